@@ -1,0 +1,254 @@
+/*
+ * cgasm.h -- C ABI of the B200-native continuous-Galerkin element assembly.
+ *
+ * One call into this library replaces one element loop of the reference:
+ *
+ *   cgasm_momentum  <->  assemble/Momentum_CG.F90:726-752  (colour loop around
+ *                        construct_momentum_element_cg, :1193-1490)
+ *   cgasm_advdiff   <->  assemble/Advection_Diffusion_CG.F90:574-598 (colour loop
+ *                        around assemble_advection_diffusion_element_cg, :702-865)
+ *
+ * Conventions follow the reference's own Fortran<->C seams (integer handle + flat
+ * arrays + integer status, femtools/Node_Owner_Finder_Fortran.F90:61-98):
+ *   - every pointer argument is HOST memory owned by the caller unless the name ends
+ *     in _dev;
+ *   - integers are 32-bit and indices are 1-BASED exactly as Fortran holds them
+ *     (mesh%ndglno, findrm, colm, halo send/receive lists);
+ *   - reals are FP64; vector fields are val(dim, nodes), tensor fields
+ *     val(dim, dim, nodes), column-major (femtools/Fields_Data_Types.F90:154-233);
+ *   - every function returns 0 on success or a CGASM_E* code; the library never aborts
+ *     (the Fortran side decides to FLAbort) and never falls back to a CPU path.
+ *
+ * All work of one handle is issued on one CUDA stream of one device.
+ */
+#ifndef CGASM_H
+#define CGASM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes ------------------------------------------------------------ */
+enum {
+  CGASM_OK = 0,
+  CGASM_EHANDLE = 1,     /* unknown / destroyed handle                              */
+  CGASM_EARG = 2,        /* invalid argument (bad dim, null pointer, bad index ...) */
+  CGASM_EUNSUPPORTED = 3,/* option combination outside the device path: caller must */
+                         /* keep the Fortran loop for this assembly                 */
+  CGASM_ESTATE = 4,      /* call order violated (e.g. assemble before coordinates)  */
+  CGASM_ECUDA = 5,       /* CUDA runtime error (cgasm_last_error has the text)      */
+  CGASM_ENCCL = 6,       /* NCCL error                                              */
+  CGASM_ENODEVICE = 7    /* no usable sm_100 device                                 */
+};
+
+/* ---- field slots (cgasm_set_field) ---------------------------------------------
+ * Names are the dummy arguments of construct_momentum_element_cg
+ * (Momentum_CG.F90:1193-1203) and assemble_advection_diffusion_element_cg
+ * (Advection_Diffusion_CG.F90:702-706). */
+enum {
+  CGASM_F_NU = 0,          /* vector: nonlinear (advecting) velocity; the tracer's      */
+                           /*         `velocity` is the same NonlinearVelocity field    */
+  CGASM_F_OLDU = 1,        /* vector: old velocity                                      */
+  CGASM_F_DENSITY = 2,     /* scalar                                                    */
+  CGASM_F_VISCOSITY = 3,   /* tensor                                                    */
+  CGASM_F_BUOYANCY = 4,    /* scalar                                                    */
+  CGASM_F_HB_DENSITY = 5,  /* scalar (subtract_out_reference_profile)                   */
+  CGASM_F_GRAVITY = 6,     /* vector: gravity direction                                 */
+  CGASM_F_ABSORPTION = 7,  /* vector                                                    */
+  CGASM_F_SOURCE = 8,      /* vector                                                    */
+  CGASM_F_T = 9,           /* scalar: tracer                                            */
+  CGASM_F_T_DIFFUSIVITY = 10, /* tensor                                                 */
+  CGASM_F_T_SOURCE = 11,   /* scalar                                                    */
+  CGASM_F_T_ABSORPTION = 12,  /* scalar                                                 */
+  CGASM_F_NSLOTS = 13
+};
+
+/* field_type, femtools/Fields_Data_Types.F90 (FIELD_TYPE_NORMAL / _CONSTANT) */
+enum { CGASM_FIELD_NORMAL = 0, CGASM_FIELD_CONSTANT = 1 };
+
+/* stabilisation_scheme, assemble/Upwind_Stabilisation.F90 + Momentum_CG.F90:118 */
+enum { CGASM_STAB_NONE = 0, CGASM_STAB_STREAMLINE_UPWIND = 1, CGASM_STAB_SUPG = 2 };
+/* nu_bar_scheme, assemble/Upwind_Stabilisation.F90:47-48 */
+enum { CGASM_NU_BAR_OPTIMAL = 1, CGASM_NU_BAR_DOUBLY_ASYMPTOTIC = 2,
+       CGASM_NU_BAR_CRITICAL_RULE = 3, CGASM_NU_BAR_UNITY = 4 };
+/* viscosity / diffusivity tensor shape, femtools/Field_Options.F90:1062-1088 */
+enum { CGASM_TENSOR_ISOTROPIC = 0, CGASM_TENSOR_DIAGONAL = 1, CGASM_TENSOR_FULL = 2 };
+
+/* how local contributions reach the CSR values (all give the same sums up to FP64
+ * summation order; north-star asks for the variants to be compared) */
+enum {
+  CGASM_SCATTER_ATOMIC = 0,   /* one thread per element, red.global.add.f64             */
+  CGASM_SCATTER_COLOURED = 1, /* femtools/Colouring.F90 colours, plain stores           */
+  CGASM_SCATTER_WARPAGG = 2,  /* warp-aggregated atomics (match.any on the slot)        */
+  CGASM_SCATTER_TILED = 3     /* node-tile owner-computes, shared-memory accumulate,    */
+                              /* every CSR value written exactly once (default)         */
+};
+
+/* ---- option structs: the module-level switches read once per assembly ----------
+ * Momentum_CG.F90:83-178 (declarations), :335-669 (population). int = Fortran logical. */
+typedef struct cgasm_momentum_opts {
+  double dt;
+  double theta;
+  double beta;                 /* conservative_advection                             */
+  double gravity_magnitude;
+  double nu_bar_scale;
+  int lump_mass;
+  int exclude_mass;
+  int exclude_advection;
+  int integrate_advection_by_parts;
+  int have_source;
+  int lump_source;
+  int have_gravity;
+  int subtract_out_reference_profile;
+  int have_absorption;
+  int lump_absorption;
+  int pressure_corrected_absorption;
+  int have_viscosity;
+  int viscosity_shape;         /* CGASM_TENSOR_*                                     */
+  int assemble_inverse_masslump;
+  int assemble_ct_matrix_here;
+  int stabilisation_scheme;    /* CGASM_STAB_*                                       */
+  int nu_bar_scheme;           /* CGASM_NU_BAR_*                                     */
+  /* switches the device path does NOT implement; any non-zero => CGASM_EUNSUPPORTED
+   * (Momentum_CG.F90 names): */
+  int have_les, multiphase, on_sphere, move_mesh, have_coriolis,
+      have_geostrophic_pressure, have_surfacetension, have_vertical_stabilization,
+      have_swe_bottom_drag, have_wd_abs, have_temperature_dependent_viscosity,
+      stress_form, partial_stress_form, radial_gravity, vel_lump_on_submesh,
+      cmc_lump_on_submesh, abs_lump_on_submesh, assemble_mass_matrix,
+      integrate_continuity_by_parts;
+} cgasm_momentum_opts;
+
+/* Advection_Diffusion_CG.F90:77-123 (declarations), :384-556 (population). */
+typedef struct cgasm_advdiff_opts {
+  double dt;
+  double theta;
+  double beta;
+  double nu_bar_scale;
+  int have_mass;
+  int lump_mass;
+  int have_advection;
+  int integrate_advection_by_parts;
+  int have_source;             /* and not add_src_directly_to_rhs                     */
+  int have_absorption;
+  int have_diffusivity;
+  int diffusivity_shape;       /* CGASM_TENSOR_ISOTROPIC or CGASM_TENSOR_FULL         */
+  int stabilisation_scheme;
+  int nu_bar_scheme;
+  /* unsupported on the device path => CGASM_EUNSUPPORTED */
+  int move_mesh, multiphase, equation_type_not_advdiff;
+} cgasm_advdiff_opts;
+
+/* ---- lifecycle ------------------------------------------------------------------- */
+
+/* Copies the P1 simplex mesh and the reference-element tables to the device.
+ * ndglno: mesh%ndglno, loc*n_elements, 1-based (femtools/Fields_Data_Types.F90:59-100).
+ * n(loc,ngi), dn(loc,ngi,dim), weight(ngi): element_type tables, column-major
+ * (femtools/Elements.F90:38-65). Only loc == dim+1 (P1) with dim in {2,3} is accepted.
+ * device < 0 selects the current CUDA device. */
+int cgasm_create(int* id, int device, int dim, int loc, int ngi, int n_nodes, int n_elements,
+                 const int* ndglno, const double* n, const double* dn, const double* weight);
+
+/* Frees every device and host resource of the handle. */
+int cgasm_destroy(int id);
+
+/* Text of the last error raised on this host thread (never NULL). */
+const char* cgasm_last_error(void);
+
+/* (Re)uploads Coordinate%val(dim, n_nodes); call again when X%refcount%id or
+ * EVENT_MESH_MOVEMENT changes (femtools/Transform_elements.F90:131-168). */
+int cgasm_set_coordinates(int id, const double* X);
+
+/* ---- sparsity (femtools/Sparsity_Patterns.F90:47-85,299-428) ----------------------- */
+
+/* Builds the first-order node-node sparsity of the mesh on its own. *nnz out. */
+int cgasm_build_sparsity(int id, int* nnz);
+/* Copies it out for the bit-exact comparison with the reference: findrm(n_nodes+1),
+ * colm(nnz), centrm(n_nodes), all 1-based (centrm as lists2csr_sparsity, :412-426). */
+int cgasm_get_sparsity(int id, int* findrm, int* colm, int* centrm);
+/* Alternatively adopt the reference-built pattern (must have sorted rows). */
+int cgasm_set_sparsity(int id, int rows, int nnz, const int* findrm, const int* colm);
+
+/* ---- colouring (femtools/Colouring.F90:85-199,250-262) ---------------------------- */
+
+/* Greedy CG1 element colouring built internally (used by CGASM_SCATTER_COLOURED). */
+int cgasm_build_colouring(int id, int* ncolours);
+/* colour_ptr(ncolours+1) (1-based offsets into colour_elements), colour_elements(n_elements)
+ * (1-based element ids ascending inside a colour == fetch(colours(clr), nnid)). */
+int cgasm_get_colouring(int id, int* colour_ptr, int* colour_elements);
+int cgasm_set_colouring(int id, int ncolours, const int* colour_ptr, const int* colour_elements);
+
+/* Selects CGASM_SCATTER_*; builds whatever plan that variant needs. */
+int cgasm_set_scatter(int id, int variant);
+
+/* ---- fields ------------------------------------------------------------------------- */
+
+/* rank 0/1/2 = scalar/vector/tensor; field_type CGASM_FIELD_*; n_val_nodes = n_nodes for a
+ * NORMAL field, 1 for a CONSTANT one (preprocessor/Populate_State.F90:1678-1724). */
+int cgasm_set_field(int id, int slot, int rank, int field_type, const double* val,
+                    int n_val_nodes);
+/* Reads a resident field back (used after cgasm_halo_update). */
+int cgasm_get_field(int id, int slot, double* val, int n_val_nodes);
+
+/* ---- the two element loops --------------------------------------------------------------
+ * Outputs are OVERWRITTEN with the assembled sums (the reference zeroes them just before
+ * the loop: Momentum_Equation.F90:593-606, Advection_Diffusion_CG.F90:560-561).
+ *
+ * big_m: dim diagonal blocks, block d (0-based) at big_m[d*nnz .. (d+1)*nnz), entries in the
+ *        order of colm -- the val(d,d)%ptr arrays of a block_csr_matrix
+ *        (femtools/Sparse_Tools.F90:117-155); the Fortran shim inserts them into the
+ *        petsc_csr_matrix row-wise.
+ * rhs(dim, n_nodes); masslump(dim, n_nodes) or NULL; ct_m: dim blocks (1,d) of nnz, or NULL.
+ */
+int cgasm_momentum(int id, const cgasm_momentum_opts* opts, double* big_m, double* rhs,
+                   double* masslump, double* ct_m);
+int cgasm_advdiff(int id, const cgasm_advdiff_opts* opts, double* matrix_val, double* rhs);
+
+/* Device-resident flavour: assemble into the handle's own device buffers and return without
+ * copying (this is what stays on the GPU between the loop and a device-side consumer).
+ * The *_fetch calls copy the last result to host buffers. */
+int cgasm_momentum_dev(int id, const cgasm_momentum_opts* opts);
+int cgasm_advdiff_dev(int id, const cgasm_advdiff_opts* opts);
+int cgasm_momentum_fetch(int id, double* big_m, double* rhs, double* masslump, double* ct_m);
+int cgasm_advdiff_fetch(int id, double* matrix_val, double* rhs);
+/* Raw device pointers of the last result (NULL if that output was not assembled). */
+int cgasm_momentum_result_dev(int id, double** big_m_dev, double** rhs_dev,
+                              double** masslump_dev, double** ct_m_dev);
+int cgasm_advdiff_result_dev(int id, double** matrix_dev, double** rhs_dev);
+
+/* Single element, for element-matrix parity checks: big_m_tensor_addto(dim,dim,loc,loc) with
+ * the lumped diagonal already folded in (Momentum_CG.F90:1462), rhs_addto(dim,loc),
+ * mass_lump(loc), grad_p_u_mat(dim,loc,loc); tracer matrix_addto(loc,loc), rhs_addto(loc).
+ * ele is 1-based. Computed on the device by the same code as the assembly kernels. */
+int cgasm_momentum_element(int id, const cgasm_momentum_opts* opts, int ele,
+                           double* big_m_tensor_addto, double* rhs_addto, double* mass_lump,
+                           double* grad_p_u_mat);
+int cgasm_advdiff_element(int id, const cgasm_advdiff_opts* opts, int ele,
+                          double* matrix_addto, double* rhs_addto);
+
+/* Blocks until everything queued on the handle's stream has finished. */
+int cgasm_synchronize(int id);
+/* The handle's cudaStream_t (as void*), so callers can record events on it. */
+int cgasm_stream(int id, void** stream);
+/* Number of CUDA kernels this library has launched on the handle so far. */
+int cgasm_launch_count(int id, long long* launches);
+/* Device time in ms of the most recent cgasm_*_dev call (CUDA events on the handle stream). */
+int cgasm_last_kernel_ms(int id, float* ms);
+
+/* ---- halo update (femtools/Halos_Communications.F90:320-412,497-567) -------------------
+ * nprocs neighbours; sends/recvs are the concatenated 1-based node lists of
+ * halo%sends(p) / halo%receives(p), nsend/nrecv their lengths per process p = 0..nprocs-1
+ * (entry for p == rank is 0). nccl_unique_id: the 128-byte ncclUniqueId made by rank 0. */
+int cgasm_halo_create(int id, int nprocs, int rank, const int* nsend, const int* sends,
+                      const int* nrecv, const int* recvs, const void* nccl_unique_id);
+/* Fills 128 bytes with a fresh ncclUniqueId (call on one rank, broadcast by the host). */
+int cgasm_nccl_unique_id(void* out128);
+/* halo_update of the resident fields whose bit (1 << slot) is set, in place, one NCCL group. */
+int cgasm_halo_update(int id, unsigned slot_mask);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CGASM_H */

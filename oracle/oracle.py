@@ -1,0 +1,275 @@
+"""ctypes wrapper of oracle/liborc.so (cg_oracle.c).
+
+TEST INFRASTRUCTURE ONLY -- see the header of cg_oracle.c. Imported by tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs; never by the
+product package.
+"""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+from fluidity_b200 import _abi as abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+c_dp = C.POINTER(C.c_double)
+c_ip = C.POINTER(C.c_int)
+
+
+def build():
+    """Compiles liborc.so with the committed Makefile (gcc; seconds)."""
+    subprocess.run(["make", "-s", "-C", _HERE], check=True)
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(_HERE, "liborc.so")
+        src = os.path.join(_HERE, "cg_oracle.c")
+        if not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(src):
+            build()
+        _LIB = C.CDLL(path)
+        _LIB.orc_make_sparsity.restype = C.c_int
+        _LIB.orc_colour_elements.restype = C.c_int
+    return _LIB
+
+
+def _dp(a):
+    return a.ctypes.data_as(c_dp) if a is not None else None
+
+
+def _ip(a):
+    return a.ctypes.data_as(c_ip) if a is not None else None
+
+
+class _Field(C.Structure):
+    _fields_ = [("val", c_dp), ("field_type", C.c_int)]
+
+
+class _Mesh(C.Structure):
+    _fields_ = [("dim", C.c_int), ("loc", C.c_int), ("ngi", C.c_int), ("n_nodes", C.c_int),
+                ("n_elements", C.c_int), ("ndglno", c_ip), ("n", c_dp), ("dn", c_dp),
+                ("weight", c_dp), ("X", c_dp)]
+
+
+class _MomFields(C.Structure):
+    _fields_ = [(k, _Field) for k in ("nu", "oldu", "density", "viscosity", "buoyancy",
+                                     "hb_density", "gravity", "absorption", "source")]
+
+
+class _AdvFields(C.Structure):
+    _fields_ = [(k, _Field) for k in ("t", "velocity", "source", "absorption", "diffusivity")]
+
+
+_MOM_SLOTS = {"nu": abi.F_NU, "oldu": abi.F_OLDU, "density": abi.F_DENSITY,
+              "viscosity": abi.F_VISCOSITY, "buoyancy": abi.F_BUOYANCY,
+              "hb_density": abi.F_HB_DENSITY, "gravity": abi.F_GRAVITY,
+              "absorption": abi.F_ABSORPTION, "source": abi.F_SOURCE}
+_ADV_SLOTS = {"t": abi.F_T, "velocity": abi.F_NU, "source": abi.F_T_SOURCE,
+              "absorption": abi.F_T_ABSORPTION, "diffusivity": abi.F_T_DIFFUSIVITY}
+
+
+def quadrature(dim):
+    """(l (ngi, loc), weight (ngi)) of the degree-3 rule."""
+    loc = dim + 1
+    l = np.zeros((loc, 5), dtype=np.float64)  # column-major (ngi, loc) with ngi<=5
+    w = np.zeros(5)
+    ngi = 5 if dim == 3 else 4
+    lbuf = np.zeros(ngi * loc)
+    lib().orc_quadrature_degree3(C.c_int(dim), _dp(lbuf), _dp(w))
+    l = lbuf.reshape(loc, ngi).T.copy()  # l[g, j]
+    return l, w[:ngi].copy()
+
+
+def tables(dim):
+    """P1 tables in the raw column-major buffers the C ABI takes:
+    n (loc*ngi), dn (loc*ngi*dim), weight (ngi)."""
+    loc = dim + 1
+    l, w = quadrature(dim)
+    ngi = len(w)
+    lbuf = np.ascontiguousarray(l.T).ravel()  # l[g + ngi*j]
+    n = np.zeros(loc * ngi)
+    dn = np.zeros(loc * ngi * dim)
+    lib().orc_shape_p1(C.c_int(dim), C.c_int(ngi), _dp(lbuf), _dp(n), _dp(dn))
+    return n, dn, w
+
+
+def transform_to_physical(dim, X_val, want_J=False):
+    """X_val (loc, dim) rows = node positions. Returns dshape (loc, ngi, dim), detwei, J."""
+    loc = dim + 1
+    n, dn, w = tables(dim)
+    ngi = len(w)
+    Xv = np.ascontiguousarray(X_val, dtype=np.float64)  # memory = X_val(dim, loc) col-major
+    dshape = np.zeros(loc * ngi * dim)
+    detwei = np.zeros(ngi)
+    J = np.zeros(dim * dim * ngi) if want_J else None
+    lib().orc_transform_to_physical(C.c_int(dim), C.c_int(ngi), _dp(Xv), _dp(dn), _dp(w),
+                                    _dp(dshape), _dp(detwei), _dp(J))
+    ds = dshape.reshape(dim, ngi, loc).transpose(2, 1, 0).copy()
+    Jm = J.reshape(ngi, dim, dim).transpose(2, 1, 0).copy() if want_J else None  # J[a,k,g]
+    return ds, detwei, Jm
+
+
+def make_sparsity(mesh):
+    """findrm (n+1), colm (nnz), centrm (n): 1-based, as lists2csr_sparsity builds them."""
+    f, c, ce = c_ip(), c_ip(), c_ip()
+    nd = np.ascontiguousarray(mesh.ndglno, dtype=np.int32)
+    nnz = lib().orc_make_sparsity(C.c_int(mesh.n_nodes), C.c_int(mesh.n_elements),
+                                  C.c_int(mesh.loc), _ip(nd), C.byref(f), C.byref(c), C.byref(ce))
+    findrm = np.ctypeslib.as_array(f, shape=(mesh.n_nodes + 1,)).copy()
+    colm = np.ctypeslib.as_array(c, shape=(max(nnz, 1),)).copy()[:nnz]
+    centrm = np.ctypeslib.as_array(ce, shape=(mesh.n_nodes,)).copy()
+    for p in (f, c, ce):
+        lib().orc_free(p)
+    return findrm, colm, centrm
+
+
+def colour_elements(mesh):
+    """(colour_of (n_elements) 1-based colours, ncolours)."""
+    nd = np.ascontiguousarray(mesh.ndglno, dtype=np.int32)
+    col = np.zeros(mesh.n_elements, dtype=np.int32)
+    nc = lib().orc_colour_elements(C.c_int(mesh.n_nodes), C.c_int(mesh.n_elements),
+                                   C.c_int(mesh.loc), _ip(nd), _ip(col))
+    return col, nc
+
+
+def colour_sets(colour_of, ncolours):
+    """colour_sets (femtools/Colouring.F90:250-262): colour_ptr (ncolours+1, 1-based offsets),
+    colour_elements (1-based ids ascending inside each colour)."""
+    order = np.argsort(colour_of, kind="stable").astype(np.int32)
+    counts = np.bincount(colour_of, minlength=ncolours + 1)[1:]
+    ptr = np.concatenate([[1], 1 + np.cumsum(counts)]).astype(np.int32)
+    return ptr, (order + 1).astype(np.int32)
+
+
+class _Ctx:
+    """Keeps numpy buffers alive while C structs point at them."""
+
+    def __init__(self, mesh, fields):
+        self.keep = []
+        dim = mesh.dim
+        n, dn, w = tables(dim)
+        nd = np.ascontiguousarray(mesh.ndglno, dtype=np.int32)
+        X = np.ascontiguousarray(mesh.X, dtype=np.float64)
+        self.keep += [n, dn, w, nd, X]
+        self.mesh = _Mesh(dim, dim + 1, len(w), mesh.n_nodes, mesh.n_elements, _ip(nd), _dp(n),
+                          _dp(dn), _dp(w), _dp(X))
+        self.fields = fields
+
+    def _field(self, slot):
+        if slot not in self.fields.data:
+            return _Field(None, 0)
+        val, ft = self.fields.get(slot)
+        self.keep.append(val)
+        return _Field(_dp(val), ft)
+
+    def mom(self):
+        return _MomFields(*[self._field(_MOM_SLOTS[k]) for k, _ in _MomFields._fields_])
+
+    def adv(self):
+        return _AdvFields(*[self._field(_ADV_SLOTS[k]) for k, _ in _AdvFields._fields_])
+
+
+def momentum_element(mesh, fields, opts, ele):
+    """Returns big_m_tensor_addto (dim,dim,loc,loc), rhs_addto (dim,loc), masslump_addto
+    (dim,loc), grad_p_u_mat (dim,loc,loc) as numpy arrays indexed like the Fortran ones."""
+    ctx = _Ctx(mesh, fields)
+    dim, loc = mesh.dim, mesh.loc
+    T = np.zeros(dim * dim * loc * loc)
+    r = np.zeros(dim * loc)
+    ml = np.zeros(dim * loc)
+    gp = np.zeros(dim * loc * loc)
+    mf = ctx.mom()
+    st = lib().orc_momentum_element(C.byref(ctx.mesh), C.byref(mf), C.byref(opts), C.c_int(ele),
+                                    _dp(T), _dp(r), _dp(ml), _dp(gp))
+    if st:
+        raise RuntimeError("oracle status %d" % st)
+    return (T.reshape(loc, loc, dim, dim).transpose(3, 2, 1, 0).copy(),
+            r.reshape(loc, dim).T.copy(), ml.reshape(loc, dim).T.copy(),
+            gp.reshape(loc, loc, dim).transpose(2, 1, 0).copy())
+
+
+def advdiff_element(mesh, fields, opts, ele):
+    ctx = _Ctx(mesh, fields)
+    loc = mesh.loc
+    A = np.zeros(loc * loc)
+    r = np.zeros(loc)
+    af = ctx.adv()
+    st = lib().orc_advdiff_element(C.byref(ctx.mesh), C.byref(af), C.byref(opts), C.c_int(ele),
+                                   _dp(A), _dp(r))
+    if st:
+        raise RuntimeError("oracle status %d" % st)
+    return A.reshape(loc, loc).T.copy(), r
+
+
+def assemble_momentum(mesh, fields, opts, findrm, colm, colouring=None, want_masslump=True,
+                      want_ct=False):
+    """Serial reference order unless colouring=(colour_ptr, colour_elements) is given (then
+    OpenMP over each colour like the reference). Returns dict of big_m (dim, nnz), rhs
+    (n_nodes, dim), masslump (n_nodes, dim) | None, ct_m (dim, nnz) | None."""
+    ctx = _Ctx(mesh, fields)
+    dim = mesh.dim
+    nnz = int(findrm[-1] - 1)
+    big_m = np.zeros((dim, nnz))
+    rhs = np.zeros((mesh.n_nodes, dim))
+    ml = np.zeros((mesh.n_nodes, dim)) if want_masslump else None
+    ct = np.zeros((dim, nnz)) if want_ct else None
+    findrm = np.ascontiguousarray(findrm, dtype=np.int32)
+    colm = np.ascontiguousarray(colm, dtype=np.int32)
+    if colouring is not None:
+        cptr = np.ascontiguousarray(colouring[0], dtype=np.int32)
+        cel = np.ascontiguousarray(colouring[1], dtype=np.int32)
+        nc = len(cptr) - 1
+    else:
+        cptr = cel = None
+        nc = 0
+    mf = ctx.mom()
+    st = lib().orc_assemble_momentum(C.byref(ctx.mesh), C.byref(mf), C.byref(opts), _ip(findrm),
+                                     _ip(colm), C.c_int(nc), _ip(cptr), _ip(cel), _dp(big_m),
+                                     _dp(rhs), _dp(ml), _dp(ct))
+    if st:
+        raise RuntimeError("oracle status %d" % st)
+    return dict(big_m=big_m, rhs=rhs, masslump=ml, ct_m=ct)
+
+
+def assemble_advdiff(mesh, fields, opts, findrm, colm, colouring=None):
+    ctx = _Ctx(mesh, fields)
+    nnz = int(findrm[-1] - 1)
+    val = np.zeros(nnz)
+    rhs = np.zeros(mesh.n_nodes)
+    findrm = np.ascontiguousarray(findrm, dtype=np.int32)
+    colm = np.ascontiguousarray(colm, dtype=np.int32)
+    if colouring is not None:
+        cptr = np.ascontiguousarray(colouring[0], dtype=np.int32)
+        cel = np.ascontiguousarray(colouring[1], dtype=np.int32)
+        nc = len(cptr) - 1
+    else:
+        cptr = cel = None
+        nc = 0
+    af = ctx.adv()
+    st = lib().orc_assemble_advdiff(C.byref(ctx.mesh), C.byref(af), C.byref(opts), _ip(findrm),
+                                    _ip(colm), C.c_int(nc), _ip(cptr), _ip(cel), _dp(val), _dp(rhs))
+    if st:
+        raise RuntimeError("oracle status %d" % st)
+    return dict(matrix=val, rhs=rhs)
+
+
+def block_addto(findrm, colm, rows, cols, vals, val):
+    """Accumulates vals (nrows, ncols) at (rows, cols) (1-based) into val in place."""
+    findrm = np.ascontiguousarray(findrm, dtype=np.int32)
+    colm = np.ascontiguousarray(colm, dtype=np.int32)
+    rows = np.ascontiguousarray(rows, dtype=np.int32)
+    cols = np.ascontiguousarray(cols, dtype=np.int32)
+    v = np.asfortranarray(vals, dtype=np.float64)
+    lib().orc_block_addto(_ip(findrm), _ip(colm), C.c_int(len(rows)), _ip(rows), C.c_int(len(cols)),
+                          _ip(cols), v.ctypes.data_as(c_dp), _dp(val))
+
+
+def halo_copy(block_size, field_p, sends_p_to_q, field_q, recvs_q_from_p):
+    s = np.ascontiguousarray(sends_p_to_q, dtype=np.int32)
+    r = np.ascontiguousarray(recvs_q_from_p, dtype=np.int32)
+    assert len(s) == len(r)
+    lib().orc_halo_copy(C.c_int(block_size), _dp(field_p), _ip(s), C.c_int(len(s)), _dp(field_q),
+                        _ip(r))
