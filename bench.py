@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""bench.py -- CG momentum + tracer element assembly throughput (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--cells C]
+
+A step = one pass of the hot path over the mesh: the momentum element loop
+(assemble/Momentum_CG.F90:726-752) followed by the tracer element loop
+(assemble/Advection_Diffusion_CG.F90:574-598) with the common option set of the four example
+configs. Workload at N=1: S3 = 256^3 x 6 = 100 663 296 Kuhn tets; at N>1
+every rank holds its own 256^3-cell slab partition (weak scaling), exchanges the halo of
+nu / oldu / T / density / buoyancy with NCCL p2p (cgasm_halo_update) and assembles all local
+elements, exactly like the reference's MPI ranks.
+
+value  = elements assembled by all ranks / device time, inputs resident in HBM.
+e2e    = same through the host-buffer C-ABI calls cgasm_set_field / cgasm_momentum /
+         cgasm_advdiff: per step the changing fields go host->device from pinned memory
+         and every assembled array comes back device->host.
+--impl reference times the CPU restatement of the reference loops (oracle/, OpenMP over the
+reference's own colouring, all host threads) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "CG momentum+tracer assembly Melements/s (whole job)"
+UNIT = "Melements/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="graft", choices=["graft", "reference"])
+    ap.add_argument("--cells", type=int, default=256, help="cells per axis per GPU (256 = S3)")
+    ap.add_argument("--scatter", default="best", choices=["best", "atomic", "coloured", "warpagg", "tiled"])
+    ap.add_argument("--cpu-cells", type=int, default=64, help="cells per axis of the CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ---- clocks sampling (B200_PROFILING.md) ------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1]))
+                smax = float(p[2])
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if p[5 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---- reference arm / cpu baseline ------------------------------------------------------------------
+def cpu_assembly_rate(cells, steps, warmup):
+    """Times the oracle port (OpenMP, reference colouring) on a cells^3 x 6 sample.
+    Returns (Melements/s, threads, ms_per_step, n_elements)."""
+    from fluidity_b200 import synthetic as syn, _abi as abi
+    from oracle import oracle as orc
+    mesh = syn.box_mesh((cells,) * 3)
+    fs = syn.standard_fields(mesh)
+    findrm, colm, _ = orc.make_sparsity(mesh)
+    col, nc = orc.colour_elements(mesh)
+    sets = orc.colour_sets(col, nc)
+    om, oa = abi.common_momentum_opts(), abi.common_advdiff_opts()
+    threads = len(os.sched_getaffinity(0))
+    os.environ.setdefault("OMP_NUM_THREADS", str(threads))
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        orc.assemble_momentum(mesh, fs, om, findrm, colm, colouring=sets)
+        orc.assemble_advdiff(mesh, fs, oa, findrm, colm, colouring=sets)
+        t1 = time.perf_counter()
+        if it >= warmup:
+            times.append(t1 - t0)
+    ms = 1e3 * float(np.mean(times))
+    return mesh.n_elements / (ms * 1e-3) / 1e6, threads, ms, mesh.n_elements
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cells = args.cpu_cells
+    rate, threads, ms, ne = cpu_assembly_rate(cells, max(1, args.steps), max(0, min(args.warmup, 1)))
+    sample = "%d^3 x 6 = %d Kuhn tets per step (bounded sample of S3), OpenMP over the reference greedy colouring" % (cells, ne)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, args.gpus),
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "reference is Fortran+PETSc and cannot be built in this image; this is the C restatement (oracle/) of its element loops",
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(args, n):
+    c = args.cells
+    return {"workload": "S3: %d^3 x 6 Kuhn tets per GPU (%d elements/GPU), P1, degree-3 quadrature, "
+                        "momentum (lumped mass, advection, isotropic viscosity, buoyancy, inverse lumped mass) "
+                        "+ tracer (consistent mass, advection, isotropic diffusivity)" % (c, 6 * c ** 3),
+            "cells_per_axis_per_gpu": c, "partition": "slab along z, one partition per GPU, L1+L2 halos" if n > 1 else "single partition",
+            "l2_policy": "inputs+outputs per step (>8 GB at S3) exceed the 126 MB L2; no explicit flush",
+            "parallelism": "dp%d" % n}
+
+
+# ---- graft arm --------------------------------------------------------------------------------------
+def run_graft(args):
+    import torch
+    import torch.distributed as dist
+    from fluidity_b200 import _abi as abi, cgasm, tables, partition as part, synthetic as syn
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE %d" % (args.gpus, world))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: libcgasm has no CPU path")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    c = args.cells
+    t_setup = time.perf_counter()
+    lp = part.slab_partition((c, c, c * world), world, rank)
+    mesh = lp.mesh
+    F = part.global_nodal_fields(3, mesh.X, lp.global_node)
+    asm = cgasm.Assembler(mesh, tables.p1_tables(3), device=local_rank)
+    nnz = asm.build_sparsity()
+    g = np.zeros((1, 3)); g[0, 2] = -1.0
+    asm.set_field(abi.F_GRAVITY, g, abi.FIELD_CONSTANT)
+    asm.set_field(abi.F_VISCOSITY, syn.iso_tensor(3, 1e-3), abi.FIELD_CONSTANT)
+    asm.set_field(abi.F_T_DIFFUSIVITY, syn.iso_tensor(3, 1e-3), abi.FIELD_CONSTANT)
+    dyn = [(abi.F_NU, F["nu"]), (abi.F_OLDU, F["oldu"]), (abi.F_DENSITY, F["density"]),
+           (abi.F_BUOYANCY, F["buoyancy"]), (abi.F_T, F["t"])]
+    if world > 1:
+        # ranks only know their owned values; the halo arrives through cgasm_halo_update
+        for _, a in dyn:
+            a[lp.n_owned:] = 0.0
+    for slot, a in dyn:
+        asm.set_field(slot, a)
+    halo_slots = [s for s, _ in dyn]
+    if world > 1:
+        uid = [cgasm.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        asm.halo_create(world, rank, lp.sends, lp.recvs, uid[0])
+    scatter = {"atomic": abi.SCATTER_ATOMIC, "coloured": abi.SCATTER_COLOURED, "warpagg": abi.SCATTER_WARPAGG,
+               "tiled": abi.SCATTER_TILED}
+    chosen = args.scatter
+    if chosen == "best":
+        try:
+            asm.set_scatter(abi.SCATTER_TILED)
+            chosen = "tiled"
+        except cgasm.CgasmError:
+            asm.set_scatter(abi.SCATTER_ATOMIC)
+            chosen = "atomic"
+    else:
+        asm.set_scatter(scatter[chosen])
+    om, oa = abi.common_momentum_opts(), abi.common_advdiff_opts()
+    setup_s = time.perf_counter() - t_setup
+
+    stream = torch.cuda.ExternalStream(asm.stream(), device=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        if world > 1:
+            asm.halo_update(halo_slots)
+        asm.momentum_dev(om)
+        asm.advdiff_dev(oa)
+
+    # ---- value: inputs resident in HBM ---------------------------------------------------
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = asm.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    mom_ms, adv_ms = [], []
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step_resident()
+    ev1.record(stream)
+    barrier()
+    total_ms = ev0.elapsed_time(ev1)
+    launches = asm.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    # per-kernel device times (separate pass so the event queries do not perturb the timed region)
+    for _ in range(max(3, min(args.steps, 5))):
+        if world > 1:
+            asm.halo_update(halo_slots)
+        asm.momentum_dev(om)
+        mom_ms.append(asm.last_kernel_ms())
+        asm.advdiff_dev(oa)
+        adv_ms.append(asm.last_kernel_ms())
+    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    n_el_local = mesh.n_elements
+    tot_el = torch.tensor([float(n_el_local)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tot_el, op=dist.ReduceOp.SUM)
+    total_elements = float(tot_el.item())
+    value = total_elements / (ms_per_step * 1e-3) / 1e6
+
+    # ---- e2e: host buffers through the C-ABI calls --------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        def pinned(shape):
+            return torch.empty(shape, dtype=torch.float64, pin_memory=True).numpy()
+        host_in = []
+        for slot, a in dyn:
+            b = pinned(a.shape)
+            b[...] = a
+            host_in.append((slot, b))
+        out_m = dict(big_m=pinned((3, nnz)), rhs=pinned((mesh.n_nodes, 3)), masslump=pinned((mesh.n_nodes, 3)))
+        out_a = dict(matrix=pinned((nnz,)), rhs=pinned((mesh.n_nodes,)))
+        h2d = sum(b.nbytes for _, b in host_in)
+        d2h = sum(v.nbytes for v in out_m.values()) + sum(v.nbytes for v in out_a.values())
+
+        def step_e2e():
+            for slot, b in host_in:
+                asm.set_field(slot, b)
+            if world > 1:
+                asm.halo_update(halo_slots)
+            asm.momentum(om, out=out_m)
+            asm.advdiff(oa, out=out_a)
+
+        n_e2e = max(2, min(args.steps, 3))
+        step_e2e()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            step_e2e()
+        barrier()
+        dt = torch.tensor([(time.perf_counter() - t0) / n_e2e], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": total_elements / float(dt.item()) / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * float(dt.item()), "steps": n_e2e,
+               "checksum": float(out_a["rhs"][: lp.n_owned].sum())}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel (momentum) -------------------------------------------
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except OSError:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    bytes_mom = syn.algorithmic_bytes(3, mesh.n_nodes, mesh.n_elements, nnz, "momentum")
+    bytes_tra = syn.algorithmic_bytes(3, mesh.n_nodes, mesh.n_elements, nnz, "tracer")
+    m_ms, a_ms = float(np.mean(mom_ms)), float(np.mean(adv_ms))
+    ach = bytes_mom * mesh.n_elements / (m_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "momentum assembly (%s scatter)" % chosen, "achieved": ach, "peak": peak,
+                "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_element": bytes_mom, "kernel_ms": m_ms,
+                "frac_of_8TBs": ach / 8000.0,
+                "tracer": {"achieved": bytes_tra * mesh.n_elements / (a_ms * 1e-3) / 1e9,
+                           "algorithmic_bytes_per_element": bytes_tra, "kernel_ms": a_ms},
+                "combined_frac": (bytes_mom + bytes_tra) * mesh.n_elements / ((m_ms + a_ms) * 1e-3) / 1e9 / peak}
+
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        rate, threads, ms, ne = cpu_assembly_rate(args.cpu_cells, 3, 1)
+        cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": "%d^3 x 6 = %d Kuhn tets, 3 timed passes of momentum+tracer, OpenMP over the reference colouring (%.0f ms/pass)" % (args.cpu_cells, ne, ms)}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
+        "per_gpu_melements_s": value / world, "scatter": chosen, "setup_s": setup_s,
+        "elements_total": total_elements, "nnz_rank0": nnz, "n_nodes_rank0": mesh.n_nodes,
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_graft(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,263 @@
+"""Host-side binding of libcgasm.so (the C ABI of include/cgasm.h) for Python callers.
+
+This is the Python twin of the Fortran shim in fluidity_b200/fortran/cgasm_fortran.F90: it
+only marshals numpy buffers (already laid out like the reference's Fortran arrays, see
+synthetic.py) into the C calls. There is no computation here and no CPU path: if the
+library or a B200 is missing every call raises.
+"""
+import ctypes as C
+import os
+import numpy as np
+
+from . import _abi as abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcgasm.so")
+_lib = None
+
+c_dp = C.POINTER(C.c_double)
+c_ip = C.POINTER(C.c_int)
+
+
+class CgasmError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("cgasm error %d: %s" % (code, msg))
+        self.code = code
+
+
+def load():
+    """Loads libcgasm.so (built in-tree by fluidity_b200/csrc/Makefile). Raises if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FileNotFoundError(
+            "%s not built: run `make -C fluidity_b200/csrc` (or __graft_entry__.build()); "
+            "there is no fallback path" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    lib.cgasm_last_error.restype = C.c_char_p
+    _lib = lib
+    return lib
+
+
+def _check(st):
+    if st != 0:
+        raise CgasmError(st, load().cgasm_last_error().decode())
+
+
+def _dp(a):
+    return a.ctypes.data_as(c_dp) if a is not None else None
+
+
+def _ip(a):
+    return a.ctypes.data_as(c_ip) if a is not None else None
+
+
+def nccl_unique_id():
+    buf = C.create_string_buffer(128)
+    _check(load().cgasm_nccl_unique_id(buf))
+    return buf.raw
+
+
+class Assembler:
+    """One handle = one mesh resident on one GPU (cgasm_create ... cgasm_destroy)."""
+
+    def __init__(self, mesh, tables, device=-1):
+        """mesh: synthetic.Mesh-like (dim, ndglno (E,loc) 1-based int32, X (N,dim));
+        tables: (n, dn, weight) raw column-major element_type tables."""
+        self.lib = load()
+        self.dim, self.loc = mesh.dim, mesh.dim + 1
+        self.n_nodes, self.n_elements = mesh.n_nodes, mesh.n_elements
+        n, dn, w = tables
+        nd = np.ascontiguousarray(mesh.ndglno, dtype=np.int32)
+        ident = C.c_int(0)
+        _check(self.lib.cgasm_create(C.byref(ident), C.c_int(device), C.c_int(self.dim),
+                                     C.c_int(self.loc), C.c_int(len(w)), C.c_int(self.n_nodes),
+                                     C.c_int(self.n_elements), _ip(nd),
+                                     _dp(np.ascontiguousarray(n)), _dp(np.ascontiguousarray(dn)),
+                                     _dp(np.ascontiguousarray(w))))
+        self.id = ident.value
+        self.nnz = None
+        self.set_coordinates(mesh.X)
+
+    def close(self):
+        if getattr(self, "id", 0):
+            self.lib.cgasm_destroy(C.c_int(self.id))
+            self.id = 0
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- mesh-level state -------------------------------------------------------------
+    def set_coordinates(self, X):
+        X = np.ascontiguousarray(X, dtype=np.float64)
+        assert X.shape == (self.n_nodes, self.dim)
+        _check(self.lib.cgasm_set_coordinates(C.c_int(self.id), _dp(X)))
+
+    def build_sparsity(self):
+        nnz = C.c_int(0)
+        _check(self.lib.cgasm_build_sparsity(C.c_int(self.id), C.byref(nnz)))
+        self.nnz = nnz.value
+        return self.nnz
+
+    def get_sparsity(self):
+        findrm = np.zeros(self.n_nodes + 1, dtype=np.int32)
+        colm = np.zeros(self.nnz, dtype=np.int32)
+        centrm = np.zeros(self.n_nodes, dtype=np.int32)
+        _check(self.lib.cgasm_get_sparsity(C.c_int(self.id), _ip(findrm), _ip(colm), _ip(centrm)))
+        return findrm, colm, centrm
+
+    def set_sparsity(self, findrm, colm):
+        findrm = np.ascontiguousarray(findrm, dtype=np.int32)
+        colm = np.ascontiguousarray(colm, dtype=np.int32)
+        _check(self.lib.cgasm_set_sparsity(C.c_int(self.id), C.c_int(len(findrm) - 1),
+                                           C.c_int(len(colm)), _ip(findrm), _ip(colm)))
+        self.nnz = len(colm)
+
+    def build_colouring(self):
+        nc = C.c_int(0)
+        _check(self.lib.cgasm_build_colouring(C.c_int(self.id), C.byref(nc)))
+        return nc.value
+
+    def get_colouring(self, ncolours):
+        ptr = np.zeros(ncolours + 1, dtype=np.int32)
+        els = np.zeros(self.n_elements, dtype=np.int32)
+        _check(self.lib.cgasm_get_colouring(C.c_int(self.id), _ip(ptr), _ip(els)))
+        return ptr, els
+
+    def set_colouring(self, colour_ptr, colour_elements):
+        ptr = np.ascontiguousarray(colour_ptr, dtype=np.int32)
+        els = np.ascontiguousarray(colour_elements, dtype=np.int32)
+        _check(self.lib.cgasm_set_colouring(C.c_int(self.id), C.c_int(len(ptr) - 1), _ip(ptr), _ip(els)))
+
+    def set_scatter(self, variant):
+        _check(self.lib.cgasm_set_scatter(C.c_int(self.id), C.c_int(variant)))
+
+    # -- fields -----------------------------------------------------------------------
+    def set_field(self, slot, val, field_type=abi.FIELD_NORMAL):
+        val = np.ascontiguousarray(val, dtype=np.float64)
+        n_val_nodes = 1 if field_type == abi.FIELD_CONSTANT else self.n_nodes
+        _check(self.lib.cgasm_set_field(C.c_int(self.id), C.c_int(slot), C.c_int(abi.FIELD_RANK[slot]),
+                                        C.c_int(field_type), _dp(val), C.c_int(n_val_nodes)))
+
+    def set_fields(self, fieldset):
+        for slot, (val, ft) in fieldset.items():
+            self.set_field(slot, val, ft)
+
+    def get_field(self, slot, shape):
+        out = np.zeros(shape, dtype=np.float64)
+        _check(self.lib.cgasm_get_field(C.c_int(self.id), C.c_int(slot), _dp(out), C.c_int(shape[0])))
+        return out
+
+    # -- the two element loops ------------------------------------------------------------
+    def momentum(self, opts, out=None):
+        """Host-buffer call (what the Fortran shim makes). Returns dict of big_m (dim,nnz),
+        rhs (N,dim), masslump (N,dim)|None, ct_m (dim,nnz)|None."""
+        dim, nnz, nn = self.dim, self.nnz, self.n_nodes
+        out = out or {}
+        big_m = out.get("big_m") if out.get("big_m") is not None else np.empty((dim, nnz))
+        rhs = out.get("rhs") if out.get("rhs") is not None else np.empty((nn, dim))
+        ml = ct = None
+        if opts.assemble_inverse_masslump:
+            ml = out.get("masslump") if out.get("masslump") is not None else np.empty((nn, dim))
+        if opts.assemble_ct_matrix_here:
+            ct = out.get("ct_m") if out.get("ct_m") is not None else np.empty((dim, nnz))
+        _check(self.lib.cgasm_momentum(C.c_int(self.id), C.byref(opts), _dp(big_m), _dp(rhs), _dp(ml), _dp(ct)))
+        return dict(big_m=big_m, rhs=rhs, masslump=ml, ct_m=ct)
+
+    def advdiff(self, opts, out=None):
+        out = out or {}
+        val = out.get("matrix") if out.get("matrix") is not None else np.empty(self.nnz)
+        rhs = out.get("rhs") if out.get("rhs") is not None else np.empty(self.n_nodes)
+        _check(self.lib.cgasm_advdiff(C.c_int(self.id), C.byref(opts), _dp(val), _dp(rhs)))
+        return dict(matrix=val, rhs=rhs)
+
+    def momentum_dev(self, opts):
+        _check(self.lib.cgasm_momentum_dev(C.c_int(self.id), C.byref(opts)))
+
+    def advdiff_dev(self, opts):
+        _check(self.lib.cgasm_advdiff_dev(C.c_int(self.id), C.byref(opts)))
+
+    def momentum_fetch(self, want_masslump=True, want_ct=False):
+        dim, nnz, nn = self.dim, self.nnz, self.n_nodes
+        big_m = np.empty((dim, nnz))
+        rhs = np.empty((nn, dim))
+        ml = np.empty((nn, dim)) if want_masslump else None
+        ct = np.empty((dim, nnz)) if want_ct else None
+        _check(self.lib.cgasm_momentum_fetch(C.c_int(self.id), _dp(big_m), _dp(rhs), _dp(ml), _dp(ct)))
+        return dict(big_m=big_m, rhs=rhs, masslump=ml, ct_m=ct)
+
+    def advdiff_fetch(self):
+        val = np.empty(self.nnz)
+        rhs = np.empty(self.n_nodes)
+        _check(self.lib.cgasm_advdiff_fetch(C.c_int(self.id), _dp(val), _dp(rhs)))
+        return dict(matrix=val, rhs=rhs)
+
+    def momentum_result_dev(self):
+        p = [C.c_void_p() for _ in range(4)]
+        _check(self.lib.cgasm_momentum_result_dev(C.c_int(self.id), *[C.byref(x) for x in p]))
+        return [x.value for x in p]
+
+    def advdiff_result_dev(self):
+        p = [C.c_void_p() for _ in range(2)]
+        _check(self.lib.cgasm_advdiff_result_dev(C.c_int(self.id), *[C.byref(x) for x in p]))
+        return [x.value for x in p]
+
+    def momentum_element(self, opts, ele):
+        dim, loc = self.dim, self.loc
+        T = np.zeros(dim * dim * loc * loc)
+        r = np.zeros(dim * loc)
+        ml = np.zeros(dim * loc)
+        gp = np.zeros(dim * loc * loc)
+        _check(self.lib.cgasm_momentum_element(C.c_int(self.id), C.byref(opts), C.c_int(ele), _dp(T),
+                                               _dp(r), _dp(ml), _dp(gp)))
+        return (T.reshape(loc, loc, dim, dim).transpose(3, 2, 1, 0).copy(), r.reshape(loc, dim).T.copy(),
+                ml.reshape(loc, dim).T.copy(), gp.reshape(loc, loc, dim).transpose(2, 1, 0).copy())
+
+    def advdiff_element(self, opts, ele):
+        loc = self.loc
+        A = np.zeros(loc * loc)
+        r = np.zeros(loc)
+        _check(self.lib.cgasm_advdiff_element(C.c_int(self.id), C.byref(opts), C.c_int(ele), _dp(A), _dp(r)))
+        return A.reshape(loc, loc).T.copy(), r
+
+    # -- plumbing -------------------------------------------------------------------------
+    def synchronize(self):
+        _check(self.lib.cgasm_synchronize(C.c_int(self.id)))
+
+    def stream(self):
+        s = C.c_void_p()
+        _check(self.lib.cgasm_stream(C.c_int(self.id), C.byref(s)))
+        return s.value
+
+    def launch_count(self):
+        n = C.c_longlong(0)
+        _check(self.lib.cgasm_launch_count(C.c_int(self.id), C.byref(n)))
+        return n.value
+
+    def last_kernel_ms(self):
+        ms = C.c_float(0)
+        _check(self.lib.cgasm_last_kernel_ms(C.c_int(self.id), C.byref(ms)))
+        return ms.value
+
+    # -- halo ---------------------------------------------------------------------------
+    def halo_create(self, nprocs, rank, sends, recvs, unique_id):
+        """sends/recvs: list (len nprocs) of 1-based node arrays (empty for rank itself)."""
+        nsend = np.array([len(s) for s in sends], dtype=np.int32)
+        nrecv = np.array([len(r) for r in recvs], dtype=np.int32)
+        s_all = np.ascontiguousarray(np.concatenate([np.asarray(s, dtype=np.int32) for s in sends])
+                                     if nsend.sum() else np.zeros(0, dtype=np.int32))
+        r_all = np.ascontiguousarray(np.concatenate([np.asarray(r, dtype=np.int32) for r in recvs])
+                                     if nrecv.sum() else np.zeros(0, dtype=np.int32))
+        uid = C.create_string_buffer(unique_id, 128) if unique_id is not None else None
+        _check(self.lib.cgasm_halo_create(C.c_int(self.id), C.c_int(nprocs), C.c_int(rank), _ip(nsend),
+                                          _ip(s_all), _ip(nrecv), _ip(r_all), uid))
+
+    def halo_update(self, slots):
+        mask = 0
+        for s in slots:
+            mask |= 1 << s
+        _check(self.lib.cgasm_halo_update(C.c_int(self.id), C.c_uint(mask)))

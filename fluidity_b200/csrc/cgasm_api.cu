@@ -1,0 +1,680 @@
+// cgasm_api.cu -- the C ABI of include/cgasm.h: handle table, device residency of mesh /
+// coordinates / fields, option guards, and dispatch to the assembly kernels.
+//
+// The guard logic mirrors what the Fortran shim evaluates before leaving the reference's
+// element loop: anything outside the device path returns
+// CGASM_EUNSUPPORTED so the caller keeps the Fortran loop; there is no CPU path in here.
+#include "cgasm_internal.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+namespace cgasm {
+
+static thread_local std::string g_last_error;
+static std::mutex g_mutex;
+static std::vector<Handle*> g_handles;  // id = index + 1
+
+void set_error(const std::string& msg) { g_last_error = msg; }
+
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+  char buf[512];
+  snprintf(buf, sizeof buf, "%s failed at %s:%d: %s", what, file, line, cudaGetErrorString(e));
+  g_last_error = buf;
+  return (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) ? CGASM_ENODEVICE : CGASM_ECUDA;
+}
+
+Handle* get_handle(int id) {
+  std::lock_guard<std::mutex> lk(g_mutex);
+  if (id < 1 || id > (int)g_handles.size()) return nullptr;
+  return g_handles[id - 1];
+}
+
+int scatter_momentum(Handle* h, const MomentumArgs& A, bool want_ml, bool want_ct);
+int scatter_advdiff(Handle* h, const AdvDiffArgs& P);
+void one_momentum(Handle* h, const MomentumArgs& A, int e, double* T, double* rhs, double* ml, double* gp);
+void one_advdiff(Handle* h, const AdvDiffArgs& P, int e, double* Aout, double* rhs);
+
+static void free_dev(void* p) {
+  if (p) cudaFree(p);
+}
+
+static void destroy_handle(Handle* h) {
+  cudaSetDevice(h->device);
+  tiles_free(h);
+  halo_free(h);
+  free_dev(h->d_ndglno);
+  free_dev(h->d_X);
+  free_dev(h->d_findrm);
+  free_dev(h->d_colm);
+  free_dev(h->d_colour_elements);
+  for (auto& f : h->fields) free_dev(f.d);
+  free_dev(h->d_big_m);
+  free_dev(h->d_mom_rhs);
+  free_dev(h->d_masslump);
+  free_dev(h->d_ct_m);
+  free_dev(h->d_adv_matrix);
+  free_dev(h->d_adv_rhs);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+static int upload_sparsity(Handle* h) {
+  free_dev(h->d_findrm);
+  free_dev(h->d_colm);
+  h->d_findrm = h->d_colm = nullptr;
+  CG_CUDA(cudaMalloc(&h->d_findrm, sizeof(int) * ((size_t)h->n_nodes + 1)));
+  CG_CUDA(cudaMalloc(&h->d_colm, sizeof(int) * (size_t)std::max(h->nnz, 1)));
+  CG_CUDA(cudaMemcpyAsync(h->d_findrm, h->h_findrm.data(), sizeof(int) * ((size_t)h->n_nodes + 1),
+                          cudaMemcpyHostToDevice, h->stream));
+  CG_CUDA(cudaMemcpyAsync(h->d_colm, h->h_colm.data(), sizeof(int) * (size_t)h->nnz,
+                          cudaMemcpyHostToDevice, h->stream));
+  CG_CUDA(cudaStreamSynchronize(h->stream));
+  // result buffers depend on nnz
+  free_dev(h->d_big_m);
+  free_dev(h->d_ct_m);
+  free_dev(h->d_adv_matrix);
+  h->d_big_m = h->d_ct_m = h->d_adv_matrix = nullptr;
+  h->mom_valid = h->adv_valid = false;
+  h->have_sparsity = true;
+  tiles_free(h);
+  return CGASM_OK;
+}
+
+static FieldView view_of(const Handle* h, int slot, int comps) {
+  const DeviceField& f = h->fields[slot];
+  FieldView v;
+  v.val = f.d;
+  v.stride = (f.field_type == CGASM_FIELD_CONSTANT) ? 0 : comps;
+  return v;
+}
+
+static int need_field(const Handle* h, int slot, const char* name) {
+  if (!h->fields[slot].set) {
+    set_error(std::string("field slot not set: ") + name);
+    return CGASM_ESTATE;
+  }
+  return CGASM_OK;
+}
+
+static int check_momentum_opts(const cgasm_momentum_opts* o) {
+  if (o->have_les || o->multiphase || o->on_sphere || o->move_mesh || o->have_coriolis ||
+      o->have_geostrophic_pressure || o->have_surfacetension || o->have_vertical_stabilization ||
+      o->have_swe_bottom_drag || o->have_wd_abs || o->have_temperature_dependent_viscosity ||
+      o->stress_form || o->partial_stress_form || o->radial_gravity || o->vel_lump_on_submesh ||
+      o->cmc_lump_on_submesh || o->abs_lump_on_submesh || o->assemble_mass_matrix ||
+      o->integrate_continuity_by_parts)
+    CG_FAIL(CGASM_EUNSUPPORTED, "momentum option outside the device path; keep the Fortran loop");
+  if (o->stabilisation_scheme != CGASM_STAB_NONE)
+    CG_FAIL(CGASM_EUNSUPPORTED, "momentum stabilisation (SU/SUPG) not on the device path yet");
+  if (o->have_viscosity && (o->viscosity_shape < 0 || o->viscosity_shape > CGASM_TENSOR_FULL))
+    CG_FAIL(CGASM_EARG, "bad viscosity_shape");
+  return CGASM_OK;
+}
+
+static int check_advdiff_opts(const cgasm_advdiff_opts* o) {
+  if (o->move_mesh || o->multiphase || o->equation_type_not_advdiff)
+    CG_FAIL(CGASM_EUNSUPPORTED, "tracer option outside the device path; keep the Fortran loop");
+  if (o->stabilisation_scheme != CGASM_STAB_NONE)
+    CG_FAIL(CGASM_EUNSUPPORTED, "tracer stabilisation (SU/SUPG) not on the device path yet");
+  if (o->have_diffusivity && o->diffusivity_shape != CGASM_TENSOR_ISOTROPIC &&
+      o->diffusivity_shape != CGASM_TENSOR_FULL)
+    CG_FAIL(CGASM_EARG, "bad diffusivity_shape");
+  return CGASM_OK;
+}
+
+static int make_momentum_args(Handle* h, const cgasm_momentum_opts* o, MomentumArgs& A) {
+  int st;
+  if ((st = check_momentum_opts(o))) return st;
+  if (!h->have_X) CG_FAIL(CGASM_ESTATE, "cgasm_set_coordinates has not been called");
+  if ((st = need_field(h, CGASM_F_OLDU, "OLDU"))) return st;
+  if ((st = need_field(h, CGASM_F_DENSITY, "DENSITY"))) return st;
+  if ((st = need_field(h, CGASM_F_NU, "NU"))) return st;
+  if (o->have_viscosity && (st = need_field(h, CGASM_F_VISCOSITY, "VISCOSITY"))) return st;
+  if (o->have_gravity) {
+    if ((st = need_field(h, CGASM_F_BUOYANCY, "BUOYANCY"))) return st;
+    if ((st = need_field(h, CGASM_F_GRAVITY, "GRAVITY"))) return st;
+    if (o->subtract_out_reference_profile && (st = need_field(h, CGASM_F_HB_DENSITY, "HB_DENSITY")))
+      return st;
+  }
+  if (o->have_absorption && (st = need_field(h, CGASM_F_ABSORPTION, "ABSORPTION"))) return st;
+  if (o->have_source && (st = need_field(h, CGASM_F_SOURCE, "SOURCE"))) return st;
+  const int dim = h->dim;
+  A.tab = h->tab;
+  A.o = *o;
+  A.ndglno = h->d_ndglno;
+  A.X = h->d_X;
+  A.nu = view_of(h, CGASM_F_NU, dim);
+  A.oldu = view_of(h, CGASM_F_OLDU, dim);
+  A.density = view_of(h, CGASM_F_DENSITY, 1);
+  A.viscosity = view_of(h, CGASM_F_VISCOSITY, dim * dim);
+  A.buoyancy = view_of(h, CGASM_F_BUOYANCY, 1);
+  A.hb_density = view_of(h, CGASM_F_HB_DENSITY, 1);
+  A.gravity = view_of(h, CGASM_F_GRAVITY, dim);
+  A.absorption = view_of(h, CGASM_F_ABSORPTION, dim);
+  A.source = view_of(h, CGASM_F_SOURCE, dim);
+  A.n_elements = h->n_elements;
+  return CGASM_OK;
+}
+
+static int make_advdiff_args(Handle* h, const cgasm_advdiff_opts* o, AdvDiffArgs& P) {
+  int st;
+  if ((st = check_advdiff_opts(o))) return st;
+  if (!h->have_X) CG_FAIL(CGASM_ESTATE, "cgasm_set_coordinates has not been called");
+  if ((st = need_field(h, CGASM_F_T, "T"))) return st;
+  if (o->have_advection && (st = need_field(h, CGASM_F_NU, "NU"))) return st;
+  if (o->have_diffusivity && (st = need_field(h, CGASM_F_T_DIFFUSIVITY, "T_DIFFUSIVITY"))) return st;
+  if (o->have_source && (st = need_field(h, CGASM_F_T_SOURCE, "T_SOURCE"))) return st;
+  if (o->have_absorption && (st = need_field(h, CGASM_F_T_ABSORPTION, "T_ABSORPTION"))) return st;
+  const int dim = h->dim;
+  P.tab = h->tab;
+  P.o = *o;
+  P.ndglno = h->d_ndglno;
+  P.X = h->d_X;
+  P.t = view_of(h, CGASM_F_T, 1);
+  P.velocity = view_of(h, CGASM_F_NU, dim);
+  P.source = view_of(h, CGASM_F_T_SOURCE, 1);
+  P.absorption = view_of(h, CGASM_F_T_ABSORPTION, 1);
+  P.diffusivity = view_of(h, CGASM_F_T_DIFFUSIVITY, dim * dim);
+  P.n_elements = h->n_elements;
+  return CGASM_OK;
+}
+
+static int ensure(double** p, size_t count) {
+  if (*p) return CGASM_OK;
+  CG_CUDA(cudaMalloc(p, sizeof(double) * std::max<size_t>(count, 1)));
+  return CGASM_OK;
+}
+
+}  // namespace cgasm
+
+using namespace cgasm;
+
+#define GET_HANDLE(h, id)                                         \
+  Handle* h = get_handle(id);                                     \
+  if (!h) CG_FAIL(CGASM_EHANDLE, "unknown cgasm handle");         \
+  CG_CUDA(cudaSetDevice(h->device))
+
+extern "C" {
+
+const char* cgasm_last_error(void) { return g_last_error.c_str(); }
+
+int cgasm_create(int* id, int device, int dim, int loc, int ngi, int n_nodes, int n_elements,
+                 const int* ndglno, const double* n, const double* dn, const double* weight) {
+  if (!id || !ndglno || !n || !dn || !weight) CG_FAIL(CGASM_EARG, "null argument");
+  if (dim != 2 && dim != 3) CG_FAIL(CGASM_EUNSUPPORTED, "only dim 2 and 3 are on the device path");
+  if (loc != dim + 1) CG_FAIL(CGASM_EUNSUPPORTED, "only P1 simplices (loc = dim+1) are on the device path");
+  if (ngi != (dim == 3 ? 5 : 4))
+    CG_FAIL(CGASM_EUNSUPPORTED, "only the degree-3 simplex quadrature (ngi 4/5) is on the device path");
+  if (n_nodes < 1 || n_elements < 1) CG_FAIL(CGASM_EARG, "empty mesh");
+  // P1 check on the derivative table: dn(i,g,k) = delta_ik, dn(loc,g,k) = -1 for all g
+  for (int k = 0; k < dim; k++)
+    for (int g = 0; g < ngi; g++)
+      for (int i = 0; i < loc; i++) {
+        const double want = (i < dim) ? (i == k ? 1.0 : 0.0) : -1.0;
+        if (std::fabs(dn[i + loc * (g + ngi * k)] - want) > 1e-14)
+          CG_FAIL(CGASM_EUNSUPPORTED, "dn is not the P1 Lagrange simplex derivative table");
+      }
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev == 0) CG_FAIL(CGASM_ENODEVICE, "no CUDA device: libcgasm has no CPU path");
+  if (device < 0) CG_CUDA(cudaGetDevice(&device));
+  if (device >= ndev) CG_FAIL(CGASM_EARG, "device index out of range");
+  CG_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CG_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) CG_FAIL(CGASM_ENODEVICE, "libcgasm is built for sm_100a only");
+
+  Handle* h = new Handle();
+  h->device = device;
+  h->dim = dim;
+  h->loc = loc;
+  h->ngi = ngi;
+  h->n_nodes = n_nodes;
+  h->n_elements = n_elements;
+  for (int i = 0; i < loc; i++)
+    for (int g = 0; g < ngi; g++) h->tab.N[i * ngi + g] = n[i + loc * g];
+  for (int g = 0; g < ngi; g++) h->tab.w[g] = weight[g];
+  h->h_nd0.resize((size_t)4 * n_elements);
+  for (int e = 0; e < n_elements; e++) {
+    for (int i = 0; i < 4; i++) {
+      int v = -1;
+      if (i < loc) {
+        v = ndglno[(size_t)loc * e + i] - 1;
+        if (v < 0 || v >= n_nodes) {
+          delete h;
+          CG_FAIL(CGASM_EARG, "ndglno entry out of range (expects 1-based node numbers)");
+        }
+      }
+      h->h_nd0[(size_t)4 * e + i] = v;
+    }
+  }
+  auto fail = [&](int code) {
+    destroy_handle(h);
+    return code;
+  };
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess ||
+      cudaMalloc(&h->d_ndglno, sizeof(int4) * (size_t)n_elements) != cudaSuccess ||
+      cudaMalloc(&h->d_X, sizeof(double) * (size_t)dim * n_nodes) != cudaSuccess ||
+      cudaMemcpy(h->d_ndglno, h->h_nd0.data(), sizeof(int4) * (size_t)n_elements,
+                 cudaMemcpyHostToDevice) != cudaSuccess) {
+    set_error(std::string("cgasm_create: ") + cudaGetErrorString(cudaGetLastError()));
+    return fail(CGASM_ECUDA);
+  }
+  build_node_to_element(n_nodes, n_elements, loc, h->h_nd0.data(), h->n2e_ptr, h->n2e);
+  std::lock_guard<std::mutex> lk(g_mutex);
+  g_handles.push_back(h);
+  *id = (int)g_handles.size();
+  return CGASM_OK;
+}
+
+int cgasm_destroy(int id) {
+  Handle* h;
+  {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    if (id < 1 || id > (int)g_handles.size() || !g_handles[id - 1])
+      CG_FAIL(CGASM_EHANDLE, "unknown cgasm handle");
+    h = g_handles[id - 1];
+    g_handles[id - 1] = nullptr;
+  }
+  destroy_handle(h);
+  return CGASM_OK;
+}
+
+int cgasm_set_coordinates(int id, const double* X) {
+  GET_HANDLE(h, id);
+  if (!X) CG_FAIL(CGASM_EARG, "null X");
+  const size_t cnt = (size_t)h->dim * h->n_nodes;
+  h->h_X.assign(X, X + cnt);
+  CG_CUDA(cudaMemcpyAsync(h->d_X, X, sizeof(double) * cnt, cudaMemcpyHostToDevice, h->stream));
+  CG_CUDA(cudaStreamSynchronize(h->stream));
+  h->have_X = true;
+  return CGASM_OK;
+}
+
+int cgasm_build_sparsity(int id, int* nnz) {
+  GET_HANDLE(h, id);
+  const int64_t total = count_nnz(h->n_nodes, h->loc, h->h_nd0.data(), h->n2e_ptr, h->n2e);
+  if (total >= (int64_t)1 << 31) CG_FAIL(CGASM_EUNSUPPORTED, "nnz does not fit the reference's 32-bit integers");
+  build_sparsity(h->n_nodes, h->n_elements, h->loc, h->h_nd0.data(), h->n2e_ptr, h->n2e, h->h_findrm,
+                 h->h_colm);
+  h->nnz = (int)total;
+  if (nnz) *nnz = h->nnz;
+  return upload_sparsity(h);
+}
+
+int cgasm_get_sparsity(int id, int* findrm, int* colm, int* centrm) {
+  GET_HANDLE(h, id);
+  if (!h->have_sparsity) CG_FAIL(CGASM_ESTATE, "no sparsity yet");
+  if (findrm)
+    for (int r = 0; r <= h->n_nodes; r++) findrm[r] = h->h_findrm[r] + 1;
+  if (colm)
+    for (int k = 0; k < h->nnz; k++) colm[k] = h->h_colm[k] + 1;
+  if (centrm)
+    for (int r = 0; r < h->n_nodes; r++) {
+      centrm[r] = 0;  // lists2csr_sparsity: 0 when the diagonal is missing
+      for (int k = h->h_findrm[r]; k < h->h_findrm[r + 1]; k++)
+        if (h->h_colm[k] == r) {
+          centrm[r] = k + 1;
+          break;
+        }
+    }
+  return CGASM_OK;
+}
+
+int cgasm_set_sparsity(int id, int rows, int nnz, const int* findrm, const int* colm) {
+  GET_HANDLE(h, id);
+  if (!findrm || !colm) CG_FAIL(CGASM_EARG, "null argument");
+  if (rows != h->n_nodes) CG_FAIL(CGASM_EARG, "sparsity rows != n_nodes");
+  if (findrm[0] != 1 || findrm[rows] != nnz + 1) CG_FAIL(CGASM_EARG, "findrm is not a 1-based CSR row pointer");
+  h->h_findrm.resize((size_t)rows + 1);
+  h->h_colm.resize((size_t)nnz);
+  for (int r = 0; r <= rows; r++) h->h_findrm[r] = findrm[r] - 1;
+  for (int r = 0; r < rows; r++) {
+    if (findrm[r + 1] < findrm[r]) CG_FAIL(CGASM_EARG, "findrm not monotone");
+    for (int k = findrm[r] - 1; k < findrm[r + 1] - 1; k++) {
+      const int c = colm[k] - 1;
+      if (c < 0 || c >= h->n_nodes) CG_FAIL(CGASM_EARG, "colm entry out of range");
+      if (k > findrm[r] - 1 && colm[k] <= colm[k - 1]) CG_FAIL(CGASM_EARG, "rows must be sorted ascending (sorted_rows)");
+      h->h_colm[k] = c;
+    }
+  }
+  // every element pair must be present (Sparse_Tools.F90:2644 would FLAbort otherwise)
+  int missing = 0;
+#pragma omp parallel for schedule(static) reduction(+ : missing)
+  for (int e = 0; e < h->n_elements; e++)
+    for (int i = 0; i < h->loc; i++) {
+      const int r = h->h_nd0[(size_t)4 * e + i];
+      for (int j = 0; j < h->loc; j++) {
+        const int c = h->h_nd0[(size_t)4 * e + j];
+        const int* b = h->h_colm.data() + h->h_findrm[r];
+        const int* en = h->h_colm.data() + h->h_findrm[r + 1];
+        if (!std::binary_search(b, en, c)) missing++;
+      }
+    }
+  if (missing) CG_FAIL(CGASM_EARG, "sparsity misses an element node pair");
+  h->nnz = nnz;
+  return upload_sparsity(h);
+}
+
+int cgasm_build_colouring(int id, int* ncolours) {
+  GET_HANDLE(h, id);
+  std::vector<int> colour_of;
+  const int nc = greedy_colouring(h->n_elements, h->loc, h->h_nd0.data(), h->n2e_ptr, h->n2e, colour_of);
+  if (nc < 0) CG_FAIL(CGASM_EUNSUPPORTED, "mesh needs more than 256 colours");
+  h->ncolours = nc;
+  colour_sets(h->n_elements, nc, colour_of, h->h_colour_ptr, h->h_colour_elements);
+  free_dev(h->d_colour_elements);
+  h->d_colour_elements = nullptr;
+  CG_CUDA(cudaMalloc(&h->d_colour_elements, sizeof(int) * (size_t)h->n_elements));
+  CG_CUDA(cudaMemcpy(h->d_colour_elements, h->h_colour_elements.data(), sizeof(int) * (size_t)h->n_elements,
+                     cudaMemcpyHostToDevice));
+  if (ncolours) *ncolours = nc;
+  return CGASM_OK;
+}
+
+int cgasm_get_colouring(int id, int* colour_ptr, int* colour_elements) {
+  GET_HANDLE(h, id);
+  if (!h->ncolours) CG_FAIL(CGASM_ESTATE, "no colouring yet");
+  if (colour_ptr)
+    for (int c = 0; c <= h->ncolours; c++) colour_ptr[c] = h->h_colour_ptr[c] + 1;
+  if (colour_elements)
+    for (int e = 0; e < h->n_elements; e++) colour_elements[e] = h->h_colour_elements[e] + 1;
+  return CGASM_OK;
+}
+
+int cgasm_set_colouring(int id, int ncolours, const int* colour_ptr, const int* colour_elements) {
+  GET_HANDLE(h, id);
+  if (ncolours < 1 || !colour_ptr || !colour_elements) CG_FAIL(CGASM_EARG, "bad colouring");
+  if (colour_ptr[0] != 1 || colour_ptr[ncolours] != h->n_elements + 1)
+    CG_FAIL(CGASM_EARG, "colour_ptr must cover every element exactly once (1-based)");
+  // validity: inside a colour no two elements may share a node, or the plain-store scatter races
+  std::vector<int> stamp((size_t)h->n_nodes, -1);
+  std::vector<char> seen((size_t)h->n_elements, 0);
+  for (int c = 0; c < ncolours; c++)
+    for (int k = colour_ptr[c] - 1; k < colour_ptr[c + 1] - 1; k++) {
+      const int e = colour_elements[k] - 1;
+      if (e < 0 || e >= h->n_elements || seen[e]) CG_FAIL(CGASM_EARG, "colour_elements is not a permutation");
+      seen[e] = 1;
+      for (int i = 0; i < h->loc; i++) {
+        const int node = h->h_nd0[(size_t)4 * e + i];
+        if (stamp[node] == c) CG_FAIL(CGASM_EARG, "invalid colouring: two elements of a colour share a node");
+        stamp[node] = c;
+      }
+    }
+  h->ncolours = ncolours;
+  h->h_colour_ptr.resize((size_t)ncolours + 1);
+  h->h_colour_elements.resize((size_t)h->n_elements);
+  for (int c = 0; c <= ncolours; c++) h->h_colour_ptr[c] = colour_ptr[c] - 1;
+  for (int e = 0; e < h->n_elements; e++) h->h_colour_elements[e] = colour_elements[e] - 1;
+  free_dev(h->d_colour_elements);
+  h->d_colour_elements = nullptr;
+  CG_CUDA(cudaMalloc(&h->d_colour_elements, sizeof(int) * (size_t)h->n_elements));
+  CG_CUDA(cudaMemcpy(h->d_colour_elements, h->h_colour_elements.data(), sizeof(int) * (size_t)h->n_elements,
+                     cudaMemcpyHostToDevice));
+  return CGASM_OK;
+}
+
+int cgasm_set_scatter(int id, int variant) {
+  GET_HANDLE(h, id);
+  if (variant < CGASM_SCATTER_ATOMIC || variant > CGASM_SCATTER_TILED) CG_FAIL(CGASM_EARG, "unknown scatter variant");
+  if (variant == CGASM_SCATTER_COLOURED && !h->ncolours) {
+    int st = cgasm_build_colouring(id, nullptr);
+    if (st) return st;
+  }
+  if (variant == CGASM_SCATTER_TILED) {
+    if (!h->have_sparsity) CG_FAIL(CGASM_ESTATE, "tiled scatter needs the sparsity first");
+    if (!h->tiles) {
+      int st = tiles_build(h);
+      if (st) return st;
+    }
+  }
+  h->scatter = variant;
+  return CGASM_OK;
+}
+
+int cgasm_set_field(int id, int slot, int rank, int field_type, const double* val, int n_val_nodes) {
+  GET_HANDLE(h, id);
+  if (slot < 0 || slot >= CGASM_F_NSLOTS || !val) CG_FAIL(CGASM_EARG, "bad slot or null val");
+  static const int kRank[CGASM_F_NSLOTS] = {1, 1, 0, 2, 0, 0, 1, 1, 1, 0, 2, 0, 0};
+  if (rank != kRank[slot]) CG_FAIL(CGASM_EARG, "field rank does not match the slot");
+  if (field_type == CGASM_FIELD_CONSTANT) {
+    if (n_val_nodes != 1) CG_FAIL(CGASM_EARG, "a CONSTANT field has one node");
+  } else if (field_type == CGASM_FIELD_NORMAL) {
+    if (n_val_nodes != h->n_nodes) CG_FAIL(CGASM_EARG, "a NORMAL field must live on the velocity mesh nodes");
+  } else {
+    CG_FAIL(CGASM_EUNSUPPORTED, "only NORMAL and CONSTANT fields are on the device path");
+  }
+  size_t comps = 1;
+  for (int r = 0; r < rank; r++) comps *= (size_t)h->dim;
+  const size_t count = comps * (size_t)n_val_nodes;
+  DeviceField& f = h->fields[slot];
+  if (f.d && f.count != count) {
+    cudaFree(f.d);
+    f.d = nullptr;
+  }
+  if (!f.d) CG_CUDA(cudaMalloc(&f.d, sizeof(double) * count));
+  CG_CUDA(cudaMemcpyAsync(f.d, val, sizeof(double) * count, cudaMemcpyHostToDevice, h->stream));
+  CG_CUDA(cudaStreamSynchronize(h->stream));
+  f.rank = rank;
+  f.field_type = field_type;
+  f.n_val_nodes = n_val_nodes;
+  f.count = count;
+  f.set = true;
+  return CGASM_OK;
+}
+
+int cgasm_get_field(int id, int slot, double* val, int n_val_nodes) {
+  GET_HANDLE(h, id);
+  if (slot < 0 || slot >= CGASM_F_NSLOTS || !val) CG_FAIL(CGASM_EARG, "bad slot or null val");
+  const DeviceField& f = h->fields[slot];
+  if (!f.set) CG_FAIL(CGASM_ESTATE, "field slot not set");
+  if (n_val_nodes != f.n_val_nodes) CG_FAIL(CGASM_EARG, "n_val_nodes mismatch");
+  CG_CUDA(cudaMemcpyAsync(val, f.d, sizeof(double) * f.count, cudaMemcpyDeviceToHost, h->stream));
+  CG_CUDA(cudaStreamSynchronize(h->stream));
+  return CGASM_OK;
+}
+
+int cgasm_momentum_dev(int id, const cgasm_momentum_opts* opts) {
+  GET_HANDLE(h, id);
+  if (!opts) CG_FAIL(CGASM_EARG, "null opts");
+  if (!h->have_sparsity) CG_FAIL(CGASM_ESTATE, "no sparsity: call cgasm_build_sparsity or cgasm_set_sparsity");
+  MomentumArgs A;
+  int st = make_momentum_args(h, opts, A);
+  if (st) return st;
+  const size_t nnz = (size_t)h->nnz, nn = (size_t)h->n_nodes, dim = (size_t)h->dim;
+  const bool want_ml = opts->assemble_inverse_masslump != 0;
+  const bool want_ct = opts->assemble_ct_matrix_here != 0;
+  if ((st = ensure(&h->d_big_m, dim * nnz))) return st;
+  if ((st = ensure(&h->d_mom_rhs, dim * nn))) return st;
+  if (want_ml && (st = ensure(&h->d_masslump, dim * nn))) return st;
+  if (want_ct && (st = ensure(&h->d_ct_m, dim * nnz))) return st;
+  CG_CUDA(cudaEventRecord(h->ev0, h->stream));
+  if (h->scatter == CGASM_SCATTER_TILED) {
+    st = tiles_momentum(h, A, want_ml, want_ct);
+  } else {
+    // zero(big_m), zero(rhs) ... (Momentum_Equation.F90:593-606) then accumulate
+    CG_CUDA(cudaMemsetAsync(h->d_big_m, 0, sizeof(double) * dim * nnz, h->stream));
+    CG_CUDA(cudaMemsetAsync(h->d_mom_rhs, 0, sizeof(double) * dim * nn, h->stream));
+    if (want_ml) CG_CUDA(cudaMemsetAsync(h->d_masslump, 0, sizeof(double) * dim * nn, h->stream));
+    if (want_ct) CG_CUDA(cudaMemsetAsync(h->d_ct_m, 0, sizeof(double) * dim * nnz, h->stream));
+    st = scatter_momentum(h, A, want_ml, want_ct);
+  }
+  if (st) return st;
+  CG_CUDA(cudaEventRecord(h->ev1, h->stream));
+  CG_CUDA(cudaGetLastError());
+  h->mom_has_masslump = want_ml;
+  h->mom_has_ct = want_ct;
+  h->mom_valid = true;
+  return CGASM_OK;
+}
+
+int cgasm_advdiff_dev(int id, const cgasm_advdiff_opts* opts) {
+  GET_HANDLE(h, id);
+  if (!opts) CG_FAIL(CGASM_EARG, "null opts");
+  if (!h->have_sparsity) CG_FAIL(CGASM_ESTATE, "no sparsity: call cgasm_build_sparsity or cgasm_set_sparsity");
+  AdvDiffArgs P;
+  int st = make_advdiff_args(h, opts, P);
+  if (st) return st;
+  const size_t nnz = (size_t)h->nnz, nn = (size_t)h->n_nodes;
+  if ((st = ensure(&h->d_adv_matrix, nnz))) return st;
+  if ((st = ensure(&h->d_adv_rhs, nn))) return st;
+  CG_CUDA(cudaEventRecord(h->ev0, h->stream));
+  if (h->scatter == CGASM_SCATTER_TILED) {
+    st = tiles_advdiff(h, P);
+  } else {
+    CG_CUDA(cudaMemsetAsync(h->d_adv_matrix, 0, sizeof(double) * nnz, h->stream));
+    CG_CUDA(cudaMemsetAsync(h->d_adv_rhs, 0, sizeof(double) * nn, h->stream));
+    st = scatter_advdiff(h, P);
+  }
+  if (st) return st;
+  CG_CUDA(cudaEventRecord(h->ev1, h->stream));
+  CG_CUDA(cudaGetLastError());
+  h->adv_valid = true;
+  return CGASM_OK;
+}
+
+int cgasm_momentum_fetch(int id, double* big_m, double* rhs, double* masslump, double* ct_m) {
+  GET_HANDLE(h, id);
+  if (!h->mom_valid) CG_FAIL(CGASM_ESTATE, "no momentum result to fetch");
+  const size_t nnz = (size_t)h->nnz, nn = (size_t)h->n_nodes, dim = (size_t)h->dim;
+  if (big_m) CG_CUDA(cudaMemcpyAsync(big_m, h->d_big_m, sizeof(double) * dim * nnz, cudaMemcpyDeviceToHost, h->stream));
+  if (rhs) CG_CUDA(cudaMemcpyAsync(rhs, h->d_mom_rhs, sizeof(double) * dim * nn, cudaMemcpyDeviceToHost, h->stream));
+  if (masslump) {
+    if (!h->mom_has_masslump) CG_FAIL(CGASM_ESTATE, "masslump was not assembled (assemble_inverse_masslump = 0)");
+    CG_CUDA(cudaMemcpyAsync(masslump, h->d_masslump, sizeof(double) * dim * nn, cudaMemcpyDeviceToHost, h->stream));
+  }
+  if (ct_m) {
+    if (!h->mom_has_ct) CG_FAIL(CGASM_ESTATE, "ct_m was not assembled (assemble_ct_matrix_here = 0)");
+    CG_CUDA(cudaMemcpyAsync(ct_m, h->d_ct_m, sizeof(double) * dim * nnz, cudaMemcpyDeviceToHost, h->stream));
+  }
+  CG_CUDA(cudaStreamSynchronize(h->stream));
+  return CGASM_OK;
+}
+
+int cgasm_advdiff_fetch(int id, double* matrix_val, double* rhs) {
+  GET_HANDLE(h, id);
+  if (!h->adv_valid) CG_FAIL(CGASM_ESTATE, "no tracer result to fetch");
+  if (matrix_val)
+    CG_CUDA(cudaMemcpyAsync(matrix_val, h->d_adv_matrix, sizeof(double) * (size_t)h->nnz, cudaMemcpyDeviceToHost, h->stream));
+  if (rhs)
+    CG_CUDA(cudaMemcpyAsync(rhs, h->d_adv_rhs, sizeof(double) * (size_t)h->n_nodes, cudaMemcpyDeviceToHost, h->stream));
+  CG_CUDA(cudaStreamSynchronize(h->stream));
+  return CGASM_OK;
+}
+
+int cgasm_momentum(int id, const cgasm_momentum_opts* opts, double* big_m, double* rhs,
+                   double* masslump, double* ct_m) {
+  int st = cgasm_momentum_dev(id, opts);
+  if (st) return st;
+  return cgasm_momentum_fetch(id, big_m, rhs, opts->assemble_inverse_masslump ? masslump : nullptr,
+                              opts->assemble_ct_matrix_here ? ct_m : nullptr);
+}
+
+int cgasm_advdiff(int id, const cgasm_advdiff_opts* opts, double* matrix_val, double* rhs) {
+  int st = cgasm_advdiff_dev(id, opts);
+  if (st) return st;
+  return cgasm_advdiff_fetch(id, matrix_val, rhs);
+}
+
+int cgasm_momentum_result_dev(int id, double** big_m_dev, double** rhs_dev, double** masslump_dev,
+                              double** ct_m_dev) {
+  GET_HANDLE(h, id);
+  if (!h->mom_valid) CG_FAIL(CGASM_ESTATE, "no momentum result");
+  if (big_m_dev) *big_m_dev = h->d_big_m;
+  if (rhs_dev) *rhs_dev = h->d_mom_rhs;
+  if (masslump_dev) *masslump_dev = h->mom_has_masslump ? h->d_masslump : nullptr;
+  if (ct_m_dev) *ct_m_dev = h->mom_has_ct ? h->d_ct_m : nullptr;
+  return CGASM_OK;
+}
+
+int cgasm_advdiff_result_dev(int id, double** matrix_dev, double** rhs_dev) {
+  GET_HANDLE(h, id);
+  if (!h->adv_valid) CG_FAIL(CGASM_ESTATE, "no tracer result");
+  if (matrix_dev) *matrix_dev = h->d_adv_matrix;
+  if (rhs_dev) *rhs_dev = h->d_adv_rhs;
+  return CGASM_OK;
+}
+
+int cgasm_momentum_element(int id, const cgasm_momentum_opts* opts, int ele, double* big_m_tensor_addto,
+                           double* rhs_addto, double* mass_lump, double* grad_p_u_mat) {
+  GET_HANDLE(h, id);
+  if (!opts) CG_FAIL(CGASM_EARG, "null opts");
+  if (ele < 1 || ele > h->n_elements) CG_FAIL(CGASM_EARG, "element number out of range");
+  MomentumArgs A;
+  int st = make_momentum_args(h, opts, A);
+  if (st) return st;
+  const int dim = h->dim, loc = h->loc;
+  const size_t nT = (size_t)dim * dim * loc * loc, nr = (size_t)dim * loc, ng = (size_t)dim * loc * loc;
+  double* buf = nullptr;
+  CG_CUDA(cudaMalloc(&buf, sizeof(double) * (nT + 2 * nr + ng)));
+  one_momentum(h, A, ele - 1, buf, buf + nT, buf + nT + nr, buf + nT + 2 * nr);
+  std::vector<double> hb(nT + 2 * nr + ng);
+  cudaError_t e = cudaMemcpyAsync(hb.data(), buf, sizeof(double) * hb.size(), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  cudaFree(buf);
+  CG_CUDA(e);
+  if (big_m_tensor_addto) memcpy(big_m_tensor_addto, hb.data(), sizeof(double) * nT);
+  if (rhs_addto) memcpy(rhs_addto, hb.data() + nT, sizeof(double) * nr);
+  if (mass_lump) memcpy(mass_lump, hb.data() + nT + nr, sizeof(double) * nr);
+  if (grad_p_u_mat) memcpy(grad_p_u_mat, hb.data() + nT + 2 * nr, sizeof(double) * ng);
+  return CGASM_OK;
+}
+
+int cgasm_advdiff_element(int id, const cgasm_advdiff_opts* opts, int ele, double* matrix_addto,
+                          double* rhs_addto) {
+  GET_HANDLE(h, id);
+  if (!opts) CG_FAIL(CGASM_EARG, "null opts");
+  if (ele < 1 || ele > h->n_elements) CG_FAIL(CGASM_EARG, "element number out of range");
+  AdvDiffArgs P;
+  int st = make_advdiff_args(h, opts, P);
+  if (st) return st;
+  const int loc = h->loc;
+  double* buf = nullptr;
+  CG_CUDA(cudaMalloc(&buf, sizeof(double) * (size_t)(loc * loc + loc)));
+  one_advdiff(h, P, ele - 1, buf, buf + loc * loc);
+  std::vector<double> hb((size_t)loc * loc + loc);
+  cudaError_t e = cudaMemcpyAsync(hb.data(), buf, sizeof(double) * hb.size(), cudaMemcpyDeviceToHost, h->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+  cudaFree(buf);
+  CG_CUDA(e);
+  if (matrix_addto) memcpy(matrix_addto, hb.data(), sizeof(double) * (size_t)loc * loc);
+  if (rhs_addto) memcpy(rhs_addto, hb.data() + loc * loc, sizeof(double) * (size_t)loc);
+  return CGASM_OK;
+}
+
+int cgasm_synchronize(int id) {
+  GET_HANDLE(h, id);
+  CG_CUDA(cudaStreamSynchronize(h->stream));
+  return CGASM_OK;
+}
+
+int cgasm_stream(int id, void** stream) {
+  GET_HANDLE(h, id);
+  if (!stream) CG_FAIL(CGASM_EARG, "null stream out");
+  *stream = (void*)h->stream;
+  return CGASM_OK;
+}
+
+int cgasm_launch_count(int id, long long* launches) {
+  GET_HANDLE(h, id);
+  if (!launches) CG_FAIL(CGASM_EARG, "null out");
+  *launches = h->launches;
+  return CGASM_OK;
+}
+
+int cgasm_last_kernel_ms(int id, float* ms) {
+  GET_HANDLE(h, id);
+  if (!ms) CG_FAIL(CGASM_EARG, "null out");
+  CG_CUDA(cudaEventSynchronize(h->ev1));
+  CG_CUDA(cudaEventElapsedTime(ms, h->ev0, h->ev1));
+  return CGASM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,113 @@
+// cgasm_internal.h -- handle layout and helpers shared by the translation units of
+// libcgasm.so. Not part of the ABI (that is include/cgasm.h).
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/cgasm.h"
+#include "element_math.cuh"
+
+namespace cgasm {
+
+struct DeviceField {
+  double* d = nullptr;
+  int rank = 0;
+  int field_type = CGASM_FIELD_NORMAL;
+  int n_val_nodes = 0;
+  size_t count = 0;  // doubles
+  bool set = false;
+};
+
+struct TilePlan;  // tiled.cu
+struct HaloPlan;  // halo.cu
+
+struct Handle {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int dim = 0, loc = 0, ngi = 0, n_nodes = 0, n_elements = 0;
+  Tables tab{};
+
+  std::vector<int> h_nd0;  // 0-based connectivity, stride 4 (4th = -1 on triangles)
+  int4* d_ndglno = nullptr;
+  double* d_X = nullptr;
+  bool have_X = false;
+  std::vector<double> h_X;  // kept for locality ordering of the tile plan
+
+  // node -> element adjacency (host)
+  std::vector<int64_t> n2e_ptr;
+  std::vector<int> n2e;
+
+  // sparsity, 0-based
+  bool have_sparsity = false;
+  int nnz = 0;
+  std::vector<int> h_findrm, h_colm;
+  int* d_findrm = nullptr;
+  int* d_colm = nullptr;
+
+  // colouring, 0-based
+  int ncolours = 0;
+  std::vector<int> h_colour_ptr, h_colour_elements;
+  int* d_colour_elements = nullptr;
+
+  DeviceField fields[CGASM_F_NSLOTS];
+
+  // results
+  double* d_big_m = nullptr;     // [dim][nnz]
+  double* d_mom_rhs = nullptr;   // (dim, n_nodes)
+  double* d_masslump = nullptr;  // (dim, n_nodes)
+  double* d_ct_m = nullptr;      // [dim][nnz]
+  double* d_adv_matrix = nullptr;  // [nnz]
+  double* d_adv_rhs = nullptr;     // (n_nodes)
+  bool mom_has_masslump = false, mom_has_ct = false, mom_valid = false, adv_valid = false;
+
+  int scatter = CGASM_SCATTER_ATOMIC;
+  TilePlan* tiles = nullptr;
+  HaloPlan* halo = nullptr;
+
+  long long launches = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  float last_ms = 0.f;
+};
+
+// error plumbing
+void set_error(const std::string& msg);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+#define CG_CUDA(call)                                                     \
+  do {                                                                    \
+    cudaError_t _e = (call);                                              \
+    if (_e != cudaSuccess) return cgasm::cuda_fail(_e, #call, __FILE__, __LINE__); \
+  } while (0)
+#define CG_FAIL(code, msg)       \
+  do {                           \
+    cgasm::set_error(msg);       \
+    return (code);               \
+  } while (0)
+
+Handle* get_handle(int id);
+
+// host_mesh.cpp
+void build_node_to_element(int n_nodes, int n_elements, int loc, const int* nd0,
+                           std::vector<int64_t>& ptr, std::vector<int>& adj);
+void build_sparsity(int n_nodes, int n_elements, int loc, const int* nd0,
+                    const std::vector<int64_t>& n2e_ptr, const std::vector<int>& n2e,
+                    std::vector<int>& findrm, std::vector<int>& colm);
+int64_t count_nnz(int n_nodes, int loc, const int* nd0, const std::vector<int64_t>& n2e_ptr,
+                  const std::vector<int>& n2e);
+int greedy_colouring(int n_elements, int loc, const int* nd0, const std::vector<int64_t>& n2e_ptr,
+                     const std::vector<int>& n2e, std::vector<int>& colour_of);
+void colour_sets(int n_elements, int ncol, const std::vector<int>& colour_of,
+                 std::vector<int>& colour_ptr, std::vector<int>& colour_elements);
+
+// tiled.cu
+int tiles_build(Handle* h);
+void tiles_free(Handle* h);
+int tiles_momentum(Handle* h, const MomentumArgs& args, bool want_ml, bool want_ct);
+int tiles_advdiff(Handle* h, const AdvDiffArgs& args);
+
+// halo.cu
+void halo_free(Handle* h);
+
+}  // namespace cgasm

@@ -1,0 +1,708 @@
+// element_math.cuh -- per-element FP64 math of the two CG element routines, written for one
+// thread = one element with everything in registers.
+//
+// What is computed (formulae: SURVEY.md 8(a); reference lines cited per block) is the same
+// local matrix / rhs as construct_momentum_element_cg (assemble/Momentum_CG.F90:1193-1490)
+// and assemble_advection_diffusion_element_cg (assemble/Advection_Diffusion_CG.F90:702-865),
+// but NOT evaluated the way the Fortran does it: for P1 simplices grad N is constant over
+// the element, so every "shape x dshape" contraction collapses from loc*loc*ngi*dim MACs
+// to a few rank-1 updates:
+//     A_ij = sum_g N_ig (u_g . gradN_j) c_g      = C_i . gradN_j,  C_i = sum_g N_ig c_g u_g
+//     K_ij = sum_g (gradN_i . gradN_j) mu_g dw_g = (mubar gradN_i) . gradN_j
+//     sum_j M_ij = sum_g N_ig c_g                  (partition of unity)
+// Summation order therefore differs from the reference; parity is 1e-12 relative
+// (tests/test_parity_gpu.py), which is what the north-star asks for.
+#pragma once
+#include <cuda_runtime.h>
+#include "../../include/cgasm.h"
+
+namespace cgasm {
+
+template <int DIM>
+struct Shape {
+  static constexpr int LOC = DIM + 1;
+  static constexpr int NGI = (DIM == 3) ? 5 : 4;  // degree-3 rules, Quadrature.F90:690-708,951-970
+};
+
+// Reference-element tables, passed by value inside the kernel parameter block so that every
+// N[i][g] / w[g] is a constant-bank operand of the DFMA that uses it.
+struct Tables {
+  double N[4 * 5];  // n(i,g) at [i*NGI + g]
+  double w[5];
+};
+
+// Device view of one nodal field (femtools/Fields_Data_Types.F90:154-233).
+// stride = 0 for FIELD_TYPE_CONSTANT (every node reads node 0), else components per node.
+struct FieldView {
+  const double* __restrict__ val;
+  int stride;
+};
+
+struct MomentumArgs {
+  Tables tab;
+  cgasm_momentum_opts o;
+  const int4* __restrict__ ndglno;  // 0-based, padded to 4 ints
+  const double* __restrict__ X;     // (dim, n_nodes)
+  FieldView nu, oldu, density, viscosity, buoyancy, hb_density, gravity, absorption, source;
+  int n_elements;
+};
+
+struct AdvDiffArgs {
+  Tables tab;
+  cgasm_advdiff_opts o;
+  const int4* __restrict__ ndglno;
+  const double* __restrict__ X;
+  FieldView t, velocity, source, absorption, diffusivity;
+  int n_elements;
+};
+
+__device__ __forceinline__ int node_of(const int4& nd, int i) {
+  return i == 0 ? nd.x : (i == 1 ? nd.y : (i == 2 ? nd.z : nd.w));
+}
+
+template <int NC>
+__device__ __forceinline__ void gather(const FieldView& f, int node, double (&out)[NC]) {
+  const double* p = f.val + (size_t)f.stride * (size_t)node;
+#pragma unroll
+  for (int c = 0; c < NC; c++) out[c] = __ldg(p + c);
+}
+
+// ---- geometry: transform_to_physical, femtools/Transform_elements.F90:807-887 -------------
+// J_T(a,k) = x_k[a] - x_loc[a] (dn(i,:,k) = delta_ik, dn(loc,:,k) = -1), cofactor inverse,
+// detJ by expanding the first column, gradN_i = invJ(:,i), gradN_loc = -sum_i gradN_i.
+template <int DIM>
+struct Geom {
+  double grad[DIM + 1][DIM];  // dN_i/dx_a
+  double absdet;              // |detJ|  (detwei_g = absdet * w_g)
+  double JT[DIM][DIM];        // J_T(a,k) = dx_a/dxi_k
+};
+
+template <int DIM>
+__device__ __forceinline__ void geometry(const double (&X)[DIM + 1][DIM], Geom<DIM>& G) {
+#pragma unroll
+  for (int a = 0; a < DIM; a++)
+#pragma unroll
+    for (int k = 0; k < DIM; k++) G.JT[a][k] = X[k][a] - X[DIM][a];
+  double C[DIM][DIM];  // cofactors: invJ(a,k)*detJ
+  if constexpr (DIM == 2) {
+    C[0][0] = G.JT[1][1];
+    C[1][0] = -G.JT[0][1];
+    C[0][1] = -G.JT[1][0];
+    C[1][1] = G.JT[0][0];
+  } else {
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        const int i1 = (i + 1) % 3, i2 = (i + 2) % 3, k1 = (k + 1) % 3, k2 = (k + 2) % 3;
+        C[i][k] = G.JT[i1][k1] * G.JT[i2][k2] - G.JT[i2][k1] * G.JT[i1][k2];
+      }
+  }
+  double det = 0.0;
+#pragma unroll
+  for (int a = 0; a < DIM; a++) det += G.JT[a][0] * C[a][0];
+  const double rdet = 1.0 / det;
+#pragma unroll
+  for (int a = 0; a < DIM; a++) {
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < DIM; k++) {
+      G.grad[k][a] = C[a][k] * rdet;  // matmul(invJ, e_k)
+      s -= G.grad[k][a];
+    }
+    G.grad[DIM][a] = s;
+  }
+  G.absdet = fabs(det);
+}
+
+// f_g = sum_i f_i N_ig  (ele_val_at_quad, femtools/Fields_Base.F90:2256-2310)
+template <int DIM>
+__device__ __forceinline__ void at_quad(const Tables& t, const double (&f)[DIM + 1],
+                                        double (&q)[Shape<DIM>::NGI]) {
+  constexpr int LOC = DIM + 1, NGI = Shape<DIM>::NGI;
+#pragma unroll
+  for (int g = 0; g < NGI; g++) {
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < LOC; i++) s += f[i] * t.N[i * NGI + g];
+    q[g] = s;
+  }
+}
+
+// ---- momentum -----------------------------------------------------------------------------
+// Result of one element. L is the part of the diagonal blocks common to every velocity
+// component; Labs[d] is added to block d only (non-lumped absorption); diag[d][i] is the
+// lumped diagonal (Momentum_CG.F90:1462, add_diagonal_to_tensor).
+template <int DIM, bool LABS>
+struct MomentumLocal {
+  static constexpr int LOC = DIM + 1;
+  double L[LOC][LOC];
+  double Labs[LABS ? DIM : 1][LOC][LOC];  // only kernels built with LABS carry it
+  double diag[DIM][LOC];
+  double rhs[DIM][LOC];
+  double ml[DIM][LOC];
+};
+
+// LABS must be true iff (have_absorption && !lump_absorption); the launcher picks the
+// instantiation, so kernels without that option never hold the dim*loc*loc extra block.
+template <int DIM, bool LABS>
+__device__ __forceinline__ void momentum_element(const MomentumArgs& A, const int4 nd,
+                                                 MomentumLocal<DIM, LABS>& R, Geom<DIM>& G) {
+  constexpr int LOC = DIM + 1, NGI = Shape<DIM>::NGI;
+  const cgasm_momentum_opts& o = A.o;
+  const Tables& t = A.tab;
+  const double dtt = o.dt * o.theta;
+
+  double X[LOC][DIM], nu[LOC][DIM], oldu[LOC][DIM], rho[LOC];
+#pragma unroll
+  for (int i = 0; i < LOC; i++) {
+    const int node = node_of(nd, i);
+    gather<DIM>(FieldView{A.X, DIM}, node, X[i]);
+    gather<DIM>(A.nu, node, nu[i]);
+    gather<DIM>(A.oldu, node, oldu[i]);
+    double r1[1];
+    gather<1>(A.density, node, r1);
+    rho[i] = r1[0];
+  }
+  geometry<DIM>(X, G);
+
+  // c_g = rho_g * detwei_g  (coefficient_detwei, :1536, :1674)
+  double c[NGI];
+  at_quad<DIM>(t, rho, c);
+#pragma unroll
+  for (int g = 0; g < NGI; g++) c[g] *= G.absdet * t.w[g];
+
+#pragma unroll
+  for (int i = 0; i < LOC; i++)
+#pragma unroll
+    for (int j = 0; j < LOC; j++) R.L[i][j] = 0.0;
+#pragma unroll
+  for (int d = 0; d < DIM; d++)
+#pragma unroll
+    for (int i = 0; i < LOC; i++) {
+      R.diag[d][i] = 0.0;
+      R.rhs[d][i] = 0.0;
+      R.ml[d][i] = 0.0;
+    }
+
+  // v[i] accumulates the vector such that (A + K)_ij = v[i] . gradN_j
+  double v[LOC][DIM];
+#pragma unroll
+  for (int i = 0; i < LOC; i++)
+#pragma unroll
+    for (int a = 0; a < DIM; a++) v[i][a] = 0.0;
+  bool have_v = false;
+
+  // Mass (add_mass_element_cg, :1492-1600)
+  if (o.assemble_inverse_masslump || !o.exclude_mass) {
+    if (!o.exclude_mass && !o.lump_mass) {
+#pragma unroll
+      for (int i = 0; i < LOC; i++)
+#pragma unroll
+        for (int j = i; j < LOC; j++) {
+          double s = 0.0;
+#pragma unroll
+          for (int g = 0; g < NGI; g++) s += (t.N[i * NGI + g] * t.N[j * NGI + g]) * c[g];
+          R.L[i][j] += s;
+          if (j != i) R.L[j][i] += s;
+        }
+    }
+    double m[LOC];  // sum(mass_mat,2) = sum_g N_ig c_g
+#pragma unroll
+    for (int i = 0; i < LOC; i++) {
+      double s = 0.0;
+#pragma unroll
+      for (int g = 0; g < NGI; g++) s += t.N[i * NGI + g] * c[g];
+      m[i] = s;
+    }
+#pragma unroll
+    for (int d = 0; d < DIM; d++)
+#pragma unroll
+      for (int i = 0; i < LOC; i++) {
+        if (!o.exclude_mass && o.lump_mass) R.diag[d][i] += m[i];
+        if (o.assemble_inverse_masslump) R.ml[d][i] += m[i];
+      }
+  }
+
+  // Advection (add_advection_element_cg, :1602-1715)
+  if (!o.exclude_advection) {
+    double ug[NGI][DIM];
+#pragma unroll
+    for (int g = 0; g < NGI; g++)
+#pragma unroll
+      for (int a = 0; a < DIM; a++) {
+        double s = 0.0;
+#pragma unroll
+        for (int i = 0; i < LOC; i++) s += nu[i][a] * t.N[i * NGI + g];
+        ug[g][a] = s;
+      }
+    double divu = 0.0;  // ele_div_at_quad: constant over the element for P1
+#pragma unroll
+    for (int i = 0; i < LOC; i++)
+#pragma unroll
+      for (int a = 0; a < DIM; a++) divu += nu[i][a] * G.grad[i][a];
+
+    if (o.integrate_advection_by_parts) {
+      // A_ij = -sum_g (u_g.gradN_i) N_jg c_g - (1-beta) divu sum_g N_ig N_jg c_g  (:1667-1668)
+      //      = -gradN_i . C_j - (1-beta) divu M_ij ; needs the transposed rank-1 form.
+      double Cj[LOC][DIM];
+#pragma unroll
+      for (int j = 0; j < LOC; j++)
+#pragma unroll
+        for (int a = 0; a < DIM; a++) {
+          double s = 0.0;
+#pragma unroll
+          for (int g = 0; g < NGI; g++) s += t.N[j * NGI + g] * (c[g] * ug[g][a]);
+          Cj[j][a] = s;
+        }
+      const double f = (1.0 - o.beta) * divu;
+#pragma unroll
+      for (int i = 0; i < LOC; i++)
+#pragma unroll
+        for (int j = 0; j < LOC; j++) {
+          double s = 0.0;
+#pragma unroll
+          for (int a = 0; a < DIM; a++) s += G.grad[i][a] * Cj[j][a];
+          double mm = 0.0;
+#pragma unroll
+          for (int g = 0; g < NGI; g++) mm += (t.N[i * NGI + g] * t.N[j * NGI + g]) * c[g];
+          const double aij = -s - f * mm;
+          R.L[i][j] += dtt * aij;
+#pragma unroll
+          for (int d = 0; d < DIM; d++) R.rhs[d][i] -= aij * oldu[j][d];
+        }
+    } else {
+      // A_ij = C_i . gradN_j + beta divu M_ij   (:1675-1680)
+#pragma unroll
+      for (int i = 0; i < LOC; i++)
+#pragma unroll
+        for (int a = 0; a < DIM; a++) {
+          double s = 0.0;
+#pragma unroll
+          for (int g = 0; g < NGI; g++) s += t.N[i * NGI + g] * (c[g] * ug[g][a]);
+          v[i][a] += s;
+        }
+      have_v = true;
+      if (o.beta != 0.0) {
+        const double f = o.beta * divu;
+#pragma unroll
+        for (int i = 0; i < LOC; i++)
+#pragma unroll
+          for (int j = 0; j < LOC; j++) {
+            double mm = 0.0;
+#pragma unroll
+            for (int g = 0; g < NGI; g++) mm += (t.N[i * NGI + g] * t.N[j * NGI + g]) * c[g];
+            const double aij = f * mm;
+            R.L[i][j] += dtt * aij;
+#pragma unroll
+            for (int d = 0; d < DIM; d++) R.rhs[d][i] -= aij * oldu[j][d];
+          }
+      }
+    }
+  }
+
+  // Viscosity, tensor form (add_viscosity_element_cg, :2286-2359)
+  if (o.have_viscosity) {
+    double visc[LOC][DIM * DIM];
+#pragma unroll
+    for (int i = 0; i < LOC; i++) gather<DIM * DIM>(A.viscosity, node_of(nd, i), visc[i]);
+    // Vbar(a,b) = sum_g (sum_i visc_i(a,b) N_ig) detwei_g ; memory index a + DIM*b
+    double Vbar[DIM * DIM];
+#pragma unroll
+    for (int ab = 0; ab < DIM * DIM; ab++) {
+      double s = 0.0;
+#pragma unroll
+      for (int i = 0; i < LOC; i++) {
+        double ni = 0.0;
+#pragma unroll
+        for (int g = 0; g < NGI; g++) ni += t.N[i * NGI + g] * t.w[g];
+        s += visc[i][ab] * ni;
+      }
+      Vbar[ab] = s * G.absdet;
+    }
+#pragma unroll
+    for (int i = 0; i < LOC; i++) {
+      if (o.viscosity_shape == CGASM_TENSOR_ISOTROPIC) {
+#pragma unroll
+        for (int a = 0; a < DIM; a++) v[i][a] += Vbar[0] * G.grad[i][a];
+      } else if (o.viscosity_shape == CGASM_TENSOR_DIAGONAL) {
+#pragma unroll
+        for (int a = 0; a < DIM; a++) v[i][a] += Vbar[a + DIM * a] * G.grad[i][a];
+      } else {
+        // K_ij = gradN_i^T V gradN_j  => v[i](b) += sum_a gradN_i(a) V(a,b)   (FETools :668-698)
+#pragma unroll
+        for (int b = 0; b < DIM; b++) {
+          double s = 0.0;
+#pragma unroll
+          for (int a = 0; a < DIM; a++) s += G.grad[i][a] * Vbar[a + DIM * b];
+          v[i][b] += s;
+        }
+      }
+    }
+    have_v = true;
+  }
+
+  if (have_v) {
+    // (A+K)_ij = v_i . gradN_j ; big_m += dt theta (A+K) ; rhs(d,i) -= (A+K)_ij oldu(d,j)
+#pragma unroll
+    for (int i = 0; i < LOC; i++)
+#pragma unroll
+      for (int j = 0; j < LOC; j++) {
+        double s = 0.0;
+#pragma unroll
+        for (int a = 0; a < DIM; a++) s += v[i][a] * G.grad[j][a];
+        R.L[i][j] += dtt * s;
+#pragma unroll
+        for (int d = 0; d < DIM; d++) R.rhs[d][i] -= s * oldu[j][d];
+      }
+  }
+
+  // Sources (add_sources_element_cg, :1717-1751)
+  if (o.have_source) {
+    double src[LOC][DIM];
+#pragma unroll
+    for (int i = 0; i < LOC; i++) gather<DIM>(A.source, node_of(nd, i), src[i]);
+#pragma unroll
+    for (int i = 0; i < LOC; i++) {
+      if (o.lump_source) {
+        double s = 0.0;
+#pragma unroll
+        for (int g = 0; g < NGI; g++) s += t.N[i * NGI + g] * c[g];
+#pragma unroll
+        for (int d = 0; d < DIM; d++) R.rhs[d][i] += s * src[i][d];
+      } else {
+#pragma unroll
+        for (int j = 0; j < LOC; j++) {
+          double mm = 0.0;
+#pragma unroll
+          for (int g = 0; g < NGI; g++) mm += (t.N[i * NGI + g] * t.N[j * NGI + g]) * c[g];
+#pragma unroll
+          for (int d = 0; d < DIM; d++) R.rhs[d][i] += mm * src[j][d];
+        }
+      }
+    }
+  }
+
+  // Buoyancy (add_buoyancy_element_cg, :1753-1792)
+  if (o.have_gravity) {
+    double b[LOC], bq[NGI], gv[LOC][DIM];
+#pragma unroll
+    for (int i = 0; i < LOC; i++) {
+      double r1[1];
+      gather<1>(A.buoyancy, node_of(nd, i), r1);
+      b[i] = r1[0];
+      if (o.subtract_out_reference_profile) {
+        gather<1>(A.hb_density, node_of(nd, i), r1);
+        b[i] -= r1[0];
+      }
+      gather<DIM>(A.gravity, node_of(nd, i), gv[i]);
+    }
+    at_quad<DIM>(t, b, bq);
+#pragma unroll
+    for (int g = 0; g < NGI; g++) bq[g] *= o.gravity_magnitude * G.absdet * t.w[g];
+#pragma unroll
+    for (int g = 0; g < NGI; g++) {
+      double gg[DIM];
+#pragma unroll
+      for (int a = 0; a < DIM; a++) {
+        double s = 0.0;
+#pragma unroll
+        for (int i = 0; i < LOC; i++) s += gv[i][a] * t.N[i * NGI + g];
+        gg[a] = s * bq[g];
+      }
+#pragma unroll
+      for (int i = 0; i < LOC; i++)
+#pragma unroll
+        for (int d = 0; d < DIM; d++) R.rhs[d][i] += t.N[i * NGI + g] * gg[d];
+    }
+  }
+
+  // Absorption, plain branch (add_absorption_element_cg, :2036-2073)
+  if (o.have_absorption) {
+    double sg[LOC][DIM], sq[NGI][DIM];
+#pragma unroll
+    for (int i = 0; i < LOC; i++) gather<DIM>(A.absorption, node_of(nd, i), sg[i]);
+#pragma unroll
+    for (int g = 0; g < NGI; g++)
+#pragma unroll
+      for (int d = 0; d < DIM; d++) {
+        double s = 0.0;
+#pragma unroll
+        for (int i = 0; i < LOC; i++) s += sg[i][d] * t.N[i * NGI + g];
+        sq[g][d] = s * c[g];
+      }
+    if (o.lump_absorption) {
+#pragma unroll
+      for (int d = 0; d < DIM; d++)
+#pragma unroll
+        for (int i = 0; i < LOC; i++) {
+          double s = 0.0;  // sum_j Ab_ij = sum_g N_ig sigma_dg c_g
+#pragma unroll
+          for (int g = 0; g < NGI; g++) s += t.N[i * NGI + g] * sq[g][d];
+          R.diag[d][i] += dtt * s;
+          R.rhs[d][i] -= s * oldu[i][d];
+          if (o.pressure_corrected_absorption && o.assemble_inverse_masslump) R.ml[d][i] += dtt * s;
+        }
+    } else if constexpr (LABS) {
+#pragma unroll
+      for (int d = 0; d < DIM; d++)
+#pragma unroll
+        for (int i = 0; i < LOC; i++)
+#pragma unroll
+          for (int j = 0; j < LOC; j++) {
+            double s = 0.0;
+#pragma unroll
+            for (int g = 0; g < NGI; g++) s += (t.N[i * NGI + g] * t.N[j * NGI + g]) * sq[g][d];
+            R.Labs[d][i][j] = dtt * s;
+            R.rhs[d][i] -= s * oldu[j][d];
+          }
+    }
+  }
+}
+
+// ct_m block: grad_p_u_mat(d,i,j) = sum_g N_ig dN_j/dx_d detwei_g   (:1401, FETools :332-362)
+template <int DIM>
+__device__ __forceinline__ double grad_p_u(const Tables& t, const Geom<DIM>& G, int d, int i, int j) {
+  constexpr int NGI = Shape<DIM>::NGI;
+  double ni = 0.0;
+#pragma unroll
+  for (int g = 0; g < NGI; g++) ni += t.N[i * NGI + g] * t.w[g];
+  return ni * G.absdet * G.grad[j][d];
+}
+
+// ---- tracer ----------------------------------------------------------------------------------
+template <int DIM>
+struct AdvDiffLocal {
+  static constexpr int LOC = DIM + 1;
+  double A[LOC][LOC];
+  double rhs[LOC];
+};
+
+template <int DIM>
+__device__ __forceinline__ void advdiff_element(const AdvDiffArgs& P, const int4 nd,
+                                                AdvDiffLocal<DIM>& R) {
+  constexpr int LOC = DIM + 1, NGI = Shape<DIM>::NGI;
+  const cgasm_advdiff_opts& o = P.o;
+  const Tables& t = P.tab;
+  const double dtt = o.dt * o.theta;
+  const double eps = 2.220446049250313e-16;  // epsilon(0.0), :1121
+  const bool implicit = fabs(dtt) > eps;
+
+  double X[LOC][DIM], T[LOC];
+#pragma unroll
+  for (int i = 0; i < LOC; i++) {
+    const int node = node_of(nd, i);
+    gather<DIM>(FieldView{P.X, DIM}, node, X[i]);
+    double r1[1];
+    gather<1>(P.t, node, r1);
+    T[i] = r1[0];
+  }
+  Geom<DIM> G;
+  geometry<DIM>(X, G);
+
+#pragma unroll
+  for (int i = 0; i < LOC; i++) {
+    R.rhs[i] = 0.0;
+#pragma unroll
+    for (int j = 0; j < LOC; j++) R.A[i][j] = 0.0;
+  }
+
+  // Mass (:867-941): M_ij = |detJ| sum_g N_ig N_jg w_g ; lumped -> |detJ| sum_g N_ig w_g
+  if (o.have_mass) {
+#pragma unroll
+    for (int i = 0; i < LOC; i++) {
+      if (o.lump_mass) {
+        double s = 0.0;
+#pragma unroll
+        for (int g = 0; g < NGI; g++) s += t.N[i * NGI + g] * t.w[g];
+        R.A[i][i] += s * G.absdet;
+      } else {
+#pragma unroll
+        for (int j = 0; j < LOC; j++) {
+          double s = 0.0;
+#pragma unroll
+          for (int g = 0; g < NGI; g++) s += (t.N[i * NGI + g] * t.N[j * NGI + g]) * t.w[g];
+          R.A[i][j] += s * G.absdet;
+        }
+      }
+    }
+  }
+
+  double v[LOC][DIM];  // (A + D)_ij = v_i . gradN_j
+#pragma unroll
+  for (int i = 0; i < LOC; i++)
+#pragma unroll
+    for (int a = 0; a < DIM; a++) v[i][a] = 0.0;
+  bool have_v = false;
+
+  // Advection (:943-1127, default equation type)
+  if (o.have_advection) {
+    double u[LOC][DIM], ug[NGI][DIM];
+#pragma unroll
+    for (int i = 0; i < LOC; i++) gather<DIM>(P.velocity, node_of(nd, i), u[i]);
+#pragma unroll
+    for (int g = 0; g < NGI; g++)
+#pragma unroll
+      for (int a = 0; a < DIM; a++) {
+        double s = 0.0;
+#pragma unroll
+        for (int i = 0; i < LOC; i++) s += u[i][a] * t.N[i * NGI + g];
+        ug[g][a] = s * (G.absdet * t.w[g]);  // u_g detwei_g
+      }
+    double divu = 0.0;
+#pragma unroll
+    for (int i = 0; i < LOC; i++)
+#pragma unroll
+      for (int a = 0; a < DIM; a++) divu += u[i][a] * G.grad[i][a];
+    if (o.integrate_advection_by_parts) {
+      const bool with_div = fabs(1.0 - o.beta) > eps;  // :1044
+      const double f = (1.0 - o.beta) * divu * G.absdet;
+#pragma unroll
+      for (int j = 0; j < LOC; j++) {
+        double Cj[DIM];
+#pragma unroll
+        for (int a = 0; a < DIM; a++) {
+          double s = 0.0;
+#pragma unroll
+          for (int g = 0; g < NGI; g++) s += t.N[j * NGI + g] * ug[g][a];
+          Cj[a] = s;
+        }
+#pragma unroll
+        for (int i = 0; i < LOC; i++) {
+          double s = 0.0;
+#pragma unroll
+          for (int a = 0; a < DIM; a++) s += G.grad[i][a] * Cj[a];
+          double aij = -s;
+          if (with_div) {
+            double mm = 0.0;
+#pragma unroll
+            for (int g = 0; g < NGI; g++) mm += (t.N[i * NGI + g] * t.N[j * NGI + g]) * t.w[g];
+            aij -= f * mm;
+          }
+          if (implicit) R.A[i][j] += dtt * aij;
+          R.rhs[i] -= aij * T[j];
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < LOC; i++)
+#pragma unroll
+        for (int a = 0; a < DIM; a++) {
+          double s = 0.0;
+#pragma unroll
+          for (int g = 0; g < NGI; g++) s += t.N[i * NGI + g] * ug[g][a];
+          v[i][a] += s;
+        }
+      have_v = true;
+      if (fabs(o.beta) > eps) {  // :1093
+        const double f = o.beta * divu * G.absdet;
+#pragma unroll
+        for (int i = 0; i < LOC; i++)
+#pragma unroll
+          for (int j = 0; j < LOC; j++) {
+            double mm = 0.0;
+#pragma unroll
+            for (int g = 0; g < NGI; g++) mm += (t.N[i * NGI + g] * t.N[j * NGI + g]) * t.w[g];
+            const double aij = f * mm;
+            if (implicit) R.A[i][j] += dtt * aij;
+            R.rhs[i] -= aij * T[j];
+          }
+      }
+    }
+  }
+
+  // Diffusivity (:1164-1202)
+  if (o.have_diffusivity) {
+    double kap[LOC][DIM * DIM], Kbar[DIM * DIM];
+#pragma unroll
+    for (int i = 0; i < LOC; i++) gather<DIM * DIM>(P.diffusivity, node_of(nd, i), kap[i]);
+#pragma unroll
+    for (int ab = 0; ab < DIM * DIM; ab++) {
+      double s = 0.0;
+#pragma unroll
+      for (int i = 0; i < LOC; i++) {
+        double ni = 0.0;
+#pragma unroll
+        for (int g = 0; g < NGI; g++) ni += t.N[i * NGI + g] * t.w[g];
+        s += kap[i][ab] * ni;
+      }
+      Kbar[ab] = s * G.absdet;
+    }
+#pragma unroll
+    for (int i = 0; i < LOC; i++) {
+      if (o.diffusivity_shape == CGASM_TENSOR_ISOTROPIC) {
+#pragma unroll
+        for (int a = 0; a < DIM; a++) v[i][a] += Kbar[0] * G.grad[i][a];
+      } else {
+#pragma unroll
+        for (int b = 0; b < DIM; b++) {
+          double s = 0.0;
+#pragma unroll
+          for (int a = 0; a < DIM; a++) s += G.grad[i][a] * Kbar[a + DIM * b];
+          v[i][b] += s;
+        }
+      }
+    }
+    have_v = true;
+  }
+
+  if (have_v) {
+#pragma unroll
+    for (int i = 0; i < LOC; i++)
+#pragma unroll
+      for (int j = 0; j < LOC; j++) {
+        double s = 0.0;
+#pragma unroll
+        for (int a = 0; a < DIM; a++) s += v[i][a] * G.grad[j][a];
+        if (implicit) R.A[i][j] += dtt * s;
+        R.rhs[i] -= s * T[j];
+      }
+  }
+
+  // Absorption (:1143-1162)
+  if (o.have_absorption) {
+    double sg[LOC], sq[NGI];
+#pragma unroll
+    for (int i = 0; i < LOC; i++) {
+      double r1[1];
+      gather<1>(P.absorption, node_of(nd, i), r1);
+      sg[i] = r1[0];
+    }
+    at_quad<DIM>(t, sg, sq);
+#pragma unroll
+    for (int g = 0; g < NGI; g++) sq[g] *= G.absdet * t.w[g];
+#pragma unroll
+    for (int i = 0; i < LOC; i++)
+#pragma unroll
+      for (int j = 0; j < LOC; j++) {
+        double s = 0.0;
+#pragma unroll
+        for (int g = 0; g < NGI; g++) s += (t.N[i * NGI + g] * t.N[j * NGI + g]) * sq[g];
+        if (implicit) R.A[i][j] += dtt * s;
+        R.rhs[i] -= s * T[j];
+      }
+  }
+
+  // Source (:1129-1141)
+  if (o.have_source) {
+    double sg[LOC], sq[NGI];
+#pragma unroll
+    for (int i = 0; i < LOC; i++) {
+      double r1[1];
+      gather<1>(P.source, node_of(nd, i), r1);
+      sg[i] = r1[0];
+    }
+    at_quad<DIM>(t, sg, sq);
+#pragma unroll
+    for (int g = 0; g < NGI; g++) sq[g] *= G.absdet * t.w[g];
+#pragma unroll
+    for (int i = 0; i < LOC; i++) {
+      double s = 0.0;
+#pragma unroll
+      for (int g = 0; g < NGI; g++) s += t.N[i * NGI + g] * sq[g];
+      R.rhs[i] += s;
+    }
+  }
+}
+
+}  // namespace cgasm

@@ -1,0 +1,140 @@
+// host_mesh.cpp -- once-per-mesh host preprocessing behind the C ABI: the first-order
+// node-node sparsity, the greedy CG1 element colouring and node->element adjacency.
+//
+// Same RESULTS as the reference routines, different algorithms:
+//   sparsity  femtools/Sparsity_Patterns.F90:299-428 inserts into per-row sorted linked lists
+//             (O(row length) per insert). Here: counting-sort the (node, element) incidences
+//             into a node->element CSR, then per row gather the incident elements' nodes into
+//             a small scratch, sort + unique. Rows are independent => OpenMP over rows.
+//   colouring femtools/Colouring.F90:159-199 greedy in element order, lowest colour unused by
+//             lower-numbered neighbours; neighbours = elements sharing a node
+//             (make_sparsity_transpose, Sparsity_Patterns.F90:87-148). Inherently sequential;
+//             here with a 64-bit colour mask per element instead of a Judy set.
+#include "cgasm_internal.h"
+
+#include <algorithm>
+#include <cstring>
+#include <numeric>
+
+namespace cgasm {
+
+// node -> element adjacency (CSR, 0-based), elements ascending inside a node.
+void build_node_to_element(int n_nodes, int n_elements, int loc, const int* nd0 /*0-based, stride 4*/,
+                           std::vector<int64_t>& ptr, std::vector<int>& adj) {
+  ptr.assign((size_t)n_nodes + 1, 0);
+  for (int e = 0; e < n_elements; e++)
+    for (int i = 0; i < loc; i++) ptr[(size_t)nd0[(size_t)4 * e + i] + 1]++;
+  for (int i = 0; i < n_nodes; i++) ptr[i + 1] += ptr[i];
+  adj.resize((size_t)ptr[n_nodes]);
+  std::vector<int64_t> fill(ptr.begin(), ptr.end() - 1);
+  for (int e = 0; e < n_elements; e++)
+    for (int i = 0; i < loc; i++) adj[(size_t)fill[nd0[(size_t)4 * e + i]]++] = e;
+}
+
+// findrm (n+1), colm (nnz), 0-based; rows sorted ascending, unique.
+void build_sparsity(int n_nodes, int n_elements, int loc, const int* nd0,
+                    const std::vector<int64_t>& n2e_ptr, const std::vector<int>& n2e,
+                    std::vector<int>& findrm, std::vector<int>& colm) {
+  (void)n_elements;
+  std::vector<int> rowlen((size_t)n_nodes);
+  // pass 1: row lengths
+#pragma omp parallel
+  {
+    std::vector<int> scratch;
+#pragma omp for schedule(dynamic, 4096)
+    for (int r = 0; r < n_nodes; r++) {
+      scratch.clear();
+      for (int64_t k = n2e_ptr[r]; k < n2e_ptr[r + 1]; k++) {
+        const int* nd = nd0 + (size_t)4 * n2e[(size_t)k];
+        for (int j = 0; j < loc; j++) scratch.push_back(nd[j]);
+      }
+      std::sort(scratch.begin(), scratch.end());
+      rowlen[r] = (int)(std::unique(scratch.begin(), scratch.end()) - scratch.begin());
+    }
+  }
+  findrm.resize((size_t)n_nodes + 1);
+  int64_t acc = 0;
+  for (int r = 0; r < n_nodes; r++) {
+    findrm[r] = (int)acc;
+    acc += rowlen[r];
+  }
+  findrm[n_nodes] = (int)acc;  // nnz < 2^31 is checked by the caller
+  colm.resize((size_t)acc);
+#pragma omp parallel
+  {
+    std::vector<int> scratch;
+#pragma omp for schedule(dynamic, 4096)
+    for (int r = 0; r < n_nodes; r++) {
+      scratch.clear();
+      for (int64_t k = n2e_ptr[r]; k < n2e_ptr[r + 1]; k++) {
+        const int* nd = nd0 + (size_t)4 * n2e[(size_t)k];
+        for (int j = 0; j < loc; j++) scratch.push_back(nd[j]);
+      }
+      std::sort(scratch.begin(), scratch.end());
+      auto end = std::unique(scratch.begin(), scratch.end());
+      std::copy(scratch.begin(), end, colm.begin() + findrm[r]);
+    }
+  }
+}
+
+int64_t count_nnz(int n_nodes, int loc, const int* nd0, const std::vector<int64_t>& n2e_ptr,
+                  const std::vector<int>& n2e) {
+  int64_t total = 0;
+#pragma omp parallel reduction(+ : total)
+  {
+    std::vector<int> scratch;
+#pragma omp for schedule(dynamic, 4096)
+    for (int r = 0; r < n_nodes; r++) {
+      scratch.clear();
+      for (int64_t k = n2e_ptr[r]; k < n2e_ptr[r + 1]; k++) {
+        const int* nd = nd0 + (size_t)4 * n2e[(size_t)k];
+        for (int j = 0; j < loc; j++) scratch.push_back(nd[j]);
+      }
+      std::sort(scratch.begin(), scratch.end());
+      total += (int64_t)(std::unique(scratch.begin(), scratch.end()) - scratch.begin());
+    }
+  }
+  return total;
+}
+
+// Greedy colouring in element order. colour_of is 0-based; returns the number of colours, or
+// -1 if more than 64*kWords colours would be needed.
+int greedy_colouring(int n_elements, int loc, const int* nd0, const std::vector<int64_t>& n2e_ptr,
+                     const std::vector<int>& n2e, std::vector<int>& colour_of) {
+  constexpr int kWords = 4;  // up to 256 colours
+  colour_of.assign((size_t)n_elements, -1);
+  int ncol = 0;
+  for (int e = 0; e < n_elements; e++) {
+    uint64_t used[kWords] = {0, 0, 0, 0};
+    const int* nd = nd0 + (size_t)4 * e;
+    for (int i = 0; i < loc; i++) {
+      const int node = nd[i];
+      for (int64_t k = n2e_ptr[node]; k < n2e_ptr[node + 1]; k++) {
+        const int e2 = n2e[(size_t)k];
+        if (e2 >= e) break;  // adjacency is ascending: only lower-numbered neighbours count
+        const int c = colour_of[e2];
+        used[c >> 6] |= (uint64_t)1 << (c & 63);
+      }
+    }
+    int c = -1;
+    for (int w = 0; w < kWords && c < 0; w++)
+      if (~used[w]) c = w * 64 + __builtin_ctzll(~used[w]);
+    if (c < 0) return -1;
+    colour_of[e] = c;
+    if (c + 1 > ncol) ncol = c + 1;
+  }
+  return ncol;
+}
+
+// colour_sets: offsets + element ids ascending inside each colour (0-based).
+void colour_sets(int n_elements, int ncol, const std::vector<int>& colour_of,
+                 std::vector<int>& colour_ptr, std::vector<int>& colour_elements) {
+  colour_ptr.assign((size_t)ncol + 1, 0);
+  for (int e = 0; e < n_elements; e++) colour_ptr[(size_t)colour_of[e] + 1]++;
+  for (int c = 0; c < ncol; c++) colour_ptr[c + 1] += colour_ptr[c];
+  colour_elements.resize((size_t)n_elements);
+  std::vector<int> fill(colour_ptr.begin(), colour_ptr.end() - 1);
+  for (int e = 0; e < n_elements; e++) colour_elements[(size_t)fill[colour_of[e]]++] = e;
+}
+
+}  // namespace cgasm

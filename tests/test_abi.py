@@ -1,0 +1,85 @@
+"""CPU-only checks of the drop-in boundary: libcgasm.so loads, exports every symbol that
+include/cgasm.h declares, the ctypes structs match the header, and (without a GPU) the
+library refuses to work instead of falling back."""
+import ctypes as C
+import os
+import re
+import subprocess
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from fluidity_b200 import _abi as abi, cgasm, tables, synthetic as syn
+
+HEADER = os.path.join(ROOT, "include", "cgasm.h")
+
+
+def _declared_symbols():
+    txt = open(HEADER).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(cgasm_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = cgasm.load()
+    syms = _declared_symbols()
+    assert len(syms) >= 25
+    for s in syms:
+        assert hasattr(lib, s), "libcgasm.so lacks " + s
+
+
+def test_struct_layout_matches_header(tmp_path):
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "cgasm.h"\n'
+                   'int main(){printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(cgasm_momentum_opts),'
+                   'sizeof(cgasm_advdiff_opts), offsetof(cgasm_momentum_opts, lump_mass),'
+                   'offsetof(cgasm_momentum_opts, integrate_continuity_by_parts),'
+                   'offsetof(cgasm_advdiff_opts, have_mass),'
+                   'offsetof(cgasm_advdiff_opts, equation_type_not_advdiff));return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.run(["/usr/bin/gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    M, A = abi.MomentumOpts, abi.AdvDiffOpts
+    want = [C.sizeof(M), C.sizeof(A), M.lump_mass.offset, M.integrate_continuity_by_parts.offset,
+            A.have_mass.offset, A.equation_type_not_advdiff.offset]
+    assert got == want
+
+
+def test_enums_match_header():
+    txt = open(HEADER).read()
+    for name, val in (("CGASM_F_T_ABSORPTION", abi.F_T_ABSORPTION), ("CGASM_F_NSLOTS", abi.F_NSLOTS),
+                      ("CGASM_SCATTER_TILED", abi.SCATTER_TILED), ("CGASM_ENODEVICE", abi.ENODEVICE)):
+        m = re.search(name + r"\s*=\s*(\d+)", txt)
+        assert m and int(m.group(1)) == val, name
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_product_tables_equal_oracle_tables(orc, dim):
+    n, dn, w = tables.p1_tables(dim)
+    on, odn, ow = orc.tables(dim)
+    assert (n == on).all() and (dn == odn).all() and (w == ow).all()
+
+
+def test_no_cpu_path_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    mesh = syn.box_mesh((2, 2, 2))
+    with pytest.raises(cgasm.CgasmError) as ei:
+        cgasm.Assembler(mesh, tables.p1_tables(3))
+    assert ei.value.code in (abi.ENODEVICE, abi.ECUDA)
+
+
+def test_bad_arguments_are_status_codes_not_aborts():
+    lib = cgasm.load()
+    ident = C.c_int(0)
+    n, dn, w = tables.p1_tables(3)
+    nd = np.ones(4, dtype=np.int32)
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    st = lib.cgasm_create(C.byref(ident), -1, 4, 5, 5, 4, 1, nd.ctypes.data_as(C.POINTER(C.c_int)), dp(n), dp(dn), dp(w))
+    assert st == abi.EUNSUPPORTED
+    st = lib.cgasm_create(C.byref(ident), -1, 3, 4, 11, 4, 1, nd.ctypes.data_as(C.POINTER(C.c_int)), dp(n), dp(dn), dp(w))
+    assert st == abi.EUNSUPPORTED  # degree-4 quadrature: caller keeps the Fortran loop
+    assert lib.cgasm_destroy(12345) == abi.EHANDLE
+    assert lib.cgasm_momentum_dev(777, None) == abi.EHANDLE
+    assert b"handle" in lib.cgasm_last_error()

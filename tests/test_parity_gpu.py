@@ -1,0 +1,289 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle. Needs a B200.
+
+Bar (north_star): findrm/colm/centrm and colouring bit-exact; element matrices, assembled
+CSR values, rhs and lumped mass within 1e-12 relative (norm-relative per block and per row,
+SURVEY.md 8(c)(ii)) because summation order differs.
+"""
+import numpy as np
+import pytest
+
+from conftest import load_golden_mesh, rel_err, row_rel_err
+from fluidity_b200 import synthetic as syn, _abi as abi, cgasm, tables
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+ALL_SCATTERS = [pytest.param(abi.SCATTER_ATOMIC, id="atomic"), pytest.param(abi.SCATTER_COLOURED, id="coloured"),
+                pytest.param(abi.SCATTER_WARPAGG, id="warpagg"), pytest.param(abi.SCATTER_TILED, id="tiled")]
+
+
+def make_asm(mesh, fields=None, scatter=None):
+    asm = cgasm.Assembler(mesh, tables.p1_tables(mesh.dim))
+    asm.build_sparsity()
+    if fields is not None:
+        asm.set_fields(fields)
+    if scatter is not None:
+        asm.set_scatter(scatter)
+    return asm
+
+
+def momentum_variants():
+    c = abi.common_momentum_opts
+    return {
+        "common": c(),
+        "common_ct": c(assemble_ct_matrix_here=1),
+        "consistent_mass": c(lump_mass=0),
+        "by_parts_beta": c(integrate_advection_by_parts=1, beta=0.3),
+        "beta1": c(beta=1.0),
+        "absorption": c(have_absorption=1),
+        "absorption_lumped_pc": c(have_absorption=1, lump_absorption=1, pressure_corrected_absorption=1),
+        "source": c(have_source=1),
+        "source_lumped": c(have_source=1, lump_source=1),
+        "ref_profile": c(subtract_out_reference_profile=1),
+        "aniso": c(viscosity_shape=abi.TENSOR_FULL),
+        "diagvisc": c(viscosity_shape=abi.TENSOR_DIAGONAL),
+        "no_adv_no_mass": c(exclude_advection=1, exclude_mass=1),
+        "stokes_no_ml": c(exclude_advection=1, have_gravity=0, assemble_inverse_masslump=0),
+    }
+
+
+def advdiff_variants():
+    c = abi.common_advdiff_opts
+    return {
+        "common": c(),
+        "lumped": c(lump_mass=1),
+        "by_parts": c(integrate_advection_by_parts=1, beta=0.25),
+        "beta": c(beta=1.0),
+        "absorb_source": c(have_absorption=1, have_source=1),
+        "tensor_diff": c(diffusivity_shape=abi.TENSOR_FULL),
+        "pure_diffusion": c(have_advection=0),
+        "mass_only": c(have_advection=0, have_diffusivity=0),
+        "theta0": c(theta=0.0),
+    }
+
+
+def fields_for(mesh, variant):
+    fs = syn.standard_fields(mesh, nodal_viscosity=(variant == "aniso"))
+    if variant in ("diagvisc", "tensor_diff"):
+        fs.set(abi.F_VISCOSITY, syn.aniso_tensor(mesh.dim), abi.FIELD_CONSTANT)
+        fs.set(abi.F_T_DIFFUSIVITY, syn.aniso_tensor(mesh.dim), abi.FIELD_CONSTANT)
+    return fs
+
+
+def check_momentum(got, ref, findrm, dim):
+    for d in range(dim):
+        assert rel_err(got["big_m"][d], ref["big_m"][d]) < TOL
+        assert row_rel_err(got["big_m"][d], ref["big_m"][d], findrm) < TOL
+        assert rel_err(got["rhs"][:, d], ref["rhs"][:, d]) < TOL
+        if ref.get("masslump") is not None and got.get("masslump") is not None:
+            assert rel_err(got["masslump"][:, d], ref["masslump"][:, d]) < TOL
+        if ref.get("ct_m") is not None and got.get("ct_m") is not None:
+            assert rel_err(got["ct_m"][d], ref["ct_m"][d]) < TOL
+
+
+# ---- sparsity / colouring: bit exact --------------------------------------------------------
+@pytest.mark.parametrize("name", ["cube.1", "cube-parallel", "square-cavity-2d", "2d_square"])
+def test_sparsity_bit_exact_reference_meshes(orc, name):
+    mesh = load_golden_mesh(name)
+    asm = make_asm(mesh)
+    f, c, ce = asm.get_sparsity()
+    of, oc, oce = orc.make_sparsity(mesh)
+    assert (f == of).all() and (c == oc).all() and (ce == oce).all()
+
+
+@pytest.mark.parametrize("shape", [(5, 4, 3), (7, 6), (1, 1, 1), (1, 1)])
+def test_sparsity_bit_exact_box_and_shuffled(orc, shape):
+    mesh = syn.box_mesh(shape)
+    for m in (mesh, syn.shuffled(mesh, seed=3)):
+        asm = make_asm(m)
+        f, c, ce = asm.get_sparsity()
+        of, oc, oce = orc.make_sparsity(m)
+        assert (f == of).all() and (c == oc).all() and (ce == oce).all()
+
+
+@pytest.mark.parametrize("name", ["square-cavity-2d", "cube-parallel"])
+def test_colouring_bit_exact(orc, name):
+    mesh = load_golden_mesh(name)
+    asm = make_asm(mesh)
+    nc = asm.build_colouring()
+    ptr, els = asm.get_colouring(nc)
+    col, onc = orc.colour_elements(mesh)
+    optr, oels = orc.colour_sets(col, onc)
+    assert nc == onc and (ptr == optr).all() and (els == oels).all()
+
+
+def test_reference_sparsity_and_colouring_can_be_adopted(orc):
+    mesh = load_golden_mesh("cube-parallel")
+    fs = syn.standard_fields(mesh)
+    findrm, colm, _ = orc.make_sparsity(mesh)
+    col, nc = orc.colour_elements(mesh)
+    asm = cgasm.Assembler(mesh, tables.p1_tables(3))
+    asm.set_sparsity(findrm, colm)
+    asm.set_colouring(*orc.colour_sets(col, nc))
+    asm.set_fields(fs)
+    asm.set_scatter(abi.SCATTER_COLOURED)
+    o = abi.common_momentum_opts()
+    check_momentum(asm.momentum(o), orc.assemble_momentum(mesh, fs, o, findrm, colm), findrm, 3)
+    # an invalid colouring (everything in one colour) must be refused, not raced
+    with pytest.raises(cgasm.CgasmError):
+        asm.set_colouring(np.array([1, mesh.n_elements + 1]), np.arange(1, mesh.n_elements + 1))
+    # a pattern with unsorted rows must be refused
+    bad = colm.copy()
+    bad[0], bad[1] = bad[1], bad[0]
+    with pytest.raises(cgasm.CgasmError):
+        asm.set_sparsity(findrm, bad)
+
+
+# ---- element matrices ---------------------------------------------------------------------
+@pytest.mark.parametrize("dim", [2, 3])
+@pytest.mark.parametrize("variant", list(momentum_variants().keys()))
+def test_momentum_element_matrices(orc, dim, variant):
+    mesh = syn.box_mesh((4, 3, 5)[:dim], seed=21)
+    o = momentum_variants()[variant]
+    fs = fields_for(mesh, variant)
+    asm = make_asm(mesh, fs)
+    rng = np.random.default_rng(0)
+    for ele in [1, mesh.n_elements] + rng.integers(1, mesh.n_elements + 1, size=6).tolist():
+        T, r, ml, gp = asm.momentum_element(o, ele)
+        oT, orr, oml, ogp = orc.momentum_element(mesh, fs, o, ele)
+        scale = max(np.abs(oT).max(), 1e-300)
+        assert np.abs(T - oT).max() <= TOL * scale, (variant, ele)
+        assert rel_err(r, orr) < TOL
+        assert rel_err(ml, oml) < TOL
+        if o.assemble_ct_matrix_here:
+            assert rel_err(gp, ogp) < TOL
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+@pytest.mark.parametrize("variant", list(advdiff_variants().keys()))
+def test_advdiff_element_matrices(orc, dim, variant):
+    mesh = syn.box_mesh((4, 3, 5)[:dim], seed=22)
+    o = advdiff_variants()[variant]
+    fs = fields_for(mesh, variant)
+    asm = make_asm(mesh, fs)
+    rng = np.random.default_rng(1)
+    for ele in [1, mesh.n_elements] + rng.integers(1, mesh.n_elements + 1, size=6).tolist():
+        A, r = asm.advdiff_element(o, ele)
+        oA, orr = orc.advdiff_element(mesh, fs, o, ele)
+        assert rel_err(A, oA) < TOL, (variant, ele)
+        assert rel_err(r, orr) < TOL
+
+
+# ---- assembled values, every scatter variant ----------------------------------------------
+@pytest.mark.parametrize("scatter", ALL_SCATTERS)
+@pytest.mark.parametrize("dim", [2, 3])
+@pytest.mark.parametrize("variant", list(momentum_variants().keys()))
+def test_momentum_assembly(orc, scatter, dim, variant):
+    mesh = syn.box_mesh((6, 5, 4)[:dim], seed=31)
+    o = momentum_variants()[variant]
+    fs = fields_for(mesh, variant)
+    asm = make_asm(mesh, fs, scatter)
+    findrm, colm, _ = asm.get_sparsity()
+    got = asm.momentum(o)
+    ref = orc.assemble_momentum(mesh, fs, o, findrm, colm, want_ct=bool(o.assemble_ct_matrix_here))
+    check_momentum(got, ref, findrm, dim)
+
+
+@pytest.mark.parametrize("scatter", ALL_SCATTERS)
+@pytest.mark.parametrize("dim", [2, 3])
+@pytest.mark.parametrize("variant", list(advdiff_variants().keys()))
+def test_advdiff_assembly(orc, scatter, dim, variant):
+    mesh = syn.box_mesh((6, 5, 4)[:dim], seed=32)
+    o = advdiff_variants()[variant]
+    fs = fields_for(mesh, variant)
+    asm = make_asm(mesh, fs, scatter)
+    findrm, colm, _ = asm.get_sparsity()
+    got = asm.advdiff(o)
+    ref = orc.assemble_advdiff(mesh, fs, o, findrm, colm)
+    assert rel_err(got["matrix"], ref["matrix"]) < TOL
+    assert row_rel_err(got["matrix"], ref["matrix"], findrm) < TOL
+    assert rel_err(got["rhs"], ref["rhs"]) < TOL
+
+
+@pytest.mark.parametrize("scatter", ALL_SCATTERS)
+@pytest.mark.parametrize("name", ["cube-parallel", "2d_square", "cube.1"])
+def test_reference_fixture_meshes(orc, scatter, name):
+    # unstructured gmsh meshes from the reference's tests/data
+    mesh = load_golden_mesh(name)
+    fs = syn.standard_fields(mesh)
+    asm = make_asm(mesh, fs, scatter)
+    findrm, colm, _ = asm.get_sparsity()
+    o = abi.common_momentum_opts(have_absorption=1)
+    check_momentum(asm.momentum(o), orc.assemble_momentum(mesh, fs, o, findrm, colm), findrm, mesh.dim)
+    oa = abi.common_advdiff_opts(have_source=1)
+    got, ref = asm.advdiff(oa), orc.assemble_advdiff(mesh, fs, oa, findrm, colm)
+    assert rel_err(got["matrix"], ref["matrix"]) < TOL and rel_err(got["rhs"], ref["rhs"]) < TOL
+
+
+@pytest.mark.parametrize("scatter", ALL_SCATTERS)
+def test_shuffled_numbering_s3_small(orc, scatter):
+    # S3-small (32^3 x 6 = 196 608 tets) with nodes and elements randomly renumbered: no
+    # structure for the kernels to lean on
+    mesh = syn.shuffled(syn.box_mesh((32, 32, 32)), seed=5)
+    fs = syn.standard_fields(mesh)
+    asm = make_asm(mesh, fs, scatter)
+    findrm, colm, _ = asm.get_sparsity()
+    o = abi.common_momentum_opts()
+    check_momentum(asm.momentum(o), orc.assemble_momentum(mesh, fs, o, findrm, colm), findrm, 3)
+    oa = abi.common_advdiff_opts()
+    got, ref = asm.advdiff(oa), orc.assemble_advdiff(mesh, fs, oa, findrm, colm)
+    assert rel_err(got["matrix"], ref["matrix"]) < TOL and rel_err(got["rhs"], ref["rhs"]) < TOL
+
+
+# ---- size-independent properties at a size the oracle would not finish quickly ---------------
+@pytest.mark.parametrize("scatter", [pytest.param(abi.SCATTER_ATOMIC, id="atomic"), pytest.param(abi.SCATTER_TILED, id="tiled")])
+def test_large_mesh_properties(scatter):
+    mesh = syn.box_mesh((96, 96, 96), jitter=0.1)
+    fs = syn.standard_fields(mesh)
+    fs.set(abi.F_T, np.ones(mesh.n_nodes))
+    fs.set(abi.F_DENSITY, np.ones(1), abi.FIELD_CONSTANT)
+    asm = make_asm(mesh, fs, scatter)
+    findrm, colm, centrm = asm.get_sparsity()
+    # (1) constants are in the kernel of advection(beta=0)+diffusion: tracer rhs == 0 for T == 1
+    out = asm.advdiff(abi.common_advdiff_opts())
+    assert np.abs(out["rhs"]).max() < 1e-12 * np.abs(out["matrix"]).max()
+    # (2) the consistent mass matrix sums to the volume of the unit cube
+    out = asm.advdiff(abi.common_advdiff_opts(have_advection=0, have_diffusivity=0))
+    assert abs(out["matrix"].sum() - 1.0) < 1e-10
+    # (3) lumped mass (rho = 1) sums to the volume too, identically for every component, and
+    #     equals the big_m diagonal when nothing else is assembled
+    o = abi.common_momentum_opts(exclude_advection=1, have_viscosity=0, have_gravity=0)
+    out = asm.momentum(o)
+    for d in range(3):
+        assert abs(out["masslump"][:, d].sum() - 1.0) < 1e-10
+        assert rel_err(out["big_m"][d][centrm - 1], out["masslump"][:, d]) < TOL
+        assert np.abs(out["rhs"]).max() == 0.0
+    # (4) linearity in oldu: rhs(2*oldu) - rhs(oldu) == rhs(oldu) - rhs(0)  (no mass in rhs)
+    o = abi.common_momentum_opts(have_gravity=0)
+    oldu, _ = fs.get(abi.F_OLDU)
+    r1 = asm.momentum(o)["rhs"].copy()
+    asm.set_field(abi.F_OLDU, 2 * oldu)
+    r2 = asm.momentum(o)["rhs"].copy()
+    assert rel_err(r2, 2 * r1) < 1e-11
+    # (5) idempotence: same call twice gives identical sums for the deterministic variant
+    a = asm.momentum(o)["big_m"].copy()
+    b = asm.momentum(o)["big_m"]
+    if scatter == abi.SCATTER_TILED:
+        assert (a == b).all()
+    else:
+        assert rel_err(a, b) < TOL
+
+
+def test_unsupported_options_are_refused():
+    mesh = syn.box_mesh((2, 2, 2))
+    asm = make_asm(mesh, syn.standard_fields(mesh))
+    for kw in (dict(have_les=1), dict(stress_form=1), dict(have_coriolis=1), dict(move_mesh=1)):
+        with pytest.raises(cgasm.CgasmError) as ei:
+            asm.momentum(abi.common_momentum_opts(**kw))
+        assert ei.value.code == abi.EUNSUPPORTED
+    with pytest.raises(cgasm.CgasmError) as ei:
+        asm.advdiff(abi.common_advdiff_opts(multiphase=1))
+    assert ei.value.code == abi.EUNSUPPORTED
+
+
+def test_missing_field_is_state_error():
+    mesh = syn.box_mesh((2, 2, 2))
+    asm = make_asm(mesh)
+    with pytest.raises(cgasm.CgasmError) as ei:
+        asm.momentum(abi.common_momentum_opts())
+    assert ei.value.code == abi.ESTATE
