@@ -42,12 +42,53 @@ static void free_dev(void* p) {
   if (p) cudaFree(p);
 }
 
+// rec[node].lane[lane0 + c] = src[node*stride + c]   (stride 0: CONSTANT field, broadcast)
+__global__ void pack_lanes_kernel(double4* __restrict__ rec, int lane0, int ncomp,
+                                  const double* __restrict__ src, int stride, const int* __restrict__ nodes, int n) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int node = nodes ? nodes[k] : k;
+  double* r = reinterpret_cast<double*>(rec + node);
+  for (int c = 0; c < ncomp; c++) r[lane0 + c] = src[(size_t)stride * node + c];
+}
+
+int repack_slot(Handle* h, int slot, const int* d_nodes, int n) {
+  double4* rec;
+  int lane0, ncomp, stride;
+  const double* src;
+  const int dim = h->dim;
+  if (slot < 0) {
+    rec = h->d_rec0; lane0 = 0; ncomp = dim; src = h->d_X; stride = dim;
+  } else {
+    const DeviceField& f = h->fields[slot];
+    const bool cst = f.field_type == CGASM_FIELD_CONSTANT;
+    src = f.d;
+    switch (slot) {
+      case CGASM_F_T: rec = h->d_rec0; lane0 = 3; ncomp = 1; stride = cst ? 0 : 1; break;
+      case CGASM_F_NU: rec = h->d_rec1; lane0 = 0; ncomp = dim; stride = cst ? 0 : dim; break;
+      case CGASM_F_DENSITY: rec = h->d_rec1; lane0 = 3; ncomp = 1; stride = cst ? 0 : 1; break;
+      case CGASM_F_OLDU: rec = h->d_rec2; lane0 = 0; ncomp = dim; stride = cst ? 0 : dim; break;
+      case CGASM_F_BUOYANCY: rec = h->d_rec2; lane0 = 3; ncomp = 1; stride = cst ? 0 : 1; break;
+      default: return CGASM_OK;  // not a packed field
+    }
+  }
+  const int count = d_nodes ? n : h->n_nodes;
+  if (count <= 0) return CGASM_OK;
+  pack_lanes_kernel<<<(count + 255) / 256, 256, 0, h->stream>>>(rec, lane0, ncomp, src, stride, d_nodes, count);
+  h->launches++;
+  CG_CUDA(cudaGetLastError());
+  return CGASM_OK;
+}
+
 static void destroy_handle(Handle* h) {
   cudaSetDevice(h->device);
   tiles_free(h);
   halo_free(h);
   free_dev(h->d_ndglno);
   free_dev(h->d_X);
+  free_dev(h->d_rec0);
+  free_dev(h->d_rec1);
+  free_dev(h->d_rec2);
   free_dev(h->d_findrm);
   free_dev(h->d_colm);
   free_dev(h->d_colour_elements);
@@ -148,12 +189,10 @@ static int make_momentum_args(Handle* h, const cgasm_momentum_opts* o, MomentumA
   A.tab = h->tab;
   A.o = *o;
   A.ndglno = h->d_ndglno;
-  A.X = h->d_X;
-  A.nu = view_of(h, CGASM_F_NU, dim);
-  A.oldu = view_of(h, CGASM_F_OLDU, dim);
-  A.density = view_of(h, CGASM_F_DENSITY, 1);
+  A.rec.r0 = h->d_rec0;
+  A.rec.r1 = h->d_rec1;
+  A.rec.r2 = h->d_rec2;
   A.viscosity = view_of(h, CGASM_F_VISCOSITY, dim * dim);
-  A.buoyancy = view_of(h, CGASM_F_BUOYANCY, 1);
   A.hb_density = view_of(h, CGASM_F_HB_DENSITY, 1);
   A.gravity = view_of(h, CGASM_F_GRAVITY, dim);
   A.absorption = view_of(h, CGASM_F_ABSORPTION, dim);
@@ -175,9 +214,9 @@ static int make_advdiff_args(Handle* h, const cgasm_advdiff_opts* o, AdvDiffArgs
   P.tab = h->tab;
   P.o = *o;
   P.ndglno = h->d_ndglno;
-  P.X = h->d_X;
-  P.t = view_of(h, CGASM_F_T, 1);
-  P.velocity = view_of(h, CGASM_F_NU, dim);
+  P.rec.r0 = h->d_rec0;
+  P.rec.r1 = h->d_rec1;
+  P.rec.r2 = h->d_rec2;
   P.source = view_of(h, CGASM_F_T_SOURCE, 1);
   P.absorption = view_of(h, CGASM_F_T_ABSORPTION, 1);
   P.diffusivity = view_of(h, CGASM_F_T_DIFFUSIVITY, dim * dim);
@@ -262,6 +301,12 @@ int cgasm_create(int* id, int device, int dim, int loc, int ngi, int n_nodes, in
       cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess ||
       cudaMalloc(&h->d_ndglno, sizeof(int4) * (size_t)n_elements) != cudaSuccess ||
       cudaMalloc(&h->d_X, sizeof(double) * (size_t)dim * n_nodes) != cudaSuccess ||
+      cudaMalloc(&h->d_rec0, sizeof(double4) * (size_t)n_nodes) != cudaSuccess ||
+      cudaMalloc(&h->d_rec1, sizeof(double4) * (size_t)n_nodes) != cudaSuccess ||
+      cudaMalloc(&h->d_rec2, sizeof(double4) * (size_t)n_nodes) != cudaSuccess ||
+      cudaMemset(h->d_rec0, 0, sizeof(double4) * (size_t)n_nodes) != cudaSuccess ||
+      cudaMemset(h->d_rec1, 0, sizeof(double4) * (size_t)n_nodes) != cudaSuccess ||
+      cudaMemset(h->d_rec2, 0, sizeof(double4) * (size_t)n_nodes) != cudaSuccess ||
       cudaMemcpy(h->d_ndglno, h->h_nd0.data(), sizeof(int4) * (size_t)n_elements,
                  cudaMemcpyHostToDevice) != cudaSuccess) {
     set_error(std::string("cgasm_create: ") + cudaGetErrorString(cudaGetLastError()));
@@ -293,6 +338,8 @@ int cgasm_set_coordinates(int id, const double* X) {
   const size_t cnt = (size_t)h->dim * h->n_nodes;
   h->h_X.assign(X, X + cnt);
   CG_CUDA(cudaMemcpyAsync(h->d_X, X, sizeof(double) * cnt, cudaMemcpyHostToDevice, h->stream));
+  int st = repack_slot(h, -1, nullptr, 0);
+  if (st) return st;
   CG_CUDA(cudaStreamSynchronize(h->stream));
   h->have_X = true;
   return CGASM_OK;
@@ -461,12 +508,14 @@ int cgasm_set_field(int id, int slot, int rank, int field_type, const double* va
   }
   if (!f.d) CG_CUDA(cudaMalloc(&f.d, sizeof(double) * count));
   CG_CUDA(cudaMemcpyAsync(f.d, val, sizeof(double) * count, cudaMemcpyHostToDevice, h->stream));
-  CG_CUDA(cudaStreamSynchronize(h->stream));
   f.rank = rank;
   f.field_type = field_type;
   f.n_val_nodes = n_val_nodes;
   f.count = count;
   f.set = true;
+  int st = repack_slot(h, slot, nullptr, 0);
+  if (st) return st;
+  CG_CUDA(cudaStreamSynchronize(h->stream));
   return CGASM_OK;
 }
 

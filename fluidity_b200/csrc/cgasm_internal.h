@@ -32,8 +32,12 @@ struct Handle {
 
   std::vector<int> h_nd0;  // 0-based connectivity, stride 4 (4th = -1 on triangles)
   int4* d_ndglno = nullptr;
-  double* d_X = nullptr;
+  double* d_X = nullptr;  // Coordinate%val(dim, n_nodes) as given
   bool have_X = false;
+  // packed node records read by the kernels (element_math.cuh NodeRecs)
+  double4* d_rec0 = nullptr;
+  double4* d_rec1 = nullptr;
+  double4* d_rec2 = nullptr;
   std::vector<double> h_X;  // kept for locality ordering of the tile plan
 
   // node -> element adjacency (host)
@@ -109,5 +113,9 @@ int tiles_advdiff(Handle* h, const AdvDiffArgs& args);
 
 // halo.cu
 void halo_free(Handle* h);
+
+// cgasm_api.cu: refresh the packed record lanes fed by `slot` (-1 = coordinates); nodes == nullptr
+// repacks every node, else only the listed ones (device array of 0-based node ids).
+int repack_slot(Handle* h, int slot, const int* d_nodes, int n);
 
 }  // namespace cgasm

@@ -38,12 +38,24 @@ struct FieldView {
   int stride;
 };
 
+// Packed per-node records of the six fields every element reads (device-private layout; the
+// caller's arrays keep the reference layout). One record = one 32-byte sector = one 256-bit
+// load, instead of dim+1 scattered 8-byte loads that each drag a whole sector through L2:
+//   r0[node] = { X(1..dim), [0], T }     r1[node] = { nu(1..dim), [0], density }
+//   r2[node] = { oldu(1..dim), [0], buoyancy }
+// CONSTANT fields are broadcast into the records when they are set.
+struct NodeRecs {
+  const double4* __restrict__ r0;
+  const double4* __restrict__ r1;
+  const double4* __restrict__ r2;
+};
+
 struct MomentumArgs {
   Tables tab;
   cgasm_momentum_opts o;
   const int4* __restrict__ ndglno;  // 0-based, padded to 4 ints
-  const double* __restrict__ X;     // (dim, n_nodes)
-  FieldView nu, oldu, density, viscosity, buoyancy, hb_density, gravity, absorption, source;
+  NodeRecs rec;
+  FieldView viscosity, hb_density, gravity, absorption, source;
   int n_elements;
 };
 
@@ -51,10 +63,24 @@ struct AdvDiffArgs {
   Tables tab;
   cgasm_advdiff_opts o;
   const int4* __restrict__ ndglno;
-  const double* __restrict__ X;
-  FieldView t, velocity, source, absorption, diffusivity;
+  NodeRecs rec;
+  FieldView source, absorption, diffusivity;
   int n_elements;
 };
+
+__device__ __forceinline__ double4 ld256(const double4* p) {
+  double4 v;
+  asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
+  return v;
+}
+
+template <int DIM>
+__device__ __forceinline__ void unpack(const double4& r, double (&v)[DIM], double& s) {
+  v[0] = r.x;
+  v[1] = r.y;
+  if constexpr (DIM == 3) v[2] = r.z;
+  s = r.w;
+}
 
 __device__ __forceinline__ int node_of(const int4& nd, int i) {
   return i == 0 ? nd.x : (i == 1 ? nd.y : (i == 2 ? nd.z : nd.w));
@@ -153,18 +179,19 @@ __device__ __forceinline__ void momentum_element(const MomentumArgs& A, const in
   const Tables& t = A.tab;
   const double dtt = o.dt * o.theta;
 
-  double X[LOC][DIM], nu[LOC][DIM], oldu[LOC][DIM], rho[LOC];
+  double X[LOC][DIM], nu[LOC][DIM], oldu[LOC][DIM], rho[LOC], buoy[LOC];
 #pragma unroll
   for (int i = 0; i < LOC; i++) {
     const int node = node_of(nd, i);
-    gather<DIM>(FieldView{A.X, DIM}, node, X[i]);
-    gather<DIM>(A.nu, node, nu[i]);
-    gather<DIM>(A.oldu, node, oldu[i]);
-    double r1[1];
-    gather<1>(A.density, node, r1);
-    rho[i] = r1[0];
+    double unused;
+    unpack<DIM>(ld256(A.rec.r0 + node), X[i], unused);
+    unpack<DIM>(ld256(A.rec.r1 + node), nu[i], rho[i]);
+    unpack<DIM>(ld256(A.rec.r2 + node), oldu[i], buoy[i]);
   }
   geometry<DIM>(X, G);
+  double wsum = 0.0;  // sum_g w_g (compile-time foldable: tables sit in the constant bank)
+#pragma unroll
+  for (int g = 0; g < NGI; g++) wsum += t.w[g];
 
   // c_g = rho_g * detwei_g  (coefficient_detwei, :1536, :1674)
   double c[NGI];
@@ -303,22 +330,29 @@ __device__ __forceinline__ void momentum_element(const MomentumArgs& A, const in
 
   // Viscosity, tensor form (add_viscosity_element_cg, :2286-2359)
   if (o.have_viscosity) {
-    double visc[LOC][DIM * DIM];
-#pragma unroll
-    for (int i = 0; i < LOC; i++) gather<DIM * DIM>(A.viscosity, node_of(nd, i), visc[i]);
     // Vbar(a,b) = sum_g (sum_i visc_i(a,b) N_ig) detwei_g ; memory index a + DIM*b
     double Vbar[DIM * DIM];
+    if (A.viscosity.stride == 0) {
+      // CONSTANT field: sum_i N_ig = 1  =>  Vbar = visc * |detJ| * sum_g w_g
+      gather<DIM * DIM>(A.viscosity, 0, Vbar);
 #pragma unroll
-    for (int ab = 0; ab < DIM * DIM; ab++) {
-      double s = 0.0;
+      for (int ab = 0; ab < DIM * DIM; ab++) Vbar[ab] *= G.absdet * wsum;
+    } else {
+      double visc[LOC][DIM * DIM];
 #pragma unroll
-      for (int i = 0; i < LOC; i++) {
-        double ni = 0.0;
+      for (int i = 0; i < LOC; i++) gather<DIM * DIM>(A.viscosity, node_of(nd, i), visc[i]);
 #pragma unroll
-        for (int g = 0; g < NGI; g++) ni += t.N[i * NGI + g] * t.w[g];
-        s += visc[i][ab] * ni;
+      for (int ab = 0; ab < DIM * DIM; ab++) {
+        double s = 0.0;
+#pragma unroll
+        for (int i = 0; i < LOC; i++) {
+          double ni = 0.0;
+#pragma unroll
+          for (int g = 0; g < NGI; g++) ni += t.N[i * NGI + g] * t.w[g];
+          s += visc[i][ab] * ni;
+        }
+        Vbar[ab] = s * G.absdet;
       }
-      Vbar[ab] = s * G.absdet;
     }
 #pragma unroll
     for (int i = 0; i < LOC; i++) {
@@ -385,35 +419,50 @@ __device__ __forceinline__ void momentum_element(const MomentumArgs& A, const in
 
   // Buoyancy (add_buoyancy_element_cg, :1753-1792)
   if (o.have_gravity) {
-    double b[LOC], bq[NGI], gv[LOC][DIM];
+    double b[LOC], bq[NGI];
 #pragma unroll
     for (int i = 0; i < LOC; i++) {
-      double r1[1];
-      gather<1>(A.buoyancy, node_of(nd, i), r1);
-      b[i] = r1[0];
+      b[i] = buoy[i];
       if (o.subtract_out_reference_profile) {
+        double r1[1];
         gather<1>(A.hb_density, node_of(nd, i), r1);
         b[i] -= r1[0];
       }
-      gather<DIM>(A.gravity, node_of(nd, i), gv[i]);
     }
     at_quad<DIM>(t, b, bq);
 #pragma unroll
     for (int g = 0; g < NGI; g++) bq[g] *= o.gravity_magnitude * G.absdet * t.w[g];
+    if (A.gravity.stride == 0) {
+      // CONSTANT gravity direction: rhs(d,i) += ghat_d * sum_g N_ig c_g
+      double gd[DIM];
+      gather<DIM>(A.gravity, 0, gd);
 #pragma unroll
-    for (int g = 0; g < NGI; g++) {
-      double gg[DIM];
-#pragma unroll
-      for (int a = 0; a < DIM; a++) {
+      for (int i = 0; i < LOC; i++) {
         double s = 0.0;
 #pragma unroll
-        for (int i = 0; i < LOC; i++) s += gv[i][a] * t.N[i * NGI + g];
-        gg[a] = s * bq[g];
+        for (int g = 0; g < NGI; g++) s += t.N[i * NGI + g] * bq[g];
+#pragma unroll
+        for (int d = 0; d < DIM; d++) R.rhs[d][i] += s * gd[d];
       }
+    } else {
+      double gv[LOC][DIM];
 #pragma unroll
-      for (int i = 0; i < LOC; i++)
+      for (int i = 0; i < LOC; i++) gather<DIM>(A.gravity, node_of(nd, i), gv[i]);
 #pragma unroll
-        for (int d = 0; d < DIM; d++) R.rhs[d][i] += t.N[i * NGI + g] * gg[d];
+      for (int g = 0; g < NGI; g++) {
+        double gg[DIM];
+#pragma unroll
+        for (int a = 0; a < DIM; a++) {
+          double s = 0.0;
+#pragma unroll
+          for (int i = 0; i < LOC; i++) s += gv[i][a] * t.N[i * NGI + g];
+          gg[a] = s * bq[g];
+        }
+#pragma unroll
+        for (int i = 0; i < LOC; i++)
+#pragma unroll
+          for (int d = 0; d < DIM; d++) R.rhs[d][i] += t.N[i * NGI + g] * gg[d];
+      }
     }
   }
 
@@ -490,15 +539,12 @@ __device__ __forceinline__ void advdiff_element(const AdvDiffArgs& P, const int4
 
   double X[LOC][DIM], T[LOC];
 #pragma unroll
-  for (int i = 0; i < LOC; i++) {
-    const int node = node_of(nd, i);
-    gather<DIM>(FieldView{P.X, DIM}, node, X[i]);
-    double r1[1];
-    gather<1>(P.t, node, r1);
-    T[i] = r1[0];
-  }
+  for (int i = 0; i < LOC; i++) unpack<DIM>(ld256(P.rec.r0 + node_of(nd, i)), X[i], T[i]);
   Geom<DIM> G;
   geometry<DIM>(X, G);
+  double wsum = 0.0;
+#pragma unroll
+  for (int g = 0; g < NGI; g++) wsum += t.w[g];
 
 #pragma unroll
   for (int i = 0; i < LOC; i++) {
@@ -539,7 +585,10 @@ __device__ __forceinline__ void advdiff_element(const AdvDiffArgs& P, const int4
   if (o.have_advection) {
     double u[LOC][DIM], ug[NGI][DIM];
 #pragma unroll
-    for (int i = 0; i < LOC; i++) gather<DIM>(P.velocity, node_of(nd, i), u[i]);
+    for (int i = 0; i < LOC; i++) {
+      double unused;
+      unpack<DIM>(ld256(P.rec.r1 + node_of(nd, i)), u[i], unused);
+    }
 #pragma unroll
     for (int g = 0; g < NGI; g++)
 #pragma unroll
@@ -613,20 +662,27 @@ __device__ __forceinline__ void advdiff_element(const AdvDiffArgs& P, const int4
 
   // Diffusivity (:1164-1202)
   if (o.have_diffusivity) {
-    double kap[LOC][DIM * DIM], Kbar[DIM * DIM];
+    double Kbar[DIM * DIM];
+    if (P.diffusivity.stride == 0) {
+      gather<DIM * DIM>(P.diffusivity, 0, Kbar);
 #pragma unroll
-    for (int i = 0; i < LOC; i++) gather<DIM * DIM>(P.diffusivity, node_of(nd, i), kap[i]);
+      for (int ab = 0; ab < DIM * DIM; ab++) Kbar[ab] *= G.absdet * wsum;
+    } else {
+      double kap[LOC][DIM * DIM];
 #pragma unroll
-    for (int ab = 0; ab < DIM * DIM; ab++) {
-      double s = 0.0;
+      for (int i = 0; i < LOC; i++) gather<DIM * DIM>(P.diffusivity, node_of(nd, i), kap[i]);
 #pragma unroll
-      for (int i = 0; i < LOC; i++) {
-        double ni = 0.0;
+      for (int ab = 0; ab < DIM * DIM; ab++) {
+        double s = 0.0;
 #pragma unroll
-        for (int g = 0; g < NGI; g++) ni += t.N[i * NGI + g] * t.w[g];
-        s += kap[i][ab] * ni;
+        for (int i = 0; i < LOC; i++) {
+          double ni = 0.0;
+#pragma unroll
+          for (int g = 0; g < NGI; g++) ni += t.N[i * NGI + g] * t.w[g];
+          s += kap[i][ab] * ni;
+        }
+        Kbar[ab] = s * G.absdet;
       }
-      Kbar[ab] = s * G.absdet;
     }
 #pragma unroll
     for (int i = 0; i < LOC; i++) {

@@ -242,6 +242,11 @@ int cgasm_halo_update(int id, unsigned slot_mask) {
         p->d_recv_kk, h->fields[slots[i]].d, p->d_recv_stage);
     h->launches++;
   }
+  // the kernels read packed node records: refresh the received nodes of the packed fields
+  for (int i = 0; i < ns && p->total_recv; i++) {
+    int st = repack_slot(h, slots[i], p->d_recv_node, p->total_recv);
+    if (st) return st;
+  }
   CG_CUDA(cudaGetLastError());
   return CGASM_OK;
 }

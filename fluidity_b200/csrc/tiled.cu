@@ -1,14 +1,705 @@
-// tiled.cu -- node-tile owner-computes assembly (CGASM_SCATTER_TILED). Placeholder until the
-// tiled kernels land: selecting the variant reports CGASM_EUNSUPPORTED.
+// tiled.cu -- CGASM_SCATTER_TILED: node-tile owner-computes assembly.
+//
+// The reference scatters every element contribution straight into the global CSR
+// (femtools/Sparse_Tools.F90:2680-2703, Sparse_Tools_Petsc.F90:848-879) and, under OpenMP,
+// serialises conflicting elements with a mesh-wide colouring (femtools/Colouring.F90).
+// On a B200 neither maps well (measured, profiles/): global FP64 reds are bound by the SM's
+// REDG issue rate (~1.3 cycles/lane, ~2e11 reds/s for the whole chip) and mesh-wide colours
+// destroy locality. This variant re-uses the reference's own PARALLEL decomposition idea one
+// level down -- node ownership + redundant assembly of halo elements
+// (every MPI rank assembles all its elements and keeps only owned rows):
+//
+//   * nodes are ordered along a Morton curve of their coordinates and cut into tiles of
+//     <= max_rows rows whose CSR rows fit in shared memory;
+//   * one CTA owns one tile: it visits EVERY element touching an owned node (elements on a
+//     tile surface are visited by each tile they touch: ~1.3-1.4x redundant element math,
+//     zero inter-CTA communication), accumulates the owned rows in shared memory and writes
+//     each CSR value / rhs entry exactly once with coalesced stores -- no atomics, no
+//     pre-zeroing of the outputs, bitwise reproducible from run to run;
+//   * inside the CTA, conflicting read-modify-writes are serialised the way Colouring.F90
+//     does it, but per tile: elements are greedily coloured (balanced, conflicts only through
+//     OWNED nodes) and the colours become __syncthreads-separated phases.
+//
+// The per-element record (node ids, tile-local row of each node, slot of every (i,j) inside
+// that row) is precomputed once per mesh+sparsity, so the hot loop does no searching at all
+// (the reference bisects every entry, Sparse_Tools.F90:2438-2497).
 #include "cgasm_internal.h"
 
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <numeric>
+
 namespace cgasm {
-struct TilePlan {};
-int tiles_build(Handle*) { CG_FAIL(CGASM_EUNSUPPORTED, "tiled scatter not built yet"); }
+
+struct TileClassPlan {
+  int nb = 0, nvec = 0;     // accumulated matrix blocks / vector components this plan is sized for
+  int ntiles = 0;
+  int max_tile_entries = 0, max_tile_rows = 0, max_phase = 0;
+  size_t smem_bytes = 0;
+  long long n_tile_elements = 0;
+  // device arrays
+  int* d_tile_row_ptr = nullptr;    // [ntiles+1] into rows
+  int* d_rows = nullptr;            // owned global node per tile row (ascending inside a tile)
+  int* d_rowoff = nullptr;          // offset of the row inside the tile's matrix accumulator
+  int* d_tile_entries = nullptr;    // [ntiles] CSR entries owned by the tile
+  int* d_tile_phase_off = nullptr;  // [ntiles+1] into phase_ptr
+  int* d_phase_ptr = nullptr;       // per tile: nphase+1 offsets into the element records
+  int* d_tile_run_ptr = nullptr;    // [ntiles+1] into runs
+  int2* d_runs = nullptr;           // {first tile-local row, nrows}: consecutive global node ids
+  int4* d_el_nodes = nullptr;       // per tile-element: global node ids (0-based)
+  uint2* d_el_rows = nullptr;       // 4 x uint16 tile-local row (0xFFFF = not owned)
+  uint4* d_el_slots = nullptr;      // 16 x uint8: slot of (i,j) inside row i  (i*4+j)
+};
+
+struct TilePlan {
+  TileClassPlan cls[2];  // [0]: one matrix block, [1]: dim matrix blocks
+  bool built[2] = {false, false};
+};
+
+static void free_class(TileClassPlan& p) {
+  void* ptrs[] = {p.d_tile_row_ptr, p.d_rows, p.d_rowoff, p.d_tile_entries, p.d_tile_phase_off,
+                  p.d_phase_ptr, p.d_tile_run_ptr, p.d_runs, p.d_el_nodes, p.d_el_rows, p.d_el_slots};
+  for (void* q : ptrs)
+    if (q) cudaFree(q);
+  p = TileClassPlan();
+}
+
 void tiles_free(Handle* h) {
+  if (!h->tiles) return;
+  for (auto& c : h->tiles->cls) free_class(c);
   delete h->tiles;
   h->tiles = nullptr;
 }
-int tiles_momentum(Handle*, const MomentumArgs&, bool, bool) { CG_FAIL(CGASM_EUNSUPPORTED, "tiled scatter not built yet"); }
-int tiles_advdiff(Handle*, const AdvDiffArgs&) { CG_FAIL(CGASM_EUNSUPPORTED, "tiled scatter not built yet"); }
+
+// ---- Morton order ----------------------------------------------------------------------------
+static inline uint64_t spread3(uint64_t x) {  // 21 bits -> every third bit
+  x &= 0x1fffff;
+  x = (x | x << 32) & 0x1f00000000ffffULL;
+  x = (x | x << 16) & 0x1f0000ff0000ffULL;
+  x = (x | x << 8) & 0x100f00f00f00f00fULL;
+  x = (x | x << 4) & 0x10c30c30c30c30c3ULL;
+  x = (x | x << 2) & 0x1249249249249249ULL;
+  return x;
+}
+static inline uint64_t spread2(uint64_t x) {  // 32 bits -> every second bit
+  x &= 0xffffffffULL;
+  x = (x | x << 16) & 0x0000ffff0000ffffULL;
+  x = (x | x << 8) & 0x00ff00ff00ff00ffULL;
+  x = (x | x << 4) & 0x0f0f0f0f0f0f0f0fULL;
+  x = (x | x << 2) & 0x3333333333333333ULL;
+  x = (x | x << 1) & 0x5555555555555555ULL;
+  return x;
+}
+
+static void morton_order(const Handle* h, std::vector<int>& order) {
+  const int n = h->n_nodes, dim = h->dim;
+  double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+  for (int i = 0; i < n; i++)
+    for (int a = 0; a < dim; a++) {
+      const double v = h->h_X[(size_t)dim * i + a];
+      lo[a] = std::min(lo[a], v);
+      hi[a] = std::max(hi[a], v);
+    }
+  // Quantise to a lattice about as fine as the mesh itself: h = (bounding volume / n)^(1/dim),
+  // cells_a = round(ext_a / h) - 1 (exact for an (m+1)^dim point lattice). Jittered lattice
+  // nodes then snap to their own lattice point, so fixed-count cuts of the Morton sequence are
+  // aligned bricks (measured redundancy 1.31 at 1024 rows vs 1.51 with a fine quantisation).
+  double vol = 1.0;
+  int live = 0;
+  for (int a = 0; a < dim; a++)
+    if (hi[a] > lo[a]) {
+      vol *= hi[a] - lo[a];
+      live++;
+    }
+  const double hcell = live ? std::pow(vol / (double)n, 1.0 / live) : 1.0;
+  double scale[3] = {0, 0, 0};
+  const double maxcells = dim == 3 ? 2097151.0 : 4294967295.0;
+  for (int a = 0; a < dim; a++)
+    if (hi[a] > lo[a]) {
+      const double cells = std::min(maxcells, std::max(1.0, std::round((hi[a] - lo[a]) / hcell) - 1.0));
+      scale[a] = cells / (hi[a] - lo[a]);
+    }
+  std::vector<uint64_t> key((size_t)n);
+#pragma omp parallel for schedule(static)
+  for (int i = 0; i < n; i++) {
+    uint64_t q[3] = {0, 0, 0};
+    for (int a = 0; a < dim; a++) q[a] = (uint64_t)std::llround((h->h_X[(size_t)dim * i + a] - lo[a]) * scale[a]);
+    key[i] = dim == 3 ? (spread3(q[0]) | spread3(q[1]) << 1 | spread3(q[2]) << 2) : (spread2(q[0]) | spread2(q[1]) << 1);
+  }
+  order.resize((size_t)n);
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return key[a] < key[b]; });
+}
+
+template <class T>
+static int upload(T** d, const std::vector<T>& v) {
+  CG_CUDA(cudaMalloc(d, sizeof(T) * std::max<size_t>(v.size(), 1)));
+  if (!v.empty()) CG_CUDA(cudaMemcpy(*d, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice));
+  return CGASM_OK;
+}
+
+// Fills el_rows-derived slots on the device: slot of column node j inside CSR row of node i.
+__global__ void tile_slots_kernel(long long n, const int4* __restrict__ el_nodes, int loc,
+                                  const int* __restrict__ findrm, const int* __restrict__ colm,
+                                  uint4* __restrict__ el_slots) {
+  const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int4 nd = el_nodes[k];
+  const int nodes[4] = {nd.x, nd.y, nd.z, nd.w};
+  unsigned packed[4] = {0, 0, 0, 0};
+  for (int i = 0; i < loc; i++) {
+    const int s = findrm[nodes[i]], e = findrm[nodes[i] + 1];
+    for (int q = s; q < e; q++) {
+      const int c = colm[q];
+      for (int j = 0; j < loc; j++)
+        if (c == nodes[j]) packed[i] |= (unsigned)((q - s) & 0xff) << (8 * j);
+    }
+  }
+  el_slots[k] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+}
+
+static int build_class(Handle* h, TileClassPlan& P, int nb, int nvec, const std::vector<int>& order) {
+  const int loc = h->loc, n_nodes = h->n_nodes;
+  const int* nd0 = h->h_nd0.data();
+  const std::vector<int>& fr = h->h_findrm;
+  int max_rows = 1024;
+  size_t smem_cap = 200 * 1024;
+  if (const char* s = getenv("CGASM_TILE_ROWS")) max_rows = std::max(32, atoi(s));
+  if (const char* s = getenv("CGASM_TILE_SMEM_KB")) smem_cap = (size_t)std::max(16, atoi(s)) * 1024;
+  max_rows = std::min(max_rows, 65534);
+  P.nb = nb;
+  P.nvec = nvec;
+
+  // ---- cut the Morton sequence into tiles ---------------------------------------------------
+  std::vector<int> tile_row_ptr{0}, rows;
+  rows.reserve((size_t)n_nodes);
+  {
+    size_t entries = 0;
+    int nrows = 0;
+    auto bytes = [&](size_t ent, int nr) {
+      return sizeof(double) * ((size_t)nb * ent + (size_t)nvec * nr) + sizeof(int) * (size_t)(nr + 1);
+    };
+    for (int k = 0; k < n_nodes; k++) {
+      const int node = order[k];
+      const int len = fr[node + 1] - fr[node];
+      if (len > 255) CG_FAIL(CGASM_EUNSUPPORTED, "CSR row longer than 255 entries: tiled scatter slot index is 8 bit");
+      if (nrows && (nrows == max_rows || bytes(entries + len, nrows + 1) > smem_cap)) {
+        tile_row_ptr.push_back((int)rows.size());
+        entries = 0;
+        nrows = 0;
+      }
+      if (bytes(len, 1) > smem_cap) CG_FAIL(CGASM_EUNSUPPORTED, "a single CSR row does not fit in shared memory");
+      rows.push_back(node);
+      entries += len;
+      nrows++;
+    }
+    tile_row_ptr.push_back((int)rows.size());
+  }
+  const int ntiles = (int)tile_row_ptr.size() - 1;
+  P.ntiles = ntiles;
+
+  std::vector<int> rowoff((size_t)n_nodes), tile_entries((size_t)ntiles), tile_of_node((size_t)n_nodes),
+      lrow_of_node((size_t)n_nodes);
+  std::vector<int> tile_run_ptr((size_t)ntiles + 1, 0);
+  std::vector<std::vector<int2>> runs_t((size_t)ntiles);
+#pragma omp parallel for schedule(dynamic, 64)
+  for (int t = 0; t < ntiles; t++) {
+    int* b = rows.data() + tile_row_ptr[t];
+    int* e = rows.data() + tile_row_ptr[t + 1];
+    std::sort(b, e);  // ascending global id => contiguous CSR ranges on output
+    int off = 0;
+    for (int* p = b; p < e; p++) {
+      const int l = (int)(p - b);
+      rowoff[tile_row_ptr[t] + l] = off;
+      off += fr[*p + 1] - fr[*p];
+      tile_of_node[*p] = t;
+      lrow_of_node[*p] = l;
+      if (l && *p == *(p - 1) + 1) runs_t[t].back().y++;
+      else runs_t[t].push_back(make_int2(l, 1));
+    }
+    tile_entries[t] = off;
+  }
+  std::vector<int2> runs;
+  for (int t = 0; t < ntiles; t++) {
+    tile_run_ptr[t] = (int)runs.size();
+    runs.insert(runs.end(), runs_t[t].begin(), runs_t[t].end());
+    runs_t[t].clear();
+    runs_t[t].shrink_to_fit();
+  }
+  tile_run_ptr[ntiles] = (int)runs.size();
+  P.max_tile_entries = *std::max_element(tile_entries.begin(), tile_entries.end());
+  for (int t = 0; t < ntiles; t++) P.max_tile_rows = std::max(P.max_tile_rows, tile_row_ptr[t + 1] - tile_row_ptr[t]);
+  P.smem_bytes = sizeof(double) * ((size_t)nb * P.max_tile_entries + (size_t)nvec * P.max_tile_rows) +
+                 sizeof(int) * (size_t)(P.max_tile_rows + 1);
+  P.smem_bytes = (P.smem_bytes + 15) & ~(size_t)15;
+
+  // ---- per tile: element set, balanced greedy colouring over owned nodes, phase order -----------
+  std::vector<long long> tile_el_count((size_t)ntiles + 1, 0);
+  std::vector<std::vector<int>> tile_elems((size_t)ntiles);   // element ids in phase order
+  std::vector<std::vector<int>> tile_phase((size_t)ntiles);   // nphase+1 offsets
+#pragma omp parallel
+  {
+    std::vector<int> els, colour, cnt, start;
+    std::vector<uint64_t> mask;  // per tile row: colours already present at that owned node
+#pragma omp for schedule(dynamic, 16)
+    for (int t = 0; t < ntiles; t++) {
+      const int r0 = tile_row_ptr[t], r1 = tile_row_ptr[t + 1], nr = r1 - r0;
+      els.clear();
+      int maxdeg = 1;
+      for (int r = r0; r < r1; r++) {
+        const int node = rows[r];
+        maxdeg = std::max(maxdeg, (int)(h->n2e_ptr[node + 1] - h->n2e_ptr[node]));
+        for (int64_t k = h->n2e_ptr[node]; k < h->n2e_ptr[node + 1]; k++) els.push_back(h->n2e[(size_t)k]);
+      }
+      std::sort(els.begin(), els.end());
+      els.erase(std::unique(els.begin(), els.end()), els.end());
+      const int ne = (int)els.size();
+      mask.assign((size_t)nr, 0);
+      colour.assign((size_t)ne, 0);
+      cnt.assign(64, 0);
+      int palette = std::min(maxdeg, 64), ncol = 0;
+      bool ok = true;
+      for (int k = 0; k < ne && ok; k++) {
+        const int* nd = nd0 + (size_t)4 * els[k];
+        uint64_t used = 0;
+        for (int i = 0; i < loc; i++)
+          if (tile_of_node[nd[i]] == t) used |= mask[lrow_of_node[nd[i]]];
+        int best = -1;
+        for (int c = 0; c < palette; c++)
+          if (!(used >> c & 1) && (best < 0 || cnt[c] < cnt[best])) best = c;
+        if (best < 0) {
+          for (int c = palette; c < 64; c++)
+            if (!(used >> c & 1)) {
+              best = c;
+              break;
+            }
+          if (best < 0) {
+            ok = false;
+            break;
+          }
+          palette = best + 1;
+        }
+        colour[k] = best;
+        cnt[best]++;
+        ncol = std::max(ncol, best + 1);
+        for (int i = 0; i < loc; i++)
+          if (tile_of_node[nd[i]] == t) mask[lrow_of_node[nd[i]]] |= (uint64_t)1 << best;
+      }
+      if (!ok) {
+        tile_phase[t].clear();  // flagged below
+        continue;
+      }
+      start.assign((size_t)ncol + 1, 0);
+      for (int c = 0; c < ncol; c++) start[c + 1] = start[c] + cnt[c];
+      tile_phase[t] = start;
+      tile_elems[t].resize((size_t)ne);
+      std::vector<int> fill(start.begin(), start.end() - 1);
+      for (int k = 0; k < ne; k++) tile_elems[t][(size_t)fill[colour[k]]++] = els[k];
+      tile_el_count[t + 1] = ne;
+    }
+  }
+  for (int t = 0; t < ntiles; t++) {
+    if (tile_phase[t].empty()) CG_FAIL(CGASM_EUNSUPPORTED, "a tile needs more than 64 colours");
+    tile_el_count[t + 1] += tile_el_count[t];
+  }
+  const long long ntel = tile_el_count[ntiles];
+  if (ntel >= ((long long)1 << 31)) CG_FAIL(CGASM_EUNSUPPORTED, "tile element records exceed 2^31");
+  P.n_tile_elements = ntel;
+
+  std::vector<int> tile_phase_off((size_t)ntiles + 1, 0), phase_ptr;
+  for (int t = 0; t < ntiles; t++) {
+    tile_phase_off[t] = (int)phase_ptr.size();
+    for (int v : tile_phase[t]) phase_ptr.push_back((int)(tile_el_count[t] + v));
+    for (size_t c = 0; c + 1 < tile_phase[t].size(); c++)
+      P.max_phase = std::max(P.max_phase, tile_phase[t][c + 1] - tile_phase[t][c]);
+  }
+  tile_phase_off[ntiles] = (int)phase_ptr.size();
+
+  std::vector<int4> el_nodes((size_t)ntel);
+  std::vector<uint2> el_rows((size_t)ntel);
+#pragma omp parallel for schedule(dynamic, 16)
+  for (int t = 0; t < ntiles; t++) {
+    long long base = tile_el_count[t];
+    for (size_t k = 0; k < tile_elems[t].size(); k++) {
+      const int* nd = nd0 + (size_t)4 * tile_elems[t][k];
+      unsigned short lr[4] = {0xFFFF, 0xFFFF, 0xFFFF, 0xFFFF};
+      for (int i = 0; i < loc; i++)
+        if (tile_of_node[nd[i]] == t) lr[i] = (unsigned short)lrow_of_node[nd[i]];
+      // unused 4th node of a triangle: repeat node 0 so gathers stay in range
+      el_nodes[(size_t)(base + k)] = make_int4(nd[0], nd[1], nd[2], loc == 4 ? nd[3] : nd[0]);
+      el_rows[(size_t)(base + k)] = make_uint2((unsigned)lr[0] | (unsigned)lr[1] << 16, (unsigned)lr[2] | (unsigned)lr[3] << 16);
+    }
+  }
+
+  int st;
+  if ((st = upload(&P.d_tile_row_ptr, tile_row_ptr)) || (st = upload(&P.d_rows, rows)) ||
+      (st = upload(&P.d_rowoff, rowoff)) || (st = upload(&P.d_tile_entries, tile_entries)) ||
+      (st = upload(&P.d_tile_phase_off, tile_phase_off)) || (st = upload(&P.d_phase_ptr, phase_ptr)) ||
+      (st = upload(&P.d_tile_run_ptr, tile_run_ptr)) || (st = upload(&P.d_runs, runs)) ||
+      (st = upload(&P.d_el_nodes, el_nodes)) || (st = upload(&P.d_el_rows, el_rows)))
+    return st;
+  CG_CUDA(cudaMalloc(&P.d_el_slots, sizeof(uint4) * (size_t)std::max<long long>(ntel, 1)));
+  {
+    const int block = 256;
+    const long long grid = (ntel + block - 1) / block;
+    tile_slots_kernel<<<(unsigned)grid, block, 0, h->stream>>>(ntel, P.d_el_nodes, loc, h->d_findrm, h->d_colm, P.d_el_slots);
+    h->launches++;
+    CG_CUDA(cudaStreamSynchronize(h->stream));
+  }
+  return CGASM_OK;
+}
+
+int tiles_build(Handle* h) {
+  if (!h->have_X) CG_FAIL(CGASM_ESTATE, "tiled scatter orders nodes by their coordinates: set coordinates first");
+  if (!h->have_sparsity) CG_FAIL(CGASM_ESTATE, "tiled scatter needs the sparsity first");
+  tiles_free(h);
+  h->tiles = new TilePlan();
+  std::vector<int> order;
+  morton_order(h, order);
+  int st = build_class(h, h->tiles->cls[0], 1, 2 * h->dim, order);
+  if (st) {
+    tiles_free(h);
+    return st;
+  }
+  h->tiles->built[0] = true;
+  return CGASM_OK;
+}
+
+static int ensure_class(Handle* h, int c) {
+  if (h->tiles->built[c]) return CGASM_OK;
+  std::vector<int> order;
+  morton_order(h, order);
+  int st = build_class(h, h->tiles->cls[c], c == 0 ? 1 : h->dim, 2 * h->dim, order);
+  if (st) return st;
+  h->tiles->built[c] = true;
+  return CGASM_OK;
+}
+
+// ---- device side ---------------------------------------------------------------------------------
+struct TileArgs {
+  const int* __restrict__ tile_row_ptr;
+  const int* __restrict__ rows;
+  const int* __restrict__ rowoff;
+  const int* __restrict__ tile_entries;
+  const int* __restrict__ tile_phase_off;
+  const int* __restrict__ phase_ptr;
+  const int* __restrict__ tile_run_ptr;
+  const int2* __restrict__ runs;
+  const int4* __restrict__ el_nodes;
+  const uint2* __restrict__ el_rows;
+  const uint4* __restrict__ el_slots;
+  const int* __restrict__ findrm;
+  size_t nnz;
+};
+
+__device__ __forceinline__ unsigned lrow_of(const uint2& r, int i) {
+  const unsigned w = i < 2 ? r.x : r.y;
+  return (i & 1) ? (w >> 16) : (w & 0xffffu);
+}
+__device__ __forceinline__ unsigned slot_of(const uint4& s, int i, int j) {
+  const unsigned w = i == 0 ? s.x : (i == 1 ? s.y : (i == 2 ? s.z : s.w));
+  return (w >> (8 * j)) & 0xffu;
+}
+
+// Shared-memory layout of one tile: [NB][entries] matrix accumulators, [rows][NVEC] vector
+// accumulators, [rows+1] row offsets.
+template <int NB, int NVEC>
+struct TileSmem {
+  double* mat;
+  double* vec;
+  int* off;
+  __device__ TileSmem(unsigned char* base, int max_entries, int max_rows) {
+    mat = reinterpret_cast<double*>(base);
+    vec = mat + (size_t)NB * max_entries;
+    off = reinterpret_cast<int*>(vec + (size_t)NVEC * max_rows);
+  }
+};
+
+// ABS: 0 = no absorption (the dim diagonal blocks are identical: ONE accumulator, written dim
+// times), 1 = lumped absorption (blocks differ on the diagonal), 2 = full absorption matrix.
+// MLD: masslump differs per component (pressure-corrected lumped absorption).
+template <int DIM, int ABS, bool MLD>
+__global__ void __launch_bounds__(384, 1)
+tiled_momentum_kernel(const MomentumArgs A, const TileArgs T, int max_entries, int max_rows,
+                      double* __restrict__ big_m, double* __restrict__ rhs, double* __restrict__ masslump) {
+  constexpr int LOC = DIM + 1;
+  constexpr bool LABS = ABS == 2;
+  constexpr bool PERD = ABS >= 1;
+  constexpr int NB = PERD ? DIM : 1;
+  constexpr int MLC = MLD ? DIM : 1;
+  constexpr int NVEC = DIM + MLC;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  TileSmem<NB, NVEC> S(smem_raw, max_entries, max_rows);
+  const int t = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
+  const int r0 = T.tile_row_ptr[t], nrows = T.tile_row_ptr[t + 1] - r0;
+  const int entries = T.tile_entries[t];
+  for (int k = tid; k < NB * max_entries; k += nthr) S.mat[k] = 0.0;
+  for (int k = tid; k < NVEC * nrows; k += nthr) S.vec[k] = 0.0;
+  for (int k = tid; k < nrows; k += nthr) S.off[k] = T.rowoff[r0 + k];
+  if (tid == 0) S.off[nrows] = entries;
+  __syncthreads();
+
+  const int p0 = T.tile_phase_off[t], nphase = T.tile_phase_off[t + 1] - p0 - 1;
+  for (int ph = 0; ph < nphase; ph++) {
+    const int kb = T.phase_ptr[p0 + ph], ke = T.phase_ptr[p0 + ph + 1];
+    for (int k = kb + tid; k < ke; k += nthr) {
+      const int4 nd = __ldg(T.el_nodes + k);
+      const uint2 lr = __ldg(T.el_rows + k);
+      const uint4 sl = __ldg(T.el_slots + k);
+      MomentumLocal<DIM, LABS> R;
+      Geom<DIM> G;
+      momentum_element<DIM, LABS>(A, nd, R, G);
+#pragma unroll
+      for (int i = 0; i < LOC; i++) {
+        const unsigned r = lrow_of(lr, i);
+        if (r != 0xffffu) {
+          const int base = S.off[r];
+#pragma unroll
+          for (int j = 0; j < LOC; j++) {
+            const int q = base + (int)slot_of(sl, i, j);
+#pragma unroll
+            for (int b = 0; b < NB; b++) {
+              double v = R.L[i][j];
+              if constexpr (LABS) v += R.Labs[b][i][j];
+              if (i == j) v += R.diag[PERD ? b : 0][i];
+              S.mat[(size_t)b * max_entries + q] += v;
+            }
+          }
+#pragma unroll
+          for (int d = 0; d < DIM; d++) S.vec[r * NVEC + d] += R.rhs[d][i];
+#pragma unroll
+          for (int d = 0; d < MLC; d++) S.vec[r * NVEC + DIM + d] += R.ml[d][i];
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- write every owned value exactly once, run by run (consecutive global rows) --------------
+  const int warp = tid >> 5, lane = tid & 31, nwarps = nthr >> 5;
+  const int ru0 = T.tile_run_ptr[t], ru1 = T.tile_run_ptr[t + 1];
+  for (int ru = ru0 + warp; ru < ru1; ru += nwarps) {
+    const int2 run = T.runs[ru];
+    const int g0 = T.rows[r0 + run.x];
+    const int src = S.off[run.x];
+    const int n = S.off[run.x + run.y] - src;
+    const size_t dst = (size_t)T.findrm[g0];
+#pragma unroll
+    for (int d = 0; d < DIM; d++) {
+      const double* s = S.mat + (size_t)(PERD ? d : 0) * max_entries + src;
+      double* o = big_m + (size_t)d * T.nnz + dst;
+      for (int k = lane; k < n; k += 32) o[k] = s[k];
+    }
+    // rhs(dim, node), masslump(dim, node): run.y consecutive nodes
+    for (int k = lane; k < run.y * DIM; k += 32) {
+      const int rr = k / DIM, d = k - rr * DIM;
+      rhs[(size_t)DIM * g0 + k] = S.vec[(run.x + rr) * NVEC + d];
+      if (masslump) masslump[(size_t)DIM * g0 + k] = S.vec[(run.x + rr) * NVEC + DIM + (MLD ? d : 0)];
+    }
+  }
+}
+
+// ct_m: dim blocks grad_p_u_mat (Momentum_CG.F90:1401,1469); first assembly only, so it is a
+// separate pass over the same plan machinery instead of widening the hot kernel.
+template <int DIM>
+__global__ void __launch_bounds__(384, 1)
+tiled_ct_kernel(const MomentumArgs A, const TileArgs T, int max_entries, int max_rows, double* __restrict__ ct_m) {
+  constexpr int LOC = DIM + 1;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  TileSmem<DIM, 0> S(smem_raw, max_entries, max_rows);
+  const int t = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
+  const int r0 = T.tile_row_ptr[t], nrows = T.tile_row_ptr[t + 1] - r0;
+  const int entries = T.tile_entries[t];
+  for (int k = tid; k < DIM * max_entries; k += nthr) S.mat[k] = 0.0;
+  for (int k = tid; k < nrows; k += nthr) S.off[k] = T.rowoff[r0 + k];
+  if (tid == 0) S.off[nrows] = entries;
+  __syncthreads();
+  const int p0 = T.tile_phase_off[t], nphase = T.tile_phase_off[t + 1] - p0 - 1;
+  for (int ph = 0; ph < nphase; ph++) {
+    const int kb = T.phase_ptr[p0 + ph], ke = T.phase_ptr[p0 + ph + 1];
+    for (int k = kb + tid; k < ke; k += nthr) {
+      const int4 nd = __ldg(T.el_nodes + k);
+      const uint2 lr = __ldg(T.el_rows + k);
+      const uint4 sl = __ldg(T.el_slots + k);
+      double X[LOC][DIM];
+#pragma unroll
+      for (int i = 0; i < LOC; i++) {
+        double unused;
+        unpack<DIM>(ld256(A.rec.r0 + node_of(nd, i)), X[i], unused);
+      }
+      Geom<DIM> G;
+      geometry<DIM>(X, G);
+#pragma unroll
+      for (int i = 0; i < LOC; i++) {
+        const unsigned r = lrow_of(lr, i);
+        if (r != 0xffffu) {
+          const int base = S.off[r];
+#pragma unroll
+          for (int j = 0; j < LOC; j++)
+#pragma unroll
+            for (int d = 0; d < DIM; d++)
+              S.mat[(size_t)d * max_entries + base + (int)slot_of(sl, i, j)] += grad_p_u<DIM>(A.tab, G, d, i, j);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  const int warp = tid >> 5, lane = tid & 31, nwarps = nthr >> 5;
+  for (int ru = T.tile_run_ptr[t] + warp; ru < T.tile_run_ptr[t + 1]; ru += nwarps) {
+    const int2 run = T.runs[ru];
+    const int g0 = T.rows[r0 + run.x];
+    const int src = S.off[run.x];
+    const int n = S.off[run.x + run.y] - src;
+    const size_t dst = (size_t)T.findrm[g0];
+#pragma unroll
+    for (int d = 0; d < DIM; d++)
+      for (int k = lane; k < n; k += 32) ct_m[(size_t)d * T.nnz + dst + k] = S.mat[(size_t)d * max_entries + src + k];
+  }
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(384, 1)
+tiled_advdiff_kernel(const AdvDiffArgs A, const TileArgs T, int max_entries, int max_rows,
+                     double* __restrict__ matrix, double* __restrict__ rhs) {
+  constexpr int LOC = DIM + 1;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  TileSmem<1, 1> S(smem_raw, max_entries, max_rows);
+  const int t = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
+  const int r0 = T.tile_row_ptr[t], nrows = T.tile_row_ptr[t + 1] - r0;
+  const int entries = T.tile_entries[t];
+  for (int k = tid; k < max_entries; k += nthr) S.mat[k] = 0.0;
+  for (int k = tid; k < nrows; k += nthr) {
+    S.vec[k] = 0.0;
+    S.off[k] = T.rowoff[r0 + k];
+  }
+  if (tid == 0) S.off[nrows] = entries;
+  __syncthreads();
+  const int p0 = T.tile_phase_off[t], nphase = T.tile_phase_off[t + 1] - p0 - 1;
+  for (int ph = 0; ph < nphase; ph++) {
+    const int kb = T.phase_ptr[p0 + ph], ke = T.phase_ptr[p0 + ph + 1];
+    for (int k = kb + tid; k < ke; k += nthr) {
+      const int4 nd = __ldg(T.el_nodes + k);
+      const uint2 lr = __ldg(T.el_rows + k);
+      const uint4 sl = __ldg(T.el_slots + k);
+      AdvDiffLocal<DIM> R;
+      advdiff_element<DIM>(A, nd, R);
+#pragma unroll
+      for (int i = 0; i < LOC; i++) {
+        const unsigned r = lrow_of(lr, i);
+        if (r != 0xffffu) {
+          const int base = S.off[r];
+#pragma unroll
+          for (int j = 0; j < LOC; j++) S.mat[base + (int)slot_of(sl, i, j)] += R.A[i][j];
+          S.vec[r] += R.rhs[i];
+        }
+      }
+    }
+    __syncthreads();
+  }
+  const int warp = tid >> 5, lane = tid & 31, nwarps = nthr >> 5;
+  for (int ru = T.tile_run_ptr[t] + warp; ru < T.tile_run_ptr[t + 1]; ru += nwarps) {
+    const int2 run = T.runs[ru];
+    const int g0 = T.rows[r0 + run.x];
+    const int src = S.off[run.x];
+    const int n = S.off[run.x + run.y] - src;
+    const size_t dst = (size_t)T.findrm[g0];
+    for (int k = lane; k < n; k += 32) matrix[dst + k] = S.mat[src + k];
+    for (int k = lane; k < run.y; k += 32) rhs[g0 + k] = S.vec[run.x + k];
+  }
+}
+
+static TileArgs tile_args(const Handle* h, const TileClassPlan& P) {
+  TileArgs T;
+  T.tile_row_ptr = P.d_tile_row_ptr;
+  T.rows = P.d_rows;
+  T.rowoff = P.d_rowoff;
+  T.tile_entries = P.d_tile_entries;
+  T.tile_phase_off = P.d_tile_phase_off;
+  T.phase_ptr = P.d_phase_ptr;
+  T.tile_run_ptr = P.d_tile_run_ptr;
+  T.runs = P.d_runs;
+  T.el_nodes = P.d_el_nodes;
+  T.el_rows = P.d_el_rows;
+  T.el_slots = P.d_el_slots;
+  T.findrm = h->d_findrm;
+  T.nnz = (size_t)h->nnz;
+  return T;
+}
+
+static int block_threads(const TileClassPlan& P) {
+  int thr = 384;
+  if (const char* s = getenv("CGASM_TILE_THREADS")) thr = atoi(s);
+  else thr = std::min(384, std::max(128, ((P.max_phase + 31) / 32) * 32));
+  return std::min(384, std::max(32, (thr / 32) * 32));
+}
+
+template <class K>
+static int set_smem(K kernel, size_t bytes) {
+  CG_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return CGASM_OK;
+}
+
+template <int DIM>
+static int tiles_momentum_dim(Handle* h, const MomentumArgs& A, bool want_ml, bool want_ct) {
+  const int abs_mode = !A.o.have_absorption ? 0 : (A.o.lump_absorption ? 1 : 2);
+  const bool mld = abs_mode == 1 && A.o.pressure_corrected_absorption;
+  int st = ensure_class(h, abs_mode ? 1 : 0);
+  if (st) return st;
+  const TileClassPlan& P = h->tiles->cls[abs_mode ? 1 : 0];
+  const TileArgs T = tile_args(h, P);
+  const int thr = block_threads(P);
+  double* ml = want_ml ? h->d_masslump : nullptr;
+#define LAUNCH_MOM(ABS_, MLD_)                                                                        \
+  do {                                                                                                \
+    if ((st = set_smem(tiled_momentum_kernel<DIM, ABS_, MLD_>, P.smem_bytes))) return st;             \
+    tiled_momentum_kernel<DIM, ABS_, MLD_><<<P.ntiles, thr, P.smem_bytes, h->stream>>>(               \
+        A, T, P.max_tile_entries, P.max_tile_rows, h->d_big_m, h->d_mom_rhs, ml);                     \
+  } while (0)
+  if (abs_mode == 2) LAUNCH_MOM(2, false);
+  else if (abs_mode == 1 && mld) LAUNCH_MOM(1, true);
+  else if (abs_mode == 1) LAUNCH_MOM(1, false);
+  else LAUNCH_MOM(0, false);
+#undef LAUNCH_MOM
+  h->launches++;
+  if (want_ct) {
+    if ((st = ensure_class(h, 1))) return st;
+    const TileClassPlan& P1 = h->tiles->cls[1];
+    const TileArgs T1 = tile_args(h, P1);
+    if ((st = set_smem(tiled_ct_kernel<DIM>, P1.smem_bytes))) return st;
+    tiled_ct_kernel<DIM><<<P1.ntiles, block_threads(P1), P1.smem_bytes, h->stream>>>(
+        A, T1, P1.max_tile_entries, P1.max_tile_rows, h->d_ct_m);
+    h->launches++;
+  }
+  CG_CUDA(cudaGetLastError());
+  return CGASM_OK;
+}
+
+int tiles_momentum(Handle* h, const MomentumArgs& A, bool want_ml, bool want_ct) {
+  if (!h->tiles) CG_FAIL(CGASM_ESTATE, "tile plan missing");
+  return h->dim == 3 ? tiles_momentum_dim<3>(h, A, want_ml, want_ct) : tiles_momentum_dim<2>(h, A, want_ml, want_ct);
+}
+
+int tiles_advdiff(Handle* h, const AdvDiffArgs& A) {
+  if (!h->tiles) CG_FAIL(CGASM_ESTATE, "tile plan missing");
+  int st = ensure_class(h, 0);
+  if (st) return st;
+  const TileClassPlan& P = h->tiles->cls[0];
+  const TileArgs T = tile_args(h, P);
+  const int thr = block_threads(P);
+  if (h->dim == 3) {
+    if ((st = set_smem(tiled_advdiff_kernel<3>, P.smem_bytes))) return st;
+    tiled_advdiff_kernel<3><<<P.ntiles, thr, P.smem_bytes, h->stream>>>(A, T, P.max_tile_entries, P.max_tile_rows,
+                                                                        h->d_adv_matrix, h->d_adv_rhs);
+  } else {
+    if ((st = set_smem(tiled_advdiff_kernel<2>, P.smem_bytes))) return st;
+    tiled_advdiff_kernel<2><<<P.ntiles, thr, P.smem_bytes, h->stream>>>(A, T, P.max_tile_entries, P.max_tile_rows,
+                                                                        h->d_adv_matrix, h->d_adv_rhs);
+  }
+  h->launches++;
+  CG_CUDA(cudaGetLastError());
+  return CGASM_OK;
+}
+
 }  // namespace cgasm
