@@ -761,4 +761,348 @@ __device__ __forceinline__ void advdiff_element(const AdvDiffArgs& P, const int4
   }
 }
 
+// =====================================================================================
+// Register-lean fused fast paths (used by the tiled kernels).
+//
+// Same formulae as momentum_element / advdiff_element for the option set shared by the
+// example configs: mass lumped or excluded, advection excluded or in
+// non-conservative form with beta = 0 and not integrated by parts, tensor-form viscosity of any
+// shape (CONSTANT or nodal), buoyancy with a CONSTANT gravity direction, lumped absorption or
+// none, no source. Instead of materialising the whole local matrix, rows are produced one at a
+// time and handed to a sink, and rows whose node the caller does not own are skipped entirely
+// (their rhs / lumped-mass contributions belong to that node too), so elements on a tile
+// surface cost only the shared part (geometry, quadrature sums).
+// =====================================================================================
+__host__ __device__ inline bool momentum_fast_ok(const cgasm_momentum_opts& o, int gravity_stride,
+                                                 int absorption_stride) {
+  (void)absorption_stride;
+  if (o.have_source) return false;
+  if (o.have_absorption && !o.lump_absorption) return false;
+  if (!o.exclude_mass && !o.lump_mass) return false;
+  if (!o.exclude_advection && (o.integrate_advection_by_parts || o.beta != 0.0)) return false;
+  if (o.have_gravity && gravity_stride != 0) return false;
+  return true;
+}
+
+// Sink concept:  bool owned(int i);  void mat(int i, int j, int d_or_0, double v)  [d only when
+// PERD];  void vec(int i, int d, double rhs_v);  void ml(int i, int d_or_0, double v)
+template <int DIM, bool PERD, class Sink>
+__device__ __forceinline__ void momentum_fast(const MomentumArgs& A, const int4 nd, Sink& sink) {
+  constexpr int LOC = DIM + 1, NGI = Shape<DIM>::NGI;
+  const cgasm_momentum_opts& o = A.o;
+  const Tables& t = A.tab;
+  const double dtt = o.dt * o.theta;
+  double wsum = 0.0;
+#pragma unroll
+  for (int g = 0; g < NGI; g++) wsum += t.w[g];
+
+  Geom<DIM> G;
+  double c[NGI];      // rho_g detwei_g
+  double v[LOC][DIM];  // (A+K)_ij = v_i . gradN_j
+  {
+    double X[LOC][DIM], nu[LOC][DIM], rho[LOC];
+#pragma unroll
+    for (int i = 0; i < LOC; i++) {
+      const int node = node_of(nd, i);
+      double unused;
+      unpack<DIM>(ld256(A.rec.r0 + node), X[i], unused);
+      unpack<DIM>(ld256(A.rec.r1 + node), nu[i], rho[i]);
+    }
+    geometry<DIM>(X, G);
+    at_quad<DIM>(t, rho, c);
+#pragma unroll
+    for (int g = 0; g < NGI; g++) c[g] *= G.absdet * t.w[g];
+#pragma unroll
+    for (int i = 0; i < LOC; i++)
+#pragma unroll
+      for (int a = 0; a < DIM; a++) v[i][a] = 0.0;
+    if (!o.exclude_advection) {
+#pragma unroll
+      for (int g = 0; g < NGI; g++) {
+        double q[DIM];  // c_g u_g
+#pragma unroll
+        for (int a = 0; a < DIM; a++) {
+          double s = 0.0;
+#pragma unroll
+          for (int i = 0; i < LOC; i++) s += nu[i][a] * t.N[i * NGI + g];
+          q[a] = s * c[g];
+        }
+#pragma unroll
+        for (int i = 0; i < LOC; i++)
+#pragma unroll
+          for (int a = 0; a < DIM; a++) v[i][a] += t.N[i * NGI + g] * q[a];
+      }
+    }
+  }
+  if (o.have_viscosity) {
+    double Vbar[DIM * DIM];
+    if (A.viscosity.stride == 0) {
+      gather<DIM * DIM>(A.viscosity, 0, Vbar);
+#pragma unroll
+      for (int ab = 0; ab < DIM * DIM; ab++) Vbar[ab] *= G.absdet * wsum;
+    } else {
+#pragma unroll
+      for (int ab = 0; ab < DIM * DIM; ab++) Vbar[ab] = 0.0;
+#pragma unroll
+      for (int i = 0; i < LOC; i++) {
+        double vi[DIM * DIM], ni = 0.0;
+        gather<DIM * DIM>(A.viscosity, node_of(nd, i), vi);
+#pragma unroll
+        for (int g = 0; g < NGI; g++) ni += t.N[i * NGI + g] * t.w[g];
+        ni *= G.absdet;
+#pragma unroll
+        for (int ab = 0; ab < DIM * DIM; ab++) Vbar[ab] += vi[ab] * ni;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < LOC; i++) {
+      if (o.viscosity_shape == CGASM_TENSOR_ISOTROPIC) {
+#pragma unroll
+        for (int a = 0; a < DIM; a++) v[i][a] += Vbar[0] * G.grad[i][a];
+      } else if (o.viscosity_shape == CGASM_TENSOR_DIAGONAL) {
+#pragma unroll
+        for (int a = 0; a < DIM; a++) v[i][a] += Vbar[a + DIM * a] * G.grad[i][a];
+      } else {
+#pragma unroll
+        for (int b = 0; b < DIM; b++) {
+          double s = 0.0;
+#pragma unroll
+          for (int a = 0; a < DIM; a++) s += G.grad[i][a] * Vbar[a + DIM * b];
+          v[i][b] += s;
+        }
+      }
+    }
+  }
+
+  double oldu[LOC][DIM], bq[NGI];
+  {
+    double b[LOC];
+#pragma unroll
+    for (int i = 0; i < LOC; i++) unpack<DIM>(ld256(A.rec.r2 + node_of(nd, i)), oldu[i], b[i]);
+    if (o.have_gravity) {
+      if (o.subtract_out_reference_profile) {
+#pragma unroll
+        for (int i = 0; i < LOC; i++) {
+          double r1[1];
+          gather<1>(A.hb_density, node_of(nd, i), r1);
+          b[i] -= r1[0];
+        }
+      }
+      at_quad<DIM>(t, b, bq);
+#pragma unroll
+      for (int g = 0; g < NGI; g++) bq[g] *= o.gravity_magnitude * G.absdet * t.w[g];
+    }
+  }
+  double gd[DIM];
+#pragma unroll
+  for (int d = 0; d < DIM; d++) gd[d] = 0.0;
+  if (o.have_gravity) gather<DIM>(A.gravity, 0, gd);
+  const bool want_m = o.assemble_inverse_masslump || !o.exclude_mass;
+  double sabs[PERD ? NGI : 1][DIM];  // sigma_dg c_g (lumped absorption only)
+  if constexpr (PERD) {
+#pragma unroll
+    for (int g = 0; g < NGI; g++)
+#pragma unroll
+      for (int d = 0; d < DIM; d++) sabs[g][d] = 0.0;
+    if (o.have_absorption) {
+#pragma unroll
+      for (int k = 0; k < LOC; k++) {
+        double ak[DIM];
+        gather<DIM>(A.absorption, node_of(nd, k), ak);
+#pragma unroll
+        for (int g = 0; g < NGI; g++)
+#pragma unroll
+          for (int d = 0; d < DIM; d++) sabs[g][d] += ak[d] * (t.N[k * NGI + g] * c[g]);
+      }
+    }
+  }
+
+#pragma unroll
+  for (int i = 0; i < LOC; i++) {
+    if (!sink.owned(i)) continue;
+    double m = 0.0, nb = 0.0;
+#pragma unroll
+    for (int g = 0; g < NGI; g++) {
+      m += t.N[i * NGI + g] * c[g];
+      if (o.have_gravity) nb += t.N[i * NGI + g] * bq[g];
+    }
+    double rhs[DIM], diag[PERD ? DIM : 1], mlv[PERD ? DIM : 1];
+#pragma unroll
+    for (int d = 0; d < DIM; d++) rhs[d] = nb * gd[d];
+#pragma unroll
+    for (int d = 0; d < (PERD ? DIM : 1); d++) {
+      diag[d] = (!o.exclude_mass && want_m) ? m : 0.0;
+      mlv[d] = o.assemble_inverse_masslump ? m : 0.0;
+    }
+    if constexpr (PERD) {
+      // lumped absorption (:2043-2050): sum_j Ab_ij = sum_g N_ig sigma_dg c_g
+      if (o.have_absorption) {
+#pragma unroll
+        for (int d = 0; d < DIM; d++) {
+          double s = 0.0;
+#pragma unroll
+          for (int g = 0; g < NGI; g++) s += t.N[i * NGI + g] * sabs[g][d];
+          diag[d] += dtt * s;
+          rhs[d] -= s * oldu[i][d];
+          if (o.pressure_corrected_absorption && o.assemble_inverse_masslump) mlv[d] += dtt * s;
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < LOC; j++) {
+      double s = 0.0;
+#pragma unroll
+      for (int a = 0; a < DIM; a++) s += v[i][a] * G.grad[j][a];
+#pragma unroll
+      for (int d = 0; d < DIM; d++) rhs[d] -= s * oldu[j][d];
+#pragma unroll
+      for (int d = 0; d < (PERD ? DIM : 1); d++) sink.mat(i, j, d, dtt * s + (i == j ? diag[d] : 0.0));
+    }
+#pragma unroll
+    for (int d = 0; d < DIM; d++) sink.vec(i, d, rhs[d]);
+#pragma unroll
+    for (int d = 0; d < (PERD ? DIM : 1); d++) sink.ml(i, d, mlv[d]);
+  }
+}
+
+__host__ __device__ inline bool advdiff_fast_ok(const cgasm_advdiff_opts& o) {
+  if (o.have_absorption) return false;
+  if (o.have_advection && (o.integrate_advection_by_parts || o.beta != 0.0)) return false;
+  return true;
+}
+
+// Sink: bool owned(i); void mat(i, j, v); void vec(i, v)
+template <int DIM, class Sink>
+__device__ __forceinline__ void advdiff_fast(const AdvDiffArgs& P, const int4 nd, Sink& sink) {
+  constexpr int LOC = DIM + 1, NGI = Shape<DIM>::NGI;
+  const cgasm_advdiff_opts& o = P.o;
+  const Tables& t = P.tab;
+  const double dtt = o.dt * o.theta;
+  const double eps = 2.220446049250313e-16;
+  const bool implicit = fabs(dtt) > eps;
+  double wsum = 0.0;
+#pragma unroll
+  for (int g = 0; g < NGI; g++) wsum += t.w[g];
+
+  Geom<DIM> G;
+  double T[LOC], v[LOC][DIM];
+  {
+    double X[LOC][DIM];
+#pragma unroll
+    for (int i = 0; i < LOC; i++) unpack<DIM>(ld256(P.rec.r0 + node_of(nd, i)), X[i], T[i]);
+    geometry<DIM>(X, G);
+  }
+#pragma unroll
+  for (int i = 0; i < LOC; i++)
+#pragma unroll
+    for (int a = 0; a < DIM; a++) v[i][a] = 0.0;
+  if (o.have_advection) {
+    double u[LOC][DIM];
+#pragma unroll
+    for (int i = 0; i < LOC; i++) {
+      double unused;
+      unpack<DIM>(ld256(P.rec.r1 + node_of(nd, i)), u[i], unused);
+    }
+#pragma unroll
+    for (int g = 0; g < NGI; g++) {
+      double q[DIM];
+#pragma unroll
+      for (int a = 0; a < DIM; a++) {
+        double s = 0.0;
+#pragma unroll
+        for (int i = 0; i < LOC; i++) s += u[i][a] * t.N[i * NGI + g];
+        q[a] = s * (G.absdet * t.w[g]);
+      }
+#pragma unroll
+      for (int i = 0; i < LOC; i++)
+#pragma unroll
+        for (int a = 0; a < DIM; a++) v[i][a] += t.N[i * NGI + g] * q[a];
+    }
+  }
+  if (o.have_diffusivity) {
+    double Kbar[DIM * DIM];
+    if (P.diffusivity.stride == 0) {
+      gather<DIM * DIM>(P.diffusivity, 0, Kbar);
+#pragma unroll
+      for (int ab = 0; ab < DIM * DIM; ab++) Kbar[ab] *= G.absdet * wsum;
+    } else {
+#pragma unroll
+      for (int ab = 0; ab < DIM * DIM; ab++) Kbar[ab] = 0.0;
+#pragma unroll
+      for (int i = 0; i < LOC; i++) {
+        double ki[DIM * DIM], ni = 0.0;
+        gather<DIM * DIM>(P.diffusivity, node_of(nd, i), ki);
+#pragma unroll
+        for (int g = 0; g < NGI; g++) ni += t.N[i * NGI + g] * t.w[g];
+        ni *= G.absdet;
+#pragma unroll
+        for (int ab = 0; ab < DIM * DIM; ab++) Kbar[ab] += ki[ab] * ni;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < LOC; i++) {
+      if (o.diffusivity_shape == CGASM_TENSOR_ISOTROPIC) {
+#pragma unroll
+        for (int a = 0; a < DIM; a++) v[i][a] += Kbar[0] * G.grad[i][a];
+      } else {
+#pragma unroll
+        for (int b = 0; b < DIM; b++) {
+          double s = 0.0;
+#pragma unroll
+          for (int a = 0; a < DIM; a++) s += G.grad[i][a] * Kbar[a + DIM * b];
+          v[i][b] += s;
+        }
+      }
+    }
+  }
+  double sq[NGI];
+  if (o.have_source) {
+    double sg[LOC];
+#pragma unroll
+    for (int i = 0; i < LOC; i++) {
+      double r1[1];
+      gather<1>(P.source, node_of(nd, i), r1);
+      sg[i] = r1[0];
+    }
+    at_quad<DIM>(t, sg, sq);
+#pragma unroll
+    for (int g = 0; g < NGI; g++) sq[g] *= G.absdet * t.w[g];
+  }
+#pragma unroll
+  for (int i = 0; i < LOC; i++) {
+    if (!sink.owned(i)) continue;
+    double rhs = 0.0;
+    if (o.have_source) {
+#pragma unroll
+      for (int g = 0; g < NGI; g++) rhs += t.N[i * NGI + g] * sq[g];
+    }
+    double mlump = 0.0;
+    if (o.have_mass && o.lump_mass) {
+#pragma unroll
+      for (int g = 0; g < NGI; g++) mlump += t.N[i * NGI + g] * t.w[g];
+      mlump *= G.absdet;
+    }
+#pragma unroll
+    for (int j = 0; j < LOC; j++) {
+      double s = 0.0;
+#pragma unroll
+      for (int a = 0; a < DIM; a++) s += v[i][a] * G.grad[j][a];
+      rhs -= s * T[j];
+      double a_ij = implicit ? dtt * s : 0.0;
+      if (o.have_mass) {
+        if (o.lump_mass) {
+          if (i == j) a_ij += mlump;
+        } else {
+          double pij = 0.0;  // sum_g N_ig N_jg w_g: constant-bank arithmetic, folded by ptxas
+#pragma unroll
+          for (int g = 0; g < NGI; g++) pij += (t.N[i * NGI + g] * t.N[j * NGI + g]) * t.w[g];
+          a_ij += pij * G.absdet;
+        }
+      }
+      sink.mat(i, j, a_ij);
+    }
+    sink.vec(i, rhs);
+  }
+}
+
 }  // namespace cgasm

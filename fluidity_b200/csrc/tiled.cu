@@ -36,7 +36,8 @@ namespace cgasm {
 struct TileClassPlan {
   int nb = 0, nvec = 0;     // accumulated matrix blocks / vector components this plan is sized for
   int ntiles = 0;
-  int max_tile_entries = 0, max_tile_rows = 0, max_phase = 0;
+  int max_tile_entries = 0, max_tile_rows = 0, max_phase = 0;  // max_phase: clusters in the largest phase
+  int cluster = 1;  // elements per cluster (records are padded to whole clusters per tile)
   size_t smem_bytes = 0;
   long long n_tile_elements = 0;
   // device arrays
@@ -45,7 +46,7 @@ struct TileClassPlan {
   int* d_rowoff = nullptr;          // offset of the row inside the tile's matrix accumulator
   int* d_tile_entries = nullptr;    // [ntiles] CSR entries owned by the tile
   int* d_tile_phase_off = nullptr;  // [ntiles+1] into phase_ptr
-  int* d_phase_ptr = nullptr;       // per tile: nphase+1 offsets into the element records
+  int* d_phase_ptr = nullptr;       // per tile: nphase+1 offsets in CLUSTER units (records = cluster*K + j)
   int* d_tile_run_ptr = nullptr;    // [ntiles+1] into runs
   int2* d_runs = nullptr;           // {first tile-local row, nrows}: consecutive global node ids
   int4* d_el_nodes = nullptr;       // per tile-element: global node ids (0-based)
@@ -93,7 +94,24 @@ static inline uint64_t spread2(uint64_t x) {  // 32 bits -> every second bit
   return x;
 }
 
-static void morton_order(const Handle* h, std::vector<int>& order) {
+struct MortonFrame {
+  double lo[3] = {0, 0, 0}, scale[3] = {0, 0, 0};
+  int dim = 3;
+  // cell of a point on the mesh-spacing lattice (nearest lattice point for nodes)
+  inline uint64_t key_round(const double* x) const {
+    uint64_t q[3] = {0, 0, 0};
+    for (int a = 0; a < dim; a++) q[a] = (uint64_t)std::llround((x[a] - lo[a]) * scale[a]);
+    return dim == 3 ? (spread3(q[0]) | spread3(q[1]) << 1 | spread3(q[2]) << 2) : (spread2(q[0]) | spread2(q[1]) << 1);
+  }
+  // containing cell (floor): element centroids of one lattice cell share a key
+  inline uint64_t key_floor(const double* x) const {
+    uint64_t q[3] = {0, 0, 0};
+    for (int a = 0; a < dim; a++) q[a] = (uint64_t)std::max(0.0, std::floor((x[a] - lo[a]) * scale[a]));
+    return dim == 3 ? (spread3(q[0]) | spread3(q[1]) << 1 | spread3(q[2]) << 2) : (spread2(q[0]) | spread2(q[1]) << 1);
+  }
+};
+
+static void morton_order(const Handle* h, std::vector<int>& order, MortonFrame& F) {
   const int n = h->n_nodes, dim = h->dim;
   double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
   for (int i = 0; i < n; i++)
@@ -114,20 +132,19 @@ static void morton_order(const Handle* h, std::vector<int>& order) {
       live++;
     }
   const double hcell = live ? std::pow(vol / (double)n, 1.0 / live) : 1.0;
-  double scale[3] = {0, 0, 0};
   const double maxcells = dim == 3 ? 2097151.0 : 4294967295.0;
-  for (int a = 0; a < dim; a++)
+  F.dim = dim;
+  for (int a = 0; a < dim; a++) {
+    F.lo[a] = lo[a];
+    F.scale[a] = 0.0;
     if (hi[a] > lo[a]) {
       const double cells = std::min(maxcells, std::max(1.0, std::round((hi[a] - lo[a]) / hcell) - 1.0));
-      scale[a] = cells / (hi[a] - lo[a]);
+      F.scale[a] = cells / (hi[a] - lo[a]);
     }
+  }
   std::vector<uint64_t> key((size_t)n);
 #pragma omp parallel for schedule(static)
-  for (int i = 0; i < n; i++) {
-    uint64_t q[3] = {0, 0, 0};
-    for (int a = 0; a < dim; a++) q[a] = (uint64_t)std::llround((h->h_X[(size_t)dim * i + a] - lo[a]) * scale[a]);
-    key[i] = dim == 3 ? (spread3(q[0]) | spread3(q[1]) << 1 | spread3(q[2]) << 2) : (spread2(q[0]) | spread2(q[1]) << 1);
-  }
+  for (int i = 0; i < n; i++) key[i] = F.key_round(&h->h_X[(size_t)dim * i]);
   order.resize((size_t)n);
   std::iota(order.begin(), order.end(), 0);
   std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return key[a] < key[b]; });
@@ -160,7 +177,8 @@ __global__ void tile_slots_kernel(long long n, const int4* __restrict__ el_nodes
   el_slots[k] = make_uint4(packed[0], packed[1], packed[2], packed[3]);
 }
 
-static int build_class(Handle* h, TileClassPlan& P, int nb, int nvec, const std::vector<int>& order) {
+static int build_class(Handle* h, TileClassPlan& P, int nb, int nvec, const std::vector<int>& order,
+                       const MortonFrame& F) {
   const int loc = h->loc, n_nodes = h->n_nodes;
   const int* nd0 = h->h_nd0.data();
   const std::vector<int>& fr = h->h_findrm;
@@ -235,44 +253,66 @@ static int build_class(Handle* h, TileClassPlan& P, int nb, int nvec, const std:
                  sizeof(int) * (size_t)(P.max_tile_rows + 1);
   P.smem_bytes = (P.smem_bytes + 15) & ~(size_t)15;
 
-  // ---- per tile: element set, balanced greedy colouring over owned nodes, phase order -----------
-  std::vector<long long> tile_el_count((size_t)ntiles + 1, 0);
-  std::vector<std::vector<int>> tile_elems((size_t)ntiles);   // element ids in phase order
-  std::vector<std::vector<int>> tile_phase((size_t)ntiles);   // nphase+1 offsets
+  // ---- per tile: element set -> clusters of K spatially adjacent elements -> balanced greedy
+  // colouring of the CLUSTERS (two clusters conflict iff they share an OWNED node); a colour is a
+  // __syncthreads-separated phase in which one thread walks one cluster element by element.
+  // Fewer, fatter phases than colouring single elements (a node has ~24 incident tets but only
+  // ~8 incident 6-tet clusters), and same-thread RMWs inside a cluster need no ordering at all.
+  int K = 1;  // measured: sequential clusters lengthen the per-thread critical path (latency-bound)
+  if (const char* s = getenv("CGASM_TILE_CLUSTER")) K = std::min(64, std::max(1, atoi(s)));
+  P.cluster = K;
+  const int dim = h->dim;
+  std::vector<long long> tile_cl_count((size_t)ntiles + 1, 0);  // clusters per tile (prefix later)
+  std::vector<std::vector<int>> tile_elems((size_t)ntiles);     // element ids, cluster-major, phase order, -1 = pad
+  std::vector<std::vector<int>> tile_phase((size_t)ntiles);     // nphase+1 offsets in clusters
 #pragma omp parallel
   {
-    std::vector<int> els, colour, cnt, start;
-    std::vector<uint64_t> mask;  // per tile row: colours already present at that owned node
+    std::vector<int> els, colour, cnt, start, perm;
+    std::vector<uint64_t> mask, ekey;
 #pragma omp for schedule(dynamic, 16)
     for (int t = 0; t < ntiles; t++) {
       const int r0 = tile_row_ptr[t], r1 = tile_row_ptr[t + 1], nr = r1 - r0;
       els.clear();
-      int maxdeg = 1;
       for (int r = r0; r < r1; r++) {
         const int node = rows[r];
-        maxdeg = std::max(maxdeg, (int)(h->n2e_ptr[node + 1] - h->n2e_ptr[node]));
         for (int64_t k = h->n2e_ptr[node]; k < h->n2e_ptr[node + 1]; k++) els.push_back(h->n2e[(size_t)k]);
       }
       std::sort(els.begin(), els.end());
       els.erase(std::unique(els.begin(), els.end()), els.end());
       const int ne = (int)els.size();
-      mask.assign((size_t)nr, 0);
-      colour.assign((size_t)ne, 0);
-      cnt.assign(64, 0);
-      int palette = std::min(maxdeg, 64), ncol = 0;
-      bool ok = true;
-      for (int k = 0; k < ne && ok; k++) {
+      // spatial order: Morton key of the containing lattice cell of the centroid
+      ekey.resize((size_t)ne);
+      perm.resize((size_t)ne);
+      for (int k = 0; k < ne; k++) {
         const int* nd = nd0 + (size_t)4 * els[k];
-        uint64_t used = 0;
+        double c[3] = {0, 0, 0};
         for (int i = 0; i < loc; i++)
-          if (tile_of_node[nd[i]] == t) used |= mask[lrow_of_node[nd[i]]];
+          for (int a = 0; a < dim; a++) c[a] += h->h_X[(size_t)dim * nd[i] + a];
+        for (int a = 0; a < dim; a++) c[a] /= loc;
+        ekey[k] = F.key_floor(c);
+        perm[k] = k;
+      }
+      std::stable_sort(perm.begin(), perm.end(), [&](int a, int b) { return ekey[a] < ekey[b]; });
+      const int ncl = (ne + K - 1) / K;
+      mask.assign((size_t)nr, 0);
+      colour.assign((size_t)ncl, 0);
+      cnt.assign(64, 0);
+      int palette = 8, ncol = 0;
+      bool ok = true;
+      for (int c = 0; c < ncl && ok; c++) {
+        uint64_t used = 0;
+        for (int k = c * K; k < std::min(ne, (c + 1) * K); k++) {
+          const int* nd = nd0 + (size_t)4 * els[perm[k]];
+          for (int i = 0; i < loc; i++)
+            if (tile_of_node[nd[i]] == t) used |= mask[lrow_of_node[nd[i]]];
+        }
         int best = -1;
-        for (int c = 0; c < palette; c++)
-          if (!(used >> c & 1) && (best < 0 || cnt[c] < cnt[best])) best = c;
+        for (int q = 0; q < palette; q++)
+          if (!(used >> q & 1) && (best < 0 || cnt[q] < cnt[best])) best = q;
         if (best < 0) {
-          for (int c = palette; c < 64; c++)
-            if (!(used >> c & 1)) {
-              best = c;
+          for (int q = palette; q < 64; q++)
+            if (!(used >> q & 1)) {
+              best = q;
               break;
             }
           if (best < 0) {
@@ -281,37 +321,43 @@ static int build_class(Handle* h, TileClassPlan& P, int nb, int nvec, const std:
           }
           palette = best + 1;
         }
-        colour[k] = best;
+        colour[c] = best;
         cnt[best]++;
         ncol = std::max(ncol, best + 1);
-        for (int i = 0; i < loc; i++)
-          if (tile_of_node[nd[i]] == t) mask[lrow_of_node[nd[i]]] |= (uint64_t)1 << best;
+        for (int k = c * K; k < std::min(ne, (c + 1) * K); k++) {
+          const int* nd = nd0 + (size_t)4 * els[perm[k]];
+          for (int i = 0; i < loc; i++)
+            if (tile_of_node[nd[i]] == t) mask[lrow_of_node[nd[i]]] |= (uint64_t)1 << best;
+        }
       }
       if (!ok) {
         tile_phase[t].clear();  // flagged below
         continue;
       }
       start.assign((size_t)ncol + 1, 0);
-      for (int c = 0; c < ncol; c++) start[c + 1] = start[c] + cnt[c];
+      for (int q = 0; q < ncol; q++) start[q + 1] = start[q] + cnt[q];
       tile_phase[t] = start;
-      tile_elems[t].resize((size_t)ne);
+      tile_elems[t].assign((size_t)ncl * K, -1);
       std::vector<int> fill(start.begin(), start.end() - 1);
-      for (int k = 0; k < ne; k++) tile_elems[t][(size_t)fill[colour[k]]++] = els[k];
-      tile_el_count[t + 1] = ne;
+      for (int c = 0; c < ncl; c++) {
+        const int dst = fill[colour[c]]++;
+        for (int k = c * K; k < std::min(ne, (c + 1) * K); k++) tile_elems[t][(size_t)dst * K + (k - c * K)] = els[perm[k]];
+      }
+      tile_cl_count[t + 1] = ncl;
     }
   }
   for (int t = 0; t < ntiles; t++) {
     if (tile_phase[t].empty()) CG_FAIL(CGASM_EUNSUPPORTED, "a tile needs more than 64 colours");
-    tile_el_count[t + 1] += tile_el_count[t];
+    tile_cl_count[t + 1] += tile_cl_count[t];
   }
-  const long long ntel = tile_el_count[ntiles];
+  const long long ntel = tile_cl_count[ntiles] * K;
   if (ntel >= ((long long)1 << 31)) CG_FAIL(CGASM_EUNSUPPORTED, "tile element records exceed 2^31");
   P.n_tile_elements = ntel;
 
   std::vector<int> tile_phase_off((size_t)ntiles + 1, 0), phase_ptr;
   for (int t = 0; t < ntiles; t++) {
     tile_phase_off[t] = (int)phase_ptr.size();
-    for (int v : tile_phase[t]) phase_ptr.push_back((int)(tile_el_count[t] + v));
+    for (int v : tile_phase[t]) phase_ptr.push_back((int)(tile_cl_count[t] + v));
     for (size_t c = 0; c + 1 < tile_phase[t].size(); c++)
       P.max_phase = std::max(P.max_phase, tile_phase[t][c + 1] - tile_phase[t][c]);
   }
@@ -321,12 +367,18 @@ static int build_class(Handle* h, TileClassPlan& P, int nb, int nvec, const std:
   std::vector<uint2> el_rows((size_t)ntel);
 #pragma omp parallel for schedule(dynamic, 16)
   for (int t = 0; t < ntiles; t++) {
-    long long base = tile_el_count[t];
+    const long long base = tile_cl_count[t] * K;
+    int last_valid = -1;
     for (size_t k = 0; k < tile_elems[t].size(); k++) {
-      const int* nd = nd0 + (size_t)4 * tile_elems[t][k];
+      const int e = tile_elems[t][k];
       unsigned short lr[4] = {0xFFFF, 0xFFFF, 0xFFFF, 0xFFFF};
-      for (int i = 0; i < loc; i++)
-        if (tile_of_node[nd[i]] == t) lr[i] = (unsigned short)lrow_of_node[nd[i]];
+      // padding record: a valid element's nodes (so the math stays finite) but no owned row
+      const int* nd = nd0 + (size_t)4 * (e >= 0 ? e : (last_valid >= 0 ? last_valid : tile_elems[t][0]));
+      if (e >= 0) {
+        last_valid = e;
+        for (int i = 0; i < loc; i++)
+          if (tile_of_node[nd[i]] == t) lr[i] = (unsigned short)lrow_of_node[nd[i]];
+      }
       // unused 4th node of a triangle: repeat node 0 so gathers stay in range
       el_nodes[(size_t)(base + k)] = make_int4(nd[0], nd[1], nd[2], loc == 4 ? nd[3] : nd[0]);
       el_rows[(size_t)(base + k)] = make_uint2((unsigned)lr[0] | (unsigned)lr[1] << 16, (unsigned)lr[2] | (unsigned)lr[3] << 16);
@@ -357,8 +409,9 @@ int tiles_build(Handle* h) {
   tiles_free(h);
   h->tiles = new TilePlan();
   std::vector<int> order;
-  morton_order(h, order);
-  int st = build_class(h, h->tiles->cls[0], 1, 2 * h->dim, order);
+  MortonFrame F;
+  morton_order(h, order, F);
+  int st = build_class(h, h->tiles->cls[0], 1, 2 * h->dim, order, F);
   if (st) {
     tiles_free(h);
     return st;
@@ -370,8 +423,9 @@ int tiles_build(Handle* h) {
 static int ensure_class(Handle* h, int c) {
   if (h->tiles->built[c]) return CGASM_OK;
   std::vector<int> order;
-  morton_order(h, order);
-  int st = build_class(h, h->tiles->cls[c], c == 0 ? 1 : h->dim, 2 * h->dim, order);
+  MortonFrame F;
+  morton_order(h, order, F);
+  int st = build_class(h, h->tiles->cls[c], c == 0 ? 1 : h->dim, 2 * h->dim, order, F);
   if (st) return st;
   h->tiles->built[c] = true;
   return CGASM_OK;
@@ -392,6 +446,7 @@ struct TileArgs {
   const uint4* __restrict__ el_slots;
   const int* __restrict__ findrm;
   size_t nnz;
+  int cluster;
 };
 
 __device__ __forceinline__ unsigned lrow_of(const uint2& r, int i) {
@@ -421,7 +476,7 @@ struct TileSmem {
 // times), 1 = lumped absorption (blocks differ on the diagonal), 2 = full absorption matrix.
 // MLD: masslump differs per component (pressure-corrected lumped absorption).
 template <int DIM, int ABS, bool MLD>
-__global__ void __launch_bounds__(384, 1)
+__global__ void __launch_bounds__(256, 1)
 tiled_momentum_kernel(const MomentumArgs A, const TileArgs T, int max_entries, int max_rows,
                       double* __restrict__ big_m, double* __restrict__ rhs, double* __restrict__ masslump) {
   constexpr int LOC = DIM + 1;
@@ -443,8 +498,10 @@ tiled_momentum_kernel(const MomentumArgs A, const TileArgs T, int max_entries, i
 
   const int p0 = T.tile_phase_off[t], nphase = T.tile_phase_off[t + 1] - p0 - 1;
   for (int ph = 0; ph < nphase; ph++) {
-    const int kb = T.phase_ptr[p0 + ph], ke = T.phase_ptr[p0 + ph + 1];
-    for (int k = kb + tid; k < ke; k += nthr) {
+    const int cb = T.phase_ptr[p0 + ph], ce = T.phase_ptr[p0 + ph + 1];
+    for (int cl = cb + tid; cl < ce; cl += nthr)
+#pragma unroll 1
+    for (int k = cl * T.cluster, kend = k + T.cluster; k < kend; k++) {
       const int4 nd = __ldg(T.el_nodes + k);
       const uint2 lr = __ldg(T.el_rows + k);
       const uint4 sl = __ldg(T.el_slots + k);
@@ -504,7 +561,7 @@ tiled_momentum_kernel(const MomentumArgs A, const TileArgs T, int max_entries, i
 // ct_m: dim blocks grad_p_u_mat (Momentum_CG.F90:1401,1469); first assembly only, so it is a
 // separate pass over the same plan machinery instead of widening the hot kernel.
 template <int DIM>
-__global__ void __launch_bounds__(384, 1)
+__global__ void __launch_bounds__(256, 1)
 tiled_ct_kernel(const MomentumArgs A, const TileArgs T, int max_entries, int max_rows, double* __restrict__ ct_m) {
   constexpr int LOC = DIM + 1;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -518,8 +575,10 @@ tiled_ct_kernel(const MomentumArgs A, const TileArgs T, int max_entries, int max
   __syncthreads();
   const int p0 = T.tile_phase_off[t], nphase = T.tile_phase_off[t + 1] - p0 - 1;
   for (int ph = 0; ph < nphase; ph++) {
-    const int kb = T.phase_ptr[p0 + ph], ke = T.phase_ptr[p0 + ph + 1];
-    for (int k = kb + tid; k < ke; k += nthr) {
+    const int cb = T.phase_ptr[p0 + ph], ce = T.phase_ptr[p0 + ph + 1];
+    for (int cl = cb + tid; cl < ce; cl += nthr)
+#pragma unroll 1
+    for (int k = cl * T.cluster, kend = k + T.cluster; k < kend; k++) {
       const int4 nd = __ldg(T.el_nodes + k);
       const uint2 lr = __ldg(T.el_rows + k);
       const uint4 sl = __ldg(T.el_slots + k);
@@ -560,7 +619,7 @@ tiled_ct_kernel(const MomentumArgs A, const TileArgs T, int max_entries, int max
 }
 
 template <int DIM>
-__global__ void __launch_bounds__(384, 1)
+__global__ void __launch_bounds__(256, 1)
 tiled_advdiff_kernel(const AdvDiffArgs A, const TileArgs T, int max_entries, int max_rows,
                      double* __restrict__ matrix, double* __restrict__ rhs) {
   constexpr int LOC = DIM + 1;
@@ -578,8 +637,10 @@ tiled_advdiff_kernel(const AdvDiffArgs A, const TileArgs T, int max_entries, int
   __syncthreads();
   const int p0 = T.tile_phase_off[t], nphase = T.tile_phase_off[t + 1] - p0 - 1;
   for (int ph = 0; ph < nphase; ph++) {
-    const int kb = T.phase_ptr[p0 + ph], ke = T.phase_ptr[p0 + ph + 1];
-    for (int k = kb + tid; k < ke; k += nthr) {
+    const int cb = T.phase_ptr[p0 + ph], ce = T.phase_ptr[p0 + ph + 1];
+    for (int cl = cb + tid; cl < ce; cl += nthr)
+#pragma unroll 1
+    for (int k = cl * T.cluster, kend = k + T.cluster; k < kend; k++) {
       const int4 nd = __ldg(T.el_nodes + k);
       const uint2 lr = __ldg(T.el_rows + k);
       const uint4 sl = __ldg(T.el_slots + k);
@@ -610,6 +671,152 @@ tiled_advdiff_kernel(const AdvDiffArgs A, const TileArgs T, int max_entries, int
   }
 }
 
+// ---- fast-path kernels: fused row-by-row accumulate (element_math.cuh momentum_fast) ---------
+template <int DIM, bool PERD, bool MLD>
+struct MomTileSink {
+  static constexpr int MLC = MLD ? DIM : 1;
+  static constexpr int NVEC = DIM + MLC;
+  double* mat_;
+  double* vec_;
+  const int* off_;
+  int max_entries;
+  uint2 lr;
+  uint4 sl;
+  int base, r;
+  __device__ __forceinline__ bool owned(int i) {
+    r = (int)lrow_of(lr, i);
+    if (r == 0xffff) return false;
+    base = off_[r];
+    return true;
+  }
+  __device__ __forceinline__ void mat(int i, int j, int d, double v) {
+    mat_[(size_t)d * max_entries + base + (int)slot_of(sl, i, j)] += v;
+  }
+  __device__ __forceinline__ void vec(int, int d, double v) { vec_[r * NVEC + d] += v; }
+  __device__ __forceinline__ void ml(int, int d, double v) {
+    if (MLD || d == 0) vec_[r * NVEC + DIM + (MLD ? d : 0)] += v;
+  }
+};
+
+template <int DIM, bool PERD, bool MLD>
+__global__ void __launch_bounds__(384, 1)
+tiled_momentum_fast_kernel(const MomentumArgs A, const TileArgs T, int max_entries, int max_rows,
+                           double* __restrict__ big_m, double* __restrict__ rhs, double* __restrict__ masslump) {
+  constexpr int NB = PERD ? DIM : 1;
+  constexpr int MLC = MLD ? DIM : 1;
+  constexpr int NVEC = DIM + MLC;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  TileSmem<NB, NVEC> S(smem_raw, max_entries, max_rows);
+  const int t = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
+  const int r0 = T.tile_row_ptr[t], nrows = T.tile_row_ptr[t + 1] - r0;
+  const int entries = T.tile_entries[t];
+  for (int k = tid; k < NB * max_entries; k += nthr) S.mat[k] = 0.0;
+  for (int k = tid; k < NVEC * nrows; k += nthr) S.vec[k] = 0.0;
+  for (int k = tid; k < nrows; k += nthr) S.off[k] = T.rowoff[r0 + k];
+  if (tid == 0) S.off[nrows] = entries;
+  __syncthreads();
+  MomTileSink<DIM, PERD, MLD> sink;
+  sink.mat_ = S.mat;
+  sink.vec_ = S.vec;
+  sink.off_ = S.off;
+  sink.max_entries = max_entries;
+  const int p0 = T.tile_phase_off[t], nphase = T.tile_phase_off[t + 1] - p0 - 1;
+  for (int ph = 0; ph < nphase; ph++) {
+    const int cb = T.phase_ptr[p0 + ph], ce = T.phase_ptr[p0 + ph + 1];
+    for (int cl = cb + tid; cl < ce; cl += nthr)
+#pragma unroll 1
+      for (int k = cl * T.cluster, kend = k + T.cluster; k < kend; k++) {
+        const int4 nd = __ldg(T.el_nodes + k);
+        sink.lr = __ldg(T.el_rows + k);
+        sink.sl = __ldg(T.el_slots + k);
+        momentum_fast<DIM, PERD>(A, nd, sink);
+      }
+    __syncthreads();
+  }
+  const int warp = tid >> 5, lane = tid & 31, nwarps = nthr >> 5;
+  for (int ru = T.tile_run_ptr[t] + warp; ru < T.tile_run_ptr[t + 1]; ru += nwarps) {
+    const int2 run = T.runs[ru];
+    const int g0 = T.rows[r0 + run.x];
+    const int src = S.off[run.x];
+    const int n = S.off[run.x + run.y] - src;
+    const size_t dst = (size_t)T.findrm[g0];
+#pragma unroll
+    for (int d = 0; d < DIM; d++) {
+      const double* s = S.mat + (size_t)(PERD ? d : 0) * max_entries + src;
+      double* o = big_m + (size_t)d * T.nnz + dst;
+      for (int k = lane; k < n; k += 32) o[k] = s[k];
+    }
+    for (int k = lane; k < run.y * DIM; k += 32) {
+      const int rr = k / DIM, d = k - rr * DIM;
+      rhs[(size_t)DIM * g0 + k] = S.vec[(run.x + rr) * NVEC + d];
+      if (masslump) masslump[(size_t)DIM * g0 + k] = S.vec[(run.x + rr) * NVEC + DIM + (MLD ? d : 0)];
+    }
+  }
+}
+
+template <int DIM>
+struct AdvTileSink {
+  double* mat_;
+  double* vec_;
+  const int* off_;
+  uint2 lr;
+  uint4 sl;
+  int base, r;
+  __device__ __forceinline__ bool owned(int i) {
+    r = (int)lrow_of(lr, i);
+    if (r == 0xffff) return false;
+    base = off_[r];
+    return true;
+  }
+  __device__ __forceinline__ void mat(int i, int j, double v) { mat_[base + (int)slot_of(sl, i, j)] += v; }
+  __device__ __forceinline__ void vec(int, double v) { vec_[r] += v; }
+};
+
+template <int DIM>
+__global__ void __launch_bounds__(384, 1)
+tiled_advdiff_fast_kernel(const AdvDiffArgs A, const TileArgs T, int max_entries, int max_rows,
+                          double* __restrict__ matrix, double* __restrict__ rhs) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  TileSmem<1, 1> S(smem_raw, max_entries, max_rows);
+  const int t = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
+  const int r0 = T.tile_row_ptr[t], nrows = T.tile_row_ptr[t + 1] - r0;
+  const int entries = T.tile_entries[t];
+  for (int k = tid; k < max_entries; k += nthr) S.mat[k] = 0.0;
+  for (int k = tid; k < nrows; k += nthr) {
+    S.vec[k] = 0.0;
+    S.off[k] = T.rowoff[r0 + k];
+  }
+  if (tid == 0) S.off[nrows] = entries;
+  __syncthreads();
+  AdvTileSink<DIM> sink;
+  sink.mat_ = S.mat;
+  sink.vec_ = S.vec;
+  sink.off_ = S.off;
+  const int p0 = T.tile_phase_off[t], nphase = T.tile_phase_off[t + 1] - p0 - 1;
+  for (int ph = 0; ph < nphase; ph++) {
+    const int cb = T.phase_ptr[p0 + ph], ce = T.phase_ptr[p0 + ph + 1];
+    for (int cl = cb + tid; cl < ce; cl += nthr)
+#pragma unroll 1
+      for (int k = cl * T.cluster, kend = k + T.cluster; k < kend; k++) {
+        const int4 nd = __ldg(T.el_nodes + k);
+        sink.lr = __ldg(T.el_rows + k);
+        sink.sl = __ldg(T.el_slots + k);
+        advdiff_fast<DIM>(A, nd, sink);
+      }
+    __syncthreads();
+  }
+  const int warp = tid >> 5, lane = tid & 31, nwarps = nthr >> 5;
+  for (int ru = T.tile_run_ptr[t] + warp; ru < T.tile_run_ptr[t + 1]; ru += nwarps) {
+    const int2 run = T.runs[ru];
+    const int g0 = T.rows[r0 + run.x];
+    const int src = S.off[run.x];
+    const int n = S.off[run.x + run.y] - src;
+    const size_t dst = (size_t)T.findrm[g0];
+    for (int k = lane; k < n; k += 32) matrix[dst + k] = S.mat[src + k];
+    for (int k = lane; k < run.y; k += 32) rhs[g0 + k] = S.vec[run.x + k];
+  }
+}
+
 static TileArgs tile_args(const Handle* h, const TileClassPlan& P) {
   TileArgs T;
   T.tile_row_ptr = P.d_tile_row_ptr;
@@ -625,14 +832,15 @@ static TileArgs tile_args(const Handle* h, const TileClassPlan& P) {
   T.el_slots = P.d_el_slots;
   T.findrm = h->d_findrm;
   T.nnz = (size_t)h->nnz;
+  T.cluster = P.cluster;
   return T;
 }
 
-static int block_threads(const TileClassPlan& P) {
-  int thr = 384;
+static int block_threads(const TileClassPlan& P, int cap) {
+  int thr;
   if (const char* s = getenv("CGASM_TILE_THREADS")) thr = atoi(s);
-  else thr = std::min(384, std::max(128, ((P.max_phase + 31) / 32) * 32));
-  return std::min(384, std::max(32, (thr / 32) * 32));
+  else thr = std::max(64, ((P.max_phase + 31) / 32) * 32);
+  return std::min(cap, std::max(32, (thr / 32) * 32));
 }
 
 template <class K>
@@ -649,8 +857,22 @@ static int tiles_momentum_dim(Handle* h, const MomentumArgs& A, bool want_ml, bo
   if (st) return st;
   const TileClassPlan& P = h->tiles->cls[abs_mode ? 1 : 0];
   const TileArgs T = tile_args(h, P);
-  const int thr = block_threads(P);
   double* ml = want_ml ? h->d_masslump : nullptr;
+  if (abs_mode != 2 && momentum_fast_ok(A.o, A.gravity.stride, A.absorption.stride) && !getenv("CGASM_TILE_GENERIC")) {
+    const int thr = block_threads(P, 384);
+#define LAUNCH_FAST(PERD_, MLD_)                                                                        \
+  do {                                                                                                  \
+    if ((st = set_smem(tiled_momentum_fast_kernel<DIM, PERD_, MLD_>, P.smem_bytes))) return st;         \
+    tiled_momentum_fast_kernel<DIM, PERD_, MLD_><<<P.ntiles, thr, P.smem_bytes, h->stream>>>(           \
+        A, T, P.max_tile_entries, P.max_tile_rows, h->d_big_m, h->d_mom_rhs, ml);                       \
+  } while (0)
+    if (abs_mode == 1 && mld) LAUNCH_FAST(true, true);
+    else if (abs_mode == 1) LAUNCH_FAST(true, false);
+    else LAUNCH_FAST(false, false);
+#undef LAUNCH_FAST
+    h->launches++;
+  } else {
+  const int thr = block_threads(P, 256);
 #define LAUNCH_MOM(ABS_, MLD_)                                                                        \
   do {                                                                                                \
     if ((st = set_smem(tiled_momentum_kernel<DIM, ABS_, MLD_>, P.smem_bytes))) return st;             \
@@ -663,12 +885,13 @@ static int tiles_momentum_dim(Handle* h, const MomentumArgs& A, bool want_ml, bo
   else LAUNCH_MOM(0, false);
 #undef LAUNCH_MOM
   h->launches++;
+  }
   if (want_ct) {
     if ((st = ensure_class(h, 1))) return st;
     const TileClassPlan& P1 = h->tiles->cls[1];
     const TileArgs T1 = tile_args(h, P1);
     if ((st = set_smem(tiled_ct_kernel<DIM>, P1.smem_bytes))) return st;
-    tiled_ct_kernel<DIM><<<P1.ntiles, block_threads(P1), P1.smem_bytes, h->stream>>>(
+    tiled_ct_kernel<DIM><<<P1.ntiles, block_threads(P1, 256), P1.smem_bytes, h->stream>>>(
         A, T1, P1.max_tile_entries, P1.max_tile_rows, h->d_ct_m);
     h->launches++;
   }
@@ -687,16 +910,22 @@ int tiles_advdiff(Handle* h, const AdvDiffArgs& A) {
   if (st) return st;
   const TileClassPlan& P = h->tiles->cls[0];
   const TileArgs T = tile_args(h, P);
-  const int thr = block_threads(P);
+  const bool fast = advdiff_fast_ok(A.o) && !getenv("CGASM_TILE_GENERIC");
+  const int thr = block_threads(P, fast ? 384 : 256);
+#define LAUNCH_ADV(KERNEL)                                                                            \
+  do {                                                                                                \
+    if ((st = set_smem(KERNEL, P.smem_bytes))) return st;                                             \
+    KERNEL<<<P.ntiles, thr, P.smem_bytes, h->stream>>>(A, T, P.max_tile_entries, P.max_tile_rows,     \
+                                                       h->d_adv_matrix, h->d_adv_rhs);                \
+  } while (0)
   if (h->dim == 3) {
-    if ((st = set_smem(tiled_advdiff_kernel<3>, P.smem_bytes))) return st;
-    tiled_advdiff_kernel<3><<<P.ntiles, thr, P.smem_bytes, h->stream>>>(A, T, P.max_tile_entries, P.max_tile_rows,
-                                                                        h->d_adv_matrix, h->d_adv_rhs);
+    if (fast) LAUNCH_ADV(tiled_advdiff_fast_kernel<3>);
+    else LAUNCH_ADV(tiled_advdiff_kernel<3>);
   } else {
-    if ((st = set_smem(tiled_advdiff_kernel<2>, P.smem_bytes))) return st;
-    tiled_advdiff_kernel<2><<<P.ntiles, thr, P.smem_bytes, h->stream>>>(A, T, P.max_tile_entries, P.max_tile_rows,
-                                                                        h->d_adv_matrix, h->d_adv_rhs);
+    if (fast) LAUNCH_ADV(tiled_advdiff_fast_kernel<2>);
+    else LAUNCH_ADV(tiled_advdiff_kernel<2>);
   }
+#undef LAUNCH_ADV
   h->launches++;
   CG_CUDA(cudaGetLastError());
   return CGASM_OK;
