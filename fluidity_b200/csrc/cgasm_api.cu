@@ -83,6 +83,7 @@ int repack_slot(Handle* h, int slot, const int* d_nodes, int n) {
 static void destroy_handle(Handle* h) {
   cudaSetDevice(h->device);
   tiles_free(h);
+  gather_free(h);
   halo_free(h);
   free_dev(h->d_ndglno);
   free_dev(h->d_X);
@@ -124,6 +125,7 @@ static int upload_sparsity(Handle* h) {
   h->mom_valid = h->adv_valid = false;
   h->have_sparsity = true;
   tiles_free(h);
+  gather_free(h);
   return CGASM_OK;
 }
 
@@ -279,6 +281,46 @@ int cgasm_create(int* id, int device, int dim, int loc, int ngi, int n_nodes, in
   for (int i = 0; i < loc; i++)
     for (int g = 0; g < ngi; g++) h->tab.N[i * ngi + g] = n[i + loc * g];
   for (int g = 0; g < ngi; g++) h->tab.w[g] = weight[g];
+  {
+    // moments of the rule and the node-permutation symmetry the quad kernels rely on
+    Tables& T = h->tab;
+    auto Nf = [&](int i, int g) { return T.N[i * ngi + g]; };
+    double P[4][4], Q[4][4][4], W1v[4];
+    T.Wsum = 0.0;
+    for (int g = 0; g < ngi; g++) T.Wsum += T.w[g];
+    for (int i = 0; i < loc; i++) {
+      W1v[i] = 0.0;
+      for (int g = 0; g < ngi; g++) W1v[i] += Nf(i, g) * T.w[g];
+      for (int k = 0; k < loc; k++) {
+        P[i][k] = 0.0;
+        for (int g = 0; g < ngi; g++) P[i][k] += Nf(i, g) * Nf(k, g) * T.w[g];
+        for (int l = 0; l < loc; l++) {
+          Q[i][k][l] = 0.0;
+          for (int g = 0; g < ngi; g++) Q[i][k][l] += Nf(i, g) * Nf(k, g) * Nf(l, g) * T.w[g];
+        }
+      }
+    }
+    T.Pd = P[0][0];
+    T.Po = P[0][1];
+    T.Qaaa = Q[0][0][0];
+    T.Qaab = Q[0][0][1];
+    T.Qabc = loc > 2 ? Q[0][1][2] : 0.0;
+    T.W1 = W1v[0];
+    bool sym = true;
+    const double tol = 1e-15;
+    for (int i = 0; i < loc; i++) {
+      sym = sym && std::fabs(W1v[i] - T.W1) < tol;
+      for (int k = 0; k < loc; k++) {
+        sym = sym && std::fabs(P[i][k] - (i == k ? T.Pd : T.Po)) < tol;
+        for (int l = 0; l < loc; l++) {
+          const int eq = (i == k) + (k == l) + (i == l);
+          const double want = eq == 3 ? T.Qaaa : (eq == 1 ? T.Qaab : T.Qabc);
+          sym = sym && std::fabs(Q[i][k][l] - want) < tol;
+        }
+      }
+    }
+    T.sym = sym ? 1 : 0;
+  }
   h->h_nd0.resize((size_t)4 * n_elements);
   for (int e = 0; e < n_elements; e++) {
     for (int i = 0; i < 4; i++) {
@@ -470,7 +512,7 @@ int cgasm_set_colouring(int id, int ncolours, const int* colour_ptr, const int* 
 
 int cgasm_set_scatter(int id, int variant) {
   GET_HANDLE(h, id);
-  if (variant < CGASM_SCATTER_ATOMIC || variant > CGASM_SCATTER_TILED) CG_FAIL(CGASM_EARG, "unknown scatter variant");
+  if (variant < CGASM_SCATTER_ATOMIC || variant > CGASM_SCATTER_GATHER) CG_FAIL(CGASM_EARG, "unknown scatter variant");
   if (variant == CGASM_SCATTER_COLOURED && !h->ncolours) {
     int st = cgasm_build_colouring(id, nullptr);
     if (st) return st;
@@ -479,6 +521,13 @@ int cgasm_set_scatter(int id, int variant) {
     if (!h->have_sparsity) CG_FAIL(CGASM_ESTATE, "tiled scatter needs the sparsity first");
     if (!h->tiles) {
       int st = tiles_build(h);
+      if (st) return st;
+    }
+  }
+  if (variant == CGASM_SCATTER_GATHER) {
+    if (!h->have_sparsity) CG_FAIL(CGASM_ESTATE, "gather scatter needs the sparsity first");
+    if (!h->gather) {
+      int st = gather_build(h);
       if (st) return st;
     }
   }
@@ -547,6 +596,8 @@ int cgasm_momentum_dev(int id, const cgasm_momentum_opts* opts) {
   CG_CUDA(cudaEventRecord(h->ev0, h->stream));
   if (h->scatter == CGASM_SCATTER_TILED) {
     st = tiles_momentum(h, A, want_ml, want_ct);
+  } else if (h->scatter == CGASM_SCATTER_GATHER) {
+    st = gather_momentum(h, A, want_ml, want_ct);
   } else {
     // zero(big_m), zero(rhs) ... (Momentum_Equation.F90:593-606) then accumulate
     CG_CUDA(cudaMemsetAsync(h->d_big_m, 0, sizeof(double) * dim * nnz, h->stream));
@@ -577,6 +628,8 @@ int cgasm_advdiff_dev(int id, const cgasm_advdiff_opts* opts) {
   CG_CUDA(cudaEventRecord(h->ev0, h->stream));
   if (h->scatter == CGASM_SCATTER_TILED) {
     st = tiles_advdiff(h, P);
+  } else if (h->scatter == CGASM_SCATTER_GATHER) {
+    st = gather_advdiff(h, P);
   } else {
     CG_CUDA(cudaMemsetAsync(h->d_adv_matrix, 0, sizeof(double) * nnz, h->stream));
     CG_CUDA(cudaMemsetAsync(h->d_adv_rhs, 0, sizeof(double) * nn, h->stream));

@@ -1,6 +1,8 @@
 // cgasm_internal.h -- handle layout and helpers shared by the translation units of
 // libcgasm.so. Not part of the ABI (that is include/cgasm.h).
 #pragma once
+#include <algorithm>
+#include <cmath>
 #include <cstdint>
 #include <string>
 #include <vector>
@@ -21,7 +23,8 @@ struct DeviceField {
   bool set = false;
 };
 
-struct TilePlan;  // tiled.cu
+struct TilePlan;    // tiled.cu
+struct GatherPlan;  // gather.cu
 struct HaloPlan;  // halo.cu
 
 struct Handle {
@@ -69,6 +72,7 @@ struct Handle {
 
   int scatter = CGASM_SCATTER_ATOMIC;
   TilePlan* tiles = nullptr;
+  GatherPlan* gather = nullptr;
   HaloPlan* halo = nullptr;
 
   long long launches = 0;
@@ -105,11 +109,56 @@ int greedy_colouring(int n_elements, int loc, const int* nd0, const std::vector<
 void colour_sets(int n_elements, int ncol, const std::vector<int>& colour_of,
                  std::vector<int>& colour_ptr, std::vector<int>& colour_elements);
 
+// ---- Morton order ----------------------------------------------------------------------------
+inline uint64_t spread3(uint64_t x) {  // 21 bits -> every third bit
+  x &= 0x1fffff;
+  x = (x | x << 32) & 0x1f00000000ffffULL;
+  x = (x | x << 16) & 0x1f0000ff0000ffULL;
+  x = (x | x << 8) & 0x100f00f00f00f00fULL;
+  x = (x | x << 4) & 0x10c30c30c30c30c3ULL;
+  x = (x | x << 2) & 0x1249249249249249ULL;
+  return x;
+}
+inline uint64_t spread2(uint64_t x) {  // 32 bits -> every second bit
+  x &= 0xffffffffULL;
+  x = (x | x << 16) & 0x0000ffff0000ffffULL;
+  x = (x | x << 8) & 0x00ff00ff00ff00ffULL;
+  x = (x | x << 4) & 0x0f0f0f0f0f0f0f0fULL;
+  x = (x | x << 2) & 0x3333333333333333ULL;
+  x = (x | x << 1) & 0x5555555555555555ULL;
+  return x;
+}
+
+struct MortonFrame {
+  double lo[3] = {0, 0, 0}, scale[3] = {0, 0, 0};
+  int dim = 3;
+  // cell of a point on the mesh-spacing lattice (nearest lattice point for nodes)
+  inline uint64_t key_round(const double* x) const {
+    uint64_t q[3] = {0, 0, 0};
+    for (int a = 0; a < dim; a++) q[a] = (uint64_t)std::llround((x[a] - lo[a]) * scale[a]);
+    return dim == 3 ? (spread3(q[0]) | spread3(q[1]) << 1 | spread3(q[2]) << 2) : (spread2(q[0]) | spread2(q[1]) << 1);
+  }
+  // containing cell (floor): element centroids of one lattice cell share a key
+  inline uint64_t key_floor(const double* x) const {
+    uint64_t q[3] = {0, 0, 0};
+    for (int a = 0; a < dim; a++) q[a] = (uint64_t)std::max(0.0, std::floor((x[a] - lo[a]) * scale[a]));
+    return dim == 3 ? (spread3(q[0]) | spread3(q[1]) << 1 | spread3(q[2]) << 2) : (spread2(q[0]) | spread2(q[1]) << 1);
+  }
+};
+
+void morton_order(const Handle* h, std::vector<int>& order, MortonFrame& F);
+
 // tiled.cu
 int tiles_build(Handle* h);
 void tiles_free(Handle* h);
 int tiles_momentum(Handle* h, const MomentumArgs& args, bool want_ml, bool want_ct);
 int tiles_advdiff(Handle* h, const AdvDiffArgs& args);
+
+// gather.cu
+int gather_build(Handle* h);
+void gather_free(Handle* h);
+int gather_momentum(Handle* h, const MomentumArgs& args, bool want_ml, bool want_ct);
+int gather_advdiff(Handle* h, const AdvDiffArgs& args);
 
 // halo.cu
 void halo_free(Handle* h);

@@ -29,6 +29,12 @@ struct Shape {
 struct Tables {
   double N[4 * 5];  // n(i,g) at [i*NGI + g]
   double w[5];
+  // Moments of a node-symmetric rule (filled and verified at cgasm_create, sym = 1 if they hold):
+  //   P_ik  = sum_g N_ig N_kg w_g       = Pd (i == k) | Po (i != k)
+  //   Q_ikl = sum_g N_ig N_kg N_lg w_g  = Qaaa | Qaab (two equal) | Qabc (all distinct)
+  //   W1    = sum_g N_ig w_g (same for every i),  Wsum = sum_g w_g
+  double Pd, Po, Qaaa, Qaab, Qabc, W1, Wsum;
+  int sym;
 };
 
 // Device view of one nodal field (femtools/Fields_Data_Types.F90:154-233).
@@ -962,6 +968,7 @@ __device__ __forceinline__ void momentum_fast(const MomentumArgs& A, const int4 
     for (int d = 0; d < DIM; d++) sink.vec(i, d, rhs[d]);
 #pragma unroll
     for (int d = 0; d < (PERD ? DIM : 1); d++) sink.ml(i, d, mlv[d]);
+    sink.row_end(i);
   }
 }
 
@@ -1102,7 +1109,253 @@ __device__ __forceinline__ void advdiff_fast(const AdvDiffArgs& P, const int4 nd
       sink.mat(i, j, a_ij);
     }
     sink.vec(i, rhs);
+    sink.row_end(i);
   }
+}
+
+// =====================================================================================
+// Row kernels for the quad mapping (one lane = one local row of one element).
+//
+// The caller passes the element's nodes rotated so that the lane's own node is local node 0;
+// the degree-3 rules are symmetric under node permutations (checked at create: Tables::sym),
+// so every quadrature sum collapses to the closed-form moments in Tables:
+//   rho-weighted mass row   M_0k = |J| sum_l Q_0kl rho_l
+//   advection               v_0  = sum_k M_0k nu_k            (A_0j = v_0 . gradN_j)
+//   lumped mass             m_0  = |J| sum_l P_0l rho_l
+//   buoyancy                n_0  = g |J| sum_k P_0k b_k
+// Option coverage = momentum_fast_ok / advdiff_fast_ok. Sink: mat(jj, d, v), vec(d, v), ml(d, v)
+// with jj the ROTATED column index.
+// =====================================================================================
+template <int DIM>
+__device__ __forceinline__ void load_rot(const double4* __restrict__ rec, const int (&n)[4], double (&v)[DIM + 1][DIM],
+                                         double (&s)[DIM + 1]) {
+#pragma unroll
+  for (int k = 0; k < DIM + 1; k++) unpack<DIM>(ld256(rec + n[k]), v[k], s[k]);
+}
+
+template <int DIM, bool PERD, class Sink>
+__device__ __forceinline__ void momentum_row0(const MomentumArgs& A, const int (&n)[4], Sink& sink) {
+  constexpr int LOC = DIM + 1;
+  const cgasm_momentum_opts& o = A.o;
+  const Tables& t = A.tab;
+  const double dtt = o.dt * o.theta;
+  Geom<DIM> G;
+  double M[LOC];  // rho-weighted mass row of local node 0
+  double v[DIM];
+  double m0;
+  {
+    double X[LOC][DIM], T_unused[LOC];
+    load_rot<DIM>(A.rec.r0, n, X, T_unused);
+    geometry<DIM>(X, G);
+  }
+  {
+    double nu[LOC][DIM], rho[LOC];
+    load_rot<DIM>(A.rec.r1, n, nu, rho);
+    double S = 0.0;
+#pragma unroll
+    for (int k = 0; k < LOC; k++) S += rho[k];
+    M[0] = G.absdet * ((t.Qaaa - t.Qaab) * rho[0] + t.Qaab * S);
+#pragma unroll
+    for (int k = 1; k < LOC; k++) M[k] = G.absdet * ((t.Qaab - t.Qabc) * (rho[0] + rho[k]) + t.Qabc * S);
+    m0 = G.absdet * ((t.Pd - t.Po) * rho[0] + t.Po * S);
+#pragma unroll
+    for (int a = 0; a < DIM; a++) v[a] = 0.0;
+    if (!o.exclude_advection) {
+#pragma unroll
+      for (int k = 0; k < LOC; k++)
+#pragma unroll
+        for (int a = 0; a < DIM; a++) v[a] += M[k] * nu[k][a];
+    }
+  }
+  if (o.have_viscosity) {
+    double Vbar[DIM * DIM];
+    if (A.viscosity.stride == 0) {
+      gather<DIM * DIM>(A.viscosity, 0, Vbar);
+#pragma unroll
+      for (int ab = 0; ab < DIM * DIM; ab++) Vbar[ab] *= G.absdet * t.Wsum;
+    } else {
+#pragma unroll
+      for (int ab = 0; ab < DIM * DIM; ab++) Vbar[ab] = 0.0;
+#pragma unroll
+      for (int k = 0; k < LOC; k++) {
+        double vk[DIM * DIM];
+        gather<DIM * DIM>(A.viscosity, n[k], vk);
+#pragma unroll
+        for (int ab = 0; ab < DIM * DIM; ab++) Vbar[ab] += vk[ab];
+      }
+#pragma unroll
+      for (int ab = 0; ab < DIM * DIM; ab++) Vbar[ab] *= G.absdet * t.W1;
+    }
+    if (o.viscosity_shape == CGASM_TENSOR_ISOTROPIC) {
+#pragma unroll
+      for (int a = 0; a < DIM; a++) v[a] += Vbar[0] * G.grad[0][a];
+    } else if (o.viscosity_shape == CGASM_TENSOR_DIAGONAL) {
+#pragma unroll
+      for (int a = 0; a < DIM; a++) v[a] += Vbar[a + DIM * a] * G.grad[0][a];
+    } else {
+#pragma unroll
+      for (int b = 0; b < DIM; b++) {
+        double s = 0.0;
+#pragma unroll
+        for (int a = 0; a < DIM; a++) s += G.grad[0][a] * Vbar[a + DIM * b];
+        v[b] += s;
+      }
+    }
+  }
+  double oldu[LOC][DIM], b[LOC];
+  load_rot<DIM>(A.rec.r2, n, oldu, b);
+  double rhs[DIM];
+#pragma unroll
+  for (int d = 0; d < DIM; d++) rhs[d] = 0.0;
+  if (o.have_gravity) {
+    if (o.subtract_out_reference_profile) {
+#pragma unroll
+      for (int k = 0; k < LOC; k++) {
+        double r1[1];
+        gather<1>(A.hb_density, n[k], r1);
+        b[k] -= r1[0];
+      }
+    }
+    double S = 0.0;
+#pragma unroll
+    for (int k = 0; k < LOC; k++) S += b[k];
+    const double nb = o.gravity_magnitude * G.absdet * ((t.Pd - t.Po) * b[0] + t.Po * S);
+    double gd[DIM];
+    gather<DIM>(A.gravity, 0, gd);
+#pragma unroll
+    for (int d = 0; d < DIM; d++) rhs[d] = nb * gd[d];
+  }
+  double diag[PERD ? DIM : 1], mlv[PERD ? DIM : 1];
+#pragma unroll
+  for (int d = 0; d < (PERD ? DIM : 1); d++) {
+    diag[d] = o.exclude_mass ? 0.0 : m0;
+    mlv[d] = o.assemble_inverse_masslump ? m0 : 0.0;
+  }
+  if constexpr (PERD) {
+    if (o.have_absorption) {  // lumped: sum_j Ab_0j(d) = sum_k M_0k sigma_k(d)
+      double sd[DIM];
+#pragma unroll
+      for (int d = 0; d < DIM; d++) sd[d] = 0.0;
+#pragma unroll
+      for (int k = 0; k < LOC; k++) {
+        double ak[DIM];
+        gather<DIM>(A.absorption, n[k], ak);
+#pragma unroll
+        for (int d = 0; d < DIM; d++) sd[d] += M[k] * ak[d];
+      }
+#pragma unroll
+      for (int d = 0; d < DIM; d++) {
+        diag[d] += dtt * sd[d];
+        rhs[d] -= sd[d] * oldu[0][d];
+        if (o.pressure_corrected_absorption && o.assemble_inverse_masslump) mlv[d] += dtt * sd[d];
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < LOC; j++) {
+    double s = 0.0;
+#pragma unroll
+    for (int a = 0; a < DIM; a++) s += v[a] * G.grad[j][a];
+#pragma unroll
+    for (int d = 0; d < DIM; d++) rhs[d] -= s * oldu[j][d];
+#pragma unroll
+    for (int d = 0; d < (PERD ? DIM : 1); d++) sink.mat(j, d, dtt * s + (j == 0 ? diag[d] : 0.0));
+  }
+#pragma unroll
+  for (int d = 0; d < DIM; d++) sink.vec(d, rhs[d]);
+#pragma unroll
+  for (int d = 0; d < (PERD ? DIM : 1); d++) sink.ml(d, mlv[d]);
+}
+
+// Sink: mat(jj, v), vec(v)
+template <int DIM, class Sink>
+__device__ __forceinline__ void advdiff_row0(const AdvDiffArgs& P, const int (&n)[4], Sink& sink) {
+  constexpr int LOC = DIM + 1;
+  const cgasm_advdiff_opts& o = P.o;
+  const Tables& t = P.tab;
+  const double dtt = o.dt * o.theta;
+  const bool implicit = fabs(dtt) > 2.220446049250313e-16;
+  Geom<DIM> G;
+  double T[LOC], v[DIM];
+  {
+    double X[LOC][DIM];
+    load_rot<DIM>(P.rec.r0, n, X, T);
+    geometry<DIM>(X, G);
+  }
+#pragma unroll
+  for (int a = 0; a < DIM; a++) v[a] = 0.0;
+  if (o.have_advection) {
+    double u[LOC][DIM], unused[LOC];
+    load_rot<DIM>(P.rec.r1, n, u, unused);
+#pragma unroll
+    for (int a = 0; a < DIM; a++) {
+      double S = 0.0;
+#pragma unroll
+      for (int k = 0; k < LOC; k++) S += u[k][a];
+      v[a] = G.absdet * ((t.Pd - t.Po) * u[0][a] + t.Po * S);
+    }
+  }
+  if (o.have_diffusivity) {
+    double Kbar[DIM * DIM];
+    if (P.diffusivity.stride == 0) {
+      gather<DIM * DIM>(P.diffusivity, 0, Kbar);
+#pragma unroll
+      for (int ab = 0; ab < DIM * DIM; ab++) Kbar[ab] *= G.absdet * t.Wsum;
+    } else {
+#pragma unroll
+      for (int ab = 0; ab < DIM * DIM; ab++) Kbar[ab] = 0.0;
+#pragma unroll
+      for (int k = 0; k < LOC; k++) {
+        double kk[DIM * DIM];
+        gather<DIM * DIM>(P.diffusivity, n[k], kk);
+#pragma unroll
+        for (int ab = 0; ab < DIM * DIM; ab++) Kbar[ab] += kk[ab];
+      }
+#pragma unroll
+      for (int ab = 0; ab < DIM * DIM; ab++) Kbar[ab] *= G.absdet * t.W1;
+    }
+    if (o.diffusivity_shape == CGASM_TENSOR_ISOTROPIC) {
+#pragma unroll
+      for (int a = 0; a < DIM; a++) v[a] += Kbar[0] * G.grad[0][a];
+    } else {
+#pragma unroll
+      for (int b = 0; b < DIM; b++) {
+        double s = 0.0;
+#pragma unroll
+        for (int a = 0; a < DIM; a++) s += G.grad[0][a] * Kbar[a + DIM * b];
+        v[b] += s;
+      }
+    }
+  }
+  double rhs = 0.0;
+  if (o.have_source) {
+    double S = 0.0, s0 = 0.0;
+#pragma unroll
+    for (int k = 0; k < LOC; k++) {
+      double r1[1];
+      gather<1>(P.source, n[k], r1);
+      S += r1[0];
+      if (k == 0) s0 = r1[0];
+    }
+    rhs = G.absdet * ((t.Pd - t.Po) * s0 + t.Po * S);
+  }
+#pragma unroll
+  for (int j = 0; j < LOC; j++) {
+    double s = 0.0;
+#pragma unroll
+    for (int a = 0; a < DIM; a++) s += v[a] * G.grad[j][a];
+    rhs -= s * T[j];
+    double a_0j = implicit ? dtt * s : 0.0;
+    if (o.have_mass) {
+      if (o.lump_mass) {
+        if (j == 0) a_0j += G.absdet * t.W1;
+      } else {
+        a_0j += G.absdet * (j == 0 ? t.Pd : t.Po);
+      }
+    }
+    sink.mat(j, a_0j);
+  }
+  sink.vec(rhs);
 }
 
 }  // namespace cgasm

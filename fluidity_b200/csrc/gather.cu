@@ -1,0 +1,654 @@
+// gather.cu -- CGASM_SCATTER_GATHER: "local rows + row gather", two barrier-free passes.
+//
+// The reference adds every element contribution into the global matrix the moment it is
+// computed (addto: femtools/Sparse_Tools.F90:2680-2703, Sparse_Tools_Petsc.F90:848-879,
+// Fields_Manipulation.F90:255-379), which on a GPU means either atomics (bound by the SM's red
+// issue rate, profiles/), colours (femtools/Colouring.F90: dozens of dependent phases) or
+// shared-memory tiles (latency-bound lock-step phases, tiled.cu). Here the addto is split:
+//
+//   pass A (one thread per element, nothing shared): the element routine runs exactly once per
+//     element and streams its loc ROW RECORDS -- row i of the local matrix block(s), rhs(:,i),
+//     lumped mass -- to a staging buffer with 256-bit stores;
+//   pass B (one thread per CSR row): walks the precomputed list of (element, local row) pairs
+//     incident to its node, reads each 64-byte record once, adds the loc matrix values into its
+//     own slots (thread-private shared-memory column, conflict-free by layout) and the vector
+//     part in registers, then the warp writes the finished row -- every output entry is written
+//     exactly once, no atomics, no pre-zeroing, summation order fixed by the plan (bitwise
+//     reproducible), no redundant element math.
+//
+// The pair list plays the role of csr_sparsity_pos (Sparse_Tools.F90:2411-2517): positions are
+// found once per mesh instead of once per entry per assembly.
+#include "cgasm_internal.h"
+
+#include <algorithm>
+#include <cstdlib>
+#include <numeric>
+
+namespace cgasm {
+
+constexpr int kBR = 128;  // rows (= threads) per gather block
+
+struct GatherPlan {
+  int nblocks = 0;
+  int maxlen = 0;                  // longest CSR row
+  int* d_rows = nullptr;           // [nblocks*kBR] node of each row slot, -1 = padding
+  long long* d_block_ptr = nullptr;  // [nblocks+1] first plan entry of a block
+  uint2* d_pairs = nullptr;        // block-interleaved: entry k of thread t at ptr + k*kBR + t
+                                   //   .x = element*4 + local row (0xFFFFFFFF = none), .y = 4 x 8-bit slot
+  long long n_entries = 0;
+  double* d_stage = nullptr;       // staging buffer (grown on demand)
+  size_t stage_doubles = 0;
+};
+
+void gather_free(Handle* h) {
+  GatherPlan* p = h->gather;
+  if (!p) return;
+  if (p->d_rows) cudaFree(p->d_rows);
+  if (p->d_block_ptr) cudaFree(p->d_block_ptr);
+  if (p->d_pairs) cudaFree(p->d_pairs);
+  if (p->d_stage) cudaFree(p->d_stage);
+  delete p;
+  h->gather = nullptr;
+}
+
+// One thread per row slot: writes the row's pair list (element order = ascending element id, the
+// order the serial reference visits them) with the slot of every element node inside the row.
+__global__ void gather_pairs_kernel(int nblocks, int loc, const int* __restrict__ rows,
+                                    const long long* __restrict__ block_ptr,
+                                    const long long* __restrict__ n2e_ptr, const int* __restrict__ n2e,
+                                    const int4* __restrict__ ndglno, const int* __restrict__ findrm,
+                                    const int* __restrict__ colm, uint2* __restrict__ pairs) {
+  const int b = blockIdx.x, t = threadIdx.x;
+  if (b >= nblocks) return;
+  const int r = rows[b * kBR + t];
+  const long long base = block_ptr[b];
+  const int deg_block = (int)((block_ptr[b + 1] - base) / kBR);
+  int deg = 0;
+  if (r >= 0) {
+    const long long k0 = n2e_ptr[r];
+    deg = (int)(n2e_ptr[r + 1] - k0);
+    const int s = findrm[r], e_ = findrm[r + 1];
+    for (int k = 0; k < deg; k++) {
+      const int e = n2e[k0 + k];
+      const int4 nd = ndglno[e];
+      const int nodes[4] = {nd.x, nd.y, nd.z, nd.w};
+      unsigned slots = 0, irow = 0;
+      for (int j = 0; j < loc; j++) {
+        if (nodes[j] == r) irow = j;
+        for (int q = s; q < e_; q++)
+          if (colm[q] == nodes[j]) slots |= (unsigned)((q - s) & 0xff) << (8 * j);
+      }
+      pairs[base + (long long)k * kBR + t] = make_uint2((unsigned)e * 4u + irow, slots);
+    }
+  }
+  for (int k = deg; k < deg_block; k++) pairs[base + (long long)k * kBR + t] = make_uint2(0xFFFFFFFFu, 0u);
+}
+
+int gather_build(Handle* h) {
+  if (!h->have_X) CG_FAIL(CGASM_ESTATE, "gather scatter orders rows by node coordinates: set coordinates first");
+  if (!h->have_sparsity) CG_FAIL(CGASM_ESTATE, "gather scatter needs the sparsity first");
+  if ((long long)h->n_elements >= (1ll << 30)) CG_FAIL(CGASM_EUNSUPPORTED, "gather scatter packs element*4+row in 32 bits");
+  gather_free(h);
+  GatherPlan* P = new GatherPlan();
+  h->gather = P;
+  const int n = h->n_nodes;
+  std::vector<int> order;
+  MortonFrame F;
+  morton_order(h, order, F);
+  P->nblocks = (n + kBR - 1) / kBR;
+  std::vector<int> rows((size_t)P->nblocks * kBR, -1);
+  std::copy(order.begin(), order.end(), rows.begin());
+  std::vector<long long> block_ptr((size_t)P->nblocks + 1, 0);
+  int maxlen = 0;
+  for (int b = 0; b < P->nblocks; b++) {
+    int deg = 0;
+    for (int t = 0; t < kBR; t++) {
+      const int r = rows[(size_t)b * kBR + t];
+      if (r < 0) continue;
+      deg = std::max(deg, (int)(h->n2e_ptr[r + 1] - h->n2e_ptr[r]));
+      maxlen = std::max(maxlen, h->h_findrm[r + 1] - h->h_findrm[r]);
+    }
+    // rows of a block are sorted by global id so that neighbouring threads write neighbouring rows
+    std::sort(rows.begin() + (size_t)b * kBR, rows.begin() + (size_t)b * kBR + std::min(kBR, n - b * kBR));
+    block_ptr[b + 1] = block_ptr[b] + (long long)deg * kBR;
+  }
+  if (maxlen > 255) CG_FAIL(CGASM_EUNSUPPORTED, "CSR row longer than 255 entries: gather slot index is 8 bit");
+  P->maxlen = maxlen;
+  P->n_entries = block_ptr[P->nblocks];
+  CG_CUDA(cudaMalloc(&P->d_rows, sizeof(int) * rows.size()));
+  CG_CUDA(cudaMemcpy(P->d_rows, rows.data(), sizeof(int) * rows.size(), cudaMemcpyHostToDevice));
+  CG_CUDA(cudaMalloc(&P->d_block_ptr, sizeof(long long) * block_ptr.size()));
+  CG_CUDA(cudaMemcpy(P->d_block_ptr, block_ptr.data(), sizeof(long long) * block_ptr.size(), cudaMemcpyHostToDevice));
+  CG_CUDA(cudaMalloc(&P->d_pairs, sizeof(uint2) * (size_t)std::max<long long>(P->n_entries, 1)));
+  // node->element adjacency goes to the device only for the duration of the plan build
+  long long* d_n2e_ptr = nullptr;
+  int* d_n2e = nullptr;
+  CG_CUDA(cudaMalloc(&d_n2e_ptr, sizeof(long long) * ((size_t)n + 1)));
+  CG_CUDA(cudaMalloc(&d_n2e, sizeof(int) * std::max<size_t>(h->n2e.size(), 1)));
+  static_assert(sizeof(long long) == sizeof(int64_t), "int64_t is long long");
+  cudaError_t e1 = cudaMemcpy(d_n2e_ptr, h->n2e_ptr.data(), sizeof(long long) * ((size_t)n + 1), cudaMemcpyHostToDevice);
+  cudaError_t e2 = cudaMemcpy(d_n2e, h->n2e.data(), sizeof(int) * h->n2e.size(), cudaMemcpyHostToDevice);
+  if (e1 == cudaSuccess && e2 == cudaSuccess) {
+    gather_pairs_kernel<<<P->nblocks, kBR, 0, h->stream>>>(P->nblocks, h->loc, P->d_rows, P->d_block_ptr, d_n2e_ptr,
+                                                          d_n2e, h->d_ndglno, h->d_findrm, h->d_colm, P->d_pairs);
+    h->launches++;
+    e1 = cudaStreamSynchronize(h->stream);
+  }
+  cudaFree(d_n2e_ptr);
+  cudaFree(d_n2e);
+  CG_CUDA(e1);
+  CG_CUDA(e2);
+  return CGASM_OK;
+}
+
+static int ensure_stage(GatherPlan* P, size_t doubles) {
+  if (P->stage_doubles >= doubles) return CGASM_OK;
+  if (P->d_stage) cudaFree(P->d_stage);
+  P->d_stage = nullptr;
+  P->stage_doubles = 0;
+  CG_CUDA(cudaMalloc(&P->d_stage, sizeof(double) * doubles));
+  P->stage_doubles = doubles;
+  return CGASM_OK;
+}
+
+// ---- record layout -------------------------------------------------------------------------------
+// record of (element e, local row i) at stage + (e*LOC + i)*RS doubles:
+//   [b*LOC + j]  matrix value (i,j) of block b, b < NB     [NB*LOC + c]  vector component c < NV
+template <int LOC, int NB, int NV>
+struct Rec {
+  static constexpr int N = NB * LOC + NV;
+  static constexpr int RS = (N + 3) / 4 * 4;  // whole 32-byte sectors
+};
+
+__device__ __forceinline__ void st256(double* p, double a, double b, double c, double d) {
+  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+
+template <int RS>
+__device__ __forceinline__ void store_rec(double* dst, const double (&v)[RS]) {
+#pragma unroll
+  for (int q = 0; q < RS; q += 4) st256(dst + q, v[q], v[q + 1], v[q + 2], v[q + 3]);
+}
+
+// ---- pass A ----------------------------------------------------------------------------------------
+// momentum, generic options: NB = 1 (no absorption) or DIM; NV = DIM + MLC
+template <int DIM, bool LABS, int NB, int MLC>
+__global__ void __launch_bounds__(128)
+gather_momentum_stage_kernel(const MomentumArgs A, double* __restrict__ stage) {
+  constexpr int LOC = DIM + 1;
+  using R_ = Rec<LOC, NB, DIM + MLC>;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= A.n_elements) return;
+  const int4 nd = __ldg(A.ndglno + e);
+  MomentumLocal<DIM, LABS> R;
+  Geom<DIM> G;
+  momentum_element<DIM, LABS>(A, nd, R, G);
+#pragma unroll
+  for (int i = 0; i < LOC; i++) {
+    double v[R_::RS];
+#pragma unroll
+    for (int q = 0; q < R_::RS; q++) v[q] = 0.0;
+#pragma unroll
+    for (int b = 0; b < NB; b++)
+#pragma unroll
+      for (int j = 0; j < LOC; j++) {
+        double x = R.L[i][j];
+        if constexpr (LABS) x += R.Labs[b][i][j];
+        if (i == j) x += R.diag[NB > 1 ? b : 0][i];
+        v[b * LOC + j] = x;
+      }
+#pragma unroll
+    for (int d = 0; d < DIM; d++) v[NB * LOC + d] = R.rhs[d][i];
+#pragma unroll
+    for (int d = 0; d < MLC; d++) v[NB * LOC + DIM + d] = R.ml[d][i];
+    store_rec<R_::RS>(stage + ((size_t)e * LOC + i) * R_::RS, v);
+  }
+}
+
+template <int DIM, bool PERD, int MLC>
+struct MomStageSink {
+  static constexpr int LOC = DIM + 1;
+  static constexpr int NB = PERD ? DIM : 1;
+  using R_ = Rec<LOC, NB, DIM + MLC>;
+  double* dst;  // first record of the element
+  double v[R_::RS];
+  __device__ __forceinline__ bool owned(int) {
+#pragma unroll
+    for (int q = 0; q < R_::RS; q++) v[q] = 0.0;
+    return true;
+  }
+  __device__ __forceinline__ void mat(int, int j, int d, double x) { v[d * LOC + j] = x; }
+  __device__ __forceinline__ void vec(int, int d, double x) { v[NB * LOC + d] = x; }
+  __device__ __forceinline__ void ml(int, int d, double x) {
+    if (d < MLC) v[NB * LOC + DIM + d] = x;
+  }
+  __device__ __forceinline__ void row_end(int i) { store_rec<R_::RS>(dst + (size_t)i * R_::RS, v); }
+};
+
+template <int DIM, bool PERD, int MLC>
+__global__ void __launch_bounds__(128)
+gather_momentum_stage_fast_kernel(const MomentumArgs A, double* __restrict__ stage) {
+  constexpr int LOC = DIM + 1;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= A.n_elements) return;
+  const int4 nd = __ldg(A.ndglno + e);
+  MomStageSink<DIM, PERD, MLC> sink;
+  sink.dst = stage + (size_t)e * LOC * MomStageSink<DIM, PERD, MLC>::R_::RS;
+  momentum_fast<DIM, PERD>(A, nd, sink);
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(128) gather_ct_stage_kernel(const MomentumArgs A, double* __restrict__ stage) {
+  constexpr int LOC = DIM + 1;
+  using R_ = Rec<LOC, DIM, 0>;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= A.n_elements) return;
+  const int4 nd = __ldg(A.ndglno + e);
+  double X[LOC][DIM];
+#pragma unroll
+  for (int i = 0; i < LOC; i++) {
+    double unused;
+    unpack<DIM>(ld256(A.rec.r0 + node_of(nd, i)), X[i], unused);
+  }
+  Geom<DIM> G;
+  geometry<DIM>(X, G);
+#pragma unroll
+  for (int i = 0; i < LOC; i++) {
+    double v[R_::RS];
+#pragma unroll
+    for (int q = 0; q < R_::RS; q++) v[q] = 0.0;
+#pragma unroll
+    for (int d = 0; d < DIM; d++)
+#pragma unroll
+      for (int j = 0; j < LOC; j++) v[d * LOC + j] = grad_p_u<DIM>(A.tab, G, d, i, j);
+    store_rec<R_::RS>(stage + ((size_t)e * LOC + i) * R_::RS, v);
+  }
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(128) gather_advdiff_stage_kernel(const AdvDiffArgs A, double* __restrict__ stage) {
+  constexpr int LOC = DIM + 1;
+  using R_ = Rec<LOC, 1, 1>;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= A.n_elements) return;
+  AdvDiffLocal<DIM> R;
+  advdiff_element<DIM>(A, __ldg(A.ndglno + e), R);
+#pragma unroll
+  for (int i = 0; i < LOC; i++) {
+    double v[R_::RS];
+#pragma unroll
+    for (int q = 0; q < R_::RS; q++) v[q] = 0.0;
+#pragma unroll
+    for (int j = 0; j < LOC; j++) v[j] = R.A[i][j];
+    v[LOC] = R.rhs[i];
+    store_rec<R_::RS>(stage + ((size_t)e * LOC + i) * R_::RS, v);
+  }
+}
+
+template <int DIM>
+struct AdvStageSink {
+  static constexpr int LOC = DIM + 1;
+  using R_ = Rec<LOC, 1, 1>;
+  double* dst;
+  double v[R_::RS];
+  __device__ __forceinline__ bool owned(int) {
+#pragma unroll
+    for (int q = 0; q < R_::RS; q++) v[q] = 0.0;
+    return true;
+  }
+  __device__ __forceinline__ void mat(int, int j, double x) { v[j] = x; }
+  __device__ __forceinline__ void vec(int, double x) { v[LOC] = x; }
+  __device__ __forceinline__ void row_end(int i) { store_rec<R_::RS>(dst + (size_t)i * R_::RS, v); }
+};
+
+template <int DIM>
+__global__ void __launch_bounds__(128)
+gather_advdiff_stage_fast_kernel(const AdvDiffArgs A, double* __restrict__ stage) {
+  constexpr int LOC = DIM + 1;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= A.n_elements) return;
+  AdvStageSink<DIM> sink;
+  sink.dst = stage + (size_t)e * LOC * AdvStageSink<DIM>::R_::RS;
+  advdiff_fast<DIM>(A, __ldg(A.ndglno + e), sink);
+}
+
+// ---- pass B ----------------------------------------------------------------------------------------
+// KIND 0: momentum (out0 = big_m [DIM blocks], out1 = rhs, out2 = masslump or null)
+// KIND 1: tracer   (out0 = matrix, out1 = rhs)        KIND 2: ct_m (out0 = ct_m [DIM blocks])
+template <int DIM, int NB, int NV, int KIND>
+__global__ void __launch_bounds__(kBR)
+gather_rows_kernel(const int* __restrict__ rows, const long long* __restrict__ block_ptr,
+                   const uint2* __restrict__ pairs, const double* __restrict__ stage,
+                   const int* __restrict__ findrm, size_t nnz, int maxlen, double* __restrict__ out0,
+                   double* __restrict__ out1, double* __restrict__ out2) {
+  constexpr int LOC = DIM + 1;
+  using R_ = Rec<LOC, NB, NV>;
+  extern __shared__ double acc[];  // [NB][maxlen][kBR]: column t is private to thread t
+  const int b = blockIdx.x, t = threadIdx.x;
+  const int r = rows[b * kBR + t];
+  const long long base = block_ptr[b];
+  const int deg = (int)((block_ptr[b + 1] - base) / kBR);
+  const int len = r >= 0 ? findrm[r + 1] - findrm[r] : 0;
+  for (int q = 0; q < NB * maxlen; q++) acc[q * kBR + t] = 0.0;
+  double vec[NV > 0 ? NV : 1];
+#pragma unroll
+  for (int c = 0; c < (NV > 0 ? NV : 1); c++) vec[c] = 0.0;
+  const uint2* p = pairs + base + t;
+#pragma unroll 2
+  for (int k = 0; k < deg; k++) {
+    const uint2 ent = __ldg(p + (long long)k * kBR);
+    if (ent.x == 0xFFFFFFFFu) continue;
+    const double* rec = stage + ((size_t)(ent.x >> 2) * LOC + (ent.x & 3u)) * R_::RS;
+    double v[R_::RS];
+#pragma unroll
+    for (int q = 0; q < R_::RS; q += 4) {
+      const double4 x = ld256(reinterpret_cast<const double4*>(rec + q));
+      v[q] = x.x;
+      v[q + 1] = x.y;
+      v[q + 2] = x.z;
+      v[q + 3] = x.w;
+    }
+#pragma unroll
+    for (int j = 0; j < LOC; j++) {
+      const int s = (ent.y >> (8 * j)) & 0xff;
+#pragma unroll
+      for (int bb = 0; bb < NB; bb++) acc[(bb * maxlen + s) * kBR + t] += v[bb * LOC + j];
+    }
+#pragma unroll
+    for (int c = 0; c < NV; c++) vec[c] += v[NB * LOC + c];
+  }
+  // vector outputs: one thread = one node
+  if (r >= 0) {
+    if (KIND == 0) {
+#pragma unroll
+      for (int d = 0; d < DIM; d++) out1[(size_t)DIM * r + d] = vec[d];
+      if (out2) {
+#pragma unroll
+        for (int d = 0; d < DIM; d++) out2[(size_t)DIM * r + d] = vec[DIM + (NV == 2 * DIM ? d : 0)];
+      }
+    } else if (KIND == 1) {
+      out1[r] = vec[0];
+    }
+  }
+  __syncthreads();
+  // matrix rows: a warp writes the rows of its 32 threads one after another, lanes = entries
+  const int warp = t >> 5, lane = t & 31;
+  for (int rr = 0; rr < 32; rr++) {
+    const int tt = warp * 32 + rr;
+    const int row = rows[b * kBR + tt];
+    if (row < 0) continue;
+    const int s0 = findrm[row], n = findrm[row + 1] - s0;
+    for (int s = lane; s < n; s += 32) {
+      if (KIND == 0) {
+#pragma unroll
+        for (int d = 0; d < DIM; d++) out0[(size_t)d * nnz + s0 + s] = acc[((NB > 1 ? d : 0) * maxlen + s) * kBR + tt];
+      } else if (KIND == 1) {
+        out0[(size_t)s0 + s] = acc[s * kBR + tt];
+      } else {
+#pragma unroll
+        for (int d = 0; d < DIM; d++) out0[(size_t)d * nnz + s0 + s] = acc[(d * maxlen + s) * kBR + tt];
+      }
+    }
+  }
+  (void)len;
+}
+
+// ---- single pass: the row thread computes its own row of every incident element ---------------------
+// For the fast option set (momentum_fast_ok / advdiff_fast_ok) with a node-symmetric quadrature rule
+// the row of local node i costs ~120 FP64 operations in closed form (element_math.cuh
+// momentum_row0), so recomputing it per (row, element) pair is cheaper than staging 64 bytes per
+// pair through HBM: no staging buffer, one kernel, every output written once.
+template <int DIM, bool PERD, bool MLD>
+struct MomDirectSink {
+  static constexpr int LOC = DIM + 1;
+  static constexpr int NV = DIM + (MLD ? DIM : 1);
+  double* acc;  // this thread's column: acc[(b*maxlen + s)*kBR]
+  int maxlen;
+  unsigned slots;
+  int i;
+  double vec_[NV];
+  __device__ __forceinline__ void mat(int jj, int d, double v) {
+    int j = i + jj;
+    if (j >= LOC) j -= LOC;
+    acc[(d * maxlen + (int)((slots >> (8 * j)) & 0xffu)) * kBR] += v;
+  }
+  __device__ __forceinline__ void vec(int d, double v) { vec_[d] += v; }
+  __device__ __forceinline__ void ml(int d, double v) {
+    if (MLD || d == 0) vec_[DIM + (MLD ? d : 0)] += v;
+  }
+};
+
+template <int DIM>
+struct AdvDirectSink {
+  static constexpr int LOC = DIM + 1;
+  double* acc;
+  unsigned slots;
+  int i;
+  double rhs;
+  __device__ __forceinline__ void mat(int jj, double v) {
+    int j = i + jj;
+    if (j >= LOC) j -= LOC;
+    acc[(int)((slots >> (8 * j)) & 0xffu) * kBR] += v;
+  }
+  __device__ __forceinline__ void vec(double v) { rhs += v; }
+};
+
+__device__ __forceinline__ int rot_node(const int4& nd, int j) { return j == 0 ? nd.x : (j == 1 ? nd.y : (j == 2 ? nd.z : nd.w)); }
+
+template <int DIM, bool PERD, bool MLD>
+__global__ void __launch_bounds__(kBR)
+gather_momentum_direct_kernel(const MomentumArgs A, const int* __restrict__ rows, const long long* __restrict__ block_ptr,
+                              const uint2* __restrict__ pairs, const int* __restrict__ findrm, size_t nnz, int maxlen,
+                              double* __restrict__ big_m, double* __restrict__ rhs, double* __restrict__ masslump) {
+  constexpr int LOC = DIM + 1;
+  constexpr int NB = PERD ? DIM : 1;
+  extern __shared__ double acc[];
+  const int b = blockIdx.x, t = threadIdx.x;
+  const int r = rows[b * kBR + t];
+  const long long base = block_ptr[b];
+  const int deg = (int)((block_ptr[b + 1] - base) / kBR);
+  for (int q = 0; q < NB * maxlen; q++) acc[q * kBR + t] = 0.0;
+  MomDirectSink<DIM, PERD, MLD> sink;
+  sink.acc = acc + t;
+  sink.maxlen = maxlen;
+#pragma unroll
+  for (int c = 0; c < MomDirectSink<DIM, PERD, MLD>::NV; c++) sink.vec_[c] = 0.0;
+  const uint2* p = pairs + base + t;
+  for (int k = 0; k < deg; k++) {
+    const uint2 ent = __ldg(p + (long long)k * kBR);
+    if (ent.x == 0xFFFFFFFFu) continue;
+    const int4 nd = __ldg(A.ndglno + (ent.x >> 2));
+    const int i = (int)(ent.x & 3u);
+    int n[4];
+#pragma unroll
+    for (int jj = 0; jj < 4; jj++) {
+      int j = i + jj;
+      if (j >= LOC) j -= LOC;
+      n[jj] = rot_node(nd, jj < LOC ? j : 0);
+    }
+    sink.slots = ent.y;
+    sink.i = i;
+    momentum_row0<DIM, PERD>(A, n, sink);
+  }
+  if (r >= 0) {
+#pragma unroll
+    for (int d = 0; d < DIM; d++) rhs[(size_t)DIM * r + d] = sink.vec_[d];
+    if (masslump) {
+#pragma unroll
+      for (int d = 0; d < DIM; d++) masslump[(size_t)DIM * r + d] = sink.vec_[DIM + (MLD ? d : 0)];
+    }
+  }
+  __syncthreads();
+  const int warp = t >> 5, lane = t & 31;
+  for (int rr = 0; rr < 32; rr++) {
+    const int tt = warp * 32 + rr;
+    const int row = rows[b * kBR + tt];
+    if (row < 0) continue;
+    const int s0 = findrm[row], n = findrm[row + 1] - s0;
+    for (int s = lane; s < n; s += 32) {
+#pragma unroll
+      for (int d = 0; d < DIM; d++) big_m[(size_t)d * nnz + s0 + s] = acc[((PERD ? d : 0) * maxlen + s) * kBR + tt];
+    }
+  }
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(kBR)
+gather_advdiff_direct_kernel(const AdvDiffArgs A, const int* __restrict__ rows, const long long* __restrict__ block_ptr,
+                             const uint2* __restrict__ pairs, const int* __restrict__ findrm, int maxlen,
+                             double* __restrict__ matrix, double* __restrict__ rhs) {
+  constexpr int LOC = DIM + 1;
+  extern __shared__ double acc[];
+  const int b = blockIdx.x, t = threadIdx.x;
+  const int r = rows[b * kBR + t];
+  const long long base = block_ptr[b];
+  const int deg = (int)((block_ptr[b + 1] - base) / kBR);
+  for (int q = 0; q < maxlen; q++) acc[q * kBR + t] = 0.0;
+  AdvDirectSink<DIM> sink;
+  sink.acc = acc + t;
+  sink.rhs = 0.0;
+  const uint2* p = pairs + base + t;
+  for (int k = 0; k < deg; k++) {
+    const uint2 ent = __ldg(p + (long long)k * kBR);
+    if (ent.x == 0xFFFFFFFFu) continue;
+    const int4 nd = __ldg(A.ndglno + (ent.x >> 2));
+    const int i = (int)(ent.x & 3u);
+    int n[4];
+#pragma unroll
+    for (int jj = 0; jj < 4; jj++) {
+      int j = i + jj;
+      if (j >= LOC) j -= LOC;
+      n[jj] = rot_node(nd, jj < LOC ? j : 0);
+    }
+    sink.slots = ent.y;
+    sink.i = i;
+    advdiff_row0<DIM>(A, n, sink);
+  }
+  if (r >= 0) rhs[r] = sink.rhs;
+  __syncthreads();
+  const int warp = t >> 5, lane = t & 31;
+  for (int rr = 0; rr < 32; rr++) {
+    const int tt = warp * 32 + rr;
+    const int row = rows[b * kBR + tt];
+    if (row < 0) continue;
+    const int s0 = findrm[row], n = findrm[row + 1] - s0;
+    for (int s = lane; s < n; s += 32) matrix[(size_t)s0 + s] = acc[s * kBR + tt];
+  }
+}
+
+template <class K>
+static int set_dyn_smem(K kernel, size_t bytes) {
+  if (bytes > 48 * 1024) CG_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return CGASM_OK;
+}
+
+template <int DIM, int NB, int NV, int KIND>
+static int launch_rows(Handle* h, double* out0, double* out1, double* out2) {
+  GatherPlan* P = h->gather;
+  const size_t smem = sizeof(double) * (size_t)NB * P->maxlen * kBR;
+  if (smem > 200 * 1024) CG_FAIL(CGASM_EUNSUPPORTED, "gather scatter: CSR rows too long for the shared-memory accumulator");
+  int st = set_dyn_smem(gather_rows_kernel<DIM, NB, NV, KIND>, smem);
+  if (st) return st;
+  gather_rows_kernel<DIM, NB, NV, KIND><<<P->nblocks, kBR, smem, h->stream>>>(
+      P->d_rows, P->d_block_ptr, P->d_pairs, P->d_stage, h->d_findrm, (size_t)h->nnz, P->maxlen, out0, out1, out2);
+  h->launches++;
+  CG_CUDA(cudaGetLastError());
+  return CGASM_OK;
+}
+
+template <int DIM>
+static int gather_momentum_dim(Handle* h, const MomentumArgs& A, bool want_ml, bool want_ct) {
+  constexpr int LOC = DIM + 1;
+  GatherPlan* P = h->gather;
+  const int ne = h->n_elements, grid = (ne + 127) / 128;
+  const int abs_mode = !A.o.have_absorption ? 0 : (A.o.lump_absorption ? 1 : 2);
+  const bool mld = abs_mode == 1 && A.o.pressure_corrected_absorption;
+  const bool fast = abs_mode != 2 && momentum_fast_ok(A.o, A.gravity.stride, A.absorption.stride) &&
+                    !getenv("CGASM_GATHER_GENERIC");
+  double* ml = want_ml ? h->d_masslump : nullptr;
+  int st;
+  const bool direct = fast && A.tab.sym && !getenv("CGASM_GATHER_STAGED");
+#define STAGE_SIZE(NB_, NV_) ((size_t)ne * LOC * Rec<LOC, NB_, NV_>::RS)
+  if (direct) {
+    const int nb = abs_mode ? DIM : 1;
+    const size_t smem = sizeof(double) * (size_t)nb * P->maxlen * kBR;
+    if (smem > 200 * 1024) CG_FAIL(CGASM_EUNSUPPORTED, "gather scatter: CSR rows too long for the shared-memory accumulator");
+#define LAUNCH_DIRECT(PERD_, MLD_)                                                                             \
+  do {                                                                                                         \
+    if ((st = set_dyn_smem(gather_momentum_direct_kernel<DIM, PERD_, MLD_>, smem))) return st;                 \
+    gather_momentum_direct_kernel<DIM, PERD_, MLD_><<<P->nblocks, kBR, smem, h->stream>>>(                     \
+        A, P->d_rows, P->d_block_ptr, P->d_pairs, h->d_findrm, (size_t)h->nnz, P->maxlen, h->d_big_m,          \
+        h->d_mom_rhs, ml);                                                                                     \
+  } while (0)
+    if (abs_mode == 0) LAUNCH_DIRECT(false, false);
+    else if (!mld) LAUNCH_DIRECT(true, false);
+    else LAUNCH_DIRECT(true, true);
+#undef LAUNCH_DIRECT
+    h->launches++;
+  } else if (abs_mode == 0) {
+    if ((st = ensure_stage(P, STAGE_SIZE(1, DIM + 1)))) return st;
+    if (fast) gather_momentum_stage_fast_kernel<DIM, false, 1><<<grid, 128, 0, h->stream>>>(A, P->d_stage);
+    else gather_momentum_stage_kernel<DIM, false, 1, 1><<<grid, 128, 0, h->stream>>>(A, P->d_stage);
+    h->launches++;
+    if ((st = launch_rows<DIM, 1, DIM + 1, 0>(h, h->d_big_m, h->d_mom_rhs, ml))) return st;
+  } else if (!mld) {
+    if ((st = ensure_stage(P, STAGE_SIZE(DIM, DIM + 1)))) return st;
+    if (fast) gather_momentum_stage_fast_kernel<DIM, true, 1><<<grid, 128, 0, h->stream>>>(A, P->d_stage);
+    else if (abs_mode == 2) gather_momentum_stage_kernel<DIM, true, DIM, 1><<<grid, 128, 0, h->stream>>>(A, P->d_stage);
+    else gather_momentum_stage_kernel<DIM, false, DIM, 1><<<grid, 128, 0, h->stream>>>(A, P->d_stage);
+    h->launches++;
+    if ((st = launch_rows<DIM, DIM, DIM + 1, 0>(h, h->d_big_m, h->d_mom_rhs, ml))) return st;
+  } else {
+    if ((st = ensure_stage(P, STAGE_SIZE(DIM, 2 * DIM)))) return st;
+    if (fast) gather_momentum_stage_fast_kernel<DIM, true, DIM><<<grid, 128, 0, h->stream>>>(A, P->d_stage);
+    else gather_momentum_stage_kernel<DIM, false, DIM, DIM><<<grid, 128, 0, h->stream>>>(A, P->d_stage);
+    h->launches++;
+    if ((st = launch_rows<DIM, DIM, 2 * DIM, 0>(h, h->d_big_m, h->d_mom_rhs, ml))) return st;
+  }
+  if (want_ct) {
+    if ((st = ensure_stage(P, STAGE_SIZE(DIM, 0)))) return st;
+    gather_ct_stage_kernel<DIM><<<grid, 128, 0, h->stream>>>(A, P->d_stage);
+    h->launches++;
+    if ((st = launch_rows<DIM, DIM, 0, 2>(h, h->d_ct_m, nullptr, nullptr))) return st;
+  }
+#undef STAGE_SIZE
+  CG_CUDA(cudaGetLastError());
+  return CGASM_OK;
+}
+
+int gather_momentum(Handle* h, const MomentumArgs& A, bool want_ml, bool want_ct) {
+  if (!h->gather) CG_FAIL(CGASM_ESTATE, "gather plan missing");
+  return h->dim == 3 ? gather_momentum_dim<3>(h, A, want_ml, want_ct) : gather_momentum_dim<2>(h, A, want_ml, want_ct);
+}
+
+template <int DIM>
+static int gather_advdiff_dim(Handle* h, const AdvDiffArgs& A) {
+  constexpr int LOC = DIM + 1;
+  GatherPlan* P = h->gather;
+  const int ne = h->n_elements, grid = (ne + 127) / 128;
+  int st;
+  if (advdiff_fast_ok(A.o) && A.tab.sym && !getenv("CGASM_GATHER_GENERIC") && !getenv("CGASM_GATHER_STAGED")) {
+    const size_t smem = sizeof(double) * (size_t)P->maxlen * kBR;
+    if (smem > 200 * 1024) CG_FAIL(CGASM_EUNSUPPORTED, "gather scatter: CSR rows too long for the shared-memory accumulator");
+    if ((st = set_dyn_smem(gather_advdiff_direct_kernel<DIM>, smem))) return st;
+    gather_advdiff_direct_kernel<DIM><<<P->nblocks, kBR, smem, h->stream>>>(
+        A, P->d_rows, P->d_block_ptr, P->d_pairs, h->d_findrm, P->maxlen, h->d_adv_matrix, h->d_adv_rhs);
+    h->launches++;
+    CG_CUDA(cudaGetLastError());
+    return CGASM_OK;
+  }
+  if ((st = ensure_stage(P, (size_t)ne * LOC * Rec<LOC, 1, 1>::RS))) return st;
+  if (advdiff_fast_ok(A.o) && !getenv("CGASM_GATHER_GENERIC"))
+    gather_advdiff_stage_fast_kernel<DIM><<<grid, 128, 0, h->stream>>>(A, P->d_stage);
+  else
+    gather_advdiff_stage_kernel<DIM><<<grid, 128, 0, h->stream>>>(A, P->d_stage);
+  h->launches++;
+  return launch_rows<DIM, 1, 1, 1>(h, h->d_adv_matrix, h->d_adv_rhs, nullptr);
+}
+
+int gather_advdiff(Handle* h, const AdvDiffArgs& A) {
+  if (!h->gather) CG_FAIL(CGASM_ESTATE, "gather plan missing");
+  return h->dim == 3 ? gather_advdiff_dim<3>(h, A) : gather_advdiff_dim<2>(h, A);
+}
+
+}  // namespace cgasm

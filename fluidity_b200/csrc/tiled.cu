@@ -74,82 +74,6 @@ void tiles_free(Handle* h) {
   h->tiles = nullptr;
 }
 
-// ---- Morton order ----------------------------------------------------------------------------
-static inline uint64_t spread3(uint64_t x) {  // 21 bits -> every third bit
-  x &= 0x1fffff;
-  x = (x | x << 32) & 0x1f00000000ffffULL;
-  x = (x | x << 16) & 0x1f0000ff0000ffULL;
-  x = (x | x << 8) & 0x100f00f00f00f00fULL;
-  x = (x | x << 4) & 0x10c30c30c30c30c3ULL;
-  x = (x | x << 2) & 0x1249249249249249ULL;
-  return x;
-}
-static inline uint64_t spread2(uint64_t x) {  // 32 bits -> every second bit
-  x &= 0xffffffffULL;
-  x = (x | x << 16) & 0x0000ffff0000ffffULL;
-  x = (x | x << 8) & 0x00ff00ff00ff00ffULL;
-  x = (x | x << 4) & 0x0f0f0f0f0f0f0f0fULL;
-  x = (x | x << 2) & 0x3333333333333333ULL;
-  x = (x | x << 1) & 0x5555555555555555ULL;
-  return x;
-}
-
-struct MortonFrame {
-  double lo[3] = {0, 0, 0}, scale[3] = {0, 0, 0};
-  int dim = 3;
-  // cell of a point on the mesh-spacing lattice (nearest lattice point for nodes)
-  inline uint64_t key_round(const double* x) const {
-    uint64_t q[3] = {0, 0, 0};
-    for (int a = 0; a < dim; a++) q[a] = (uint64_t)std::llround((x[a] - lo[a]) * scale[a]);
-    return dim == 3 ? (spread3(q[0]) | spread3(q[1]) << 1 | spread3(q[2]) << 2) : (spread2(q[0]) | spread2(q[1]) << 1);
-  }
-  // containing cell (floor): element centroids of one lattice cell share a key
-  inline uint64_t key_floor(const double* x) const {
-    uint64_t q[3] = {0, 0, 0};
-    for (int a = 0; a < dim; a++) q[a] = (uint64_t)std::max(0.0, std::floor((x[a] - lo[a]) * scale[a]));
-    return dim == 3 ? (spread3(q[0]) | spread3(q[1]) << 1 | spread3(q[2]) << 2) : (spread2(q[0]) | spread2(q[1]) << 1);
-  }
-};
-
-static void morton_order(const Handle* h, std::vector<int>& order, MortonFrame& F) {
-  const int n = h->n_nodes, dim = h->dim;
-  double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
-  for (int i = 0; i < n; i++)
-    for (int a = 0; a < dim; a++) {
-      const double v = h->h_X[(size_t)dim * i + a];
-      lo[a] = std::min(lo[a], v);
-      hi[a] = std::max(hi[a], v);
-    }
-  // Quantise to a lattice about as fine as the mesh itself: h = (bounding volume / n)^(1/dim),
-  // cells_a = round(ext_a / h) - 1 (exact for an (m+1)^dim point lattice). Jittered lattice
-  // nodes then snap to their own lattice point, so fixed-count cuts of the Morton sequence are
-  // aligned bricks (measured redundancy 1.31 at 1024 rows vs 1.51 with a fine quantisation).
-  double vol = 1.0;
-  int live = 0;
-  for (int a = 0; a < dim; a++)
-    if (hi[a] > lo[a]) {
-      vol *= hi[a] - lo[a];
-      live++;
-    }
-  const double hcell = live ? std::pow(vol / (double)n, 1.0 / live) : 1.0;
-  const double maxcells = dim == 3 ? 2097151.0 : 4294967295.0;
-  F.dim = dim;
-  for (int a = 0; a < dim; a++) {
-    F.lo[a] = lo[a];
-    F.scale[a] = 0.0;
-    if (hi[a] > lo[a]) {
-      const double cells = std::min(maxcells, std::max(1.0, std::round((hi[a] - lo[a]) / hcell) - 1.0));
-      F.scale[a] = cells / (hi[a] - lo[a]);
-    }
-  }
-  std::vector<uint64_t> key((size_t)n);
-#pragma omp parallel for schedule(static)
-  for (int i = 0; i < n; i++) key[i] = F.key_round(&h->h_X[(size_t)dim * i]);
-  order.resize((size_t)n);
-  std::iota(order.begin(), order.end(), 0);
-  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return key[a] < key[b]; });
-}
-
 template <class T>
 static int upload(T** d, const std::vector<T>& v) {
   CG_CUDA(cudaMalloc(d, sizeof(T) * std::max<size_t>(v.size(), 1)));
@@ -696,6 +620,7 @@ struct MomTileSink {
   __device__ __forceinline__ void ml(int, int d, double v) {
     if (MLD || d == 0) vec_[r * NVEC + DIM + (MLD ? d : 0)] += v;
   }
+  __device__ __forceinline__ void row_end(int) {}
 };
 
 template <int DIM, bool PERD, bool MLD>
@@ -770,6 +695,7 @@ struct AdvTileSink {
   }
   __device__ __forceinline__ void mat(int i, int j, double v) { mat_[base + (int)slot_of(sl, i, j)] += v; }
   __device__ __forceinline__ void vec(int, double v) { vec_[r] += v; }
+  __device__ __forceinline__ void row_end(int) {}
 };
 
 template <int DIM>
@@ -817,6 +743,169 @@ tiled_advdiff_fast_kernel(const AdvDiffArgs A, const TileArgs T, int max_entries
   }
 }
 
+// ---- quad kernels: one lane = one local row of one element (element_math.cuh momentum_row0) ----
+__device__ __forceinline__ int sel4(const int4& v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w)); }
+__device__ __forceinline__ unsigned sel4u(const uint4& v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w)); }
+
+template <int DIM, bool PERD, bool MLD>
+struct MomQuadSink {
+  static constexpr int LOC = DIM + 1;
+  static constexpr int MLC = MLD ? DIM : 1;
+  static constexpr int NVEC = DIM + MLC;
+  double* mat_;   // accumulator of block 0 at this row's base
+  double* vec_;   // this row's vector accumulators
+  int max_entries;
+  unsigned slots;  // 4 x 8 bit slot of column j inside this row
+  int i;
+  __device__ __forceinline__ void mat(int jj, int d, double v) {
+    int j = i + jj;
+    if (j >= LOC) j -= LOC;
+    mat_[(size_t)d * max_entries + ((slots >> (8 * j)) & 0xffu)] += v;
+  }
+  __device__ __forceinline__ void vec(int d, double v) { vec_[d] += v; }
+  __device__ __forceinline__ void ml(int d, double v) {
+    if (MLD || d == 0) vec_[DIM + (MLD ? d : 0)] += v;
+  }
+};
+
+template <int DIM, bool PERD, bool MLD>
+__global__ void __launch_bounds__(768, 1)
+tiled_momentum_quad_kernel(const MomentumArgs A, const TileArgs T, int max_entries, int max_rows,
+                           double* __restrict__ big_m, double* __restrict__ rhs, double* __restrict__ masslump) {
+  constexpr int LOC = DIM + 1;
+  constexpr int NB = PERD ? DIM : 1;
+  constexpr int MLC = MLD ? DIM : 1;
+  constexpr int NVEC = DIM + MLC;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  TileSmem<NB, NVEC> S(smem_raw, max_entries, max_rows);
+  const int t = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
+  const int r0 = T.tile_row_ptr[t], nrows = T.tile_row_ptr[t + 1] - r0;
+  const int entries = T.tile_entries[t];
+  for (int k = tid; k < NB * max_entries; k += nthr) S.mat[k] = 0.0;
+  for (int k = tid; k < NVEC * nrows; k += nthr) S.vec[k] = 0.0;
+  for (int k = tid; k < nrows; k += nthr) S.off[k] = T.rowoff[r0 + k];
+  if (tid == 0) S.off[nrows] = entries;
+  __syncthreads();
+  const int p0 = T.tile_phase_off[t], nphase = T.tile_phase_off[t + 1] - p0 - 1;
+  for (int ph = 0; ph < nphase; ph++) {
+    const int cb = T.phase_ptr[p0 + ph], nwork = (T.phase_ptr[p0 + ph + 1] - cb) * 4;
+    for (int w = tid; w < nwork; w += nthr) {
+      const int k = cb + (w >> 2), i = w & 3;
+      if (DIM == 2 && i == 3) continue;
+      const uint2 lr = __ldg(T.el_rows + k);
+      const unsigned r = ((i < 2 ? lr.x : lr.y) >> (16 * (i & 1))) & 0xffffu;
+      if (r == 0xffffu) continue;  // row of a node another tile owns
+      const int4 nd = __ldg(T.el_nodes + k);
+      const uint4 sl = __ldg(T.el_slots + k);
+      int n[4];
+#pragma unroll
+      for (int jj = 0; jj < 4; jj++) {
+        int j = i + jj;
+        if (j >= LOC) j -= LOC;
+        n[jj] = sel4(nd, jj < LOC ? j : 0);
+      }
+      MomQuadSink<DIM, PERD, MLD> sink;
+      sink.mat_ = S.mat + S.off[r];
+      sink.vec_ = S.vec + r * NVEC;
+      sink.max_entries = max_entries;
+      sink.slots = sel4u(sl, i);
+      sink.i = i;
+      momentum_row0<DIM, PERD>(A, n, sink);
+    }
+    __syncthreads();
+  }
+  const int warp = tid >> 5, lane = tid & 31, nwarps = nthr >> 5;
+  for (int ru = T.tile_run_ptr[t] + warp; ru < T.tile_run_ptr[t + 1]; ru += nwarps) {
+    const int2 run = T.runs[ru];
+    const int g0 = T.rows[r0 + run.x];
+    const int src = S.off[run.x];
+    const int n = S.off[run.x + run.y] - src;
+    const size_t dst = (size_t)T.findrm[g0];
+#pragma unroll
+    for (int d = 0; d < DIM; d++) {
+      const double* s = S.mat + (size_t)(PERD ? d : 0) * max_entries + src;
+      double* o = big_m + (size_t)d * T.nnz + dst;
+      for (int k = lane; k < n; k += 32) o[k] = s[k];
+    }
+    for (int k = lane; k < run.y * DIM; k += 32) {
+      const int rr = k / DIM, d = k - rr * DIM;
+      rhs[(size_t)DIM * g0 + k] = S.vec[(run.x + rr) * NVEC + d];
+      if (masslump) masslump[(size_t)DIM * g0 + k] = S.vec[(run.x + rr) * NVEC + DIM + (MLD ? d : 0)];
+    }
+  }
+}
+
+template <int DIM>
+struct AdvQuadSink {
+  static constexpr int LOC = DIM + 1;
+  double* mat_;
+  double* vec_;
+  unsigned slots;
+  int i;
+  __device__ __forceinline__ void mat(int jj, double v) {
+    int j = i + jj;
+    if (j >= LOC) j -= LOC;
+    mat_[(slots >> (8 * j)) & 0xffu] += v;
+  }
+  __device__ __forceinline__ void vec(double v) { *vec_ += v; }
+};
+
+template <int DIM>
+__global__ void __launch_bounds__(768, 1)
+tiled_advdiff_quad_kernel(const AdvDiffArgs A, const TileArgs T, int max_entries, int max_rows,
+                          double* __restrict__ matrix, double* __restrict__ rhs) {
+  constexpr int LOC = DIM + 1;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  TileSmem<1, 1> S(smem_raw, max_entries, max_rows);
+  const int t = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
+  const int r0 = T.tile_row_ptr[t], nrows = T.tile_row_ptr[t + 1] - r0;
+  const int entries = T.tile_entries[t];
+  for (int k = tid; k < max_entries; k += nthr) S.mat[k] = 0.0;
+  for (int k = tid; k < nrows; k += nthr) {
+    S.vec[k] = 0.0;
+    S.off[k] = T.rowoff[r0 + k];
+  }
+  if (tid == 0) S.off[nrows] = entries;
+  __syncthreads();
+  const int p0 = T.tile_phase_off[t], nphase = T.tile_phase_off[t + 1] - p0 - 1;
+  for (int ph = 0; ph < nphase; ph++) {
+    const int cb = T.phase_ptr[p0 + ph], nwork = (T.phase_ptr[p0 + ph + 1] - cb) * 4;
+    for (int w = tid; w < nwork; w += nthr) {
+      const int k = cb + (w >> 2), i = w & 3;
+      if (DIM == 2 && i == 3) continue;
+      const uint2 lr = __ldg(T.el_rows + k);
+      const unsigned r = ((i < 2 ? lr.x : lr.y) >> (16 * (i & 1))) & 0xffffu;
+      if (r == 0xffffu) continue;
+      const int4 nd = __ldg(T.el_nodes + k);
+      const uint4 sl = __ldg(T.el_slots + k);
+      int n[4];
+#pragma unroll
+      for (int jj = 0; jj < 4; jj++) {
+        int j = i + jj;
+        if (j >= LOC) j -= LOC;
+        n[jj] = sel4(nd, jj < LOC ? j : 0);
+      }
+      AdvQuadSink<DIM> sink;
+      sink.mat_ = S.mat + S.off[r];
+      sink.vec_ = S.vec + r;
+      sink.slots = sel4u(sl, i);
+      sink.i = i;
+      advdiff_row0<DIM>(A, n, sink);
+    }
+    __syncthreads();
+  }
+  const int warp = tid >> 5, lane = tid & 31, nwarps = nthr >> 5;
+  for (int ru = T.tile_run_ptr[t] + warp; ru < T.tile_run_ptr[t + 1]; ru += nwarps) {
+    const int2 run = T.runs[ru];
+    const int g0 = T.rows[r0 + run.x];
+    const int src = S.off[run.x];
+    const int n = S.off[run.x + run.y] - src;
+    const size_t dst = (size_t)T.findrm[g0];
+    for (int k = lane; k < n; k += 32) matrix[dst + k] = S.mat[src + k];
+    for (int k = lane; k < run.y; k += 32) rhs[g0 + k] = S.vec[run.x + k];
+  }
+}
+
 static TileArgs tile_args(const Handle* h, const TileClassPlan& P) {
   TileArgs T;
   T.tile_row_ptr = P.d_tile_row_ptr;
@@ -843,6 +932,16 @@ static int block_threads(const TileClassPlan& P, int cap) {
   return std::min(cap, std::max(32, (thr / 32) * 32));
 }
 
+// quad kernels: 4 work items per element; pick the thread count that splits the largest phase into
+// equal rounds
+static int quad_threads(const TileClassPlan& P, int cap) {
+  if (const char* s = getenv("CGASM_TILE_THREADS")) return std::min(cap, std::max(32, (atoi(s) / 32) * 32));
+  const int work = std::max(1, P.max_phase * 4);
+  const int rounds = (work + cap - 1) / cap;
+  const int thr = (((work + rounds - 1) / rounds) + 31) / 32 * 32;
+  return std::min(cap, std::max(64, thr));
+}
+
 template <class K>
 static int set_smem(K kernel, size_t bytes) {
   CG_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
@@ -858,7 +957,22 @@ static int tiles_momentum_dim(Handle* h, const MomentumArgs& A, bool want_ml, bo
   const TileClassPlan& P = h->tiles->cls[abs_mode ? 1 : 0];
   const TileArgs T = tile_args(h, P);
   double* ml = want_ml ? h->d_masslump : nullptr;
-  if (abs_mode != 2 && momentum_fast_ok(A.o, A.gravity.stride, A.absorption.stride) && !getenv("CGASM_TILE_GENERIC")) {
+  const bool fast_ok = abs_mode != 2 && momentum_fast_ok(A.o, A.gravity.stride, A.absorption.stride) &&
+                       !getenv("CGASM_TILE_GENERIC");
+  if (fast_ok && A.tab.sym && P.cluster == 1 && !getenv("CGASM_TILE_NOQUAD")) {
+    const int thr = quad_threads(P, 768);
+#define LAUNCH_QUAD(PERD_, MLD_)                                                                        \
+  do {                                                                                                  \
+    if ((st = set_smem(tiled_momentum_quad_kernel<DIM, PERD_, MLD_>, P.smem_bytes))) return st;         \
+    tiled_momentum_quad_kernel<DIM, PERD_, MLD_><<<P.ntiles, thr, P.smem_bytes, h->stream>>>(           \
+        A, T, P.max_tile_entries, P.max_tile_rows, h->d_big_m, h->d_mom_rhs, ml);                       \
+  } while (0)
+    if (abs_mode == 1 && mld) LAUNCH_QUAD(true, true);
+    else if (abs_mode == 1) LAUNCH_QUAD(true, false);
+    else LAUNCH_QUAD(false, false);
+#undef LAUNCH_QUAD
+    h->launches++;
+  } else if (fast_ok) {
     const int thr = block_threads(P, 384);
 #define LAUNCH_FAST(PERD_, MLD_)                                                                        \
   do {                                                                                                  \
@@ -911,7 +1025,8 @@ int tiles_advdiff(Handle* h, const AdvDiffArgs& A) {
   const TileClassPlan& P = h->tiles->cls[0];
   const TileArgs T = tile_args(h, P);
   const bool fast = advdiff_fast_ok(A.o) && !getenv("CGASM_TILE_GENERIC");
-  const int thr = block_threads(P, fast ? 384 : 256);
+  const bool quad = fast && A.tab.sym && P.cluster == 1 && !getenv("CGASM_TILE_NOQUAD");
+  const int thr = quad ? quad_threads(P, 768) : block_threads(P, fast ? 384 : 256);
 #define LAUNCH_ADV(KERNEL)                                                                            \
   do {                                                                                                \
     if ((st = set_smem(KERNEL, P.smem_bytes))) return st;                                             \
@@ -919,10 +1034,12 @@ int tiles_advdiff(Handle* h, const AdvDiffArgs& A) {
                                                        h->d_adv_matrix, h->d_adv_rhs);                \
   } while (0)
   if (h->dim == 3) {
-    if (fast) LAUNCH_ADV(tiled_advdiff_fast_kernel<3>);
+    if (quad) LAUNCH_ADV(tiled_advdiff_quad_kernel<3>);
+    else if (fast) LAUNCH_ADV(tiled_advdiff_fast_kernel<3>);
     else LAUNCH_ADV(tiled_advdiff_kernel<3>);
   } else {
-    if (fast) LAUNCH_ADV(tiled_advdiff_fast_kernel<2>);
+    if (quad) LAUNCH_ADV(tiled_advdiff_quad_kernel<2>);
+    else if (fast) LAUNCH_ADV(tiled_advdiff_fast_kernel<2>);
     else LAUNCH_ADV(tiled_advdiff_kernel<2>);
   }
 #undef LAUNCH_ADV

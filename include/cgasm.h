@@ -82,8 +82,11 @@ enum {
   CGASM_SCATTER_ATOMIC = 0,   /* one thread per element, red.global.add.f64             */
   CGASM_SCATTER_COLOURED = 1, /* femtools/Colouring.F90 colours, plain stores           */
   CGASM_SCATTER_WARPAGG = 2,  /* warp-aggregated atomics (match.any on the slot)        */
-  CGASM_SCATTER_TILED = 3     /* node-tile owner-computes, shared-memory accumulate,    */
-                              /* every CSR value written exactly once (default)         */
+  CGASM_SCATTER_TILED = 3,    /* node-tile owner-computes, shared-memory accumulate,    */
+                              /* every CSR value written exactly once                   */
+  CGASM_SCATTER_GATHER = 4    /* two passes: element kernel streams local rows to a     */
+                              /* staging buffer, row kernel gathers them (no atomics,   */
+                              /* no colouring, no redundant element math)               */
 };
 
 /* ---- option structs: the module-level switches read once per assembly ----------

@@ -3,7 +3,7 @@ mkdir -p gpurun_out
 timeout 1200 python -m pytest tests -m gpu -x -q -k "tiled or sparsity or element" > gpurun_out/pytest_gpu.log 2>&1
 echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
 tail -6 gpurun_out/pytest_gpu.log
-for cfg in "1024 1 0" "1024 1 256" "512 1 0" "1024 2 0" "768 1 0"; do
+for cfg in "1024 1 0" "1024 1 768" "1024 1 512" "512 1 0"; do
   set -- $cfg
   export CGASM_TILE_ROWS=$1 CGASM_TILE_CLUSTER=$2
   if [ "$3" != "0" ]; then export CGASM_TILE_THREADS=$3; else unset CGASM_TILE_THREADS; fi
@@ -13,7 +13,7 @@ done
 unset CGASM_TILE_ROWS CGASM_TILE_CLUSTER CGASM_TILE_THREADS
 timeout 900 python bench.py --cells 256 --scatter tiled --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench256_tiled.json 2> gpurun_out/bench256_tiled.err
 tail -3 gpurun_out/bench256_tiled.err
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:tiled_momentum -s 2 -c 1 -o gpurun_out/prof_tiled_mom3 -f \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:tiled_momentum -s 2 -c 1 -o gpurun_out/prof_tiled_mom4 -f \
   python bench.py --cells 96 --scatter tiled --steps 2 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/ncu_tiled.log 2>&1
 python - <<'PY'
 import json,glob

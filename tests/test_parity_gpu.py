@@ -14,7 +14,8 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-12
 
 ALL_SCATTERS = [pytest.param(abi.SCATTER_ATOMIC, id="atomic"), pytest.param(abi.SCATTER_COLOURED, id="coloured"),
-                pytest.param(abi.SCATTER_WARPAGG, id="warpagg"), pytest.param(abi.SCATTER_TILED, id="tiled")]
+                pytest.param(abi.SCATTER_WARPAGG, id="warpagg"), pytest.param(abi.SCATTER_TILED, id="tiled"),
+                pytest.param(abi.SCATTER_GATHER, id="gather")]
 
 
 def make_asm(mesh, fields=None, scatter=None):
@@ -231,7 +232,8 @@ def test_shuffled_numbering_s3_small(orc, scatter):
 
 
 # ---- size-independent properties at a size the oracle would not finish quickly ---------------
-@pytest.mark.parametrize("scatter", [pytest.param(abi.SCATTER_ATOMIC, id="atomic"), pytest.param(abi.SCATTER_TILED, id="tiled")])
+@pytest.mark.parametrize("scatter", [pytest.param(abi.SCATTER_ATOMIC, id="atomic"), pytest.param(abi.SCATTER_TILED, id="tiled"),
+                                     pytest.param(abi.SCATTER_GATHER, id="gather")])
 def test_large_mesh_properties(scatter):
     mesh = syn.box_mesh((96, 96, 96), jitter=0.1)
     fs = syn.standard_fields(mesh)
@@ -263,7 +265,7 @@ def test_large_mesh_properties(scatter):
     # (5) idempotence: same call twice gives identical sums for the deterministic variant
     a = asm.momentum(o)["big_m"].copy()
     b = asm.momentum(o)["big_m"]
-    if scatter == abi.SCATTER_TILED:
+    if scatter in (abi.SCATTER_TILED, abi.SCATTER_GATHER):
         assert (a == b).all()
     else:
         assert rel_err(a, b) < TOL
