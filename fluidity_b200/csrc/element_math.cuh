@@ -1133,8 +1133,42 @@ __device__ __forceinline__ void load_rot(const double4* __restrict__ rec, const 
   for (int k = 0; k < DIM + 1; k++) unpack<DIM>(ld256(rec + n[k]), v[k], s[k]);
 }
 
-template <int DIM, bool PERD, class Sink>
-__device__ __forceinline__ void momentum_row0(const MomentumArgs& A, const int (&n)[4], Sink& sink) {
+// Option views: the runtime one reads the option struct (uniform branches), the "common" ones
+// are compile-time constants for the option set shared by the example configs, so the hot
+// instantiation carries no option branches at all.
+struct MomRuntimeFlags {
+  const cgasm_momentum_opts& o;
+  int visc_stride;
+  __device__ __forceinline__ bool adv() const { return !o.exclude_advection; }
+  __device__ __forceinline__ bool visc() const { return o.have_viscosity != 0; }
+  __device__ __forceinline__ bool visc_const() const { return visc_stride == 0; }
+  __device__ __forceinline__ int visc_shape() const { return o.viscosity_shape; }
+  __device__ __forceinline__ bool grav() const { return o.have_gravity != 0; }
+  __device__ __forceinline__ bool hb() const { return o.subtract_out_reference_profile != 0; }
+  __device__ __forceinline__ bool mass() const { return !o.exclude_mass; }
+  __device__ __forceinline__ bool mlump() const { return o.assemble_inverse_masslump != 0; }
+};
+// lumped mass, advection, CONSTANT isotropic viscosity, buoyancy (no reference profile), inverse
+// lumped mass: driven_cavity / lock_exchange / flow_past_sphere(isotropic part) / S3
+struct MomCommonFlags {
+  __device__ __forceinline__ MomCommonFlags() {}
+  __device__ __forceinline__ constexpr bool adv() const { return true; }
+  __device__ __forceinline__ constexpr bool visc() const { return true; }
+  __device__ __forceinline__ constexpr bool visc_const() const { return true; }
+  __device__ __forceinline__ constexpr int visc_shape() const { return CGASM_TENSOR_ISOTROPIC; }
+  __device__ __forceinline__ constexpr bool grav() const { return true; }
+  __device__ __forceinline__ constexpr bool hb() const { return false; }
+  __device__ __forceinline__ constexpr bool mass() const { return true; }
+  __device__ __forceinline__ constexpr bool mlump() const { return true; }
+};
+__host__ __device__ inline bool momentum_common_ok(const cgasm_momentum_opts& o, int visc_stride) {
+  return !o.exclude_advection && o.have_viscosity && visc_stride == 0 &&
+         o.viscosity_shape == CGASM_TENSOR_ISOTROPIC && o.have_gravity && !o.subtract_out_reference_profile &&
+         !o.exclude_mass && o.assemble_inverse_masslump && !o.have_absorption;
+}
+
+template <int DIM, bool PERD, class Sink, class F>
+__device__ __forceinline__ void momentum_row0(const MomentumArgs& A, const int (&n)[4], Sink& sink, const F f) {
   constexpr int LOC = DIM + 1;
   const cgasm_momentum_opts& o = A.o;
   const Tables& t = A.tab;
@@ -1160,16 +1194,16 @@ __device__ __forceinline__ void momentum_row0(const MomentumArgs& A, const int (
     m0 = G.absdet * ((t.Pd - t.Po) * rho[0] + t.Po * S);
 #pragma unroll
     for (int a = 0; a < DIM; a++) v[a] = 0.0;
-    if (!o.exclude_advection) {
+    if (f.adv()) {
 #pragma unroll
       for (int k = 0; k < LOC; k++)
 #pragma unroll
         for (int a = 0; a < DIM; a++) v[a] += M[k] * nu[k][a];
     }
   }
-  if (o.have_viscosity) {
+  if (f.visc()) {
     double Vbar[DIM * DIM];
-    if (A.viscosity.stride == 0) {
+    if (f.visc_const()) {
       gather<DIM * DIM>(A.viscosity, 0, Vbar);
 #pragma unroll
       for (int ab = 0; ab < DIM * DIM; ab++) Vbar[ab] *= G.absdet * t.Wsum;
@@ -1186,10 +1220,10 @@ __device__ __forceinline__ void momentum_row0(const MomentumArgs& A, const int (
 #pragma unroll
       for (int ab = 0; ab < DIM * DIM; ab++) Vbar[ab] *= G.absdet * t.W1;
     }
-    if (o.viscosity_shape == CGASM_TENSOR_ISOTROPIC) {
+    if (f.visc_shape() == CGASM_TENSOR_ISOTROPIC) {
 #pragma unroll
       for (int a = 0; a < DIM; a++) v[a] += Vbar[0] * G.grad[0][a];
-    } else if (o.viscosity_shape == CGASM_TENSOR_DIAGONAL) {
+    } else if (f.visc_shape() == CGASM_TENSOR_DIAGONAL) {
 #pragma unroll
       for (int a = 0; a < DIM; a++) v[a] += Vbar[a + DIM * a] * G.grad[0][a];
     } else {
@@ -1207,8 +1241,8 @@ __device__ __forceinline__ void momentum_row0(const MomentumArgs& A, const int (
   double rhs[DIM];
 #pragma unroll
   for (int d = 0; d < DIM; d++) rhs[d] = 0.0;
-  if (o.have_gravity) {
-    if (o.subtract_out_reference_profile) {
+  if (f.grav()) {
+    if (f.hb()) {
 #pragma unroll
       for (int k = 0; k < LOC; k++) {
         double r1[1];
@@ -1228,8 +1262,8 @@ __device__ __forceinline__ void momentum_row0(const MomentumArgs& A, const int (
   double diag[PERD ? DIM : 1], mlv[PERD ? DIM : 1];
 #pragma unroll
   for (int d = 0; d < (PERD ? DIM : 1); d++) {
-    diag[d] = o.exclude_mass ? 0.0 : m0;
-    mlv[d] = o.assemble_inverse_masslump ? m0 : 0.0;
+    diag[d] = f.mass() ? m0 : 0.0;
+    mlv[d] = f.mlump() ? m0 : 0.0;
   }
   if constexpr (PERD) {
     if (o.have_absorption) {  // lumped: sum_j Ab_0j(d) = sum_k M_0k sigma_k(d)
@@ -1268,8 +1302,35 @@ __device__ __forceinline__ void momentum_row0(const MomentumArgs& A, const int (
 }
 
 // Sink: mat(jj, v), vec(v)
-template <int DIM, class Sink>
-__device__ __forceinline__ void advdiff_row0(const AdvDiffArgs& P, const int (&n)[4], Sink& sink) {
+struct AdvRuntimeFlags {
+  const cgasm_advdiff_opts& o;
+  int diff_stride;
+  __device__ __forceinline__ bool adv() const { return o.have_advection != 0; }
+  __device__ __forceinline__ bool diff() const { return o.have_diffusivity != 0; }
+  __device__ __forceinline__ bool diff_const() const { return diff_stride == 0; }
+  __device__ __forceinline__ int diff_shape() const { return o.diffusivity_shape; }
+  __device__ __forceinline__ bool source() const { return o.have_source != 0; }
+  __device__ __forceinline__ bool mass() const { return o.have_mass != 0; }
+  __device__ __forceinline__ bool lump() const { return o.lump_mass != 0; }
+};
+// consistent mass, advection, CONSTANT isotropic diffusivity, no source: the default CG tracer
+struct AdvCommonFlags {
+  __device__ __forceinline__ AdvCommonFlags() {}
+  __device__ __forceinline__ constexpr bool adv() const { return true; }
+  __device__ __forceinline__ constexpr bool diff() const { return true; }
+  __device__ __forceinline__ constexpr bool diff_const() const { return true; }
+  __device__ __forceinline__ constexpr int diff_shape() const { return CGASM_TENSOR_ISOTROPIC; }
+  __device__ __forceinline__ constexpr bool source() const { return false; }
+  __device__ __forceinline__ constexpr bool mass() const { return true; }
+  __device__ __forceinline__ constexpr bool lump() const { return false; }
+};
+__host__ __device__ inline bool advdiff_common_ok(const cgasm_advdiff_opts& o, int diff_stride) {
+  return o.have_advection && o.have_diffusivity && diff_stride == 0 && o.diffusivity_shape == CGASM_TENSOR_ISOTROPIC &&
+         !o.have_source && o.have_mass && !o.lump_mass;
+}
+
+template <int DIM, class Sink, class F>
+__device__ __forceinline__ void advdiff_row0(const AdvDiffArgs& P, const int (&n)[4], Sink& sink, const F f) {
   constexpr int LOC = DIM + 1;
   const cgasm_advdiff_opts& o = P.o;
   const Tables& t = P.tab;
@@ -1284,7 +1345,7 @@ __device__ __forceinline__ void advdiff_row0(const AdvDiffArgs& P, const int (&n
   }
 #pragma unroll
   for (int a = 0; a < DIM; a++) v[a] = 0.0;
-  if (o.have_advection) {
+  if (f.adv()) {
     double u[LOC][DIM], unused[LOC];
     load_rot<DIM>(P.rec.r1, n, u, unused);
 #pragma unroll
@@ -1295,9 +1356,9 @@ __device__ __forceinline__ void advdiff_row0(const AdvDiffArgs& P, const int (&n
       v[a] = G.absdet * ((t.Pd - t.Po) * u[0][a] + t.Po * S);
     }
   }
-  if (o.have_diffusivity) {
+  if (f.diff()) {
     double Kbar[DIM * DIM];
-    if (P.diffusivity.stride == 0) {
+    if (f.diff_const()) {
       gather<DIM * DIM>(P.diffusivity, 0, Kbar);
 #pragma unroll
       for (int ab = 0; ab < DIM * DIM; ab++) Kbar[ab] *= G.absdet * t.Wsum;
@@ -1314,7 +1375,7 @@ __device__ __forceinline__ void advdiff_row0(const AdvDiffArgs& P, const int (&n
 #pragma unroll
       for (int ab = 0; ab < DIM * DIM; ab++) Kbar[ab] *= G.absdet * t.W1;
     }
-    if (o.diffusivity_shape == CGASM_TENSOR_ISOTROPIC) {
+    if (f.diff_shape() == CGASM_TENSOR_ISOTROPIC) {
 #pragma unroll
       for (int a = 0; a < DIM; a++) v[a] += Kbar[0] * G.grad[0][a];
     } else {
@@ -1328,7 +1389,7 @@ __device__ __forceinline__ void advdiff_row0(const AdvDiffArgs& P, const int (&n
     }
   }
   double rhs = 0.0;
-  if (o.have_source) {
+  if (f.source()) {
     double S = 0.0, s0 = 0.0;
 #pragma unroll
     for (int k = 0; k < LOC; k++) {
@@ -1346,8 +1407,8 @@ __device__ __forceinline__ void advdiff_row0(const AdvDiffArgs& P, const int (&n
     for (int a = 0; a < DIM; a++) s += v[a] * G.grad[j][a];
     rhs -= s * T[j];
     double a_0j = implicit ? dtt * s : 0.0;
-    if (o.have_mass) {
-      if (o.lump_mass) {
+    if (f.mass()) {
+      if (f.lump()) {
         if (j == 0) a_0j += G.absdet * t.W1;
       } else {
         a_0j += G.absdet * (j == 0 ? t.Pd : t.Po);

@@ -435,11 +435,62 @@ struct AdvDirectSink {
 
 __device__ __forceinline__ int rot_node(const int4& nd, int j) { return j == 0 ? nd.x : (j == 1 ? nd.y : (j == 2 ? nd.z : nd.w)); }
 
-template <int DIM, bool PERD, bool MLD>
-__global__ void __launch_bounds__(kBR)
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+// Pair stream of one row thread, software-pipelined: the plan entry two pairs ahead and the
+// element connectivity one pair ahead are in flight while the current pair is computed, and the
+// next pair's node records are pulled into L1 (prefetch needs no registers).
+struct PairStream {
+  const uint2* p;
+  const int4* ndglno;
+  int deg, k;
+  uint2 ent0, ent1, ent2;
+  int4 nd0, nd1;
+  __device__ __forceinline__ uint2 load_ent(int kk) const {
+    return kk < deg ? __ldg(p + (long long)kk * kBR) : make_uint2(0xFFFFFFFFu, 0u);
+  }
+  __device__ __forceinline__ int4 load_nd(const uint2& e) const {
+    return e.x != 0xFFFFFFFFu ? __ldg(ndglno + (e.x >> 2)) : make_int4(0, 0, 0, 0);
+  }
+  __device__ __forceinline__ void init(const uint2* p_, const int4* nd_, int deg_) {
+    p = p_;
+    ndglno = nd_;
+    deg = deg_;
+    k = 0;
+    ent0 = load_ent(0);
+    ent1 = load_ent(1);
+    ent2 = load_ent(2);
+    nd0 = load_nd(ent0);
+    nd1 = load_nd(ent1);
+  }
+  __device__ __forceinline__ void advance() {
+    ent0 = ent1;
+    nd0 = nd1;
+    ent1 = ent2;
+    nd1 = load_nd(ent1);
+    k++;
+    ent2 = load_ent(k + 2);
+  }
+};
+
+template <int NREC>
+__device__ __forceinline__ void prefetch_nodes(const NodeRecs& rec, const int4& nd, bool valid) {
+  if (!valid) return;
+  const int nn[4] = {nd.x, nd.y, nd.z, nd.w};
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    prefetch_l1(rec.r0 + nn[q]);
+    prefetch_l1(rec.r1 + nn[q]);
+    if (NREC > 2) prefetch_l1(rec.r2 + nn[q]);
+  }
+}
+
+template <int DIM, bool PERD, bool MLD, bool COMMON, int MINB>
+__global__ void __launch_bounds__(kBR, MINB)
 gather_momentum_direct_kernel(const MomentumArgs A, const int* __restrict__ rows, const long long* __restrict__ block_ptr,
                               const uint2* __restrict__ pairs, const int* __restrict__ findrm, size_t nnz, int maxlen,
-                              double* __restrict__ big_m, double* __restrict__ rhs, double* __restrict__ masslump) {
+                              int prefetch, double* __restrict__ big_m, double* __restrict__ rhs,
+                              double* __restrict__ masslump) {
   constexpr int LOC = DIM + 1;
   constexpr int NB = PERD ? DIM : 1;
   extern __shared__ double acc[];
@@ -447,28 +498,29 @@ gather_momentum_direct_kernel(const MomentumArgs A, const int* __restrict__ rows
   const int r = rows[b * kBR + t];
   const long long base = block_ptr[b];
   const int deg = (int)((block_ptr[b + 1] - base) / kBR);
+  PairStream ps;
+  ps.init(pairs + base + t, A.ndglno, deg);
   for (int q = 0; q < NB * maxlen; q++) acc[q * kBR + t] = 0.0;
   MomDirectSink<DIM, PERD, MLD> sink;
   sink.acc = acc + t;
   sink.maxlen = maxlen;
 #pragma unroll
   for (int c = 0; c < MomDirectSink<DIM, PERD, MLD>::NV; c++) sink.vec_[c] = 0.0;
-  const uint2* p = pairs + base + t;
-  for (int k = 0; k < deg; k++) {
-    const uint2 ent = __ldg(p + (long long)k * kBR);
-    if (ent.x == 0xFFFFFFFFu) continue;
-    const int4 nd = __ldg(A.ndglno + (ent.x >> 2));
-    const int i = (int)(ent.x & 3u);
+  for (; ps.k < deg; ps.advance()) {
+    if (prefetch) prefetch_nodes<3>(A.rec, ps.nd1, ps.ent1.x != 0xFFFFFFFFu);
+    if (ps.ent0.x == 0xFFFFFFFFu) continue;
+    const int i = (int)(ps.ent0.x & 3u);
     int n[4];
 #pragma unroll
     for (int jj = 0; jj < 4; jj++) {
       int j = i + jj;
       if (j >= LOC) j -= LOC;
-      n[jj] = rot_node(nd, jj < LOC ? j : 0);
+      n[jj] = rot_node(ps.nd0, jj < LOC ? j : 0);
     }
-    sink.slots = ent.y;
+    sink.slots = ps.ent0.y;
     sink.i = i;
-    momentum_row0<DIM, PERD>(A, n, sink);
+    if constexpr (COMMON) momentum_row0<DIM, PERD>(A, n, sink, MomCommonFlags());
+    else momentum_row0<DIM, PERD>(A, n, sink, MomRuntimeFlags{A.o, A.viscosity.stride});
   }
   if (r >= 0) {
 #pragma unroll
@@ -492,10 +544,10 @@ gather_momentum_direct_kernel(const MomentumArgs A, const int* __restrict__ rows
   }
 }
 
-template <int DIM>
-__global__ void __launch_bounds__(kBR)
+template <int DIM, bool COMMON, int MINB>
+__global__ void __launch_bounds__(kBR, MINB)
 gather_advdiff_direct_kernel(const AdvDiffArgs A, const int* __restrict__ rows, const long long* __restrict__ block_ptr,
-                             const uint2* __restrict__ pairs, const int* __restrict__ findrm, int maxlen,
+                             const uint2* __restrict__ pairs, const int* __restrict__ findrm, int maxlen, int prefetch,
                              double* __restrict__ matrix, double* __restrict__ rhs) {
   constexpr int LOC = DIM + 1;
   extern __shared__ double acc[];
@@ -503,26 +555,27 @@ gather_advdiff_direct_kernel(const AdvDiffArgs A, const int* __restrict__ rows, 
   const int r = rows[b * kBR + t];
   const long long base = block_ptr[b];
   const int deg = (int)((block_ptr[b + 1] - base) / kBR);
+  PairStream ps;
+  ps.init(pairs + base + t, A.ndglno, deg);
   for (int q = 0; q < maxlen; q++) acc[q * kBR + t] = 0.0;
   AdvDirectSink<DIM> sink;
   sink.acc = acc + t;
   sink.rhs = 0.0;
-  const uint2* p = pairs + base + t;
-  for (int k = 0; k < deg; k++) {
-    const uint2 ent = __ldg(p + (long long)k * kBR);
-    if (ent.x == 0xFFFFFFFFu) continue;
-    const int4 nd = __ldg(A.ndglno + (ent.x >> 2));
-    const int i = (int)(ent.x & 3u);
+  for (; ps.k < deg; ps.advance()) {
+    if (prefetch) prefetch_nodes<2>(A.rec, ps.nd1, ps.ent1.x != 0xFFFFFFFFu);
+    if (ps.ent0.x == 0xFFFFFFFFu) continue;
+    const int i = (int)(ps.ent0.x & 3u);
     int n[4];
 #pragma unroll
     for (int jj = 0; jj < 4; jj++) {
       int j = i + jj;
       if (j >= LOC) j -= LOC;
-      n[jj] = rot_node(nd, jj < LOC ? j : 0);
+      n[jj] = rot_node(ps.nd0, jj < LOC ? j : 0);
     }
-    sink.slots = ent.y;
+    sink.slots = ps.ent0.y;
     sink.i = i;
-    advdiff_row0<DIM>(A, n, sink);
+    if constexpr (COMMON) advdiff_row0<DIM>(A, n, sink, AdvCommonFlags());
+    else advdiff_row0<DIM>(A, n, sink, AdvRuntimeFlags{A.o, A.diffusivity.stride});
   }
   if (r >= 0) rhs[r] = sink.rhs;
   __syncthreads();
@@ -573,16 +626,22 @@ static int gather_momentum_dim(Handle* h, const MomentumArgs& A, bool want_ml, b
     const int nb = abs_mode ? DIM : 1;
     const size_t smem = sizeof(double) * (size_t)nb * P->maxlen * kBR;
     if (smem > 200 * 1024) CG_FAIL(CGASM_EUNSUPPORTED, "gather scatter: CSR rows too long for the shared-memory accumulator");
-#define LAUNCH_DIRECT(PERD_, MLD_)                                                                             \
+    const int prefetch = getenv("CGASM_GATHER_PREFETCH") ? atoi(getenv("CGASM_GATHER_PREFETCH")) : 0;
+    const int minb = getenv("CGASM_GATHER_MINB") ? atoi(getenv("CGASM_GATHER_MINB")) : 5;
+#define LAUNCH_DIRECT(PERD_, MLD_, COMMON_, MINB_)                                                             \
   do {                                                                                                         \
-    if ((st = set_dyn_smem(gather_momentum_direct_kernel<DIM, PERD_, MLD_>, smem))) return st;                 \
-    gather_momentum_direct_kernel<DIM, PERD_, MLD_><<<P->nblocks, kBR, smem, h->stream>>>(                     \
-        A, P->d_rows, P->d_block_ptr, P->d_pairs, h->d_findrm, (size_t)h->nnz, P->maxlen, h->d_big_m,          \
+    if ((st = set_dyn_smem(gather_momentum_direct_kernel<DIM, PERD_, MLD_, COMMON_, MINB_>, smem))) return st; \
+    gather_momentum_direct_kernel<DIM, PERD_, MLD_, COMMON_, MINB_><<<P->nblocks, kBR, smem, h->stream>>>(     \
+        A, P->d_rows, P->d_block_ptr, P->d_pairs, h->d_findrm, (size_t)h->nnz, P->maxlen, prefetch, h->d_big_m,\
         h->d_mom_rhs, ml);                                                                                     \
   } while (0)
-    if (abs_mode == 0) LAUNCH_DIRECT(false, false);
-    else if (!mld) LAUNCH_DIRECT(true, false);
-    else LAUNCH_DIRECT(true, true);
+    if (abs_mode == 0 && momentum_common_ok(A.o, A.viscosity.stride) && want_ml) {
+      if (minb >= 6) LAUNCH_DIRECT(false, false, true, 6);
+      else if (minb == 5) LAUNCH_DIRECT(false, false, true, 5);
+      else LAUNCH_DIRECT(false, false, true, 4);
+    } else if (abs_mode == 0) LAUNCH_DIRECT(false, false, false, 4);
+    else if (!mld) LAUNCH_DIRECT(true, false, false, 4);
+    else LAUNCH_DIRECT(true, true, false, 4);
 #undef LAUNCH_DIRECT
     h->launches++;
   } else if (abs_mode == 0) {
@@ -630,9 +689,21 @@ static int gather_advdiff_dim(Handle* h, const AdvDiffArgs& A) {
   if (advdiff_fast_ok(A.o) && A.tab.sym && !getenv("CGASM_GATHER_GENERIC") && !getenv("CGASM_GATHER_STAGED")) {
     const size_t smem = sizeof(double) * (size_t)P->maxlen * kBR;
     if (smem > 200 * 1024) CG_FAIL(CGASM_EUNSUPPORTED, "gather scatter: CSR rows too long for the shared-memory accumulator");
-    if ((st = set_dyn_smem(gather_advdiff_direct_kernel<DIM>, smem))) return st;
-    gather_advdiff_direct_kernel<DIM><<<P->nblocks, kBR, smem, h->stream>>>(
-        A, P->d_rows, P->d_block_ptr, P->d_pairs, h->d_findrm, P->maxlen, h->d_adv_matrix, h->d_adv_rhs);
+    const int prefetch = getenv("CGASM_GATHER_PREFETCH") ? atoi(getenv("CGASM_GATHER_PREFETCH")) : 0;
+    const int minb = getenv("CGASM_GATHER_MINB") ? atoi(getenv("CGASM_GATHER_MINB")) : 5;
+#define LAUNCH_ADIRECT(COMMON_, MINB_)                                                                   \
+  do {                                                                                                   \
+    if ((st = set_dyn_smem(gather_advdiff_direct_kernel<DIM, COMMON_, MINB_>, smem))) return st;         \
+    gather_advdiff_direct_kernel<DIM, COMMON_, MINB_><<<P->nblocks, kBR, smem, h->stream>>>(             \
+        A, P->d_rows, P->d_block_ptr, P->d_pairs, h->d_findrm, P->maxlen, prefetch, h->d_adv_matrix,     \
+        h->d_adv_rhs);                                                                                   \
+  } while (0)
+    if (advdiff_common_ok(A.o, A.diffusivity.stride)) {
+      if (minb >= 6) LAUNCH_ADIRECT(true, 6);
+      else if (minb == 5) LAUNCH_ADIRECT(true, 5);
+      else LAUNCH_ADIRECT(true, 4);
+    } else LAUNCH_ADIRECT(false, 4);
+#undef LAUNCH_ADIRECT
     h->launches++;
     CG_CUDA(cudaGetLastError());
     return CGASM_OK;
