@@ -1126,6 +1126,59 @@ __device__ __forceinline__ void advdiff_fast(const AdvDiffArgs& P, const int4 nd
 // Option coverage = momentum_fast_ok / advdiff_fast_ok. Sink: mat(jj, d, v), vec(d, v), ml(d, v)
 // with jj the ROTATED column index.
 // =====================================================================================
+// Lean geometry for the row kernels: cofactors + 1/det only. gradN_k = C(:,k)/det for k < dim and
+// gradN_loc = -sum_k gradN_k, so v.gradN_j = (v.C(:,j))/det and the last product is minus the sum
+// of the others; only gradN_0 (the row's own node) is ever formed explicitly.
+template <int DIM>
+struct GeomLean {
+  double C[DIM][DIM];
+  double rdet, absdet;
+  __device__ __forceinline__ void grad0(double (&g)[DIM]) const {
+#pragma unroll
+    for (int a = 0; a < DIM; a++) g[a] = C[a][0] * rdet;
+  }
+  __device__ __forceinline__ void dots(const double (&v)[DIM], double (&s)[DIM + 1]) const {
+    double tot = 0.0;
+#pragma unroll
+    for (int j = 0; j < DIM; j++) {
+      double t = 0.0;
+#pragma unroll
+      for (int a = 0; a < DIM; a++) t += v[a] * C[a][j];
+      s[j] = t * rdet;
+      tot += s[j];
+    }
+    s[DIM] = -tot;
+  }
+};
+
+template <int DIM>
+__device__ __forceinline__ void geometry_lean(const double (&X)[DIM + 1][DIM], GeomLean<DIM>& G) {
+  double JT[DIM][DIM];
+#pragma unroll
+  for (int a = 0; a < DIM; a++)
+#pragma unroll
+    for (int k = 0; k < DIM; k++) JT[a][k] = X[k][a] - X[DIM][a];
+  if constexpr (DIM == 2) {
+    G.C[0][0] = JT[1][1];
+    G.C[1][0] = -JT[0][1];
+    G.C[0][1] = -JT[1][0];
+    G.C[1][1] = JT[0][0];
+  } else {
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        const int i1 = (i + 1) % 3, i2 = (i + 2) % 3, k1 = (k + 1) % 3, k2 = (k + 2) % 3;
+        G.C[i][k] = JT[i1][k1] * JT[i2][k2] - JT[i2][k1] * JT[i1][k2];
+      }
+  }
+  double det = 0.0;
+#pragma unroll
+  for (int a = 0; a < DIM; a++) det += JT[a][0] * G.C[a][0];
+  G.rdet = 1.0 / det;
+  G.absdet = fabs(det);
+}
+
 template <int DIM>
 __device__ __forceinline__ void load_rot(const double4* __restrict__ rec, const int (&n)[4], double (&v)[DIM + 1][DIM],
                                          double (&s)[DIM + 1]) {
@@ -1173,14 +1226,16 @@ __device__ __forceinline__ void momentum_row0(const MomentumArgs& A, const int (
   const cgasm_momentum_opts& o = A.o;
   const Tables& t = A.tab;
   const double dtt = o.dt * o.theta;
-  Geom<DIM> G;
+  GeomLean<DIM> G;
+  double g0[DIM];  // gradN of the row's own node
   double M[LOC];  // rho-weighted mass row of local node 0
   double v[DIM];
   double m0;
   {
     double X[LOC][DIM], T_unused[LOC];
     load_rot<DIM>(A.rec.r0, n, X, T_unused);
-    geometry<DIM>(X, G);
+    geometry_lean<DIM>(X, G);
+    G.grad0(g0);
   }
   {
     double nu[LOC][DIM], rho[LOC];
@@ -1222,16 +1277,16 @@ __device__ __forceinline__ void momentum_row0(const MomentumArgs& A, const int (
     }
     if (f.visc_shape() == CGASM_TENSOR_ISOTROPIC) {
 #pragma unroll
-      for (int a = 0; a < DIM; a++) v[a] += Vbar[0] * G.grad[0][a];
+      for (int a = 0; a < DIM; a++) v[a] += Vbar[0] * g0[a];
     } else if (f.visc_shape() == CGASM_TENSOR_DIAGONAL) {
 #pragma unroll
-      for (int a = 0; a < DIM; a++) v[a] += Vbar[a + DIM * a] * G.grad[0][a];
+      for (int a = 0; a < DIM; a++) v[a] += Vbar[a + DIM * a] * g0[a];
     } else {
 #pragma unroll
       for (int b = 0; b < DIM; b++) {
         double s = 0.0;
 #pragma unroll
-        for (int a = 0; a < DIM; a++) s += G.grad[0][a] * Vbar[a + DIM * b];
+        for (int a = 0; a < DIM; a++) s += g0[a] * Vbar[a + DIM * b];
         v[b] += s;
       }
     }
@@ -1285,11 +1340,11 @@ __device__ __forceinline__ void momentum_row0(const MomentumArgs& A, const int (
       }
     }
   }
+  double sj[LOC];
+  G.dots(v, sj);
 #pragma unroll
   for (int j = 0; j < LOC; j++) {
-    double s = 0.0;
-#pragma unroll
-    for (int a = 0; a < DIM; a++) s += v[a] * G.grad[j][a];
+    const double s = sj[j];
 #pragma unroll
     for (int d = 0; d < DIM; d++) rhs[d] -= s * oldu[j][d];
 #pragma unroll
@@ -1336,12 +1391,14 @@ __device__ __forceinline__ void advdiff_row0(const AdvDiffArgs& P, const int (&n
   const Tables& t = P.tab;
   const double dtt = o.dt * o.theta;
   const bool implicit = fabs(dtt) > 2.220446049250313e-16;
-  Geom<DIM> G;
+  GeomLean<DIM> G;
+  double g0[DIM];
   double T[LOC], v[DIM];
   {
     double X[LOC][DIM];
     load_rot<DIM>(P.rec.r0, n, X, T);
-    geometry<DIM>(X, G);
+    geometry_lean<DIM>(X, G);
+    G.grad0(g0);
   }
 #pragma unroll
   for (int a = 0; a < DIM; a++) v[a] = 0.0;
@@ -1377,13 +1434,13 @@ __device__ __forceinline__ void advdiff_row0(const AdvDiffArgs& P, const int (&n
     }
     if (f.diff_shape() == CGASM_TENSOR_ISOTROPIC) {
 #pragma unroll
-      for (int a = 0; a < DIM; a++) v[a] += Kbar[0] * G.grad[0][a];
+      for (int a = 0; a < DIM; a++) v[a] += Kbar[0] * g0[a];
     } else {
 #pragma unroll
       for (int b = 0; b < DIM; b++) {
         double s = 0.0;
 #pragma unroll
-        for (int a = 0; a < DIM; a++) s += G.grad[0][a] * Kbar[a + DIM * b];
+        for (int a = 0; a < DIM; a++) s += g0[a] * Kbar[a + DIM * b];
         v[b] += s;
       }
     }
@@ -1400,11 +1457,11 @@ __device__ __forceinline__ void advdiff_row0(const AdvDiffArgs& P, const int (&n
     }
     rhs = G.absdet * ((t.Pd - t.Po) * s0 + t.Po * S);
   }
+  double sj[LOC];
+  G.dots(v, sj);
 #pragma unroll
   for (int j = 0; j < LOC; j++) {
-    double s = 0.0;
-#pragma unroll
-    for (int a = 0; a < DIM; a++) s += v[a] * G.grad[j][a];
+    const double s = sj[j];
     rhs -= s * T[j];
     double a_0j = implicit ? dtt * s : 0.0;
     if (f.mass()) {

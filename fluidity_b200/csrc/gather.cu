@@ -35,6 +35,9 @@ struct GatherPlan {
   long long* d_block_ptr = nullptr;  // [nblocks+1] first plan entry of a block
   uint2* d_pairs = nullptr;        // block-interleaved: entry k of thread t at ptr + k*kBR + t
                                    //   .x = element*4 + local row (0xFFFFFFFF = none), .y = 4 x 8-bit slot
+  int4* d_pair_nodes = nullptr;    // same indexing: the element's nodes ROTATED so the row's own node is
+                                   //   first (.x < 0 = none); slot byte j of .y belongs to rotated node j
+  unsigned* d_pair_rslots = nullptr;  // slots in rotated order
   long long n_entries = 0;
   double* d_stage = nullptr;       // staging buffer (grown on demand)
   size_t stage_doubles = 0;
@@ -46,6 +49,8 @@ void gather_free(Handle* h) {
   if (p->d_rows) cudaFree(p->d_rows);
   if (p->d_block_ptr) cudaFree(p->d_block_ptr);
   if (p->d_pairs) cudaFree(p->d_pairs);
+  if (p->d_pair_nodes) cudaFree(p->d_pair_nodes);
+  if (p->d_pair_rslots) cudaFree(p->d_pair_rslots);
   if (p->d_stage) cudaFree(p->d_stage);
   delete p;
   h->gather = nullptr;
@@ -57,7 +62,8 @@ __global__ void gather_pairs_kernel(int nblocks, int loc, const int* __restrict_
                                     const long long* __restrict__ block_ptr,
                                     const long long* __restrict__ n2e_ptr, const int* __restrict__ n2e,
                                     const int4* __restrict__ ndglno, const int* __restrict__ findrm,
-                                    const int* __restrict__ colm, uint2* __restrict__ pairs) {
+                                    const int* __restrict__ colm, uint2* __restrict__ pairs,
+                                    int4* __restrict__ pair_nodes, unsigned* __restrict__ pair_rslots) {
   const int b = blockIdx.x, t = threadIdx.x;
   if (b >= nblocks) return;
   const int r = rows[b * kBR + t];
@@ -79,9 +85,24 @@ __global__ void gather_pairs_kernel(int nblocks, int loc, const int* __restrict_
           if (colm[q] == nodes[j]) slots |= (unsigned)((q - s) & 0xff) << (8 * j);
       }
       pairs[base + (long long)k * kBR + t] = make_uint2((unsigned)e * 4u + irow, slots);
+      int rn[4];
+      unsigned rs = 0;
+      for (int jj = 0; jj < 4; jj++) {
+        int j = (int)irow + jj;
+        if (j >= loc) j -= loc;
+        if (jj >= loc) j = (int)irow;
+        rn[jj] = nodes[j];
+        rs |= ((slots >> (8 * j)) & 0xffu) << (8 * jj);
+      }
+      pair_nodes[base + (long long)k * kBR + t] = make_int4(rn[0], rn[1], rn[2], rn[3]);
+      pair_rslots[base + (long long)k * kBR + t] = rs;
     }
   }
-  for (int k = deg; k < deg_block; k++) pairs[base + (long long)k * kBR + t] = make_uint2(0xFFFFFFFFu, 0u);
+  for (int k = deg; k < deg_block; k++) {
+    pairs[base + (long long)k * kBR + t] = make_uint2(0xFFFFFFFFu, 0u);
+    pair_nodes[base + (long long)k * kBR + t] = make_int4(-1, -1, -1, -1);
+    pair_rslots[base + (long long)k * kBR + t] = 0u;
+  }
 }
 
 int gather_build(Handle* h) {
@@ -120,6 +141,8 @@ int gather_build(Handle* h) {
   CG_CUDA(cudaMalloc(&P->d_block_ptr, sizeof(long long) * block_ptr.size()));
   CG_CUDA(cudaMemcpy(P->d_block_ptr, block_ptr.data(), sizeof(long long) * block_ptr.size(), cudaMemcpyHostToDevice));
   CG_CUDA(cudaMalloc(&P->d_pairs, sizeof(uint2) * (size_t)std::max<long long>(P->n_entries, 1)));
+  CG_CUDA(cudaMalloc(&P->d_pair_nodes, sizeof(int4) * (size_t)std::max<long long>(P->n_entries, 1)));
+  CG_CUDA(cudaMalloc(&P->d_pair_rslots, sizeof(unsigned) * (size_t)std::max<long long>(P->n_entries, 1)));
   // node->element adjacency goes to the device only for the duration of the plan build
   long long* d_n2e_ptr = nullptr;
   int* d_n2e = nullptr;
@@ -130,7 +153,8 @@ int gather_build(Handle* h) {
   cudaError_t e2 = cudaMemcpy(d_n2e, h->n2e.data(), sizeof(int) * h->n2e.size(), cudaMemcpyHostToDevice);
   if (e1 == cudaSuccess && e2 == cudaSuccess) {
     gather_pairs_kernel<<<P->nblocks, kBR, 0, h->stream>>>(P->nblocks, h->loc, P->d_rows, P->d_block_ptr, d_n2e_ptr,
-                                                          d_n2e, h->d_ndglno, h->d_findrm, h->d_colm, P->d_pairs);
+                                                          d_n2e, h->d_ndglno, h->d_findrm, h->d_colm, P->d_pairs,
+                                                          P->d_pair_nodes, P->d_pair_rslots);
     h->launches++;
     e1 = cudaStreamSynchronize(h->stream);
   }
@@ -408,9 +432,7 @@ struct MomDirectSink {
   int i;
   double vec_[NV];
   __device__ __forceinline__ void mat(int jj, int d, double v) {
-    int j = i + jj;
-    if (j >= LOC) j -= LOC;
-    acc[(d * maxlen + (int)((slots >> (8 * j)) & 0xffu)) * kBR] += v;
+    acc[(d * maxlen + (int)((slots >> (8 * jj)) & 0xffu)) * kBR] += v;
   }
   __device__ __forceinline__ void vec(int d, double v) { vec_[d] += v; }
   __device__ __forceinline__ void ml(int d, double v) {
@@ -425,11 +447,7 @@ struct AdvDirectSink {
   unsigned slots;
   int i;
   double rhs;
-  __device__ __forceinline__ void mat(int jj, double v) {
-    int j = i + jj;
-    if (j >= LOC) j -= LOC;
-    acc[(int)((slots >> (8 * j)) & 0xffu) * kBR] += v;
-  }
+  __device__ __forceinline__ void mat(int jj, double v) { acc[(int)((slots >> (8 * jj)) & 0xffu) * kBR] += v; }
   __device__ __forceinline__ void vec(double v) { rhs += v; }
 };
 
@@ -437,40 +455,51 @@ __device__ __forceinline__ int rot_node(const int4& nd, int j) { return j == 0 ?
 
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
-// Pair stream of one row thread, software-pipelined: the plan entry two pairs ahead and the
-// element connectivity one pair ahead are in flight while the current pair is computed, and the
-// next pair's node records are pulled into L1 (prefetch needs no registers).
+// Pair stream of one row thread: rotated node ids + slots of the current pair, with the next
+// pair already in flight. Plan data is read once, so it bypasses L1 (L1::no_allocate) and leaves
+// the cache to the node records, which neighbouring rows re-read ~24 times.
+__device__ __forceinline__ int4 ldg_stream(const int4* p) {
+  int4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ unsigned ldg_stream(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
 struct PairStream {
-  const uint2* p;
-  const int4* ndglno;
+  const int4* pn;
+  const unsigned* psl;
   int deg, k;
-  uint2 ent0, ent1, ent2;
   int4 nd0, nd1;
-  __device__ __forceinline__ uint2 load_ent(int kk) const {
-    return kk < deg ? __ldg(p + (long long)kk * kBR) : make_uint2(0xFFFFFFFFu, 0u);
+  unsigned sl0, sl1;
+  __device__ __forceinline__ void load_next(int kk) {
+    if (kk < deg) {
+      nd1 = ldg_stream(pn + (long long)kk * kBR);
+      sl1 = ldg_stream(psl + (long long)kk * kBR);
+    } else {
+      nd1 = make_int4(-1, -1, -1, -1);
+      sl1 = 0u;
+    }
   }
-  __device__ __forceinline__ int4 load_nd(const uint2& e) const {
-    return e.x != 0xFFFFFFFFu ? __ldg(ndglno + (e.x >> 2)) : make_int4(0, 0, 0, 0);
-  }
-  __device__ __forceinline__ void init(const uint2* p_, const int4* nd_, int deg_) {
-    p = p_;
-    ndglno = nd_;
+  __device__ __forceinline__ void init(const int4* pn_, const unsigned* psl_, int deg_) {
+    pn = pn_;
+    psl = psl_;
     deg = deg_;
     k = 0;
-    ent0 = load_ent(0);
-    ent1 = load_ent(1);
-    ent2 = load_ent(2);
-    nd0 = load_nd(ent0);
-    nd1 = load_nd(ent1);
+    load_next(0);
+    nd0 = nd1;
+    sl0 = sl1;
+    load_next(1);
   }
   __device__ __forceinline__ void advance() {
-    ent0 = ent1;
     nd0 = nd1;
-    ent1 = ent2;
-    nd1 = load_nd(ent1);
+    sl0 = sl1;
     k++;
-    ent2 = load_ent(k + 2);
+    load_next(k + 1);
   }
+  __device__ __forceinline__ bool valid() const { return nd0.x >= 0; }
 };
 
 template <int NREC>
@@ -488,7 +517,8 @@ __device__ __forceinline__ void prefetch_nodes(const NodeRecs& rec, const int4& 
 template <int DIM, bool PERD, bool MLD, bool COMMON, int MINB>
 __global__ void __launch_bounds__(kBR, MINB)
 gather_momentum_direct_kernel(const MomentumArgs A, const int* __restrict__ rows, const long long* __restrict__ block_ptr,
-                              const uint2* __restrict__ pairs, const int* __restrict__ findrm, size_t nnz, int maxlen,
+                              const int4* __restrict__ pair_nodes, const unsigned* __restrict__ pair_rslots,
+                              const int* __restrict__ findrm, size_t nnz, int maxlen,
                               int prefetch, double* __restrict__ big_m, double* __restrict__ rhs,
                               double* __restrict__ masslump) {
   constexpr int LOC = DIM + 1;
@@ -499,7 +529,7 @@ gather_momentum_direct_kernel(const MomentumArgs A, const int* __restrict__ rows
   const long long base = block_ptr[b];
   const int deg = (int)((block_ptr[b + 1] - base) / kBR);
   PairStream ps;
-  ps.init(pairs + base + t, A.ndglno, deg);
+  ps.init(pair_nodes + base + t, pair_rslots + base + t, deg);
   for (int q = 0; q < NB * maxlen; q++) acc[q * kBR + t] = 0.0;
   MomDirectSink<DIM, PERD, MLD> sink;
   sink.acc = acc + t;
@@ -507,18 +537,11 @@ gather_momentum_direct_kernel(const MomentumArgs A, const int* __restrict__ rows
 #pragma unroll
   for (int c = 0; c < MomDirectSink<DIM, PERD, MLD>::NV; c++) sink.vec_[c] = 0.0;
   for (; ps.k < deg; ps.advance()) {
-    if (prefetch) prefetch_nodes<3>(A.rec, ps.nd1, ps.ent1.x != 0xFFFFFFFFu);
-    if (ps.ent0.x == 0xFFFFFFFFu) continue;
-    const int i = (int)(ps.ent0.x & 3u);
-    int n[4];
-#pragma unroll
-    for (int jj = 0; jj < 4; jj++) {
-      int j = i + jj;
-      if (j >= LOC) j -= LOC;
-      n[jj] = rot_node(ps.nd0, jj < LOC ? j : 0);
-    }
-    sink.slots = ps.ent0.y;
-    sink.i = i;
+    if (prefetch) prefetch_nodes<3>(A.rec, ps.nd1, ps.nd1.x >= 0);
+    if (!ps.valid()) continue;
+    const int n[4] = {ps.nd0.x, ps.nd0.y, ps.nd0.z, ps.nd0.w};
+    sink.slots = ps.sl0;
+    sink.i = 0;
     if constexpr (COMMON) momentum_row0<DIM, PERD>(A, n, sink, MomCommonFlags());
     else momentum_row0<DIM, PERD>(A, n, sink, MomRuntimeFlags{A.o, A.viscosity.stride});
   }
@@ -547,7 +570,8 @@ gather_momentum_direct_kernel(const MomentumArgs A, const int* __restrict__ rows
 template <int DIM, bool COMMON, int MINB>
 __global__ void __launch_bounds__(kBR, MINB)
 gather_advdiff_direct_kernel(const AdvDiffArgs A, const int* __restrict__ rows, const long long* __restrict__ block_ptr,
-                             const uint2* __restrict__ pairs, const int* __restrict__ findrm, int maxlen, int prefetch,
+                             const int4* __restrict__ pair_nodes, const unsigned* __restrict__ pair_rslots,
+                             const int* __restrict__ findrm, int maxlen, int prefetch,
                              double* __restrict__ matrix, double* __restrict__ rhs) {
   constexpr int LOC = DIM + 1;
   extern __shared__ double acc[];
@@ -556,24 +580,17 @@ gather_advdiff_direct_kernel(const AdvDiffArgs A, const int* __restrict__ rows, 
   const long long base = block_ptr[b];
   const int deg = (int)((block_ptr[b + 1] - base) / kBR);
   PairStream ps;
-  ps.init(pairs + base + t, A.ndglno, deg);
+  ps.init(pair_nodes + base + t, pair_rslots + base + t, deg);
   for (int q = 0; q < maxlen; q++) acc[q * kBR + t] = 0.0;
   AdvDirectSink<DIM> sink;
   sink.acc = acc + t;
   sink.rhs = 0.0;
   for (; ps.k < deg; ps.advance()) {
-    if (prefetch) prefetch_nodes<2>(A.rec, ps.nd1, ps.ent1.x != 0xFFFFFFFFu);
-    if (ps.ent0.x == 0xFFFFFFFFu) continue;
-    const int i = (int)(ps.ent0.x & 3u);
-    int n[4];
-#pragma unroll
-    for (int jj = 0; jj < 4; jj++) {
-      int j = i + jj;
-      if (j >= LOC) j -= LOC;
-      n[jj] = rot_node(ps.nd0, jj < LOC ? j : 0);
-    }
-    sink.slots = ps.ent0.y;
-    sink.i = i;
+    if (prefetch) prefetch_nodes<2>(A.rec, ps.nd1, ps.nd1.x >= 0);
+    if (!ps.valid()) continue;
+    const int n[4] = {ps.nd0.x, ps.nd0.y, ps.nd0.z, ps.nd0.w};
+    sink.slots = ps.sl0;
+    sink.i = 0;
     if constexpr (COMMON) advdiff_row0<DIM>(A, n, sink, AdvCommonFlags());
     else advdiff_row0<DIM>(A, n, sink, AdvRuntimeFlags{A.o, A.diffusivity.stride});
   }
@@ -632,7 +649,8 @@ static int gather_momentum_dim(Handle* h, const MomentumArgs& A, bool want_ml, b
   do {                                                                                                         \
     if ((st = set_dyn_smem(gather_momentum_direct_kernel<DIM, PERD_, MLD_, COMMON_, MINB_>, smem))) return st; \
     gather_momentum_direct_kernel<DIM, PERD_, MLD_, COMMON_, MINB_><<<P->nblocks, kBR, smem, h->stream>>>(     \
-        A, P->d_rows, P->d_block_ptr, P->d_pairs, h->d_findrm, (size_t)h->nnz, P->maxlen, prefetch, h->d_big_m,\
+        A, P->d_rows, P->d_block_ptr, P->d_pair_nodes, P->d_pair_rslots, h->d_findrm, (size_t)h->nnz,          \
+        P->maxlen, prefetch, h->d_big_m,                                                                       \
         h->d_mom_rhs, ml);                                                                                     \
   } while (0)
     if (abs_mode == 0 && momentum_common_ok(A.o, A.viscosity.stride) && want_ml) {
@@ -690,12 +708,13 @@ static int gather_advdiff_dim(Handle* h, const AdvDiffArgs& A) {
     const size_t smem = sizeof(double) * (size_t)P->maxlen * kBR;
     if (smem > 200 * 1024) CG_FAIL(CGASM_EUNSUPPORTED, "gather scatter: CSR rows too long for the shared-memory accumulator");
     const int prefetch = getenv("CGASM_GATHER_PREFETCH") ? atoi(getenv("CGASM_GATHER_PREFETCH")) : 0;
-    const int minb = getenv("CGASM_GATHER_MINB") ? atoi(getenv("CGASM_GATHER_MINB")) : 5;
+    const int minb = getenv("CGASM_GATHER_MINB") ? atoi(getenv("CGASM_GATHER_MINB")) : 6;
 #define LAUNCH_ADIRECT(COMMON_, MINB_)                                                                   \
   do {                                                                                                   \
     if ((st = set_dyn_smem(gather_advdiff_direct_kernel<DIM, COMMON_, MINB_>, smem))) return st;         \
     gather_advdiff_direct_kernel<DIM, COMMON_, MINB_><<<P->nblocks, kBR, smem, h->stream>>>(             \
-        A, P->d_rows, P->d_block_ptr, P->d_pairs, h->d_findrm, P->maxlen, prefetch, h->d_adv_matrix,     \
+        A, P->d_rows, P->d_block_ptr, P->d_pair_nodes, P->d_pair_rslots, h->d_findrm, P->maxlen,         \
+        prefetch, h->d_adv_matrix,                                                                       \
         h->d_adv_rhs);                                                                                   \
   } while (0)
     if (advdiff_common_ok(A.o, A.diffusivity.stride)) {
