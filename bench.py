@@ -246,6 +246,16 @@ def run_graft(args):
     launches = asm.launch_count() - l0
     clocks = sampler.stop() if rank == 0 else None
     # per-kernel device times (separate pass so the event queries do not perturb the timed region)
+    halo_ms = None
+    if world > 1:
+        h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        h0.record(stream)
+        for _ in range(5):
+            asm.halo_update(halo_slots)
+        h1.record(stream)
+        barrier()
+        halo_ms = h0.elapsed_time(h1) / 5
     for _ in range(max(3, min(args.steps, 5))):
         if world > 1:
             asm.halo_update(halo_slots)
@@ -341,6 +351,7 @@ def run_graft(args):
         "per_gpu_melements_s": value / world, "scatter": chosen, "setup_s": setup_s,
         "elements_total": total_elements, "nnz_rank0": nnz, "n_nodes_rank0": mesh.n_nodes,
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        "halo_update_ms_rank0": halo_ms, "halo_nodes_sent_rank0": int(sum(len(s) for s in lp.sends)),
     }
     print(json.dumps(line))
     if world > 1:

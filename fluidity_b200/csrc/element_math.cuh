@@ -1220,8 +1220,37 @@ __host__ __device__ inline bool momentum_common_ok(const cgasm_momentum_opts& o,
          !o.exclude_mass && o.assemble_inverse_masslump && !o.have_absorption;
 }
 
+// Records of the row's own node (rotated local node 0): identical for every pair of the row, so the
+// row kernels load them once per row instead of once per pair.
+template <int DIM>
+struct OwnNode {
+  double X[DIM], nu[DIM], oldu[DIM];
+  double T, rho, b;
+  __device__ __forceinline__ void load(const NodeRecs& rec, int node) {
+    unpack<DIM>(ld256(rec.r0 + node), X, T);
+    unpack<DIM>(ld256(rec.r1 + node), nu, rho);
+    unpack<DIM>(ld256(rec.r2 + node), oldu, b);
+  }
+  __device__ __forceinline__ void load_tracer(const NodeRecs& rec, int node) {
+    unpack<DIM>(ld256(rec.r0 + node), X, T);
+    unpack<DIM>(ld256(rec.r1 + node), nu, rho);
+  }
+};
+
+// loads local nodes 1..LOC-1 from the records, node 0 from `own`
+template <int DIM>
+__device__ __forceinline__ void load_rot_own(const double4* __restrict__ rec, const int (&n)[4], const double (&own_v)[DIM],
+                                             double own_s, double (&v)[DIM + 1][DIM], double (&s)[DIM + 1]) {
+#pragma unroll
+  for (int a = 0; a < DIM; a++) v[0][a] = own_v[a];
+  s[0] = own_s;
+#pragma unroll
+  for (int k = 1; k < DIM + 1; k++) unpack<DIM>(ld256(rec + n[k]), v[k], s[k]);
+}
+
 template <int DIM, bool PERD, class Sink, class F>
-__device__ __forceinline__ void momentum_row0(const MomentumArgs& A, const int (&n)[4], Sink& sink, const F f) {
+__device__ __forceinline__ void momentum_row0(const MomentumArgs& A, const int (&n)[4], const OwnNode<DIM>& own,
+                                              Sink& sink, const F f) {
   constexpr int LOC = DIM + 1;
   const cgasm_momentum_opts& o = A.o;
   const Tables& t = A.tab;
@@ -1233,13 +1262,13 @@ __device__ __forceinline__ void momentum_row0(const MomentumArgs& A, const int (
   double m0;
   {
     double X[LOC][DIM], T_unused[LOC];
-    load_rot<DIM>(A.rec.r0, n, X, T_unused);
+    load_rot_own<DIM>(A.rec.r0, n, own.X, own.T, X, T_unused);
     geometry_lean<DIM>(X, G);
     G.grad0(g0);
   }
   {
     double nu[LOC][DIM], rho[LOC];
-    load_rot<DIM>(A.rec.r1, n, nu, rho);
+    load_rot_own<DIM>(A.rec.r1, n, own.nu, own.rho, nu, rho);
     double S = 0.0;
 #pragma unroll
     for (int k = 0; k < LOC; k++) S += rho[k];
@@ -1292,7 +1321,7 @@ __device__ __forceinline__ void momentum_row0(const MomentumArgs& A, const int (
     }
   }
   double oldu[LOC][DIM], b[LOC];
-  load_rot<DIM>(A.rec.r2, n, oldu, b);
+  load_rot_own<DIM>(A.rec.r2, n, own.oldu, own.b, oldu, b);
   double rhs[DIM];
 #pragma unroll
   for (int d = 0; d < DIM; d++) rhs[d] = 0.0;
@@ -1385,7 +1414,8 @@ __host__ __device__ inline bool advdiff_common_ok(const cgasm_advdiff_opts& o, i
 }
 
 template <int DIM, class Sink, class F>
-__device__ __forceinline__ void advdiff_row0(const AdvDiffArgs& P, const int (&n)[4], Sink& sink, const F f) {
+__device__ __forceinline__ void advdiff_row0(const AdvDiffArgs& P, const int (&n)[4], const OwnNode<DIM>& own,
+                                             Sink& sink, const F f) {
   constexpr int LOC = DIM + 1;
   const cgasm_advdiff_opts& o = P.o;
   const Tables& t = P.tab;
@@ -1396,7 +1426,7 @@ __device__ __forceinline__ void advdiff_row0(const AdvDiffArgs& P, const int (&n
   double T[LOC], v[DIM];
   {
     double X[LOC][DIM];
-    load_rot<DIM>(P.rec.r0, n, X, T);
+    load_rot_own<DIM>(P.rec.r0, n, own.X, own.T, X, T);
     geometry_lean<DIM>(X, G);
     G.grad0(g0);
   }
@@ -1404,7 +1434,7 @@ __device__ __forceinline__ void advdiff_row0(const AdvDiffArgs& P, const int (&n
   for (int a = 0; a < DIM; a++) v[a] = 0.0;
   if (f.adv()) {
     double u[LOC][DIM], unused[LOC];
-    load_rot<DIM>(P.rec.r1, n, u, unused);
+    load_rot_own<DIM>(P.rec.r1, n, own.nu, own.rho, u, unused);
 #pragma unroll
     for (int a = 0; a < DIM; a++) {
       double S = 0.0;

@@ -536,14 +536,16 @@ gather_momentum_direct_kernel(const MomentumArgs A, const int* __restrict__ rows
   sink.maxlen = maxlen;
 #pragma unroll
   for (int c = 0; c < MomDirectSink<DIM, PERD, MLD>::NV; c++) sink.vec_[c] = 0.0;
+  OwnNode<DIM> own;
+  own.load(A.rec, r >= 0 ? r : 0);
   for (; ps.k < deg; ps.advance()) {
     if (prefetch) prefetch_nodes<3>(A.rec, ps.nd1, ps.nd1.x >= 0);
     if (!ps.valid()) continue;
     const int n[4] = {ps.nd0.x, ps.nd0.y, ps.nd0.z, ps.nd0.w};
     sink.slots = ps.sl0;
     sink.i = 0;
-    if constexpr (COMMON) momentum_row0<DIM, PERD>(A, n, sink, MomCommonFlags());
-    else momentum_row0<DIM, PERD>(A, n, sink, MomRuntimeFlags{A.o, A.viscosity.stride});
+    if constexpr (COMMON) momentum_row0<DIM, PERD>(A, n, own, sink, MomCommonFlags());
+    else momentum_row0<DIM, PERD>(A, n, own, sink, MomRuntimeFlags{A.o, A.viscosity.stride});
   }
   if (r >= 0) {
 #pragma unroll
@@ -585,14 +587,16 @@ gather_advdiff_direct_kernel(const AdvDiffArgs A, const int* __restrict__ rows, 
   AdvDirectSink<DIM> sink;
   sink.acc = acc + t;
   sink.rhs = 0.0;
+  OwnNode<DIM> own;
+  own.load_tracer(A.rec, r >= 0 ? r : 0);
   for (; ps.k < deg; ps.advance()) {
     if (prefetch) prefetch_nodes<2>(A.rec, ps.nd1, ps.nd1.x >= 0);
     if (!ps.valid()) continue;
     const int n[4] = {ps.nd0.x, ps.nd0.y, ps.nd0.z, ps.nd0.w};
     sink.slots = ps.sl0;
     sink.i = 0;
-    if constexpr (COMMON) advdiff_row0<DIM>(A, n, sink, AdvCommonFlags());
-    else advdiff_row0<DIM>(A, n, sink, AdvRuntimeFlags{A.o, A.diffusivity.stride});
+    if constexpr (COMMON) advdiff_row0<DIM>(A, n, own, sink, AdvCommonFlags());
+    else advdiff_row0<DIM>(A, n, own, sink, AdvRuntimeFlags{A.o, A.diffusivity.stride});
   }
   if (r >= 0) rhs[r] = sink.rhs;
   __syncthreads();
@@ -644,7 +648,7 @@ static int gather_momentum_dim(Handle* h, const MomentumArgs& A, bool want_ml, b
     const size_t smem = sizeof(double) * (size_t)nb * P->maxlen * kBR;
     if (smem > 200 * 1024) CG_FAIL(CGASM_EUNSUPPORTED, "gather scatter: CSR rows too long for the shared-memory accumulator");
     const int prefetch = getenv("CGASM_GATHER_PREFETCH") ? atoi(getenv("CGASM_GATHER_PREFETCH")) : 0;
-    const int minb = getenv("CGASM_GATHER_MINB") ? atoi(getenv("CGASM_GATHER_MINB")) : 5;
+    const int minb = getenv("CGASM_GATHER_MINB") ? atoi(getenv("CGASM_GATHER_MINB")) : 4;
 #define LAUNCH_DIRECT(PERD_, MLD_, COMMON_, MINB_)                                                             \
   do {                                                                                                         \
     if ((st = set_dyn_smem(gather_momentum_direct_kernel<DIM, PERD_, MLD_, COMMON_, MINB_>, smem))) return st; \

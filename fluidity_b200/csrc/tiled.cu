@@ -810,7 +810,9 @@ tiled_momentum_quad_kernel(const MomentumArgs A, const TileArgs T, int max_entri
       sink.max_entries = max_entries;
       sink.slots = sel4u(sl, i);
       sink.i = i;
-      momentum_row0<DIM, PERD>(A, n, sink, MomRuntimeFlags{A.o, A.viscosity.stride});
+      OwnNode<DIM> own;
+      own.load(A.rec, n[0]);
+      momentum_row0<DIM, PERD>(A, n, own, sink, MomRuntimeFlags{A.o, A.viscosity.stride});
     }
     __syncthreads();
   }
@@ -890,7 +892,9 @@ tiled_advdiff_quad_kernel(const AdvDiffArgs A, const TileArgs T, int max_entries
       sink.vec_ = S.vec + r;
       sink.slots = sel4u(sl, i);
       sink.i = i;
-      advdiff_row0<DIM>(A, n, sink, AdvRuntimeFlags{A.o, A.diffusivity.stride});
+      OwnNode<DIM> own;
+      own.load_tracer(A.rec, n[0]);
+      advdiff_row0<DIM>(A, n, own, sink, AdvRuntimeFlags{A.o, A.diffusivity.stride});
     }
     __syncthreads();
   }

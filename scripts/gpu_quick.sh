@@ -4,7 +4,7 @@ mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -x -q -k "gather or tiled" > gpurun_out/pytest_gpu.log 2>&1
 echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
 tail -4 gpurun_out/pytest_gpu.log
-for mb in 5 6; do
+for mb in 4 5 6; do
 CGASM_GATHER_MINB=$mb timeout 600 python bench.py --cells 128 --scatter gather --steps 5 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/bench128_gather_mb$mb.json 2> gpurun_out/bench128_gather_mb$mb.err
 tail -2 gpurun_out/bench128_gather_mb$mb.err
 done
