@@ -21,6 +21,7 @@ reference's own colouring, all host threads) on a bounded sample of the same wor
 import argparse
 import json
 import os
+import resource
 import subprocess
 import sys
 import threading
@@ -213,6 +214,14 @@ def run_graft(args):
         asm.set_scatter(scatter[chosen])
     om, oa = abi.common_momentum_opts(), abi.common_advdiff_opts()
     setup_s = time.perf_counter() - t_setup
+    # the library holds its own copies; drop the generator's arrays before the pinned e2e buffers
+    n_el_local, n_nodes_local, n_owned = mesh.n_elements, mesh.n_nodes, lp.n_owned
+    n_sent = int(sum(len(s) for s in lp.sends))
+    mesh.ndglno = None
+    mesh.X = None
+    lp.global_node = lp.global_element = None
+    import gc
+    gc.collect()
 
     stream = torch.cuda.ExternalStream(asm.stream(), device=torch.device("cuda", local_rank))
 
@@ -268,7 +277,6 @@ def run_graft(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
     ms_per_step = total_ms / args.steps
-    n_el_local = mesh.n_elements
     tot_el = torch.tensor([float(n_el_local)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tot_el, op=dist.ReduceOp.SUM)
@@ -285,8 +293,8 @@ def run_graft(args):
             b = pinned(a.shape)
             b[...] = a
             host_in.append((slot, b))
-        out_m = dict(big_m=pinned((3, nnz)), rhs=pinned((mesh.n_nodes, 3)), masslump=pinned((mesh.n_nodes, 3)))
-        out_a = dict(matrix=pinned((nnz,)), rhs=pinned((mesh.n_nodes,)))
+        out_m = dict(big_m=pinned((3, nnz)), rhs=pinned((n_nodes_local, 3)), masslump=pinned((n_nodes_local, 3)))
+        out_a = dict(matrix=pinned((nnz,)), rhs=pinned((n_nodes_local,)))
         h2d = sum(b.nbytes for _, b in host_in)
         d2h = sum(v.nbytes for v in out_m.values()) + sum(v.nbytes for v in out_a.values())
 
@@ -310,7 +318,7 @@ def run_graft(args):
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         e2e = {"value": total_elements / float(dt.item()) / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * float(dt.item()), "steps": n_e2e,
-               "checksum": float(out_a["rhs"][: lp.n_owned].sum())}
+               "checksum": float(out_a["rhs"][:n_owned].sum())}
 
     if rank != 0:
         if world > 1:
@@ -326,17 +334,17 @@ def run_graft(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    bytes_mom = syn.algorithmic_bytes(3, mesh.n_nodes, mesh.n_elements, nnz, "momentum")
-    bytes_tra = syn.algorithmic_bytes(3, mesh.n_nodes, mesh.n_elements, nnz, "tracer")
+    bytes_mom = syn.algorithmic_bytes(3, n_nodes_local, n_el_local, nnz, "momentum")
+    bytes_tra = syn.algorithmic_bytes(3, n_nodes_local, n_el_local, nnz, "tracer")
     m_ms, a_ms = float(np.mean(mom_ms)), float(np.mean(adv_ms))
-    ach = bytes_mom * mesh.n_elements / (m_ms * 1e-3) / 1e9
+    ach = bytes_mom * n_el_local / (m_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "momentum assembly (%s scatter)" % chosen, "achieved": ach, "peak": peak,
                 "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
                 "algorithmic_bytes_per_element": bytes_mom, "kernel_ms": m_ms,
                 "frac_of_8TBs": ach / 8000.0,
-                "tracer": {"achieved": bytes_tra * mesh.n_elements / (a_ms * 1e-3) / 1e9,
+                "tracer": {"achieved": bytes_tra * n_el_local / (a_ms * 1e-3) / 1e9,
                            "algorithmic_bytes_per_element": bytes_tra, "kernel_ms": a_ms},
-                "combined_frac": (bytes_mom + bytes_tra) * mesh.n_elements / ((m_ms + a_ms) * 1e-3) / 1e9 / peak}
+                "combined_frac": (bytes_mom + bytes_tra) * n_el_local / ((m_ms + a_ms) * 1e-3) / 1e9 / peak}
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
@@ -349,9 +357,10 @@ def run_graft(args):
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
         "per_gpu_melements_s": value / world, "scatter": chosen, "setup_s": setup_s,
-        "elements_total": total_elements, "nnz_rank0": nnz, "n_nodes_rank0": mesh.n_nodes,
+        "elements_total": total_elements, "nnz_rank0": nnz, "n_nodes_rank0": n_nodes_local,
+        "host_peak_rss_gb_rank0": resource.getrusage(resource.RUSAGE_SELF).ru_maxrss / 1048576.0,
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-        "halo_update_ms_rank0": halo_ms, "halo_nodes_sent_rank0": int(sum(len(s) for s in lp.sends)),
+        "halo_update_ms_rank0": halo_ms, "halo_nodes_sent_rank0": n_sent,
     }
     print(json.dumps(line))
     if world > 1:

@@ -147,25 +147,64 @@ void morton_order(const Handle* h, std::vector<int>& order, MortonFrame& F) {
       lo[a] = std::min(lo[a], v);
       hi[a] = std::max(hi[a], v);
     }
-  // Quantise to a lattice about as fine as the mesh itself: h = (bounding volume / n)^(1/dim),
-  // cells_a = round(ext_a / h) - 1 (exact for an (m+1)^dim point lattice). Jittered lattice
-  // nodes then snap to their own lattice point, so fixed-count cuts of the Morton sequence are
-  // aligned bricks (measured redundancy 1.31 at 1024 rows vs 1.51 with a fine quantisation).
-  double vol = 1.0;
-  int live = 0;
-  for (int a = 0; a < dim; a++)
-    if (hi[a] > lo[a]) {
-      vol *= hi[a] - lo[a];
-      live++;
+  // Quantise to a lattice about as fine as the mesh itself, per axis: the spacing ratio between axes
+  // comes from the mean |edge component| over all element edges, the absolute scale from
+  // prod_a(ext_a / h_a + 1) = n (points per axis), and cells_a = round(ext_a / h_a): exact for a
+  // lattice also when the spacing differs between axes, e.g. slab partitions of a box.
+  // Jittered lattice nodes then snap to their own lattice point, so fixed-count cuts of the Morton
+  // sequence are aligned bricks (measured tile redundancy 1.31 at 1024 rows vs 1.51 with a fine
+  // quantisation).
+  double mean_edge[3] = {0, 0, 0};
+  {
+    const int loc = h->loc, ne = h->n_elements;
+    const int stride = std::max(1, ne / 2000000);  // a sample is enough
+    double acc0 = 0, acc1 = 0, acc2 = 0;
+#pragma omp parallel for schedule(static) reduction(+ : acc0, acc1, acc2)
+    for (int e = 0; e < ne; e += stride) {
+      const int* nd = h->h_nd0.data() + (size_t)4 * e;
+      for (int i = 0; i < loc; i++)
+        for (int j = i + 1; j < loc; j++) {
+          const double* xi = &h->h_X[(size_t)dim * nd[i]];
+          const double* xj = &h->h_X[(size_t)dim * nd[j]];
+          acc0 += std::fabs(xi[0] - xj[0]);
+          acc1 += std::fabs(xi[1] - xj[1]);
+          if (dim == 3) acc2 += std::fabs(xi[2] - xj[2]);
+        }
     }
-  const double hcell = live ? std::pow(vol / (double)n, 1.0 / live) : 1.0;
+    mean_edge[0] = acc0;
+    mean_edge[1] = acc1;
+    mean_edge[2] = acc2;
+  }
+  // h_a = c * mean_edge_a with c solving prod_a(ext_a / h_a + 1) = n (points per axis = cells + 1)
+  double lo_c = 1e-300, hi_c = 1e300;
+  {
+    auto points = [&](double c) {
+      double p = 1.0;
+      for (int a = 0; a < dim; a++)
+        if (hi[a] > lo[a] && mean_edge[a] > 0.0) p *= (hi[a] - lo[a]) / (c * mean_edge[a]) + 1.0;
+      return p;
+    };
+    // bracket: points(c) decreases with c
+    double c0 = 1.0;
+    while (points(c0) < (double)n && c0 > 1e-280) c0 *= 0.5;
+    lo_c = c0;
+    hi_c = c0;
+    while (points(hi_c) > (double)n && hi_c < 1e280) hi_c *= 2.0;
+    for (int it = 0; it < 200; it++) {
+      const double mid = 0.5 * (lo_c + hi_c);
+      if (points(mid) > (double)n) lo_c = mid;
+      else hi_c = mid;
+    }
+  }
+  const double cscale = 0.5 * (lo_c + hi_c);
   const double maxcells = dim == 3 ? 2097151.0 : 4294967295.0;
   F.dim = dim;
   for (int a = 0; a < dim; a++) {
     F.lo[a] = lo[a];
     F.scale[a] = 0.0;
-    if (hi[a] > lo[a]) {
-      const double cells = std::min(maxcells, std::max(1.0, std::round((hi[a] - lo[a]) / hcell) - 1.0));
+    if (hi[a] > lo[a] && mean_edge[a] > 0.0) {
+      const double ha = cscale * mean_edge[a];
+      const double cells = std::min(maxcells, std::max(1.0, std::round((hi[a] - lo[a]) / ha)));
       F.scale[a] = cells / (hi[a] - lo[a]);
     }
   }
