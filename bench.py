@@ -175,6 +175,10 @@ def run_graft(args):
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # torchrun pins OMP_NUM_THREADS=1; the once-per-mesh host preprocessing (sparsity, plans) is
+        # OpenMP code, so give every rank its share of the host cores
+        if os.environ.get("OMP_NUM_THREADS", "1") == "1":
+            os.environ["OMP_NUM_THREADS"] = str(max(1, len(os.sched_getaffinity(0)) // world))
 
     c = args.cells
     t_setup = time.perf_counter()
