@@ -342,8 +342,18 @@ def run_graft(args):
     bytes_tra = syn.algorithmic_bytes(3, n_nodes_local, n_el_local, nnz, "tracer")
     m_ms, a_ms = float(np.mean(mom_ms)), float(np.mean(adv_ms))
     ach = bytes_mom * n_el_local / (m_ms * 1e-3) / 1e9
+    # measured DRAM bytes per launch of the same kernel (ncu capture of this command, profiles/)
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            tr = json.load(f)["kernels"]["momentum"]
+        if chosen == "gather" and world == 1 and tr["elements"] == n_el_local:
+            traffic = tr["dram_bytes_per_launch"]
+    except (OSError, KeyError, ValueError):
+        pass
     roofline = {"bound": "hbm", "kernel": "momentum assembly (%s scatter)" % chosen, "achieved": ach, "peak": peak,
-                "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": bytes_mom * n_el_local,
                 "algorithmic_bytes_per_element": bytes_mom, "kernel_ms": m_ms,
                 "frac_of_8TBs": ach / 8000.0,
                 "tracer": {"achieved": bytes_tra * n_el_local / (a_ms * 1e-3) / 1e9,

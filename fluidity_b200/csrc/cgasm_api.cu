@@ -153,8 +153,11 @@ static int check_momentum_opts(const cgasm_momentum_opts* o) {
       o->cmc_lump_on_submesh || o->abs_lump_on_submesh || o->assemble_mass_matrix ||
       o->integrate_continuity_by_parts)
     CG_FAIL(CGASM_EUNSUPPORTED, "momentum option outside the device path; keep the Fortran loop");
-  if (o->stabilisation_scheme != CGASM_STAB_NONE)
-    CG_FAIL(CGASM_EUNSUPPORTED, "momentum stabilisation (SU/SUPG) not on the device path yet");
+  if (o->stabilisation_scheme < CGASM_STAB_NONE || o->stabilisation_scheme > CGASM_STAB_SUPG)
+    CG_FAIL(CGASM_EARG, "bad stabilisation_scheme");
+  if (o->stabilisation_scheme != CGASM_STAB_NONE &&
+      (o->nu_bar_scheme < CGASM_NU_BAR_OPTIMAL || o->nu_bar_scheme > CGASM_NU_BAR_UNITY || o->nu_bar_scale < 0.0))
+    CG_FAIL(CGASM_EARG, "bad nu_bar scheme / scale");
   if (o->have_viscosity && (o->viscosity_shape < 0 || o->viscosity_shape > CGASM_TENSOR_FULL))
     CG_FAIL(CGASM_EARG, "bad viscosity_shape");
   return CGASM_OK;
@@ -163,8 +166,11 @@ static int check_momentum_opts(const cgasm_momentum_opts* o) {
 static int check_advdiff_opts(const cgasm_advdiff_opts* o) {
   if (o->move_mesh || o->multiphase || o->equation_type_not_advdiff)
     CG_FAIL(CGASM_EUNSUPPORTED, "tracer option outside the device path; keep the Fortran loop");
-  if (o->stabilisation_scheme != CGASM_STAB_NONE)
-    CG_FAIL(CGASM_EUNSUPPORTED, "tracer stabilisation (SU/SUPG) not on the device path yet");
+  if (o->stabilisation_scheme < CGASM_STAB_NONE || o->stabilisation_scheme > CGASM_STAB_SUPG)
+    CG_FAIL(CGASM_EARG, "bad stabilisation_scheme");
+  if (o->stabilisation_scheme != CGASM_STAB_NONE &&
+      (o->nu_bar_scheme < CGASM_NU_BAR_OPTIMAL || o->nu_bar_scheme > CGASM_NU_BAR_UNITY || o->nu_bar_scale < 0.0))
+    CG_FAIL(CGASM_EARG, "bad nu_bar scheme / scale");
   if (o->have_diffusivity && o->diffusivity_shape != CGASM_TENSOR_ISOTROPIC &&
       o->diffusivity_shape != CGASM_TENSOR_FULL)
     CG_FAIL(CGASM_EARG, "bad diffusivity_shape");
@@ -593,6 +599,9 @@ int cgasm_momentum_dev(int id, const cgasm_momentum_opts* opts) {
   if ((st = ensure(&h->d_mom_rhs, dim * nn))) return st;
   if (want_ml && (st = ensure(&h->d_masslump, dim * nn))) return st;
   if (want_ct && (st = ensure(&h->d_ct_m, dim * nnz))) return st;
+  if (opts->stabilisation_scheme != CGASM_STAB_NONE && h->scatter != CGASM_SCATTER_ATOMIC &&
+      h->scatter != CGASM_SCATTER_GATHER)
+    CG_FAIL(CGASM_EUNSUPPORTED, "SU/SUPG stabilisation runs on the ATOMIC and GATHER scatter variants only");
   CG_CUDA(cudaEventRecord(h->ev0, h->stream));
   if (h->scatter == CGASM_SCATTER_TILED) {
     st = tiles_momentum(h, A, want_ml, want_ct);
@@ -625,6 +634,9 @@ int cgasm_advdiff_dev(int id, const cgasm_advdiff_opts* opts) {
   const size_t nnz = (size_t)h->nnz, nn = (size_t)h->n_nodes;
   if ((st = ensure(&h->d_adv_matrix, nnz))) return st;
   if ((st = ensure(&h->d_adv_rhs, nn))) return st;
+  if (opts->stabilisation_scheme != CGASM_STAB_NONE && h->scatter != CGASM_SCATTER_ATOMIC &&
+      h->scatter != CGASM_SCATTER_GATHER)
+    CG_FAIL(CGASM_EUNSUPPORTED, "SU/SUPG stabilisation runs on the ATOMIC and GATHER scatter variants only");
   CG_CUDA(cudaEventRecord(h->ev0, h->stream));
   if (h->scatter == CGASM_SCATTER_TILED) {
     st = tiles_advdiff(h, P);

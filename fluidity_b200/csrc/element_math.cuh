@@ -161,6 +161,142 @@ __device__ __forceinline__ void at_quad(const Tables& t, const double (&f)[DIM +
   }
 }
 
+// ---- upwind stabilisation (assemble/Upwind_Stabilisation.F90) ------------------------------------
+// nu_bar_scaled_q :225-320 with xi_optimal :133-162, xi_doubly_asymptotic :164-192,
+// xi_critical_rule :194-223. Jm(a,k) = J(a,k,g) (constant over a P1 element); diff = NULL-like flag
+// have_diff false => NU_BAR_UNITY (:248-251). inverse() of the dim x dim diffusivity by cofactors.
+template <int DIM>
+__device__ __forceinline__ void small_inverse(const double (&A)[DIM * DIM], double (&B)[DIM * DIM]) {
+  if constexpr (DIM == 2) {
+    const double det = A[0] * A[3] - A[2] * A[1];
+    B[0] = A[3] / det;
+    B[1] = -A[1] / det;
+    B[2] = -A[2] / det;
+    B[3] = A[0] / det;
+  } else {
+#define A_(i, j) A[(i) + 3 * (j)]
+    const double c00 = A_(1, 1) * A_(2, 2) - A_(1, 2) * A_(2, 1);
+    const double c01 = A_(1, 2) * A_(2, 0) - A_(1, 0) * A_(2, 2);
+    const double c02 = A_(1, 0) * A_(2, 1) - A_(1, 1) * A_(2, 0);
+    const double det = A_(0, 0) * c00 + A_(0, 1) * c01 + A_(0, 2) * c02;
+    B[0 + 3 * 0] = c00 / det;
+    B[1 + 3 * 0] = c01 / det;
+    B[2 + 3 * 0] = c02 / det;
+    B[0 + 3 * 1] = (A_(0, 2) * A_(2, 1) - A_(0, 1) * A_(2, 2)) / det;
+    B[1 + 3 * 1] = (A_(0, 0) * A_(2, 2) - A_(0, 2) * A_(2, 0)) / det;
+    B[2 + 3 * 1] = (A_(0, 1) * A_(2, 0) - A_(0, 0) * A_(2, 1)) / det;
+    B[0 + 3 * 2] = (A_(0, 1) * A_(1, 2) - A_(0, 2) * A_(1, 1)) / det;
+    B[1 + 3 * 2] = (A_(0, 2) * A_(1, 0) - A_(0, 0) * A_(1, 2)) / det;
+    B[2 + 3 * 2] = (A_(0, 0) * A_(1, 1) - A_(0, 1) * A_(1, 0)) / det;
+#undef A_
+  }
+}
+
+template <int DIM>
+__device__ __forceinline__ double nu_bar_scaled(const double (&u)[DIM], const double (&Jm)[DIM][DIM], bool have_diff,
+                                                const double (&diff)[DIM * DIM], int scheme, double scale) {
+  const double tolerance = 1.0e-10, tanh_tolerance = 11.859499013855018;  // :50-51
+  double norm_u = 0.0;
+#pragma unroll
+  for (int d = 0; d < DIM; d++) norm_u += u[d] * u[d];
+  if (norm_u < tolerance) return 0.0;
+  double uJ[DIM];
+#pragma unroll
+  for (int k = 0; k < DIM; k++) {
+    double s = 0.0;
+#pragma unroll
+    for (int a = 0; a < DIM; a++) s += u[a] * Jm[a][k];
+    uJ[k] = s;
+  }
+  double val = 0.0;
+  if (!have_diff || scheme == CGASM_NU_BAR_UNITY) {
+#pragma unroll
+    for (int k = 0; k < DIM; k++) val += fabs(uJ[k]);
+  } else {
+    double inv[DIM * DIM];
+    small_inverse<DIM>(diff, inv);
+#pragma unroll
+    for (int k = 0; k < DIM; k++) {
+      double p = 0.0;  // pe = 0.5 * u . (J . inverse(diff))
+#pragma unroll
+      for (int a = 0; a < DIM; a++) {
+        double jd = 0.0;
+#pragma unroll
+        for (int b = 0; b < DIM; b++) jd += Jm[a][b] * inv[b + DIM * k];
+        p += u[a] * jd;
+      }
+      p *= 0.5;
+      double xi;
+      if (scheme == CGASM_NU_BAR_OPTIMAL) {
+        if (fabs(p) < tolerance) xi = 0.0;
+        else if (p > tanh_tolerance) xi = 1.0 - (1.0 / p);
+        else if (p < -tanh_tolerance) xi = -1.0 - (1.0 / p);
+        else xi = (1.0 / tanh(p)) - (1.0 / p);
+      } else if (scheme == CGASM_NU_BAR_DOUBLY_ASYMPTOTIC) {
+        if (fabs(p) <= 3.0) xi = p / 3.0;
+        else xi = p > 0.0 ? 1.0 : -1.0;
+      } else {
+        if (fabs(p) <= 1.0) xi = 0.0;
+        else xi = p > 0.0 ? 1.0 - 1.0 / p : -1.0 - 1.0 / p;
+      }
+      val += xi * uJ[k];
+    }
+  }
+  return val / norm_u * scale;
+}
+
+// Everything the stabilised element routines need beyond the Galerkin terms:
+//   STAB 1 (SU):   stab_ij = sum_g (u_g.gradN_i)(u_g.gradN_j) nubar_g detwei_g      (:82-131)
+//   STAB 2 (SUPG): test function n(i,g) + nubar_g (u_g.gradN_i)                      (:418-454)
+template <int DIM, int STAB>
+struct Stabilisation {
+  static constexpr int LOC = DIM + 1, NGI = Shape<DIM>::NGI;
+  double nt[STAB == 2 ? LOC * NGI : 1];    // SUPG test function
+  double udn[STAB == 1 ? LOC * NGI : 1];   // u_g . gradN_i
+  double wq[STAB == 1 ? NGI : 1];          // nubar_g * detwei_g
+  __device__ __forceinline__ double test(const Tables& t, int i, int g) const {
+    if constexpr (STAB == 2) return nt[i * NGI + g];
+    else return t.N[i * NGI + g];
+  }
+  // ug: u at quadrature points; diffq(g): diffusivity at g (dim x dim, column-major) if have_diff
+  template <class DiffAt>
+  __device__ __forceinline__ void setup(const Tables& t, const Geom<DIM>& G, const double (&ug)[NGI][DIM], bool have_diff,
+                                        DiffAt diff_at, int scheme, double scale) {
+    if constexpr (STAB != 0) {
+      double Jm[DIM][DIM];  // J(:,:,gi) = transpose(J_local_T), Transform_elements.F90:878-882
+#pragma unroll
+      for (int a = 0; a < DIM; a++)
+#pragma unroll
+        for (int k = 0; k < DIM; k++) Jm[a][k] = G.JT[k][a];
+#pragma unroll
+      for (int g = 0; g < NGI; g++) {
+        double dq[DIM * DIM];
+#pragma unroll
+        for (int ab = 0; ab < DIM * DIM; ab++) dq[ab] = 0.0;
+        if (have_diff) diff_at(g, dq);
+        const double nb = nu_bar_scaled<DIM>(ug[g], Jm, have_diff, dq, scheme, scale);
+#pragma unroll
+        for (int i = 0; i < LOC; i++) {
+          double s = 0.0;
+#pragma unroll
+          for (int a = 0; a < DIM; a++) s += ug[g][a] * G.grad[i][a];
+          if constexpr (STAB == 2) nt[i * NGI + g] = t.N[i * NGI + g] + nb * s;
+          if constexpr (STAB == 1) udn[i * NGI + g] = s;
+        }
+        if constexpr (STAB == 1) wq[g] = nb * G.absdet * t.w[g];
+      }
+    }
+  }
+  __device__ __forceinline__ double su(int i, int j) const {
+    double s = 0.0;
+    if constexpr (STAB == 1) {
+#pragma unroll
+      for (int g = 0; g < NGI; g++) s += (udn[i * NGI + g] * wq[g]) * udn[j * NGI + g];
+    }
+    return s;
+  }
+};
+
 // ---- momentum -----------------------------------------------------------------------------
 // Result of one element. L is the part of the diagonal blocks common to every velocity
 // component; Labs[d] is added to block d only (non-lumped absorption); diag[d][i] is the
@@ -177,7 +313,8 @@ struct MomentumLocal {
 
 // LABS must be true iff (have_absorption && !lump_absorption); the launcher picks the
 // instantiation, so kernels without that option never hold the dim*loc*loc extra block.
-template <int DIM, bool LABS>
+// STAB: CGASM_STAB_* (0 none, 1 streamline upwind, 2 SUPG), Momentum_CG.F90:1345-1372, :1686-1708.
+template <int DIM, bool LABS, int STAB = 0>
 __device__ __forceinline__ void momentum_element(const MomentumArgs& A, const int4 nd,
                                                  MomentumLocal<DIM, LABS>& R, Geom<DIM>& G) {
   constexpr int LOC = DIM + 1, NGI = Shape<DIM>::NGI;
@@ -218,6 +355,37 @@ __device__ __forceinline__ void momentum_element(const MomentumArgs& A, const in
       R.ml[d][i] = 0.0;
     }
 
+  // relu_gi = ele_val_at_quad(nu) (:1347, :1639)
+  double ug[NGI][DIM];
+#pragma unroll
+  for (int g = 0; g < NGI; g++)
+#pragma unroll
+    for (int a = 0; a < DIM; a++) {
+      double s = 0.0;
+#pragma unroll
+      for (int i = 0; i < LOC; i++) s += nu[i][a] * t.N[i * NGI + g];
+      ug[g][a] = s;
+    }
+  Stabilisation<DIM, STAB> ST;
+  if constexpr (STAB != 0) {
+    // diff_q = viscosity at the quadrature points with the off-diagonal entries zeroed (:1351-1360)
+    auto diff_at = [&](int g, double (&dq)[DIM * DIM]) {
+#pragma unroll
+      for (int a = 0; a < DIM; a++) {
+        double vv = 0.0;
+        if (A.viscosity.stride == 0) {
+          vv = __ldg(A.viscosity.val + a + DIM * a);
+        } else {
+#pragma unroll
+          for (int i = 0; i < LOC; i++)
+            vv += __ldg(A.viscosity.val + (size_t)A.viscosity.stride * node_of(nd, i) + a + DIM * a) * t.N[i * NGI + g];
+        }
+        dq[a + DIM * a] = vv;
+      }
+    };
+    ST.setup(t, G, ug, o.have_viscosity != 0, diff_at, o.nu_bar_scheme, o.nu_bar_scale);
+  }
+
   // v[i] accumulates the vector such that (A + K)_ij = v[i] . gradN_j
   double v[LOC][DIM];
 #pragma unroll
@@ -232,20 +400,19 @@ __device__ __forceinline__ void momentum_element(const MomentumArgs& A, const in
 #pragma unroll
       for (int i = 0; i < LOC; i++)
 #pragma unroll
-        for (int j = i; j < LOC; j++) {
+        for (int j = 0; j < LOC; j++) {
           double s = 0.0;
 #pragma unroll
-          for (int g = 0; g < NGI; g++) s += (t.N[i * NGI + g] * t.N[j * NGI + g]) * c[g];
+          for (int g = 0; g < NGI; g++) s += (ST.test(t, i, g) * t.N[j * NGI + g]) * c[g];
           R.L[i][j] += s;
-          if (j != i) R.L[j][i] += s;
         }
     }
-    double m[LOC];  // sum(mass_mat,2) = sum_g N_ig c_g
+    double m[LOC];  // sum(mass_mat,2) = sum_g test_ig c_g
 #pragma unroll
     for (int i = 0; i < LOC; i++) {
       double s = 0.0;
 #pragma unroll
-      for (int g = 0; g < NGI; g++) s += t.N[i * NGI + g] * c[g];
+      for (int g = 0; g < NGI; g++) s += ST.test(t, i, g) * c[g];
       m[i] = s;
     }
 #pragma unroll
@@ -259,16 +426,6 @@ __device__ __forceinline__ void momentum_element(const MomentumArgs& A, const in
 
   // Advection (add_advection_element_cg, :1602-1715)
   if (!o.exclude_advection) {
-    double ug[NGI][DIM];
-#pragma unroll
-    for (int g = 0; g < NGI; g++)
-#pragma unroll
-      for (int a = 0; a < DIM; a++) {
-        double s = 0.0;
-#pragma unroll
-        for (int i = 0; i < LOC; i++) s += nu[i][a] * t.N[i * NGI + g];
-        ug[g][a] = s;
-      }
     double divu = 0.0;  // ele_div_at_quad: constant over the element for P1
 #pragma unroll
     for (int i = 0; i < LOC; i++)
@@ -298,8 +455,8 @@ __device__ __forceinline__ void momentum_element(const MomentumArgs& A, const in
           for (int a = 0; a < DIM; a++) s += G.grad[i][a] * Cj[j][a];
           double mm = 0.0;
 #pragma unroll
-          for (int g = 0; g < NGI; g++) mm += (t.N[i * NGI + g] * t.N[j * NGI + g]) * c[g];
-          const double aij = -s - f * mm;
+          for (int g = 0; g < NGI; g++) mm += (ST.test(t, i, g) * t.N[j * NGI + g]) * c[g];
+          const double aij = -s - f * mm + ST.su(i, j);
           R.L[i][j] += dtt * aij;
 #pragma unroll
           for (int d = 0; d < DIM; d++) R.rhs[d][i] -= aij * oldu[j][d];
@@ -312,11 +469,11 @@ __device__ __forceinline__ void momentum_element(const MomentumArgs& A, const in
         for (int a = 0; a < DIM; a++) {
           double s = 0.0;
 #pragma unroll
-          for (int g = 0; g < NGI; g++) s += t.N[i * NGI + g] * (c[g] * ug[g][a]);
+          for (int g = 0; g < NGI; g++) s += ST.test(t, i, g) * (c[g] * ug[g][a]);
           v[i][a] += s;
         }
       have_v = true;
-      if (o.beta != 0.0) {
+      if (o.beta != 0.0 || STAB == 1) {
         const double f = o.beta * divu;
 #pragma unroll
         for (int i = 0; i < LOC; i++)
@@ -324,8 +481,8 @@ __device__ __forceinline__ void momentum_element(const MomentumArgs& A, const in
           for (int j = 0; j < LOC; j++) {
             double mm = 0.0;
 #pragma unroll
-            for (int g = 0; g < NGI; g++) mm += (t.N[i * NGI + g] * t.N[j * NGI + g]) * c[g];
-            const double aij = f * mm;
+            for (int g = 0; g < NGI; g++) mm += (ST.test(t, i, g) * t.N[j * NGI + g]) * c[g];
+            const double aij = f * mm + ST.su(i, j);
             R.L[i][j] += dtt * aij;
 #pragma unroll
             for (int d = 0; d < DIM; d++) R.rhs[d][i] -= aij * oldu[j][d];
@@ -407,7 +564,7 @@ __device__ __forceinline__ void momentum_element(const MomentumArgs& A, const in
       if (o.lump_source) {
         double s = 0.0;
 #pragma unroll
-        for (int g = 0; g < NGI; g++) s += t.N[i * NGI + g] * c[g];
+        for (int g = 0; g < NGI; g++) s += ST.test(t, i, g) * c[g];
 #pragma unroll
         for (int d = 0; d < DIM; d++) R.rhs[d][i] += s * src[i][d];
       } else {
@@ -415,7 +572,7 @@ __device__ __forceinline__ void momentum_element(const MomentumArgs& A, const in
         for (int j = 0; j < LOC; j++) {
           double mm = 0.0;
 #pragma unroll
-          for (int g = 0; g < NGI; g++) mm += (t.N[i * NGI + g] * t.N[j * NGI + g]) * c[g];
+          for (int g = 0; g < NGI; g++) mm += (ST.test(t, i, g) * t.N[j * NGI + g]) * c[g];
 #pragma unroll
           for (int d = 0; d < DIM; d++) R.rhs[d][i] += mm * src[j][d];
         }
@@ -446,7 +603,7 @@ __device__ __forceinline__ void momentum_element(const MomentumArgs& A, const in
       for (int i = 0; i < LOC; i++) {
         double s = 0.0;
 #pragma unroll
-        for (int g = 0; g < NGI; g++) s += t.N[i * NGI + g] * bq[g];
+        for (int g = 0; g < NGI; g++) s += ST.test(t, i, g) * bq[g];
 #pragma unroll
         for (int d = 0; d < DIM; d++) R.rhs[d][i] += s * gd[d];
       }
@@ -467,7 +624,7 @@ __device__ __forceinline__ void momentum_element(const MomentumArgs& A, const in
 #pragma unroll
         for (int i = 0; i < LOC; i++)
 #pragma unroll
-          for (int d = 0; d < DIM; d++) R.rhs[d][i] += t.N[i * NGI + g] * gg[d];
+          for (int d = 0; d < DIM; d++) R.rhs[d][i] += ST.test(t, i, g) * gg[d];
       }
     }
   }
@@ -491,9 +648,9 @@ __device__ __forceinline__ void momentum_element(const MomentumArgs& A, const in
       for (int d = 0; d < DIM; d++)
 #pragma unroll
         for (int i = 0; i < LOC; i++) {
-          double s = 0.0;  // sum_j Ab_ij = sum_g N_ig sigma_dg c_g
+          double s = 0.0;  // sum_j Ab_ij = sum_g test_ig sigma_dg c_g
 #pragma unroll
-          for (int g = 0; g < NGI; g++) s += t.N[i * NGI + g] * sq[g][d];
+          for (int g = 0; g < NGI; g++) s += ST.test(t, i, g) * sq[g][d];
           R.diag[d][i] += dtt * s;
           R.rhs[d][i] -= s * oldu[i][d];
           if (o.pressure_corrected_absorption && o.assemble_inverse_masslump) R.ml[d][i] += dtt * s;
@@ -507,7 +664,7 @@ __device__ __forceinline__ void momentum_element(const MomentumArgs& A, const in
           for (int j = 0; j < LOC; j++) {
             double s = 0.0;
 #pragma unroll
-            for (int g = 0; g < NGI; g++) s += (t.N[i * NGI + g] * t.N[j * NGI + g]) * sq[g][d];
+            for (int g = 0; g < NGI; g++) s += (ST.test(t, i, g) * t.N[j * NGI + g]) * sq[g][d];
             R.Labs[d][i][j] = dtt * s;
             R.rhs[d][i] -= s * oldu[j][d];
           }
@@ -533,7 +690,7 @@ struct AdvDiffLocal {
   double rhs[LOC];
 };
 
-template <int DIM>
+template <int DIM, int STAB = 0>
 __device__ __forceinline__ void advdiff_element(const AdvDiffArgs& P, const int4 nd,
                                                 AdvDiffLocal<DIM>& R) {
   constexpr int LOC = DIM + 1, NGI = Shape<DIM>::NGI;
@@ -559,6 +716,43 @@ __device__ __forceinline__ void advdiff_element(const AdvDiffArgs& P, const int4
     for (int j = 0; j < LOC; j++) R.A[i][j] = 0.0;
   }
 
+  // velocity at the quadrature points + stabilisation (:813-826, :1107-1119)
+  double u[LOC][DIM], uq[NGI][DIM];
+  Stabilisation<DIM, STAB> ST;
+  if (o.have_advection || STAB != 0) {
+#pragma unroll
+    for (int i = 0; i < LOC; i++) {
+      double unused;
+      unpack<DIM>(ld256(P.rec.r1 + node_of(nd, i)), u[i], unused);
+    }
+#pragma unroll
+    for (int g = 0; g < NGI; g++)
+#pragma unroll
+      for (int a = 0; a < DIM; a++) {
+        double s = 0.0;
+#pragma unroll
+        for (int i = 0; i < LOC; i++) s += u[i][a] * t.N[i * NGI + g];
+        uq[g][a] = s;
+      }
+  }
+  if constexpr (STAB != 0) {
+    auto diff_at = [&](int g, double (&dq)[DIM * DIM]) {
+#pragma unroll
+      for (int ab = 0; ab < DIM * DIM; ab++) {
+        double vv = 0.0;
+        if (P.diffusivity.stride == 0) {
+          vv = __ldg(P.diffusivity.val + ab);
+        } else {
+#pragma unroll
+          for (int i = 0; i < LOC; i++)
+            vv += __ldg(P.diffusivity.val + (size_t)P.diffusivity.stride * node_of(nd, i) + ab) * t.N[i * NGI + g];
+        }
+        dq[ab] = vv;
+      }
+    };
+    ST.setup(t, G, uq, o.have_diffusivity != 0, diff_at, o.nu_bar_scheme, o.nu_bar_scale);
+  }
+
   // Mass (:867-941): M_ij = |detJ| sum_g N_ig N_jg w_g ; lumped -> |detJ| sum_g N_ig w_g
   if (o.have_mass) {
 #pragma unroll
@@ -566,14 +760,14 @@ __device__ __forceinline__ void advdiff_element(const AdvDiffArgs& P, const int4
       if (o.lump_mass) {
         double s = 0.0;
 #pragma unroll
-        for (int g = 0; g < NGI; g++) s += t.N[i * NGI + g] * t.w[g];
+        for (int g = 0; g < NGI; g++) s += ST.test(t, i, g) * t.w[g];
         R.A[i][i] += s * G.absdet;
       } else {
 #pragma unroll
         for (int j = 0; j < LOC; j++) {
           double s = 0.0;
 #pragma unroll
-          for (int g = 0; g < NGI; g++) s += (t.N[i * NGI + g] * t.N[j * NGI + g]) * t.w[g];
+          for (int g = 0; g < NGI; g++) s += (ST.test(t, i, g) * t.N[j * NGI + g]) * t.w[g];
           R.A[i][j] += s * G.absdet;
         }
       }
@@ -589,21 +783,11 @@ __device__ __forceinline__ void advdiff_element(const AdvDiffArgs& P, const int4
 
   // Advection (:943-1127, default equation type)
   if (o.have_advection) {
-    double u[LOC][DIM], ug[NGI][DIM];
-#pragma unroll
-    for (int i = 0; i < LOC; i++) {
-      double unused;
-      unpack<DIM>(ld256(P.rec.r1 + node_of(nd, i)), u[i], unused);
-    }
+    double ug[NGI][DIM];  // u_g detwei_g
 #pragma unroll
     for (int g = 0; g < NGI; g++)
 #pragma unroll
-      for (int a = 0; a < DIM; a++) {
-        double s = 0.0;
-#pragma unroll
-        for (int i = 0; i < LOC; i++) s += u[i][a] * t.N[i * NGI + g];
-        ug[g][a] = s * (G.absdet * t.w[g]);  // u_g detwei_g
-      }
+      for (int a = 0; a < DIM; a++) ug[g][a] = uq[g][a] * (G.absdet * t.w[g]);
     double divu = 0.0;
 #pragma unroll
     for (int i = 0; i < LOC; i++)
@@ -631,9 +815,10 @@ __device__ __forceinline__ void advdiff_element(const AdvDiffArgs& P, const int4
           if (with_div) {
             double mm = 0.0;
 #pragma unroll
-            for (int g = 0; g < NGI; g++) mm += (t.N[i * NGI + g] * t.N[j * NGI + g]) * t.w[g];
+            for (int g = 0; g < NGI; g++) mm += (ST.test(t, i, g) * t.N[j * NGI + g]) * t.w[g];
             aij -= f * mm;
           }
+          aij += ST.su(i, j);
           if (implicit) R.A[i][j] += dtt * aij;
           R.rhs[i] -= aij * T[j];
         }
@@ -645,20 +830,21 @@ __device__ __forceinline__ void advdiff_element(const AdvDiffArgs& P, const int4
         for (int a = 0; a < DIM; a++) {
           double s = 0.0;
 #pragma unroll
-          for (int g = 0; g < NGI; g++) s += t.N[i * NGI + g] * ug[g][a];
+          for (int g = 0; g < NGI; g++) s += ST.test(t, i, g) * ug[g][a];
           v[i][a] += s;
         }
       have_v = true;
-      if (fabs(o.beta) > eps) {  // :1093
-        const double f = o.beta * divu * G.absdet;
+      const bool with_div = fabs(o.beta) > eps;  // :1093
+      if (with_div || STAB == 1) {
+        const double f = with_div ? o.beta * divu * G.absdet : 0.0;
 #pragma unroll
         for (int i = 0; i < LOC; i++)
 #pragma unroll
           for (int j = 0; j < LOC; j++) {
             double mm = 0.0;
 #pragma unroll
-            for (int g = 0; g < NGI; g++) mm += (t.N[i * NGI + g] * t.N[j * NGI + g]) * t.w[g];
-            const double aij = f * mm;
+            for (int g = 0; g < NGI; g++) mm += (ST.test(t, i, g) * t.N[j * NGI + g]) * t.w[g];
+            const double aij = f * mm + ST.su(i, j);
             if (implicit) R.A[i][j] += dtt * aij;
             R.rhs[i] -= aij * T[j];
           }
@@ -739,7 +925,7 @@ __device__ __forceinline__ void advdiff_element(const AdvDiffArgs& P, const int4
       for (int j = 0; j < LOC; j++) {
         double s = 0.0;
 #pragma unroll
-        for (int g = 0; g < NGI; g++) s += (t.N[i * NGI + g] * t.N[j * NGI + g]) * sq[g];
+        for (int g = 0; g < NGI; g++) s += (ST.test(t, i, g) * t.N[j * NGI + g]) * sq[g];
         if (implicit) R.A[i][j] += dtt * s;
         R.rhs[i] -= s * T[j];
       }
@@ -761,7 +947,7 @@ __device__ __forceinline__ void advdiff_element(const AdvDiffArgs& P, const int4
     for (int i = 0; i < LOC; i++) {
       double s = 0.0;
 #pragma unroll
-      for (int g = 0; g < NGI; g++) s += t.N[i * NGI + g] * sq[g];
+      for (int g = 0; g < NGI; g++) s += ST.test(t, i, g) * sq[g];
       R.rhs[i] += s;
     }
   }
@@ -782,6 +968,7 @@ __device__ __forceinline__ void advdiff_element(const AdvDiffArgs& P, const int4
 __host__ __device__ inline bool momentum_fast_ok(const cgasm_momentum_opts& o, int gravity_stride,
                                                  int absorption_stride) {
   (void)absorption_stride;
+  if (o.stabilisation_scheme != CGASM_STAB_NONE) return false;
   if (o.have_source) return false;
   if (o.have_absorption && !o.lump_absorption) return false;
   if (!o.exclude_mass && !o.lump_mass) return false;
@@ -973,6 +1160,7 @@ __device__ __forceinline__ void momentum_fast(const MomentumArgs& A, const int4 
 }
 
 __host__ __device__ inline bool advdiff_fast_ok(const cgasm_advdiff_opts& o) {
+  if (o.stabilisation_scheme != CGASM_STAB_NONE) return false;
   if (o.have_absorption) return false;
   if (o.have_advection && (o.integrate_advection_by_parts || o.beta != 0.0)) return false;
   return true;

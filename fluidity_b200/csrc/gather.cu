@@ -35,9 +35,9 @@ struct GatherPlan {
   long long* d_block_ptr = nullptr;  // [nblocks+1] first plan entry of a block
   uint2* d_pairs = nullptr;        // block-interleaved: entry k of thread t at ptr + k*kBR + t
                                    //   .x = element*4 + local row (0xFFFFFFFF = none), .y = 4 x 8-bit slot
-  int4* d_pair_nodes = nullptr;    // same indexing: the element's nodes ROTATED so the row's own node is
-                                   //   first (.x < 0 = none); slot byte j of .y belongs to rotated node j
-  unsigned* d_pair_rslots = nullptr;  // slots in rotated order
+  int4* d_pair_nodes = nullptr;    // same indexing, ONE 16-byte load per pair: {n1, n2, n3, slots} = the element's
+                                   //   other nodes in rotated order (the row's own node is rotated node 0;
+                                   //   n1 < 0 = none) and the 4 x 8-bit CSR slots of rotated nodes 0..3
   long long n_entries = 0;
   double* d_stage = nullptr;       // staging buffer (grown on demand)
   size_t stage_doubles = 0;
@@ -50,7 +50,6 @@ void gather_free(Handle* h) {
   if (p->d_block_ptr) cudaFree(p->d_block_ptr);
   if (p->d_pairs) cudaFree(p->d_pairs);
   if (p->d_pair_nodes) cudaFree(p->d_pair_nodes);
-  if (p->d_pair_rslots) cudaFree(p->d_pair_rslots);
   if (p->d_stage) cudaFree(p->d_stage);
   delete p;
   h->gather = nullptr;
@@ -63,7 +62,7 @@ __global__ void gather_pairs_kernel(int nblocks, int loc, const int* __restrict_
                                     const long long* __restrict__ n2e_ptr, const int* __restrict__ n2e,
                                     const int4* __restrict__ ndglno, const int* __restrict__ findrm,
                                     const int* __restrict__ colm, uint2* __restrict__ pairs,
-                                    int4* __restrict__ pair_nodes, unsigned* __restrict__ pair_rslots) {
+                                    int4* __restrict__ pair_nodes) {
   const int b = blockIdx.x, t = threadIdx.x;
   if (b >= nblocks) return;
   const int r = rows[b * kBR + t];
@@ -94,14 +93,12 @@ __global__ void gather_pairs_kernel(int nblocks, int loc, const int* __restrict_
         rn[jj] = nodes[j];
         rs |= ((slots >> (8 * j)) & 0xffu) << (8 * jj);
       }
-      pair_nodes[base + (long long)k * kBR + t] = make_int4(rn[0], rn[1], rn[2], rn[3]);
-      pair_rslots[base + (long long)k * kBR + t] = rs;
+      pair_nodes[base + (long long)k * kBR + t] = make_int4(rn[1], rn[2], loc == 4 ? rn[3] : rn[0], (int)rs);
     }
   }
   for (int k = deg; k < deg_block; k++) {
     pairs[base + (long long)k * kBR + t] = make_uint2(0xFFFFFFFFu, 0u);
-    pair_nodes[base + (long long)k * kBR + t] = make_int4(-1, -1, -1, -1);
-    pair_rslots[base + (long long)k * kBR + t] = 0u;
+    pair_nodes[base + (long long)k * kBR + t] = make_int4(-1, -1, -1, 0);
   }
 }
 
@@ -142,7 +139,6 @@ int gather_build(Handle* h) {
   CG_CUDA(cudaMemcpy(P->d_block_ptr, block_ptr.data(), sizeof(long long) * block_ptr.size(), cudaMemcpyHostToDevice));
   CG_CUDA(cudaMalloc(&P->d_pairs, sizeof(uint2) * (size_t)std::max<long long>(P->n_entries, 1)));
   CG_CUDA(cudaMalloc(&P->d_pair_nodes, sizeof(int4) * (size_t)std::max<long long>(P->n_entries, 1)));
-  CG_CUDA(cudaMalloc(&P->d_pair_rslots, sizeof(unsigned) * (size_t)std::max<long long>(P->n_entries, 1)));
   // node->element adjacency goes to the device only for the duration of the plan build
   long long* d_n2e_ptr = nullptr;
   int* d_n2e = nullptr;
@@ -154,7 +150,7 @@ int gather_build(Handle* h) {
   if (e1 == cudaSuccess && e2 == cudaSuccess) {
     gather_pairs_kernel<<<P->nblocks, kBR, 0, h->stream>>>(P->nblocks, h->loc, P->d_rows, P->d_block_ptr, d_n2e_ptr,
                                                           d_n2e, h->d_ndglno, h->d_findrm, h->d_colm, P->d_pairs,
-                                                          P->d_pair_nodes, P->d_pair_rslots);
+                                                          P->d_pair_nodes);
     h->launches++;
     e1 = cudaStreamSynchronize(h->stream);
   }
@@ -196,7 +192,7 @@ __device__ __forceinline__ void store_rec(double* dst, const double (&v)[RS]) {
 
 // ---- pass A ----------------------------------------------------------------------------------------
 // momentum, generic options: NB = 1 (no absorption) or DIM; NV = DIM + MLC
-template <int DIM, bool LABS, int NB, int MLC>
+template <int DIM, bool LABS, int NB, int MLC, int STAB>
 __global__ void __launch_bounds__(128)
 gather_momentum_stage_kernel(const MomentumArgs A, double* __restrict__ stage) {
   constexpr int LOC = DIM + 1;
@@ -206,7 +202,7 @@ gather_momentum_stage_kernel(const MomentumArgs A, double* __restrict__ stage) {
   const int4 nd = __ldg(A.ndglno + e);
   MomentumLocal<DIM, LABS> R;
   Geom<DIM> G;
-  momentum_element<DIM, LABS>(A, nd, R, G);
+  momentum_element<DIM, LABS, STAB>(A, nd, R, G);
 #pragma unroll
   for (int i = 0; i < LOC; i++) {
     double v[R_::RS];
@@ -289,14 +285,14 @@ __global__ void __launch_bounds__(128) gather_ct_stage_kernel(const MomentumArgs
   }
 }
 
-template <int DIM>
+template <int DIM, int STAB>
 __global__ void __launch_bounds__(128) gather_advdiff_stage_kernel(const AdvDiffArgs A, double* __restrict__ stage) {
   constexpr int LOC = DIM + 1;
   using R_ = Rec<LOC, 1, 1>;
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= A.n_elements) return;
   AdvDiffLocal<DIM> R;
-  advdiff_element<DIM>(A, __ldg(A.ndglno + e), R);
+  advdiff_element<DIM, STAB>(A, __ldg(A.ndglno + e), R);
 #pragma unroll
   for (int i = 0; i < LOC; i++) {
     double v[R_::RS];
@@ -463,39 +459,24 @@ __device__ __forceinline__ int4 ldg_stream(const int4* p) {
   asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
   return v;
 }
-__device__ __forceinline__ unsigned ldg_stream(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
-  return v;
-}
 struct PairStream {
   const int4* pn;
-  const unsigned* psl;
   int deg, k;
   int4 nd0, nd1;
-  unsigned sl0, sl1;
   __device__ __forceinline__ void load_next(int kk) {
-    if (kk < deg) {
-      nd1 = ldg_stream(pn + (long long)kk * kBR);
-      sl1 = ldg_stream(psl + (long long)kk * kBR);
-    } else {
-      nd1 = make_int4(-1, -1, -1, -1);
-      sl1 = 0u;
-    }
+    if (kk < deg) nd1 = ldg_stream(pn + (long long)kk * kBR);
+    else nd1 = make_int4(-1, -1, -1, 0);
   }
-  __device__ __forceinline__ void init(const int4* pn_, const unsigned* psl_, int deg_) {
+  __device__ __forceinline__ void init(const int4* pn_, int deg_) {
     pn = pn_;
-    psl = psl_;
     deg = deg_;
     k = 0;
     load_next(0);
     nd0 = nd1;
-    sl0 = sl1;
     load_next(1);
   }
   __device__ __forceinline__ void advance() {
     nd0 = nd1;
-    sl0 = sl1;
     k++;
     load_next(k + 1);
   }
@@ -505,9 +486,9 @@ struct PairStream {
 template <int NREC>
 __device__ __forceinline__ void prefetch_nodes(const NodeRecs& rec, const int4& nd, bool valid) {
   if (!valid) return;
-  const int nn[4] = {nd.x, nd.y, nd.z, nd.w};
+  const int nn[3] = {nd.x, nd.y, nd.z};
 #pragma unroll
-  for (int q = 0; q < 4; q++) {
+  for (int q = 0; q < 3; q++) {
     prefetch_l1(rec.r0 + nn[q]);
     prefetch_l1(rec.r1 + nn[q]);
     if (NREC > 2) prefetch_l1(rec.r2 + nn[q]);
@@ -517,8 +498,7 @@ __device__ __forceinline__ void prefetch_nodes(const NodeRecs& rec, const int4& 
 template <int DIM, bool PERD, bool MLD, bool COMMON, int MINB>
 __global__ void __launch_bounds__(kBR, MINB)
 gather_momentum_direct_kernel(const MomentumArgs A, const int* __restrict__ rows, const long long* __restrict__ block_ptr,
-                              const int4* __restrict__ pair_nodes, const unsigned* __restrict__ pair_rslots,
-                              const int* __restrict__ findrm, size_t nnz, int maxlen,
+                              const int4* __restrict__ pair_nodes, const int* __restrict__ findrm, size_t nnz, int maxlen,
                               int prefetch, double* __restrict__ big_m, double* __restrict__ rhs,
                               double* __restrict__ masslump) {
   constexpr int LOC = DIM + 1;
@@ -529,7 +509,7 @@ gather_momentum_direct_kernel(const MomentumArgs A, const int* __restrict__ rows
   const long long base = block_ptr[b];
   const int deg = (int)((block_ptr[b + 1] - base) / kBR);
   PairStream ps;
-  ps.init(pair_nodes + base + t, pair_rslots + base + t, deg);
+  ps.init(pair_nodes + base + t, deg);
   for (int q = 0; q < NB * maxlen; q++) acc[q * kBR + t] = 0.0;
   MomDirectSink<DIM, PERD, MLD> sink;
   sink.acc = acc + t;
@@ -541,8 +521,8 @@ gather_momentum_direct_kernel(const MomentumArgs A, const int* __restrict__ rows
   for (; ps.k < deg; ps.advance()) {
     if (prefetch) prefetch_nodes<3>(A.rec, ps.nd1, ps.nd1.x >= 0);
     if (!ps.valid()) continue;
-    const int n[4] = {ps.nd0.x, ps.nd0.y, ps.nd0.z, ps.nd0.w};
-    sink.slots = ps.sl0;
+    const int n[4] = {r, ps.nd0.x, ps.nd0.y, ps.nd0.z};
+    sink.slots = (unsigned)ps.nd0.w;
     sink.i = 0;
     if constexpr (COMMON) momentum_row0<DIM, PERD>(A, n, own, sink, MomCommonFlags());
     else momentum_row0<DIM, PERD>(A, n, own, sink, MomRuntimeFlags{A.o, A.viscosity.stride});
@@ -572,8 +552,7 @@ gather_momentum_direct_kernel(const MomentumArgs A, const int* __restrict__ rows
 template <int DIM, bool COMMON, int MINB>
 __global__ void __launch_bounds__(kBR, MINB)
 gather_advdiff_direct_kernel(const AdvDiffArgs A, const int* __restrict__ rows, const long long* __restrict__ block_ptr,
-                             const int4* __restrict__ pair_nodes, const unsigned* __restrict__ pair_rslots,
-                             const int* __restrict__ findrm, int maxlen, int prefetch,
+                             const int4* __restrict__ pair_nodes, const int* __restrict__ findrm, int maxlen, int prefetch,
                              double* __restrict__ matrix, double* __restrict__ rhs) {
   constexpr int LOC = DIM + 1;
   extern __shared__ double acc[];
@@ -582,7 +561,7 @@ gather_advdiff_direct_kernel(const AdvDiffArgs A, const int* __restrict__ rows, 
   const long long base = block_ptr[b];
   const int deg = (int)((block_ptr[b + 1] - base) / kBR);
   PairStream ps;
-  ps.init(pair_nodes + base + t, pair_rslots + base + t, deg);
+  ps.init(pair_nodes + base + t, deg);
   for (int q = 0; q < maxlen; q++) acc[q * kBR + t] = 0.0;
   AdvDirectSink<DIM> sink;
   sink.acc = acc + t;
@@ -592,8 +571,8 @@ gather_advdiff_direct_kernel(const AdvDiffArgs A, const int* __restrict__ rows, 
   for (; ps.k < deg; ps.advance()) {
     if (prefetch) prefetch_nodes<2>(A.rec, ps.nd1, ps.nd1.x >= 0);
     if (!ps.valid()) continue;
-    const int n[4] = {ps.nd0.x, ps.nd0.y, ps.nd0.z, ps.nd0.w};
-    sink.slots = ps.sl0;
+    const int n[4] = {r, ps.nd0.x, ps.nd0.y, ps.nd0.z};
+    sink.slots = (unsigned)ps.nd0.w;
     sink.i = 0;
     if constexpr (COMMON) advdiff_row0<DIM>(A, n, own, sink, AdvCommonFlags());
     else advdiff_row0<DIM>(A, n, own, sink, AdvRuntimeFlags{A.o, A.diffusivity.stride});
@@ -643,6 +622,13 @@ static int gather_momentum_dim(Handle* h, const MomentumArgs& A, bool want_ml, b
   int st;
   const bool direct = fast && A.tab.sym && !getenv("CGASM_GATHER_STAGED");
 #define STAGE_SIZE(NB_, NV_) ((size_t)ne * LOC * Rec<LOC, NB_, NV_>::RS)
+  const int stab = A.o.stabilisation_scheme;
+#define STAGE_GENERIC(LABS_, NB_, MLC_)                                                                             \
+  do {                                                                                                              \
+    if (stab == 1) gather_momentum_stage_kernel<DIM, LABS_, NB_, MLC_, 1><<<grid, 128, 0, h->stream>>>(A, P->d_stage);      \
+    else if (stab == 2) gather_momentum_stage_kernel<DIM, LABS_, NB_, MLC_, 2><<<grid, 128, 0, h->stream>>>(A, P->d_stage); \
+    else gather_momentum_stage_kernel<DIM, LABS_, NB_, MLC_, 0><<<grid, 128, 0, h->stream>>>(A, P->d_stage);                \
+  } while (0)
   if (direct) {
     const int nb = abs_mode ? DIM : 1;
     const size_t smem = sizeof(double) * (size_t)nb * P->maxlen * kBR;
@@ -653,7 +639,7 @@ static int gather_momentum_dim(Handle* h, const MomentumArgs& A, bool want_ml, b
   do {                                                                                                         \
     if ((st = set_dyn_smem(gather_momentum_direct_kernel<DIM, PERD_, MLD_, COMMON_, MINB_>, smem))) return st; \
     gather_momentum_direct_kernel<DIM, PERD_, MLD_, COMMON_, MINB_><<<P->nblocks, kBR, smem, h->stream>>>(     \
-        A, P->d_rows, P->d_block_ptr, P->d_pair_nodes, P->d_pair_rslots, h->d_findrm, (size_t)h->nnz,          \
+        A, P->d_rows, P->d_block_ptr, P->d_pair_nodes, h->d_findrm, (size_t)h->nnz,                           \
         P->maxlen, prefetch, h->d_big_m,                                                                       \
         h->d_mom_rhs, ml);                                                                                     \
   } while (0)
@@ -669,20 +655,20 @@ static int gather_momentum_dim(Handle* h, const MomentumArgs& A, bool want_ml, b
   } else if (abs_mode == 0) {
     if ((st = ensure_stage(P, STAGE_SIZE(1, DIM + 1)))) return st;
     if (fast) gather_momentum_stage_fast_kernel<DIM, false, 1><<<grid, 128, 0, h->stream>>>(A, P->d_stage);
-    else gather_momentum_stage_kernel<DIM, false, 1, 1><<<grid, 128, 0, h->stream>>>(A, P->d_stage);
+    else STAGE_GENERIC(false, 1, 1);
     h->launches++;
     if ((st = launch_rows<DIM, 1, DIM + 1, 0>(h, h->d_big_m, h->d_mom_rhs, ml))) return st;
   } else if (!mld) {
     if ((st = ensure_stage(P, STAGE_SIZE(DIM, DIM + 1)))) return st;
     if (fast) gather_momentum_stage_fast_kernel<DIM, true, 1><<<grid, 128, 0, h->stream>>>(A, P->d_stage);
-    else if (abs_mode == 2) gather_momentum_stage_kernel<DIM, true, DIM, 1><<<grid, 128, 0, h->stream>>>(A, P->d_stage);
-    else gather_momentum_stage_kernel<DIM, false, DIM, 1><<<grid, 128, 0, h->stream>>>(A, P->d_stage);
+    else if (abs_mode == 2) STAGE_GENERIC(true, DIM, 1);
+    else STAGE_GENERIC(false, DIM, 1);
     h->launches++;
     if ((st = launch_rows<DIM, DIM, DIM + 1, 0>(h, h->d_big_m, h->d_mom_rhs, ml))) return st;
   } else {
     if ((st = ensure_stage(P, STAGE_SIZE(DIM, 2 * DIM)))) return st;
     if (fast) gather_momentum_stage_fast_kernel<DIM, true, DIM><<<grid, 128, 0, h->stream>>>(A, P->d_stage);
-    else gather_momentum_stage_kernel<DIM, false, DIM, DIM><<<grid, 128, 0, h->stream>>>(A, P->d_stage);
+    else STAGE_GENERIC(false, DIM, DIM);
     h->launches++;
     if ((st = launch_rows<DIM, DIM, 2 * DIM, 0>(h, h->d_big_m, h->d_mom_rhs, ml))) return st;
   }
@@ -693,6 +679,7 @@ static int gather_momentum_dim(Handle* h, const MomentumArgs& A, bool want_ml, b
     if ((st = launch_rows<DIM, DIM, 0, 2>(h, h->d_ct_m, nullptr, nullptr))) return st;
   }
 #undef STAGE_SIZE
+#undef STAGE_GENERIC
   CG_CUDA(cudaGetLastError());
   return CGASM_OK;
 }
@@ -717,7 +704,7 @@ static int gather_advdiff_dim(Handle* h, const AdvDiffArgs& A) {
   do {                                                                                                   \
     if ((st = set_dyn_smem(gather_advdiff_direct_kernel<DIM, COMMON_, MINB_>, smem))) return st;         \
     gather_advdiff_direct_kernel<DIM, COMMON_, MINB_><<<P->nblocks, kBR, smem, h->stream>>>(             \
-        A, P->d_rows, P->d_block_ptr, P->d_pair_nodes, P->d_pair_rslots, h->d_findrm, P->maxlen,         \
+        A, P->d_rows, P->d_block_ptr, P->d_pair_nodes, h->d_findrm, P->maxlen,                          \
         prefetch, h->d_adv_matrix,                                                                       \
         h->d_adv_rhs);                                                                                   \
   } while (0)
@@ -734,8 +721,12 @@ static int gather_advdiff_dim(Handle* h, const AdvDiffArgs& A) {
   if ((st = ensure_stage(P, (size_t)ne * LOC * Rec<LOC, 1, 1>::RS))) return st;
   if (advdiff_fast_ok(A.o) && !getenv("CGASM_GATHER_GENERIC"))
     gather_advdiff_stage_fast_kernel<DIM><<<grid, 128, 0, h->stream>>>(A, P->d_stage);
+  else if (A.o.stabilisation_scheme == 1)
+    gather_advdiff_stage_kernel<DIM, 1><<<grid, 128, 0, h->stream>>>(A, P->d_stage);
+  else if (A.o.stabilisation_scheme == 2)
+    gather_advdiff_stage_kernel<DIM, 2><<<grid, 128, 0, h->stream>>>(A, P->d_stage);
   else
-    gather_advdiff_stage_kernel<DIM><<<grid, 128, 0, h->stream>>>(A, P->d_stage);
+    gather_advdiff_stage_kernel<DIM, 0><<<grid, 128, 0, h->stream>>>(A, P->d_stage);
   h->launches++;
   return launch_rows<DIM, 1, 1, 1>(h, h->d_adv_matrix, h->d_adv_rhs, nullptr);
 }

@@ -47,7 +47,7 @@ __device__ __forceinline__ void row_positions(const int* __restrict__ findrm,
   }
 }
 
-template <int DIM, int MODE, bool LABS>
+template <int DIM, int MODE, bool LABS, int STAB>
 __global__ void __launch_bounds__(128)
 momentum_scatter_kernel(const MomentumArgs A, const int* __restrict__ elist, int count,
                         const int* __restrict__ findrm, const int* __restrict__ colm, size_t nnz,
@@ -60,7 +60,7 @@ momentum_scatter_kernel(const MomentumArgs A, const int* __restrict__ elist, int
   const int4 nd = __ldg(A.ndglno + e);
   MomentumLocal<DIM, LABS> R;
   Geom<DIM> G;
-  momentum_element<DIM, LABS>(A, nd, R, G);
+  momentum_element<DIM, LABS, STAB>(A, nd, R, G);
 
   int cols[LOC];
 #pragma unroll
@@ -88,7 +88,7 @@ momentum_scatter_kernel(const MomentumArgs A, const int* __restrict__ elist, int
   }
 }
 
-template <int DIM, int MODE>
+template <int DIM, int MODE, int STAB>
 __global__ void __launch_bounds__(128)
 advdiff_scatter_kernel(const AdvDiffArgs P, const int* __restrict__ elist, int count,
                        const int* __restrict__ findrm, const int* __restrict__ colm,
@@ -99,7 +99,7 @@ advdiff_scatter_kernel(const AdvDiffArgs P, const int* __restrict__ elist, int c
   const int e = elist ? __ldg(elist + tid) : tid;
   const int4 nd = __ldg(P.ndglno + e);
   AdvDiffLocal<DIM> R;
-  advdiff_element<DIM>(P, nd, R);
+  advdiff_element<DIM, STAB>(P, nd, R);
   int cols[LOC];
 #pragma unroll
   for (int j = 0; j < LOC; j++) cols[j] = node_of(nd, j);
@@ -114,7 +114,7 @@ advdiff_scatter_kernel(const AdvDiffArgs P, const int* __restrict__ elist, int c
 }
 
 // Single element -> dense local arrays (element-matrix parity checks).
-template <int DIM>
+template <int DIM, int STAB>
 __global__ void momentum_one_kernel(const MomentumArgs A, int e, double* __restrict__ T,
                                     double* __restrict__ rhs, double* __restrict__ ml,
                                     double* __restrict__ gp) {
@@ -129,7 +129,7 @@ __global__ void momentum_one_kernel(const MomentumArgs A, int e, double* __restr
     for (int i = 0; i < LOC; i++)
 #pragma unroll
       for (int j = 0; j < LOC; j++) R.Labs[d][i][j] = 0.0;
-  momentum_element<DIM, true>(A, nd, R, G);
+  momentum_element<DIM, true, STAB>(A, nd, R, G);
   for (int a = 0; a < DIM * DIM * LOC * LOC; a++) T[a] = 0.0;
   for (int d = 0; d < DIM; d++)
     for (int i = 0; i < LOC; i++) {
@@ -144,13 +144,13 @@ __global__ void momentum_one_kernel(const MomentumArgs A, int e, double* __restr
     }
 }
 
-template <int DIM>
+template <int DIM, int STAB>
 __global__ void advdiff_one_kernel(const AdvDiffArgs P, int e, double* __restrict__ Aout,
                                    double* __restrict__ rhs) {
   constexpr int LOC = DIM + 1;
   if (threadIdx.x || blockIdx.x) return;
   AdvDiffLocal<DIM> R;
-  advdiff_element<DIM>(P, P.ndglno[e], R);
+  advdiff_element<DIM, STAB>(P, P.ndglno[e], R);
   for (int i = 0; i < LOC; i++) {
     for (int j = 0; j < LOC; j++) Aout[i + LOC * j] = R.A[i][j];
     rhs[i] = R.rhs[i];
@@ -164,12 +164,27 @@ static void launch_momentum_mode(Handle* h, const MomentumArgs& A, const int* el
   if (count <= 0) return;
   const int block = 128, grid = (count + block - 1) / block;
   const bool labs = A.o.have_absorption && !A.o.lump_absorption;
-  if (labs)
-    momentum_scatter_kernel<DIM, MODE, true><<<grid, block, 0, h->stream>>>(
-        A, elist, count, h->d_findrm, h->d_colm, (size_t)h->nnz, h->d_big_m, h->d_mom_rhs, ml, ct);
-  else
-    momentum_scatter_kernel<DIM, MODE, false><<<grid, block, 0, h->stream>>>(
-        A, elist, count, h->d_findrm, h->d_colm, (size_t)h->nnz, h->d_big_m, h->d_mom_rhs, ml, ct);
+  const int stab = A.o.stabilisation_scheme;
+#define LAUNCH(LABS_, STAB_)                                                                       \
+  momentum_scatter_kernel<DIM, MODE, LABS_, STAB_><<<grid, block, 0, h->stream>>>(                 \
+      A, elist, count, h->d_findrm, h->d_colm, (size_t)h->nnz, h->d_big_m, h->d_mom_rhs, ml, ct)
+  if constexpr (MODE == MODE_ATOMIC) {
+    if (stab == CGASM_STAB_STREAMLINE_UPWIND) {
+      if (labs) LAUNCH(true, 1);
+      else LAUNCH(false, 1);
+      h->launches++;
+      return;
+    }
+    if (stab == CGASM_STAB_SUPG) {
+      if (labs) LAUNCH(true, 2);
+      else LAUNCH(false, 2);
+      h->launches++;
+      return;
+    }
+  }
+  if (labs) LAUNCH(true, 0);
+  else LAUNCH(false, 0);
+#undef LAUNCH
   h->launches++;
 }
 
@@ -177,8 +192,24 @@ template <int DIM, int MODE>
 static void launch_advdiff_mode(Handle* h, const AdvDiffArgs& P, const int* elist, int count) {
   if (count <= 0) return;
   const int block = 128, grid = (count + block - 1) / block;
-  advdiff_scatter_kernel<DIM, MODE><<<grid, block, 0, h->stream>>>(
-      P, elist, count, h->d_findrm, h->d_colm, h->d_adv_matrix, h->d_adv_rhs);
+  const int stab = P.o.stabilisation_scheme;
+#define LAUNCH(STAB_)                                                              \
+  advdiff_scatter_kernel<DIM, MODE, STAB_><<<grid, block, 0, h->stream>>>(         \
+      P, elist, count, h->d_findrm, h->d_colm, h->d_adv_matrix, h->d_adv_rhs)
+  if constexpr (MODE == MODE_ATOMIC) {
+    if (stab == CGASM_STAB_STREAMLINE_UPWIND) {
+      LAUNCH(1);
+      h->launches++;
+      return;
+    }
+    if (stab == CGASM_STAB_SUPG) {
+      LAUNCH(2);
+      h->launches++;
+      return;
+    }
+  }
+  LAUNCH(0);
+#undef LAUNCH
   h->launches++;
 }
 
@@ -236,13 +267,29 @@ int scatter_advdiff(Handle* h, const AdvDiffArgs& P) {
 
 void one_momentum(Handle* h, const MomentumArgs& A, int e, double* T, double* rhs, double* ml,
                   double* gp) {
-  if (h->dim == 3) momentum_one_kernel<3><<<1, 32, 0, h->stream>>>(A, e, T, rhs, ml, gp);
-  else momentum_one_kernel<2><<<1, 32, 0, h->stream>>>(A, e, T, rhs, ml, gp);
+  const int stab = A.o.stabilisation_scheme;
+#define ONE(DIM_)                                                                        \
+  do {                                                                                   \
+    if (stab == 1) momentum_one_kernel<DIM_, 1><<<1, 32, 0, h->stream>>>(A, e, T, rhs, ml, gp);      \
+    else if (stab == 2) momentum_one_kernel<DIM_, 2><<<1, 32, 0, h->stream>>>(A, e, T, rhs, ml, gp); \
+    else momentum_one_kernel<DIM_, 0><<<1, 32, 0, h->stream>>>(A, e, T, rhs, ml, gp);                \
+  } while (0)
+  if (h->dim == 3) ONE(3);
+  else ONE(2);
+#undef ONE
   h->launches++;
 }
 void one_advdiff(Handle* h, const AdvDiffArgs& P, int e, double* Aout, double* rhs) {
-  if (h->dim == 3) advdiff_one_kernel<3><<<1, 32, 0, h->stream>>>(P, e, Aout, rhs);
-  else advdiff_one_kernel<2><<<1, 32, 0, h->stream>>>(P, e, Aout, rhs);
+  const int stab = P.o.stabilisation_scheme;
+#define ONE(DIM_)                                                                     \
+  do {                                                                                \
+    if (stab == 1) advdiff_one_kernel<DIM_, 1><<<1, 32, 0, h->stream>>>(P, e, Aout, rhs);      \
+    else if (stab == 2) advdiff_one_kernel<DIM_, 2><<<1, 32, 0, h->stream>>>(P, e, Aout, rhs); \
+    else advdiff_one_kernel<DIM_, 0><<<1, 32, 0, h->stream>>>(P, e, Aout, rhs);                \
+  } while (0)
+  if (h->dim == 3) ONE(3);
+  else ONE(2);
+#undef ONE
   h->launches++;
 }
 

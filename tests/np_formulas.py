@@ -34,6 +34,42 @@ def _gather(mesh, fields, slot, kind):
     return val[nd]
 
 
+def nu_bar(u_g, J, diff_g, scheme, scale):
+    """nu_bar_scaled_q (assemble/Upwind_Stabilisation.F90:225-320), vectorised over (e, g).
+    u_g (E,G,d); J (E,d,d) with J[e,a,k] = J(a,k); diff_g (E,G,d,d) [a,b] or None."""
+    norm = np.einsum("ega,ega->eg", u_g, u_g)
+    uJ = np.einsum("ega,eak->egk", u_g, J)
+    if diff_g is None or scheme == abi.NU_BAR_UNITY:
+        val = np.abs(uJ).sum(axis=2)
+    else:
+        inv = np.linalg.inv(diff_g)
+        pe = 0.5 * np.einsum("ega,eab,egbk->egk", u_g, J, inv)
+        if scheme == abi.NU_BAR_OPTIMAL:
+            with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
+                xi = 1.0 / np.tanh(pe) - 1.0 / pe
+                xi = np.where(pe > 11.859499013855018, 1.0 - 1.0 / pe, xi)
+                xi = np.where(pe < -11.859499013855018, -1.0 - 1.0 / pe, xi)
+                xi = np.where(np.abs(pe) < 1e-10, 0.0, xi)
+        elif scheme == abi.NU_BAR_DOUBLY_ASYMPTOTIC:
+            xi = np.where(np.abs(pe) <= 3.0, pe / 3.0, np.sign(pe))
+        else:
+            with np.errstate(divide="ignore"):
+                xi = np.where(np.abs(pe) <= 1.0, 0.0, np.sign(pe) - 1.0 / pe)
+        val = np.einsum("egk,egk->eg", xi, uJ)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        out = np.where(norm < 1e-10, 0.0, val / norm)
+    return out * scale
+
+
+def jacobian(orc, mesh):
+    """J[e,a,k] = J(a,k,gi) = transpose(J_local_T) (Transform_elements.F90:878-882)."""
+    dim = mesh.dim
+    _, DN, _ = _tables(orc, dim)
+    Xe = mesh.X[mesh.ndglno.astype(np.int64) - 1]
+    JT = np.einsum("eia,ik->eak", Xe, DN)
+    return JT.transpose(0, 2, 1)
+
+
 def momentum_local(orc, mesh, fields, o):
     """Returns L[e,d,i,j] (diagonal blocks incl. lumped diagonal), rhs[e,d,i], ml[e,d,i]."""
     dim, loc = mesh.dim, mesh.loc
@@ -50,7 +86,23 @@ def momentum_local(orc, mesh, fields, o):
     rhs = np.zeros((E, dim, loc))
     ml = np.zeros((E, dim, loc))
     dtt = o.dt * o.theta
-    M = np.einsum("ig,jg,eg->eij", N, N, rho_g * detwei)
+    Nt = np.broadcast_to(N[None], (E,) + N.shape)      # test function (E,i,g)
+    stab_mat = None
+    if o.stabilisation_scheme != abi.STAB_NONE:
+        dq = None
+        if o.have_viscosity:
+            visc0 = _gather(mesh, fields, abi.F_VISCOSITY, 2)
+            Vq = np.einsum("eiba,ig->egab", visc0, N)
+            dq = np.zeros_like(Vq)
+            for a in range(dim):
+                dq[:, :, a, a] = Vq[:, :, a, a]
+        nb = nu_bar(u_g, jacobian(orc, mesh), dq, o.nu_bar_scheme, o.nu_bar_scale)
+        udn = np.einsum("ega,eia->eig", u_g, grad)
+        if o.stabilisation_scheme == abi.STAB_SUPG:
+            Nt = N[None] + nb[:, None, :] * udn
+        else:
+            stab_mat = np.einsum("eig,ejg,eg->eij", udn, udn, nb * detwei)
+    M = np.einsum("eig,jg,eg->eij", Nt, N, rho_g * detwei)
     m = M.sum(axis=2)
     if not o.exclude_mass:
         if o.lump_mass:
@@ -61,15 +113,17 @@ def momentum_local(orc, mesh, fields, o):
         ml += m[:, None, :]
     if not o.exclude_advection:
         ugradN = np.einsum("egd,ejd->egj", u_g, grad)      # u_g . grad N_j
-        NN = np.einsum("ig,jg,eg->eij", N, N, divu[:, None] * rho_g * detwei)
+        NN = np.einsum("eig,jg,eg->eij", Nt, N, divu[:, None] * rho_g * detwei)
         if o.integrate_advection_by_parts:
             A = -np.einsum("egi,jg,eg->eij", ugradN, N, rho_g * detwei) - (1 - o.beta) * NN
         else:
-            A = np.einsum("ig,egj,eg->eij", N, ugradN, rho_g * detwei) + o.beta * NN
+            A = np.einsum("eig,egj,eg->eij", Nt, ugradN, rho_g * detwei) + o.beta * NN
+        if stab_mat is not None:
+            A = A + stab_mat
         L += dtt * A[:, None]
         rhs -= np.einsum("eij,edj->edi", A, oldu.transpose(0, 2, 1))
     if o.have_source:
-        S = np.einsum("ig,jg,eg->eij", N, N, rho_g * detwei)
+        S = np.einsum("eig,jg,eg->eij", Nt, N, rho_g * detwei)
         src = _gather(mesh, fields, abi.F_SOURCE, 1)
         if o.lump_source:
             rhs += S.sum(axis=2)[:, None, :] * src.transpose(0, 2, 1)
@@ -80,10 +134,10 @@ def momentum_local(orc, mesh, fields, o):
         if o.subtract_out_reference_profile:
             b_g = b_g - _gather(mesh, fields, abi.F_HB_DENSITY, 0) @ N
         g_g = np.einsum("eid,ig->egd", _gather(mesh, fields, abi.F_GRAVITY, 1), N)
-        rhs += np.einsum("ig,egd,eg->edi", N, g_g, o.gravity_magnitude * b_g * detwei)
+        rhs += np.einsum("eig,egd,eg->edi", Nt, g_g, o.gravity_magnitude * b_g * detwei)
     if o.have_absorption:
         s_g = np.einsum("eid,ig->egd", _gather(mesh, fields, abi.F_ABSORPTION, 1), N)
-        Ab = np.einsum("ig,jg,egd,eg->edij", N, N, s_g, rho_g * detwei)
+        Ab = np.einsum("eig,jg,egd,eg->edij", Nt, N, s_g, rho_g * detwei)
         if o.lump_absorption:
             al = Ab.sum(axis=3)
             diag += dtt * al
@@ -119,8 +173,23 @@ def advdiff_local(orc, mesh, fields, o):
     A_tot = np.zeros((E, loc, loc))
     rhs = np.zeros((E, loc))
     dtt = o.dt * o.theta
+    Nt = np.broadcast_to(N[None], (E,) + N.shape)
+    stab_mat = None
+    if o.stabilisation_scheme != abi.STAB_NONE:
+        uu = _gather(mesh, fields, abi.F_NU, 1)
+        uq = np.einsum("eid,ig->egd", uu, N)
+        dq = None
+        if o.have_diffusivity:
+            kap0 = _gather(mesh, fields, abi.F_T_DIFFUSIVITY, 2)
+            dq = np.einsum("eiba,ig->egab", kap0, N)
+        nb = nu_bar(uq, jacobian(orc, mesh), dq, o.nu_bar_scheme, o.nu_bar_scale)
+        udn = np.einsum("ega,eia->eig", uq, grad)
+        if o.stabilisation_scheme == abi.STAB_SUPG:
+            Nt = N[None] + nb[:, None, :] * udn
+        else:
+            stab_mat = np.einsum("eig,ejg,eg->eij", udn, udn, nb * detwei)
     if o.have_mass:
-        M = np.einsum("ig,jg,eg->eij", N, N, detwei)
+        M = np.einsum("eig,jg,eg->eij", Nt, N, detwei)
         if o.lump_mass:
             idx = np.arange(loc)
             A_tot[:, idx, idx] += M.sum(axis=2)
@@ -131,16 +200,18 @@ def advdiff_local(orc, mesh, fields, o):
         u_g = np.einsum("eid,ig->egd", u, N)
         divu = np.einsum("eid,eid->e", u, grad)
         ugradN = np.einsum("egd,ejd->egj", u_g, grad)
-        NN = np.einsum("ig,jg,eg->eij", N, N, divu[:, None] * detwei)
+        NN = np.einsum("eig,jg,eg->eij", Nt, N, divu[:, None] * detwei)
         if o.integrate_advection_by_parts:
             A = -np.einsum("egi,jg,eg->eij", ugradN, N, detwei) - (1 - o.beta) * NN
         else:
-            A = np.einsum("ig,egj,eg->eij", N, ugradN, detwei) + o.beta * NN
+            A = np.einsum("eig,egj,eg->eij", Nt, ugradN, detwei) + o.beta * NN
+        if stab_mat is not None:
+            A = A + stab_mat
         A_tot += dtt * A
         rhs -= np.einsum("eij,ej->ei", A, T)
     if o.have_absorption:
         s_g = _gather(mesh, fields, abi.F_T_ABSORPTION, 0) @ N
-        Ab = np.einsum("ig,jg,eg->eij", N, N, s_g * detwei)
+        Ab = np.einsum("eig,jg,eg->eij", Nt, N, s_g * detwei)
         A_tot += dtt * Ab
         rhs -= np.einsum("eij,ej->ei", Ab, T)
     if o.have_diffusivity:
@@ -154,7 +225,7 @@ def advdiff_local(orc, mesh, fields, o):
         rhs -= np.einsum("eij,ej->ei", D, T)
     if o.have_source:
         s_g = _gather(mesh, fields, abi.F_T_SOURCE, 0) @ N
-        rhs += np.einsum("ig,eg->ei", N, s_g * detwei)
+        rhs += np.einsum("eig,eg->ei", Nt, s_g * detwei)
     return A_tot, rhs
 
 

@@ -26,6 +26,12 @@ def _variants_momentum():
         "diagvisc": c(viscosity_shape=abi.TENSOR_DIAGONAL),
         "no_adv_no_mass": c(exclude_advection=1, exclude_mass=1),
         "stokes": c(exclude_advection=1, have_gravity=0),
+        "su_optimal": c(stabilisation_scheme=abi.STAB_STREAMLINE_UPWIND, nu_bar_scheme=abi.NU_BAR_OPTIMAL),
+        "su_unity_noviscosity": c(stabilisation_scheme=abi.STAB_STREAMLINE_UPWIND, have_viscosity=0),
+        "supg_critical": c(stabilisation_scheme=abi.STAB_SUPG, nu_bar_scheme=abi.NU_BAR_CRITICAL_RULE, nu_bar_scale=1.0,
+                           lump_mass=0, have_absorption=1, have_source=1),
+        "supg_asymptotic_by_parts": c(stabilisation_scheme=abi.STAB_SUPG, nu_bar_scheme=abi.NU_BAR_DOUBLY_ASYMPTOTIC,
+                                      integrate_advection_by_parts=1, beta=0.5),
     }
 
 
@@ -41,12 +47,18 @@ def _variants_advdiff():
         "pure_diffusion": c(have_advection=0),
         "mass_only": c(have_advection=0, have_diffusivity=0),
         "theta0": c(theta=0.0),
+        "su_optimal": c(stabilisation_scheme=abi.STAB_STREAMLINE_UPWIND),
+        "su_unity_nodiff": c(stabilisation_scheme=abi.STAB_STREAMLINE_UPWIND, have_diffusivity=0),
+        "supg_optimal_tensor": c(stabilisation_scheme=abi.STAB_SUPG, diffusivity_shape=abi.TENSOR_FULL, have_source=1,
+                                 have_absorption=1, lump_mass=1),
+        "supg_critical_by_parts": c(stabilisation_scheme=abi.STAB_SUPG, nu_bar_scheme=abi.NU_BAR_CRITICAL_RULE,
+                                    integrate_advection_by_parts=1, beta=0.3),
     }
 
 
 def _fields(mesh, variant):
     fs = syn.standard_fields(mesh)
-    if variant in ("aniso", "diagvisc", "tensor_diff"):
+    if variant in ("aniso", "diagvisc", "tensor_diff", "supg_optimal_tensor"):
         fs.set(abi.F_VISCOSITY, syn.aniso_tensor(mesh.dim), abi.FIELD_CONSTANT)
         fs.set(abi.F_T_DIFFUSIVITY, syn.aniso_tensor(mesh.dim), abi.FIELD_CONSTANT)
     return fs

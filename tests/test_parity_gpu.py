@@ -45,6 +45,12 @@ def momentum_variants():
         "diagvisc": c(viscosity_shape=abi.TENSOR_DIAGONAL),
         "no_adv_no_mass": c(exclude_advection=1, exclude_mass=1),
         "stokes_no_ml": c(exclude_advection=1, have_gravity=0, assemble_inverse_masslump=0),
+        "su_optimal": c(stabilisation_scheme=abi.STAB_STREAMLINE_UPWIND, nu_bar_scheme=abi.NU_BAR_OPTIMAL),
+        "su_unity_noviscosity": c(stabilisation_scheme=abi.STAB_STREAMLINE_UPWIND, have_viscosity=0),
+        "supg_critical": c(stabilisation_scheme=abi.STAB_SUPG, nu_bar_scheme=abi.NU_BAR_CRITICAL_RULE, nu_bar_scale=1.0,
+                           lump_mass=0, have_absorption=1, have_source=1),
+        "supg_asymptotic_by_parts": c(stabilisation_scheme=abi.STAB_SUPG, nu_bar_scheme=abi.NU_BAR_DOUBLY_ASYMPTOTIC,
+                                      integrate_advection_by_parts=1, beta=0.5),
     }
 
 
@@ -60,12 +66,18 @@ def advdiff_variants():
         "pure_diffusion": c(have_advection=0),
         "mass_only": c(have_advection=0, have_diffusivity=0),
         "theta0": c(theta=0.0),
+        "su_optimal": c(stabilisation_scheme=abi.STAB_STREAMLINE_UPWIND),
+        "su_unity_nodiff": c(stabilisation_scheme=abi.STAB_STREAMLINE_UPWIND, have_diffusivity=0),
+        "supg_optimal_tensor": c(stabilisation_scheme=abi.STAB_SUPG, diffusivity_shape=abi.TENSOR_FULL, have_source=1,
+                                 have_absorption=1, lump_mass=1),
+        "supg_critical_by_parts": c(stabilisation_scheme=abi.STAB_SUPG, nu_bar_scheme=abi.NU_BAR_CRITICAL_RULE,
+                                    integrate_advection_by_parts=1, beta=0.3),
     }
 
 
 def fields_for(mesh, variant):
     fs = syn.standard_fields(mesh, nodal_viscosity=(variant == "aniso"))
-    if variant in ("diagvisc", "tensor_diff"):
+    if variant in ("diagvisc", "tensor_diff", "supg_optimal_tensor"):
         fs.set(abi.F_VISCOSITY, syn.aniso_tensor(mesh.dim), abi.FIELD_CONSTANT)
         fs.set(abi.F_T_DIFFUSIVITY, syn.aniso_tensor(mesh.dim), abi.FIELD_CONSTANT)
     return fs
@@ -177,6 +189,12 @@ def test_advdiff_element_matrices(orc, dim, variant):
 def test_momentum_assembly(orc, scatter, dim, variant):
     mesh = syn.box_mesh((6, 5, 4)[:dim], seed=31)
     o = momentum_variants()[variant]
+    if o.stabilisation_scheme and scatter not in (abi.SCATTER_ATOMIC, abi.SCATTER_GATHER):
+        asm = make_asm(mesh, fields_for(mesh, variant), scatter)
+        with pytest.raises(cgasm.CgasmError) as ei:
+            asm.momentum(o)
+        assert ei.value.code == abi.EUNSUPPORTED  # the caller keeps the Fortran loop (or picks GATHER)
+        return
     fs = fields_for(mesh, variant)
     asm = make_asm(mesh, fs, scatter)
     findrm, colm, _ = asm.get_sparsity()
@@ -191,6 +209,12 @@ def test_momentum_assembly(orc, scatter, dim, variant):
 def test_advdiff_assembly(orc, scatter, dim, variant):
     mesh = syn.box_mesh((6, 5, 4)[:dim], seed=32)
     o = advdiff_variants()[variant]
+    if o.stabilisation_scheme and scatter not in (abi.SCATTER_ATOMIC, abi.SCATTER_GATHER):
+        asm = make_asm(mesh, fields_for(mesh, variant), scatter)
+        with pytest.raises(cgasm.CgasmError) as ei:
+            asm.advdiff(o)
+        assert ei.value.code == abi.EUNSUPPORTED
+        return
     fs = fields_for(mesh, variant)
     asm = make_asm(mesh, fs, scatter)
     findrm, colm, _ = asm.get_sparsity()
