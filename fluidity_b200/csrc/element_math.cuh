@@ -1436,9 +1436,13 @@ __device__ __forceinline__ void load_rot_own(const double4* __restrict__ rec, co
   for (int k = 1; k < DIM + 1; k++) unpack<DIM>(ld256(rec + n[k]), v[k], s[k]);
 }
 
+// Core of the momentum row: node data already in registers. X/nu/oldu are (LOC, DIM) with the row's
+// own node first, rho/b (LOC); n[] = node ids (only used by the runtime-flag gathers).
 template <int DIM, bool PERD, class Sink, class F>
-__device__ __forceinline__ void momentum_row0(const MomentumArgs& A, const int (&n)[4], const OwnNode<DIM>& own,
-                                              Sink& sink, const F f) {
+__device__ __forceinline__ void momentum_row0_data(const MomentumArgs& A, const int (&n)[4],
+                                                   const double (&X)[DIM + 1][DIM], const double (&nu)[DIM + 1][DIM],
+                                                   const double (&rho)[DIM + 1], const double (&oldu)[DIM + 1][DIM],
+                                                   const double (&b_in)[DIM + 1], Sink& sink, const F f) {
   constexpr int LOC = DIM + 1;
   const cgasm_momentum_opts& o = A.o;
   const Tables& t = A.tab;
@@ -1448,15 +1452,9 @@ __device__ __forceinline__ void momentum_row0(const MomentumArgs& A, const int (
   double M[LOC];  // rho-weighted mass row of local node 0
   double v[DIM];
   double m0;
+  geometry_lean<DIM>(X, G);
+  G.grad0(g0);
   {
-    double X[LOC][DIM], T_unused[LOC];
-    load_rot_own<DIM>(A.rec.r0, n, own.X, own.T, X, T_unused);
-    geometry_lean<DIM>(X, G);
-    G.grad0(g0);
-  }
-  {
-    double nu[LOC][DIM], rho[LOC];
-    load_rot_own<DIM>(A.rec.r1, n, own.nu, own.rho, nu, rho);
     double S = 0.0;
 #pragma unroll
     for (int k = 0; k < LOC; k++) S += rho[k];
@@ -1508,8 +1506,9 @@ __device__ __forceinline__ void momentum_row0(const MomentumArgs& A, const int (
       }
     }
   }
-  double oldu[LOC][DIM], b[LOC];
-  load_rot_own<DIM>(A.rec.r2, n, own.oldu, own.b, oldu, b);
+  double b[LOC];
+#pragma unroll
+  for (int k = 0; k < LOC; k++) b[k] = b_in[k];
   double rhs[DIM];
 #pragma unroll
   for (int d = 0; d < DIM; d++) rhs[d] = 0.0;
@@ -1574,6 +1573,18 @@ __device__ __forceinline__ void momentum_row0(const MomentumArgs& A, const int (
 }
 
 // Sink: mat(jj, v), vec(v)
+
+template <int DIM, bool PERD, class Sink, class F>
+__device__ __forceinline__ void momentum_row0(const MomentumArgs& A, const int (&n)[4], const OwnNode<DIM>& own,
+                                              Sink& sink, const F f) {
+  constexpr int LOC = DIM + 1;
+  double X[LOC][DIM], nu[LOC][DIM], oldu[LOC][DIM], T_unused[LOC], rho[LOC], b[LOC];
+  load_rot_own<DIM>(A.rec.r0, n, own.X, own.T, X, T_unused);
+  load_rot_own<DIM>(A.rec.r1, n, own.nu, own.rho, nu, rho);
+  load_rot_own<DIM>(A.rec.r2, n, own.oldu, own.b, oldu, b);
+  momentum_row0_data<DIM, PERD>(A, n, X, nu, rho, oldu, b, sink, f);
+}
+
 struct AdvRuntimeFlags {
   const cgasm_advdiff_opts& o;
   int diff_stride;
@@ -1602,8 +1613,9 @@ __host__ __device__ inline bool advdiff_common_ok(const cgasm_advdiff_opts& o, i
 }
 
 template <int DIM, class Sink, class F>
-__device__ __forceinline__ void advdiff_row0(const AdvDiffArgs& P, const int (&n)[4], const OwnNode<DIM>& own,
-                                             Sink& sink, const F f) {
+__device__ __forceinline__ void advdiff_row0_data(const AdvDiffArgs& P, const int (&n)[4], const double (&X)[DIM + 1][DIM],
+                                                  const double (&T)[DIM + 1], const double (&u)[DIM + 1][DIM], Sink& sink,
+                                                  const F f) {
   constexpr int LOC = DIM + 1;
   const cgasm_advdiff_opts& o = P.o;
   const Tables& t = P.tab;
@@ -1611,18 +1623,12 @@ __device__ __forceinline__ void advdiff_row0(const AdvDiffArgs& P, const int (&n
   const bool implicit = fabs(dtt) > 2.220446049250313e-16;
   GeomLean<DIM> G;
   double g0[DIM];
-  double T[LOC], v[DIM];
-  {
-    double X[LOC][DIM];
-    load_rot_own<DIM>(P.rec.r0, n, own.X, own.T, X, T);
-    geometry_lean<DIM>(X, G);
-    G.grad0(g0);
-  }
+  double v[DIM];
+  geometry_lean<DIM>(X, G);
+  G.grad0(g0);
 #pragma unroll
   for (int a = 0; a < DIM; a++) v[a] = 0.0;
   if (f.adv()) {
-    double u[LOC][DIM], unused[LOC];
-    load_rot_own<DIM>(P.rec.r1, n, own.nu, own.rho, u, unused);
 #pragma unroll
     for (int a = 0; a < DIM; a++) {
       double S = 0.0;
@@ -1692,6 +1698,17 @@ __device__ __forceinline__ void advdiff_row0(const AdvDiffArgs& P, const int (&n
     sink.mat(j, a_0j);
   }
   sink.vec(rhs);
+}
+
+
+template <int DIM, class Sink, class F>
+__device__ __forceinline__ void advdiff_row0(const AdvDiffArgs& P, const int (&n)[4], const OwnNode<DIM>& own,
+                                             Sink& sink, const F f) {
+  constexpr int LOC = DIM + 1;
+  double X[LOC][DIM], T[LOC], u[LOC][DIM], unused[LOC];
+  load_rot_own<DIM>(P.rec.r0, n, own.X, own.T, X, T);
+  load_rot_own<DIM>(P.rec.r1, n, own.nu, own.rho, u, unused);
+  advdiff_row0_data<DIM>(P, n, X, T, u, sink, f);
 }
 
 }  // namespace cgasm

@@ -21,6 +21,7 @@
 #include "cgasm_internal.h"
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <numeric>
 
@@ -39,6 +40,15 @@ struct GatherPlan {
                                    //   other nodes in rotated order (the row's own node is rotated node 0;
                                    //   n1 < 0 = none) and the 4 x 8-bit CSR slots of rotated nodes 0..3
   long long n_entries = 0;
+  // walk plan (single-pass kernels for the common option set): per row the incident elements are
+  // ordered as a face-adjacent walk around the node, so consecutive elements share two of their
+  // three other nodes; an entry loads ONE node into one of the three register positions.
+  //   .x = node to load (-1 = padding), .y = position (bits 0-1) | compute flag (bit 2) | CSR slot << 8
+  long long* d_walk_ptr = nullptr;  // [nblocks+1]
+  int2* d_walk = nullptr;           // block-interleaved like d_pairs
+  unsigned char* d_own_slot = nullptr;  // [nblocks*kBR] slot of the diagonal inside the row
+  long long n_walk = 0;
+  double walk_entries_per_pair = 0.0;
   double* d_stage = nullptr;       // staging buffer (grown on demand)
   size_t stage_doubles = 0;
 };
@@ -51,6 +61,9 @@ void gather_free(Handle* h) {
   if (p->d_pairs) cudaFree(p->d_pairs);
   if (p->d_pair_nodes) cudaFree(p->d_pair_nodes);
   if (p->d_stage) cudaFree(p->d_stage);
+  if (p->d_walk_ptr) cudaFree(p->d_walk_ptr);
+  if (p->d_walk) cudaFree(p->d_walk);
+  if (p->d_own_slot) cudaFree(p->d_own_slot);
   delete p;
   h->gather = nullptr;
 }
@@ -100,6 +113,159 @@ __global__ void gather_pairs_kernel(int nblocks, int loc, const int* __restrict_
     pairs[base + (long long)k * kBR + t] = make_uint2(0xFFFFFFFFu, 0u);
     pair_nodes[base + (long long)k * kBR + t] = make_int4(-1, -1, -1, 0);
   }
+}
+
+// ---- walk plan -------------------------------------------------------------------------------------
+// For one row (node r) with incident elements E_r: two elements are face-adjacent around r when they
+// share two of their other nodes. A greedy walk (next = unvisited face-neighbour with the fewest
+// unvisited neighbours, else any unvisited element sharing most nodes with the held ones) orders
+// E_r; each step emits one entry per node of the next element that is not already held.
+static void build_walk_row(const Handle* h, int r, std::vector<int2>& out) {
+  const int loc = h->loc, no = loc - 1;  // other nodes per element
+  const int64_t k0 = h->n2e_ptr[r];
+  const int m = (int)(h->n2e_ptr[r + 1] - k0);
+  out.clear();
+  if (m == 0) return;
+  // other nodes of each incident element
+  std::vector<int> oth((size_t)m * 3, -1);
+  for (int k = 0; k < m; k++) {
+    const int* nd = h->h_nd0.data() + (size_t)4 * h->n2e[(size_t)(k0 + k)];
+    int q = 0;
+    for (int i = 0; i < loc; i++)
+      if (nd[i] != r) oth[(size_t)k * 3 + q++] = nd[i];
+  }
+  auto shared = [&](int a, int b) {
+    int c = 0;
+    for (int i = 0; i < no; i++)
+      for (int j = 0; j < no; j++) c += oth[(size_t)a * 3 + i] == oth[(size_t)b * 3 + j];
+    return c;
+  };
+  // face adjacency (shares no-1 other nodes); m is ~24 (3-D) / ~6 (2-D): quadratic is fine
+  std::vector<std::vector<int>> adj((size_t)m);
+  for (int a = 0; a < m; a++)
+    for (int b = a + 1; b < m; b++)
+      if (shared(a, b) == no - 1) {
+        adj[a].push_back(b);
+        adj[b].push_back(a);
+      }
+  std::vector<char> visited((size_t)m, 0);
+  auto unvisited_deg = [&](int e) {
+    int c = 0;
+    for (int x : adj[e]) c += !visited[x];
+    return c;
+  };
+  int held[4] = {r, -1, -1, -1};
+  const int s0 = h->h_findrm[r], s1 = h->h_findrm[r + 1];
+  auto slot_of = [&](int node) {
+    const int* b = h->h_colm.data() + s0;
+    const int* e = h->h_colm.data() + s1;
+    return (int)(std::lower_bound(b, e, node) - b);
+  };
+  auto emit = [&](int e) {
+    // which positions keep a node of e, which nodes of e are missing
+    bool keep[4] = {true, false, false, false};
+    int missing[3], nmiss = 0;
+    for (int i = 0; i < no; i++) {
+      const int node = oth[(size_t)e * 3 + i];
+      bool found = false;
+      for (int p = 1; p <= no; p++)
+        if (held[p] == node) {
+          keep[p] = true;
+          found = true;
+        }
+      if (!found) missing[nmiss++] = node;
+    }
+    int p = 1;
+    for (int q = 0; q < nmiss; q++) {
+      while (keep[p]) p++;
+      held[p] = missing[q];
+      keep[p] = true;
+      const int compute = (q == nmiss - 1) ? 4 : 0;
+      out.push_back(make_int2(missing[q], p | compute | (slot_of(missing[q]) << 8)));
+    }
+  };
+  // start from an element with the fewest face neighbours (an end of the fan on boundaries)
+  int cur = 0;
+  for (int e = 1; e < m; e++)
+    if (adj[e].size() < adj[cur].size()) cur = e;
+  for (int step = 0; step < m; step++) {
+    visited[cur] = 1;
+    emit(cur);
+    int next = -1, best = 1 << 30;
+    for (int x : adj[cur])
+      if (!visited[x]) {
+        const int d = unvisited_deg(x);
+        if (d < best) {
+          best = d;
+          next = x;
+        }
+      }
+    if (next < 0) {  // dead end: jump to the unvisited element sharing most held nodes
+      int bs = -1;
+      for (int e = 0; e < m; e++)
+        if (!visited[e]) {
+          int c = 0;
+          for (int i = 0; i < no; i++)
+            for (int p = 1; p <= no; p++) c += held[p] == oth[(size_t)e * 3 + i];
+          if (c > bs) {
+            bs = c;
+            next = e;
+          }
+        }
+    }
+    if (next < 0) break;
+    cur = next;
+  }
+}
+
+static int build_walk_plan(Handle* h, GatherPlan* P, const std::vector<int>& rows) {
+  const int nb = P->nblocks;
+  std::vector<long long> walk_ptr((size_t)nb + 1, 0);
+  std::vector<std::vector<int2>> rowplans(rows.size());
+  std::vector<unsigned char> own_slot(rows.size(), 0);
+  std::vector<int> block_deg((size_t)nb, 0);
+#pragma omp parallel
+  {
+    std::vector<int2> tmp;
+#pragma omp for schedule(dynamic, 8)
+    for (int b = 0; b < nb; b++) {
+      int deg = 0;
+      for (int t = 0; t < kBR; t++) {
+        const size_t q = (size_t)b * kBR + t;
+        const int r = rows[q];
+        if (r < 0) continue;
+        build_walk_row(h, r, tmp);
+        rowplans[q] = tmp;
+        deg = std::max(deg, (int)tmp.size());
+        const int* cb = h->h_colm.data() + h->h_findrm[r];
+        const int* ce = h->h_colm.data() + h->h_findrm[r + 1];
+        own_slot[q] = (unsigned char)(std::lower_bound(cb, ce, r) - cb);
+      }
+      block_deg[b] = deg;
+    }
+  }
+  long long total_real = 0;
+  for (int b = 0; b < nb; b++) walk_ptr[b + 1] = walk_ptr[b] + (long long)block_deg[b] * kBR;
+  P->n_walk = walk_ptr[nb];
+  std::vector<int2> walk((size_t)std::max<long long>(P->n_walk, 1), make_int2(-1, 0));
+#pragma omp parallel for schedule(dynamic, 8) reduction(+ : total_real)
+  for (int b = 0; b < nb; b++)
+    for (int t = 0; t < kBR; t++) {
+      const auto& rp = rowplans[(size_t)b * kBR + t];
+      for (size_t k = 0; k < rp.size(); k++) walk[(size_t)(walk_ptr[b] + (long long)k * kBR + t)] = rp[k];
+      total_real += (long long)rp.size();
+    }
+  P->walk_entries_per_pair = h->n2e.empty() ? 0.0 : (double)total_real / (double)h->n2e.size();
+  if (getenv("CGASM_DEBUG"))
+    fprintf(stderr, "[cgasm] walk plan: %.3f entries per (row, element) pair, %lld padded entries\n",
+            P->walk_entries_per_pair, P->n_walk);
+  CG_CUDA(cudaMalloc(&P->d_walk_ptr, sizeof(long long) * walk_ptr.size()));
+  CG_CUDA(cudaMemcpy(P->d_walk_ptr, walk_ptr.data(), sizeof(long long) * walk_ptr.size(), cudaMemcpyHostToDevice));
+  CG_CUDA(cudaMalloc(&P->d_walk, sizeof(int2) * walk.size()));
+  CG_CUDA(cudaMemcpy(P->d_walk, walk.data(), sizeof(int2) * walk.size(), cudaMemcpyHostToDevice));
+  CG_CUDA(cudaMalloc(&P->d_own_slot, own_slot.size()));
+  CG_CUDA(cudaMemcpy(P->d_own_slot, own_slot.data(), own_slot.size(), cudaMemcpyHostToDevice));
+  return CGASM_OK;
 }
 
 int gather_build(Handle* h) {
@@ -158,6 +324,7 @@ int gather_build(Handle* h) {
   cudaFree(d_n2e);
   CG_CUDA(e1);
   CG_CUDA(e2);
+  if (!getenv("CGASM_GATHER_NOWALK")) return build_walk_plan(h, P, rows);
   return CGASM_OK;
 }
 
@@ -589,6 +756,162 @@ gather_advdiff_direct_kernel(const AdvDiffArgs A, const int* __restrict__ rows, 
   }
 }
 
+// ---- single pass, walk order: one new node per entry ---------------------------------------------------
+__device__ __forceinline__ int2 ldg_stream(const int2* p) {
+  int2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.s32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+  return v;
+}
+
+template <int DIM, bool COMMON, int MINB>
+__global__ void __launch_bounds__(kBR, MINB)
+gather_momentum_walk_kernel(const MomentumArgs A, const int* __restrict__ rows, const long long* __restrict__ walk_ptr,
+                            const int2* __restrict__ walk, const unsigned char* __restrict__ own_slot,
+                            const int* __restrict__ findrm, size_t nnz, int maxlen, double* __restrict__ big_m,
+                            double* __restrict__ rhs, double* __restrict__ masslump) {
+  constexpr int LOC = DIM + 1;
+  extern __shared__ double acc[];
+  const int b = blockIdx.x, t = threadIdx.x;
+  const int r = rows[b * kBR + t];
+  const long long base = walk_ptr[b];
+  const int deg = (int)((walk_ptr[b + 1] - base) / kBR);
+  const int2* p = walk + base + t;
+  int2 e0 = deg > 0 ? ldg_stream(p) : make_int2(-1, 0);
+  int2 e1 = deg > 1 ? ldg_stream(p + kBR) : make_int2(-1, 0);
+  for (int q = 0; q < maxlen; q++) acc[q * kBR + t] = 0.0;
+  MomDirectSink<DIM, false, false> sink;
+  sink.acc = acc + t;
+  sink.maxlen = maxlen;
+  sink.i = 0;
+#pragma unroll
+  for (int c = 0; c < MomDirectSink<DIM, false, false>::NV; c++) sink.vec_[c] = 0.0;
+  // node data in registers: position 0 = the row's own node, 1..LOC-1 = the walk's current element
+  double X[LOC][DIM], nu[LOC][DIM], oldu[LOC][DIM], rho[LOC], bb[LOC];
+  int n[4] = {r >= 0 ? r : 0, 0, 0, 0};
+  unsigned slots = own_slot[b * kBR + t];
+  {
+    double unused;
+    unpack<DIM>(ld256(A.rec.r0 + n[0]), X[0], unused);
+    unpack<DIM>(ld256(A.rec.r1 + n[0]), nu[0], rho[0]);
+    unpack<DIM>(ld256(A.rec.r2 + n[0]), oldu[0], bb[0]);
+#pragma unroll
+    for (int q = 1; q < LOC; q++) {
+#pragma unroll
+      for (int a = 0; a < DIM; a++) X[q][a] = nu[q][a] = oldu[q][a] = 0.0;
+      rho[q] = bb[q] = 0.0;
+    }
+  }
+  for (int k = 0; k < deg; k++) {
+    const int2 ent = e0;
+    e0 = e1;
+    e1 = (k + 2 < deg) ? ldg_stream(p + (long long)(k + 2) * kBR) : make_int2(-1, 0);
+    if (ent.x < 0) continue;
+    const int pos = ent.y & 3;
+#pragma unroll
+    for (int q = 1; q < LOC; q++)
+      if (pos == q) {
+        double unused;
+        unpack<DIM>(ld256(A.rec.r0 + ent.x), X[q], unused);
+        unpack<DIM>(ld256(A.rec.r1 + ent.x), nu[q], rho[q]);
+        unpack<DIM>(ld256(A.rec.r2 + ent.x), oldu[q], bb[q]);
+        n[q] = ent.x;
+        slots = (slots & ~(0xffu << (8 * q))) | (((unsigned)ent.y >> 8 & 0xffu) << (8 * q));
+      }
+    if (ent.y & 4) {
+      sink.slots = slots;
+      if constexpr (COMMON) momentum_row0_data<DIM, false>(A, n, X, nu, rho, oldu, bb, sink, MomCommonFlags());
+      else momentum_row0_data<DIM, false>(A, n, X, nu, rho, oldu, bb, sink, MomRuntimeFlags{A.o, A.viscosity.stride});
+    }
+  }
+  if (r >= 0) {
+#pragma unroll
+    for (int d = 0; d < DIM; d++) rhs[(size_t)DIM * r + d] = sink.vec_[d];
+    if (masslump) {
+#pragma unroll
+      for (int d = 0; d < DIM; d++) masslump[(size_t)DIM * r + d] = sink.vec_[DIM];
+    }
+  }
+  __syncthreads();
+  const int warp = t >> 5, lane = t & 31;
+  for (int rr = 0; rr < 32; rr++) {
+    const int tt = warp * 32 + rr;
+    const int row = rows[b * kBR + tt];
+    if (row < 0) continue;
+    const int s0 = findrm[row], nn = findrm[row + 1] - s0;
+    for (int s = lane; s < nn; s += 32) {
+#pragma unroll
+      for (int d = 0; d < DIM; d++) big_m[(size_t)d * nnz + s0 + s] = acc[s * kBR + tt];
+    }
+  }
+}
+
+template <int DIM, bool COMMON, int MINB>
+__global__ void __launch_bounds__(kBR, MINB)
+gather_advdiff_walk_kernel(const AdvDiffArgs A, const int* __restrict__ rows, const long long* __restrict__ walk_ptr,
+                           const int2* __restrict__ walk, const unsigned char* __restrict__ own_slot,
+                           const int* __restrict__ findrm, int maxlen, double* __restrict__ matrix,
+                           double* __restrict__ rhs) {
+  constexpr int LOC = DIM + 1;
+  extern __shared__ double acc[];
+  const int b = blockIdx.x, t = threadIdx.x;
+  const int r = rows[b * kBR + t];
+  const long long base = walk_ptr[b];
+  const int deg = (int)((walk_ptr[b + 1] - base) / kBR);
+  const int2* p = walk + base + t;
+  int2 e0 = deg > 0 ? ldg_stream(p) : make_int2(-1, 0);
+  int2 e1 = deg > 1 ? ldg_stream(p + kBR) : make_int2(-1, 0);
+  for (int q = 0; q < maxlen; q++) acc[q * kBR + t] = 0.0;
+  AdvDirectSink<DIM> sink;
+  sink.acc = acc + t;
+  sink.rhs = 0.0;
+  sink.i = 0;
+  double X[LOC][DIM], u[LOC][DIM], T[LOC];
+  int n[4] = {r >= 0 ? r : 0, 0, 0, 0};
+  unsigned slots = own_slot[b * kBR + t];
+  {
+    double unused;
+    unpack<DIM>(ld256(A.rec.r0 + n[0]), X[0], T[0]);
+    unpack<DIM>(ld256(A.rec.r1 + n[0]), u[0], unused);
+#pragma unroll
+    for (int q = 1; q < LOC; q++) {
+#pragma unroll
+      for (int a = 0; a < DIM; a++) X[q][a] = u[q][a] = 0.0;
+      T[q] = 0.0;
+    }
+  }
+  for (int k = 0; k < deg; k++) {
+    const int2 ent = e0;
+    e0 = e1;
+    e1 = (k + 2 < deg) ? ldg_stream(p + (long long)(k + 2) * kBR) : make_int2(-1, 0);
+    if (ent.x < 0) continue;
+    const int pos = ent.y & 3;
+#pragma unroll
+    for (int q = 1; q < LOC; q++)
+      if (pos == q) {
+        double unused;
+        unpack<DIM>(ld256(A.rec.r0 + ent.x), X[q], T[q]);
+        unpack<DIM>(ld256(A.rec.r1 + ent.x), u[q], unused);
+        n[q] = ent.x;
+        slots = (slots & ~(0xffu << (8 * q))) | (((unsigned)ent.y >> 8 & 0xffu) << (8 * q));
+      }
+    if (ent.y & 4) {
+      sink.slots = slots;
+      if constexpr (COMMON) advdiff_row0_data<DIM>(A, n, X, T, u, sink, AdvCommonFlags());
+      else advdiff_row0_data<DIM>(A, n, X, T, u, sink, AdvRuntimeFlags{A.o, A.diffusivity.stride});
+    }
+  }
+  if (r >= 0) rhs[r] = sink.rhs;
+  __syncthreads();
+  const int warp = t >> 5, lane = t & 31;
+  for (int rr = 0; rr < 32; rr++) {
+    const int tt = warp * 32 + rr;
+    const int row = rows[b * kBR + tt];
+    if (row < 0) continue;
+    const int s0 = findrm[row], nn = findrm[row + 1] - s0;
+    for (int s = lane; s < nn; s += 32) matrix[(size_t)s0 + s] = acc[s * kBR + tt];
+  }
+}
+
 template <class K>
 static int set_dyn_smem(K kernel, size_t bytes) {
   if (bytes > 48 * 1024) CG_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
@@ -643,7 +966,23 @@ static int gather_momentum_dim(Handle* h, const MomentumArgs& A, bool want_ml, b
         P->maxlen, prefetch, h->d_big_m,                                                                       \
         h->d_mom_rhs, ml);                                                                                     \
   } while (0)
-    if (abs_mode == 0 && momentum_common_ok(A.o, A.viscosity.stride) && want_ml) {
+    const bool use_walk = P->d_walk && abs_mode == 0 && !getenv("CGASM_GATHER_DIRECT");
+    if (use_walk) {
+      const int wminb = getenv("CGASM_WALK_MINB") ? atoi(getenv("CGASM_WALK_MINB")) : 3;
+#define LAUNCH_WALK(COMMON_, MINB_)                                                                            \
+  do {                                                                                                         \
+    if ((st = set_dyn_smem(gather_momentum_walk_kernel<DIM, COMMON_, MINB_>, smem))) return st;                \
+    gather_momentum_walk_kernel<DIM, COMMON_, MINB_><<<P->nblocks, kBR, smem, h->stream>>>(                    \
+        A, P->d_rows, P->d_walk_ptr, P->d_walk, P->d_own_slot, h->d_findrm, (size_t)h->nnz, P->maxlen,         \
+        h->d_big_m, h->d_mom_rhs, ml);                                                                         \
+  } while (0)
+      if (momentum_common_ok(A.o, A.viscosity.stride) && want_ml) {
+        if (wminb >= 4) LAUNCH_WALK(true, 4);
+        else if (wminb == 3) LAUNCH_WALK(true, 3);
+        else LAUNCH_WALK(true, 2);
+      } else LAUNCH_WALK(false, 2);
+#undef LAUNCH_WALK
+    } else if (abs_mode == 0 && momentum_common_ok(A.o, A.viscosity.stride) && want_ml) {
       if (minb >= 6) LAUNCH_DIRECT(false, false, true, 6);
       else if (minb == 5) LAUNCH_DIRECT(false, false, true, 5);
       else LAUNCH_DIRECT(false, false, true, 4);
@@ -708,7 +1047,22 @@ static int gather_advdiff_dim(Handle* h, const AdvDiffArgs& A) {
         prefetch, h->d_adv_matrix,                                                                       \
         h->d_adv_rhs);                                                                                   \
   } while (0)
-    if (advdiff_common_ok(A.o, A.diffusivity.stride)) {
+    if (P->d_walk && !getenv("CGASM_GATHER_DIRECT")) {
+      const int wminb = getenv("CGASM_WALK_MINB") ? atoi(getenv("CGASM_WALK_MINB")) : 4;
+#define LAUNCH_AWALK(COMMON_, MINB_)                                                                     \
+  do {                                                                                                   \
+    if ((st = set_dyn_smem(gather_advdiff_walk_kernel<DIM, COMMON_, MINB_>, smem))) return st;           \
+    gather_advdiff_walk_kernel<DIM, COMMON_, MINB_><<<P->nblocks, kBR, smem, h->stream>>>(               \
+        A, P->d_rows, P->d_walk_ptr, P->d_walk, P->d_own_slot, h->d_findrm, P->maxlen, h->d_adv_matrix,  \
+        h->d_adv_rhs);                                                                                   \
+  } while (0)
+      if (advdiff_common_ok(A.o, A.diffusivity.stride)) {
+        if (wminb >= 5) LAUNCH_AWALK(true, 5);
+        else if (wminb == 4) LAUNCH_AWALK(true, 4);
+        else LAUNCH_AWALK(true, 3);
+      } else LAUNCH_AWALK(false, 3);
+#undef LAUNCH_AWALK
+    } else if (advdiff_common_ok(A.o, A.diffusivity.stride)) {
       if (minb >= 6) LAUNCH_ADIRECT(true, 6);
       else if (minb == 5) LAUNCH_ADIRECT(true, 5);
       else LAUNCH_ADIRECT(true, 4);
