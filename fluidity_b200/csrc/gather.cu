@@ -767,8 +767,8 @@ template <int DIM, bool COMMON, int MINB>
 __global__ void __launch_bounds__(kBR, MINB)
 gather_momentum_walk_kernel(const MomentumArgs A, const int* __restrict__ rows, const long long* __restrict__ walk_ptr,
                             const int2* __restrict__ walk, const unsigned char* __restrict__ own_slot,
-                            const int* __restrict__ findrm, size_t nnz, int maxlen, double* __restrict__ big_m,
-                            double* __restrict__ rhs, double* __restrict__ masslump) {
+                            const int* __restrict__ findrm, size_t nnz, int maxlen, int prefetch,
+                            double* __restrict__ big_m, double* __restrict__ rhs, double* __restrict__ masslump) {
   constexpr int LOC = DIM + 1;
   extern __shared__ double acc[];
   const int b = blockIdx.x, t = threadIdx.x;
@@ -805,6 +805,11 @@ gather_momentum_walk_kernel(const MomentumArgs A, const int* __restrict__ rows, 
     const int2 ent = e0;
     e0 = e1;
     e1 = (k + 2 < deg) ? ldg_stream(p + (long long)(k + 2) * kBR) : make_int2(-1, 0);
+    if (prefetch && e0.x >= 0) {
+      prefetch_l1(A.rec.r0 + e0.x);
+      prefetch_l1(A.rec.r1 + e0.x);
+      prefetch_l1(A.rec.r2 + e0.x);
+    }
     if (ent.x < 0) continue;
     const int pos = ent.y & 3;
 #pragma unroll
@@ -849,7 +854,7 @@ template <int DIM, bool COMMON, int MINB>
 __global__ void __launch_bounds__(kBR, MINB)
 gather_advdiff_walk_kernel(const AdvDiffArgs A, const int* __restrict__ rows, const long long* __restrict__ walk_ptr,
                            const int2* __restrict__ walk, const unsigned char* __restrict__ own_slot,
-                           const int* __restrict__ findrm, int maxlen, double* __restrict__ matrix,
+                           const int* __restrict__ findrm, int maxlen, int prefetch, double* __restrict__ matrix,
                            double* __restrict__ rhs) {
   constexpr int LOC = DIM + 1;
   extern __shared__ double acc[];
@@ -883,6 +888,10 @@ gather_advdiff_walk_kernel(const AdvDiffArgs A, const int* __restrict__ rows, co
     const int2 ent = e0;
     e0 = e1;
     e1 = (k + 2 < deg) ? ldg_stream(p + (long long)(k + 2) * kBR) : make_int2(-1, 0);
+    if (prefetch && e0.x >= 0) {
+      prefetch_l1(A.rec.r0 + e0.x);
+      prefetch_l1(A.rec.r1 + e0.x);
+    }
     if (ent.x < 0) continue;
     const int pos = ent.y & 3;
 #pragma unroll
@@ -969,12 +978,13 @@ static int gather_momentum_dim(Handle* h, const MomentumArgs& A, bool want_ml, b
     const bool use_walk = P->d_walk && abs_mode == 0 && !getenv("CGASM_GATHER_DIRECT");
     if (use_walk) {
       const int wminb = getenv("CGASM_WALK_MINB") ? atoi(getenv("CGASM_WALK_MINB")) : 3;
+      const int wprefetch = getenv("CGASM_WALK_PREFETCH") ? atoi(getenv("CGASM_WALK_PREFETCH")) : 0;
 #define LAUNCH_WALK(COMMON_, MINB_)                                                                            \
   do {                                                                                                         \
     if ((st = set_dyn_smem(gather_momentum_walk_kernel<DIM, COMMON_, MINB_>, smem))) return st;                \
     gather_momentum_walk_kernel<DIM, COMMON_, MINB_><<<P->nblocks, kBR, smem, h->stream>>>(                    \
         A, P->d_rows, P->d_walk_ptr, P->d_walk, P->d_own_slot, h->d_findrm, (size_t)h->nnz, P->maxlen,         \
-        h->d_big_m, h->d_mom_rhs, ml);                                                                         \
+        wprefetch, h->d_big_m, h->d_mom_rhs, ml);                                                              \
   } while (0)
       if (momentum_common_ok(A.o, A.viscosity.stride) && want_ml) {
         if (wminb >= 4) LAUNCH_WALK(true, 4);
@@ -1049,12 +1059,13 @@ static int gather_advdiff_dim(Handle* h, const AdvDiffArgs& A) {
   } while (0)
     if (P->d_walk && !getenv("CGASM_GATHER_DIRECT")) {
       const int wminb = getenv("CGASM_WALK_MINB") ? atoi(getenv("CGASM_WALK_MINB")) : 4;
+      const int wprefetch = getenv("CGASM_WALK_PREFETCH") ? atoi(getenv("CGASM_WALK_PREFETCH")) : 0;
 #define LAUNCH_AWALK(COMMON_, MINB_)                                                                     \
   do {                                                                                                   \
     if ((st = set_dyn_smem(gather_advdiff_walk_kernel<DIM, COMMON_, MINB_>, smem))) return st;           \
     gather_advdiff_walk_kernel<DIM, COMMON_, MINB_><<<P->nblocks, kBR, smem, h->stream>>>(               \
-        A, P->d_rows, P->d_walk_ptr, P->d_walk, P->d_own_slot, h->d_findrm, P->maxlen, h->d_adv_matrix,  \
-        h->d_adv_rhs);                                                                                   \
+        A, P->d_rows, P->d_walk_ptr, P->d_walk, P->d_own_slot, h->d_findrm, P->maxlen, wprefetch,        \
+        h->d_adv_matrix, h->d_adv_rhs);                                                                  \
   } while (0)
       if (advdiff_common_ok(A.o, A.diffusivity.stride)) {
         if (wminb >= 5) LAUNCH_AWALK(true, 5);
