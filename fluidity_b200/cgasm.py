@@ -190,6 +190,26 @@ class Assembler:
         _check(self.lib.cgasm_momentum_fetch(C.c_int(self.id), _dp(big_m), _dp(rhs), _dp(ml), _dp(ct)))
         return dict(big_m=big_m, rhs=rhs, masslump=ml, ct_m=ct)
 
+    def momentum_identical_blocks(self):
+        f = C.c_int(0)
+        _check(self.lib.cgasm_momentum_identical_blocks(C.c_int(self.id), C.byref(f)))
+        return bool(f.value)
+
+    def momentum_fetch_blocks(self, first, nblocks, out):
+        _check(self.lib.cgasm_momentum_fetch_blocks(C.c_int(self.id), C.c_int(first), C.c_int(nblocks), _dp(out)))
+        return out
+
+    def momentum_host(self, opts, out):
+        """Host-buffer momentum call that moves only what is distinct: when the dim diagonal blocks are
+        identical (cgasm_momentum_identical_blocks) one block crosses PCIe and out['big_m'] has shape
+        (1, nnz); the caller inserts it dim times."""
+        self.momentum_dev(opts)
+        nb = 1 if self.momentum_identical_blocks() else self.dim
+        self.momentum_fetch_blocks(0, nb, out["big_m"])
+        ml = out.get("masslump") if opts.assemble_inverse_masslump else None
+        _check(self.lib.cgasm_momentum_fetch(C.c_int(self.id), None, _dp(out["rhs"]), _dp(ml), None))
+        return nb
+
     def advdiff_fetch(self):
         val = np.empty(self.nnz)
         rhs = np.empty(self.n_nodes)

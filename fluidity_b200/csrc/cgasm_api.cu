@@ -620,6 +620,7 @@ int cgasm_momentum_dev(int id, const cgasm_momentum_opts* opts) {
   CG_CUDA(cudaGetLastError());
   h->mom_has_masslump = want_ml;
   h->mom_has_ct = want_ct;
+  h->mom_identical_blocks = !opts->have_absorption;
   h->mom_valid = true;
   return CGASM_OK;
 }
@@ -668,6 +669,25 @@ int cgasm_momentum_fetch(int id, double* big_m, double* rhs, double* masslump, d
     if (!h->mom_has_ct) CG_FAIL(CGASM_ESTATE, "ct_m was not assembled (assemble_ct_matrix_here = 0)");
     CG_CUDA(cudaMemcpyAsync(ct_m, h->d_ct_m, sizeof(double) * dim * nnz, cudaMemcpyDeviceToHost, h->stream));
   }
+  CG_CUDA(cudaStreamSynchronize(h->stream));
+  return CGASM_OK;
+}
+
+int cgasm_momentum_identical_blocks(int id, int* identical) {
+  GET_HANDLE(h, id);
+  if (!identical) CG_FAIL(CGASM_EARG, "null out");
+  if (!h->mom_valid) CG_FAIL(CGASM_ESTATE, "no momentum result");
+  *identical = h->mom_identical_blocks ? 1 : 0;
+  return CGASM_OK;
+}
+
+int cgasm_momentum_fetch_blocks(int id, int first_block, int nblocks, double* big_m) {
+  GET_HANDLE(h, id);
+  if (!h->mom_valid) CG_FAIL(CGASM_ESTATE, "no momentum result to fetch");
+  if (!big_m || first_block < 0 || nblocks < 1 || first_block + nblocks > h->dim) CG_FAIL(CGASM_EARG, "bad block range");
+  const size_t nnz = (size_t)h->nnz;
+  CG_CUDA(cudaMemcpyAsync(big_m, h->d_big_m + (size_t)first_block * nnz, sizeof(double) * nnz * nblocks,
+                          cudaMemcpyDeviceToHost, h->stream));
   CG_CUDA(cudaStreamSynchronize(h->stream));
   return CGASM_OK;
 }

@@ -69,6 +69,7 @@ struct Handle {
   double* d_adv_matrix = nullptr;  // [nnz]
   double* d_adv_rhs = nullptr;     // (n_nodes)
   bool mom_has_masslump = false, mom_has_ct = false, mom_valid = false, adv_valid = false;
+  bool mom_identical_blocks = false;
 
   int scatter = CGASM_SCATTER_ATOMIC;
   TilePlan* tiles = nullptr;

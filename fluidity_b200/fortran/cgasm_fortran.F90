@@ -19,7 +19,8 @@ module cgasm_interface
        & cgasm_build_sparsity, cgasm_get_sparsity, cgasm_set_colouring, cgasm_build_colouring, &
        & cgasm_get_colouring, cgasm_set_scatter, cgasm_set_field, cgasm_get_field, &
        & cgasm_momentum, cgasm_advdiff, cgasm_momentum_dev, cgasm_advdiff_dev, &
-       & cgasm_momentum_fetch, cgasm_advdiff_fetch, cgasm_momentum_element, &
+       & cgasm_momentum_fetch, cgasm_advdiff_fetch, cgasm_momentum_identical_blocks, &
+       & cgasm_momentum_fetch_blocks, cgasm_momentum_element, &
        & cgasm_advdiff_element, cgasm_synchronize, cgasm_halo_create, cgasm_halo_update, &
        & cgasm_nccl_unique_id, cgasm_last_error
   public :: CGASM_OK, CGASM_EUNSUPPORTED
@@ -197,6 +198,22 @@ module cgasm_interface
        type(c_ptr), value :: big_m, rhs, masslump, ct_m
        integer(c_int) :: stat
      end function cgasm_momentum_fetch
+
+     function cgasm_momentum_identical_blocks(id, identical) &
+          & bind(c, name="cgasm_momentum_identical_blocks") result(stat)
+       use iso_c_binding
+       integer(c_int), value :: id
+       integer(c_int), intent(out) :: identical
+       integer(c_int) :: stat
+     end function cgasm_momentum_identical_blocks
+
+     function cgasm_momentum_fetch_blocks(id, first_block, nblocks, big_m) &
+          & bind(c, name="cgasm_momentum_fetch_blocks") result(stat)
+       use iso_c_binding
+       integer(c_int), value :: id, first_block, nblocks
+       real(c_double), dimension(*), intent(out) :: big_m
+       integer(c_int) :: stat
+     end function cgasm_momentum_fetch_blocks
 
      function cgasm_advdiff_fetch(id, matrix_val, rhs) bind(c, name="cgasm_advdiff_fetch") result(stat)
        use iso_c_binding

@@ -216,6 +216,12 @@ int cgasm_momentum_dev(int id, const cgasm_momentum_opts* opts);
 int cgasm_advdiff_dev(int id, const cgasm_advdiff_opts* opts);
 int cgasm_momentum_fetch(int id, double* big_m, double* rhs, double* masslump, double* ct_m);
 int cgasm_advdiff_fetch(int id, double* matrix_val, double* rhs);
+/* 1 if the dim diagonal blocks of the last momentum result are identical (no absorption term:
+ * mass, advection and tensor-form viscosity add the same loc x loc matrix to every (d,d) block,
+ * Momentum_CG.F90:1550,1711,2312-2317), so one block can be fetched and inserted dim times. */
+int cgasm_momentum_identical_blocks(int id, int* identical);
+/* Copies blocks first_block .. first_block+nblocks-1 (0-based) of big_m to the host. */
+int cgasm_momentum_fetch_blocks(int id, int first_block, int nblocks, double* big_m);
 /* Raw device pointers of the last result (NULL if that output was not assembled). */
 int cgasm_momentum_result_dev(int id, double** big_m_dev, double** rhs_dev,
                               double** masslump_dev, double** ct_m_dev);

@@ -295,6 +295,28 @@ def test_large_mesh_properties(scatter):
         assert rel_err(a, b) < TOL
 
 
+def test_identical_blocks_partial_fetch(orc):
+    mesh = syn.box_mesh((5, 4, 3))
+    fs = syn.standard_fields(mesh)
+    asm = make_asm(mesh, fs, abi.SCATTER_GATHER)
+    findrm, colm, _ = asm.get_sparsity()
+    o = abi.common_momentum_opts()
+    ref = orc.assemble_momentum(mesh, fs, o, findrm, colm)
+    out = dict(big_m=np.empty((1, asm.nnz)), rhs=np.empty((mesh.n_nodes, 3)), masslump=np.empty((mesh.n_nodes, 3)))
+    assert asm.momentum_host(o, out) == 1
+    for d in range(3):  # one fetched block stands for all three
+        assert rel_err(out["big_m"][0], ref["big_m"][d]) < TOL
+    assert rel_err(out["rhs"], ref["rhs"]) < TOL and rel_err(out["masslump"], ref["masslump"]) < TOL
+    o2 = abi.common_momentum_opts(have_absorption=1)
+    out3 = dict(big_m=np.empty((3, asm.nnz)), rhs=np.empty((mesh.n_nodes, 3)), masslump=np.empty((mesh.n_nodes, 3)))
+    assert asm.momentum_host(o2, out3) == 3
+    ref2 = orc.assemble_momentum(mesh, fs, o2, findrm, colm)
+    for d in range(3):
+        assert rel_err(out3["big_m"][d], ref2["big_m"][d]) < TOL
+    with pytest.raises(cgasm.CgasmError):
+        asm.momentum_fetch_blocks(2, 2, np.empty((2, asm.nnz)))
+
+
 def test_unsupported_options_are_refused():
     mesh = syn.box_mesh((2, 2, 2))
     asm = make_asm(mesh, syn.standard_fields(mesh))
