@@ -43,7 +43,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="graft", choices=["graft", "reference"])
     ap.add_argument("--cells", type=int, default=256, help="cells per axis per GPU (256 = S3)")
-    ap.add_argument("--scatter", default="best", choices=["best", "atomic", "coloured", "warpagg", "tiled", "gather"])
+    ap.add_argument("--scatter", default="best", choices=["best", "atomic", "coloured", "warpagg", "tiled", "gather", "strip"])
     ap.add_argument("--cpu-cells", type=int, default=64, help="cells per axis of the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -205,12 +205,12 @@ def run_graft(args):
         dist.broadcast_object_list(uid, src=0)
         asm.halo_create(world, rank, lp.sends, lp.recvs, uid[0])
     scatter = {"atomic": abi.SCATTER_ATOMIC, "coloured": abi.SCATTER_COLOURED, "warpagg": abi.SCATTER_WARPAGG,
-               "tiled": abi.SCATTER_TILED, "gather": abi.SCATTER_GATHER}
+               "tiled": abi.SCATTER_TILED, "gather": abi.SCATTER_GATHER, "strip": abi.SCATTER_STRIP}
     chosen = args.scatter
     if chosen == "best":
         try:
-            asm.set_scatter(abi.SCATTER_GATHER)
-            chosen = "gather"
+            asm.set_scatter(abi.SCATTER_STRIP)
+            chosen = "strip"
         except cgasm.CgasmError:
             asm.set_scatter(abi.SCATTER_ATOMIC)
             chosen = "atomic"

@@ -22,7 +22,7 @@ FIELD_NORMAL, FIELD_CONSTANT = 0, 1
 STAB_NONE, STAB_STREAMLINE_UPWIND, STAB_SUPG = 0, 1, 2
 NU_BAR_OPTIMAL, NU_BAR_DOUBLY_ASYMPTOTIC, NU_BAR_CRITICAL_RULE, NU_BAR_UNITY = 1, 2, 3, 4
 TENSOR_ISOTROPIC, TENSOR_DIAGONAL, TENSOR_FULL = 0, 1, 2
-SCATTER_ATOMIC, SCATTER_COLOURED, SCATTER_WARPAGG, SCATTER_TILED, SCATTER_GATHER = 0, 1, 2, 3, 4
+SCATTER_ATOMIC, SCATTER_COLOURED, SCATTER_WARPAGG, SCATTER_TILED, SCATTER_GATHER, SCATTER_STRIP = 0, 1, 2, 3, 4, 5
 
 _M_DOUBLES = ["dt", "theta", "beta", "gravity_magnitude", "nu_bar_scale"]
 _M_INTS = [

@@ -76,6 +76,10 @@ int repack_slot(Handle* h, int slot, const int* d_nodes, int n) {
   if (count <= 0) return CGASM_OK;
   pack_lanes_kernel<<<(count + 255) / 256, 256, 0, h->stream>>>(rec, lane0, ncomp, src, stride, d_nodes, count);
   h->launches++;
+  if (slot < 0 || slot == CGASM_F_BUOYANCY) {  // rec3 = { X, buoyancy } mirrors these two
+    pack_lanes_kernel<<<(count + 255) / 256, 256, 0, h->stream>>>(h->d_rec3, lane0, ncomp, src, stride, d_nodes, count);
+    h->launches++;
+  }
   CG_CUDA(cudaGetLastError());
   return CGASM_OK;
 }
@@ -90,6 +94,7 @@ static void destroy_handle(Handle* h) {
   free_dev(h->d_rec0);
   free_dev(h->d_rec1);
   free_dev(h->d_rec2);
+  free_dev(h->d_rec3);
   free_dev(h->d_findrm);
   free_dev(h->d_colm);
   free_dev(h->d_colour_elements);
@@ -352,6 +357,8 @@ int cgasm_create(int* id, int device, int dim, int loc, int ngi, int n_nodes, in
       cudaMalloc(&h->d_rec0, sizeof(double4) * (size_t)n_nodes) != cudaSuccess ||
       cudaMalloc(&h->d_rec1, sizeof(double4) * (size_t)n_nodes) != cudaSuccess ||
       cudaMalloc(&h->d_rec2, sizeof(double4) * (size_t)n_nodes) != cudaSuccess ||
+      cudaMalloc(&h->d_rec3, sizeof(double4) * (size_t)n_nodes) != cudaSuccess ||
+      cudaMemset(h->d_rec3, 0, sizeof(double4) * (size_t)n_nodes) != cudaSuccess ||
       cudaMemset(h->d_rec0, 0, sizeof(double4) * (size_t)n_nodes) != cudaSuccess ||
       cudaMemset(h->d_rec1, 0, sizeof(double4) * (size_t)n_nodes) != cudaSuccess ||
       cudaMemset(h->d_rec2, 0, sizeof(double4) * (size_t)n_nodes) != cudaSuccess ||
@@ -518,7 +525,7 @@ int cgasm_set_colouring(int id, int ncolours, const int* colour_ptr, const int* 
 
 int cgasm_set_scatter(int id, int variant) {
   GET_HANDLE(h, id);
-  if (variant < CGASM_SCATTER_ATOMIC || variant > CGASM_SCATTER_GATHER) CG_FAIL(CGASM_EARG, "unknown scatter variant");
+  if (variant < CGASM_SCATTER_ATOMIC || variant > CGASM_SCATTER_STRIP) CG_FAIL(CGASM_EARG, "unknown scatter variant");
   if (variant == CGASM_SCATTER_COLOURED && !h->ncolours) {
     int st = cgasm_build_colouring(id, nullptr);
     if (st) return st;
@@ -530,10 +537,14 @@ int cgasm_set_scatter(int id, int variant) {
       if (st) return st;
     }
   }
-  if (variant == CGASM_SCATTER_GATHER) {
+  if (variant == CGASM_SCATTER_GATHER || variant == CGASM_SCATTER_STRIP) {
     if (!h->have_sparsity) CG_FAIL(CGASM_ESTATE, "gather scatter needs the sparsity first");
     if (!h->gather) {
       int st = gather_build(h);
+      if (st) return st;
+    }
+    if (variant == CGASM_SCATTER_STRIP) {
+      int st = strip_build(h);
       if (st) return st;
     }
   }
@@ -600,12 +611,12 @@ int cgasm_momentum_dev(int id, const cgasm_momentum_opts* opts) {
   if (want_ml && (st = ensure(&h->d_masslump, dim * nn))) return st;
   if (want_ct && (st = ensure(&h->d_ct_m, dim * nnz))) return st;
   if (opts->stabilisation_scheme != CGASM_STAB_NONE && h->scatter != CGASM_SCATTER_ATOMIC &&
-      h->scatter != CGASM_SCATTER_GATHER)
+      h->scatter != CGASM_SCATTER_GATHER && h->scatter != CGASM_SCATTER_STRIP)
     CG_FAIL(CGASM_EUNSUPPORTED, "SU/SUPG stabilisation runs on the ATOMIC and GATHER scatter variants only");
   CG_CUDA(cudaEventRecord(h->ev0, h->stream));
   if (h->scatter == CGASM_SCATTER_TILED) {
     st = tiles_momentum(h, A, want_ml, want_ct);
-  } else if (h->scatter == CGASM_SCATTER_GATHER) {
+  } else if (h->scatter == CGASM_SCATTER_GATHER || h->scatter == CGASM_SCATTER_STRIP) {
     st = gather_momentum(h, A, want_ml, want_ct);
   } else {
     // zero(big_m), zero(rhs) ... (Momentum_Equation.F90:593-606) then accumulate
@@ -636,12 +647,12 @@ int cgasm_advdiff_dev(int id, const cgasm_advdiff_opts* opts) {
   if ((st = ensure(&h->d_adv_matrix, nnz))) return st;
   if ((st = ensure(&h->d_adv_rhs, nn))) return st;
   if (opts->stabilisation_scheme != CGASM_STAB_NONE && h->scatter != CGASM_SCATTER_ATOMIC &&
-      h->scatter != CGASM_SCATTER_GATHER)
+      h->scatter != CGASM_SCATTER_GATHER && h->scatter != CGASM_SCATTER_STRIP)
     CG_FAIL(CGASM_EUNSUPPORTED, "SU/SUPG stabilisation runs on the ATOMIC and GATHER scatter variants only");
   CG_CUDA(cudaEventRecord(h->ev0, h->stream));
   if (h->scatter == CGASM_SCATTER_TILED) {
     st = tiles_advdiff(h, P);
-  } else if (h->scatter == CGASM_SCATTER_GATHER) {
+  } else if (h->scatter == CGASM_SCATTER_GATHER || h->scatter == CGASM_SCATTER_STRIP) {
     st = gather_advdiff(h, P);
   } else {
     CG_CUDA(cudaMemsetAsync(h->d_adv_matrix, 0, sizeof(double) * nnz, h->stream));

@@ -41,6 +41,7 @@ struct Handle {
   double4* d_rec0 = nullptr;
   double4* d_rec1 = nullptr;
   double4* d_rec2 = nullptr;
+  double4* d_rec3 = nullptr;  // { X, buoyancy }: with rec1 everything the strip momentum loop reads
   std::vector<double> h_X;  // kept for locality ordering of the tile plan
 
   // node -> element adjacency (host)
@@ -160,6 +161,14 @@ int gather_build(Handle* h);
 void gather_free(Handle* h);
 int gather_momentum(Handle* h, const MomentumArgs& args, bool want_ml, bool want_ct);
 int gather_advdiff(Handle* h, const AdvDiffArgs& args);
+
+// strip.cu
+int strip_build(Handle* h);
+void strip_free(GatherPlan* P);
+bool strip_momentum_ok(const Handle* h, const MomentumArgs& args, bool want_ml);
+bool strip_advdiff_ok(const Handle* h, const AdvDiffArgs& args);
+int strip_momentum(Handle* h, const MomentumArgs& args);
+int strip_advdiff(Handle* h, const AdvDiffArgs& args);
 
 // halo.cu
 void halo_free(Handle* h);

@@ -19,6 +19,7 @@
 // The pair list plays the role of csr_sparsity_pos (Sparse_Tools.F90:2411-2517): positions are
 // found once per mesh instead of once per entry per assembly.
 #include "cgasm_internal.h"
+#include "gather_plan.h"
 
 #include <algorithm>
 #include <cstdio>
@@ -26,32 +27,6 @@
 #include <numeric>
 
 namespace cgasm {
-
-constexpr int kBR = 128;  // rows (= threads) per gather block
-
-struct GatherPlan {
-  int nblocks = 0;
-  int maxlen = 0;                  // longest CSR row
-  int* d_rows = nullptr;           // [nblocks*kBR] node of each row slot, -1 = padding
-  long long* d_block_ptr = nullptr;  // [nblocks+1] first plan entry of a block
-  uint2* d_pairs = nullptr;        // block-interleaved: entry k of thread t at ptr + k*kBR + t
-                                   //   .x = element*4 + local row (0xFFFFFFFF = none), .y = 4 x 8-bit slot
-  int4* d_pair_nodes = nullptr;    // same indexing, ONE 16-byte load per pair: {n1, n2, n3, slots} = the element's
-                                   //   other nodes in rotated order (the row's own node is rotated node 0;
-                                   //   n1 < 0 = none) and the 4 x 8-bit CSR slots of rotated nodes 0..3
-  long long n_entries = 0;
-  // walk plan (single-pass kernels for the common option set): per row the incident elements are
-  // ordered as a face-adjacent walk around the node, so consecutive elements share two of their
-  // three other nodes; an entry loads ONE node into one of the three register positions.
-  //   .x = node to load (-1 = padding), .y = position (bits 0-1) | compute flag (bit 2) | CSR slot << 8
-  long long* d_walk_ptr = nullptr;  // [nblocks+1]
-  int2* d_walk = nullptr;           // block-interleaved like d_pairs
-  unsigned char* d_own_slot = nullptr;  // [nblocks*kBR] slot of the diagonal inside the row
-  long long n_walk = 0;
-  double walk_entries_per_pair = 0.0;
-  double* d_stage = nullptr;       // staging buffer (grown on demand)
-  size_t stage_doubles = 0;
-};
 
 void gather_free(Handle* h) {
   GatherPlan* p = h->gather;
@@ -64,6 +39,7 @@ void gather_free(Handle* h) {
   if (p->d_walk_ptr) cudaFree(p->d_walk_ptr);
   if (p->d_walk) cudaFree(p->d_walk);
   if (p->d_own_slot) cudaFree(p->d_own_slot);
+  strip_free(p);
   delete p;
   h->gather = nullptr;
 }
@@ -296,6 +272,7 @@ int gather_build(Handle* h) {
     std::sort(rows.begin() + (size_t)b * kBR, rows.begin() + (size_t)b * kBR + std::min(kBR, n - b * kBR));
     block_ptr[b + 1] = block_ptr[b] + (long long)deg * kBR;
   }
+  P->h_rows = rows;
   if (maxlen > 255) CG_FAIL(CGASM_EUNSUPPORTED, "CSR row longer than 255 entries: gather slot index is 8 bit");
   P->maxlen = maxlen;
   P->n_entries = block_ptr[P->nblocks];
@@ -976,7 +953,10 @@ static int gather_momentum_dim(Handle* h, const MomentumArgs& A, bool want_ml, b
         h->d_mom_rhs, ml);                                                                                     \
   } while (0)
     const bool use_walk = P->d_walk && abs_mode == 0 && !getenv("CGASM_GATHER_DIRECT");
-    if (use_walk) {
+    if (h->scatter == CGASM_SCATTER_STRIP && strip_momentum_ok(h, A, want_ml)) {
+      if ((st = strip_momentum(h, A))) return st;
+      h->launches--;  // counted by strip_momentum
+    } else if (use_walk) {
       const int wminb = getenv("CGASM_WALK_MINB") ? atoi(getenv("CGASM_WALK_MINB")) : 3;
       const int wprefetch = getenv("CGASM_WALK_PREFETCH") ? atoi(getenv("CGASM_WALK_PREFETCH")) : 0;
 #define LAUNCH_WALK(COMMON_, MINB_)                                                                            \
@@ -1057,7 +1037,10 @@ static int gather_advdiff_dim(Handle* h, const AdvDiffArgs& A) {
         prefetch, h->d_adv_matrix,                                                                       \
         h->d_adv_rhs);                                                                                   \
   } while (0)
-    if (P->d_walk && !getenv("CGASM_GATHER_DIRECT")) {
+    if (h->scatter == CGASM_SCATTER_STRIP && strip_advdiff_ok(h, A)) {
+      if ((st = strip_advdiff(h, A))) return st;
+      h->launches--;  // counted by strip_advdiff
+    } else if (P->d_walk && !getenv("CGASM_GATHER_DIRECT")) {
       const int wminb = getenv("CGASM_WALK_MINB") ? atoi(getenv("CGASM_WALK_MINB")) : 4;
       const int wprefetch = getenv("CGASM_WALK_PREFETCH") ? atoi(getenv("CGASM_WALK_PREFETCH")) : 0;
 #define LAUNCH_AWALK(COMMON_, MINB_)                                                                     \

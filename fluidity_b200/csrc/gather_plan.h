@@ -1,0 +1,41 @@
+// gather_plan.h -- row-block plans shared by the row-owner kernels (gather.cu, strip.cu).
+#pragma once
+#include "cgasm_internal.h"
+
+namespace cgasm {
+
+constexpr int kBR = 128;  // rows (= threads) per gather block
+
+struct GatherPlan {
+  int nblocks = 0;
+  int maxlen = 0;                  // longest CSR row
+  int* d_rows = nullptr;           // [nblocks*kBR] node of each row slot, -1 = padding
+  long long* d_block_ptr = nullptr;  // [nblocks+1] first plan entry of a block
+  uint2* d_pairs = nullptr;        // block-interleaved: entry k of thread t at ptr + k*kBR + t
+                                   //   .x = element*4 + local row (0xFFFFFFFF = none), .y = 4 x 8-bit slot
+  int4* d_pair_nodes = nullptr;    // same indexing, ONE 16-byte load per pair: {n1, n2, n3, slots} = the element's
+                                   //   other nodes in rotated order (the row's own node is rotated node 0;
+                                   //   n1 < 0 = none) and the 4 x 8-bit CSR slots of rotated nodes 0..3
+  long long n_entries = 0;
+  // walk plan (single-pass kernels for the common option set): per row the incident elements are
+  // ordered as a face-adjacent walk around the node, so consecutive elements share two of their
+  // three other nodes; an entry loads ONE node into one of the three register positions.
+  //   .x = node to load (-1 = padding), .y = position (bits 0-1) | compute flag (bit 2) | CSR slot << 8
+  long long* d_walk_ptr = nullptr;  // [nblocks+1]
+  int2* d_walk = nullptr;           // block-interleaved like d_pairs
+  unsigned char* d_own_slot = nullptr;  // [nblocks*kBR] slot of the diagonal inside the row
+  long long n_walk = 0;
+  double walk_entries_per_pair = 0.0;
+  // strip plan (strip.cu / strip_plan.h): block-interleaved {node, slot | compute << 8}, block degree
+  // padded to a multiple of strip_mult (= register buffers of the kernel) with no-op entries
+  std::vector<int> h_rows;           // host copy of d_rows
+  long long* d_strip_ptr = nullptr;  // [nblocks+1]
+  int2* d_strip = nullptr;
+  long long n_strip = 0;
+  int strip_mult = 0;
+  double strip_entries_per_pair = 0.0;
+  double* d_stage = nullptr;       // staging buffer (grown on demand)
+  size_t stage_doubles = 0;
+};
+
+}  // namespace cgasm

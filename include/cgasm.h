@@ -84,9 +84,13 @@ enum {
   CGASM_SCATTER_WARPAGG = 2,  /* warp-aggregated atomics (match.any on the slot)        */
   CGASM_SCATTER_TILED = 3,    /* node-tile owner-computes, shared-memory accumulate,    */
                               /* every CSR value written exactly once                   */
-  CGASM_SCATTER_GATHER = 4    /* two passes: element kernel streams local rows to a     */
+  CGASM_SCATTER_GATHER = 4,   /* two passes: element kernel streams local rows to a     */
                               /* staging buffer, row kernel gathers them (no atomics,   */
                               /* no colouring, no redundant element math)               */
+  CGASM_SCATTER_STRIP = 5     /* row owner, elements streamed as a strip around the     */
+                              /* node (one node load per entry, register accumulators,  */
+                              /* rhs as one sparse dot per row); option sets outside    */
+                              /* the common one run the GATHER kernels                  */
 };
 
 /* ---- option structs: the module-level switches read once per assembly ----------
@@ -245,6 +249,14 @@ int cgasm_stream(int id, void** stream);
 int cgasm_launch_count(int id, long long* launches);
 /* Device time in ms of the most recent cgasm_*_dev call (CUDA events on the handle stream). */
 int cgasm_last_kernel_ms(int id, float* ms);
+
+/* Diagnostics (host only, no GPU): the strip ordering CGASM_SCATTER_STRIP uses for every row of
+ * a P1 simplex mesh. ndglno as in cgasm_create. row_ptr(n_nodes+1): 0-based offsets; entries:
+ * pairs {node (1-based), meta} with meta bits 0-7 = 0-based CSR slot of the node inside the row,
+ * bit 8 = "the last loc-1 pushed nodes plus the row node form an element: compute it now".
+ * At most `capacity` pairs are written; *needed returns the total. */
+int cgasm_strip_plan_host(int loc, int n_nodes, int n_elements, const int* ndglno,
+                          long long* row_ptr, int* entries, long long capacity, long long* needed);
 
 /* ---- halo update (femtools/Halos_Communications.F90:320-412,497-567) -------------------
  * nprocs neighbours; sends/recvs are the concatenated 1-based node lists of

@@ -1,0 +1,153 @@
+"""numpy emulation of the STRIP row-owner kernels (fluidity_b200/csrc/strip.cu), run on the CPU
+from the plan that cgasm_strip_plan_host builds: same FIFO windows, same closed forms, same
+per-row epilogue. It is TEST infrastructure: it lets the CPU suite check the plan and the
+algebra of the device code against the oracle without a GPU. Common option set only.
+"""
+import ctypes as C
+
+import numpy as np
+
+from fluidity_b200 import _abi as abi, cgasm, tables
+
+COMPUTE = 0x100
+
+
+def strip_plan(mesh):
+    """row_ptr (n_nodes+1), entries (n, 2): node (1-based), meta."""
+    lib = cgasm.load()
+    nd = np.ascontiguousarray(mesh.ndglno, dtype=np.int32)
+    row_ptr = np.zeros(mesh.n_nodes + 1, dtype=np.int64)
+    needed = C.c_longlong(0)
+    args = [C.c_int(mesh.loc), C.c_int(mesh.n_nodes), C.c_int(mesh.n_elements), nd.ctypes.data_as(C.POINTER(C.c_int)),
+            row_ptr.ctypes.data_as(C.POINTER(C.c_longlong))]
+    st = lib.cgasm_strip_plan_host(*args, None, C.c_longlong(0), C.byref(needed))
+    assert st == 0, lib.cgasm_last_error()
+    ent = np.zeros((max(needed.value, 1), 2), dtype=np.int32)
+    st = lib.cgasm_strip_plan_host(*args, ent.ctypes.data_as(C.POINTER(C.c_int)), C.c_longlong(needed.value),
+                                   C.byref(needed))
+    assert st == 0, lib.cgasm_last_error()
+    return row_ptr, ent[:needed.value]
+
+
+def moments(dim):
+    """Pd, Po, Qaaa, Qaab, Qabc, Wsum of the degree-3 rule (element_math.cuh Tables)."""
+    l, w = tables.quadrature_degree3(dim)
+    N = l.T  # N[i, g]
+    P = np.einsum("ig,kg,g->ik", N, N, w)
+    Q = np.einsum("ig,kg,lg,g->ikl", N, N, N, w)
+    return dict(Pd=P[0, 0], Po=P[0, 1], Qaaa=Q[0, 0, 0], Qaab=Q[0, 0, 1], Qabc=Q[0, 1, 2], Wsum=w.sum())
+
+
+def _geometry(e):
+    """cofactor vectors c[k] (gradN_k = c[k]/det) and det of the window edges e (dim, dim)."""
+    dim = e.shape[0]
+    if dim == 3:
+        c = np.array([np.cross(e[1], e[2]), np.cross(e[2], e[0]), np.cross(e[0], e[1])])
+    else:
+        c = np.array([[e[1][1], -e[1][0]], [-e[0][1], e[0][0]]])
+    return c, float(e[0] @ c[0])
+
+
+def emulate_momentum(mesh, fs, o, findrm, colm):
+    dim, nn = mesh.dim, mesh.n_nodes
+    m = moments(dim)
+    X = mesh.X
+    nu, oldu = fs.get(abi.F_NU)[0], fs.get(abi.F_OLDU)[0]
+    rho, bb = fs.get(abi.F_DENSITY)[0], fs.get(abi.F_BUOYANCY)[0]
+    mu = fs.get(abi.F_VISCOSITY)[0].reshape(-1)[0]
+    g = fs.get(abi.F_GRAVITY)[0].reshape(-1)[:dim]
+    row_ptr, ent = strip_plan(mesh)
+    f0, c0 = findrm - 1, colm - 1
+    nnz = len(colm)
+    big_m = np.zeros((dim, nnz))
+    rhs = np.zeros((nn, dim))
+    ml = np.zeros((nn, dim))
+    dtt = o.dt * o.theta
+    Qa, Qd = m["Qaaa"] - m["Qaab"], m["Qaab"] - m["Qabc"]
+    for r in range(nn):
+        s0, s1 = f0[r], f0[r + 1]
+        acc = np.zeros(s1 - s0)
+        own = int(np.searchsorted(c0[s0:s1], r))
+        fifo = []  # (node, slot)
+        msum = nbsum = 0.0
+        for node1, meta in ent[row_ptr[r]:row_ptr[r + 1]]:
+            fifo.append((node1 - 1, meta & 0xff))
+            fifo = fifo[-dim:]
+            if not (meta & COMPUTE):
+                continue
+            nodes = [q for q, _ in fifo]
+            e = X[nodes] - X[r]
+            c, det = _geometry(e)
+            rd = 1.0 / det
+            sc = c.sum(axis=0)
+            S = rho[r] + rho[nodes].sum()
+            M0 = Qa * rho[r] + m["Qaab"] * S
+            w = M0 * nu[r]
+            for k, q in enumerate(nodes):
+                w = w + (Qd * (rho[r] + rho[q]) + m["Qabc"] * S) * nu[q]
+            u = np.sign(det) * (w - (mu * m["Wsum"] * rd) * sc)
+            tot = 0.0
+            for k, (q, slot) in enumerate(fifo):
+                sk = float(u @ c[k])
+                acc[slot] += sk
+                tot += sk
+            acc[own] -= tot
+            ad = abs(det)
+            msum += ad * ((m["Pd"] - m["Po"]) * rho[r] + m["Po"] * S)
+            nbsum += ad * ((m["Pd"] - m["Po"]) * bb[r] + m["Po"] * (bb[r] + bb[nodes].sum()))
+        cols = c0[s0:s1]
+        rhs[r] = o.gravity_magnitude * g * nbsum - acc @ oldu[cols]
+        vals = dtt * acc
+        vals[own] += msum
+        big_m[:, s0:s1] = vals
+        ml[r] = msum
+    return dict(big_m=big_m, rhs=rhs, masslump=ml)
+
+
+def emulate_advdiff(mesh, fs, o, findrm, colm):
+    dim, nn = mesh.dim, mesh.n_nodes
+    m = moments(dim)
+    X = mesh.X
+    nu, T = fs.get(abi.F_NU)[0], fs.get(abi.F_T)[0]
+    kappa = fs.get(abi.F_T_DIFFUSIVITY)[0].reshape(-1)[0]
+    row_ptr, ent = strip_plan(mesh)
+    f0, c0 = findrm - 1, colm - 1
+    matrix = np.zeros(len(colm))
+    rhs = np.zeros(nn)
+    dtt = o.dt * o.theta
+    dtt = dtt if abs(dtt) > 2.220446049250313e-16 else 0.0
+    for r in range(nn):
+        s0, s1 = f0[r], f0[r + 1]
+        a = np.zeros(s1 - s0)
+        vol = np.zeros(s1 - s0)
+        own = int(np.searchsorted(c0[s0:s1], r))
+        fifo = []
+        rh = 0.0
+        for node1, meta in ent[row_ptr[r]:row_ptr[r + 1]]:
+            fifo.append((node1 - 1, meta & 0xff))
+            fifo = fifo[-dim:]
+            if not (meta & COMPUTE):
+                continue
+            nodes = [q for q, _ in fifo]
+            e = X[nodes] - X[r]
+            c, det = _geometry(e)
+            sc = c.sum(axis=0)
+            Su = nu[r] + nu[nodes].sum(axis=0)
+            v = (m["Pd"] - m["Po"]) * nu[r] + m["Po"] * Su
+            u = np.sign(det) * (v - (kappa * m["Wsum"] / det) * sc)
+            tot = 0.0
+            ad = abs(det)
+            for k, (q, slot) in enumerate(fifo):
+                sk = float(u @ c[k])
+                a[slot] += sk
+                vol[slot] += ad
+                rh -= sk * T[q]
+                tot += sk
+            a[own] -= tot
+            vol[own] += ad
+            rh += tot * T[r]
+        vals = dtt * a + m["Po"] * vol
+        vals[own] = dtt * a[own] + m["Pd"] * vol[own]
+        matrix[s0:s1] = vals
+        rhs[r] = rh
+    return dict(matrix=matrix, rhs=rhs)

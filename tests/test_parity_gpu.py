@@ -15,7 +15,7 @@ TOL = 1e-12
 
 ALL_SCATTERS = [pytest.param(abi.SCATTER_ATOMIC, id="atomic"), pytest.param(abi.SCATTER_COLOURED, id="coloured"),
                 pytest.param(abi.SCATTER_WARPAGG, id="warpagg"), pytest.param(abi.SCATTER_TILED, id="tiled"),
-                pytest.param(abi.SCATTER_GATHER, id="gather")]
+                pytest.param(abi.SCATTER_GATHER, id="gather"), pytest.param(abi.SCATTER_STRIP, id="strip")]
 
 
 def make_asm(mesh, fields=None, scatter=None):
@@ -189,7 +189,7 @@ def test_advdiff_element_matrices(orc, dim, variant):
 def test_momentum_assembly(orc, scatter, dim, variant):
     mesh = syn.box_mesh((6, 5, 4)[:dim], seed=31)
     o = momentum_variants()[variant]
-    if o.stabilisation_scheme and scatter not in (abi.SCATTER_ATOMIC, abi.SCATTER_GATHER):
+    if o.stabilisation_scheme and scatter not in (abi.SCATTER_ATOMIC, abi.SCATTER_GATHER, abi.SCATTER_STRIP):
         asm = make_asm(mesh, fields_for(mesh, variant), scatter)
         with pytest.raises(cgasm.CgasmError) as ei:
             asm.momentum(o)
@@ -209,7 +209,7 @@ def test_momentum_assembly(orc, scatter, dim, variant):
 def test_advdiff_assembly(orc, scatter, dim, variant):
     mesh = syn.box_mesh((6, 5, 4)[:dim], seed=32)
     o = advdiff_variants()[variant]
-    if o.stabilisation_scheme and scatter not in (abi.SCATTER_ATOMIC, abi.SCATTER_GATHER):
+    if o.stabilisation_scheme and scatter not in (abi.SCATTER_ATOMIC, abi.SCATTER_GATHER, abi.SCATTER_STRIP):
         asm = make_asm(mesh, fields_for(mesh, variant), scatter)
         with pytest.raises(cgasm.CgasmError) as ei:
             asm.advdiff(o)
@@ -257,7 +257,7 @@ def test_shuffled_numbering_s3_small(orc, scatter):
 
 # ---- size-independent properties at a size the oracle would not finish quickly ---------------
 @pytest.mark.parametrize("scatter", [pytest.param(abi.SCATTER_ATOMIC, id="atomic"), pytest.param(abi.SCATTER_TILED, id="tiled"),
-                                     pytest.param(abi.SCATTER_GATHER, id="gather")])
+                                     pytest.param(abi.SCATTER_GATHER, id="gather"), pytest.param(abi.SCATTER_STRIP, id="strip")])
 def test_large_mesh_properties(scatter):
     mesh = syn.box_mesh((96, 96, 96), jitter=0.1)
     fs = syn.standard_fields(mesh)
@@ -289,10 +289,31 @@ def test_large_mesh_properties(scatter):
     # (5) idempotence: same call twice gives identical sums for the deterministic variant
     a = asm.momentum(o)["big_m"].copy()
     b = asm.momentum(o)["big_m"]
-    if scatter in (abi.SCATTER_TILED, abi.SCATTER_GATHER):
+    if scatter in (abi.SCATTER_TILED, abi.SCATTER_GATHER, abi.SCATTER_STRIP):
         assert (a == b).all()
     else:
         assert rel_err(a, b) < TOL
+
+
+def test_strip_matches_gather_at_size():
+    """STRIP and GATHER kernels are independent formulations of the same sums: at 64^3 (1.57 M tets,
+    jittered, every boundary shape) they must agree to 1e-12, and STRIP must be bitwise reproducible."""
+    mesh = syn.box_mesh((64, 64, 64), jitter=0.1)
+    fs = syn.standard_fields(mesh)
+    asm = make_asm(mesh, fs, abi.SCATTER_GATHER)
+    findrm, _, _ = asm.get_sparsity()
+    om, oa = abi.common_momentum_opts(), abi.common_advdiff_opts()
+    gm = {k: v.copy() for k, v in asm.momentum(om).items() if v is not None}
+    ga = {k: v.copy() for k, v in asm.advdiff(oa).items()}
+    asm.set_scatter(abi.SCATTER_STRIP)
+    sm = {k: v.copy() for k, v in asm.momentum(om).items() if v is not None}
+    sa = {k: v.copy() for k, v in asm.advdiff(oa).items()}
+    check_momentum(sm, gm, findrm, 3)
+    assert rel_err(sa["matrix"], ga["matrix"]) < TOL and row_rel_err(sa["matrix"], ga["matrix"], findrm) < TOL
+    assert rel_err(sa["rhs"], ga["rhs"]) < TOL
+    sm2, sa2 = asm.momentum(om), asm.advdiff(oa)
+    assert (sm2["big_m"] == sm["big_m"]).all() and (sm2["rhs"] == sm["rhs"]).all()
+    assert (sa2["matrix"] == sa["matrix"]).all() and (sa2["rhs"] == sa["rhs"]).all()
 
 
 def test_identical_blocks_partial_fetch(orc):
