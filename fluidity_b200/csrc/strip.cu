@@ -23,144 +23,13 @@
 // interior node). Summation order is fixed by the plan: results are bitwise reproducible.
 // Option coverage: the common option set only (momentum_common_ok / advdiff_common_ok); everything
 // else runs the GATHER kernels (gather.cu).
-#include "gather_plan.h"
-#include "strip_plan.h"
+#include "strip_common.cuh"
 
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 
 namespace cgasm {
-
-constexpr int kAS = kBR + 1;  // stride (doubles) between slots of the accumulator: odd, so that the
-                              // write-out (one row spread over consecutive lanes) is conflict-free
-
-struct StripConsts {  // passed by value: operands are read straight from the constant bank
-  double Qa, Qaab, Qd, Qabc;  // Qa = Qaaa - Qaab, Qd = Qaab - Qabc (Tables)
-  double PdPo, Po, Pd;        // PdPo = Pd - Po
-  double Wsum;
-  double dtt;                 // dt*theta (tracer: 0 unless |dt*theta| > epsilon, Advection_Diffusion_CG.F90:1121)
-  double gmag;                // gravity_magnitude
-};
-
-struct StripPlanView {
-  const int* __restrict__ rows;
-  const long long* __restrict__ ptr;
-  const int2* __restrict__ ent;
-  const unsigned char* __restrict__ own_slot;
-  const int* __restrict__ findrm;
-  const int* __restrict__ colm;
-  int maxlen, lpr_shift;
-};
-
-__device__ __forceinline__ int2 ldg_stream2(const int2* p) {
-  int2 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v2.s32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
-  return v;
-}
-
-// 1/x: MUFU.RCP64H seed + two Newton steps (what the compiler's own division starts from, minus
-// the special-case branch; det of a valid element is a normal number)
-__device__ __forceinline__ double rcp_nr(double x) {
-  double r;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-  double e = fma(-x, r, 1.0);
-  r = fma(r, e, r);
-  e = fma(-x, r, 1.0);
-  r = fma(r, e, r);
-  return r;
-}
-
-__device__ __forceinline__ double flip_sign(double v, unsigned sgn) {
-  return __hiloint2double(__double2hiint(v) ^ (int)sgn, __double2loint(v));
-}
-
-// cofactor vectors of the window: gradN_k = c[k] / det, det = e_0 . c[0], with e_k = X_k - X_r the
-// edges from the row's own node (femtools/Transform_elements.F90:807-887 with r as the origin)
-#define WQ(k) ((QC + N - (DIM - 1) + (k)) % N)
-template <int DIM, int N, int QC>
-__device__ __forceinline__ double window_geometry(const double (&X)[N][DIM], double (&c)[DIM][DIM]) {
-  if constexpr (DIM == 3) {
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-      const double(&p)[3] = X[WQ((k + 1) % 3)];
-      const double(&q)[3] = X[WQ((k + 2) % 3)];
-      c[k][0] = p[1] * q[2] - p[2] * q[1];
-      c[k][1] = p[2] * q[0] - p[0] * q[2];
-      c[k][2] = p[0] * q[1] - p[1] * q[0];
-    }
-  } else {
-    c[0][0] = X[WQ(1)][1];
-    c[0][1] = -X[WQ(1)][0];
-    c[1][0] = -X[WQ(0)][1];
-    c[1][1] = X[WQ(0)][0];
-  }
-  double det = 0.0;
-#pragma unroll
-  for (int a = 0; a < DIM; a++) det = fma(X[WQ(0)][a], c[0][a], det);
-  return det;
-}
-
-// ---- momentum -----------------------------------------------------------------------------------------
-template <int DIM, int N>
-struct MomState {
-  double X[N][DIM], U[N][DIM], R[N], B[N], A[N];  // edge (after install), nu, density, buoyancy, accumulator
-  int meta[N];
-  double X0[DIM], U0[DIM], rho0, b0;
-  double a0, msum, nbsum;
-};
-
-// row 0 (the row's own node) of the element {r, window}: Momentum_CG.F90:1535-1552 (lumped mass),
-// :1675-1680 with beta = 0 (advection), :2304-2317 (constant isotropic viscosity), :1770-1789 (buoyancy)
-template <int DIM, int N, int QC>
-__device__ __forceinline__ void mom_compute(MomState<DIM, N>& s, const StripConsts& k_, double muW) {
-  double c[DIM][DIM];
-  const double det = window_geometry<DIM, N, QC>(s.X, c);
-  const double rd = rcp_nr(det);
-  double sc[DIM];
-#pragma unroll
-  for (int a = 0; a < DIM; a++) {
-    sc[a] = c[0][a];
-#pragma unroll
-    for (int k = 1; k < DIM; k++) sc[a] += c[k][a];
-  }
-  double S = s.rho0;
-#pragma unroll
-  for (int k = 0; k < DIM; k++) S += s.R[WQ(k)];
-  const double QS = k_.Qabc * S;
-  const double M0 = fma(k_.Qa, s.rho0, k_.Qaab * S);
-  double w[DIM];
-#pragma unroll
-  for (int a = 0; a < DIM; a++) w[a] = M0 * s.U0[a];
-#pragma unroll
-  for (int k = 0; k < DIM; k++) {
-    const double Mk = fma(k_.Qd, s.rho0 + s.R[WQ(k)], QS);
-#pragma unroll
-    for (int a = 0; a < DIM; a++) w[a] = fma(Mk, s.U[WQ(k)][a], w[a]);
-  }
-  // v / det with v = |det| (w + mu Wsum gradN_0), gradN_0 = -sc / det
-  const double tt = muW * rd;
-  const unsigned sgn = (unsigned)__double2hiint(det) & 0x80000000u;
-  double u[DIM];
-#pragma unroll
-  for (int a = 0; a < DIM; a++) u[a] = flip_sign(fma(-tt, sc[a], w[a]), sgn);
-  double tot = 0.0;
-#pragma unroll
-  for (int k = 0; k < DIM; k++) {
-    double sk = 0.0;
-#pragma unroll
-    for (int a = 0; a < DIM; a++) sk = fma(u[a], c[k][a], sk);
-    s.A[WQ(k)] += sk;
-    tot += sk;
-  }
-  s.a0 -= tot;
-  const double ad = fabs(det);
-  s.msum = fma(ad, fma(k_.PdPo, s.rho0, k_.Po * S), s.msum);
-  double Sb = s.b0;
-#pragma unroll
-  for (int k = 0; k < DIM; k++) Sb += s.B[WQ(k)];
-  s.nbsum = fma(ad, fma(k_.PdPo, s.b0, k_.Po * Sb), s.nbsum);
-}
 
 template <int DIM, int N, int QC>
 __device__ __forceinline__ void mom_step(MomState<DIM, N>& s, const StripConsts& k_, double muW, int j, int deg,
@@ -177,8 +46,8 @@ __device__ __forceinline__ void mom_step(MomState<DIM, N>& s, const StripConsts&
     *sl += s.A[QE];
     s.A[QE] = 0.0;
   }
-  unpack<DIM>(ld256(rX + en.x), s.X[QE], s.B[QE]);
-  unpack<DIM>(ld256(rU + en.x), s.U[QE], s.R[QE]);
+  unpack<DIM>(ld256v(rX + en.x), s.X[QE], s.B[QE]);
+  unpack<DIM>(ld256v(rU + en.x), s.U[QE], s.R[QE]);
   s.meta[QE] = en.y;
 #pragma unroll
   for (int a = 0; a < DIM; a++) s.X[QC][a] -= s.X0[a];
@@ -193,25 +62,6 @@ struct MomUnroll {
     if constexpr (Q + 1 < N) MomUnroll<DIM, N, Q + 1>::run(s, k_, muW, j0, args...);
   }
 };
-
-// rows of the warp -> global memory, LPR = 1 << lpr_shift lanes per row
-template <int NOUT>
-__device__ __forceinline__ void write_rows(const double* __restrict__ acc, int t, int my_s0, int my_len, int lpr_shift,
-                                           size_t nnz, double* __restrict__ out) {
-  const int lane = t & 31, wbase = t & ~31;
-  const int lpr = 1 << lpr_shift, rpi = 32 >> lpr_shift;
-  const int sub = lane >> lpr_shift, sl = lane & (lpr - 1);
-  for (int rr = 0; rr < 32; rr += rpi) {
-    const int src = rr + sub;
-    const int s0r = __shfl_sync(0xffffffffu, my_s0, src);
-    const int lr = __shfl_sync(0xffffffffu, my_len, src);
-    for (int ss = sl; ss < lr; ss += lpr) {
-      const double v = acc[ss * kAS + wbase + src];
-#pragma unroll
-      for (int d = 0; d < NOUT; d++) __stcs(out + (size_t)d * nnz + s0r + ss, v);
-    }
-  }
-}
 
 template <int DIM, int N, int MINB>
 __global__ void __launch_bounds__(kBR, MINB)
@@ -285,54 +135,6 @@ strip_momentum_kernel(const StripConsts k_, const StripPlanView P, const double4
 }
 
 // ---- tracer -------------------------------------------------------------------------------------------
-template <int DIM, int N>
-struct AdvState {
-  double X[N][DIM], U[N][DIM], T[N], A[N], C[N];  // C: sum of |det| over the elements sharing the edge (mass)
-  int meta[N];
-  double X0[DIM], U0[DIM], T0;
-  double a0, c0, rhs;
-};
-
-// Advection_Diffusion_CG.F90:909-920 (consistent mass), :1093-1098 with beta = 0, :1192 (constant
-// isotropic diffusivity), :1125,1200 (rhs -= (A + D) T)
-template <int DIM, int N, int QC>
-__device__ __forceinline__ void adv_compute(AdvState<DIM, N>& s, const StripConsts& k_, double kW) {
-  double c[DIM][DIM];
-  const double det = window_geometry<DIM, N, QC>(s.X, c);
-  const double rd = rcp_nr(det);
-  double sc[DIM], v[DIM];
-#pragma unroll
-  for (int a = 0; a < DIM; a++) {
-    sc[a] = c[0][a];
-    double Su = s.U0[a];
-#pragma unroll
-    for (int k = 1; k < DIM; k++) sc[a] += c[k][a];
-#pragma unroll
-    for (int k = 0; k < DIM; k++) Su += s.U[WQ(k)][a];
-    v[a] = fma(k_.PdPo, s.U0[a], k_.Po * Su);
-  }
-  const double tt = kW * rd;
-  const unsigned sgn = (unsigned)__double2hiint(det) & 0x80000000u;
-  double u[DIM];
-#pragma unroll
-  for (int a = 0; a < DIM; a++) u[a] = flip_sign(fma(-tt, sc[a], v[a]), sgn);
-  const double ad = fabs(det);
-  double tot = 0.0;
-#pragma unroll
-  for (int k = 0; k < DIM; k++) {
-    double sk = 0.0;
-#pragma unroll
-    for (int a = 0; a < DIM; a++) sk = fma(u[a], c[k][a], sk);
-    s.A[WQ(k)] += sk;
-    s.C[WQ(k)] += ad;
-    s.rhs = fma(-sk, s.T[WQ(k)], s.rhs);
-    tot += sk;
-  }
-  s.a0 -= tot;
-  s.c0 += ad;
-  s.rhs = fma(tot, s.T0, s.rhs);
-}
-
 template <int DIM, int N, int QC>
 __device__ __forceinline__ void adv_step(AdvState<DIM, N>& s, const StripConsts& k_, double kW, int j, int deg,
                                          const int2* __restrict__ p, int2& pq0, int2& pq1, const int2 pad,
@@ -350,8 +152,8 @@ __device__ __forceinline__ void adv_step(AdvState<DIM, N>& s, const StripConsts&
     s.C[QE] = 0.0;
   }
   double unused;
-  unpack<DIM>(ld256(rX + en.x), s.X[QE], s.T[QE]);
-  unpack<DIM>(ld256(rU + en.x), s.U[QE], unused);
+  unpack<DIM>(ld256v(rX + en.x), s.X[QE], s.T[QE]);
+  unpack<DIM>(ld256v(rU + en.x), s.U[QE], unused);
   s.meta[QE] = en.y;
 #pragma unroll
   for (int a = 0; a < DIM; a++) s.X[QC][a] -= s.X0[a];
@@ -419,7 +221,6 @@ strip_advdiff_kernel(const StripConsts k_, const StripPlanView P, const double4*
   __syncwarp();
   write_rows<1>(acc, t, my_s0, my_len, P.lpr_shift, 0, matrix);
 }
-#undef WQ
 
 // ---- plan ---------------------------------------------------------------------------------------------
 static int strip_nbuf(int dim) {
@@ -464,9 +265,22 @@ int strip_build(Handle* h) {
   P->strip_mult = mult;
   P->n_strip = ptr[nb];
   std::vector<int2> ent((size_t)std::max<long long>(P->n_strip, 1));
+  // staged flavour: the sorted distinct nodes of each block and the same entries with block-local indices
+  std::vector<unsigned> lent(ent.size());
+  std::vector<unsigned> own_local(rows.size(), 0);
+  std::vector<std::vector<int>> blk_nodes((size_t)nb);
 #pragma omp parallel for schedule(dynamic, 8)
   for (int b = 0; b < nb; b++) {
     const int deg = (int)((ptr[b + 1] - ptr[b]) / kBR);
+    std::vector<int>& bn = blk_nodes[b];
+    for (int t = 0; t < kBR; t++) {
+      const size_t q = (size_t)b * kBR + t;
+      bn.push_back(rows[q] >= 0 ? rows[q] : 0);
+      for (const StripEntry& e : rowplans[q]) bn.push_back(e.node);
+    }
+    std::sort(bn.begin(), bn.end());
+    bn.erase(std::unique(bn.begin(), bn.end()), bn.end());
+    auto local_of = [&](int node) { return (unsigned)(std::lower_bound(bn.begin(), bn.end(), node) - bn.begin()); };
     for (int t = 0; t < kBR; t++) {
       const size_t q = (size_t)b * kBR + t;
       const int r = rows[q];
@@ -476,17 +290,42 @@ int strip_build(Handle* h) {
         const int* cb = h->h_colm.data() + h->h_findrm[r];
         own = (int)(std::lower_bound(cb, (const int*)h->h_colm.data() + h->h_findrm[r + 1], r) - cb);
       }
+      const unsigned ol = local_of(r >= 0 ? r : 0) | (unsigned)own << 16;
+      own_local[q] = ol;
       for (int k = 0; k < deg; k++) {
         int2 v = make_int2(r >= 0 ? r : 0, own);  // padding: re-push the own node, nothing computed
-        if (k < (int)rp.size()) v = make_int2(rp[k].node, rp[k].meta);
+        unsigned lv = ol;
+        if (k < (int)rp.size()) {
+          v = make_int2(rp[k].node, rp[k].meta);
+          lv = local_of(rp[k].node) | (unsigned)(rp[k].meta & 0xff) << 16 | ((rp[k].meta & kStripCompute) ? 1u << 24 : 0u);
+        }
         ent[(size_t)(ptr[b] + (long long)k * kBR + t)] = v;
+        lent[(size_t)(ptr[b] + (long long)k * kBR + t)] = lv;
       }
     }
   }
+  std::vector<int> blk_ptr((size_t)nb + 1, 0);
+  P->blk_nodes_max = 0;
+  for (int b = 0; b < nb; b++) {
+    blk_ptr[b + 1] = blk_ptr[b] + (int)blk_nodes[b].size();
+    P->blk_nodes_max = std::max(P->blk_nodes_max, (int)blk_nodes[b].size());
+  }
+  std::vector<int> blk_flat((size_t)std::max(blk_ptr[nb], 1));
+  for (int b = 0; b < nb; b++) std::copy(blk_nodes[b].begin(), blk_nodes[b].end(), blk_flat.begin() + blk_ptr[b]);
+  if (P->blk_nodes_max < 65536) {
+    CG_CUDA(cudaMalloc(&P->d_blk_ptr, sizeof(int) * blk_ptr.size()));
+    CG_CUDA(cudaMemcpy(P->d_blk_ptr, blk_ptr.data(), sizeof(int) * blk_ptr.size(), cudaMemcpyHostToDevice));
+    CG_CUDA(cudaMalloc(&P->d_blk_nodes, sizeof(int) * blk_flat.size()));
+    CG_CUDA(cudaMemcpy(P->d_blk_nodes, blk_flat.data(), sizeof(int) * blk_flat.size(), cudaMemcpyHostToDevice));
+    CG_CUDA(cudaMalloc(&P->d_strip_local, sizeof(unsigned) * lent.size()));
+    CG_CUDA(cudaMemcpy(P->d_strip_local, lent.data(), sizeof(unsigned) * lent.size(), cudaMemcpyHostToDevice));
+    CG_CUDA(cudaMalloc(&P->d_own_local, sizeof(unsigned) * own_local.size()));
+    CG_CUDA(cudaMemcpy(P->d_own_local, own_local.data(), sizeof(unsigned) * own_local.size(), cudaMemcpyHostToDevice));
+  }
   P->strip_entries_per_pair = h->n2e.empty() ? 0.0 : (double)total_real / (double)h->n2e.size();
   if (getenv("CGASM_DEBUG"))
-    fprintf(stderr, "[cgasm] strip plan: %.3f entries per (row, element) pair, %lld padded entries\n",
-            P->strip_entries_per_pair, P->n_strip);
+    fprintf(stderr, "[cgasm] strip plan: %.3f entries per (row, element) pair, %lld padded entries, <= %d nodes per block\n",
+            P->strip_entries_per_pair, P->n_strip, P->blk_nodes_max);
   CG_CUDA(cudaMalloc(&P->d_strip_ptr, sizeof(long long) * ptr.size()));
   CG_CUDA(cudaMemcpy(P->d_strip_ptr, ptr.data(), sizeof(long long) * ptr.size(), cudaMemcpyHostToDevice));
   CG_CUDA(cudaMalloc(&P->d_strip, sizeof(int2) * ent.size()));
@@ -508,48 +347,17 @@ int strip_build(Handle* h) {
 void strip_free(GatherPlan* P) {
   if (P->d_strip_ptr) cudaFree(P->d_strip_ptr);
   if (P->d_strip) cudaFree(P->d_strip);
+  if (P->d_blk_ptr) cudaFree(P->d_blk_ptr);
+  if (P->d_blk_nodes) cudaFree(P->d_blk_nodes);
+  if (P->d_strip_local) cudaFree(P->d_strip_local);
+  if (P->d_own_local) cudaFree(P->d_own_local);
   P->d_strip_ptr = nullptr;
   P->d_strip = nullptr;
+  P->d_blk_ptr = P->d_blk_nodes = nullptr;
+  P->d_strip_local = P->d_own_local = nullptr;
 }
 
 // ---- launch -------------------------------------------------------------------------------------------
-static StripPlanView plan_view(const Handle* h) {
-  const GatherPlan* P = h->gather;
-  StripPlanView v;
-  v.rows = P->d_rows;
-  v.ptr = P->d_strip_ptr;
-  v.ent = P->d_strip;
-  v.own_slot = P->d_own_slot;
-  v.findrm = h->d_findrm;
-  v.colm = h->d_colm;
-  v.maxlen = P->maxlen;
-  int sh = 0;
-  while ((1 << sh) < P->maxlen && sh < 5) sh++;
-  v.lpr_shift = sh;
-  return v;
-}
-
-static StripConsts consts_of(const Tables& t, double dtt, double gmag) {
-  StripConsts c;
-  c.Qa = t.Qaaa - t.Qaab;
-  c.Qaab = t.Qaab;
-  c.Qd = t.Qaab - t.Qabc;
-  c.Qabc = t.Qabc;
-  c.PdPo = t.Pd - t.Po;
-  c.Po = t.Po;
-  c.Pd = t.Pd;
-  c.Wsum = t.Wsum;
-  c.dtt = dtt;
-  c.gmag = gmag;
-  return c;
-}
-
-template <class K>
-static int strip_smem(K kernel, size_t bytes) {
-  if (bytes > 48 * 1024) CG_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-  return CGASM_OK;
-}
-
 bool strip_momentum_ok(const Handle* h, const MomentumArgs& A, bool want_ml) {
   const GatherPlan* P = h->gather;
   return P && P->d_strip && A.tab.sym && want_ml && !A.o.have_absorption &&
@@ -568,7 +376,7 @@ static int strip_momentum_dim(Handle* h, const MomentumArgs& A) {
   if (smem > 200 * 1024) CG_FAIL(CGASM_EUNSUPPORTED, "strip scatter: CSR rows too long for the shared-memory accumulator");
   const StripConsts c = consts_of(A.tab, A.o.dt * A.o.theta, A.o.gravity_magnitude);
   const StripPlanView v = plan_view(h);
-  const int minb = getenv("CGASM_STRIP_MINB") ? atoi(getenv("CGASM_STRIP_MINB")) : 3;
+  const int minb = getenv("CGASM_STRIP_MINB") ? atoi(getenv("CGASM_STRIP_MINB")) : 4;
   int st;
 #define LAUNCH(N_, MINB_)                                                                                      \
   do {                                                                                                         \
@@ -592,6 +400,7 @@ static int strip_momentum_dim(Handle* h, const MomentumArgs& A) {
 }
 
 int strip_momentum(Handle* h, const MomentumArgs& A) {
+  if (strip_staged_ok(h, true)) return strip_staged_momentum(h, A);
   return h->dim == 3 ? strip_momentum_dim<3>(h, A) : strip_momentum_dim<2>(h, A);
 }
 
@@ -626,6 +435,7 @@ static int strip_advdiff_dim(Handle* h, const AdvDiffArgs& A) {
 }
 
 int strip_advdiff(Handle* h, const AdvDiffArgs& A) {
+  if (strip_staged_ok(h, false)) return strip_staged_advdiff(h, A);
   return h->dim == 3 ? strip_advdiff_dim<3>(h, A) : strip_advdiff_dim<2>(h, A);
 }
 

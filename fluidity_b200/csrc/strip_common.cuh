@@ -1,0 +1,260 @@
+// strip_common.cuh -- device code shared by the STRIP kernels (strip.cu: node records fetched per entry
+// from global memory; strip_staged.cu: node records of the row block staged in shared memory).
+#pragma once
+#include "gather_plan.h"
+#include "strip_plan.h"
+
+namespace cgasm {
+
+constexpr int kAS = kBR + 1;  // stride (doubles) between slots of the accumulator: odd, so that the
+                              // write-out (one row spread over consecutive lanes) is conflict-free
+
+struct StripConsts {  // passed by value: operands are read straight from the constant bank
+  double Qa, Qaab, Qd, Qabc;  // Qa = Qaaa - Qaab, Qd = Qaab - Qabc (Tables)
+  double PdPo, Po, Pd;        // PdPo = Pd - Po
+  double Wsum;
+  double dtt;                 // dt*theta (tracer: 0 unless |dt*theta| > epsilon, Advection_Diffusion_CG.F90:1121)
+  double gmag;                // gravity_magnitude
+};
+
+struct StripPlanView {
+  const int* __restrict__ rows;
+  const long long* __restrict__ ptr;
+  const int2* __restrict__ ent;
+  const unsigned char* __restrict__ own_slot;
+  const int* __restrict__ findrm;
+  const int* __restrict__ colm;
+  int maxlen, lpr_shift;
+};
+
+__device__ __forceinline__ int2 ldg_stream2(const int2* p) {
+  int2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.s32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+  return v;
+}
+
+// volatile: the request must be issued HERE (one step ahead of its use); the plain ld256 is sunk by the
+// compiler to just before the first use, behind the divergent compute block
+__device__ __forceinline__ double4 ld256v(const double4* p) {
+  double4 v;
+  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
+  return v;
+}
+
+// 1/x: MUFU.RCP64H seed + two Newton steps (what the compiler's own division starts from, minus
+// the special-case branch; det of a valid element is a normal number)
+__device__ __forceinline__ double rcp_nr(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  return r;
+}
+
+__device__ __forceinline__ double flip_sign(double v, unsigned sgn) {
+  return __hiloint2double(__double2hiint(v) ^ (int)sgn, __double2loint(v));
+}
+
+// cofactor vectors of the window: gradN_k = c[k] / det, det = e_0 . c[0], with e_k = X_k - X_r the
+// edges from the row's own node (femtools/Transform_elements.F90:807-887 with r as the origin)
+#define WQ(k) ((QC + N - (DIM - 1) + (k)) % N)
+template <int DIM, int N, int QC>
+__device__ __forceinline__ double window_geometry(const double (&X)[N][DIM], double (&c)[DIM][DIM]) {
+  if constexpr (DIM == 3) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      const double(&p)[3] = X[WQ((k + 1) % 3)];
+      const double(&q)[3] = X[WQ((k + 2) % 3)];
+      c[k][0] = p[1] * q[2] - p[2] * q[1];
+      c[k][1] = p[2] * q[0] - p[0] * q[2];
+      c[k][2] = p[0] * q[1] - p[1] * q[0];
+    }
+  } else {
+    c[0][0] = X[WQ(1)][1];
+    c[0][1] = -X[WQ(1)][0];
+    c[1][0] = -X[WQ(0)][1];
+    c[1][1] = X[WQ(0)][0];
+  }
+  double det = 0.0;
+#pragma unroll
+  for (int a = 0; a < DIM; a++) det = fma(X[WQ(0)][a], c[0][a], det);
+  return det;
+}
+
+// ---- momentum -----------------------------------------------------------------------------------------
+template <int DIM, int N>
+struct MomState {
+  double X[N][DIM], U[N][DIM], R[N], B[N], A[N];  // edge (after install), nu, density, buoyancy, accumulator
+  int meta[N];
+  double X0[DIM], U0[DIM], rho0, b0;
+  double a0, msum, nbsum;
+};
+
+// row 0 (the row's own node) of the element {r, window}: Momentum_CG.F90:1535-1552 (lumped mass),
+// :1675-1680 with beta = 0 (advection), :2304-2317 (constant isotropic viscosity), :1770-1789 (buoyancy)
+template <int DIM, int N, int QC>
+__device__ __forceinline__ void mom_compute(MomState<DIM, N>& s, const StripConsts& k_, double muW) {
+  double c[DIM][DIM];
+  const double det = window_geometry<DIM, N, QC>(s.X, c);
+  const double rd = rcp_nr(det);
+  double sc[DIM];
+#pragma unroll
+  for (int a = 0; a < DIM; a++) {
+    sc[a] = c[0][a];
+#pragma unroll
+    for (int k = 1; k < DIM; k++) sc[a] += c[k][a];
+  }
+  double S = s.rho0;
+#pragma unroll
+  for (int k = 0; k < DIM; k++) S += s.R[WQ(k)];
+  const double QS = k_.Qabc * S;
+  const double M0 = fma(k_.Qa, s.rho0, k_.Qaab * S);
+  double w[DIM];
+#pragma unroll
+  for (int a = 0; a < DIM; a++) w[a] = M0 * s.U0[a];
+#pragma unroll
+  for (int k = 0; k < DIM; k++) {
+    const double Mk = fma(k_.Qd, s.rho0 + s.R[WQ(k)], QS);
+#pragma unroll
+    for (int a = 0; a < DIM; a++) w[a] = fma(Mk, s.U[WQ(k)][a], w[a]);
+  }
+  // v / det with v = |det| (w + mu Wsum gradN_0), gradN_0 = -sc / det
+  const double tt = muW * rd;
+  const unsigned sgn = (unsigned)__double2hiint(det) & 0x80000000u;
+  double u[DIM];
+#pragma unroll
+  for (int a = 0; a < DIM; a++) u[a] = flip_sign(fma(-tt, sc[a], w[a]), sgn);
+  double tot = 0.0;
+#pragma unroll
+  for (int k = 0; k < DIM; k++) {
+    double sk = 0.0;
+#pragma unroll
+    for (int a = 0; a < DIM; a++) sk = fma(u[a], c[k][a], sk);
+    s.A[WQ(k)] += sk;
+    tot += sk;
+  }
+  s.a0 -= tot;
+  const double ad = fabs(det);
+  s.msum = fma(ad, fma(k_.PdPo, s.rho0, k_.Po * S), s.msum);
+  double Sb = s.b0;
+#pragma unroll
+  for (int k = 0; k < DIM; k++) Sb += s.B[WQ(k)];
+  s.nbsum = fma(ad, fma(k_.PdPo, s.b0, k_.Po * Sb), s.nbsum);
+}
+
+// rows of the warp -> global memory, LPR = 1 << lpr_shift lanes per row
+template <int NOUT>
+__device__ __forceinline__ void write_rows(const double* __restrict__ acc, int t, int my_s0, int my_len, int lpr_shift,
+                                           size_t nnz, double* __restrict__ out) {
+  const int lane = t & 31, wbase = t & ~31;
+  const int lpr = 1 << lpr_shift, rpi = 32 >> lpr_shift;
+  const int sub = lane >> lpr_shift, sl = lane & (lpr - 1);
+  for (int rr = 0; rr < 32; rr += rpi) {
+    const int src = rr + sub;
+    const int s0r = __shfl_sync(0xffffffffu, my_s0, src);
+    const int lr = __shfl_sync(0xffffffffu, my_len, src);
+    for (int ss = sl; ss < lr; ss += lpr) {
+      const double v = acc[ss * kAS + wbase + src];
+#pragma unroll
+      for (int d = 0; d < NOUT; d++) __stcs(out + (size_t)d * nnz + s0r + ss, v);
+    }
+  }
+}
+
+// ---- tracer state and element math ----------------------------------------------------------------------
+template <int DIM, int N>
+struct AdvState {
+  double X[N][DIM], U[N][DIM], T[N], A[N], C[N];  // C: sum of |det| over the elements sharing the edge (mass)
+  int meta[N];
+  double X0[DIM], U0[DIM], T0;
+  double a0, c0, rhs;
+};
+
+// Advection_Diffusion_CG.F90:909-920 (consistent mass), :1093-1098 with beta = 0, :1192 (constant
+// isotropic diffusivity), :1125,1200 (rhs -= (A + D) T)
+template <int DIM, int N, int QC>
+__device__ __forceinline__ void adv_compute(AdvState<DIM, N>& s, const StripConsts& k_, double kW) {
+  double c[DIM][DIM];
+  const double det = window_geometry<DIM, N, QC>(s.X, c);
+  const double rd = rcp_nr(det);
+  double sc[DIM], v[DIM];
+#pragma unroll
+  for (int a = 0; a < DIM; a++) {
+    sc[a] = c[0][a];
+    double Su = s.U0[a];
+#pragma unroll
+    for (int k = 1; k < DIM; k++) sc[a] += c[k][a];
+#pragma unroll
+    for (int k = 0; k < DIM; k++) Su += s.U[WQ(k)][a];
+    v[a] = fma(k_.PdPo, s.U0[a], k_.Po * Su);
+  }
+  const double tt = kW * rd;
+  const unsigned sgn = (unsigned)__double2hiint(det) & 0x80000000u;
+  double u[DIM];
+#pragma unroll
+  for (int a = 0; a < DIM; a++) u[a] = flip_sign(fma(-tt, sc[a], v[a]), sgn);
+  const double ad = fabs(det);
+  double tot = 0.0;
+#pragma unroll
+  for (int k = 0; k < DIM; k++) {
+    double sk = 0.0;
+#pragma unroll
+    for (int a = 0; a < DIM; a++) sk = fma(u[a], c[k][a], sk);
+    s.A[WQ(k)] += sk;
+    s.C[WQ(k)] += ad;
+    s.rhs = fma(-sk, s.T[WQ(k)], s.rhs);
+    tot += sk;
+  }
+  s.a0 -= tot;
+  s.c0 += ad;
+  s.rhs = fma(tot, s.T0, s.rhs);
+}
+
+#undef WQ
+
+// ---- host helpers ---------------------------------------------------------------------------------------
+inline StripPlanView plan_view(const Handle* h) {
+  const GatherPlan* P = h->gather;
+  StripPlanView v;
+  v.rows = P->d_rows;
+  v.ptr = P->d_strip_ptr;
+  v.ent = P->d_strip;
+  v.own_slot = P->d_own_slot;
+  v.findrm = h->d_findrm;
+  v.colm = h->d_colm;
+  v.maxlen = P->maxlen;
+  int sh = 0;
+  while ((1 << sh) < P->maxlen && sh < 5) sh++;
+  v.lpr_shift = sh;
+  return v;
+}
+
+inline StripConsts consts_of(const Tables& t, double dtt, double gmag) {
+  StripConsts c;
+  c.Qa = t.Qaaa - t.Qaab;
+  c.Qaab = t.Qaab;
+  c.Qd = t.Qaab - t.Qabc;
+  c.Qabc = t.Qabc;
+  c.PdPo = t.Pd - t.Po;
+  c.Po = t.Po;
+  c.Pd = t.Pd;
+  c.Wsum = t.Wsum;
+  c.dtt = dtt;
+  c.gmag = gmag;
+  return c;
+}
+
+template <class K>
+inline int strip_smem(K kernel, size_t bytes) {
+  if (bytes > 48 * 1024) CG_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return CGASM_OK;
+}
+
+// strip_staged.cu
+bool strip_staged_ok(const Handle* h, bool momentum);
+int strip_staged_momentum(Handle* h, const MomentumArgs& A);
+int strip_staged_advdiff(Handle* h, const AdvDiffArgs& A);
+
+}  // namespace cgasm

@@ -1,0 +1,423 @@
+// strip_staged.cu -- STRIP kernels with the node records of a row block staged in shared memory.
+//
+// ncu on the first STRIP kernels (strip.cu; profiles/r1_kernel_history.md #14): every lane fetches its
+// own 2 x 32-byte records per entry, so a warp-level load waits for its slowest lane (L1 hit rate
+// 68 %, L2 39 %: usually a DRAM round trip, more than one loop body of prefetch distance) and the
+// L1 data pipe runs at 57 % moving 1 KB per LDG.256 through 64-byte wavefronts.
+// A block of 128 Morton-adjacent rows touches only ~360 distinct nodes (its own 8x4x4 patch plus one
+// layer), each of them ~14 x 1.9 times. So:
+//   phase 0  the block copies the records of its distinct nodes (sorted list in the plan) into
+//            shared memory with cp.async, coalesced, bypassing L1 and registers; one barrier;
+//   loop     entries carry block-LOCAL node indices (32-bit entries instead of 64-bit): the FIFO
+//            buffers are filled by LDS.128 from a structure-of-16-byte-chunks layout (neighbouring
+//            rows read neighbouring indices: conflict-free), nothing in the loop waits on DRAM
+//            except the plan stream, which is requested two steps ahead;
+//   flush    when a node leaves the FIFO its accumulated entry goes to the row's slot AND into
+//            rhs -= entry * oldu(node) (Momentum_CG.F90:1712,2346 is linear in the entries), with
+//            oldu read from the staged records: no epilogue pass over colm;
+//   write    dt*theta and the lumped mass on the diagonal (:1550, :1484-1486) are applied while the
+//            warp streams its rows out.
+#include "strip_common.cuh"
+
+#include <cstdlib>
+
+namespace cgasm {
+
+struct StagedView {
+  const int* __restrict__ rows;
+  const long long* __restrict__ ptr;      // strip entries of the block (block-interleaved)
+  const unsigned* __restrict__ ent;       // local index | slot << 16 | compute << 24
+  const unsigned* __restrict__ own_local; // own node: local index | own slot << 16
+  const int* __restrict__ blk_ptr;
+  const int* __restrict__ blk_nodes;
+  const int* __restrict__ findrm;
+  int maxlen, lpr_shift;
+  int nl;         // chunk stride (nodes) of the staged records
+  int acc_bytes;  // bytes of the accumulator in front of them (multiple of 16)
+};
+
+constexpr unsigned kLocalCompute = 1u << 24;
+
+__device__ __forceinline__ unsigned ldg_stream1(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
+// copies NCH 16-byte chunks of every node of the block: chunk c of local node i at nodes[c*nl + i]
+template <int NREC>
+__device__ __forceinline__ void stage_nodes(const StagedView& P, int b, int t, double2* __restrict__ nodes,
+                                            const double4* const (&rec)[NREC]) {
+  const int n0 = P.blk_ptr[b], nloc = P.blk_ptr[b + 1] - n0;
+  for (int i = t; i < nloc; i += kBR) {
+    const int node = __ldg(P.blk_nodes + n0 + i);
+#pragma unroll
+    for (int q = 0; q < NREC; q++) {
+      const double2* src = reinterpret_cast<const double2*>(rec[q] + node);
+      cp_async16(nodes + (2 * q) * P.nl + i, src);
+      cp_async16(nodes + (2 * q + 1) * P.nl + i, src + 1);
+    }
+  }
+}
+
+template <int DIM>
+__device__ __forceinline__ void load_rec(const double2* __restrict__ nodes, int nl, int rec, int li, double (&v)[DIM], double& s) {
+  const double2 a = nodes[(2 * rec) * nl + li];
+  const double2 b = nodes[(2 * rec + 1) * nl + li];
+  v[0] = a.x;
+  v[1] = a.y;
+  if constexpr (DIM == 3) v[2] = b.x;
+  s = b.y;
+}
+
+// ---- momentum -----------------------------------------------------------------------------------------
+template <int DIM, int N, int QC>
+__device__ __forceinline__ void smom_step(MomState<DIM, N>& s, double (&rh)[DIM], const StripConsts& k_, double muW, int j,
+                                          int deg, const unsigned* __restrict__ p, unsigned& pq0, unsigned& pq1,
+                                          const unsigned pad, double* __restrict__ acc_t,
+                                          const double2* __restrict__ nodes, int nl) {
+  constexpr int PD = N - DIM;
+  constexpr int QE = (QC + PD) % N;  // holds entry j - DIM: evicted now, refilled with entry j + PD
+  const unsigned en = pq0;
+  pq0 = pq1;
+  pq1 = (j + PD + 2 < deg) ? ldg_stream1(p + (long long)(j + PD + 2) * kBR) : pad;
+  {
+    const unsigned m = (unsigned)s.meta[QE];
+    const int lo = (int)(m & 0xffffu);
+    double* sl = acc_t + ((m >> 16) & 0xffu) * kAS;
+    const double a = s.A[QE];
+    *sl += a;
+    const double2 o0 = nodes[4 * nl + lo];
+    rh[0] = fma(-a, o0.x, rh[0]);
+    rh[1] = fma(-a, o0.y, rh[1]);
+    if constexpr (DIM == 3) rh[2] = fma(-a, nodes[5 * nl + lo].x, rh[2]);
+    s.A[QE] = 0.0;
+  }
+  const int li = (int)(en & 0xffffu);
+  load_rec<DIM>(nodes, nl, 0, li, s.X[QE], s.B[QE]);
+  load_rec<DIM>(nodes, nl, 1, li, s.U[QE], s.R[QE]);
+  s.meta[QE] = (int)en;
+#pragma unroll
+  for (int a = 0; a < DIM; a++) s.X[QC][a] -= s.X0[a];
+  if ((unsigned)s.meta[QC] & kLocalCompute) mom_compute<DIM, N, QC>(s, k_, muW);
+}
+
+template <int DIM, int N, int Q>
+struct SMomUnroll {
+  template <class... Args>
+  static __device__ __forceinline__ void run(MomState<DIM, N>& s, double (&rh)[DIM], const StripConsts& k_, double muW,
+                                             int j0, Args&&... args) {
+    smom_step<DIM, N, Q>(s, rh, k_, muW, j0 + Q, args...);
+    if constexpr (Q + 1 < N) SMomUnroll<DIM, N, Q + 1>::run(s, rh, k_, muW, j0, args...);
+  }
+};
+
+// rows of the warp -> the dim identical diagonal blocks: dt*theta * entry (+ lumped mass on the diagonal)
+template <int DIM>
+__device__ __forceinline__ void write_rows_scaled(const double* __restrict__ acc, int t, int my_s0, int my_len, int my_own,
+                                                  double my_mass, double dtt, int lpr_shift, size_t nnz,
+                                                  double* __restrict__ out) {
+  const int lane = t & 31, wbase = t & ~31;
+  const int lpr = 1 << lpr_shift, rpi = 32 >> lpr_shift;
+  const int sub = lane >> lpr_shift, sl = lane & (lpr - 1);
+  for (int rr = 0; rr < 32; rr += rpi) {
+    const int src = rr + sub;
+    const int s0r = __shfl_sync(0xffffffffu, my_s0, src);
+    const int lr = __shfl_sync(0xffffffffu, my_len, src);
+    const int own = __shfl_sync(0xffffffffu, my_own, src);
+    const double mass = __shfl_sync(0xffffffffu, my_mass, src);
+    for (int ss = sl; ss < lr; ss += lpr) {
+      const double v = fma(dtt, acc[ss * kAS + wbase + src], ss == own ? mass : 0.0);
+#pragma unroll
+      for (int d = 0; d < DIM; d++) __stcs(out + (size_t)d * nnz + s0r + ss, v);
+    }
+  }
+}
+
+template <int DIM, int N, int MINB>
+__global__ void __launch_bounds__(kBR, MINB)
+staged_momentum_kernel(const StripConsts k_, const StagedView P, const double4* __restrict__ rX,
+                       const double4* __restrict__ rU, const double4* __restrict__ rO,
+                       const double* __restrict__ viscosity, const double* __restrict__ gravity, size_t nnz,
+                       double* __restrict__ big_m, double* __restrict__ rhs, double* __restrict__ masslump) {
+  constexpr int PD = N - DIM;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* acc = reinterpret_cast<double*>(smem_raw);
+  double2* nodes = reinterpret_cast<double2*>(smem_raw + P.acc_bytes);
+  const int b = blockIdx.x, t = threadIdx.x, nl = P.nl;
+  {
+    const double4* const rec[3] = {rX, rU, rO};
+    stage_nodes<3>(P, b, t, nodes, rec);
+  }
+  const int r = P.rows[b * kBR + t];
+  const long long base = P.ptr[b];
+  const int deg = (int)((P.ptr[b + 1] - base) / kBR);  // a multiple of N
+  const unsigned* p = P.ent + base + t;
+  double* acc_t = acc + t;
+  for (int q = 0; q < P.maxlen; q++) acc_t[q * kAS] = 0.0;
+  const unsigned pad = P.own_local[b * kBR + t];
+  const int own = (int)((pad >> 16) & 0xffu), own_li = (int)(pad & 0xffffu);
+  const double muW = __ldg(viscosity) * k_.Wsum;
+  unsigned first[PD];
+#pragma unroll
+  for (int q = 0; q < PD; q++) first[q] = q < deg ? ldg_stream1(p + (long long)q * kBR) : pad;
+  unsigned pq0 = PD < deg ? ldg_stream1(p + (long long)PD * kBR) : pad;
+  unsigned pq1 = PD + 1 < deg ? ldg_stream1(p + (long long)(PD + 1) * kBR) : pad;
+  cp_async_commit_wait_all();
+  __syncthreads();
+  MomState<DIM, N> s;
+  load_rec<DIM>(nodes, nl, 0, own_li, s.X0, s.b0);
+  load_rec<DIM>(nodes, nl, 1, own_li, s.U0, s.rho0);
+  s.a0 = s.msum = s.nbsum = 0.0;
+  double rh[DIM];
+#pragma unroll
+  for (int d = 0; d < DIM; d++) rh[d] = 0.0;
+#pragma unroll
+  for (int q = 0; q < N; q++) {
+#pragma unroll
+    for (int a = 0; a < DIM; a++) s.X[q][a] = s.U[q][a] = 0.0;
+    s.R[q] = s.B[q] = s.A[q] = 0.0;
+    s.meta[q] = (int)pad;
+  }
+#pragma unroll
+  for (int q = 0; q < PD; q++) {
+    const int li = (int)(first[q] & 0xffffu);
+    load_rec<DIM>(nodes, nl, 0, li, s.X[q], s.B[q]);
+    load_rec<DIM>(nodes, nl, 1, li, s.U[q], s.R[q]);
+    s.meta[q] = (int)first[q];
+  }
+  for (int j0 = 0; j0 < deg; j0 += N) SMomUnroll<DIM, N, 0>::run(s, rh, k_, muW, j0, deg, p, pq0, pq1, pad, acc_t, nodes, nl);
+  // drain the FIFO, then the diagonal (the row's own node never leaves)
+#pragma unroll
+  for (int q = 0; q < N; q++) {
+    const unsigned m = (unsigned)s.meta[q];
+    const int lo = (int)(m & 0xffffu);
+    acc_t[((m >> 16) & 0xffu) * kAS] += s.A[q];
+    const double2 o0 = nodes[4 * nl + lo];
+    rh[0] = fma(-s.A[q], o0.x, rh[0]);
+    rh[1] = fma(-s.A[q], o0.y, rh[1]);
+    if constexpr (DIM == 3) rh[2] = fma(-s.A[q], nodes[5 * nl + lo].x, rh[2]);
+  }
+  acc_t[own * kAS] += s.a0;
+  int my_s0 = 0, my_len = 0;
+  if (r >= 0) {
+    my_s0 = P.findrm[r];
+    my_len = P.findrm[r + 1] - my_s0;
+    double ou[DIM], unused;
+    load_rec<DIM>(nodes, nl, 2, own_li, ou, unused);
+#pragma unroll
+    for (int d = 0; d < DIM; d++) {
+      rhs[(size_t)DIM * r + d] = fma(-s.a0, ou[d], fma(k_.gmag * __ldg(gravity + d), s.nbsum, rh[d]));
+      if (masslump) masslump[(size_t)DIM * r + d] = s.msum;
+    }
+  }
+  __syncwarp();
+  write_rows_scaled<DIM>(acc, t, my_s0, my_len, own, s.msum, k_.dtt, P.lpr_shift, nnz, big_m);
+}
+
+// ---- tracer -------------------------------------------------------------------------------------------
+template <int DIM, int N, int QC>
+__device__ __forceinline__ void sadv_step(AdvState<DIM, N>& s, const StripConsts& k_, double kW, int j, int deg,
+                                          const unsigned* __restrict__ p, unsigned& pq0, unsigned& pq1, const unsigned pad,
+                                          double* __restrict__ acc_t, const double2* __restrict__ nodes, int nl) {
+  constexpr int PD = N - DIM;
+  constexpr int QE = (QC + PD) % N;
+  const unsigned en = pq0;
+  pq0 = pq1;
+  pq1 = (j + PD + 2 < deg) ? ldg_stream1(p + (long long)(j + PD + 2) * kBR) : pad;
+  {
+    double* sl = acc_t + (((unsigned)s.meta[QE] >> 16) & 0xffu) * kAS;
+    *sl += fma(k_.dtt, s.A[QE], k_.Po * s.C[QE]);
+    s.A[QE] = 0.0;
+    s.C[QE] = 0.0;
+  }
+  const int li = (int)(en & 0xffffu);
+  double unused;
+  load_rec<DIM>(nodes, nl, 0, li, s.X[QE], s.T[QE]);
+  load_rec<DIM>(nodes, nl, 1, li, s.U[QE], unused);
+  s.meta[QE] = (int)en;
+#pragma unroll
+  for (int a = 0; a < DIM; a++) s.X[QC][a] -= s.X0[a];
+  if ((unsigned)s.meta[QC] & kLocalCompute) adv_compute<DIM, N, QC>(s, k_, kW);
+}
+
+template <int DIM, int N, int Q>
+struct SAdvUnroll {
+  template <class... Args>
+  static __device__ __forceinline__ void run(AdvState<DIM, N>& s, const StripConsts& k_, double kW, int j0, Args&&... args) {
+    sadv_step<DIM, N, Q>(s, k_, kW, j0 + Q, args...);
+    if constexpr (Q + 1 < N) SAdvUnroll<DIM, N, Q + 1>::run(s, k_, kW, j0, args...);
+  }
+};
+
+template <int DIM, int N, int MINB>
+__global__ void __launch_bounds__(kBR, MINB)
+staged_advdiff_kernel(const StripConsts k_, const StagedView P, const double4* __restrict__ rX,
+                      const double4* __restrict__ rU, const double* __restrict__ diffusivity,
+                      double* __restrict__ matrix, double* __restrict__ rhs) {
+  constexpr int PD = N - DIM;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* acc = reinterpret_cast<double*>(smem_raw);
+  double2* nodes = reinterpret_cast<double2*>(smem_raw + P.acc_bytes);
+  const int b = blockIdx.x, t = threadIdx.x, nl = P.nl;
+  {
+    const double4* const rec[2] = {rX, rU};
+    stage_nodes<2>(P, b, t, nodes, rec);
+  }
+  const int r = P.rows[b * kBR + t];
+  const long long base = P.ptr[b];
+  const int deg = (int)((P.ptr[b + 1] - base) / kBR);
+  const unsigned* p = P.ent + base + t;
+  double* acc_t = acc + t;
+  for (int q = 0; q < P.maxlen; q++) acc_t[q * kAS] = 0.0;
+  const unsigned pad = P.own_local[b * kBR + t];
+  const int own = (int)((pad >> 16) & 0xffu), own_li = (int)(pad & 0xffffu);
+  const double kW = __ldg(diffusivity) * k_.Wsum;
+  unsigned first[PD];
+#pragma unroll
+  for (int q = 0; q < PD; q++) first[q] = q < deg ? ldg_stream1(p + (long long)q * kBR) : pad;
+  unsigned pq0 = PD < deg ? ldg_stream1(p + (long long)PD * kBR) : pad;
+  unsigned pq1 = PD + 1 < deg ? ldg_stream1(p + (long long)(PD + 1) * kBR) : pad;
+  cp_async_commit_wait_all();
+  __syncthreads();
+  AdvState<DIM, N> s;
+  double unused;
+  load_rec<DIM>(nodes, nl, 0, own_li, s.X0, s.T0);
+  load_rec<DIM>(nodes, nl, 1, own_li, s.U0, unused);
+  s.a0 = s.c0 = s.rhs = 0.0;
+#pragma unroll
+  for (int q = 0; q < N; q++) {
+#pragma unroll
+    for (int a = 0; a < DIM; a++) s.X[q][a] = s.U[q][a] = 0.0;
+    s.T[q] = s.A[q] = s.C[q] = 0.0;
+    s.meta[q] = (int)pad;
+  }
+#pragma unroll
+  for (int q = 0; q < PD; q++) {
+    const int li = (int)(first[q] & 0xffffu);
+    load_rec<DIM>(nodes, nl, 0, li, s.X[q], s.T[q]);
+    load_rec<DIM>(nodes, nl, 1, li, s.U[q], unused);
+    s.meta[q] = (int)first[q];
+  }
+  for (int j0 = 0; j0 < deg; j0 += N) SAdvUnroll<DIM, N, 0>::run(s, k_, kW, j0, deg, p, pq0, pq1, pad, acc_t, nodes, nl);
+#pragma unroll
+  for (int q = 0; q < N; q++)
+    acc_t[(((unsigned)s.meta[q] >> 16) & 0xffu) * kAS] += fma(k_.dtt, s.A[q], k_.Po * s.C[q]);
+  acc_t[own * kAS] += fma(k_.dtt, s.a0, k_.Pd * s.c0);
+  int my_s0 = 0, my_len = 0;
+  if (r >= 0) {
+    my_s0 = P.findrm[r];
+    my_len = P.findrm[r + 1] - my_s0;
+    rhs[r] = s.rhs;
+  }
+  __syncwarp();
+  write_rows<1>(acc, t, my_s0, my_len, P.lpr_shift, 0, matrix);
+}
+
+// ---- launch -------------------------------------------------------------------------------------------
+static size_t acc_bytes_of(const GatherPlan* P) {
+  return (sizeof(double) * (size_t)P->maxlen * kAS + 15) & ~(size_t)15;
+}
+static int nl_of(const GatherPlan* P) { return (P->blk_nodes_max + 7) & ~7; }
+static size_t staged_smem(const GatherPlan* P, int nrec) { return acc_bytes_of(P) + (size_t)nl_of(P) * 32 * nrec; }
+
+bool strip_staged_ok(const Handle* h, bool momentum) {
+  const GatherPlan* P = h->gather;
+  if (!P || !P->d_strip_local || getenv("CGASM_STRIP_GLOBAL")) return false;
+  return staged_smem(P, momentum ? 3 : 2) <= 100 * 1024;  // at least two blocks per SM, else the per-entry kernels
+}
+
+static StagedView staged_view(const Handle* h) {
+  const GatherPlan* P = h->gather;
+  StagedView v;
+  v.rows = P->d_rows;
+  v.ptr = P->d_strip_ptr;
+  v.ent = P->d_strip_local;
+  v.own_local = P->d_own_local;
+  v.blk_ptr = P->d_blk_ptr;
+  v.blk_nodes = P->d_blk_nodes;
+  v.findrm = h->d_findrm;
+  v.maxlen = P->maxlen;
+  int sh = 0;
+  while ((1 << sh) < P->maxlen && sh < 5) sh++;
+  v.lpr_shift = sh;
+  v.nl = nl_of(P);
+  v.acc_bytes = (int)acc_bytes_of(P);
+  return v;
+}
+
+template <int DIM>
+static int staged_momentum_dim(Handle* h, const MomentumArgs& A) {
+  GatherPlan* P = h->gather;
+  const size_t smem = staged_smem(P, 3);
+  const StripConsts c = consts_of(A.tab, A.o.dt * A.o.theta, A.o.gravity_magnitude);
+  const StagedView v = staged_view(h);
+  const int minb = getenv("CGASM_STRIP_MINB") ? atoi(getenv("CGASM_STRIP_MINB")) : 4;
+  int st;
+#define LAUNCH(N_, MINB_)                                                                                       \
+  do {                                                                                                          \
+    if ((st = strip_smem(staged_momentum_kernel<DIM, N_, MINB_>, smem))) return st;                             \
+    staged_momentum_kernel<DIM, N_, MINB_><<<P->nblocks, kBR, smem, h->stream>>>(                               \
+        c, v, h->d_rec3, h->d_rec1, h->d_rec2, A.viscosity.val, A.gravity.val, (size_t)h->nnz, h->d_big_m,       \
+        h->d_mom_rhs, h->d_masslump);                                                                           \
+  } while (0)
+  if (P->strip_mult == DIM + 2) {
+    if (minb >= 3) LAUNCH(DIM + 2, 3);
+    else LAUNCH(DIM + 2, 2);
+  } else {
+    if (minb >= 4) LAUNCH(DIM + 1, 4);
+    else if (minb == 3) LAUNCH(DIM + 1, 3);
+    else LAUNCH(DIM + 1, 2);
+  }
+#undef LAUNCH
+  h->launches++;
+  CG_CUDA(cudaGetLastError());
+  return CGASM_OK;
+}
+
+int strip_staged_momentum(Handle* h, const MomentumArgs& A) {
+  return h->dim == 3 ? staged_momentum_dim<3>(h, A) : staged_momentum_dim<2>(h, A);
+}
+
+template <int DIM>
+static int staged_advdiff_dim(Handle* h, const AdvDiffArgs& A) {
+  GatherPlan* P = h->gather;
+  const size_t smem = staged_smem(P, 2);
+  const double dtt = A.o.dt * A.o.theta;
+  const StripConsts c = consts_of(A.tab, fabs(dtt) > 2.220446049250313e-16 ? dtt : 0.0, 0.0);
+  const StagedView v = staged_view(h);
+  const int minb = getenv("CGASM_STRIP_MINB_ADV") ? atoi(getenv("CGASM_STRIP_MINB_ADV")) : 4;
+  int st;
+#define LAUNCH(N_, MINB_)                                                                                       \
+  do {                                                                                                          \
+    if ((st = strip_smem(staged_advdiff_kernel<DIM, N_, MINB_>, smem))) return st;                              \
+    staged_advdiff_kernel<DIM, N_, MINB_><<<P->nblocks, kBR, smem, h->stream>>>(                                \
+        c, v, h->d_rec0, h->d_rec1, A.diffusivity.val, h->d_adv_matrix, h->d_adv_rhs);                           \
+  } while (0)
+  if (P->strip_mult == DIM + 2) {
+    if (minb >= 4) LAUNCH(DIM + 2, 4);
+    else LAUNCH(DIM + 2, 3);
+  } else {
+    if (minb >= 5) LAUNCH(DIM + 1, 5);
+    else if (minb == 4) LAUNCH(DIM + 1, 4);
+    else LAUNCH(DIM + 1, 3);
+  }
+#undef LAUNCH
+  h->launches++;
+  CG_CUDA(cudaGetLastError());
+  return CGASM_OK;
+}
+
+int strip_staged_advdiff(Handle* h, const AdvDiffArgs& A) {
+  return h->dim == 3 ? staged_advdiff_dim<3>(h, A) : staged_advdiff_dim<2>(h, A);
+}
+
+}  // namespace cgasm
