@@ -157,10 +157,13 @@ void morton_order(const Handle* h, std::vector<int>& order, MortonFrame& F) {
   double mean_edge[3] = {0, 0, 0};
   {
     const int loc = h->loc, ne = h->n_elements;
-    const int stride = std::max(1, ne / 2000000);  // a sample is enough
+    // a sample is enough, but not a strided one: structured meshes repeat their element shapes with a
+    // short period (6 Kuhn tets per cube), and a stride sharing a factor with it sees one shape only
+    const long long nsample = std::min<long long>(ne, 4000000);
     double acc0 = 0, acc1 = 0, acc2 = 0;
 #pragma omp parallel for schedule(static) reduction(+ : acc0, acc1, acc2)
-    for (int e = 0; e < ne; e += stride) {
+    for (long long s = 0; s < nsample; s++) {
+      const int e = nsample == ne ? (int)s : (int)(((unsigned long long)s * 2654435761ull + 12345ull) % (unsigned long long)ne);
       const int* nd = h->h_nd0.data() + (size_t)4 * e;
       for (int i = 0; i < loc; i++)
         for (int j = i + 1; j < loc; j++) {

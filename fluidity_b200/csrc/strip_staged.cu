@@ -40,7 +40,7 @@ constexpr unsigned kLocalCompute = 1u << 24;
 
 __device__ __forceinline__ unsigned ldg_stream1(const unsigned* p) {
   unsigned v;
-  asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
 
@@ -52,59 +52,101 @@ __device__ __forceinline__ void cp_async_commit_wait_all() {
   asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
 
-// copies NCH 16-byte chunks of every node of the block: chunk c of local node i at nodes[c*nl + i]
-template <int NREC>
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+
+// Copies the records of every node of the block: 16-byte chunk c of local node i at nodes[c*nl + i]
+// (chunks 2q, 2q+1 = record q). If OLDU, chunk 4 = oldu(x, y) and the z components follow as a plain
+// double array (an 8-byte read from a 16-byte-strided chunk would be a 2-way bank conflict).
+template <int DIM, bool OLDU>
 __device__ __forceinline__ void stage_nodes(const StagedView& P, int b, int t, double2* __restrict__ nodes,
-                                            const double4* const (&rec)[NREC]) {
+                                            const double4* __restrict__ r0, const double4* __restrict__ r1,
+                                            const double4* __restrict__ rO) {
   const int n0 = P.blk_ptr[b], nloc = P.blk_ptr[b + 1] - n0;
+  double* oz = reinterpret_cast<double*>(nodes + 5 * P.nl);
   for (int i = t; i < nloc; i += kBR) {
     const int node = __ldg(P.blk_nodes + n0 + i);
-#pragma unroll
-    for (int q = 0; q < NREC; q++) {
-      const double2* src = reinterpret_cast<const double2*>(rec[q] + node);
-      cp_async16(nodes + (2 * q) * P.nl + i, src);
-      cp_async16(nodes + (2 * q + 1) * P.nl + i, src + 1);
+    const double2* s0 = reinterpret_cast<const double2*>(r0 + node);
+    const double2* s1 = reinterpret_cast<const double2*>(r1 + node);
+    cp_async16(nodes + 0 * P.nl + i, s0);
+    cp_async16(nodes + 1 * P.nl + i, s0 + 1);
+    cp_async16(nodes + 2 * P.nl + i, s1);
+    cp_async16(nodes + 3 * P.nl + i, s1 + 1);
+    if constexpr (OLDU) {
+      const double2* s2 = reinterpret_cast<const double2*>(rO + node);
+      cp_async16(nodes + 4 * P.nl + i, s2);
+      if constexpr (DIM == 3) cp_async8(oz + i, s2 + 1);
     }
   }
 }
 
+// Shared-memory reads of the staged records are volatile asm with a memory clobber: they must be ISSUED
+// where they are written (one step ahead of their use) -- left to the compiler they sink to the first
+// use and every step pays the LDS latency in its prologue (ncu: short_scoreboard on the install DADDs).
+__device__ __forceinline__ double2 lds128(unsigned sa) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(sa) : "memory");
+  return v;
+}
+__device__ __forceinline__ double lds64(unsigned sa) {
+  double v;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(sa) : "memory");
+  return v;
+}
+
+// chunk c of local node li (16-byte chunks; nsa = shared address of the staged records)
+__device__ __forceinline__ unsigned chunk_sa(unsigned nsa, int nl, int c, int li) { return nsa + (unsigned)(c * nl + li) * 16u; }
+
 template <int DIM>
-__device__ __forceinline__ void load_rec(const double2* __restrict__ nodes, int nl, int rec, int li, double (&v)[DIM], double& s) {
-  const double2 a = nodes[(2 * rec) * nl + li];
-  const double2 b = nodes[(2 * rec + 1) * nl + li];
+__device__ __forceinline__ void load_rec(unsigned nsa, int nl, int rec, int li, double (&v)[DIM], double& s) {
+  const double2 a = lds128(chunk_sa(nsa, nl, 2 * rec, li));
+  const double2 b = lds128(chunk_sa(nsa, nl, 2 * rec + 1, li));
   v[0] = a.x;
   v[1] = a.y;
   if constexpr (DIM == 3) v[2] = b.x;
   s = b.y;
 }
 
+// oldu of local node li: chunk 4 = {x, y}; the z components sit behind chunk 4 as a plain double array
+template <int DIM>
+__device__ __forceinline__ void load_oldu(unsigned nsa, int nl, int li, double (&o)[DIM]) {
+  const double2 a = lds128(chunk_sa(nsa, nl, 4, li));
+  o[0] = a.x;
+  o[1] = a.y;
+  if constexpr (DIM == 3) o[2] = lds64(nsa + (unsigned)(5 * nl) * 16u + (unsigned)li * 8u);
+}
+
 // ---- momentum -----------------------------------------------------------------------------------------
+// One strip entry. Program order = issue order (all memory asm is volatile):
+//   flush the evicted buffer with the oldu fetched one step ago; request the records of entry j+PD, the
+//   oldu of the node evicted NEXT step and plan entry j+PD+3; then install and compute entry j.
 template <int DIM, int N, int QC>
-__device__ __forceinline__ void smom_step(MomState<DIM, N>& s, double (&rh)[DIM], const StripConsts& k_, double muW, int j,
-                                          int deg, const unsigned* __restrict__ p, unsigned& pq0, unsigned& pq1,
-                                          const unsigned pad, double* __restrict__ acc_t,
-                                          const double2* __restrict__ nodes, int nl) {
+__device__ __forceinline__ void smom_step(MomState<DIM, N>& s, double (&rh)[DIM], double (&on)[DIM], const StripConsts& k_,
+                                          double muW, int j, int deg, const unsigned* __restrict__ p, unsigned& pq0,
+                                          unsigned& pq1, unsigned& pq2, const unsigned pad, double* __restrict__ acc_t,
+                                          unsigned nsa, int nl) {
   constexpr int PD = N - DIM;
   constexpr int QE = (QC + PD) % N;  // holds entry j - DIM: evicted now, refilled with entry j + PD
+  constexpr int QN = (QE + 1) % N;   // evicted at the next step
   const unsigned en = pq0;
   pq0 = pq1;
-  pq1 = (j + PD + 2 < deg) ? ldg_stream1(p + (long long)(j + PD + 2) * kBR) : pad;
+  pq1 = pq2;
   {
-    const unsigned m = (unsigned)s.meta[QE];
-    const int lo = (int)(m & 0xffffu);
-    double* sl = acc_t + ((m >> 16) & 0xffu) * kAS;
+    double* sl = acc_t + (((unsigned)s.meta[QE] >> 16) & 0xffu) * kAS;
     const double a = s.A[QE];
     *sl += a;
-    const double2 o0 = nodes[4 * nl + lo];
-    rh[0] = fma(-a, o0.x, rh[0]);
-    rh[1] = fma(-a, o0.y, rh[1]);
-    if constexpr (DIM == 3) rh[2] = fma(-a, nodes[5 * nl + lo].x, rh[2]);
+#pragma unroll
+    for (int d = 0; d < DIM; d++) rh[d] = fma(-a, on[d], rh[d]);
     s.A[QE] = 0.0;
   }
   const int li = (int)(en & 0xffffu);
-  load_rec<DIM>(nodes, nl, 0, li, s.X[QE], s.B[QE]);
-  load_rec<DIM>(nodes, nl, 1, li, s.U[QE], s.R[QE]);
+  load_rec<DIM>(nsa, nl, 0, li, s.X[QE], s.B[QE]);
+  load_rec<DIM>(nsa, nl, 1, li, s.U[QE], s.R[QE]);
   s.meta[QE] = (int)en;
+  load_oldu<DIM>(nsa, nl, (int)((unsigned)s.meta[QN] & 0xffffu), on);
+  pq2 = (j + PD + 3 < deg) ? ldg_stream1(p + (long long)(j + PD + 3) * kBR) : pad;
 #pragma unroll
   for (int a = 0; a < DIM; a++) s.X[QC][a] -= s.X0[a];
   if ((unsigned)s.meta[QC] & kLocalCompute) mom_compute<DIM, N, QC>(s, k_, muW);
@@ -113,10 +155,10 @@ __device__ __forceinline__ void smom_step(MomState<DIM, N>& s, double (&rh)[DIM]
 template <int DIM, int N, int Q>
 struct SMomUnroll {
   template <class... Args>
-  static __device__ __forceinline__ void run(MomState<DIM, N>& s, double (&rh)[DIM], const StripConsts& k_, double muW,
-                                             int j0, Args&&... args) {
-    smom_step<DIM, N, Q>(s, rh, k_, muW, j0 + Q, args...);
-    if constexpr (Q + 1 < N) SMomUnroll<DIM, N, Q + 1>::run(s, rh, k_, muW, j0, args...);
+  static __device__ __forceinline__ void run(MomState<DIM, N>& s, double (&rh)[DIM], double (&on)[DIM], const StripConsts& k_,
+                                             double muW, int j0, Args&&... args) {
+    smom_step<DIM, N, Q>(s, rh, on, k_, muW, j0 + Q, args...);
+    if constexpr (Q + 1 < N) SMomUnroll<DIM, N, Q + 1>::run(s, rh, on, k_, muW, j0, args...);
   }
 };
 
@@ -152,11 +194,9 @@ staged_momentum_kernel(const StripConsts k_, const StagedView P, const double4* 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* acc = reinterpret_cast<double*>(smem_raw);
   double2* nodes = reinterpret_cast<double2*>(smem_raw + P.acc_bytes);
+  const unsigned nsa = (unsigned)__cvta_generic_to_shared(nodes);
   const int b = blockIdx.x, t = threadIdx.x, nl = P.nl;
-  {
-    const double4* const rec[3] = {rX, rU, rO};
-    stage_nodes<3>(P, b, t, nodes, rec);
-  }
+  stage_nodes<DIM, true>(P, b, t, nodes, rX, rU, rO);
   const int r = P.rows[b * kBR + t];
   const long long base = P.ptr[b];
   const int deg = (int)((P.ptr[b + 1] - base) / kBR);  // a multiple of N
@@ -171,15 +211,16 @@ staged_momentum_kernel(const StripConsts k_, const StagedView P, const double4* 
   for (int q = 0; q < PD; q++) first[q] = q < deg ? ldg_stream1(p + (long long)q * kBR) : pad;
   unsigned pq0 = PD < deg ? ldg_stream1(p + (long long)PD * kBR) : pad;
   unsigned pq1 = PD + 1 < deg ? ldg_stream1(p + (long long)(PD + 1) * kBR) : pad;
+  unsigned pq2 = PD + 2 < deg ? ldg_stream1(p + (long long)(PD + 2) * kBR) : pad;
   cp_async_commit_wait_all();
   __syncthreads();
   MomState<DIM, N> s;
-  load_rec<DIM>(nodes, nl, 0, own_li, s.X0, s.b0);
-  load_rec<DIM>(nodes, nl, 1, own_li, s.U0, s.rho0);
+  load_rec<DIM>(nsa, nl, 0, own_li, s.X0, s.b0);
+  load_rec<DIM>(nsa, nl, 1, own_li, s.U0, s.rho0);
   s.a0 = s.msum = s.nbsum = 0.0;
-  double rh[DIM];
+  double rh[DIM], on[DIM];
 #pragma unroll
-  for (int d = 0; d < DIM; d++) rh[d] = 0.0;
+  for (int d = 0; d < DIM; d++) rh[d] = on[d] = 0.0;
 #pragma unroll
   for (int q = 0; q < N; q++) {
 #pragma unroll
@@ -190,29 +231,30 @@ staged_momentum_kernel(const StripConsts k_, const StagedView P, const double4* 
 #pragma unroll
   for (int q = 0; q < PD; q++) {
     const int li = (int)(first[q] & 0xffffu);
-    load_rec<DIM>(nodes, nl, 0, li, s.X[q], s.B[q]);
-    load_rec<DIM>(nodes, nl, 1, li, s.U[q], s.R[q]);
+    load_rec<DIM>(nsa, nl, 0, li, s.X[q], s.B[q]);
+    load_rec<DIM>(nsa, nl, 1, li, s.U[q], s.R[q]);
     s.meta[q] = (int)first[q];
   }
-  for (int j0 = 0; j0 < deg; j0 += N) SMomUnroll<DIM, N, 0>::run(s, rh, k_, muW, j0, deg, p, pq0, pq1, pad, acc_t, nodes, nl);
+  // `on` = oldu of the node the first step evicts: nothing has accumulated there yet (A = 0), zeros do
+  for (int j0 = 0; j0 < deg; j0 += N)
+    SMomUnroll<DIM, N, 0>::run(s, rh, on, k_, muW, j0, deg, p, pq0, pq1, pq2, pad, acc_t, nsa, nl);
   // drain the FIFO, then the diagonal (the row's own node never leaves)
 #pragma unroll
   for (int q = 0; q < N; q++) {
     const unsigned m = (unsigned)s.meta[q];
-    const int lo = (int)(m & 0xffffu);
     acc_t[((m >> 16) & 0xffu) * kAS] += s.A[q];
-    const double2 o0 = nodes[4 * nl + lo];
-    rh[0] = fma(-s.A[q], o0.x, rh[0]);
-    rh[1] = fma(-s.A[q], o0.y, rh[1]);
-    if constexpr (DIM == 3) rh[2] = fma(-s.A[q], nodes[5 * nl + lo].x, rh[2]);
+    double o[DIM];
+    load_oldu<DIM>(nsa, nl, (int)(m & 0xffffu), o);
+#pragma unroll
+    for (int d = 0; d < DIM; d++) rh[d] = fma(-s.A[q], o[d], rh[d]);
   }
   acc_t[own * kAS] += s.a0;
   int my_s0 = 0, my_len = 0;
   if (r >= 0) {
     my_s0 = P.findrm[r];
     my_len = P.findrm[r + 1] - my_s0;
-    double ou[DIM], unused;
-    load_rec<DIM>(nodes, nl, 2, own_li, ou, unused);
+    double ou[DIM];
+    load_oldu<DIM>(nsa, nl, own_li, ou);
 #pragma unroll
     for (int d = 0; d < DIM; d++) {
       rhs[(size_t)DIM * r + d] = fma(-s.a0, ou[d], fma(k_.gmag * __ldg(gravity + d), s.nbsum, rh[d]));
@@ -226,13 +268,13 @@ staged_momentum_kernel(const StripConsts k_, const StagedView P, const double4* 
 // ---- tracer -------------------------------------------------------------------------------------------
 template <int DIM, int N, int QC>
 __device__ __forceinline__ void sadv_step(AdvState<DIM, N>& s, const StripConsts& k_, double kW, int j, int deg,
-                                          const unsigned* __restrict__ p, unsigned& pq0, unsigned& pq1, const unsigned pad,
-                                          double* __restrict__ acc_t, const double2* __restrict__ nodes, int nl) {
+                                          const unsigned* __restrict__ p, unsigned& pq0, unsigned& pq1, unsigned& pq2,
+                                          const unsigned pad, double* __restrict__ acc_t, unsigned nsa, int nl) {
   constexpr int PD = N - DIM;
   constexpr int QE = (QC + PD) % N;
   const unsigned en = pq0;
   pq0 = pq1;
-  pq1 = (j + PD + 2 < deg) ? ldg_stream1(p + (long long)(j + PD + 2) * kBR) : pad;
+  pq1 = pq2;
   {
     double* sl = acc_t + (((unsigned)s.meta[QE] >> 16) & 0xffu) * kAS;
     *sl += fma(k_.dtt, s.A[QE], k_.Po * s.C[QE]);
@@ -241,9 +283,10 @@ __device__ __forceinline__ void sadv_step(AdvState<DIM, N>& s, const StripConsts
   }
   const int li = (int)(en & 0xffffu);
   double unused;
-  load_rec<DIM>(nodes, nl, 0, li, s.X[QE], s.T[QE]);
-  load_rec<DIM>(nodes, nl, 1, li, s.U[QE], unused);
+  load_rec<DIM>(nsa, nl, 0, li, s.X[QE], s.T[QE]);
+  load_rec<DIM>(nsa, nl, 1, li, s.U[QE], unused);
   s.meta[QE] = (int)en;
+  pq2 = (j + PD + 3 < deg) ? ldg_stream1(p + (long long)(j + PD + 3) * kBR) : pad;
 #pragma unroll
   for (int a = 0; a < DIM; a++) s.X[QC][a] -= s.X0[a];
   if ((unsigned)s.meta[QC] & kLocalCompute) adv_compute<DIM, N, QC>(s, k_, kW);
@@ -267,11 +310,9 @@ staged_advdiff_kernel(const StripConsts k_, const StagedView P, const double4* _
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* acc = reinterpret_cast<double*>(smem_raw);
   double2* nodes = reinterpret_cast<double2*>(smem_raw + P.acc_bytes);
+  const unsigned nsa = (unsigned)__cvta_generic_to_shared(nodes);
   const int b = blockIdx.x, t = threadIdx.x, nl = P.nl;
-  {
-    const double4* const rec[2] = {rX, rU};
-    stage_nodes<2>(P, b, t, nodes, rec);
-  }
+  stage_nodes<DIM, false>(P, b, t, nodes, rX, rU, nullptr);
   const int r = P.rows[b * kBR + t];
   const long long base = P.ptr[b];
   const int deg = (int)((P.ptr[b + 1] - base) / kBR);
@@ -286,12 +327,13 @@ staged_advdiff_kernel(const StripConsts k_, const StagedView P, const double4* _
   for (int q = 0; q < PD; q++) first[q] = q < deg ? ldg_stream1(p + (long long)q * kBR) : pad;
   unsigned pq0 = PD < deg ? ldg_stream1(p + (long long)PD * kBR) : pad;
   unsigned pq1 = PD + 1 < deg ? ldg_stream1(p + (long long)(PD + 1) * kBR) : pad;
+  unsigned pq2 = PD + 2 < deg ? ldg_stream1(p + (long long)(PD + 2) * kBR) : pad;
   cp_async_commit_wait_all();
   __syncthreads();
   AdvState<DIM, N> s;
   double unused;
-  load_rec<DIM>(nodes, nl, 0, own_li, s.X0, s.T0);
-  load_rec<DIM>(nodes, nl, 1, own_li, s.U0, unused);
+  load_rec<DIM>(nsa, nl, 0, own_li, s.X0, s.T0);
+  load_rec<DIM>(nsa, nl, 1, own_li, s.U0, unused);
   s.a0 = s.c0 = s.rhs = 0.0;
 #pragma unroll
   for (int q = 0; q < N; q++) {
@@ -303,11 +345,11 @@ staged_advdiff_kernel(const StripConsts k_, const StagedView P, const double4* _
 #pragma unroll
   for (int q = 0; q < PD; q++) {
     const int li = (int)(first[q] & 0xffffu);
-    load_rec<DIM>(nodes, nl, 0, li, s.X[q], s.T[q]);
-    load_rec<DIM>(nodes, nl, 1, li, s.U[q], unused);
+    load_rec<DIM>(nsa, nl, 0, li, s.X[q], s.T[q]);
+    load_rec<DIM>(nsa, nl, 1, li, s.U[q], unused);
     s.meta[q] = (int)first[q];
   }
-  for (int j0 = 0; j0 < deg; j0 += N) SAdvUnroll<DIM, N, 0>::run(s, k_, kW, j0, deg, p, pq0, pq1, pad, acc_t, nodes, nl);
+  for (int j0 = 0; j0 < deg; j0 += N) SAdvUnroll<DIM, N, 0>::run(s, k_, kW, j0, deg, p, pq0, pq1, pq2, pad, acc_t, nsa, nl);
 #pragma unroll
   for (int q = 0; q < N; q++)
     acc_t[(((unsigned)s.meta[q] >> 16) & 0xffu) * kAS] += fma(k_.dtt, s.A[q], k_.Po * s.C[q]);
@@ -327,12 +369,12 @@ static size_t acc_bytes_of(const GatherPlan* P) {
   return (sizeof(double) * (size_t)P->maxlen * kAS + 15) & ~(size_t)15;
 }
 static int nl_of(const GatherPlan* P) { return (P->blk_nodes_max + 7) & ~7; }
-static size_t staged_smem(const GatherPlan* P, int nrec) { return acc_bytes_of(P) + (size_t)nl_of(P) * 32 * nrec; }
+static size_t staged_smem(const GatherPlan* P, bool momentum) { return acc_bytes_of(P) + (size_t)nl_of(P) * (momentum ? 88 : 64); }
 
 bool strip_staged_ok(const Handle* h, bool momentum) {
   const GatherPlan* P = h->gather;
   if (!P || !P->d_strip_local || getenv("CGASM_STRIP_GLOBAL")) return false;
-  return staged_smem(P, momentum ? 3 : 2) <= 100 * 1024;  // at least two blocks per SM, else the per-entry kernels
+  return staged_smem(P, momentum) <= 100 * 1024;  // at least two blocks per SM, else the per-entry kernels
 }
 
 static StagedView staged_view(const Handle* h) {
@@ -357,7 +399,7 @@ static StagedView staged_view(const Handle* h) {
 template <int DIM>
 static int staged_momentum_dim(Handle* h, const MomentumArgs& A) {
   GatherPlan* P = h->gather;
-  const size_t smem = staged_smem(P, 3);
+  const size_t smem = staged_smem(P, true);
   const StripConsts c = consts_of(A.tab, A.o.dt * A.o.theta, A.o.gravity_magnitude);
   const StagedView v = staged_view(h);
   const int minb = getenv("CGASM_STRIP_MINB") ? atoi(getenv("CGASM_STRIP_MINB")) : 4;
@@ -390,7 +432,7 @@ int strip_staged_momentum(Handle* h, const MomentumArgs& A) {
 template <int DIM>
 static int staged_advdiff_dim(Handle* h, const AdvDiffArgs& A) {
   GatherPlan* P = h->gather;
-  const size_t smem = staged_smem(P, 2);
+  const size_t smem = staged_smem(P, false);
   const double dtt = A.o.dt * A.o.theta;
   const StripConsts c = consts_of(A.tab, fabs(dtt) > 2.220446049250313e-16 ? dtt : 0.0, 0.0);
   const StagedView v = staged_view(h);
