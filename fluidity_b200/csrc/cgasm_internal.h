@@ -149,6 +149,10 @@ struct MortonFrame {
 };
 
 void morton_order(const Handle* h, std::vector<int>& order, MortonFrame& F);
+// Cuts the Morton sequence into blocks of at most block_rows rows (rows: nblocks * block_rows node ids,
+// -1 = padding at the end of a block); returns the number of blocks. Needs the sparsity.
+int form_row_blocks(const Handle* h, const std::vector<int>& order, const MortonFrame& F, int block_rows,
+                    std::vector<int>& rows);
 
 // tiled.cu
 int tiles_build(Handle* h);

@@ -255,52 +255,8 @@ int gather_build(Handle* h) {
   std::vector<int> order;
   MortonFrame F;
   morton_order(h, order, F);
-  // Row blocks = runs of the Morton sequence. Cutting every kBR nodes drifts off the lattice bricks as
-  // soon as one brick is partly filled (domain boundary), and a block that straddles two bricks touches
-  // up to twice as many distinct nodes. So: group the sequence by brick (kBR lattice points: the low
-  // log2(kBR) key bits), merge consecutive groups while they fit, split over-full ones; keep that
-  // only if the padding stays below 15 %.
   std::vector<int> rows;
-  {
-    int shift = 0;
-    while ((1 << shift) < kBR) shift++;
-    std::vector<int> cut;  // start of every block in `order`
-    int start = 0, count = 0;
-    uint64_t brick = ~0ull;
-    for (int i = 0; i < n; i++) {
-      const uint64_t k = F.key_round(&h->h_X[(size_t)h->dim * order[i]]) >> shift;
-      if (k != brick) {  // a new group starts at i: find its end, then merge or cut
-        int e = i;
-        while (e < n && (F.key_round(&h->h_X[(size_t)h->dim * order[e]]) >> shift) == k) e++;
-        const int len = e - i;
-        if (count > 0 && count + len > kBR) {
-          cut.push_back(start);
-          start = i;
-          count = 0;
-        }
-        brick = k;
-      }
-      if (count == kBR) {
-        cut.push_back(start);
-        start = i;
-        count = 0;
-      }
-      count++;
-    }
-    if (count > 0) cut.push_back(start);
-    cut.push_back(n);
-    const int nb_aligned = (int)cut.size() - 1, nb_plain = (n + kBR - 1) / kBR;
-    if ((double)nb_aligned <= 1.15 * nb_plain && !getenv("CGASM_GATHER_PLAIN_BLOCKS")) {
-      P->nblocks = nb_aligned;
-      rows.assign((size_t)nb_aligned * kBR, -1);
-      for (int b = 0; b < nb_aligned; b++) std::copy(order.begin() + cut[b], order.begin() + cut[b + 1], rows.begin() + (size_t)b * kBR);
-    } else {
-      P->nblocks = nb_plain;
-      rows.assign((size_t)nb_plain * kBR, -1);
-      std::copy(order.begin(), order.end(), rows.begin());
-    }
-    if (getenv("CGASM_DEBUG")) fprintf(stderr, "[cgasm] row blocks: %d (plain %d, brick-aligned %d)\n", P->nblocks, nb_plain, nb_aligned);
-  }
+  P->nblocks = form_row_blocks(h, order, F, kBR, rows);
   std::vector<long long> block_ptr((size_t)P->nblocks + 1, 0);
   int maxlen = 0;
   for (int b = 0; b < P->nblocks; b++) {

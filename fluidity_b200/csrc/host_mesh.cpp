@@ -12,6 +12,9 @@
 //             here with a 64-bit colour mask per element instead of a Judy set.
 #include "cgasm_internal.h"
 
+#include <cstdio>
+#include <cstdlib>
+
 #include <algorithm>
 #include <cstring>
 #include <numeric>
@@ -219,5 +222,94 @@ void morton_order(const Handle* h, std::vector<int>& order, MortonFrame& F) {
   std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return key[a] < key[b]; });
 }
 
+
+int form_row_blocks(const Handle* h, const std::vector<int>& order, const MortonFrame& F, int block_rows,
+                    std::vector<int>& rows) {
+  const int n = h->n_nodes;
+  int nblocks = 0;
+  // Row blocks = runs of the Morton sequence. Cutting every block_rows nodes drifts off the lattice bricks as
+  // soon as one brick is partly filled (domain boundary), and a block that straddles two bricks touches
+  // up to twice as many distinct nodes. So: group the sequence by brick (block_rows lattice points: the low
+  // log2(block_rows) key bits), merge consecutive groups while they fit AND while the distinct nodes the
+  // block touches (the union of its CSR rows: what the staged kernels keep in shared memory) stay
+  // near what a full brick needs, split over-full groups; keep that only if the padding stays below 15 %.
+    int shift = 0;
+    while ((1 << shift) < block_rows) shift++;
+    std::vector<int> gstart;  // start of every brick group in `order`
+    {
+      uint64_t brick = ~0ull;
+      for (int i = 0; i < n; i++) {
+        const uint64_t k = F.key_round(&h->h_X[(size_t)h->dim * order[i]]) >> shift;
+        if (k != brick || i - gstart.back() == block_rows) gstart.push_back(i);
+        brick = k;
+      }
+      gstart.push_back(n);
+    }
+    const int ng = (int)gstart.size() - 1;
+    std::vector<int> mark((size_t)n, -1);
+    // distinct columns of rows order[i0..i1) not yet stamped; stamps them if commit
+    auto touch = [&](int i0, int i1, int stamp, bool commit) {
+      int fresh = 0;
+      for (int i = i0; i < i1; i++) {
+        const int r = order[i];
+        for (int q = h->h_findrm[r]; q < h->h_findrm[r + 1]; q++) {
+          const int c = h->h_colm[q];
+          if (mark[c] != stamp && mark[c] != -2 - stamp) {
+            fresh++;
+            mark[c] = commit ? stamp : -2 - stamp;
+          }
+        }
+      }
+      if (!commit)  // undo the tentative marks
+        for (int i = i0; i < i1; i++) {
+          const int r = order[i];
+          for (int q = h->h_findrm[r]; q < h->h_findrm[r + 1]; q++)
+            if (mark[h->h_colm[q]] == -2 - stamp) mark[h->h_colm[q]] = -1;
+        }
+      return fresh;
+    };
+    // what a full brick touches (median over a sample of full groups)
+    int cap = 1 << 30;
+    {
+      std::vector<int> sizes;
+      const int step = std::max(1, ng / 2000);
+      for (int g = 0; g < ng; g += step)
+        if (gstart[g + 1] - gstart[g] == block_rows) sizes.push_back(touch(gstart[g], gstart[g + 1], 0, false));
+      if (!sizes.empty()) {
+        std::nth_element(sizes.begin(), sizes.begin() + sizes.size() / 2, sizes.end());
+        cap = (int)(1.15 * sizes[sizes.size() / 2]);
+      }
+    }
+    std::vector<int> cut;  // start of every block in `order`
+    int count = 0, touched = 0, stamp = 1;
+    for (int g = 0; g < ng; g++) {
+      const int len = gstart[g + 1] - gstart[g];
+      if (count > 0) {
+        const bool fits = count + len <= block_rows && touched + touch(gstart[g], gstart[g + 1], stamp, false) <= cap;
+        if (!fits) {
+          count = 0;
+          touched = 0;
+          stamp++;
+        }
+      }
+      if (count == 0) cut.push_back(gstart[g]);
+      touched += touch(gstart[g], gstart[g + 1], stamp, true);
+      count += len;
+    }
+    cut.push_back(n);
+    const int nb_aligned = (int)cut.size() - 1, nb_plain = (n + block_rows - 1) / block_rows;
+    if ((double)nb_aligned <= 1.15 * nb_plain && !getenv("CGASM_GATHER_PLAIN_BLOCKS")) {
+      nblocks = nb_aligned;
+      rows.assign((size_t)nb_aligned * block_rows, -1);
+      for (int b = 0; b < nb_aligned; b++) std::copy(order.begin() + cut[b], order.begin() + cut[b + 1], rows.begin() + (size_t)b * block_rows);
+    } else {
+      nblocks = nb_plain;
+      rows.assign((size_t)nb_plain * block_rows, -1);
+      std::copy(order.begin(), order.end(), rows.begin());
+    }
+    if (getenv("CGASM_DEBUG"))
+      fprintf(stderr, "[cgasm] row blocks: %d (plain %d, brick-aligned %d, node cap %d)\n", nblocks, nb_plain, nb_aligned, cap);
+  return nblocks;
+}
 
 }  // namespace cgasm

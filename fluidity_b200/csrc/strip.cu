@@ -223,11 +223,9 @@ strip_advdiff_kernel(const StripConsts k_, const StripPlanView P, const double4*
 }
 
 // ---- plan ---------------------------------------------------------------------------------------------
-static int strip_nbuf(int dim) {
-  const char* e = getenv("CGASM_STRIP_NBUF");
-  int n = e ? atoi(e) : dim + 1;
-  return std::min(std::max(n, dim + 1), dim + 2);
-}
+// block degrees are padded to a multiple of every buffer count the kernels are built for (dim: FIFO
+// only, dim + 1: one entry of prefetch), so the unrolled loops need no tail
+static int strip_nbuf(int dim) { return dim * (dim + 1); }
 
 int strip_build(Handle* h) {
   GatherPlan* P = h->gather;
@@ -385,14 +383,9 @@ static int strip_momentum_dim(Handle* h, const MomentumArgs& A) {
         c, v, h->d_rec3, h->d_rec1, h->d_rec2, A.viscosity.val, A.gravity.val, (size_t)h->nnz, h->d_big_m,      \
         h->d_mom_rhs, h->d_masslump);                                                                          \
   } while (0)
-  if (P->strip_mult == DIM + 2) {
-    if (minb >= 3) LAUNCH(DIM + 2, 3);
-    else LAUNCH(DIM + 2, 2);
-  } else {
-    if (minb >= 4) LAUNCH(DIM + 1, 4);
-    else if (minb == 3) LAUNCH(DIM + 1, 3);
-    else LAUNCH(DIM + 1, 2);
-  }
+  if (minb >= 4) LAUNCH(DIM + 1, 4);
+  else if (minb == 3) LAUNCH(DIM + 1, 3);
+  else LAUNCH(DIM + 1, 2);
 #undef LAUNCH
   h->launches++;
   CG_CUDA(cudaGetLastError());
@@ -420,14 +413,9 @@ static int strip_advdiff_dim(Handle* h, const AdvDiffArgs& A) {
     strip_advdiff_kernel<DIM, N_, MINB_><<<P->nblocks, kBR, smem, h->stream>>>(                                \
         c, v, h->d_rec0, h->d_rec1, A.diffusivity.val, h->d_adv_matrix, h->d_adv_rhs);                          \
   } while (0)
-  if (P->strip_mult == DIM + 2) {
-    if (minb >= 4) LAUNCH(DIM + 2, 4);
-    else LAUNCH(DIM + 2, 3);
-  } else {
-    if (minb >= 5) LAUNCH(DIM + 1, 5);
-    else if (minb == 4) LAUNCH(DIM + 1, 4);
-    else LAUNCH(DIM + 1, 3);
-  }
+  if (minb >= 5) LAUNCH(DIM + 1, 5);
+  else if (minb == 4) LAUNCH(DIM + 1, 4);
+  else LAUNCH(DIM + 1, 3);
 #undef LAUNCH
   h->launches++;
   CG_CUDA(cudaGetLastError());

@@ -122,7 +122,7 @@ __device__ __forceinline__ void load_oldu(unsigned nsa, int nl, int li, double (
 // One strip entry. Program order = issue order (all memory asm is volatile):
 //   flush the evicted buffer with the oldu fetched one step ago; request the records of entry j+PD, the
 //   oldu of the node evicted NEXT step and plan entry j+PD+3; then install and compute entry j.
-template <int DIM, int N, int QC>
+template <int DIM, int N, int QC, bool ONPF>
 __device__ __forceinline__ void smom_step(MomState<DIM, N>& s, double (&rh)[DIM], double (&on)[DIM], const StripConsts& k_,
                                           double muW, int j, int deg, const unsigned* __restrict__ p, unsigned& pq0,
                                           unsigned& pq1, unsigned& pq2, const unsigned pad, double* __restrict__ acc_t,
@@ -134,7 +134,9 @@ __device__ __forceinline__ void smom_step(MomState<DIM, N>& s, double (&rh)[DIM]
   pq0 = pq1;
   pq1 = pq2;
   {
-    double* sl = acc_t + (((unsigned)s.meta[QE] >> 16) & 0xffu) * kAS;
+    const unsigned m = (unsigned)s.meta[QE];
+    if constexpr (!ONPF) load_oldu<DIM>(nsa, nl, (int)(m & 0xffffu), on);
+    double* sl = acc_t + ((m >> 16) & 0xffu) * kAS;
     const double a = s.A[QE];
     *sl += a;
 #pragma unroll
@@ -145,20 +147,20 @@ __device__ __forceinline__ void smom_step(MomState<DIM, N>& s, double (&rh)[DIM]
   load_rec<DIM>(nsa, nl, 0, li, s.X[QE], s.B[QE]);
   load_rec<DIM>(nsa, nl, 1, li, s.U[QE], s.R[QE]);
   s.meta[QE] = (int)en;
-  load_oldu<DIM>(nsa, nl, (int)((unsigned)s.meta[QN] & 0xffffu), on);
+  if constexpr (ONPF) load_oldu<DIM>(nsa, nl, (int)((unsigned)s.meta[QN] & 0xffffu), on);
   pq2 = (j + PD + 3 < deg) ? ldg_stream1(p + (long long)(j + PD + 3) * kBR) : pad;
 #pragma unroll
   for (int a = 0; a < DIM; a++) s.X[QC][a] -= s.X0[a];
   if ((unsigned)s.meta[QC] & kLocalCompute) mom_compute<DIM, N, QC>(s, k_, muW);
 }
 
-template <int DIM, int N, int Q>
+template <int DIM, int N, int Q, bool ONPF>
 struct SMomUnroll {
   template <class... Args>
   static __device__ __forceinline__ void run(MomState<DIM, N>& s, double (&rh)[DIM], double (&on)[DIM], const StripConsts& k_,
                                              double muW, int j0, Args&&... args) {
-    smom_step<DIM, N, Q>(s, rh, on, k_, muW, j0 + Q, args...);
-    if constexpr (Q + 1 < N) SMomUnroll<DIM, N, Q + 1>::run(s, rh, on, k_, muW, j0, args...);
+    smom_step<DIM, N, Q, ONPF>(s, rh, on, k_, muW, j0 + Q, args...);
+    if constexpr (Q + 1 < N) SMomUnroll<DIM, N, Q + 1, ONPF>::run(s, rh, on, k_, muW, j0, args...);
   }
 };
 
@@ -184,7 +186,7 @@ __device__ __forceinline__ void write_rows_scaled(const double* __restrict__ acc
   }
 }
 
-template <int DIM, int N, int MINB>
+template <int DIM, int N, int MINB, bool ONPF>
 __global__ void __launch_bounds__(kBR, MINB)
 staged_momentum_kernel(const StripConsts k_, const StagedView P, const double4* __restrict__ rX,
                        const double4* __restrict__ rU, const double4* __restrict__ rO,
@@ -206,7 +208,7 @@ staged_momentum_kernel(const StripConsts k_, const StagedView P, const double4* 
   const unsigned pad = P.own_local[b * kBR + t];
   const int own = (int)((pad >> 16) & 0xffu), own_li = (int)(pad & 0xffffu);
   const double muW = __ldg(viscosity) * k_.Wsum;
-  unsigned first[PD];
+  unsigned first[PD > 0 ? PD : 1];
 #pragma unroll
   for (int q = 0; q < PD; q++) first[q] = q < deg ? ldg_stream1(p + (long long)q * kBR) : pad;
   unsigned pq0 = PD < deg ? ldg_stream1(p + (long long)PD * kBR) : pad;
@@ -237,7 +239,7 @@ staged_momentum_kernel(const StripConsts k_, const StagedView P, const double4* 
   }
   // `on` = oldu of the node the first step evicts: nothing has accumulated there yet (A = 0), zeros do
   for (int j0 = 0; j0 < deg; j0 += N)
-    SMomUnroll<DIM, N, 0>::run(s, rh, on, k_, muW, j0, deg, p, pq0, pq1, pq2, pad, acc_t, nsa, nl);
+    SMomUnroll<DIM, N, 0, ONPF>::run(s, rh, on, k_, muW, j0, deg, p, pq0, pq1, pq2, pad, acc_t, nsa, nl);
   // drain the FIFO, then the diagonal (the row's own node never leaves)
 #pragma unroll
   for (int q = 0; q < N; q++) {
@@ -322,7 +324,7 @@ staged_advdiff_kernel(const StripConsts k_, const StagedView P, const double4* _
   const unsigned pad = P.own_local[b * kBR + t];
   const int own = (int)((pad >> 16) & 0xffu), own_li = (int)(pad & 0xffffu);
   const double kW = __ldg(diffusivity) * k_.Wsum;
-  unsigned first[PD];
+  unsigned first[PD > 0 ? PD : 1];
 #pragma unroll
   for (int q = 0; q < PD; q++) first[q] = q < deg ? ldg_stream1(p + (long long)q * kBR) : pad;
   unsigned pq0 = PD < deg ? ldg_stream1(p + (long long)PD * kBR) : pad;
@@ -404,20 +406,24 @@ static int staged_momentum_dim(Handle* h, const MomentumArgs& A) {
   const StagedView v = staged_view(h);
   const int minb = getenv("CGASM_STRIP_MINB") ? atoi(getenv("CGASM_STRIP_MINB")) : 4;
   int st;
-#define LAUNCH(N_, MINB_)                                                                                       \
+#define LAUNCH(N_, MINB_, ONPF_)                                                                                       \
   do {                                                                                                          \
-    if ((st = strip_smem(staged_momentum_kernel<DIM, N_, MINB_>, smem))) return st;                             \
-    staged_momentum_kernel<DIM, N_, MINB_><<<P->nblocks, kBR, smem, h->stream>>>(                               \
+    if ((st = strip_smem(staged_momentum_kernel<DIM, N_, MINB_, ONPF_>, smem))) return st;                             \
+    staged_momentum_kernel<DIM, N_, MINB_, ONPF_><<<P->nblocks, kBR, smem, h->stream>>>(                               \
         c, v, h->d_rec3, h->d_rec1, h->d_rec2, A.viscosity.val, A.gravity.val, (size_t)h->nnz, h->d_big_m,       \
         h->d_mom_rhs, h->d_masslump);                                                                           \
   } while (0)
-  if (P->strip_mult == DIM + 2) {
-    if (minb >= 3) LAUNCH(DIM + 2, 3);
-    else LAUNCH(DIM + 2, 2);
+  const int nbuf = getenv("CGASM_STRIP_NBUF") ? atoi(getenv("CGASM_STRIP_NBUF")) : DIM;
+  const bool onpf = getenv("CGASM_STRIP_ONPF") && atoi(getenv("CGASM_STRIP_ONPF"));
+  if (nbuf > DIM) {
+    if (minb >= 4) LAUNCH(DIM + 1, 4, true);
+    else if (onpf) LAUNCH(DIM + 1, 3, true);
+    else LAUNCH(DIM + 1, 3, false);
   } else {
-    if (minb >= 4) LAUNCH(DIM + 1, 4);
-    else if (minb == 3) LAUNCH(DIM + 1, 3);
-    else LAUNCH(DIM + 1, 2);
+    if (minb >= 4 && onpf) LAUNCH(DIM, 4, true);
+    else if (minb >= 4) LAUNCH(DIM, 4, false);
+    else if (onpf) LAUNCH(DIM, 3, true);
+    else LAUNCH(DIM, 3, false);
   }
 #undef LAUNCH
   h->launches++;
@@ -444,13 +450,14 @@ static int staged_advdiff_dim(Handle* h, const AdvDiffArgs& A) {
     staged_advdiff_kernel<DIM, N_, MINB_><<<P->nblocks, kBR, smem, h->stream>>>(                                \
         c, v, h->d_rec0, h->d_rec1, A.diffusivity.val, h->d_adv_matrix, h->d_adv_rhs);                           \
   } while (0)
-  if (P->strip_mult == DIM + 2) {
-    if (minb >= 4) LAUNCH(DIM + 2, 4);
-    else LAUNCH(DIM + 2, 3);
-  } else {
-    if (minb >= 5) LAUNCH(DIM + 1, 5);
-    else if (minb == 4) LAUNCH(DIM + 1, 4);
+  const int nbuf = getenv("CGASM_STRIP_NBUF") ? atoi(getenv("CGASM_STRIP_NBUF")) : DIM;
+  if (nbuf > DIM) {
+    if (minb >= 4) LAUNCH(DIM + 1, 4);
     else LAUNCH(DIM + 1, 3);
+  } else {
+    if (minb >= 5) LAUNCH(DIM, 5);
+    else if (minb == 4) LAUNCH(DIM, 4);
+    else LAUNCH(DIM, 3);
   }
 #undef LAUNCH
   h->launches++;
