@@ -37,12 +37,19 @@ struct StagedView {
 };
 
 constexpr unsigned kLocalCompute = 1u << 24;
+// ptxas sinks the plan loads to about one step before their use whatever the source order says (it
+// shortens the live range), which exposes a DRAM round trip per step: so the plan line of step
+// j + kPlanAhead is pulled into L2 by a prefetch (no destination register, nothing to sink) and the
+// sunk load then hits L2.
+constexpr int kPlanAhead = 10;
 
 __device__ __forceinline__ unsigned ldg_stream1(const unsigned* p) {
   unsigned v;
   asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -66,18 +73,26 @@ __device__ __forceinline__ void stage_nodes(const StagedView& P, int b, int t, d
                                             const double4* __restrict__ rO) {
   const int n0 = P.blk_ptr[b], nloc = P.blk_ptr[b + 1] - n0;
   double* oz = reinterpret_cast<double*>(nodes + 5 * P.nl);
-  for (int i = t; i < nloc; i += kBR) {
-    const int node = __ldg(P.blk_nodes + n0 + i);
-    const double2* s0 = reinterpret_cast<const double2*>(r0 + node);
-    const double2* s1 = reinterpret_cast<const double2*>(r1 + node);
-    cp_async16(nodes + 0 * P.nl + i, s0);
-    cp_async16(nodes + 1 * P.nl + i, s0 + 1);
-    cp_async16(nodes + 2 * P.nl + i, s1);
-    cp_async16(nodes + 3 * P.nl + i, s1 + 1);
-    if constexpr (OLDU) {
-      const double2* s2 = reinterpret_cast<const double2*>(rO + node);
-      cp_async16(nodes + 4 * P.nl + i, s2);
-      if constexpr (DIM == 3) cp_async8(oz + i, s2 + 1);
+  constexpr int U = 4;  // node ids of U rounds are requested together, then their copies are issued
+  for (int i0 = t; i0 < nloc; i0 += U * kBR) {
+    int node[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) node[u] = i0 + u * kBR < nloc ? __ldg(P.blk_nodes + n0 + i0 + u * kBR) : -1;
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      if (node[u] < 0) continue;
+      const int i = i0 + u * kBR;
+      const double2* s0 = reinterpret_cast<const double2*>(r0 + node[u]);
+      const double2* s1 = reinterpret_cast<const double2*>(r1 + node[u]);
+      cp_async16(nodes + 0 * P.nl + i, s0);
+      cp_async16(nodes + 1 * P.nl + i, s0 + 1);
+      cp_async16(nodes + 2 * P.nl + i, s1);
+      cp_async16(nodes + 3 * P.nl + i, s1 + 1);
+      if constexpr (OLDU) {
+        const double2* s2 = reinterpret_cast<const double2*>(rO + node[u]);
+        cp_async16(nodes + 4 * P.nl + i, s2);
+        if constexpr (DIM == 3) cp_async8(oz + i, s2 + 1);
+      }
     }
   }
 }
@@ -149,6 +164,7 @@ __device__ __forceinline__ void smom_step(MomState<DIM, N>& s, double (&rh)[DIM]
   s.meta[QE] = (int)en;
   if constexpr (ONPF) load_oldu<DIM>(nsa, nl, (int)((unsigned)s.meta[QN] & 0xffffu), on);
   pq2 = (j + PD + 3 < deg) ? ldg_stream1(p + (long long)(j + PD + 3) * kBR) : pad;
+  if (j + kPlanAhead < deg) prefetch_l2(p + (long long)(j + kPlanAhead) * kBR);
 #pragma unroll
   for (int a = 0; a < DIM; a++) s.X[QC][a] -= s.X0[a];
   if ((unsigned)s.meta[QC] & kLocalCompute) mom_compute<DIM, N, QC>(s, k_, muW);
@@ -208,12 +224,16 @@ staged_momentum_kernel(const StripConsts k_, const StagedView P, const double4* 
   const unsigned pad = P.own_local[b * kBR + t];
   const int own = (int)((pad >> 16) & 0xffu), own_li = (int)(pad & 0xffffu);
   const double muW = __ldg(viscosity) * k_.Wsum;
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(gravity));  // read at the very end of the row
   unsigned first[PD > 0 ? PD : 1];
 #pragma unroll
   for (int q = 0; q < PD; q++) first[q] = q < deg ? ldg_stream1(p + (long long)q * kBR) : pad;
   unsigned pq0 = PD < deg ? ldg_stream1(p + (long long)PD * kBR) : pad;
   unsigned pq1 = PD + 1 < deg ? ldg_stream1(p + (long long)(PD + 1) * kBR) : pad;
   unsigned pq2 = PD + 2 < deg ? ldg_stream1(p + (long long)(PD + 2) * kBR) : pad;
+#pragma unroll
+  for (int q = PD + 3; q < kPlanAhead; q++)
+    if (q < deg) prefetch_l2(p + (long long)q * kBR);
   cp_async_commit_wait_all();
   __syncthreads();
   MomState<DIM, N> s;
@@ -289,6 +309,7 @@ __device__ __forceinline__ void sadv_step(AdvState<DIM, N>& s, const StripConsts
   load_rec<DIM>(nsa, nl, 1, li, s.U[QE], unused);
   s.meta[QE] = (int)en;
   pq2 = (j + PD + 3 < deg) ? ldg_stream1(p + (long long)(j + PD + 3) * kBR) : pad;
+  if (j + kPlanAhead < deg) prefetch_l2(p + (long long)(j + kPlanAhead) * kBR);
 #pragma unroll
   for (int a = 0; a < DIM; a++) s.X[QC][a] -= s.X0[a];
   if ((unsigned)s.meta[QC] & kLocalCompute) adv_compute<DIM, N, QC>(s, k_, kW);
@@ -330,6 +351,9 @@ staged_advdiff_kernel(const StripConsts k_, const StagedView P, const double4* _
   unsigned pq0 = PD < deg ? ldg_stream1(p + (long long)PD * kBR) : pad;
   unsigned pq1 = PD + 1 < deg ? ldg_stream1(p + (long long)(PD + 1) * kBR) : pad;
   unsigned pq2 = PD + 2 < deg ? ldg_stream1(p + (long long)(PD + 2) * kBR) : pad;
+#pragma unroll
+  for (int q = PD + 3; q < kPlanAhead; q++)
+    if (q < deg) prefetch_l2(p + (long long)q * kBR);
   cp_async_commit_wait_all();
   __syncthreads();
   AdvState<DIM, N> s;
