@@ -36,10 +36,10 @@ struct GatherPlan {
   double strip_entries_per_pair = 0.0;
   // staged strip plan (strip_staged.cu): the distinct nodes each row block touches (sorted) and the
   // strip entries re-expressed with block-local node indices:
-  //   bits 0-15 local node index, bits 16-23 CSR slot, bit 24 compute, bit 25 last push of the node
+  //   bits 0-15 local node index, bits 16-23 CSR slot, bit 24 compute
   int* d_blk_ptr = nullptr;          // [nblocks+1] into d_blk_nodes
   int* d_blk_nodes = nullptr;
-  unsigned* d_strip_local = nullptr; // same d_strip_ptr; 16-byte chunks of 4 entries: chunk c of thread t at (c*kBR + t)*4
+  unsigned* d_strip_local = nullptr; // block-interleaved like d_strip, same d_strip_ptr
   unsigned* d_own_local = nullptr;   // [nblocks*kBR] own node: local index | own slot << 16
   int blk_nodes_max = 0;
   double* d_stage = nullptr;       // staging buffer (grown on demand)

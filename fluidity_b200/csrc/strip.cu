@@ -225,8 +225,7 @@ strip_advdiff_kernel(const StripConsts k_, const StripPlanView P, const double4*
 // ---- plan ---------------------------------------------------------------------------------------------
 // block degrees are padded to a multiple of every buffer count the kernels are built for (dim: FIFO
 // only, dim + 1: one entry of prefetch), so the unrolled loops need no tail
-// ... and of 4: the staged kernels fetch their entries in 16-byte chunks
-static int strip_nbuf(int dim) { return dim == 3 ? 12 : 12; }
+static int strip_nbuf(int dim) { return dim * (dim + 1); }
 
 int strip_build(Handle* h) {
   GatherPlan* P = h->gather;
@@ -296,12 +295,10 @@ int strip_build(Handle* h) {
         unsigned lv = ol;
         if (k < (int)rp.size()) {
           v = make_int2(rp[k].node, rp[k].meta);
-          lv = local_of(rp[k].node) | (unsigned)(rp[k].meta & 0xff) << 16 | ((rp[k].meta & kStripCompute) ? 1u << 24 : 0u) |
-               ((rp[k].meta & kStripFinal) ? 1u << 25 : 0u);
+          lv = local_of(rp[k].node) | (unsigned)(rp[k].meta & 0xff) << 16 | ((rp[k].meta & kStripCompute) ? 1u << 24 : 0u);
         }
         ent[(size_t)(ptr[b] + (long long)k * kBR + t)] = v;
-        // staged flavour: 16-byte chunks of 4 consecutive entries per thread, chunk c of thread t at (c*kBR + t)*4
-        lent[(size_t)(ptr[b] + ((long long)(k / 4) * kBR + t) * 4 + (k % 4))] = lv;
+        lent[(size_t)(ptr[b] + (long long)k * kBR + t)] = lv;
       }
     }
   }

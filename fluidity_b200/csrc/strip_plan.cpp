@@ -231,11 +231,6 @@ void build_strip_row(int loc, const int* nd0, const int64_t* n2e_ptr, const int*
     out[k].node = best.node[k];
     out[k].meta = (slot & 0xff) | (best.comp[k] ? kStripCompute : 0);
   }
-  for (size_t k = 0; k < out.size(); k++) {
-    bool last = true;
-    for (size_t q = k + 1; q < out.size() && last; q++) last = out[q].node != out[k].node;
-    if (last) out[k].meta |= kStripFinal;
-  }
 }
 
 }  // namespace cgasm

@@ -16,10 +16,9 @@ namespace cgasm {
 struct StripEntry {
   int node;  // 0-based node to push
   int meta;  // bits 0-7: CSR slot of `node` inside row r; bit 8: the window ending here is an
-             // element of r that has not been computed yet -> compute it; bit 9: kStripFinal
+             // element of r that has not been computed yet -> compute it
 };
 constexpr int kStripCompute = 0x100;
-constexpr int kStripFinal = 0x200;  // bit 9: last push of this node in the row (its slot is complete when it leaves)
 
 // Strip of row r. nd0: 0-based connectivity with stride 4; n2e_ptr/n2e: node -> element adjacency
 // (ascending element ids); findrm/colm: 0-based sorted CSR rows. Deterministic in the relative

@@ -37,16 +37,11 @@ struct StagedView {
 };
 
 constexpr unsigned kLocalCompute = 1u << 24;
-constexpr unsigned kLocalFinal = 1u << 25;
-
-// Plan feed. ptxas sinks register loads of the plan stream to about one step before their use whatever
-// the source order says (shorter live range), which exposes a DRAM round trip per step (ncu: one
-// IMAD on the entry = 17 % of all stall samples). So the entries travel through shared memory instead:
-// every thread owns a ring of three 16-byte chunks (4 entries each), refilled by cp.async two chunks
-// (8-11 steps) ahead of their use -- no destination register, nothing to sink -- and reads one entry
-// per step with LDS, one step ahead.
-constexpr int kRingChunks = 3;
-constexpr int kRingBytes = kRingChunks * kBR * 16;
+// ptxas sinks the plan loads to about one step before their use whatever the source order says (it
+// shortens the live range), which exposes a DRAM round trip per step: so the plan line of step
+// j + kPlanAhead is pulled into L2 by a prefetch (no destination register, nothing to sink) and the
+// sunk load then hits L2.
+constexpr int kPlanAhead = 10;
 
 __device__ __forceinline__ unsigned ldg_stream1(const unsigned* p) {
   unsigned v;
@@ -63,46 +58,6 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 __device__ __forceinline__ void cp_async_commit_wait_all() {
   asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
-__device__ __forceinline__ void cp_async16_sa(unsigned smem_dst, const void* gmem_src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ unsigned lds32(unsigned sa) {
-  unsigned v;
-  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(sa) : "memory");
-  return v;
-}
-
-struct PlanRing {
-  unsigned sa;     // shared address of this thread's slot in ring chunk 0
-  const uint4* g;  // chunk 0 of this thread in global memory; chunk c at g[c * kBR]
-  int deg;         // entries of the block (a multiple of 4)
-  unsigned next;   // entry of the next pop
-  unsigned pad;    // what a pop past the end returns (re-push of the own node)
-  __device__ __forceinline__ void issue(int c) {
-    if (4 * c < deg) cp_async16_sa(sa + (unsigned)(c % kRingChunks) * (kBR * 16), g + (long long)c * kBR);
-    cp_async_commit();
-  }
-  __device__ __forceinline__ unsigned read(int e) const {
-    return e < deg ? lds32(sa + (unsigned)((e >> 2) % kRingChunks) * (kBR * 16) + (unsigned)(e & 3) * 4u) : pad;
-  }
-  // chunks 0..2 requested; the caller waits for all outstanding copies, then calls start()
-  __device__ __forceinline__ void prime() {
-#pragma unroll
-    for (int c = 0; c < kRingChunks; c++) issue(c);
-  }
-  // returns entry e (the previous `next`) and fetches entry e + 1; e is uniform over the block
-  __device__ __forceinline__ unsigned pop(int e) {
-    const unsigned en = next;
-    if (((e + 1) & 3) == 0) {  // entry e was the last of its chunk: its slot is free for the chunk 3 ahead
-      cp_async_wait_1();       // the next chunk has landed (only the newest request may be in flight)
-      issue(((e + 1) >> 2) + kRingChunks - 1);
-    }
-    next = read(e + 1);
-    return en;
-  }
-};
 
 __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -179,43 +134,49 @@ __device__ __forceinline__ void load_oldu(unsigned nsa, int nl, int li, double (
 }
 
 // ---- momentum -----------------------------------------------------------------------------------------
-// One strip entry. Program order = issue order (all memory asm is volatile): flush the evicted buffer,
-// request the records of entry j + PD, then install and compute entry j.
-template <int DIM, int N, int QC>
-__device__ __forceinline__ void smom_step(MomState<DIM, N>& s, double (&rh)[DIM], const StripConsts& k_, double muW, int j,
-                                          PlanRing& ring, double* __restrict__ acc_t, unsigned nsa, int nl) {
+// One strip entry. Program order = issue order (all memory asm is volatile):
+//   flush the evicted buffer with the oldu fetched one step ago; request the records of entry j+PD, the
+//   oldu of the node evicted NEXT step and plan entry j+PD+3; then install and compute entry j.
+template <int DIM, int N, int QC, bool ONPF>
+__device__ __forceinline__ void smom_step(MomState<DIM, N>& s, double (&rh)[DIM], double (&on)[DIM], const StripConsts& k_,
+                                          double muW, int j, int deg, const unsigned* __restrict__ p, unsigned& pq0,
+                                          unsigned& pq1, unsigned& pq2, const unsigned pad, double* __restrict__ acc_t,
+                                          unsigned nsa, int nl) {
   constexpr int PD = N - DIM;
   constexpr int QE = (QC + PD) % N;  // holds entry j - DIM: evicted now, refilled with entry j + PD
-  const unsigned en = ring.pop(j + PD);
+  constexpr int QN = (QE + 1) % N;   // evicted at the next step
+  const unsigned en = pq0;
+  pq0 = pq1;
+  pq1 = pq2;
   {
     const unsigned m = (unsigned)s.meta[QE];
+    if constexpr (!ONPF) load_oldu<DIM>(nsa, nl, (int)(m & 0xffffu), on);
     double* sl = acc_t + ((m >> 16) & 0xffu) * kAS;
-    const double tot = *sl + s.A[QE];
-    *sl = tot;
-    s.A[QE] = 0.0;
-    if (m & kLocalFinal) {  // the slot is complete: rhs -= (A + K)(r, node) oldu(node)
-      double o[DIM];
-      load_oldu<DIM>(nsa, nl, (int)(m & 0xffffu), o);
+    const double a = s.A[QE];
+    *sl += a;
 #pragma unroll
-      for (int d = 0; d < DIM; d++) rh[d] = fma(-tot, o[d], rh[d]);
-    }
+    for (int d = 0; d < DIM; d++) rh[d] = fma(-a, on[d], rh[d]);
+    s.A[QE] = 0.0;
   }
   const int li = (int)(en & 0xffffu);
   load_rec<DIM>(nsa, nl, 0, li, s.X[QE], s.B[QE]);
   load_rec<DIM>(nsa, nl, 1, li, s.U[QE], s.R[QE]);
   s.meta[QE] = (int)en;
+  if constexpr (ONPF) load_oldu<DIM>(nsa, nl, (int)((unsigned)s.meta[QN] & 0xffffu), on);
+  pq2 = (j + PD + 3 < deg) ? ldg_stream1(p + (long long)(j + PD + 3) * kBR) : pad;
+  if (j + kPlanAhead < deg) prefetch_l2(p + (long long)(j + kPlanAhead) * kBR);
 #pragma unroll
   for (int a = 0; a < DIM; a++) s.X[QC][a] -= s.X0[a];
   if ((unsigned)s.meta[QC] & kLocalCompute) mom_compute<DIM, N, QC>(s, k_, muW);
 }
 
-template <int DIM, int N, int Q>
+template <int DIM, int N, int Q, bool ONPF>
 struct SMomUnroll {
   template <class... Args>
-  static __device__ __forceinline__ void run(MomState<DIM, N>& s, double (&rh)[DIM], const StripConsts& k_, double muW,
-                                             int j0, Args&&... args) {
-    smom_step<DIM, N, Q>(s, rh, k_, muW, j0 + Q, args...);
-    if constexpr (Q + 1 < N) SMomUnroll<DIM, N, Q + 1>::run(s, rh, k_, muW, j0, args...);
+  static __device__ __forceinline__ void run(MomState<DIM, N>& s, double (&rh)[DIM], double (&on)[DIM], const StripConsts& k_,
+                                             double muW, int j0, Args&&... args) {
+    smom_step<DIM, N, Q, ONPF>(s, rh, on, k_, muW, j0 + Q, args...);
+    if constexpr (Q + 1 < N) SMomUnroll<DIM, N, Q + 1, ONPF>::run(s, rh, on, k_, muW, j0, args...);
   }
 };
 
@@ -241,7 +202,7 @@ __device__ __forceinline__ void write_rows_scaled(const double* __restrict__ acc
   }
 }
 
-template <int DIM, int N, int MINB>
+template <int DIM, int N, int MINB, bool ONPF>
 __global__ void __launch_bounds__(kBR, MINB)
 staged_momentum_kernel(const StripConsts k_, const StagedView P, const double4* __restrict__ rX,
                        const double4* __restrict__ rU, const double4* __restrict__ rO,
@@ -250,33 +211,38 @@ staged_momentum_kernel(const StripConsts k_, const StagedView P, const double4* 
   constexpr int PD = N - DIM;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* acc = reinterpret_cast<double*>(smem_raw);
-  double2* nodes = reinterpret_cast<double2*>(smem_raw + P.acc_bytes + kRingBytes);
+  double2* nodes = reinterpret_cast<double2*>(smem_raw + P.acc_bytes);
   const unsigned nsa = (unsigned)__cvta_generic_to_shared(nodes);
   const int b = blockIdx.x, t = threadIdx.x, nl = P.nl;
-  const long long base = P.ptr[b];
-  PlanRing ring;
-  ring.sa = (unsigned)__cvta_generic_to_shared(smem_raw + P.acc_bytes) + (unsigned)t * 16u;
-  ring.g = reinterpret_cast<const uint4*>(P.ent + base) + t;
-  ring.deg = (int)((P.ptr[b + 1] - base) / kBR);  // a multiple of 12
-  ring.pad = P.own_local[b * kBR + t];
-  ring.prime();
   stage_nodes<DIM, true>(P, b, t, nodes, rX, rU, rO);
   const int r = P.rows[b * kBR + t];
+  const long long base = P.ptr[b];
+  const int deg = (int)((P.ptr[b + 1] - base) / kBR);  // a multiple of N
+  const unsigned* p = P.ent + base + t;
   double* acc_t = acc + t;
   for (int q = 0; q < P.maxlen; q++) acc_t[q * kAS] = 0.0;
-  const unsigned pad = ring.pad;
+  const unsigned pad = P.own_local[b * kBR + t];
   const int own = (int)((pad >> 16) & 0xffu), own_li = (int)(pad & 0xffffu);
   const double muW = __ldg(viscosity) * k_.Wsum;
   asm volatile("prefetch.global.L1 [%0];" ::"l"(gravity));  // read at the very end of the row
+  unsigned first[PD > 0 ? PD : 1];
+#pragma unroll
+  for (int q = 0; q < PD; q++) first[q] = q < deg ? ldg_stream1(p + (long long)q * kBR) : pad;
+  unsigned pq0 = PD < deg ? ldg_stream1(p + (long long)PD * kBR) : pad;
+  unsigned pq1 = PD + 1 < deg ? ldg_stream1(p + (long long)(PD + 1) * kBR) : pad;
+  unsigned pq2 = PD + 2 < deg ? ldg_stream1(p + (long long)(PD + 2) * kBR) : pad;
+#pragma unroll
+  for (int q = PD + 3; q < kPlanAhead; q++)
+    if (q < deg) prefetch_l2(p + (long long)q * kBR);
   cp_async_commit_wait_all();
   __syncthreads();
   MomState<DIM, N> s;
   load_rec<DIM>(nsa, nl, 0, own_li, s.X0, s.b0);
   load_rec<DIM>(nsa, nl, 1, own_li, s.U0, s.rho0);
   s.a0 = s.msum = s.nbsum = 0.0;
-  double rh[DIM];
+  double rh[DIM], on[DIM];
 #pragma unroll
-  for (int d = 0; d < DIM; d++) rh[d] = 0.0;
+  for (int d = 0; d < DIM; d++) rh[d] = on[d] = 0.0;
 #pragma unroll
   for (int q = 0; q < N; q++) {
 #pragma unroll
@@ -284,32 +250,27 @@ staged_momentum_kernel(const StripConsts k_, const StagedView P, const double4* 
     s.R[q] = s.B[q] = s.A[q] = 0.0;
     s.meta[q] = (int)pad;
   }
-  ring.next = ring.read(0);
 #pragma unroll
-  for (int q = 0; q < PD; q++) {  // entries 0 .. PD-1 go into their buffers ahead of the loop
-    const unsigned en = ring.pop(q);
-    const int li = (int)(en & 0xffffu);
+  for (int q = 0; q < PD; q++) {
+    const int li = (int)(first[q] & 0xffffu);
     load_rec<DIM>(nsa, nl, 0, li, s.X[q], s.B[q]);
     load_rec<DIM>(nsa, nl, 1, li, s.U[q], s.R[q]);
-    s.meta[q] = (int)en;
+    s.meta[q] = (int)first[q];
   }
-  for (int j0 = 0; j0 < ring.deg; j0 += N) SMomUnroll<DIM, N, 0>::run(s, rh, k_, muW, j0, ring, acc_t, nsa, nl);
+  // `on` = oldu of the node the first step evicts: nothing has accumulated there yet (A = 0), zeros do
+  for (int j0 = 0; j0 < deg; j0 += N)
+    SMomUnroll<DIM, N, 0, ONPF>::run(s, rh, on, k_, muW, j0, deg, p, pq0, pq1, pq2, pad, acc_t, nsa, nl);
   // drain the FIFO, then the diagonal (the row's own node never leaves)
 #pragma unroll
   for (int q = 0; q < N; q++) {
     const unsigned m = (unsigned)s.meta[q];
-    double* sl = acc_t + ((m >> 16) & 0xffu) * kAS;
-    const double tot = *sl + s.A[q];
-    *sl = tot;
-    if (m & kLocalFinal) {
-      double o[DIM];
-      load_oldu<DIM>(nsa, nl, (int)(m & 0xffffu), o);
+    acc_t[((m >> 16) & 0xffu) * kAS] += s.A[q];
+    double o[DIM];
+    load_oldu<DIM>(nsa, nl, (int)(m & 0xffffu), o);
 #pragma unroll
-      for (int d = 0; d < DIM; d++) rh[d] = fma(-tot, o[d], rh[d]);
-    }
+    for (int d = 0; d < DIM; d++) rh[d] = fma(-s.A[q], o[d], rh[d]);
   }
-  const double diag = acc_t[own * kAS] + s.a0;
-  acc_t[own * kAS] = diag;
+  acc_t[own * kAS] += s.a0;
   int my_s0 = 0, my_len = 0;
   if (r >= 0) {
     my_s0 = P.findrm[r];
@@ -318,7 +279,7 @@ staged_momentum_kernel(const StripConsts k_, const StagedView P, const double4* 
     load_oldu<DIM>(nsa, nl, own_li, ou);
 #pragma unroll
     for (int d = 0; d < DIM; d++) {
-      rhs[(size_t)DIM * r + d] = fma(-diag, ou[d], fma(k_.gmag * __ldg(gravity + d), s.nbsum, rh[d]));
+      rhs[(size_t)DIM * r + d] = fma(-s.a0, ou[d], fma(k_.gmag * __ldg(gravity + d), s.nbsum, rh[d]));
       if (masslump) masslump[(size_t)DIM * r + d] = s.msum;
     }
   }
@@ -328,11 +289,14 @@ staged_momentum_kernel(const StripConsts k_, const StagedView P, const double4* 
 
 // ---- tracer -------------------------------------------------------------------------------------------
 template <int DIM, int N, int QC>
-__device__ __forceinline__ void sadv_step(AdvState<DIM, N>& s, const StripConsts& k_, double kW, int j, PlanRing& ring,
-                                          double* __restrict__ acc_t, unsigned nsa, int nl) {
+__device__ __forceinline__ void sadv_step(AdvState<DIM, N>& s, const StripConsts& k_, double kW, int j, int deg,
+                                          const unsigned* __restrict__ p, unsigned& pq0, unsigned& pq1, unsigned& pq2,
+                                          const unsigned pad, double* __restrict__ acc_t, unsigned nsa, int nl) {
   constexpr int PD = N - DIM;
   constexpr int QE = (QC + PD) % N;
-  const unsigned en = ring.pop(j + PD);
+  const unsigned en = pq0;
+  pq0 = pq1;
+  pq1 = pq2;
   {
     double* sl = acc_t + (((unsigned)s.meta[QE] >> 16) & 0xffu) * kAS;
     *sl += fma(k_.dtt, s.A[QE], k_.Po * s.C[QE]);
@@ -344,6 +308,8 @@ __device__ __forceinline__ void sadv_step(AdvState<DIM, N>& s, const StripConsts
   load_rec<DIM>(nsa, nl, 0, li, s.X[QE], s.T[QE]);
   load_rec<DIM>(nsa, nl, 1, li, s.U[QE], unused);
   s.meta[QE] = (int)en;
+  pq2 = (j + PD + 3 < deg) ? ldg_stream1(p + (long long)(j + PD + 3) * kBR) : pad;
+  if (j + kPlanAhead < deg) prefetch_l2(p + (long long)(j + kPlanAhead) * kBR);
 #pragma unroll
   for (int a = 0; a < DIM; a++) s.X[QC][a] -= s.X0[a];
   if ((unsigned)s.meta[QC] & kLocalCompute) adv_compute<DIM, N, QC>(s, k_, kW);
@@ -366,23 +332,28 @@ staged_advdiff_kernel(const StripConsts k_, const StagedView P, const double4* _
   constexpr int PD = N - DIM;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* acc = reinterpret_cast<double*>(smem_raw);
-  double2* nodes = reinterpret_cast<double2*>(smem_raw + P.acc_bytes + kRingBytes);
+  double2* nodes = reinterpret_cast<double2*>(smem_raw + P.acc_bytes);
   const unsigned nsa = (unsigned)__cvta_generic_to_shared(nodes);
   const int b = blockIdx.x, t = threadIdx.x, nl = P.nl;
-  const long long base = P.ptr[b];
-  PlanRing ring;
-  ring.sa = (unsigned)__cvta_generic_to_shared(smem_raw + P.acc_bytes) + (unsigned)t * 16u;
-  ring.g = reinterpret_cast<const uint4*>(P.ent + base) + t;
-  ring.deg = (int)((P.ptr[b + 1] - base) / kBR);
-  ring.pad = P.own_local[b * kBR + t];
-  ring.prime();
   stage_nodes<DIM, false>(P, b, t, nodes, rX, rU, nullptr);
   const int r = P.rows[b * kBR + t];
+  const long long base = P.ptr[b];
+  const int deg = (int)((P.ptr[b + 1] - base) / kBR);
+  const unsigned* p = P.ent + base + t;
   double* acc_t = acc + t;
   for (int q = 0; q < P.maxlen; q++) acc_t[q * kAS] = 0.0;
-  const unsigned pad = ring.pad;
+  const unsigned pad = P.own_local[b * kBR + t];
   const int own = (int)((pad >> 16) & 0xffu), own_li = (int)(pad & 0xffffu);
   const double kW = __ldg(diffusivity) * k_.Wsum;
+  unsigned first[PD > 0 ? PD : 1];
+#pragma unroll
+  for (int q = 0; q < PD; q++) first[q] = q < deg ? ldg_stream1(p + (long long)q * kBR) : pad;
+  unsigned pq0 = PD < deg ? ldg_stream1(p + (long long)PD * kBR) : pad;
+  unsigned pq1 = PD + 1 < deg ? ldg_stream1(p + (long long)(PD + 1) * kBR) : pad;
+  unsigned pq2 = PD + 2 < deg ? ldg_stream1(p + (long long)(PD + 2) * kBR) : pad;
+#pragma unroll
+  for (int q = PD + 3; q < kPlanAhead; q++)
+    if (q < deg) prefetch_l2(p + (long long)q * kBR);
   cp_async_commit_wait_all();
   __syncthreads();
   AdvState<DIM, N> s;
@@ -397,16 +368,14 @@ staged_advdiff_kernel(const StripConsts k_, const StagedView P, const double4* _
     s.T[q] = s.A[q] = s.C[q] = 0.0;
     s.meta[q] = (int)pad;
   }
-  ring.next = ring.read(0);
 #pragma unroll
   for (int q = 0; q < PD; q++) {
-    const unsigned en = ring.pop(q);
-    const int li = (int)(en & 0xffffu);
+    const int li = (int)(first[q] & 0xffffu);
     load_rec<DIM>(nsa, nl, 0, li, s.X[q], s.T[q]);
     load_rec<DIM>(nsa, nl, 1, li, s.U[q], unused);
-    s.meta[q] = (int)en;
+    s.meta[q] = (int)first[q];
   }
-  for (int j0 = 0; j0 < ring.deg; j0 += N) SAdvUnroll<DIM, N, 0>::run(s, k_, kW, j0, ring, acc_t, nsa, nl);
+  for (int j0 = 0; j0 < deg; j0 += N) SAdvUnroll<DIM, N, 0>::run(s, k_, kW, j0, deg, p, pq0, pq1, pq2, pad, acc_t, nsa, nl);
 #pragma unroll
   for (int q = 0; q < N; q++)
     acc_t[(((unsigned)s.meta[q] >> 16) & 0xffu) * kAS] += fma(k_.dtt, s.A[q], k_.Po * s.C[q]);
@@ -426,9 +395,7 @@ static size_t acc_bytes_of(const GatherPlan* P) {
   return (sizeof(double) * (size_t)P->maxlen * kAS + 15) & ~(size_t)15;
 }
 static int nl_of(const GatherPlan* P) { return (P->blk_nodes_max + 7) & ~7; }
-static size_t staged_smem(const GatherPlan* P, bool momentum) {
-  return acc_bytes_of(P) + kRingBytes + (size_t)nl_of(P) * (momentum ? 88 : 64);
-}
+static size_t staged_smem(const GatherPlan* P, bool momentum) { return acc_bytes_of(P) + (size_t)nl_of(P) * (momentum ? 88 : 64); }
 
 bool strip_staged_ok(const Handle* h, bool momentum) {
   const GatherPlan* P = h->gather;
@@ -463,20 +430,24 @@ static int staged_momentum_dim(Handle* h, const MomentumArgs& A) {
   const StagedView v = staged_view(h);
   const int minb = getenv("CGASM_STRIP_MINB") ? atoi(getenv("CGASM_STRIP_MINB")) : 4;
   int st;
-#define LAUNCH(N_, MINB_)                                                                                       \
+#define LAUNCH(N_, MINB_, ONPF_)                                                                                       \
   do {                                                                                                          \
-    if ((st = strip_smem(staged_momentum_kernel<DIM, N_, MINB_>, smem))) return st;                             \
-    staged_momentum_kernel<DIM, N_, MINB_><<<P->nblocks, kBR, smem, h->stream>>>(                               \
+    if ((st = strip_smem(staged_momentum_kernel<DIM, N_, MINB_, ONPF_>, smem))) return st;                             \
+    staged_momentum_kernel<DIM, N_, MINB_, ONPF_><<<P->nblocks, kBR, smem, h->stream>>>(                               \
         c, v, h->d_rec3, h->d_rec1, h->d_rec2, A.viscosity.val, A.gravity.val, (size_t)h->nnz, h->d_big_m,       \
         h->d_mom_rhs, h->d_masslump);                                                                           \
   } while (0)
   const int nbuf = getenv("CGASM_STRIP_NBUF") ? atoi(getenv("CGASM_STRIP_NBUF")) : DIM;
+  const bool onpf = getenv("CGASM_STRIP_ONPF") && atoi(getenv("CGASM_STRIP_ONPF"));
   if (nbuf > DIM) {
-    if (minb >= 4) LAUNCH(DIM + 1, 4);
-    else LAUNCH(DIM + 1, 3);
+    if (minb >= 4) LAUNCH(DIM + 1, 4, true);
+    else if (onpf) LAUNCH(DIM + 1, 3, true);
+    else LAUNCH(DIM + 1, 3, false);
   } else {
-    if (minb >= 4) LAUNCH(DIM, 4);
-    else LAUNCH(DIM, 3);
+    if (minb >= 4 && onpf) LAUNCH(DIM, 4, true);
+    else if (minb >= 4) LAUNCH(DIM, 4, false);
+    else if (onpf) LAUNCH(DIM, 3, true);
+    else LAUNCH(DIM, 3, false);
   }
 #undef LAUNCH
   h->launches++;

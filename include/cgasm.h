@@ -253,8 +253,7 @@ int cgasm_last_kernel_ms(int id, float* ms);
 /* Diagnostics (host only, no GPU): the strip ordering CGASM_SCATTER_STRIP uses for every row of
  * a P1 simplex mesh. ndglno as in cgasm_create. row_ptr(n_nodes+1): 0-based offsets; entries:
  * pairs {node (1-based), meta} with meta bits 0-7 = 0-based CSR slot of the node inside the row,
- * bit 8 = "the last loc-1 pushed nodes plus the row node form an element: compute it now",
- * bit 9 = "last push of this node in the row".
+ * bit 8 = "the last loc-1 pushed nodes plus the row node form an element: compute it now".
  * At most `capacity` pairs are written; *needed returns the total. */
 int cgasm_strip_plan_host(int loc, int n_nodes, int n_elements, const int* ndglno,
                           long long* row_ptr, int* entries, long long capacity, long long* needed);

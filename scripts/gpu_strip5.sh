@@ -7,13 +7,13 @@ run() { # name cells scatter env...
   name=$1; cells=$2; sc=$3; shift 3
   env "$@" timeout 900 python bench.py --cells $cells --scatter $sc --steps 5 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/bench_$name.json 2> gpurun_out/bench_$name.err
 }
-run s5_n3_mb4 128 strip CGASM_STRIP_NBUF=3 CGASM_STRIP_MINB=4 CGASM_STRIP_MINB_ADV=4
-run s5_n3_mb4 128 strip CGASM_STRIP_NBUF=3 CGASM_STRIP_MINB=4 CGASM_STRIP_MINB_ADV=5
-run s5_n3_mb3 128 strip CGASM_STRIP_NBUF=3 CGASM_STRIP_MINB=3 CGASM_STRIP_MINB_ADV=3
-run s5_n4_mb3 128 strip CGASM_STRIP_NBUF=4 CGASM_STRIP_MINB=3 CGASM_STRIP_MINB_ADV=4
-run s5_n4_mb3 128 strip CGASM_STRIP_NBUF=4 CGASM_STRIP_MINB=3 CGASM_STRIP_MINB_ADV=3
-run s5_256_n3_mb4 256 strip CGASM_STRIP_NBUF=3 CGASM_STRIP_MINB=4 CGASM_STRIP_MINB_ADV=4
-run s5_256_n4_mb3 256 strip CGASM_STRIP_NBUF=4 CGASM_STRIP_MINB=3 CGASM_STRIP_MINB_ADV=4
+run s5_n3_mb4_on0 128 strip CGASM_STRIP_NBUF=3 CGASM_STRIP_MINB=4 CGASM_STRIP_ONPF=0 CGASM_STRIP_MINB_ADV=4
+run s5_n3_mb4_on1 128 strip CGASM_STRIP_NBUF=3 CGASM_STRIP_MINB=4 CGASM_STRIP_ONPF=1 CGASM_STRIP_MINB_ADV=5
+run s5_n3_mb3_on1 128 strip CGASM_STRIP_NBUF=3 CGASM_STRIP_MINB=3 CGASM_STRIP_ONPF=1 CGASM_STRIP_MINB_ADV=3
+run s5_n4_mb3_on1 128 strip CGASM_STRIP_NBUF=4 CGASM_STRIP_MINB=3 CGASM_STRIP_ONPF=1 CGASM_STRIP_MINB_ADV=4
+run s5_n4_mb3_on0 128 strip CGASM_STRIP_NBUF=4 CGASM_STRIP_MINB=3 CGASM_STRIP_ONPF=0 CGASM_STRIP_MINB_ADV=3
+run s5_256_n3_mb4_on0 256 strip CGASM_STRIP_NBUF=3 CGASM_STRIP_MINB=4 CGASM_STRIP_ONPF=0 CGASM_STRIP_MINB_ADV=4
+run s5_256_n4_mb3_on1 256 strip CGASM_STRIP_NBUF=4 CGASM_STRIP_MINB=3 CGASM_STRIP_ONPF=1 CGASM_STRIP_MINB_ADV=4
 python - <<'PY'
 import json,glob
 for f in sorted(glob.glob('gpurun_out/bench_s5_*.json')):

@@ -10,7 +10,6 @@ import numpy as np
 from fluidity_b200 import _abi as abi, cgasm, tables
 
 COMPUTE = 0x100
-FINAL = 0x200
 
 
 def strip_plan(mesh):
