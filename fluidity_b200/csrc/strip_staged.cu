@@ -137,7 +137,7 @@ __device__ __forceinline__ void load_oldu(unsigned nsa, int nl, int li, double (
 // One strip entry. Program order = issue order (all memory asm is volatile):
 //   flush the evicted buffer with the oldu fetched one step ago; request the records of entry j+PD, the
 //   oldu of the node evicted NEXT step and plan entry j+PD+3; then install and compute entry j.
-template <int DIM, int N, int QC, bool ONPF>
+template <int DIM, int N, int QC, bool ONPF, bool PF>
 __device__ __forceinline__ void smom_step(MomState<DIM, N>& s, double (&rh)[DIM], double (&on)[DIM], const StripConsts& k_,
                                           double muW, int j, int deg, const unsigned* __restrict__ p, unsigned& pq0,
                                           unsigned& pq1, unsigned& pq2, const unsigned pad, double* __restrict__ acc_t,
@@ -164,19 +164,19 @@ __device__ __forceinline__ void smom_step(MomState<DIM, N>& s, double (&rh)[DIM]
   s.meta[QE] = (int)en;
   if constexpr (ONPF) load_oldu<DIM>(nsa, nl, (int)((unsigned)s.meta[QN] & 0xffffu), on);
   pq2 = (j + PD + 3 < deg) ? ldg_stream1(p + (long long)(j + PD + 3) * kBR) : pad;
-  if (j + kPlanAhead < deg) prefetch_l2(p + (long long)(j + kPlanAhead) * kBR);
+  if (PF && j + kPlanAhead < deg) prefetch_l2(p + (long long)(j + kPlanAhead) * kBR);
 #pragma unroll
   for (int a = 0; a < DIM; a++) s.X[QC][a] -= s.X0[a];
   if ((unsigned)s.meta[QC] & kLocalCompute) mom_compute<DIM, N, QC>(s, k_, muW);
 }
 
-template <int DIM, int N, int Q, bool ONPF>
+template <int DIM, int N, int Q, bool ONPF, bool PF>
 struct SMomUnroll {
   template <class... Args>
   static __device__ __forceinline__ void run(MomState<DIM, N>& s, double (&rh)[DIM], double (&on)[DIM], const StripConsts& k_,
                                              double muW, int j0, Args&&... args) {
-    smom_step<DIM, N, Q, ONPF>(s, rh, on, k_, muW, j0 + Q, args...);
-    if constexpr (Q + 1 < N) SMomUnroll<DIM, N, Q + 1, ONPF>::run(s, rh, on, k_, muW, j0, args...);
+    smom_step<DIM, N, Q, ONPF, PF>(s, rh, on, k_, muW, j0 + Q, args...);
+    if constexpr (Q + 1 < N) SMomUnroll<DIM, N, Q + 1, ONPF, PF>::run(s, rh, on, k_, muW, j0, args...);
   }
 };
 
@@ -202,7 +202,7 @@ __device__ __forceinline__ void write_rows_scaled(const double* __restrict__ acc
   }
 }
 
-template <int DIM, int N, int MINB, bool ONPF>
+template <int DIM, int N, int MINB, bool ONPF, bool PF>
 __global__ void __launch_bounds__(kBR, MINB)
 staged_momentum_kernel(const StripConsts k_, const StagedView P, const double4* __restrict__ rX,
                        const double4* __restrict__ rU, const double4* __restrict__ rO,
@@ -231,9 +231,11 @@ staged_momentum_kernel(const StripConsts k_, const StagedView P, const double4* 
   unsigned pq0 = PD < deg ? ldg_stream1(p + (long long)PD * kBR) : pad;
   unsigned pq1 = PD + 1 < deg ? ldg_stream1(p + (long long)(PD + 1) * kBR) : pad;
   unsigned pq2 = PD + 2 < deg ? ldg_stream1(p + (long long)(PD + 2) * kBR) : pad;
+  if constexpr (PF) {
 #pragma unroll
-  for (int q = PD + 3; q < kPlanAhead; q++)
-    if (q < deg) prefetch_l2(p + (long long)q * kBR);
+    for (int q = PD + 3; q < kPlanAhead; q++)
+      if (q < deg) prefetch_l2(p + (long long)q * kBR);
+  }
   cp_async_commit_wait_all();
   __syncthreads();
   MomState<DIM, N> s;
@@ -259,7 +261,7 @@ staged_momentum_kernel(const StripConsts k_, const StagedView P, const double4* 
   }
   // `on` = oldu of the node the first step evicts: nothing has accumulated there yet (A = 0), zeros do
   for (int j0 = 0; j0 < deg; j0 += N)
-    SMomUnroll<DIM, N, 0, ONPF>::run(s, rh, on, k_, muW, j0, deg, p, pq0, pq1, pq2, pad, acc_t, nsa, nl);
+    SMomUnroll<DIM, N, 0, ONPF, PF>::run(s, rh, on, k_, muW, j0, deg, p, pq0, pq1, pq2, pad, acc_t, nsa, nl);
   // drain the FIFO, then the diagonal (the row's own node never leaves)
 #pragma unroll
   for (int q = 0; q < N; q++) {
@@ -288,7 +290,7 @@ staged_momentum_kernel(const StripConsts k_, const StagedView P, const double4* 
 }
 
 // ---- tracer -------------------------------------------------------------------------------------------
-template <int DIM, int N, int QC>
+template <int DIM, int N, int QC, bool PF>
 __device__ __forceinline__ void sadv_step(AdvState<DIM, N>& s, const StripConsts& k_, double kW, int j, int deg,
                                           const unsigned* __restrict__ p, unsigned& pq0, unsigned& pq1, unsigned& pq2,
                                           const unsigned pad, double* __restrict__ acc_t, unsigned nsa, int nl) {
@@ -309,22 +311,22 @@ __device__ __forceinline__ void sadv_step(AdvState<DIM, N>& s, const StripConsts
   load_rec<DIM>(nsa, nl, 1, li, s.U[QE], unused);
   s.meta[QE] = (int)en;
   pq2 = (j + PD + 3 < deg) ? ldg_stream1(p + (long long)(j + PD + 3) * kBR) : pad;
-  if (j + kPlanAhead < deg) prefetch_l2(p + (long long)(j + kPlanAhead) * kBR);
+  if (PF && j + kPlanAhead < deg) prefetch_l2(p + (long long)(j + kPlanAhead) * kBR);
 #pragma unroll
   for (int a = 0; a < DIM; a++) s.X[QC][a] -= s.X0[a];
   if ((unsigned)s.meta[QC] & kLocalCompute) adv_compute<DIM, N, QC>(s, k_, kW);
 }
 
-template <int DIM, int N, int Q>
+template <int DIM, int N, int Q, bool PF>
 struct SAdvUnroll {
   template <class... Args>
   static __device__ __forceinline__ void run(AdvState<DIM, N>& s, const StripConsts& k_, double kW, int j0, Args&&... args) {
-    sadv_step<DIM, N, Q>(s, k_, kW, j0 + Q, args...);
-    if constexpr (Q + 1 < N) SAdvUnroll<DIM, N, Q + 1>::run(s, k_, kW, j0, args...);
+    sadv_step<DIM, N, Q, PF>(s, k_, kW, j0 + Q, args...);
+    if constexpr (Q + 1 < N) SAdvUnroll<DIM, N, Q + 1, PF>::run(s, k_, kW, j0, args...);
   }
 };
 
-template <int DIM, int N, int MINB>
+template <int DIM, int N, int MINB, bool PF>
 __global__ void __launch_bounds__(kBR, MINB)
 staged_advdiff_kernel(const StripConsts k_, const StagedView P, const double4* __restrict__ rX,
                       const double4* __restrict__ rU, const double* __restrict__ diffusivity,
@@ -351,9 +353,11 @@ staged_advdiff_kernel(const StripConsts k_, const StagedView P, const double4* _
   unsigned pq0 = PD < deg ? ldg_stream1(p + (long long)PD * kBR) : pad;
   unsigned pq1 = PD + 1 < deg ? ldg_stream1(p + (long long)(PD + 1) * kBR) : pad;
   unsigned pq2 = PD + 2 < deg ? ldg_stream1(p + (long long)(PD + 2) * kBR) : pad;
+  if constexpr (PF) {
 #pragma unroll
-  for (int q = PD + 3; q < kPlanAhead; q++)
-    if (q < deg) prefetch_l2(p + (long long)q * kBR);
+    for (int q = PD + 3; q < kPlanAhead; q++)
+      if (q < deg) prefetch_l2(p + (long long)q * kBR);
+  }
   cp_async_commit_wait_all();
   __syncthreads();
   AdvState<DIM, N> s;
@@ -375,7 +379,7 @@ staged_advdiff_kernel(const StripConsts k_, const StagedView P, const double4* _
     load_rec<DIM>(nsa, nl, 1, li, s.U[q], unused);
     s.meta[q] = (int)first[q];
   }
-  for (int j0 = 0; j0 < deg; j0 += N) SAdvUnroll<DIM, N, 0>::run(s, k_, kW, j0, deg, p, pq0, pq1, pq2, pad, acc_t, nsa, nl);
+  for (int j0 = 0; j0 < deg; j0 += N) SAdvUnroll<DIM, N, 0, PF>::run(s, k_, kW, j0, deg, p, pq0, pq1, pq2, pad, acc_t, nsa, nl);
 #pragma unroll
   for (int q = 0; q < N; q++)
     acc_t[(((unsigned)s.meta[q] >> 16) & 0xffu) * kAS] += fma(k_.dtt, s.A[q], k_.Po * s.C[q]);
@@ -422,33 +426,44 @@ static StagedView staged_view(const Handle* h) {
   return v;
 }
 
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
 template <int DIM>
 static int staged_momentum_dim(Handle* h, const MomentumArgs& A) {
   GatherPlan* P = h->gather;
   const size_t smem = staged_smem(P, true);
   const StripConsts c = consts_of(A.tab, A.o.dt * A.o.theta, A.o.gravity_magnitude);
   const StagedView v = staged_view(h);
-  const int minb = getenv("CGASM_STRIP_MINB") ? atoi(getenv("CGASM_STRIP_MINB")) : 4;
+  // tuning switches (defaults = best measured on S3, profiles/r1_kernel_history.md)
+  const int minb = env_int("CGASM_STRIP_MINB", 4), nbuf = env_int("CGASM_STRIP_NBUF", DIM);
+  const bool onpf = env_int("CGASM_STRIP_ONPF", 0) != 0, pf = env_int("CGASM_STRIP_PF", 1) != 0;
   int st;
-#define LAUNCH(N_, MINB_, ONPF_)                                                                                       \
+#define LAUNCH(N_, MINB_, ONPF_, PF_)                                                                           \
   do {                                                                                                          \
-    if ((st = strip_smem(staged_momentum_kernel<DIM, N_, MINB_, ONPF_>, smem))) return st;                             \
-    staged_momentum_kernel<DIM, N_, MINB_, ONPF_><<<P->nblocks, kBR, smem, h->stream>>>(                               \
+    if ((st = strip_smem(staged_momentum_kernel<DIM, N_, MINB_, ONPF_, PF_>, smem))) return st;                 \
+    staged_momentum_kernel<DIM, N_, MINB_, ONPF_, PF_><<<P->nblocks, kBR, smem, h->stream>>>(                   \
         c, v, h->d_rec3, h->d_rec1, h->d_rec2, A.viscosity.val, A.gravity.val, (size_t)h->nnz, h->d_big_m,       \
         h->d_mom_rhs, h->d_masslump);                                                                           \
   } while (0)
-  const int nbuf = getenv("CGASM_STRIP_NBUF") ? atoi(getenv("CGASM_STRIP_NBUF")) : DIM;
-  const bool onpf = getenv("CGASM_STRIP_ONPF") && atoi(getenv("CGASM_STRIP_ONPF"));
+#define LAUNCH_PF(N_, MINB_, ONPF_) \
+  do {                              \
+    if (pf) LAUNCH(N_, MINB_, ONPF_, true); \
+    else LAUNCH(N_, MINB_, ONPF_, false);   \
+  } while (0)
   if (nbuf > DIM) {
-    if (minb >= 4) LAUNCH(DIM + 1, 4, true);
-    else if (onpf) LAUNCH(DIM + 1, 3, true);
-    else LAUNCH(DIM + 1, 3, false);
+    if (minb >= 4) LAUNCH_PF(DIM + 1, 4, true);
+    else if (onpf) LAUNCH_PF(DIM + 1, 3, true);
+    else LAUNCH_PF(DIM + 1, 3, false);
   } else {
-    if (minb >= 4 && onpf) LAUNCH(DIM, 4, true);
-    else if (minb >= 4) LAUNCH(DIM, 4, false);
-    else if (onpf) LAUNCH(DIM, 3, true);
-    else LAUNCH(DIM, 3, false);
+    if (minb >= 4 && onpf) LAUNCH_PF(DIM, 4, true);
+    else if (minb >= 4) LAUNCH_PF(DIM, 4, false);
+    else if (onpf) LAUNCH_PF(DIM, 3, true);
+    else LAUNCH_PF(DIM, 3, false);
   }
+#undef LAUNCH_PF
 #undef LAUNCH
   h->launches++;
   CG_CUDA(cudaGetLastError());
@@ -466,23 +481,29 @@ static int staged_advdiff_dim(Handle* h, const AdvDiffArgs& A) {
   const double dtt = A.o.dt * A.o.theta;
   const StripConsts c = consts_of(A.tab, fabs(dtt) > 2.220446049250313e-16 ? dtt : 0.0, 0.0);
   const StagedView v = staged_view(h);
-  const int minb = getenv("CGASM_STRIP_MINB_ADV") ? atoi(getenv("CGASM_STRIP_MINB_ADV")) : 4;
+  const int minb = env_int("CGASM_STRIP_MINB_ADV", 4), nbuf = env_int("CGASM_STRIP_NBUF_ADV", DIM + 1);
+  const bool pf = env_int("CGASM_STRIP_PF_ADV", 0) != 0;
   int st;
-#define LAUNCH(N_, MINB_)                                                                                       \
+#define LAUNCH(N_, MINB_, PF_)                                                                                  \
   do {                                                                                                          \
-    if ((st = strip_smem(staged_advdiff_kernel<DIM, N_, MINB_>, smem))) return st;                              \
-    staged_advdiff_kernel<DIM, N_, MINB_><<<P->nblocks, kBR, smem, h->stream>>>(                                \
+    if ((st = strip_smem(staged_advdiff_kernel<DIM, N_, MINB_, PF_>, smem))) return st;                         \
+    staged_advdiff_kernel<DIM, N_, MINB_, PF_><<<P->nblocks, kBR, smem, h->stream>>>(                           \
         c, v, h->d_rec0, h->d_rec1, A.diffusivity.val, h->d_adv_matrix, h->d_adv_rhs);                           \
   } while (0)
-  const int nbuf = getenv("CGASM_STRIP_NBUF") ? atoi(getenv("CGASM_STRIP_NBUF")) : DIM;
+#define LAUNCH_PF(N_, MINB_)        \
+  do {                              \
+    if (pf) LAUNCH(N_, MINB_, true); \
+    else LAUNCH(N_, MINB_, false);   \
+  } while (0)
   if (nbuf > DIM) {
-    if (minb >= 4) LAUNCH(DIM + 1, 4);
-    else LAUNCH(DIM + 1, 3);
+    if (minb >= 4) LAUNCH_PF(DIM + 1, 4);
+    else LAUNCH_PF(DIM + 1, 3);
   } else {
-    if (minb >= 5) LAUNCH(DIM, 5);
-    else if (minb == 4) LAUNCH(DIM, 4);
-    else LAUNCH(DIM, 3);
+    if (minb >= 5) LAUNCH_PF(DIM, 5);
+    else if (minb == 4) LAUNCH_PF(DIM, 4);
+    else LAUNCH_PF(DIM, 3);
   }
+#undef LAUNCH_PF
 #undef LAUNCH
   h->launches++;
   CG_CUDA(cudaGetLastError());
