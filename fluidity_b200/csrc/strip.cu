@@ -58,8 +58,7 @@ template <int DIM, int N, int Q>
 struct MomUnroll {
   template <class... Args>
   static __device__ __forceinline__ void run(MomState<DIM, N>& s, const StripConsts& k_, double muW, int j0, Args&&... args) {
-    if (Q == 0 || j0 + Q < deg_of(args...))
-      mom_step<DIM, N, Q>(s, k_, muW, j0 + Q, args...);
+    mom_step<DIM, N, Q>(s, k_, muW, j0 + Q, args...);
     if constexpr (Q + 1 < N) MomUnroll<DIM, N, Q + 1>::run(s, k_, muW, j0, args...);
   }
 };
@@ -76,7 +75,7 @@ strip_momentum_kernel(const StripConsts k_, const StripPlanView P, const double4
   const int r = P.rows[b * kBR + t];
   const int r0 = r >= 0 ? r : 0;
   const long long base = P.ptr[b];
-  const int deg = (int)((P.ptr[b + 1] - base) / kBR);  
+  const int deg = (int)((P.ptr[b + 1] - base) / kBR);  // a multiple of N
   const int2* p = P.ent + base + t;
   double* acc_t = acc + t;
   for (int q = 0; q < P.maxlen; q++) acc_t[q * kAS] = 0.0;
@@ -165,8 +164,7 @@ template <int DIM, int N, int Q>
 struct AdvUnroll {
   template <class... Args>
   static __device__ __forceinline__ void run(AdvState<DIM, N>& s, const StripConsts& k_, double kW, int j0, Args&&... args) {
-    if (Q == 0 || j0 + Q < deg_of(args...))
-      adv_step<DIM, N, Q>(s, k_, kW, j0 + Q, args...);
+    adv_step<DIM, N, Q>(s, k_, kW, j0 + Q, args...);
     if constexpr (Q + 1 < N) AdvUnroll<DIM, N, Q + 1>::run(s, k_, kW, j0, args...);
   }
 };
@@ -225,8 +223,9 @@ strip_advdiff_kernel(const StripConsts k_, const StripPlanView P, const double4*
 }
 
 // ---- plan ---------------------------------------------------------------------------------------------
-// block degrees need no padding: the unrolled loops skip the steps past the end (uniform branch)
-static int strip_nbuf(int) { return 1; }
+// block degrees are padded to a multiple of every buffer count the kernels are built for (dim: FIFO
+// only, dim + 1: one entry of prefetch), so the unrolled loops need no tail
+static int strip_nbuf(int dim) { return dim * (dim + 1); }
 
 int strip_build(Handle* h) {
   GatherPlan* P = h->gather;

@@ -214,10 +214,6 @@ __device__ __forceinline__ void adv_compute(AdvState<DIM, N>& s, const StripCons
 
 #undef WQ
 
-// first of the trailing step arguments = the block's entry count (steps past it are skipped)
-template <class... Rest>
-__device__ __forceinline__ int deg_of(int deg, Rest&&...) { return deg; }
-
 // ---- host helpers ---------------------------------------------------------------------------------------
 inline StripPlanView plan_view(const Handle* h) {
   const GatherPlan* P = h->gather;

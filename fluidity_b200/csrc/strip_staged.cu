@@ -175,8 +175,7 @@ struct SMomUnroll {
   template <class... Args>
   static __device__ __forceinline__ void run(MomState<DIM, N>& s, double (&rh)[DIM], double (&on)[DIM], const StripConsts& k_,
                                              double muW, int j0, Args&&... args) {
-    if (Q == 0 || j0 + Q < deg_of(args...))
-      smom_step<DIM, N, Q, ONPF, PF>(s, rh, on, k_, muW, j0 + Q, args...);
+    smom_step<DIM, N, Q, ONPF, PF>(s, rh, on, k_, muW, j0 + Q, args...);
     if constexpr (Q + 1 < N) SMomUnroll<DIM, N, Q + 1, ONPF, PF>::run(s, rh, on, k_, muW, j0, args...);
   }
 };
@@ -218,7 +217,7 @@ staged_momentum_kernel(const StripConsts k_, const StagedView P, const double4* 
   stage_nodes<DIM, true>(P, b, t, nodes, rX, rU, rO);
   const int r = P.rows[b * kBR + t];
   const long long base = P.ptr[b];
-  const int deg = (int)((P.ptr[b + 1] - base) / kBR);  
+  const int deg = (int)((P.ptr[b + 1] - base) / kBR);  // a multiple of N
   const unsigned* p = P.ent + base + t;
   double* acc_t = acc + t;
   for (int q = 0; q < P.maxlen; q++) acc_t[q * kAS] = 0.0;
@@ -322,8 +321,7 @@ template <int DIM, int N, int Q, bool PF>
 struct SAdvUnroll {
   template <class... Args>
   static __device__ __forceinline__ void run(AdvState<DIM, N>& s, const StripConsts& k_, double kW, int j0, Args&&... args) {
-    if (Q == 0 || j0 + Q < deg_of(args...))
-      sadv_step<DIM, N, Q, PF>(s, k_, kW, j0 + Q, args...);
+    sadv_step<DIM, N, Q, PF>(s, k_, kW, j0 + Q, args...);
     if constexpr (Q + 1 < N) SAdvUnroll<DIM, N, Q + 1, PF>::run(s, k_, kW, j0, args...);
   }
 };
