@@ -12,7 +12,8 @@ import numpy as np
 from . import _abi as abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcgasm.so")
+# CGASM_LIB: another build of the same library (A/B timing of two builds on one GPU box)
+LIB_PATH = os.environ.get("CGASM_LIB") or os.path.join(_HERE, "libcgasm.so")
 _lib = None
 
 c_dp = C.POINTER(C.c_double)
@@ -210,6 +211,11 @@ class Assembler:
         _check(self.lib.cgasm_momentum_fetch(C.c_int(self.id), None, _dp(out["rhs"]), _dp(ml), None))
         return nb
 
+    def advdiff_fetch_into(self, out):
+        """cgasm_advdiff_fetch into caller-owned (pinned) buffers out['matrix'], out['rhs']."""
+        _check(self.lib.cgasm_advdiff_fetch(C.c_int(self.id), _dp(out["matrix"]), _dp(out["rhs"])))
+        return out
+
     def advdiff_fetch(self):
         val = np.empty(self.nnz)
         rhs = np.empty(self.n_nodes)
@@ -245,6 +251,10 @@ class Assembler:
         return A.reshape(loc, loc).T.copy(), r
 
     # -- plumbing -------------------------------------------------------------------------
+    def set_async(self, on=True):
+        """cgasm_set_async: uploads and result downloads are queued, cgasm_synchronize waits."""
+        _check(self.lib.cgasm_set_async(C.c_int(self.id), C.c_int(1 if on else 0)))
+
     def synchronize(self):
         _check(self.lib.cgasm_synchronize(C.c_int(self.id)))
 

@@ -107,6 +107,10 @@ static void destroy_handle(Handle* h) {
   free_dev(h->d_adv_rhs);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->ev_ready) cudaEventDestroy(h->ev_ready);
+  if (h->ev_mom_copied) cudaEventDestroy(h->ev_mom_copied);
+  if (h->ev_adv_copied) cudaEventDestroy(h->ev_adv_copied);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -581,7 +585,7 @@ int cgasm_set_field(int id, int slot, int rank, int field_type, const double* va
   f.set = true;
   int st = repack_slot(h, slot, nullptr, 0);
   if (st) return st;
-  CG_CUDA(cudaStreamSynchronize(h->stream));
+  if (!h->async) CG_CUDA(cudaStreamSynchronize(h->stream));
   return CGASM_OK;
 }
 
@@ -613,6 +617,10 @@ int cgasm_momentum_dev(int id, const cgasm_momentum_opts* opts) {
   if (opts->stabilisation_scheme != CGASM_STAB_NONE && h->scatter != CGASM_SCATTER_ATOMIC &&
       h->scatter != CGASM_SCATTER_GATHER && h->scatter != CGASM_SCATTER_STRIP)
     CG_FAIL(CGASM_EUNSUPPORTED, "SU/SUPG stabilisation runs on the ATOMIC and GATHER scatter variants only");
+  if (h->mom_copy_pending) {  // an asynchronous fetch may still be reading the previous result
+    CG_CUDA(cudaStreamWaitEvent(h->stream, h->ev_mom_copied, 0));
+    h->mom_copy_pending = false;
+  }
   CG_CUDA(cudaEventRecord(h->ev0, h->stream));
   if (h->scatter == CGASM_SCATTER_TILED) {
     st = tiles_momentum(h, A, want_ml, want_ct);
@@ -649,6 +657,10 @@ int cgasm_advdiff_dev(int id, const cgasm_advdiff_opts* opts) {
   if (opts->stabilisation_scheme != CGASM_STAB_NONE && h->scatter != CGASM_SCATTER_ATOMIC &&
       h->scatter != CGASM_SCATTER_GATHER && h->scatter != CGASM_SCATTER_STRIP)
     CG_FAIL(CGASM_EUNSUPPORTED, "SU/SUPG stabilisation runs on the ATOMIC and GATHER scatter variants only");
+  if (h->adv_copy_pending) {
+    CG_CUDA(cudaStreamWaitEvent(h->stream, h->ev_adv_copied, 0));
+    h->adv_copy_pending = false;
+  }
   CG_CUDA(cudaEventRecord(h->ev0, h->stream));
   if (h->scatter == CGASM_SCATTER_TILED) {
     st = tiles_advdiff(h, P);
@@ -666,22 +678,49 @@ int cgasm_advdiff_dev(int id, const cgasm_advdiff_opts* opts) {
   return CGASM_OK;
 }
 
+// Device -> host copies of a result. Synchronous flavour: on the handle's stream, returns when the data
+// is in the caller's buffers. Asynchronous flavour (cgasm_set_async): the copies are queued on the copy
+// stream behind an event that marks the result complete, the call returns at once and the compute
+// stream is free for the next element loop; cgasm_synchronize waits for everything.
+static int fetch_begin(Handle* h, cudaStream_t* s) {
+  if (!h->async) {
+    *s = h->stream;
+    return CGASM_OK;
+  }
+  CG_CUDA(cudaEventRecord(h->ev_ready, h->stream));
+  CG_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_ready, 0));
+  *s = h->copy_stream;
+  return CGASM_OK;
+}
+static int fetch_end(Handle* h, bool momentum) {
+  if (!h->async) {
+    CG_CUDA(cudaStreamSynchronize(h->stream));
+    return CGASM_OK;
+  }
+  if (momentum) {
+    CG_CUDA(cudaEventRecord(h->ev_mom_copied, h->copy_stream));
+    h->mom_copy_pending = true;
+  } else {
+    CG_CUDA(cudaEventRecord(h->ev_adv_copied, h->copy_stream));
+    h->adv_copy_pending = true;
+  }
+  return CGASM_OK;
+}
+
 int cgasm_momentum_fetch(int id, double* big_m, double* rhs, double* masslump, double* ct_m) {
   GET_HANDLE(h, id);
   if (!h->mom_valid) CG_FAIL(CGASM_ESTATE, "no momentum result to fetch");
   const size_t nnz = (size_t)h->nnz, nn = (size_t)h->n_nodes, dim = (size_t)h->dim;
-  if (big_m) CG_CUDA(cudaMemcpyAsync(big_m, h->d_big_m, sizeof(double) * dim * nnz, cudaMemcpyDeviceToHost, h->stream));
-  if (rhs) CG_CUDA(cudaMemcpyAsync(rhs, h->d_mom_rhs, sizeof(double) * dim * nn, cudaMemcpyDeviceToHost, h->stream));
-  if (masslump) {
-    if (!h->mom_has_masslump) CG_FAIL(CGASM_ESTATE, "masslump was not assembled (assemble_inverse_masslump = 0)");
-    CG_CUDA(cudaMemcpyAsync(masslump, h->d_masslump, sizeof(double) * dim * nn, cudaMemcpyDeviceToHost, h->stream));
-  }
-  if (ct_m) {
-    if (!h->mom_has_ct) CG_FAIL(CGASM_ESTATE, "ct_m was not assembled (assemble_ct_matrix_here = 0)");
-    CG_CUDA(cudaMemcpyAsync(ct_m, h->d_ct_m, sizeof(double) * dim * nnz, cudaMemcpyDeviceToHost, h->stream));
-  }
-  CG_CUDA(cudaStreamSynchronize(h->stream));
-  return CGASM_OK;
+  if (masslump && !h->mom_has_masslump) CG_FAIL(CGASM_ESTATE, "masslump was not assembled (assemble_inverse_masslump = 0)");
+  if (ct_m && !h->mom_has_ct) CG_FAIL(CGASM_ESTATE, "ct_m was not assembled (assemble_ct_matrix_here = 0)");
+  cudaStream_t cs;
+  int st = fetch_begin(h, &cs);
+  if (st) return st;
+  if (big_m) CG_CUDA(cudaMemcpyAsync(big_m, h->d_big_m, sizeof(double) * dim * nnz, cudaMemcpyDeviceToHost, cs));
+  if (rhs) CG_CUDA(cudaMemcpyAsync(rhs, h->d_mom_rhs, sizeof(double) * dim * nn, cudaMemcpyDeviceToHost, cs));
+  if (masslump) CG_CUDA(cudaMemcpyAsync(masslump, h->d_masslump, sizeof(double) * dim * nn, cudaMemcpyDeviceToHost, cs));
+  if (ct_m) CG_CUDA(cudaMemcpyAsync(ct_m, h->d_ct_m, sizeof(double) * dim * nnz, cudaMemcpyDeviceToHost, cs));
+  return fetch_end(h, true);
 }
 
 int cgasm_momentum_identical_blocks(int id, int* identical) {
@@ -697,20 +736,40 @@ int cgasm_momentum_fetch_blocks(int id, int first_block, int nblocks, double* bi
   if (!h->mom_valid) CG_FAIL(CGASM_ESTATE, "no momentum result to fetch");
   if (!big_m || first_block < 0 || nblocks < 1 || first_block + nblocks > h->dim) CG_FAIL(CGASM_EARG, "bad block range");
   const size_t nnz = (size_t)h->nnz;
+  cudaStream_t cs;
+  int st = fetch_begin(h, &cs);
+  if (st) return st;
   CG_CUDA(cudaMemcpyAsync(big_m, h->d_big_m + (size_t)first_block * nnz, sizeof(double) * nnz * nblocks,
-                          cudaMemcpyDeviceToHost, h->stream));
-  CG_CUDA(cudaStreamSynchronize(h->stream));
-  return CGASM_OK;
+                          cudaMemcpyDeviceToHost, cs));
+  return fetch_end(h, true);
 }
 
 int cgasm_advdiff_fetch(int id, double* matrix_val, double* rhs) {
   GET_HANDLE(h, id);
   if (!h->adv_valid) CG_FAIL(CGASM_ESTATE, "no tracer result to fetch");
+  cudaStream_t cs;
+  int st = fetch_begin(h, &cs);
+  if (st) return st;
   if (matrix_val)
-    CG_CUDA(cudaMemcpyAsync(matrix_val, h->d_adv_matrix, sizeof(double) * (size_t)h->nnz, cudaMemcpyDeviceToHost, h->stream));
-  if (rhs)
-    CG_CUDA(cudaMemcpyAsync(rhs, h->d_adv_rhs, sizeof(double) * (size_t)h->n_nodes, cudaMemcpyDeviceToHost, h->stream));
-  CG_CUDA(cudaStreamSynchronize(h->stream));
+    CG_CUDA(cudaMemcpyAsync(matrix_val, h->d_adv_matrix, sizeof(double) * (size_t)h->nnz, cudaMemcpyDeviceToHost, cs));
+  if (rhs) CG_CUDA(cudaMemcpyAsync(rhs, h->d_adv_rhs, sizeof(double) * (size_t)h->n_nodes, cudaMemcpyDeviceToHost, cs));
+  return fetch_end(h, false);
+}
+
+int cgasm_set_async(int id, int on) {
+  GET_HANDLE(h, id);
+  if (on && !h->copy_stream) {
+    CG_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    CG_CUDA(cudaEventCreateWithFlags(&h->ev_ready, cudaEventDisableTiming));
+    CG_CUDA(cudaEventCreateWithFlags(&h->ev_mom_copied, cudaEventDisableTiming));
+    CG_CUDA(cudaEventCreateWithFlags(&h->ev_adv_copied, cudaEventDisableTiming));
+  }
+  if (!on && h->async) {
+    CG_CUDA(cudaStreamSynchronize(h->stream));
+    CG_CUDA(cudaStreamSynchronize(h->copy_stream));
+    h->mom_copy_pending = h->adv_copy_pending = false;
+  }
+  h->async = on != 0;
   return CGASM_OK;
 }
 
@@ -797,6 +856,10 @@ int cgasm_advdiff_element(int id, const cgasm_advdiff_opts* opts, int ele, doubl
 int cgasm_synchronize(int id) {
   GET_HANDLE(h, id);
   CG_CUDA(cudaStreamSynchronize(h->stream));
+  if (h->copy_stream) {
+    CG_CUDA(cudaStreamSynchronize(h->copy_stream));
+    h->mom_copy_pending = h->adv_copy_pending = false;
+  }
   return CGASM_OK;
 }
 

@@ -80,6 +80,13 @@ struct Handle {
   long long launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   float last_ms = 0.f;
+  // asynchronous host flavour (cgasm_set_async): results leave on copy_stream while the next loop runs
+  bool async = false;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_ready = nullptr;       // compute stream -> copy stream: the result is complete
+  cudaEvent_t ev_mom_copied = nullptr;  // copy stream -> compute stream: momentum buffers may be overwritten
+  cudaEvent_t ev_adv_copied = nullptr;
+  bool mom_copy_pending = false, adv_copy_pending = false;
 };
 
 // error plumbing

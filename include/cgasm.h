@@ -241,7 +241,15 @@ int cgasm_momentum_element(int id, const cgasm_momentum_opts* opts, int ele,
 int cgasm_advdiff_element(int id, const cgasm_advdiff_opts* opts, int ele,
                           double* matrix_addto, double* rhs_addto);
 
-/* Blocks until everything queued on the handle's stream has finished. */
+/* Asynchronous host flavour. With on != 0: cgasm_set_field returns once the upload is queued (val must
+ * stay valid, ideally pinned, until cgasm_synchronize) and the *_fetch calls queue their device -> host
+ * copies on a second stream behind the result and return at once, so the next element loop and the
+ * uploads of its fields overlap with the download of the previous result (PCIe is full duplex). The
+ * host buffers are valid after cgasm_synchronize. A new cgasm_momentum_dev / cgasm_advdiff_dev waits on
+ * the device for a pending download of the buffers it overwrites. Default: off (every call blocks). */
+int cgasm_set_async(int id, int on);
+
+/* Blocks until everything queued on the handle's streams has finished. */
 int cgasm_synchronize(int id);
 /* The handle's cudaStream_t (as void*), so callers can record events on it. */
 int cgasm_stream(int id, void** stream);

@@ -316,6 +316,45 @@ def test_strip_matches_gather_at_size():
     assert (sa2["matrix"] == sa["matrix"]).all() and (sa2["rhs"] == sa["rhs"]).all()
 
 
+def test_async_host_flavour_matches_blocking_calls():
+    """cgasm_set_async: uploads and downloads are queued on two streams; after cgasm_synchronize the host
+    buffers hold exactly what the blocking calls return, also when a loop is re-run while the previous
+    download may still be in flight."""
+    mesh = syn.box_mesh((12, 10, 8))
+    fs = syn.standard_fields(mesh)
+    asm = make_asm(mesh, fs, abi.SCATTER_STRIP)
+    om, oa = abi.common_momentum_opts(), abi.common_advdiff_opts()
+    nu, _ = fs.get(abi.F_NU)
+    T, _ = fs.get(abi.F_T)
+    ref = []
+    for scale in (1.0, 2.0):
+        asm.set_field(abi.F_NU, scale * nu)
+        asm.set_field(abi.F_T, scale * T)
+        m = asm.momentum(om)
+        a = asm.advdiff(oa)
+        ref.append(({k: v.copy() for k, v in m.items() if v is not None}, {k: v.copy() for k, v in a.items()}))
+    asm.set_async(True)
+    nn, nnz = mesh.n_nodes, asm.nnz
+    for rep in range(2):
+        for scale, (rm, ra) in zip((1.0, 2.0), ref):
+            out_m = dict(big_m=np.empty((1, nnz)), rhs=np.empty((nn, 3)), masslump=np.empty((nn, 3)))
+            out_a = dict(matrix=np.empty(nnz), rhs=np.empty(nn))
+            up_nu, up_T = scale * nu, scale * T  # must stay alive until synchronize
+            asm.set_field(abi.F_NU, up_nu)
+            asm.set_field(abi.F_T, up_T)
+            asm.advdiff_dev(oa)
+            asm.advdiff_fetch_into(out_a)
+            assert asm.momentum_host(om, out_m) == 1
+            asm.advdiff_dev(oa)  # re-run while the first tracer download may still be in flight
+            asm.synchronize()
+            assert (out_a["matrix"] == ra["matrix"]).all() and (out_a["rhs"] == ra["rhs"]).all()
+            assert (out_m["big_m"][0] == rm["big_m"][0]).all() and (out_m["rhs"] == rm["rhs"]).all()
+            assert (out_m["masslump"] == rm["masslump"]).all()
+    asm.set_async(False)
+    m = asm.momentum(om)
+    assert (m["big_m"] == ref[1][0]["big_m"]).all()
+
+
 def test_identical_blocks_partial_fetch(orc):
     mesh = syn.box_mesh((5, 4, 3))
     fs = syn.standard_fields(mesh)
