@@ -366,7 +366,7 @@ def run_graft(args):
     try:
         with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
             tr = json.load(f)["kernels"]["momentum"]
-        if chosen == "gather" and world == 1 and tr["elements"] == n_el_local:
+        if chosen == "strip" and world == 1 and tr["elements"] == n_el_local:
             traffic = tr["dram_bytes_per_launch"]
     except (OSError, KeyError, ValueError):
         pass

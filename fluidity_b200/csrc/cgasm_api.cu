@@ -583,6 +583,8 @@ int cgasm_set_field(int id, int slot, int rank, int field_type, const double* va
   f.n_val_nodes = n_val_nodes;
   f.count = count;
   f.set = true;
+  if (field_type == CGASM_FIELD_CONSTANT)
+    for (size_t c = 0; c < count && c < 9; c++) f.h_const[c] = val[c];
   int st = repack_slot(h, slot, nullptr, 0);
   if (st) return st;
   if (!h->async) CG_CUDA(cudaStreamSynchronize(h->stream));

@@ -21,6 +21,7 @@ struct DeviceField {
   int n_val_nodes = 0;
   size_t count = 0;  // doubles
   bool set = false;
+  double h_const[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // host copy of a CONSTANT field's single node (<= dim*dim values)
 };
 
 struct TilePlan;    // tiled.cu

@@ -10,11 +10,15 @@ constexpr int kAS = kBR + 1;  // stride (doubles) between slots of the accumulat
                               // write-out (one row spread over consecutive lanes) is conflict-free
 
 struct StripConsts {  // passed by value: operands are read straight from the constant bank
-  double Qa, Qaab, Qd, Qabc;  // Qa = Qaaa - Qaab, Qd = Qaab - Qabc (Tables)
-  double PdPo, Po, Pd;        // PdPo = Pd - Po
-  double Wsum;
+  // Option switches are folded into these numbers on the host (consts_momentum / consts_advdiff): a term
+  // that is switched off has zero coefficients, so one kernel serves every combination.
+  double Qa, Qaab, Qd, Qabc;  // advection: Qa = Qaaa - Qaab, Qd = Qaab - Qabc (Tables); 0 if no advection
+  double PdPo, Po;            // momentum: lumped mass / buoyancy moments; tracer: advection moments (0 if none)
+  double mPd, mPo;            // tracer mass matrix: (Pd, Po) consistent, (W1, 0) lumped, (0, 0) none
+  double mass_on;             // momentum: 1 if the lumped mass goes on the diagonal of big_m (not exclude_mass)
+  double V[9];                // constant viscosity / diffusivity tensor * Wsum, [a + dim*b]; V[0] if isotropic
+  double grav[3];             // gravity_magnitude * gravity direction (0 if no gravity)
   double dtt;                 // dt*theta (tracer: 0 unless |dt*theta| > epsilon, Advection_Diffusion_CG.F90:1121)
-  double gmag;                // gravity_magnitude
 };
 
 struct StripPlanView {
@@ -94,8 +98,29 @@ struct MomState {
 
 // row 0 (the row's own node) of the element {r, window}: Momentum_CG.F90:1535-1552 (lumped mass),
 // :1675-1680 with beta = 0 (advection), :2304-2317 (constant isotropic viscosity), :1770-1789 (buoyancy)
-template <int DIM, int N, int QC>
-__device__ __forceinline__ void mom_compute(MomState<DIM, N>& s, const StripConsts& k_, double muW) {
+// u = sign(det) (w - (1/det) V^T sc): the viscous/diffusive part of the row vector. FULLV: V is a full constant
+// tensor (dshape_tensor_dshape, Momentum_CG.F90:2331-2339), else isotropic (V[0]).
+template <int DIM, bool FULLV>
+__device__ __forceinline__ void row_vector(const StripConsts& k_, const double (&w)[DIM], const double (&sc)[DIM], double rd,
+                                           double det, double (&u)[DIM]) {
+  const unsigned sgn = (unsigned)__double2hiint(det) & 0x80000000u;
+  if constexpr (FULLV) {
+#pragma unroll
+    for (int b = 0; b < DIM; b++) {
+      double t = 0.0;
+#pragma unroll
+      for (int a = 0; a < DIM; a++) t = fma(sc[a], k_.V[a + DIM * b], t);
+      u[b] = flip_sign(fma(-rd, t, w[b]), sgn);
+    }
+  } else {
+    const double tt = k_.V[0] * rd;
+#pragma unroll
+    for (int a = 0; a < DIM; a++) u[a] = flip_sign(fma(-tt, sc[a], w[a]), sgn);
+  }
+}
+
+template <int DIM, int N, int QC, bool FULLV>
+__device__ __forceinline__ void mom_compute(MomState<DIM, N>& s, const StripConsts& k_) {
   double c[DIM][DIM];
   const double det = window_geometry<DIM, N, QC>(s.X, c);
   const double rd = rcp_nr(det);
@@ -120,12 +145,9 @@ __device__ __forceinline__ void mom_compute(MomState<DIM, N>& s, const StripCons
 #pragma unroll
     for (int a = 0; a < DIM; a++) w[a] = fma(Mk, s.U[WQ(k)][a], w[a]);
   }
-  // v / det with v = |det| (w + mu Wsum gradN_0), gradN_0 = -sc / det
-  const double tt = muW * rd;
-  const unsigned sgn = (unsigned)__double2hiint(det) & 0x80000000u;
+  // v / det with v = |det| (w + Wsum V gradN_0), gradN_0 = -sc / det
   double u[DIM];
-#pragma unroll
-  for (int a = 0; a < DIM; a++) u[a] = flip_sign(fma(-tt, sc[a], w[a]), sgn);
+  row_vector<DIM, FULLV>(k_, w, sc, rd, det, u);
   double tot = 0.0;
 #pragma unroll
   for (int k = 0; k < DIM; k++) {
@@ -174,8 +196,8 @@ struct AdvState {
 
 // Advection_Diffusion_CG.F90:909-920 (consistent mass), :1093-1098 with beta = 0, :1192 (constant
 // isotropic diffusivity), :1125,1200 (rhs -= (A + D) T)
-template <int DIM, int N, int QC>
-__device__ __forceinline__ void adv_compute(AdvState<DIM, N>& s, const StripConsts& k_, double kW) {
+template <int DIM, int N, int QC, bool FULLV>
+__device__ __forceinline__ void adv_compute(AdvState<DIM, N>& s, const StripConsts& k_) {
   double c[DIM][DIM];
   const double det = window_geometry<DIM, N, QC>(s.X, c);
   const double rd = rcp_nr(det);
@@ -190,11 +212,8 @@ __device__ __forceinline__ void adv_compute(AdvState<DIM, N>& s, const StripCons
     for (int k = 0; k < DIM; k++) Su += s.U[WQ(k)][a];
     v[a] = fma(k_.PdPo, s.U0[a], k_.Po * Su);
   }
-  const double tt = kW * rd;
-  const unsigned sgn = (unsigned)__double2hiint(det) & 0x80000000u;
   double u[DIM];
-#pragma unroll
-  for (int a = 0; a < DIM; a++) u[a] = flip_sign(fma(-tt, sc[a], v[a]), sgn);
+  row_vector<DIM, FULLV>(k_, v, sc, rd, det, u);
   const double ad = fabs(det);
   double tot = 0.0;
 #pragma unroll
@@ -231,18 +250,62 @@ inline StripPlanView plan_view(const Handle* h) {
   return v;
 }
 
-inline StripConsts consts_of(const Tables& t, double dtt, double gmag) {
-  StripConsts c;
-  c.Qa = t.Qaaa - t.Qaab;
-  c.Qaab = t.Qaab;
-  c.Qd = t.Qaab - t.Qabc;
-  c.Qabc = t.Qabc;
+// which option sets the STRIP kernels cover (everything else runs the GATHER kernels)
+inline bool strip_momentum_opts_ok(const MomentumArgs& A) {
+  const cgasm_momentum_opts& o = A.o;
+  return A.tab.sym && momentum_fast_ok(o, A.gravity.stride, A.absorption.stride) && !o.have_absorption &&
+         !(o.have_gravity && o.subtract_out_reference_profile) && (!o.have_viscosity || A.viscosity.stride == 0);
+}
+inline bool strip_advdiff_opts_ok(const AdvDiffArgs& A) {
+  const cgasm_advdiff_opts& o = A.o;
+  return A.tab.sym && advdiff_fast_ok(o) && !o.have_source && (!o.have_diffusivity || A.diffusivity.stride == 0);
+}
+// full constant tensor needed? (isotropic fields only use V[0])
+inline bool strip_full_tensor(int have, int shape) { return have && shape != CGASM_TENSOR_ISOTROPIC; }
+
+inline void consts_tensor(StripConsts& c, int dim, int have, int shape, const double* t, double wsum) {
+  for (int q = 0; q < 9; q++) c.V[q] = 0.0;
+  if (!have) return;
+  if (shape == CGASM_TENSOR_ISOTROPIC) {
+    c.V[0] = t[0] * wsum;
+  } else {
+    for (int b = 0; b < dim; b++)
+      for (int a = 0; a < dim; a++)
+        c.V[a + dim * b] = (shape == CGASM_TENSOR_DIAGONAL && a != b) ? 0.0 : t[a + dim * b] * wsum;
+  }
+}
+
+inline StripConsts consts_momentum(const Handle* h, const MomentumArgs& A) {
+  const Tables& t = A.tab;
+  const cgasm_momentum_opts& o = A.o;
+  StripConsts c{};
+  const double adv = o.exclude_advection ? 0.0 : 1.0;
+  c.Qa = adv * (t.Qaaa - t.Qaab);
+  c.Qaab = adv * t.Qaab;
+  c.Qd = adv * (t.Qaab - t.Qabc);
+  c.Qabc = adv * t.Qabc;
   c.PdPo = t.Pd - t.Po;
   c.Po = t.Po;
-  c.Pd = t.Pd;
-  c.Wsum = t.Wsum;
-  c.dtt = dtt;
-  c.gmag = gmag;
+  c.mass_on = o.exclude_mass ? 0.0 : 1.0;
+  consts_tensor(c, h->dim, o.have_viscosity, o.viscosity_shape, h->fields[CGASM_F_VISCOSITY].h_const, t.Wsum);
+  for (int d = 0; d < 3; d++)
+    c.grav[d] = (o.have_gravity && d < h->dim) ? o.gravity_magnitude * h->fields[CGASM_F_GRAVITY].h_const[d] : 0.0;
+  c.dtt = o.dt * o.theta;
+  return c;
+}
+
+inline StripConsts consts_advdiff(const Handle* h, const AdvDiffArgs& A) {
+  const Tables& t = A.tab;
+  const cgasm_advdiff_opts& o = A.o;
+  StripConsts c{};
+  const double adv = o.have_advection ? 1.0 : 0.0;
+  c.PdPo = adv * (t.Pd - t.Po);
+  c.Po = adv * t.Po;
+  c.mPd = !o.have_mass ? 0.0 : (o.lump_mass ? t.W1 : t.Pd);
+  c.mPo = !o.have_mass ? 0.0 : (o.lump_mass ? 0.0 : t.Po);
+  consts_tensor(c, h->dim, o.have_diffusivity, o.diffusivity_shape, h->fields[CGASM_F_T_DIFFUSIVITY].h_const, t.Wsum);
+  const double dtt = o.dt * o.theta;
+  c.dtt = fabs(dtt) > 2.220446049250313e-16 ? dtt : 0.0;
   return c;
 }
 

@@ -21,14 +21,14 @@ module cgasm_interface
        & cgasm_momentum, cgasm_advdiff, cgasm_momentum_dev, cgasm_advdiff_dev, &
        & cgasm_momentum_fetch, cgasm_advdiff_fetch, cgasm_momentum_identical_blocks, &
        & cgasm_momentum_fetch_blocks, cgasm_momentum_element, &
-       & cgasm_advdiff_element, cgasm_synchronize, cgasm_halo_create, cgasm_halo_update, &
+       & cgasm_advdiff_element, cgasm_synchronize, cgasm_set_async, cgasm_halo_create, cgasm_halo_update, &
        & cgasm_nccl_unique_id, cgasm_last_error
   public :: CGASM_OK, CGASM_EUNSUPPORTED
   public :: CGASM_F_NU, CGASM_F_OLDU, CGASM_F_DENSITY, CGASM_F_VISCOSITY, CGASM_F_BUOYANCY, &
        & CGASM_F_HB_DENSITY, CGASM_F_GRAVITY, CGASM_F_ABSORPTION, CGASM_F_SOURCE, CGASM_F_T, &
        & CGASM_F_T_DIFFUSIVITY, CGASM_F_T_SOURCE, CGASM_F_T_ABSORPTION
   public :: CGASM_SCATTER_ATOMIC, CGASM_SCATTER_COLOURED, CGASM_SCATTER_WARPAGG, &
-       & CGASM_SCATTER_TILED, CGASM_SCATTER_GATHER
+       & CGASM_SCATTER_TILED, CGASM_SCATTER_GATHER, CGASM_SCATTER_STRIP
 
   integer(c_int), parameter :: CGASM_OK = 0, CGASM_EUNSUPPORTED = 3
   integer(c_int), parameter :: CGASM_F_NU = 0, CGASM_F_OLDU = 1, CGASM_F_DENSITY = 2, &
@@ -36,7 +36,8 @@ module cgasm_interface
        & CGASM_F_GRAVITY = 6, CGASM_F_ABSORPTION = 7, CGASM_F_SOURCE = 8, CGASM_F_T = 9, &
        & CGASM_F_T_DIFFUSIVITY = 10, CGASM_F_T_SOURCE = 11, CGASM_F_T_ABSORPTION = 12
   integer(c_int), parameter :: CGASM_SCATTER_ATOMIC = 0, CGASM_SCATTER_COLOURED = 1, &
-       & CGASM_SCATTER_WARPAGG = 2, CGASM_SCATTER_TILED = 3, CGASM_SCATTER_GATHER = 4
+       & CGASM_SCATTER_WARPAGG = 2, CGASM_SCATTER_TILED = 3, CGASM_SCATTER_GATHER = 4, &
+       & CGASM_SCATTER_STRIP = 5
 
   !! Mirrors struct cgasm_momentum_opts: the module-level switches of
   !! assemble/Momentum_CG.F90:83-178. Logicals travel as integer(c_int) (0/1).
@@ -241,6 +242,13 @@ module cgasm_interface
        real(c_double), dimension(*), intent(out) :: matrix_addto, rhs_addto
        integer(c_int) :: stat
      end function cgasm_advdiff_element
+
+     !! on /= 0: uploads and result downloads are queued (two streams); cgasm_synchronize waits
+     function cgasm_set_async(id, on) bind(c, name="cgasm_set_async") result(stat)
+       use iso_c_binding
+       integer(c_int), value :: id, on
+       integer(c_int) :: stat
+     end function cgasm_set_async
 
      function cgasm_synchronize(id) bind(c, name="cgasm_synchronize") result(stat)
        use iso_c_binding
