@@ -21,8 +21,12 @@
 //
 // Entries per (row, element) pair: 1.375 on Kuhn meshes (33 pushes for the 24 elements of an
 // interior node). Summation order is fixed by the plan: results are bitwise reproducible.
-// Option coverage: the common option set only (momentum_common_ok / advdiff_common_ok); everything
-// else runs the GATHER kernels (gather.cu).
+// Option coverage (strip_momentum_opts_ok / strip_advdiff_opts_ok): lumped or excluded mass, advection
+// on/off (not by parts, beta = 0), CONSTANT viscosity / diffusivity of any tensor shape or none, constant
+// gravity direction with nodal buoyancy or no gravity, tracer mass consistent / lumped / none -- the switches
+// are folded into the coefficients on the host (strip_common.cuh), so one kernel (two with the full-tensor
+// variant) serves them all: driven_cavity, lock_exchange, flow_past_sphere_Re100 and S3 take this path.
+// Absorption, sources, SU/SUPG, by-parts advection, nodal viscosity run the GATHER kernels (gather.cu).
 #include "strip_common.cuh"
 
 #include <algorithm>
@@ -32,7 +36,7 @@
 namespace cgasm {
 
 template <int DIM, int N, int QC>
-__device__ __forceinline__ void mom_step(MomState<DIM, N>& s, const StripConsts& k_, double muW, int j, int deg,
+__device__ __forceinline__ void mom_step(MomState<DIM, N>& s, const StripConsts& k_, int j, int deg,
                                          const int2* __restrict__ p, int2& pq0, int2& pq1, const int2 pad,
                                          double* __restrict__ acc_t, const double4* __restrict__ rX,
                                          const double4* __restrict__ rU) {
@@ -51,23 +55,22 @@ __device__ __forceinline__ void mom_step(MomState<DIM, N>& s, const StripConsts&
   s.meta[QE] = en.y;
 #pragma unroll
   for (int a = 0; a < DIM; a++) s.X[QC][a] -= s.X0[a];
-  if (s.meta[QC] & kStripCompute) mom_compute<DIM, N, QC>(s, k_, muW);
+  if (s.meta[QC] & kStripCompute) mom_compute<DIM, N, QC, false>(s, k_);
 }
 
 template <int DIM, int N, int Q>
 struct MomUnroll {
   template <class... Args>
-  static __device__ __forceinline__ void run(MomState<DIM, N>& s, const StripConsts& k_, double muW, int j0, Args&&... args) {
-    mom_step<DIM, N, Q>(s, k_, muW, j0 + Q, args...);
-    if constexpr (Q + 1 < N) MomUnroll<DIM, N, Q + 1>::run(s, k_, muW, j0, args...);
+  static __device__ __forceinline__ void run(MomState<DIM, N>& s, const StripConsts& k_, int j0, Args&&... args) {
+    mom_step<DIM, N, Q>(s, k_, j0 + Q, args...);
+    if constexpr (Q + 1 < N) MomUnroll<DIM, N, Q + 1>::run(s, k_, j0, args...);
   }
 };
 
 template <int DIM, int N, int MINB>
 __global__ void __launch_bounds__(kBR, MINB)
 strip_momentum_kernel(const StripConsts k_, const StripPlanView P, const double4* __restrict__ rX,
-                      const double4* __restrict__ rU, const double4* __restrict__ rO,
-                      const double* __restrict__ viscosity, const double* __restrict__ gravity, size_t nnz,
+                      const double4* __restrict__ rU, const double4* __restrict__ rO, size_t nnz,
                       double* __restrict__ big_m, double* __restrict__ rhs, double* __restrict__ masslump) {
   constexpr int PD = N - DIM;
   extern __shared__ double acc[];
@@ -81,7 +84,6 @@ strip_momentum_kernel(const StripConsts k_, const StripPlanView P, const double4
   for (int q = 0; q < P.maxlen; q++) acc_t[q * kAS] = 0.0;
   const int own = P.own_slot[b * kBR + t];
   const int2 pad = make_int2(r0, own);
-  const double muW = __ldg(viscosity) * k_.Wsum;
   MomState<DIM, N> s;
   unpack<DIM>(ld256(rX + r0), s.X0, s.b0);
   unpack<DIM>(ld256(rU + r0), s.U0, s.rho0);
@@ -103,7 +105,7 @@ strip_momentum_kernel(const StripConsts k_, const StripPlanView P, const double4
   }
   int2 pq0 = PD < deg ? ldg_stream2(p + (long long)PD * kBR) : pad;
   int2 pq1 = PD + 1 < deg ? ldg_stream2(p + (long long)(PD + 1) * kBR) : pad;
-  for (int j0 = 0; j0 < deg; j0 += N) MomUnroll<DIM, N, 0>::run(s, k_, muW, j0, deg, p, pq0, pq1, pad, acc_t, rX, rU);
+  for (int j0 = 0; j0 < deg; j0 += N) MomUnroll<DIM, N, 0>::run(s, k_, j0, deg, p, pq0, pq1, pad, acc_t, rX, rU);
 #pragma unroll
   for (int q = 0; q < N; q++) acc_t[(s.meta[q] & 0xff) * kAS] += s.A[q];
   acc_t[own * kAS] += s.a0;
@@ -114,7 +116,7 @@ strip_momentum_kernel(const StripConsts k_, const StripPlanView P, const double4
     my_len = P.findrm[r + 1] - my_s0;
     double rh[DIM];
 #pragma unroll
-    for (int d = 0; d < DIM; d++) rh[d] = (k_.gmag * __ldg(gravity + d)) * s.nbsum;
+    for (int d = 0; d < DIM; d++) rh[d] = k_.grav[d] * s.nbsum;
     for (int q = 0; q < my_len; q++) {
       const int col = __ldg(P.colm + my_s0 + q);
       const double4 o = ld256(rO + col);
@@ -122,7 +124,7 @@ strip_momentum_kernel(const StripConsts k_, const StripPlanView P, const double4
       rh[0] = fma(-v, o.x, rh[0]);
       rh[1] = fma(-v, o.y, rh[1]);
       if constexpr (DIM == 3) rh[2] = fma(-v, o.z, rh[2]);
-      acc_t[q * kAS] = fma(k_.dtt, v, q == own ? s.msum : 0.0);
+      acc_t[q * kAS] = fma(k_.dtt, v, q == own ? s.msum * k_.mass_on : 0.0);
     }
 #pragma unroll
     for (int d = 0; d < DIM; d++) {
@@ -136,7 +138,7 @@ strip_momentum_kernel(const StripConsts k_, const StripPlanView P, const double4
 
 // ---- tracer -------------------------------------------------------------------------------------------
 template <int DIM, int N, int QC>
-__device__ __forceinline__ void adv_step(AdvState<DIM, N>& s, const StripConsts& k_, double kW, int j, int deg,
+__device__ __forceinline__ void adv_step(AdvState<DIM, N>& s, const StripConsts& k_, int j, int deg,
                                          const int2* __restrict__ p, int2& pq0, int2& pq1, const int2 pad,
                                          double* __restrict__ acc_t, const double4* __restrict__ rX,
                                          const double4* __restrict__ rU) {
@@ -147,7 +149,7 @@ __device__ __forceinline__ void adv_step(AdvState<DIM, N>& s, const StripConsts&
   pq1 = (j + PD + 2 < deg) ? ldg_stream2(p + (long long)(j + PD + 2) * kBR) : pad;
   {
     double* sl = acc_t + (s.meta[QE] & 0xff) * kAS;
-    *sl += fma(k_.dtt, s.A[QE], k_.Po * s.C[QE]);
+    *sl += fma(k_.dtt, s.A[QE], k_.mPo * s.C[QE]);
     s.A[QE] = 0.0;
     s.C[QE] = 0.0;
   }
@@ -157,23 +159,22 @@ __device__ __forceinline__ void adv_step(AdvState<DIM, N>& s, const StripConsts&
   s.meta[QE] = en.y;
 #pragma unroll
   for (int a = 0; a < DIM; a++) s.X[QC][a] -= s.X0[a];
-  if (s.meta[QC] & kStripCompute) adv_compute<DIM, N, QC>(s, k_, kW);
+  if (s.meta[QC] & kStripCompute) adv_compute<DIM, N, QC, false>(s, k_);
 }
 
 template <int DIM, int N, int Q>
 struct AdvUnroll {
   template <class... Args>
-  static __device__ __forceinline__ void run(AdvState<DIM, N>& s, const StripConsts& k_, double kW, int j0, Args&&... args) {
-    adv_step<DIM, N, Q>(s, k_, kW, j0 + Q, args...);
-    if constexpr (Q + 1 < N) AdvUnroll<DIM, N, Q + 1>::run(s, k_, kW, j0, args...);
+  static __device__ __forceinline__ void run(AdvState<DIM, N>& s, const StripConsts& k_, int j0, Args&&... args) {
+    adv_step<DIM, N, Q>(s, k_, j0 + Q, args...);
+    if constexpr (Q + 1 < N) AdvUnroll<DIM, N, Q + 1>::run(s, k_, j0, args...);
   }
 };
 
 template <int DIM, int N, int MINB>
 __global__ void __launch_bounds__(kBR, MINB)
 strip_advdiff_kernel(const StripConsts k_, const StripPlanView P, const double4* __restrict__ rX,
-                     const double4* __restrict__ rU, const double* __restrict__ diffusivity,
-                     double* __restrict__ matrix, double* __restrict__ rhs) {
+                     const double4* __restrict__ rU, double* __restrict__ matrix, double* __restrict__ rhs) {
   constexpr int PD = N - DIM;
   extern __shared__ double acc[];
   const int b = blockIdx.x, t = threadIdx.x;
@@ -186,7 +187,6 @@ strip_advdiff_kernel(const StripConsts k_, const StripPlanView P, const double4*
   for (int q = 0; q < P.maxlen; q++) acc_t[q * kAS] = 0.0;
   const int own = P.own_slot[b * kBR + t];
   const int2 pad = make_int2(r0, own);
-  const double kW = __ldg(diffusivity) * k_.Wsum;
   AdvState<DIM, N> s;
   double unused;
   unpack<DIM>(ld256(rX + r0), s.X0, s.T0);
@@ -208,10 +208,10 @@ strip_advdiff_kernel(const StripConsts k_, const StripPlanView P, const double4*
   }
   int2 pq0 = PD < deg ? ldg_stream2(p + (long long)PD * kBR) : pad;
   int2 pq1 = PD + 1 < deg ? ldg_stream2(p + (long long)(PD + 1) * kBR) : pad;
-  for (int j0 = 0; j0 < deg; j0 += N) AdvUnroll<DIM, N, 0>::run(s, k_, kW, j0, deg, p, pq0, pq1, pad, acc_t, rX, rU);
+  for (int j0 = 0; j0 < deg; j0 += N) AdvUnroll<DIM, N, 0>::run(s, k_, j0, deg, p, pq0, pq1, pad, acc_t, rX, rU);
 #pragma unroll
-  for (int q = 0; q < N; q++) acc_t[(s.meta[q] & 0xff) * kAS] += fma(k_.dtt, s.A[q], k_.Po * s.C[q]);
-  acc_t[own * kAS] += fma(k_.dtt, s.a0, k_.Pd * s.c0);
+  for (int q = 0; q < N; q++) acc_t[(s.meta[q] & 0xff) * kAS] += fma(k_.dtt, s.A[q], k_.mPo * s.C[q]);
+  acc_t[own * kAS] += fma(k_.dtt, s.a0, k_.mPd * s.c0);
   int my_s0 = 0, my_len = 0;
   if (r >= 0) {
     my_s0 = P.findrm[r];
@@ -357,14 +357,17 @@ void strip_free(GatherPlan* P) {
 
 // ---- launch -------------------------------------------------------------------------------------------
 bool strip_momentum_ok(const Handle* h, const MomentumArgs& A, bool want_ml) {
+  (void)want_ml;
   const GatherPlan* P = h->gather;
-  return P && P->d_strip && A.tab.sym && want_ml && !A.o.have_absorption &&
-         momentum_fast_ok(A.o, A.gravity.stride, A.absorption.stride) && momentum_common_ok(A.o, A.viscosity.stride);
+  if (!P || !P->d_strip || !strip_momentum_opts_ok(A)) return false;
+  // a full constant tensor needs the staged kernels
+  return strip_staged_ok(h, true) || !strip_full_tensor(A.o.have_viscosity, A.o.viscosity_shape);
 }
 
 bool strip_advdiff_ok(const Handle* h, const AdvDiffArgs& A) {
   const GatherPlan* P = h->gather;
-  return P && P->d_strip && A.tab.sym && advdiff_fast_ok(A.o) && advdiff_common_ok(A.o, A.diffusivity.stride);
+  if (!P || !P->d_strip || !strip_advdiff_opts_ok(A)) return false;
+  return strip_staged_ok(h, false) || !strip_full_tensor(A.o.have_diffusivity, A.o.diffusivity_shape);
 }
 
 template <int DIM>
@@ -372,7 +375,7 @@ static int strip_momentum_dim(Handle* h, const MomentumArgs& A) {
   GatherPlan* P = h->gather;
   const size_t smem = sizeof(double) * (size_t)P->maxlen * kAS;
   if (smem > 200 * 1024) CG_FAIL(CGASM_EUNSUPPORTED, "strip scatter: CSR rows too long for the shared-memory accumulator");
-  const StripConsts c = consts_of(A.tab, A.o.dt * A.o.theta, A.o.gravity_magnitude);
+  const StripConsts c = consts_momentum(h, A);
   const StripPlanView v = plan_view(h);
   const int minb = getenv("CGASM_STRIP_MINB") ? atoi(getenv("CGASM_STRIP_MINB")) : 4;
   int st;
@@ -380,8 +383,8 @@ static int strip_momentum_dim(Handle* h, const MomentumArgs& A) {
   do {                                                                                                         \
     if ((st = strip_smem(strip_momentum_kernel<DIM, N_, MINB_>, smem))) return st;                             \
     strip_momentum_kernel<DIM, N_, MINB_><<<P->nblocks, kBR, smem, h->stream>>>(                               \
-        c, v, h->d_rec3, h->d_rec1, h->d_rec2, A.viscosity.val, A.gravity.val, (size_t)h->nnz, h->d_big_m,      \
-        h->d_mom_rhs, h->d_masslump);                                                                          \
+        c, v, h->d_rec3, h->d_rec1, h->d_rec2, (size_t)h->nnz, h->d_big_m, h->d_mom_rhs,                        \
+        A.o.assemble_inverse_masslump ? h->d_masslump : nullptr);                                                                        \
   } while (0)
   if (minb >= 4) LAUNCH(DIM + 1, 4);
   else if (minb == 3) LAUNCH(DIM + 1, 3);
@@ -402,8 +405,7 @@ static int strip_advdiff_dim(Handle* h, const AdvDiffArgs& A) {
   GatherPlan* P = h->gather;
   const size_t smem = sizeof(double) * (size_t)P->maxlen * kAS;
   if (smem > 200 * 1024) CG_FAIL(CGASM_EUNSUPPORTED, "strip scatter: CSR rows too long for the shared-memory accumulator");
-  const double dtt = A.o.dt * A.o.theta;
-  const StripConsts c = consts_of(A.tab, fabs(dtt) > 2.220446049250313e-16 ? dtt : 0.0, 0.0);
+  const StripConsts c = consts_advdiff(h, A);
   const StripPlanView v = plan_view(h);
   const int minb = getenv("CGASM_STRIP_MINB_ADV") ? atoi(getenv("CGASM_STRIP_MINB_ADV")) : 4;
   int st;
@@ -411,7 +413,7 @@ static int strip_advdiff_dim(Handle* h, const AdvDiffArgs& A) {
   do {                                                                                                         \
     if ((st = strip_smem(strip_advdiff_kernel<DIM, N_, MINB_>, smem))) return st;                              \
     strip_advdiff_kernel<DIM, N_, MINB_><<<P->nblocks, kBR, smem, h->stream>>>(                                \
-        c, v, h->d_rec0, h->d_rec1, A.diffusivity.val, h->d_adv_matrix, h->d_adv_rhs);                          \
+        c, v, h->d_rec0, h->d_rec1, h->d_adv_matrix, h->d_adv_rhs);                         \
   } while (0)
   if (minb >= 5) LAUNCH(DIM + 1, 5);
   else if (minb == 4) LAUNCH(DIM + 1, 4);

@@ -134,23 +134,22 @@ __device__ __forceinline__ void load_oldu(unsigned nsa, int nl, int li, double (
 }
 
 // ---- momentum -----------------------------------------------------------------------------------------
-// One strip entry. Program order = issue order (all memory asm is volatile):
-//   flush the evicted buffer with the oldu fetched one step ago; request the records of entry j+PD, the
-//   oldu of the node evicted NEXT step and plan entry j+PD+3; then install and compute entry j.
-template <int DIM, int N, int QC, bool ONPF, bool PF>
-__device__ __forceinline__ void smom_step(MomState<DIM, N>& s, double (&rh)[DIM], double (&on)[DIM], const StripConsts& k_,
-                                          double muW, int j, int deg, const unsigned* __restrict__ p, unsigned& pq0,
-                                          unsigned& pq1, unsigned& pq2, const unsigned pad, double* __restrict__ acc_t,
-                                          unsigned nsa, int nl) {
+// One strip entry. Program order = issue order (all memory asm is volatile): flush the evicted buffer
+// (slot accumulator and rhs -= entry * oldu of the evicted node), request the records of entry j + PD and
+// plan entry j + PD + 3, then install and compute entry j.
+template <int DIM, int N, int QC, bool FULLV, bool PF>
+__device__ __forceinline__ void smom_step(MomState<DIM, N>& s, double (&rh)[DIM], const StripConsts& k_, int j, int deg,
+                                          const unsigned* __restrict__ p, unsigned& pq0, unsigned& pq1, unsigned& pq2,
+                                          const unsigned pad, double* __restrict__ acc_t, unsigned nsa, int nl) {
   constexpr int PD = N - DIM;
   constexpr int QE = (QC + PD) % N;  // holds entry j - DIM: evicted now, refilled with entry j + PD
-  constexpr int QN = (QE + 1) % N;   // evicted at the next step
   const unsigned en = pq0;
   pq0 = pq1;
   pq1 = pq2;
   {
     const unsigned m = (unsigned)s.meta[QE];
-    if constexpr (!ONPF) load_oldu<DIM>(nsa, nl, (int)(m & 0xffffu), on);
+    double on[DIM];
+    load_oldu<DIM>(nsa, nl, (int)(m & 0xffffu), on);
     double* sl = acc_t + ((m >> 16) & 0xffu) * kAS;
     const double a = s.A[QE];
     *sl += a;
@@ -162,21 +161,20 @@ __device__ __forceinline__ void smom_step(MomState<DIM, N>& s, double (&rh)[DIM]
   load_rec<DIM>(nsa, nl, 0, li, s.X[QE], s.B[QE]);
   load_rec<DIM>(nsa, nl, 1, li, s.U[QE], s.R[QE]);
   s.meta[QE] = (int)en;
-  if constexpr (ONPF) load_oldu<DIM>(nsa, nl, (int)((unsigned)s.meta[QN] & 0xffffu), on);
   pq2 = (j + PD + 3 < deg) ? ldg_stream1(p + (long long)(j + PD + 3) * kBR) : pad;
   if (PF && j + kPlanAhead < deg) prefetch_l2(p + (long long)(j + kPlanAhead) * kBR);
 #pragma unroll
   for (int a = 0; a < DIM; a++) s.X[QC][a] -= s.X0[a];
-  if ((unsigned)s.meta[QC] & kLocalCompute) mom_compute<DIM, N, QC>(s, k_, muW);
+  if ((unsigned)s.meta[QC] & kLocalCompute) mom_compute<DIM, N, QC, FULLV>(s, k_);
 }
 
-template <int DIM, int N, int Q, bool ONPF, bool PF>
+template <int DIM, int N, int Q, bool FULLV, bool PF>
 struct SMomUnroll {
   template <class... Args>
-  static __device__ __forceinline__ void run(MomState<DIM, N>& s, double (&rh)[DIM], double (&on)[DIM], const StripConsts& k_,
-                                             double muW, int j0, Args&&... args) {
-    smom_step<DIM, N, Q, ONPF, PF>(s, rh, on, k_, muW, j0 + Q, args...);
-    if constexpr (Q + 1 < N) SMomUnroll<DIM, N, Q + 1, ONPF, PF>::run(s, rh, on, k_, muW, j0, args...);
+  static __device__ __forceinline__ void run(MomState<DIM, N>& s, double (&rh)[DIM], const StripConsts& k_, int j0,
+                                             Args&&... args) {
+    smom_step<DIM, N, Q, FULLV, PF>(s, rh, k_, j0 + Q, args...);
+    if constexpr (Q + 1 < N) SMomUnroll<DIM, N, Q + 1, FULLV, PF>::run(s, rh, k_, j0, args...);
   }
 };
 
@@ -202,11 +200,10 @@ __device__ __forceinline__ void write_rows_scaled(const double* __restrict__ acc
   }
 }
 
-template <int DIM, int N, int MINB, bool ONPF, bool PF>
+template <int DIM, int N, int MINB, bool FULLV, bool PF>
 __global__ void __launch_bounds__(kBR, MINB)
 staged_momentum_kernel(const StripConsts k_, const StagedView P, const double4* __restrict__ rX,
-                       const double4* __restrict__ rU, const double4* __restrict__ rO,
-                       const double* __restrict__ viscosity, const double* __restrict__ gravity, size_t nnz,
+                       const double4* __restrict__ rU, const double4* __restrict__ rO, size_t nnz,
                        double* __restrict__ big_m, double* __restrict__ rhs, double* __restrict__ masslump) {
   constexpr int PD = N - DIM;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -223,8 +220,6 @@ staged_momentum_kernel(const StripConsts k_, const StagedView P, const double4* 
   for (int q = 0; q < P.maxlen; q++) acc_t[q * kAS] = 0.0;
   const unsigned pad = P.own_local[b * kBR + t];
   const int own = (int)((pad >> 16) & 0xffu), own_li = (int)(pad & 0xffffu);
-  const double muW = __ldg(viscosity) * k_.Wsum;
-  asm volatile("prefetch.global.L1 [%0];" ::"l"(gravity));  // read at the very end of the row
   unsigned first[PD > 0 ? PD : 1];
 #pragma unroll
   for (int q = 0; q < PD; q++) first[q] = q < deg ? ldg_stream1(p + (long long)q * kBR) : pad;
@@ -242,9 +237,9 @@ staged_momentum_kernel(const StripConsts k_, const StagedView P, const double4* 
   load_rec<DIM>(nsa, nl, 0, own_li, s.X0, s.b0);
   load_rec<DIM>(nsa, nl, 1, own_li, s.U0, s.rho0);
   s.a0 = s.msum = s.nbsum = 0.0;
-  double rh[DIM], on[DIM];
+  double rh[DIM];
 #pragma unroll
-  for (int d = 0; d < DIM; d++) rh[d] = on[d] = 0.0;
+  for (int d = 0; d < DIM; d++) rh[d] = 0.0;
 #pragma unroll
   for (int q = 0; q < N; q++) {
 #pragma unroll
@@ -259,9 +254,8 @@ staged_momentum_kernel(const StripConsts k_, const StagedView P, const double4* 
     load_rec<DIM>(nsa, nl, 1, li, s.U[q], s.R[q]);
     s.meta[q] = (int)first[q];
   }
-  // `on` = oldu of the node the first step evicts: nothing has accumulated there yet (A = 0), zeros do
   for (int j0 = 0; j0 < deg; j0 += N)
-    SMomUnroll<DIM, N, 0, ONPF, PF>::run(s, rh, on, k_, muW, j0, deg, p, pq0, pq1, pq2, pad, acc_t, nsa, nl);
+    SMomUnroll<DIM, N, 0, FULLV, PF>::run(s, rh, k_, j0, deg, p, pq0, pq1, pq2, pad, acc_t, nsa, nl);
   // drain the FIFO, then the diagonal (the row's own node never leaves)
 #pragma unroll
   for (int q = 0; q < N; q++) {
@@ -281,17 +275,17 @@ staged_momentum_kernel(const StripConsts k_, const StagedView P, const double4* 
     load_oldu<DIM>(nsa, nl, own_li, ou);
 #pragma unroll
     for (int d = 0; d < DIM; d++) {
-      rhs[(size_t)DIM * r + d] = fma(-s.a0, ou[d], fma(k_.gmag * __ldg(gravity + d), s.nbsum, rh[d]));
+      rhs[(size_t)DIM * r + d] = fma(-s.a0, ou[d], fma(k_.grav[d], s.nbsum, rh[d]));
       if (masslump) masslump[(size_t)DIM * r + d] = s.msum;
     }
   }
   __syncwarp();
-  write_rows_scaled<DIM>(acc, t, my_s0, my_len, own, s.msum, k_.dtt, P.lpr_shift, nnz, big_m);
+  write_rows_scaled<DIM>(acc, t, my_s0, my_len, own, s.msum * k_.mass_on, k_.dtt, P.lpr_shift, nnz, big_m);
 }
 
 // ---- tracer -------------------------------------------------------------------------------------------
-template <int DIM, int N, int QC, bool PF>
-__device__ __forceinline__ void sadv_step(AdvState<DIM, N>& s, const StripConsts& k_, double kW, int j, int deg,
+template <int DIM, int N, int QC, bool FULLV, bool PF>
+__device__ __forceinline__ void sadv_step(AdvState<DIM, N>& s, const StripConsts& k_, int j, int deg,
                                           const unsigned* __restrict__ p, unsigned& pq0, unsigned& pq1, unsigned& pq2,
                                           const unsigned pad, double* __restrict__ acc_t, unsigned nsa, int nl) {
   constexpr int PD = N - DIM;
@@ -301,7 +295,7 @@ __device__ __forceinline__ void sadv_step(AdvState<DIM, N>& s, const StripConsts
   pq1 = pq2;
   {
     double* sl = acc_t + (((unsigned)s.meta[QE] >> 16) & 0xffu) * kAS;
-    *sl += fma(k_.dtt, s.A[QE], k_.Po * s.C[QE]);
+    *sl += fma(k_.dtt, s.A[QE], k_.mPo * s.C[QE]);
     s.A[QE] = 0.0;
     s.C[QE] = 0.0;
   }
@@ -314,23 +308,22 @@ __device__ __forceinline__ void sadv_step(AdvState<DIM, N>& s, const StripConsts
   if (PF && j + kPlanAhead < deg) prefetch_l2(p + (long long)(j + kPlanAhead) * kBR);
 #pragma unroll
   for (int a = 0; a < DIM; a++) s.X[QC][a] -= s.X0[a];
-  if ((unsigned)s.meta[QC] & kLocalCompute) adv_compute<DIM, N, QC>(s, k_, kW);
+  if ((unsigned)s.meta[QC] & kLocalCompute) adv_compute<DIM, N, QC, FULLV>(s, k_);
 }
 
-template <int DIM, int N, int Q, bool PF>
+template <int DIM, int N, int Q, bool FULLV, bool PF>
 struct SAdvUnroll {
   template <class... Args>
-  static __device__ __forceinline__ void run(AdvState<DIM, N>& s, const StripConsts& k_, double kW, int j0, Args&&... args) {
-    sadv_step<DIM, N, Q, PF>(s, k_, kW, j0 + Q, args...);
-    if constexpr (Q + 1 < N) SAdvUnroll<DIM, N, Q + 1, PF>::run(s, k_, kW, j0, args...);
+  static __device__ __forceinline__ void run(AdvState<DIM, N>& s, const StripConsts& k_, int j0, Args&&... args) {
+    sadv_step<DIM, N, Q, FULLV, PF>(s, k_, j0 + Q, args...);
+    if constexpr (Q + 1 < N) SAdvUnroll<DIM, N, Q + 1, FULLV, PF>::run(s, k_, j0, args...);
   }
 };
 
-template <int DIM, int N, int MINB, bool PF>
+template <int DIM, int N, int MINB, bool FULLV, bool PF>
 __global__ void __launch_bounds__(kBR, MINB)
 staged_advdiff_kernel(const StripConsts k_, const StagedView P, const double4* __restrict__ rX,
-                      const double4* __restrict__ rU, const double* __restrict__ diffusivity,
-                      double* __restrict__ matrix, double* __restrict__ rhs) {
+                      const double4* __restrict__ rU, double* __restrict__ matrix, double* __restrict__ rhs) {
   constexpr int PD = N - DIM;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* acc = reinterpret_cast<double*>(smem_raw);
@@ -346,7 +339,6 @@ staged_advdiff_kernel(const StripConsts k_, const StagedView P, const double4* _
   for (int q = 0; q < P.maxlen; q++) acc_t[q * kAS] = 0.0;
   const unsigned pad = P.own_local[b * kBR + t];
   const int own = (int)((pad >> 16) & 0xffu), own_li = (int)(pad & 0xffffu);
-  const double kW = __ldg(diffusivity) * k_.Wsum;
   unsigned first[PD > 0 ? PD : 1];
 #pragma unroll
   for (int q = 0; q < PD; q++) first[q] = q < deg ? ldg_stream1(p + (long long)q * kBR) : pad;
@@ -379,11 +371,11 @@ staged_advdiff_kernel(const StripConsts k_, const StagedView P, const double4* _
     load_rec<DIM>(nsa, nl, 1, li, s.U[q], unused);
     s.meta[q] = (int)first[q];
   }
-  for (int j0 = 0; j0 < deg; j0 += N) SAdvUnroll<DIM, N, 0, PF>::run(s, k_, kW, j0, deg, p, pq0, pq1, pq2, pad, acc_t, nsa, nl);
+  for (int j0 = 0; j0 < deg; j0 += N) SAdvUnroll<DIM, N, 0, FULLV, PF>::run(s, k_, j0, deg, p, pq0, pq1, pq2, pad, acc_t, nsa, nl);
 #pragma unroll
   for (int q = 0; q < N; q++)
-    acc_t[(((unsigned)s.meta[q] >> 16) & 0xffu) * kAS] += fma(k_.dtt, s.A[q], k_.Po * s.C[q]);
-  acc_t[own * kAS] += fma(k_.dtt, s.a0, k_.Pd * s.c0);
+    acc_t[(((unsigned)s.meta[q] >> 16) & 0xffu) * kAS] += fma(k_.dtt, s.A[q], k_.mPo * s.C[q]);
+  acc_t[own * kAS] += fma(k_.dtt, s.a0, k_.mPd * s.c0);
   int my_s0 = 0, my_len = 0;
   if (r >= 0) {
     my_s0 = P.findrm[r];
@@ -435,35 +427,36 @@ template <int DIM>
 static int staged_momentum_dim(Handle* h, const MomentumArgs& A) {
   GatherPlan* P = h->gather;
   const size_t smem = staged_smem(P, true);
-  const StripConsts c = consts_of(A.tab, A.o.dt * A.o.theta, A.o.gravity_magnitude);
+  const StripConsts c = consts_momentum(h, A);
   const StagedView v = staged_view(h);
   // tuning switches (defaults = best measured on S3, profiles/r1_kernel_history.md)
   const int minb = env_int("CGASM_STRIP_MINB", 4), nbuf = env_int("CGASM_STRIP_NBUF", DIM);
-  const bool onpf = env_int("CGASM_STRIP_ONPF", 0) != 0, pf = env_int("CGASM_STRIP_PF", 1) != 0;
+  const bool pf = env_int("CGASM_STRIP_PF", 1) != 0;
+  const bool fullv = strip_full_tensor(A.o.have_viscosity, A.o.viscosity_shape);
+  double* ml = A.o.assemble_inverse_masslump ? h->d_masslump : nullptr;
   int st;
-#define LAUNCH(N_, MINB_, ONPF_, PF_)                                                                           \
+#define LAUNCH(N_, MINB_, FULLV_, PF_)                                                                          \
   do {                                                                                                          \
-    if ((st = strip_smem(staged_momentum_kernel<DIM, N_, MINB_, ONPF_, PF_>, smem))) return st;                 \
-    staged_momentum_kernel<DIM, N_, MINB_, ONPF_, PF_><<<P->nblocks, kBR, smem, h->stream>>>(                   \
-        c, v, h->d_rec3, h->d_rec1, h->d_rec2, A.viscosity.val, A.gravity.val, (size_t)h->nnz, h->d_big_m,       \
-        h->d_mom_rhs, h->d_masslump);                                                                           \
+    if ((st = strip_smem(staged_momentum_kernel<DIM, N_, MINB_, FULLV_, PF_>, smem))) return st;                \
+    staged_momentum_kernel<DIM, N_, MINB_, FULLV_, PF_><<<P->nblocks, kBR, smem, h->stream>>>(                  \
+        c, v, h->d_rec3, h->d_rec1, h->d_rec2, (size_t)h->nnz, h->d_big_m, h->d_mom_rhs, ml);                    \
   } while (0)
-#define LAUNCH_PF(N_, MINB_, ONPF_) \
-  do {                              \
-    if (pf) LAUNCH(N_, MINB_, ONPF_, true); \
-    else LAUNCH(N_, MINB_, ONPF_, false);   \
+#define LAUNCH_V(N_, MINB_, PF_)                    \
+  do {                                              \
+    if (fullv) LAUNCH(N_, MINB_, true, PF_);        \
+    else LAUNCH(N_, MINB_, false, PF_);             \
   } while (0)
   if (nbuf > DIM) {
-    if (minb >= 4) LAUNCH_PF(DIM + 1, 4, true);
-    else if (onpf) LAUNCH_PF(DIM + 1, 3, true);
-    else LAUNCH_PF(DIM + 1, 3, false);
+    if (pf) LAUNCH_V(DIM + 1, 3, true);
+    else LAUNCH_V(DIM + 1, 3, false);
+  } else if (minb >= 4) {
+    if (pf) LAUNCH_V(DIM, 4, true);
+    else LAUNCH_V(DIM, 4, false);
   } else {
-    if (minb >= 4 && onpf) LAUNCH_PF(DIM, 4, true);
-    else if (minb >= 4) LAUNCH_PF(DIM, 4, false);
-    else if (onpf) LAUNCH_PF(DIM, 3, true);
-    else LAUNCH_PF(DIM, 3, false);
+    if (pf) LAUNCH_V(DIM, 3, true);
+    else LAUNCH_V(DIM, 3, false);
   }
-#undef LAUNCH_PF
+#undef LAUNCH_V
 #undef LAUNCH
   h->launches++;
   CG_CUDA(cudaGetLastError());
@@ -478,32 +471,32 @@ template <int DIM>
 static int staged_advdiff_dim(Handle* h, const AdvDiffArgs& A) {
   GatherPlan* P = h->gather;
   const size_t smem = staged_smem(P, false);
-  const double dtt = A.o.dt * A.o.theta;
-  const StripConsts c = consts_of(A.tab, fabs(dtt) > 2.220446049250313e-16 ? dtt : 0.0, 0.0);
+  const StripConsts c = consts_advdiff(h, A);
   const StagedView v = staged_view(h);
   const int minb = env_int("CGASM_STRIP_MINB_ADV", 4), nbuf = env_int("CGASM_STRIP_NBUF_ADV", DIM + 1);
   const bool pf = env_int("CGASM_STRIP_PF_ADV", 0) != 0;
+  const bool fullv = strip_full_tensor(A.o.have_diffusivity, A.o.diffusivity_shape);
   int st;
-#define LAUNCH(N_, MINB_, PF_)                                                                                  \
+#define LAUNCH(N_, MINB_, FULLV_, PF_)                                                                          \
   do {                                                                                                          \
-    if ((st = strip_smem(staged_advdiff_kernel<DIM, N_, MINB_, PF_>, smem))) return st;                         \
-    staged_advdiff_kernel<DIM, N_, MINB_, PF_><<<P->nblocks, kBR, smem, h->stream>>>(                           \
-        c, v, h->d_rec0, h->d_rec1, A.diffusivity.val, h->d_adv_matrix, h->d_adv_rhs);                           \
+    if ((st = strip_smem(staged_advdiff_kernel<DIM, N_, MINB_, FULLV_, PF_>, smem))) return st;                 \
+    staged_advdiff_kernel<DIM, N_, MINB_, FULLV_, PF_><<<P->nblocks, kBR, smem, h->stream>>>(                   \
+        c, v, h->d_rec0, h->d_rec1, h->d_adv_matrix, h->d_adv_rhs);                                              \
   } while (0)
-#define LAUNCH_PF(N_, MINB_)        \
-  do {                              \
-    if (pf) LAUNCH(N_, MINB_, true); \
-    else LAUNCH(N_, MINB_, false);   \
+#define LAUNCH_V(N_, MINB_, PF_)                    \
+  do {                                              \
+    if (fullv) LAUNCH(N_, MINB_, true, PF_);        \
+    else LAUNCH(N_, MINB_, false, PF_);             \
   } while (0)
   if (nbuf > DIM) {
-    if (minb >= 4) LAUNCH_PF(DIM + 1, 4);
-    else LAUNCH_PF(DIM + 1, 3);
+    if (minb >= 4 && pf) LAUNCH_V(DIM + 1, 4, true);
+    else if (minb >= 4) LAUNCH_V(DIM + 1, 4, false);
+    else LAUNCH_V(DIM + 1, 3, false);
   } else {
-    if (minb >= 5) LAUNCH_PF(DIM, 5);
-    else if (minb == 4) LAUNCH_PF(DIM, 4);
-    else LAUNCH_PF(DIM, 3);
+    if (pf) LAUNCH_V(DIM, 4, true);
+    else LAUNCH_V(DIM, 4, false);
   }
-#undef LAUNCH_PF
+#undef LAUNCH_V
 #undef LAUNCH
   h->launches++;
   CG_CUDA(cudaGetLastError());
