@@ -107,7 +107,7 @@ def _nccl_worker(rank, world, port, q):
     for s, name in slots:
         got = asm.get_field(s, F[name].shape)
         ok = ok and bool((got == F[name]).all())
-    asm.set_scatter(abi.SCATTER_GATHER)
+    asm.set_scatter(abi.SCATTER_STRIP)  # after the halo update: the received nodes' records were repacked
     om, oa = abi.common_momentum_opts(), abi.common_advdiff_opts()
     out_m, out_a = asm.momentum(om), asm.advdiff(oa)
     findrm, colm, _ = asm.get_sparsity()
