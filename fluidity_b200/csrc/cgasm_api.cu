@@ -544,13 +544,12 @@ int cgasm_set_scatter(int id, int variant) {
   if (variant == CGASM_SCATTER_GATHER || variant == CGASM_SCATTER_STRIP) {
     if (!h->have_sparsity) CG_FAIL(CGASM_ESTATE, "gather scatter needs the sparsity first");
     if (!h->gather) {
-      int st = gather_build(h);
+      int st = gather_build_rows(h);
       if (st) return st;
     }
-    if (variant == CGASM_SCATTER_STRIP) {
-      int st = strip_build(h);
-      if (st) return st;
-    }
+    // GATHER needs its pair lists now; STRIP builds them only if an option set falls back to them
+    int st = variant == CGASM_SCATTER_GATHER ? gather_build_pairs(h) : strip_build(h);
+    if (st) return st;
   }
   h->scatter = variant;
   return CGASM_OK;

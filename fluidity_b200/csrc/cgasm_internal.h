@@ -169,7 +169,9 @@ int tiles_momentum(Handle* h, const MomentumArgs& args, bool want_ml, bool want_
 int tiles_advdiff(Handle* h, const AdvDiffArgs& args);
 
 // gather.cu
-int gather_build(Handle* h);
+int gather_build(Handle* h);        // rows + pairs/walk plans (GATHER)
+int gather_build_rows(Handle* h);   // row blocks only
+int gather_build_pairs(Handle* h);  // pair lists + walk plan, on demand
 void gather_free(Handle* h);
 int gather_momentum(Handle* h, const MomentumArgs& args, bool want_ml, bool want_ct);
 int gather_advdiff(Handle* h, const AdvDiffArgs& args);

@@ -239,19 +239,21 @@ static int build_walk_plan(Handle* h, GatherPlan* P, const std::vector<int>& row
   CG_CUDA(cudaMemcpy(P->d_walk_ptr, walk_ptr.data(), sizeof(long long) * walk_ptr.size(), cudaMemcpyHostToDevice));
   CG_CUDA(cudaMalloc(&P->d_walk, sizeof(int2) * walk.size()));
   CG_CUDA(cudaMemcpy(P->d_walk, walk.data(), sizeof(int2) * walk.size(), cudaMemcpyHostToDevice));
-  CG_CUDA(cudaMalloc(&P->d_own_slot, own_slot.size()));
-  CG_CUDA(cudaMemcpy(P->d_own_slot, own_slot.data(), own_slot.size(), cudaMemcpyHostToDevice));
+  if (!P->d_own_slot) {  // the STRIP plan may have made it already
+    CG_CUDA(cudaMalloc(&P->d_own_slot, own_slot.size()));
+    CG_CUDA(cudaMemcpy(P->d_own_slot, own_slot.data(), own_slot.size(), cudaMemcpyHostToDevice));
+  }
   return CGASM_OK;
 }
 
-int gather_build(Handle* h) {
+// Row blocks only: what every row-owner variant needs (rows of each block, block degrees, longest row).
+int gather_build_rows(Handle* h) {
   if (!h->have_X) CG_FAIL(CGASM_ESTATE, "gather scatter orders rows by node coordinates: set coordinates first");
   if (!h->have_sparsity) CG_FAIL(CGASM_ESTATE, "gather scatter needs the sparsity first");
   if ((long long)h->n_elements >= (1ll << 30)) CG_FAIL(CGASM_EUNSUPPORTED, "gather scatter packs element*4+row in 32 bits");
   gather_free(h);
   GatherPlan* P = new GatherPlan();
   h->gather = P;
-  const int n = h->n_nodes;
   std::vector<int> order;
   MortonFrame F;
   morton_order(h, order, F);
@@ -282,6 +284,16 @@ int gather_build(Handle* h) {
   CG_CUDA(cudaMemcpy(P->d_rows, rows.data(), sizeof(int) * rows.size(), cudaMemcpyHostToDevice));
   CG_CUDA(cudaMalloc(&P->d_block_ptr, sizeof(long long) * block_ptr.size()));
   CG_CUDA(cudaMemcpy(P->d_block_ptr, block_ptr.data(), sizeof(long long) * block_ptr.size(), cudaMemcpyHostToDevice));
+  return CGASM_OK;
+}
+
+// Pair lists + walk plan of the GATHER kernels. The STRIP variant builds them only when an option set
+// outside its own kernels is first assembled (they are 13 GB and ~40 % of the plan time at S3).
+int gather_build_pairs(Handle* h) {
+  GatherPlan* P = h->gather;
+  if (!P) CG_FAIL(CGASM_ESTATE, "gather plan missing");
+  if (P->d_pairs) return CGASM_OK;
+  const int n = h->n_nodes;
   CG_CUDA(cudaMalloc(&P->d_pairs, sizeof(uint2) * (size_t)std::max<long long>(P->n_entries, 1)));
   CG_CUDA(cudaMalloc(&P->d_pair_nodes, sizeof(int4) * (size_t)std::max<long long>(P->n_entries, 1)));
   // node->element adjacency goes to the device only for the duration of the plan build
@@ -303,8 +315,14 @@ int gather_build(Handle* h) {
   cudaFree(d_n2e);
   CG_CUDA(e1);
   CG_CUDA(e2);
-  if (!getenv("CGASM_GATHER_NOWALK")) return build_walk_plan(h, P, rows);
+  if (!getenv("CGASM_GATHER_NOWALK")) return build_walk_plan(h, P, P->h_rows);
   return CGASM_OK;
+}
+
+int gather_build(Handle* h) {
+  int st = gather_build_rows(h);
+  if (st) return st;
+  return gather_build_pairs(h);
 }
 
 static int ensure_stage(GatherPlan* P, size_t doubles) {
@@ -1017,6 +1035,10 @@ static int gather_momentum_dim(Handle* h, const MomentumArgs& A, bool want_ml, b
 
 int gather_momentum(Handle* h, const MomentumArgs& A, bool want_ml, bool want_ct) {
   if (!h->gather) CG_FAIL(CGASM_ESTATE, "gather plan missing");
+  if (!(h->scatter == CGASM_SCATTER_STRIP && strip_momentum_ok(h, A, want_ml) && !want_ct)) {
+    int st = gather_build_pairs(h);  // no-op when they exist
+    if (st) return st;
+  }
   return h->dim == 3 ? gather_momentum_dim<3>(h, A, want_ml, want_ct) : gather_momentum_dim<2>(h, A, want_ml, want_ct);
 }
 
@@ -1083,6 +1105,10 @@ static int gather_advdiff_dim(Handle* h, const AdvDiffArgs& A) {
 
 int gather_advdiff(Handle* h, const AdvDiffArgs& A) {
   if (!h->gather) CG_FAIL(CGASM_ESTATE, "gather plan missing");
+  if (!(h->scatter == CGASM_SCATTER_STRIP && strip_advdiff_ok(h, A))) {
+    int st = gather_build_pairs(h);
+    if (st) return st;
+  }
   return h->dim == 3 ? gather_advdiff_dim<3>(h, A) : gather_advdiff_dim<2>(h, A);
 }
 
