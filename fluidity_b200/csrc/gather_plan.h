@@ -27,19 +27,18 @@ struct GatherPlan {
   long long n_walk = 0;
   double walk_entries_per_pair = 0.0;
   // strip plan (strip.cu / strip_plan.h): block-interleaved {node, slot | compute << 8}, block degree
-  // padded to a multiple of strip_mult (= register buffers of the kernel) with no-op entries
+  // padded to a multiple of dim + 1 (= register buffers of the per-entry-fetch kernels) with no-op entries
   std::vector<int> h_rows;           // host copy of d_rows
   long long* d_strip_ptr = nullptr;  // [nblocks+1]
   int2* d_strip = nullptr;
   long long n_strip = 0;
-  int strip_mult = 0;
   double strip_entries_per_pair = 0.0;
   // staged strip plan (strip_staged.cu): the distinct nodes each row block touches (sorted) and the
   // strip entries re-expressed with block-local node indices:
   //   bits 0-15 local node index, bits 16-23 CSR slot, bit 24 compute
-  int* d_blk_ptr = nullptr;          // [nblocks+1] into d_blk_nodes
-  int* d_blk_nodes = nullptr;
-  unsigned* d_strip_local = nullptr; // block-interleaved like d_strip, same d_strip_ptr
+  int* d_blk_nodes = nullptr;        // [nblocks][nl], nl = blk_nodes_max rounded up to 8, -1 padded
+  long long* d_strip_local_ptr = nullptr;  // [nblocks+1] into d_strip_local (degrees padded to a multiple of dim)
+  unsigned* d_strip_local = nullptr; // block-interleaved like d_strip
   unsigned* d_own_local = nullptr;   // [nblocks*kBR] own node: local index | own slot << 16
   int blk_nodes_max = 0;
   double* d_stage = nullptr;       // staging buffer (grown on demand)

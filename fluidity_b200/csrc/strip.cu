@@ -223,9 +223,9 @@ strip_advdiff_kernel(const StripConsts k_, const StripPlanView P, const double4*
 }
 
 // ---- plan ---------------------------------------------------------------------------------------------
-// block degrees are padded to a multiple of every buffer count the kernels are built for (dim: FIFO
-// only, dim + 1: one entry of prefetch), so the unrolled loops need no tail
-static int strip_nbuf(int dim) { return dim * (dim + 1); }
+// Block degrees are padded to a multiple of the kernels' unroll factor so the loops need no tail: dim + 1
+// buffers for the per-entry-fetch kernels (one entry of prefetch), dim for the staged ones (FIFO only).
+static int pad_to(int deg, int mult) { return (deg + mult - 1) / mult * mult; }
 
 int strip_build(Handle* h) {
   GatherPlan* P = h->gather;
@@ -254,22 +254,20 @@ int strip_build(Handle* h) {
       block_deg[b] = deg;
     }
   }
-  std::vector<long long> ptr((size_t)nb + 1, 0);
-  const int mult = strip_nbuf(h->dim);
+  std::vector<long long> ptr((size_t)nb + 1, 0), lptr((size_t)nb + 1, 0);
   for (int b = 0; b < nb; b++) {
-    const int deg = (block_deg[b] + mult - 1) / mult * mult;
-    ptr[b + 1] = ptr[b] + (long long)deg * kBR;
+    ptr[b + 1] = ptr[b] + (long long)pad_to(block_deg[b], h->dim + 1) * kBR;
+    lptr[b + 1] = lptr[b] + (long long)pad_to(block_deg[b], h->dim) * kBR;
   }
-  P->strip_mult = mult;
   P->n_strip = ptr[nb];
   std::vector<int2> ent((size_t)std::max<long long>(P->n_strip, 1));
   // staged flavour: the sorted distinct nodes of each block and the same entries with block-local indices
-  std::vector<unsigned> lent(ent.size());
+  std::vector<unsigned> lent((size_t)std::max<long long>(lptr[nb], 1));
   std::vector<unsigned> own_local(rows.size(), 0);
   std::vector<std::vector<int>> blk_nodes((size_t)nb);
 #pragma omp parallel for schedule(dynamic, 8)
   for (int b = 0; b < nb; b++) {
-    const int deg = (int)((ptr[b + 1] - ptr[b]) / kBR);
+    const int deg = (int)((ptr[b + 1] - ptr[b]) / kBR), ldeg = (int)((lptr[b + 1] - lptr[b]) / kBR);
     std::vector<int>& bn = blk_nodes[b];
     for (int t = 0; t < kBR; t++) {
       const size_t q = (size_t)b * kBR + t;
@@ -292,29 +290,28 @@ int strip_build(Handle* h) {
       own_local[q] = ol;
       for (int k = 0; k < deg; k++) {
         int2 v = make_int2(r >= 0 ? r : 0, own);  // padding: re-push the own node, nothing computed
-        unsigned lv = ol;
-        if (k < (int)rp.size()) {
-          v = make_int2(rp[k].node, rp[k].meta);
-          lv = local_of(rp[k].node) | (unsigned)(rp[k].meta & 0xff) << 16 | ((rp[k].meta & kStripCompute) ? 1u << 24 : 0u);
-        }
+        if (k < (int)rp.size()) v = make_int2(rp[k].node, rp[k].meta);
         ent[(size_t)(ptr[b] + (long long)k * kBR + t)] = v;
-        lent[(size_t)(ptr[b] + (long long)k * kBR + t)] = lv;
+      }
+      for (int k = 0; k < ldeg; k++) {
+        unsigned lv = ol;
+        if (k < (int)rp.size())
+          lv = local_of(rp[k].node) | (unsigned)(rp[k].meta & 0xff) << 16 | ((rp[k].meta & kStripCompute) ? 1u << 24 : 0u);
+        lent[(size_t)(lptr[b] + (long long)k * kBR + t)] = lv;
       }
     }
   }
-  std::vector<int> blk_ptr((size_t)nb + 1, 0);
   P->blk_nodes_max = 0;
-  for (int b = 0; b < nb; b++) {
-    blk_ptr[b + 1] = blk_ptr[b] + (int)blk_nodes[b].size();
-    P->blk_nodes_max = std::max(P->blk_nodes_max, (int)blk_nodes[b].size());
-  }
-  std::vector<int> blk_flat((size_t)std::max(blk_ptr[nb], 1));
-  for (int b = 0; b < nb; b++) std::copy(blk_nodes[b].begin(), blk_nodes[b].end(), blk_flat.begin() + blk_ptr[b]);
+  for (int b = 0; b < nb; b++) P->blk_nodes_max = std::max(P->blk_nodes_max, (int)blk_nodes[b].size());
+  // fixed stride (= the shared-memory chunk stride), -1 padded: a block finds its list without a pointer load
+  const int nl = (P->blk_nodes_max + 7) & ~7;
   if (P->blk_nodes_max < 65536) {
-    CG_CUDA(cudaMalloc(&P->d_blk_ptr, sizeof(int) * blk_ptr.size()));
-    CG_CUDA(cudaMemcpy(P->d_blk_ptr, blk_ptr.data(), sizeof(int) * blk_ptr.size(), cudaMemcpyHostToDevice));
+    std::vector<int> blk_flat((size_t)std::max(nb, 1) * nl, -1);
+    for (int b = 0; b < nb; b++) std::copy(blk_nodes[b].begin(), blk_nodes[b].end(), blk_flat.begin() + (size_t)b * nl);
     CG_CUDA(cudaMalloc(&P->d_blk_nodes, sizeof(int) * blk_flat.size()));
     CG_CUDA(cudaMemcpy(P->d_blk_nodes, blk_flat.data(), sizeof(int) * blk_flat.size(), cudaMemcpyHostToDevice));
+    CG_CUDA(cudaMalloc(&P->d_strip_local_ptr, sizeof(long long) * lptr.size()));
+    CG_CUDA(cudaMemcpy(P->d_strip_local_ptr, lptr.data(), sizeof(long long) * lptr.size(), cudaMemcpyHostToDevice));
     CG_CUDA(cudaMalloc(&P->d_strip_local, sizeof(unsigned) * lent.size()));
     CG_CUDA(cudaMemcpy(P->d_strip_local, lent.data(), sizeof(unsigned) * lent.size(), cudaMemcpyHostToDevice));
     CG_CUDA(cudaMalloc(&P->d_own_local, sizeof(unsigned) * own_local.size()));
@@ -345,13 +342,14 @@ int strip_build(Handle* h) {
 void strip_free(GatherPlan* P) {
   if (P->d_strip_ptr) cudaFree(P->d_strip_ptr);
   if (P->d_strip) cudaFree(P->d_strip);
-  if (P->d_blk_ptr) cudaFree(P->d_blk_ptr);
+  if (P->d_strip_local_ptr) cudaFree(P->d_strip_local_ptr);
   if (P->d_blk_nodes) cudaFree(P->d_blk_nodes);
   if (P->d_strip_local) cudaFree(P->d_strip_local);
   if (P->d_own_local) cudaFree(P->d_own_local);
   P->d_strip_ptr = nullptr;
   P->d_strip = nullptr;
-  P->d_blk_ptr = P->d_blk_nodes = nullptr;
+  P->d_strip_local_ptr = nullptr;
+  P->d_blk_nodes = nullptr;
   P->d_strip_local = P->d_own_local = nullptr;
 }
 

@@ -8,7 +8,8 @@
 // layer), each of them ~14 x 1.9 times. So:
 //   phase 0  the block copies the records of its distinct nodes (sorted list in the plan) into
 //            shared memory with cp.async, coalesced, bypassing L1 and registers; one barrier;
-//   loop     entries carry block-LOCAL node indices (32-bit entries instead of 64-bit): the FIFO
+//   loop     N = dim register buffers (the FIFO itself: shared-memory latency needs no prefetch buffer);
+//            entries carry block-LOCAL node indices (32-bit entries instead of 64-bit): the FIFO
 //            buffers are filled by LDS.128 from a structure-of-16-byte-chunks layout (neighbouring
 //            rows read neighbouring indices: conflict-free), nothing in the loop waits on DRAM
 //            except the plan stream, which is requested two steps ahead;
@@ -28,8 +29,7 @@ struct StagedView {
   const long long* __restrict__ ptr;      // strip entries of the block (block-interleaved)
   const unsigned* __restrict__ ent;       // local index | slot << 16 | compute << 24
   const unsigned* __restrict__ own_local; // own node: local index | own slot << 16
-  const int* __restrict__ blk_ptr;
-  const int* __restrict__ blk_nodes;
+  const int* __restrict__ blk_nodes;      // [nblocks][nl], -1 padded
   const int* __restrict__ findrm;
   int maxlen, lpr_shift;
   int nl;         // chunk stride (nodes) of the staged records
@@ -71,13 +71,13 @@ template <int DIM, bool OLDU>
 __device__ __forceinline__ void stage_nodes(const StagedView& P, int b, int t, double2* __restrict__ nodes,
                                             const double4* __restrict__ r0, const double4* __restrict__ r1,
                                             const double4* __restrict__ rO) {
-  const int n0 = P.blk_ptr[b], nloc = P.blk_ptr[b + 1] - n0;
+  const int* ids = P.blk_nodes + (size_t)b * P.nl;  // fixed stride: no pointer load in front of the id loads
   double* oz = reinterpret_cast<double*>(nodes + 5 * P.nl);
   constexpr int U = 4;  // node ids of U rounds are requested together, then their copies are issued
-  for (int i0 = t; i0 < nloc; i0 += U * kBR) {
+  for (int i0 = t; i0 < P.nl; i0 += U * kBR) {
     int node[U];
 #pragma unroll
-    for (int u = 0; u < U; u++) node[u] = i0 + u * kBR < nloc ? __ldg(P.blk_nodes + n0 + i0 + u * kBR) : -1;
+    for (int u = 0; u < U; u++) node[u] = i0 + u * kBR < P.nl ? __ldg(ids + i0 + u * kBR) : -1;
 #pragma unroll
     for (int u = 0; u < U; u++) {
       if (node[u] < 0) continue;
@@ -403,10 +403,9 @@ static StagedView staged_view(const Handle* h) {
   const GatherPlan* P = h->gather;
   StagedView v;
   v.rows = P->d_rows;
-  v.ptr = P->d_strip_ptr;
+  v.ptr = P->d_strip_local_ptr;
   v.ent = P->d_strip_local;
   v.own_local = P->d_own_local;
-  v.blk_ptr = P->d_blk_ptr;
   v.blk_nodes = P->d_blk_nodes;
   v.findrm = h->d_findrm;
   v.maxlen = P->maxlen;
@@ -430,7 +429,7 @@ static int staged_momentum_dim(Handle* h, const MomentumArgs& A) {
   const StripConsts c = consts_momentum(h, A);
   const StagedView v = staged_view(h);
   // tuning switches (defaults = best measured on S3, profiles/r1_kernel_history.md)
-  const int minb = env_int("CGASM_STRIP_MINB", 4), nbuf = env_int("CGASM_STRIP_NBUF", DIM);
+  const int minb = env_int("CGASM_STRIP_MINB", 4);
   const bool pf = env_int("CGASM_STRIP_PF", 1) != 0;
   const bool fullv = strip_full_tensor(A.o.have_viscosity, A.o.viscosity_shape);
   double* ml = A.o.assemble_inverse_masslump ? h->d_masslump : nullptr;
@@ -446,10 +445,7 @@ static int staged_momentum_dim(Handle* h, const MomentumArgs& A) {
     if (fullv) LAUNCH(N_, MINB_, true, PF_);        \
     else LAUNCH(N_, MINB_, false, PF_);             \
   } while (0)
-  if (nbuf > DIM) {
-    if (pf) LAUNCH_V(DIM + 1, 3, true);
-    else LAUNCH_V(DIM + 1, 3, false);
-  } else if (minb >= 4) {
+  if (minb >= 4) {
     if (pf) LAUNCH_V(DIM, 4, true);
     else LAUNCH_V(DIM, 4, false);
   } else {
@@ -473,8 +469,8 @@ static int staged_advdiff_dim(Handle* h, const AdvDiffArgs& A) {
   const size_t smem = staged_smem(P, false);
   const StripConsts c = consts_advdiff(h, A);
   const StagedView v = staged_view(h);
-  const int minb = env_int("CGASM_STRIP_MINB_ADV", 4), nbuf = env_int("CGASM_STRIP_NBUF_ADV", DIM + 1);
-  const bool pf = env_int("CGASM_STRIP_PF_ADV", 0) != 0;
+  const int minb = env_int("CGASM_STRIP_MINB_ADV", 4);
+  const bool pf = env_int("CGASM_STRIP_PF_ADV", 1) != 0;
   const bool fullv = strip_full_tensor(A.o.have_diffusivity, A.o.diffusivity_shape);
   int st;
 #define LAUNCH(N_, MINB_, FULLV_, PF_)                                                                          \
@@ -488,13 +484,12 @@ static int staged_advdiff_dim(Handle* h, const AdvDiffArgs& A) {
     if (fullv) LAUNCH(N_, MINB_, true, PF_);        \
     else LAUNCH(N_, MINB_, false, PF_);             \
   } while (0)
-  if (nbuf > DIM) {
-    if (minb >= 4 && pf) LAUNCH_V(DIM + 1, 4, true);
-    else if (minb >= 4) LAUNCH_V(DIM + 1, 4, false);
-    else LAUNCH_V(DIM + 1, 3, false);
-  } else {
+  if (minb >= 4) {
     if (pf) LAUNCH_V(DIM, 4, true);
     else LAUNCH_V(DIM, 4, false);
+  } else {
+    if (pf) LAUNCH_V(DIM, 3, true);
+    else LAUNCH_V(DIM, 3, false);
   }
 #undef LAUNCH_V
 #undef LAUNCH

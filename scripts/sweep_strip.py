@@ -19,18 +19,10 @@ sys.path.insert(0, ROOT)
 
 DEFAULT = [
     "default=",
-    "m_n3_mb4_pf1=CGASM_STRIP_NBUF=3,CGASM_STRIP_MINB=4,CGASM_STRIP_PF=1",
-    "m_n3_mb4_pf0=CGASM_STRIP_NBUF=3,CGASM_STRIP_MINB=4,CGASM_STRIP_PF=0",
-    "m_n3_mb3_pf1=CGASM_STRIP_NBUF=3,CGASM_STRIP_MINB=3,CGASM_STRIP_PF=1",
-    "m_n3_mb4_pf1_on=CGASM_STRIP_NBUF=3,CGASM_STRIP_MINB=4,CGASM_STRIP_PF=1,CGASM_STRIP_ONPF=1",
-    "m_n4_mb3_pf1=CGASM_STRIP_NBUF=4,CGASM_STRIP_MINB=3,CGASM_STRIP_PF=1",
-    "m_n4_mb3_pf0=CGASM_STRIP_NBUF=4,CGASM_STRIP_MINB=3,CGASM_STRIP_PF=0",
-    "a_n3_mb4_pf1=CGASM_STRIP_NBUF_ADV=3,CGASM_STRIP_MINB_ADV=4,CGASM_STRIP_PF_ADV=1",
-    "a_n3_mb4_pf0=CGASM_STRIP_NBUF_ADV=3,CGASM_STRIP_MINB_ADV=4,CGASM_STRIP_PF_ADV=0",
-    "a_n3_mb5_pf1=CGASM_STRIP_NBUF_ADV=3,CGASM_STRIP_MINB_ADV=5,CGASM_STRIP_PF_ADV=1",
-    "a_n4_mb4_pf1=CGASM_STRIP_NBUF_ADV=4,CGASM_STRIP_MINB_ADV=4,CGASM_STRIP_PF_ADV=1",
-    "a_n4_mb4_pf0=CGASM_STRIP_NBUF_ADV=4,CGASM_STRIP_MINB_ADV=4,CGASM_STRIP_PF_ADV=0",
-    "a_n4_mb3_pf0=CGASM_STRIP_NBUF_ADV=4,CGASM_STRIP_MINB_ADV=3,CGASM_STRIP_PF_ADV=0",
+    "m_mb4_pf0=CGASM_STRIP_MINB=4,CGASM_STRIP_PF=0",
+    "m_mb3_pf1=CGASM_STRIP_MINB=3,CGASM_STRIP_PF=1",
+    "a_mb4_pf0=CGASM_STRIP_MINB_ADV=4,CGASM_STRIP_PF_ADV=0",
+    "a_mb3_pf1=CGASM_STRIP_MINB_ADV=3,CGASM_STRIP_PF_ADV=1",
     "global=CGASM_STRIP_GLOBAL=1",
 ]
 
