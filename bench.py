@@ -450,6 +450,10 @@ def run_graft(args):
 
 def main():
     args = parse()
+    # stdout carries exactly one JSON line: NCCL's version banner (NCCL_DEBUG=VERSION, printed to stdout by
+    # the first communicator) would be a second one
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
     if args.impl == "reference":
         return run_reference(args)
     return run_graft(args)
