@@ -179,6 +179,10 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    # torchrun exports OMP_NUM_THREADS=1 to every rank; the reference arm runs on rank 0 alone with all the
+    # host threads it can use (set before the OpenMP runtime of the oracle library starts)
+    if "WORLD_SIZE" in os.environ and os.environ.get("OMP_NUM_THREADS", "1") == "1":
+        os.environ["OMP_NUM_THREADS"] = str(len(os.sched_getaffinity(0)))
     cells = args.cpu_cells
     rate, threads, ms, ne = cpu_assembly_rate(cells, max(1, args.steps), max(0, min(args.warmup, 1)))
     sample = "%d^3 x 6 = %d Kuhn tets per step (bounded sample of S3), OpenMP over the reference greedy colouring" % (cells, ne)
@@ -192,7 +196,7 @@ def run_reference(args):
         "gpu_launches": 0,
         "note": "reference is Fortran+PETSc and cannot be built in this image; this is the C restatement (oracle/) of its element loops",
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -442,18 +446,34 @@ def run_graft(args):
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         "halo_update_ms_rank0": halo_ms, "halo_nodes_sent_rank0": n_sent,
     }
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
 
 
+_JSON_FD = None
+
+
+def emit(line):
+    """The one JSON line of the contract, on the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    global _JSON_FD
     args = parse()
-    # stdout carries exactly one JSON line: NCCL's version banner (NCCL_DEBUG=VERSION, printed to stdout by
-    # the first communicator) would be a second one
-    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"
+    # stdout carries exactly one JSON line. Native libraries write there too (NCCL prints its version banner
+    # when the first communicator is made), so fd 1 points at stderr for the duration of the run and the
+    # JSON line goes to a duplicate of the original stdout.
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference(args)
     return run_graft(args)
