@@ -267,3 +267,36 @@ extern "C" int cgasm_strip_plan_host(int loc, int n_nodes, int n_elements, const
   *needed = total;
   return CGASM_OK;
 }
+
+// ---- diagnostics ABI: the row blocks of the row-owner variants, built on the host (no GPU needed) -----
+extern "C" int cgasm_row_blocks_host(int dim, int n_nodes, int n_elements, const int* ndglno, const double* X,
+                                     int block_rows, int* rows, int capacity_blocks, int* nblocks, double* lattice_scale) {
+  using namespace cgasm;
+  const int loc = dim + 1;
+  if ((dim != 2 && dim != 3) || n_nodes <= 0 || n_elements <= 0 || !ndglno || !X || !nblocks || block_rows < 1)
+    CG_FAIL(CGASM_EARG, "cgasm_row_blocks_host: bad argument");
+  Handle h;
+  h.dim = dim;
+  h.loc = loc;
+  h.n_nodes = n_nodes;
+  h.n_elements = n_elements;
+  h.h_nd0.assign((size_t)4 * n_elements, -1);
+  for (int e = 0; e < n_elements; e++)
+    for (int i = 0; i < loc; i++) {
+      const int v = ndglno[(size_t)loc * e + i] - 1;
+      if (v < 0 || v >= n_nodes) CG_FAIL(CGASM_EARG, "cgasm_row_blocks_host: node id out of range");
+      h.h_nd0[(size_t)4 * e + i] = v;
+    }
+  h.h_X.assign(X, X + (size_t)dim * n_nodes);
+  build_node_to_element(n_nodes, n_elements, loc, h.h_nd0.data(), h.n2e_ptr, h.n2e);
+  build_sparsity(n_nodes, n_elements, loc, h.h_nd0.data(), h.n2e_ptr, h.n2e, h.h_findrm, h.h_colm);
+  std::vector<int> order, r;
+  MortonFrame F;
+  morton_order(&h, order, F);
+  *nblocks = form_row_blocks(&h, order, F, block_rows, r);
+  if (lattice_scale)
+    for (int a = 0; a < dim; a++) lattice_scale[a] = F.scale[a];
+  if (rows && *nblocks <= capacity_blocks)
+    for (size_t q = 0; q < r.size(); q++) rows[q] = r[q] >= 0 ? r[q] + 1 : 0;
+  return CGASM_OK;
+}

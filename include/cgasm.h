@@ -266,6 +266,15 @@ int cgasm_last_kernel_ms(int id, float* ms);
 int cgasm_strip_plan_host(int loc, int n_nodes, int n_elements, const int* ndglno,
                           long long* row_ptr, int* entries, long long capacity, long long* needed);
 
+/* Diagnostics (host only, no GPU): the row blocks the GATHER / STRIP variants work on. Nodes are quantised
+ * to a lattice as fine as the mesh (lattice_scale(dim) = cells per unit length, out, may be NULL), ordered
+ * along the Morton curve and cut into blocks of at most block_rows rows (bricks of the lattice where the
+ * mesh is structured). rows(nblocks*block_rows): 1-based node of every row slot, 0 = padding; written only
+ * if *nblocks <= capacity_blocks. X(dim, n_nodes) and ndglno as in cgasm_create / cgasm_set_coordinates. */
+int cgasm_row_blocks_host(int dim, int n_nodes, int n_elements, const int* ndglno, const double* X,
+                          int block_rows, int* rows, int capacity_blocks, int* nblocks,
+                          double* lattice_scale);
+
 /* ---- halo update (femtools/Halos_Communications.F90:320-412,497-567) -------------------
  * nprocs neighbours; sends/recvs are the concatenated 1-based node lists of
  * halo%sends(p) / halo%receives(p), nsend/nrecv their lengths per process p = 0..nprocs-1
