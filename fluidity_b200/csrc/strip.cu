@@ -1,4 +1,7 @@
 // strip.cu -- CGASM_SCATTER_STRIP: row-owner assembly with a strip-ordered element stream.
+// This file: the plan (strip_build), the dispatch, and the kernels that fetch each node's records from
+// global memory per entry. They are the FALLBACK: the default kernels stage a block's node records in
+// shared memory (strip_staged.cu) and run whenever that staging fits (strip_staged_ok).
 //
 // One thread owns one CSR row (node r) and recomputes ITS row of every incident element in closed
 // form (element_math.cuh row kernels: P1 simplices + node-symmetric degree-3 rule,
@@ -10,13 +13,14 @@
 //    one node into a FIFO of dim nodes and the oldest node drops out, so all threads replace the
 //    same register set at the same step -- the node loop is unrolled over N rotating register
 //    buffers (N = dim + prefetch distance) with no selects and no divergence in the load path.
-//  * The records of entry j+PD are requested while entry j is being computed (register prefetch).
+//  * The records of entry j+1 are requested while entry j is being computed (register prefetch; the
+//    staged kernels read shared memory instead and need no prefetch buffer: N = dim there).
 //  * A contribution to column v accumulates in a REGISTER for as long as v sits in the FIFO and is
 //    added to the row's shared-memory slot once, when v is evicted (1.4 RMW per pair instead of 4).
 //  * rhs -= (A + K) oldu (Momentum_CG.F90:1712,2346) is linear in the assembled row, so it is one
-//    sparse dot product per row after the loop (colm + the {oldu, buoyancy} records) instead of
-//    dim*loc FMAs and one more 32-byte record per pair. Likewise the constant gravity direction
-//    (:1786-1789) and dt*theta (:1484-1486) are applied once per row.
+//    sparse dot product per row after the loop (colm + the {oldu, buoyancy} records; the staged kernels
+//    fold it into the eviction instead) rather than dim*loc FMAs and one more 32-byte record per pair.
+//    Likewise the constant gravity direction (:1786-1789) and dt*theta (:1484-1486) are applied once per row.
 //  * Momentum reads two records per node, {X, buoyancy} and {nu, density}.
 //
 // Entries per (row, element) pair: 1.375 on Kuhn meshes (33 pushes for the 24 elements of an

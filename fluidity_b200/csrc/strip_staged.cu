@@ -4,15 +4,15 @@
 // own 2 x 32-byte records per entry, so a warp-level load waits for its slowest lane (L1 hit rate
 // 68 %, L2 39 %: usually a DRAM round trip, more than one loop body of prefetch distance) and the
 // L1 data pipe runs at 57 % moving 1 KB per LDG.256 through 64-byte wavefronts.
-// A block of 128 Morton-adjacent rows touches only ~360 distinct nodes (its own 8x4x4 patch plus one
-// layer), each of them ~14 x 1.9 times. So:
+// A block of 128 Morton-adjacent rows touches only ~320-370 distinct nodes (its own 8x4x4 brick plus one
+// layer), each of them ~14 x 2.4 times. So:
 //   phase 0  the block copies the records of its distinct nodes (sorted list in the plan) into
 //            shared memory with cp.async, coalesced, bypassing L1 and registers; one barrier;
 //   loop     N = dim register buffers (the FIFO itself: shared-memory latency needs no prefetch buffer);
 //            entries carry block-LOCAL node indices (32-bit entries instead of 64-bit): the FIFO
 //            buffers are filled by LDS.128 from a structure-of-16-byte-chunks layout (neighbouring
 //            rows read neighbouring indices: conflict-free), nothing in the loop waits on DRAM
-//            except the plan stream, which is requested two steps ahead;
+//            except the plan stream (three entries ahead in registers, its lines pulled into L2 ten ahead);
 //   flush    when a node leaves the FIFO its accumulated entry goes to the row's slot AND into
 //            rhs -= entry * oldu(node) (Momentum_CG.F90:1712,2346 is linear in the entries), with
 //            oldu read from the staged records: no epilogue pass over colm;
