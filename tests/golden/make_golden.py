@@ -7,6 +7,7 @@ Inputs (reference data files, not source code):
     tests/data/square-cavity-2d.msh                            the test_colouring mesh
     tests/data/2d_square.msh
     tests/meshconv_test/src/prectangle_{0,1}.halo             a real 2-rank L1+L2 halo pair
+    tests/meshconv_test/src/prectangle_{0,1}.msh              its two local meshes (binary gmsh)
 Only node coordinates and the volume elements (gmsh type 4 = tet, type 2 = triangle on 2-D
 meshes) are kept, as float64 / int32 arrays.
 """
@@ -69,6 +70,18 @@ def main():
     with open(os.path.join(OUT, "prectangle_halos.json"), "w") as f:
         json.dump(halos, f, indent=1)
     print("halos", {k: {l: v["n_private_nodes"] for l, v in h["levels"].items()} for k, h in halos.items()})
+    # the matching decomposed meshes (binary gmsh 2.1 with 4 face tags) and the serial mesh they
+    # were cut from, through the package's own reader (fluidity_b200/formats.py; its ASCII path
+    # is cross-checked against read_gmsh_ascii above by tests/test_formats.py)
+    sys.path.insert(0, os.path.dirname(os.path.dirname(OUT)))
+    from fluidity_b200 import formats
+    src = os.path.join(REF, "tests", "meshconv_test", "src")
+    for r in (0, 1):
+        g = formats.read_gmsh(os.path.join(src, "prectangle_%d.msh" % r))
+        np.savez_compressed(os.path.join(OUT, "prectangle_%d.npz" % r), X=g.mesh.X, ndglno=g.mesh.ndglno, dim=g.mesh.dim,
+                            sndgln=g.sndgln, boundary_ids=g.boundary_ids, element_owner=g.element_owner,
+                            region_ids=g.region_ids)
+        print("prectangle_%d" % r, g.mesh.X.shape, g.mesh.ndglno.shape, g.sndgln.shape)
 
 
 if __name__ == "__main__":

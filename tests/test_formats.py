@@ -1,0 +1,340 @@
+"""On-disk formats either side of the path: gmsh 2.x,
+.halo XML, `_<rank>` decompositions, PETSc binary dumps. CPU only.
+
+Pins: (1) the reference's own fixture files, read where they lie when /root/reference exists
+(this container) and compared with the independent line parser of tests/golden/make_golden.py;
+(2) the committed conversions of the reference's real 2-rank decomposition `prectangle`, which
+must drop into the multi-rank path unchanged: halo lists pair up node for node and the owned
+rows assembled per rank equal the rows of the re-joined global mesh."""
+import json
+import os
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, load_golden_mesh, rel_err
+from fluidity_b200 import formats as fmt, partition as part, synthetic as syn, _abi as abi
+
+REF = os.environ.get("FLUIDITY_REFERENCE", "/root/reference")
+needs_reference = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "tests", "data")),
+                                     reason="reference fixtures are only present in the build container")
+
+
+# ---- gmsh ------------------------------------------------------------------------------------------------
+@needs_reference
+@pytest.mark.parametrize("name", ["cube.1", "cube-parallel", "square-cavity-2d", "2d_square"])
+def test_gmsh_reader_against_reference_fixtures(name):
+    g = fmt.read_gmsh(os.path.join(REF, "tests", "data", name + ".msh"))
+    ref = load_golden_mesh(name)  # converted by make_golden.read_gmsh_ascii
+    assert g.mesh.dim == ref.dim and not g.binary
+    assert (g.mesh.ndglno == ref.ndglno).all()
+    assert (g.mesh.X == ref.X).all()
+    sloc = g.mesh.dim
+    assert g.sndgln.shape[1] == sloc
+    if len(g.sndgln):
+        # every face is a face of some element
+        faces = {tuple(sorted(f)) for e in g.mesh.ndglno for f in
+                 [tuple(np.delete(e, k)) for k in range(g.mesh.loc)]}
+        assert all(tuple(sorted(f)) in faces for f in g.sndgln)
+
+
+@needs_reference
+def test_gmsh_binary_reader_reads_the_reference_decomposition():
+    src = os.path.join(REF, "tests", "meshconv_test", "src")
+    for r in (0, 1):
+        g = fmt.read_gmsh(os.path.join(src, "prectangle_%d.msh" % r))
+        z = np.load(os.path.join(GOLDEN, "prectangle_%d.npz" % r))
+        assert g.binary and g.version == (2, 1)
+        assert (g.mesh.ndglno == z["ndglno"]).all() and (g.mesh.X == z["X"]).all()
+        assert g.element_owner is not None  # 4 face tags: surface id, 0, 0, owning element
+        own = g.mesh.ndglno[g.element_owner - 1]
+        assert all(set(f) <= set(e) for f, e in zip(g.sndgln, own))
+        h = fmt.read_halo(os.path.join(src, "prectangle_%d.halo" % r))
+        with open(os.path.join(GOLDEN, "prectangle_halos.json")) as f:
+            ref = json.load(f)[str(r)]
+        for lv, hl in h.levels.items():
+            assert hl.n_private_nodes == ref["levels"][str(lv)]["n_private_nodes"]
+            for p in range(h.nprocs):
+                assert hl.sends[p].tolist() == ref["levels"][str(lv)]["sends"][str(p)]
+                assert hl.receives[p].tolist() == ref["levels"][str(lv)]["receives"][str(p)]
+
+
+@needs_reference
+def test_serial_dummy_halo_with_comment_and_legacy_tag():
+    # tests/data/cube-parallel_0.halo: a comment in front of the declaration, `tag=` instead of `level=`
+    h = fmt.read_halo(os.path.join(REF, "tests", "data", "cube-parallel_0.halo"))
+    assert (h.process, h.nprocs) == (0, 1) and sorted(h.levels) == [1, 2]
+    assert h.levels[1].n_private_nodes == 665
+    assert h.levels[2].receives[0].min() == 666  # "665 private nodes, receives 666..."
+
+
+@pytest.mark.parametrize("binary", [False, True])
+@pytest.mark.parametrize("name", ["cube.1", "square-cavity-2d"])
+def test_gmsh_round_trip(tmp_path, name, binary):
+    m = load_golden_mesh(name)
+    rng = np.random.default_rng(4)
+    sloc = m.dim
+    faces = np.array([np.delete(m.ndglno[e], e % m.loc) for e in range(min(7, m.n_elements))], dtype=np.int32)
+    g = fmt.GmshMesh(mesh=m, sndgln=faces, boundary_ids=rng.integers(1, 9, len(faces)).astype(np.int32),
+                     element_owner=np.arange(1, len(faces) + 1, dtype=np.int32),
+                     region_ids=rng.integers(1, 4, m.n_elements).astype(np.int32))
+    p = str(tmp_path / "m.msh")
+    fmt.write_gmsh(p, g, binary=binary)
+    b = fmt.read_gmsh(p)
+    assert b.binary == binary and b.mesh.dim == m.dim and b.sndgln.shape == (len(faces), sloc)
+    assert (b.mesh.ndglno == m.ndglno).all() and (b.mesh.X == m.X).all()  # exact, also in ASCII
+    assert (b.sndgln == faces).all() and (b.boundary_ids == g.boundary_ids).all()
+    assert (b.element_owner == g.element_owner).all() and (b.region_ids == g.region_ids).all()
+
+
+def test_gmsh_reader_refuses_what_the_reference_refuses(tmp_path):
+    def write(text):
+        p = tmp_path / "bad.msh"
+        p.write_text(text)
+        return str(p)
+    with pytest.raises(fmt.FormatError, match="version"):
+        fmt.read_gmsh(write("$MeshFormat\n3.0 0 8\n$EndMeshFormat\n"))
+    with pytest.raises(fmt.FormatError, match="data size"):
+        fmt.read_gmsh(write("$MeshFormat\n2.2 0 4\n$EndMeshFormat\n"))
+    with pytest.raises(fmt.FormatError, match="nodes field < 2"):
+        fmt.read_gmsh(write("$MeshFormat\n2.2 0 8\n$EndMeshFormat\n$Nodes\n1\n1 0 0 0\n$EndNodes\n"))
+    body = "$MeshFormat\n2.2 0 8\n$EndMeshFormat\n$Nodes\n3\n1 0 0 0\n2 1 0 0\n3 0 1 0\n$EndNodes\n$Elements\n"
+    with pytest.raises(fmt.FormatError, match="Unsupported element type"):
+        fmt.read_gmsh(write(body + "1\n1 9 2 0 0 1 2 3 1 2 3\n$EndElements\n"))
+    with pytest.raises(fmt.FormatError, match="Inconsistent number of element tags"):
+        fmt.read_gmsh(write(body + "2\n1 2 2 0 0 1 2 3\n2 2 3 0 0 0 1 2 3\n$EndElements\n"))
+    with pytest.raises(fmt.FormatError, match=r"\$EndElements"):
+        fmt.read_gmsh(write(body + "1\n1 2 2 0 0 1 2 3\n"))
+    g = fmt.read_gmsh(write(body + "1\n1 2 2 5 0 1 2 3\n$EndElements\n"))
+    assert g.mesh.n_elements == 1 and g.region_ids.tolist() == [5] and g.boundary_ids is None
+
+
+# ---- .halo -----------------------------------------------------------------------------------------------
+def _golden_halos(r):
+    with open(os.path.join(GOLDEN, "prectangle_halos.json")) as f:
+        H = json.load(f)[str(r)]
+    out = fmt.Halos(process=H["process"], nprocs=H["nprocs"])
+    for lv, e in H["levels"].items():
+        out.levels[int(lv)] = fmt.HaloLevel(e["n_private_nodes"],
+                                            [np.array(e["sends"][str(p)], dtype=np.int32) for p in range(H["nprocs"])],
+                                            [np.array(e["receives"][str(p)], dtype=np.int32) for p in range(H["nprocs"])])
+    return out
+
+
+def test_halo_round_trip_and_validity_rules(tmp_path):
+    h = _golden_halos(0)
+    p = str(tmp_path / "x_0.halo")
+    fmt.write_halo(p, h)
+    b = fmt.read_halo(p)
+    assert (b.process, b.nprocs) == (0, 2) and sorted(b.levels) == [1, 2]
+    for lv in (1, 2):
+        assert b.levels[lv].n_private_nodes == h.levels[lv].n_private_nodes
+        for q in range(2):
+            assert (b.levels[lv].sends[q] == h.levels[lv].sends[q]).all()
+            assert (b.levels[lv].receives[q] == h.levels[lv].receives[q]).all()
+        assert fmt.trailing_receives_consistent(b.levels[lv])
+    text = open(p).read()
+    if os.path.isdir(os.path.join(REF, "tests", "meshconv_test", "src")):
+        # byte-identical with the file WriteHalos produced (TinyXML layout: 4-blank indent, "id " lists)
+        assert text == open(os.path.join(REF, "tests", "meshconv_test", "src", "prectangle_0.halo")).read()
+    for bad in (text.replace('process="0" nprocs="2"', 'process="2" nprocs="2"'),       # process >= nprocs
+                text.replace('n_private_nodes="16"', 'n_private_nodes="-1"', 1),        # negative
+                text.replace('<halo_data process="1">', '<halo_data process="0">', 1),  # repeated process
+                text.replace('<halo_data process="1">', '<halo_data process="5">', 1),  # out of range
+                text.replace(' level="1"', "", 1),                                       # neither level nor tag
+                text[:200]):                                                             # truncated XML
+        q = tmp_path / "bad_0.halo"
+        q.write_text(bad)
+        with pytest.raises(fmt.FormatError):
+            fmt.read_halo(str(q))
+    with pytest.raises(fmt.FormatError):
+        fmt.read_halo(str(tmp_path / "absent_0.halo"))
+
+
+# ---- decompositions --------------------------------------------------------------------------------------
+def _owned_rows_match(orc, parts, gmesh, l2g):
+    """Every rank assembles all its local elements; rows of owned nodes == global rows."""
+    dim = gmesh.dim
+    fs = syn.standard_fields(gmesh)
+    findrm, colm, _ = orc.make_sparsity(gmesh)
+    om, oa = abi.common_momentum_opts(), abi.common_advdiff_opts()
+    gm = orc.assemble_momentum(gmesh, fs, om, findrm, colm)
+    ga = orc.assemble_advdiff(gmesh, fs, oa, findrm, colm)
+    slots = [abi.F_NU, abi.F_OLDU, abi.F_DENSITY, abi.F_BUOYANCY, abi.F_T]
+    local_fs = []
+    for lp, g in zip(parts, l2g):
+        lf = syn.standard_fields(lp.mesh)
+        for s in slots:
+            v = fs.get(s)[0][g].copy()
+            v[lp.n_owned:] = 0.0  # stale halo values, to be filled by the exchange
+            lf.set(s, v)
+        local_fs.append(lf)
+    for s in slots:
+        arrays = [lf.get(s)[0] for lf in local_fs]
+        block = arrays[0].shape[1] if arrays[0].ndim > 1 else 1
+        for p, lp in enumerate(parts):
+            for q, lq in enumerate(parts):
+                if p != q and len(lp.sends[q]):
+                    orc.halo_copy(block, arrays[p], lp.sends[q], arrays[q], lq.recvs[p])
+    for lp, lf, g in zip(parts, local_fs, l2g):
+        for s in slots:
+            assert (lf.get(s)[0] == fs.get(s)[0][g]).all()  # the halo lists reach every non-owned node
+        lfind, lcolm, _ = orc.make_sparsity(lp.mesh)
+        lm = orc.assemble_momentum(lp.mesh, lf, om, lfind, lcolm)
+        la = orc.assemble_advdiff(lp.mesh, lf, oa, lfind, lcolm)
+        for i in range(lp.n_owned):
+            lrow = slice(lfind[i] - 1, lfind[i + 1] - 1)
+            grow = slice(findrm[g[i]] - 1, findrm[g[i] + 1] - 1)
+            lcols = g[lcolm[lrow] - 1]
+            perm = np.argsort(lcols)
+            assert (lcols[perm] == colm[grow] - 1).all()
+            for d in range(dim):
+                assert np.abs(lm["big_m"][d][lrow][perm] - gm["big_m"][d][grow]).max() <= 1e-12 * np.abs(gm["big_m"][d]).max()
+            assert np.abs(la["matrix"][lrow][perm] - ga["matrix"][grow]).max() <= 1e-12 * np.abs(ga["matrix"]).max()
+        own = g[:lp.n_owned]
+        assert rel_err(lm["rhs"][:lp.n_owned], gm["rhs"][own]) < 1e-12
+        assert rel_err(la["rhs"][:lp.n_owned], ga["rhs"][own]) < 1e-12
+
+
+def test_reference_decomposition_drops_into_the_multirank_path(orc, tmp_path):
+    """prectangle_{0,1}: flredecomp output of the reference (binary gmsh + L1/L2 .halo). Written back
+    with our writers, read with read_decomposition, joined by coordinates into the global mesh."""
+    base = str(tmp_path / "prectangle")
+    for r in (0, 1):
+        z = np.load(os.path.join(GOLDEN, "prectangle_%d.npz" % r))
+        g = fmt.GmshMesh(mesh=syn.Mesh(dim=int(z["dim"]), ndglno=z["ndglno"], X=z["X"]), sndgln=z["sndgln"],
+                         boundary_ids=z["boundary_ids"], element_owner=z["element_owner"], region_ids=z["region_ids"])
+        fmt.write_gmsh(fmt.parallel_filename(base, r, ".msh"), g, binary=True)
+        fmt.write_halo(fmt.parallel_filename(base, r, ".halo"), _golden_halos(r))
+    parts = [fmt.read_decomposition(base, r)[0] for r in (0, 1)]
+    assert [lp.n_owned for lp in parts] == [16, 7] and [lp.n_l1 for lp in parts] == [6, 7]
+    # both sides of every list are the same points, in the same order
+    for r, p in ((0, 1), (1, 0)):
+        assert len(parts[r].sends[p]) == len(parts[p].recvs[r]) > 0
+        assert (parts[r].mesh.X[parts[r].sends[p] - 1] == parts[p].mesh.X[parts[p].recvs[r] - 1]).all()
+    # global numbering: owned nodes of rank 0, then of rank 1; halo nodes found by their coordinates
+    owned_X = np.concatenate([lp.mesh.X[:lp.n_owned] for lp in parts])
+    assert len(np.unique(owned_X, axis=0)) == 23
+    key = {tuple(x): i for i, x in enumerate(owned_X)}
+    l2g = [np.array([key[tuple(x)] for x in lp.mesh.X]) for lp in parts]
+    eles = {}
+    for lp, g in zip(parts, l2g):
+        for e in g[lp.mesh.ndglno - 1]:
+            eles.setdefault(tuple(sorted(e)), e)
+    gmesh = syn.Mesh(dim=2, ndglno=(np.array(list(eles.values())) + 1).astype(np.int32), X=owned_X)
+    # every element around an owned node is present locally
+    nd0 = gmesh.ndglno - 1
+    for r, (lp, g) in enumerate(zip(parts, l2g)):
+        mine = np.isin(nd0, g[:lp.n_owned]).any(axis=1).sum()
+        local = np.isin(g[lp.mesh.ndglno - 1], g[:lp.n_owned]).any(axis=1).sum()
+        assert mine == local
+    _owned_rows_match(orc, parts, gmesh, l2g)
+
+
+@pytest.mark.parametrize("binary", [False, True])
+def test_our_decomposition_round_trips_through_the_reference_formats(orc, tmp_path, binary):
+    mesh = load_golden_mesh("cube-parallel")
+    nprocs = 3
+    order = np.argsort(mesh.X[:, 0], kind="stable")
+    owner = np.zeros(mesh.n_nodes, dtype=np.int64)
+    for r, chunk in enumerate(np.array_split(order, nprocs)):
+        owner[chunk] = r
+    parts = part.partition_by_owner(mesh, owner, nprocs)
+    base = str(tmp_path / "cube")
+    fmt.write_decomposition(base, parts, binary=binary)
+    for r, lp in enumerate(parts):
+        assert os.path.exists("%s_%d.msh" % (base, r)) and os.path.exists("%s_%d.halo" % (base, r))
+        back, gm, hs = fmt.read_decomposition(base, r)
+        assert back.n_owned == lp.n_owned and back.n_l1 == lp.n_l1
+        assert (back.mesh.ndglno == lp.mesh.ndglno).all() and (back.mesh.X == lp.mesh.X).all()
+        for p in range(nprocs):
+            assert (back.sends[p] == lp.sends[p]).all() and (back.recvs[p] == lp.recvs[p]).all()
+        # level 1 is the level-2 list restricted to the first n_l1 receive nodes, pairwise consistent
+        l1 = hs.levels[1]
+        assert fmt.trailing_receives_consistent(l1) and fmt.trailing_receives_consistent(hs.levels[2])
+        allr = np.concatenate(l1.receives)
+        assert sorted(allr.tolist()) == list(range(lp.n_owned + 1, lp.n_owned + lp.n_l1 + 1))
+        for p in range(nprocs):
+            other = fmt.read_halo("%s_%d.halo" % (base, p)).levels[1]
+            assert len(l1.sends[p]) == len(other.receives[r])
+            assert (lp.global_node[l1.sends[p] - 1] == parts[p].global_node[other.receives[r] - 1]).all()
+    with pytest.raises(fmt.FormatError, match="process number"):
+        os.replace("%s_1.halo" % base, "%s_7.halo" % base)
+        os.replace("%s_1.msh" % base, "%s_7.msh" % base)
+        fmt.read_decomposition(base, 7)
+
+
+# ---- PETSc binary dumps ----------------------------------------------------------------------------------
+def test_petsc_binary_layout_is_the_published_one(tmp_path):
+    # 2 x 3 matrix [[1, 0, 2], [0, 3, 0]] and a vector, written by hand byte for byte
+    import struct
+    raw = struct.pack(">4i", 1211216, 2, 3, 3) + struct.pack(">2i", 2, 1) + struct.pack(">3i", 0, 2, 1) + \
+        struct.pack(">3d", 1.0, 2.0, 3.0) + struct.pack(">2i", 1211214, 2) + struct.pack(">2d", 0.5, -4.0)
+    p = tmp_path / "matrixdump"
+    p.write_bytes(raw)
+    A, b = fmt.read_petsc_binary(str(p))
+    assert (A.rows, A.cols) == (2, 3) and A.findrm.tolist() == [0, 2, 3] and A.colm.tolist() == [0, 2, 1]
+    assert A.val.tolist() == [1.0, 2.0, 3.0] and b.tolist() == [0.5, -4.0]
+    q = tmp_path / "again"
+    fmt.write_petsc_binary(str(q), [A, b])
+    assert q.read_bytes() == raw
+    fmt.write_petsc_binary(str(q), [A, b], int64=True)
+    A8, b8 = fmt.read_petsc_binary(str(q), int64=True)
+    assert A8.colm.tolist() == [0, 2, 1] and b8.tolist() == [0.5, -4.0]
+    (tmp_path / "cut").write_bytes(raw[:40])
+    with pytest.raises(fmt.FormatError, match="truncated"):
+        fmt.read_petsc_binary(str(tmp_path / "cut"))
+    (tmp_path / "junk").write_bytes(struct.pack(">2i", 77, 1))
+    with pytest.raises(fmt.FormatError, match="class id"):
+        fmt.read_petsc_binary(str(tmp_path / "junk"))
+    assert fmt.dump_name_parts("/x/Velocity_12") == ("Velocity", 12) and fmt.dump_name_parts("matrixdump") == ("matrixdump", None)
+
+
+def test_petsc_numbering_and_block_expansion(orc):
+    # femtools/Petsc_Tools.F90:184-199: field-major without groups, node-major inside a group
+    n = fmt.petsc_row_numbering(4, 3)
+    assert n[:, 0].tolist() == [0, 1, 2, 3] and n[:, 2].tolist() == [8, 9, 10, 11]
+    g = fmt.petsc_row_numbering(4, 3, group_size=3)
+    assert g[0].tolist() == [0, 1, 2] and g[3].tolist() == [9, 10, 11]
+    # femtools/tests/test_petsc_csr_matrix.F90: 2 x 2 blocks of a 2-node dense sparsity, entry
+    # values 1..16 in (block, node) order land at gnn2unn rows/columns
+    findrm, colm = np.array([1, 3, 5]), np.array([1, 2, 1, 2])
+    blocks = np.arange(1.0, 17.0).reshape(2, 2, 4)
+    M = fmt.blocks_to_petsc(findrm, colm, blocks, 2, diagonal=False)
+    import scipy.sparse as sp
+    D = sp.csr_matrix((M.val, M.colm, M.findrm), shape=(4, 4)).toarray()
+    for bi in range(2):
+        for bj in range(2):
+            assert (D[2 * bi:2 * bi + 2, 2 * bj:2 * bj + 2].ravel() == blocks[bi, bj]).all()
+    # an assembled momentum matrix survives dump -> read -> compare, and a 1e-9 perturbation does not
+    mesh = load_golden_mesh("cube.1")
+    fs = syn.standard_fields(mesh)
+    fr, cm, _ = orc.make_sparsity(mesh)
+    res = orc.assemble_momentum(mesh, fs, abi.common_momentum_opts(), fr, cm)
+    A = fmt.blocks_to_petsc(fr, cm, np.array(res["big_m"]), mesh.n_nodes)
+    assert A.rows == 3 * mesh.n_nodes and (np.diff(A.colm)[np.diff(np.repeat(np.arange(A.rows), np.diff(A.findrm))) == 0] > 0).all()
+    same = fmt.compare_petsc_mats(A, A)
+    assert same["ok"] and same["block_rel"] == 0.0
+    # PETSc drops nothing, but a dump made with MAT_IGNORE_ZERO_ENTRIES has fewer stored entries
+    B = fmt.blocks_to_petsc(fr, cm, np.array(res["big_m"]), mesh.n_nodes, keep_zeros=False)
+    assert fmt.compare_petsc_mats(A, B)["ok"]
+    C = fmt.PetscMat(A.rows, A.cols, A.findrm, A.colm, A.val * (1 + 1e-9))
+    assert not fmt.compare_petsc_mats(C, A)["ok"]
+
+
+def test_compare_matrixdump_tool(orc, tmp_path):
+    import subprocess
+    import sys
+    mesh = load_golden_mesh("cube.1")
+    fs = syn.standard_fields(mesh)
+    fr, cm, _ = orc.make_sparsity(mesh)
+    res = orc.assemble_advdiff(mesh, fs, abi.common_advdiff_opts(), fr, cm)
+    A = fmt.csr_to_petsc(fr, cm, res["matrix"], mesh.n_nodes)
+    x0 = np.zeros(mesh.n_nodes)
+    fmt.write_petsc_binary(str(tmp_path / "T_1"), [A, res["rhs"], x0])
+    fmt.write_petsc_binary(str(tmp_path / "T_ours"), [A, res["rhs"] * (1 + 1e-14), x0])
+    fmt.write_petsc_binary(str(tmp_path / "T_off"), [A, res["rhs"] * (1 + 1e-8), x0])
+    tool = os.path.join(os.path.dirname(GOLDEN), "..", "scripts", "compare_matrixdump.py")
+    good = subprocess.run([sys.executable, tool, str(tmp_path / "T_1"), str(tmp_path / "T_ours")], capture_output=True, text=True)
+    assert good.returncode == 0 and json.loads(good.stdout)["ok"]
+    bad = subprocess.run([sys.executable, tool, str(tmp_path / "T_1"), str(tmp_path / "T_off")], capture_output=True, text=True)
+    assert bad.returncode == 1 and not json.loads(bad.stdout)["objects"][1]["ok"]
