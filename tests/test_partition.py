@@ -158,3 +158,32 @@ def test_global_fields_agree_on_shared_nodes():
     assert len(common) > 0
     for k in F[0]:
         assert (F[0][k][i0] == F[1][k][i1]).all()
+
+
+@pytest.mark.parametrize("name,nprocs", [("cube-parallel", 5), ("2d_square", 8), ("square-cavity-2d", 3)])
+def test_rcb_partition(orc, name, nprocs):
+    """Geometric stand-in for Zoltan/METIS: balanced, deterministic, every rank a
+    box of the bisection tree, and valid input for partition_by_owner."""
+    mesh = load_golden_mesh(name)
+    owner = part.rcb_owner(mesh.X, nprocs)
+    assert (owner == part.rcb_owner(mesh.X, nprocs)).all()
+    counts = np.bincount(owner, minlength=nprocs)
+    assert counts.min() >= mesh.n_nodes // nprocs - 1 and counts.max() <= -(-mesh.n_nodes // nprocs) + 1
+    parts = part.partition_by_owner(mesh, owner, nprocs)
+    q = part.partition_quality(mesh, parts)
+    assert q["owned_imbalance"] < 1.01
+    # compact parts: far less halo than a random owner map of the same balance
+    rnd = np.random.default_rng(0).permutation(owner)
+    q_rnd = part.partition_quality(mesh, part.partition_by_owner(mesh, rnd, nprocs))
+    assert q["halo_nodes_sent_total"] < 0.5 * q_rnd["halo_nodes_sent_total"]
+    assert q["element_redundancy"] < q_rnd["element_redundancy"]
+    for r, lp in enumerate(parts):
+        for p in range(nprocs):
+            assert len(lp.sends[p]) == len(parts[p].recvs[r])
+    # the bounding boxes of two parts overlap at most in a thin layer along one axis
+    lo = np.array([mesh.X[owner == r].min(axis=0) for r in range(nprocs)])
+    hi = np.array([mesh.X[owner == r].max(axis=0) for r in range(nprocs)])
+    for a in range(nprocs):
+        for b in range(a + 1, nprocs):
+            overlap = np.minimum(hi[a], hi[b]) - np.maximum(lo[a], lo[b])
+            assert (overlap <= 1e-12).any() or overlap.min() < 0.05 * (mesh.X.max() - mesh.X.min())
