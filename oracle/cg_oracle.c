@@ -11,11 +11,19 @@
  * elements in ascending order, (iloc,jloc) row-major scatter). Every function cites the
  * reference file:line it follows (paths relative to the Fluidity source tree).
  *
- * PARITY PINNING: the reference's own unit tests pin the tables, the transform, the
+ * PARITY PINNING: (1) the reference's own unit tests pin the tables, the transform, the
  * colouring and the block addto (tests/test_oracle_golden.py re-runs those known answers
- * against this file); the assembled VALUES of the two element loops are pinned by no
- * reference test => for those, "parity unpinned" beyond the closed
- * forms checked in tests/test_oracle_closed_forms.py.
+ * against this file). (2) Outputs of the reference itself: python/fluidity/state_types.py,
+ * the reference's Python implementation of transform_to_physical / shape_shape /
+ * shape_dshape / ele_val_at_quad / addto, imported unmodified by
+ * tests/golden/make_pyref_golden.py, pins detwei, the physical gradients, the momentum mass
+ * and lumped mass, the tracer mass matrix and grad_p_u_mat / ct_m, per element and
+ * assembled (tests/golden/pyref_*.npz, tests/test_pyref_golden.py), and supplies every
+ * ingredient of the common-option-set matrices (the `c_*` arrays). (3) The contractions of
+ * the advection / viscosity / absorption / source / buoyancy terms exist only in the
+ * Fortran, which cannot run here: for those the VALUES are "parity unpinned" against a real
+ * Fortran run, beyond (2)'s ingredients, the closed forms and the independent numpy
+ * evaluation in tests/test_oracle_closed_forms.py.
  *
  * Array conventions are the Fortran ones: column-major, 1-based node/element numbers in
  * the integer arrays (ndglno, findrm, colm), FP64 reals.

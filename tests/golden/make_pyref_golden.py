@@ -1,0 +1,193 @@
+"""Golden vectors computed by the REFERENCE'S OWN Python implementation of pieces of this path.
+
+The reference ships a Python restatement of its element machinery for python diagnostics:
+`python/fluidity/state_types.py` -- `Transform` (Jacobian J = X.dn, |det J|, detwei, inverse;
+:338-377 = femtools/Transform_elements.F90:807-887), `Transform.grad` (physical shape-function
+gradients, :379-386), `Transform.shape_shape` (mass matrix with an optional quadrature-point
+coefficient, :388-406 = femtools/FETools.F90:206-226), `Transform.shape_dshape` (:408-427 =
+FETools.F90:332-362), `Field.ele_val_at_quad` (:113-117 = femtools/Fields_Base.F90:2256-2310),
+`Field.addto` (:71-81). This script IMPORTS that module unmodified from /root/reference (build
+container only; the GPU box has no reference, so the outputs are committed) and runs it on
+reference fixture meshes, producing what the momentum / tracer element loops are built from:
+
+  per element   detwei(ngi), du_t = dshape(loc,ngi,dim)       transform_to_physical
+                M      = shape_shape(N, N, detwei)            tracer consistent mass (Advection_Diffusion_CG.F90:909)
+                M_rho  = shape_shape(N, N, detwei*rho_g)      momentum mass (Momentum_CG.F90:1535), rho_g = ele_val_at_quad
+                G      = shape_dshape(N, du_t)                grad_p_u_mat / ct_m entries (Momentum_CG.F90:1401)
+  assembled     lumped mass sum_j M_rho_ij per node           masslump (Momentum_CG.F90:1541,1560-1565), via Field.addto as
+                                                              the module's own test_shape_dshape does (:452-458)
+                dense tracer mass matrix and dense ct blocks  (plain += of the element matrices)
+  composed      the momentum / tracer element matrices and rhs of the common option set (+ absorption, sources), CONTRACTED
+                here by numpy.einsum following Momentum_CG.F90:1535-1552,1675-1680,1737-1748,1770-1789,2038-2059,2304-2346
+                and Advection_Diffusion_CG.F90:909-920,1093-1125,1139,1156-1160,1192-1200 from ingredients that are ALL
+                reference-computed: detwei, du_t (Transform.grad), N, and every field at the quadrature points
+                (Field.ele_val_at_quad); mass-type terms go through Transform.shape_shape itself. A weaker pin than the
+                direct ones above (the contraction is restated), kept apart in the file as `c_*`.
+
+The element tables n / dn / weights handed to `Element` / `Quadrature` are the degree-3 P1 tables
+of fluidity_b200/tables.py (at run time the reference fills these objects from its Fortran
+element_type; the tables are pinned separately against femtools/tests/test_quadrature.F90 and
+test_shape_functions.F90 by tests/test_oracle_golden.py).
+
+    python tests/golden/make_pyref_golden.py        # writes tests/golden/pyref_<mesh>.npz
+"""
+import os
+import sys
+import numpy as np
+
+REF = os.environ.get("FLUIDITY_REFERENCE", "/root/reference")
+OUT = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(OUT))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(REF, "python"))
+
+from fluidity import state_types as st  # noqa: E402  (the reference module, unmodified)
+from fluidity_b200 import tables, synthetic  # noqa: E402
+
+# (fixture, elements taken): whole small meshes, the first elements of the unstructured ones
+CASES = [("cube.1", None), ("cube-parallel", 160), ("square-cavity-2d", 200), ("prectangle_0", None)]
+
+
+def reference_shape(dim):
+    n, dn, w = tables.p1_tables(dim)
+    loc, ngi = dim + 1, len(w)
+    n = n.reshape(ngi, loc).T.copy()            # n[i, g]
+    dn = dn.reshape(dim, ngi, loc).transpose(2, 1, 0).copy()  # dn[i, g, k]
+    el = st.Element(dim, loc, ngi, 1, n, dn, np.zeros((loc, dim)), 0, 0, 0, 0, "lagrangian", "simplex")
+    l, _ = tables.quadrature_degree3(dim)
+    el.set_quadrature(st.Quadrature(w, l, dim, 3, loc, ngi))
+    return el
+
+
+def density_of(mesh):
+    return synthetic.standard_fields(mesh).get(synthetic.abi.F_DENSITY)[0]
+
+
+DT, THETA, GMAG = 0.01, 0.5, 10.0  # _abi.common_momentum_opts / common_advdiff_opts
+
+
+def scalar_components(name, val, mesh):
+    """A (n_nodes, k) array as k reference ScalarFields (ele_val_at_quad is scalar-only, state_types.py:113-117)."""
+    val = np.asarray(val)
+    if val.ndim == 1:
+        val = val[:, None]
+    out = []
+    for k in range(val.shape[1]):
+        f = st.ScalarField("%s%d" % (name, k), np.ascontiguousarray(val[:, k]), 0, "")
+        f.set_mesh(mesh)
+        out.append(f)
+    return out
+
+
+def composed(e, t, du_t, shape, F, dim, loc):
+    """Element matrices of the common option set with absorption and sources switched on or off."""
+    A = synthetic.abi
+    N = np.asarray(shape.n)                       # [i, g]
+    dN = np.asarray(du_t.dn)                      # [i, g, k]
+    dw = np.asarray(t.detwei)
+    q = lambda comps: np.array([c.ele_val_at_quad(e) for c in comps])  # [k, g]
+    nodes = F["rho"][0].ele_nodes(e)
+    nv = lambda comps: np.array([[c.node_val(n) for n in nodes] for c in comps])  # [k, i]
+    rho_g, u_g, b_g = q(F["rho"])[0], q(F["nu"]), q(F["buoy"])[0]
+    sig_g, tsig_g, ts_g = q(F["absn"]), q(F["t_abs"])[0], q(F["t_src"])[0]
+    oldu, src, T = nv(F["oldu"]), nv(F["src"]), nv(F["T"])[0]
+    Mr = t.shape_shape(shape, shape, rho_g)
+    M = t.shape_shape(shape, shape)
+    m = Mr.sum(1)
+    udn = np.einsum("kg,jgk->jg", u_g, dN)       # u_g . grad N_j
+    Adv = np.einsum("ig,jg,g->ij", N, udn, rho_g * dw)
+    K = np.einsum("igk,jgk,g->ij", dN, dN, F["mu"] * dw)
+    out = {}
+    for tag, have_abs, have_src in (("common", 0, 0), ("abs_src", 1, 1)):
+        Tm = np.zeros((dim, dim, loc, loc))
+        rhs = np.zeros((dim, loc))
+        for d in range(dim):
+            Ab = t.shape_shape(shape, shape, rho_g * sig_g[d]) if have_abs else np.zeros((loc, loc))
+            L = Adv + K + Ab
+            Tm[d, d] = np.diag(m) + DT * THETA * L
+            rhs[d] = -L @ oldu[d] + N @ (F["gdir"][d] * GMAG * b_g * dw)
+            if have_src:
+                rhs[d] += Mr @ src[d]
+        out["c_mom_T_" + tag], out["c_mom_rhs_" + tag] = Tm, rhs
+    Atr = np.einsum("ig,jg,g->ij", N, udn, dw)
+    D = np.einsum("igk,jgk,g->ij", dN, dN, F["kappa"] * dw)
+    for tag, on in (("common", 0), ("abs_src", 1)):
+        Ab = t.shape_shape(shape, shape, tsig_g) if on else np.zeros((loc, loc))
+        L = Atr + D + Ab
+        out["c_adv_A_" + tag] = M + DT * THETA * L
+        out["c_adv_rhs_" + tag] = -L @ T + (N @ (ts_g * dw) if on else 0.0)
+    return out
+
+
+def run(name, nele):
+    z = np.load(os.path.join(OUT, name + ".npz"))
+    dim = int(z["dim"])
+    nd = np.ascontiguousarray(z["ndglno"], dtype=np.int32)
+    if nele is not None:
+        # keep the first `nele` elements and renumber their nodes compactly (ascending old id)
+        nd = nd[:nele]
+        used = np.unique(nd)
+        remap = np.zeros(int(used.max()) + 1, dtype=np.int32)
+        remap[used] = np.arange(1, len(used) + 1)
+        nd = remap[nd]
+        X = np.ascontiguousarray(z["X"][used - 1])
+    else:
+        X = np.ascontiguousarray(z["X"])
+    loc = dim + 1
+    n_nodes, n_ele = X.shape[0], nd.shape[0]
+    mesh = st.Mesh(nd.ravel(), n_ele, n_nodes, 0, "CoordinateMesh", "", None)
+    mesh.shape = reference_shape(dim)
+    ngi = mesh.shape.ngi
+    coord = st.VectorField("Coordinate", X, 0, "", dim)
+    coord.set_mesh(mesh)
+    rho_val = density_of(synthetic.Mesh(dim=dim, ndglno=nd, X=X))
+    rho = st.ScalarField("Density", rho_val, 0, "")
+    rho.set_mesh(mesh)
+    lump = st.ScalarField("LumpMass", np.zeros(n_nodes), 0, "")
+    lump.set_mesh(mesh)
+    A = synthetic.abi
+    fs = synthetic.standard_fields(synthetic.Mesh(dim=dim, ndglno=nd, X=X))
+    F = dict(rho=[rho], nu=scalar_components("nu", fs.get(A.F_NU)[0], mesh), oldu=scalar_components("oldu", fs.get(A.F_OLDU)[0], mesh),
+             buoy=scalar_components("b", fs.get(A.F_BUOYANCY)[0], mesh), absn=scalar_components("abs", fs.get(A.F_ABSORPTION)[0], mesh),
+             src=scalar_components("src", fs.get(A.F_SOURCE)[0], mesh), T=scalar_components("T", fs.get(A.F_T)[0], mesh),
+             t_abs=scalar_components("tabs", fs.get(A.F_T_ABSORPTION)[0], mesh), t_src=scalar_components("tsrc", fs.get(A.F_T_SOURCE)[0], mesh),
+             mu=float(fs.get(A.F_VISCOSITY)[0][0, 0, 0]), kappa=float(fs.get(A.F_T_DIFFUSIVITY)[0][0, 0, 0]),
+             gdir=fs.get(A.F_GRAVITY)[0][0])
+    comp = {}
+
+    detwei = np.zeros((n_ele, ngi))
+    dshape = np.zeros((n_ele, loc, ngi, dim))
+    M = np.zeros((n_ele, loc, loc))
+    M_rho = np.zeros((n_ele, loc, loc))
+    G = np.zeros((n_ele, loc, loc, dim))
+    rho_q = np.zeros((n_ele, ngi))
+    mass_dense = np.zeros((n_nodes, n_nodes))
+    ct_dense = np.zeros((dim, n_nodes, n_nodes))
+    for e in range(n_ele):
+        t = st.Transform(e, coord)
+        du_t = t.grad(mesh.shape)
+        detwei[e] = t.detwei
+        dshape[e] = du_t.dn
+        rho_q[e] = rho.ele_val_at_quad(e)
+        M[e] = t.shape_shape(mesh.shape, mesh.shape)
+        M_rho[e] = t.shape_shape(mesh.shape, mesh.shape, rho_q[e])
+        G[e] = np.asarray(t.shape_dshape(mesh.shape, du_t))
+        for k, v in composed(e, t, du_t, mesh.shape, F, dim, loc).items():
+            comp.setdefault(k, []).append(v)
+        nodes = lump.ele_nodes(e)
+        lump.addto(nodes, M_rho[e].sum(1))
+        for i in range(loc):
+            for j in range(loc):
+                mass_dense[nodes[i], nodes[j]] += M[e][i, j]
+                for d in range(dim):
+                    ct_dense[d, nodes[i], nodes[j]] += G[e][i, j, d]
+    out = os.path.join(OUT, "pyref_%s.npz" % name)
+    np.savez_compressed(out, dim=dim, ndglno=nd, X=X, density=rho_val, rho_q=rho_q, detwei=detwei, dshape=dshape,
+                        M=M, M_rho=M_rho, G=G, masslump=lump.val, mass_dense=mass_dense, ct_dense=ct_dense,
+                        **{k: np.array(v) for k, v in comp.items()})
+    print(name, "dim", dim, "elements", n_ele, "nodes", n_nodes, "-> %s (%d bytes)" % (out, os.path.getsize(out)))
+
+
+if __name__ == "__main__":
+    for name, nele in CASES:
+        run(name, nele)

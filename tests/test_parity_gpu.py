@@ -255,6 +255,35 @@ def test_shuffled_numbering_s3_small(orc, scatter):
     assert rel_err(got["matrix"], ref["matrix"]) < TOL and rel_err(got["rhs"], ref["rhs"]) < TOL
 
 
+# ---- golden vectors from the reference's own Python element machinery ------------------------------
+@pytest.mark.parametrize("name", ["cube.1", "cube-parallel", "square-cavity-2d", "prectangle_0"])
+def test_element_matrices_match_reference_python(name):
+    """tests/golden/pyref_*.npz were computed by python/fluidity/state_types.py of the reference
+    (imported unmodified, tests/golden/make_pyref_golden.py): mass, lumped mass, tracer mass and
+    grad_p_u_mat of every element, here against cgasm_momentum_element / cgasm_advdiff_element."""
+    import pyref_checks as pc
+    mesh, fs, z = pc.load(name)
+    asm = make_asm(mesh, fs)
+    worst = pc.check_elements(mesh, fs, z, asm.momentum_element, asm.advdiff_element, zero_tol=TOL)
+    assert worst < TOL
+    # the common option set (+ absorption + sources) from reference-computed ingredients
+    assert pc.check_composed(mesh, fs, z, asm.momentum_element, asm.advdiff_element) < TOL
+
+
+@pytest.mark.parametrize("scatter", ALL_SCATTERS)
+@pytest.mark.parametrize("name", ["cube.1", "cube-parallel", "square-cavity-2d", "prectangle_0"])
+def test_assembled_mass_and_ct_match_reference_python(scatter, name):
+    """Assembled lumped mass, ct_m blocks and the tracer mass matrix of every scatter variant against
+    what the reference's Python accumulated with its own Field.addto."""
+    import pyref_checks as pc
+    mesh, fs, z = pc.load(name)
+    asm = make_asm(mesh, fs, scatter)
+    findrm, colm, _ = asm.get_sparsity()
+    pc.check_assembled(mesh, fs, z, findrm, colm, asm.momentum, asm.advdiff, zero_tol=TOL)
+    # assembled CSR values and rhs of the common option set (+ absorption + sources)
+    pc.check_assembled_composed(mesh, fs, z, findrm, colm, asm.momentum, asm.advdiff)
+
+
 # ---- size-independent properties at a size the oracle would not finish quickly ---------------
 @pytest.mark.parametrize("scatter", [pytest.param(abi.SCATTER_ATOMIC, id="atomic"), pytest.param(abi.SCATTER_TILED, id="tiled"),
                                      pytest.param(abi.SCATTER_GATHER, id="gather"), pytest.param(abi.SCATTER_STRIP, id="strip")])
