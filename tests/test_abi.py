@@ -83,3 +83,38 @@ def test_bad_arguments_are_status_codes_not_aborts():
     assert lib.cgasm_destroy(12345) == abi.EHANDLE
     assert lib.cgasm_momentum_dev(777, None) == abi.EHANDLE
     assert b"handle" in lib.cgasm_last_error()
+
+
+# ---- the uncompiled Fortran half of the boundary must not drift from the header ----------------------
+FORTRAN = os.path.join(ROOT, "fluidity_b200", "fortran", "cgasm_fortran.F90")
+# diagnostics / device-pointer accessors a Fortran caller has no use for
+_NOT_BOUND_IN_FORTRAN = {"cgasm_advdiff_result_dev", "cgasm_momentum_result_dev", "cgasm_last_kernel_ms",
+                         "cgasm_launch_count", "cgasm_row_blocks_host", "cgasm_strip_plan_host", "cgasm_stream"}
+
+
+def _fortran_type_fields(txt, name):
+    body = re.search(r"type,\s*bind\(c\)\s*::\s*%s(.*?)end type" % name, txt, flags=re.S | re.I).group(1)
+    fields = []
+    for line in body.splitlines():
+        line = line.split("!")[0]
+        m = re.match(r"\s*(real\(c_double\)|integer\(c_int\))\s*::\s*(.*)", line)
+        if m:
+            fields += [(m.group(1), f.strip()) for f in m.group(2).split(",") if f.strip()]
+    return fields
+
+
+def test_fortran_module_binds_the_header():
+    txt = open(FORTRAN).read()
+    bound = set(re.findall(r'name\s*=\s*"(cgasm_[a-z0-9_]+)"', txt))
+    declared = set(_declared_symbols())
+    assert bound <= declared, bound - declared
+    assert declared - bound == _NOT_BOUND_IN_FORTRAN
+    # derived types: same members, same order, same kinds as the C structs (= the ctypes twins)
+    for tname, cls in (("cgasm_momentum_opts", abi.MomentumOpts), ("cgasm_advdiff_opts", abi.AdvDiffOpts)):
+        want = [("real(c_double)" if t is C.c_double else "integer(c_int)", k) for k, t in cls._fields_]
+        assert _fortran_type_fields(txt, tname) == want, tname
+    # enumerators repeated as Fortran parameters
+    hdr = open(HEADER).read()
+    for name, val in re.findall(r"\b(CGASM_[A-Z0-9_]+)\s*=\s*(\d+)", txt):
+        m = re.search(r"\b%s\s*=\s*(\d+)" % name, hdr)
+        assert m and m.group(1) == val, name
