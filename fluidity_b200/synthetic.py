@@ -128,6 +128,23 @@ def shuffled(mesh, seed=7):
     return Mesh(dim=mesh.dim, ndglno=np.ascontiguousarray(nd.astype(np.int32)), X=X, shape=())
 
 
+def boundary_faces(mesh):
+    """Surface mesh of `mesh` the way femtools add_faces leaves it for a mesh without a surface file:
+    the facets that belong to exactly one element (femtools/Fields_Allocates.F90:1166-1296), here in
+    ascending (element, local facet) order; local facet k is the one opposite local node k
+    (femtools/Element_Numbering.F90 boundary numbering of simplices). Returns
+    sndgln (n_faces, sloc) int32 1-based global nodes (ascending local-node order) and face_ele
+    (n_faces,) int32 1-based owning element."""
+    nd = mesh.ndglno.astype(np.int64)
+    loc = mesh.loc
+    faces = np.stack([np.delete(nd, k, axis=1) for k in range(loc)], axis=1)  # (ne, loc, sloc)
+    key = np.sort(faces, axis=2).reshape(-1, loc - 1)
+    _, inv, cnt = np.unique(key, axis=0, return_inverse=True, return_counts=True)
+    on_boundary = (cnt[inv.ravel()] == 1).reshape(nd.shape[0], loc)
+    e, k = np.nonzero(on_boundary)
+    return np.ascontiguousarray(faces[e, k], dtype=np.int32), (e + 1).astype(np.int32)
+
+
 @dataclass
 class FieldSet:
     """slot -> (values, field_type); values laid out as the module docstring says."""

@@ -41,3 +41,35 @@ def p1_tables(dim):
             for k in range(dim):
                 dn[i + loc * (g + ngi * k)] = (1.0 if i == k else 0.0) if i < dim else -1.0
     return n, dn, w
+
+
+def face_quadrature_degree3(dim):
+    """(l (sngi, sloc), weight (sngi)) of the faces of a dim-dimensional P1 simplex mesh: the rule of
+    the mesh's degree on the (dim-1)-simplex (femtools/Fields_Allocates.F90:1302-1320). dim 3: the
+    triangle rule above; dim 2: the 3-point degree-3 interval rule, constants as truncated in
+    femtools/Quadrature.F90:1181-1199, point order of interval_permutations (:1893-1905)."""
+    if dim == 3:
+        return quadrature_degree3(2)
+    if dim != 2:
+        raise ValueError("dim must be 2 or 3")
+    a = 0.887298334620742
+    b = 1.0 - a
+    l = np.array([[a, b], [b, a], [0.5, 0.5]])
+    w = np.array([0.277777777777777, 0.277777777777777, 0.444444444444444])
+    return l, w
+
+
+def p1_face_tables(dim):
+    """n_f (sloc*sngi), dn_f (sloc*sngi*(dim-1)), weight_f (sngi) of mesh%faces%shape, raw column-major:
+    n_f[i + sloc*g], dn_f[i + sloc*(g + sngi*k)] (P1: dn(i,g,k) = delta_ik, last node -1)."""
+    sloc, fd = dim, dim - 1
+    l, w = face_quadrature_degree3(dim)
+    sngi = len(w)
+    n = np.zeros(sloc * sngi)
+    dn = np.zeros(sloc * sngi * fd)
+    for g in range(sngi):
+        for i in range(sloc):
+            n[i + sloc * g] = l[g, i]
+            for k in range(fd):
+                dn[i + sloc * (g + sngi * k)] = (1.0 if i == k else 0.0) if i < fd else -1.0
+    return n, dn, w

@@ -1240,3 +1240,331 @@ void orc_block_addto(const int* findrm, const int* colm, int nrows, const int* r
       if (pos > 0) val[pos - 1] += vals[i + nrows * j];
     }
 }
+
+/* ====================================================================================
+ * Surface-element loops and strong Dirichlet conditions: the step right after the element
+ * loops. Same status as the rest of this file: TEST
+ * INFRASTRUCTURE, restated from the cited lines; values pinned by closed forms and an
+ * independent numpy evaluation (tests/test_surface_oracle.py) -- the reference has no unit
+ * test at this level ("parity unpinned" against a Fortran run).
+ * ==================================================================================== */
+
+/* Face quadrature = rule of the mesh's degree on the (dim-1)-simplex
+ * (femtools/Fields_Allocates.F90:1302-1320). dim == 3: the 4-point triangle rule above;
+ * dim == 2: the 3-point degree-3 interval rule, femtools/Quadrature.F90:1181-1199 with
+ * interval_permutations :1893-1905 (the constants are truncated in the source: kept as
+ * written). l is (sngi, sloc) column-major; returns sngi. */
+int orc_quadrature_face_degree3(int dim, double* l, double* weight) {
+  if (dim == 3) return orc_quadrature_degree3(2, l, weight);
+  if (dim != 2) return 0;
+  const int ngi = 3;
+  double coords[2];
+  coords[0] = 0.887298334620742;
+  coords[1] = 1.0 - coords[0];
+  static const int p2[2][2] = {{1, 2}, {2, 1}};
+  for (int k = 0; k < 2; k++) {
+    for (int j = 0; j < 2; j++) l[k + ngi * j] = coords[p2[k][j] - 1];
+    weight[k] = 0.277777777777777;
+  }
+  coords[0] = 0.5;
+  for (int j = 0; j < 2; j++) l[2 + ngi * j] = coords[0];
+  weight[2] = 0.444444444444444;
+  return ngi;
+}
+
+typedef struct orc_surface {
+  int n_faces, sloc, sngi;
+  const int* sndgln;      /* sloc*n_faces, 1-based global nodes (face_global_nodes)   */
+  const int* face_ele;    /* n_faces, 1-based owning element (face_ele)               */
+  const double* n_f;      /* faces%shape%n(sloc,sngi)                                 */
+  const double* dn_f;     /* faces%shape%dn(sloc,sngi,dim-1)                          */
+  const double* weight_f; /* faces%shape%quadrature%weight(sngi)                      */
+} orc_surface;
+
+/* transform_facet_to_physical_full, femtools/Transform_elements.F90:1353-1525, linear simplex
+ * branch: Jacobian at gi == 1 only (:1427), outward_vector = facet centroid - element centroid
+ * (:1445), facet_normal :1527-1553, detwei_f = detJ*weight (:1498, :1514-1517), normal copied to
+ * every gi (:1520-1522). X_f(dim,sloc), X_val(dim,loc). */
+void orc_transform_facet_to_physical(int dim, int sloc, int sngi, const double* X_f, const double* X_val,
+                                     const double* dn_f, const double* weight_f, double* detwei_f,
+                                     double* normal /*(dim,sngi)*/) {
+  const int loc = dim + 1;
+  double outward[MAXDIM], J[MAXDIM * 2], nrm[MAXDIM];
+  for (int a = 0; a < dim; a++) {
+    double sf = 0.0, sv = 0.0;
+    for (int i = 0; i < sloc; i++) sf += X_f[a + dim * i];
+    for (int i = 0; i < loc; i++) sv += X_val[a + dim * i];
+    outward[a] = sf / sloc - sv / loc;
+  }
+  /* J = matmul(X_f, dn(:,1,:)): J(a,k) */
+  for (int k = 0; k < dim - 1; k++)
+    for (int a = 0; a < dim; a++) {
+      double s = 0.0;
+      for (int i = 0; i < sloc; i++) s += X_f[a + dim * i] * dn_f[i + sloc * (0 + sngi * k)];
+      J[a + dim * k] = s;
+    }
+#define J_(a, k) J[((a) - 1) + dim * ((k) - 1)]
+  double detJ = 0.0;
+  if (dim == 2) {
+    detJ = sqrt(J_(1, 1) * J_(1, 1) + J_(2, 1) * J_(2, 1));
+    nrm[0] = -J_(2, 1);
+    nrm[1] = J_(1, 1);
+  } else {
+    for (int i = 1; i <= 3; i++) {
+      double c = J_(cyc3(i + 2), 1) * J_(cyc3(i + 1), 2) - J_(cyc3(i + 2), 2) * J_(cyc3(i + 1), 1);
+      detJ = detJ + c * c;
+    }
+    detJ = sqrt(detJ);
+    nrm[0] = J_(2, 1) * J_(3, 2) - J_(3, 1) * J_(2, 2);
+    nrm[1] = J_(3, 1) * J_(1, 2) - J_(1, 1) * J_(3, 2);
+    nrm[2] = J_(1, 1) * J_(2, 2) - J_(2, 1) * J_(1, 2);
+  }
+#undef J_
+  double dotp = 0.0, nn = 0.0;
+  for (int a = 0; a < dim; a++) dotp += nrm[a] * outward[a];
+  for (int a = 0; a < dim; a++) nrm[a] = nrm[a] * dotp;
+  for (int a = 0; a < dim; a++) nn += nrm[a] * nrm[a];
+  nn = sqrt(nn);
+  for (int g = 0; g < sngi; g++) {
+    if (detwei_f) detwei_f[g] = detJ * weight_f[g];
+    for (int a = 0; a < dim; a++) normal[a + dim * g] = nrm[a] / nn;
+  }
+}
+
+#define MAXSLOC 3
+#define MAXSNGI 4
+
+static void face_geometry(const orc_mesh* m, const orc_surface* s, int face, double* detwei, double* normal) {
+  const int dim = m->dim;
+  const int* fn = s->sndgln + (size_t)s->sloc * (size_t)(face - 1);
+  const int* en = ele_nodes(m, s->face_ele[face - 1]);
+  double X_f[MAXDIM * MAXSLOC], X_val[MAXDIM * MAXLOC];
+  for (int i = 0; i < s->sloc; i++)
+    for (int a = 0; a < dim; a++) X_f[a + dim * i] = m->X[a + (size_t)dim * (size_t)(fn[i] - 1)];
+  for (int i = 0; i < m->loc; i++)
+    for (int a = 0; a < dim; a++) X_val[a + dim * i] = m->X[a + (size_t)dim * (size_t)(en[i] - 1)];
+  orc_transform_facet_to_physical(dim, s->sloc, s->sngi, X_f, X_val, s->dn_f, s->weight_f, detwei, normal);
+}
+
+/* face_val (Fields_Base.F90:2172-2254) of a nodal field with ncomp components: out(ncomp,sloc) */
+static void face_val_multi(const orc_surface* s, const orc_field* f, int ncomp, int face, double* out) {
+  const int* fn = s->sndgln + (size_t)s->sloc * (size_t)(face - 1);
+  for (int i = 0; i < s->sloc; i++)
+    for (int c = 0; c < ncomp; c++)
+      out[c + ncomp * i] = (f->field_type == CGASM_FIELD_CONSTANT) ? f->val[c] : f->val[c + (size_t)ncomp * (size_t)(fn[i] - 1)];
+}
+/* face_val_at_quad (Fields_Base.F90:2374-2400): matmul(face_val, faces%shape%n) */
+static void face_at_quad(const orc_surface* s, int ncomp, const double* fv, double* q /*(ncomp,sngi)*/) {
+  for (int g = 0; g < s->sngi; g++)
+    for (int c = 0; c < ncomp; c++) {
+      double v = 0.0;
+      for (int i = 0; i < s->sloc; i++) v += fv[c + ncomp * i] * s->n_f[i + s->sloc * g];
+      q[c + ncomp * g] = v;
+    }
+}
+
+/* assemble_advection_diffusion_face_cg, assemble/Advection_Diffusion_CG.F90:1228-1283 with
+ * add_advection_face_cg :1285-1340 (default equation type) and add_diffusivity_face_cg :1342-1379.
+ * bc_type: 0, BC_TYPE_NEUMANN = 1, BC_TYPE_WEAKDIRICHLET = 2, BC_TYPE_ROBIN = 4 (:74-75; internal = 3 faces are
+ * skipped by the caller, :629). t_bc / t_bc_2 (sloc): ele_val of the surface fields on this face.
+ * Outputs overwritten: matrix_addto(sloc,sloc), rhs_addto(sloc). */
+int orc_advdiff_face(const orc_mesh* m, const orc_surface* s, const orc_advdiff_fields* f, const cgasm_advdiff_opts* o,
+                     int face, int bc_type, const double* t_bc, const double* t_bc_2, double* matrix_addto,
+                     double* rhs_addto) {
+  const int dim = m->dim, sloc = s->sloc, sngi = s->sngi;
+  const double dt_theta = o->dt * o->theta;
+  const double eps = 2.220446049250313e-16;
+  if (o->move_mesh || o->multiphase || o->equation_type_not_advdiff) return CGASM_EUNSUPPORTED;
+  if (!(bc_type == 0 || bc_type == 1 || bc_type == 2 || bc_type == 4)) return CGASM_EARG; /* assert :1253 */
+  double detwei[MAXSNGI], normal[MAXDIM * MAXSNGI], t_face[MAXSLOC], c_g[MAXSNGI], mat[MAXSLOC * MAXSLOC], q[MAXSNGI];
+  for (int k = 0; k < sloc * sloc; k++) matrix_addto[k] = 0.0;
+  for (int i = 0; i < sloc; i++) rhs_addto[i] = 0.0;
+  const int by_parts_adv = o->have_advection && o->integrate_advection_by_parts;
+  if (by_parts_adv || (o->have_diffusivity && (bc_type == 1 || bc_type == 4))) face_geometry(m, s, face, detwei, normal);
+  face_val_multi(s, &f->t, 1, face, t_face);
+  if (by_parts_adv) { /* :1285-1340 */
+    double u_f[MAXDIM * MAXSLOC], u_q[MAXDIM * MAXSNGI];
+    face_val_multi(s, &f->velocity, dim, face, u_f);
+    face_at_quad(s, dim, u_f, u_q);
+    for (int g = 0; g < sngi; g++) {
+      double un = 0.0;
+      for (int a = 0; a < dim; a++) un += u_q[a + dim * g] * normal[a + dim * g];
+      c_g[g] = detwei[g] * un;
+    }
+    shape_shape2(sloc, sngi, s->n_f, s->n_f, c_g, mat);
+    if (fabs(dt_theta) > eps) {
+      if (bc_type == 2) {
+        for (int i = 0; i < sloc; i++) {
+          double v = 0.0;
+          for (int j = 0; j < sloc; j++) v += mat[i + sloc * j] * (t_bc[j] - t_face[j]);
+          rhs_addto[i] = rhs_addto[i] - o->theta * v;
+        }
+      } else {
+        for (int k = 0; k < sloc * sloc; k++) matrix_addto[k] = matrix_addto[k] + dt_theta * mat[k];
+      }
+    }
+    for (int i = 0; i < sloc; i++) {
+      double v = 0.0;
+      for (int j = 0; j < sloc; j++) v += mat[i + sloc * j] * t_face[j];
+      rhs_addto[i] = rhs_addto[i] - v;
+    }
+  }
+  if (o->have_diffusivity) { /* :1342-1379 */
+    if (bc_type == 1 || bc_type == 4) {
+      double r[MAXSLOC];
+      face_at_quad(s, 1, t_bc, q);
+      for (int g = 0; g < sngi; g++) c_g[g] = detwei[g] * q[g];
+      shape_rhs(sloc, sngi, s->n_f, c_g, r);
+      for (int i = 0; i < sloc; i++) rhs_addto[i] = rhs_addto[i] + r[i];
+    }
+    if (bc_type == 4) {
+      face_at_quad(s, 1, t_bc_2, q);
+      for (int g = 0; g < sngi; g++) c_g[g] = detwei[g] * q[g];
+      shape_shape2(sloc, sngi, s->n_f, s->n_f, c_g, mat);
+      if (fabs(dt_theta) > eps)
+        for (int k = 0; k < sloc * sloc; k++) matrix_addto[k] = matrix_addto[k] + dt_theta * mat[k];
+      for (int i = 0; i < sloc; i++) {
+        double v = 0.0;
+        for (int j = 0; j < sloc; j++) v += mat[i + sloc * j] * t_face[j];
+        rhs_addto[i] = rhs_addto[i] - v;
+      }
+    } else if (bc_type == 2) {
+      return CGASM_EUNSUPPORTED; /* FLExit :1375: weak Dirichlet with diffusivity */
+    }
+  }
+  return 0;
+}
+
+/* The face loop of assemble_advection_diffusion_cg, assemble/Advection_Diffusion_CG.F90:609-643: runs only
+ * with by-parts advection or diffusivity; internal faces skipped; ascending faces; csr addto of
+ * (face_nodes, face_nodes) (exact zeros skipped, Sparse_Tools.F90:2640) and rhs addto. ADDS to
+ * matrix_val / rhs (they hold the element-loop result). bc arrays: bc_type(n_faces), t_bc and t_bc_2
+ * (sloc, n_faces) (either may be NULL when no face needs it). */
+int orc_assemble_advdiff_surface(const orc_mesh* m, const orc_surface* s, const orc_advdiff_fields* f,
+                                 const cgasm_advdiff_opts* o, const int* findrm, const int* colm, const int* bc_type,
+                                 const double* t_bc, const double* t_bc_2, double* matrix_val, double* rhs) {
+  if (!((o->integrate_advection_by_parts && o->have_advection) || o->have_diffusivity)) return 0;
+  const int sloc = s->sloc;
+  const double zero[MAXSLOC] = {0, 0, 0};
+  for (int face = 1; face <= s->n_faces; face++) {
+    if (bc_type[face - 1] == 3) continue;
+    double A[MAXSLOC * MAXSLOC], r[MAXSLOC];
+    int st = orc_advdiff_face(m, s, f, o, face, bc_type[face - 1], t_bc ? t_bc + (size_t)sloc * (face - 1) : zero,
+                              t_bc_2 ? t_bc_2 + (size_t)sloc * (face - 1) : zero, A, r);
+    if (st) return st;
+    const int* fn = s->sndgln + (size_t)sloc * (size_t)(face - 1);
+    for (int i = 0; i < sloc; i++)
+      for (int j = 0; j < sloc; j++) {
+        double v = A[i + sloc * j];
+        if (v == 0) continue;
+        matrix_val[csr_sparsity_pos(findrm, colm, fn[i], fn[j]) - 1] += v;
+      }
+    for (int i = 0; i < sloc; i++) rhs[fn[i] - 1] += r[i];
+  }
+  return 0;
+}
+
+/* apply_dirichlet_conditions_scalar, femtools/Boundary_Conditions.F90:1982-2024, for one boundary condition:
+ * rhs(node_j) = (value_j - field(node_j))/dt with dt given ("rate of change form"), else value_j. The matrix
+ * rows are only flagged inactive there (set_inactive, :2006): `inactive` (n_nodes, may be NULL) receives
+ * the flags. nodes 1-based. */
+void orc_apply_dirichlet_scalar(int n, const int* nodes, const double* values, const double* field,
+                                int have_dt, double dt, double* rhs, int* inactive) {
+  for (int j = 0; j < n; j++) {
+    const int node = nodes[j] - 1;
+    if (inactive) inactive[node] = 1;
+    rhs[node] = have_dt ? (values[j] - field[node]) / dt : values[j];
+  }
+}
+
+/* construct_momentum_surface_element_cg, assemble/Momentum_CG.F90:959-1191, the branches inside the device
+ * path's guard (no free-surface stabilisation, continuity not by parts, single phase, static mesh):
+ *   by-parts advection boundary term :1029-1071, flux boundary condition :1180-1187.
+ * velocity_bc_type(dim): 0, BC_TYPE_WEAKDIRICHLET = 1, NO_NORMAL_FLOW = 2, INTERNAL = 3, FREE_SURFACE = 4,
+ * FLUX = 5 (:138-140). velocity_bc(dim, sloc): ele_val of the surface field. Outputs overwritten:
+ * big_m_addto(dim, sloc, sloc) (diagonal blocks only), rhs_addto(dim, sloc). */
+int orc_momentum_face(const orc_mesh* m, const orc_surface* s, const orc_momentum_fields* f,
+                      const cgasm_momentum_opts* o, int face, const int* velocity_bc_type, const double* velocity_bc,
+                      double* big_m_addto, double* rhs_addto) {
+  const int dim = m->dim, sloc = s->sloc, sngi = s->sngi;
+  if (momentum_opts_unsupported(o)) return CGASM_EUNSUPPORTED;
+  double detwei[MAXSNGI], normal[MAXDIM * MAXSNGI], c_g[MAXSNGI], mat[MAXSLOC * MAXSLOC];
+  for (int k = 0; k < dim * sloc * sloc; k++) big_m_addto[k] = 0.0;
+  for (int k = 0; k < dim * sloc; k++) rhs_addto[k] = 0.0;
+  face_geometry(m, s, face, detwei, normal);
+  double oldu_val[MAXDIM * MAXSLOC];
+  face_val_multi(s, &f->oldu, dim, face, oldu_val);
+  if (velocity_bc_type[0] != 2) {
+    if (o->integrate_advection_by_parts && !o->exclude_advection) {
+      double nu_f[MAXDIM * MAXSLOC], relu_gi[MAXDIM * MAXSNGI], rho_f[MAXSLOC], rho_q[MAXSNGI];
+      face_val_multi(s, &f->nu, dim, face, nu_f);
+      face_at_quad(s, dim, nu_f, relu_gi);
+      face_val_multi(s, &f->density, 1, face, rho_f);
+      face_at_quad(s, 1, rho_f, rho_q);
+      for (int g = 0; g < sngi; g++) {
+        double un = 0.0;
+        for (int a = 0; a < dim; a++) un += relu_gi[a + dim * g] * normal[a + dim * g];
+        c_g[g] = detwei[g] * un * rho_q[g];
+      }
+      shape_shape2(sloc, sngi, s->n_f, s->n_f, c_g, mat);
+      for (int d = 0; d < dim; d++) {
+        if (velocity_bc_type[d] == 1) {
+          for (int i = 0; i < sloc; i++) {
+            double v = 0.0;
+            for (int j = 0; j < sloc; j++) v += mat[i + sloc * j] * velocity_bc[d + dim * j];
+            rhs_addto[d + dim * i] += -v;
+          }
+        } else {
+          for (int k = 0; k < sloc * sloc; k++) big_m_addto[d + dim * k] += o->dt * o->theta * mat[k];
+          for (int i = 0; i < sloc; i++) {
+            double v = 0.0;
+            for (int j = 0; j < sloc; j++) v += mat[i + sloc * j] * oldu_val[d + dim * j];
+            rhs_addto[d + dim * i] += -v;
+          }
+        }
+      }
+    }
+  }
+  for (int d = 0; d < dim; d++)
+    if (velocity_bc_type[d] == 5) { /* shape_rhs(u_shape, ele_val_at_quad(velocity_bc, sele, dim)*detwei_bdy) */
+      double bc_d[MAXSLOC], q[MAXSNGI] = {0, 0, 0, 0}, r[MAXSLOC];
+      for (int i = 0; i < sloc; i++) bc_d[i] = velocity_bc[d + dim * i];
+      face_at_quad(s, 1, bc_d, q);
+      for (int g = 0; g < sngi; g++) c_g[g] = q[g] * detwei[g];
+      shape_rhs(sloc, sngi, s->n_f, c_g, r);
+      for (int i = 0; i < sloc; i++) rhs_addto[d + dim * i] += r[i];
+    }
+  return 0;
+}
+
+/* surface_element_loop of construct_momentum_cg, assemble/Momentum_CG.F90:795-812: faces whose only
+ * condition is no-normal-flow, or that are internal, are skipped unless they carry a pressure condition
+ * (:799-803). pressure_bc_type may be NULL (= all zero). ADDS to big_m [dim][nnz] and rhs (dim, N). */
+int orc_assemble_momentum_surface(const orc_mesh* m, const orc_surface* s, const orc_momentum_fields* f,
+                                  const cgasm_momentum_opts* o, const int* findrm, const int* colm,
+                                  const int* velocity_bc_type /*(dim,n_faces)*/, const double* velocity_bc /*(dim,sloc,n_faces)*/,
+                                  const int* pressure_bc_type, double* big_m, double* rhs) {
+  const int dim = m->dim, sloc = s->sloc;
+  const size_t nnz = (size_t)(findrm[m->n_nodes] - 1);
+  for (int face = 1; face <= s->n_faces; face++) {
+    const int* bt = velocity_bc_type + (size_t)dim * (face - 1);
+    int sum = 0, any_internal = 0;
+    for (int d = 0; d < dim; d++) {
+      sum += bt[d];
+      any_internal |= bt[d] == 3;
+    }
+    if (((bt[0] == 2 && sum == 2) || any_internal) && (!pressure_bc_type || pressure_bc_type[face - 1] == 0)) continue;
+    double B[MAXDIM * MAXSLOC * MAXSLOC], r[MAXDIM * MAXSLOC];
+    int st = orc_momentum_face(m, s, f, o, face, bt, velocity_bc + (size_t)dim * sloc * (face - 1), B, r);
+    if (st) return st;
+    const int* fn = s->sndgln + (size_t)sloc * (size_t)(face - 1);
+    for (int i = 0; i < sloc; i++)
+      for (int j = 0; j < sloc; j++) {
+        int pos = csr_sparsity_pos(findrm, colm, fn[i], fn[j]);
+        for (int d = 0; d < dim; d++) big_m[d * nnz + (size_t)(pos - 1)] += B[d + dim * (i + sloc * j)];
+      }
+    for (int i = 0; i < sloc; i++)
+      for (int d = 0; d < dim; d++) rhs[d + (size_t)dim * (fn[i] - 1)] += r[d + dim * i];
+  }
+  return 0;
+}

@@ -273,3 +273,117 @@ def halo_copy(block_size, field_p, sends_p_to_q, field_q, recvs_q_from_p):
     assert len(s) == len(r)
     lib().orc_halo_copy(C.c_int(block_size), _dp(field_p), _ip(s), C.c_int(len(s)), _dp(field_q),
                         _ip(r))
+
+
+# ---- surface loops and Dirichlet conditions -------------------------------------------
+class _Surface(C.Structure):
+    _fields_ = [("n_faces", C.c_int), ("sloc", C.c_int), ("sngi", C.c_int), ("sndgln", c_ip), ("face_ele", c_ip),
+                ("n_f", c_dp), ("dn_f", c_dp), ("weight_f", c_dp)]
+
+
+def face_tables(dim):
+    """n_f, dn_f, weight_f of the face element in the raw column-major layout (restated rule)."""
+    sloc = dim
+    l = np.zeros(4 * sloc)
+    w = np.zeros(4)
+    sngi = lib().orc_quadrature_face_degree3(C.c_int(dim), _dp(l), _dp(w))
+    n = np.zeros(sloc * sngi)
+    dn = np.zeros(sloc * sngi * (dim - 1))
+    lib().orc_shape_p1(C.c_int(dim - 1), C.c_int(sngi), _dp(l), _dp(n), _dp(dn))
+    return n, dn, w[:sngi].copy()
+
+
+def transform_facet_to_physical(dim, X_f, X_val):
+    """X_f (sloc, dim), X_val (loc, dim) rows = node positions. Returns detwei_f (sngi), normal (sngi, dim)."""
+    n, dn, w = face_tables(dim)
+    sngi = len(w)
+    detwei = np.zeros(sngi)
+    normal = np.zeros(dim * sngi)
+    lib().orc_transform_facet_to_physical(C.c_int(dim), C.c_int(dim), C.c_int(sngi),
+                                          _dp(np.ascontiguousarray(X_f, dtype=np.float64)),
+                                          _dp(np.ascontiguousarray(X_val, dtype=np.float64)), _dp(dn), _dp(w),
+                                          _dp(detwei), _dp(normal))
+    return detwei, normal.reshape(sngi, dim)
+
+
+class _SurfCtx(_Ctx):
+    def __init__(self, mesh, fields, sndgln, face_ele):
+        super().__init__(mesh, fields)
+        n, dn, w = face_tables(mesh.dim)
+        sn = np.ascontiguousarray(sndgln, dtype=np.int32)
+        fe = np.ascontiguousarray(face_ele, dtype=np.int32)
+        self.keep += [n, dn, w, sn, fe]
+        self.n_faces = len(fe)
+        self.surface = _Surface(len(fe), mesh.dim, len(w), _ip(sn), _ip(fe), _dp(n), _dp(dn), _dp(w))
+
+
+def advdiff_face(mesh, fields, opts, sndgln, face_ele, face, bc_type, t_bc=None, t_bc_2=None):
+    """matrix_addto (sloc, sloc), rhs_addto (sloc) of one face (1-based)."""
+    ctx = _SurfCtx(mesh, fields, sndgln, face_ele)
+    sloc = mesh.dim
+    A = np.zeros(sloc * sloc)
+    r = np.zeros(sloc)
+    b1 = np.ascontiguousarray(t_bc if t_bc is not None else np.zeros(sloc), dtype=np.float64)
+    b2 = np.ascontiguousarray(t_bc_2 if t_bc_2 is not None else np.zeros(sloc), dtype=np.float64)
+    af = ctx.adv()
+    st = lib().orc_advdiff_face(C.byref(ctx.mesh), C.byref(ctx.surface), C.byref(af), C.byref(opts), C.c_int(face),
+                                C.c_int(bc_type), _dp(b1), _dp(b2), _dp(A), _dp(r))
+    if st:
+        raise RuntimeError("oracle status %d" % st)
+    return A.reshape(sloc, sloc).T.copy(), r
+
+
+def assemble_advdiff_surface(mesh, fields, opts, findrm, colm, sndgln, face_ele, bc_type, t_bc, t_bc_2, matrix, rhs):
+    """ADDS the face loop to matrix (nnz) / rhs (n_nodes) in place. t_bc, t_bc_2: (n_faces, sloc) or None."""
+    ctx = _SurfCtx(mesh, fields, sndgln, face_ele)
+    bt = np.ascontiguousarray(bc_type, dtype=np.int32)
+    b1 = np.ascontiguousarray(t_bc, dtype=np.float64) if t_bc is not None else None
+    b2 = np.ascontiguousarray(t_bc_2, dtype=np.float64) if t_bc_2 is not None else None
+    af = ctx.adv()
+    st = lib().orc_assemble_advdiff_surface(C.byref(ctx.mesh), C.byref(ctx.surface), C.byref(af), C.byref(opts),
+                                            _ip(np.ascontiguousarray(findrm, dtype=np.int32)),
+                                            _ip(np.ascontiguousarray(colm, dtype=np.int32)), _ip(bt), _dp(b1), _dp(b2),
+                                            _dp(matrix), _dp(rhs))
+    if st:
+        raise RuntimeError("oracle status %d" % st)
+
+
+def apply_dirichlet_scalar(nodes, values, field, dt, rhs, inactive=None):
+    """In place on rhs (and the int32 `inactive` flags). dt None: the rhs receives the value itself."""
+    nd = np.ascontiguousarray(nodes, dtype=np.int32)
+    lib().orc_apply_dirichlet_scalar(C.c_int(len(nd)), _ip(nd), _dp(np.ascontiguousarray(values, dtype=np.float64)),
+                                     _dp(np.ascontiguousarray(field, dtype=np.float64)), C.c_int(0 if dt is None else 1),
+                                     C.c_double(dt or 0.0), _dp(rhs), _ip(inactive))
+
+
+def momentum_face(mesh, fields, opts, sndgln, face_ele, face, velocity_bc_type, velocity_bc=None):
+    """big_m_addto (dim, sloc, sloc), rhs_addto (dim, sloc) of one face. velocity_bc (sloc, dim)."""
+    ctx = _SurfCtx(mesh, fields, sndgln, face_ele)
+    dim = sloc = mesh.dim
+    B = np.zeros(dim * sloc * sloc)
+    r = np.zeros(dim * sloc)
+    bt = np.ascontiguousarray(velocity_bc_type, dtype=np.int32)
+    bv = np.ascontiguousarray(velocity_bc if velocity_bc is not None else np.zeros((sloc, dim)), dtype=np.float64)
+    mf = ctx.mom()
+    st = lib().orc_momentum_face(C.byref(ctx.mesh), C.byref(ctx.surface), C.byref(mf), C.byref(opts), C.c_int(face),
+                                 _ip(bt), _dp(bv), _dp(B), _dp(r))
+    if st:
+        raise RuntimeError("oracle status %d" % st)
+    return B.reshape(sloc, sloc, dim).transpose(2, 1, 0).copy(), r.reshape(sloc, dim).T.copy()
+
+
+def assemble_momentum_surface(mesh, fields, opts, findrm, colm, sndgln, face_ele, velocity_bc_type, velocity_bc,
+                              big_m, rhs, pressure_bc_type=None):
+    """ADDS the surface loop to big_m (dim, nnz) / rhs (n_nodes, dim) in place. velocity_bc_type (n_faces, dim),
+    velocity_bc (n_faces, sloc, dim)."""
+    ctx = _SurfCtx(mesh, fields, sndgln, face_ele)
+    bt = np.ascontiguousarray(velocity_bc_type, dtype=np.int32)
+    bv = np.ascontiguousarray(velocity_bc, dtype=np.float64)
+    pt = np.ascontiguousarray(pressure_bc_type, dtype=np.int32) if pressure_bc_type is not None else None
+    mf = ctx.mom()
+    st = lib().orc_assemble_momentum_surface(C.byref(ctx.mesh), C.byref(ctx.surface), C.byref(mf), C.byref(opts),
+                                             _ip(np.ascontiguousarray(findrm, dtype=np.int32)),
+                                             _ip(np.ascontiguousarray(colm, dtype=np.int32)), _ip(bt), _dp(bv), _ip(pt),
+                                             _dp(big_m), _dp(rhs))
+    if st:
+        raise RuntimeError("oracle status %d" % st)
