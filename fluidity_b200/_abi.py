@@ -23,6 +23,9 @@ STAB_NONE, STAB_STREAMLINE_UPWIND, STAB_SUPG = 0, 1, 2
 NU_BAR_OPTIMAL, NU_BAR_DOUBLY_ASYMPTOTIC, NU_BAR_CRITICAL_RULE, NU_BAR_UNITY = 1, 2, 3, 4
 TENSOR_ISOTROPIC, TENSOR_DIAGONAL, TENSOR_FULL = 0, 1, 2
 SCATTER_ATOMIC, SCATTER_COLOURED, SCATTER_WARPAGG, SCATTER_TILED, SCATTER_GATHER, SCATTER_STRIP = 0, 1, 2, 3, 4, 5
+# boundary-condition types of the surface loops (Advection_Diffusion_CG.F90:74-75, Momentum_CG.F90:138-140)
+TBC_NONE, TBC_NEUMANN, TBC_WEAKDIRICHLET, TBC_INTERNAL, TBC_ROBIN = range(5)
+VBC_NONE, VBC_WEAKDIRICHLET, VBC_NO_NORMAL_FLOW, VBC_INTERNAL, VBC_FREE_SURFACE, VBC_FLUX = range(6)
 
 _M_DOUBLES = ["dt", "theta", "beta", "gravity_magnitude", "nu_bar_scale"]
 _M_INTS = [

@@ -222,6 +222,38 @@ class Assembler:
         _check(self.lib.cgasm_advdiff_fetch(C.c_int(self.id), _dp(val), _dp(rhs)))
         return dict(matrix=val, rhs=rhs)
 
+    # -- surface loops and strong Dirichlet conditions (add to the device-resident result) ----
+    def set_surface(self, sndgln, face_ele, face_tables):
+        """sndgln (n_faces, sloc) 1-based, face_ele (n_faces,) 1-based, face_tables = (n_f, dn_f, weight_f)."""
+        n, dn, w = face_tables
+        sn = np.ascontiguousarray(sndgln, dtype=np.int32)
+        fe = np.ascontiguousarray(face_ele, dtype=np.int32)
+        self.n_faces = len(fe)
+        sloc = sn.shape[1] if sn.ndim == 2 else self.dim
+        _check(self.lib.cgasm_set_surface(C.c_int(self.id), C.c_int(len(fe)), C.c_int(sloc), C.c_int(len(w)), _ip(sn), _ip(fe),
+                                          _dp(np.ascontiguousarray(n)), _dp(np.ascontiguousarray(dn)),
+                                          _dp(np.ascontiguousarray(w))))
+
+    def advdiff_surface_dev(self, opts, bc_type, t_bc=None, t_bc_2=None):
+        """bc_type (n_faces,), t_bc / t_bc_2 (n_faces, sloc) or None."""
+        bt = np.ascontiguousarray(bc_type, dtype=np.int32)
+        b1 = np.ascontiguousarray(t_bc, dtype=np.float64) if t_bc is not None else None
+        b2 = np.ascontiguousarray(t_bc_2, dtype=np.float64) if t_bc_2 is not None else None
+        _check(self.lib.cgasm_advdiff_surface_dev(C.c_int(self.id), C.byref(opts), _ip(bt), _dp(b1), _dp(b2)))
+
+    def advdiff_dirichlet_dev(self, nodes, values, dt=None):
+        nd = np.ascontiguousarray(nodes, dtype=np.int32)
+        v = np.ascontiguousarray(values, dtype=np.float64)
+        _check(self.lib.cgasm_advdiff_dirichlet_dev(C.c_int(self.id), C.c_int(len(nd)), _ip(nd), _dp(v),
+                                                    C.c_int(0 if dt is None else 1), C.c_double(dt or 0.0)))
+
+    def momentum_surface_dev(self, opts, velocity_bc_type, velocity_bc=None, pressure_bc_type=None):
+        """velocity_bc_type (n_faces, dim), velocity_bc (n_faces, sloc, dim) or None, pressure_bc_type (n_faces,) or None."""
+        bt = np.ascontiguousarray(velocity_bc_type, dtype=np.int32)
+        bv = np.ascontiguousarray(velocity_bc, dtype=np.float64) if velocity_bc is not None else None
+        pt = np.ascontiguousarray(pressure_bc_type, dtype=np.int32) if pressure_bc_type is not None else None
+        _check(self.lib.cgasm_momentum_surface_dev(C.c_int(self.id), C.byref(opts), _ip(bt), _dp(bv), _ip(pt)))
+
     def momentum_result_dev(self):
         p = [C.c_void_p() for _ in range(4)]
         _check(self.lib.cgasm_momentum_result_dev(C.c_int(self.id), *[C.byref(x) for x in p]))

@@ -89,6 +89,7 @@ static void destroy_handle(Handle* h) {
   tiles_free(h);
   gather_free(h);
   halo_free(h);
+  surface_free(h);
   free_dev(h->d_ndglno);
   free_dev(h->d_X);
   free_dev(h->d_rec0);

@@ -27,6 +27,7 @@ struct DeviceField {
 struct TilePlan;    // tiled.cu
 struct GatherPlan;  // gather.cu
 struct HaloPlan;  // halo.cu
+struct SurfacePlan;  // surface.cu
 
 struct Handle {
   int device = 0;
@@ -77,6 +78,7 @@ struct Handle {
   TilePlan* tiles = nullptr;
   GatherPlan* gather = nullptr;
   HaloPlan* halo = nullptr;
+  SurfacePlan* surface = nullptr;
 
   long long launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -186,6 +188,9 @@ int strip_advdiff(Handle* h, const AdvDiffArgs& args);
 
 // halo.cu
 void halo_free(Handle* h);
+
+// surface.cu
+void surface_free(Handle* h);
 
 // cgasm_api.cu: refresh the packed record lanes fed by `slot` (-1 = coordinates); nodes == nullptr
 // repacks every node, else only the listed ones (device array of 0-based node ids).

@@ -22,7 +22,8 @@ module cgasm_interface
        & cgasm_momentum_fetch, cgasm_advdiff_fetch, cgasm_momentum_identical_blocks, &
        & cgasm_momentum_fetch_blocks, cgasm_momentum_element, &
        & cgasm_advdiff_element, cgasm_synchronize, cgasm_set_async, cgasm_halo_create, cgasm_halo_update, &
-       & cgasm_nccl_unique_id, cgasm_last_error
+       & cgasm_nccl_unique_id, cgasm_last_error, cgasm_set_surface, cgasm_advdiff_surface_dev, &
+       & cgasm_advdiff_dirichlet_dev, cgasm_momentum_surface_dev
   public :: CGASM_OK, CGASM_EUNSUPPORTED
   public :: CGASM_F_NU, CGASM_F_OLDU, CGASM_F_DENSITY, CGASM_F_VISCOSITY, CGASM_F_BUOYANCY, &
        & CGASM_F_HB_DENSITY, CGASM_F_GRAVITY, CGASM_F_ABSORPTION, CGASM_F_SOURCE, CGASM_F_T, &
@@ -242,6 +243,54 @@ module cgasm_interface
        real(c_double), dimension(*), intent(out) :: matrix_addto, rhs_addto
        integer(c_int) :: stat
      end function cgasm_advdiff_element
+
+     !! Boundary faces of the mesh: sndgln = face_global_nodes of every surface element, face_ele, and the
+     !! tables of mesh%faces%shape (n, dn, quadrature%weight)
+     function cgasm_set_surface(id, n_faces, sloc, sngi, sndgln, face_ele, n_f, dn_f, weight_f) &
+          & bind(c, name="cgasm_set_surface") result(stat)
+       use iso_c_binding
+       integer(c_int), value :: id, n_faces, sloc, sngi
+       integer(c_int), dimension(*), intent(in) :: sndgln, face_ele
+       real(c_double), dimension(*), intent(in) :: n_f, dn_f, weight_f
+       integer(c_int) :: stat
+     end function cgasm_set_surface
+
+     !! Face loop of assemble_advection_diffusion_cg (Advection_Diffusion_CG.F90:609-643), added to the
+     !! device-resident result of cgasm_advdiff_dev. t_bc, t_bc_2: (sloc, n_faces) = ele_val(t_bc, face)
+     function cgasm_advdiff_surface_dev(id, opts, bc_type, t_bc, t_bc_2) &
+          & bind(c, name="cgasm_advdiff_surface_dev") result(stat)
+       use iso_c_binding
+       import :: cgasm_advdiff_opts
+       integer(c_int), value :: id
+       type(cgasm_advdiff_opts), intent(in) :: opts
+       integer(c_int), dimension(*), intent(in) :: bc_type
+       real(c_double), dimension(*), intent(in) :: t_bc, t_bc_2
+       integer(c_int) :: stat
+     end function cgasm_advdiff_surface_dev
+
+     !! apply_dirichlet_conditions (Boundary_Conditions.F90:1982-2024) for one boundary condition
+     function cgasm_advdiff_dirichlet_dev(id, n, nodes, values, have_dt, dt) &
+          & bind(c, name="cgasm_advdiff_dirichlet_dev") result(stat)
+       use iso_c_binding
+       integer(c_int), value :: id, n, have_dt
+       integer(c_int), dimension(*), intent(in) :: nodes
+       real(c_double), dimension(*), intent(in) :: values
+       real(c_double), value :: dt
+       integer(c_int) :: stat
+     end function cgasm_advdiff_dirichlet_dev
+
+     !! surface_element_loop of construct_momentum_cg (Momentum_CG.F90:795-812): velocity_bc_type(dim, n_faces),
+     !! velocity_bc(dim, sloc, n_faces), pressure_bc_type(n_faces)
+     function cgasm_momentum_surface_dev(id, opts, velocity_bc_type, velocity_bc, pressure_bc_type) &
+          & bind(c, name="cgasm_momentum_surface_dev") result(stat)
+       use iso_c_binding
+       import :: cgasm_momentum_opts
+       integer(c_int), value :: id
+       type(cgasm_momentum_opts), intent(in) :: opts
+       integer(c_int), dimension(*), intent(in) :: velocity_bc_type, pressure_bc_type
+       real(c_double), dimension(*), intent(in) :: velocity_bc
+       integer(c_int) :: stat
+     end function cgasm_momentum_surface_dev
 
      !! on /= 0: uploads and result downloads are queued (two streams); cgasm_synchronize waits
      function cgasm_set_async(id, on) bind(c, name="cgasm_set_async") result(stat)

@@ -241,6 +241,59 @@ int cgasm_momentum_element(int id, const cgasm_momentum_opts* opts, int ele,
 int cgasm_advdiff_element(int id, const cgasm_advdiff_opts* opts, int ele,
                           double* matrix_addto, double* rhs_addto);
 
+/* ---- surface-element loops and strong Dirichlet conditions: the step right after the element loops ----
+ * (SURVEY.md 8(f) #1). They ADD to the device-resident result of the preceding cgasm_advdiff_dev /
+ * cgasm_momentum_dev call, so a shim replaces
+ *     element loop; face loop; apply_dirichlet_conditions          (Advection_Diffusion_CG.F90:569-645)
+ * by  cgasm_advdiff_dev; cgasm_advdiff_surface_dev; cgasm_advdiff_dirichlet_dev; cgasm_advdiff_fetch.
+ *
+ * cgasm_set_surface: the boundary faces of the mesh (mesh%faces: surface_element_count, face_global_nodes,
+ * face_ele, faces%shape; femtools/Fields_Base.F90:597-608,1317-1325,1917-1932). sndgln(sloc*n_faces) 1-based global nodes,
+ * face_ele(n_faces) 1-based owning element; n_f(sloc,sngi), dn_f(sloc,sngi,dim-1), weight_f(sngi): the face
+ * element's tables, column-major as in cgasm_create. P1 simplex faces only (sloc = dim, sngi <= 4). */
+int cgasm_set_surface(int id, int n_faces, int sloc, int sngi, const int* sndgln, const int* face_ele,
+                      const double* n_f, const double* dn_f, const double* weight_f);
+
+/* Tracer boundary-condition types of assemble/Advection_Diffusion_CG.F90:74-75 */
+enum {
+  CGASM_TBC_NONE = 0,
+  CGASM_TBC_NEUMANN = 1,
+  CGASM_TBC_WEAKDIRICHLET = 2,
+  CGASM_TBC_INTERNAL = 3,
+  CGASM_TBC_ROBIN = 4
+};
+/* Face loop of assemble_advection_diffusion_cg (Advection_Diffusion_CG.F90:609-643 calling
+ * assemble_advection_diffusion_face_cg :1228-1379): by-parts advection boundary term (weak Dirichlet or
+ * free), Neumann and Robin conditions of the diffusive term. bc_type(n_faces); t_bc, t_bc_2(sloc, n_faces) =
+ * ele_val of the "entire boundary condition" surface fields (either may be NULL if no face reads it). Does
+ * nothing unless (integrate_advection_by_parts and have_advection) or have_diffusivity, like the reference.
+ * CGASM_EUNSUPPORTED: a weak Dirichlet face with have_diffusivity (the reference FLExits, :1375). */
+int cgasm_advdiff_surface_dev(int id, const cgasm_advdiff_opts* opts, const int* bc_type, const double* t_bc,
+                              const double* t_bc_2);
+/* apply_dirichlet_conditions for a scalar field (femtools/Boundary_Conditions.F90:1982-2024), one call per
+ * boundary condition: rhs(nodes(j)) = (values(j) - T(nodes(j))) / dt if have_dt, else values(j). nodes are
+ * 1-based. The matrix itself is untouched: the reference only flags the rows inactive (set_inactive), which
+ * stays with the caller's csr_matrix. */
+int cgasm_advdiff_dirichlet_dev(int id, int n, const int* nodes, const double* values, int have_dt, double dt);
+
+/* Velocity boundary-condition types of assemble/Momentum_CG.F90:138-140 */
+enum {
+  CGASM_VBC_NONE = 0,
+  CGASM_VBC_WEAKDIRICHLET = 1,
+  CGASM_VBC_NO_NORMAL_FLOW = 2,
+  CGASM_VBC_INTERNAL = 3,
+  CGASM_VBC_FREE_SURFACE = 4,
+  CGASM_VBC_FLUX = 5
+};
+/* surface_element_loop of construct_momentum_cg (Momentum_CG.F90:795-812 calling
+ * construct_momentum_surface_element_cg :959-1191), the branches inside the device path's guard: by-parts
+ * advection boundary term (:1029-1071) and flux conditions (:1180-1187). velocity_bc_type(dim, n_faces),
+ * velocity_bc(dim, sloc, n_faces) = ele_val of the boundary-condition surface field (NULL if no face is weak
+ * Dirichlet or flux), pressure_bc_type(n_faces) or NULL (only enters the skip rule :799-803). The caller keeps
+ * the Fortran loop when have_fs_stab(u) (free-surface stabilisation) or integrate_continuity_by_parts. */
+int cgasm_momentum_surface_dev(int id, const cgasm_momentum_opts* opts, const int* velocity_bc_type,
+                               const double* velocity_bc, const int* pressure_bc_type);
+
 /* Asynchronous host flavour. With on != 0: cgasm_set_field returns once the upload is queued (val must
  * stay valid, ideally pinned, until cgasm_synchronize) and the *_fetch calls queue their device -> host
  * copies on a second stream behind the result and return at once, so the next element loop and the

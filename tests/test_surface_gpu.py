@@ -1,0 +1,160 @@
+"""Surface-element loops and strong Dirichlet conditions on the device, through the C ABI, against the
+oracle. Needs a B200. The per-face arithmetic is additionally checked on the CPU by
+tests/test_surface_math.py; here the kernels, the CSR position search and the atomics around it."""
+import numpy as np
+import pytest
+
+from conftest import load_golden_mesh, rel_err, row_rel_err
+from fluidity_b200 import synthetic as syn, _abi as abi, cgasm, tables
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+def make(mesh, fs, scatter=None):
+    asm = cgasm.Assembler(mesh, tables.p1_tables(mesh.dim))
+    asm.build_sparsity()
+    asm.set_fields(fs)
+    if scatter is not None:
+        asm.set_scatter(scatter)
+    sn, fe = syn.boundary_faces(mesh)
+    asm.set_surface(sn, fe, tables.p1_face_tables(mesh.dim))
+    return asm, sn, fe
+
+
+def meshes():
+    return {"box2": syn.box_mesh((9, 7), seed=3), "box3": syn.box_mesh((5, 4, 6), seed=5),
+            "cube-parallel": load_golden_mesh("cube-parallel"), "cavity": load_golden_mesh("square-cavity-2d")}
+
+
+SCATTERS = [pytest.param(abi.SCATTER_ATOMIC, id="atomic"), pytest.param(abi.SCATTER_GATHER, id="gather"),
+            pytest.param(abi.SCATTER_STRIP, id="strip")]
+
+
+@pytest.mark.parametrize("scatter", SCATTERS)
+@pytest.mark.parametrize("name", ["box2", "box3", "cube-parallel", "cavity"])
+def test_tracer_surface_loop_and_dirichlet(orc, scatter, name):
+    mesh = meshes()[name]
+    fs = syn.standard_fields(mesh)
+    asm, sn, fe = make(mesh, fs, scatter)
+    findrm, colm, _ = asm.get_sparsity()
+    rng = np.random.default_rng(7)
+    nf, sloc = len(fe), mesh.dim
+    t_bc, t_bc_2 = rng.uniform(size=(nf, sloc)), rng.uniform(0.5, 2.0, size=(nf, sloc))
+    nodes = np.unique(sn[: nf // 3].ravel())
+    vals = rng.uniform(size=len(nodes))
+    cases = [(abi.common_advdiff_opts(), rng.choice([0, 1, 3, 4], size=nf)),                                   # Neumann / Robin
+             (abi.common_advdiff_opts(integrate_advection_by_parts=1, beta=0.25), rng.choice([0, 1, 3, 4], size=nf)),
+             (abi.common_advdiff_opts(integrate_advection_by_parts=1, have_diffusivity=0), rng.choice([0, 2, 3], size=nf)),
+             (abi.common_advdiff_opts(integrate_advection_by_parts=1, have_diffusivity=0, theta=0.0), rng.choice([0, 2], size=nf))]
+    for o, bt in cases:
+        ref = orc.assemble_advdiff(mesh, fs, o, findrm, colm)
+        orc.assemble_advdiff_surface(mesh, fs, o, findrm, colm, sn, fe, bt, t_bc, t_bc_2, ref["matrix"], ref["rhs"])
+        orc.apply_dirichlet_scalar(nodes, vals, fs.get(abi.F_T)[0], o.dt, ref["rhs"])
+        asm.advdiff_dev(o)
+        asm.advdiff_surface_dev(o, bt, t_bc, t_bc_2)
+        asm.advdiff_dirichlet_dev(nodes, vals, o.dt)
+        got = asm.advdiff_fetch()
+        assert rel_err(got["matrix"], ref["matrix"]) < TOL and row_rel_err(got["matrix"], ref["matrix"], findrm) < TOL
+        assert rel_err(got["rhs"], ref["rhs"]) < TOL
+    # without a time step the Dirichlet rows receive the boundary value itself
+    asm.advdiff_dev(cases[0][0])
+    asm.advdiff_dirichlet_dev(nodes, vals)
+    assert (asm.advdiff_fetch()["rhs"][nodes - 1] == vals).all()
+
+
+@pytest.mark.parametrize("name", ["box2", "box3"])
+def test_by_parts_identity_on_the_device(name):
+    """by-parts volume loop + face loop (no boundary condition) == plain volume loop: ties the face kernel's
+    normals, measures and face mass matrices to the element kernels without the oracle."""
+    mesh = meshes()[name]
+    fs = syn.standard_fields(mesh)
+    fs.set(abi.F_DENSITY, np.array([1.3]), abi.FIELD_CONSTANT)
+    asm, sn, fe = make(mesh, fs)
+    plain = asm.advdiff(abi.common_advdiff_opts(beta=0.3))
+    o = abi.common_advdiff_opts(beta=0.3, integrate_advection_by_parts=1)
+    asm.advdiff_dev(o)
+    asm.advdiff_surface_dev(o, np.zeros(len(fe), dtype=np.int32))
+    got = asm.advdiff_fetch()
+    assert rel_err(got["matrix"], plain["matrix"]) < TOL and rel_err(got["rhs"], plain["rhs"]) < TOL
+    pm = asm.momentum(abi.common_momentum_opts(beta=0.4))
+    om = abi.common_momentum_opts(beta=0.4, integrate_advection_by_parts=1)
+    asm.momentum_dev(om)
+    asm.momentum_surface_dev(om, np.zeros((len(fe), mesh.dim), dtype=np.int32))
+    gm = asm.momentum_fetch()
+    for d in range(mesh.dim):
+        assert rel_err(gm["big_m"][d], pm["big_m"][d]) < TOL and rel_err(gm["rhs"][:, d], pm["rhs"][:, d]) < TOL
+    assert asm.momentum_identical_blocks()
+
+
+@pytest.mark.parametrize("scatter", SCATTERS)
+@pytest.mark.parametrize("name", ["box2", "box3", "cube-parallel"])
+def test_momentum_surface_loop(orc, scatter, name):
+    mesh = meshes()[name]
+    dim = mesh.dim
+    fs = syn.standard_fields(mesh)
+    asm, sn, fe = make(mesh, fs, scatter)
+    findrm, colm, _ = asm.get_sparsity()
+    rng = np.random.default_rng(9)
+    nf = len(fe)
+    vbc = rng.uniform(-1, 1, size=(nf, dim, dim))
+    vt = rng.choice([0, 1, 2, 3, 4, 5], size=(nf, dim))
+    pt = rng.choice([0, 1], size=nf)
+    for o in (abi.common_momentum_opts(integrate_advection_by_parts=1, beta=0.5), abi.common_momentum_opts(),
+              abi.common_momentum_opts(integrate_advection_by_parts=1, have_absorption=1)):
+        for ptype in (None, pt):
+            ref = orc.assemble_momentum(mesh, fs, o, findrm, colm)
+            orc.assemble_momentum_surface(mesh, fs, o, findrm, colm, sn, fe, vt, vbc, ref["big_m"], ref["rhs"], ptype)
+            asm.momentum_dev(o)
+            asm.momentum_surface_dev(o, vt, vbc, ptype)
+            got = asm.momentum_fetch()
+            for d in range(dim):
+                assert rel_err(got["big_m"][d], ref["big_m"][d]) < TOL
+                assert row_rel_err(got["big_m"][d], ref["big_m"][d], findrm) < TOL
+                assert rel_err(got["rhs"][:, d], ref["rhs"][:, d]) < TOL
+                assert rel_err(got["masslump"][:, d], ref["masslump"][:, d]) < TOL
+    # weak Dirichlet on some components only: the diagonal blocks are no longer identical
+    o = abi.common_momentum_opts(integrate_advection_by_parts=1)
+    asm.momentum_dev(o)
+    assert asm.momentum_identical_blocks()
+    asm.momentum_surface_dev(o, vt, vbc)
+    assert not asm.momentum_identical_blocks()
+
+
+def test_surface_calls_refuse_what_they_must():
+    mesh = syn.box_mesh((3, 3), seed=1)
+    fs = syn.standard_fields(mesh)
+    asm = cgasm.Assembler(mesh, tables.p1_tables(2))
+    asm.build_sparsity()
+    asm.set_fields(fs)
+    sn, fe = syn.boundary_faces(mesh)
+    o = abi.common_advdiff_opts()
+
+    def code(fn, *a):
+        with pytest.raises(cgasm.CgasmError) as ei:
+            fn(*a)
+        return ei.value.code
+
+    asm.advdiff_dev(o)
+    assert code(asm.advdiff_surface_dev, o, np.zeros(len(fe))) == abi.ESTATE           # no surface yet
+    bad = sn.copy()
+    bad[0, 0] = (set(range(1, mesh.n_nodes + 1)) - set(mesh.ndglno[fe[0] - 1].tolist())).pop()
+    assert code(asm.set_surface, bad, fe, tables.p1_face_tables(2)) == abi.EARG        # face node outside its element
+    assert code(asm.set_surface, sn, fe, tables.p1_tables(2)) == abi.EUNSUPPORTED      # wrong face element
+    asm.set_surface(sn, fe, tables.p1_face_tables(2))
+    assert code(asm.advdiff_surface_dev, o, np.full(len(fe), abi.TBC_WEAKDIRICHLET), np.zeros((len(fe), 2))) == abi.EUNSUPPORTED
+    assert code(asm.advdiff_surface_dev, o, np.full(len(fe), 9)) == abi.EARG
+    assert code(asm.advdiff_surface_dev, o, np.full(len(fe), abi.TBC_NEUMANN)) == abi.EARG   # values missing
+    assert code(asm.advdiff_dirichlet_dev, [mesh.n_nodes + 1], [0.0], 0.1) == abi.EARG
+    assert code(asm.advdiff_dirichlet_dev, [1], [0.0], 0.0) == abi.EARG
+    om = abi.common_momentum_opts()
+    assert code(asm.momentum_surface_dev, om, np.zeros((len(fe), 2))) == abi.ESTATE    # no momentum result yet
+    asm.momentum_dev(om)
+    assert code(asm.momentum_surface_dev, om, np.full((len(fe), 2), abi.VBC_FLUX)) == abi.EARG   # values missing
+    assert code(asm.momentum_surface_dev, om, np.full((len(fe), 2), 6)) == abi.EARG
+    # nothing was added by the refused calls
+    ref = asm.advdiff(o)
+    asm.advdiff_dev(o)
+    asm.advdiff_surface_dev(abi.common_advdiff_opts(have_diffusivity=0), np.full(len(fe), abi.TBC_NEUMANN))  # loop does not run
+    got = asm.advdiff_fetch()
+    assert (got["matrix"] == ref["matrix"]).all() and (got["rhs"] == ref["rhs"]).all()
