@@ -54,6 +54,20 @@ def _ip(a):
     return a.ctypes.data_as(c_ip) if a is not None else None
 
 
+def cmc_sparsity_host(findrm, colm):
+    """cgasm_cmc_sparsity_host: second-order pattern (1-based) of a first-order one, on the host."""
+    lib = load()
+    f = np.ascontiguousarray(findrm, dtype=np.int32)
+    c = np.ascontiguousarray(colm, dtype=np.int32)
+    n = len(f) - 1
+    f2 = np.zeros(n + 1, dtype=np.int32)
+    need = C.c_longlong(0)
+    _check(lib.cgasm_cmc_sparsity_host(C.c_int(n), _ip(f), _ip(c), _ip(f2), None, C.c_longlong(0), C.byref(need)))
+    c2 = np.zeros(need.value, dtype=np.int32)
+    _check(lib.cgasm_cmc_sparsity_host(C.c_int(n), _ip(f), _ip(c), _ip(f2), _ip(c2), C.c_longlong(need.value), C.byref(need)))
+    return f2, c2
+
+
 def nccl_unique_id():
     buf = C.create_string_buffer(128)
     _check(load().cgasm_nccl_unique_id(buf))
@@ -253,6 +267,35 @@ class Assembler:
         bv = np.ascontiguousarray(velocity_bc, dtype=np.float64) if velocity_bc is not None else None
         pt = np.ascontiguousarray(pressure_bc_type, dtype=np.int32) if pressure_bc_type is not None else None
         _check(self.lib.cgasm_momentum_surface_dev(C.c_int(self.id), C.byref(opts), _ip(bt), _dp(bv), _ip(pt)))
+
+    # -- lumped-mass pressure matrix C M_L^-1 C^T --------------------------------------------
+    def cmc_build_sparsity(self):
+        n = C.c_longlong(0)
+        _check(self.lib.cgasm_cmc_build_sparsity(C.c_int(self.id), C.byref(n)))
+        self.nnz2 = n.value
+        return self.nnz2
+
+    def cmc_get_sparsity(self):
+        f = np.zeros(self.n_nodes + 1, dtype=np.int32)
+        c = np.zeros(self.nnz2, dtype=np.int32)
+        _check(self.lib.cgasm_cmc_get_sparsity(C.c_int(self.id), _ip(f), _ip(c)))
+        return f, c
+
+    def cmc_set_sparsity(self, findrm2, colm2):
+        f = np.ascontiguousarray(findrm2, dtype=np.int32)
+        c = np.ascontiguousarray(colm2, dtype=np.int32)
+        _check(self.lib.cgasm_cmc_set_sparsity(C.c_int(self.id), C.c_int(len(f) - 1), C.c_int(len(c)), _ip(f), _ip(c)))
+        self.nnz2 = len(c)
+
+    def cmc_dev(self, ct_m=None, inverse_masslump=None):
+        ct = np.ascontiguousarray(ct_m, dtype=np.float64) if ct_m is not None else None
+        iv = np.ascontiguousarray(inverse_masslump, dtype=np.float64) if inverse_masslump is not None else None
+        _check(self.lib.cgasm_cmc_dev(C.c_int(self.id), _dp(ct), _dp(iv)))
+
+    def cmc_fetch(self):
+        out = np.empty(self.nnz2)
+        _check(self.lib.cgasm_cmc_fetch(C.c_int(self.id), _dp(out)))
+        return out
 
     def momentum_result_dev(self):
         p = [C.c_void_p() for _ in range(4)]

@@ -90,6 +90,7 @@ static void destroy_handle(Handle* h) {
   gather_free(h);
   halo_free(h);
   surface_free(h);
+  cmc_free(h);
   free_dev(h->d_ndglno);
   free_dev(h->d_X);
   free_dev(h->d_rec0);

@@ -28,6 +28,7 @@ struct TilePlan;    // tiled.cu
 struct GatherPlan;  // gather.cu
 struct HaloPlan;  // halo.cu
 struct SurfacePlan;  // surface.cu
+struct CmcPlan;  // cmc.cu
 
 struct Handle {
   int device = 0;
@@ -79,6 +80,7 @@ struct Handle {
   GatherPlan* gather = nullptr;
   HaloPlan* halo = nullptr;
   SurfacePlan* surface = nullptr;
+  CmcPlan* cmc = nullptr;
 
   long long launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -191,6 +193,9 @@ void halo_free(Handle* h);
 
 // surface.cu
 void surface_free(Handle* h);
+
+// cmc.cu
+void cmc_free(Handle* h);
 
 // cgasm_api.cu: refresh the packed record lanes fed by `slot` (-1 = coordinates); nodes == nullptr
 // repacks every node, else only the listed ones (device array of 0-based node ids).

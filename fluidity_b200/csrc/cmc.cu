@@ -1,0 +1,255 @@
+// cmc.cu -- lumped-mass pressure matrix cmc_m = C_P^T M_L^-1 C next to the momentum loop (SURVEY.md 8(f) #3;
+// assemble_masslumped_cmc, assemble/Assemble_CMC.F90:119-135 -> mult_div_vector_div_T,
+// femtools/Sparse_Matrices_Fields.F90:590-671). Its inputs are results of cgasm_momentum_dev that are already
+// resident: ct_m (assemble_ct_matrix_here) and the lumped mass; P1-P1, ctp_m = ct_m (single phase, not
+// compressible). The second-order sparsity is the reference's make_sparsity_mult
+// (femtools/Sparsity_Patterns.F90:150-210), adopted from the caller or built here bit-identically.
+//
+// Integer/byte-bound sparse work, no tensor-core shape: one warp per row i, lanes over the entries j of the
+// second-order row; every lane merges the two sorted first-order rows i and j (row i is the same for the whole
+// warp: broadcast loads). No atomics, every entry written once, summation in the reference's order.
+#include <omp.h>
+
+#include "cgasm_internal.h"
+#include "cmc_math.h"
+
+namespace cgasm {
+
+struct CmcPlan {
+  long long nnz2 = 0;
+  std::vector<int> h_findrm2, h_colm2;  // 0-based
+  int* d_findrm2 = nullptr;
+  int* d_colm2 = nullptr;
+  double* d_val = nullptr;
+  double* d_ct = nullptr;   // uploaded ct_m when the caller passes one
+  double* d_inv = nullptr;  // inverse lumped mass (dim, n_nodes)
+  bool valid = false;
+};
+
+void cmc_free(Handle* h) {
+  CmcPlan* P = h->cmc;
+  if (!P) return;
+  cudaFree(P->d_findrm2);
+  cudaFree(P->d_colm2);
+  cudaFree(P->d_val);
+  cudaFree(P->d_ct);
+  cudaFree(P->d_inv);
+  delete P;
+  h->cmc = nullptr;
+}
+
+// Row i of the second-order pattern = ascending union of the first-order rows of the nodes in row i.
+static void second_order_sparsity(int n, const std::vector<int>& findrm, const std::vector<int>& colm,
+                                  std::vector<int>& findrm2, std::vector<int>& colm2, long long* nnz2) {
+  std::vector<long long> ptr((size_t)n + 1, 0);
+#pragma omp parallel
+  {
+    std::vector<int> mark((size_t)n, -1);
+#pragma omp for schedule(static)
+    for (int i = 0; i < n; i++) {
+      long long c = 0;
+      for (int a = findrm[i]; a < findrm[i + 1]; a++) {
+        const int k = colm[a];
+        for (int b = findrm[k]; b < findrm[k + 1]; b++)
+          if (mark[colm[b]] != i) {
+            mark[colm[b]] = i;
+            c++;
+          }
+      }
+      ptr[(size_t)i + 1] = c;
+    }
+  }
+  for (int i = 0; i < n; i++) ptr[(size_t)i + 1] += ptr[i];
+  *nnz2 = ptr[n];
+  if (*nnz2 > 2147483647LL) return;  // the reference's integer findrm cannot hold it either
+  findrm2.resize((size_t)n + 1);
+  for (int i = 0; i <= n; i++) findrm2[i] = (int)ptr[i];
+  colm2.resize((size_t)*nnz2);
+#pragma omp parallel
+  {
+    std::vector<int> mark((size_t)n, -1);
+#pragma omp for schedule(static)
+    for (int i = 0; i < n; i++) {
+      int* out = colm2.data() + findrm2[i];
+      int c = 0;
+      for (int a = findrm[i]; a < findrm[i + 1]; a++) {
+        const int k = colm[a];
+        for (int b = findrm[k]; b < findrm[k + 1]; b++)
+          if (mark[colm[b]] != i) {
+            mark[colm[b]] = i;
+            out[c++] = colm[b];
+          }
+      }
+      std::sort(out, out + c);
+    }
+  }
+}
+
+static int upload_pattern(Handle* h) {
+  CmcPlan* P = h->cmc;
+  cudaFree(P->d_findrm2);
+  cudaFree(P->d_colm2);
+  cudaFree(P->d_val);
+  P->d_findrm2 = P->d_colm2 = nullptr;
+  P->d_val = nullptr;
+  P->valid = false;
+  CG_CUDA(cudaMalloc(&P->d_findrm2, sizeof(int) * P->h_findrm2.size()));
+  CG_CUDA(cudaMalloc(&P->d_colm2, sizeof(int) * std::max<size_t>(P->h_colm2.size(), 1)));
+  CG_CUDA(cudaMalloc(&P->d_val, sizeof(double) * std::max<size_t>(P->h_colm2.size(), 1)));
+  CG_CUDA(cudaMemcpyAsync(P->d_findrm2, P->h_findrm2.data(), sizeof(int) * P->h_findrm2.size(), cudaMemcpyHostToDevice, h->stream));
+  CG_CUDA(cudaMemcpyAsync(P->d_colm2, P->h_colm2.data(), sizeof(int) * P->h_colm2.size(), cudaMemcpyHostToDevice, h->stream));
+  CG_CUDA(cudaStreamSynchronize(h->stream));
+  return CGASM_OK;
+}
+
+constexpr int kCmcWarps = 8;  // rows per block
+
+template <int DIM>
+__global__ void __launch_bounds__(kCmcWarps * 32)
+cmc_kernel(int n_rows, const int* __restrict__ findrm, const int* __restrict__ colm, const double* __restrict__ ct, size_t nnz,
+           const double* __restrict__ inv, const int* __restrict__ findrm2, const int* __restrict__ colm2,
+           double* __restrict__ out) {
+  const int i = blockIdx.x * kCmcWarps + (threadIdx.x >> 5);
+  if (i >= n_rows) return;
+  const int lane = threadIdx.x & 31;
+  for (int e = findrm2[i] + lane; e < findrm2[i + 1]; e += 32)
+    out[e] = cmc_entry<DIM>(findrm, colm, ct, ct, nnz, inv, i, colm2[e]);
+}
+
+// invert(inverse_masslump) (assemble/Momentum_CG.F90:873): 1/x per entry
+__global__ void invert_kernel(size_t n, const double* __restrict__ x, double* __restrict__ y) {
+  const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) y[k] = 1.0 / x[k];
+}
+
+}  // namespace cgasm
+
+using namespace cgasm;
+
+#define GET_HANDLE(h, id)                                         \
+  Handle* h = get_handle(id);                                     \
+  if (!h) CG_FAIL(CGASM_EHANDLE, "unknown cgasm handle");         \
+  CG_CUDA(cudaSetDevice(h->device))
+
+extern "C" {
+
+int cgasm_cmc_build_sparsity(int id, long long* nnz2) {
+  GET_HANDLE(h, id);
+  if (!h->have_sparsity) CG_FAIL(CGASM_ESTATE, "no first-order sparsity: call cgasm_build_sparsity or cgasm_set_sparsity");
+  if (!h->cmc) h->cmc = new CmcPlan();
+  CmcPlan* P = h->cmc;
+  second_order_sparsity(h->n_nodes, h->h_findrm, h->h_colm, P->h_findrm2, P->h_colm2, &P->nnz2);
+  if (nnz2) *nnz2 = P->nnz2;
+  if (P->nnz2 > 2147483647LL) CG_FAIL(CGASM_EUNSUPPORTED, "second-order sparsity exceeds 32-bit indices: partition the mesh");
+  return upload_pattern(h);
+}
+
+int cgasm_cmc_sparsity_host(int n_nodes, const int* findrm, const int* colm, int* findrm2, int* colm2, long long capacity,
+                            long long* needed) {
+  if (n_nodes < 1 || !findrm || !colm || !needed) CG_FAIL(CGASM_EARG, "null argument");
+  std::vector<int> f0((size_t)n_nodes + 1), c0((size_t)(findrm[n_nodes] - 1)), f2, c2;
+  for (int i = 0; i <= n_nodes; i++) f0[i] = findrm[i] - 1;
+  for (size_t k = 0; k < c0.size(); k++) c0[k] = colm[k] - 1;
+  second_order_sparsity(n_nodes, f0, c0, f2, c2, needed);
+  if (*needed > 2147483647LL) CG_FAIL(CGASM_EUNSUPPORTED, "second-order sparsity exceeds 32-bit indices");
+  if (findrm2)
+    for (int i = 0; i <= n_nodes; i++) findrm2[i] = f2[i] + 1;
+  if (colm2 && *needed <= capacity)
+    for (size_t k = 0; k < c2.size(); k++) colm2[k] = c2[k] + 1;
+  return CGASM_OK;
+}
+
+int cgasm_cmc_get_sparsity(int id, int* findrm2, int* colm2) {
+  GET_HANDLE(h, id);
+  CmcPlan* P = h->cmc;
+  if (!P || P->h_findrm2.empty()) CG_FAIL(CGASM_ESTATE, "no second-order sparsity");
+  if (findrm2)
+    for (size_t i = 0; i < P->h_findrm2.size(); i++) findrm2[i] = P->h_findrm2[i] + 1;
+  if (colm2)
+    for (size_t k = 0; k < P->h_colm2.size(); k++) colm2[k] = P->h_colm2[k] + 1;
+  return CGASM_OK;
+}
+
+int cgasm_cmc_set_sparsity(int id, int rows, int nnz2, const int* findrm2, const int* colm2) {
+  GET_HANDLE(h, id);
+  if (!findrm2 || !colm2 || rows != h->n_nodes || nnz2 < 0) CG_FAIL(CGASM_EARG, "bad second-order sparsity");
+  if (findrm2[0] != 1 || findrm2[rows] != nnz2 + 1) CG_FAIL(CGASM_EARG, "findrm does not span colm");
+  for (int i = 0; i < rows; i++) {
+    if (findrm2[i + 1] < findrm2[i]) CG_FAIL(CGASM_EARG, "findrm is not monotone");
+    for (int k = findrm2[i] - 1; k < findrm2[i + 1] - 1; k++)
+      if (colm2[k] < 1 || colm2[k] > rows || (k > findrm2[i] - 1 && colm2[k] <= colm2[k - 1]))
+        CG_FAIL(CGASM_EARG, "rows of the second-order sparsity must be sorted, unique and in range");
+  }
+  if (!h->cmc) h->cmc = new CmcPlan();
+  CmcPlan* P = h->cmc;
+  P->nnz2 = nnz2;
+  P->h_findrm2.resize((size_t)rows + 1);
+  P->h_colm2.resize((size_t)nnz2);
+  for (int i = 0; i <= rows; i++) P->h_findrm2[i] = findrm2[i] - 1;
+  for (int k = 0; k < nnz2; k++) P->h_colm2[k] = colm2[k] - 1;
+  return upload_pattern(h);
+}
+
+int cgasm_cmc_dev(int id, const double* ct_m, const double* inverse_masslump) {
+  GET_HANDLE(h, id);
+  CmcPlan* P = h->cmc;
+  if (!P || !P->d_findrm2) CG_FAIL(CGASM_ESTATE, "no second-order sparsity: call cgasm_cmc_build_sparsity or cgasm_cmc_set_sparsity");
+  if (!h->have_sparsity) CG_FAIL(CGASM_ESTATE, "no first-order sparsity");
+  const size_t nnz = (size_t)h->nnz, nn = (size_t)h->n_nodes, dim = (size_t)h->dim;
+  const double* ct = nullptr;
+  if (ct_m) {
+    if (!P->d_ct) CG_CUDA(cudaMalloc(&P->d_ct, sizeof(double) * dim * std::max<size_t>(nnz, 1)));
+    CG_CUDA(cudaMemcpyAsync(P->d_ct, ct_m, sizeof(double) * dim * nnz, cudaMemcpyHostToDevice, h->stream));
+    CG_CUDA(cudaStreamSynchronize(h->stream));
+    ct = P->d_ct;
+  } else {
+    if (!h->mom_valid || !h->mom_has_ct)
+      CG_FAIL(CGASM_ESTATE, "no resident ct_m: run cgasm_momentum_dev with assemble_ct_matrix_here, or pass ct_m");
+    ct = h->d_ct_m;
+  }
+  if (!P->d_inv) CG_CUDA(cudaMalloc(&P->d_inv, sizeof(double) * dim * nn));
+  if (inverse_masslump) {
+    CG_CUDA(cudaMemcpyAsync(P->d_inv, inverse_masslump, sizeof(double) * dim * nn, cudaMemcpyHostToDevice, h->stream));
+    CG_CUDA(cudaStreamSynchronize(h->stream));
+  } else {
+    if (!h->mom_valid || !h->mom_has_masslump)
+      CG_FAIL(CGASM_ESTATE, "no resident lumped mass: run cgasm_momentum_dev with assemble_inverse_masslump, or pass inverse_masslump");
+    const size_t cnt = dim * nn;
+    invert_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, h->stream>>>(cnt, h->d_masslump, P->d_inv);
+    h->launches++;
+  }
+  CG_CUDA(cudaEventRecord(h->ev0, h->stream));
+  const int blocks = (h->n_nodes + kCmcWarps - 1) / kCmcWarps;
+  if (h->dim == 3)
+    cmc_kernel<3><<<blocks, kCmcWarps * 32, 0, h->stream>>>(h->n_nodes, h->d_findrm, h->d_colm, ct, nnz, P->d_inv, P->d_findrm2,
+                                                            P->d_colm2, P->d_val);
+  else
+    cmc_kernel<2><<<blocks, kCmcWarps * 32, 0, h->stream>>>(h->n_nodes, h->d_findrm, h->d_colm, ct, nnz, P->d_inv, P->d_findrm2,
+                                                            P->d_colm2, P->d_val);
+  h->launches++;
+  CG_CUDA(cudaEventRecord(h->ev1, h->stream));
+  CG_CUDA(cudaGetLastError());
+  P->valid = true;
+  return CGASM_OK;
+}
+
+int cgasm_cmc_fetch(int id, double* cmc_val) {
+  GET_HANDLE(h, id);
+  CmcPlan* P = h->cmc;
+  if (!P || !P->valid) CG_FAIL(CGASM_ESTATE, "no cmc result to fetch");
+  if (!cmc_val) CG_FAIL(CGASM_EARG, "null output");
+  CG_CUDA(cudaMemcpyAsync(cmc_val, P->d_val, sizeof(double) * (size_t)P->nnz2, cudaMemcpyDeviceToHost, h->stream));
+  CG_CUDA(cudaStreamSynchronize(h->stream));
+  return CGASM_OK;
+}
+
+int cgasm_cmc_result_dev(int id, double** cmc_val_dev) {
+  GET_HANDLE(h, id);
+  CmcPlan* P = h->cmc;
+  if (!P || !P->valid) CG_FAIL(CGASM_ESTATE, "no cmc result");
+  if (!cmc_val_dev) CG_FAIL(CGASM_EARG, "null output");
+  *cmc_val_dev = P->d_val;
+  return CGASM_OK;
+}
+
+}  // extern "C"

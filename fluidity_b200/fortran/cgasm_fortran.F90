@@ -23,7 +23,8 @@ module cgasm_interface
        & cgasm_momentum_fetch_blocks, cgasm_momentum_element, &
        & cgasm_advdiff_element, cgasm_synchronize, cgasm_set_async, cgasm_halo_create, cgasm_halo_update, &
        & cgasm_nccl_unique_id, cgasm_last_error, cgasm_set_surface, cgasm_advdiff_surface_dev, &
-       & cgasm_advdiff_dirichlet_dev, cgasm_momentum_surface_dev
+       & cgasm_advdiff_dirichlet_dev, cgasm_momentum_surface_dev, cgasm_cmc_build_sparsity, &
+       & cgasm_cmc_get_sparsity, cgasm_cmc_set_sparsity, cgasm_cmc_dev, cgasm_cmc_fetch
   public :: CGASM_OK, CGASM_EUNSUPPORTED
   public :: CGASM_F_NU, CGASM_F_OLDU, CGASM_F_DENSITY, CGASM_F_VISCOSITY, CGASM_F_BUOYANCY, &
        & CGASM_F_HB_DENSITY, CGASM_F_GRAVITY, CGASM_F_ABSORPTION, CGASM_F_SOURCE, CGASM_F_T, &
@@ -291,6 +292,45 @@ module cgasm_interface
        real(c_double), dimension(*), intent(in) :: velocity_bc
        integer(c_int) :: stat
      end function cgasm_momentum_surface_dev
+
+     !! Lumped-mass pressure matrix (assemble_masslumped_cmc, Assemble_CMC.F90:119-135) on the second-order
+     !! sparsity of get_csr_sparsity_secondorder: adopt cmc_m%sparsity (findrm, colm) or build the same pattern
+     function cgasm_cmc_set_sparsity(id, rows, nnz2, findrm2, colm2) bind(c, name="cgasm_cmc_set_sparsity") result(stat)
+       use iso_c_binding
+       integer(c_int), value :: id, rows, nnz2
+       integer(c_int), dimension(*), intent(in) :: findrm2, colm2
+       integer(c_int) :: stat
+     end function cgasm_cmc_set_sparsity
+
+     function cgasm_cmc_build_sparsity(id, nnz2) bind(c, name="cgasm_cmc_build_sparsity") result(stat)
+       use iso_c_binding
+       integer(c_int), value :: id
+       integer(c_long_long), intent(out) :: nnz2
+       integer(c_int) :: stat
+     end function cgasm_cmc_build_sparsity
+
+     function cgasm_cmc_get_sparsity(id, findrm2, colm2) bind(c, name="cgasm_cmc_get_sparsity") result(stat)
+       use iso_c_binding
+       integer(c_int), value :: id
+       integer(c_int), dimension(*), intent(out) :: findrm2, colm2
+       integer(c_int) :: stat
+     end function cgasm_cmc_get_sparsity
+
+     !! ct_m: the dim blocks of ct_m%val(1,d)%ptr back to back; inverse_masslump%val(dim, nodes). Pass
+     !! c_null_ptr-associated arrays (or use the *_resident wrapper of INTEGRATION.md) to use the device copies
+     function cgasm_cmc_dev(id, ct_m, inverse_masslump) bind(c, name="cgasm_cmc_dev") result(stat)
+       use iso_c_binding
+       integer(c_int), value :: id
+       type(c_ptr), value :: ct_m, inverse_masslump
+       integer(c_int) :: stat
+     end function cgasm_cmc_dev
+
+     function cgasm_cmc_fetch(id, cmc_val) bind(c, name="cgasm_cmc_fetch") result(stat)
+       use iso_c_binding
+       integer(c_int), value :: id
+       real(c_double), dimension(*), intent(out) :: cmc_val
+       integer(c_int) :: stat
+     end function cgasm_cmc_fetch
 
      !! on /= 0: uploads and result downloads are queued (two streams); cgasm_synchronize waits
      function cgasm_set_async(id, on) bind(c, name="cgasm_set_async") result(stat)

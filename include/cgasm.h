@@ -294,6 +294,28 @@ enum {
 int cgasm_momentum_surface_dev(int id, const cgasm_momentum_opts* opts, const int* velocity_bc_type,
                                const double* velocity_bc, const int* pressure_bc_type);
 
+/* ---- lumped-mass pressure matrix next to the momentum loop -------------------------
+ * cmc_m = C_P^T M_L^-1 C: assemble_masslumped_cmc (assemble/Assemble_CMC.F90:119-135) ->
+ * mult_div_vector_div_T (femtools/Sparse_Matrices_Fields.F90:590-671), for P1-P1 with ctp_m = ct_m (single
+ * phase, not compressible). Values live on the SECOND-ORDER sparsity get_csr_sparsity_secondorder builds with
+ * make_sparsity_mult (femtools/Sparsity_Patterns.F90:150-210): adopt the reference's pattern with
+ * cgasm_cmc_set_sparsity(rows, nnz2, findrm, colm) (1-based, sorted rows) or let the library build the same
+ * pattern (cgasm_cmc_build_sparsity; cgasm_cmc_get_sparsity returns it 1-based for the bit-exact check). */
+int cgasm_cmc_build_sparsity(int id, long long* nnz2);
+int cgasm_cmc_get_sparsity(int id, int* findrm2, int* colm2);
+int cgasm_cmc_set_sparsity(int id, int rows, int nnz2, const int* findrm2, const int* colm2);
+/* ct_m: host [dim][nnz] blocks on the first-order sparsity, or NULL = the ct_m left on the device by the last
+ * cgasm_momentum_dev with assemble_ct_matrix_here. inverse_masslump: host (dim, n_nodes) -- what the caller
+ * holds after invert() and apply_dirichlet_conditions_inverse_mass (Momentum_CG.F90:873-876) -- or NULL =
+ * 1 / (lumped mass of the last cgasm_momentum_dev), i.e. no strong Dirichlet rows. */
+int cgasm_cmc_dev(int id, const double* ct_m, const double* inverse_masslump);
+int cgasm_cmc_fetch(int id, double* cmc_val);            /* nnz2 values in the order of the second-order colm */
+int cgasm_cmc_result_dev(int id, double** cmc_val_dev);  /* raw device pointer of the last result */
+/* Diagnostics (host only, no GPU): the second-order pattern of a first-order one (both 1-based). findrm2
+ * (n_nodes+1) is always written; colm2 only if *needed <= capacity. */
+int cgasm_cmc_sparsity_host(int n_nodes, const int* findrm, const int* colm, int* findrm2, int* colm2,
+                            long long capacity, long long* needed);
+
 /* Asynchronous host flavour. With on != 0: cgasm_set_field returns once the upload is queued (val must
  * stay valid, ideally pinned, until cgasm_synchronize) and the *_fetch calls queue their device -> host
  * copies on a second stream behind the result and return at once, so the next element loop and the

@@ -1568,3 +1568,74 @@ int orc_assemble_momentum_surface(const orc_mesh* m, const orc_surface* s, const
   }
   return 0;
 }
+
+/* ====================================================================================
+ * Lumped-mass pressure matrix C M_L^-1 C^T next to the path.
+ * ==================================================================================== */
+
+/* make_sparsity_mult, femtools/Sparsity_Patterns.F90:150-210, for mesh1 = mesh2 = mesh3 (P1-P1): the
+ * second-order sparsity get_csr_sparsity_secondorder hands to cmc_m
+ * (femtools/Sparsity_Patterns_Meshes.F90:122-148). Row i = ascending union of the first-order rows of
+ * the nodes in first-order row i (insert_ascending :182). 1-based in and out; caller frees with orc_free. */
+int orc_make_sparsity_mult(int n_nodes, const int* findrm, const int* colm, int** findrm_out, int** colm_out) {
+  ilist_pool pool = {0};
+  int* head = (int*)malloc(sizeof(int) * (size_t)n_nodes);
+  int* length = (int*)calloc((size_t)n_nodes, sizeof(int));
+  for (int i = 0; i < n_nodes; i++) head[i] = -1;
+  /* do i = 1, count_2: row_1 = row_3 = first-order row of node i (lists of mesh2 x mesh1 / mesh3) */
+  for (int i = 0; i < n_nodes; i++)
+    for (int j = findrm[i] - 1; j < findrm[i + 1] - 1; j++)
+      for (int k = findrm[i] - 1; k < findrm[i + 1] - 1; k++)
+        insert_ascending(&pool, &head[colm[k] - 1], &length[colm[k] - 1], colm[j]);
+  int* fr = (int*)malloc(sizeof(int) * (size_t)(n_nodes + 1));
+  fr[0] = 1;
+  for (int i = 0; i < n_nodes; i++) fr[i + 1] = fr[i] + length[i];
+  const int nnz = fr[n_nodes] - 1;
+  int* cm = (int*)malloc(sizeof(int) * (size_t)(nnz > 0 ? nnz : 1));
+  for (int i = 0; i < n_nodes; i++) {
+    int p = fr[i] - 1;
+    for (int node = head[i]; node >= 0; node = pool.pool[node].next) cm[p++] = pool.pool[node].value;
+  }
+  free(pool.pool);
+  free(head);
+  free(length);
+  *findrm_out = fr;
+  *colm_out = cm;
+  return nnz;
+}
+
+/* mult_div_vector_div_T, femtools/Sparse_Matrices_Fields.F90:590-671, called by assemble_masslumped_cmc
+ * (assemble/Assemble_CMC.F90:119-135) with matrix1 = ctp_m, matrix2 = ct_m (1 x dim blocks on the
+ * first-order sparsity, sorted rows) and vfield = inverse_masslump(dim, N):
+ *   product_ij = sum_k sum_d A_d(i,k) B_d(j,k) v(d,k), both rows walked left to right (:643-656).
+ * ct1 / ct2: [dim][nnz]. product: values on the second-order sparsity, overwritten. */
+void orc_mult_div_vector_div_T(int dim, int n_nodes, const int* findrm, const int* colm, const double* ct1,
+                               const double* ct2, const double* vfield, const int* findrm2, const int* colm2,
+                               double* product) {
+  const size_t nnz = (size_t)(findrm[n_nodes] - 1);
+  size_t nentry0 = 0;
+  for (int i = 1; i <= n_nodes; i++) {
+    const int r0 = findrm[i - 1] - 1, rn = findrm[i] - findrm[i - 1];
+    for (int jcol = findrm2[i - 1] - 1; jcol < findrm2[i] - 1; jcol++) {
+      const int j = colm2[jcol];
+      const int c0 = findrm[j - 1] - 1, cn = findrm[j] - findrm[j - 1];
+      double entry0 = 0.0;
+      int k1 = 1, k2 = 1;
+      while (k1 <= rn && k2 <= cn) {
+        const int a = colm[r0 + k1 - 1], b = colm[c0 + k2 - 1];
+        if (a < b) {
+          k1 = k1 + 1;
+        } else if (a == b) {
+          for (int d = 0; d < dim; d++)
+            entry0 = entry0 + ct1[d * nnz + (size_t)(r0 + k1 - 1)] * ct2[d * nnz + (size_t)(c0 + k2 - 1)] *
+                                  vfield[d + (size_t)dim * (size_t)(a - 1)];
+          k1 = k1 + 1;
+          k2 = k2 + 1;
+        } else {
+          k2 = k2 + 1;
+        }
+      }
+      product[nentry0++] = entry0;
+    }
+  }
+}

@@ -387,3 +387,31 @@ def assemble_momentum_surface(mesh, fields, opts, findrm, colm, sndgln, face_ele
                                              _dp(big_m), _dp(rhs))
     if st:
         raise RuntimeError("oracle status %d" % st)
+
+
+# ---- lumped-mass pressure matrix ----------------------------------------------------------
+def make_sparsity_mult(n_nodes, findrm, colm):
+    """Second-order sparsity (make_sparsity_mult, P1-P1): findrm2, colm2, 1-based."""
+    f, c = c_ip(), c_ip()
+    lib().orc_make_sparsity_mult.restype = C.c_int
+    nnz = lib().orc_make_sparsity_mult(C.c_int(n_nodes), _ip(np.ascontiguousarray(findrm, dtype=np.int32)),
+                                       _ip(np.ascontiguousarray(colm, dtype=np.int32)), C.byref(f), C.byref(c))
+    findrm2 = np.ctypeslib.as_array(f, shape=(n_nodes + 1,)).copy()
+    colm2 = np.ctypeslib.as_array(c, shape=(max(nnz, 1),)).copy()[:nnz]
+    lib().orc_free(f)
+    lib().orc_free(c)
+    return findrm2, colm2
+
+
+def mult_div_vector_div_T(findrm, colm, ct1, ct2, vfield, findrm2, colm2):
+    """product = ct1 . diag(vfield) . ct2^T on the second-order sparsity. ct (dim, nnz); vfield (n_nodes, dim)."""
+    ct1 = np.ascontiguousarray(ct1, dtype=np.float64)
+    ct2 = np.ascontiguousarray(ct2, dtype=np.float64)
+    v = np.ascontiguousarray(vfield, dtype=np.float64)
+    dim, n_nodes = ct1.shape[0], len(findrm) - 1
+    out = np.zeros(len(colm2))
+    lib().orc_mult_div_vector_div_T(C.c_int(dim), C.c_int(n_nodes), _ip(np.ascontiguousarray(findrm, dtype=np.int32)),
+                                    _ip(np.ascontiguousarray(colm, dtype=np.int32)), _dp(ct1), _dp(ct2), _dp(v),
+                                    _ip(np.ascontiguousarray(findrm2, dtype=np.int32)),
+                                    _ip(np.ascontiguousarray(colm2, dtype=np.int32)), _dp(out))
+    return out
