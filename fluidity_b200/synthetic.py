@@ -139,7 +139,14 @@ def boundary_faces(mesh):
     loc = mesh.loc
     faces = np.stack([np.delete(nd, k, axis=1) for k in range(loc)], axis=1)  # (ne, loc, sloc)
     key = np.sort(faces, axis=2).reshape(-1, loc - 1)
-    _, inv, cnt = np.unique(key, axis=0, return_inverse=True, return_counts=True)
+    n = mesh.n_nodes + 1
+    if n ** (loc - 1) < 2 ** 62:  # one integer per facet: much faster than a row-wise unique
+        k1 = key[:, 0].copy()
+        for c in range(1, loc - 1):
+            k1 = k1 * n + key[:, c]
+        _, inv, cnt = np.unique(k1, return_inverse=True, return_counts=True)
+    else:
+        _, inv, cnt = np.unique(key, axis=0, return_inverse=True, return_counts=True)
     on_boundary = (cnt[inv.ravel()] == 1).reshape(nd.shape[0], loc)
     e, k = np.nonzero(on_boundary)
     return np.ascontiguousarray(faces[e, k], dtype=np.int32), (e + 1).astype(np.int32)
