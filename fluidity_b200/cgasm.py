@@ -68,6 +68,24 @@ def cmc_sparsity_host(findrm, colm):
     return f2, c2
 
 
+def cmc_expand_plan_host(findrm, colm, findrm2, colm2):
+    """cgasm_cmc_expand_plan_host: (tpos, pptr, slots, n2max) or None if the patterns admit no expansion plan."""
+    lib = load()
+    a = [np.ascontiguousarray(x, dtype=np.int32) for x in (findrm, colm, findrm2, colm2)]
+    n = len(a[0]) - 1
+    tpos = np.zeros(len(a[1]), dtype=np.int32)
+    pptr = np.zeros(n + 1, dtype=np.int64)
+    need, n2max = C.c_longlong(0), C.c_int(0)
+    args = [C.c_int(n)] + [_ip(x) for x in a] + [_ip(tpos), pptr.ctypes.data_as(C.POINTER(C.c_longlong))]
+    _check(lib.cgasm_cmc_expand_plan_host(*args, None, C.c_longlong(0), C.byref(need), C.byref(n2max)))
+    if need.value < 0:
+        return None
+    slots = np.zeros(need.value, dtype=np.uint16)
+    _check(lib.cgasm_cmc_expand_plan_host(*args, slots.ctypes.data_as(C.POINTER(C.c_ushort)), C.c_longlong(need.value),
+                                          C.byref(need), C.byref(n2max)))
+    return tpos, pptr, slots, n2max.value
+
+
 def nccl_unique_id():
     buf = C.create_string_buffer(128)
     _check(load().cgasm_nccl_unique_id(buf))

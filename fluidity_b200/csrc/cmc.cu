@@ -5,10 +5,15 @@
 // compressible). The second-order sparsity is the reference's make_sparsity_mult
 // (femtools/Sparsity_Patterns.F90:150-210), adopted from the caller or built here bit-identically.
 //
-// Integer/byte-bound sparse work, no tensor-core shape: one warp per row i, lanes over the entries j of the
-// second-order row; every lane merges the two sorted first-order rows i and j (row i is the same for the whole
-// warp: broadcast loads). No atomics, every entry written once, summation in the reference's order.
+// Integer/byte-bound sparse work, no tensor-core shape. Two kernels, same bits:
+//   expand (default)  half-warp per row i, the second-order row accumulated in shared memory by expanding
+//                     (k in row i) x (j in row k) with precomputed slots and transposed positions;
+//   merge (fallback: asymmetric first-order pattern, rows longer than the accumulator, CGASM_CMC_MERGE=1)
+//                     warp per row i, every lane merges the sorted rows i and j like the reference's loop.
+// No atomics, every entry written once, summation in the reference's order.
 #include <omp.h>
+
+#include <cstdlib>
 
 #include "cgasm_internal.h"
 #include "cmc_math.h"
@@ -24,6 +29,17 @@ struct CmcPlan {
   double* d_ct = nullptr;   // uploaded ct_m when the caller passes one
   double* d_inv = nullptr;  // inverse lumped mass (dim, n_nodes)
   bool valid = false;
+  // expansion plan (expand kernel): transposed positions of the first-order entries, and for every row i the
+  // second-order slot of each (k in row i, j in row k) pair, rows of k back to back
+  bool have_expand = false;
+  int n2max = 0;
+  int slot_bytes = 0;  // 1 or 2
+  std::vector<int> h_tpos;
+  std::vector<long long> h_pptr;
+  std::vector<unsigned char> h_slots;
+  int* d_tpos = nullptr;
+  long long* d_pptr = nullptr;
+  unsigned char* d_slots = nullptr;
 };
 
 void cmc_free(Handle* h) {
@@ -34,6 +50,9 @@ void cmc_free(Handle* h) {
   cudaFree(P->d_val);
   cudaFree(P->d_ct);
   cudaFree(P->d_inv);
+  cudaFree(P->d_tpos);
+  cudaFree(P->d_pptr);
+  cudaFree(P->d_slots);
   delete P;
   h->cmc = nullptr;
 }
@@ -85,6 +104,61 @@ static void second_order_sparsity(int n, const std::vector<int>& findrm, const s
   }
 }
 
+// Expansion plan. Returns false (no plan: the merge kernel runs) if the first-order pattern is not structurally
+// symmetric, a second-order row is not the union the expansion needs, or a row is too long for the accumulator.
+constexpr int kExpandMaxRow2 = 384;  // 16 half-warps x 384 doubles = 48 KB of shared memory per block
+static bool build_expand_plan(int n, const std::vector<int>& findrm, const std::vector<int>& colm,
+                              const std::vector<int>& findrm2, const std::vector<int>& colm2, CmcPlan* P) {
+  P->have_expand = false;
+  const size_t nnz = colm.size();
+  P->h_tpos.assign(nnz, -1);
+  bool ok = true;
+  int n2max = 0;
+#pragma omp parallel for schedule(static) reduction(&& : ok) reduction(max : n2max)
+  for (int k = 0; k < n; k++) {
+    n2max = std::max(n2max, findrm2[k + 1] - findrm2[k]);
+    for (int p = findrm[k]; p < findrm[k + 1]; p++) {
+      const int j = colm[p];
+      const int* b = colm.data() + findrm[j];
+      const int* e = colm.data() + findrm[j + 1];
+      const int* it = std::lower_bound(b, e, k);
+      if (it == e || *it != k) ok = false;
+      else P->h_tpos[p] = (int)(it - colm.data());
+    }
+  }
+  if (!ok || n2max > kExpandMaxRow2) return false;
+  P->n2max = n2max;
+  P->slot_bytes = n2max <= 256 ? 1 : 2;
+  P->h_pptr.assign((size_t)n + 1, 0);
+  for (int i = 0; i < n; i++) {
+    long long c = 0;
+    for (int a = findrm[i]; a < findrm[i + 1]; a++) c += findrm[colm[a] + 1] - findrm[colm[a]];
+    P->h_pptr[(size_t)i + 1] = P->h_pptr[i] + c;
+  }
+  P->h_slots.assign((size_t)P->h_pptr[n] * P->slot_bytes, 0);
+#pragma omp parallel
+  {
+    std::vector<int> slot_of((size_t)n, -1);
+#pragma omp for schedule(static) reduction(&& : ok)
+    for (int i = 0; i < n; i++) {
+      for (int s = findrm2[i]; s < findrm2[i + 1]; s++) slot_of[colm2[s]] = s - findrm2[i];
+      long long w = P->h_pptr[i];
+      for (int a = findrm[i]; a < findrm[i + 1]; a++) {
+        const int k = colm[a];
+        for (int p = findrm[k]; p < findrm[k + 1]; p++, w++) {
+          const int s = slot_of[colm[p]];
+          if (s < 0) ok = false;  // the adopted second-order pattern lacks an entry of S.S
+          else if (P->slot_bytes == 1) P->h_slots[(size_t)w] = (unsigned char)s;
+          else reinterpret_cast<unsigned short*>(P->h_slots.data())[(size_t)w] = (unsigned short)s;
+        }
+      }
+      for (int s = findrm2[i]; s < findrm2[i + 1]; s++) slot_of[colm2[s]] = -1;
+    }
+  }
+  P->have_expand = ok;
+  return ok;
+}
+
 static int upload_pattern(Handle* h) {
   CmcPlan* P = h->cmc;
   cudaFree(P->d_findrm2);
@@ -99,6 +173,25 @@ static int upload_pattern(Handle* h) {
   CG_CUDA(cudaMemcpyAsync(P->d_findrm2, P->h_findrm2.data(), sizeof(int) * P->h_findrm2.size(), cudaMemcpyHostToDevice, h->stream));
   CG_CUDA(cudaMemcpyAsync(P->d_colm2, P->h_colm2.data(), sizeof(int) * P->h_colm2.size(), cudaMemcpyHostToDevice, h->stream));
   CG_CUDA(cudaStreamSynchronize(h->stream));
+  cudaFree(P->d_tpos);
+  cudaFree(P->d_pptr);
+  cudaFree(P->d_slots);
+  P->d_tpos = nullptr;
+  P->d_pptr = nullptr;
+  P->d_slots = nullptr;
+  if (build_expand_plan(h->n_nodes, h->h_findrm, h->h_colm, P->h_findrm2, P->h_colm2, P)) {
+    CG_CUDA(cudaMalloc(&P->d_tpos, sizeof(int) * std::max<size_t>(P->h_tpos.size(), 1)));
+    CG_CUDA(cudaMalloc(&P->d_pptr, sizeof(long long) * P->h_pptr.size()));
+    CG_CUDA(cudaMalloc(&P->d_slots, std::max<size_t>(P->h_slots.size(), 1)));
+    CG_CUDA(cudaMemcpyAsync(P->d_tpos, P->h_tpos.data(), sizeof(int) * P->h_tpos.size(), cudaMemcpyHostToDevice, h->stream));
+    CG_CUDA(cudaMemcpyAsync(P->d_pptr, P->h_pptr.data(), sizeof(long long) * P->h_pptr.size(), cudaMemcpyHostToDevice, h->stream));
+    CG_CUDA(cudaMemcpyAsync(P->d_slots, P->h_slots.data(), P->h_slots.size(), cudaMemcpyHostToDevice, h->stream));
+    CG_CUDA(cudaStreamSynchronize(h->stream));
+  }
+  // the host copies of the plan are only needed by the diagnostics entry point
+  std::vector<unsigned char>().swap(P->h_slots);
+  std::vector<int>().swap(P->h_tpos);
+  std::vector<long long>().swap(P->h_pptr);
   return CGASM_OK;
 }
 
@@ -114,6 +207,51 @@ cmc_kernel(int n_rows, const int* __restrict__ findrm, const int* __restrict__ c
   const int lane = threadIdx.x & 31;
   for (int e = findrm2[i] + lane; e < findrm2[i + 1]; e += 32)
     out[e] = cmc_entry<DIM>(findrm, colm, ct, ct, nnz, inv, i, colm2[e]);
+}
+
+// Expansion kernel: one HALF-warp per row i (first-order rows of P1 meshes have ~15-27 entries: 16 lanes keep them
+// busy), 16 rows per block. The second-order row is accumulated in shared memory; for each column k of row i, in
+// ascending order, the lanes take the entries (k, j) of row k -- distinct j, so distinct accumulator slots, plain
+// read-modify-write -- and a __syncwarp separates the k steps. Slots and transposed positions come from the plan:
+// no searching, no merging, the plan and row k are read coalesced. Same bits as the merge kernel.
+constexpr int kExpandRows = 16;
+
+template <int DIM, class SLOT>
+__global__ void __launch_bounds__(kExpandRows * 16)
+cmc_expand_kernel(int n_rows, const int* __restrict__ findrm, const int* __restrict__ colm, const double* __restrict__ ct,
+                  size_t nnz, const double* __restrict__ inv, const int* __restrict__ tpos, const long long* __restrict__ pptr,
+                  const SLOT* __restrict__ slots, const int* __restrict__ findrm2, int n2max, double* __restrict__ out) {
+  extern __shared__ double cmc_acc[];
+  const int hw = threadIdx.x >> 4, hl = threadIdx.x & 15;
+  const int i = blockIdx.x * kExpandRows + hw;
+  double* acc = cmc_acc + (size_t)hw * n2max;
+  const bool live = i < n_rows;
+  const int r0 = live ? findrm[i] : 0;
+  const int n1 = live ? findrm[i + 1] - r0 : 0;
+  const int o0 = live ? findrm2[i] : 0;
+  const int n2 = live ? findrm2[i + 1] - o0 : 0;
+  for (int s = hl; s < n2; s += 16) acc[s] = 0.0;
+  const int n1_both = max(n1, __shfl_xor_sync(0xffffffffu, n1, 16));  // the two halves of a warp step together
+  __syncwarp();
+  long long pp = live ? pptr[i] : 0;
+  for (int a = 0; a < n1_both; a++) {
+    if (a < n1) {
+      const int k = colm[r0 + a];
+      double Ad[DIM], Wd[DIM];
+      for (int d = 0; d < DIM; d++) {
+        Ad[d] = ct[d * nnz + r0 + a];
+        Wd[d] = inv[(size_t)DIM * k + d];
+      }
+      const int kb = findrm[k], kn = findrm[k + 1] - kb;
+      for (int q = hl; q < kn; q += 16) {
+        const int s = (int)slots[pp + q];
+        acc[s] = cmc_accumulate<DIM>(acc[s], Ad, Wd, ct, nnz, tpos[kb + q]);
+      }
+      pp += kn;
+    }
+    __syncwarp();
+  }
+  for (int s = hl; s < n2; s += 16) out[o0 + s] = acc[s];
 }
 
 // invert(inverse_masslump) (assemble/Momentum_CG.F90:873): 1/x per entry
@@ -156,6 +294,35 @@ int cgasm_cmc_sparsity_host(int n_nodes, const int* findrm, const int* colm, int
     for (int i = 0; i <= n_nodes; i++) findrm2[i] = f2[i] + 1;
   if (colm2 && *needed <= capacity)
     for (size_t k = 0; k < c2.size(); k++) colm2[k] = c2[k] + 1;
+  return CGASM_OK;
+}
+
+int cgasm_cmc_expand_plan_host(int n_nodes, const int* findrm, const int* colm, const int* findrm2, const int* colm2,
+                               int* tpos, long long* pptr, unsigned short* slots, long long capacity, long long* needed,
+                               int* n2max) {
+  if (n_nodes < 1 || !findrm || !colm || !findrm2 || !colm2 || !needed) CG_FAIL(CGASM_EARG, "null argument");
+  auto zero_based = [](const int* a, size_t n) {
+    std::vector<int> v(n);
+    for (size_t k = 0; k < n; k++) v[k] = a[k] - 1;
+    return v;
+  };
+  const std::vector<int> f0 = zero_based(findrm, (size_t)n_nodes + 1), c0 = zero_based(colm, (size_t)(findrm[n_nodes] - 1));
+  const std::vector<int> f2 = zero_based(findrm2, (size_t)n_nodes + 1), c2 = zero_based(colm2, (size_t)(findrm2[n_nodes] - 1));
+  CmcPlan P;
+  if (!build_expand_plan(n_nodes, f0, c0, f2, c2, &P)) {
+    *needed = -1;  // no expansion plan for these patterns: the merge kernel would run
+    return CGASM_OK;
+  }
+  *needed = P.h_pptr[n_nodes];
+  if (n2max) *n2max = P.n2max;
+  if (tpos)
+    for (size_t k = 0; k < P.h_tpos.size(); k++) tpos[k] = P.h_tpos[k];
+  if (pptr)
+    for (size_t k = 0; k < P.h_pptr.size(); k++) pptr[k] = P.h_pptr[k];
+  if (slots && *needed <= capacity)
+    for (long long k = 0; k < *needed; k++)
+      slots[k] = P.slot_bytes == 1 ? (unsigned short)P.h_slots[(size_t)k]
+                                   : reinterpret_cast<const unsigned short*>(P.h_slots.data())[(size_t)k];
   return CGASM_OK;
 }
 
@@ -219,13 +386,31 @@ int cgasm_cmc_dev(int id, const double* ct_m, const double* inverse_masslump) {
     h->launches++;
   }
   CG_CUDA(cudaEventRecord(h->ev0, h->stream));
-  const int blocks = (h->n_nodes + kCmcWarps - 1) / kCmcWarps;
-  if (h->dim == 3)
-    cmc_kernel<3><<<blocks, kCmcWarps * 32, 0, h->stream>>>(h->n_nodes, h->d_findrm, h->d_colm, ct, nnz, P->d_inv, P->d_findrm2,
-                                                            P->d_colm2, P->d_val);
-  else
-    cmc_kernel<2><<<blocks, kCmcWarps * 32, 0, h->stream>>>(h->n_nodes, h->d_findrm, h->d_colm, ct, nnz, P->d_inv, P->d_findrm2,
-                                                            P->d_colm2, P->d_val);
+  const bool expand = P->d_slots && !getenv("CGASM_CMC_MERGE");
+  if (expand) {
+    const int blocks = (h->n_nodes + kExpandRows - 1) / kExpandRows;
+    const size_t smem = sizeof(double) * (size_t)kExpandRows * P->n2max;
+#define EXPAND(DIM_, SLOT_)                                                                                              \
+  cmc_expand_kernel<DIM_, SLOT_><<<blocks, kExpandRows * 16, smem, h->stream>>>(                                          \
+      h->n_nodes, h->d_findrm, h->d_colm, ct, nnz, P->d_inv, P->d_tpos, P->d_pptr, reinterpret_cast<const SLOT_*>(P->d_slots), \
+      P->d_findrm2, P->n2max, P->d_val)
+    if (h->dim == 3) {
+      if (P->slot_bytes == 1) EXPAND(3, unsigned char);
+      else EXPAND(3, unsigned short);
+    } else {
+      if (P->slot_bytes == 1) EXPAND(2, unsigned char);
+      else EXPAND(2, unsigned short);
+    }
+#undef EXPAND
+  } else {
+    const int blocks = (h->n_nodes + kCmcWarps - 1) / kCmcWarps;
+    if (h->dim == 3)
+      cmc_kernel<3><<<blocks, kCmcWarps * 32, 0, h->stream>>>(h->n_nodes, h->d_findrm, h->d_colm, ct, nnz, P->d_inv, P->d_findrm2,
+                                                              P->d_colm2, P->d_val);
+    else
+      cmc_kernel<2><<<blocks, kCmcWarps * 32, 0, h->stream>>>(h->n_nodes, h->d_findrm, h->d_colm, ct, nnz, P->d_inv, P->d_findrm2,
+                                                              P->d_colm2, P->d_val);
+  }
   h->launches++;
   CG_CUDA(cudaEventRecord(h->ev1, h->stream));
   CG_CUDA(cudaGetLastError());

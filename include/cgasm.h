@@ -315,6 +315,14 @@ int cgasm_cmc_result_dev(int id, double** cmc_val_dev);  /* raw device pointer o
  * (n_nodes+1) is always written; colm2 only if *needed <= capacity. */
 int cgasm_cmc_sparsity_host(int n_nodes, const int* findrm, const int* colm, int* findrm2, int* colm2,
                             long long capacity, long long* needed);
+/* Diagnostics (host only, no GPU): the plan of the expansion kernel for 1-based first- and second-order patterns.
+ * tpos(nnz): 0-based position of the transposed entry of every first-order entry; pptr(n_nodes+1): offsets into
+ * slots; slots: for row i, for every column k of row i in order, for every entry (k, j) of row k in order, the 0-based
+ * position of j in second-order row i. *needed = number of slots, or -1 if the patterns admit no plan (the merge
+ * kernel runs). slots are written only if *needed <= capacity. */
+int cgasm_cmc_expand_plan_host(int n_nodes, const int* findrm, const int* colm, const int* findrm2, const int* colm2,
+                               int* tpos, long long* pptr, unsigned short* slots, long long capacity, long long* needed,
+                               int* n2max);
 
 /* Asynchronous host flavour. With on != 0: cgasm_set_field returns once the upload is queued (val must
  * stay valid, ideally pinned, until cgasm_synchronize) and the *_fetch calls queue their device -> host

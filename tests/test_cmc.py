@@ -86,6 +86,59 @@ def test_device_entry_function_on_the_host_is_bitwise_the_oracle(orc, harness, n
     assert (out == ref).all()  # same operations in the same order, no contraction
 
 
+@pytest.mark.parametrize("name", list(cases()))
+def test_expansion_plan_and_kernel_emulation_are_bitwise_the_oracle(orc, harness, name):
+    """The default device kernel expands (k in row i) x (j in row k) with a plan built by the library on the host:
+    plan invariants, and a lane-level emulation of the kernel with that plan against the oracle, bit for bit."""
+    mesh = cases()[name]
+    fs, findrm, colm, ct, w = inputs(orc, mesh)
+    f2, c2 = orc.make_sparsity_mult(mesh.n_nodes, findrm, colm)
+    plan = cgasm.cmc_expand_plan_host(findrm, colm, f2, c2)
+    assert plan is not None
+    tpos, pptr, slots, n2max = plan
+    f0, c0 = findrm - 1, colm - 1
+    rows = np.repeat(np.arange(mesh.n_nodes), np.diff(f0))
+    assert (c0[tpos] == rows).all() and (rows[tpos] == c0).all()          # transposed positions
+    assert n2max == np.diff(f2).max() and pptr[-1] == len(slots)
+    per_row = np.array([np.diff(f0)[c0[f0[i]:f0[i + 1]]].sum() for i in range(mesh.n_nodes)])
+    assert (np.diff(pptr) == per_row).all()
+    i = mesh.n_nodes // 2                                                   # slots of one row, spelled out
+    want = [np.searchsorted(c2[f2[i] - 1:f2[i + 1] - 1], colm[p]) for a in range(f0[i], f0[i + 1])
+            for p in range(f0[c0[a]], f0[c0[a] + 1])]
+    assert slots[pptr[i]:pptr[i + 1]].tolist() == want
+    ref = orc.mult_div_vector_div_T(findrm, colm, ct, ct, w, f2, c2)
+    i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+    ip, dp = C.POINTER(C.c_int), C.POINTER(C.c_double)
+    out = np.zeros(len(c2))
+    ctc, wc, f0c, c0c, g0 = np.ascontiguousarray(ct), np.ascontiguousarray(w), i32(f0), i32(c0), i32(f2 - 1)
+    harness.harness_cmc_expand.restype = C.c_longlong
+    bad = harness.harness_cmc_expand(C.c_int(mesh.dim), C.c_int(mesh.n_nodes), f0c.ctypes.data_as(ip), c0c.ctypes.data_as(ip),
+                                     ctc.ctypes.data_as(dp), C.c_longlong(len(colm)), wc.ctypes.data_as(dp),
+                                     tpos.ctypes.data_as(ip), pptr.ctypes.data_as(C.POINTER(C.c_longlong)),
+                                     slots.ctypes.data_as(C.POINTER(C.c_ushort)), g0.ctypes.data_as(ip), C.c_int(n2max),
+                                     out.ctypes.data_as(dp))
+    assert bad == 0          # no two lanes of a step share a slot; the plan covers each row exactly
+    assert (out == ref).all()
+
+
+def test_expansion_plan_is_refused_for_patterns_it_cannot_serve(orc):
+    mesh = cases()["box2"]
+    findrm, colm, _ = orc.make_sparsity(mesh)
+    f2, c2 = orc.make_sparsity_mult(mesh.n_nodes, findrm, colm)
+    # a second-order pattern that lacks an entry of S.S
+    keep = np.ones(len(c2), dtype=bool)
+    keep[f2[5] - 1 + 1] = False
+    g2 = f2.copy()
+    g2[6:] -= 1
+    assert cgasm.cmc_expand_plan_host(findrm, colm, g2, c2[keep]) is None
+    # a structurally asymmetric first-order pattern (entry (1, j) dropped, (j, 1) kept)
+    drop = np.ones(len(colm), dtype=bool)
+    drop[findrm[0] - 1 + 1] = False
+    gf = findrm.copy()
+    gf[1:] -= 1
+    assert cgasm.cmc_expand_plan_host(gf, colm[drop], f2, c2) is None
+
+
 # ---- CUDA path ---------------------------------------------------------------------------------------------
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", list(cases()))
@@ -118,6 +171,13 @@ def test_cmc_on_the_device(orc, name):
     ref = orc.mult_div_vector_div_T(findrm, colm, ref_m["ct_m"], ref_m["ct_m"], w, of2, oc2)
     assert rel_err(got, ref) < 1e-12
     assert (got == ref).all()
+    # the merge kernel (fallback for patterns without an expansion plan) gives the same bits
+    os.environ["CGASM_CMC_MERGE"] = "1"
+    try:
+        asm.cmc_dev(ref_m["ct_m"], w)
+        assert (asm.cmc_fetch() == ref).all()
+    finally:
+        del os.environ["CGASM_CMC_MERGE"]
 
 
 @pytest.mark.gpu
