@@ -40,6 +40,7 @@ struct CmcPlan {
   int* d_tpos = nullptr;
   long long* d_pptr = nullptr;
   unsigned char* d_slots = nullptr;
+  double* d_ctT = nullptr;  // ct_m with every entry moved to its transposed position: row k holds C(j,k) for j in row k
 };
 
 void cmc_free(Handle* h) {
@@ -53,6 +54,7 @@ void cmc_free(Handle* h) {
   cudaFree(P->d_tpos);
   cudaFree(P->d_pptr);
   cudaFree(P->d_slots);
+  cudaFree(P->d_ctT);
   delete P;
   h->cmc = nullptr;
 }
@@ -176,6 +178,8 @@ static int upload_pattern(Handle* h) {
   cudaFree(P->d_tpos);
   cudaFree(P->d_pptr);
   cudaFree(P->d_slots);
+  cudaFree(P->d_ctT);
+  P->d_ctT = nullptr;
   P->d_tpos = nullptr;
   P->d_pptr = nullptr;
   P->d_slots = nullptr;
@@ -216,10 +220,21 @@ cmc_kernel(int n_rows, const int* __restrict__ findrm, const int* __restrict__ c
 // no searching, no merging, the plan and row k are read coalesced. Same bits as the merge kernel.
 constexpr int kExpandRows = 16;
 
+// ctT[d][p] = ct[d][tpos[p]]: one gathered pass over the first-order entries, so that the expansion reads the
+// factors C(j,k), j in row k, contiguously (every row k is read by all ~15-27 rows i that contain k)
+template <int DIM>
+__global__ void transpose_ct_kernel(size_t nnz, const int* __restrict__ tpos, const double* __restrict__ ct,
+                                    double* __restrict__ ctT) {
+  const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= nnz) return;
+  const int t = tpos[p];
+  for (int d = 0; d < DIM; d++) ctT[d * nnz + p] = ct[d * nnz + t];
+}
+
 template <int DIM, class SLOT>
 __global__ void __launch_bounds__(kExpandRows * 16)
 cmc_expand_kernel(int n_rows, const int* __restrict__ findrm, const int* __restrict__ colm, const double* __restrict__ ct,
-                  size_t nnz, const double* __restrict__ inv, const int* __restrict__ tpos, const long long* __restrict__ pptr,
+                  const double* __restrict__ ctT, size_t nnz, const double* __restrict__ inv, const long long* __restrict__ pptr,
                   const SLOT* __restrict__ slots, const int* __restrict__ findrm2, int n2max, double* __restrict__ out) {
   extern __shared__ double cmc_acc[];
   const int hw = threadIdx.x >> 4, hl = threadIdx.x & 15;
@@ -245,7 +260,7 @@ cmc_expand_kernel(int n_rows, const int* __restrict__ findrm, const int* __restr
       const int kb = findrm[k], kn = findrm[k + 1] - kb;
       for (int q = hl; q < kn; q += 16) {
         const int s = (int)slots[pp + q];
-        acc[s] = cmc_accumulate<DIM>(acc[s], Ad, Wd, ct, nnz, tpos[kb + q]);
+        acc[s] = cmc_accumulate<DIM>(acc[s], Ad, Wd, ctT, nnz, kb + q);
       }
       pp += kn;
     }
@@ -390,9 +405,14 @@ int cgasm_cmc_dev(int id, const double* ct_m, const double* inverse_masslump) {
   if (expand) {
     const int blocks = (h->n_nodes + kExpandRows - 1) / kExpandRows;
     const size_t smem = sizeof(double) * (size_t)kExpandRows * P->n2max;
+    if (!P->d_ctT) CG_CUDA(cudaMalloc(&P->d_ctT, sizeof(double) * dim * std::max<size_t>(nnz, 1)));
+    const unsigned tb = (unsigned)((nnz + 255) / 256);
+    if (h->dim == 3) transpose_ct_kernel<3><<<tb, 256, 0, h->stream>>>(nnz, P->d_tpos, ct, P->d_ctT);
+    else transpose_ct_kernel<2><<<tb, 256, 0, h->stream>>>(nnz, P->d_tpos, ct, P->d_ctT);
+    h->launches++;
 #define EXPAND(DIM_, SLOT_)                                                                                              \
   cmc_expand_kernel<DIM_, SLOT_><<<blocks, kExpandRows * 16, smem, h->stream>>>(                                          \
-      h->n_nodes, h->d_findrm, h->d_colm, ct, nnz, P->d_inv, P->d_tpos, P->d_pptr, reinterpret_cast<const SLOT_*>(P->d_slots), \
+      h->n_nodes, h->d_findrm, h->d_colm, ct, P->d_ctT, nnz, P->d_inv, P->d_pptr, reinterpret_cast<const SLOT_*>(P->d_slots), \
       P->d_findrm2, P->n2max, P->d_val)
     if (h->dim == 3) {
       if (P->slot_bytes == 1) EXPAND(3, unsigned char);

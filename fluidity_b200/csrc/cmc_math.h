@@ -40,17 +40,18 @@ CG_HD double cmc_entry(const int* findrm, const int* colm, const double* ct1, co
 
 // The same sum by EXPANSION (cmc.cu, expand kernel): for a fixed row i the columns k of row i are visited in
 // ascending order and every entry (k, j) of row k adds A_d(i,k) B_d(j,k) v(d,k) to the accumulator of (i, j);
-// B_d(j,k) sits at the transposed position tpos of entry (k, j). For a fixed (i, j) the terms arrive in ascending k,
+// B_d(j,k) is read from the transposed copy of ct (ctT[d][p] = ct[d][tpos[p]]) at the position p of entry (k, j).
+// For a fixed (i, j) the terms arrive in ascending k,
 // components innermost: the order of the merge above, hence the same bits. One call = one (k, j) entry.
 template <int DIM>
-CG_HD double cmc_accumulate(double acc, const double (&Ad)[DIM], const double (&Wd)[DIM], const double* ct2, size_t nnz,
-                            int tpos) {
+CG_HD double cmc_accumulate(double acc, const double (&Ad)[DIM], const double (&Wd)[DIM], const double* ctT, size_t nnz,
+                            int p) {
   for (int d = 0; d < DIM; d++) {
 #if defined(__CUDA_ARCH__)
-    acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(Ad[d], ct2[d * nnz + tpos]), Wd[d]));
+    acc = __dadd_rn(acc, __dmul_rn(__dmul_rn(Ad[d], ctT[d * nnz + p]), Wd[d]));
 #else
-    const volatile double p = Ad[d] * ct2[d * nnz + tpos];
-    const volatile double q = p * Wd[d];
+    const volatile double m = Ad[d] * ctT[d * nnz + p];
+    const volatile double q = m * Wd[d];
     acc = acc + q;
 #endif
   }

@@ -16,6 +16,10 @@ extern "C" long long harness_cmc_expand(int dim, int n, const int* findrm, const
                                         const double* v, const int* tpos, const long long* pptr, const unsigned short* slots,
                                         const int* findrm2, int n2max, double* out) {
   long long collisions = 0;
+  // transpose_ct_kernel: ctT[d][p] = ct[d][tpos[p]]
+  double* ctT = new double[(size_t)dim * nnz];
+  for (int d = 0; d < dim; d++)
+    for (long long p = 0; p < nnz; p++) ctT[d * nnz + p] = ct[d * nnz + tpos[p]];
   double* acc = new double[n2max];
   int* stamp = new int[n2max];
   for (int i = 0; i < n; i++) {
@@ -33,11 +37,11 @@ extern "C" long long harness_cmc_expand(int dim, int n, const int* findrm, const
           if (dim == 3) {
             double Ad[3], Wd[3];
             for (int d = 0; d < 3; d++) { Ad[d] = ct[d * nnz + r0 + a]; Wd[d] = v[(size_t)3 * k + d]; }
-            acc[s] = cgasm::cmc_accumulate<3>(acc[s], Ad, Wd, ct, (size_t)nnz, tpos[kb + q]);
+            acc[s] = cgasm::cmc_accumulate<3>(acc[s], Ad, Wd, ctT, (size_t)nnz, kb + q);
           } else {
             double Ad[2], Wd[2];
             for (int d = 0; d < 2; d++) { Ad[d] = ct[d * nnz + r0 + a]; Wd[d] = v[(size_t)2 * k + d]; }
-            acc[s] = cgasm::cmc_accumulate<2>(acc[s], Ad, Wd, ct, (size_t)nnz, tpos[kb + q]);
+            acc[s] = cgasm::cmc_accumulate<2>(acc[s], Ad, Wd, ctT, (size_t)nnz, kb + q);
           }
         }
       pp += kn;
@@ -46,6 +50,7 @@ extern "C" long long harness_cmc_expand(int dim, int n, const int* findrm, const
     for (int s = 0; s < n2; s++) out[o0 + s] = acc[s];
   }
   delete[] acc;
+  delete[] ctT;
   delete[] stamp;
   return collisions;
 }
