@@ -157,4 +157,5 @@ def test_surface_calls_refuse_what_they_must():
     asm.advdiff_dev(o)
     asm.advdiff_surface_dev(abi.common_advdiff_opts(have_diffusivity=0), np.full(len(fe), abi.TBC_NEUMANN))  # loop does not run
     got = asm.advdiff_fetch()
-    assert (got["matrix"] == ref["matrix"]).all() and (got["rhs"] == ref["rhs"]).all()
+    # (two runs of the default ATOMIC scatter variant: equal up to the order of the atomic additions)
+    assert rel_err(got["matrix"], ref["matrix"]) < 1e-14 and rel_err(got["rhs"], ref["rhs"]) < 1e-14
