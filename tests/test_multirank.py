@@ -79,6 +79,60 @@ def test_halo_lists_over_gloo(world):
     assert all(ok for _, ok in res)
 
 
+def _decomposed_worker(rank, world, port, q, base):
+    """Every rank reads ITS files of a decomposition in the reference's formats (<base>_<rank>.msh + .halo,
+    fluidity_b200/formats.py) and runs the halo update of a coordinate-derived field with those lists."""
+    sys.path.insert(0, ROOT)
+    from fluidity_b200 import formats as fmt
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lp, gm, hs = fmt.read_decomposition(base, rank)
+    want = np.stack([np.sin(3 * lp.mesh.X[:, 0]) + lp.mesh.X[:, 1] ** 2, np.cos(2 * lp.mesh.X[:, -1])], axis=1)
+    have = want.copy()
+    have[lp.n_owned:] = -777.0
+    reqs, bufs = [], []
+    for p in range(world):
+        if len(lp.sends[p]):
+            reqs.append(dist.isend(torch.from_numpy(np.ascontiguousarray(have[lp.sends[p] - 1])), dst=p))
+        if len(lp.recvs[p]):
+            b = torch.empty((len(lp.recvs[p]), 2), dtype=torch.float64)
+            bufs.append((p, b))
+            reqs.append(dist.irecv(b, src=p))
+    for r in reqs:
+        r.wait()
+    for p, b in bufs:
+        have[lp.recvs[p] - 1] = b.numpy()
+    ok = bool((have == want).all()) and hs.nprocs == world and sorted(hs.levels) == [1, 2]
+    # owned-node counts add up to the global mesh
+    t = torch.tensor([float(lp.n_owned)], dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    q.put((rank, ok, int(t.item())))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_rcb_decomposition_through_the_reference_formats_over_gloo(world, tmp_path):
+    sys.path.insert(0, ROOT)
+    from conftest import load_golden_mesh
+    from fluidity_b200 import formats as fmt, partition as part
+    mesh = load_golden_mesh("cube-parallel")  # unstructured gmsh mesh from the reference's tests/data
+    parts = part.partition_by_owner(mesh, part.rcb_owner(mesh.X, world), world)
+    base = str(tmp_path / "cube")
+    fmt.write_decomposition(base, parts, binary=True)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_decomposed_worker, args=(r, world, port, q, base)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(r for r, _, _ in res) == list(range(world))
+    assert all(ok for _, ok, _ in res) and all(n == mesh.n_nodes for _, _, n in res)
+
+
 def _nccl_worker(rank, world, port, q):
     sys.path.insert(0, ROOT)
     from fluidity_b200 import partition as part, cgasm, tables, _abi as abi, synthetic as syn
