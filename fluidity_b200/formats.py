@@ -186,10 +186,15 @@ def read_gmsh(path, coordinate_dim=None):
     return out
 
 
-def write_gmsh(path, gm, binary=False):
-    """Write_GMSH.F90:165-430: "2.1 <0|1> 8", faces first (2 tags, or 4 with element owners), then
-    the volume elements with 2 tags (region id, 0). ASCII coordinates use repr() instead of the
-    reference's F0.10 so that a round trip is exact."""
+def write_gmsh(path, gm, binary=False, style="femtools"):
+    """style "femtools": Write_GMSH.F90:165-430: "2.1 <0|1> 8", faces first (2 tags, or 4 with element
+    owners), then the volume elements with 2 tags (region id, 0). ASCII coordinates use repr() instead of
+    the reference's F0.10 so that a round trip is exact.
+    style "fldecomp": the files fldecomp writes for every partition (fldecomp/fldgmsh.cpp
+    write_part_main_mesh :99-300): binary, ONE tag per face (the boundary id; none if there are no ids)
+    and one per element (the region id), a face group header even when there is no face."""
+    if style == "fldecomp":
+        return _write_gmsh_fldecomp(path, gm)
     m = gm.mesh
     etype = {1: GMSH_LINE, 2: GMSH_TRIANGLE, 3: GMSH_TET}[m.dim]
     ftype = {1: GMSH_NODE, 2: GMSH_LINE, 3: GMSH_TRIANGLE}[m.dim]
@@ -236,6 +241,31 @@ def write_gmsh(path, gm, binary=False):
                 row = [nf + k + 1, etype, 2] + list(etags[k]) + list(m.ndglno[k])
                 f.write((" ".join(str(int(v)) for v in row) + "\n").encode())
         f.write(b"$EndElements\n")
+
+
+def _write_gmsh_fldecomp(path, gm):
+    m = gm.mesh
+    etype = {2: GMSH_TRIANGLE, 3: GMSH_TET}[m.dim]
+    ftype = {2: GMSH_LINE, 3: GMSH_TRIANGLE}[m.dim]
+    nf, ne = len(gm.sndgln), m.n_elements
+    xyz = np.zeros((m.n_nodes, 3))
+    xyz[:, :m.X.shape[1]] = m.X
+    with open(path, "wb") as f:
+        f.write(b"$MeshFormat\n2.1 1 8\n" + struct.pack("<i", 1) + b"\n$EndMeshFormat\n$Nodes\n")
+        f.write(("%d\n" % m.n_nodes).encode())
+        rec = np.zeros(m.n_nodes, dtype=[("id", "<i4"), ("x", "<f8", (3,))])
+        rec["id"] = np.arange(1, m.n_nodes + 1)
+        rec["x"] = xyz
+        f.write(rec.tobytes() + b"\n$EndNodes\n$Elements\n")
+        f.write(("%d\n" % (nf + ne)).encode())
+        have_bid = gm.boundary_ids is not None and len(gm.boundary_ids) > 0
+        f.write(struct.pack("<3i", ftype, nf, 1 if have_bid else 0))
+        cols = [np.arange(1, nf + 1)[:, None]] + ([np.asarray(gm.boundary_ids)[:, None]] if have_bid else []) + [gm.sndgln]
+        f.write(np.hstack(cols).astype("<i4").tobytes())
+        rid = gm.region_ids if gm.region_ids is not None else np.zeros(ne, dtype=np.int32)
+        f.write(struct.pack("<3i", etype, ne, 1))
+        f.write(np.hstack([np.arange(nf + 1, nf + ne + 1)[:, None], np.asarray(rid)[:, None], m.ndglno]).astype("<i4").tobytes())
+        f.write(b"\n$EndElements\n")
 
 
 # ---- .halo ---------------------------------------------------------------------------------------------
@@ -327,11 +357,14 @@ def trailing_receives_consistent(h):
                 and len(np.unique(rec)) == len(rec))
 
 
-def write_decomposition(basename, parts, binary=False):
+def write_decomposition(basename, parts, binary=False, style="femtools", region_ids=None):
     """Writes `<basename>_<rank>.msh` + `.halo` for every LocalPart the way fldecomp/flredecomp
     leave them: local numbering, owned nodes first; level-1 and level-2 halos. The level-1 lists
     are the level-2 lists restricted to the level-1 receive nodes (ids <= n_owned + n_l1) on the
-    receiving side and to their images on the sending side."""
+    receiving side and to their images on the sending side. The boundary faces a LocalPart carries
+    (partition_by_owner(..., sndgln, boundary_ids)) are written too. style "fldecomp" (+ the GLOBAL
+    region_ids, default 0) gives byte for byte the files of fldecomp/fldgmsh.cpp for the same node ->
+    partition map (tests/test_formats.py, against the compiled reference in oracle/_ref)."""
     from .partition import LocalPart  # noqa: F401  (documented type of `parts`)
     nprocs = len(parts)
     # position of the level-1 entries inside each rank's level-2 receive list
@@ -339,7 +372,11 @@ def write_decomposition(basename, parts, binary=False):
              for r in range(nprocs)]
     for r, lp in enumerate(parts):
         gm = GmshMesh(mesh=lp.mesh, sndgln=np.zeros((0, lp.mesh.dim), dtype=np.int32))
-        write_gmsh(parallel_filename(basename, r, ".msh"), gm, binary=binary)
+        if getattr(lp, "sndgln", None) is not None:
+            gm.sndgln, gm.boundary_ids = lp.sndgln, lp.boundary_ids
+        if region_ids is not None and lp.global_element is not None:
+            gm.region_ids = np.asarray(region_ids)[lp.global_element].astype(np.int32)
+        write_gmsh(parallel_filename(basename, r, ".msh"), gm, binary=binary, style=style)
         l2 = HaloLevel(lp.n_owned, [np.asarray(s) for s in lp.sends], [np.asarray(v) for v in lp.recvs])
         l1 = HaloLevel(lp.n_owned,
                        [np.asarray(lp.sends[p])[l1pos[p][r]] for p in range(nprocs)],

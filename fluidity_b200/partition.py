@@ -6,8 +6,8 @@ here): every rank owns a set of nodes and additionally holds
   level-2 halo nodes  = nodes of elements that contain an owned or level-1 node,
 numbered "trailing receives" (femtools/Halo_Data_Types.F90 HALO_ORDER_TRAILING_RECEIVES:
 owned nodes first, then the level-1 receives, then the level-2-only receives; see the real
-fixture tests/golden/prectangle_halos.json). The local mesh is every element whose nodes
-all lie in that set; each rank assembles ALL of them (no ownership test, SURVEY.md section
+fixture tests/golden/prectangle_halos.json). The local mesh is every element with an owned or
+a level-1 node (fldecomp/fldgmsh.cpp:375-455); each rank assembles ALL of them (no ownership test, SURVEY.md section
 0 fact 5) and only the rows of owned nodes are used. halo_update uses the largest (level-2)
 halo: sends(p) = owned nodes that rank p receives, in the order of p's receives.
 
@@ -33,6 +33,9 @@ class LocalPart:
     sends: list                # per process: 1-based LOCAL node ids (level-2 halo)
     recvs: list                # per process: 1-based LOCAL node ids (level-2 halo)
     n_l1: int = 0              # number of level-1 receive nodes (they precede the L2-only ones)
+    sndgln: np.ndarray = None  # (n_local_faces, sloc) 1-based LOCAL nodes of the boundary faces held locally
+    boundary_ids: np.ndarray = None
+    global_face: np.ndarray = None  # 0-based global surface-element id of each local face
 
 
 def _grow(ndglno0, mask):
@@ -43,37 +46,52 @@ def _grow(ndglno0, mask):
     return out
 
 
-def partition_by_owner(mesh, owner, nprocs):
-    """Returns [LocalPart] for every rank. owner: (n_nodes,) rank of each global node."""
+def partition_by_owner(mesh, owner, nprocs, sndgln=None, boundary_ids=None):
+    """Returns [LocalPart] for every rank from a node -> rank map, in the conventions of the reference's own
+    decomposition writer (fldecomp/fldgmsh.cpp write_partitions_gmsh :310-626; tests/test_formats.py compares
+    the two bit for bit through oracle/_ref):
+      nodes     owned (ascending global id), then the level-1 halo nodes (ascending), then the level-2-only ones;
+      elements  those with an owned node -- first the ones whose lowest-ranked node owner is this rank, then the
+                others, each ascending (:375-425) -- then the level-2 elements: no owned node but a level-1 node
+                (:431-455);
+      halos     receives from p = the halo nodes p owns in ascending GLOBAL id; sends to p = p's receives from us in
+                the same order (:589-611); the level-2 lists contain the level-1 ones (:458-459);
+      faces     (if sndgln is given) the global surface elements all of whose nodes lie in one local element, in
+                global order (:518-556).
+    owner: (n_nodes,) rank of each global node; sndgln (n_faces, sloc) 1-based, boundary_ids (n_faces,)."""
     nd0 = mesh.ndglno.astype(np.int64) - 1
     owner = np.asarray(owner)
+    eown = owner[nd0]                                   # (n_elements, loc)
+    emin = eown.min(axis=1)
     parts = []
     local_of = []  # per rank: global -> local (0-based) map, -1 if absent
+    l2_sets = []
     for r in range(nprocs):
         own = owner == r
-        l1 = _grow(nd0, own) & ~own
-        l2 = _grow(nd0, own | l1) & ~own & ~l1
-        g_own = np.flatnonzero(own)
-        # receives sorted by sending process, then global id (stable, deterministic)
-        g_l1 = np.flatnonzero(l1)
-        g_l1 = g_l1[np.lexsort((g_l1, owner[g_l1]))]
-        g_l2 = np.flatnonzero(l2)
-        g_l2 = g_l2[np.lexsort((g_l2, owner[g_l2]))]
+        n_own_in_e = (eown == r).sum(axis=1)
+        e_owned = n_own_in_e > 0
+        l1 = np.zeros(mesh.n_nodes, dtype=bool)
+        l1[nd0[e_owned].ravel()] = True
+        l1 &= ~own
+        e_halo2 = (~e_owned) & l1[nd0].any(axis=1)
+        l2 = np.zeros(mesh.n_nodes, dtype=bool)
+        l2[nd0[e_halo2].ravel()] = True
+        l2 &= ~l1                                       # (no owned node in these elements)
+        g_own, g_l1, g_l2 = np.flatnonzero(own), np.flatnonzero(l1), np.flatnonzero(l2)
         gl = np.concatenate([g_own, g_l1, g_l2])
         g2l = -np.ones(mesh.n_nodes, dtype=np.int64)
         g2l[gl] = np.arange(len(gl))
-        present = g2l >= 0
-        keep = present[nd0].all(axis=1)
-        ge = np.flatnonzero(keep)
+        eo = np.flatnonzero(e_owned)
+        ge = np.concatenate([eo[emin[eo] == r], eo[emin[eo] != r], np.flatnonzero(e_halo2)])
         lnd = (g2l[nd0[ge]] + 1).astype(np.int32)
         lm = Mesh(dim=mesh.dim, ndglno=np.ascontiguousarray(lnd), X=np.ascontiguousarray(mesh.X[gl]))
-        recvs = []
-        halo_g = np.concatenate([g_l1, g_l2])
-        for p in range(nprocs):
-            sel = halo_g[owner[halo_g] == p]
-            recvs.append((g2l[sel] + 1).astype(np.int32))
-        parts.append(LocalPart(mesh=lm, n_owned=len(g_own), global_node=gl, global_element=ge,
-                               sends=[None] * nprocs, recvs=recvs, n_l1=len(g_l1)))
+        halo_g = np.flatnonzero(l1 | l2)                 # ascending global id, level 1 and 2 together
+        recvs = [(g2l[halo_g[owner[halo_g] == p]] + 1).astype(np.int32) for p in range(nprocs)]
+        lp = LocalPart(mesh=lm, n_owned=len(g_own), global_node=gl, global_element=ge,
+                       sends=[None] * nprocs, recvs=recvs, n_l1=len(g_l1))
+        if sndgln is not None:
+            lp.sndgln, lp.boundary_ids, lp.global_face = _local_faces(lm, g2l, np.asarray(sndgln), boundary_ids)
+        parts.append(lp)
         local_of.append(g2l)
     # sends(p) on rank r = what p receives from r, in p's receive order, in r's numbering
     for r in range(nprocs):
@@ -81,6 +99,27 @@ def partition_by_owner(mesh, owner, nprocs):
             gp = parts[p].global_node[parts[p].recvs[r] - 1] if len(parts[p].recvs[r]) else np.zeros(0, dtype=np.int64)
             parts[r].sends[p] = (local_of[r][gp] + 1).astype(np.int32)
     return parts
+
+
+def _local_faces(lmesh, g2l, sndgln, boundary_ids):
+    """Global surface elements whose nodes all belong to one local volume element (fldgmsh.cpp:518-556)."""
+    lf = g2l[sndgln.astype(np.int64) - 1]               # (n_faces, sloc) local 0-based, -1 = absent
+    cand = np.flatnonzero((lf >= 0).all(axis=1))
+    loc = lmesh.loc
+    nd = lmesh.ndglno.astype(np.int64) - 1
+    facets = np.stack([np.sort(np.delete(nd, k, axis=1), axis=1) for k in range(loc)], axis=1).reshape(-1, loc - 1)
+    n = lmesh.n_nodes + 1
+
+    def key(a):
+        k = a[:, 0].copy()
+        for c in range(1, a.shape[1]):
+            k = k * n + a[:, c]
+        return k
+
+    present = np.isin(key(np.sort(lf[cand], axis=1)), key(facets))
+    keep = cand[present]
+    bid = np.asarray(boundary_ids)[keep].astype(np.int32) if boundary_ids is not None else None
+    return (lf[keep] + 1).astype(np.int32), bid, keep
 
 
 def rcb_owner(X, nprocs):

@@ -5,8 +5,9 @@
  * link or import this file; only tests/, __graft_entry__.smoke() and bench.py's
  * cpu_baseline / --impl reference legs use it, as the checker / CPU baseline.
  *
- * The reference (Fortran + PETSc) cannot be compiled in this image (no Fortran compiler,
- * no PETSc), so this is a line-for-line restatement in plain C of the reference algorithm,
+ * The reference's element loops (Fortran + PETSc) cannot be compiled in this image (no Fortran
+ * compiler, no PETSc; only its C++ halo IO and fldecomp writer build, see oracle/Makefile `ref`),
+ * so this is a line-for-line restatement in plain C of the reference algorithm,
  * keeping its loop nests and summation order (gi innermost in the FETools contractions,
  * elements in ascending order, (iloc,jloc) row-major scatter). Every function cites the
  * reference file:line it follows (paths relative to the Fluidity source tree).

@@ -338,3 +338,108 @@ def test_compare_matrixdump_tool(orc, tmp_path):
     assert good.returncode == 0 and json.loads(good.stdout)["ok"]
     bad = subprocess.run([sys.executable, tool, str(tmp_path / "T_1"), str(tmp_path / "T_off")], capture_output=True, text=True)
     assert bad.returncode == 1 and not json.loads(bad.stdout)["objects"][1]["ok"]
+
+
+# ---- against the reference's own compiled halo reader / writer (oracle/_ref) ------------------------------
+def _ref_halos():
+    from oracle import ref_halos
+    if not ref_halos.available():
+        pytest.skip("oracle/_ref/libref_halos_io.so is built from /root/reference (build container only)")
+    return ref_halos
+
+
+def test_our_halo_files_are_read_by_the_reference_reader(tmp_path):
+    """Halos_IO.cpp, compiled unmodified from the reference tree (`make -C oracle ref`), reads the files
+    formats.write_decomposition produces and returns the lists we wrote."""
+    rh = _ref_halos()
+    mesh = load_golden_mesh("cube-parallel")
+    nprocs = 3
+    parts = part.partition_by_owner(mesh, part.rcb_owner(mesh.X, nprocs), nprocs)
+    base = str(tmp_path / "cube")
+    fmt.write_decomposition(base, parts, binary=True)
+    for r, lp in enumerate(parts):
+        got = rh.read(base, r, nprocs)
+        ours = fmt.read_halo(fmt.parallel_filename(base, r, ".halo"))
+        for lv in (1, 2):
+            npn, sends, recvs = got[lv]
+            assert npn == lp.n_owned == ours.levels[lv].n_private_nodes
+            for p in range(nprocs):
+                assert (sends[p] == ours.levels[lv].sends[p]).all() and (recvs[p] == ours.levels[lv].receives[p]).all()
+        assert all((got[2][1][p] == lp.sends[p]).all() and (got[2][2][p] == lp.recvs[p]).all() for p in range(nprocs))
+    # a file for the wrong process and a corrupt file are refused by the reference reader as by ours
+    os.replace("%s_1.halo" % base, "%s_5.halo" % base)
+    os.replace("%s_1.msh" % base, "%s_5.msh" % base)
+    with pytest.raises(ValueError):
+        rh.read(base, 5, 6)
+    with pytest.raises(fmt.FormatError):
+        fmt.read_decomposition(base, 5)
+
+
+def test_reference_writer_and_ours_produce_the_same_bytes(tmp_path):
+    rh = _ref_halos()
+    mesh = load_golden_mesh("2d_square")
+    nprocs = 4
+    parts = part.partition_by_owner(mesh, part.rcb_owner(mesh.X, nprocs), nprocs)
+    ours, theirs = str(tmp_path / "ours"), str(tmp_path / "theirs")
+    fmt.write_decomposition(ours, parts)
+    for r in range(nprocs):
+        h = fmt.read_halo(fmt.parallel_filename(ours, r, ".halo"))
+        rh.write(theirs, r, nprocs, {lv: (hl.n_private_nodes, hl.sends, hl.receives) for lv, hl in h.levels.items()})
+        a = open(fmt.parallel_filename(ours, r, ".halo"), "rb").read()
+        b = open(fmt.parallel_filename(theirs, r, ".halo"), "rb").read()
+        assert a == b
+        back = fmt.read_halo(fmt.parallel_filename(theirs, r, ".halo"))
+        assert all((back.levels[2].sends[p] == parts[r].sends[p]).all() for p in range(nprocs))
+
+
+@needs_reference
+def test_reference_reader_and_ours_agree_on_the_reference_fixtures():
+    rh = _ref_halos()
+    src = os.path.join(REF, "tests", "meshconv_test", "src", "prectangle")
+    for r in (0, 1):
+        got = rh.read(src, r, 2)
+        ours = fmt.read_halo(fmt.parallel_filename(src, r, ".halo"))
+        for lv in (1, 2):
+            assert got[lv][0] == ours.levels[lv].n_private_nodes
+            for p in range(2):
+                assert (got[lv][1][p] == ours.levels[lv].sends[p]).all() and (got[lv][2][p] == ours.levels[lv].receives[p]).all()
+    serial = rh.read(os.path.join(REF, "tests", "data", "cube-parallel"), 0, 1)   # comment before the declaration, `tag=`
+    ours = fmt.read_halo(os.path.join(REF, "tests", "data", "cube-parallel_0.halo"))
+    assert serial[1][0] == 665 and (serial[2][2][0] == ours.levels[2].receives[0]).all()
+
+
+@pytest.mark.parametrize("name,nparts", [("cube-parallel", 3), ("2d_square", 4), ("square-cavity-2d", 2), ("cube.1", 2)])
+def test_partition_by_owner_is_the_reference_decomposition_writer(tmp_path, name, nparts):
+    """fldecomp/fldgmsh.cpp write_partitions_gmsh -- the reference's own code that turns a node -> partition map
+    into per-rank meshes and halos -- compiled unmodified into oracle/_ref and fed OUR owner map: our LocalParts
+    and the files we write for them are identical, byte for byte (.msh: nodes, faces, elements; .halo: both levels)."""
+    from oracle import ref_fldecomp as rf
+    if not rf.available():
+        pytest.skip("oracle/_ref/libref_fldecomp.so is built from /root/reference (build container only)")
+    mesh = load_golden_mesh(name)
+    owner = part.rcb_owner(mesh.X, nparts)
+    sn, fe = syn.boundary_faces(mesh)
+    bid = (np.arange(len(sn)) % 5 + 1).astype(np.int32)
+    rid = (np.arange(mesh.n_elements) % 3 + 7).astype(np.int32)
+    theirs, ours = str(tmp_path / "theirs"), str(tmp_path / "ours")
+    rf.write_partitions(theirs, mesh, owner, nparts, sn, bid, rid)
+    parts = part.partition_by_owner(mesh, owner, nparts, sn, bid)
+    fmt.write_decomposition(ours, parts, style="fldecomp", region_ids=rid)
+    for r, mine in enumerate(parts):
+        lp, gm, hs = fmt.read_decomposition(theirs, r)
+        assert lp.n_owned == mine.n_owned and lp.n_l1 == mine.n_l1
+        assert (lp.mesh.X == mine.mesh.X).all() and (lp.mesh.ndglno == mine.mesh.ndglno).all()
+        assert (gm.sndgln == mine.sndgln).all() and (gm.boundary_ids == mine.boundary_ids).all()
+        assert (gm.region_ids == rid[mine.global_element]).all()
+        for p in range(nparts):
+            assert (lp.recvs[p] == mine.recvs[p]).all() and (lp.sends[p] == mine.sends[p]).all()
+        for ext in (".msh", ".halo"):
+            a = open(fmt.parallel_filename(theirs, r, ext), "rb").read()
+            b = open(fmt.parallel_filename(ours, r, ext), "rb").read()
+            assert a == b, (r, ext)
+        # every local face lies in one local element, and every global boundary face of an owned node is held
+        if len(mine.sndgln):
+            ele_sets = {tuple(sorted(np.delete(e, k))) for e in mine.mesh.ndglno for k in range(mesh.loc)}
+            assert all(tuple(sorted(f)) in ele_sets for f in mine.sndgln)
+        touching = np.flatnonzero((owner[sn - 1] == r).any(axis=1))
+        assert np.isin(touching, mine.global_face).all()
