@@ -443,3 +443,42 @@ def test_partition_by_owner_is_the_reference_decomposition_writer(tmp_path, name
             assert all(tuple(sorted(f)) in ele_sets for f in mine.sndgln)
         touching = np.flatnonzero((owner[sn - 1] == r).any(axis=1))
         assert np.isin(touching, mine.global_face).all()
+
+
+@needs_reference
+@pytest.mark.parametrize("rel", ["tests/data/cube-parallel.msh", "tests/data/square-cavity-2d.msh", "tests/data/cube.1.msh",
+                                 "tests/meshconv_test/src/prectangle_0.msh", "tests/meshconv_test/src/prectangle_1.msh"])
+def test_gmsh_reader_against_the_reference_python_reader(rel):
+    """python/fluidity/diagnostics/gmshtools.py ReadMsh (the reference's own Python gmsh reader, imported
+    unmodified) on ASCII and binary fixtures. Its package imports vtk at module level for unrelated VTU helpers;
+    vtk is absent here, so a MagicMock stands in for it -- the gmsh parsing code never touches it."""
+    import sys
+    from unittest import mock
+    sys.modules.setdefault("vtk", mock.MagicMock())
+    sys.path.insert(0, os.path.join(REF, "python"))
+    try:
+        import fluidity.diagnostics.gmshtools as gmshtools
+        path = os.path.join(REF, rel)
+        cwd = os.getcwd()
+        os.chdir(os.path.dirname(path))  # ReadMsh looks for a .halo file next to the mesh
+        try:
+            ref = gmshtools.ReadMsh(path)
+        finally:
+            os.chdir(cwd)
+    finally:
+        sys.path.remove(os.path.join(REF, "python"))
+    g = fmt.read_gmsh(path)
+    m = g.mesh
+    assert ref.NodeCount() == m.n_nodes and ref.VolumeElementCount() == m.n_elements and ref.SurfaceElementCount() == len(g.sndgln)
+    assert (np.array([ref.GetNodeCoord(i)[:m.dim] for i in range(m.n_nodes)]) == m.X).all()
+    assert (np.array([ref.GetVolumeElement(e).GetNodes() for e in range(m.n_elements)]) + 1 == m.ndglno).all()
+    if g.region_ids is not None:
+        assert [ref.GetVolumeElement(e).GetIds()[0] for e in range(m.n_elements)] == g.region_ids.tolist()
+    if len(g.sndgln):
+        assert (np.array([ref.GetSurfaceElement(f).GetNodes() for f in range(len(g.sndgln))]) + 1 == g.sndgln).all()
+        if g.boundary_ids is not None:
+            assert [ref.GetSurfaceElement(f).GetIds()[0] for f in range(len(g.sndgln))] == g.boundary_ids.tolist()
+        else:
+            assert all(len(ref.GetSurfaceElement(f).GetIds()) == 0 for f in range(len(g.sndgln)))
+        if g.element_owner is not None:
+            assert [ref.GetSurfaceElement(f).GetIds()[3] for f in range(len(g.sndgln))] == g.element_owner.tolist()
