@@ -16,7 +16,10 @@ Producers:
   rcb_owner           a node->rank map by recursive coordinate bisection (the geometric stand-in
                       for Zoltan/METIS; any nprocs, balanced to within one node)
   slab_partition      box meshes cut into slabs along the last axis, generated directly per
-                      rank without ever building the global mesh (bench sizes)
+                      rank without ever building the global mesh (bench sizes). Same node, element and
+                      halo SETS as partition_by_owner (= fldecomp's writer) for the slab owner map
+                      (tests/test_partition.py), in its own order: cells lexicographic, receive lists layer
+                      by layer (nearest layer first) instead of ascending global id
 """
 from dataclasses import dataclass
 import numpy as np
