@@ -17,12 +17,16 @@ reference fixture meshes, producing what the momentum / tracer element loops are
   assembled     lumped mass sum_j M_rho_ij per node           masslump (Momentum_CG.F90:1541,1560-1565), via Field.addto as
                                                               the module's own test_shape_dshape does (:452-458)
                 dense tracer mass matrix and dense ct blocks  (plain += of the element matrices)
-  composed      the momentum / tracer element matrices and rhs of the common option set (+ absorption, sources), CONTRACTED
-                here by numpy.einsum following Momentum_CG.F90:1535-1552,1675-1680,1737-1748,1770-1789,2038-2059,2304-2346
-                and Advection_Diffusion_CG.F90:909-920,1093-1125,1139,1156-1160,1192-1200 from ingredients that are ALL
-                reference-computed: detwei, du_t (Transform.grad), N, and every field at the quadrature points
-                (Field.ele_val_at_quad); mass-type terms go through Transform.shape_shape itself. A weaker pin than the
-                direct ones above (the contraction is restated), kept apart in the file as `c_*`.
+  composed      the momentum / tracer element matrices and rhs of the common option set (+ absorption, sources), following
+                Momentum_CG.F90:1535-1552,1675-1680,1737-1748,1770-1789,2038-2059,2304-2346 and
+                Advection_Diffusion_CG.F90:909-920,1093-1125,1139,1156-1160,1192-1200. Every ingredient is
+                reference-computed (detwei, du_t = Transform.grad, N, every field at the quadrature points through
+                Field.ele_val_at_quad) and every quadrature contraction runs in the reference's own loops: mass,
+                absorption and source matrices through Transform.shape_shape(coeff), advection and
+                viscosity / diffusivity through Transform.shape_dshape with the coefficient folded into detwei (and, for
+                the stiffness term, dN/dx_k in the place of N). What is restated here is only the assembly of those
+                pieces (dt*theta scaling, sums, products with oldu / T, the buoyancy and tracer-source vectors). Kept
+                apart in the file as `c_*`.
 
 The element tables n / dn / weights handed to `Element` / `Quadrature` are the degree-3 P1 tables
 of fluidity_b200/tables.py (at run time the reference fills these objects from its Fortran
@@ -31,6 +35,7 @@ test_shape_functions.F90 by tests/test_oracle_golden.py).
 
     python tests/golden/make_pyref_golden.py        # writes tests/golden/pyref_<mesh>.npz
 """
+import copy
 import os
 import sys
 import numpy as np
@@ -94,9 +99,32 @@ def composed(e, t, du_t, shape, F, dim, loc):
     Mr = t.shape_shape(shape, shape, rho_g)
     M = t.shape_shape(shape, shape)
     m = Mr.sum(1)
-    udn = np.einsum("kg,jgk->jg", u_g, dN)       # u_g . grad N_j
-    Adv = np.einsum("ig,jg,g->ij", N, udn, rho_g * dw)
-    K = np.einsum("igk,jgk,g->ij", dN, dN, F["mu"] * dw)
+    def with_detwei(weights, fn):
+        """Runs a reference contraction with a quadrature-point coefficient folded into detwei, the way the Fortran
+        passes detwei*coefficient to FETools (e.g. Momentum_CG.F90:1675-1680)."""
+        keep = t.detwei
+        t.detwei = np.asarray(weights)
+        try:
+            return np.asarray(fn())
+        finally:
+            t.detwei = keep
+
+    def advection(weight_g):
+        # shape_vector_dot_dshape (FETools.F90:749-772) = sum_k shape_dshape(N, du_t, detwei*u_k)[:, :, k], through
+        # the reference's Transform.shape_dshape
+        return sum(with_detwei(weight_g * u_g[k], lambda: t.shape_dshape(shape, du_t))[:, :, k] for k in range(dim))
+
+    def stiffness(weight_g):
+        # dshape_dot_dshape (FETools.F90:391-453): the same reference loop with dN_i/dx_k in the place of N_i
+        out = np.zeros((loc, loc))
+        for k in range(dim):
+            grad_k = copy.copy(shape)
+            grad_k.n = dN[:, :, k]
+            out += with_detwei(weight_g, lambda: t.shape_dshape(grad_k, du_t))[:, :, k]
+        return out
+
+    Adv = advection(rho_g * dw)
+    K = stiffness(F["mu"] * dw)
     out = {}
     for tag, have_abs, have_src in (("common", 0, 0), ("abs_src", 1, 1)):
         Tm = np.zeros((dim, dim, loc, loc))
@@ -109,8 +137,8 @@ def composed(e, t, du_t, shape, F, dim, loc):
             if have_src:
                 rhs[d] += Mr @ src[d]
         out["c_mom_T_" + tag], out["c_mom_rhs_" + tag] = Tm, rhs
-    Atr = np.einsum("ig,jg,g->ij", N, udn, dw)
-    D = np.einsum("igk,jgk,g->ij", dN, dN, F["kappa"] * dw)
+    Atr = advection(dw)
+    D = stiffness(F["kappa"] * dw)
     for tag, on in (("common", 0), ("abs_src", 1)):
         Ab = t.shape_shape(shape, shape, tsig_g) if on else np.zeros((loc, loc))
         L = Atr + D + Ab
