@@ -187,3 +187,58 @@ def test_rcb_partition(orc, name, nprocs):
         for b in range(a + 1, nprocs):
             overlap = np.minimum(hi[a], hi[b]) - np.maximum(lo[a], lo[b])
             assert (overlap <= 1e-12).any() or overlap.min() < 0.05 * (mesh.X.max() - mesh.X.min())
+
+
+@pytest.mark.parametrize("name,nprocs", [("cube-parallel", 3), ("square-cavity-2d", 2)])
+def test_surface_loops_shard_like_the_element_loops(orc, name, nprocs):
+    """Every rank runs the face loop over the boundary faces it holds (partition_by_owner(..., sndgln): the faces
+    fldecomp writes into its mesh file); the rows of owned nodes equal the global element + face assembly."""
+    mesh = load_golden_mesh(name)
+    dim = mesh.dim
+    fs = syn.standard_fields(mesh)
+    sn, fe = syn.boundary_faces(mesh)
+    rng = np.random.default_rng(3)
+    bt = rng.choice([0, 1, 4], size=len(fe)).astype(np.int32)
+    t_bc, t_bc_2 = rng.uniform(size=(len(fe), dim)), rng.uniform(0.5, 2.0, size=(len(fe), dim))
+    vt = rng.choice([0, 1, 5], size=(len(fe), dim)).astype(np.int32)
+    vbc = rng.uniform(-1, 1, size=(len(fe), dim, dim))
+    findrm, colm, _ = orc.make_sparsity(mesh)
+    oa = abi.common_advdiff_opts(integrate_advection_by_parts=1, beta=0.2)
+    om = abi.common_momentum_opts(integrate_advection_by_parts=1)
+    ga = orc.assemble_advdiff(mesh, fs, oa, findrm, colm)
+    orc.assemble_advdiff_surface(mesh, fs, oa, findrm, colm, sn, fe, bt, t_bc, t_bc_2, ga["matrix"], ga["rhs"])
+    gm = orc.assemble_momentum(mesh, fs, om, findrm, colm)
+    orc.assemble_momentum_surface(mesh, fs, om, findrm, colm, sn, fe, vt, vbc, gm["big_m"], gm["rhs"])
+    parts = part.partition_by_owner(mesh, part.rcb_owner(mesh.X, nprocs), nprocs, sn, np.arange(len(sn)))
+    slots = [abi.F_NU, abi.F_OLDU, abi.F_DENSITY, abi.F_BUOYANCY, abi.F_T]
+    for lp in parts:
+        lf = syn.standard_fields(lp.mesh)
+        for s in slots:
+            lf.set(s, fs.get(s)[0][lp.global_node])
+        lfind, lcolm, _ = orc.make_sparsity(lp.mesh)
+        # owning element of every local face: the local element that contains all its nodes
+        ele_of = {}
+        for e, nd in enumerate(lp.mesh.ndglno):
+            for k in range(mesh.loc):
+                ele_of.setdefault(tuple(sorted(np.delete(nd, k))), e + 1)
+        lfe = np.array([ele_of[tuple(sorted(f))] for f in lp.sndgln], dtype=np.int32)
+        gf = lp.global_face
+        # the same face may list its nodes in a different local order than the global file: boundary values follow the nodes
+        order = np.array([[list(sn[g]).index(n) for n in lp.global_node[f - 1] + 1] for f, g in zip(lp.sndgln, gf)])
+        take = lambda a: np.take_along_axis(a[gf], order, axis=1)
+        la = orc.assemble_advdiff(lp.mesh, lf, oa, lfind, lcolm)
+        orc.assemble_advdiff_surface(lp.mesh, lf, oa, lfind, lcolm, lp.sndgln, lfe, bt[gf], take(t_bc), take(t_bc_2),
+                                     la["matrix"], la["rhs"])
+        lm = orc.assemble_momentum(lp.mesh, lf, om, lfind, lcolm)
+        orc.assemble_momentum_surface(lp.mesh, lf, om, lfind, lcolm, lp.sndgln, lfe, vt[gf],
+                                      np.take_along_axis(vbc[gf], order[:, :, None], axis=1), lm["big_m"], lm["rhs"])
+        for i in range(lp.n_owned):
+            gi = lp.global_node[i]
+            lrow, grow = slice(lfind[i] - 1, lfind[i + 1] - 1), slice(findrm[gi] - 1, findrm[gi + 1] - 1)
+            perm = np.argsort(lp.global_node[lcolm[lrow] - 1])
+            assert np.abs(la["matrix"][lrow][perm] - ga["matrix"][grow]).max() <= 1e-12 * np.abs(ga["matrix"]).max()
+            for d in range(dim):
+                assert np.abs(lm["big_m"][d][lrow][perm] - gm["big_m"][d][grow]).max() <= 1e-12 * np.abs(gm["big_m"][d]).max()
+        own = lp.global_node[:lp.n_owned]
+        assert rel_err(la["rhs"][:lp.n_owned], ga["rhs"][own]) < 1e-12
+        assert rel_err(lm["rhs"][:lp.n_owned], gm["rhs"][own]) < 1e-12
