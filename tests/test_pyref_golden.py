@@ -6,7 +6,6 @@ and grad_p_u_mat / ct_m. (Advection, viscosity, absorption, sources and buoyancy
 implementation outside the Fortran; they stay pinned by closed forms and the independent numpy
 evaluation, tests/test_oracle_closed_forms.py.) CPU only; tests/test_parity_gpu.py runs the same
 checks on the CUDA path."""
-import numpy as np
 import pytest
 
 import pyref_checks as pc
