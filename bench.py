@@ -229,7 +229,12 @@ def run_graft(args):
         # torchrun pins OMP_NUM_THREADS=1; the once-per-mesh host preprocessing (sparsity, plans) is
         # OpenMP code, so give every rank its share of the host cores
         if os.environ.get("OMP_NUM_THREADS", "1") == "1":
-            os.environ["OMP_NUM_THREADS"] = str(max(1, len(os.sched_getaffinity(0)) // world))
+            share = max(1, len(os.sched_getaffinity(0)) // world)
+            os.environ["OMP_NUM_THREADS"] = str(share)
+            # libcgasm.so resolves libgomp.so.1 to the copy torch bundles, which read OMP_NUM_THREADS=1 when torch
+            # was imported: the environment alone no longer reaches it (measured: 390 s of single-threaded plan
+            # building per rank at N=2 against 45 s at N=1), so set the thread count through the runtime as well
+            torch.set_num_threads(share)
 
     c = args.cells
     t_setup = time.perf_counter()
