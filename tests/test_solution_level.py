@@ -88,3 +88,35 @@ def test_advection_diffusion_wave_with_strong_dirichlet_converges(orc, lumped):
         errs.append(l2_error(mesh, T, exact(mesh.X, t)))
     rates = np.log2(np.array(errs[:-1]) / np.array(errs[1:]))
     assert errs[-1] < 5e-3 and (rates > 1.7).all(), (errs, rates)
+
+
+@pytest.mark.parametrize("lump", [1, 0])
+def test_momentum_shear_layer_decay_converges_at_second_order(orc, lump):
+    """Momentum equation without pressure gradient: u = (cos(pi y) exp(-nu pi^2 t), 0) is an exact solution
+    (u.grad u = 0, zero-stress walls are natural). big_m . delta_u = rhs per component for the rate of change
+    (assemble/Momentum_Equation.F90: the velocity change is solved for and added with dt), advecting velocity and
+    oldu = u^n, constant density."""
+    nu_, dt, t_end = 0.2, 0.0025, 0.05
+    errs = []
+    for n in (8, 16, 32):
+        mesh = syn.box_mesh((n, n), seed=13)
+        fs = syn.standard_fields(mesh)
+        fs.set(abi.F_DENSITY, np.array([1.0]), abi.FIELD_CONSTANT)
+        fs.set(abi.F_VISCOSITY, syn.iso_tensor(2, nu_), abi.FIELD_CONSTANT)
+        findrm, colm, _ = orc.make_sparsity(mesh)
+        o = abi.common_momentum_opts(dt=dt, theta=0.5, have_gravity=0, lump_mass=lump)
+        N = mesh.n_nodes
+        u = np.zeros((N, 2))
+        u[:, 0] = np.cos(np.pi * mesh.X[:, 1])
+        for _ in range(int(round(t_end / dt))):
+            fs.set(abi.F_NU, u)
+            fs.set(abi.F_OLDU, u)
+            s = orc.assemble_momentum(mesh, fs, o, findrm, colm)
+            for d in range(2):
+                A = sp.csr_matrix((s["big_m"][d], colm - 1, findrm - 1), shape=(N, N)).tocsc()
+                u[:, d] = u[:, d] + dt * spla.spsolve(A, s["rhs"][:, d])
+        exact = np.cos(np.pi * mesh.X[:, 1]) * np.exp(-nu_ * np.pi ** 2 * t_end)
+        errs.append(l2_error(mesh, u[:, 0], exact))
+        assert np.abs(u[:, 1]).max() < 1e-10       # no spurious cross-flow
+    rates = np.log2(np.array(errs[:-1]) / np.array(errs[1:]))
+    assert errs[-1] < 3e-4 and (rates > 1.8).all(), (errs, rates)
