@@ -120,3 +120,28 @@ def test_momentum_shear_layer_decay_converges_at_second_order(orc, lump):
         assert np.abs(u[:, 1]).max() < 1e-10       # no spurious cross-flow
     rates = np.log2(np.array(errs[:-1]) / np.array(errs[1:]))
     assert errs[-1] < 3e-4 and (rates > 1.8).all(), (errs, rates)
+
+
+def test_pressure_matrix_is_a_consistent_discrete_laplacian(orc):
+    """ct_m(d)(i, j) = int N_i d_d N_j (Momentum_CG.F90:1401) is the weak divergence; for p vanishing on the
+    boundary C^T p = -int grad p_h N_j, so cmc_m = C M_L^-1 C^T (Assemble_CMC.F90:119-135) is the stiffness form
+    q^T cmc p -> int grad q . grad p, at second order on jittered meshes (pointwise it is only first order there:
+    the stencil is two elements wide). p = sin(pi x) sin(2 pi y), q = x(1-x) sin(2 pi y):
+    int |grad p|^2 = 5 pi^2 / 4, int grad q . grad p = 10 / pi."""
+    errs = []
+    for n in (8, 16, 32):
+        mesh = syn.box_mesh((n, n), seed=14)
+        fs = syn.standard_fields(mesh)
+        fs.set(abi.F_DENSITY, np.array([1.0]), abi.FIELD_CONSTANT)
+        findrm, colm, _ = orc.make_sparsity(mesh)
+        s = orc.assemble_momentum(mesh, fs, abi.common_momentum_opts(assemble_ct_matrix_here=1), findrm, colm, want_ct=True)
+        f2, c2 = orc.make_sparsity_mult(mesh.n_nodes, findrm, colm)
+        cmc = orc.mult_div_vector_div_T(findrm, colm, s["ct_m"], s["ct_m"], 1.0 / s["masslump"], f2, c2)
+        N = mesh.n_nodes
+        M = sp.csr_matrix((cmc, c2 - 1, f2 - 1), shape=(N, N))
+        x, y = mesh.X[:, 0], mesh.X[:, 1]
+        p = np.sin(np.pi * x) * np.sin(2 * np.pi * y)
+        q = x * (1 - x) * np.sin(2 * np.pi * y)
+        errs.append(max(abs(p @ (M @ p) - 5 * np.pi ** 2 / 4) / (5 * np.pi ** 2 / 4), abs(q @ (M @ p) - 10 / np.pi) / (10 / np.pi)))
+    rates = np.log2(np.array(errs[:-1]) / np.array(errs[1:]))
+    assert errs[-1] < 0.02 and (rates > 1.8).all(), (errs, rates)
