@@ -99,3 +99,34 @@ def test_emulated_advdiff_matches_oracle(orc, name, theta):
     assert rel_err(got["matrix"], ref["matrix"]) < TOL
     assert row_rel_err(got["matrix"], ref["matrix"], findrm) < TOL
     assert rel_err(got["rhs"], ref["rhs"]) < TOL
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_absorption_row_closed_form_for_the_strip_kernels(orc, dim):
+    """The row-owner closed form planned for absorption in the strip kernels: with
+    constant density, row 0 of Ab^d = shape_shape_vector(test, u, detwei*rho, sigma) (Momentum_CG.F90:2038) is
+    rho |J| [Qa sigma_0 + Qaab S] on the diagonal and rho |J| [Qd (sigma_0 + sigma_k) + Qabc S] off it, S = sum of
+    sigma_d over the element -- the density-weighted mass row with sigma_d in the place of rho. Checked per element
+    against the oracle (difference of the element matrices with and without absorption)."""
+    mesh = syn.box_mesh((3, 2, 2)[:dim], seed=9)
+    fs = syn.standard_fields(mesh)
+    rho = 1.3
+    fs.set(abi.F_DENSITY, np.array([rho]), abi.FIELD_CONSTANT)
+    m = se.moments(dim)
+    Qa, Qd = m["Qaaa"] - m["Qaab"], m["Qaab"] - m["Qabc"]
+    sig = fs.get(abi.F_ABSORPTION)[0]
+    o0, o1 = abi.common_momentum_opts(), abi.common_momentum_opts(have_absorption=1)
+    dtt = o0.dt * o0.theta
+    for ele in range(1, mesh.n_elements + 1):
+        nd = mesh.ndglno[ele - 1] - 1
+        T0 = orc.momentum_element(mesh, fs, o0, ele)[0]
+        T1 = orc.momentum_element(mesh, fs, o1, ele)[0]
+        X = mesh.X[nd]
+        adet = abs(np.linalg.det(X[1:] - X[0]))
+        for d in range(dim):
+            Ab = (T1[d, d] - T0[d, d]) / dtt
+            s = sig[nd, d]
+            S = s.sum()
+            want = np.array([[rho * adet * ((Qa * s[i] + m["Qaab"] * S) if i == k else (Qd * (s[i] + s[k]) + m["Qabc"] * S))
+                              for k in range(dim + 1)] for i in range(dim + 1)])
+            assert np.abs(Ab - want).max() <= 1e-9 * np.abs(want).max()   # (difference of two O(1) numbers / dt theta)
