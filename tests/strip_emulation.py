@@ -151,3 +151,41 @@ def emulate_advdiff(mesh, fs, o, findrm, colm):
         matrix[s0:s1] = vals
         rhs[r] = rh
     return dict(matrix=matrix, rhs=rhs)
+
+
+def emulate_absorption_pass(mesh, fs, o, findrm, colm):
+    """The second strip pass planned for round 2, emulated: per row the same strip,
+    per computed window only |J| (one triple product) and the closed-form absorption row
+    rho |J| [Qa s_0 + Qaab S | Qd (s_0 + s_k) + Qabc S] for every component d. Constant density (Boussinesq).
+    Returns what has to be ADDED to the common result: big_m (dim, nnz) and rhs (n_nodes, dim)."""
+    dim, nn = mesh.dim, mesh.n_nodes
+    m = moments(dim)
+    Qa, Qd = m["Qaaa"] - m["Qaab"], m["Qaab"] - m["Qabc"]
+    X = mesh.X
+    rho = float(fs.get(abi.F_DENSITY)[0].reshape(-1)[0])
+    sig, oldu = fs.get(abi.F_ABSORPTION)[0], fs.get(abi.F_OLDU)[0]
+    row_ptr, ent = strip_plan(mesh)
+    f0, c0 = findrm - 1, colm - 1
+    big_m = np.zeros((dim, len(colm)))
+    rhs = np.zeros((nn, dim))
+    dtt = o.dt * o.theta
+    for r in range(nn):
+        s0, s1 = f0[r], f0[r + 1]
+        acc = np.zeros((dim, s1 - s0))
+        own = int(np.searchsorted(c0[s0:s1], r))
+        fifo = []
+        for node1, meta in ent[row_ptr[r]:row_ptr[r + 1]]:
+            fifo.append((node1 - 1, meta & 0xff))
+            fifo = fifo[-dim:]
+            if not (meta & COMPUTE):
+                continue
+            nodes = [q for q, _ in fifo]
+            ad = rho * abs(np.linalg.det(X[nodes] - X[r]))
+            S = sig[r] + sig[nodes].sum(axis=0)                      # (dim,)
+            acc[:, own] += ad * (Qa * sig[r] + m["Qaab"] * S)
+            for q, slot in fifo:
+                acc[:, slot] += ad * (Qd * (sig[r] + sig[q]) + m["Qabc"] * S)
+        cols = c0[s0:s1]
+        big_m[:, s0:s1] = dtt * acc
+        rhs[r] = -np.einsum("ds,sd->d", acc, oldu[cols])
+    return dict(big_m=big_m, rhs=rhs)

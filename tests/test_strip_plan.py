@@ -130,3 +130,22 @@ def test_absorption_row_closed_form_for_the_strip_kernels(orc, dim):
             want = np.array([[rho * adet * ((Qa * s[i] + m["Qaab"] * S) if i == k else (Qd * (s[i] + s[k]) + m["Qabc"] * S))
                               for k in range(dim + 1)] for i in range(dim + 1)])
             assert np.abs(Ab - want).max() <= 1e-9 * np.abs(want).max()   # (difference of two O(1) numbers / dt theta)
+
+
+@pytest.mark.parametrize("name", ["box3", "box2_shuffled", "cube.1"])
+def test_emulated_absorption_pass_matches_oracle(orc, name):
+    """common strip result + the planned absorption pass == the oracle's assembly with have_absorption
+    (the backward_facing_step_3d option set: constant density, nodal vector absorption)."""
+    mesh = meshes()[name]
+    fs = syn.standard_fields(mesh)
+    fs.set(abi.F_DENSITY, np.full(mesh.n_nodes, 1.25))  # uniform, stored nodally (the emulation indexes it by node)
+    findrm, colm, _ = orc.make_sparsity(mesh)
+    o = abi.common_momentum_opts(have_absorption=1)
+    ref = orc.assemble_momentum(mesh, fs, o, findrm, colm)
+    base = se.emulate_momentum(mesh, fs, abi.common_momentum_opts(), findrm, colm)
+    add = se.emulate_absorption_pass(mesh, fs, o, findrm, colm)
+    for d in range(mesh.dim):
+        got = base["big_m"][d] + add["big_m"][d]
+        assert rel_err(got, ref["big_m"][d]) < TOL and row_rel_err(got, ref["big_m"][d], findrm) < TOL
+        assert rel_err(base["rhs"][:, d] + add["rhs"][:, d], ref["rhs"][:, d]) < TOL
+    assert rel_err(base["masslump"], ref["masslump"]) < TOL
