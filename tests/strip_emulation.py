@@ -105,10 +105,16 @@ def emulate_momentum(mesh, fs, o, findrm, colm):
 
 
 def emulate_advdiff(mesh, fs, o, findrm, colm):
+    """have_absorption / have_source (not in the device strip kernels yet: the closed forms planned for round 2,
+    DESIGN.md section 7 item 2): Ab_0k = |J| [Qa s_0 + Qaab S | Qd (s_0 + s_k) + Qabc S]
+    (Advection_Diffusion_CG.F90:1156), source rhs_0 += |J| [(Pd - Po) q_0 + Po sum q] (:1139)."""
     dim, nn = mesh.dim, mesh.n_nodes
     m = moments(dim)
     X = mesh.X
     nu, T = fs.get(abi.F_NU)[0], fs.get(abi.F_T)[0]
+    sig = fs.get(abi.F_T_ABSORPTION)[0] if o.have_absorption else np.zeros(nn)
+    src = fs.get(abi.F_T_SOURCE)[0] if o.have_source else np.zeros(nn)
+    Qa, Qd = m["Qaaa"] - m["Qaab"], m["Qaab"] - m["Qabc"]
     kappa = fs.get(abi.F_T_DIFFUSIVITY)[0].reshape(-1)[0]
     row_ptr, ent = strip_plan(mesh)
     f0, c0 = findrm - 1, colm - 1
@@ -137,15 +143,19 @@ def emulate_advdiff(mesh, fs, o, findrm, colm):
             u = np.sign(det) * (v - (kappa * m["Wsum"] / det) * sc)
             tot = 0.0
             ad = abs(det)
+            Ss = sig[r] + sig[nodes].sum()
             for k, (q, slot) in enumerate(fifo):
                 sk = float(u @ c[k])
-                a[slot] += sk
+                ab = ad * (Qd * (sig[r] + sig[q]) + m["Qabc"] * Ss)
+                a[slot] += sk + ab
                 vol[slot] += ad
-                rh -= sk * T[q]
+                rh -= (sk + ab) * T[q]
                 tot += sk
-            a[own] -= tot
+            ab0 = ad * (Qa * sig[r] + m["Qaab"] * Ss)
+            a[own] += ab0 - tot
             vol[own] += ad
-            rh += tot * T[r]
+            rh += (tot - ab0) * T[r]
+            rh += ad * ((m["Pd"] - m["Po"]) * src[r] + m["Po"] * (src[r] + src[nodes].sum()))
         vals = dtt * a + m["Po"] * vol
         vals[own] = dtt * a[own] + m["Pd"] * vol[own]
         matrix[s0:s1] = vals

@@ -101,6 +101,20 @@ def test_emulated_advdiff_matches_oracle(orc, name, theta):
     assert rel_err(got["rhs"], ref["rhs"]) < TOL
 
 
+@pytest.mark.parametrize("name", ["box3", "box2_shuffled", "cube.1", "2d_square"])
+def test_emulated_advdiff_with_absorption_and_source_matches_oracle(orc, name):
+    # the tracer closed forms planned for the strip kernels in round 2 (absorption, nodal source)
+    mesh = meshes()[name]
+    fs = syn.standard_fields(mesh)
+    findrm, colm, _ = orc.make_sparsity(mesh)
+    for o in (abi.common_advdiff_opts(have_absorption=1), abi.common_advdiff_opts(have_source=1),
+              abi.common_advdiff_opts(have_absorption=1, have_source=1, theta=1.0)):
+        ref = orc.assemble_advdiff(mesh, fs, o, findrm, colm)
+        got = se.emulate_advdiff(mesh, fs, o, findrm, colm)
+        assert rel_err(got["matrix"], ref["matrix"]) < TOL and row_rel_err(got["matrix"], ref["matrix"], findrm) < TOL
+        assert rel_err(got["rhs"], ref["rhs"]) < TOL
+
+
 @pytest.mark.parametrize("dim", [2, 3])
 def test_absorption_row_closed_form_for_the_strip_kernels(orc, dim):
     """The row-owner closed form planned for absorption in the strip kernels: with
