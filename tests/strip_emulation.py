@@ -54,6 +54,10 @@ def emulate_momentum(mesh, fs, o, findrm, colm):
     X = mesh.X
     nu, oldu = fs.get(abi.F_NU)[0], fs.get(abi.F_OLDU)[0]
     rho, bb = fs.get(abi.F_DENSITY)[0], fs.get(abi.F_BUOYANCY)[0]
+    if o.have_gravity and o.subtract_out_reference_profile:
+        bb = bb - fs.get(abi.F_HB_DENSITY)[0]       # Momentum_CG.F90:1781-1784: (buoyancy - hb_density) at the quadrature points
+    src = fs.get(abi.F_SOURCE)[0] if (o.have_source and not o.lump_source) else None
+    rsrc = np.zeros((nn, dim))
     mu = fs.get(abi.F_VISCOSITY)[0].reshape(-1)[0]
     g = fs.get(abi.F_GRAVITY)[0].reshape(-1)[:dim]
     row_ptr, ent = strip_plan(mesh)
@@ -85,6 +89,12 @@ def emulate_momentum(mesh, fs, o, findrm, colm):
             w = M0 * nu[r]
             for k, q in enumerate(nodes):
                 w = w + (Qd * (rho[r] + rho[q]) + m["Qabc"] * S) * nu[q]
+            if src is not None:
+                # add_sources_element_cg (:1737-1748): rhs(d, 0) += sum_k M_0k src(d, k), M = the density-weighted mass row
+                ws = M0 * src[r]
+                for k, q in enumerate(nodes):
+                    ws = ws + (Qd * (rho[r] + rho[q]) + m["Qabc"] * S) * src[q]
+                rsrc[r] += abs(det) * ws
             u = np.sign(det) * (w - (mu * m["Wsum"] * rd) * sc)
             tot = 0.0
             for k, (q, slot) in enumerate(fifo):
@@ -96,7 +106,7 @@ def emulate_momentum(mesh, fs, o, findrm, colm):
             msum += ad * ((m["Pd"] - m["Po"]) * rho[r] + m["Po"] * S)
             nbsum += ad * ((m["Pd"] - m["Po"]) * bb[r] + m["Po"] * (bb[r] + bb[nodes].sum()))
         cols = c0[s0:s1]
-        rhs[r] = o.gravity_magnitude * g * nbsum - acc @ oldu[cols]
+        rhs[r] = o.gravity_magnitude * g * nbsum - acc @ oldu[cols] + rsrc[r]
         vals = dtt * acc
         vals[own] += msum
         big_m[:, s0:s1] = vals

@@ -101,6 +101,21 @@ def test_emulated_advdiff_matches_oracle(orc, name, theta):
     assert rel_err(got["rhs"], ref["rhs"]) < TOL
 
 
+@pytest.mark.parametrize("name", ["box3", "box2_shuffled", "cube.1"])
+def test_emulated_momentum_with_source_and_reference_profile_matches_oracle(orc, name):
+    # momentum closed forms planned for the strip kernels in round 2: nodal source, subtract_out_reference_profile
+    mesh = meshes()[name]
+    fs = syn.standard_fields(mesh)
+    findrm, colm, _ = orc.make_sparsity(mesh)
+    for o in (abi.common_momentum_opts(have_source=1), abi.common_momentum_opts(subtract_out_reference_profile=1),
+              abi.common_momentum_opts(have_source=1, subtract_out_reference_profile=1, theta=1.0)):
+        ref = orc.assemble_momentum(mesh, fs, o, findrm, colm)
+        got = se.emulate_momentum(mesh, fs, o, findrm, colm)
+        for d in range(mesh.dim):
+            assert rel_err(got["big_m"][d], ref["big_m"][d]) < TOL
+            assert rel_err(got["rhs"][:, d], ref["rhs"][:, d]) < TOL
+
+
 @pytest.mark.parametrize("name", ["box3", "box2_shuffled", "cube.1", "2d_square"])
 def test_emulated_advdiff_with_absorption_and_source_matches_oracle(orc, name):
     # the tracer closed forms planned for the strip kernels in round 2 (absorption, nodal source)
