@@ -71,6 +71,7 @@ def emulate_momentum(mesh, fs, o, findrm, colm):
     for r in range(nn):
         s0, s1 = f0[r], f0[r + 1]
         acc = np.zeros(s1 - s0)
+        mass = np.zeros(s1 - s0)
         own = int(np.searchsorted(c0[s0:s1], r))
         fifo = []  # (node, slot)
         msum = nbsum = 0.0
@@ -97,18 +98,28 @@ def emulate_momentum(mesh, fs, o, findrm, colm):
                 rsrc[r] += abs(det) * ws
             u = np.sign(det) * (w - (mu * m["Wsum"] * rd) * sc)
             tot = 0.0
+            ad = abs(det)
+            # beta term of the plain form (:1675-1680): beta * div(nu) * density-weighted mass row; for P1 div(nu) is
+            # constant on the element: sum_k nu_k . gradN_k with gradN_0 = -sc/det, gradN_k = c[k]/det
+            divu = (float(-nu[r] @ sc) + sum(float(nu[q] @ c[k]) for k, q in enumerate(nodes))) * rd
+            bm = o.beta * divu * ad
             for k, (q, slot) in enumerate(fifo):
                 sk = float(u @ c[k])
-                acc[slot] += sk
+                Mk = Qd * (rho[r] + rho[q]) + m["Qabc"] * S
+                acc[slot] += sk + bm * Mk
+                if not o.lump_mass and not o.exclude_mass:
+                    mass[slot] += ad * Mk               # consistent mass block (:1554-1556), not scaled by dt*theta
                 tot += sk
-            acc[own] -= tot
-            ad = abs(det)
+            acc[own] += bm * M0 - tot
+            if not o.lump_mass and not o.exclude_mass:
+                mass[own] += ad * M0
             msum += ad * ((m["Pd"] - m["Po"]) * rho[r] + m["Po"] * S)
             nbsum += ad * ((m["Pd"] - m["Po"]) * bb[r] + m["Po"] * (bb[r] + bb[nodes].sum()))
         cols = c0[s0:s1]
         rhs[r] = o.gravity_magnitude * g * nbsum - acc @ oldu[cols] + rsrc[r]
-        vals = dtt * acc
-        vals[own] += msum
+        vals = dtt * acc + mass
+        if o.lump_mass and not o.exclude_mass:
+            vals[own] += msum
         big_m[:, s0:s1] = vals
         ml[r] = msum
     return dict(big_m=big_m, rhs=rhs, masslump=ml)
