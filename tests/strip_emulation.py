@@ -165,17 +165,23 @@ def emulate_advdiff(mesh, fs, o, findrm, colm):
             tot = 0.0
             ad = abs(det)
             Ss = sig[r] + sig[nodes].sum()
+            # beta term (:1093-1098): beta * div(nu) * mass row, div(nu) constant on a P1 element
+            divu = (float(-nu[r] @ sc) + sum(float(nu[q] @ c[k]) for k, q in enumerate(nodes))) / det
+            bm = o.beta * divu * ad if o.have_advection else 0.0
             for k, (q, slot) in enumerate(fifo):
-                sk = float(u @ c[k])
+                sk = float(u @ c[k]) + bm * m["Po"]
                 ab = ad * (Qd * (sig[r] + sig[q]) + m["Qabc"] * Ss)
                 a[slot] += sk + ab
                 vol[slot] += ad
                 rh -= (sk + ab) * T[q]
                 tot += sk
             ab0 = ad * (Qa * sig[r] + m["Qaab"] * Ss)
-            a[own] += ab0 - tot
+            # diagonal of the advective + diffusive part: minus the off-diagonal row sum of the beta-free part, plus
+            # the beta mass diagonal
+            d0 = -(tot - dim * bm * m["Po"]) + bm * m["Pd"]
+            a[own] += ab0 + d0
             vol[own] += ad
-            rh += (tot - ab0) * T[r]
+            rh -= (ab0 + d0) * T[r]
             rh += ad * ((m["Pd"] - m["Po"]) * src[r] + m["Po"] * (src[r] + src[nodes].sum()))
         vals = dtt * a + m["Po"] * vol
         vals[own] = dtt * a[own] + m["Pd"] * vol[own]
