@@ -99,6 +99,29 @@ def emulate_momentum(mesh, fs, o, findrm, colm):
             u = np.sign(det) * (w - (mu * m["Wsum"] * rd) * sc)
             tot = 0.0
             ad = abs(det)
+            if o.integrate_advection_by_parts and not o.exclude_advection:
+                # by-parts volume form (:1646-1669): A_0j = -gradN_0 . W_j - (1 - beta) div(nu) M_0j with
+                # W_j = sum_g u_g N_jg rho_g detwei = |J| sum_k M~_jk nu_k (M~ = density-weighted mass moments, every row j)
+                ids = [r] + nodes
+                Mt = np.array([[(Qa * rho[a] + m["Qaab"] * S) if a == b else (Qd * (rho[a] + rho[b]) + m["Qabc"] * S)
+                                for b in ids] for a in ids])
+                Wj = Mt @ nu[ids]                                           # (loc, dim), without |J|
+                divu = (float(-nu[r] @ sc) + sum(float(nu[q] @ c[k]) for k, q in enumerate(nodes))) * rd
+                visc = -np.sign(det) * (mu * m["Wsum"] * rd)                # K_0k = visc * sc . c[k]
+                row = np.sign(det) * (Wj @ sc) - (1.0 - o.beta) * divu * ad * Mt[0]      # advective part, columns ids
+                tot_k = 0.0
+                for k, (q, slot) in enumerate(fifo):
+                    kk = visc * float(sc @ c[k])
+                    acc[slot] += row[k + 1] + kk
+                    tot_k += kk
+                    if not o.lump_mass and not o.exclude_mass:
+                        mass[slot] += ad * Mt[0, k + 1]
+                acc[own] += row[0] - tot_k
+                if not o.lump_mass and not o.exclude_mass:
+                    mass[own] += ad * M0
+                msum += ad * ((m["Pd"] - m["Po"]) * rho[r] + m["Po"] * S)
+                nbsum += ad * ((m["Pd"] - m["Po"]) * bb[r] + m["Po"] * (bb[r] + bb[nodes].sum()))
+                continue
             # beta term of the plain form (:1675-1680): beta * div(nu) * density-weighted mass row; for P1 div(nu) is
             # constant on the element: sum_k nu_k . gradN_k with gradN_0 = -sc/det, gradN_k = c[k]/det
             divu = (float(-nu[r] @ sc) + sum(float(nu[q] @ c[k]) for k, q in enumerate(nodes))) * rd
