@@ -191,6 +191,29 @@ def emulate_advdiff(mesh, fs, o, findrm, colm):
             # beta term (:1093-1098): beta * div(nu) * mass row, div(nu) constant on a P1 element
             divu = (float(-nu[r] @ sc) + sum(float(nu[q] @ c[k]) for k, q in enumerate(nodes))) / det
             bm = o.beta * divu * ad if o.have_advection else 0.0
+            if o.have_advection and o.integrate_advection_by_parts:
+                # by-parts volume form (:1043-1049): A_0j = -gradN_0 . W_j - (1 - beta) div(nu) P_0j, W_j = |J| [(Pd - Po) nu_j
+                # + Po sum nu]; the second term is skipped when |1 - beta| <= epsilon. Diffusion as in the plain form.
+                ids = [r] + nodes
+                Wj = (m["Pd"] - m["Po"]) * nu[ids] + m["Po"] * Su                 # (loc, dim), without |J|
+                row = np.sign(det) * (Wj @ sc)
+                if abs(1.0 - o.beta) > 2.220446049250313e-16:
+                    row = row - (1.0 - o.beta) * divu * ad * np.array([m["Pd"]] + [m["Po"]] * dim)
+                dif = -np.sign(det) * (kappa * m["Wsum"] / det)
+                tot_k = 0.0
+                for k, (q, slot) in enumerate(fifo):
+                    kk = dif * float(sc @ c[k])
+                    ab = ad * (Qd * (sig[r] + sig[q]) + m["Qabc"] * Ss)
+                    a[slot] += row[k + 1] + kk + ab
+                    vol[slot] += ad
+                    rh -= (row[k + 1] + kk + ab) * T[q]
+                    tot_k += kk
+                ab0 = ad * (Qa * sig[r] + m["Qaab"] * Ss)
+                a[own] += row[0] - tot_k + ab0
+                vol[own] += ad
+                rh -= (row[0] - tot_k + ab0) * T[r]
+                rh += ad * ((m["Pd"] - m["Po"]) * src[r] + m["Po"] * (src[r] + src[nodes].sum()))
+                continue
             for k, (q, slot) in enumerate(fifo):
                 sk = float(u @ c[k]) + bm * m["Po"]
                 ab = ad * (Qd * (sig[r] + sig[q]) + m["Qabc"] * Ss)

@@ -128,7 +128,9 @@ def test_emulated_advdiff_with_absorption_and_source_matches_oracle(orc, name):
     findrm, colm, _ = orc.make_sparsity(mesh)
     for o in (abi.common_advdiff_opts(have_absorption=1), abi.common_advdiff_opts(have_source=1),
               abi.common_advdiff_opts(have_absorption=1, have_source=1, theta=1.0), abi.common_advdiff_opts(beta=1.0),
-              abi.common_advdiff_opts(beta=0.4, have_absorption=1)):
+              abi.common_advdiff_opts(beta=0.4, have_absorption=1), abi.common_advdiff_opts(integrate_advection_by_parts=1),
+              abi.common_advdiff_opts(integrate_advection_by_parts=1, beta=1.0),
+              abi.common_advdiff_opts(integrate_advection_by_parts=1, beta=0.25, have_source=1)):
         ref = orc.assemble_advdiff(mesh, fs, o, findrm, colm)
         got = se.emulate_advdiff(mesh, fs, o, findrm, colm)
         assert rel_err(got["matrix"], ref["matrix"]) < TOL and row_rel_err(got["matrix"], ref["matrix"], findrm) < TOL
