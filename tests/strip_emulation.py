@@ -58,7 +58,9 @@ def emulate_momentum(mesh, fs, o, findrm, colm):
         bb = bb - fs.get(abi.F_HB_DENSITY)[0]       # Momentum_CG.F90:1781-1784: (buoyancy - hb_density) at the quadrature points
     src = fs.get(abi.F_SOURCE)[0] if (o.have_source and not o.lump_source) else None
     rsrc = np.zeros((nn, dim))
-    mu = fs.get(abi.F_VISCOSITY)[0].reshape(-1)[0]
+    visc_field = fs.get(abi.F_VISCOSITY)[0]            # (1 | n_nodes, dim, dim), [node, b, a] = V(a, b)
+    mu = visc_field.reshape(-1)[0]
+    general_visc = o.have_viscosity and (o.viscosity_shape != abi.TENSOR_ISOTROPIC or visc_field.shape[0] > 1)
     g = fs.get(abi.F_GRAVITY)[0].reshape(-1)[:dim]
     row_ptr, ent = strip_plan(mesh)
     f0, c0 = findrm - 1, colm - 1
@@ -96,7 +98,18 @@ def emulate_momentum(mesh, fs, o, findrm, colm):
                 for k, q in enumerate(nodes):
                     ws = ws + (Qd * (rho[r] + rho[q]) + m["Qabc"] * S) * src[q]
                 rsrc[r] += abs(det) * ws
-            u = np.sign(det) * (w - (mu * m["Wsum"] * rd) * sc)
+            if general_visc:
+                # dshape_tensor_dshape / dshape_diagtensor_dshape (:2318-2339): K_0k = |J| sum_g w_g gradN_0^T V_g gradN_k; V is P1
+                # and the rule symmetric, so sum_g w_g V_g = (Wsum / loc) sum_l V_l (constant fields: Wsum V)
+                ids_v = ([r] + nodes) if visc_field.shape[0] > 1 else [0]
+                Vbar = m["Wsum"] * visc_field[ids_v].mean(axis=0).T        # Vbar[a, b]
+                if o.viscosity_shape == abi.TENSOR_DIAGONAL:
+                    Vbar = np.diag(np.diag(Vbar))
+                elif o.viscosity_shape == abi.TENSOR_ISOTROPIC:
+                    Vbar = Vbar[0, 0] * np.eye(dim)
+                u = np.sign(det) * (w - rd * (sc @ Vbar))
+            else:
+                u = np.sign(det) * (w - (mu * m["Wsum"] * rd) * sc)
             tot = 0.0
             ad = abs(det)
             if o.integrate_advection_by_parts and not o.exclude_advection:

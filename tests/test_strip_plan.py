@@ -120,6 +120,23 @@ def test_emulated_momentum_option_variants_match_oracle(orc, name):
             assert rel_err(got["rhs"][:, d], ref["rhs"][:, d]) < TOL
 
 
+@pytest.mark.parametrize("name", ["box3", "box2_shuffled", "cube.1"])
+def test_emulated_momentum_tensor_viscosity_matches_oracle(orc, name):
+    # nodal full-tensor viscosity (element average x Wsum), constant anisotropic and diagonal tensors
+    mesh = meshes()[name]
+    findrm, colm, _ = orc.make_sparsity(mesh)
+    cases = [(syn.standard_fields(mesh, nodal_viscosity=True), abi.common_momentum_opts(viscosity_shape=abi.TENSOR_FULL))]
+    for shape in (abi.TENSOR_FULL, abi.TENSOR_DIAGONAL):
+        fs = syn.standard_fields(mesh)
+        fs.set(abi.F_VISCOSITY, syn.aniso_tensor(mesh.dim), abi.FIELD_CONSTANT)
+        cases.append((fs, abi.common_momentum_opts(viscosity_shape=shape)))
+    for fs, o in cases:
+        ref = orc.assemble_momentum(mesh, fs, o, findrm, colm)
+        got = se.emulate_momentum(mesh, fs, o, findrm, colm)
+        for d in range(mesh.dim):
+            assert rel_err(got["big_m"][d], ref["big_m"][d]) < TOL and rel_err(got["rhs"][:, d], ref["rhs"][:, d]) < TOL
+
+
 @pytest.mark.parametrize("name", ["box3", "box2_shuffled", "cube.1", "2d_square"])
 def test_emulated_advdiff_with_absorption_and_source_matches_oracle(orc, name):
     # the tracer closed forms planned for the strip kernels in round 2 (absorption, nodal source)
