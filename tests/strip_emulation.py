@@ -58,6 +58,10 @@ def emulate_momentum(mesh, fs, o, findrm, colm):
         bb = bb - fs.get(abi.F_HB_DENSITY)[0]       # Momentum_CG.F90:1781-1784: (buoyancy - hb_density) at the quadrature points
     src = fs.get(abi.F_SOURCE)[0] if (o.have_source and not o.lump_source) else None
     rsrc = np.zeros((nn, dim))
+    lump_abs = bool(o.have_absorption and o.lump_absorption)
+    sig = fs.get(abi.F_ABSORPTION)[0] if lump_abs else None
+    l, wq = tables.quadrature_degree3(dim)
+    Q3 = np.einsum("g,gl,gm->lm", wq * l[:, 0], l, l)      # Q_{0lm} = sum_g w_g N_0g N_lg N_mg (row node first)
     visc_field = fs.get(abi.F_VISCOSITY)[0]            # (1 | n_nodes, dim, dim), [node, b, a] = V(a, b)
     mu = visc_field.reshape(-1)[0]
     general_visc = o.have_viscosity and (o.viscosity_shape != abi.TENSOR_ISOTROPIC or visc_field.shape[0] > 1)
@@ -77,6 +81,7 @@ def emulate_momentum(mesh, fs, o, findrm, colm):
         own = int(np.searchsorted(c0[s0:s1], r))
         fifo = []  # (node, slot)
         msum = nbsum = 0.0
+        alump = np.zeros(dim)
         for node1, meta in ent[row_ptr[r]:row_ptr[r + 1]]:
             fifo.append((node1 - 1, meta & 0xff))
             fifo = fifo[-dim:]
@@ -86,6 +91,10 @@ def emulate_momentum(mesh, fs, o, findrm, colm):
             e = X[nodes] - X[r]
             c, det = _geometry(e)
             rd = 1.0 / det
+            if lump_abs:
+                # lumped absorption (:2041-2056): sum_j Ab^d_0j = sum_g N_0g sigma_dg rho_g detwei = |J| sum_lm Q_0lm sigma_dl rho_m
+                ids_a = [r] + nodes
+                alump += abs(det) * np.einsum("lm,ld,m->d", Q3, sig[ids_a], rho[ids_a])
             sc = c.sum(axis=0)
             S = rho[r] + rho[nodes].sum()
             M0 = Qa * rho[r] + m["Qaab"] * S
@@ -152,12 +161,15 @@ def emulate_momentum(mesh, fs, o, findrm, colm):
             msum += ad * ((m["Pd"] - m["Po"]) * rho[r] + m["Po"] * S)
             nbsum += ad * ((m["Pd"] - m["Po"]) * bb[r] + m["Po"] * (bb[r] + bb[nodes].sum()))
         cols = c0[s0:s1]
-        rhs[r] = o.gravity_magnitude * g * nbsum - acc @ oldu[cols] + rsrc[r]
+        if o.have_source and o.lump_source:
+            rsrc[r] = msum * fs.get(abi.F_SOURCE)[0][r]     # (:1739-1742): lumped density-weighted mass times the nodal source
+        rhs[r] = o.gravity_magnitude * g * nbsum - acc @ oldu[cols] + rsrc[r] - alump * oldu[r]
         vals = dtt * acc + mass
         if o.lump_mass and not o.exclude_mass:
             vals[own] += msum
         big_m[:, s0:s1] = vals
-        ml[r] = msum
+        big_m[:, s0 + own] += dtt * alump
+        ml[r] = msum + (dtt * alump if (lump_abs and o.pressure_corrected_absorption) else 0.0)
     return dict(big_m=big_m, rhs=rhs, masslump=ml)
 
 

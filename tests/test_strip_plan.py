@@ -104,7 +104,8 @@ def test_emulated_advdiff_matches_oracle(orc, name, theta):
 @pytest.mark.parametrize("name", ["box3", "box2_shuffled", "cube.1"])
 def test_emulated_momentum_option_variants_match_oracle(orc, name):
     # momentum closed forms planned for the strip kernels in round 2: nodal source, subtract_out_reference_profile,
-    # consistent mass, the beta term of the plain advection form, the by-parts volume form
+    # consistent mass, the beta term of the plain advection form, the by-parts volume form, lumped source, lumped
+    # (and pressure-corrected) absorption
     mesh = meshes()[name]
     fs = syn.standard_fields(mesh)
     findrm, colm, _ = orc.make_sparsity(mesh)
@@ -112,12 +113,16 @@ def test_emulated_momentum_option_variants_match_oracle(orc, name):
               abi.common_momentum_opts(have_source=1, subtract_out_reference_profile=1, theta=1.0),
               abi.common_momentum_opts(lump_mass=0), abi.common_momentum_opts(beta=1.0), abi.common_momentum_opts(beta=0.3, lump_mass=0),
               abi.common_momentum_opts(exclude_mass=1), abi.common_momentum_opts(integrate_advection_by_parts=1),
-              abi.common_momentum_opts(integrate_advection_by_parts=1, beta=0.3, lump_mass=0)):
+              abi.common_momentum_opts(integrate_advection_by_parts=1, beta=0.3, lump_mass=0),
+              abi.common_momentum_opts(have_source=1, lump_source=1),
+              abi.common_momentum_opts(have_absorption=1, lump_absorption=1),
+              abi.common_momentum_opts(have_absorption=1, lump_absorption=1, pressure_corrected_absorption=1)):
         ref = orc.assemble_momentum(mesh, fs, o, findrm, colm)
         got = se.emulate_momentum(mesh, fs, o, findrm, colm)
         for d in range(mesh.dim):
             assert rel_err(got["big_m"][d], ref["big_m"][d]) < TOL
             assert rel_err(got["rhs"][:, d], ref["rhs"][:, d]) < TOL
+            assert rel_err(got["masslump"][:, d], ref["masslump"][:, d]) < TOL
 
 
 @pytest.mark.parametrize("name", ["box3", "box2_shuffled", "cube.1"])
