@@ -523,6 +523,19 @@ def blocks_to_petsc(findrm, colm, blocks, n_nodes, group_size=1, diagonal=True, 
     return PetscMat(nrows, nrows, np.cumsum(fr), Cc, V)
 
 
+def field_to_petsc(val, group_size=1):
+    """A scalar (n_nodes,) or vector (n_nodes, dim) field as the PETSc Vec field2petsc builds with the serial
+    numbering above (femtools/Petsc_Tools.F90 field2petsc): entry gnn2unn(node, component)."""
+    val = np.asarray(val, dtype=np.float64)
+    if val.ndim == 1:
+        return val.copy()
+    n, dim = val.shape
+    num = petsc_row_numbering(n, dim, group_size)
+    out = np.zeros(n * dim)
+    out[num.ravel()] = val.ravel()
+    return out
+
+
 def csr_to_petsc(findrm, colm, val, n_nodes):
     """A femtools csr_matrix (1-based sparsity) as the PETSc matrix csr2petsc produces for a scalar
     field (femtools/Petsc_Tools.F90:1154-1301): same rows, 0-based sorted columns."""

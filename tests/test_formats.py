@@ -321,6 +321,21 @@ def test_petsc_numbering_and_block_expansion(orc):
     assert not fmt.compare_petsc_mats(C, A)["ok"]
 
 
+def test_vector_fields_follow_the_matrix_numbering(orc):
+    mesh = load_golden_mesh("cube.1")
+    fs = syn.standard_fields(mesh)
+    fr, cm, _ = orc.make_sparsity(mesh)
+    res = orc.assemble_momentum(mesh, fs, abi.common_momentum_opts(), fr, cm)
+    x = np.random.default_rng(0).uniform(size=(mesh.n_nodes, 3))
+    import scipy.sparse as sp
+    want = np.stack([sp.csr_matrix((res["big_m"][d], cm - 1, fr - 1), shape=(mesh.n_nodes,) * 2) @ x[:, d] for d in range(3)], axis=1)
+    for gs in (1, 3):
+        A = fmt.blocks_to_petsc(fr, cm, np.array(res["big_m"]), mesh.n_nodes, group_size=gs)
+        M = sp.csr_matrix((A.val, A.colm, A.findrm), shape=(A.rows, A.cols))
+        assert np.abs(M @ fmt.field_to_petsc(x, gs) - fmt.field_to_petsc(want, gs)).max() < 1e-14
+    assert (fmt.field_to_petsc(x[:, 0]) == x[:, 0]).all()
+
+
 def test_compare_matrixdump_tool(orc, tmp_path):
     import subprocess
     import sys
