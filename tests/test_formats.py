@@ -469,7 +469,9 @@ def test_gmsh_reader_against_the_reference_python_reader(rel):
     vtk is absent here, so a MagicMock stands in for it -- the gmsh parsing code never touches it."""
     import sys
     from unittest import mock
-    sys.modules.setdefault("vtk", mock.MagicMock())
+    stub_vtk = "vtk" not in sys.modules
+    if stub_vtk:
+        sys.modules["vtk"] = mock.MagicMock()
     sys.path.insert(0, os.path.join(REF, "python"))
     try:
         import fluidity.diagnostics.gmshtools as gmshtools
@@ -482,6 +484,8 @@ def test_gmsh_reader_against_the_reference_python_reader(rel):
             os.chdir(cwd)
     finally:
         sys.path.remove(os.path.join(REF, "python"))
+        if stub_vtk:
+            del sys.modules["vtk"]
     g = fmt.read_gmsh(path)
     m = g.mesh
     assert ref.NodeCount() == m.n_nodes and ref.VolumeElementCount() == m.n_elements and ref.SurfaceElementCount() == len(g.sndgln)
