@@ -550,7 +550,7 @@ static int momentum_opts_unsupported(const cgasm_momentum_opts* o) {
          o->have_vertical_stabilization || o->have_swe_bottom_drag || o->have_wd_abs ||
          o->have_temperature_dependent_viscosity || o->stress_form || o->partial_stress_form ||
          o->radial_gravity || o->vel_lump_on_submesh || o->cmc_lump_on_submesh ||
-         o->abs_lump_on_submesh || o->assemble_mass_matrix || o->integrate_continuity_by_parts;
+         o->abs_lump_on_submesh || o->assemble_mass_matrix;
 }
 
 int orc_momentum_element(const orc_mesh* m, const orc_momentum_fields* f,
@@ -620,8 +620,22 @@ int orc_momentum_element(const orc_mesh* m, const orc_momentum_fields* f,
   }
 
   /* ct_m block (:1377-1404), P1-P1: p_shape == u_shape tables */
-  if (o->assemble_ct_matrix_here && grad_p_u_mat)
-    shape_dshape(dim, loc, ngi, n, dshape, detwei, grad_p_u_mat);
+  if (o->assemble_ct_matrix_here && grad_p_u_mat) {
+    if (o->integrate_continuity_by_parts) {
+      /* :1377-1383: grad_p_u_mat = -dshape_shape(dp_t, u_shape, detwei), femtools/FETools.F90:364-389:
+       * (d, i, j) = -sum_g detwei_g dshape(i,g,d) n(j,g). Restated ahead of the device path (which still
+       * refuses the option): the boundary half is orc_momentum_face_ct below. */
+      for (int j = 0; j < loc; j++)
+        for (int i = 0; i < loc; i++)
+          for (int d = 0; d < dim; d++) {
+            double sacc = 0.0;
+            for (int g = 0; g < ngi; g++) sacc += detwei[g] * (DS_(i, g, d) * N_(j, g));
+            grad_p_u_mat[d + dim * (i + loc * j)] = -sacc;
+          }
+    } else {
+      shape_dshape(dim, loc, ngi, n, dshape, detwei, grad_p_u_mat);
+    }
+  }
 
   /* Mass terms (:1411 -> :1492-1600) */
   if (o->assemble_inverse_masslump || !o->exclude_mass) {
@@ -1639,4 +1653,83 @@ void orc_mult_div_vector_div_T(int dim, int n_nodes, const int* findrm, const in
       product[nentry0++] = entry0;
     }
   }
+}
+
+
+/* The continuity half of construct_momentum_surface_element_cg, assemble/Momentum_CG.F90:1073-1111, taken when
+ * integrate_continuity_by_parts and (assemble_ct_matrix_here or include_pressure_and_continuity_bcs): on faces that are
+ * neither no-normal-flow nor free-surface (:1075) ct_mat_bdy = shape_shape_vector(p_shape, u_shape, detwei_bdy,
+ * normal_bdy) (:1080); per component: a weak Dirichlet velocity (type 1) with include_pressure_and_continuity_bcs moves
+ * -ct_mat_bdy . velocity_bc to ct_rhs (:1084-1086), otherwise the block is added to ct_m (:1087-1088); a pressure
+ * condition adds -(pressure_bc [- hb_pressure]) . ct_mat_bdy to the momentum rhs (:1090-1098). Outputs overwritten:
+ * ct_addto(dim, sloc, sloc) [p node, u node], ct_rhs_addto(sloc), rhs_addto(dim, sloc). pressure_bc / hb_pressure:
+ * ele_val on the face (sloc), may be NULL (= 0). */
+int orc_momentum_face_ct(const orc_mesh* m, const orc_surface* s, const cgasm_momentum_opts* o, int face,
+                         const int* velocity_bc_type, const double* velocity_bc, int pressure_bc_type,
+                         const double* pressure_bc, const double* hb_pressure, int include_pressure_and_continuity_bcs,
+                         double* ct_addto, double* ct_rhs_addto, double* rhs_addto) {
+  const int dim = m->dim, sloc = s->sloc, sngi = s->sngi;
+  for (int k = 0; k < dim * sloc * sloc; k++) ct_addto[k] = 0.0;
+  for (int k = 0; k < sloc; k++) ct_rhs_addto[k] = 0.0;
+  for (int k = 0; k < dim * sloc; k++) rhs_addto[k] = 0.0;
+  if (!(o->integrate_continuity_by_parts && (o->assemble_ct_matrix_here || include_pressure_and_continuity_bcs))) return 0;
+  if (velocity_bc_type[0] == 2 || velocity_bc_type[0] == 4) return 0;
+  double detwei[MAXSNGI], normal[MAXDIM * MAXSNGI], ct_mat_bdy[MAXDIM * MAXSLOC * MAXSLOC];
+  face_geometry(m, s, face, detwei, normal);
+  shape_shape_vector2(dim, sloc, sngi, s->n_f, s->n_f, detwei, normal, ct_mat_bdy);
+#define CB_(d, i, j) ct_mat_bdy[(d) + dim * ((i) + sloc * (j))]
+  for (int d = 0; d < dim; d++) {
+    if (include_pressure_and_continuity_bcs && velocity_bc_type[d] == 1) {
+      for (int i = 0; i < sloc; i++) {
+        double v = 0.0;
+        for (int j = 0; j < sloc; j++) v += CB_(d, i, j) * velocity_bc[d + dim * j];
+        ct_rhs_addto[i] += -v;
+      }
+    } else if (o->assemble_ct_matrix_here) {
+      for (int j = 0; j < sloc; j++)
+        for (int i = 0; i < sloc; i++) ct_addto[d + dim * (i + sloc * j)] += CB_(d, i, j);
+    }
+    if (pressure_bc_type > 0) {
+      for (int j = 0; j < sloc; j++) { /* matmul(vector(ploc), ct_mat_bdy(dim,:,:)) -> u node j */
+        double v = 0.0;
+        for (int i = 0; i < sloc; i++) {
+          double pv = pressure_bc ? pressure_bc[i] : 0.0;
+          if (o->subtract_out_reference_profile && hb_pressure) pv -= hb_pressure[i];
+          v += pv * CB_(d, i, j);
+        }
+        rhs_addto[d + dim * j] += -v;
+      }
+    }
+  }
+#undef CB_
+  return 0;
+}
+
+/* Adds the continuity boundary blocks of every face to ct_m [dim][nnz] (rows = pressure nodes): the loop
+ * :795-812 restricted to the ct_m part, with the skip rule :799-803. */
+int orc_assemble_ct_surface(const orc_mesh* m, const orc_surface* s, const cgasm_momentum_opts* o, const int* findrm,
+                            const int* colm, const int* velocity_bc_type, const int* pressure_bc_type, double* ct_m) {
+  const int dim = m->dim, sloc = s->sloc;
+  const size_t nnz = (size_t)(findrm[m->n_nodes] - 1);
+  const double zero[MAXDIM * MAXSLOC] = {0};
+  for (int face = 1; face <= s->n_faces; face++) {
+    const int* bt = velocity_bc_type + (size_t)dim * (face - 1);
+    int sum = 0, any_internal = 0;
+    for (int d = 0; d < dim; d++) {
+      sum += bt[d];
+      any_internal |= bt[d] == 3;
+    }
+    const int pt = pressure_bc_type ? pressure_bc_type[face - 1] : 0;
+    if (((bt[0] == 2 && sum == 2) || any_internal) && pt == 0) continue;
+    double C[MAXDIM * MAXSLOC * MAXSLOC], cr[MAXSLOC], r[MAXDIM * MAXSLOC];
+    int st = orc_momentum_face_ct(m, s, o, face, bt, zero, pt, NULL, NULL, 0, C, cr, r);
+    if (st) return st;
+    const int* fn = s->sndgln + (size_t)sloc * (size_t)(face - 1);
+    for (int i = 0; i < sloc; i++)
+      for (int j = 0; j < sloc; j++) {
+        int pos = csr_sparsity_pos(findrm, colm, fn[i], fn[j]);
+        for (int d = 0; d < dim; d++) ct_m[d * nnz + (size_t)(pos - 1)] += C[d + dim * (i + sloc * j)];
+      }
+  }
+  return 0;
 }

@@ -415,3 +415,34 @@ def mult_div_vector_div_T(findrm, colm, ct1, ct2, vfield, findrm2, colm2):
                                     _ip(np.ascontiguousarray(findrm2, dtype=np.int32)),
                                     _ip(np.ascontiguousarray(colm2, dtype=np.int32)), _dp(out))
     return out
+
+
+def momentum_face_ct(mesh, fields, opts, sndgln, face_ele, face, velocity_bc_type, velocity_bc=None, pressure_bc_type=0,
+                     pressure_bc=None, hb_pressure=None, include_pressure_and_continuity_bcs=False):
+    """Continuity half of the momentum surface element: ct_addto (dim, sloc [p], sloc [u]), ct_rhs_addto (sloc),
+    rhs_addto (dim, sloc)."""
+    ctx = _SurfCtx(mesh, fields, sndgln, face_ele)
+    dim = sloc = mesh.dim
+    Cb, cr, r = np.zeros(dim * sloc * sloc), np.zeros(sloc), np.zeros(dim * sloc)
+    bt = np.ascontiguousarray(velocity_bc_type, dtype=np.int32)
+    bv = np.ascontiguousarray(velocity_bc if velocity_bc is not None else np.zeros((sloc, dim)), dtype=np.float64)
+    pb = np.ascontiguousarray(pressure_bc, dtype=np.float64) if pressure_bc is not None else None
+    hb = np.ascontiguousarray(hb_pressure, dtype=np.float64) if hb_pressure is not None else None
+    st = lib().orc_momentum_face_ct(C.byref(ctx.mesh), C.byref(ctx.surface), C.byref(opts), C.c_int(face), _ip(bt), _dp(bv),
+                                    C.c_int(pressure_bc_type), _dp(pb), _dp(hb),
+                                    C.c_int(1 if include_pressure_and_continuity_bcs else 0), _dp(Cb), _dp(cr), _dp(r))
+    if st:
+        raise RuntimeError("oracle status %d" % st)
+    return Cb.reshape(sloc, sloc, dim).transpose(2, 1, 0).copy(), cr, r.reshape(sloc, dim).T.copy()
+
+
+def assemble_ct_surface(mesh, fields, opts, findrm, colm, sndgln, face_ele, velocity_bc_type, ct_m, pressure_bc_type=None):
+    """ADDS the continuity boundary blocks to ct_m (dim, nnz) in place."""
+    ctx = _SurfCtx(mesh, fields, sndgln, face_ele)
+    bt = np.ascontiguousarray(velocity_bc_type, dtype=np.int32)
+    pt = np.ascontiguousarray(pressure_bc_type, dtype=np.int32) if pressure_bc_type is not None else None
+    st = lib().orc_assemble_ct_surface(C.byref(ctx.mesh), C.byref(ctx.surface), C.byref(opts),
+                                       _ip(np.ascontiguousarray(findrm, dtype=np.int32)),
+                                       _ip(np.ascontiguousarray(colm, dtype=np.int32)), _ip(bt), _ip(pt), _dp(ct_m))
+    if st:
+        raise RuntimeError("oracle status %d" % st)

@@ -241,3 +241,47 @@ def test_strong_dirichlet_scalar(orc):
     assert (rhs == want).all() and flags.sum() == 4 and flags[[2, 6, 19, 0]].all()
     orc.apply_dirichlet_scalar(nodes, vals, T, None, rhs)
     assert (rhs[nodes - 1] == vals).all()
+
+
+@pytest.mark.parametrize("name", ["box2", "box3", "cavity"])
+def test_continuity_by_parts_plus_boundary_blocks_equals_the_plain_form(orc, name):
+    """int N_i d_d N_j = -int d_d N_i N_j + oint N_i N_j n_d: the by-parts ct_m (Momentum_CG.F90:1377-1383) plus the
+    boundary blocks of the surface loop (:1073-1088) is the plain ct_m (:1401). (Oracle only: the device path still
+    returns CGASM_EUNSUPPORTED for integrate_continuity_by_parts.)"""
+    mesh = meshes()[name]
+    dim = mesh.dim
+    fs = syn.standard_fields(mesh)
+    findrm, colm, _ = orc.make_sparsity(mesh)
+    sn, fe = syn.boundary_faces(mesh)
+    plain = orc.assemble_momentum(mesh, fs, abi.common_momentum_opts(assemble_ct_matrix_here=1), findrm, colm, want_ct=True)
+    o = abi.common_momentum_opts(assemble_ct_matrix_here=1, integrate_continuity_by_parts=1)
+    got = orc.assemble_momentum(mesh, fs, o, findrm, colm, want_ct=True)
+    for k in ("big_m", "rhs", "masslump"):
+        assert (got[k] == plain[k]).all()           # only ct_m depends on the option
+    assert rel_err(got["ct_m"], plain["ct_m"]) > 1e-3
+    bt = np.zeros((len(fe), dim), dtype=np.int32)
+    orc.assemble_ct_surface(mesh, fs, o, findrm, colm, sn, fe, bt, got["ct_m"])
+    for d in range(dim):
+        assert rel_err(got["ct_m"][d], plain["ct_m"][d]) < TOL
+    # no-normal-flow faces carry no boundary block: ct_m keeps the by-parts volume form there (the condition is natural)
+    skip = orc.assemble_momentum(mesh, fs, o, findrm, colm, want_ct=True)
+    vol = skip["ct_m"].copy()
+    bt[:, 0] = V_NNF
+    orc.assemble_ct_surface(mesh, fs, o, findrm, colm, sn, fe, bt, skip["ct_m"], pressure_bc_type=np.ones(len(fe), dtype=np.int32))
+    assert (skip["ct_m"] == vol).all()
+    # one face: blocks, weak Dirichlet moved to ct_rhs, pressure condition on the momentum rhs
+    f = 0
+    F, n, M, Q = _face_mats(mesh, sn, fe, f)
+    bc = np.random.default_rng(5).uniform(size=(dim, dim))
+    pbc = np.random.default_rng(6).uniform(size=dim)
+    vt = np.zeros(dim, dtype=np.int32)
+    vt[0] = V_WEAK
+    Cb, cr, r = orc.momentum_face_ct(mesh, fs, o, sn, fe, f + 1, vt, bc, pressure_bc_type=1, pressure_bc=pbc,
+                                     include_pressure_and_continuity_bcs=True)
+    for d in range(dim):
+        blk = M * n[d]
+        assert rel_err(r[d], -(pbc @ blk)) < TOL
+        if d == 0:
+            assert np.abs(Cb[d]).max() == 0.0 and rel_err(cr, -(blk @ bc[:, 0])) < TOL
+        else:
+            assert rel_err(Cb[d], blk) < TOL
