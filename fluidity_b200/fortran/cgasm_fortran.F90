@@ -265,7 +265,7 @@ module cgasm_interface
        integer(c_int), value :: id
        type(cgasm_advdiff_opts), intent(in) :: opts
        integer(c_int), dimension(*), intent(in) :: bc_type
-       real(c_double), dimension(*), intent(in) :: t_bc, t_bc_2
+       type(c_ptr), value :: t_bc, t_bc_2   ! c_loc of the (sloc, n_faces) values, or c_null_ptr if no face reads them
        integer(c_int) :: stat
      end function cgasm_advdiff_surface_dev
 
@@ -288,8 +288,8 @@ module cgasm_interface
        import :: cgasm_momentum_opts
        integer(c_int), value :: id
        type(cgasm_momentum_opts), intent(in) :: opts
-       integer(c_int), dimension(*), intent(in) :: velocity_bc_type, pressure_bc_type
-       real(c_double), dimension(*), intent(in) :: velocity_bc
+       integer(c_int), dimension(*), intent(in) :: velocity_bc_type
+       type(c_ptr), value :: velocity_bc, pressure_bc_type   ! c_loc(...) or c_null_ptr
        integer(c_int) :: stat
      end function cgasm_momentum_surface_dev
 
