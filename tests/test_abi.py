@@ -119,3 +119,15 @@ def test_fortran_module_binds_the_header():
     for name, val in re.findall(r"\b(CGASM_[A-Z0-9_]+)\s*=\s*(\d+)", txt):
         m = re.search(r"\b%s\s*=\s*(\d+)" % name, hdr)
         assert m and m.group(1) == val, name
+
+
+def test_integration_guide_only_names_declared_symbols():
+    """Every cgasm_* identifier the maintainer-facing documents mention exists in the header (or is one of its types)."""
+    declared = set(_declared_symbols()) | {"cgasm_momentum_opts", "cgasm_advdiff_opts", "cgasm_interface", "cgasm_fortran"}
+    for doc in ("INTEGRATION.md", "README.md", "DESIGN.md"):
+        txt = open(os.path.join(ROOT, doc)).read()
+        used = set(re.findall(r"\bcgasm_[a-z0-9_]+\b", txt))
+        # prefixes written with a wildcard in prose (`cgasm_cmc_*`, `cgasm_*_surface_dev`) leave a trailing underscore
+        used = {u for u in used if not u.endswith("_")}
+        unknown = sorted(u for u in used if u not in declared and not any(d.startswith(u) for d in declared))
+        assert not unknown, (doc, unknown)
