@@ -501,3 +501,23 @@ def test_gmsh_reader_against_the_reference_python_reader(rel):
             assert all(len(ref.GetSurfaceElement(f).GetIds()) == 0 for f in range(len(g.sndgln)))
         if g.element_owner is not None:
             assert [ref.GetSurfaceElement(f).GetIds()[3] for f in range(len(g.sndgln))] == g.element_owner.tolist()
+
+
+@pytest.mark.parametrize("kind", ["random", "stripes"])
+def test_reference_decomposition_writer_with_pathological_owner_maps(tmp_path, kind):
+    """Scattered ownership (every rank neighbours every other, halos cover most of the mesh): still the same bytes as
+    fldecomp's writer."""
+    from oracle import ref_fldecomp as rf
+    if not rf.available():
+        pytest.skip("oracle/_ref/libref_fldecomp.so is built from /root/reference (build container only)")
+    mesh = syn.shuffled(syn.box_mesh((5, 4, 4)), seed=3) if kind == "random" else syn.box_mesh((7, 6), seed=2)
+    nparts = 5 if kind == "random" else 3
+    owner = np.random.default_rng(1).integers(0, nparts, mesh.n_nodes) if kind == "random" else np.arange(mesh.n_nodes) % nparts
+    sn, _ = syn.boundary_faces(mesh)
+    bid = np.ones(len(sn), dtype=np.int32)
+    theirs, ours = str(tmp_path / "theirs"), str(tmp_path / "ours")
+    rf.write_partitions(theirs, mesh, owner, nparts, sn, bid)
+    fmt.write_decomposition(ours, part.partition_by_owner(mesh, owner, nparts, sn, bid), style="fldecomp")
+    for r in range(nparts):
+        for ext in (".msh", ".halo"):
+            assert open(fmt.parallel_filename(theirs, r, ext), "rb").read() == open(fmt.parallel_filename(ours, r, ext), "rb").read()
