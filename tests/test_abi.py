@@ -131,3 +131,21 @@ def test_integration_guide_only_names_declared_symbols():
         used = {u for u in used if not u.endswith("_")}
         unknown = sorted(u for u in used if u not in declared and not any(d.startswith(u) for d in declared))
         assert not unknown, (doc, unknown)
+
+
+def test_plain_c_client_compiles_links_and_is_refused_without_a_gpu(tmp_path):
+    """examples/c_client.c: the ABI from C99 with nothing but the header and the shared library. In this container
+    (no GPU) the library must refuse at cgasm_create with CGASM_ENODEVICE -- there is no CPU path to fall into."""
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("a GPU is present: the client would run")
+    except ImportError:
+        pass
+    exe = tmp_path / "c_client"
+    libdir = os.path.join(ROOT, "fluidity_b200")
+    subprocess.run(["/usr/bin/gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "examples", "c_client.c"), "-L", libdir, "-lcgasm", "-Wl,-rpath," + libdir, "-o", str(exe)],
+                   check=True)
+    p = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert p.returncode == abi.ENODEVICE and "no CPU path" in p.stderr and p.stdout == ""
