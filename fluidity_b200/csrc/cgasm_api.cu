@@ -135,8 +135,11 @@ static int upload_sparsity(Handle* h) {
   h->d_big_m = h->d_ct_m = h->d_adv_matrix = nullptr;
   h->mom_valid = h->adv_valid = false;
   h->have_sparsity = true;
+  // every plan derived from the first-order pattern is stale now (the CMC plan holds slots / transposed positions
+  // sized for the old nnz: cgasm_cmc_dev answers CGASM_ESTATE until the second-order pattern is set again)
   tiles_free(h);
   gather_free(h);
+  cmc_free(h);
   return CGASM_OK;
 }
 
@@ -339,17 +342,22 @@ int cgasm_create(int* id, int device, int dim, int loc, int ngi, int n_nodes, in
     T.sym = sym ? 1 : 0;
   }
   h->h_nd0.resize((size_t)4 * n_elements);
-  for (int e = 0; e < n_elements; e++) {
-    for (int i = 0; i < 4; i++) {
-      int v = -1;
-      if (i < loc) {
-        v = ndglno[(size_t)loc * e + i] - 1;
-        if (v < 0 || v >= n_nodes) {
-          delete h;
-          CG_FAIL(CGASM_EARG, "ndglno entry out of range (expects 1-based node numbers)");
+  {
+    int bad = 0;
+    int* nd0 = h->h_nd0.data();
+#pragma omp parallel for schedule(static) reduction(+ : bad)
+    for (int e = 0; e < n_elements; e++)
+      for (int i = 0; i < 4; i++) {
+        int v = -1;
+        if (i < loc) {
+          v = ndglno[(size_t)loc * e + i] - 1;
+          if (v < 0 || v >= n_nodes) bad++;
         }
+        nd0[(size_t)4 * e + i] = v;
       }
-      h->h_nd0[(size_t)4 * e + i] = v;
+    if (bad) {
+      delete h;
+      CG_FAIL(CGASM_EARG, "ndglno entry out of range (expects 1-based node numbers)");
     }
   }
   auto fail = [&](int code) {
@@ -408,10 +416,11 @@ int cgasm_set_coordinates(int id, const double* X) {
 
 int cgasm_build_sparsity(int id, int* nnz) {
   GET_HANDLE(h, id);
-  const int64_t total = count_nnz(h->n_nodes, h->loc, h->h_nd0.data(), h->n2e_ptr, h->n2e);
+  IVec findrm, colm;
+  const int64_t total = build_sparsity(h->n_nodes, h->n_elements, h->loc, h->h_nd0.data(), h->n2e_ptr, h->n2e, findrm, colm);
   if (total >= (int64_t)1 << 31) CG_FAIL(CGASM_EUNSUPPORTED, "nnz does not fit the reference's 32-bit integers");
-  build_sparsity(h->n_nodes, h->n_elements, h->loc, h->h_nd0.data(), h->n2e_ptr, h->n2e, h->h_findrm,
-                 h->h_colm);
+  h->h_findrm.swap(findrm);
+  h->h_colm.swap(colm);
   h->nnz = (int)total;
   if (nnz) *nnz = h->nnz;
   return upload_sparsity(h);
@@ -440,19 +449,26 @@ int cgasm_set_sparsity(int id, int rows, int nnz, const int* findrm, const int* 
   GET_HANDLE(h, id);
   if (!findrm || !colm) CG_FAIL(CGASM_EARG, "null argument");
   if (rows != h->n_nodes) CG_FAIL(CGASM_EARG, "sparsity rows != n_nodes");
-  if (findrm[0] != 1 || findrm[rows] != nnz + 1) CG_FAIL(CGASM_EARG, "findrm is not a 1-based CSR row pointer");
-  h->h_findrm.resize((size_t)rows + 1);
-  h->h_colm.resize((size_t)nnz);
-  for (int r = 0; r <= rows; r++) h->h_findrm[r] = findrm[r] - 1;
+  if (nnz < 0 || findrm[0] != 1 || findrm[rows] != nnz + 1) CG_FAIL(CGASM_EARG, "findrm is not a 1-based CSR row pointer");
+  // Validate everything against the caller's arrays into temporaries first; the handle keeps its previous
+  // pattern (host copy, nnz, device copy, plans) unless every check passes.
+  for (int r = 0; r < rows; r++)
+    if (findrm[r] < 1 || findrm[r + 1] < findrm[r] || findrm[r + 1] > nnz + 1) CG_FAIL(CGASM_EARG, "findrm not monotone inside [1, nnz+1]");
+  IVec new_findrm((size_t)rows + 1), new_colm((size_t)nnz);
+  int bad_range = 0, bad_order = 0;
+#pragma omp parallel for schedule(static) reduction(+ : bad_range, bad_order)
   for (int r = 0; r < rows; r++) {
-    if (findrm[r + 1] < findrm[r]) CG_FAIL(CGASM_EARG, "findrm not monotone");
+    new_findrm[r] = findrm[r] - 1;
     for (int k = findrm[r] - 1; k < findrm[r + 1] - 1; k++) {
       const int c = colm[k] - 1;
-      if (c < 0 || c >= h->n_nodes) CG_FAIL(CGASM_EARG, "colm entry out of range");
-      if (k > findrm[r] - 1 && colm[k] <= colm[k - 1]) CG_FAIL(CGASM_EARG, "rows must be sorted ascending (sorted_rows)");
-      h->h_colm[k] = c;
+      if (c < 0 || c >= h->n_nodes) bad_range++;
+      if (k > findrm[r] - 1 && colm[k] <= colm[k - 1]) bad_order++;
+      new_colm[k] = c;
     }
   }
+  new_findrm[rows] = nnz;
+  if (bad_range) CG_FAIL(CGASM_EARG, "colm entry out of range");
+  if (bad_order) CG_FAIL(CGASM_EARG, "rows must be sorted ascending (sorted_rows)");
   // every element pair must be present (Sparse_Tools.F90:2644 would FLAbort otherwise)
   int missing = 0;
 #pragma omp parallel for schedule(static) reduction(+ : missing)
@@ -461,12 +477,14 @@ int cgasm_set_sparsity(int id, int rows, int nnz, const int* findrm, const int* 
       const int r = h->h_nd0[(size_t)4 * e + i];
       for (int j = 0; j < h->loc; j++) {
         const int c = h->h_nd0[(size_t)4 * e + j];
-        const int* b = h->h_colm.data() + h->h_findrm[r];
-        const int* en = h->h_colm.data() + h->h_findrm[r + 1];
+        const int* b = new_colm.data() + new_findrm[r];
+        const int* en = new_colm.data() + new_findrm[r + 1];
         if (!std::binary_search(b, en, c)) missing++;
       }
     }
   if (missing) CG_FAIL(CGASM_EARG, "sparsity misses an element node pair");
+  h->h_findrm.swap(new_findrm);
+  h->h_colm.swap(new_colm);
   h->nnz = nnz;
   return upload_sparsity(h);
 }

@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -13,6 +14,24 @@
 #include "element_math.cuh"
 
 namespace cgasm {
+
+// std::vector whose resize() leaves new elements uninitialised: the big host arrays (connectivity, adjacency,
+// sparsity) are filled by parallel loops right after they are sized, and the serial zero-fill of a plain
+// std::vector (1.6 GB for the connectivity of a 100 M-tet mesh) was a visible part of the set-up time.
+template <class T>
+struct DefaultInitAlloc : std::allocator<T> {
+  template <class U>
+  struct rebind {
+    using other = DefaultInitAlloc<U>;
+  };
+  template <class U, class... A>
+  void construct(U* p, A&&... a) {
+    if constexpr (sizeof...(A) == 0) ::new ((void*)p) U;
+    else ::new ((void*)p) U(std::forward<A>(a)...);
+  }
+};
+using IVec = std::vector<int, DefaultInitAlloc<int>>;
+using I64Vec = std::vector<int64_t, DefaultInitAlloc<int64_t>>;
 
 struct DeviceField {
   double* d = nullptr;
@@ -36,7 +55,7 @@ struct Handle {
   int dim = 0, loc = 0, ngi = 0, n_nodes = 0, n_elements = 0;
   Tables tab{};
 
-  std::vector<int> h_nd0;  // 0-based connectivity, stride 4 (4th = -1 on triangles)
+  IVec h_nd0;  // 0-based connectivity, stride 4 (4th = -1 on triangles)
   int4* d_ndglno = nullptr;
   double* d_X = nullptr;  // Coordinate%val(dim, n_nodes) as given
   bool have_X = false;
@@ -48,13 +67,13 @@ struct Handle {
   std::vector<double> h_X;  // kept for locality ordering of the tile plan
 
   // node -> element adjacency (host)
-  std::vector<int64_t> n2e_ptr;
-  std::vector<int> n2e;
+  I64Vec n2e_ptr;
+  IVec n2e;
 
   // sparsity, 0-based
   bool have_sparsity = false;
   int nnz = 0;
-  std::vector<int> h_findrm, h_colm;
+  IVec h_findrm, h_colm;
   int* d_findrm = nullptr;
   int* d_colm = nullptr;
 
@@ -112,14 +131,14 @@ Handle* get_handle(int id);
 
 // host_mesh.cpp
 void build_node_to_element(int n_nodes, int n_elements, int loc, const int* nd0,
-                           std::vector<int64_t>& ptr, std::vector<int>& adj);
-void build_sparsity(int n_nodes, int n_elements, int loc, const int* nd0,
-                    const std::vector<int64_t>& n2e_ptr, const std::vector<int>& n2e,
-                    std::vector<int>& findrm, std::vector<int>& colm);
-int64_t count_nnz(int n_nodes, int loc, const int* nd0, const std::vector<int64_t>& n2e_ptr,
-                  const std::vector<int>& n2e);
-int greedy_colouring(int n_elements, int loc, const int* nd0, const std::vector<int64_t>& n2e_ptr,
-                     const std::vector<int>& n2e, std::vector<int>& colour_of);
+                           I64Vec& ptr, IVec& adj);
+int64_t build_sparsity(int n_nodes, int n_elements, int loc, const int* nd0,
+                       const I64Vec& n2e_ptr, const IVec& n2e,
+                       IVec& findrm, IVec& colm);  // returns nnz (>= 2^31: nothing filled)
+int64_t count_nnz(int n_nodes, int loc, const int* nd0, const I64Vec& n2e_ptr,
+                  const IVec& n2e);
+int greedy_colouring(int n_elements, int loc, const int* nd0, const I64Vec& n2e_ptr,
+                     const IVec& n2e, std::vector<int>& colour_of);
 void colour_sets(int n_elements, int ncol, const std::vector<int>& colour_of,
                  std::vector<int>& colour_ptr, std::vector<int>& colour_elements);
 

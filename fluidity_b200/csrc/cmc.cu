@@ -60,7 +60,8 @@ void cmc_free(Handle* h) {
 }
 
 // Row i of the second-order pattern = ascending union of the first-order rows of the nodes in row i.
-static void second_order_sparsity(int n, const std::vector<int>& findrm, const std::vector<int>& colm,
+template <class V>
+static void second_order_sparsity(int n, const V& findrm, const V& colm,
                                   std::vector<int>& findrm2, std::vector<int>& colm2, long long* nnz2) {
   std::vector<long long> ptr((size_t)n + 1, 0);
 #pragma omp parallel
@@ -109,7 +110,8 @@ static void second_order_sparsity(int n, const std::vector<int>& findrm, const s
 // Expansion plan. Returns false (no plan: the merge kernel runs) if the first-order pattern is not structurally
 // symmetric, a second-order row is not the union the expansion needs, or a row is too long for the accumulator.
 constexpr int kExpandMaxRow2 = 384;  // 16 half-warps x 384 doubles = 48 KB of shared memory per block
-static bool build_expand_plan(int n, const std::vector<int>& findrm, const std::vector<int>& colm,
+template <class V>
+static bool build_expand_plan(int n, const V& findrm, const V& colm,
                               const std::vector<int>& findrm2, const std::vector<int>& colm2, CmcPlan* P) {
   P->have_expand = false;
   const size_t nnz = colm.size();

@@ -25,5 +25,9 @@ constexpr int kStripCompute = 0x100;
 // order of the ids, so rows with the same local topology get the same compute pattern.
 void build_strip_row(int loc, const int* nd0, const int64_t* n2e_ptr, const int* n2e, const int* findrm,
                      const int* colm, int r, std::vector<StripEntry>& out);
+// The same greedy without the fixed-size local tables (O(m^2) per step): what build_strip_row falls back to
+// for links that do not fit them, and the reference implementation the CPU tests compare it with.
+void build_strip_row_generic(int loc, const int* nd0, const int64_t* n2e_ptr, const int* n2e, const int* findrm,
+                             const int* colm, int r, std::vector<StripEntry>& out);
 
 }  // namespace cgasm

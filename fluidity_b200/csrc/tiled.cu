@@ -105,7 +105,7 @@ static int build_class(Handle* h, TileClassPlan& P, int nb, int nvec, const std:
                        const MortonFrame& F) {
   const int loc = h->loc, n_nodes = h->n_nodes;
   const int* nd0 = h->h_nd0.data();
-  const std::vector<int>& fr = h->h_findrm;
+  const IVec& fr = h->h_findrm;
   int max_rows = 1024;
   size_t smem_cap = 200 * 1024;
   if (const char* s = getenv("CGASM_TILE_ROWS")) max_rows = std::max(32, atoi(s));
