@@ -43,18 +43,19 @@ static void free_dev(void* p) {
 }
 
 // rec[node].lane[lane0 + c] = src[node*stride + c]   (stride 0: CONSTANT field, broadcast)
-__global__ void pack_lanes_kernel(double4* __restrict__ rec, int lane0, int ncomp,
+// (recw = doubles per record: 4 for the 32-byte node records, 2 for the tracer absorption / source pairs)
+__global__ void pack_lanes_kernel(double* __restrict__ rec, int recw, int lane0, int ncomp,
                                   const double* __restrict__ src, int stride, const int* __restrict__ nodes, int n) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
   const int node = nodes ? nodes[k] : k;
-  double* r = reinterpret_cast<double*>(rec + node);
+  double* r = rec + (size_t)recw * node;
   for (int c = 0; c < ncomp; c++) r[lane0 + c] = src[(size_t)stride * node + c];
 }
 
 int repack_slot(Handle* h, int slot, const int* d_nodes, int n) {
   double4* rec;
-  int lane0, ncomp, stride;
+  int lane0, ncomp, stride, recw = 4;
   const double* src;
   const int dim = h->dim;
   if (slot < 0) {
@@ -69,15 +70,26 @@ int repack_slot(Handle* h, int slot, const int* d_nodes, int n) {
       case CGASM_F_DENSITY: rec = h->d_rec1; lane0 = 3; ncomp = 1; stride = cst ? 0 : 1; break;
       case CGASM_F_OLDU: rec = h->d_rec2; lane0 = 0; ncomp = dim; stride = cst ? 0 : dim; break;
       case CGASM_F_BUOYANCY: rec = h->d_rec2; lane0 = 3; ncomp = 1; stride = cst ? 0 : 1; break;
+      case CGASM_F_T_ABSORPTION:
+      case CGASM_F_T_SOURCE:
+        // { absorption, source } pairs of the tracer STRIP kernel, made on first use and zeroed (a lane that is
+        // never set is multiplied by a zero coefficient: it must hold a finite number)
+        if (!h->d_rec4) {
+          CG_CUDA(cudaMalloc(&h->d_rec4, sizeof(double2) * (size_t)h->n_nodes));
+          CG_CUDA(cudaMemsetAsync(h->d_rec4, 0, sizeof(double2) * (size_t)h->n_nodes, h->stream));
+        }
+        rec = reinterpret_cast<double4*>(h->d_rec4); recw = 2; lane0 = slot == CGASM_F_T_ABSORPTION ? 0 : 1; ncomp = 1;
+        stride = cst ? 0 : 1;
+        break;
       default: return CGASM_OK;  // not a packed field
     }
   }
   const int count = d_nodes ? n : h->n_nodes;
   if (count <= 0) return CGASM_OK;
-  pack_lanes_kernel<<<(count + 255) / 256, 256, 0, h->stream>>>(rec, lane0, ncomp, src, stride, d_nodes, count);
+  pack_lanes_kernel<<<(count + 255) / 256, 256, 0, h->stream>>>(reinterpret_cast<double*>(rec), recw, lane0, ncomp, src, stride, d_nodes, count);
   h->launches++;
   if (slot < 0 || slot == CGASM_F_BUOYANCY) {  // rec3 = { X, buoyancy } mirrors these two
-    pack_lanes_kernel<<<(count + 255) / 256, 256, 0, h->stream>>>(h->d_rec3, lane0, ncomp, src, stride, d_nodes, count);
+    pack_lanes_kernel<<<(count + 255) / 256, 256, 0, h->stream>>>(reinterpret_cast<double*>(h->d_rec3), 4, lane0, ncomp, src, stride, d_nodes, count);
     h->launches++;
   }
   CG_CUDA(cudaGetLastError());
@@ -97,6 +109,7 @@ static void destroy_handle(Handle* h) {
   free_dev(h->d_rec1);
   free_dev(h->d_rec2);
   free_dev(h->d_rec3);
+  free_dev(h->d_rec4);
   free_dev(h->d_findrm);
   free_dev(h->d_colm);
   free_dev(h->d_colour_elements);

@@ -64,6 +64,7 @@ struct Handle {
   double4* d_rec1 = nullptr;
   double4* d_rec2 = nullptr;
   double4* d_rec3 = nullptr;  // { X, buoyancy }: with rec1 everything the strip momentum loop reads
+  double2* d_rec4 = nullptr;  // { tracer absorption, tracer source }: made when one of them is first set
   std::vector<double> h_X;  // kept for locality ordering of the tile plan
 
   // node -> element adjacency (host)

@@ -252,8 +252,9 @@ int gather_build_rows(Handle* h) {
   if (!h->have_sparsity) CG_FAIL(CGASM_ESTATE, "gather scatter needs the sparsity first");
   if ((long long)h->n_elements >= (1ll << 30)) CG_FAIL(CGASM_EUNSUPPORTED, "gather scatter packs element*4+row in 32 bits");
   gather_free(h);
+  // built into a local plan and installed on the handle only when everything succeeded: a half-built plan
+  // (e.g. rows longer than the slot index allows) must not make the next cgasm_set_scatter skip the rebuild
   GatherPlan* P = new GatherPlan();
-  h->gather = P;
   std::vector<int> order;
   MortonFrame F;
   morton_order(h, order, F);
@@ -261,6 +262,7 @@ int gather_build_rows(Handle* h) {
   P->nblocks = form_row_blocks(h, order, F, kBR, rows);
   std::vector<long long> block_ptr((size_t)P->nblocks + 1, 0);
   int maxlen = 0;
+#pragma omp parallel for schedule(static) reduction(max : maxlen)
   for (int b = 0; b < P->nblocks; b++) {
     int deg = 0;
     for (int t = 0; t < kBR; t++) {
@@ -274,16 +276,29 @@ int gather_build_rows(Handle* h) {
       int* rb = rows.data() + (size_t)b * kBR;
       std::sort(rb, std::find(rb, rb + kBR, -1));
     }
-    block_ptr[b + 1] = block_ptr[b] + (long long)deg * kBR;
+    block_ptr[b + 1] = (long long)deg * kBR;
   }
-  P->h_rows = rows;
-  if (maxlen > 255) CG_FAIL(CGASM_EUNSUPPORTED, "CSR row longer than 255 entries: gather slot index is 8 bit");
+  for (int b = 0; b < P->nblocks; b++) block_ptr[b + 1] += block_ptr[b];
   P->maxlen = maxlen;
   P->n_entries = block_ptr[P->nblocks];
-  CG_CUDA(cudaMalloc(&P->d_rows, sizeof(int) * rows.size()));
-  CG_CUDA(cudaMemcpy(P->d_rows, rows.data(), sizeof(int) * rows.size(), cudaMemcpyHostToDevice));
-  CG_CUDA(cudaMalloc(&P->d_block_ptr, sizeof(long long) * block_ptr.size()));
-  CG_CUDA(cudaMemcpy(P->d_block_ptr, block_ptr.data(), sizeof(long long) * block_ptr.size(), cudaMemcpyHostToDevice));
+  auto fail = [&](int code) {
+    h->gather = P;  // gather_free releases whatever was allocated
+    gather_free(h);
+    return code;
+  };
+  if (maxlen > 255) {
+    set_error("CSR row longer than 255 entries: gather slot index is 8 bit");
+    return fail(CGASM_EUNSUPPORTED);
+  }
+  if (cudaMalloc(&P->d_rows, sizeof(int) * rows.size()) != cudaSuccess ||
+      cudaMemcpy(P->d_rows, rows.data(), sizeof(int) * rows.size(), cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMalloc(&P->d_block_ptr, sizeof(long long) * block_ptr.size()) != cudaSuccess ||
+      cudaMemcpy(P->d_block_ptr, block_ptr.data(), sizeof(long long) * block_ptr.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+    set_error(std::string("gather_build_rows: ") + cudaGetErrorString(cudaGetLastError()));
+    return fail(CGASM_ECUDA);
+  }
+  P->h_rows.swap(rows);
+  h->gather = P;
   return CGASM_OK;
 }
 

@@ -5,6 +5,8 @@
 namespace cgasm {
 
 constexpr int kBR = 128;  // rows (= threads) per gather block
+constexpr int kAS = kBR + 1;  // stride (doubles) between slots of the STRIP accumulator: odd, so that the
+                              // write-out (one row spread over consecutive lanes) is conflict-free
 
 struct GatherPlan {
   int nblocks = 0;
@@ -33,14 +35,18 @@ struct GatherPlan {
   int2* d_strip = nullptr;
   long long n_strip = 0;
   double strip_entries_per_pair = 0.0;
-  // staged strip plan (strip_staged.cu): the distinct nodes each row block touches (sorted) and the
-  // strip entries re-expressed with block-local node indices:
-  //   bits 0-15 local node index, bits 16-23 CSR slot, bit 24 compute
-  int* d_blk_nodes = nullptr;        // [nblocks][nl], nl = blk_nodes_max rounded up to 8, -1 padded
+  // staged strip plan (strip_staged.cu, built by strip_plan.cpp build_staged_plan_host): the distinct nodes each
+  // row block touches (sorted) and the strip entries re-expressed with block-local node indices, pre-scaled to
+  // the byte offsets the kernel adds to its shared-memory bases:
+  //   bit 0 compute, bits 4-15 local node index (<< 4 = byte offset of its 16-byte chunk), bits 16-31 CSR slot * kAS
+  //   (<< 3 = byte offset of the slot in the thread's accumulator column)
+  int* d_blk_nodes = nullptr;        // [nblocks][nl], -1 padded
   long long* d_strip_local_ptr = nullptr;  // [nblocks+1] into d_strip_local (degrees padded to a multiple of dim)
-  unsigned* d_strip_local = nullptr; // block-interleaved like d_strip
-  unsigned* d_own_local = nullptr;   // [nblocks*kBR] own node: local index | own slot << 16
+  unsigned* d_strip_local = nullptr; // block-interleaved like d_strip, kStagedTailRows rows of padding at the end
+  unsigned* d_own_local = nullptr;   // [nblocks*kBR] own node in the same encoding (compute = 0)
   int blk_nodes_max = 0;
+  int nl = 0;                        // chunk stride of the staged records (one of kStagedNL)
+  bool staged_ok = false;            // the mesh fits the staged encoding
   double* d_stage = nullptr;       // staging buffer (grown on demand)
   size_t stage_doubles = 0;
 };

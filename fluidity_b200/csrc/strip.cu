@@ -32,6 +32,7 @@
 // variant) serves them all: driven_cavity, lock_exchange, flow_past_sphere_Re100 and S3 take this path.
 // Absorption, sources, SU/SUPG, by-parts advection, nodal viscosity run the GATHER kernels (gather.cu).
 #include "strip_common.cuh"
+#include "strip_plan.h"
 
 #include <algorithm>
 #include <cstdio>
@@ -231,9 +232,9 @@ strip_advdiff_kernel(const StripConsts k_, const StripPlanView P, const double4*
 // buffers for the per-entry-fetch kernels (one entry of prefetch), dim for the staged ones (FIFO only).
 static int pad_to(int deg, int mult) { return (deg + mult - 1) / mult * mult; }
 
-int strip_build(Handle* h) {
+// per-entry-fetch plan (64-bit entries, global node ids): only for meshes the staged kernels cannot take
+static int strip_build_global(Handle* h) {
   GatherPlan* P = h->gather;
-  if (!P) CG_FAIL(CGASM_ESTATE, "strip scatter: the gather row blocks must exist first");
   if (P->d_strip) return CGASM_OK;
   const int nb = P->nblocks, loc = h->loc;
   const std::vector<int>& rows = P->h_rows;
@@ -258,29 +259,13 @@ int strip_build(Handle* h) {
       block_deg[b] = deg;
     }
   }
-  std::vector<long long> ptr((size_t)nb + 1, 0), lptr((size_t)nb + 1, 0);
-  for (int b = 0; b < nb; b++) {
-    ptr[b + 1] = ptr[b] + (long long)pad_to(block_deg[b], h->dim + 1) * kBR;
-    lptr[b + 1] = lptr[b] + (long long)pad_to(block_deg[b], h->dim) * kBR;
-  }
+  std::vector<long long> ptr((size_t)nb + 1, 0);
+  for (int b = 0; b < nb; b++) ptr[b + 1] = ptr[b] + (long long)pad_to(block_deg[b], h->dim + 1) * kBR;
   P->n_strip = ptr[nb];
   std::vector<int2> ent((size_t)std::max<long long>(P->n_strip, 1));
-  // staged flavour: the sorted distinct nodes of each block and the same entries with block-local indices
-  std::vector<unsigned> lent((size_t)std::max<long long>(lptr[nb], 1));
-  std::vector<unsigned> own_local(rows.size(), 0);
-  std::vector<std::vector<int>> blk_nodes((size_t)nb);
 #pragma omp parallel for schedule(dynamic, 8)
   for (int b = 0; b < nb; b++) {
-    const int deg = (int)((ptr[b + 1] - ptr[b]) / kBR), ldeg = (int)((lptr[b + 1] - lptr[b]) / kBR);
-    std::vector<int>& bn = blk_nodes[b];
-    for (int t = 0; t < kBR; t++) {
-      const size_t q = (size_t)b * kBR + t;
-      bn.push_back(rows[q] >= 0 ? rows[q] : 0);
-      for (const StripEntry& e : rowplans[q]) bn.push_back(e.node);
-    }
-    std::sort(bn.begin(), bn.end());
-    bn.erase(std::unique(bn.begin(), bn.end()), bn.end());
-    auto local_of = [&](int node) { return (unsigned)(std::lower_bound(bn.begin(), bn.end(), node) - bn.begin()); };
+    const int deg = (int)((ptr[b + 1] - ptr[b]) / kBR);
     for (int t = 0; t < kBR; t++) {
       const size_t q = (size_t)b * kBR + t;
       const int r = rows[q];
@@ -290,41 +275,14 @@ int strip_build(Handle* h) {
         const int* cb = h->h_colm.data() + h->h_findrm[r];
         own = (int)(std::lower_bound(cb, (const int*)h->h_colm.data() + h->h_findrm[r + 1], r) - cb);
       }
-      const unsigned ol = local_of(r >= 0 ? r : 0) | (unsigned)own << 16;
-      own_local[q] = ol;
       for (int k = 0; k < deg; k++) {
         int2 v = make_int2(r >= 0 ? r : 0, own);  // padding: re-push the own node, nothing computed
         if (k < (int)rp.size()) v = make_int2(rp[k].node, rp[k].meta);
         ent[(size_t)(ptr[b] + (long long)k * kBR + t)] = v;
       }
-      for (int k = 0; k < ldeg; k++) {
-        unsigned lv = ol;
-        if (k < (int)rp.size())
-          lv = local_of(rp[k].node) | (unsigned)(rp[k].meta & 0xff) << 16 | ((rp[k].meta & kStripCompute) ? 1u << 24 : 0u);
-        lent[(size_t)(lptr[b] + (long long)k * kBR + t)] = lv;
-      }
     }
   }
-  P->blk_nodes_max = 0;
-  for (int b = 0; b < nb; b++) P->blk_nodes_max = std::max(P->blk_nodes_max, (int)blk_nodes[b].size());
-  // fixed stride (= the shared-memory chunk stride), -1 padded: a block finds its list without a pointer load
-  const int nl = (P->blk_nodes_max + 7) & ~7;
-  if (P->blk_nodes_max < 65536) {
-    std::vector<int> blk_flat((size_t)std::max(nb, 1) * nl, -1);
-    for (int b = 0; b < nb; b++) std::copy(blk_nodes[b].begin(), blk_nodes[b].end(), blk_flat.begin() + (size_t)b * nl);
-    CG_CUDA(cudaMalloc(&P->d_blk_nodes, sizeof(int) * blk_flat.size()));
-    CG_CUDA(cudaMemcpy(P->d_blk_nodes, blk_flat.data(), sizeof(int) * blk_flat.size(), cudaMemcpyHostToDevice));
-    CG_CUDA(cudaMalloc(&P->d_strip_local_ptr, sizeof(long long) * lptr.size()));
-    CG_CUDA(cudaMemcpy(P->d_strip_local_ptr, lptr.data(), sizeof(long long) * lptr.size(), cudaMemcpyHostToDevice));
-    CG_CUDA(cudaMalloc(&P->d_strip_local, sizeof(unsigned) * lent.size()));
-    CG_CUDA(cudaMemcpy(P->d_strip_local, lent.data(), sizeof(unsigned) * lent.size(), cudaMemcpyHostToDevice));
-    CG_CUDA(cudaMalloc(&P->d_own_local, sizeof(unsigned) * own_local.size()));
-    CG_CUDA(cudaMemcpy(P->d_own_local, own_local.data(), sizeof(unsigned) * own_local.size(), cudaMemcpyHostToDevice));
-  }
   P->strip_entries_per_pair = h->n2e.empty() ? 0.0 : (double)total_real / (double)h->n2e.size();
-  if (getenv("CGASM_DEBUG"))
-    fprintf(stderr, "[cgasm] strip plan: %.3f entries per (row, element) pair, %lld padded entries, <= %d nodes per block\n",
-            P->strip_entries_per_pair, P->n_strip, P->blk_nodes_max);
   CG_CUDA(cudaMalloc(&P->d_strip_ptr, sizeof(long long) * ptr.size()));
   CG_CUDA(cudaMemcpy(P->d_strip_ptr, ptr.data(), sizeof(long long) * ptr.size(), cudaMemcpyHostToDevice));
   CG_CUDA(cudaMalloc(&P->d_strip, sizeof(int2) * ent.size()));
@@ -340,6 +298,43 @@ int strip_build(Handle* h) {
     CG_CUDA(cudaMalloc(&P->d_own_slot, own_slot.size()));
     CG_CUDA(cudaMemcpy(P->d_own_slot, own_slot.data(), own_slot.size(), cudaMemcpyHostToDevice));
   }
+  return CGASM_OK;
+}
+
+// The staged plan is built first (strip_plan.cpp, host only); the per-entry-fetch plan only if the mesh does not fit
+// the staged kernels (more than 1024 distinct nodes around a 128-row block, very long rows) or CGASM_STRIP_GLOBAL asks.
+int strip_build(Handle* h) {
+  GatherPlan* P = h->gather;
+  if (!P) CG_FAIL(CGASM_ESTATE, "strip scatter: the gather row blocks must exist first");
+  if (P->d_strip || P->d_strip_local) return CGASM_OK;
+  StagedPlanHost sp;
+  build_staged_plan_host(h, P->h_rows, P->nblocks, P->maxlen, sp);
+  P->blk_nodes_max = sp.blk_nodes_max;
+  P->strip_entries_per_pair = h->n2e.empty() ? 0.0 : (double)sp.total_real / (double)h->n2e.size();
+  if (getenv("CGASM_DEBUG"))
+    fprintf(stderr, "[cgasm] strip plan: %.3f entries per (row, element) pair, %lld padded entries, <= %d nodes per block (stride %d)%s\n",
+            P->strip_entries_per_pair, sp.ptr[P->nblocks], sp.blk_nodes_max, sp.nl, sp.ok ? "" : " -- staged kernels not applicable");
+  if (sp.ok) {
+    const size_t total = (size_t)sp.ptr[P->nblocks], tail = (size_t)kStagedTailRows * kBR;
+    CG_CUDA(cudaMalloc(&P->d_strip_local, sizeof(unsigned) * (total + tail)));
+    CG_CUDA(cudaMemsetAsync(P->d_strip_local + total, 0, sizeof(unsigned) * tail, h->stream));
+    for (size_t k = 0; k < sp.ent.size(); k++) {
+      const int b0 = (int)k * sp.task_blocks;
+      if (b0 >= P->nblocks || sp.ent[k].empty()) continue;
+      CG_CUDA(cudaMemcpyAsync(P->d_strip_local + sp.ptr[b0], sp.ent[k].data(), sizeof(unsigned) * sp.ent[k].size(),
+                              cudaMemcpyHostToDevice, h->stream));
+    }
+    CG_CUDA(cudaMalloc(&P->d_blk_nodes, sizeof(int) * sp.blk_nodes.size()));
+    CG_CUDA(cudaMemcpyAsync(P->d_blk_nodes, sp.blk_nodes.data(), sizeof(int) * sp.blk_nodes.size(), cudaMemcpyHostToDevice, h->stream));
+    CG_CUDA(cudaMalloc(&P->d_strip_local_ptr, sizeof(long long) * sp.ptr.size()));
+    CG_CUDA(cudaMemcpyAsync(P->d_strip_local_ptr, sp.ptr.data(), sizeof(long long) * sp.ptr.size(), cudaMemcpyHostToDevice, h->stream));
+    CG_CUDA(cudaMalloc(&P->d_own_local, sizeof(unsigned) * sp.own_local.size()));
+    CG_CUDA(cudaMemcpyAsync(P->d_own_local, sp.own_local.data(), sizeof(unsigned) * sp.own_local.size(), cudaMemcpyHostToDevice, h->stream));
+    CG_CUDA(cudaStreamSynchronize(h->stream));  // the host vectors go out of scope
+    P->nl = sp.nl;
+    P->staged_ok = true;
+  }
+  if (!strip_staged_ok(h, true) || !strip_staged_ok(h, false)) return strip_build_global(h);
   return CGASM_OK;
 }
 
@@ -361,15 +356,17 @@ void strip_free(GatherPlan* P) {
 bool strip_momentum_ok(const Handle* h, const MomentumArgs& A, bool want_ml) {
   (void)want_ml;
   const GatherPlan* P = h->gather;
-  if (!P || !P->d_strip || !strip_momentum_opts_ok(A)) return false;
+  if (!P || !(P->d_strip || P->d_strip_local) || !strip_momentum_opts_ok(A)) return false;
   // a full constant tensor needs the staged kernels
-  return strip_staged_ok(h, true) || !strip_full_tensor(A.o.have_viscosity, A.o.viscosity_shape);
+  return strip_staged_ok(h, true) || (P->d_strip && !strip_full_tensor(A.o.have_viscosity, A.o.viscosity_shape));
 }
 
 bool strip_advdiff_ok(const Handle* h, const AdvDiffArgs& A) {
   const GatherPlan* P = h->gather;
-  if (!P || !P->d_strip || !strip_advdiff_opts_ok(A)) return false;
-  return strip_staged_ok(h, false) || !strip_full_tensor(A.o.have_diffusivity, A.o.diffusivity_shape);
+  if (!P || !(P->d_strip || P->d_strip_local) || !strip_advdiff_opts_ok(A)) return false;
+  // a full constant tensor, absorption and sources need the staged kernels
+  return strip_staged_ok(h, false) ||
+         (P->d_strip && !strip_full_tensor(A.o.have_diffusivity, A.o.diffusivity_shape) && !strip_advdiff_needs_extra(A));
 }
 
 template <int DIM>

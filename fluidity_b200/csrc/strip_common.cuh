@@ -6,9 +6,6 @@
 
 namespace cgasm {
 
-constexpr int kAS = kBR + 1;  // stride (doubles) between slots of the accumulator: odd, so that the
-                              // write-out (one row spread over consecutive lanes) is conflict-free
-
 struct StripConsts {  // passed by value: operands are read straight from the constant bank
   // Option switches are folded into these numbers on the host (consts_momentum / consts_advdiff): a term
   // that is switched off has zero coefficients, so one kernel serves every combination.
@@ -19,6 +16,8 @@ struct StripConsts {  // passed by value: operands are read straight from the co
   double V[9];                // constant viscosity / diffusivity tensor * Wsum, [a + dim*b]; V[0] if isotropic
   double grav[3];             // gravity_magnitude * gravity direction (0 if no gravity)
   double dtt;                 // dt*theta (tracer: 0 unless |dt*theta| > epsilon, Advection_Diffusion_CG.F90:1121)
+  double sPdPo, sPo;          // tracer source moments (Pd - Po, Po), 0 without a source; with absorption the tracer
+                              // kernel reads Qa, Qaab, Qd, Qabc as the absorption moments (0 without absorption)
 };
 
 struct StripPlanView {
@@ -50,11 +49,11 @@ __device__ __forceinline__ double4 ld256v(const double4* p) {
 __device__ __forceinline__ double rcp_nr(double x) {
   double r;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-  double e = fma(-x, r, 1.0);
-  r = fma(r, e, r);
-  e = fma(-x, r, 1.0);
-  r = fma(r, e, r);
-  return r;
+  // r1 = r0 (1 + e0), r2 = r1 (1 + e0^2) with e0 = 1 - x r0: the residual of r1 is e0^2 exactly, so the second
+  // Newton step needs no second residual evaluation (the dependent chain is one FMA shorter; |e0| < 2^-20)
+  const double e = fma(-x, r, 1.0);
+  const double r1 = fma(r, e, r);
+  return fma(r1, e * e, r1);
 }
 
 __device__ __forceinline__ double flip_sign(double v, unsigned sgn) {
@@ -231,6 +230,60 @@ __device__ __forceinline__ void adv_compute(AdvState<DIM, N>& s, const StripCons
   s.rhs = fma(tot, s.T0, s.rhs);
 }
 
+// the row's own absorption / source values (tracer kernel with ABS)
+struct AdvOwnExtra {
+  double sg0, sq0;
+};
+
+// adv_compute plus nodal absorption and source: Ab_0k = |J| [Qa s_0 + Qaab S | Qd (s_0 + s_k) + Qabc S]
+// (Advection_Diffusion_CG.F90:1156: shape_shape with the absorption at the quadrature points; scaled by dt*theta
+// with the advective / diffusive entries, rhs -= Ab T), source rhs_0 += |J| [(Pd - Po) q_0 + Po sum q] (:1139)
+template <int DIM, int N, int QC, bool FULLV>
+__device__ __forceinline__ void adv_compute_abs(AdvState<DIM, N>& s, const double (&sg)[N], const double (&sq)[N],
+                                                const AdvOwnExtra& ox, const StripConsts& k_) {
+  double c[DIM][DIM];
+  const double det = window_geometry<DIM, N, QC>(s.X, c);
+  const double rd = rcp_nr(det);
+  double sc[DIM], v[DIM];
+#pragma unroll
+  for (int a = 0; a < DIM; a++) {
+    sc[a] = c[0][a];
+    double Su = s.U0[a];
+#pragma unroll
+    for (int k = 1; k < DIM; k++) sc[a] += c[k][a];
+#pragma unroll
+    for (int k = 0; k < DIM; k++) Su += s.U[WQ(k)][a];
+    v[a] = fma(k_.PdPo, s.U0[a], k_.Po * Su);
+  }
+  double u[DIM];
+  row_vector<DIM, FULLV>(k_, v, sc, rd, det, u);
+  const double ad = fabs(det);
+  double Ss = ox.sg0, Sq = ox.sq0;
+#pragma unroll
+  for (int k = 0; k < DIM; k++) {
+    Ss += sg[WQ(k)];
+    Sq += sq[WQ(k)];
+  }
+  const double QS = k_.Qabc * Ss;
+  double tot = 0.0;
+#pragma unroll
+  for (int k = 0; k < DIM; k++) {
+    double sk = 0.0;
+#pragma unroll
+    for (int a = 0; a < DIM; a++) sk = fma(u[a], c[k][a], sk);
+    const double e = fma(ad, fma(k_.Qd, ox.sg0 + sg[WQ(k)], QS), sk);
+    s.A[WQ(k)] += e;
+    s.C[WQ(k)] += ad;
+    s.rhs = fma(-e, s.T[WQ(k)], s.rhs);
+    tot += sk;
+  }
+  const double d0 = fma(ad, fma(k_.Qa, ox.sg0, k_.Qaab * Ss), -tot);
+  s.a0 += d0;
+  s.c0 += ad;
+  s.rhs = fma(-d0, s.T0, s.rhs);
+  s.rhs = fma(ad, fma(k_.sPdPo, ox.sq0, k_.sPo * Sq), s.rhs);
+}
+
 #undef WQ
 
 // ---- host helpers ---------------------------------------------------------------------------------------
@@ -256,10 +309,14 @@ inline bool strip_momentum_opts_ok(const MomentumArgs& A) {
   return A.tab.sym && momentum_fast_ok(o, A.gravity.stride, A.absorption.stride) && !o.have_absorption &&
          !(o.have_gravity && o.subtract_out_reference_profile) && (!o.have_viscosity || A.viscosity.stride == 0);
 }
+// (nodal or constant absorption and source: staged kernels only, strip_advdiff_ok checks that)
 inline bool strip_advdiff_opts_ok(const AdvDiffArgs& A) {
   const cgasm_advdiff_opts& o = A.o;
-  return A.tab.sym && advdiff_fast_ok(o) && !o.have_source && (!o.have_diffusivity || A.diffusivity.stride == 0);
+  if (o.stabilisation_scheme != CGASM_STAB_NONE) return false;
+  if (o.have_advection && (o.integrate_advection_by_parts || o.beta != 0.0)) return false;
+  return A.tab.sym && (!o.have_diffusivity || A.diffusivity.stride == 0);
 }
+inline bool strip_advdiff_needs_extra(const AdvDiffArgs& A) { return A.o.have_absorption || A.o.have_source; }
 // full constant tensor needed? (isotropic fields only use V[0])
 inline bool strip_full_tensor(int have, int shape) { return have && shape != CGASM_TENSOR_ISOTROPIC; }
 
@@ -306,6 +363,13 @@ inline StripConsts consts_advdiff(const Handle* h, const AdvDiffArgs& A) {
   consts_tensor(c, h->dim, o.have_diffusivity, o.diffusivity_shape, h->fields[CGASM_F_T_DIFFUSIVITY].h_const, t.Wsum);
   const double dtt = o.dt * o.theta;
   c.dtt = fabs(dtt) > 2.220446049250313e-16 ? dtt : 0.0;
+  const double ab = o.have_absorption ? 1.0 : 0.0, sr = o.have_source ? 1.0 : 0.0;
+  c.Qa = ab * (t.Qaaa - t.Qaab);
+  c.Qaab = ab * t.Qaab;
+  c.Qd = ab * (t.Qaab - t.Qabc);
+  c.Qabc = ab * t.Qabc;
+  c.sPdPo = sr * (t.Pd - t.Po);
+  c.sPo = sr * t.Po;
   return c;
 }
 

@@ -10,6 +10,7 @@
 #include <omp.h>
 
 #include "cgasm_internal.h"
+#include "gather_plan.h"
 
 namespace cgasm {
 
@@ -657,6 +658,156 @@ void build_strip_row_generic(int loc, const int* nd0, const int64_t* n2e_ptr, co
   build_strip_row_impl(loc, nd0, n2e_ptr, n2e, findrm, colm, r, out, false);
 }
 
+// ---- staged plan ------------------------------------------------------------------------------------------
+namespace {
+// node -> small index, O(1) clear by generation stamps (a block touches a few hundred nodes)
+struct NodeIndexMap {
+  std::vector<int> key, val;
+  std::vector<unsigned> gen;
+  unsigned cur = 1;
+  size_t mask, count = 0;
+  explicit NodeIndexMap(size_t cap = 16384) : key(cap), val(cap), gen(cap, 0), mask(cap - 1) {}
+  static size_t hash(int v) { return (size_t)((uint32_t)v * 2654435761u) >> 9; }
+  void clear() {
+    count = 0;
+    if (++cur == 0) {
+      std::fill(gen.begin(), gen.end(), 0u);
+      cur = 1;
+    }
+  }
+  void grow() {
+    std::vector<int> k2, v2;
+    for (size_t p = 0; p <= mask; p++)
+      if (gen[p] == cur) {
+        k2.push_back(key[p]);
+        v2.push_back(val[p]);
+      }
+    const size_t cap = 2 * (mask + 1);
+    key.assign(cap, 0);
+    val.assign(cap, 0);
+    gen.assign(cap, 0);
+    mask = cap - 1;
+    cur = 1;
+    count = 0;
+    for (size_t i = 0; i < k2.size(); i++) *slot(k2[i]) = v2[i];
+  }
+  // pointer to the value of `node`, inserted with value -1 if absent
+  int* slot(int node) {
+    if (2 * (count + 1) > mask + 1) grow();
+    size_t p = hash(node) & mask;
+    while (gen[p] == cur) {
+      if (key[p] == node) return &val[p];
+      p = (p + 1) & mask;
+    }
+    key[p] = node;
+    val[p] = -1;
+    gen[p] = cur;
+    count++;
+    return &val[p];
+  }
+};
+}  // namespace
+
+void build_staged_plan_host(const Handle* h, const std::vector<int>& rows, int nblocks, int maxlen, StagedPlanHost& out) {
+  const int loc = h->loc, dim = h->dim;
+  constexpr int kTask = 128;  // blocks per task: fixed, so the layout does not depend on the thread count
+  const int ntasks = (nblocks + kTask - 1) / kTask;
+  out.nblocks = nblocks;
+  out.task_blocks = kTask;
+  out.ent.assign((size_t)std::max(ntasks, 1), {});
+  out.own_local.assign(rows.size(), 0);
+  out.ptr.assign((size_t)nblocks + 1, 0);
+  std::vector<int> block_ldeg((size_t)nblocks, 0), block_nn((size_t)nblocks, 0);
+  std::vector<std::vector<int>> task_nodes((size_t)std::max(ntasks, 1));  // node lists of the task's blocks, concatenated
+  long long total_real = 0;
+  int overflow = 0;
+#pragma omp parallel reduction(+ : total_real, overflow)
+  {
+    std::vector<StripEntry> rp[kBR];
+    NodeIndexMap map;
+    std::vector<int> bn;
+#pragma omp for schedule(dynamic, 1)
+    for (int task = 0; task < ntasks; task++) {
+      std::vector<unsigned>& ent = out.ent[task];
+      std::vector<int>& tn = task_nodes[task];
+      const int b0 = task * kTask, b1 = std::min(nblocks, b0 + kTask);
+      ent.reserve((size_t)(b1 - b0) * kBR * 36);
+      for (int b = b0; b < b1; b++) {
+        int deg = 0;
+        map.clear();
+        bn.clear();
+        auto note = [&](int node) {
+          int* v = map.slot(node);
+          if (*v < 0) {
+            *v = 0;
+            bn.push_back(node);
+          }
+        };
+        for (int t = 0; t < kBR; t++) {
+          const int r = rows[(size_t)b * kBR + t];
+          rp[t].clear();
+          note(r >= 0 ? r : 0);
+          if (r < 0) continue;
+          build_strip_row(loc, h->h_nd0.data(), h->n2e_ptr.data(), h->n2e.data(), h->h_findrm.data(), h->h_colm.data(), r, rp[t]);
+          deg = std::max(deg, (int)rp[t].size());
+          total_real += (long long)rp[t].size();
+          for (const StripEntry& e : rp[t]) note(e.node);
+        }
+        std::sort(bn.begin(), bn.end());
+        for (size_t i = 0; i < bn.size(); i++) *map.slot(bn[i]) = (int)i;
+        block_nn[b] = (int)bn.size();
+        tn.insert(tn.end(), bn.begin(), bn.end());
+        if (bn.size() > 4095) overflow++;
+        const int ldeg = (deg + dim - 1) / dim * dim;
+        block_ldeg[b] = ldeg;
+        const size_t base = ent.size();
+        ent.resize(base + (size_t)ldeg * kBR);
+        for (int t = 0; t < kBR; t++) {
+          const size_t q = (size_t)b * kBR + t;
+          const int r = rows[q];
+          int own = 0;
+          if (r >= 0) {
+            const int* cb = h->h_colm.data() + h->h_findrm[r];
+            own = (int)(std::lower_bound(cb, (const int*)h->h_colm.data() + h->h_findrm[r + 1], r) - cb);
+          }
+          const unsigned ol = (unsigned)(own * kAS) << 16 | (unsigned)(*map.slot(r >= 0 ? r : 0) & 0xfff) << 4;
+          out.own_local[q] = ol;
+          const int n = (int)rp[t].size();
+          for (int k = 0; k < ldeg; k++) {
+            unsigned lv = ol;  // padding: re-push the own node, nothing computed
+            if (k < n) {
+              const StripEntry& e = rp[t][k];
+              lv = (unsigned)((e.meta & 0xff) * kAS) << 16 | (unsigned)(*map.slot(e.node) & 0xfff) << 4 |
+                   ((e.meta & kStripCompute) ? kStagedCompute : 0u);
+            }
+            ent[base + (size_t)k * kBR + t] = lv;
+          }
+        }
+      }
+    }
+  }
+  for (int b = 0; b < nblocks; b++) out.ptr[(size_t)b + 1] = out.ptr[b] + (long long)block_ldeg[b] * kBR;
+  out.total_real = total_real;
+  out.blk_nodes_max = 0;
+  for (int b = 0; b < nblocks; b++) out.blk_nodes_max = std::max(out.blk_nodes_max, block_nn[b]);
+  out.nl = 0;
+  for (int c : kStagedNL)
+    if (!out.nl && c >= out.blk_nodes_max) out.nl = c;
+  out.ok = !overflow && out.nl > 0 && (long long)maxlen * kAS < 65536;
+  if (!out.ok) return;
+  const int nl = out.nl;
+  out.blk_nodes.assign((size_t)std::max(nblocks, 1) * nl, -1);
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int task = 0; task < ntasks; task++) {
+    const int b0 = task * kTask, b1 = std::min(nblocks, b0 + kTask);
+    size_t off = 0;
+    for (int b = b0; b < b1; b++) {
+      std::copy(task_nodes[task].begin() + off, task_nodes[task].begin() + off + block_nn[b], out.blk_nodes.begin() + (size_t)b * nl);
+      off += (size_t)block_nn[b];
+    }
+  }
+}
+
 }  // namespace cgasm
 
 // ---- diagnostics ABI: the strips of every row of a mesh, built on the host (no GPU needed) ----------
@@ -780,19 +931,10 @@ extern "C" int cgasm_plan_host_timing(int dim, int n_nodes, int n_elements, cons
   const int nb = form_row_blocks(&h, order, F, 128, rows);
   times[4] = now() - t0;
   t0 = now();
-  long long total = 0;
-#pragma omp parallel reduction(+ : total)
-  {
-    std::vector<StripEntry> row;
-#pragma omp for schedule(dynamic, 8)
-    for (int b = 0; b < nb; b++)
-      for (int t = 0; t < 128; t++) {
-        const int r = rows[(size_t)b * 128 + t];
-        if (r < 0) continue;
-        build_strip_row(loc, h.h_nd0.data(), h.n2e_ptr.data(), h.n2e.data(), h.h_findrm.data(), h.h_colm.data(), r, row);
-        total += (long long)row.size();
-      }
-  }
+  h.h_nd0.shrink_to_fit();
+  StagedPlanHost sp;
+  build_staged_plan_host(&h, rows, nb, 64, sp);
+  const long long total = sp.total_real;
   times[5] = now() - t0;
   if (entries_per_pair) *entries_per_pair = h.n2e.empty() ? 0.0 : (double)total / (double)h.n2e.size();
   return CGASM_OK;

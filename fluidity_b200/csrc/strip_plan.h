@@ -30,4 +30,26 @@ void build_strip_row(int loc, const int* nd0, const int64_t* n2e_ptr, const int*
 void build_strip_row_generic(int loc, const int* nd0, const int64_t* n2e_ptr, const int* n2e, const int* findrm,
                              const int* colm, int r, std::vector<StripEntry>& out);
 
+// ---- staged strip plan (host side of strip_staged.cu) ---------------------------------------------------
+constexpr unsigned kStagedCompute = 1u;
+constexpr int kStagedNL[] = {128, 256, 384, 512, 768, 1024};  // chunk strides the staged kernels are instantiated for
+constexpr int kStagedTailRows = 16;  // rows of padding behind the last block: the kernels read / prefetch ahead unguarded
+
+struct StagedPlanHost {
+  int nblocks = 0;
+  int blk_nodes_max = 0, nl = 0;
+  bool ok = false;                     // false: the mesh does not fit the encoding (use the per-entry-fetch kernels)
+  std::vector<long long> ptr;          // [nblocks+1] first entry of a block; degrees padded to a multiple of dim
+  int task_blocks = 0;                 // blocks per chunk of `ent`
+  std::vector<std::vector<unsigned>> ent;  // entries of blocks [k*task_blocks, (k+1)*task_blocks), block-interleaved
+  std::vector<unsigned> own_local;     // [nblocks*block_rows]
+  std::vector<int> blk_nodes;          // [nblocks][nl] sorted distinct nodes of the block, -1 padded
+  long long total_real = 0;            // strip entries before padding
+};
+
+struct Handle;
+// rows: nblocks*block_rows node ids (-1 = padding), block_rows = kBR. Needs connectivity, adjacency and sparsity
+// of the handle (host copies only).
+void build_staged_plan_host(const Handle* h, const std::vector<int>& rows, int nblocks, int maxlen, StagedPlanHost& out);
+
 }  // namespace cgasm

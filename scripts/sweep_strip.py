@@ -32,13 +32,21 @@ def main():
     ap.add_argument("--cells", type=int, default=256)
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--configs", nargs="*", default=DEFAULT)
+    ap.add_argument("--shuffle", action="store_true", help="random node and element numbering (synthetic.shuffled)")
+    ap.add_argument("--tag", default="")
     args = ap.parse_args()
     from fluidity_b200 import synthetic as syn, _abi as abi, cgasm, tables, partition as part
 
     c = args.cells
+    import time
     lp = part.slab_partition((c, c, c), 1, 0)
     mesh = lp.mesh
-    F = part.global_nodal_fields(3, mesh.X, lp.global_node)
+    gnode = lp.global_node
+    if args.shuffle:
+        mesh = syn.shuffled(mesh)
+        gnode = np.arange(mesh.n_nodes)
+    F = part.global_nodal_fields(3, mesh.X, gnode)
+    t0 = time.perf_counter()
     asm = cgasm.Assembler(mesh, tables.p1_tables(3), device=0)
     asm.build_sparsity()
     g = np.zeros((1, 3))
@@ -50,6 +58,7 @@ def main():
                     (abi.F_BUOYANCY, F["buoyancy"]), (abi.F_T, F["t"])]:
         asm.set_field(slot, a)
     asm.set_scatter(abi.SCATTER_STRIP)
+    print("library set-up (create + sparsity + fields + strip plans): %.2f s" % (time.perf_counter() - t0), flush=True)
     om, oa = abi.common_momentum_opts(), abi.common_advdiff_opts()
     n_el = mesh.n_elements
     touched = set()
@@ -78,7 +87,7 @@ def main():
         print("%-22s mom %.3f (min %.3f)  tracer %.3f (min %.3f)  %.2f G el/s" %
               (name, rec["mom_ms"], rec["mom_min"], rec["adv_ms"], rec["adv_min"], rec["gel_s"]), flush=True)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    with open(os.path.join(ROOT, "gpurun_out", "sweep_strip_%d.json" % c), "w") as f:
+    with open(os.path.join(ROOT, "gpurun_out", "sweep_strip_%d%s.json" % (c, args.tag)), "w") as f:
         json.dump(out, f, indent=1)
     asm.close()
 
