@@ -1063,6 +1063,12 @@ static int gather_advdiff_dim(Handle* h, const AdvDiffArgs& A) {
   GatherPlan* P = h->gather;
   const int ne = h->n_elements, grid = (ne + 127) / 128;
   int st;
+  // the STRIP kernels cover more option sets than the GATHER fast path (absorption, sources): ask them first
+  if (h->scatter == CGASM_SCATTER_STRIP && strip_advdiff_ok(h, A)) {
+    if ((st = strip_advdiff(h, A))) return st;
+    CG_CUDA(cudaGetLastError());
+    return CGASM_OK;
+  }
   if (advdiff_fast_ok(A.o) && A.tab.sym && !getenv("CGASM_GATHER_GENERIC") && !getenv("CGASM_GATHER_STAGED")) {
     const size_t smem = sizeof(double) * (size_t)P->maxlen * kBR;
     if (smem > 200 * 1024) CG_FAIL(CGASM_EUNSUPPORTED, "gather scatter: CSR rows too long for the shared-memory accumulator");
@@ -1076,10 +1082,7 @@ static int gather_advdiff_dim(Handle* h, const AdvDiffArgs& A) {
         prefetch, h->d_adv_matrix,                                                                       \
         h->d_adv_rhs);                                                                                   \
   } while (0)
-    if (h->scatter == CGASM_SCATTER_STRIP && strip_advdiff_ok(h, A)) {
-      if ((st = strip_advdiff(h, A))) return st;
-      h->launches--;  // counted by strip_advdiff
-    } else if (P->d_walk && !getenv("CGASM_GATHER_DIRECT")) {
+    if (P->d_walk && !getenv("CGASM_GATHER_DIRECT")) {
       const int wminb = getenv("CGASM_WALK_MINB") ? atoi(getenv("CGASM_WALK_MINB")) : 4;
       const int wprefetch = getenv("CGASM_WALK_PREFETCH") ? atoi(getenv("CGASM_WALK_PREFETCH")) : 0;
 #define LAUNCH_AWALK(COMMON_, MINB_)                                                                     \
