@@ -6,12 +6,15 @@
 A step = one pass of the hot path over the mesh: the momentum element loop
 (assemble/Momentum_CG.F90:726-752) followed by the tracer element loop
 (assemble/Advection_Diffusion_CG.F90:574-598) with the common option set of the four example
-configs. Workload at N=1: S3 = 256^3 x 6 = 100 663 296 Kuhn tets; at N>1
-every rank holds its own 256^3-cell slab partition (weak scaling), exchanges the halo of
-nu / oldu / T / density / buoyancy with NCCL p2p (cgasm_halo_update) and assembles all local
-elements, exactly like the reference's MPI ranks.
+configs. Workload: S3 = 256^3 x 6 = 100 663 296 Kuhn tets. At N>1 the default is STRONG
+scaling, BASELINE.json's configs[4]: the ONE 100 M-tet mesh is decomposed into N node blocks
+(1x1x2, 1x2x2, 2x2x2) with the reference's fldecomp conventions (partition.block_partition: owned nodes +
+level-1/2 halos, trailing receives), one partition per GPU; every rank exchanges the halo of
+nu / oldu / T / density / buoyancy with NCCL p2p (cgasm_halo_update, overlapped with the row blocks that read
+no received node) and assembles ALL its local elements, like the reference's MPI ranks. `--scaling weak`
+keeps round 1's layout (every rank its own 256^3-cell slab).
 
-value  = elements assembled by all ranks / device time, inputs resident in HBM.
+value  = OWNED elements (= the mesh's elements) / device time (max over ranks), inputs resident in HBM.
 e2e    = same through the host-buffer C-ABI calls cgasm_set_field / cgasm_momentum /
          cgasm_advdiff: per step the changing fields go host->device from pinned memory
          and every assembled array comes back device->host.
@@ -44,7 +47,12 @@ def parse():
     ap.add_argument("--impl", default="graft", choices=["graft", "reference"])
     ap.add_argument("--cells", type=int, default=256, help="cells per axis per GPU (256 = S3)")
     ap.add_argument("--scatter", default="best", choices=["best", "atomic", "coloured", "warpagg", "tiled", "gather", "strip"])
-    ap.add_argument("--cpu-cells", type=int, default=64, help="cells per axis of the CPU-baseline sample")
+    ap.add_argument("--cpu-cells", type=int, default=128, help="cells per axis of the CPU-baseline sample")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="N>1: strong = one cells^3 mesh split into N blocks (default); weak = cells^3 per GPU")
+    ap.add_argument("--no-overlap", action="store_true", help="halo exchange in front of the kernels instead of beside them")
+    ap.add_argument("--no-configs", action="store_true", help="skip the example-config option sets (N=1 only)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the multi-GPU parity check against the oracle (N>1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -150,19 +158,22 @@ class ClockSampler:
 
 
 # ---- reference arm / cpu baseline ------------------------------------------------------------------
-def cpu_assembly_rate(cells, steps, warmup):
-    """Times the oracle port (OpenMP, reference colouring) on a cells^3 x 6 sample.
-    Returns (Melements/s, threads, ms_per_step, n_elements)."""
+def cpu_assembly_rate(cells, steps, warmup, threads=None):
+    """Times the oracle port (OpenMP, reference colouring) on a cells^3 x 6 sample with the TIMING build of the oracle
+    (oracle/liborc_fast.so: -O3 -march=native, FMA contraction allowed, compiled on this host; parity tests keep the
+    strict -ffp-contract=off build). Returns (Melements/s, threads, ms_per_step, n_elements)."""
     from fluidity_b200 import synthetic as syn, _abi as abi
     from oracle import oracle as orc
+    orc.select("fast")
     mesh = syn.box_mesh((cells,) * 3)
     fs = syn.standard_fields(mesh)
     findrm, colm, _ = orc.make_sparsity(mesh)
     col, nc = orc.colour_elements(mesh)
     sets = orc.colour_sets(col, nc)
     om, oa = abi.common_momentum_opts(), abi.common_advdiff_opts()
-    threads = len(os.sched_getaffinity(0))
-    os.environ.setdefault("OMP_NUM_THREADS", str(threads))
+    avail = len(os.sched_getaffinity(0))
+    threads = avail if threads is None else threads
+    orc.set_threads(threads)
     times = []
     for it in range(warmup + steps):
         t0 = time.perf_counter()
@@ -173,6 +184,19 @@ def cpu_assembly_rate(cells, steps, warmup):
             times.append(t1 - t0)
     ms = 1e3 * float(np.mean(times))
     return mesh.n_elements / (ms * 1e-3) / 1e6, threads, ms, mesh.n_elements
+
+
+def cpu_baseline_block(cells):
+    """All-core and single-thread rates of the CPU restatement on bounded samples of S3."""
+    rate, threads, ms, ne = cpu_assembly_rate(cells, 3, 1)
+    c1 = max(16, cells // 2)
+    r1, _, ms1, ne1 = cpu_assembly_rate(c1, 1, 0, threads=1)
+    return {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+            "build": "oracle/liborc_fast.so: gcc -O3 -march=native -fopenmp (FMA contraction on), built on this host",
+            "sample": "%d^3 x 6 = %d Kuhn tets, 3 timed passes of momentum+tracer, OpenMP over the reference colouring "
+                      "(%.0f ms/pass)" % (cells, ne, ms),
+            "single_thread": {"value": r1, "unit": UNIT, "cores": 1,
+                              "sample": "%d^3 x 6 = %d Kuhn tets, 1 pass (%.0f ms)" % (c1, ne1, ms1)}}
 
 
 def run_reference(args):
@@ -189,9 +213,10 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "scaling": scaling_of(args, args.gpus), "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args, args.gpus),
-        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                         "build": "oracle/liborc_fast.so: gcc -O3 -march=native -fopenmp, built on this host"},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
         "note": "reference is Fortran+PETSc and cannot be built in this image; this is the C restatement (oracle/) of its element loops",
@@ -200,17 +225,172 @@ def run_reference(args):
     return 0
 
 
+def scaling_of(args, n):
+    """"strong": the total work (one cells^3 mesh) is fixed as N grows; "weak": cells^3 per GPU."""
+    return args.scaling
+
+
 def workload_config(args, n):
     c = args.cells
-    return {"workload": "S3: %d^3 x 6 Kuhn tets per GPU (%d elements/GPU), P1, degree-3 quadrature, "
-                        "momentum (lumped mass, advection, isotropic viscosity, buoyancy, inverse lumped mass) "
-                        "+ tracer (consistent mass, advection, isotropic diffusivity)" % (c, 6 * c ** 3),
-            "cells_per_axis_per_gpu": c, "partition": "slab along z, one partition per GPU, L1+L2 halos" if n > 1 else "single partition",
-            "l2_policy": "inputs+outputs per step (>8 GB at S3) exceed the 126 MB L2; no explicit flush",
+    strong = args.scaling == "strong" or n == 1
+    from fluidity_b200 import partition as part
+    what = ("S3: ONE %d^3 x 6 Kuhn tet mesh (%d elements), " % (c, 6 * c ** 3)) if strong else \
+           ("S3 per GPU: %d^3 x 6 Kuhn tets per GPU (%d elements/GPU), " % (c, 6 * c ** 3))
+    if n == 1:
+        partition = "single partition"
+    elif strong:
+        partition = ("node blocks %s (x, y, z), one partition per GPU, fldecomp conventions: owned + level-1/2 halo nodes, "
+                     "every element with an owned or level-1 node" % "x".join(str(p) for p in part.block_grid(n)))
+    else:
+        partition = "slab along z, one partition per GPU, L1+L2 halos"
+    return {"workload": what + "P1, degree-3 quadrature, momentum (lumped mass, advection, isotropic viscosity, buoyancy, "
+                        "inverse lumped mass) + tracer (consistent mass, advection, isotropic diffusivity)",
+            "cells_per_axis": c, "partition": partition,
+            "l2_policy": "inputs+outputs per step (>1 GB per GPU) exceed the 126 MB L2; no explicit flush",
             "parallelism": "dp%d" % n}
 
 
 # ---- graft arm --------------------------------------------------------------------------------------
+def setup_fields(asm, abi, syn, F, n_owned, world):
+    g = np.zeros((1, 3)); g[0, 2] = -1.0
+    asm.set_field(abi.F_GRAVITY, g, abi.FIELD_CONSTANT)
+    asm.set_field(abi.F_VISCOSITY, syn.iso_tensor(3, 1e-3), abi.FIELD_CONSTANT)
+    asm.set_field(abi.F_T_DIFFUSIVITY, syn.iso_tensor(3, 1e-3), abi.FIELD_CONSTANT)
+    dyn = [(abi.F_NU, F["nu"]), (abi.F_OLDU, F["oldu"]), (abi.F_DENSITY, F["density"]),
+           (abi.F_BUOYANCY, F["buoyancy"]), (abi.F_T, F["t"])]
+    if world > 1:
+        # ranks only know their owned values; the halo arrives through cgasm_halo_update
+        for _, a in dyn:
+            a[n_owned:] = 0.0
+    for slot, a in dyn:
+        asm.set_field(slot, a)
+    return dyn
+
+
+def multi_gpu_parity(args, world, rank, local_rank, dist, overlap):
+    """N>1 correctness inside the bench (the GPU test lease has one GPU): a small box, 24 cells per block and axis,
+    decomposed exactly like the timed mesh; every rank assembles its partition (halo values arrive through
+    cgasm_halo_update only), rank 0 assembles the GLOBAL mesh with the CPU oracle and compares every owned row.
+    Returns the largest relative error over big_m, rhs, masslump, tracer matrix and rhs (rank 0), else None."""
+    from fluidity_b200 import _abi as abi, cgasm, tables, partition as part, synthetic as syn
+    pg = part.block_grid(world)
+    shape = tuple(24 * p for p in pg)
+    lp = part.block_partition(shape, pg, rank)
+    mesh = lp.mesh
+    F = part.global_nodal_fields(3, mesh.X, lp.global_node)
+    asm = cgasm.Assembler(mesh, tables.p1_tables(3), device=local_rank)
+    asm.build_sparsity()
+    dyn = setup_fields(asm, abi, syn, F, lp.n_owned, world)
+    uid = [cgasm.nccl_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    asm.halo_create(world, rank, lp.sends, lp.recvs, uid[0])
+    asm.halo_set_overlap(overlap)
+    asm.set_scatter(abi.SCATTER_STRIP)
+    om, oa = abi.common_momentum_opts(), abi.common_advdiff_opts()
+    asm.halo_update([s for s, _ in dyn])
+    got_m = asm.momentum(om)
+    got_a = asm.advdiff(oa)
+    findrm, colm, _ = asm.get_sparsity()
+    no = lp.n_owned
+    g = lp.global_node
+    rows = np.repeat(np.arange(mesh.n_nodes), np.diff(findrm))
+    keep = rows < no
+    nn_glob = int(np.prod([c + 1 for c in shape]))
+    key = g[rows[keep]] * nn_glob + g[colm[keep] - 1]
+    mine = dict(key=key, big_m=got_m["big_m"][0][keep], matrix=got_a["matrix"][keep], gnode=g[:no],
+                rhs=got_m["rhs"][:no], masslump=got_m["masslump"][:no], arhs=got_a["rhs"][:no])
+    asm.close()
+    parts = [None] * world if rank == 0 else None
+    dist.gather_object(mine, parts, dst=0)
+    if rank != 0:
+        return None
+    from oracle import oracle as orc
+    whole = part.block_partition(shape, (1, 1, 1), 0)
+    gm = whole.mesh
+    GF = part.global_nodal_fields(3, gm.X, whole.global_node)
+    fs = syn.standard_fields(gm)
+    for slot, name in ((abi.F_NU, "nu"), (abi.F_OLDU, "oldu"), (abi.F_DENSITY, "density"), (abi.F_BUOYANCY, "buoyancy"),
+                       (abi.F_T, "t")):
+        fs.set(slot, GF[name])
+    gvec = np.zeros((1, 3)); gvec[0, 2] = -1.0
+    fs.set(abi.F_GRAVITY, gvec, abi.FIELD_CONSTANT)
+    fs.set(abi.F_VISCOSITY, syn.iso_tensor(3, 1e-3), abi.FIELD_CONSTANT)
+    fs.set(abi.F_T_DIFFUSIVITY, syn.iso_tensor(3, 1e-3), abi.FIELD_CONSTANT)
+    gf, gc, _ = orc.make_sparsity(gm)
+    ref_m = orc.assemble_momentum(gm, fs, om, gf, gc)
+    ref_a = orc.assemble_advdiff(gm, fs, oa, gf, gc)
+    grows = np.repeat(np.arange(gm.n_nodes), np.diff(gf))
+    gkey = grows.astype(np.int64) * nn_glob + (gc.astype(np.int64) - 1)   # ascending: rows ascending, columns sorted
+    worst, seen = 0.0, 0
+    for pr in parts:
+        pos = np.searchsorted(gkey, pr["key"])
+        assert (gkey[pos] == pr["key"]).all(), "a partition holds an entry the global sparsity lacks"
+        seen += len(pr["gnode"])
+        for got, ref in ((pr["big_m"], ref_m["big_m"][0][pos]), (pr["matrix"], ref_a["matrix"][pos]),
+                         (pr["rhs"], ref_m["rhs"][pr["gnode"]]), (pr["masslump"], ref_m["masslump"][pr["gnode"]]),
+                         (pr["arhs"], ref_a["rhs"][pr["gnode"]])):
+            worst = max(worst, float(np.abs(got - ref).max() / np.abs(ref).max()))
+    assert seen == gm.n_nodes, "the partitions' owned nodes do not cover the mesh"
+    return worst
+
+
+def example_configs(device, cells3, cells2, reps=5):
+    """Kernel time of the two element loops for the option sets of BASELINE.json configs[0..3] (their meshes are not
+    in the reference tree: option sets on synthetic meshes of the same dimension), plus the S3 option set on a randomly
+    renumbered mesh. STRIP variant, CUDA events on the handle's stream."""
+    import statistics
+    from fluidity_b200 import synthetic as syn, _abi as abi, cgasm, tables
+    cm, ca = abi.common_momentum_opts, abi.common_advdiff_opts
+    cases = [
+        ("driven_cavity: 2-D, nodal density, constant isotropic viscosity, no gravity", 2, cm(have_gravity=0), ca(), None, False),
+        ("lock_exchange: 2-D, Boussinesq, nodal buoyancy, gravity; tracer", 2, cm(), ca(), "const_density", False),
+        ("backward_facing_step_3d: 3-D, constant density, nodal vector absorption", 3,
+         cm(have_absorption=1, have_gravity=0), ca(), "const_density", False),
+        ("flow_past_sphere_Re100: 3-D, constant anisotropic viscosity", 3,
+         cm(viscosity_shape=abi.TENSOR_FULL, have_gravity=0), ca(), "aniso", False),
+        ("S3 option set, tracer with nodal absorption and source", 3, cm(), ca(have_absorption=1, have_source=1), None, False),
+        ("S3 option set at this size", 3, cm(), ca(), None, False),
+        ("S3 option set, nodes and elements randomly renumbered", 3, cm(), ca(), None, True),
+    ]
+    meshes, out = {}, []
+    for name, dim, om, oa, tweak, shuffle in cases:
+        keym = (dim, shuffle)
+        if keym not in meshes:
+            c = cells3 if dim == 3 else cells2
+            mesh = syn.box_mesh((c,) * dim)
+            if shuffle:
+                mesh = syn.shuffled(mesh)
+            meshes[keym] = (mesh, syn.standard_fields(mesh))
+        mesh, fs0 = meshes[keym]
+        t0 = time.perf_counter()
+        asm = cgasm.Assembler(mesh, tables.p1_tables(dim), device=device)
+        asm.build_sparsity()
+        asm.set_fields(fs0)
+        if tweak == "const_density":
+            asm.set_field(abi.F_DENSITY, np.ones(1), abi.FIELD_CONSTANT)
+        if tweak == "aniso":
+            asm.set_field(abi.F_VISCOSITY, syn.aniso_tensor(dim), abi.FIELD_CONSTANT)
+        asm.set_scatter(abi.SCATTER_STRIP)
+        setup = time.perf_counter() - t0
+        mom, adv = [], []
+        l0 = asm.launch_count()
+        for i in range(reps + 2):
+            asm.momentum_dev(om)
+            m = asm.last_kernel_ms()
+            asm.advdiff_dev(oa)
+            a = asm.last_kernel_ms()
+            if i >= 2:
+                mom.append(m)
+                adv.append(a)
+        launches = (asm.launch_count() - l0) / (reps + 2)
+        mm, aa = statistics.median(mom), statistics.median(adv)
+        out.append({"config": name, "dim": dim, "elements": mesh.n_elements, "momentum_ms": mm, "tracer_ms": aa,
+                    "gel_s": mesh.n_elements / ((mm + aa) * 1e-3) / 1e9, "kernel_launches_per_step": launches,
+                    "library_setup_s": setup})
+        asm.close()
+    return out
+
+
 def run_graft(args):
     import torch
     import torch.distributed as dist
@@ -232,34 +412,29 @@ def run_graft(args):
             share = max(1, len(os.sched_getaffinity(0)) // world)
             os.environ["OMP_NUM_THREADS"] = str(share)
             # libcgasm.so resolves libgomp.so.1 to the copy torch bundles, which read OMP_NUM_THREADS=1 when torch
-            # was imported: the environment alone no longer reaches it (measured: 390 s of single-threaded plan
-            # building per rank at N=2 against 45 s at N=1), so set the thread count through the runtime as well
+            # was imported: the environment alone no longer reaches it, so set the thread count through the runtime too
             torch.set_num_threads(share)
+    strong = args.scaling == "strong" or world == 1
+    overlap = world > 1 and not args.no_overlap
+
+    parity = None
+    if world > 1 and not args.no_parity:
+        parity = multi_gpu_parity(args, world, rank, local_rank, dist, overlap)
 
     c = args.cells
-    t_setup = time.perf_counter()
-    lp = part.slab_partition((c, c, c * world), world, rank)
+    t_gen = time.perf_counter()
+    if strong:
+        lp = part.block_partition((c, c, c), part.block_grid(world), rank)
+    else:
+        lp = part.slab_partition((c, c, c * world), world, rank)
     mesh = lp.mesh
     F = part.global_nodal_fields(3, mesh.X, lp.global_node)
+    mesh_gen_s = time.perf_counter() - t_gen
+    t_setup = time.perf_counter()
     asm = cgasm.Assembler(mesh, tables.p1_tables(3), device=local_rank)
     nnz = asm.build_sparsity()
-    g = np.zeros((1, 3)); g[0, 2] = -1.0
-    asm.set_field(abi.F_GRAVITY, g, abi.FIELD_CONSTANT)
-    asm.set_field(abi.F_VISCOSITY, syn.iso_tensor(3, 1e-3), abi.FIELD_CONSTANT)
-    asm.set_field(abi.F_T_DIFFUSIVITY, syn.iso_tensor(3, 1e-3), abi.FIELD_CONSTANT)
-    dyn = [(abi.F_NU, F["nu"]), (abi.F_OLDU, F["oldu"]), (abi.F_DENSITY, F["density"]),
-           (abi.F_BUOYANCY, F["buoyancy"]), (abi.F_T, F["t"])]
-    if world > 1:
-        # ranks only know their owned values; the halo arrives through cgasm_halo_update
-        for _, a in dyn:
-            a[lp.n_owned:] = 0.0
-    for slot, a in dyn:
-        asm.set_field(slot, a)
+    dyn = setup_fields(asm, abi, syn, F, lp.n_owned, world)
     halo_slots = [s for s, _ in dyn]
-    if world > 1:
-        uid = [cgasm.nccl_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        asm.halo_create(world, rank, lp.sends, lp.recvs, uid[0])
     scatter = {"atomic": abi.SCATTER_ATOMIC, "coloured": abi.SCATTER_COLOURED, "warpagg": abi.SCATTER_WARPAGG,
                "tiled": abi.SCATTER_TILED, "gather": abi.SCATTER_GATHER, "strip": abi.SCATTER_STRIP}
     chosen = args.scatter
@@ -272,11 +447,17 @@ def run_graft(args):
             chosen = "atomic"
     else:
         asm.set_scatter(scatter[chosen])
-    om, oa = abi.common_momentum_opts(), abi.common_advdiff_opts()
     setup_s = time.perf_counter() - t_setup
+    if world > 1:
+        uid = [cgasm.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        asm.halo_create(world, rank, lp.sends, lp.recvs, uid[0])
+        asm.halo_set_overlap(overlap)
+    om, oa = abi.common_momentum_opts(), abi.common_advdiff_opts()
     # the library holds its own copies; drop the generator's arrays before the pinned e2e buffers
     n_el_local, n_nodes_local, n_owned = mesh.n_elements, mesh.n_nodes, lp.n_owned
     n_sent = int(sum(len(s) for s in lp.sends))
+    n_neighbours = int(sum(1 for s in lp.sends if len(s)))
     mesh.ndglno = None
     mesh.X = None
     lp.global_node = lp.global_element = None
@@ -311,37 +492,53 @@ def run_graft(args):
         step_resident()
     ev1.record(stream)
     barrier()
-    total_ms = ev0.elapsed_time(ev1)
+    my_total_ms = ev0.elapsed_time(ev1)
     launches = asm.launch_count() - l0
     clocks = sampler.stop() if rank == 0 else None
     # per-kernel device times (separate pass so the event queries do not perturb the timed region)
     halo_ms = None
     if world > 1:
+        # the exchange alone (no kernels beside it): pack + NCCL group + unpack, joined back onto the compute stream
         h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         h0.record(stream)
         for _ in range(5):
             asm.halo_update(halo_slots)
+            asm.synchronize()
         h1.record(stream)
         barrier()
         halo_ms = h0.elapsed_time(h1) / 5
     for _ in range(max(3, min(args.steps, 5))):
         if world > 1:
             asm.halo_update(halo_slots)
+            asm.synchronize()
         asm.momentum_dev(om)
         mom_ms.append(asm.last_kernel_ms())
         asm.advdiff_dev(oa)
         adv_ms.append(asm.last_kernel_ms())
-    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    t = torch.tensor([my_total_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
     ms_per_step = total_ms / args.steps
-    tot_el = torch.tensor([float(n_el_local)], dtype=torch.float64, device="cuda")
-    if world > 1:
+    # units of work: the mesh's elements (strong: every element is owned by exactly one block's rows; the halo
+    # elements a rank assembles on top are redundant work, not throughput) / weak: every rank's own mesh
+    if strong:
+        total_elements = float(6 * c ** 3)
+    else:
+        tot_el = torch.tensor([float(n_el_local)], dtype=torch.float64, device="cuda")
         dist.all_reduce(tot_el, op=dist.ReduceOp.SUM)
-    total_elements = float(tot_el.item())
+        total_elements = float(tot_el.item())
     value = total_elements / (ms_per_step * 1e-3) / 1e6
+    m_ms, a_ms = float(np.mean(mom_ms)), float(np.mean(adv_ms))
+    per_rank = None
+    if world > 1:
+        mine = dict(rank=rank, step_ms=my_total_ms / args.steps, momentum_ms=m_ms, tracer_ms=a_ms, halo_ms=halo_ms,
+                    local_elements=n_el_local, local_nodes=n_nodes_local, owned_nodes=n_owned, halo_nodes_sent=n_sent,
+                    neighbours=n_neighbours, library_setup_s=setup_s, mesh_gen_s=mesh_gen_s)
+        allr = [None] * world if rank == 0 else None
+        dist.gather_object(mine, allr, dst=0)
+        per_rank = allr
 
     # ---- e2e: host buffers through the C-ABI calls --------------------------------------------------
     e2e = None
@@ -395,9 +592,15 @@ def run_graft(args):
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         asm.set_async(False)
-        e2e = {"value": total_elements / float(dt.item()) / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * float(dt.item()), "steps": n_e2e,
+        tb = torch.tensor([float(h2d), float(d2h)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tb, op=dist.ReduceOp.SUM)
+        e2e = {"value": total_elements / float(dt.item()) / 1e6, "unit": UNIT,
+               "h2d_bytes_per_step": int(tb[0].item()), "d2h_bytes_per_step": int(tb[1].item()),
+               "per_gpu_melements_s": total_elements / float(dt.item()) / 1e6 / world,
+               "ms_per_step": 1e3 * float(dt.item()), "steps": n_e2e,
                "checksum": float(out_a["rhs"][:n_owned].sum())}
+    asm.close()
 
     if rank != 0:
         if world > 1:
@@ -415,41 +618,43 @@ def run_graft(args):
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     bytes_mom = syn.algorithmic_bytes(3, n_nodes_local, n_el_local, nnz, "momentum")
     bytes_tra = syn.algorithmic_bytes(3, n_nodes_local, n_el_local, nnz, "tracer")
-    m_ms, a_ms = float(np.mean(mom_ms)), float(np.mean(adv_ms))
     ach = bytes_mom * n_el_local / (m_ms * 1e-3) / 1e9
     # measured DRAM bytes per launch of the same kernel (ncu capture of this command, profiles/)
     traffic = None
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as f:
             tr = json.load(f)["kernels"]["momentum"]
         if chosen == "strip" and world == 1 and tr["elements"] == n_el_local:
             traffic = tr["dram_bytes_per_launch"]
     except (OSError, KeyError, ValueError):
         pass
-    roofline = {"bound": "hbm", "kernel": "momentum assembly (%s scatter)" % chosen, "achieved": ach, "peak": peak,
-                "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
+    roofline = {"bound": "hbm", "kernel": "momentum assembly (%s scatter), rank 0's partition" % chosen, "achieved": ach,
+                "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": bytes_mom * n_el_local,
                 "algorithmic_bytes_per_element": bytes_mom, "kernel_ms": m_ms,
                 "frac_of_8TBs": ach / 8000.0,
                 "tracer": {"achieved": bytes_tra * n_el_local / (a_ms * 1e-3) / 1e9,
+                           "frac": bytes_tra * n_el_local / (a_ms * 1e-3) / 1e9 / peak,
                            "algorithmic_bytes_per_element": bytes_tra, "kernel_ms": a_ms},
                 "combined_frac": (bytes_mom + bytes_tra) * n_el_local / ((m_ms + a_ms) * 1e-3) / 1e9 / peak}
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
-        rate, threads, ms, ne = cpu_assembly_rate(args.cpu_cells, 3, 1)
-        cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": "%d^3 x 6 = %d Kuhn tets, 3 timed passes of momentum+tracer, OpenMP over the reference colouring (%.0f ms/pass)" % (args.cpu_cells, ne, ms)}
+        cpu = cpu_baseline_block(args.cpu_cells)
+    configs = None
+    if world == 1 and not args.no_configs:
+        configs = example_configs(local_rank, 128, 2048)
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling_of(args, world), "vs_baseline": None,
         "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
-        "per_gpu_melements_s": value / world, "scatter": chosen, "setup_s": setup_s,
-        "elements_total": total_elements, "nnz_rank0": nnz, "n_nodes_rank0": n_nodes_local,
+        "per_gpu_melements_s": value / world, "scatter": chosen, "setup_s": setup_s, "mesh_gen_s": mesh_gen_s,
+        "elements_total": total_elements, "local_elements_rank0": n_el_local, "nnz_rank0": nnz, "n_nodes_rank0": n_nodes_local,
         "host_peak_rss_gb_rank0": resource.getrusage(resource.RUSAGE_SELF).ru_maxrss / 1048576.0,
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-        "halo_update_ms_rank0": halo_ms, "halo_nodes_sent_rank0": n_sent,
+        "halo_update_ms_rank0": halo_ms, "halo_nodes_sent_rank0": n_sent, "halo_overlap": overlap,
+        "multi_gpu_parity_max_rel_err": parity, "per_rank": per_rank, "configs": configs,
     }
     emit(line)
     if world > 1:

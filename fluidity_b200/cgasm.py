@@ -379,6 +379,9 @@ class Assembler:
         _check(self.lib.cgasm_halo_create(C.c_int(self.id), C.c_int(nprocs), C.c_int(rank), _ip(nsend),
                                           _ip(s_all), _ip(nrecv), _ip(r_all), uid))
 
+    def halo_set_overlap(self, on):
+        _check(self.lib.cgasm_halo_set_overlap(C.c_int(self.id), C.c_int(1 if on else 0)))
+
     def halo_update(self, slots):
         mask = 0
         for s in slots:

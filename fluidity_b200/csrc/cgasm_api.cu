@@ -53,43 +53,58 @@ __global__ void pack_lanes_kernel(double* __restrict__ rec, int recw, int lane0,
   for (int c = 0; c < ncomp; c++) r[lane0 + c] = src[(size_t)stride * node + c];
 }
 
-int repack_slot(Handle* h, int slot, const int* d_nodes, int n) {
-  double4* rec;
-  int lane0, ncomp, stride, recw = 4;
-  const double* src;
+// Which packed-record lanes mirror field `slot` (-1 = coordinates): up to two targets {record array, doubles per
+// record, first lane}; ncomp components each. Returns the number of targets (0: not a packed field).
+int record_targets(Handle* h, int slot, double* rec[2], int recw[2], int lane0[2], int* ncomp) {
   const int dim = h->dim;
+  rec[0] = rec[1] = nullptr;
+  recw[0] = recw[1] = 4;
+  lane0[0] = lane0[1] = 0;
+  auto r4 = [](double4* p) { return reinterpret_cast<double*>(p); };
+  switch (slot) {
+    case -1:  // X: rec0 and rec3
+      rec[0] = r4(h->d_rec0); rec[1] = r4(h->d_rec3); *ncomp = dim; return 2;
+    case CGASM_F_T: rec[0] = r4(h->d_rec0); lane0[0] = 3; *ncomp = 1; return 1;
+    case CGASM_F_NU: rec[0] = r4(h->d_rec1); *ncomp = dim; return 1;
+    case CGASM_F_DENSITY: rec[0] = r4(h->d_rec1); lane0[0] = 3; *ncomp = 1; return 1;
+    case CGASM_F_OLDU: rec[0] = r4(h->d_rec2); *ncomp = dim; return 1;
+    case CGASM_F_BUOYANCY:  // rec2 and rec3 = { X, buoyancy }
+      rec[0] = r4(h->d_rec2); rec[1] = r4(h->d_rec3); lane0[0] = lane0[1] = 3; *ncomp = 1; return 2;
+    case CGASM_F_T_ABSORPTION:
+    case CGASM_F_T_SOURCE:
+      // { absorption, source } pairs of the tracer STRIP kernel, made on first use and zeroed (a lane that is
+      // never set is multiplied by a zero coefficient: it must hold a finite number)
+      if (!h->d_rec4) {
+        if (cudaMalloc(&h->d_rec4, sizeof(double2) * (size_t)h->n_nodes) != cudaSuccess) return -1;
+        if (cudaMemsetAsync(h->d_rec4, 0, sizeof(double2) * (size_t)h->n_nodes, h->stream) != cudaSuccess) return -1;
+      }
+      rec[0] = reinterpret_cast<double*>(h->d_rec4); recw[0] = 2; lane0[0] = slot == CGASM_F_T_ABSORPTION ? 0 : 1;
+      *ncomp = 1;
+      return 1;
+    default: return 0;
+  }
+}
+
+int repack_slot(Handle* h, int slot, const int* d_nodes, int n) {
+  double* rec[2];
+  int recw[2], lane0[2], ncomp = 0;
+  const int nt = record_targets(h, slot, rec, recw, lane0, &ncomp);
+  if (nt < 0) CG_FAIL(CGASM_ECUDA, "cannot allocate the tracer absorption / source records");
+  if (nt == 0) return CGASM_OK;  // not a packed field
+  const double* src;
+  int stride;
   if (slot < 0) {
-    rec = h->d_rec0; lane0 = 0; ncomp = dim; src = h->d_X; stride = dim;
+    src = h->d_X;
+    stride = h->dim;
   } else {
     const DeviceField& f = h->fields[slot];
-    const bool cst = f.field_type == CGASM_FIELD_CONSTANT;
     src = f.d;
-    switch (slot) {
-      case CGASM_F_T: rec = h->d_rec0; lane0 = 3; ncomp = 1; stride = cst ? 0 : 1; break;
-      case CGASM_F_NU: rec = h->d_rec1; lane0 = 0; ncomp = dim; stride = cst ? 0 : dim; break;
-      case CGASM_F_DENSITY: rec = h->d_rec1; lane0 = 3; ncomp = 1; stride = cst ? 0 : 1; break;
-      case CGASM_F_OLDU: rec = h->d_rec2; lane0 = 0; ncomp = dim; stride = cst ? 0 : dim; break;
-      case CGASM_F_BUOYANCY: rec = h->d_rec2; lane0 = 3; ncomp = 1; stride = cst ? 0 : 1; break;
-      case CGASM_F_T_ABSORPTION:
-      case CGASM_F_T_SOURCE:
-        // { absorption, source } pairs of the tracer STRIP kernel, made on first use and zeroed (a lane that is
-        // never set is multiplied by a zero coefficient: it must hold a finite number)
-        if (!h->d_rec4) {
-          CG_CUDA(cudaMalloc(&h->d_rec4, sizeof(double2) * (size_t)h->n_nodes));
-          CG_CUDA(cudaMemsetAsync(h->d_rec4, 0, sizeof(double2) * (size_t)h->n_nodes, h->stream));
-        }
-        rec = reinterpret_cast<double4*>(h->d_rec4); recw = 2; lane0 = slot == CGASM_F_T_ABSORPTION ? 0 : 1; ncomp = 1;
-        stride = cst ? 0 : 1;
-        break;
-      default: return CGASM_OK;  // not a packed field
-    }
+    stride = f.field_type == CGASM_FIELD_CONSTANT ? 0 : ncomp;
   }
   const int count = d_nodes ? n : h->n_nodes;
   if (count <= 0) return CGASM_OK;
-  pack_lanes_kernel<<<(count + 255) / 256, 256, 0, h->stream>>>(reinterpret_cast<double*>(rec), recw, lane0, ncomp, src, stride, d_nodes, count);
-  h->launches++;
-  if (slot < 0 || slot == CGASM_F_BUOYANCY) {  // rec3 = { X, buoyancy } mirrors these two
-    pack_lanes_kernel<<<(count + 255) / 256, 256, 0, h->stream>>>(reinterpret_cast<double*>(h->d_rec3), 4, lane0, ncomp, src, stride, d_nodes, count);
+  for (int m = 0; m < nt; m++) {
+    pack_lanes_kernel<<<(count + 255) / 256, 256, 0, h->stream>>>(rec[m], recw[m], lane0[m], ncomp, src, stride, d_nodes, count);
     h->launches++;
   }
   CG_CUDA(cudaGetLastError());
@@ -591,6 +606,7 @@ int cgasm_set_scatter(int id, int variant) {
 int cgasm_set_field(int id, int slot, int rank, int field_type, const double* val, int n_val_nodes) {
   GET_HANDLE(h, id);
   if (slot < 0 || slot >= CGASM_F_NSLOTS || !val) CG_FAIL(CGASM_EARG, "bad slot or null val");
+  if (int js = halo_join(h)) return js;  // a pending halo exchange writes the fields
   static const int kRank[CGASM_F_NSLOTS] = {1, 1, 0, 2, 0, 0, 1, 1, 1, 0, 2, 0, 0};
   if (rank != kRank[slot]) CG_FAIL(CGASM_EARG, "field rank does not match the slot");
   if (field_type == CGASM_FIELD_CONSTANT) {
@@ -629,6 +645,7 @@ int cgasm_get_field(int id, int slot, double* val, int n_val_nodes) {
   const DeviceField& f = h->fields[slot];
   if (!f.set) CG_FAIL(CGASM_ESTATE, "field slot not set");
   if (n_val_nodes != f.n_val_nodes) CG_FAIL(CGASM_EARG, "n_val_nodes mismatch");
+  if (int js = halo_join(h)) return js;
   CG_CUDA(cudaMemcpyAsync(val, f.d, sizeof(double) * f.count, cudaMemcpyDeviceToHost, h->stream));
   CG_CUDA(cudaStreamSynchronize(h->stream));
   return CGASM_OK;
@@ -655,6 +672,7 @@ int cgasm_momentum_dev(int id, const cgasm_momentum_opts* opts) {
     CG_CUDA(cudaStreamWaitEvent(h->stream, h->ev_mom_copied, 0));
     h->mom_copy_pending = false;
   }
+  if (h->scatter != CGASM_SCATTER_GATHER && h->scatter != CGASM_SCATTER_STRIP && (st = halo_join(h))) return st;
   CG_CUDA(cudaEventRecord(h->ev0, h->stream));
   if (h->scatter == CGASM_SCATTER_TILED) {
     st = tiles_momentum(h, A, want_ml, want_ct);
@@ -695,6 +713,7 @@ int cgasm_advdiff_dev(int id, const cgasm_advdiff_opts* opts) {
     CG_CUDA(cudaStreamWaitEvent(h->stream, h->ev_adv_copied, 0));
     h->adv_copy_pending = false;
   }
+  if (h->scatter != CGASM_SCATTER_GATHER && h->scatter != CGASM_SCATTER_STRIP && (st = halo_join(h))) return st;
   CG_CUDA(cudaEventRecord(h->ev0, h->stream));
   if (h->scatter == CGASM_SCATTER_TILED) {
     st = tiles_advdiff(h, P);
@@ -889,6 +908,7 @@ int cgasm_advdiff_element(int id, const cgasm_advdiff_opts* opts, int ele, doubl
 
 int cgasm_synchronize(int id) {
   GET_HANDLE(h, id);
+  if (int js = halo_join(h)) return js;
   CG_CUDA(cudaStreamSynchronize(h->stream));
   if (h->copy_stream) {
     CG_CUDA(cudaStreamSynchronize(h->copy_stream));

@@ -220,5 +220,12 @@ void cmc_free(Handle* h);
 // cgasm_api.cu: refresh the packed record lanes fed by `slot` (-1 = coordinates); nodes == nullptr
 // repacks every node, else only the listed ones (device array of 0-based node ids).
 int repack_slot(Handle* h, int slot, const int* d_nodes, int n);
+// packed-record lanes that mirror a field slot (cgasm_api.cu); returns the number of targets, -1 on allocation failure
+int record_targets(Handle* h, int slot, double* rec[2], int recw[2], int lane0[2], int* ncomp);
+
+// halo.cu: overlap of the halo exchange with the assembly
+int halo_join(Handle* h);  // compute stream waits for a pending exchange (no-op if none)
+// if an exchange is pending and the STRIP block split exists: the two block lists (device) and their lengths; else false
+bool halo_split(Handle* h, const int** indep, int* n_indep, const int** dep, int* n_dep);
 
 }  // namespace cgasm

@@ -255,6 +255,8 @@ int gather_build_rows(Handle* h) {
   // built into a local plan and installed on the handle only when everything succeeded: a half-built plan
   // (e.g. rows longer than the slot index allows) must not make the next cgasm_set_scatter skip the rebuild
   GatherPlan* P = new GatherPlan();
+  static long long plan_serial = 0;
+  P->serial = ++plan_serial;
   std::vector<int> order;
   MortonFrame F;
   morton_order(h, order, F);
@@ -990,7 +992,7 @@ static int gather_momentum_dim(Handle* h, const MomentumArgs& A, bool want_ml, b
     const bool use_walk = P->d_walk && abs_mode == 0 && !getenv("CGASM_GATHER_DIRECT");
     if (h->scatter == CGASM_SCATTER_STRIP && strip_momentum_ok(h, A, want_ml)) {
       if ((st = strip_momentum(h, A))) return st;
-      h->launches--;  // counted by strip_momentum
+      h->launches--;  // the branches of this chain share one count below; strip_momentum counted its own
     } else if (use_walk) {
       const int wminb = getenv("CGASM_WALK_MINB") ? atoi(getenv("CGASM_WALK_MINB")) : 3;
       const int wprefetch = getenv("CGASM_WALK_PREFETCH") ? atoi(getenv("CGASM_WALK_PREFETCH")) : 0;
@@ -1050,8 +1052,13 @@ static int gather_momentum_dim(Handle* h, const MomentumArgs& A, bool want_ml, b
 
 int gather_momentum(Handle* h, const MomentumArgs& A, bool want_ml, bool want_ct) {
   if (!h->gather) CG_FAIL(CGASM_ESTATE, "gather plan missing");
-  if (!(h->scatter == CGASM_SCATTER_STRIP && strip_momentum_ok(h, A, want_ml) && !want_ct)) {
+  const bool strip = h->scatter == CGASM_SCATTER_STRIP && strip_momentum_ok(h, A, want_ml);
+  if (!strip || want_ct) {
     int st = gather_build_pairs(h);  // no-op when they exist
+    if (st) return st;
+  }
+  if (!strip) {  // only the STRIP kernels overlap a pending halo exchange with their halo-independent blocks
+    int st = halo_join(h);
     if (st) return st;
   }
   return h->dim == 3 ? gather_momentum_dim<3>(h, A, want_ml, want_ct) : gather_momentum_dim<2>(h, A, want_ml, want_ct);
@@ -1126,6 +1133,7 @@ int gather_advdiff(Handle* h, const AdvDiffArgs& A) {
   if (!(h->scatter == CGASM_SCATTER_STRIP && strip_advdiff_ok(h, A))) {
     int st = gather_build_pairs(h);
     if (st) return st;
+    if ((st = halo_join(h))) return st;
   }
   return h->dim == 3 ? gather_advdiff_dim<3>(h, A) : gather_advdiff_dim<2>(h, A);
 }

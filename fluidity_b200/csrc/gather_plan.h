@@ -9,6 +9,7 @@ constexpr int kAS = kBR + 1;  // stride (doubles) between slots of the STRIP acc
                               // write-out (one row spread over consecutive lanes) is conflict-free
 
 struct GatherPlan {
+  long long serial = 0;            // unique per built plan (plans derived from this one remember it)
   int nblocks = 0;
   int maxlen = 0;                  // longest CSR row
   int* d_rows = nullptr;           // [nblocks*kBR] node of each row slot, -1 = padding

@@ -396,6 +396,7 @@ static int strip_momentum_dim(Handle* h, const MomentumArgs& A) {
 
 int strip_momentum(Handle* h, const MomentumArgs& A) {
   if (strip_staged_ok(h, true)) return strip_staged_momentum(h, A);
+  if (int js = halo_join(h)) return js;
   return h->dim == 3 ? strip_momentum_dim<3>(h, A) : strip_momentum_dim<2>(h, A);
 }
 
@@ -425,6 +426,7 @@ static int strip_advdiff_dim(Handle* h, const AdvDiffArgs& A) {
 
 int strip_advdiff(Handle* h, const AdvDiffArgs& A) {
   if (strip_staged_ok(h, false)) return strip_staged_advdiff(h, A);
+  if (int js = halo_join(h)) return js;
   return h->dim == 3 ? strip_advdiff_dim<3>(h, A) : strip_advdiff_dim<2>(h, A);
 }
 

@@ -38,6 +38,7 @@ struct StagedView {
   const unsigned* __restrict__ own_local; // own node in the same encoding
   const int* __restrict__ blk_nodes;      // [nblocks][NL], -1 padded
   const int* __restrict__ findrm;
+  const int* __restrict__ blocks;         // the row blocks this launch works on (nullptr: all, in order)
   int maxlen, lpr_shift;
   int acc_bytes;  // bytes of the accumulator in front of the staged records (multiple of 16)
 };
@@ -212,7 +213,7 @@ staged_momentum_kernel(const StripConsts k_, const StagedView P, const double4* 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* acc = reinterpret_cast<double*>(smem_raw);
   const unsigned nsa = (unsigned)__cvta_generic_to_shared(smem_raw) + (unsigned)P.acc_bytes;
-  const int b = blockIdx.x, t = threadIdx.x;
+  const int b = P.blocks ? P.blocks[blockIdx.x] : (int)blockIdx.x, t = threadIdx.x;
   stage_nodes<DIM, NL, 1>(P, b, t, nsa, rX, rU, rO);
   const int r = P.rows[b * kBR + t];
   const long long base = P.ptr[b];
@@ -327,7 +328,7 @@ staged_advdiff_kernel(const StripConsts k_, const StagedView P, const double4* _
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* acc = reinterpret_cast<double*>(smem_raw);
   const unsigned nsa = (unsigned)__cvta_generic_to_shared(smem_raw) + (unsigned)P.acc_bytes;
-  const int b = blockIdx.x, t = threadIdx.x;
+  const int b = P.blocks ? P.blocks[blockIdx.x] : (int)blockIdx.x, t = threadIdx.x;
   stage_nodes<DIM, NL, ABS ? 2 : 0>(P, b, t, nsa, rX, rU, rE);
   const int r = P.rows[b * kBR + t];
   const long long base = P.ptr[b];
@@ -406,6 +407,7 @@ static StagedView staged_view(const Handle* h) {
   v.own_local = P->d_own_local;
   v.blk_nodes = P->d_blk_nodes;
   v.findrm = h->d_findrm;
+  v.blocks = nullptr;
   v.maxlen = P->maxlen;
   int sh = 0;
   while ((1 << sh) < P->maxlen && sh < 5) sh++;
@@ -432,25 +434,39 @@ static int staged_momentum_dim(Handle* h, const MomentumArgs& A) {
   GatherPlan* P = h->gather;
   const size_t smem = staged_smem(P, true, false);
   const StripConsts c = consts_momentum(h, A);
-  const StagedView v = staged_view(h);
+  StagedView v = staged_view(h);
   const bool fullv = strip_full_tensor(A.o.have_viscosity, A.o.viscosity_shape);
   double* ml = A.o.assemble_inverse_masslump ? h->d_masslump : nullptr;
-  int st = CGASM_OK;
+  int st = CGASM_OK, grid = P->nblocks;
 #define LAUNCH(NL_, FULLV_)                                                                                     \
   do {                                                                                                          \
     if ((st = strip_smem(staged_momentum_kernel<DIM, NL_, FULLV_>, smem))) return st;                           \
-    staged_momentum_kernel<DIM, NL_, FULLV_><<<P->nblocks, kBR, smem, h->stream>>>(                             \
+    staged_momentum_kernel<DIM, NL_, FULLV_><<<grid, kBR, smem, h->stream>>>(                                   \
         c, v, h->d_rec3, h->d_rec1, h->d_rec2, (size_t)h->nnz, h->d_big_m, h->d_mom_rhs, ml);                    \
+    h->launches++;                                                                                              \
   } while (0)
 #define LAUNCH_NL(NL_)                   \
   do {                                   \
     if (fullv) LAUNCH(NL_, true);        \
     else LAUNCH(NL_, false);             \
   } while (0)
-  CGASM_FOR_NL(DIM, LAUNCH_NL);
+  // A pending halo exchange (cgasm_halo_set_overlap): the blocks that read no received node run beside it
+  const int *ia = nullptr, *ib = nullptr;
+  int na = 0, nb = 0;
+  const bool split = halo_split(h, &ia, &na, &ib, &nb);
+  if (split) {
+    v.blocks = ia;
+    grid = na;
+    CGASM_FOR_NL(DIM, LAUNCH_NL);
+  }
+  if ((st = halo_join(h))) return st;
+  if (split) {
+    v.blocks = ib;
+    grid = nb;
+  }
+  if (grid > 0) CGASM_FOR_NL(DIM, LAUNCH_NL);
 #undef LAUNCH_NL
 #undef LAUNCH
-  h->launches++;
   CG_CUDA(cudaGetLastError());
   return st;
 }
@@ -465,14 +481,15 @@ static int staged_advdiff_dim(Handle* h, const AdvDiffArgs& A) {
   const bool abs = A.o.have_absorption || A.o.have_source;
   const size_t smem = staged_smem(P, false, abs);
   const StripConsts c = consts_advdiff(h, A);
-  const StagedView v = staged_view(h);
+  StagedView v = staged_view(h);
   const bool fullv = strip_full_tensor(A.o.have_diffusivity, A.o.diffusivity_shape);
-  int st = CGASM_OK;
+  int st = CGASM_OK, grid = P->nblocks;
 #define LAUNCH(NL_, FULLV_, ABS_)                                                                               \
   do {                                                                                                          \
     if ((st = strip_smem(staged_advdiff_kernel<DIM, NL_, FULLV_, ABS_>, smem))) return st;                      \
-    staged_advdiff_kernel<DIM, NL_, FULLV_, ABS_><<<P->nblocks, kBR, smem, h->stream>>>(                        \
+    staged_advdiff_kernel<DIM, NL_, FULLV_, ABS_><<<grid, kBR, smem, h->stream>>>(                              \
         c, v, h->d_rec0, h->d_rec1, h->d_rec4, h->d_adv_matrix, h->d_adv_rhs);                                   \
+    h->launches++;                                                                                              \
   } while (0)
 #define LAUNCH_NL(NL_)                              \
   do {                                              \
@@ -484,10 +501,22 @@ static int staged_advdiff_dim(Handle* h, const AdvDiffArgs& A) {
       else LAUNCH(NL_, false, false);               \
     }                                               \
   } while (0)
-  CGASM_FOR_NL(DIM, LAUNCH_NL);
+  const int *ia = nullptr, *ib = nullptr;
+  int na = 0, nb = 0;
+  const bool split = halo_split(h, &ia, &na, &ib, &nb);
+  if (split) {
+    v.blocks = ia;
+    grid = na;
+    CGASM_FOR_NL(DIM, LAUNCH_NL);
+  }
+  if ((st = halo_join(h))) return st;
+  if (split) {
+    v.blocks = ib;
+    grid = nb;
+  }
+  if (grid > 0) CGASM_FOR_NL(DIM, LAUNCH_NL);
 #undef LAUNCH_NL
 #undef LAUNCH
-  h->launches++;
   CG_CUDA(cudaGetLastError());
   return st;
 }

@@ -21,7 +21,7 @@ module cgasm_interface
        & cgasm_momentum, cgasm_advdiff, cgasm_momentum_dev, cgasm_advdiff_dev, &
        & cgasm_momentum_fetch, cgasm_advdiff_fetch, cgasm_momentum_identical_blocks, &
        & cgasm_momentum_fetch_blocks, cgasm_momentum_element, &
-       & cgasm_advdiff_element, cgasm_synchronize, cgasm_set_async, cgasm_halo_create, cgasm_halo_update, &
+       & cgasm_advdiff_element, cgasm_synchronize, cgasm_set_async, cgasm_halo_create, cgasm_halo_update, cgasm_halo_set_overlap, &
        & cgasm_nccl_unique_id, cgasm_last_error, cgasm_set_surface, cgasm_advdiff_surface_dev, &
        & cgasm_advdiff_dirichlet_dev, cgasm_momentum_surface_dev, cgasm_cmc_build_sparsity, &
        & cgasm_cmc_get_sparsity, cgasm_cmc_set_sparsity, cgasm_cmc_dev, cgasm_cmc_fetch
@@ -366,6 +366,13 @@ module cgasm_interface
        integer(c_int), value :: slot_mask
        integer(c_int) :: stat
      end function cgasm_halo_update
+
+     function cgasm_halo_set_overlap(id, on) bind(c, name="cgasm_halo_set_overlap") result(stat)
+       use iso_c_binding
+       integer(c_int), value :: id
+       integer(c_int), value :: on
+       integer(c_int) :: stat
+     end function cgasm_halo_set_overlap
   end interface
 
 end module cgasm_interface

@@ -284,3 +284,124 @@ def global_nodal_fields(dim, X, gid, seeds=(1, 2, 3, 4, 5)):
     return dict(nu=velocity(seeds[0]), oldu=velocity(seeds[1]),
                 density=1.0 + 0.1 * _hash_uniform(gid, seeds[2], 0),
                 buoyancy=_hash_uniform(gid, seeds[3], 0), t=_hash_uniform(gid, seeds[4], 0))
+
+
+def block_grid(nprocs):
+    """Process grid (px, py, pz) for a box: powers of two are split along the last axes first
+    (1 -> 1x1x1, 2 -> 1x1x2, 4 -> 1x2x2, 8 -> 2x2x2); other counts are factorised greedily the same way."""
+    p = [1, 1, 1]
+    n, axis, f = int(nprocs), 2, 2
+    while n > 1:
+        while n % f:
+            f += 1
+        p[axis] *= f
+        n //= f
+        axis = (axis - 1) % 3
+    return tuple(p)
+
+
+def block_partition(ncells_global, pgrid, rank, jitter=0.1, seed=20240601):
+    """LocalPart of `rank` for ONE Kuhn box mesh of ncells_global cells decomposed into pgrid = (px, py, pz) blocks
+    of nodes (strong scaling: the mesh is fixed, the blocks shrink). Generated from the block's own neighbourhood --
+    the sub-box of node layers within two cells of the owned block -- without ever building the global mesh; on that
+    sub-box the sets are made exactly as partition_by_owner makes them on the global mesh (= the reference's
+    fldecomp writer, fldecomp/fldgmsh.cpp:310-626): owned nodes, level-1 halo (nodes of elements with an owned node),
+    level-2 halo, the elements with an owned or level-1 node, receive lists in ascending global id, send lists in the
+    receiver's order. tests/test_partition.py compares the two on small boxes, every rank, every list.
+    Ranks are numbered x fastest: rank = rx + px * (ry + py * rz)."""
+    ncells_global = tuple(int(c) for c in ncells_global)
+    dim = len(ncells_global)
+    pgrid = tuple(int(p) for p in pgrid)
+    assert len(pgrid) == dim
+    nprocs = int(np.prod(pgrid))
+    npts = tuple(c + 1 for c in ncells_global)
+    L = [slab_layers(npts[k], pgrid[k]) for k in range(dim)]
+    rc, rem = [], rank
+    for k in range(dim):
+        rc.append(rem % pgrid[k])
+        rem //= pgrid[k]
+    lo_own = [L[k][rc[k]] for k in range(dim)]
+    hi_own = [L[k][rc[k] + 1] for k in range(dim)]
+    lo = [max(lo_own[k] - 2, 0) for k in range(dim)]
+    hi = [min(hi_own[k] + 2, npts[k]) for k in range(dim)]
+    ncl = tuple(hi[k] - lo[k] - 1 for k in range(dim))
+    m = box_mesh(ncl, jitter=0.0)
+    lpts = tuple(c + 1 for c in ncl)
+    n_sub = m.n_nodes
+    lidx = np.arange(n_sub, dtype=np.int64)
+    gi, r_ = [], lidx
+    for k in range(dim):
+        gi.append(r_ % lpts[k] + lo[k])
+        r_ = r_ // lpts[k]
+    gid = np.zeros(n_sub, dtype=np.int64)
+    for k in reversed(range(dim)):
+        gid = gid * npts[k] + gi[k]
+    X = np.empty((n_sub, dim))
+    interior = np.ones(n_sub, dtype=bool)
+    for k in range(dim):
+        X[:, k] = gi[k].astype(np.float64) / ncells_global[k]   # from the GLOBAL index: identical bits on every rank
+        interior &= (gi[k] > 0) & (gi[k] < npts[k] - 1)
+    if jitter:
+        for k in range(dim):
+            d = (2.0 * _hash_uniform(gid, seed, k) - 1.0) * jitter * (1.0 / ncells_global[k])   # as slab_partition: same bits
+            X[:, k] += np.where(interior, d, 0.0)
+    # owner of every sub-box node
+    owner = np.zeros(n_sub, dtype=np.int64)
+    for k in reversed(range(dim)):
+        bk = np.searchsorted(np.asarray(L[k]), gi[k], side="right") - 1
+        owner = owner * pgrid[k] + bk
+    nd0 = m.ndglno.astype(np.int64) - 1
+    if nprocs == 1:
+        lm = Mesh(dim=dim, ndglno=m.ndglno, X=np.ascontiguousarray(X), shape=ncl)
+        return LocalPart(mesh=lm, n_owned=n_sub, global_node=gid, global_element=np.arange(m.n_elements, dtype=np.int64),
+                         sends=[np.zeros(0, dtype=np.int32)], recvs=[np.zeros(0, dtype=np.int32)], n_l1=0)
+    eown = owner[nd0]
+
+    def halo_sets(p):
+        """(own, l1, l2, e_owned, e_halo2) of rank p, restricted to this sub-box"""
+        own = owner == p
+        e_owned = (eown == p).any(axis=1)
+        l1 = np.zeros(n_sub, dtype=bool)
+        l1[nd0[e_owned].ravel()] = True
+        l1 &= ~own
+        e_halo2 = (~e_owned) & l1[nd0].any(axis=1)
+        l2 = np.zeros(n_sub, dtype=bool)
+        l2[nd0[e_halo2].ravel()] = True
+        l2 &= ~l1
+        l2 &= ~own
+        return own, l1, l2, e_owned, e_halo2
+
+    own, l1, l2, e_owned, e_halo2 = halo_sets(rank)
+    s_own, s_l1, s_l2 = np.flatnonzero(own), np.flatnonzero(l1), np.flatnonzero(l2)
+    sl = np.concatenate([s_own, s_l1, s_l2])                # sub-box ids in local order
+    s2l = -np.ones(n_sub, dtype=np.int64)
+    s2l[sl] = np.arange(len(sl))
+    emin = eown.min(axis=1)
+    eo = np.flatnonzero(e_owned)
+    se = np.concatenate([eo[emin[eo] == rank], eo[emin[eo] != rank], np.flatnonzero(e_halo2)])
+    lnd = (s2l[nd0[se]] + 1).astype(np.int32)
+    lm = Mesh(dim=dim, ndglno=np.ascontiguousarray(lnd), X=np.ascontiguousarray(X[sl]), shape=ncl)
+    # global element ids: cell (global lexicographic) * dim! + simplex
+    nsimp = m.n_elements // int(np.prod(ncl))
+    cell = se // nsimp
+    gc, r_, stride = np.zeros(len(se), dtype=np.int64), cell, 1
+    for k in range(dim):
+        gc += (r_ % ncl[k] + lo[k]) * stride
+        stride *= ncells_global[k]
+        r_ = r_ // ncl[k]
+    ge = gc * nsimp + se % nsimp
+    halo = l1 | l2
+    recvs, sends = [], []
+    for p in range(nprocs):
+        if p == rank:
+            recvs.append(np.zeros(0, dtype=np.int32))
+            sends.append(np.zeros(0, dtype=np.int32))
+            continue
+        recvs.append((s2l[np.flatnonzero(halo & (owner == p))] + 1).astype(np.int32))
+        if not (owner == p).any():
+            sends.append(np.zeros(0, dtype=np.int32))
+            continue
+        _, pl1, pl2, _, _ = halo_sets(p)
+        sends.append((s2l[np.flatnonzero(own & (pl1 | pl2))] + 1).astype(np.int32))
+    return LocalPart(mesh=lm, n_owned=len(s_own), global_node=gid[sl], global_element=ge, sends=sends, recvs=recvs,
+                     n_l1=len(s_l1))

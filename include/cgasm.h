@@ -358,6 +358,12 @@ int cgasm_row_blocks_host(int dim, int n_nodes, int n_elements, const int* ndgln
                           int block_rows, int* rows, int capacity_blocks, int* nblocks,
                           double* lattice_scale);
 
+/* Diagnostics (host only, no GPU): wall-clock seconds of the host phases of a handle's set-up on this mesh --
+ * times(6) = connectivity conversion, node->element adjacency, sparsity, Morton order, row blocks, strip plans
+ * (the staged STRIP plan); entries_per_pair (may be NULL) = strip entries per (row, element) pair. */
+int cgasm_plan_host_timing(int dim, int n_nodes, int n_elements, const int* ndglno, const double* X,
+                           double* times, double* entries_per_pair);
+
 /* ---- halo update (femtools/Halos_Communications.F90:320-412,497-567) -------------------
  * nprocs neighbours; sends/recvs are the concatenated 1-based node lists of
  * halo%sends(p) / halo%receives(p), nsend/nrecv their lengths per process p = 0..nprocs-1
@@ -366,8 +372,16 @@ int cgasm_halo_create(int id, int nprocs, int rank, const int* nsend, const int*
                       const int* nrecv, const int* recvs, const void* nccl_unique_id);
 /* Fills 128 bytes with a fresh ncclUniqueId (call on one rank, broadcast by the host). */
 int cgasm_nccl_unique_id(void* out128);
-/* halo_update of the resident fields whose bit (1 << slot) is set, in place, one NCCL group. */
+/* halo_update of the resident fields whose bit (1 << slot) is set, in place: one pack kernel, one NCCL group
+ * (one message per neighbour carrying every field), one unpack kernel that also refreshes the packed node
+ * records of the received nodes. */
 int cgasm_halo_update(int id, unsigned slot_mask);
+/* Overlap (Halos_Communications.F90 has none: halo_update blocks in MPI_Waitall; SURVEY.md section 5 asks for
+ * it). on = 1: cgasm_halo_update queues the exchange on a stream of its own and returns; the next
+ * cgasm_momentum_dev / cgasm_advdiff_dev with the STRIP variant first launches the row blocks that read no
+ * received node, then makes the compute stream wait for the exchange and launches the rest. Every other call
+ * that reads or writes resident fields waits for a pending exchange first. Results are identical. Default 0. */
+int cgasm_halo_set_overlap(int id, int on);
 
 #ifdef __cplusplus
 }

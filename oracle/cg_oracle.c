@@ -1733,3 +1733,11 @@ int orc_assemble_ct_surface(const orc_mesh* m, const orc_surface* s, const cgasm
   }
   return 0;
 }
+
+/* Thread count of the OpenMP loops above (bench.py's CPU legs: all cores and one core). */
+#ifdef _OPENMP
+#include <omp.h>
+void orc_set_threads(int n) { omp_set_num_threads(n > 0 ? n : 1); }
+#else
+void orc_set_threads(int n) { (void)n; }
+#endif

@@ -23,17 +23,39 @@ def build():
     subprocess.run(["make", "-s", "-C", _HERE], check=True)
 
 
+_FLAVOUR = "strict"
+
+
+def select(flavour):
+    """"strict" (default): liborc.so, -ffp-contract=off, baseline x86-64-v2 -- the build every parity test uses.
+    "fast": liborc_fast.so, -O3 -march=native with FMA contraction, compiled on THIS host on first use -- only for
+    the timing legs of bench.py (cpu_baseline, --impl reference): the CPU arm at its best, not a parity oracle."""
+    global _FLAVOUR, _LIB
+    assert flavour in ("strict", "fast")
+    if flavour != _FLAVOUR:
+        _FLAVOUR, _LIB = flavour, None
+
+
 def lib():
     global _LIB
     if _LIB is None:
-        path = os.path.join(_HERE, "liborc.so")
+        name = "liborc.so" if _FLAVOUR == "strict" else "liborc_fast.so"
+        path = os.path.join(_HERE, name)
         src = os.path.join(_HERE, "cg_oracle.c")
-        if not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(src):
+        if _FLAVOUR == "fast":
+            # -march=native: always rebuilt where it runs (a copy built on another host may not run here)
+            subprocess.run(["make", "-s", "-B", "-C", _HERE, name], check=True)
+        elif not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(src):
             build()
         _LIB = C.CDLL(path)
         _LIB.orc_make_sparsity.restype = C.c_int
         _LIB.orc_colour_elements.restype = C.c_int
     return _LIB
+
+
+def set_threads(n):
+    """OpenMP threads of the assembly loops (omp_set_num_threads in the library's own runtime)."""
+    lib().orc_set_threads(C.c_int(int(n)))
 
 
 def _dp(a):

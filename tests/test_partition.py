@@ -242,3 +242,42 @@ def test_surface_loops_shard_like_the_element_loops(orc, name, nprocs):
         own = lp.global_node[:lp.n_owned]
         assert rel_err(la["rhs"][:lp.n_owned], ga["rhs"][own]) < 1e-12
         assert rel_err(lm["rhs"][:lp.n_owned], gm["rhs"][own]) < 1e-12
+
+
+# ---- block partition (strong scaling of ONE box: bench.py --gpus N) ----------------------------------------------
+def _block_owner(shape, pgrid, gid):
+    npts = [c + 1 for c in shape]
+    L = [part.slab_layers(npts[k], pgrid[k]) for k in range(3)]
+    idx = [gid % npts[0], (gid // npts[0]) % npts[1], gid // (npts[0] * npts[1])]
+    owner = np.zeros(len(gid), dtype=np.int64)
+    for k in (2, 1, 0):
+        owner = owner * pgrid[k] + (np.searchsorted(np.asarray(L[k]), idx[k], side="right") - 1)
+    return owner
+
+
+@pytest.mark.parametrize("shape,pgrid", [((6, 5, 7), (2, 2, 2)), ((5, 5, 9), (1, 2, 2)), ((4, 4, 8), (1, 1, 2)),
+                                         ((7, 6, 5), (2, 1, 3))])
+def test_block_partition_is_the_fldecomp_partition_of_the_block_owner_map(shape, pgrid):
+    """block_partition never builds the global mesh; on small boxes it must equal partition_by_owner (= the reference's
+    fldgmsh.cpp writer, tests/test_formats.py) list for list: numbering, elements, coordinates, both halo lists."""
+    whole = part.block_partition(shape, (1, 1, 1), 0)
+    nprocs = int(np.prod(pgrid))
+    ref = part.partition_by_owner(whole.mesh, _block_owner(shape, pgrid, whole.global_node), nprocs)
+    n_owned = 0
+    for r in range(nprocs):
+        lp, a = part.block_partition(shape, pgrid, r), ref[r]
+        assert lp.n_owned == a.n_owned and lp.n_l1 == a.n_l1
+        assert (lp.global_node == a.global_node).all() and (lp.global_element == a.global_element).all()
+        assert (lp.mesh.ndglno == a.mesh.ndglno).all() and (lp.mesh.X == a.mesh.X).all()
+        for p in range(nprocs):
+            assert (lp.recvs[p] == a.recvs[p]).all() and (lp.sends[p] == a.sends[p]).all()
+        n_owned += lp.n_owned
+    assert n_owned == whole.mesh.n_nodes
+    # the one-block case is the slab generator's whole box (same coordinates bit for bit: bench N=1 is unchanged)
+    w2 = part.slab_partition(shape, 1, 0)
+    assert (whole.mesh.X == w2.mesh.X).all() and (whole.mesh.ndglno == w2.mesh.ndglno).all()
+
+
+def test_block_grid():
+    assert [part.block_grid(n) for n in (1, 2, 4, 8)] == [(1, 1, 1), (1, 1, 2), (1, 2, 2), (2, 2, 2)]
+    assert int(np.prod(part.block_grid(6))) == 6 and int(np.prod(part.block_grid(3))) == 3
