@@ -81,15 +81,38 @@ int record_targets(Handle* h, int slot, double* rec[2], int recw[2], int lane0[2
       rec[0] = reinterpret_cast<double*>(h->d_rec4); recw[0] = 2; lane0[0] = slot == CGASM_F_T_ABSORPTION ? 0 : 1;
       *ncomp = 1;
       return 1;
+    case CGASM_F_ABSORPTION:
+    case CGASM_F_HB_DENSITY:
+    case CGASM_F_SOURCE:
+      if (ensure_extra_records(h) != CGASM_OK) return -1;
+      if (slot == CGASM_F_SOURCE) {
+        rec[0] = r4(h->d_rec6); *ncomp = dim;
+      } else if (slot == CGASM_F_ABSORPTION) {
+        rec[0] = r4(h->d_rec5); *ncomp = dim;
+      } else {
+        rec[0] = r4(h->d_rec5); lane0[0] = 3; *ncomp = 1;
+      }
+      return 1;
     default: return 0;
   }
+}
+
+// { absorption, hb_density } and { source, - } records of the additive STRIP pass: zeroed when made (unset lanes
+// are multiplied by zero coefficients and must hold finite numbers)
+int ensure_extra_records(Handle* h) {
+  for (double4** p : {&h->d_rec5, &h->d_rec6})
+    if (!*p) {
+      CG_CUDA(cudaMalloc(p, sizeof(double4) * (size_t)h->n_nodes));
+      CG_CUDA(cudaMemsetAsync(*p, 0, sizeof(double4) * (size_t)h->n_nodes, h->stream));
+    }
+  return CGASM_OK;
 }
 
 int repack_slot(Handle* h, int slot, const int* d_nodes, int n) {
   double* rec[2];
   int recw[2], lane0[2], ncomp = 0;
   const int nt = record_targets(h, slot, rec, recw, lane0, &ncomp);
-  if (nt < 0) CG_FAIL(CGASM_ECUDA, "cannot allocate the tracer absorption / source records");
+  if (nt < 0) CG_FAIL(CGASM_ECUDA, "cannot allocate the absorption / source records");
   if (nt == 0) return CGASM_OK;  // not a packed field
   const double* src;
   int stride;
@@ -125,6 +148,8 @@ static void destroy_handle(Handle* h) {
   free_dev(h->d_rec2);
   free_dev(h->d_rec3);
   free_dev(h->d_rec4);
+  free_dev(h->d_rec5);
+  free_dev(h->d_rec6);
   free_dev(h->d_findrm);
   free_dev(h->d_colm);
   free_dev(h->d_colour_elements);

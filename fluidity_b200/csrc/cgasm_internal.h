@@ -65,6 +65,8 @@ struct Handle {
   double4* d_rec2 = nullptr;
   double4* d_rec3 = nullptr;  // { X, buoyancy }: with rec1 everything the strip momentum loop reads
   double2* d_rec4 = nullptr;  // { tracer absorption, tracer source }: made when one of them is first set
+  double4* d_rec5 = nullptr;  // { momentum absorption, hb_density } and
+  double4* d_rec6 = nullptr;  // { momentum source, - }: read by the additive STRIP pass (strip_extra.cu), made on demand
   std::vector<double> h_X;  // kept for locality ordering of the tile plan
 
   // node -> element adjacency (host)
@@ -199,6 +201,12 @@ int gather_build_pairs(Handle* h);  // pair lists + walk plan, on demand
 void gather_free(Handle* h);
 int gather_momentum(Handle* h, const MomentumArgs& args, bool want_ml, bool want_ct);
 int gather_advdiff(Handle* h, const AdvDiffArgs& args);
+
+// strip_extra.cu: the additive momentum pass (absorption, sources, reference profile; constant density)
+bool strip_extra_needed(const MomentumArgs& args);
+bool strip_extra_ok(const Handle* h, const MomentumArgs& args);
+int strip_extra(Handle* h, const MomentumArgs& args);
+int ensure_extra_records(Handle* h);  // cgasm_api.cu
 
 // strip.cu
 int strip_build(Handle* h);

@@ -357,6 +357,7 @@ bool strip_momentum_ok(const Handle* h, const MomentumArgs& A, bool want_ml) {
   (void)want_ml;
   const GatherPlan* P = h->gather;
   if (!P || !(P->d_strip || P->d_strip_local) || !strip_momentum_opts_ok(A)) return false;
+  if (strip_extra_needed(A) && !(strip_staged_ok(h, true) && strip_extra_ok(h, A))) return false;
   // a full constant tensor needs the staged kernels
   return strip_staged_ok(h, true) || (P->d_strip && !strip_full_tensor(A.o.have_viscosity, A.o.viscosity_shape));
 }
@@ -395,7 +396,11 @@ static int strip_momentum_dim(Handle* h, const MomentumArgs& A) {
 }
 
 int strip_momentum(Handle* h, const MomentumArgs& A) {
-  if (strip_staged_ok(h, true)) return strip_staged_momentum(h, A);
+  if (strip_staged_ok(h, true)) {
+    int st = strip_staged_momentum(h, A);
+    if (st == CGASM_OK && strip_extra_needed(A)) st = strip_extra(h, A);  // adds to the common result in place
+    return st;
+  }
   if (int js = halo_join(h)) return js;
   return h->dim == 3 ? strip_momentum_dim<3>(h, A) : strip_momentum_dim<2>(h, A);
 }

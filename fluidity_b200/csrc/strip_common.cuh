@@ -304,10 +304,15 @@ inline StripPlanView plan_view(const Handle* h) {
 }
 
 // which option sets the STRIP kernels cover (everything else runs the GATHER kernels)
+// (absorption, sources and the reference profile are added by the additive pass, strip_extra.cu: strip_momentum_ok
+// asks strip_extra_ok for them)
 inline bool strip_momentum_opts_ok(const MomentumArgs& A) {
   const cgasm_momentum_opts& o = A.o;
-  return A.tab.sym && momentum_fast_ok(o, A.gravity.stride, A.absorption.stride) && !o.have_absorption &&
-         !(o.have_gravity && o.subtract_out_reference_profile) && (!o.have_viscosity || A.viscosity.stride == 0);
+  if (o.stabilisation_scheme != CGASM_STAB_NONE) return false;
+  if (!o.exclude_mass && !o.lump_mass) return false;
+  if (!o.exclude_advection && (o.integrate_advection_by_parts || o.beta != 0.0)) return false;
+  if (o.have_gravity && A.gravity.stride != 0) return false;
+  return A.tab.sym && (!o.have_viscosity || A.viscosity.stride == 0);
 }
 // (nodal or constant absorption and source: staged kernels only, strip_advdiff_ok checks that)
 inline bool strip_advdiff_opts_ok(const AdvDiffArgs& A) {

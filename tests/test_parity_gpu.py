@@ -424,3 +424,47 @@ def test_missing_field_is_state_error():
     with pytest.raises(cgasm.CgasmError) as ei:
         asm.momentum(abi.common_momentum_opts())
     assert ei.value.code == abi.ESTATE
+
+
+# ---- STRIP: the additive momentum pass (absorption, sources, reference profile; constant density) ---------------
+def boussinesq_variants():
+    c = abi.common_momentum_opts
+    return {
+        "absorption": c(have_absorption=1),
+        "absorption_nogravity": c(have_absorption=1, have_gravity=0),          # backward_facing_step_3d's option set
+        "absorption_lumped": c(have_absorption=1, lump_absorption=1),
+        "absorption_lumped_pc": c(have_absorption=1, lump_absorption=1, pressure_corrected_absorption=1),
+        "absorption_pc_full": c(have_absorption=1, pressure_corrected_absorption=1),
+        "source": c(have_source=1),
+        "source_lumped": c(have_source=1, lump_source=1),
+        "ref_profile": c(subtract_out_reference_profile=1),
+        "everything": c(have_absorption=1, have_source=1, subtract_out_reference_profile=1, viscosity_shape=abi.TENSOR_FULL),
+        "everything_lumped_noml": c(have_absorption=1, lump_absorption=1, pressure_corrected_absorption=1, have_source=1,
+                                    lump_source=1, subtract_out_reference_profile=1, assemble_inverse_masslump=0),
+        "exclude_mass_adv": c(have_absorption=1, have_source=1, exclude_mass=1, exclude_advection=1),
+    }
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+@pytest.mark.parametrize("variant", list(boussinesq_variants().keys()))
+def test_strip_additive_pass_constant_density(orc, dim, variant):
+    """Constant density (every example config is Boussinesq): the STRIP variant assembles these option sets in its own
+    kernels -- common kernel + the additive pass of strip_extra.cu -- and must agree with the oracle like any other."""
+    mesh = syn.box_mesh((6, 5, 4)[:dim], seed=33)
+    o = boussinesq_variants()[variant]
+    fs = syn.standard_fields(mesh)
+    fs.set(abi.F_DENSITY, np.array([1.3]), abi.FIELD_CONSTANT)
+    if variant == "everything":
+        fs.set(abi.F_VISCOSITY, syn.aniso_tensor(dim), abi.FIELD_CONSTANT)
+    asm = make_asm(mesh, fs, abi.SCATTER_STRIP)
+    findrm, colm, _ = asm.get_sparsity()
+    l0 = asm.launch_count()
+    got = asm.momentum(o)
+    # one common kernel + one additive pass: not the two-pass GATHER staging path (3 launches and more)
+    assert asm.launch_count() - l0 == 2, "the option set did not take the STRIP kernels"
+    ref = orc.assemble_momentum(mesh, fs, o, findrm, colm, want_masslump=bool(o.assemble_inverse_masslump))
+    check_momentum(got, ref, findrm, dim)
+    # a second assembly overwrites, it does not accumulate on top of the first
+    got2 = asm.momentum(o)
+    for k in ("big_m", "rhs"):
+        assert (got2[k] == got[k]).all()
