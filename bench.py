@@ -118,6 +118,11 @@ class ClockSampler:
         for ln in self.proc.stdout:
             self.lines.append(ln.strip())
 
+    def mark(self):
+        """Forget what was sampled so far (warm-up): only the timed region is reported."""
+        self.samples = []
+        self.lines = []
+
     def stop(self):
         if self.nvml:
             self._stop.set()
@@ -478,15 +483,22 @@ def run_graft(args):
         asm.advdiff_dev(oa)
 
     # ---- value: inputs resident in HBM ---------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()     # before the barrier: NVML start-up on rank 0 must not skew the ranks' entry into the timed region
     for _ in range(args.warmup):
         step_resident()
     barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    # one more untimed step AFTER the barrier + synchronize: the ranks leave the host barrier microseconds to
+    # milliseconds apart, and the first halo exchange makes the early ones wait for the late ones -- that wait belongs
+    # to the barrier, not to the K timed steps. Its exchange lines the ranks up on the device; ev0 follows on-stream.
+    if world > 1:
+        step_resident()
     l0 = asm.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     mom_ms, adv_ms = [], []
+    if rank == 0:
+        sampler.mark()
     ev0.record(stream)
     for _ in range(args.steps):
         step_resident()

@@ -966,7 +966,11 @@ static int gather_momentum_dim(Handle* h, const MomentumArgs& A, bool want_ml, b
                     !getenv("CGASM_GATHER_GENERIC");
   double* ml = want_ml ? h->d_masslump : nullptr;
   int st;
-  const bool direct = fast && A.tab.sym && !getenv("CGASM_GATHER_STAGED");
+  // the STRIP kernels cover more option sets than the GATHER fast path (full absorption, sources, the reference
+  // profile through the additive pass): ask them first; ct_m is a separate pass over the pair lists either way
+  const bool strip = h->scatter == CGASM_SCATTER_STRIP && strip_momentum_ok(h, A, want_ml);
+  if (strip && (st = strip_momentum(h, A))) return st;
+  const bool direct = !strip && fast && A.tab.sym && !getenv("CGASM_GATHER_STAGED");
 #define STAGE_SIZE(NB_, NV_) ((size_t)ne * LOC * Rec<LOC, NB_, NV_>::RS)
   const int stab = A.o.stabilisation_scheme;
 #define STAGE_GENERIC(LABS_, NB_, MLC_)                                                                             \
@@ -990,10 +994,7 @@ static int gather_momentum_dim(Handle* h, const MomentumArgs& A, bool want_ml, b
         h->d_mom_rhs, ml);                                                                                     \
   } while (0)
     const bool use_walk = P->d_walk && abs_mode == 0 && !getenv("CGASM_GATHER_DIRECT");
-    if (h->scatter == CGASM_SCATTER_STRIP && strip_momentum_ok(h, A, want_ml)) {
-      if ((st = strip_momentum(h, A))) return st;
-      h->launches--;  // the branches of this chain share one count below; strip_momentum counted its own
-    } else if (use_walk) {
+    if (use_walk) {
       const int wminb = getenv("CGASM_WALK_MINB") ? atoi(getenv("CGASM_WALK_MINB")) : 3;
       const int wprefetch = getenv("CGASM_WALK_PREFETCH") ? atoi(getenv("CGASM_WALK_PREFETCH")) : 0;
 #define LAUNCH_WALK(COMMON_, MINB_)                                                                            \
@@ -1018,6 +1019,8 @@ static int gather_momentum_dim(Handle* h, const MomentumArgs& A, bool want_ml, b
     else LAUNCH_DIRECT(true, true, false, 4);
 #undef LAUNCH_DIRECT
     h->launches++;
+  } else if (strip) {
+    // done above
   } else if (abs_mode == 0) {
     if ((st = ensure_stage(P, STAGE_SIZE(1, DIM + 1)))) return st;
     if (fast) gather_momentum_stage_fast_kernel<DIM, false, 1><<<grid, 128, 0, h->stream>>>(A, P->d_stage);

@@ -28,6 +28,17 @@ reference fixture meshes, producing what the momentum / tracer element loops are
                 pieces (dt*theta scaling, sums, products with oldu / T, the buoyancy and tracer-source vectors). Kept
                 apart in the file as `c_*`.
 
+  variants      `v_mom_T_<tag>` (diagonal blocks), `v_mom_rhs_<tag>`, `v_mom_ml_<tag>`, `v_adv_A_<tag>`, `v_adv_rhs_<tag>` for EVERY
+                non-stabilised entry of tests/variants.py (momentum_variants, advdiff_variants, boussinesq_variants = the
+                four example option sets and their neighbours) on the first VARIANT_ELEMENTS elements: consistent / lumped /
+                excluded mass, plain / by-parts advection with the beta term (Momentum_CG.F90:1646-1680: by parts =
+                minus the TRANSPOSE of the reference's shape_dshape contraction; div(nu) from Transform.grad), isotropic /
+                diagonal / full tensor viscosity and diffusivity (dshape_tensor_dshape, FETools.F90:551-698 = the reference's
+                shape_dshape loop with dN/dx_a in the place of N and V_ab folded into detwei), full / lumped /
+                pressure-corrected absorption (:2036-2073), consistent / lumped sources (:1717-1751),
+                subtract_out_reference_profile (:1767-1771), constant or nodal density. What stays Fortran-only (no
+                reference implementation outside the Fortran): SU / SUPG and their nu_bar schemes.
+
 The element tables n / dn / weights handed to `Element` / `Quadrature` are the degree-3 P1 tables
 of fluidity_b200/tables.py (at run time the reference fills these objects from its Fortran
 element_type; the tables are pinned separately against femtools/tests/test_quadrature.F90 and
@@ -46,8 +57,14 @@ ROOT = os.path.dirname(os.path.dirname(OUT))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(REF, "python"))
 
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
 from fluidity import state_types as st  # noqa: E402  (the reference module, unmodified)
 from fluidity_b200 import tables, synthetic  # noqa: E402
+import variants  # noqa: E402  (tests/variants.py: the option tables the parity tests run)
+
+VARIANT_ELEMENTS = 40
+EPS = 2.220446049250313e-16
 
 # (fixture, elements taken): whole small meshes, the first elements of the unstructured ones
 CASES = [("cube.1", None), ("cube-parallel", 160), ("square-cavity-2d", 200), ("prectangle_0", None)]
@@ -147,6 +164,183 @@ def composed(e, t, du_t, shape, F, dim, loc):
     return out
 
 
+class RefFields:
+    """The fields of a variant as reference ScalarFields per component (CONSTANT fields become nodal fields holding the
+    constant: ele_val_at_quad of a constant is the constant)."""
+    def __init__(self, fs, mesh, n_nodes, dim):
+        A = synthetic.abi
+        self.dim = dim
+
+        def comps(slot, shape):
+            val, ftype = fs.get(slot)
+            val = np.asarray(val, dtype=np.float64)
+            if ftype == A.FIELD_CONSTANT:
+                val = np.broadcast_to(val.reshape((1,) + shape), (n_nodes,) + shape)
+            return scalar_components("f%d_" % slot, np.ascontiguousarray(val.reshape(n_nodes, -1)), mesh)
+
+        self.rho = comps(A.F_DENSITY, ())
+        self.nu, self.oldu = comps(A.F_NU, (dim,)), comps(A.F_OLDU, (dim,))
+        self.buoy, self.hb = comps(A.F_BUOYANCY, ()), comps(A.F_HB_DENSITY, ())
+        self.absn, self.src = comps(A.F_ABSORPTION, (dim,)), comps(A.F_SOURCE, (dim,))
+        self.grav = comps(A.F_GRAVITY, (dim,))
+        self.visc = comps(A.F_VISCOSITY, (dim, dim))       # component b*dim + a holds V(a, b) (synthetic.py layout)
+        self.T = comps(A.F_T, ())
+        self.t_abs, self.t_src = comps(A.F_T_ABSORPTION, ()), comps(A.F_T_SOURCE, ())
+        self.kappa = comps(A.F_T_DIFFUSIVITY, (dim, dim))
+
+
+class RefElement:
+    """Reference-computed ingredients of one element and the reference's own contraction loops."""
+    def __init__(self, e, t, du_t, shape, dim, loc):
+        self.e, self.t, self.du_t, self.shape, self.dim, self.loc = e, t, du_t, shape, dim, loc
+        self.N = np.asarray(shape.n)
+        self.dN = np.asarray(du_t.dn)
+        self.dw = np.asarray(t.detwei)
+
+    def q(self, comps):
+        return np.array([c.ele_val_at_quad(self.e) for c in comps])    # [k, g]
+
+    def nv(self, comps):
+        nodes = comps[0].ele_nodes(self.e)
+        return np.array([[c.node_val(n) for n in nodes] for c in comps])  # [k, i]
+
+    def with_detwei(self, weights, fn):
+        keep = self.t.detwei
+        self.t.detwei = np.asarray(weights)
+        try:
+            return np.asarray(fn())
+        finally:
+            self.t.detwei = keep
+
+    def mass(self, coeff_g=None):
+        return np.asarray(self.t.shape_shape(self.shape, self.shape, coeff_g) if coeff_g is not None
+                          else self.t.shape_shape(self.shape, self.shape))
+
+    def advection(self, weight_g, u_g):
+        # shape_vector_dot_dshape (FETools.F90:749-772): sum_k shape_dshape(N, du_t, detwei*u_k)[:, :, k]
+        return sum(self.with_detwei(weight_g * u_g[k], lambda: self.t.shape_dshape(self.shape, self.du_t))[:, :, k]
+                   for k in range(self.dim))
+
+    def tensor_stiffness(self, V_g, which):
+        """dshape_dot_dshape / dshape_diagtensor_dshape / dshape_tensor_dshape (FETools.F90:391-453,551-698) through the
+        reference's shape_dshape loop: dN/dx_a in the place of N, V_ab(g) * detwei as the weight, component b taken.
+        V_g[a, b, g]; which: 0 isotropic (V_11 on every a = b), 1 diagonal, 2 full."""
+        out = np.zeros((self.loc, self.loc))
+        for a in range(self.dim):
+            grad_a = copy.copy(self.shape)
+            grad_a.n = self.dN[:, :, a]
+            for b in range(self.dim):
+                if which < 2 and a != b:
+                    continue
+                w = V_g[0, 0] if which == 0 else V_g[a, b]
+                out += self.with_detwei(w * self.dw, lambda: self.t.shape_dshape(grad_a, self.du_t))[:, :, b]
+        return out
+
+    def div_at_quad(self, comps):
+        # ele_div_at_quad (Fields_Base.F90): sum_k sum_i u_k(i) dN_i/dx_k, from the reference's Transform.grad
+        u = self.nv(comps)                                               # [k, i]
+        return np.einsum("ki,igk->g", u, self.dN)
+
+    def tensor_at_quad(self, comps):
+        v = self.q(comps)                                                # [b*dim + a, g]
+        return v.reshape(self.dim, self.dim, -1).transpose(1, 0, 2)      # [a, b, g]
+
+
+def momentum_variant_element(o, R, F):
+    """construct_momentum_element_cg for the option set o (no stabilisation): every contraction in the reference's
+    Python loops, only the assembly of the terms restated (Momentum_CG.F90:1492-1575 mass, :1602-1714 advection,
+    :1717-1751 sources, :1753-1795 buoyancy, :2036-2073 absorption, :2286-2359 viscosity)."""
+    A = synthetic.abi
+    dim, loc = R.dim, R.loc
+    dtt = o.dt * o.theta
+    rho_g = R.q(F.rho)[0]
+    oldu = R.nv(F.oldu)
+    Mr = R.mass(rho_g)
+    m = Mr.sum(1)
+    T = np.zeros((dim, loc, loc))
+    rhs = np.zeros((dim, loc))
+    ml = np.zeros((dim, loc))
+    if o.assemble_inverse_masslump:
+        ml += m
+    if not o.exclude_mass:
+        T += np.diag(m) if o.lump_mass else Mr
+    if not o.exclude_advection:
+        u_g = R.q(F.nu)
+        div_g = R.div_at_quad(F.nu)
+        if o.integrate_advection_by_parts:
+            adv = -R.advection(rho_g * R.dw, u_g).T - (1.0 - o.beta) * R.mass(div_g * rho_g)
+        else:
+            adv = R.advection(rho_g * R.dw, u_g) + o.beta * R.mass(div_g * rho_g)
+        T += dtt * adv
+        rhs -= oldu @ adv.T
+    if o.have_source:
+        src = R.nv(F.src)
+        rhs += (m * src) if o.lump_source else src @ Mr.T
+    if o.have_gravity:
+        b_g = R.q(F.buoy)[0]
+        if o.subtract_out_reference_profile:
+            b_g = b_g - R.q(F.hb)[0]
+        g_g = R.q(F.grav)
+        for d in range(dim):
+            rhs[d] += R.N @ (g_g[d] * o.gravity_magnitude * b_g * R.dw)
+    if o.have_absorption:
+        sig_g = R.q(F.absn)
+        for d in range(dim):
+            Ab = R.mass(rho_g * sig_g[d])
+            if o.lump_absorption:
+                al = Ab.sum(1)
+                T[d] += dtt * np.diag(al)
+                rhs[d] -= al * oldu[d]
+                if o.pressure_corrected_absorption and o.assemble_inverse_masslump:
+                    ml[d] += dtt * al
+            else:
+                T[d] += dtt * Ab
+                rhs[d] -= Ab @ oldu[d]
+    if o.have_viscosity:
+        K = R.tensor_stiffness(R.tensor_at_quad(F.visc), o.viscosity_shape)
+        T += dtt * K
+        rhs -= oldu @ K.T
+    return T, rhs, ml
+
+
+def advdiff_variant_element(o, R, F):
+    """assemble_advection_diffusion_element_cg (Advection_Diffusion_CG.F90:867-944 mass, :946-1127 advection,
+    :1129-1162 source / absorption, :1164-1202 diffusivity), default equation type, no stabilisation."""
+    dim, loc = R.dim, R.loc
+    dtt = o.dt * o.theta
+    implicit = abs(dtt) > EPS
+    Tn = R.nv(F.T)[0]
+    Amat = np.zeros((loc, loc))
+    rhs = np.zeros(loc)
+    if o.have_mass:
+        M = R.mass()
+        Amat += np.diag(M.sum(1)) if o.lump_mass else M
+    terms = []
+    if o.have_advection:
+        u_g = R.q(F.nu)
+        if o.integrate_advection_by_parts:
+            adv = -R.advection(R.dw, u_g).T
+            if abs(1.0 - o.beta) > EPS:
+                adv = adv - (1.0 - o.beta) * R.mass(R.div_at_quad(F.nu))
+        else:
+            adv = R.advection(R.dw, u_g)
+            if abs(o.beta) > EPS:
+                adv = adv + o.beta * R.mass(R.div_at_quad(F.nu))
+        terms.append(adv)
+    if o.have_absorption:
+        terms.append(R.mass(R.q(F.t_abs)[0]))
+    if o.have_diffusivity:
+        which = 0 if o.diffusivity_shape == synthetic.abi.TENSOR_ISOTROPIC else 2
+        terms.append(R.tensor_stiffness(R.tensor_at_quad(F.kappa), which))
+    for L in terms:
+        if implicit:
+            Amat += dtt * L
+        rhs -= L @ Tn
+    if o.have_source:
+        rhs += R.N @ (R.q(F.t_src)[0] * R.dw)
+    return Amat, rhs
+
+
 def run(name, nele):
     z = np.load(os.path.join(OUT, name + ".npz"))
     dim = int(z["dim"])
@@ -209,8 +403,29 @@ def run(name, nele):
                 mass_dense[nodes[i], nodes[j]] += M[e][i, j]
                 for d in range(dim):
                     ct_dense[d, nodes[i], nodes[j]] += G[e][i, j, d]
+    # every non-stabilised option variant of the parity tests on the first elements
+    smesh = synthetic.Mesh(dim=dim, ndglno=nd, X=X)
+    nvar = min(n_ele, VARIANT_ELEMENTS)
+    field_cache = {}
+    for tag, kind, o, ftag in variants.variant_cases():
+        fkey = variants.variant_field_key(ftag)
+        if fkey not in field_cache:
+            field_cache[fkey] = RefFields(variants.variant_fields(smesh, ftag), mesh, n_nodes, dim)
+        RF = field_cache[fkey]
+        for e in range(nvar):
+            t = st.Transform(e, coord)
+            R = RefElement(e, t, t.grad(mesh.shape), mesh.shape, dim, loc)
+            if kind == "mom":
+                Tm, r, mlv = momentum_variant_element(o, R, RF)
+                comp.setdefault("v_mom_T_" + tag, []).append(Tm)
+                comp.setdefault("v_mom_rhs_" + tag, []).append(r)
+                comp.setdefault("v_mom_ml_" + tag, []).append(mlv)
+            else:
+                Am, r = advdiff_variant_element(o, R, RF)
+                comp.setdefault("v_adv_A_" + tag, []).append(Am)
+                comp.setdefault("v_adv_rhs_" + tag, []).append(r)
     out = os.path.join(OUT, "pyref_%s.npz" % name)
-    np.savez_compressed(out, dim=dim, ndglno=nd, X=X, density=rho_val, rho_q=rho_q, detwei=detwei, dshape=dshape,
+    np.savez_compressed(out, dim=dim, n_variant_elements=nvar, ndglno=nd, X=X, density=rho_val, rho_q=rho_q, detwei=detwei, dshape=dshape,
                         M=M, M_rho=M_rho, G=G, masslump=lump.val, mass_dense=mass_dense, ct_dense=ct_dense,
                         **{k: np.array(v) for k, v in comp.items()})
     print(name, "dim", dim, "elements", n_ele, "nodes", n_nodes, "-> %s (%d bytes)" % (out, os.path.getsize(out)))

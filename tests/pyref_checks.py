@@ -147,3 +147,37 @@ def check_assembled_composed(mesh, fs, z, findrm, colm, assemble_momentum, assem
         a = assemble_advdiff(adv[tag])
         assert rel_err(a["matrix"], _dense_at(findrm, colm, mat)) < TOL, tag
         assert rel_err(a["rhs"], trhs) < TOL, tag
+
+
+def check_variants(mesh, z, elements_for):
+    """Every non-stabilised option variant of tests/variants.py against its `v_*` golden (reference Python loops on
+    reference-computed ingredients; only the assembly of the terms is restated in the generator).
+    elements_for(fs) -> (momentum_element(opts, ele), advdiff_element(opts, ele)) for a field set."""
+    import variants as V
+    dim = mesh.dim
+    nvar = int(z["n_variant_elements"])
+    cache = {}
+    worst = 0.0
+    for tag, kind, o, ftag in V.variant_cases():
+        key = V.variant_field_key(ftag)
+        if key not in cache:
+            cache[key] = elements_for(V.variant_fields(mesh, ftag))
+        mom_el, adv_el = cache[key]
+        for e in range(nvar):
+            if kind == "mom":
+                T, r, ml, _ = mom_el(o, e + 1)
+                refT, refr, refml = z["v_mom_T_" + tag][e], z["v_mom_rhs_" + tag][e], z["v_mom_ml_" + tag][e]
+                scale = np.abs(refT).max()
+                errs = [rel_err(r, refr)]
+                for d1 in range(dim):
+                    for d2 in range(dim):
+                        ref = refT[d1] if d1 == d2 else np.zeros_like(refT[0])
+                        errs.append(np.abs(T[d1, d2] - ref).max() / scale)
+                if o.assemble_inverse_masslump:
+                    errs.append(rel_err(ml, refml))
+            else:
+                A, r = adv_el(o, e + 1)
+                errs = [rel_err(A, z["v_adv_A_" + tag][e]), rel_err(r, z["v_adv_rhs_" + tag][e])]
+            assert max(errs) < TOL, (tag, e, errs)
+            worst = max(worst, *errs)
+    return worst

@@ -9,6 +9,7 @@ import pytest
 
 from conftest import load_golden_mesh, rel_err, row_rel_err
 from fluidity_b200 import synthetic as syn, _abi as abi, cgasm, tables
+from variants import momentum_variants, advdiff_variants, boussinesq_variants, fields_for
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-12
@@ -26,61 +27,6 @@ def make_asm(mesh, fields=None, scatter=None):
     if scatter is not None:
         asm.set_scatter(scatter)
     return asm
-
-
-def momentum_variants():
-    c = abi.common_momentum_opts
-    return {
-        "common": c(),
-        "common_ct": c(assemble_ct_matrix_here=1),
-        "consistent_mass": c(lump_mass=0),
-        "by_parts_beta": c(integrate_advection_by_parts=1, beta=0.3),
-        "beta1": c(beta=1.0),
-        "absorption": c(have_absorption=1),
-        "absorption_lumped_pc": c(have_absorption=1, lump_absorption=1, pressure_corrected_absorption=1),
-        "source": c(have_source=1),
-        "source_lumped": c(have_source=1, lump_source=1),
-        "ref_profile": c(subtract_out_reference_profile=1),
-        "aniso": c(viscosity_shape=abi.TENSOR_FULL),
-        "diagvisc": c(viscosity_shape=abi.TENSOR_DIAGONAL),
-        "no_adv_no_mass": c(exclude_advection=1, exclude_mass=1),
-        "stokes_no_ml": c(exclude_advection=1, have_gravity=0, assemble_inverse_masslump=0),
-        "su_optimal": c(stabilisation_scheme=abi.STAB_STREAMLINE_UPWIND, nu_bar_scheme=abi.NU_BAR_OPTIMAL),
-        "su_unity_noviscosity": c(stabilisation_scheme=abi.STAB_STREAMLINE_UPWIND, have_viscosity=0),
-        "supg_critical": c(stabilisation_scheme=abi.STAB_SUPG, nu_bar_scheme=abi.NU_BAR_CRITICAL_RULE, nu_bar_scale=1.0,
-                           lump_mass=0, have_absorption=1, have_source=1),
-        "supg_asymptotic_by_parts": c(stabilisation_scheme=abi.STAB_SUPG, nu_bar_scheme=abi.NU_BAR_DOUBLY_ASYMPTOTIC,
-                                      integrate_advection_by_parts=1, beta=0.5),
-    }
-
-
-def advdiff_variants():
-    c = abi.common_advdiff_opts
-    return {
-        "common": c(),
-        "lumped": c(lump_mass=1),
-        "by_parts": c(integrate_advection_by_parts=1, beta=0.25),
-        "beta": c(beta=1.0),
-        "absorb_source": c(have_absorption=1, have_source=1),
-        "tensor_diff": c(diffusivity_shape=abi.TENSOR_FULL),
-        "pure_diffusion": c(have_advection=0),
-        "mass_only": c(have_advection=0, have_diffusivity=0),
-        "theta0": c(theta=0.0),
-        "su_optimal": c(stabilisation_scheme=abi.STAB_STREAMLINE_UPWIND),
-        "su_unity_nodiff": c(stabilisation_scheme=abi.STAB_STREAMLINE_UPWIND, have_diffusivity=0),
-        "supg_optimal_tensor": c(stabilisation_scheme=abi.STAB_SUPG, diffusivity_shape=abi.TENSOR_FULL, have_source=1,
-                                 have_absorption=1, lump_mass=1),
-        "supg_critical_by_parts": c(stabilisation_scheme=abi.STAB_SUPG, nu_bar_scheme=abi.NU_BAR_CRITICAL_RULE,
-                                    integrate_advection_by_parts=1, beta=0.3),
-    }
-
-
-def fields_for(mesh, variant):
-    fs = syn.standard_fields(mesh, nodal_viscosity=(variant == "aniso"))
-    if variant in ("diagvisc", "tensor_diff", "supg_optimal_tensor"):
-        fs.set(abi.F_VISCOSITY, syn.aniso_tensor(mesh.dim), abi.FIELD_CONSTANT)
-        fs.set(abi.F_T_DIFFUSIVITY, syn.aniso_tensor(mesh.dim), abi.FIELD_CONSTANT)
-    return fs
 
 
 def check_momentum(got, ref, findrm, dim):
@@ -426,25 +372,23 @@ def test_missing_field_is_state_error():
     assert ei.value.code == abi.ESTATE
 
 
+@pytest.mark.parametrize("name", ["cube.1", "cube-parallel", "square-cavity-2d", "prectangle_0"])
+def test_every_non_stabilised_variant_matches_reference_python(name):
+    """The CUDA element routines (cgasm_momentum_element / cgasm_advdiff_element) against the `v_*` goldens: every
+    non-stabilised option variant of tests/variants.py, contractions run by the reference's own Python loops."""
+    import pyref_checks as pc
+    mesh, fs, z = pc.load(name)
+    asms = []
+
+    def elements_for(f):
+        asm = make_asm(mesh, f)
+        asms.append(asm)
+        return asm.momentum_element, asm.advdiff_element
+
+    assert pc.check_variants(mesh, z, elements_for) < TOL
+
+
 # ---- STRIP: the additive momentum pass (absorption, sources, reference profile; constant density) ---------------
-def boussinesq_variants():
-    c = abi.common_momentum_opts
-    return {
-        "absorption": c(have_absorption=1),
-        "absorption_nogravity": c(have_absorption=1, have_gravity=0),          # backward_facing_step_3d's option set
-        "absorption_lumped": c(have_absorption=1, lump_absorption=1),
-        "absorption_lumped_pc": c(have_absorption=1, lump_absorption=1, pressure_corrected_absorption=1),
-        "absorption_pc_full": c(have_absorption=1, pressure_corrected_absorption=1),
-        "source": c(have_source=1),
-        "source_lumped": c(have_source=1, lump_source=1),
-        "ref_profile": c(subtract_out_reference_profile=1),
-        "everything": c(have_absorption=1, have_source=1, subtract_out_reference_profile=1, viscosity_shape=abi.TENSOR_FULL),
-        "everything_lumped_noml": c(have_absorption=1, lump_absorption=1, pressure_corrected_absorption=1, have_source=1,
-                                    lump_source=1, subtract_out_reference_profile=1, assemble_inverse_masslump=0),
-        "exclude_mass_adv": c(have_absorption=1, have_source=1, exclude_mass=1, exclude_advection=1),
-    }
-
-
 @pytest.mark.parametrize("dim", [2, 3])
 @pytest.mark.parametrize("variant", list(boussinesq_variants().keys()))
 def test_strip_additive_pass_constant_density(orc, dim, variant):

@@ -52,6 +52,17 @@ def test_common_option_set_from_reference_python_ingredients(orc, name):
     assert worst < pc.TOL
 
 
+@pytest.mark.parametrize("name", pc.CASES)
+def test_every_non_stabilised_variant_from_reference_python_loops(orc, name):
+    """Tensor / diagonal viscosity and diffusivity, by-parts advection, the beta term, consistent / lumped / excluded mass,
+    full / lumped / pressure-corrected absorption, sources, the reference profile, constant density: the oracle against
+    goldens whose every quadrature contraction ran in the reference's own Python loops."""
+    mesh, fs, z = pc.load(name)
+    worst = pc.check_variants(mesh, z, lambda f: (lambda o, ele: orc.momentum_element(mesh, f, o, ele),
+                                                  lambda o, ele: orc.advdiff_element(mesh, f, o, ele)))
+    assert worst < pc.TOL
+
+
 def test_quadrature_point_gather_matches_reference_python(orc):
     # Field.ele_val_at_quad (state_types.py:113-117) == ele_val . shape%n (Fields_Base.F90:2256-2310)
     mesh, fs, z = pc.load("cube-parallel")
