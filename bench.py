@@ -51,6 +51,9 @@ def parse():
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
                     help="N>1: strong = one cells^3 mesh split into N blocks (default); weak = cells^3 per GPU")
     ap.add_argument("--no-overlap", action="store_true", help="halo exchange in front of the kernels instead of beside them")
+    ap.add_argument("--step", default="separate", choices=["separate", "fused"],
+                    help="timed step = cgasm_momentum_dev + cgasm_advdiff_dev (the reference's two loops, default) or the "
+                         "one-call cgasm_momentum_advdiff_dev (one fused kernel); the other one is reported beside it")
     ap.add_argument("--no-configs", action="store_true", help="skip the example-config option sets (N=1 only)")
     ap.add_argument("--no-parity", action="store_true", help="skip the multi-GPU parity check against the oracle (N>1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -388,9 +391,11 @@ def example_configs(device, cells3, cells2, reps=5):
                 mom.append(m)
                 adv.append(a)
         launches = (asm.launch_count() - l0) / (reps + 2)
+        paths = asm.last_path()
         mm, aa = statistics.median(mom), statistics.median(adv)
         out.append({"config": name, "dim": dim, "elements": mesh.n_elements, "momentum_ms": mm, "tracer_ms": aa,
                     "gel_s": mesh.n_elements / ((mm + aa) * 1e-3) / 1e9, "kernel_launches_per_step": launches,
+                    "momentum_path": paths[0], "tracer_path": paths[1],
                     "library_setup_s": setup})
         asm.close()
     return out
@@ -479,8 +484,11 @@ def run_graft(args):
     def step_resident():
         if world > 1:
             asm.halo_update(halo_slots)
-        asm.momentum_dev(om)
-        asm.advdiff_dev(oa)
+        if args.step == "fused":
+            asm.momentum_advdiff_dev(om, oa)
+        else:
+            asm.momentum_dev(om)
+            asm.advdiff_dev(oa)
 
     # ---- value: inputs resident in HBM ---------------------------------------------------
     sampler = ClockSampler(local_rank)
@@ -528,6 +536,15 @@ def run_graft(args):
         mom_ms.append(asm.last_kernel_ms())
         asm.advdiff_dev(oa)
         adv_ms.append(asm.last_kernel_ms())
+    # the one-call flavour of the step (one fused kernel for this option set), timed alone
+    fused_ms = []
+    for _ in range(max(3, min(args.steps, 5))):
+        if world > 1:
+            asm.halo_update(halo_slots)
+            asm.synchronize()
+        asm.momentum_advdiff_dev(om, oa)
+        fused_ms.append(asm.last_kernel_ms())
+    fused_ms = float(np.mean(fused_ms))
     t = torch.tensor([my_total_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -545,7 +562,7 @@ def run_graft(args):
     m_ms, a_ms = float(np.mean(mom_ms)), float(np.mean(adv_ms))
     per_rank = None
     if world > 1:
-        mine = dict(rank=rank, step_ms=my_total_ms / args.steps, momentum_ms=m_ms, tracer_ms=a_ms, halo_ms=halo_ms,
+        mine = dict(rank=rank, step_ms=my_total_ms / args.steps, momentum_ms=m_ms, tracer_ms=a_ms, fused_ms=fused_ms, halo_ms=halo_ms,
                     local_elements=n_el_local, local_nodes=n_nodes_local, owned_nodes=n_owned, halo_nodes_sent=n_sent,
                     neighbours=n_neighbours, library_setup_s=setup_s, mesh_gen_s=mesh_gen_s)
         allr = [None] * world if rank == 0 else None
@@ -665,6 +682,7 @@ def run_graft(args):
         "elements_total": total_elements, "local_elements_rank0": n_el_local, "nnz_rank0": nnz, "n_nodes_rank0": n_nodes_local,
         "host_peak_rss_gb_rank0": resource.getrusage(resource.RUSAGE_SELF).ru_maxrss / 1048576.0,
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        "step_flavour": args.step, "separate_kernels_ms_rank0": m_ms + a_ms, "fused_kernel_ms_rank0": fused_ms,
         "halo_update_ms_rank0": halo_ms, "halo_nodes_sent_rank0": n_sent, "halo_overlap": overlap,
         "multi_gpu_parity_max_rel_err": parity, "per_rank": per_rank, "configs": configs,
     }

@@ -214,6 +214,10 @@ class Assembler:
     def advdiff_dev(self, opts):
         _check(self.lib.cgasm_advdiff_dev(C.c_int(self.id), C.byref(opts)))
 
+    def momentum_advdiff_dev(self, mopts, aopts):
+        """Both element loops in one call (one fused kernel for the common STRIP option sets)."""
+        _check(self.lib.cgasm_momentum_advdiff_dev(C.c_int(self.id), C.byref(mopts), C.byref(aopts)))
+
     def momentum_fetch(self, want_masslump=True, want_ct=False):
         dim, nnz, nn = self.dim, self.nnz, self.n_nodes
         big_m = np.empty((dim, nnz))
@@ -378,6 +382,14 @@ class Assembler:
         uid = C.create_string_buffer(unique_id, 128) if unique_id is not None else None
         _check(self.lib.cgasm_halo_create(C.c_int(self.id), C.c_int(nprocs), C.c_int(rank), _ip(nsend),
                                           _ip(s_all), _ip(nrecv), _ip(r_all), uid))
+
+    PATHS = {0: "none", 1: "element", 2: "tiled", 3: "gather_staged", 4: "gather_rows", 5: "strip", 6: "strip_staged"}
+
+    def last_path(self):
+        """(momentum, tracer) kernel family of the last assemblies (cgasm_last_path)."""
+        m, a = C.c_int(0), C.c_int(0)
+        _check(self.lib.cgasm_last_path(C.c_int(self.id), C.byref(m), C.byref(a)))
+        return self.PATHS[m.value], self.PATHS[a.value]
 
     def halo_set_overlap(self, on):
         _check(self.lib.cgasm_halo_set_overlap(C.c_int(self.id), C.c_int(1 if on else 0)))

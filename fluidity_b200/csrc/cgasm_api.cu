@@ -162,6 +162,8 @@ static void destroy_handle(Handle* h) {
   free_dev(h->d_adv_rhs);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->evc0) cudaEventDestroy(h->evc0);
+  if (h->evc1) cudaEventDestroy(h->evc1);
   if (h->ev_ready) cudaEventDestroy(h->ev_ready);
   if (h->ev_mom_copied) cudaEventDestroy(h->ev_mom_copied);
   if (h->ev_adv_copied) cudaEventDestroy(h->ev_adv_copied);
@@ -419,6 +421,7 @@ int cgasm_create(int* id, int device, int dim, int loc, int ngi, int n_nodes, in
   };
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreate(&h->ev0) != cudaSuccess || cudaEventCreate(&h->ev1) != cudaSuccess ||
+      cudaEventCreate(&h->evc0) != cudaSuccess || cudaEventCreate(&h->evc1) != cudaSuccess ||
       cudaMalloc(&h->d_ndglno, sizeof(int4) * (size_t)n_elements) != cudaSuccess ||
       cudaMalloc(&h->d_X, sizeof(double) * (size_t)dim * n_nodes) != cudaSuccess ||
       cudaMalloc(&h->d_rec0, sizeof(double4) * (size_t)n_nodes) != cudaSuccess ||
@@ -701,6 +704,7 @@ int cgasm_momentum_dev(int id, const cgasm_momentum_opts* opts) {
   CG_CUDA(cudaEventRecord(h->ev0, h->stream));
   if (h->scatter == CGASM_SCATTER_TILED) {
     st = tiles_momentum(h, A, want_ml, want_ct);
+    h->mom_path = CGASM_PATH_TILED;
   } else if (h->scatter == CGASM_SCATTER_GATHER || h->scatter == CGASM_SCATTER_STRIP) {
     st = gather_momentum(h, A, want_ml, want_ct);
   } else {
@@ -710,10 +714,12 @@ int cgasm_momentum_dev(int id, const cgasm_momentum_opts* opts) {
     if (want_ml) CG_CUDA(cudaMemsetAsync(h->d_masslump, 0, sizeof(double) * dim * nn, h->stream));
     if (want_ct) CG_CUDA(cudaMemsetAsync(h->d_ct_m, 0, sizeof(double) * dim * nnz, h->stream));
     st = scatter_momentum(h, A, want_ml, want_ct);
+    h->mom_path = CGASM_PATH_ELEMENT;
   }
   if (st) return st;
   CG_CUDA(cudaEventRecord(h->ev1, h->stream));
   CG_CUDA(cudaGetLastError());
+  h->last_combined = false;
   h->mom_has_masslump = want_ml;
   h->mom_has_ct = want_ct;
   h->mom_identical_blocks = !opts->have_absorption;
@@ -742,17 +748,64 @@ int cgasm_advdiff_dev(int id, const cgasm_advdiff_opts* opts) {
   CG_CUDA(cudaEventRecord(h->ev0, h->stream));
   if (h->scatter == CGASM_SCATTER_TILED) {
     st = tiles_advdiff(h, P);
+    h->adv_path = CGASM_PATH_TILED;
   } else if (h->scatter == CGASM_SCATTER_GATHER || h->scatter == CGASM_SCATTER_STRIP) {
     st = gather_advdiff(h, P);
   } else {
     CG_CUDA(cudaMemsetAsync(h->d_adv_matrix, 0, sizeof(double) * nnz, h->stream));
     CG_CUDA(cudaMemsetAsync(h->d_adv_rhs, 0, sizeof(double) * nn, h->stream));
     st = scatter_advdiff(h, P);
+    h->adv_path = CGASM_PATH_ELEMENT;
   }
   if (st) return st;
   CG_CUDA(cudaEventRecord(h->ev1, h->stream));
   CG_CUDA(cudaGetLastError());
+  h->last_combined = false;
   h->adv_valid = true;
+  return CGASM_OK;
+}
+
+// Both element loops of a time step in one call. When both option sets are the common STRIP sets (lumped or excluded
+// mass, plain advection, constant isotropic viscosity / diffusivity, constant gravity direction, no absorption / sources)
+// one kernel assembles both systems, sharing the strip, the staged node records and the element geometry
+// (strip_fused.cu); otherwise the two loops run one after the other. Results: exactly those of the two calls.
+int cgasm_momentum_advdiff_dev(int id, const cgasm_momentum_opts* mopts, const cgasm_advdiff_opts* aopts) {
+  GET_HANDLE(h, id);
+  if (!mopts || !aopts) CG_FAIL(CGASM_EARG, "null opts");
+  if (!h->have_sparsity) CG_FAIL(CGASM_ESTATE, "no sparsity: call cgasm_build_sparsity or cgasm_set_sparsity");
+  MomentumArgs M;
+  AdvDiffArgs A;
+  int st = make_momentum_args(h, mopts, M);
+  if (st) return st;
+  if ((st = make_advdiff_args(h, aopts, A))) return st;
+  CG_CUDA(cudaEventRecord(h->evc0, h->stream));
+  if (aopts->have_advection && strip_fused_ok(h, M, A)) {
+    const size_t nnz = (size_t)h->nnz, nn = (size_t)h->n_nodes, dim = (size_t)h->dim;
+    const bool want_ml = mopts->assemble_inverse_masslump != 0;
+    if ((st = ensure(&h->d_big_m, dim * nnz)) || (st = ensure(&h->d_mom_rhs, dim * nn)) ||
+        (want_ml && (st = ensure(&h->d_masslump, dim * nn))) || (st = ensure(&h->d_adv_matrix, nnz)) ||
+        (st = ensure(&h->d_adv_rhs, nn)))
+      return st;
+    if (h->mom_copy_pending) {
+      CG_CUDA(cudaStreamWaitEvent(h->stream, h->ev_mom_copied, 0));
+      h->mom_copy_pending = false;
+    }
+    if (h->adv_copy_pending) {
+      CG_CUDA(cudaStreamWaitEvent(h->stream, h->ev_adv_copied, 0));
+      h->adv_copy_pending = false;
+    }
+    if ((st = strip_fused(h, M, A))) return st;
+    h->mom_has_masslump = want_ml;
+    h->mom_has_ct = false;
+    h->mom_identical_blocks = true;
+    h->mom_valid = h->adv_valid = true;
+  } else {
+    if ((st = cgasm_momentum_dev(id, mopts))) return st;
+    if ((st = cgasm_advdiff_dev(id, aopts))) return st;
+  }
+  CG_CUDA(cudaEventRecord(h->evc1, h->stream));
+  CG_CUDA(cudaGetLastError());
+  h->last_combined = true;
   return CGASM_OK;
 }
 
@@ -956,11 +1009,19 @@ int cgasm_launch_count(int id, long long* launches) {
   return CGASM_OK;
 }
 
+int cgasm_last_path(int id, int* momentum_path, int* advdiff_path) {
+  GET_HANDLE(h, id);
+  if (momentum_path) *momentum_path = h->mom_path;
+  if (advdiff_path) *advdiff_path = h->adv_path;
+  return CGASM_OK;
+}
+
 int cgasm_last_kernel_ms(int id, float* ms) {
   GET_HANDLE(h, id);
   if (!ms) CG_FAIL(CGASM_EARG, "null out");
-  CG_CUDA(cudaEventSynchronize(h->ev1));
-  CG_CUDA(cudaEventElapsedTime(ms, h->ev0, h->ev1));
+  cudaEvent_t e0 = h->last_combined ? h->evc0 : h->ev0, e1 = h->last_combined ? h->evc1 : h->ev1;
+  CG_CUDA(cudaEventSynchronize(e1));
+  CG_CUDA(cudaEventElapsedTime(ms, e0, e1));
   return CGASM_OK;
 }
 

@@ -105,7 +105,10 @@ struct Handle {
   CmcPlan* cmc = nullptr;
 
   long long launches = 0;
+  int mom_path = 0, adv_path = 0;  // CGASM_PATH_* of the last assembly (cgasm_last_path)
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t evc0 = nullptr, evc1 = nullptr;  // around cgasm_momentum_advdiff_dev (both loops)
+  bool last_combined = false;                   // cgasm_last_kernel_ms reads evc0..evc1 instead of ev0..ev1
   float last_ms = 0.f;
   // asynchronous host flavour (cgasm_set_async): results leave on copy_stream while the next loop runs
   bool async = false;
@@ -207,6 +210,10 @@ bool strip_extra_needed(const MomentumArgs& args);
 bool strip_extra_ok(const Handle* h, const MomentumArgs& args);
 int strip_extra(Handle* h, const MomentumArgs& args);
 int ensure_extra_records(Handle* h);  // cgasm_api.cu
+
+// strip_fused.cu: both element loops in one kernel (common STRIP option sets)
+bool strip_fused_ok(const Handle* h, const MomentumArgs& m, const AdvDiffArgs& a);
+int strip_fused(Handle* h, const MomentumArgs& m, const AdvDiffArgs& a);
 
 // strip.cu
 int strip_build(Handle* h);

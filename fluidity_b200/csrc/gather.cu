@@ -970,6 +970,7 @@ static int gather_momentum_dim(Handle* h, const MomentumArgs& A, bool want_ml, b
   // profile through the additive pass): ask them first; ct_m is a separate pass over the pair lists either way
   const bool strip = h->scatter == CGASM_SCATTER_STRIP && strip_momentum_ok(h, A, want_ml);
   if (strip && (st = strip_momentum(h, A))) return st;
+  if (!strip) h->mom_path = (fast && A.tab.sym && !getenv("CGASM_GATHER_STAGED")) ? CGASM_PATH_GATHER_ROWS : CGASM_PATH_GATHER_STAGED;
   const bool direct = !strip && fast && A.tab.sym && !getenv("CGASM_GATHER_STAGED");
 #define STAGE_SIZE(NB_, NV_) ((size_t)ne * LOC * Rec<LOC, NB_, NV_>::RS)
   const int stab = A.o.stabilisation_scheme;
@@ -1079,7 +1080,9 @@ static int gather_advdiff_dim(Handle* h, const AdvDiffArgs& A) {
     CG_CUDA(cudaGetLastError());
     return CGASM_OK;
   }
+  h->adv_path = CGASM_PATH_GATHER_STAGED;
   if (advdiff_fast_ok(A.o) && A.tab.sym && !getenv("CGASM_GATHER_GENERIC") && !getenv("CGASM_GATHER_STAGED")) {
+    h->adv_path = CGASM_PATH_GATHER_ROWS;
     const size_t smem = sizeof(double) * (size_t)P->maxlen * kBR;
     if (smem > 200 * 1024) CG_FAIL(CGASM_EUNSUPPORTED, "gather scatter: CSR rows too long for the shared-memory accumulator");
     const int prefetch = getenv("CGASM_GATHER_PREFETCH") ? atoi(getenv("CGASM_GATHER_PREFETCH")) : 0;

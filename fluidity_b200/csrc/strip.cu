@@ -195,7 +195,11 @@ strip_advdiff_kernel(const StripConsts k_, const StripPlanView P, const double4*
   AdvState<DIM, N> s;
   double unused;
   unpack<DIM>(ld256(rX + r0), s.X0, s.T0);
-  unpack<DIM>(ld256(rU + r0), s.U0, unused);
+  {
+    double U0[DIM];
+    unpack<DIM>(ld256(rU + r0), U0, unused);
+    adv_row_const<DIM>(k_, U0, s.cU0);
+  }
   s.a0 = s.c0 = s.rhs = 0.0;
 #pragma unroll
   for (int q = 0; q < N; q++) {
@@ -396,7 +400,9 @@ static int strip_momentum_dim(Handle* h, const MomentumArgs& A) {
 }
 
 int strip_momentum(Handle* h, const MomentumArgs& A) {
+  h->mom_path = CGASM_PATH_STRIP;
   if (strip_staged_ok(h, true)) {
+    h->mom_path = CGASM_PATH_STRIP_STAGED;
     int st = strip_staged_momentum(h, A);
     if (st == CGASM_OK && strip_extra_needed(A)) st = strip_extra(h, A);  // adds to the common result in place
     return st;
@@ -430,7 +436,11 @@ static int strip_advdiff_dim(Handle* h, const AdvDiffArgs& A) {
 }
 
 int strip_advdiff(Handle* h, const AdvDiffArgs& A) {
-  if (strip_staged_ok(h, false)) return strip_staged_advdiff(h, A);
+  h->adv_path = CGASM_PATH_STRIP;
+  if (strip_staged_ok(h, false)) {
+    h->adv_path = CGASM_PATH_STRIP_STAGED;
+    return strip_staged_advdiff(h, A);
+  }
   if (int js = halo_join(h)) return js;
   return h->dim == 3 ? strip_advdiff_dim<3>(h, A) : strip_advdiff_dim<2>(h, A);
 }

@@ -118,18 +118,25 @@ __device__ __forceinline__ void row_vector(const StripConsts& k_, const double (
   }
 }
 
-template <int DIM, int N, int QC, bool FULLV>
-__device__ __forceinline__ void mom_compute(MomState<DIM, N>& s, const StripConsts& k_) {
-  double c[DIM][DIM];
-  const double det = window_geometry<DIM, N, QC>(s.X, c);
-  const double rd = rcp_nr(det);
-  double sc[DIM];
+// cofactors, determinant, its reciprocal and the cofactor sum of the window: shared by every term of the element
+template <int DIM>
+struct WindowGeom {
+  double c[DIM][DIM], sc[DIM], det, rd;
+};
+template <int DIM, int N, int QC>
+__device__ __forceinline__ void window_geom(const double (&X)[N][DIM], WindowGeom<DIM>& g) {
+  g.det = window_geometry<DIM, N, QC>(X, g.c);
+  g.rd = rcp_nr(g.det);
 #pragma unroll
   for (int a = 0; a < DIM; a++) {
-    sc[a] = c[0][a];
+    g.sc[a] = g.c[0][a];
 #pragma unroll
-    for (int k = 1; k < DIM; k++) sc[a] += c[k][a];
+    for (int k = 1; k < DIM; k++) g.sc[a] += g.c[k][a];
   }
+}
+
+template <int DIM, int N, int QC, bool FULLV>
+__device__ __forceinline__ void mom_terms(MomState<DIM, N>& s, const StripConsts& k_, const WindowGeom<DIM>& g) {
   double S = s.rho0;
 #pragma unroll
   for (int k = 0; k < DIM; k++) S += s.R[WQ(k)];
@@ -146,23 +153,30 @@ __device__ __forceinline__ void mom_compute(MomState<DIM, N>& s, const StripCons
   }
   // v / det with v = |det| (w + Wsum V gradN_0), gradN_0 = -sc / det
   double u[DIM];
-  row_vector<DIM, FULLV>(k_, w, sc, rd, det, u);
+  row_vector<DIM, FULLV>(k_, w, g.sc, g.rd, g.det, u);
   double tot = 0.0;
 #pragma unroll
   for (int k = 0; k < DIM; k++) {
     double sk = 0.0;
 #pragma unroll
-    for (int a = 0; a < DIM; a++) sk = fma(u[a], c[k][a], sk);
+    for (int a = 0; a < DIM; a++) sk = fma(u[a], g.c[k][a], sk);
     s.A[WQ(k)] += sk;
     tot += sk;
   }
   s.a0 -= tot;
-  const double ad = fabs(det);
+  const double ad = fabs(g.det);
   s.msum = fma(ad, fma(k_.PdPo, s.rho0, k_.Po * S), s.msum);
   double Sb = s.b0;
 #pragma unroll
   for (int k = 0; k < DIM; k++) Sb += s.B[WQ(k)];
   s.nbsum = fma(ad, fma(k_.PdPo, s.b0, k_.Po * Sb), s.nbsum);
+}
+
+template <int DIM, int N, int QC, bool FULLV>
+__device__ __forceinline__ void mom_compute(MomState<DIM, N>& s, const StripConsts& k_) {
+  WindowGeom<DIM> g;
+  window_geom<DIM, N, QC>(s.X, g);
+  mom_terms<DIM, N, QC, FULLV>(s, k_, g);
 }
 
 // rows of the warp -> global memory, LPR = 1 << lpr_shift lanes per row
@@ -189,45 +203,58 @@ template <int DIM, int N>
 struct AdvState {
   double X[N][DIM], U[N][DIM], T[N], A[N], C[N];  // C: sum of |det| over the elements sharing the edge (mass)
   int meta[N];
-  double X0[DIM], U0[DIM], T0;
+  double X0[DIM], cU0[DIM], T0;  // cU0 = Pd * nu(row node): adv_row_const
   double a0, c0, rhs;
 };
 
+// the row-constant part of the advecting-velocity moment: (Pd - Po) nu_0 + Po nu_0
+template <int DIM>
+__device__ __forceinline__ void adv_row_const(const StripConsts& k_, const double (&U0)[DIM], double (&cU0)[DIM]) {
+#pragma unroll
+  for (int a = 0; a < DIM; a++) cU0[a] = (k_.PdPo + k_.Po) * U0[a];
+}
+
 // Advection_Diffusion_CG.F90:909-920 (consistent mass), :1093-1098 with beta = 0, :1192 (constant
 // isotropic diffusivity), :1125,1200 (rhs -= (A + D) T)
+// the tracer terms of one window on explicit operands (the fused momentum + tracer kernel shares the momentum state's
+// velocity buffers and the geometry)
 template <int DIM, int N, int QC, bool FULLV>
-__device__ __forceinline__ void adv_compute(AdvState<DIM, N>& s, const StripConsts& k_) {
-  double c[DIM][DIM];
-  const double det = window_geometry<DIM, N, QC>(s.X, c);
-  const double rd = rcp_nr(det);
-  double sc[DIM], v[DIM];
+__device__ __forceinline__ void adv_terms(const StripConsts& k_, const WindowGeom<DIM>& g, const double (&U)[N][DIM],
+                                          const double (&cU0)[DIM], const double (&T)[N], double T0, double (&A)[N],
+                                          double (&C)[N], double& a0, double& c0, double& rhs) {
+  // v = (Pd - Po) nu_0 + Po (nu_0 + sum_k nu_k); cU0 = Pd nu_0 is the same for every element of the row
+  double v[DIM];
 #pragma unroll
   for (int a = 0; a < DIM; a++) {
-    sc[a] = c[0][a];
-    double Su = s.U0[a];
+    double Su = U[WQ(0)][a];
 #pragma unroll
-    for (int k = 1; k < DIM; k++) sc[a] += c[k][a];
-#pragma unroll
-    for (int k = 0; k < DIM; k++) Su += s.U[WQ(k)][a];
-    v[a] = fma(k_.PdPo, s.U0[a], k_.Po * Su);
+    for (int k = 1; k < DIM; k++) Su += U[WQ(k)][a];
+    v[a] = fma(k_.Po, Su, cU0[a]);
   }
   double u[DIM];
-  row_vector<DIM, FULLV>(k_, v, sc, rd, det, u);
-  const double ad = fabs(det);
+  row_vector<DIM, FULLV>(k_, v, g.sc, g.rd, g.det, u);
+  const double ad = fabs(g.det);
   double tot = 0.0;
 #pragma unroll
   for (int k = 0; k < DIM; k++) {
     double sk = 0.0;
 #pragma unroll
-    for (int a = 0; a < DIM; a++) sk = fma(u[a], c[k][a], sk);
-    s.A[WQ(k)] += sk;
-    s.C[WQ(k)] += ad;
-    s.rhs = fma(-sk, s.T[WQ(k)], s.rhs);
+    for (int a = 0; a < DIM; a++) sk = fma(u[a], g.c[k][a], sk);
+    A[WQ(k)] += sk;
+    C[WQ(k)] += ad;
+    rhs = fma(-sk, T[WQ(k)], rhs);
     tot += sk;
   }
-  s.a0 -= tot;
-  s.c0 += ad;
-  s.rhs = fma(tot, s.T0, s.rhs);
+  a0 -= tot;
+  c0 += ad;
+  rhs = fma(tot, T0, rhs);
+}
+
+template <int DIM, int N, int QC, bool FULLV>
+__device__ __forceinline__ void adv_compute(AdvState<DIM, N>& s, const StripConsts& k_) {
+  WindowGeom<DIM> g;
+  window_geom<DIM, N, QC>(s.X, g);
+  adv_terms<DIM, N, QC, FULLV>(k_, g, s.U, s.cU0, s.T, s.T0, s.A, s.C, s.a0, s.c0, s.rhs);
 }
 
 // the row's own absorption / source values (tracer kernel with ABS)
@@ -248,12 +275,12 @@ __device__ __forceinline__ void adv_compute_abs(AdvState<DIM, N>& s, const doubl
 #pragma unroll
   for (int a = 0; a < DIM; a++) {
     sc[a] = c[0][a];
-    double Su = s.U0[a];
+    double Su = s.U[WQ(0)][a];
 #pragma unroll
     for (int k = 1; k < DIM; k++) sc[a] += c[k][a];
 #pragma unroll
-    for (int k = 0; k < DIM; k++) Su += s.U[WQ(k)][a];
-    v[a] = fma(k_.PdPo, s.U0[a], k_.Po * Su);
+    for (int k = 1; k < DIM; k++) Su += s.U[WQ(k)][a];
+    v[a] = fma(k_.Po, Su, s.cU0[a]);
   }
   double u[DIM];
   row_vector<DIM, FULLV>(k_, v, sc, rd, det, u);

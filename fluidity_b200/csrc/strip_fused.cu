@@ -1,0 +1,259 @@
+// strip_fused.cu -- ONE kernel for construct_momentum_element_cg + assemble_advection_diffusion_element_cg when both
+// loops run the common STRIP option sets on the same mesh with the same advecting velocity (a passive tracer advected
+// by nu: SURVEY.md 2.1 "fused momentum + tracer", VERDICT r1 missing #6).
+//
+// What the two staged kernels do twice and this one does once per (row, element) pair: the strip plan stream, the
+// staging of {X}, {nu} in shared memory, the FIFO rotation, the cofactor geometry with its reciprocal (32 of the ~80 /
+// ~93 FP64 instructions of the tracer / momentum pair) and the prologue / epilogue bookkeeping of a row. The terms
+// themselves are the same device functions the separate kernels call (strip_common.cuh: mom_terms, adv_terms), in the
+// same order on the same operands: the results are BITWISE those of cgasm_momentum_dev followed by cgasm_advdiff_dev.
+// Isotropic constant viscosity / diffusivity only (the full-tensor and additive variants keep the separate kernels).
+#include "strip_staged.cuh"
+
+namespace cgasm {
+
+// staged chunks (16 bytes, stride NL): 0,1 = {X | z, buoyancy}  2,3 = {nu | z, density}  4 = oldu {x, y};
+// then plain double arrays: oldu z (at chunk 5's place), T behind it
+template <int NL>
+__device__ __forceinline__ unsigned fused_t_sa(unsigned nsa, unsigned noff) {
+  return nsa + (unsigned)(5 * NL * 16 + NL * 8) + (noff >> 1);
+}
+
+template <int DIM, int NL>
+__device__ __forceinline__ void stage_fused(const StagedView& P, int b, int t, unsigned nsa, const double4* __restrict__ rX,
+                                            const double4* __restrict__ rU, const double4* __restrict__ rO,
+                                            const double4* __restrict__ rT) {
+  const int* ids = P.blk_nodes + (size_t)b * NL;
+  constexpr int U = NL / kBR >= 2 ? 2 : 1;
+  for (int i0 = t; i0 < NL; i0 += U * kBR) {
+    int node[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) node[u] = i0 + u * kBR < NL ? __ldg(ids + i0 + u * kBR) : -1;
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      if (node[u] < 0) continue;
+      const unsigned i = (unsigned)(i0 + u * kBR), d = nsa + i * 16u;
+      const double2* s0 = reinterpret_cast<const double2*>(rX + node[u]);
+      const double2* s1 = reinterpret_cast<const double2*>(rU + node[u]);
+      const double2* s2 = reinterpret_cast<const double2*>(rO + node[u]);
+      cp_async16(d + 0 * NL * 16, s0);
+      cp_async16(d + 1 * NL * 16, s0 + 1);
+      cp_async16(d + 2 * NL * 16, s1);
+      cp_async16(d + 3 * NL * 16, s1 + 1);
+      cp_async16(d + 4 * NL * 16, s2);
+      if constexpr (DIM == 3) cp_async8(nsa + 5 * NL * 16 + i * 8u, s2 + 1);
+      cp_async8(nsa + (unsigned)(5 * NL * 16 + NL * 8) + i * 8u, reinterpret_cast<const double*>(rT + node[u]) + 3);
+    }
+  }
+}
+
+template <int DIM>
+struct TracerSide {
+  double T[DIM], A[DIM], C[DIM];
+  double T0, a0, c0, rhs;
+  double cU0[DIM];
+};
+
+template <int DIM, int QC, int NL>
+__device__ __forceinline__ void fused_step(MomState<DIM, DIM>& s, TracerSide<DIM>& q, double (&rh)[DIM], const StripConsts& km,
+                                           const StripConsts& ka, const unsigned* __restrict__ p, unsigned& pq0, unsigned& pq1,
+                                           unsigned& pq2, unsigned acc_sa, unsigned acc2_sa, unsigned nsa) {
+  const unsigned en = pq0;
+  pq0 = pq1;
+  pq1 = pq2;
+  const unsigned m = (unsigned)s.meta[QC];
+  double on[DIM];
+  load_oldu<DIM, NL>(nsa, m & 0xfff0u, on);
+  const unsigned so = (m >> 16) << 3;
+  const double slot = lds64(acc_sa + so), slot2 = lds64(acc2_sa + so);
+  const unsigned noff = en & 0xfff0u, nb = nsa + noff;
+  load_rec<DIM, NL>(nb, 0, s.X[QC], s.B[QC]);
+  load_rec<DIM, NL>(nb, 1, s.U[QC], s.R[QC]);
+  const double tnew = lds64(fused_t_sa<NL>(nsa, noff));
+  s.meta[QC] = (int)en;
+  pq2 = ldg_stream1(p + (QC + 3) * kBR);
+  prefetch_l2(p + (QC + kPlanAhead) * kBR);
+  {
+    const double a = s.A[QC];
+    sts64(acc_sa + so, slot + a);
+    sts64(acc2_sa + so, slot2 + fma(ka.dtt, q.A[QC], ka.mPo * q.C[QC]));
+#pragma unroll
+    for (int d = 0; d < DIM; d++) rh[d] = fma(-a, on[d], rh[d]);
+    s.A[QC] = 0.0;
+    q.A[QC] = 0.0;
+    q.C[QC] = 0.0;
+    q.T[QC] = tnew;
+  }
+#pragma unroll
+  for (int a = 0; a < DIM; a++) s.X[QC][a] -= s.X0[a];
+  if (en & kStagedCompute) {
+    WindowGeom<DIM> g;
+    window_geom<DIM, DIM, QC>(s.X, g);
+    mom_terms<DIM, DIM, QC, false>(s, km, g);
+    adv_terms<DIM, DIM, QC, false>(ka, g, s.U, q.cU0, q.T, q.T0, q.A, q.C, q.a0, q.c0, q.rhs);
+  }
+}
+
+template <int DIM, int Q, int NL>
+struct FusedUnroll {
+  template <class... Args>
+  static __device__ __forceinline__ void run(MomState<DIM, DIM>& s, Args&&... args) {
+    fused_step<DIM, Q, NL>(s, args...);
+    if constexpr (Q + 1 < DIM) FusedUnroll<DIM, Q + 1, NL>::run(s, args...);
+  }
+};
+
+template <int DIM, int NL>
+__global__ void __launch_bounds__(kBR, (NL <= 512 ? 3 : 2))
+staged_fused_kernel(const StripConsts km, const StripConsts ka, const StagedView P, const double4* __restrict__ rX,
+                    const double4* __restrict__ rU, const double4* __restrict__ rO, const double4* __restrict__ rT,
+                    size_t nnz, double* __restrict__ big_m, double* __restrict__ rhs, double* __restrict__ masslump,
+                    double* __restrict__ matrix, double* __restrict__ arhs) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* acc = reinterpret_cast<double*>(smem_raw);
+  double* acc2 = acc + P.maxlen * kAS;
+  const unsigned nsa = (unsigned)__cvta_generic_to_shared(smem_raw) + (unsigned)P.acc_bytes;
+  const int b = P.blocks ? P.blocks[blockIdx.x] : (int)blockIdx.x, t = threadIdx.x;
+  stage_fused<DIM, NL>(P, b, t, nsa, rX, rU, rO, rT);
+  const int r = P.rows[b * kBR + t];
+  const long long base = P.ptr[b];
+  const int deg = (int)((P.ptr[b + 1] - base) / kBR);
+  const unsigned* p = P.ent + base + t;
+  double* acc_t = acc + t;
+  double* acc2_t = acc2 + t;
+  const unsigned acc_sa = (unsigned)__cvta_generic_to_shared(acc_t), acc2_sa = (unsigned)__cvta_generic_to_shared(acc2_t);
+  for (int q = 0; q < P.maxlen; q++) acc_t[q * kAS] = acc2_t[q * kAS] = 0.0;
+  const unsigned pad = P.own_local[b * kBR + t];
+  const unsigned own_off = pad & 0xfff0u;
+  const int own = (int)(pad >> 16) / kAS;
+  unsigned pq0 = ldg_stream1(p);
+  unsigned pq1 = ldg_stream1(p + kBR);
+  unsigned pq2 = ldg_stream1(p + 2 * kBR);
+#pragma unroll
+  for (int q = 3; q < kPlanAhead; q++) prefetch_l2(p + q * kBR);
+  cp_async_commit_wait_all();
+  __syncthreads();
+  MomState<DIM, DIM> s;
+  TracerSide<DIM> q;
+  load_rec<DIM, NL>(nsa + own_off, 0, s.X0, s.b0);
+  load_rec<DIM, NL>(nsa + own_off, 1, s.U0, s.rho0);
+  q.T0 = lds64(fused_t_sa<NL>(nsa, own_off));
+  adv_row_const<DIM>(ka, s.U0, q.cU0);
+  s.a0 = s.msum = s.nbsum = 0.0;
+  q.a0 = q.c0 = q.rhs = 0.0;
+  double rh[DIM];
+#pragma unroll
+  for (int d = 0; d < DIM; d++) rh[d] = 0.0;
+#pragma unroll
+  for (int k = 0; k < DIM; k++) {
+#pragma unroll
+    for (int a = 0; a < DIM; a++) s.X[k][a] = s.U[k][a] = 0.0;
+    s.R[k] = s.B[k] = s.A[k] = 0.0;
+    q.T[k] = q.A[k] = q.C[k] = 0.0;
+    s.meta[k] = (int)pad;
+  }
+  for (int j0 = 0; j0 < deg; j0 += DIM, p += DIM * kBR)
+    FusedUnroll<DIM, 0, NL>::run(s, q, rh, km, ka, p, pq0, pq1, pq2, acc_sa, acc2_sa, nsa);
+  // drain the FIFO, then the diagonals
+#pragma unroll
+  for (int k = 0; k < DIM; k++) {
+    const unsigned m = (unsigned)s.meta[k];
+    acc_t[m >> 16] += s.A[k];
+    acc2_t[m >> 16] += fma(ka.dtt, q.A[k], ka.mPo * q.C[k]);
+    double o[DIM];
+    load_oldu<DIM, NL>(nsa, m & 0xfff0u, o);
+#pragma unroll
+    for (int d = 0; d < DIM; d++) rh[d] = fma(-s.A[k], o[d], rh[d]);
+  }
+  acc_t[own * kAS] += s.a0;
+  acc2_t[own * kAS] += fma(ka.dtt, q.a0, ka.mPd * q.c0);
+  int my_s0 = 0, my_len = 0;
+  if (r >= 0) {
+    my_s0 = P.findrm[r];
+    my_len = P.findrm[r + 1] - my_s0;
+    double ou[DIM];
+    load_oldu<DIM, NL>(nsa, own_off, ou);
+#pragma unroll
+    for (int d = 0; d < DIM; d++) {
+      rhs[(size_t)DIM * r + d] = fma(-s.a0, ou[d], fma(km.grav[d], s.nbsum, rh[d]));
+      if (masslump) masslump[(size_t)DIM * r + d] = s.msum;
+    }
+    arhs[r] = q.rhs;
+  }
+  __syncwarp();
+  // rows of the warp: the dim identical momentum blocks (dt*theta * entry + lumped mass on the diagonal) and the tracer matrix
+  const double my_mass = s.msum * km.mass_on;
+  const int lane = t & 31, wbase = t & ~31;
+  const int lpr = 1 << P.lpr_shift, rpi = 32 >> P.lpr_shift;
+  const int sub = lane >> P.lpr_shift, sl = lane & (lpr - 1);
+  for (int rr = 0; rr < 32; rr += rpi) {
+    const int src = rr + sub;
+    const int s0r = __shfl_sync(0xffffffffu, my_s0, src);
+    const int lr = __shfl_sync(0xffffffffu, my_len, src);
+    const int ownr = __shfl_sync(0xffffffffu, own, src);
+    const double mass = __shfl_sync(0xffffffffu, my_mass, src);
+    for (int ss = sl; ss < lr; ss += lpr) {
+      const double v = fma(km.dtt, acc[ss * kAS + wbase + src], ss == ownr ? mass : 0.0);
+#pragma unroll
+      for (int d = 0; d < DIM; d++) __stcs(big_m + (size_t)d * nnz + s0r + ss, v);
+      __stcs(matrix + s0r + ss, acc2[ss * kAS + wbase + src]);
+    }
+  }
+}
+
+// ---- host side ----------------------------------------------------------------------------------------
+static size_t fused_smem(const GatherPlan* P) { return staged_acc_bytes(P, 2) + (size_t)P->nl * 96; }
+
+bool strip_fused_ok(const Handle* h, const MomentumArgs& M, const AdvDiffArgs& A) {
+  const GatherPlan* P = h->gather;
+  if (h->scatter != CGASM_SCATTER_STRIP || !P || !P->staged_ok || !P->d_strip_local || getenv("CGASM_STRIP_GLOBAL") ||
+      getenv("CGASM_NO_FUSED"))
+    return false;
+  if (!strip_momentum_opts_ok(M) || strip_extra_needed(M) || strip_full_tensor(M.o.have_viscosity, M.o.viscosity_shape)) return false;
+  if (M.o.assemble_ct_matrix_here) return false;
+  if (!strip_advdiff_opts_ok(A) || strip_advdiff_needs_extra(A) || strip_full_tensor(A.o.have_diffusivity, A.o.diffusivity_shape))
+    return false;
+  return fused_smem(P) <= 110 * 1024;
+}
+
+template <int DIM>
+static int strip_fused_dim(Handle* h, const MomentumArgs& M, const AdvDiffArgs& A) {
+  GatherPlan* P = h->gather;
+  const size_t smem = fused_smem(P);
+  const StripConsts km = consts_momentum(h, M), ka = consts_advdiff(h, A);
+  StagedView v = staged_view(h, 2);
+  double* ml = M.o.assemble_inverse_masslump ? h->d_masslump : nullptr;
+  int st = CGASM_OK, grid = P->nblocks;
+#define LAUNCH_NL(NL_)                                                                                          \
+  do {                                                                                                          \
+    if ((st = strip_smem(staged_fused_kernel<DIM, NL_>, smem))) return st;                                      \
+    staged_fused_kernel<DIM, NL_><<<grid, kBR, smem, h->stream>>>(km, ka, v, h->d_rec3, h->d_rec1, h->d_rec2,   \
+                                                                  h->d_rec0, (size_t)h->nnz, h->d_big_m,        \
+                                                                  h->d_mom_rhs, ml, h->d_adv_matrix, h->d_adv_rhs); \
+    h->launches++;                                                                                              \
+  } while (0)
+  const int *ia = nullptr, *ib = nullptr;
+  int na = 0, nb = 0;
+  const bool split = halo_split(h, &ia, &na, &ib, &nb);
+  if (split) {
+    v.blocks = ia;
+    grid = na;
+    CGASM_FOR_NL(LAUNCH_NL);
+  }
+  if ((st = halo_join(h))) return st;
+  if (split) {
+    v.blocks = ib;
+    grid = nb;
+  }
+  if (grid > 0) CGASM_FOR_NL(LAUNCH_NL);
+#undef LAUNCH_NL
+  CG_CUDA(cudaGetLastError());
+  return st;
+}
+
+int strip_fused(Handle* h, const MomentumArgs& M, const AdvDiffArgs& A) {
+  h->mom_path = h->adv_path = CGASM_PATH_STRIP_STAGED;
+  return h->dim == 3 ? strip_fused_dim<3>(h, M, A) : strip_fused_dim<2>(h, M, A);
+}
+
+}  // namespace cgasm

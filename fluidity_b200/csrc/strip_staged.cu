@@ -73,23 +73,26 @@ __device__ __forceinline__ void smom_step(MomState<DIM, DIM>& s, double (&rh)[DI
   const unsigned en = pq0;
   pq0 = pq1;
   pq1 = pq2;
-  {
-    const unsigned m = (unsigned)s.meta[QC];
-    double on[DIM];
-    load_oldu<DIM, NL>(nsa, m & 0xfff0u, on);
-    const unsigned sa = acc_sa + ((m >> 16) << 3);
-    const double a = s.A[QC];
-    sts64(sa, lds64(sa) + a);
-#pragma unroll
-    for (int d = 0; d < DIM; d++) rh[d] = fma(-a, on[d], rh[d]);
-    s.A[QC] = 0.0;
-  }
+  // every shared-memory read of the step is issued before the first one is consumed (one exposed LDS latency per
+  // step instead of three): the evicted node's oldu and slot, then the records of the node that takes its buffer
+  const unsigned m = (unsigned)s.meta[QC];
+  double on[DIM];
+  load_oldu<DIM, NL>(nsa, m & 0xfff0u, on);
+  const unsigned sa = acc_sa + ((m >> 16) << 3);
+  const double slot = lds64(sa);
   const unsigned nb = nsa + (en & 0xfff0u);
   load_rec<DIM, NL>(nb, 0, s.X[QC], s.B[QC]);
   load_rec<DIM, NL>(nb, 1, s.U[QC], s.R[QC]);
   s.meta[QC] = (int)en;
   pq2 = ldg_stream1(p + (QC + 3) * kBR);
   prefetch_l2(p + (QC + kPlanAhead) * kBR);
+  {
+    const double a = s.A[QC];
+    sts64(sa, slot + a);
+#pragma unroll
+    for (int d = 0; d < DIM; d++) rh[d] = fma(-a, on[d], rh[d]);
+    s.A[QC] = 0.0;
+  }
 #pragma unroll
   for (int a = 0; a < DIM; a++) s.X[QC][a] -= s.X0[a];
   if (en & kStagedCompute) mom_compute<DIM, DIM, QC, FULLV>(s, k_);
@@ -206,16 +209,15 @@ __device__ __forceinline__ void sadv_step(AdvState<DIM, DIM>& s, double (&sg)[AB
   const unsigned en = pq0;
   pq0 = pq1;
   pq1 = pq2;
-  {
-    const unsigned sa = acc_sa + (((unsigned)s.meta[QC] >> 16) << 3);
-    sts64(sa, lds64(sa) + fma(k_.dtt, s.A[QC], k_.mPo * s.C[QC]));
-    s.A[QC] = 0.0;
-    s.C[QC] = 0.0;
-  }
+  const unsigned sa = acc_sa + (((unsigned)s.meta[QC] >> 16) << 3);
+  const double slot = lds64(sa);
   const unsigned nb = nsa + (en & 0xfff0u);
   double unused;
   load_rec<DIM, NL>(nb, 0, s.X[QC], s.T[QC]);
   load_rec<DIM, NL>(nb, 1, s.U[QC], unused);
+  sts64(sa, slot + fma(k_.dtt, s.A[QC], k_.mPo * s.C[QC]));
+  s.A[QC] = 0.0;
+  s.C[QC] = 0.0;
   if constexpr (ABS) {
     const double2 e = lds128(nb + (unsigned)(4 * NL * 16));
     sg[QC] = e.x;
@@ -270,8 +272,12 @@ staged_advdiff_kernel(const StripConsts k_, const StagedView P, const double4* _
   __syncthreads();
   AdvState<DIM, DIM> s;
   double unused;
-  load_rec<DIM, NL>(nsa + own_off, 0, s.X0, s.T0);
-  load_rec<DIM, NL>(nsa + own_off, 1, s.U0, unused);
+  {
+    double U0[DIM];
+    load_rec<DIM, NL>(nsa + own_off, 0, s.X0, s.T0);
+    load_rec<DIM, NL>(nsa + own_off, 1, U0, unused);
+    adv_row_const<DIM>(k_, U0, s.cU0);
+  }
   s.a0 = s.c0 = s.rhs = 0.0;
   double sg[ABS ? DIM : 1], sq[ABS ? DIM : 1];
   AdvOwnExtra ox;

@@ -18,7 +18,7 @@ module cgasm_interface
   public :: cgasm_create, cgasm_destroy, cgasm_set_coordinates, cgasm_set_sparsity, &
        & cgasm_build_sparsity, cgasm_get_sparsity, cgasm_set_colouring, cgasm_build_colouring, &
        & cgasm_get_colouring, cgasm_set_scatter, cgasm_set_field, cgasm_get_field, &
-       & cgasm_momentum, cgasm_advdiff, cgasm_momentum_dev, cgasm_advdiff_dev, &
+       & cgasm_momentum, cgasm_advdiff, cgasm_momentum_dev, cgasm_advdiff_dev, cgasm_momentum_advdiff_dev, &
        & cgasm_momentum_fetch, cgasm_advdiff_fetch, cgasm_momentum_identical_blocks, &
        & cgasm_momentum_fetch_blocks, cgasm_momentum_element, &
        & cgasm_advdiff_element, cgasm_synchronize, cgasm_set_async, cgasm_halo_create, cgasm_halo_update, cgasm_halo_set_overlap, &
@@ -194,6 +194,15 @@ module cgasm_interface
        type(cgasm_advdiff_opts), intent(in) :: opts
        integer(c_int) :: stat
      end function cgasm_advdiff_dev
+
+     function cgasm_momentum_advdiff_dev(id, mopts, aopts) bind(c, name="cgasm_momentum_advdiff_dev") result(stat)
+       use iso_c_binding
+       import :: cgasm_momentum_opts, cgasm_advdiff_opts
+       integer(c_int), value :: id
+       type(cgasm_momentum_opts), intent(in) :: mopts
+       type(cgasm_advdiff_opts), intent(in) :: aopts
+       integer(c_int) :: stat
+     end function cgasm_momentum_advdiff_dev
 
      function cgasm_momentum_fetch(id, big_m, rhs, masslump, ct_m) bind(c, name="cgasm_momentum_fetch") result(stat)
        use iso_c_binding

@@ -218,6 +218,13 @@ int cgasm_advdiff(int id, const cgasm_advdiff_opts* opts, double* matrix_val, do
  * The *_fetch calls copy the last result to host buffers. */
 int cgasm_momentum_dev(int id, const cgasm_momentum_opts* opts);
 int cgasm_advdiff_dev(int id, const cgasm_advdiff_opts* opts);
+/* Both element loops of a time step in one call (a tracer advected by the same nonlinear velocity the momentum
+ * equation uses). When both option sets are the common ones of the STRIP variant -- lumped or excluded momentum mass,
+ * plain advection, constant isotropic viscosity / diffusivity, constant gravity direction, no absorption or sources,
+ * no ct_m -- ONE kernel assembles both systems (shared strip, staged node records and element geometry); any other
+ * combination runs cgasm_momentum_dev then cgasm_advdiff_dev. The results are those of the two calls; fetch them
+ * with cgasm_momentum_fetch / cgasm_advdiff_fetch. cgasm_last_kernel_ms afterwards covers the whole call. */
+int cgasm_momentum_advdiff_dev(int id, const cgasm_momentum_opts* mopts, const cgasm_advdiff_opts* aopts);
 int cgasm_momentum_fetch(int id, double* big_m, double* rhs, double* masslump, double* ct_m);
 int cgasm_advdiff_fetch(int id, double* matrix_val, double* rhs);
 /* 1 if the dim diagonal blocks of the last momentum result are identical (no absorption term:
@@ -338,6 +345,18 @@ int cgasm_synchronize(int id);
 int cgasm_stream(int id, void** stream);
 /* Number of CUDA kernels this library has launched on the handle so far. */
 int cgasm_launch_count(int id, long long* launches);
+/* Which kernel family the most recent cgasm_momentum_dev / cgasm_advdiff_dev ran (diagnostics: the option set
+ * decides whether a scatter variant's own kernels apply or a slower general path of the same variant). */
+enum cgasm_path {
+  CGASM_PATH_NONE = 0,
+  CGASM_PATH_ELEMENT = 1,       /* thread per element: ATOMIC / COLOURED / WARPAGG */
+  CGASM_PATH_TILED = 2,
+  CGASM_PATH_GATHER_STAGED = 3, /* two passes: element kernel -> row records -> row kernel */
+  CGASM_PATH_GATHER_ROWS = 4,   /* single-pass row kernels (direct / walk) */
+  CGASM_PATH_STRIP = 5,         /* strip kernels, node records fetched per entry */
+  CGASM_PATH_STRIP_STAGED = 6   /* strip kernels, node records staged in shared memory (+ additive passes) */
+};
+int cgasm_last_path(int id, int* momentum_path, int* advdiff_path);
 /* Device time in ms of the most recent cgasm_*_dev call (CUDA events on the handle stream). */
 int cgasm_last_kernel_ms(int id, float* ms);
 

@@ -404,11 +404,53 @@ def test_strip_additive_pass_constant_density(orc, dim, variant):
     findrm, colm, _ = asm.get_sparsity()
     l0 = asm.launch_count()
     got = asm.momentum(o)
-    # one common kernel + one additive pass: not the two-pass GATHER staging path (3 launches and more)
-    assert asm.launch_count() - l0 == 2, "the option set did not take the STRIP kernels"
+    # the common kernel + the additive passes it needs (per-row pass: lumped absorption / sources / reference profile;
+    # per-component pass: full absorption matrix), not the two-pass GATHER staging path (element kernel + row kernel)
+    full = bool(o.have_absorption and not o.lump_absorption)
+    light = bool((o.have_absorption and o.lump_absorption) or o.have_source or (o.have_gravity and o.subtract_out_reference_profile))
+    assert asm.launch_count() - l0 == 1 + int(full) + int(light), "the option set did not take the STRIP kernels"
+    assert asm.last_path()[0] == "strip_staged"
     ref = orc.assemble_momentum(mesh, fs, o, findrm, colm, want_masslump=bool(o.assemble_inverse_masslump))
     check_momentum(got, ref, findrm, dim)
     # a second assembly overwrites, it does not accumulate on top of the first
     got2 = asm.momentum(o)
     for k in ("big_m", "rhs"):
         assert (got2[k] == got[k]).all()
+
+
+# ---- both loops in one call ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dim", [2, 3])
+@pytest.mark.parametrize("case", ["common", "excluded_mass_lumped_tracer", "no_gravity_no_ml", "fallback_absorption",
+                                  "fallback_tensor"])
+def test_fused_momentum_tracer_call_equals_the_two_calls(orc, dim, case):
+    """cgasm_momentum_advdiff_dev: one fused STRIP kernel for the common option sets (same device functions, same
+    operand order as the separate kernels: the results must be BITWISE those of the two calls), the two loops one
+    after the other for anything else."""
+    mesh = syn.box_mesh((7, 5, 4)[:dim], seed=35)
+    fs = syn.standard_fields(mesh)
+    cm, ca = abi.common_momentum_opts, abi.common_advdiff_opts
+    om, oa, fused = {
+        "common": (cm(), ca(), True),
+        "excluded_mass_lumped_tracer": (cm(exclude_mass=1), ca(lump_mass=1), True),
+        "no_gravity_no_ml": (cm(have_gravity=0, assemble_inverse_masslump=0), ca(have_diffusivity=0), True),
+        "fallback_absorption": (cm(), ca(have_absorption=1), False),
+        "fallback_tensor": (cm(viscosity_shape=abi.TENSOR_FULL), ca(), False),
+    }[case]
+    asm = make_asm(mesh, fs, abi.SCATTER_STRIP)
+    findrm, colm, _ = asm.get_sparsity()
+    asm.momentum_dev(om)
+    asm.advdiff_dev(oa)
+    want_ml = bool(om.assemble_inverse_masslump)
+    sep_m, sep_a = asm.momentum_fetch(want_masslump=want_ml), asm.advdiff_fetch()
+    l0 = asm.launch_count()
+    asm.momentum_advdiff_dev(om, oa)
+    assert asm.launch_count() - l0 == (1 if fused else 2)
+    got_m, got_a = asm.momentum_fetch(want_masslump=want_ml), asm.advdiff_fetch()
+    for k in ("big_m", "rhs") + (("masslump",) if want_ml else ()):
+        assert (got_m[k] == sep_m[k]).all(), k
+    for k in ("matrix", "rhs"):
+        assert (got_a[k] == sep_a[k]).all(), k
+    ref_m = orc.assemble_momentum(mesh, fs, om, findrm, colm, want_masslump=want_ml)
+    ref_a = orc.assemble_advdiff(mesh, fs, oa, findrm, colm)
+    check_momentum(got_m, ref_m, findrm, dim)
+    assert rel_err(got_a["matrix"], ref_a["matrix"]) < TOL and rel_err(got_a["rhs"], ref_a["rhs"]) < TOL
