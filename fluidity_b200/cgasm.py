@@ -391,6 +391,26 @@ class Assembler:
         _check(self.lib.cgasm_last_path(C.c_int(self.id), C.byref(m), C.byref(a)))
         return self.PATHS[m.value], self.PATHS[a.value]
 
+    # -- device hand-off to PETSc (COO triplets in universal numbering) --------------------------------
+    def coo_pattern(self, which, row_gnn2unn, col_gnn2unn=None, compact=False):
+        """which: 0 momentum (dim diagonal blocks), 1 tracer. gnn2unn: (n_nodes, nfields) int array as
+        petsc_numbering%gnn2unn (0-based, -1 = masked). Returns ncoo; the device pointers stay with the handle."""
+        r = np.asfortranarray(np.asarray(row_gnn2unn, dtype=np.int32))
+        c = np.asfortranarray(np.asarray(col_gnn2unn, dtype=np.int32)) if col_gnn2unn is not None else None
+        n = C.c_longlong(0)
+        pi, pj = C.c_void_p(), C.c_void_p()
+        _check(self.lib.cgasm_coo_pattern_dev(C.c_int(self.id), C.c_int(which), r.ctypes.data_as(c_ip),
+                                              c.ctypes.data_as(c_ip) if c is not None else None, C.c_int(1 if compact else 0),
+                                              C.byref(n), C.byref(pi), C.byref(pj)))
+        return n.value
+
+    def coo_fetch(self, which, ncoo):
+        i = np.empty(ncoo, dtype=np.int32)
+        j = np.empty(ncoo, dtype=np.int32)
+        v = np.empty(ncoo)
+        _check(self.lib.cgasm_coo_fetch(C.c_int(self.id), C.c_int(which), C.c_longlong(ncoo), _ip(i), _ip(j), _dp(v)))
+        return i, j, v
+
     def halo_set_overlap(self, on):
         _check(self.lib.cgasm_halo_set_overlap(C.c_int(self.id), C.c_int(1 if on else 0)))
 

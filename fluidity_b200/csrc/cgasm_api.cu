@@ -141,6 +141,7 @@ static void destroy_handle(Handle* h) {
   halo_free(h);
   surface_free(h);
   cmc_free(h);
+  coo_free(h);
   free_dev(h->d_ndglno);
   free_dev(h->d_X);
   free_dev(h->d_rec0);
@@ -195,6 +196,7 @@ static int upload_sparsity(Handle* h) {
   tiles_free(h);
   gather_free(h);
   cmc_free(h);
+  coo_free(h);
   return CGASM_OK;
 }
 

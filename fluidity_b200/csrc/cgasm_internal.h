@@ -48,6 +48,7 @@ struct GatherPlan;  // gather.cu
 struct HaloPlan;  // halo.cu
 struct SurfacePlan;  // surface.cu
 struct CmcPlan;  // cmc.cu
+struct CooPlan;  // coo.cu
 
 struct Handle {
   int device = 0;
@@ -103,6 +104,7 @@ struct Handle {
   HaloPlan* halo = nullptr;
   SurfacePlan* surface = nullptr;
   CmcPlan* cmc = nullptr;
+  CooPlan* coo[2] = {nullptr, nullptr};  // CGASM_COO_MOMENTUM, CGASM_COO_TRACER
 
   long long launches = 0;
   int mom_path = 0, adv_path = 0;  // CGASM_PATH_* of the last assembly (cgasm_last_path)
@@ -231,6 +233,9 @@ void surface_free(Handle* h);
 
 // cmc.cu
 void cmc_free(Handle* h);
+
+// coo.cu
+void coo_free(Handle* h);
 
 // cgasm_api.cu: refresh the packed record lanes fed by `slot` (-1 = coordinates); nodes == nullptr
 // repacks every node, else only the listed ones (device array of 0-based node ids).

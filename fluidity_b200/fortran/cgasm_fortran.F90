@@ -22,6 +22,7 @@ module cgasm_interface
        & cgasm_momentum_fetch, cgasm_advdiff_fetch, cgasm_momentum_identical_blocks, &
        & cgasm_momentum_fetch_blocks, cgasm_momentum_element, &
        & cgasm_advdiff_element, cgasm_synchronize, cgasm_set_async, cgasm_halo_create, cgasm_halo_update, cgasm_halo_set_overlap, &
+       & cgasm_coo_pattern_dev, cgasm_coo_values_dev, cgasm_coo_fetch, &
        & cgasm_nccl_unique_id, cgasm_last_error, cgasm_set_surface, cgasm_advdiff_surface_dev, &
        & cgasm_advdiff_dirichlet_dev, cgasm_momentum_surface_dev, cgasm_cmc_build_sparsity, &
        & cgasm_cmc_get_sparsity, cgasm_cmc_set_sparsity, cgasm_cmc_dev, cgasm_cmc_fetch
@@ -382,6 +383,35 @@ module cgasm_interface
        integer(c_int), value :: on
        integer(c_int) :: stat
      end function cgasm_halo_set_overlap
+
+     ! device hand-off to PETSc: the (i, j) pattern once per sparsity for MatSetPreallocationCOO, the values per assembly
+     ! for MatSetValuesCOO. row_gnn2unn / col_gnn2unn = petsc_numbering%gnn2unn of the matrix (col: c_null_ptr = rows).
+     function cgasm_coo_pattern_dev(id, which, row_gnn2unn, col_gnn2unn, compact, ncoo, coo_i_dev, coo_j_dev) &
+          & bind(c, name="cgasm_coo_pattern_dev") result(stat)
+       use iso_c_binding
+       integer(c_int), value :: id, which
+       integer(c_int), intent(in) :: row_gnn2unn(*)
+       type(c_ptr), value :: col_gnn2unn
+       integer(c_int), value :: compact
+       integer(c_long_long), intent(out) :: ncoo
+       type(c_ptr), intent(out) :: coo_i_dev, coo_j_dev
+       integer(c_int) :: stat
+     end function cgasm_coo_pattern_dev
+
+     function cgasm_coo_values_dev(id, which, coo_v_dev) bind(c, name="cgasm_coo_values_dev") result(stat)
+       use iso_c_binding
+       integer(c_int), value :: id, which
+       type(c_ptr), intent(out) :: coo_v_dev
+       integer(c_int) :: stat
+     end function cgasm_coo_values_dev
+
+     function cgasm_coo_fetch(id, which, ncoo, coo_i, coo_j, coo_v) bind(c, name="cgasm_coo_fetch") result(stat)
+       use iso_c_binding
+       integer(c_int), value :: id, which
+       integer(c_long_long), value :: ncoo
+       type(c_ptr), value :: coo_i, coo_j, coo_v
+       integer(c_int) :: stat
+     end function cgasm_coo_fetch
   end interface
 
 end module cgasm_interface

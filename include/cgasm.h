@@ -377,6 +377,28 @@ int cgasm_row_blocks_host(int dim, int n_nodes, int n_elements, const int* ndgln
                           int block_rows, int* rows, int capacity_blocks, int* nblocks,
                           double* lattice_scale);
 
+/* ---- device hand-off to PETSc (femtools/Sparse_Tools_Petsc.F90:848-879, femtools/Petsc_Tools.F90:141-306) --------
+ * The assembled matrices as COO triplets in PETSc's universal numbering, on the device, in the layout
+ * MatSetPreallocationCOO(A, ncoo, i, j) / MatSetValuesCOO(A, v, INSERT_VALUES) take (device pointers with PETSc's
+ * CUDA matrix types): no host round trip of the values.
+ *   which        CGASM_COO_MOMENTUM: the dim diagonal blocks of big_m, entries ordered [block d][CSR entry];
+ *                CGASM_COO_TRACER: the tracer matrix.
+ *   row_gnn2unn  petsc_numbering%gnn2unn(n_nodes, nfields) of the rows as Fluidity built it (column-major, 0-based
+ *                universal numbers; nfields = dim for big_m, 1 for the tracer); -1 = masked (the rows of nodes this
+ *                process does not own, Sparse_Tools_Petsc.F90:220-227, and ghost nodes, Petsc_Tools.F90:255-297).
+ *   col_gnn2unn  the column numbering, NULL = the row numbering.
+ *   compact      0: ncoo = nblocks * nnz, masked entries keep index -1 (PETSc ignores negative indices) and the values
+ *                   are the assembly's own result buffer (cgasm_coo_values_dev returns it: zero copy);
+ *                1: masked entries are removed; cgasm_coo_values_dev gathers the values with one kernel per call.
+ * The pattern belongs to the current sparsity: cgasm_build_sparsity / cgasm_set_sparsity drop it. */
+enum cgasm_coo_matrix { CGASM_COO_MOMENTUM = 0, CGASM_COO_TRACER = 1 };
+int cgasm_coo_pattern_dev(int id, int which, const int* row_gnn2unn, const int* col_gnn2unn, int compact,
+                          long long* ncoo, int** coo_i_dev, int** coo_j_dev);
+/* Values of the most recent assembly in the order of the pattern (device pointer, valid until the next assembly). */
+int cgasm_coo_values_dev(int id, int which, double** coo_v_dev);
+/* The same triplets copied to the host (any of the three may be NULL): for callers without a CUDA-aware PETSc. */
+int cgasm_coo_fetch(int id, int which, long long ncoo, int* coo_i, int* coo_j, double* coo_v);
+
 /* Diagnostics (host only, no GPU): wall-clock seconds of the host phases of a handle's set-up on this mesh --
  * times(6) = connectivity conversion, node->element adjacency, sparsity, Morton order, row blocks, strip plans
  * (the staged STRIP plan); entries_per_pair (may be NULL) = strip entries per (row, element) pair. */

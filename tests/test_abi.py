@@ -149,3 +149,38 @@ def test_plain_c_client_compiles_links_and_is_refused_without_a_gpu(tmp_path):
                    check=True)
     p = subprocess.run([str(exe)], capture_output=True, text=True)
     assert p.returncode == abi.ENODEVICE and "no CPU path" in p.stderr and p.stdout == ""
+
+
+@pytest.mark.gpu
+def test_plain_c_client_runs_on_the_gpu_and_prints_the_oracles_matrix(tmp_path, orc):
+    """examples/c_client.c built with gcc against the header and the shared library only, RUN on the B200: the matrix and
+    right-hand side it prints (two triangles, default tracer options) are the oracle's."""
+    exe = tmp_path / "c_client"
+    libdir = os.path.join(ROOT, "fluidity_b200")
+    subprocess.run(["/usr/bin/gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "examples", "c_client.c"), "-L", libdir, "-lcgasm", "-Wl,-rpath," + libdir, "-o", str(exe)],
+                   check=True)
+    p = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr
+    rows = [ln for ln in p.stdout.splitlines() if ln.startswith("row ")]
+    assert len(rows) == 4
+    mesh = syn.Mesh(dim=2, ndglno=np.array([[1, 2, 3], [2, 4, 3]], dtype=np.int32),
+                    X=np.array([[0, 0], [1, 0], [0, 1], [1, 1]], dtype=np.float64))
+    fs = syn.FieldSet()
+    fs.set(abi.F_T, np.array([0.0, 1.0, 0.5, 0.25]))
+    fs.set(abi.F_NU, np.array([[1.0, 0.0]] * 4))
+    fs.set(abi.F_T_DIFFUSIVITY, np.array([[[1e-3, 0.0], [0.0, 1e-3]]]), abi.FIELD_CONSTANT)
+    o = abi.common_advdiff_opts()
+    findrm, colm, _ = orc.make_sparsity(mesh)
+    ref = orc.assemble_advdiff(mesh, fs, o, findrm, colm)
+    got_vals, got_rhs, got_cols = [], [], []
+    for ln in rows:
+        body, rhs = ln.split("| rhs")
+        got_rhs.append(float(rhs))
+        for col, val in re.findall(r"\((\d+)\)\s+(\S+)", body):
+            got_cols.append(int(col))
+            got_vals.append(float(val))
+    assert got_cols == list(colm)
+    # the client prints 7 significant digits
+    assert np.abs(np.array(got_vals) - ref["matrix"]).max() <= 1e-6 * np.abs(ref["matrix"]).max()
+    assert np.abs(np.array(got_rhs) - ref["rhs"]).max() <= 1e-6 * np.abs(ref["rhs"]).max()
