@@ -45,6 +45,7 @@ struct GatherPlan {
   long long* d_strip_local_ptr = nullptr;  // [nblocks+1] into d_strip_local (degrees padded to a multiple of dim)
   unsigned* d_strip_local = nullptr; // block-interleaved like d_strip, kStagedTailRows rows of padding at the end
   unsigned* d_own_local = nullptr;   // [nblocks*kBR] own node in the same encoding (compute = 0)
+  int4* d_row_meta = nullptr;        // [nblocks*kBR] {row node, first CSR entry, length | own slot << 16, own_local}
   int blk_nodes_max = 0;
   int nl = 0;                        // chunk stride of the staged records (one of kStagedNL)
   bool staged_ok = false;            // the mesh fits the staged encoding

@@ -334,6 +334,8 @@ int strip_build(Handle* h) {
     CG_CUDA(cudaMemcpyAsync(P->d_strip_local_ptr, sp.ptr.data(), sizeof(long long) * sp.ptr.size(), cudaMemcpyHostToDevice, h->stream));
     CG_CUDA(cudaMalloc(&P->d_own_local, sizeof(unsigned) * sp.own_local.size()));
     CG_CUDA(cudaMemcpyAsync(P->d_own_local, sp.own_local.data(), sizeof(unsigned) * sp.own_local.size(), cudaMemcpyHostToDevice, h->stream));
+    CG_CUDA(cudaMalloc(&P->d_row_meta, sizeof(int) * sp.row_meta.size()));
+    CG_CUDA(cudaMemcpyAsync(P->d_row_meta, sp.row_meta.data(), sizeof(int) * sp.row_meta.size(), cudaMemcpyHostToDevice, h->stream));
     CG_CUDA(cudaStreamSynchronize(h->stream));  // the host vectors go out of scope
     P->nl = sp.nl;
     P->staged_ok = true;
@@ -349,6 +351,8 @@ void strip_free(GatherPlan* P) {
   if (P->d_blk_nodes) cudaFree(P->d_blk_nodes);
   if (P->d_strip_local) cudaFree(P->d_strip_local);
   if (P->d_own_local) cudaFree(P->d_own_local);
+  if (P->d_row_meta) cudaFree(P->d_row_meta);
+  P->d_row_meta = nullptr;
   P->d_strip_ptr = nullptr;
   P->d_strip = nullptr;
   P->d_strip_local_ptr = nullptr;

@@ -20,30 +20,24 @@ __device__ __forceinline__ unsigned fused_t_sa(unsigned nsa, unsigned noff) {
 }
 
 template <int DIM, int NL>
-__device__ __forceinline__ void stage_fused(const StagedView& P, int b, int t, unsigned nsa, const double4* __restrict__ rX,
+__device__ __forceinline__ void stage_fused(const BlockIds<NL>& ids, int t, unsigned nsa, const double4* __restrict__ rX,
                                             const double4* __restrict__ rU, const double4* __restrict__ rO,
                                             const double4* __restrict__ rT) {
-  const int* ids = P.blk_nodes + (size_t)b * NL;
-  constexpr int U = NL / kBR >= 2 ? 2 : 1;
-  for (int i0 = t; i0 < NL; i0 += U * kBR) {
-    int node[U];
 #pragma unroll
-    for (int u = 0; u < U; u++) node[u] = i0 + u * kBR < NL ? __ldg(ids + i0 + u * kBR) : -1;
-#pragma unroll
-    for (int u = 0; u < U; u++) {
-      if (node[u] < 0) continue;
-      const unsigned i = (unsigned)(i0 + u * kBR), d = nsa + i * 16u;
-      const double2* s0 = reinterpret_cast<const double2*>(rX + node[u]);
-      const double2* s1 = reinterpret_cast<const double2*>(rU + node[u]);
-      const double2* s2 = reinterpret_cast<const double2*>(rO + node[u]);
-      cp_async16(d + 0 * NL * 16, s0);
-      cp_async16(d + 1 * NL * 16, s0 + 1);
-      cp_async16(d + 2 * NL * 16, s1);
-      cp_async16(d + 3 * NL * 16, s1 + 1);
-      cp_async16(d + 4 * NL * 16, s2);
-      if constexpr (DIM == 3) cp_async8(nsa + 5 * NL * 16 + i * 8u, s2 + 1);
-      cp_async8(nsa + (unsigned)(5 * NL * 16 + NL * 8) + i * 8u, reinterpret_cast<const double*>(rT + node[u]) + 3);
-    }
+  for (int u = 0; u < BlockIds<NL>::PER; u++) {
+    const int node = ids.node[u];
+    if (node < 0) continue;
+    const unsigned i = (unsigned)(t + u * kBR), d = nsa + i * 16u;
+    const double2* s0 = reinterpret_cast<const double2*>(rX + node);
+    const double2* s1 = reinterpret_cast<const double2*>(rU + node);
+    const double2* s2 = reinterpret_cast<const double2*>(rO + node);
+    cp_async16(d + 0 * NL * 16, s0);
+    cp_async16(d + 1 * NL * 16, s0 + 1);
+    cp_async16(d + 2 * NL * 16, s1);
+    cp_async16(d + 3 * NL * 16, s1 + 1);
+    cp_async16(d + 4 * NL * 16, s2);
+    if constexpr (DIM == 3) cp_async8(nsa + 5 * NL * 16 + i * 8u, s2 + 1);
+    cp_async8(nsa + (unsigned)(5 * NL * 16 + NL * 8) + i * 8u, reinterpret_cast<const double*>(rT + node) + 3);
   }
 }
 
@@ -56,11 +50,9 @@ struct TracerSide {
 
 template <int DIM, int QC, int NL>
 __device__ __forceinline__ void fused_step(MomState<DIM, DIM>& s, TracerSide<DIM>& q, double (&rh)[DIM], const StripConsts& km,
-                                           const StripConsts& ka, const unsigned* __restrict__ p, unsigned& pq0, unsigned& pq1,
-                                           unsigned& pq2, unsigned acc_sa, unsigned acc2_sa, unsigned nsa) {
-  const unsigned en = pq0;
-  pq0 = pq1;
-  pq1 = pq2;
+                                           const StripConsts& ka, const unsigned* __restrict__ p, unsigned (&pq)[DIM],
+                                           unsigned acc_sa, unsigned acc2_sa, unsigned nsa) {
+  const unsigned en = pq[QC];
   const unsigned m = (unsigned)s.meta[QC];
   double on[DIM];
   load_oldu<DIM, NL>(nsa, m & 0xfff0u, on);
@@ -71,7 +63,7 @@ __device__ __forceinline__ void fused_step(MomState<DIM, DIM>& s, TracerSide<DIM
   load_rec<DIM, NL>(nb, 1, s.U[QC], s.R[QC]);
   const double tnew = lds64(fused_t_sa<NL>(nsa, noff));
   s.meta[QC] = (int)en;
-  pq2 = ldg_stream1(p + (QC + 3) * kBR);
+  pq[QC] = ldg_stream1(p + (QC + DIM) * kBR);
   prefetch_l2(p + (QC + kPlanAhead) * kBR);
   {
     const double a = s.A[QC];
@@ -113,24 +105,29 @@ staged_fused_kernel(const StripConsts km, const StripConsts ka, const StagedView
   double* acc = reinterpret_cast<double*>(smem_raw);
   double* acc2 = acc + P.maxlen * kAS;
   const unsigned nsa = (unsigned)__cvta_generic_to_shared(smem_raw) + (unsigned)P.acc_bytes;
+  const unsigned tbl_sa = nsa + (unsigned)(NL * 96);
   const int b = P.blocks ? P.blocks[blockIdx.x] : (int)blockIdx.x, t = threadIdx.x;
-  stage_fused<DIM, NL>(P, b, t, nsa, rX, rU, rO, rT);
-  const int r = P.rows[b * kBR + t];
-  const long long base = P.ptr[b];
-  const int deg = (int)((P.ptr[b + 1] - base) / kBR);
-  const unsigned* p = P.ent + base + t;
+  BlockIds<NL> ids;
+  issue_block_ids<NL>(P, b, t, ids);
+  const int4 meta = ldg_nc_v4(P.row_meta + (size_t)b * kBR + t);
+  const long long base = ldg_nc_s64(P.ptr + b), end = ldg_nc_s64(P.ptr + b + 1);
+  prefetch_next_block<NL>(P, b, t);
   double* acc_t = acc + t;
   double* acc2_t = acc2 + t;
   const unsigned acc_sa = (unsigned)__cvta_generic_to_shared(acc_t), acc2_sa = (unsigned)__cvta_generic_to_shared(acc2_t);
   for (int q = 0; q < P.maxlen; q++) acc_t[q * kAS] = acc2_t[q * kAS] = 0.0;
-  const unsigned pad = P.own_local[b * kBR + t];
-  const unsigned own_off = pad & 0xfff0u;
-  const int own = (int)(pad >> 16) / kAS;
-  unsigned pq0 = ldg_stream1(p);
-  unsigned pq1 = ldg_stream1(p + kBR);
-  unsigned pq2 = ldg_stream1(p + 2 * kBR);
+  stage_fused<DIM, NL>(ids, t, nsa, rX, rU, rO, rT);
+  const int deg = (int)((end - base) / kBR);
+  const unsigned* p = P.ent + base + t;
+  unsigned pq[DIM];
 #pragma unroll
-  for (int q = 3; q < kPlanAhead; q++) prefetch_l2(p + q * kBR);
+  for (int q = 0; q < DIM; q++) pq[q] = ldg_stream1(p + q * kBR);
+#pragma unroll
+  for (int q = DIM; q < kPlanAhead; q++) prefetch_l2(p + q * kBR);
+  const int r = meta.x;
+  const unsigned pad = (unsigned)meta.w;
+  const unsigned own_off = pad & 0xfff0u;
+  const int own = meta.z >> 16;
   cp_async_commit_wait_all();
   __syncthreads();
   MomState<DIM, DIM> s;
@@ -153,7 +150,7 @@ staged_fused_kernel(const StripConsts km, const StripConsts ka, const StagedView
     s.meta[k] = (int)pad;
   }
   for (int j0 = 0; j0 < deg; j0 += DIM, p += DIM * kBR)
-    FusedUnroll<DIM, 0, NL>::run(s, q, rh, km, ka, p, pq0, pq1, pq2, acc_sa, acc2_sa, nsa);
+    FusedUnroll<DIM, 0, NL>::run(s, q, rh, km, ka, p, pq, acc_sa, acc2_sa, nsa);
   // drain the FIFO, then the diagonals
 #pragma unroll
   for (int k = 0; k < DIM; k++) {
@@ -167,10 +164,7 @@ staged_fused_kernel(const StripConsts km, const StripConsts ka, const StagedView
   }
   acc_t[own * kAS] += s.a0;
   acc2_t[own * kAS] += fma(ka.dtt, q.a0, ka.mPd * q.c0);
-  int my_s0 = 0, my_len = 0;
   if (r >= 0) {
-    my_s0 = P.findrm[r];
-    my_len = P.findrm[r + 1] - my_s0;
     double ou[DIM];
     load_oldu<DIM, NL>(nsa, own_off, ou);
 #pragma unroll
@@ -180,29 +174,18 @@ staged_fused_kernel(const StripConsts km, const StripConsts ka, const StagedView
     }
     arhs[r] = q.rhs;
   }
+  // rows of the warp: the dim identical momentum blocks (dt*theta * entry + lumped mass on the diagonal), then the tracer matrix
+  row_table_store(tbl_sa, t, meta.y, meta.z, s.msum * km.mass_on);
   __syncwarp();
-  // rows of the warp: the dim identical momentum blocks (dt*theta * entry + lumped mass on the diagonal) and the tracer matrix
-  const double my_mass = s.msum * km.mass_on;
-  const int lane = t & 31, wbase = t & ~31;
-  const int lpr = 1 << P.lpr_shift, rpi = 32 >> P.lpr_shift;
-  const int sub = lane >> P.lpr_shift, sl = lane & (lpr - 1);
-  for (int rr = 0; rr < 32; rr += rpi) {
-    const int src = rr + sub;
-    const int s0r = __shfl_sync(0xffffffffu, my_s0, src);
-    const int lr = __shfl_sync(0xffffffffu, my_len, src);
-    const int ownr = __shfl_sync(0xffffffffu, own, src);
-    const double mass = __shfl_sync(0xffffffffu, my_mass, src);
-    for (int ss = sl; ss < lr; ss += lpr) {
-      const double v = fma(km.dtt, acc[ss * kAS + wbase + src], ss == ownr ? mass : 0.0);
-#pragma unroll
-      for (int d = 0; d < DIM; d++) __stcs(big_m + (size_t)d * nnz + s0r + ss, v);
-      __stcs(matrix + s0r + ss, acc2[ss * kAS + wbase + src]);
-    }
-  }
+  write_rows_table<DIM>(acc, tbl_sa, t, km.dtt, P.lpr_shift, nnz, big_m);
+  __syncwarp();
+  sts64(tbl_sa + (unsigned)t * 16u + 8u, 0.0);
+  __syncwarp();
+  write_rows_table<1>(acc2, tbl_sa, t, 1.0, P.lpr_shift, 0, matrix);
 }
 
 // ---- host side ----------------------------------------------------------------------------------------
-static size_t fused_smem(const GatherPlan* P) { return staged_acc_bytes(P, 2) + (size_t)P->nl * 96; }
+static size_t fused_smem(const GatherPlan* P) { return staged_acc_bytes(P, 2) + (size_t)P->nl * 96 + kBR * 16; }
 
 bool strip_fused_ok(const Handle* h, const MomentumArgs& M, const AdvDiffArgs& A) {
   const GatherPlan* P = h->gather;

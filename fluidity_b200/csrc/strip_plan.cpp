@@ -716,6 +716,7 @@ void build_staged_plan_host(const Handle* h, const std::vector<int>& rows, int n
   out.task_blocks = kTask;
   out.ent.assign((size_t)std::max(ntasks, 1), {});
   out.own_local.assign(rows.size(), 0);
+  out.row_meta.assign(rows.size() * 4, 0);
   out.ptr.assign((size_t)nblocks + 1, 0);
   std::vector<int> block_ldeg((size_t)nblocks, 0), block_nn((size_t)nblocks, 0);
   std::vector<std::vector<int>> task_nodes((size_t)std::max(ntasks, 1));  // node lists of the task's blocks, concatenated
@@ -772,6 +773,10 @@ void build_staged_plan_host(const Handle* h, const std::vector<int>& rows, int n
           }
           const unsigned ol = (unsigned)(own * kAS) << 16 | (unsigned)(*map.slot(r >= 0 ? r : 0) & 0xfff) << 4;
           out.own_local[q] = ol;
+          out.row_meta[4 * q + 0] = r;
+          out.row_meta[4 * q + 1] = r >= 0 ? h->h_findrm[r] : 0;
+          out.row_meta[4 * q + 2] = (r >= 0 ? h->h_findrm[r + 1] - h->h_findrm[r] : 0) | own << 16;
+          out.row_meta[4 * q + 3] = (int)ol;
           const int n = (int)rp[t].size();
           for (int k = 0; k < ldeg; k++) {
             unsigned lv = ol;  // padding: re-push the own node, nothing computed

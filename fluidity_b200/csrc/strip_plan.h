@@ -43,6 +43,8 @@ struct StagedPlanHost {
   int task_blocks = 0;                 // blocks per chunk of `ent`
   std::vector<std::vector<unsigned>> ent;  // entries of blocks [k*task_blocks, (k+1)*task_blocks), block-interleaved
   std::vector<unsigned> own_local;     // [nblocks*block_rows]
+  std::vector<int> row_meta;           // [nblocks*block_rows][4] = {row node (-1 = padding), first CSR entry of the row,
+                                       //   row length | own slot << 16, own_local}: everything a row thread needs, one load
   std::vector<int> blk_nodes;          // [nblocks][nl] sorted distinct nodes of the block, -1 padded
   long long total_real = 0;            // strip entries before padding
 };

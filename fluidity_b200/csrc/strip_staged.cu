@@ -30,34 +30,28 @@
 
 namespace cgasm {
 
-// Copies the records of every node of the block. EXTRA: 0 none, 1 oldu (momentum), 2 one more 16-byte chunk
-// from a double2 array (tracer absorption / source).
+// Copies the records of every node of the block (ids already in registers, issue_block_ids). EXTRA: 0 none, 1 oldu
+// (momentum), 2 one more 16-byte chunk from a double2 array (tracer absorption / source).
 template <int DIM, int NL, int EXTRA>
-__device__ __forceinline__ void stage_nodes(const StagedView& P, int b, int t, unsigned nsa, const double4* __restrict__ r0,
+__device__ __forceinline__ void stage_nodes(const BlockIds<NL>& ids, int t, unsigned nsa, const double4* __restrict__ r0,
                                             const double4* __restrict__ r1, const void* __restrict__ rE) {
-  const int* ids = P.blk_nodes + (size_t)b * NL;  // fixed stride: no pointer load in front of the id loads
-  constexpr int U = NL / kBR >= 4 ? 4 : (NL / kBR >= 2 ? 2 : 1);  // node ids of U rounds are requested together
-  for (int i0 = t; i0 < NL; i0 += U * kBR) {
-    int node[U];
 #pragma unroll
-    for (int u = 0; u < U; u++) node[u] = i0 + u * kBR < NL ? __ldg(ids + i0 + u * kBR) : -1;
-#pragma unroll
-    for (int u = 0; u < U; u++) {
-      if (node[u] < 0) continue;
-      const unsigned d = nsa + (unsigned)(i0 + u * kBR) * 16u;
-      const double2* s0 = reinterpret_cast<const double2*>(r0 + node[u]);
-      const double2* s1 = reinterpret_cast<const double2*>(r1 + node[u]);
-      cp_async16(d + 0 * NL * 16, s0);
-      cp_async16(d + 1 * NL * 16, s0 + 1);
-      cp_async16(d + 2 * NL * 16, s1);
-      cp_async16(d + 3 * NL * 16, s1 + 1);
-      if constexpr (EXTRA == 1) {
-        const double2* s2 = reinterpret_cast<const double2*>(reinterpret_cast<const double4*>(rE) + node[u]);
-        cp_async16(d + 4 * NL * 16, s2);
-        if constexpr (DIM == 3) cp_async8(nsa + 5 * NL * 16 + (unsigned)(i0 + u * kBR) * 8u, s2 + 1);
-      } else if constexpr (EXTRA == 2) {
-        cp_async16(d + 4 * NL * 16, reinterpret_cast<const double2*>(rE) + node[u]);
-      }
+  for (int u = 0; u < BlockIds<NL>::PER; u++) {
+    const int node = ids.node[u];
+    if (node < 0) continue;
+    const unsigned i = (unsigned)(t + u * kBR), d = nsa + i * 16u;
+    const double2* s0 = reinterpret_cast<const double2*>(r0 + node);
+    const double2* s1 = reinterpret_cast<const double2*>(r1 + node);
+    cp_async16(d + 0 * NL * 16, s0);
+    cp_async16(d + 1 * NL * 16, s0 + 1);
+    cp_async16(d + 2 * NL * 16, s1);
+    cp_async16(d + 3 * NL * 16, s1 + 1);
+    if constexpr (EXTRA == 1) {
+      const double2* s2 = reinterpret_cast<const double2*>(reinterpret_cast<const double4*>(rE) + node);
+      cp_async16(d + 4 * NL * 16, s2);
+      if constexpr (DIM == 3) cp_async8(nsa + 5 * NL * 16 + i * 8u, s2 + 1);
+    } else if constexpr (EXTRA == 2) {
+      cp_async16(d + 4 * NL * 16, reinterpret_cast<const double2*>(rE) + node);
     }
   }
 }
@@ -68,11 +62,10 @@ __device__ __forceinline__ void stage_nodes(const StagedView& P, int b, int t, u
 // plan entry j + 3, then install and compute entry j.
 template <int DIM, int QC, int NL, bool FULLV>
 __device__ __forceinline__ void smom_step(MomState<DIM, DIM>& s, double (&rh)[DIM], const StripConsts& k_,
-                                          const unsigned* __restrict__ p, unsigned& pq0, unsigned& pq1, unsigned& pq2,
-                                          unsigned acc_sa, unsigned nsa) {
-  const unsigned en = pq0;
-  pq0 = pq1;
-  pq1 = pq2;
+                                          const unsigned* __restrict__ p, unsigned (&pq)[DIM], unsigned acc_sa, unsigned nsa) {
+  // plan queue: slot QC holds entry j, refilled with entry j + DIM (static indices: the unroll factor is the queue
+  // length, so nothing is moved between registers at the loop's back edge)
+  const unsigned en = pq[QC];
   // every shared-memory read of the step is issued before the first one is consumed (one exposed LDS latency per
   // step instead of three): the evicted node's oldu and slot, then the records of the node that takes its buffer
   const unsigned m = (unsigned)s.meta[QC];
@@ -84,7 +77,7 @@ __device__ __forceinline__ void smom_step(MomState<DIM, DIM>& s, double (&rh)[DI
   load_rec<DIM, NL>(nb, 0, s.X[QC], s.B[QC]);
   load_rec<DIM, NL>(nb, 1, s.U[QC], s.R[QC]);
   s.meta[QC] = (int)en;
-  pq2 = ldg_stream1(p + (QC + 3) * kBR);
+  pq[QC] = ldg_stream1(p + (QC + DIM) * kBR);
   prefetch_l2(p + (QC + kPlanAhead) * kBR);
   {
     const double a = s.A[QC];
@@ -107,28 +100,6 @@ struct SMomUnroll {
   }
 };
 
-// rows of the warp -> the dim identical diagonal blocks: dt*theta * entry (+ lumped mass on the diagonal)
-template <int DIM>
-__device__ __forceinline__ void write_rows_scaled(const double* __restrict__ acc, int t, int my_s0, int my_len, int my_own,
-                                                  double my_mass, double dtt, int lpr_shift, size_t nnz,
-                                                  double* __restrict__ out) {
-  const int lane = t & 31, wbase = t & ~31;
-  const int lpr = 1 << lpr_shift, rpi = 32 >> lpr_shift;
-  const int sub = lane >> lpr_shift, sl = lane & (lpr - 1);
-  for (int rr = 0; rr < 32; rr += rpi) {
-    const int src = rr + sub;
-    const int s0r = __shfl_sync(0xffffffffu, my_s0, src);
-    const int lr = __shfl_sync(0xffffffffu, my_len, src);
-    const int own = __shfl_sync(0xffffffffu, my_own, src);
-    const double mass = __shfl_sync(0xffffffffu, my_mass, src);
-    for (int ss = sl; ss < lr; ss += lpr) {
-      const double v = fma(dtt, acc[ss * kAS + wbase + src], ss == own ? mass : 0.0);
-#pragma unroll
-      for (int d = 0; d < DIM; d++) __stcs(out + (size_t)d * nnz + s0r + ss, v);
-    }
-  }
-}
-
 template <int DIM, int NL, bool FULLV>
 __global__ void __launch_bounds__(kBR, (NL <= 512 ? 4 : (NL <= 768 ? 3 : 2)))
 staged_momentum_kernel(const StripConsts k_, const StagedView P, const double4* __restrict__ rX,
@@ -137,23 +108,29 @@ staged_momentum_kernel(const StripConsts k_, const StagedView P, const double4* 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* acc = reinterpret_cast<double*>(smem_raw);
   const unsigned nsa = (unsigned)__cvta_generic_to_shared(smem_raw) + (unsigned)P.acc_bytes;
+  const unsigned tbl_sa = nsa + (unsigned)(NL * 88);
   const int b = P.blocks ? P.blocks[blockIdx.x] : (int)blockIdx.x, t = threadIdx.x;
-  stage_nodes<DIM, NL, 1>(P, b, t, nsa, rX, rU, rO);
-  const int r = P.rows[b * kBR + t];
-  const long long base = P.ptr[b];
-  const int deg = (int)((P.ptr[b + 1] - base) / kBR);  // a multiple of DIM
-  const unsigned* p = P.ent + base + t;
+  // every independent load of the block first
+  BlockIds<NL> ids;
+  issue_block_ids<NL>(P, b, t, ids);
+  const int4 meta = ldg_nc_v4(P.row_meta + (size_t)b * kBR + t);
+  const long long base = ldg_nc_s64(P.ptr + b), end = ldg_nc_s64(P.ptr + b + 1);
+  prefetch_next_block<NL>(P, b, t);
   double* acc_t = acc + t;
   const unsigned acc_sa = (unsigned)__cvta_generic_to_shared(acc_t);
   for (int q = 0; q < P.maxlen; q++) acc_t[q * kAS] = 0.0;
-  const unsigned pad = P.own_local[b * kBR + t];
-  const unsigned own_off = pad & 0xfff0u;
-  const int own = (int)(pad >> 16) / kAS;
-  unsigned pq0 = ldg_stream1(p);
-  unsigned pq1 = ldg_stream1(p + kBR);
-  unsigned pq2 = ldg_stream1(p + 2 * kBR);
+  stage_nodes<DIM, NL, 1>(ids, t, nsa, rX, rU, rO);
+  const int deg = (int)((end - base) / kBR);  // a multiple of DIM
+  const unsigned* p = P.ent + base + t;
+  unsigned pq[DIM];
 #pragma unroll
-  for (int q = 3; q < kPlanAhead; q++) prefetch_l2(p + q * kBR);
+  for (int q = 0; q < DIM; q++) pq[q] = ldg_stream1(p + q * kBR);
+#pragma unroll
+  for (int q = DIM; q < kPlanAhead; q++) prefetch_l2(p + q * kBR);
+  const int r = meta.x;
+  const unsigned pad = (unsigned)meta.w;
+  const unsigned own_off = pad & 0xfff0u;
+  const int own = meta.z >> 16;
   cp_async_commit_wait_all();
   __syncthreads();
   MomState<DIM, DIM> s;
@@ -170,8 +147,7 @@ staged_momentum_kernel(const StripConsts k_, const StagedView P, const double4* 
     s.R[q] = s.B[q] = s.A[q] = 0.0;
     s.meta[q] = (int)pad;
   }
-  for (int j0 = 0; j0 < deg; j0 += DIM, p += DIM * kBR)
-    SMomUnroll<DIM, 0, NL, FULLV>::run(s, rh, k_, p, pq0, pq1, pq2, acc_sa, nsa);
+  for (int j0 = 0; j0 < deg; j0 += DIM, p += DIM * kBR) SMomUnroll<DIM, 0, NL, FULLV>::run(s, rh, k_, p, pq, acc_sa, nsa);
   // drain the FIFO, then the diagonal (the row's own node never leaves)
 #pragma unroll
   for (int q = 0; q < DIM; q++) {
@@ -183,10 +159,7 @@ staged_momentum_kernel(const StripConsts k_, const StagedView P, const double4* 
     for (int d = 0; d < DIM; d++) rh[d] = fma(-s.A[q], o[d], rh[d]);
   }
   acc_t[own * kAS] += s.a0;
-  int my_s0 = 0, my_len = 0;
   if (r >= 0) {
-    my_s0 = P.findrm[r];
-    my_len = P.findrm[r + 1] - my_s0;
     double ou[DIM];
     load_oldu<DIM, NL>(nsa, own_off, ou);
 #pragma unroll
@@ -195,8 +168,10 @@ staged_momentum_kernel(const StripConsts k_, const StagedView P, const double4* 
       if (masslump) masslump[(size_t)DIM * r + d] = s.msum;
     }
   }
+  // rows of the warp -> the dim identical diagonal blocks: dt*theta * entry (+ lumped mass on the diagonal)
+  row_table_store(tbl_sa, t, meta.y, meta.z, s.msum * k_.mass_on);
   __syncwarp();
-  write_rows_scaled<DIM>(acc, t, my_s0, my_len, own, s.msum * k_.mass_on, k_.dtt, P.lpr_shift, nnz, big_m);
+  write_rows_table<DIM>(acc, tbl_sa, t, k_.dtt, P.lpr_shift, nnz, big_m);
 }
 
 // ---- tracer -------------------------------------------------------------------------------------------
@@ -205,10 +180,8 @@ staged_momentum_kernel(const StripConsts k_, const StagedView P, const double4* 
 template <int DIM, int QC, int NL, bool FULLV, bool ABS>
 __device__ __forceinline__ void sadv_step(AdvState<DIM, DIM>& s, double (&sg)[ABS ? DIM : 1], double (&sq)[ABS ? DIM : 1],
                                           AdvOwnExtra& ox, const StripConsts& k_, const unsigned* __restrict__ p,
-                                          unsigned& pq0, unsigned& pq1, unsigned& pq2, unsigned acc_sa, unsigned nsa) {
-  const unsigned en = pq0;
-  pq0 = pq1;
-  pq1 = pq2;
+                                          unsigned (&pq)[DIM], unsigned acc_sa, unsigned nsa) {
+  const unsigned en = pq[QC];
   const unsigned sa = acc_sa + (((unsigned)s.meta[QC] >> 16) << 3);
   const double slot = lds64(sa);
   const unsigned nb = nsa + (en & 0xfff0u);
@@ -224,7 +197,7 @@ __device__ __forceinline__ void sadv_step(AdvState<DIM, DIM>& s, double (&sg)[AB
     sq[QC] = e.y;
   }
   s.meta[QC] = (int)en;
-  pq2 = ldg_stream1(p + (QC + 3) * kBR);
+  pq[QC] = ldg_stream1(p + (QC + DIM) * kBR);
   prefetch_l2(p + (QC + kPlanAhead) * kBR);
 #pragma unroll
   for (int a = 0; a < DIM; a++) s.X[QC][a] -= s.X0[a];
@@ -251,23 +224,28 @@ staged_advdiff_kernel(const StripConsts k_, const StagedView P, const double4* _
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* acc = reinterpret_cast<double*>(smem_raw);
   const unsigned nsa = (unsigned)__cvta_generic_to_shared(smem_raw) + (unsigned)P.acc_bytes;
+  const unsigned tbl_sa = nsa + (unsigned)(NL * (ABS ? 80 : 64));
   const int b = P.blocks ? P.blocks[blockIdx.x] : (int)blockIdx.x, t = threadIdx.x;
-  stage_nodes<DIM, NL, ABS ? 2 : 0>(P, b, t, nsa, rX, rU, rE);
-  const int r = P.rows[b * kBR + t];
-  const long long base = P.ptr[b];
-  const int deg = (int)((P.ptr[b + 1] - base) / kBR);
-  const unsigned* p = P.ent + base + t;
+  BlockIds<NL> ids;
+  issue_block_ids<NL>(P, b, t, ids);
+  const int4 meta = ldg_nc_v4(P.row_meta + (size_t)b * kBR + t);
+  const long long base = ldg_nc_s64(P.ptr + b), end = ldg_nc_s64(P.ptr + b + 1);
+  prefetch_next_block<NL>(P, b, t);
   double* acc_t = acc + t;
   const unsigned acc_sa = (unsigned)__cvta_generic_to_shared(acc_t);
   for (int q = 0; q < P.maxlen; q++) acc_t[q * kAS] = 0.0;
-  const unsigned pad = P.own_local[b * kBR + t];
-  const unsigned own_off = pad & 0xfff0u;
-  const int own = (int)(pad >> 16) / kAS;
-  unsigned pq0 = ldg_stream1(p);
-  unsigned pq1 = ldg_stream1(p + kBR);
-  unsigned pq2 = ldg_stream1(p + 2 * kBR);
+  stage_nodes<DIM, NL, ABS ? 2 : 0>(ids, t, nsa, rX, rU, rE);
+  const int deg = (int)((end - base) / kBR);
+  const unsigned* p = P.ent + base + t;
+  unsigned pq[DIM];
 #pragma unroll
-  for (int q = 3; q < kPlanAhead; q++) prefetch_l2(p + q * kBR);
+  for (int q = 0; q < DIM; q++) pq[q] = ldg_stream1(p + q * kBR);
+#pragma unroll
+  for (int q = DIM; q < kPlanAhead; q++) prefetch_l2(p + q * kBR);
+  const int r = meta.x;
+  const unsigned pad = (unsigned)meta.w;
+  const unsigned own_off = pad & 0xfff0u;
+  const int own = meta.z >> 16;
   cp_async_commit_wait_all();
   __syncthreads();
   AdvState<DIM, DIM> s;
@@ -296,24 +274,20 @@ staged_advdiff_kernel(const StripConsts k_, const StagedView P, const double4* _
     if constexpr (ABS) sg[q] = sq[q] = 0.0;
   }
   for (int j0 = 0; j0 < deg; j0 += DIM, p += DIM * kBR)
-    SAdvUnroll<DIM, 0, NL, FULLV, ABS>::run(s, sg, sq, ox, k_, p, pq0, pq1, pq2, acc_sa, nsa);
+    SAdvUnroll<DIM, 0, NL, FULLV, ABS>::run(s, sg, sq, ox, k_, p, pq, acc_sa, nsa);
 #pragma unroll
   for (int q = 0; q < DIM; q++) acc_t[(unsigned)s.meta[q] >> 16] += fma(k_.dtt, s.A[q], k_.mPo * s.C[q]);
   acc_t[own * kAS] += fma(k_.dtt, s.a0, k_.mPd * s.c0);
-  int my_s0 = 0, my_len = 0;
-  if (r >= 0) {
-    my_s0 = P.findrm[r];
-    my_len = P.findrm[r + 1] - my_s0;
-    rhs[r] = s.rhs;
-  }
+  if (r >= 0) rhs[r] = s.rhs;
+  row_table_store(tbl_sa, t, meta.y, meta.z, 0.0);
   __syncwarp();
-  write_rows<1>(acc, t, my_s0, my_len, P.lpr_shift, 0, matrix);
+  write_rows_table<1>(acc, tbl_sa, t, 1.0, P.lpr_shift, 0, matrix);
 }
 
 // ---- launch -------------------------------------------------------------------------------------------
 // bytes per staged node: 4 chunks (two records) + momentum: oldu (24) / tracer with absorption+source: one chunk
 static size_t staged_smem(const GatherPlan* P, bool momentum, bool extra) {
-  return staged_acc_bytes(P, 1) + (size_t)P->nl * (momentum ? 88 : (extra ? 80 : 64));
+  return staged_acc_bytes(P, 1) + (size_t)P->nl * (momentum ? 88 : (extra ? 80 : 64)) + kBR * 16;  // + the row table
 }
 
 bool strip_staged_ok(const Handle* h, bool momentum) {

@@ -14,6 +14,8 @@ struct StagedView {
   const int* __restrict__ blk_nodes;      // [nblocks][NL], -1 padded
   const int* __restrict__ findrm;
   const int* __restrict__ blocks;         // the row blocks this launch works on (nullptr: all, in order)
+  const int4* __restrict__ row_meta;      // {row node, first CSR entry, length | own slot << 16, own_local}
+  int nblocks, ahead;                     // blocks in the plan; how far ahead a block pulls its successor's metadata into L2
   int maxlen, lpr_shift;
   int acc_bytes;  // bytes of the accumulator in front of the staged records (multiple of 16)
 };
@@ -84,6 +86,81 @@ __device__ __forceinline__ void load_oldu(unsigned nsa, unsigned noff, double (&
   if constexpr (DIM == 3) o[2] = lds64(nsa + (noff >> 1) + (unsigned)(5 * NL * 16));
 }
 
+
+// ---- block prologue / epilogue shared by the staged kernels -----------------------------------------------------
+// ncu (profiles/r2_kernel_history.md): a quarter of a warp's life went into FOUR dependent DRAM round trips around the
+// loop -- node ids, then (rows, ptr, own_local), then the first plan entries, and findrm in the epilogue. Now every
+// independent load of the block is issued back to back at the top (ids, the row's int4 meta record that replaces rows /
+// own_local / findrm, the block's plan pointers), the accumulator is zeroed while they fly, and the block pulls the
+// same lines of the block `ahead` positions further on into L2, so its successor's first round trip is an L2 hit.
+__device__ __forceinline__ int ldg_nc_s32(const int* p) {
+  int v;
+  asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ int4 ldg_nc_v4(const int4* p) {
+  int4 v;
+  asm volatile("ld.global.nc.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ long long ldg_nc_s64(const long long* p) {
+  long long v;
+  asm volatile("ld.global.nc.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+template <int NL>
+struct BlockIds {
+  static constexpr int PER = NL / kBR;
+  int node[PER];
+};
+
+template <int NL>
+__device__ __forceinline__ void issue_block_ids(const StagedView& P, int b, int t, BlockIds<NL>& ids) {
+  const int* p = P.blk_nodes + (size_t)b * NL + t;  // fixed stride: no pointer load in front of the id loads
+#pragma unroll
+  for (int u = 0; u < BlockIds<NL>::PER; u++) ids.node[u] = ldg_nc_s32(p + u * kBR);
+}
+
+template <int NL>
+__device__ __forceinline__ void prefetch_next_block(const StagedView& P, int b, int t) {
+  if (P.blocks) return;
+  const int nb = b + P.ahead;
+  if (nb >= P.nblocks) return;
+  if (t < 16) prefetch_l2(P.row_meta + (size_t)nb * kBR + t * 8);                      // 128 rows x 16 bytes
+  else if (t < 16 + NL / 32) prefetch_l2(P.blk_nodes + (size_t)nb * NL + (t - 16) * 32);  // NL ids
+  else if (t == 16 + NL / 32) prefetch_l2(P.ptr + nb);
+}
+
+// per-row table for the write-out: {first CSR entry, length | own slot << 16, value for the diagonal}, 16 bytes per row
+__device__ __forceinline__ void row_table_store(unsigned tbl_sa, int t, int s0, int lenown, double diag) {
+  asm volatile("st.shared.v2.s32 [%0], {%1,%2};" ::"r"(tbl_sa + (unsigned)t * 16u), "r"(s0), "r"(lenown) : "memory");
+  sts64(tbl_sa + (unsigned)t * 16u + 8u, diag);
+}
+
+// rows of the warp -> global memory, LPR = 1 << lpr_shift lanes per row: out[d*nnz + s0 + ss] = scale * acc[ss] (+ diag
+// on the own slot), for d < NOUT. The row table replaces four shuffles per row by one broadcast LDS.128.
+template <int NOUT>
+__device__ __forceinline__ void write_rows_table(const double* __restrict__ acc, unsigned tbl_sa, int t, double scale,
+                                                 int lpr_shift, size_t nnz, double* __restrict__ out) {
+  const int lane = t & 31, wbase = t & ~31;
+  const int lpr = 1 << lpr_shift, rpi = 32 >> lpr_shift;
+  const int sub = lane >> lpr_shift, sl = lane & (lpr - 1);
+  for (int rr = 0; rr < 32; rr += rpi) {
+    const int src = wbase + rr + sub;
+    int s0r, lo;
+    double diag;
+    asm volatile("ld.shared.v2.s32 {%0,%1}, [%2];" : "=r"(s0r), "=r"(lo) : "r"(tbl_sa + (unsigned)src * 16u) : "memory");
+    diag = lds64(tbl_sa + (unsigned)src * 16u + 8u);
+    const int lr = lo & 0xffff, own = lo >> 16;
+    for (int ss = sl; ss < lr; ss += lpr) {
+      const double v = fma(scale, acc[ss * kAS + src], ss == own ? diag : 0.0);
+#pragma unroll
+      for (int d = 0; d < NOUT; d++) __stcs(out + (size_t)d * nnz + s0r + ss, v);
+    }
+  }
+}
+
 static inline size_t staged_acc_bytes(const GatherPlan* P, int nblocks_acc) {
   return (sizeof(double) * (size_t)nblocks_acc * P->maxlen * kAS + 15) & ~(size_t)15;
 }
@@ -98,6 +175,9 @@ static inline StagedView staged_view(const Handle* h, int nblocks_acc = 1) {
   v.blk_nodes = P->d_blk_nodes;
   v.findrm = h->d_findrm;
   v.blocks = nullptr;
+  v.row_meta = P->d_row_meta;
+  v.nblocks = P->nblocks;
+  v.ahead = 4 * 148;  // about the number of blocks resident on the chip
   v.maxlen = P->maxlen;
   int sh = 0;
   while ((1 << sh) < P->maxlen && sh < 5) sh++;
