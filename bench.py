@@ -259,6 +259,39 @@ def workload_config(args, n):
 
 
 # ---- graft arm --------------------------------------------------------------------------------------
+def bind_to_gpu_numa(index):
+    """Pins this rank's host threads to the CPUs of the NUMA node its GPU hangs off (sysfs numa_node of the GPU's PCI
+    function), BEFORE the pinned staging buffers of the e2e leg are allocated and first touched. Round 1's e2e
+    collapsed with N (918 -> 218 Melements/s per GPU at N = 8): every rank's pinned memory sat on NUMA node 0 and all
+    host<->device traffic crossed one socket's memory controllers and the inter-socket link. Returns a description."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(phys)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        dev = bus.lower()
+        if len(dev.split(":")[0]) == 8:        # NVML prints an 8-digit domain, sysfs a 4-digit one
+            dev = dev[4:]
+        with open("/sys/bus/pci/devices/%s/numa_node" % dev) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return {"numa_node": node, "bound": False, "why": "the platform reports no NUMA affinity for the GPU"}
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if not allowed:
+            return {"numa_node": node, "bound": False, "why": "none of the node's CPUs is in this process's affinity mask"}
+        os.sched_setaffinity(0, allowed)
+        return {"numa_node": node, "bound": True, "cpus": len(allowed)}
+    except Exception as exc:  # no NVML / sysfs: run unbound
+        return {"bound": False, "why": "%s: %s" % (type(exc).__name__, exc)}
+
+
 def setup_fields(asm, abi, syn, F, n_owned, world):
     g = np.zeros((1, 3)); g[0, 2] = -1.0
     asm.set_field(abi.F_GRAVITY, g, abi.FIELD_CONSTANT)
@@ -414,12 +447,16 @@ def run_graft(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: libcgasm has no CPU path")
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa(local_rank) if world > 1 else {"bound": False, "why": "single rank"}
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         # torchrun pins OMP_NUM_THREADS=1; the once-per-mesh host preprocessing (sparsity, plans) is
         # OpenMP code, so give every rank its share of the host cores
         if os.environ.get("OMP_NUM_THREADS", "1") == "1":
-            share = max(1, len(os.sched_getaffinity(0)) // world)
+            share = max(1, len(os.sched_getaffinity(0)) // (1 if numa.get("bound") else world))
+            if numa.get("bound"):
+                # the node's CPUs are shared by the ranks bound to it
+                share = max(1, share // max(1, world // 2))
             os.environ["OMP_NUM_THREADS"] = str(share)
             # libcgasm.so resolves libgomp.so.1 to the copy torch bundles, which read OMP_NUM_THREADS=1 when torch
             # was imported: the environment alone no longer reaches it, so set the thread count through the runtime too
@@ -564,7 +601,7 @@ def run_graft(args):
     if world > 1:
         mine = dict(rank=rank, step_ms=my_total_ms / args.steps, momentum_ms=m_ms, tracer_ms=a_ms, fused_ms=fused_ms, halo_ms=halo_ms,
                     local_elements=n_el_local, local_nodes=n_nodes_local, owned_nodes=n_owned, halo_nodes_sent=n_sent,
-                    neighbours=n_neighbours, library_setup_s=setup_s, mesh_gen_s=mesh_gen_s)
+                    neighbours=n_neighbours, library_setup_s=setup_s, mesh_gen_s=mesh_gen_s, numa=numa)
         allr = [None] * world if rank == 0 else None
         dist.gather_object(mine, allr, dst=0)
         per_rank = allr

@@ -39,8 +39,11 @@ _M_INTS = [
     "have_geostrophic_pressure", "have_surfacetension", "have_vertical_stabilization",
     "have_swe_bottom_drag", "have_wd_abs", "have_temperature_dependent_viscosity",
     "stress_form", "partial_stress_form", "radial_gravity", "vel_lump_on_submesh",
-    "cmc_lump_on_submesh", "abs_lump_on_submesh", "assemble_mass_matrix",
-    "integrate_continuity_by_parts",
+    "cmc_lump_on_submesh", "abs_lump_on_submesh",
+    # implemented since round 2
+    "assemble_mass_matrix", "integrate_continuity_by_parts",
+    # surface loop only: free-surface stabilisation (unsupported)
+    "have_surface_fs_stabilisation",
 ]
 
 

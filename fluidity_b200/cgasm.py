@@ -227,6 +227,12 @@ class Assembler:
         _check(self.lib.cgasm_momentum_fetch(C.c_int(self.id), _dp(big_m), _dp(rhs), _dp(ml), _dp(ct)))
         return dict(big_m=big_m, rhs=rhs, masslump=ml, ct_m=ct)
 
+    def momentum_mass_fetch(self):
+        """The `mass` matrix (opts.assemble_mass_matrix): (dim, nnz) diagonal blocks."""
+        mass = np.empty((self.dim, self.nnz))
+        _check(self.lib.cgasm_momentum_mass_fetch(C.c_int(self.id), _dp(mass)))
+        return mass
+
     def momentum_identical_blocks(self):
         f = C.c_int(0)
         _check(self.lib.cgasm_momentum_identical_blocks(C.c_int(self.id), C.byref(f)))
@@ -289,6 +295,23 @@ class Assembler:
         bv = np.ascontiguousarray(velocity_bc, dtype=np.float64) if velocity_bc is not None else None
         pt = np.ascontiguousarray(pressure_bc_type, dtype=np.int32) if pressure_bc_type is not None else None
         _check(self.lib.cgasm_momentum_surface_dev(C.c_int(self.id), C.byref(opts), _ip(bt), _dp(bv), _ip(pt)))
+
+    def momentum_dirichlet_dev(self, nodes, comps, values):
+        """Strong Dirichlet conditions on the resident big_m / rhs: nodes, comps 1-based, values as
+        collect_vector_dirichlet_conditions writes them into rhs."""
+        nd = np.ascontiguousarray(nodes, dtype=np.int32)
+        cp = np.ascontiguousarray(comps, dtype=np.int32)
+        v = np.ascontiguousarray(values, dtype=np.float64)
+        _check(self.lib.cgasm_momentum_dirichlet_dev(C.c_int(self.id), C.c_int(len(nd)), _ip(nd), _ip(cp), _dp(v)))
+
+    def correct_masslumped_velocity(self, inverse_masslump, delta_p, u, ct_m=None):
+        """u (n_nodes, dim) corrected in place (returns it)."""
+        iml = np.ascontiguousarray(inverse_masslump, dtype=np.float64)
+        dp = np.ascontiguousarray(delta_p, dtype=np.float64)
+        assert u.flags.c_contiguous and u.dtype == np.float64
+        ct = np.ascontiguousarray(ct_m, dtype=np.float64) if ct_m is not None else None
+        _check(self.lib.cgasm_correct_masslumped_velocity(C.c_int(self.id), _dp(ct), _dp(iml), _dp(dp), _dp(u)))
+        return u
 
     # -- lumped-mass pressure matrix C M_L^-1 C^T --------------------------------------------
     def cmc_build_sparsity(self):

@@ -158,6 +158,8 @@ static void destroy_handle(Handle* h) {
   free_dev(h->d_big_m);
   free_dev(h->d_mom_rhs);
   free_dev(h->d_masslump);
+  free_dev(h->d_mass);
+  free_dev(h->d_mass_rhs);
   free_dev(h->d_ct_m);
   free_dev(h->d_adv_matrix);
   free_dev(h->d_adv_rhs);
@@ -188,7 +190,8 @@ static int upload_sparsity(Handle* h) {
   free_dev(h->d_big_m);
   free_dev(h->d_ct_m);
   free_dev(h->d_adv_matrix);
-  h->d_big_m = h->d_ct_m = h->d_adv_matrix = nullptr;
+  free_dev(h->d_mass);
+  h->d_big_m = h->d_ct_m = h->d_adv_matrix = h->d_mass = nullptr;
   h->mom_valid = h->adv_valid = false;
   h->have_sparsity = true;
   // every plan derived from the first-order pattern is stale now (the CMC plan holds slots / transposed positions
@@ -221,8 +224,7 @@ static int check_momentum_opts(const cgasm_momentum_opts* o) {
       o->have_geostrophic_pressure || o->have_surfacetension || o->have_vertical_stabilization ||
       o->have_swe_bottom_drag || o->have_wd_abs || o->have_temperature_dependent_viscosity ||
       o->stress_form || o->partial_stress_form || o->radial_gravity || o->vel_lump_on_submesh ||
-      o->cmc_lump_on_submesh || o->abs_lump_on_submesh || o->assemble_mass_matrix ||
-      o->integrate_continuity_by_parts)
+      o->cmc_lump_on_submesh || o->abs_lump_on_submesh)
     CG_FAIL(CGASM_EUNSUPPORTED, "momentum option outside the device path; keep the Fortran loop");
   if (o->stabilisation_scheme < CGASM_STAB_NONE || o->stabilisation_scheme > CGASM_STAB_SUPG)
     CG_FAIL(CGASM_EARG, "bad stabilisation_scheme");
@@ -681,6 +683,28 @@ int cgasm_get_field(int id, int slot, double* val, int n_val_nodes) {
   return CGASM_OK;
 }
 
+// runs the momentum element loop of the handle's scatter variant into the handle's result buffers
+static int run_momentum(Handle* h, const MomentumArgs& A, bool want_ml, bool want_ct) {
+  const size_t nnz = (size_t)h->nnz, nn = (size_t)h->n_nodes, dim = (size_t)h->dim;
+  int st;
+  if (h->scatter != CGASM_SCATTER_GATHER && h->scatter != CGASM_SCATTER_STRIP && (st = halo_join(h))) return st;
+  if (h->scatter == CGASM_SCATTER_TILED) {
+    st = tiles_momentum(h, A, want_ml, want_ct);
+    h->mom_path = CGASM_PATH_TILED;
+  } else if (h->scatter == CGASM_SCATTER_GATHER || h->scatter == CGASM_SCATTER_STRIP) {
+    st = gather_momentum(h, A, want_ml, want_ct);
+  } else {
+    // zero(big_m), zero(rhs) ... (Momentum_Equation.F90:593-606) then accumulate
+    CG_CUDA(cudaMemsetAsync(h->d_big_m, 0, sizeof(double) * dim * nnz, h->stream));
+    CG_CUDA(cudaMemsetAsync(h->d_mom_rhs, 0, sizeof(double) * dim * nn, h->stream));
+    if (want_ml) CG_CUDA(cudaMemsetAsync(h->d_masslump, 0, sizeof(double) * dim * nn, h->stream));
+    if (want_ct) CG_CUDA(cudaMemsetAsync(h->d_ct_m, 0, sizeof(double) * dim * nnz, h->stream));
+    st = scatter_momentum(h, A, want_ml, want_ct);
+    h->mom_path = CGASM_PATH_ELEMENT;
+  }
+  return st;
+}
+
 int cgasm_momentum_dev(int id, const cgasm_momentum_opts* opts) {
   GET_HANDLE(h, id);
   if (!opts) CG_FAIL(CGASM_EARG, "null opts");
@@ -698,27 +722,46 @@ int cgasm_momentum_dev(int id, const cgasm_momentum_opts* opts) {
   if (opts->stabilisation_scheme != CGASM_STAB_NONE && h->scatter != CGASM_SCATTER_ATOMIC &&
       h->scatter != CGASM_SCATTER_GATHER && h->scatter != CGASM_SCATTER_STRIP)
     CG_FAIL(CGASM_EUNSUPPORTED, "SU/SUPG stabilisation runs on the ATOMIC and GATHER scatter variants only");
+  if (opts->assemble_mass_matrix && opts->stabilisation_scheme == CGASM_STAB_SUPG)
+    CG_FAIL(CGASM_EUNSUPPORTED, "assemble_mass_matrix with a SUPG test function is outside the device path");
   if (h->mom_copy_pending) {  // an asynchronous fetch may still be reading the previous result
     CG_CUDA(cudaStreamWaitEvent(h->stream, h->ev_mom_copied, 0));
     h->mom_copy_pending = false;
   }
-  if (h->scatter != CGASM_SCATTER_GATHER && h->scatter != CGASM_SCATTER_STRIP && (st = halo_join(h))) return st;
   CG_CUDA(cudaEventRecord(h->ev0, h->stream));
-  if (h->scatter == CGASM_SCATTER_TILED) {
-    st = tiles_momentum(h, A, want_ml, want_ct);
-    h->mom_path = CGASM_PATH_TILED;
-  } else if (h->scatter == CGASM_SCATTER_GATHER || h->scatter == CGASM_SCATTER_STRIP) {
-    st = gather_momentum(h, A, want_ml, want_ct);
-  } else {
-    // zero(big_m), zero(rhs) ... (Momentum_Equation.F90:593-606) then accumulate
-    CG_CUDA(cudaMemsetAsync(h->d_big_m, 0, sizeof(double) * dim * nnz, h->stream));
-    CG_CUDA(cudaMemsetAsync(h->d_mom_rhs, 0, sizeof(double) * dim * nn, h->stream));
-    if (want_ml) CG_CUDA(cudaMemsetAsync(h->d_masslump, 0, sizeof(double) * dim * nn, h->stream));
-    if (want_ct) CG_CUDA(cudaMemsetAsync(h->d_ct_m, 0, sizeof(double) * dim * nnz, h->stream));
-    st = scatter_momentum(h, A, want_ml, want_ct);
-    h->mom_path = CGASM_PATH_ELEMENT;
+  if ((st = run_momentum(h, A, want_ml, want_ct))) return st;
+  h->mom_has_mass = false;
+  if (opts->assemble_mass_matrix) {
+    // The `mass` matrix (Momentum_CG.F90:1567-1571, :2073-2078) is the big_m of ANOTHER option set of the same loop:
+    // consistent mass, no advection / viscosity / gravity / sources, and the full absorption matrix when the
+    // absorption is pressure-corrected -- T = mass_mat + dt theta absorption_mat. Run that set into the mass buffers.
+    if ((st = ensure(&h->d_mass, dim * nnz)) || (st = ensure(&h->d_mass_rhs, dim * nn))) return st;
+    cgasm_momentum_opts mo = *opts;
+    mo.assemble_mass_matrix = 0;
+    mo.lump_mass = 0;
+    mo.exclude_mass = 0;
+    mo.exclude_advection = 1;
+    mo.have_viscosity = 0;
+    mo.have_gravity = 0;
+    mo.have_source = 0;
+    mo.have_absorption = (opts->have_absorption && opts->pressure_corrected_absorption) ? 1 : 0;
+    mo.lump_absorption = 0;
+    mo.pressure_corrected_absorption = 0;
+    mo.stabilisation_scheme = CGASM_STAB_NONE;
+    mo.assemble_inverse_masslump = 0;
+    mo.assemble_ct_matrix_here = 0;
+    MomentumArgs Am;
+    if ((st = make_momentum_args(h, &mo, Am))) return st;
+    const int path = h->mom_path;
+    std::swap(h->d_big_m, h->d_mass);
+    std::swap(h->d_mom_rhs, h->d_mass_rhs);
+    st = run_momentum(h, Am, false, false);
+    std::swap(h->d_big_m, h->d_mass);
+    std::swap(h->d_mom_rhs, h->d_mass_rhs);
+    h->mom_path = path;
+    if (st) return st;
+    h->mom_has_mass = true;
   }
-  if (st) return st;
   CG_CUDA(cudaEventRecord(h->ev1, h->stream));
   CG_CUDA(cudaGetLastError());
   h->last_combined = false;
@@ -726,6 +769,23 @@ int cgasm_momentum_dev(int id, const cgasm_momentum_opts* opts) {
   h->mom_has_ct = want_ct;
   h->mom_identical_blocks = !opts->have_absorption;
   h->mom_valid = true;
+  return CGASM_OK;
+}
+
+int cgasm_momentum_mass_fetch(int id, double* mass) {
+  GET_HANDLE(h, id);
+  if (!mass) CG_FAIL(CGASM_EARG, "null mass");
+  if (!h->mom_valid || !h->mom_has_mass) CG_FAIL(CGASM_ESTATE, "the mass matrix was not assembled (assemble_mass_matrix = 0)");
+  CG_CUDA(cudaMemcpyAsync(mass, h->d_mass, sizeof(double) * (size_t)h->dim * (size_t)h->nnz, cudaMemcpyDeviceToHost, h->stream));
+  CG_CUDA(cudaStreamSynchronize(h->stream));
+  return CGASM_OK;
+}
+
+int cgasm_momentum_mass_dev(int id, double** mass_dev) {
+  GET_HANDLE(h, id);
+  if (!mass_dev) CG_FAIL(CGASM_EARG, "null out");
+  if (!h->mom_valid || !h->mom_has_mass) CG_FAIL(CGASM_ESTATE, "the mass matrix was not assembled (assemble_mass_matrix = 0)");
+  *mass_dev = h->d_mass;
   return CGASM_OK;
 }
 

@@ -93,10 +93,13 @@ struct Handle {
   double* d_mom_rhs = nullptr;   // (dim, n_nodes)
   double* d_masslump = nullptr;  // (dim, n_nodes)
   double* d_ct_m = nullptr;      // [dim][nnz]
+  double* d_mass = nullptr;      // [dim][nnz] the `mass` matrix (assemble_mass_matrix)
+  double* d_mass_rhs = nullptr;  // scratch of the pass that makes it
   double* d_adv_matrix = nullptr;  // [nnz]
   double* d_adv_rhs = nullptr;     // (n_nodes)
   bool mom_has_masslump = false, mom_has_ct = false, mom_valid = false, adv_valid = false;
   bool mom_identical_blocks = false;
+  bool mom_has_mass = false;
 
   int scatter = CGASM_SCATTER_ATOMIC;
   TilePlan* tiles = nullptr;

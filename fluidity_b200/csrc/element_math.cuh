@@ -672,14 +672,18 @@ __device__ __forceinline__ void momentum_element(const MomentumArgs& A, const in
   }
 }
 
-// ct_m block: grad_p_u_mat(d,i,j) = sum_g N_ig dN_j/dx_d detwei_g   (:1401, FETools :332-362)
+// ct_m block: grad_p_u_mat(d,i,j) = sum_g N_ig dN_j/dx_d detwei_g   (:1401, FETools :332-362); with
+// integrate_continuity_by_parts -dshape_shape(dp_t, u_shape, detwei): (d,i,j) = -sum_g dN_i/dx_d N_jg detwei_g
+// (:1379-1383, FETools :364-389) -- for P1 minus the transpose of the plain form; the boundary half is the surface loop's
 template <int DIM>
-__device__ __forceinline__ double grad_p_u(const Tables& t, const Geom<DIM>& G, int d, int i, int j) {
+__device__ __forceinline__ double grad_p_u(const Tables& t, const Geom<DIM>& G, int d, int i, int j, bool by_parts = false) {
   constexpr int NGI = Shape<DIM>::NGI;
-  double ni = 0.0;
+  const int a = by_parts ? j : i, b = by_parts ? i : j;
+  double na = 0.0;
 #pragma unroll
-  for (int g = 0; g < NGI; g++) ni += t.N[i * NGI + g] * t.w[g];
-  return ni * G.absdet * G.grad[j][d];
+  for (int g = 0; g < NGI; g++) na += t.N[a * NGI + g] * t.w[g];
+  const double v = na * G.absdet * G.grad[b][d];
+  return by_parts ? -v : v;
 }
 
 // ---- tracer ----------------------------------------------------------------------------------

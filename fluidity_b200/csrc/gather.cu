@@ -461,7 +461,7 @@ __global__ void __launch_bounds__(128) gather_ct_stage_kernel(const MomentumArgs
 #pragma unroll
     for (int d = 0; d < DIM; d++)
 #pragma unroll
-      for (int j = 0; j < LOC; j++) v[d * LOC + j] = grad_p_u<DIM>(A.tab, G, d, i, j);
+      for (int j = 0; j < LOC; j++) v[d * LOC + j] = grad_p_u<DIM>(A.tab, G, d, i, j, A.o.integrate_continuity_by_parts != 0);
     store_rec<R_::RS>(stage + ((size_t)e * LOC + i) * R_::RS, v);
   }
 }

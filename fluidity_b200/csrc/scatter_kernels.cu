@@ -77,7 +77,7 @@ momentum_scatter_kernel(const MomentumArgs A, const int* __restrict__ elist, int
         if constexpr (LABS) v += R.Labs[d][i][j];
         if (i == j) v += R.diag[d][i];
         add_to<MODE>(big_m + (size_t)d * nnz + (size_t)pos[j], v);
-        if (ct_m) add_to<MODE>(ct_m + (size_t)d * nnz + (size_t)pos[j], grad_p_u<DIM>(A.tab, G, d, i, j));
+        if (ct_m) add_to<MODE>(ct_m + (size_t)d * nnz + (size_t)pos[j], grad_p_u<DIM>(A.tab, G, d, i, j, A.o.integrate_continuity_by_parts != 0));
       }
     }
 #pragma unroll
@@ -137,7 +137,7 @@ __global__ void momentum_one_kernel(const MomentumArgs A, int e, double* __restr
         double v = R.L[i][j] + R.Labs[d][i][j];
         if (i == j) v += R.diag[d][i];
         T[d + DIM * (d + DIM * (i + LOC * j))] = v;
-        gp[d + DIM * (i + LOC * j)] = grad_p_u<DIM>(A.tab, G, d, i, j);
+        gp[d + DIM * (i + LOC * j)] = grad_p_u<DIM>(A.tab, G, d, i, j, A.o.integrate_continuity_by_parts != 0);
       }
       rhs[d + DIM * i] = R.rhs[d][i];
       ml[d + DIM * i] = R.ml[d][i];

@@ -177,11 +177,24 @@ staged_fused_kernel(const StripConsts km, const StripConsts ka, const StagedView
   // rows of the warp: the dim identical momentum blocks (dt*theta * entry + lumped mass on the diagonal), then the tracer matrix
   row_table_store(tbl_sa, t, meta.y, meta.z, s.msum * km.mass_on);
   __syncwarp();
-  write_rows_table<DIM>(acc, tbl_sa, t, km.dtt, P.lpr_shift, nnz, big_m);
-  __syncwarp();
-  sts64(tbl_sa + (unsigned)t * 16u + 8u, 0.0);
-  __syncwarp();
-  write_rows_table<1>(acc2, tbl_sa, t, 1.0, P.lpr_shift, 0, matrix);
+  {
+    const int lane = t & 31, wbase = t & ~31;
+    const int lpr = 1 << P.lpr_shift, rpi = 32 >> P.lpr_shift;
+    const int sub = lane >> P.lpr_shift, sl = lane & (lpr - 1);
+    for (int rr = 0; rr < 32; rr += rpi) {
+      const int src = wbase + rr + sub;
+      int s0r, lo;
+      asm volatile("ld.shared.v2.s32 {%0,%1}, [%2];" : "=r"(s0r), "=r"(lo) : "r"(tbl_sa + (unsigned)src * 16u) : "memory");
+      const double diag = lds64(tbl_sa + (unsigned)src * 16u + 8u);
+      const int lr = lo & 0xffff, ownr = lo >> 16;
+      for (int ss = sl; ss < lr; ss += lpr) {
+        const double v = fma(km.dtt, acc[ss * kAS + src], ss == ownr ? diag : 0.0);
+#pragma unroll
+        for (int d = 0; d < DIM; d++) __stcs(big_m + (size_t)d * nnz + s0r + ss, v);
+        __stcs(matrix + s0r + ss, acc2[ss * kAS + src]);
+      }
+    }
+  }
 }
 
 // ---- host side ----------------------------------------------------------------------------------------

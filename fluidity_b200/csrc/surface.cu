@@ -137,7 +137,7 @@ template <int DIM>
 __global__ void momentum_surface_kernel(const SurfTables t, const FaceMesh m, const cgasm_momentum_opts o, const RawField U,
                                         const RawField O, const RawField R, const int* __restrict__ vtype,
                                         const double* __restrict__ vbc, const int* __restrict__ ptype, size_t nnz,
-                                        double* __restrict__ big_m, double* __restrict__ rhs) {
+                                        double* __restrict__ big_m, double* __restrict__ rhs, double* __restrict__ ct_m) {
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
   if (f >= m.n_faces) return;
   int bt[DIM];
@@ -164,6 +164,18 @@ __global__ void momentum_surface_kernel(const SurfTables t, const FaceMesh m, co
     }
     for (int d = 0; d < DIM; d++)
       if (r[d][i] != 0.0) atomicAdd(rhs + (size_t)DIM * nodes[i] + d, r[d][i]);
+  }
+  // continuity by parts: the boundary blocks of ct_m (:1073-1088; weak-Dirichlet ct_rhs and pressure conditions are
+  // outside the device path: cgasm_momentum_surface_dev refuses them)
+  if (ct_m && bt[0] != CGASM_VBC_NO_NORMAL_FLOW && bt[0] != CGASM_VBC_FREE_SURFACE) {
+    double CB[DIM][DIM][DIM];
+    momentum_face_ct<DIM>(t, Xf, Xc, CB);
+    for (int i = 0; i < DIM; i++)
+      for (int j = 0; j < DIM; j++) {
+        const int pos = csr_pos0(m.findrm, m.colm, nodes[i], nodes[j]);
+        if (pos < 0) continue;
+        for (int d = 0; d < DIM; d++) atomicAdd(ct_m + (size_t)d * nnz + pos, CB[d][i][j]);
+      }
   }
 }
 
@@ -335,8 +347,16 @@ int cgasm_momentum_surface_dev(int id, const cgasm_momentum_opts* opts, const in
   SurfacePlan* S = h->surface;
   if (!S || !S->d_sndgln) CG_FAIL(CGASM_ESTATE, "cgasm_set_surface has not been called");
   if (!h->mom_valid) CG_FAIL(CGASM_ESTATE, "no momentum result to add to: call cgasm_momentum_dev first");
-  if (opts->have_les || opts->multiphase || opts->on_sphere || opts->move_mesh || opts->integrate_continuity_by_parts)
+  if (opts->have_les || opts->multiphase || opts->on_sphere || opts->move_mesh)
     CG_FAIL(CGASM_EUNSUPPORTED, "momentum option outside the device path; keep the Fortran loop");
+  // integrate_continuity_by_parts: the boundary blocks go into the ct_m of the element loop; the ct_rhs of weak-Dirichlet
+  // velocities and the pressure-condition terms (:1084-1098) need data this call does not take
+  const bool ct_bdy = opts->integrate_continuity_by_parts && opts->assemble_ct_matrix_here;
+  if (ct_bdy && !h->mom_has_ct) CG_FAIL(CGASM_ESTATE, "no ct_m to add the boundary blocks to: run cgasm_momentum_dev with assemble_ct_matrix_here");
+  if (opts->integrate_continuity_by_parts && pressure_bc_type)
+    for (int f = 0; f < S->n_faces; f++)
+      if (pressure_bc_type[f] > 0)
+        CG_FAIL(CGASM_EUNSUPPORTED, "pressure boundary conditions with integrate_continuity_by_parts are outside the device path");
   if (S->n_faces == 0) return CGASM_OK;
   if (!velocity_bc_type) CG_FAIL(CGASM_EARG, "null velocity_bc_type");
   const int dim = h->dim;
@@ -347,6 +367,8 @@ int cgasm_momentum_surface_dev(int id, const cgasm_momentum_opts* opts, const in
     if (t < CGASM_VBC_NONE || t > CGASM_VBC_FLUX) CG_FAIL(CGASM_EARG, "bad velocity boundary-condition type");
     need_bc = need_bc || t == CGASM_VBC_FLUX || (t == CGASM_VBC_WEAKDIRICHLET && by_parts);
     adds_matrix = adds_matrix || (by_parts && t != CGASM_VBC_WEAKDIRICHLET);
+    if (t == CGASM_VBC_FREE_SURFACE && opts->have_surface_fs_stabilisation)
+      CG_FAIL(CGASM_EUNSUPPORTED, "free-surface stabilisation (have_fs_stab) is outside the device path; keep the Fortran surface loop");
   }
   if (need_bc && !velocity_bc) CG_FAIL(CGASM_EARG, "a face needs boundary values that were not given");
   const size_t nf = (size_t)S->n_faces;
@@ -371,11 +393,11 @@ int cgasm_momentum_surface_dev(int id, const cgasm_momentum_opts* opts, const in
   if (dim == 3)
     momentum_surface_kernel<3><<<blocks, threads, 0, h->stream>>>(S->tab, m, *opts, U, O, R, S->d_itype, need_bc ? S->d_bc : nullptr,
                                                                   pressure_bc_type ? S->d_ptype : nullptr, (size_t)h->nnz,
-                                                                  h->d_big_m, h->d_mom_rhs);
+                                                                  h->d_big_m, h->d_mom_rhs, ct_bdy ? h->d_ct_m : nullptr);
   else
     momentum_surface_kernel<2><<<blocks, threads, 0, h->stream>>>(S->tab, m, *opts, U, O, R, S->d_itype, need_bc ? S->d_bc : nullptr,
                                                                   pressure_bc_type ? S->d_ptype : nullptr, (size_t)h->nnz,
-                                                                  h->d_big_m, h->d_mom_rhs);
+                                                                  h->d_big_m, h->d_mom_rhs, ct_bdy ? h->d_ct_m : nullptr);
   h->launches++;
   CG_CUDA(cudaGetLastError());
   // weak Dirichlet on some components only makes the diagonal blocks differ

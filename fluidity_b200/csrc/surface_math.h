@@ -208,6 +208,22 @@ CG_HD void momentum_face(const SurfTables& t, const cgasm_momentum_opts& o, cons
     }
 }
 
+// The continuity half of construct_momentum_surface_element_cg with integrate_continuity_by_parts
+// (assemble/Momentum_CG.F90:1073-1088): ct_mat_bdy = shape_shape_vector(p_shape, u_shape, detwei_bdy, normal_bdy),
+// CB[d][i][j] = normal_d sum_g N_i N_j detwei (P1 faces: the normal is constant), added to block d of ct_m at
+// (pressure node i, velocity node j) on faces that are neither no-normal-flow nor free-surface.
+template <int DIM>
+CG_HD void momentum_face_ct(const SurfTables& t, const double (&Xf)[DIM][DIM], const double (&Xc)[DIM],
+                            double (&CB)[DIM][DIM][DIM]) {
+  double detJ, nrm[DIM], c[kMaxSngi], M[DIM][DIM];
+  facet_geometry<DIM>(t, Xf, Xc, detJ, nrm);
+  for (int g = 0; g < t.sngi; g++) c[g] = detJ * t.w[g];
+  face_shape_shape<DIM>(t, c, M);
+  for (int d = 0; d < DIM; d++)
+    for (int i = 0; i < DIM; i++)
+      for (int j = 0; j < DIM; j++) CB[d][i][j] = nrm[d] * M[i][j];
+}
+
 // csr_sparsity_pos on a sorted row (femtools/Sparse_Tools.F90:2438-2497), 0-based: position of column j in
 // row i, or -1
 CG_HD int csr_pos0(const int* findrm, const int* colm, int i, int j) {

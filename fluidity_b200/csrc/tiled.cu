@@ -523,7 +523,7 @@ tiled_ct_kernel(const MomentumArgs A, const TileArgs T, int max_entries, int max
           for (int j = 0; j < LOC; j++)
 #pragma unroll
             for (int d = 0; d < DIM; d++)
-              S.mat[(size_t)d * max_entries + base + (int)slot_of(sl, i, j)] += grad_p_u<DIM>(A.tab, G, d, i, j);
+              S.mat[(size_t)d * max_entries + base + (int)slot_of(sl, i, j)] += grad_p_u<DIM>(A.tab, G, d, i, j, A.o.integrate_continuity_by_parts != 0);
         }
       }
     }

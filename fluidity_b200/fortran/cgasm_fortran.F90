@@ -20,11 +20,13 @@ module cgasm_interface
        & cgasm_get_colouring, cgasm_set_scatter, cgasm_set_field, cgasm_get_field, &
        & cgasm_momentum, cgasm_advdiff, cgasm_momentum_dev, cgasm_advdiff_dev, cgasm_momentum_advdiff_dev, &
        & cgasm_momentum_fetch, cgasm_advdiff_fetch, cgasm_momentum_identical_blocks, &
+       & cgasm_momentum_mass_fetch, cgasm_momentum_mass_dev, &
        & cgasm_momentum_fetch_blocks, cgasm_momentum_element, &
        & cgasm_advdiff_element, cgasm_synchronize, cgasm_set_async, cgasm_halo_create, cgasm_halo_update, cgasm_halo_set_overlap, &
        & cgasm_coo_pattern_dev, cgasm_coo_values_dev, cgasm_coo_fetch, &
        & cgasm_nccl_unique_id, cgasm_last_error, cgasm_set_surface, cgasm_advdiff_surface_dev, &
-       & cgasm_advdiff_dirichlet_dev, cgasm_momentum_surface_dev, cgasm_cmc_build_sparsity, &
+       & cgasm_advdiff_dirichlet_dev, cgasm_momentum_surface_dev, cgasm_momentum_dirichlet_dev, &
+       & cgasm_correct_masslumped_velocity, cgasm_cmc_build_sparsity, &
        & cgasm_cmc_get_sparsity, cgasm_cmc_set_sparsity, cgasm_cmc_dev, cgasm_cmc_fetch
   public :: CGASM_OK, CGASM_EUNSUPPORTED
   public :: CGASM_F_NU, CGASM_F_OLDU, CGASM_F_DENSITY, CGASM_F_VISCOSITY, CGASM_F_BUOYANCY, &
@@ -56,7 +58,7 @@ module cgasm_interface
      integer(c_int) :: have_swe_bottom_drag, have_wd_abs, have_temperature_dependent_viscosity
      integer(c_int) :: stress_form, partial_stress_form, radial_gravity, vel_lump_on_submesh
      integer(c_int) :: cmc_lump_on_submesh, abs_lump_on_submesh, assemble_mass_matrix
-     integer(c_int) :: integrate_continuity_by_parts
+     integer(c_int) :: integrate_continuity_by_parts, have_surface_fs_stabilisation
   end type cgasm_momentum_opts
 
   !! Mirrors struct cgasm_advdiff_opts: assemble/Advection_Diffusion_CG.F90:77-123.
@@ -204,6 +206,21 @@ module cgasm_interface
        type(cgasm_advdiff_opts), intent(in) :: aopts
        integer(c_int) :: stat
      end function cgasm_momentum_advdiff_dev
+
+     ! the `mass` matrix of construct_momentum_cg (assemble_mass_matrix): dim diagonal blocks of nnz values
+     function cgasm_momentum_mass_fetch(id, mass) bind(c, name="cgasm_momentum_mass_fetch") result(stat)
+       use iso_c_binding
+       integer(c_int), value :: id
+       real(c_double), intent(out) :: mass(*)
+       integer(c_int) :: stat
+     end function cgasm_momentum_mass_fetch
+
+     function cgasm_momentum_mass_dev(id, mass_dev) bind(c, name="cgasm_momentum_mass_dev") result(stat)
+       use iso_c_binding
+       integer(c_int), value :: id
+       type(c_ptr), intent(out) :: mass_dev
+       integer(c_int) :: stat
+     end function cgasm_momentum_mass_dev
 
      function cgasm_momentum_fetch(id, big_m, rhs, masslump, ct_m) bind(c, name="cgasm_momentum_fetch") result(stat)
        use iso_c_binding
@@ -383,6 +400,26 @@ module cgasm_interface
        integer(c_int), value :: on
        integer(c_int) :: stat
      end function cgasm_halo_set_overlap
+
+     ! strong Dirichlet conditions of the velocity on the resident big_m / rhs (lift_boundary_conditions)
+     function cgasm_momentum_dirichlet_dev(id, n, nodes, comps, values) bind(c, name="cgasm_momentum_dirichlet_dev") result(stat)
+       use iso_c_binding
+       integer(c_int), value :: id, n
+       integer(c_int), intent(in) :: nodes(*), comps(*)
+       real(c_double), intent(in) :: values(*)
+       integer(c_int) :: stat
+     end function cgasm_momentum_dirichlet_dev
+
+     ! correct_masslumped_velocity: u += inverse_masslump * ct_m^T delta_p (ct_m: c_null_ptr = the resident one)
+     function cgasm_correct_masslumped_velocity(id, ct_m, inverse_masslump, delta_p, u) &
+          & bind(c, name="cgasm_correct_masslumped_velocity") result(stat)
+       use iso_c_binding
+       integer(c_int), value :: id
+       type(c_ptr), value :: ct_m
+       real(c_double), intent(in) :: inverse_masslump(*), delta_p(*)
+       real(c_double), intent(inout) :: u(*)
+       integer(c_int) :: stat
+     end function cgasm_correct_masslumped_velocity
 
      ! device hand-off to PETSc: the (i, j) pattern once per sparsity for MatSetPreallocationCOO, the values per assembly
      ! for MatSetValuesCOO. row_gnn2unn / col_gnn2unn = petsc_numbering%gnn2unn of the matrix (col: c_null_ptr = rows).

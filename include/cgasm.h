@@ -124,8 +124,13 @@ typedef struct cgasm_momentum_opts {
       have_geostrophic_pressure, have_surfacetension, have_vertical_stabilization,
       have_swe_bottom_drag, have_wd_abs, have_temperature_dependent_viscosity,
       stress_form, partial_stress_form, radial_gravity, vel_lump_on_submesh,
-      cmc_lump_on_submesh, abs_lump_on_submesh, assemble_mass_matrix,
-      integrate_continuity_by_parts;
+      cmc_lump_on_submesh, abs_lump_on_submesh;
+  /* implemented since round 2 (they keep their place in the struct): the `mass` matrix (cgasm_momentum_mass_fetch) and
+   * continuity by parts (volume form in the element loop, boundary blocks in cgasm_momentum_surface_dev) */
+  int assemble_mass_matrix, integrate_continuity_by_parts;
+  /* have_fs_stab(u): free-surface stabilisation of the surface loop (Momentum_CG.F90:1108-1178). Not implemented:
+   * cgasm_momentum_surface_dev answers CGASM_EUNSUPPORTED when it is set and a face has type FREE_SURFACE. */
+  int have_surface_fs_stabilisation;
 } cgasm_momentum_opts;
 
 /* Advection_Diffusion_CG.F90:77-123 (declarations), :384-556 (population). */
@@ -230,6 +235,11 @@ int cgasm_advdiff_fetch(int id, double* matrix_val, double* rhs);
 /* 1 if the dim diagonal blocks of the last momentum result are identical (no absorption term:
  * mass, advection and tensor-form viscosity add the same loc x loc matrix to every (d,d) block,
  * Momentum_CG.F90:1550,1711,2312-2317), so one block can be fetched and inserted dim times. */
+/* The `mass` matrix of construct_momentum_cg when opts.assemble_mass_matrix = 1 (Momentum_CG.F90:1567-1571: the
+ * density-weighted consistent mass matrix on every diagonal block, plus dt*theta*absorption_mat with
+ * pressure_corrected_absorption, :2073-2078), as [dim][nnz] diagonal blocks in colm order like big_m. */
+int cgasm_momentum_mass_fetch(int id, double* mass);
+int cgasm_momentum_mass_dev(int id, double** mass_dev);
 int cgasm_momentum_identical_blocks(int id, int* identical);
 /* Copies blocks first_block .. first_block+nblocks-1 (0-based) of big_m to the host. */
 int cgasm_momentum_fetch_blocks(int id, int first_block, int nblocks, double* big_m);
@@ -282,6 +292,24 @@ int cgasm_advdiff_surface_dev(int id, const cgasm_advdiff_opts* opts, const int*
  * 1-based. The matrix itself is untouched: the reference only flags the rows inactive (set_inactive), which
  * stays with the caller's csr_matrix. */
 int cgasm_advdiff_dirichlet_dev(int id, int n, const int* nodes, const double* values, int have_dt, double dt);
+
+/* Strong Dirichlet conditions of the velocity on big_m / rhs, device-resident (apply_dirichlet_conditions for a
+ * petsc_csr_matrix: femtools/Boundary_Conditions.F90:2198-2218 = collect_vector_dirichlet_conditions :2125-2178 +
+ * lift_boundary_conditions, femtools/Sparse_Tools_Petsc.F90:1139-1254 = MatZeroRowsColumns with pivot 1, then
+ * fix_scaling). ONE call carries every strong condition: nodes(n) 1-based, comps(n) 1-based component, values(n) = what
+ * collect_vector_dirichlet_conditions writes into rhs ((bc - u)/dt in acceleration form, else bc); a pair listed twice
+ * takes the later value. For every listed (r, d): rhs(d, i) -= big_m_d(i, r) * value for the rows i not listed
+ * themselves, row r and column r of block d are zeroed except the diagonal, which keeps its value, and
+ * rhs(d, r) = diagonal * value. */
+int cgasm_momentum_dirichlet_dev(int id, int n, const int* nodes, const int* comps, const double* values);
+
+/* correct_masslumped_velocity (assemble/Momentum_CG.F90:2544-2575): u(d, :) += inverse_masslump(d, :) * (ct_m(1,d)^T
+ * delta_p), every component. ct_m: host [dim][nnz] blocks or NULL = the ct_m left on the device by the last
+ * cgasm_momentum_dev with assemble_ct_matrix_here; inverse_masslump host (dim, n_nodes) (the caller inverts masslump as
+ * Momentum_Equation does); delta_p host (n_nodes); u host (dim, n_nodes), corrected in place. Same summation order as the
+ * reference's mult_T. The halo_update(u) that follows stays with the caller. */
+int cgasm_correct_masslumped_velocity(int id, const double* ct_m, const double* inverse_masslump, const double* delta_p,
+                                      double* u);
 
 /* Velocity boundary-condition types of assemble/Momentum_CG.F90:138-140 */
 enum {

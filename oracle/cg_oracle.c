@@ -550,7 +550,7 @@ static int momentum_opts_unsupported(const cgasm_momentum_opts* o) {
          o->have_vertical_stabilization || o->have_swe_bottom_drag || o->have_wd_abs ||
          o->have_temperature_dependent_viscosity || o->stress_form || o->partial_stress_form ||
          o->radial_gravity || o->vel_lump_on_submesh || o->cmc_lump_on_submesh ||
-         o->abs_lump_on_submesh || o->assemble_mass_matrix;
+         o->abs_lump_on_submesh; /* assemble_mass_matrix: the `mass` matrix is orc_assemble_momentum_mass below */
 }
 
 int orc_momentum_element(const orc_mesh* m, const orc_momentum_fields* f,
@@ -1198,6 +1198,49 @@ int orc_assemble_momentum(const orc_mesh* m, const orc_momentum_fields* f,
   return status;
 }
 
+/* The `mass` matrix of construct_momentum_cg (assemble_mass_matrix, Momentum_CG.F90:1567-1571): every element adds its
+ * density-weighted consistent mass matrix mass_mat = shape_shape(test_function, u_shape, detwei*density_gi) to each
+ * diagonal block -- whatever lump_mass / exclude_mass say about big_m -- and, with pressure_corrected_absorption,
+ * dt*theta*absorption_mat(dim,:,:) on top (:2073-2078, the full absorption matrix also when the absorption in big_m is
+ * lumped). mass: [dim][nnz] diagonal blocks in colm order. Test function = u_shape (no SUPG). */
+int orc_assemble_momentum_mass(const orc_mesh* m, const orc_momentum_fields* f, const cgasm_momentum_opts* o,
+                               const int* findrm, const int* colm, double* mass) {
+  const int dim = m->dim, loc = m->loc, ngi = m->ngi;
+  const size_t nnz = (size_t)(findrm[m->n_nodes] - 1);
+  if (momentum_opts_unsupported(o) || o->stabilisation_scheme == CGASM_STAB_SUPG) return CGASM_EUNSUPPORTED;
+  memset(mass, 0, sizeof(double) * dim * nnz);
+  for (int ele = 1; ele <= m->n_elements; ele++) {
+    double X_val[MAXDIM * MAXLOC], du_t[MAXLOC * MAXNGI * MAXDIM], detwei[MAXNGI];
+    orc_field Xf = {m->X, CGASM_FIELD_NORMAL};
+    ele_val_vector(m, &Xf, ele, X_val);
+    orc_transform_to_physical(dim, ngi, X_val, m->dn, m->weight, du_t, detwei, NULL);
+    double density_gi[MAXNGI], ev_s[MAXLOC], cd[MAXNGI], mass_mat[MAXLOC * MAXLOC];
+    ele_val_scalar(m, &f->density, ele, ev_s);
+    at_quad_scalar(m, ev_s, density_gi);
+    for (int g = 0; g < ngi; g++) cd[g] = density_gi[g] * detwei[g];
+    shape_shape2(loc, ngi, m->n, m->n, cd, mass_mat);
+    double absorption_mat[MAXDIM * MAXLOC * MAXLOC];
+    const int pc = o->have_absorption && o->pressure_corrected_absorption;
+    if (pc) {
+      double a_val[MAXDIM * MAXLOC], absorption_gi[MAXDIM * MAXNGI];
+      ele_val_vector(m, &f->absorption, ele, a_val);
+      at_quad_multi(m, dim, a_val, absorption_gi);
+      shape_shape_vector2(dim, loc, ngi, m->n, m->n, cd, absorption_gi, absorption_mat);
+    }
+    const int* nd = ele_nodes(m, ele);
+    for (int i = 0; i < loc; i++)
+      for (int j = 0; j < loc; j++) {
+        const int pos = csr_sparsity_pos(findrm, colm, nd[i], nd[j]);
+        for (int d = 0; d < dim; d++) {
+          double v = mass_mat[i + loc * j];
+          if (pc) v = v + o->dt * o->theta * absorption_mat[d + dim * (i + loc * j)];
+          mass[d * nnz + (size_t)(pos - 1)] += v;
+        }
+      }
+  }
+  return 0;
+}
+
 int orc_assemble_advdiff(const orc_mesh* m, const orc_advdiff_fields* f, const cgasm_advdiff_opts* o,
                          const int* findrm, const int* colm, int ncolours, const int* colour_ptr,
                          const int* colour_elements, double* matrix_val /*nnz*/, double* rhs /*N*/) {
@@ -1741,3 +1784,64 @@ void orc_set_threads(int n) { omp_set_num_threads(n > 0 ? n : 1); }
 #else
 void orc_set_threads(int n) { (void)n; }
 #endif
+
+/* correct_masslumped_velocity, assemble/Momentum_CG.F90:2544-2575: per component d
+ *   delta_u = mult_T(block(ct_m, 1, d), delta_p)      femtools/Sparse_Tools.F90:3889-3916: rows of ct_m ascending,
+ *                                                      vector_out(colm(j)) += val(j) * vector_in(i)
+ *   delta_u = delta_u * inverse_masslump(d, :)         scale
+ *   u(d, :) = u(d, :) + delta_u                        addto
+ * ct_m [dim][nnz] on the first-order sparsity (rows = pressure nodes), inverse_masslump and u (dim, n_nodes). */
+void orc_correct_masslumped_velocity(int dim, int n_nodes, const int* findrm, const int* colm, const double* ct_m,
+                                     const double* inverse_masslump, const double* delta_p, double* u) {
+  const size_t nnz = (size_t)(findrm[n_nodes] - 1);
+  double* delta_u = (double*)malloc(sizeof(double) * (size_t)n_nodes);
+  for (int d = 0; d < dim; d++) {
+    for (int k = 0; k < n_nodes; k++) delta_u[k] = 0.0;
+    for (int i = 1; i <= n_nodes; i++)
+      for (int j = findrm[i - 1]; j <= findrm[i] - 1; j++) {
+        const int k = colm[j - 1];
+        delta_u[k - 1] = delta_u[k - 1] + ct_m[d * nnz + (size_t)(j - 1)] * delta_p[i - 1];
+      }
+    for (int k = 0; k < n_nodes; k++) {
+      delta_u[k] = delta_u[k] * inverse_masslump[d + (size_t)dim * k];
+      u[d + (size_t)dim * k] = u[d + (size_t)dim * k] + delta_u[k];
+    }
+  }
+  free(delta_u);
+}
+
+/* Strong Dirichlet conditions on big_m: apply_dirichlet_conditions_vector_petsc_csr, femtools/Boundary_Conditions.F90
+ * :2198-2218 = collect_vector_dirichlet_conditions (:2125-2178: rhs(d, node) = value) + lift_boundary_conditions,
+ * femtools/Sparse_Tools_Petsc.F90:1139-1254. The latter is PETSc's MatZeroRowsColumns(A, rows, pivot = 1.0, x, b)
+ * (PETSc is an un-vendored dependency, debian/control names 3.8.3; its documented algorithm: for every listed row r
+ * b_r = pivot * x_r, for every other row i b_i -= A_ir x_r, row r and column r are zeroed, A_rr = pivot; x is a copy of b
+ * taken beforehand, :1185-1190) followed by fix_scaling (:1213-1235): A_rr = its old diagonal value and
+ * b_r = old diagonal * b_r. big_m is held as its dim diagonal blocks [dim][nnz] (block_mask, Momentum_CG.F90:1293-1300),
+ * rhs (dim, n_nodes). bc_nodes / bc_comps (1-based) list the (node, component) pairs with a strong condition. */
+void orc_lift_boundary_conditions(int dim, int n_nodes, const int* findrm, const int* colm, double* big_m, double* rhs,
+                                  int nbc, const int* bc_nodes, const int* bc_comps) {
+  const size_t nnz = (size_t)(findrm[n_nodes] - 1);
+  char* flag = (char*)calloc((size_t)dim * (size_t)n_nodes, 1);
+  double* x = (double*)malloc(sizeof(double) * (size_t)dim * (size_t)n_nodes);
+  for (size_t k = 0; k < (size_t)dim * (size_t)n_nodes; k++) x[k] = rhs[k]; /* xvec = copy of bvec */
+  for (int b = 0; b < nbc; b++) flag[(bc_comps[b] - 1) + (size_t)dim * (bc_nodes[b] - 1)] = 1;
+  for (int d = 0; d < dim; d++)
+    for (int i = 1; i <= n_nodes; i++) {
+      const int mine = flag[d + (size_t)dim * (i - 1)];
+      double old_diag = 0.0;
+      for (int j = findrm[i - 1]; j <= findrm[i] - 1; j++) {
+        const int c = colm[j - 1];
+        double* a = &big_m[d * nnz + (size_t)(j - 1)];
+        if (mine) {
+          if (c == i) old_diag = *a; /* kept: MatSetValue(j, j, old_diagonal_values) */
+          else *a = 0.0;
+        } else if (flag[d + (size_t)dim * (c - 1)]) {
+          rhs[d + (size_t)dim * (i - 1)] = rhs[d + (size_t)dim * (i - 1)] - *a * x[d + (size_t)dim * (c - 1)];
+          *a = 0.0;
+        }
+      }
+      if (mine) rhs[d + (size_t)dim * (i - 1)] = old_diag * (1.0 * x[d + (size_t)dim * (i - 1)]);
+    }
+  free(flag);
+  free(x);
+}

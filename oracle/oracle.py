@@ -256,6 +256,20 @@ def assemble_momentum(mesh, fields, opts, findrm, colm, colouring=None, want_mas
     return dict(big_m=big_m, rhs=rhs, masslump=ml, ct_m=ct)
 
 
+def assemble_momentum_mass(mesh, fields, opts, findrm, colm):
+    """The `mass` matrix of construct_momentum_cg (assemble_mass_matrix): (dim, nnz) diagonal blocks."""
+    ctx = _Ctx(mesh, fields)
+    nnz = int(findrm[-1] - 1)
+    mass = np.zeros((mesh.dim, nnz))
+    mf = ctx.mom()
+    st = lib().orc_assemble_momentum_mass(C.byref(ctx.mesh), C.byref(mf), C.byref(opts),
+                                          _ip(np.ascontiguousarray(findrm, dtype=np.int32)),
+                                          _ip(np.ascontiguousarray(colm, dtype=np.int32)), _dp(mass))
+    if st:
+        raise RuntimeError("orc_assemble_momentum_mass status %d" % st)
+    return mass
+
+
 def assemble_advdiff(mesh, fields, opts, findrm, colm, colouring=None):
     ctx = _Ctx(mesh, fields)
     nnz = int(findrm[-1] - 1)
@@ -468,3 +482,24 @@ def assemble_ct_surface(mesh, fields, opts, findrm, colm, sndgln, face_ele, velo
                                        _ip(np.ascontiguousarray(colm, dtype=np.int32)), _ip(bt), _ip(pt), _dp(ct_m))
     if st:
         raise RuntimeError("oracle status %d" % st)
+
+
+def correct_masslumped_velocity(findrm, colm, ct_m, inverse_masslump, delta_p, u):
+    """u (n_nodes, dim) corrected IN PLACE: u_d += inverse_masslump_d * (ct_m_d^T delta_p) (Momentum_CG.F90:2544-2575)."""
+    n, dim = u.shape
+    lib().orc_correct_masslumped_velocity(C.c_int(dim), C.c_int(n), _ip(np.ascontiguousarray(findrm, dtype=np.int32)),
+                                          _ip(np.ascontiguousarray(colm, dtype=np.int32)),
+                                          _dp(np.ascontiguousarray(ct_m)), _dp(np.ascontiguousarray(inverse_masslump)),
+                                          _dp(np.ascontiguousarray(delta_p)), _dp(u))
+    return u
+
+
+def lift_boundary_conditions(findrm, colm, big_m, rhs, nodes, comps):
+    """Strong Dirichlet rows of big_m (dim, nnz) / rhs (n_nodes, dim), IN PLACE; rhs already holds the boundary values in
+    the listed (node, component) entries (collect_vector_dirichlet_conditions)."""
+    n, dim = rhs.shape
+    nodes = np.ascontiguousarray(nodes, dtype=np.int32)
+    comps = np.ascontiguousarray(comps, dtype=np.int32)
+    lib().orc_lift_boundary_conditions(C.c_int(dim), C.c_int(n), _ip(np.ascontiguousarray(findrm, dtype=np.int32)),
+                                       _ip(np.ascontiguousarray(colm, dtype=np.int32)), _dp(big_m), _dp(rhs),
+                                       C.c_int(len(nodes)), _ip(nodes), _ip(comps))

@@ -454,3 +454,53 @@ def test_fused_momentum_tracer_call_equals_the_two_calls(orc, dim, case):
     ref_a = orc.assemble_advdiff(mesh, fs, oa, findrm, colm)
     check_momentum(got_m, ref_m, findrm, dim)
     assert rel_err(got_a["matrix"], ref_a["matrix"]) < TOL and rel_err(got_a["rhs"], ref_a["rhs"]) < TOL
+
+
+# ---- the `mass` matrix (assemble_mass_matrix) and continuity by parts ------------------------------------------------
+@pytest.mark.parametrize("scatter", [pytest.param(abi.SCATTER_ATOMIC, id="atomic"), pytest.param(abi.SCATTER_STRIP, id="strip")])
+@pytest.mark.parametrize("dim", [2, 3])
+@pytest.mark.parametrize("case", ["plain", "lumped_excluded", "pressure_corrected_absorption"])
+def test_assemble_mass_matrix(orc, scatter, dim, case):
+    """Momentum_CG.F90:1567-1571 / :2073-2078: the consistent density-weighted mass matrix on every diagonal block,
+    independent of what lump_mass / exclude_mass do to big_m, plus dt*theta*absorption_mat when pressure-corrected."""
+    mesh = syn.box_mesh((5, 4, 3)[:dim], seed=36)
+    fs = syn.standard_fields(mesh)
+    c = abi.common_momentum_opts
+    o = {"plain": c(assemble_mass_matrix=1, lump_mass=0),
+         "lumped_excluded": c(assemble_mass_matrix=1, exclude_mass=1),
+         "pressure_corrected_absorption": c(assemble_mass_matrix=1, have_absorption=1, lump_absorption=1,
+                                            pressure_corrected_absorption=1)}[case]
+    asm = make_asm(mesh, fs, scatter)
+    findrm, colm, _ = asm.get_sparsity()
+    got = asm.momentum(o)
+    mass = asm.momentum_mass_fetch()
+    ref_mass = orc.assemble_momentum_mass(mesh, fs, o, findrm, colm)
+    for d in range(dim):
+        assert rel_err(mass[d], ref_mass[d]) < TOL and row_rel_err(mass[d], ref_mass[d], findrm) < TOL
+    # big_m itself is what it is without the flag
+    o2 = abi.MomentumOpts.from_buffer_copy(o)
+    o2.assemble_mass_matrix = 0
+    check_momentum(got, orc.assemble_momentum(mesh, fs, o2, findrm, colm), findrm, dim)
+    # and the matrix is not there when it was not asked for
+    asm.momentum_dev(o2)
+    with pytest.raises(cgasm.CgasmError):
+        asm.momentum_mass_fetch()
+
+
+@pytest.mark.parametrize("scatter", [pytest.param(abi.SCATTER_ATOMIC, id="atomic"), pytest.param(abi.SCATTER_GATHER, id="gather"),
+                                     pytest.param(abi.SCATTER_STRIP, id="strip")])
+@pytest.mark.parametrize("dim", [2, 3])
+def test_continuity_by_parts_volume_form(orc, scatter, dim):
+    """integrate_continuity_by_parts: ct_m's volume form is -dshape_shape (Momentum_CG.F90:1379-1383)."""
+    mesh = syn.box_mesh((5, 4, 3)[:dim], seed=37)
+    fs = syn.standard_fields(mesh)
+    o = abi.common_momentum_opts(assemble_ct_matrix_here=1, integrate_continuity_by_parts=1)
+    asm = make_asm(mesh, fs, scatter)
+    findrm, colm, _ = asm.get_sparsity()
+    got = asm.momentum(o)
+    ref = orc.assemble_momentum(mesh, fs, o, findrm, colm, want_ct=True)
+    check_momentum(got, ref, findrm, dim)
+    for ele in (1, mesh.n_elements // 2, mesh.n_elements):
+        _, _, _, gp = asm.momentum_element(o, ele)
+        _, _, _, ogp = orc.momentum_element(mesh, fs, o, ele)
+        assert rel_err(gp, ogp) < TOL

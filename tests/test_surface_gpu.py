@@ -159,3 +159,83 @@ def test_surface_calls_refuse_what_they_must():
     got = asm.advdiff_fetch()
     # (two runs of the default ATOMIC scatter variant: equal up to the order of the atomic additions)
     assert rel_err(got["matrix"], ref["matrix"]) < 1e-14 and rel_err(got["rhs"], ref["rhs"]) < 1e-14
+
+
+@pytest.mark.parametrize("name", ["box2", "box3", "cube-parallel"])
+def test_continuity_by_parts_boundary_blocks(orc, name):
+    """integrate_continuity_by_parts: the element loop makes -dshape_shape, the surface loop adds
+    shape_shape_vector(p_shape, u_shape, detwei_bdy, normal_bdy) on every face that is neither no-normal-flow nor
+    free-surface (Momentum_CG.F90:1073-1088). By the divergence theorem the two together equal the plain form on rows
+    whose faces all take part; here simply against the oracle."""
+    mesh = meshes()[name]
+    fs = syn.standard_fields(mesh)
+    asm, sn, fe = make(mesh, fs, abi.SCATTER_STRIP)
+    findrm, colm, _ = asm.get_sparsity()
+    dim, nf = mesh.dim, len(fe)
+    rng = np.random.default_rng(11)
+    bt = np.zeros((nf, dim), dtype=np.int32)
+    kind = rng.choice([0, 1, 2, 4], size=nf)          # none / weak Dirichlet / no normal flow / free surface
+    bt[:, 0] = kind
+    bt[kind == 1, 1:] = 1
+    o = abi.common_momentum_opts(assemble_ct_matrix_here=1, integrate_continuity_by_parts=1, integrate_advection_by_parts=1)
+    vbc = rng.uniform(size=(nf, dim, dim))
+    ref = orc.assemble_momentum(mesh, fs, o, findrm, colm, want_ct=True)
+    orc.assemble_momentum_surface(mesh, fs, o, findrm, colm, sn, fe, bt, vbc, ref["big_m"], ref["rhs"])
+    orc.assemble_ct_surface(mesh, fs, o, findrm, colm, sn, fe, bt, ref["ct_m"])
+    asm.momentum_dev(o)
+    asm.momentum_surface_dev(o, bt, vbc)
+    got = asm.momentum_fetch(want_masslump=True, want_ct=True)
+    for d in range(dim):
+        assert rel_err(got["ct_m"][d], ref["ct_m"][d]) < TOL
+        assert rel_err(got["big_m"][d], ref["big_m"][d]) < TOL
+    assert rel_err(got["rhs"], ref["rhs"]) < TOL
+    # pressure conditions with by-parts continuity stay with the Fortran loop
+    with pytest.raises(cgasm.CgasmError) as ei:
+        asm.momentum_surface_dev(o, bt, vbc, np.ones(nf, dtype=np.int32))
+    assert ei.value.code == abi.EUNSUPPORTED
+
+
+@pytest.mark.parametrize("name", ["box2", "box3", "cube-parallel"])
+def test_vector_dirichlet_lifting_and_velocity_correction(orc, name):
+    """Strong Dirichlet conditions on big_m (lift_boundary_conditions: MatZeroRowsColumns + fix_scaling) and
+    correct_masslumped_velocity, both on the device-resident results, against the C restatements in the oracle."""
+    mesh = meshes()[name]
+    fs = syn.standard_fields(mesh)
+    asm, sn, fe = make(mesh, fs, abi.SCATTER_STRIP)
+    findrm, colm, _ = asm.get_sparsity()
+    dim, nn = mesh.dim, mesh.n_nodes
+    rng = np.random.default_rng(13)
+    o = abi.common_momentum_opts(assemble_ct_matrix_here=1, have_absorption=1)
+    ref = orc.assemble_momentum(mesh, fs, o, findrm, colm, want_ct=True)
+    # conditions: all components on a third of the boundary nodes, the first component only on another third,
+    # a few pairs listed twice (the later value wins)
+    bnodes = np.unique(sn.ravel())
+    a, b = bnodes[: len(bnodes) // 3], bnodes[len(bnodes) // 3: 2 * len(bnodes) // 3]
+    nodes = np.concatenate([np.repeat(a, dim), b, a[:3]])
+    comps = np.concatenate([np.tile(np.arange(1, dim + 1), len(a)), np.ones(len(b), dtype=np.int64), np.ones(3, dtype=np.int64)])
+    vals = rng.uniform(-1, 1, size=len(nodes))
+    want_rhs = ref["rhs"].copy()
+    want_rhs[nodes - 1, comps - 1] = vals          # numpy fancy assignment: later entries win, like the reference's set()
+    want_bigm = ref["big_m"].copy()
+    orc.lift_boundary_conditions(findrm, colm, want_bigm, want_rhs, nodes, comps)
+    asm.momentum_dev(o)
+    asm.momentum_dirichlet_dev(nodes, comps, vals)
+    got = asm.momentum_fetch(want_masslump=True, want_ct=True)
+    for d in range(dim):
+        assert rel_err(got["big_m"][d], want_bigm[d]) < TOL
+        lifted = np.zeros(nn, dtype=bool)
+        lifted[nodes[comps == d + 1] - 1] = True
+        rows = np.repeat(np.arange(nn), np.diff(findrm))
+        offdiag = (colm - 1) != rows
+        assert (got["big_m"][d][lifted[rows] & offdiag] == 0.0).all() and (got["big_m"][d][lifted[colm - 1] & offdiag] == 0.0).all()
+    assert rel_err(got["rhs"], want_rhs) < TOL
+    assert not asm.momentum_identical_blocks()
+    # velocity correction with the resident ct_m and with a host copy
+    iml = 1.0 / ref["masslump"]
+    dp = rng.uniform(-1, 1, size=nn)
+    u0 = fs.get(abi.F_NU)[0].copy()
+    want_u = orc.correct_masslumped_velocity(findrm, colm, ref["ct_m"], iml, dp, u0.copy())
+    got_u = asm.correct_masslumped_velocity(iml, dp, u0.copy())
+    assert rel_err(got_u, want_u) < TOL
+    got_u2 = asm.correct_masslumped_velocity(iml, dp, u0.copy(), ct_m=ref["ct_m"])
+    assert (got_u2 == want_u).all()      # same inputs, same summation order, explicit multiplies and adds: bitwise
