@@ -108,6 +108,88 @@ int ensure_extra_records(Handle* h) {
   return CGASM_OK;
 }
 
+void* rec_array(const Handle* h, int k) {
+  switch (k) {
+    case 0: return h->d_rec0;
+    case 1: return h->d_rec1;
+    case 2: return h->d_rec2;
+    case 3: return h->d_rec3;
+    case 4: return h->d_rec4;
+    case 5: return h->d_rec5;
+    default: return h->d_rec6;
+  }
+}
+int rec_width(int k) { return k == 4 ? 2 : 4; }  // doubles per record
+
+const void* staged_rec(const Handle* h, int k) { return (h->d_perm && h->d_prec[k]) ? h->d_prec[k] : rec_array(h, k); }
+
+// dst[perm[node]] = src[node], whole records
+__global__ void permute_records_kernel(double* __restrict__ dst, const double* __restrict__ src, int recw,
+                                       const int* __restrict__ perm, const int* __restrict__ nodes, int n) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int node = nodes ? nodes[k] : k;
+  const double* a = src + (size_t)recw * node;
+  double* b = dst + (size_t)recw * perm[node];
+  if (recw == 4) *reinterpret_cast<double4*>(b) = *reinterpret_cast<const double4*>(a);
+  else *reinterpret_cast<double2*>(b) = *reinterpret_cast<const double2*>(a);
+}
+
+int refresh_permuted(Handle* h, unsigned recmask, const int* d_nodes, int n, cudaStream_t stream) {
+  if (!h->d_perm) return CGASM_OK;
+  const int count = d_nodes ? n : h->n_nodes;
+  if (count <= 0) return CGASM_OK;
+  for (int k = 0; k < 7; k++) {
+    if (!(recmask & (1u << k)) || !rec_array(h, k)) continue;
+    if (!h->d_prec[k]) {
+      CG_CUDA(cudaMalloc(&h->d_prec[k], sizeof(double) * rec_width(k) * (size_t)h->n_nodes));
+      // a mirror made late starts as a full copy
+      permute_records_kernel<<<(h->n_nodes + 255) / 256, 256, 0, stream>>>(
+          (double*)h->d_prec[k], (const double*)rec_array(h, k), rec_width(k), h->d_perm, nullptr, h->n_nodes);
+      h->launches++;
+      continue;
+    }
+    permute_records_kernel<<<(count + 255) / 256, 256, 0, stream>>>((double*)h->d_prec[k], (const double*)rec_array(h, k),
+                                                                    rec_width(k), h->d_perm, d_nodes, count);
+    h->launches++;
+  }
+  CG_CUDA(cudaGetLastError());
+  return CGASM_OK;
+}
+
+int set_permutation(Handle* h, const std::vector<int>& perm) {
+  free_dev(h->d_perm);
+  h->d_perm = nullptr;
+  for (void*& p : h->d_prec) {
+    free_dev(p);
+    p = nullptr;
+  }
+  if (perm.empty()) return CGASM_OK;
+  CG_CUDA(cudaMalloc(&h->d_perm, sizeof(int) * perm.size()));
+  CG_CUDA(cudaMemcpyAsync(h->d_perm, perm.data(), sizeof(int) * perm.size(), cudaMemcpyHostToDevice, h->stream));
+  CG_CUDA(cudaStreamSynchronize(h->stream));
+  return refresh_permuted(h, 0x7f, nullptr, 0, h->stream);
+}
+
+// which record arrays mirror a field slot (bit k = record k)
+static unsigned slot_recmask(int slot) {
+  switch (slot) {
+    case -1: return 1u << 0 | 1u << 3;
+    case CGASM_F_T: return 1u << 0;
+    case CGASM_F_NU:
+    case CGASM_F_DENSITY: return 1u << 1;
+    case CGASM_F_OLDU: return 1u << 2;
+    case CGASM_F_BUOYANCY: return 1u << 2 | 1u << 3;
+    case CGASM_F_T_ABSORPTION:
+    case CGASM_F_T_SOURCE: return 1u << 4;
+    case CGASM_F_ABSORPTION:
+    case CGASM_F_HB_DENSITY: return 1u << 5;
+    case CGASM_F_SOURCE: return 1u << 6;
+    default: return 0;
+  }
+}
+unsigned slot_record_mask(int slot) { return slot_recmask(slot); }
+
 int repack_slot(Handle* h, int slot, const int* d_nodes, int n) {
   double* rec[2];
   int recw[2], lane0[2], ncomp = 0;
@@ -131,7 +213,7 @@ int repack_slot(Handle* h, int slot, const int* d_nodes, int n) {
     h->launches++;
   }
   CG_CUDA(cudaGetLastError());
-  return CGASM_OK;
+  return refresh_permuted(h, slot_recmask(slot), d_nodes, n, h->stream);
 }
 
 static void destroy_handle(Handle* h) {
@@ -151,6 +233,8 @@ static void destroy_handle(Handle* h) {
   free_dev(h->d_rec4);
   free_dev(h->d_rec5);
   free_dev(h->d_rec6);
+  free_dev(h->d_perm);
+  for (void* p : h->d_prec) free_dev(p);
   free_dev(h->d_findrm);
   free_dev(h->d_colm);
   free_dev(h->d_colour_elements);

@@ -69,6 +69,11 @@ struct Handle {
   double4* d_rec5 = nullptr;  // { momentum absorption, hb_density } and
   double4* d_rec6 = nullptr;  // { momentum source, - }: read by the additive STRIP pass (strip_extra.cu), made on demand
   std::vector<double> h_X;  // kept for locality ordering of the tile plan
+  // Node records in the order of the STRIP row blocks (Morton), made when the caller's numbering is scattered: the staging
+  // gathers of a row block then read a few contiguous runs instead of ~370 random sectors. d_perm[node] = position;
+  // s_rec[k] = what the staged kernels read (the permuted mirror of d_rec<k>, or d_rec<k> itself when d_perm is null).
+  int* d_perm = nullptr;
+  void* d_prec[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 
   // node -> element adjacency (host)
   I64Vec n2e_ptr;
@@ -215,6 +220,14 @@ bool strip_extra_needed(const MomentumArgs& args);
 bool strip_extra_ok(const Handle* h, const MomentumArgs& args);
 int strip_extra(Handle* h, const MomentumArgs& args);
 int ensure_extra_records(Handle* h);  // cgasm_api.cu
+// record k (0..6) as the staged kernels read it; refresh of the permuted mirrors after record k changed (all nodes, or the
+// listed ones) on `stream`
+const void* staged_rec(const Handle* h, int k);
+int refresh_permuted(Handle* h, unsigned recmask, const int* d_nodes, int n, cudaStream_t stream);
+int set_permutation(Handle* h, const std::vector<int>& perm);  // empty = none
+void* rec_array(const Handle* h, int k);
+int rec_width(int k);
+unsigned slot_record_mask(int slot);  // bit k = record k mirrors the slot (-1 = coordinates)
 
 // strip_fused.cu: both element loops in one kernel (common STRIP option sets)
 bool strip_fused_ok(const Handle* h, const MomentumArgs& m, const AdvDiffArgs& a);

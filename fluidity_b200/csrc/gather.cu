@@ -42,6 +42,7 @@ void gather_free(Handle* h) {
   strip_free(p);
   delete p;
   h->gather = nullptr;
+  set_permutation(h, std::vector<int>());  // the mirrors follow the row blocks
 }
 
 // One thread per row slot: writes the row's pair list (element order = ascending element id, the

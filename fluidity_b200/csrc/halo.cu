@@ -160,9 +160,11 @@ __global__ void halo_block_dep_kernel(int nblocks, int nl, const int* __restrict
   if (threadIdx.x == 0) dep[b] = (unsigned char)any;
 }
 
-__global__ void halo_mark_kernel(int n, const int* __restrict__ node, unsigned char* __restrict__ mark) {
+// (perm: the block node lists hold record positions when the records are permuted)
+__global__ void halo_mark_kernel(int n, const int* __restrict__ node, const int* __restrict__ perm,
+                                 unsigned char* __restrict__ mark) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k < n) mark[node[k]] = 1;
+  if (k < n) mark[perm ? perm[node[k]] : node[k]] = 1;
 }
 
 static int upload_ints(int** d, const std::vector<int>& v) {
@@ -357,6 +359,12 @@ int cgasm_halo_update(int id, unsigned slot_mask) {
     h->launches++;
   }
   CG_CUDA(cudaGetLastError());
+  if (h->d_perm && p->total_recv) {  // the staged kernels read the permuted mirrors of the records just refreshed
+    unsigned recmask = 0;
+    for (int s = 0; s < CGASM_F_NSLOTS; s++)
+      if ((slot_mask & (1u << s)) && h->fields[s].set && h->fields[s].field_type == CGASM_FIELD_NORMAL) recmask |= slot_record_mask(s);
+    if ((st = refresh_permuted(h, recmask, p->d_recv_node, p->total_recv, cs))) return st;
+  }
   if (p->overlap) {
     CG_CUDA(cudaEventRecord(p->ev_done, cs));
     p->pending = true;
@@ -390,7 +398,7 @@ static int halo_build_split(Handle* h) {
   CG_CUDA(cudaMalloc(&d_mark, (size_t)h->n_nodes));
   CG_CUDA(cudaMalloc(&d_dep, (size_t)std::max(nb, 1)));
   CG_CUDA(cudaMemsetAsync(d_mark, 0, (size_t)h->n_nodes, h->stream));
-  if (p->total_recv) halo_mark_kernel<<<(p->total_recv + 255) / 256, 256, 0, h->stream>>>(p->total_recv, p->d_recv_node, d_mark);
+  if (p->total_recv) halo_mark_kernel<<<(p->total_recv + 255) / 256, 256, 0, h->stream>>>(p->total_recv, p->d_recv_node, h->d_perm, d_mark);
   halo_block_dep_kernel<<<nb, 128, 0, h->stream>>>(nb, P->nl, P->d_blk_nodes, d_mark, d_dep);
   h->launches += 2;
   std::vector<unsigned char> dep((size_t)nb);

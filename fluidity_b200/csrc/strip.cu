@@ -311,8 +311,36 @@ int strip_build(Handle* h) {
   GatherPlan* P = h->gather;
   if (!P) CG_FAIL(CGASM_ESTATE, "strip scatter: the gather row blocks must exist first");
   if (P->d_strip || P->d_strip_local) return CGASM_OK;
+  // Scattered numbering (a gmsh / adapted mesh without renumbering; tests: synthetic.shuffled): the rows of a block, sorted
+  // by node id, are hardly ever consecutive. The staged kernels then read permuted mirrors of the node records, laid out in
+  // the order of the row blocks. CGASM_STRIP_PERMUTE=0/1 overrides the choice.
+  std::vector<int> perm;
+  {
+    long long pairs = 0, consecutive = 0;
+    const std::vector<int>& rows = P->h_rows;
+    for (size_t q = 1; q < rows.size(); q++) {
+      if (q % kBR == 0 || rows[q] < 0 || rows[q - 1] < 0) continue;
+      pairs++;
+      consecutive += rows[q] == rows[q - 1] + 1;
+    }
+    bool scattered = pairs > 0 && (double)consecutive < 0.25 * (double)pairs;
+    if (const char* e = getenv("CGASM_STRIP_PERMUTE")) scattered = atoi(e) != 0;
+    if (scattered) {
+      perm.assign((size_t)h->n_nodes, 0);
+      int next = 0;
+      for (size_t q = 0; q < rows.size(); q++)
+        if (rows[q] >= 0) perm[rows[q]] = next++;
+      if (getenv("CGASM_DEBUG"))
+        fprintf(stderr, "[cgasm] scattered numbering (%.1f %% of a block's rows consecutive): node records mirrored in row-block order\n",
+                pairs ? 100.0 * consecutive / pairs : 0.0);
+    }
+  }
+  {
+    int pst = set_permutation(h, perm);
+    if (pst) return pst;
+  }
   StagedPlanHost sp;
-  build_staged_plan_host(h, P->h_rows, P->nblocks, P->maxlen, sp);
+  build_staged_plan_host(h, P->h_rows, P->nblocks, P->maxlen, perm, sp);
   P->blk_nodes_max = sp.blk_nodes_max;
   P->strip_entries_per_pair = h->n2e.empty() ? 0.0 : (double)sp.total_real / (double)h->n2e.size();
   if (getenv("CGASM_DEBUG"))

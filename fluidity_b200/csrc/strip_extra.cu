@@ -425,6 +425,7 @@ static int strip_extra_dim(Handle* h, const MomentumArgs& A) {
   c.ml_on = (o.have_absorption && o.lump_absorption && o.pressure_corrected_absorption) ? 1.0 : 0.0;
   int st = ensure_extra_records(h);
   if (st) return st;
+  if (h->d_perm && (!h->d_prec[5] || !h->d_prec[6]) && (st = refresh_permuted(h, 1u << 5 | 1u << 6, nullptr, 0, h->stream))) return st;
   double* ml = o.assemble_inverse_masslump ? h->d_masslump : nullptr;
   if (light) {
     const StagedView v = staged_view(h, 0);
@@ -433,7 +434,8 @@ static int strip_extra_dim(Handle* h, const MomentumArgs& A) {
   do {                                                                                                          \
     if ((st = strip_smem(staged_momentum_extra_kernel<DIM, NL_>, smem))) return st;                      \
     staged_momentum_extra_kernel<DIM, NL_><<<P->nblocks, kBR, smem, h->stream>>>(                        \
-        c, v, h->d_rec3, h->d_rec5, h->d_rec6, h->d_rec2, (size_t)h->nnz, h->d_big_m, h->d_mom_rhs, ml);         \
+        c, v, (const double4*)staged_rec(h, 3), (const double4*)staged_rec(h, 5), (const double4*)staged_rec(h, 6),                 \
+        (const double4*)staged_rec(h, 2), (size_t)h->nnz, h->d_big_m, h->d_mom_rhs, ml);         \
     h->launches++;                                                                                              \
   } while (0)
     CGASM_FOR_NL(LAUNCH_NL);
@@ -446,7 +448,8 @@ static int strip_extra_dim(Handle* h, const MomentumArgs& A) {
   do {                                                                                                          \
     if ((st = strip_smem(staged_momentum_abs_kernel<DIM, NL_>, smem))) return st;                               \
     staged_momentum_abs_kernel<DIM, NL_><<<dim3(P->nblocks, DIM), kBR, smem, h->stream>>>(                      \
-        c, v, h->d_rec3, h->d_rec5, h->d_rec2, (size_t)h->nnz, h->d_big_m, h->d_mom_rhs);                        \
+        c, v, (const double4*)staged_rec(h, 3), (const double4*)staged_rec(h, 5), (const double4*)staged_rec(h, 2),                 \
+        (size_t)h->nnz, h->d_big_m, h->d_mom_rhs);                        \
     h->launches++;                                                                                              \
   } while (0)
     CGASM_FOR_NL(LAUNCH_NL);

@@ -223,8 +223,9 @@ static int strip_fused_dim(Handle* h, const MomentumArgs& M, const AdvDiffArgs& 
 #define LAUNCH_NL(NL_)                                                                                          \
   do {                                                                                                          \
     if ((st = strip_smem(staged_fused_kernel<DIM, NL_>, smem))) return st;                                      \
-    staged_fused_kernel<DIM, NL_><<<grid, kBR, smem, h->stream>>>(km, ka, v, h->d_rec3, h->d_rec1, h->d_rec2,   \
-                                                                  h->d_rec0, (size_t)h->nnz, h->d_big_m,        \
+    staged_fused_kernel<DIM, NL_><<<grid, kBR, smem, h->stream>>>(                                              \
+        km, ka, v, (const double4*)staged_rec(h, 3), (const double4*)staged_rec(h, 1),                          \
+        (const double4*)staged_rec(h, 2), (const double4*)staged_rec(h, 0), (size_t)h->nnz, h->d_big_m,         \
                                                                   h->d_mom_rhs, ml, h->d_adv_matrix, h->d_adv_rhs); \
     h->launches++;                                                                                              \
   } while (0)

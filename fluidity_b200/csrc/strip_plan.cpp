@@ -708,7 +708,9 @@ struct NodeIndexMap {
 };
 }  // namespace
 
-void build_staged_plan_host(const Handle* h, const std::vector<int>& rows, int nblocks, int maxlen, StagedPlanHost& out) {
+void build_staged_plan_host(const Handle* h, const std::vector<int>& rows, int nblocks, int maxlen,
+                            const std::vector<int>& perm, StagedPlanHost& out) {
+  const bool permuted = !perm.empty();
   const int loc = h->loc, dim = h->dim;
   constexpr int kTask = 128;  // blocks per task: fixed, so the layout does not depend on the thread count
   const int ntasks = (nblocks + kTask - 1) / kTask;
@@ -737,11 +739,13 @@ void build_staged_plan_host(const Handle* h, const std::vector<int>& rows, int n
         int deg = 0;
         map.clear();
         bn.clear();
+        // the map and the block list are keyed by the record position (perm[node] when the records are permuted)
+        auto key_of = [&](int node) { return permuted ? perm[node] : node; };
         auto note = [&](int node) {
-          int* v = map.slot(node);
+          int* v = map.slot(key_of(node));
           if (*v < 0) {
             *v = 0;
-            bn.push_back(node);
+            bn.push_back(key_of(node));
           }
         };
         for (int t = 0; t < kBR; t++) {
@@ -771,7 +775,7 @@ void build_staged_plan_host(const Handle* h, const std::vector<int>& rows, int n
             const int* cb = h->h_colm.data() + h->h_findrm[r];
             own = (int)(std::lower_bound(cb, (const int*)h->h_colm.data() + h->h_findrm[r + 1], r) - cb);
           }
-          const unsigned ol = (unsigned)(own * kAS) << 16 | (unsigned)(*map.slot(r >= 0 ? r : 0) & 0xfff) << 4;
+          const unsigned ol = (unsigned)(own * kAS) << 16 | (unsigned)(*map.slot(key_of(r >= 0 ? r : 0)) & 0xfff) << 4;
           out.own_local[q] = ol;
           out.row_meta[4 * q + 0] = r;
           out.row_meta[4 * q + 1] = r >= 0 ? h->h_findrm[r] : 0;
@@ -782,7 +786,7 @@ void build_staged_plan_host(const Handle* h, const std::vector<int>& rows, int n
             unsigned lv = ol;  // padding: re-push the own node, nothing computed
             if (k < n) {
               const StripEntry& e = rp[t][k];
-              lv = (unsigned)((e.meta & 0xff) * kAS) << 16 | (unsigned)(*map.slot(e.node) & 0xfff) << 4 |
+              lv = (unsigned)((e.meta & 0xff) * kAS) << 16 | (unsigned)(*map.slot(key_of(e.node)) & 0xfff) << 4 |
                    ((e.meta & kStripCompute) ? kStagedCompute : 0u);
             }
             ent[base + (size_t)k * kBR + t] = lv;
@@ -938,7 +942,7 @@ extern "C" int cgasm_plan_host_timing(int dim, int n_nodes, int n_elements, cons
   t0 = now();
   h.h_nd0.shrink_to_fit();
   StagedPlanHost sp;
-  build_staged_plan_host(&h, rows, nb, 64, sp);
+  build_staged_plan_host(&h, rows, nb, 64, std::vector<int>(), sp);
   const long long total = sp.total_real;
   times[5] = now() - t0;
   if (entries_per_pair) *entries_per_pair = h.n2e.empty() ? 0.0 : (double)total / (double)h.n2e.size();

@@ -52,6 +52,9 @@ struct StagedPlanHost {
 struct Handle;
 // rows: nblocks*block_rows node ids (-1 = padding), block_rows = kBR. Needs connectivity, adjacency and sparsity
 // of the handle (host copies only).
-void build_staged_plan_host(const Handle* h, const std::vector<int>& rows, int nblocks, int maxlen, StagedPlanHost& out);
+// perm (empty, or n_nodes entries): the staged records are stored at perm[node]; the block node lists then hold and are
+// sorted by those positions.
+void build_staged_plan_host(const Handle* h, const std::vector<int>& rows, int nblocks, int maxlen,
+                            const std::vector<int>& perm, StagedPlanHost& out);
 
 }  // namespace cgasm

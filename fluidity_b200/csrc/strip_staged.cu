@@ -309,7 +309,8 @@ static int staged_momentum_dim(Handle* h, const MomentumArgs& A) {
   do {                                                                                                          \
     if ((st = strip_smem(staged_momentum_kernel<DIM, NL_, FULLV_>, smem))) return st;                           \
     staged_momentum_kernel<DIM, NL_, FULLV_><<<grid, kBR, smem, h->stream>>>(                                   \
-        c, v, h->d_rec3, h->d_rec1, h->d_rec2, (size_t)h->nnz, h->d_big_m, h->d_mom_rhs, ml);                    \
+        c, v, (const double4*)staged_rec(h, 3), (const double4*)staged_rec(h, 1), (const double4*)staged_rec(h, 2), (size_t)h->nnz,    \
+        h->d_big_m, h->d_mom_rhs, ml);                    \
     h->launches++;                                                                                              \
   } while (0)
 #define LAUNCH_NL(NL_)                   \
@@ -355,7 +356,8 @@ static int staged_advdiff_dim(Handle* h, const AdvDiffArgs& A) {
   do {                                                                                                          \
     if ((st = strip_smem(staged_advdiff_kernel<DIM, NL_, FULLV_, ABS_>, smem))) return st;                      \
     staged_advdiff_kernel<DIM, NL_, FULLV_, ABS_><<<grid, kBR, smem, h->stream>>>(                              \
-        c, v, h->d_rec0, h->d_rec1, h->d_rec4, h->d_adv_matrix, h->d_adv_rhs);                                   \
+        c, v, (const double4*)staged_rec(h, 0), (const double4*)staged_rec(h, 1), (const double2*)staged_rec(h, 4),                  \
+        h->d_adv_matrix, h->d_adv_rhs);                                   \
     h->launches++;                                                                                              \
   } while (0)
 #define LAUNCH_NL(NL_)                              \
