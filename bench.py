@@ -55,6 +55,8 @@ def parse():
                     help="timed step = cgasm_momentum_dev + cgasm_advdiff_dev (the reference's two loops, default) or the "
                          "one-call cgasm_momentum_advdiff_dev (one fused kernel); the other one is reported beside it")
     ap.add_argument("--no-configs", action="store_true", help="skip the example-config option sets (N=1 only)")
+    ap.add_argument("--delaunay-points", type=int, default=1500000,
+                    help="points of the unstructured (scipy Delaunay) mesh of the configs block; 0 = skip it")
     ap.add_argument("--no-parity", action="store_true", help="skip the multi-GPU parity check against the oracle (N>1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -375,7 +377,27 @@ def multi_gpu_parity(args, world, rank, local_rank, dist, overlap):
     return worst
 
 
-def example_configs(device, cells3, cells2, reps=5):
+DELAUNAY_CODE = """
+import sys, numpy as np
+sys.path.insert(0, %r)
+from fluidity_b200 import synthetic as syn
+m = syn.delaunay_mesh(int(sys.argv[1]))
+np.save(sys.argv[2] + '.X.npy', m.X); np.save(sys.argv[2] + '.nd.npy', m.ndglno)
+"""
+
+
+def start_delaunay(points):
+    """The unstructured leg of the configs block needs a scipy (qhull) Delaunay triangulation of `points` graded random
+    points (~6.5 tets per point: 1.5 M points = 10 M tets, ~90 s on one core): built by a child process beside the
+    S3 set-up and timing, which do not need that core."""
+    import tempfile
+    base = os.path.join(tempfile.mkdtemp(prefix="cgasm_delaunay_"), "mesh")
+    proc = subprocess.Popen([sys.executable, "-c", DELAUNAY_CODE % ROOT, str(points), base],
+                            stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    return proc, base, time.perf_counter()
+
+
+def example_configs(device, cells3, cells2, reps=5, delaunay=None):
     """Kernel time of the two element loops for the option sets of BASELINE.json configs[0..3] (their meshes are not
     in the reference tree: option sets on synthetic meshes of the same dimension), plus the S3 option set on a randomly
     renumbered mesh. STRIP variant, CUDA events on the handle's stream."""
@@ -392,15 +414,32 @@ def example_configs(device, cells3, cells2, reps=5):
         ("S3 option set, tracer with nodal absorption and source", 3, cm(), ca(have_absorption=1, have_source=1), None, False),
         ("S3 option set at this size", 3, cm(), ca(), None, False),
         ("S3 option set, nodes and elements randomly renumbered", 3, cm(), ca(), None, True),
+        ("S3 option set with streamline-upwind stabilisation (nu_bar optimal) in both loops: per-element nu_bar at every "
+         "quadrature point, so the element-owner two-pass path by design", 3,
+         cm(stabilisation_scheme=abi.STAB_STREAMLINE_UPWIND), ca(stabilisation_scheme=abi.STAB_STREAMLINE_UPWIND), None, False),
     ]
+    if delaunay is not None:
+        cases.append(("flow_past_sphere_Re100 option set on an UNSTRUCTURED mesh: Delaunay triangulation of graded random "
+                      "points (scipy/qhull), generator-like numbering", 3,
+                      cm(viscosity_shape=abi.TENSOR_FULL, have_gravity=0), ca(), "aniso", "delaunay"))
     meshes, out = {}, []
     for name, dim, om, oa, tweak, shuffle in cases:
         keym = (dim, shuffle)
         if keym not in meshes:
-            c = cells3 if dim == 3 else cells2
-            mesh = syn.box_mesh((c,) * dim)
-            if shuffle:
-                mesh = syn.shuffled(mesh)
+            if shuffle == "delaunay":
+                proc, base, t_start = delaunay
+                proc.wait()
+                if proc.returncode != 0:
+                    out.append({"config": name, "error": "Delaunay child process failed (%d)" % proc.returncode})
+                    continue
+                mesh = syn.Mesh(dim=3, ndglno=np.load(base + ".nd.npy"), X=np.load(base + ".X.npy"))
+                for suffix in (".nd.npy", ".X.npy"):
+                    os.remove(base + suffix)
+            else:
+                c = cells3 if dim == 3 else cells2
+                mesh = syn.box_mesh((c,) * dim)
+                if shuffle:
+                    mesh = syn.shuffled(mesh)
             meshes[keym] = (mesh, syn.standard_fields(mesh))
         mesh, fs0 = meshes[keym]
         t0 = time.perf_counter()
@@ -426,10 +465,16 @@ def example_configs(device, cells3, cells2, reps=5):
         launches = (asm.launch_count() - l0) / (reps + 2)
         paths = asm.last_path()
         mm, aa = statistics.median(mom), statistics.median(adv)
-        out.append({"config": name, "dim": dim, "elements": mesh.n_elements, "momentum_ms": mm, "tracer_ms": aa,
-                    "gel_s": mesh.n_elements / ((mm + aa) * 1e-3) / 1e9, "kernel_launches_per_step": launches,
-                    "momentum_path": paths[0], "tracer_path": paths[1],
-                    "library_setup_s": setup})
+        rec = {"config": name, "dim": dim, "elements": mesh.n_elements, "momentum_ms": mm, "tracer_ms": aa,
+               "gel_s": mesh.n_elements / ((mm + aa) * 1e-3) / 1e9, "kernel_launches_per_step": launches,
+               "momentum_path": paths[0], "tracer_path": paths[1],
+               "library_setup_s": setup}
+        if shuffle:
+            nnz = asm.nnz
+            rec.update({"nodes": mesh.n_nodes, "nnz": int(nnz), "mean_row_length": nnz / mesh.n_nodes,
+                        "elements_per_node": mesh.n_elements * (dim + 1) / mesh.n_nodes,
+                        "plan": asm.plan_stats()})
+        out.append(rec)
         asm.close()
     return out
 
@@ -463,6 +508,9 @@ def run_graft(args):
             torch.set_num_threads(share)
     strong = args.scaling == "strong" or world == 1
     overlap = world > 1 and not args.no_overlap
+    delaunay = None
+    if world == 1 and not args.no_configs and args.delaunay_points > 0:
+        delaunay = start_delaunay(args.delaunay_points)
 
     parity = None
     if world > 1 and not args.no_parity:
@@ -709,7 +757,9 @@ def run_graft(args):
         cpu = cpu_baseline_block(args.cpu_cells)
     configs = None
     if world == 1 and not args.no_configs:
-        configs = example_configs(local_rank, 128, 2048)
+        configs = example_configs(local_rank, 128, 2048, delaunay=delaunay)
+    elif delaunay is not None:
+        delaunay[0].kill()
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

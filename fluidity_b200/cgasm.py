@@ -414,6 +414,14 @@ class Assembler:
         _check(self.lib.cgasm_last_path(C.c_int(self.id), C.byref(m), C.byref(a)))
         return self.PATHS[m.value], self.PATHS[a.value]
 
+    def plan_stats(self):
+        """Shape of the row-block plan (cgasm_plan_stats)."""
+        st = (C.c_double * 8)()
+        _check(self.lib.cgasm_plan_stats(C.c_int(self.id), st))
+        keys = ("row_blocks", "rows_per_block", "longest_row", "strip_entries_per_pair", "staged", "max_nodes_per_block",
+                "staged_node_capacity", "momentum_smem_bytes_per_block")
+        return dict(zip(keys, [float(v) for v in st]))
+
     # -- device hand-off to PETSc (COO triplets in universal numbering) --------------------------------
     def coo_pattern(self, which, row_gnn2unn, col_gnn2unn=None, compact=False):
         """which: 0 momentum (dim diagonal blocks), 1 tracer. gnn2unn: (n_nodes, nfields) int array as

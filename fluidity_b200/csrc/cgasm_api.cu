@@ -5,6 +5,7 @@
 // element loop: anything outside the device path returns
 // CGASM_EUNSUPPORTED so the caller keeps the Fortran loop; there is no CPU path in here.
 #include "cgasm_internal.h"
+#include "gather_plan.h"
 
 #include <algorithm>
 #include <cmath>
@@ -1159,6 +1160,22 @@ int cgasm_last_path(int id, int* momentum_path, int* advdiff_path) {
   GET_HANDLE(h, id);
   if (momentum_path) *momentum_path = h->mom_path;
   if (advdiff_path) *advdiff_path = h->adv_path;
+  return CGASM_OK;
+}
+
+int cgasm_plan_stats(int id, double* stats) {
+  GET_HANDLE(h, id);
+  if (!stats) CG_FAIL(CGASM_EARG, "null out");
+  const GatherPlan* P = h->gather;
+  if (!P) CG_FAIL(CGASM_ESTATE, "no row-block plan: call cgasm_set_scatter(GATHER | STRIP) first");
+  stats[0] = P->nblocks;
+  stats[1] = kBR;
+  stats[2] = P->maxlen;
+  stats[3] = P->strip_entries_per_pair;
+  stats[4] = P->staged_ok ? 1.0 : 0.0;
+  stats[5] = P->blk_nodes_max;
+  stats[6] = P->nl;
+  stats[7] = P->staged_ok ? (double)(sizeof(double) * (size_t)P->maxlen * kAS + (size_t)P->nl * 88 + kBR * 16) : 0.0;
   return CGASM_OK;
 }
 

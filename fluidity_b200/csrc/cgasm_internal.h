@@ -218,7 +218,10 @@ int gather_advdiff(Handle* h, const AdvDiffArgs& args);
 // strip_extra.cu: the additive momentum pass (absorption, sources, reference profile; constant density)
 bool strip_extra_needed(const MomentumArgs& args);
 bool strip_extra_ok(const Handle* h, const MomentumArgs& args);
-int strip_extra(Handle* h, const MomentumArgs& args);
+int strip_extra(Handle* h, const MomentumArgs& args, bool skip_full_absorption = false);
+// strip_absorb.cu: the common STRIP momentum kernel with the full absorption matrix in the same pass
+bool strip_absorb_ok(const Handle* h, const MomentumArgs& args);
+int strip_absorb_momentum(Handle* h, const MomentumArgs& args);
 int ensure_extra_records(Handle* h);  // cgasm_api.cu
 // record k (0..6) as the staged kernels read it; refresh of the permuted mirrors after record k changed (all nodes, or the
 // listed ones) on `stream`

@@ -435,8 +435,10 @@ int strip_momentum(Handle* h, const MomentumArgs& A) {
   h->mom_path = CGASM_PATH_STRIP;
   if (strip_staged_ok(h, true)) {
     h->mom_path = CGASM_PATH_STRIP_STAGED;
-    int st = strip_staged_momentum(h, A);
-    if (st == CGASM_OK && strip_extra_needed(A)) st = strip_extra(h, A);  // adds to the common result in place
+    // full absorption matrix: carried by the common kernel's own loop (strip_absorb.cu) where it fits
+    const bool absorb = strip_extra_needed(A) && strip_absorb_ok(h, A);
+    int st = absorb ? strip_absorb_momentum(h, A) : strip_staged_momentum(h, A);
+    if (st == CGASM_OK && strip_extra_needed(A)) st = strip_extra(h, A, absorb);  // adds to the common result in place
     return st;
   }
   if (int js = halo_join(h)) return js;

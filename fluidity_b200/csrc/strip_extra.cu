@@ -394,11 +394,11 @@ bool strip_extra_ok(const Handle* h, const MomentumArgs& A) {
 }
 
 template <int DIM>
-static int strip_extra_dim(Handle* h, const MomentumArgs& A) {
+static int strip_extra_dim(Handle* h, const MomentumArgs& A, bool skip_full) {
   GatherPlan* P = h->gather;
   const cgasm_momentum_opts& o = A.o;
   const Tables& t = A.tab;
-  const bool full = o.have_absorption && !o.lump_absorption;
+  const bool full = o.have_absorption && !o.lump_absorption && !skip_full;
   const bool light = (o.have_absorption && o.lump_absorption) || o.have_source ||
                      (o.have_gravity && o.subtract_out_reference_profile);
   ExtraConsts c{};
@@ -459,8 +459,8 @@ static int strip_extra_dim(Handle* h, const MomentumArgs& A) {
   return st;
 }
 
-int strip_extra(Handle* h, const MomentumArgs& A) {
-  return h->dim == 3 ? strip_extra_dim<3>(h, A) : strip_extra_dim<2>(h, A);
+int strip_extra(Handle* h, const MomentumArgs& A, bool skip_full_absorption) {
+  return h->dim == 3 ? strip_extra_dim<3>(h, A, skip_full_absorption) : strip_extra_dim<2>(h, A, skip_full_absorption);
 }
 
 }  // namespace cgasm

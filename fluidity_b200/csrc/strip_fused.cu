@@ -23,21 +23,16 @@ template <int DIM, int NL>
 __device__ __forceinline__ void stage_fused(const BlockIds<NL>& ids, int t, unsigned nsa, const double4* __restrict__ rX,
                                             const double4* __restrict__ rU, const double4* __restrict__ rO,
                                             const double4* __restrict__ rT) {
+  const int h = t & 1;
 #pragma unroll
-  for (int u = 0; u < BlockIds<NL>::PER; u++) {
-    const int node = ids.node[u];
+  for (int v = 0; v < BlockIds<NL>::PER; v++) {
+    const int node = ids.node[v];
     if (node < 0) continue;
-    const unsigned i = (unsigned)(t + u * kBR), d = nsa + i * 16u;
-    const double2* s0 = reinterpret_cast<const double2*>(rX + node);
-    const double2* s1 = reinterpret_cast<const double2*>(rU + node);
-    const double2* s2 = reinterpret_cast<const double2*>(rO + node);
-    cp_async16(d + 0 * NL * 16, s0);
-    cp_async16(d + 1 * NL * 16, s0 + 1);
-    cp_async16(d + 2 * NL * 16, s1);
-    cp_async16(d + 3 * NL * 16, s1 + 1);
-    cp_async16(d + 4 * NL * 16, s2);
-    if constexpr (DIM == 3) cp_async8(nsa + 5 * NL * 16 + i * 8u, s2 + 1);
-    cp_async8(nsa + (unsigned)(5 * NL * 16 + NL * 8) + i * 8u, reinterpret_cast<const double*>(rT + node) + 3);
+    const unsigned i = (unsigned)((t >> 1) + v * (kBR / 2));
+    stage_record<NL>(nsa, 0, i, h, rX, node);
+    stage_record<NL>(nsa, 2, i, h, rU, node);
+    stage_record_3<NL, DIM == 3>(nsa, 4, (unsigned)(5 * NL * 16), i, h, rO, node);
+    if (h == 1) cp_async8(nsa + (unsigned)(5 * NL * 16 + NL * 8) + i * 8u, reinterpret_cast<const double*>(rT + node) + 3);
   }
 }
 

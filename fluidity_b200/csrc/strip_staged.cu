@@ -35,23 +35,18 @@ namespace cgasm {
 template <int DIM, int NL, int EXTRA>
 __device__ __forceinline__ void stage_nodes(const BlockIds<NL>& ids, int t, unsigned nsa, const double4* __restrict__ r0,
                                             const double4* __restrict__ r1, const void* __restrict__ rE) {
+  const int h = t & 1;
 #pragma unroll
-  for (int u = 0; u < BlockIds<NL>::PER; u++) {
-    const int node = ids.node[u];
+  for (int v = 0; v < BlockIds<NL>::PER; v++) {
+    const int node = ids.node[v];
     if (node < 0) continue;
-    const unsigned i = (unsigned)(t + u * kBR), d = nsa + i * 16u;
-    const double2* s0 = reinterpret_cast<const double2*>(r0 + node);
-    const double2* s1 = reinterpret_cast<const double2*>(r1 + node);
-    cp_async16(d + 0 * NL * 16, s0);
-    cp_async16(d + 1 * NL * 16, s0 + 1);
-    cp_async16(d + 2 * NL * 16, s1);
-    cp_async16(d + 3 * NL * 16, s1 + 1);
+    const unsigned i = (unsigned)((t >> 1) + v * (kBR / 2));
+    stage_record<NL>(nsa, 0, i, h, r0, node);
+    stage_record<NL>(nsa, 2, i, h, r1, node);
     if constexpr (EXTRA == 1) {
-      const double2* s2 = reinterpret_cast<const double2*>(reinterpret_cast<const double4*>(rE) + node);
-      cp_async16(d + 4 * NL * 16, s2);
-      if constexpr (DIM == 3) cp_async8(nsa + 5 * NL * 16 + i * 8u, s2 + 1);
+      stage_record_3<NL, DIM == 3>(nsa, 4, (unsigned)(5 * NL * 16), i, h, reinterpret_cast<const double4*>(rE), node);
     } else if constexpr (EXTRA == 2) {
-      cp_async16(d + 4 * NL * 16, reinterpret_cast<const double2*>(rE) + node);
+      if (h == 0) cp_async16(nsa + (unsigned)(4 * NL * 16) + i * 16u, reinterpret_cast<const double2*>(rE) + node);
     }
   }
 }

@@ -109,17 +109,35 @@ __device__ __forceinline__ long long ldg_nc_s64(const long long* p) {
   return v;
 }
 
+// Staging map: a PAIR of lanes copies one 32-byte node record -- lane 2i the first 16 bytes of the record of local node
+// i, lane 2i+1 the second -- so a warp-wide cp.async reads 16 records = 512 contiguous bytes wherever the block's
+// (sorted) node list runs through consecutive ids. ncu (profiles/r2_kernel_history.md #32): with one lane per record and
+// two copies per lane every LDGSTS.128 touched 32 half-used sectors and took 16 shared-memory wavefronts where 2-4
+// suffice; staging was 14 % of the kernel's wavefronts on the busiest pipe (L1 data, 67 %).
 template <int NL>
 struct BlockIds {
-  static constexpr int PER = NL / kBR;
-  int node[PER];
+  static constexpr int PER = 2 * NL / kBR;
+  int node[PER];  // node of local index (t >> 1) + v * (kBR / 2)
 };
 
 template <int NL>
 __device__ __forceinline__ void issue_block_ids(const StagedView& P, int b, int t, BlockIds<NL>& ids) {
-  const int* p = P.blk_nodes + (size_t)b * NL + t;  // fixed stride: no pointer load in front of the id loads
+  const int* p = P.blk_nodes + (size_t)b * NL + (t >> 1);  // fixed stride: no pointer load in front of the id loads
 #pragma unroll
-  for (int u = 0; u < BlockIds<NL>::PER; u++) ids.node[u] = ldg_nc_s32(p + u * kBR);
+  for (int v = 0; v < BlockIds<NL>::PER; v++) ids.node[v] = ldg_nc_s32(p + v * (kBR / 2));
+}
+
+// half h of the record of `node` -> chunk (chunk0 + h) of local node i
+template <int NL>
+__device__ __forceinline__ void stage_record(unsigned nsa, int chunk0, unsigned i, int h, const double4* __restrict__ rec, int node) {
+  cp_async16(nsa + (unsigned)((chunk0 + h) * NL * 16) + i * 16u, reinterpret_cast<const double2*>(rec + node) + h);
+}
+// {a, b | c, -} record: a, b -> chunk `chunk` (16 bytes), c -> the plain double array at byte offset arr_off
+template <int NL, bool THIRD>
+__device__ __forceinline__ void stage_record_3(unsigned nsa, int chunk, unsigned arr_off, unsigned i, int h,
+                                               const double4* __restrict__ rec, int node) {
+  if (h == 0) cp_async16(nsa + (unsigned)(chunk * NL * 16) + i * 16u, reinterpret_cast<const double2*>(rec + node));
+  else if (THIRD) cp_async8(nsa + arr_off + i * 8u, reinterpret_cast<const double*>(rec + node) + 2);
 }
 
 template <int NL>

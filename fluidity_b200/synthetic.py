@@ -128,6 +128,53 @@ def shuffled(mesh, seed=7):
     return Mesh(dim=mesh.dim, ndglno=np.ascontiguousarray(nd.astype(np.int32)), X=X, shape=())
 
 
+def delaunay_points(npoints, dim=3, seed=11, graded=True):
+    """Points of an unstructured test mesh in the unit box: uniform background plus (graded) a cloud concentrated
+    around the centre, like the refinement around the obstacle of examples/flow_past_sphere_Re100. Numbered the way
+    a mesh generator leaves them: sorted by a coarse lattice cell (lexicographic), arbitrary inside a cell."""
+    rng = np.random.default_rng(seed)
+    n_bg = npoints if not graded else (npoints * 3) // 5
+    pts = [rng.random((n_bg, dim))]
+    if graded:
+        c = 0.5 + 0.12 * rng.standard_normal((npoints - n_bg, dim))
+        pts.append(np.clip(c, 0.0, 1.0))
+    # the corners keep the hull the unit box
+    corners = np.array(list(itertools.product((0.0, 1.0), repeat=dim)))
+    P = np.concatenate(pts + [corners])
+    P = np.unique(P, axis=0)
+    cells = max(2, int(round((P.shape[0] / 64.0) ** (1.0 / dim))))
+    key = np.zeros(P.shape[0], dtype=np.int64)
+    for k in range(dim - 1, -1, -1):
+        key = key * cells + np.minimum((P[:, k] * cells).astype(np.int64), cells - 1)
+    return np.ascontiguousarray(P[np.argsort(key, kind="stable")])
+
+
+def delaunay_mesh(npoints, dim=3, seed=11, graded=True, min_quality=0.02):
+    """scipy.spatial.Delaunay of `delaunay_points`: an UNSTRUCTURED simplex mesh (node degrees, strip lengths and row
+    lengths all vary; ~6.5 tets per point in 3-D). Slivers (|det J| below min_quality x longest edge^dim; a regular
+    tetrahedron has 0.71) are dropped, as a mesh generator would -- the Delaunay triangulation of random points has
+    many flat ones on the hull; local node order is whatever qhull returns (both orientations occur)."""
+    from scipy.spatial import Delaunay
+    P = delaunay_points(npoints, dim, seed, graded)
+    simp = Delaunay(P).simplices.astype(np.int64)
+    V = P[simp]
+    det = np.abs(np.linalg.det(V[:, 1:] - V[:, :1]))
+    lmax = np.zeros(simp.shape[0])
+    for a in range(dim + 1):
+        for b in range(a + 1, dim + 1):
+            lmax = np.maximum(lmax, np.linalg.norm(V[:, a] - V[:, b], axis=1))
+    keep = det > min_quality * lmax ** dim
+    nd = simp[keep]
+    # drop nodes no kept element uses (none in practice) by compacting the numbering
+    used = np.zeros(P.shape[0], dtype=bool)
+    used[nd.ravel()] = True
+    if not used.all():
+        new_id = np.cumsum(used) - 1
+        nd = new_id[nd]
+        P = P[used]
+    return Mesh(dim=dim, ndglno=np.ascontiguousarray((nd + 1).astype(np.int32)), X=np.ascontiguousarray(P), shape=())
+
+
 def boundary_faces(mesh):
     """Surface mesh of `mesh` the way femtools add_faces leaves it for a mesh without a surface file:
     the facets that belong to exactly one element (femtools/Fields_Allocates.F90:1166-1296), here in

@@ -385,6 +385,11 @@ enum cgasm_path {
   CGASM_PATH_STRIP_STAGED = 6   /* strip kernels, node records staged in shared memory (+ additive passes) */
 };
 int cgasm_last_path(int id, int* momentum_path, int* advdiff_path);
+/* Diagnostics: shape of the row-block plan behind CGASM_SCATTER_GATHER / STRIP (after cgasm_set_scatter).
+ * stats(8) = row blocks, rows per block, longest CSR row, strip entries per (row, element) pair, staged STRIP plan
+ * usable (0/1), largest number of distinct nodes a block touches, staged node capacity per block (NL), bytes of
+ * shared memory per block of the staged momentum kernel. */
+int cgasm_plan_stats(int id, double* stats);
 /* Device time in ms of the most recent cgasm_*_dev call (CUDA events on the handle stream). */
 int cgasm_last_kernel_ms(int id, float* ms);
 

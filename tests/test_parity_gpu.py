@@ -201,6 +201,32 @@ def test_shuffled_numbering_s3_small(orc, scatter):
     assert rel_err(got["matrix"], ref["matrix"]) < TOL and rel_err(got["rhs"], ref["rhs"]) < TOL
 
 
+@pytest.mark.parametrize("scatter", ALL_SCATTERS)
+@pytest.mark.parametrize("dim", [2, 3])
+def test_delaunay_unstructured_mesh(orc, scatter, dim):
+    """A Delaunay triangulation of graded random points (what examples/flow_past_sphere_Re100 looks like to the
+    kernels: node degrees 8-58, row lengths and strip lengths all different, both local orientations), with the
+    anisotropic-viscosity option set of that example, the common set and the constant-density absorption set."""
+    mesh = syn.delaunay_mesh(4000 if dim == 3 else 6000, dim=dim, seed=3)
+    fs = syn.standard_fields(mesh)
+    asm = make_asm(mesh, fs, scatter)
+    findrm, colm, _ = asm.get_sparsity()
+    of, oc, _ = orc.make_sparsity(mesh)
+    assert (findrm == of).all() and (colm == oc).all()
+    oa = abi.common_advdiff_opts()
+    got, ref = asm.advdiff(oa), orc.assemble_advdiff(mesh, fs, oa, findrm, colm)
+    assert rel_err(got["matrix"], ref["matrix"]) < TOL and rel_err(got["rhs"], ref["rhs"]) < TOL
+    o = abi.common_momentum_opts()
+    check_momentum(asm.momentum(o), orc.assemble_momentum(mesh, fs, o, findrm, colm), findrm, dim)
+    fs.set(abi.F_VISCOSITY, syn.aniso_tensor(dim), abi.FIELD_CONSTANT)
+    fs.set(abi.F_DENSITY, np.array([1.1]), abi.FIELD_CONSTANT)
+    asm.set_field(abi.F_VISCOSITY, syn.aniso_tensor(dim), abi.FIELD_CONSTANT)
+    asm.set_field(abi.F_DENSITY, np.array([1.1]), abi.FIELD_CONSTANT)
+    for o in (abi.common_momentum_opts(viscosity_shape=abi.TENSOR_FULL, have_gravity=0),
+              abi.common_momentum_opts(have_absorption=1, have_gravity=0)):
+        check_momentum(asm.momentum(o), orc.assemble_momentum(mesh, fs, o, findrm, colm), findrm, dim)
+
+
 # ---- golden vectors from the reference's own Python element machinery ------------------------------
 @pytest.mark.parametrize("name", ["cube.1", "cube-parallel", "square-cavity-2d", "prectangle_0"])
 def test_element_matrices_match_reference_python(name):
@@ -388,14 +414,24 @@ def test_every_non_stabilised_variant_matches_reference_python(name):
     assert pc.check_variants(mesh, z, elements_for) < TOL
 
 
-# ---- STRIP: the additive momentum pass (absorption, sources, reference profile; constant density) ---------------
+# ---- STRIP: absorption, sources, reference profile with a constant density -----------------------------------------
 @pytest.mark.parametrize("dim", [2, 3])
+@pytest.mark.parametrize("in_loop", [True, False])
 @pytest.mark.parametrize("variant", list(boussinesq_variants().keys()))
-def test_strip_additive_pass_constant_density(orc, dim, variant):
+def test_strip_additive_pass_constant_density(orc, dim, variant, in_loop, monkeypatch):
     """Constant density (every example config is Boussinesq): the STRIP variant assembles these option sets in its own
-    kernels -- common kernel + the additive pass of strip_extra.cu -- and must agree with the oracle like any other."""
+    kernels and must agree with the oracle like any other. The full absorption matrix is carried by the common kernel's
+    own loop (strip_absorb.cu; in_loop) or, where that does not fit, by one more strip pass per component
+    (strip_extra.cu; forced here with CGASM_STRIP_NO_ABSORB); the per-row quantities (lumped absorption, sources,
+    reference profile) by strip_extra.cu's per-row pass."""
     mesh = syn.box_mesh((6, 5, 4)[:dim], seed=33)
     o = boussinesq_variants()[variant]
+    full = bool(o.have_absorption and not o.lump_absorption)
+    light = bool((o.have_absorption and o.lump_absorption) or o.have_source or (o.have_gravity and o.subtract_out_reference_profile))
+    if not in_loop:
+        if not full:
+            pytest.skip("no full absorption matrix: same kernels as in_loop")
+        monkeypatch.setenv("CGASM_STRIP_NO_ABSORB", "1")
     fs = syn.standard_fields(mesh)
     fs.set(abi.F_DENSITY, np.array([1.3]), abi.FIELD_CONSTANT)
     if variant == "everything":
@@ -404,11 +440,8 @@ def test_strip_additive_pass_constant_density(orc, dim, variant):
     findrm, colm, _ = asm.get_sparsity()
     l0 = asm.launch_count()
     got = asm.momentum(o)
-    # the common kernel + the additive passes it needs (per-row pass: lumped absorption / sources / reference profile;
-    # per-component pass: full absorption matrix), not the two-pass GATHER staging path (element kernel + row kernel)
-    full = bool(o.have_absorption and not o.lump_absorption)
-    light = bool((o.have_absorption and o.lump_absorption) or o.have_source or (o.have_gravity and o.subtract_out_reference_profile))
-    assert asm.launch_count() - l0 == 1 + int(full) + int(light), "the option set did not take the STRIP kernels"
+    # not the two-pass GATHER staging path (element kernel + row kernel)
+    assert asm.launch_count() - l0 == 1 + int(full and not in_loop) + int(light), "the option set did not take the STRIP kernels"
     assert asm.last_path()[0] == "strip_staged"
     ref = orc.assemble_momentum(mesh, fs, o, findrm, colm, want_masslump=bool(o.assemble_inverse_masslump))
     check_momentum(got, ref, findrm, dim)
