@@ -342,6 +342,15 @@ class Assembler:
         _check(self.lib.cgasm_cmc_fetch(C.c_int(self.id), _dp(out)))
         return out
 
+    def kmk(self, theta_pg=1.0, want_parts=False):
+        """assemble_kmk_matrix on the device: kmk (nnz2), optionally kt (nnz) and the lumped pressure mass (n_nodes)."""
+        _check(self.lib.cgasm_kmk_dev(C.c_int(self.id), C.c_double(theta_pg)))
+        out = np.empty(self.nnz2)
+        kt = np.empty(self.nnz) if want_parts else None
+        ml = np.empty(self.n_nodes) if want_parts else None
+        _check(self.lib.cgasm_kmk_fetch(C.c_int(self.id), _dp(out), _dp(kt), _dp(ml)))
+        return (out, kt, ml) if want_parts else out
+
     def momentum_result_dev(self):
         p = [C.c_void_p() for _ in range(4)]
         _check(self.lib.cgasm_momentum_result_dev(C.c_int(self.id), *[C.byref(x) for x in p]))

@@ -17,31 +17,10 @@
 
 #include "cgasm_internal.h"
 #include "cmc_math.h"
+#include "cmc_plan.h"
 
 namespace cgasm {
 
-struct CmcPlan {
-  long long nnz2 = 0;
-  std::vector<int> h_findrm2, h_colm2;  // 0-based
-  int* d_findrm2 = nullptr;
-  int* d_colm2 = nullptr;
-  double* d_val = nullptr;
-  double* d_ct = nullptr;   // uploaded ct_m when the caller passes one
-  double* d_inv = nullptr;  // inverse lumped mass (dim, n_nodes)
-  bool valid = false;
-  // expansion plan (expand kernel): transposed positions of the first-order entries, and for every row i the
-  // second-order slot of each (k in row i, j in row k) pair, rows of k back to back
-  bool have_expand = false;
-  int n2max = 0;
-  int slot_bytes = 0;  // 1 or 2
-  std::vector<int> h_tpos;
-  std::vector<long long> h_pptr;
-  std::vector<unsigned char> h_slots;
-  int* d_tpos = nullptr;
-  long long* d_pptr = nullptr;
-  unsigned char* d_slots = nullptr;
-  double* d_ctT = nullptr;  // ct_m with every entry moved to its transposed position: row k holds C(j,k) for j in row k
-};
 
 void cmc_free(Handle* h) {
   CmcPlan* P = h->cmc;
@@ -55,6 +34,11 @@ void cmc_free(Handle* h) {
   cudaFree(P->d_pptr);
   cudaFree(P->d_slots);
   cudaFree(P->d_ctT);
+  cudaFree(P->d_kt);
+  cudaFree(P->d_ktT);
+  cudaFree(P->d_pml);
+  cudaFree(P->d_pinv);
+  cudaFree(P->d_kmk);
   delete P;
   h->cmc = nullptr;
 }
@@ -171,6 +155,9 @@ static int upload_pattern(Handle* h) {
   P->d_findrm2 = P->d_colm2 = nullptr;
   P->d_val = nullptr;
   P->valid = false;
+  cudaFree(P->d_kmk);
+  P->d_kmk = nullptr;
+  P->kmk_valid = false;
   CG_CUDA(cudaMalloc(&P->d_findrm2, sizeof(int) * P->h_findrm2.size()));
   CG_CUDA(cudaMalloc(&P->d_colm2, sizeof(int) * std::max<size_t>(P->h_colm2.size(), 1)));
   CG_CUDA(cudaMalloc(&P->d_val, sizeof(double) * std::max<size_t>(P->h_colm2.size(), 1)));
@@ -220,7 +207,6 @@ cmc_kernel(int n_rows, const int* __restrict__ findrm, const int* __restrict__ c
 // ascending order, the lanes take the entries (k, j) of row k -- distinct j, so distinct accumulator slots, plain
 // read-modify-write -- and a __syncwarp separates the k steps. Slots and transposed positions come from the plan:
 // no searching, no merging, the plan and row k are read coalesced. Same bits as the merge kernel.
-constexpr int kExpandRows = 16;
 
 // ctT[d][p] = ct[d][tpos[p]]: one gathered pass over the first-order entries, so that the expansion reads the
 // factors C(j,k), j in row k, contiguously (every row k is read by all ~15-27 rows i that contain k)
@@ -275,6 +261,33 @@ cmc_expand_kernel(int n_rows, const int* __restrict__ findrm, const int* __restr
 __global__ void invert_kernel(size_t n, const double* __restrict__ x, double* __restrict__ y) {
   const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (k < n) y[k] = 1.0 / x[k];
+}
+
+// K diag(w) K^T for a scalar matrix on the first-order sparsity (kmk.cu): the DIM = 1 instances of the kernels above
+int cmc_scalar_product(Handle* h, const double* d_a, double* d_aT, const double* d_w, double* d_out) {
+  CmcPlan* P = h->cmc;
+  const size_t nnz = (size_t)h->nnz;
+  const bool expand = P->d_slots && !getenv("CGASM_CMC_MERGE");
+  if (expand) {
+    const int blocks = (h->n_nodes + kExpandRows - 1) / kExpandRows;
+    const size_t smem = sizeof(double) * (size_t)kExpandRows * P->n2max;
+    transpose_ct_kernel<1><<<(unsigned)((nnz + 255) / 256), 256, 0, h->stream>>>(nnz, P->d_tpos, d_a, d_aT);
+    h->launches++;
+    if (P->slot_bytes == 1)
+      cmc_expand_kernel<1, unsigned char><<<blocks, kExpandRows * 16, smem, h->stream>>>(
+          h->n_nodes, h->d_findrm, h->d_colm, d_a, d_aT, nnz, d_w, P->d_pptr, P->d_slots, P->d_findrm2, P->n2max, d_out);
+    else
+      cmc_expand_kernel<1, unsigned short><<<blocks, kExpandRows * 16, smem, h->stream>>>(
+          h->n_nodes, h->d_findrm, h->d_colm, d_a, d_aT, nnz, d_w, P->d_pptr, reinterpret_cast<const unsigned short*>(P->d_slots),
+          P->d_findrm2, P->n2max, d_out);
+  } else {
+    const int blocks = (h->n_nodes + kCmcWarps - 1) / kCmcWarps;
+    cmc_kernel<1><<<blocks, kCmcWarps * 32, 0, h->stream>>>(h->n_nodes, h->d_findrm, h->d_colm, d_a, nnz, d_w, P->d_findrm2,
+                                                            P->d_colm2, d_out);
+  }
+  h->launches++;
+  CG_CUDA(cudaGetLastError());
+  return CGASM_OK;
 }
 
 }  // namespace cgasm

@@ -274,10 +274,18 @@ int gather_build_rows(Handle* h) {
       deg = std::max(deg, (int)(h->n2e_ptr[r + 1] - h->n2e_ptr[r]));
       maxlen = std::max(maxlen, h->h_findrm[r + 1] - h->h_findrm[r]);
     }
-    // rows of a block are sorted by global id so that neighbouring threads write neighbouring rows
+    // Rows of a block: by descending number of incident elements, then by global id. Rows with equally long
+    // element lists share a warp, so a warp of the row-owner kernels stops after ITS longest row instead of the
+    // block's (unstructured meshes: node degrees 8-58 made a warp execute 1.9x the element computations its lanes
+    // needed); where the degree is uniform (the interior of a structured mesh) this is the plain order by global id,
+    // in which neighbouring threads write neighbouring rows.
     {
       int* rb = rows.data() + (size_t)b * kBR;
-      std::sort(rb, std::find(rb, rb + kBR, -1));
+      const int64_t* np = h->n2e_ptr.data();
+      std::sort(rb, std::find(rb, rb + kBR, -1), [np](int x, int y) {
+        const int64_t dx = np[x + 1] - np[x], dy = np[y + 1] - np[y];
+        return dx != dy ? dx > dy : x < y;
+      });
     }
     block_ptr[b + 1] = (long long)deg * kBR;
   }

@@ -318,10 +318,16 @@ int strip_build(Handle* h) {
   {
     long long pairs = 0, consecutive = 0;
     const std::vector<int>& rows = P->h_rows;
-    for (size_t q = 1; q < rows.size(); q++) {
-      if (q % kBR == 0 || rows[q] < 0 || rows[q - 1] < 0) continue;
-      pairs++;
-      consecutive += rows[q] == rows[q - 1] + 1;
+    std::vector<int> ids;
+    for (size_t b0 = 0; b0 < rows.size(); b0 += kBR) {  // (the rows of a block are ordered by node degree first)
+      ids.clear();
+      for (size_t q = b0; q < b0 + kBR && q < rows.size(); q++)
+        if (rows[q] >= 0) ids.push_back(rows[q]);
+      std::sort(ids.begin(), ids.end());
+      for (size_t q = 1; q < ids.size(); q++) {
+        pairs++;
+        consecutive += ids[q] == ids[q - 1] + 1;
+      }
     }
     bool scattered = pairs > 0 && (double)consecutive < 0.25 * (double)pairs;
     if (const char* e = getenv("CGASM_STRIP_PERMUTE")) scattered = atoi(e) != 0;

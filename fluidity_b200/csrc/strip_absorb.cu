@@ -138,14 +138,14 @@ staged_momentum_absorb_kernel(const StripConsts k_, const AbsorbConsts ka, const
   BlockIds<NL> ids;
   issue_block_ids<NL>(P, b, t, ids);
   const int4 meta = ldg_nc_v4(P.row_meta + (size_t)b * kBR + t);
-  const long long base = ldg_nc_s64(P.ptr + b), end = ldg_nc_s64(P.ptr + b + 1);
+  const long long base = ldg_nc_s64(P.ptr + b);
   prefetch_next_block<NL>(P, b, t);
   double* acc_t = acc + t;
   const unsigned acc_sa = (unsigned)__cvta_generic_to_shared(acc_t);
   for (int d = 0; d < DIM; d++)
     for (int q = 0; q < P.maxlen; q++) acc_t[d * (acc_stride >> 3) + q * kAS] = 0.0;
   stage_nodes_absorb<DIM, NL>(ids, t, nsa, rX, rU, rO, rS);
-  const int deg = (int)((end - base) / kBR);
+  const int deg = warp_trip_count<DIM>(meta.z);
   const unsigned* p = P.ent + base + t;
   unsigned pq[DIM];
 #pragma unroll
@@ -155,7 +155,7 @@ staged_momentum_absorb_kernel(const StripConsts k_, const AbsorbConsts ka, const
   const int r = meta.x;
   const unsigned pad = (unsigned)meta.w;
   const unsigned own_off = pad & 0xfff0u;
-  const int own = meta.z >> 16;
+  const int own = (meta.z >> 16) & 0xff;
   cp_async_commit_wait_all();
   __syncthreads();
   MomState<DIM, DIM> s;
@@ -213,7 +213,7 @@ staged_momentum_absorb_kernel(const StripConsts k_, const AbsorbConsts ka, const
       int s0r, lo;
       asm volatile("ld.shared.v2.s32 {%0,%1}, [%2];" : "=r"(s0r), "=r"(lo) : "r"(tbl_sa + (unsigned)src * 16u) : "memory");
       const double diag = lds64(tbl_sa + (unsigned)src * 16u + 8u);
-      const int lr = lo & 0xffff, own_s = lo >> 16;
+      const int lr = lo & 0xff, own_s = (lo >> 16) & 0xff;
       for (int ss = sl; ss < lr; ss += lpr) {
         const double dg = ss == own_s ? diag : 0.0;
 #pragma unroll

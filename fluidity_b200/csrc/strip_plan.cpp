@@ -779,7 +779,10 @@ void build_staged_plan_host(const Handle* h, const std::vector<int>& rows, int n
           out.own_local[q] = ol;
           out.row_meta[4 * q + 0] = r;
           out.row_meta[4 * q + 1] = r >= 0 ? h->h_findrm[r] : 0;
-          out.row_meta[4 * q + 2] = (r >= 0 ? h->h_findrm[r + 1] - h->h_findrm[r] : 0) | own << 16;
+          // bits 0-7 row length, 16-23 own slot, 24-31 strip length in units of dim entries (the warp's trip count)
+          const int steps = ((int)rp[t].size() + dim - 1) / dim;
+          if (steps > 255) overflow++;
+          out.row_meta[4 * q + 2] = (r >= 0 ? h->h_findrm[r + 1] - h->h_findrm[r] : 0) | own << 16 | (int)((unsigned)(steps & 0xff) << 24);
           out.row_meta[4 * q + 3] = (int)ol;
           const int n = (int)rp[t].size();
           for (int k = 0; k < ldeg; k++) {

@@ -109,13 +109,13 @@ staged_momentum_kernel(const StripConsts k_, const StagedView P, const double4* 
   BlockIds<NL> ids;
   issue_block_ids<NL>(P, b, t, ids);
   const int4 meta = ldg_nc_v4(P.row_meta + (size_t)b * kBR + t);
-  const long long base = ldg_nc_s64(P.ptr + b), end = ldg_nc_s64(P.ptr + b + 1);
+  const long long base = ldg_nc_s64(P.ptr + b);
   prefetch_next_block<NL>(P, b, t);
   double* acc_t = acc + t;
   const unsigned acc_sa = (unsigned)__cvta_generic_to_shared(acc_t);
   for (int q = 0; q < P.maxlen; q++) acc_t[q * kAS] = 0.0;
   stage_nodes<DIM, NL, 1>(ids, t, nsa, rX, rU, rO);
-  const int deg = (int)((end - base) / kBR);  // a multiple of DIM
+  const int deg = warp_trip_count<DIM>(meta.z);
   const unsigned* p = P.ent + base + t;
   unsigned pq[DIM];
 #pragma unroll
@@ -125,7 +125,7 @@ staged_momentum_kernel(const StripConsts k_, const StagedView P, const double4* 
   const int r = meta.x;
   const unsigned pad = (unsigned)meta.w;
   const unsigned own_off = pad & 0xfff0u;
-  const int own = meta.z >> 16;
+  const int own = (meta.z >> 16) & 0xff;
   cp_async_commit_wait_all();
   __syncthreads();
   MomState<DIM, DIM> s;
@@ -224,13 +224,13 @@ staged_advdiff_kernel(const StripConsts k_, const StagedView P, const double4* _
   BlockIds<NL> ids;
   issue_block_ids<NL>(P, b, t, ids);
   const int4 meta = ldg_nc_v4(P.row_meta + (size_t)b * kBR + t);
-  const long long base = ldg_nc_s64(P.ptr + b), end = ldg_nc_s64(P.ptr + b + 1);
+  const long long base = ldg_nc_s64(P.ptr + b);
   prefetch_next_block<NL>(P, b, t);
   double* acc_t = acc + t;
   const unsigned acc_sa = (unsigned)__cvta_generic_to_shared(acc_t);
   for (int q = 0; q < P.maxlen; q++) acc_t[q * kAS] = 0.0;
   stage_nodes<DIM, NL, ABS ? 2 : 0>(ids, t, nsa, rX, rU, rE);
-  const int deg = (int)((end - base) / kBR);
+  const int deg = warp_trip_count<DIM>(meta.z);
   const unsigned* p = P.ent + base + t;
   unsigned pq[DIM];
 #pragma unroll
@@ -240,7 +240,7 @@ staged_advdiff_kernel(const StripConsts k_, const StagedView P, const double4* _
   const int r = meta.x;
   const unsigned pad = (unsigned)meta.w;
   const unsigned own_off = pad & 0xfff0u;
-  const int own = meta.z >> 16;
+  const int own = (meta.z >> 16) & 0xff;
   cp_async_commit_wait_all();
   __syncthreads();
   AdvState<DIM, DIM> s;

@@ -150,6 +150,13 @@ __device__ __forceinline__ void prefetch_next_block(const StagedView& P, int b, 
   else if (t == 16 + NL / 32) prefetch_l2(P.ptr + nb);
 }
 
+// Strip entries this WARP walks: its longest row's, in the row record's bits 24-31 in units of DIM entries (the plan pads
+// every row of the block to the block's longest with no-op entries; a warp whose rows are shorter skips them).
+template <int DIM>
+__device__ __forceinline__ int warp_trip_count(int meta_z) {
+  return (int)__reduce_max_sync(0xffffffffu, (unsigned)meta_z >> 24) * DIM;
+}
+
 // per-row table for the write-out: {first CSR entry, length | own slot << 16, value for the diagonal}, 16 bytes per row
 __device__ __forceinline__ void row_table_store(unsigned tbl_sa, int t, int s0, int lenown, double diag) {
   asm volatile("st.shared.v2.s32 [%0], {%1,%2};" ::"r"(tbl_sa + (unsigned)t * 16u), "r"(s0), "r"(lenown) : "memory");
@@ -170,7 +177,7 @@ __device__ __forceinline__ void write_rows_table(const double* __restrict__ acc,
     double diag;
     asm volatile("ld.shared.v2.s32 {%0,%1}, [%2];" : "=r"(s0r), "=r"(lo) : "r"(tbl_sa + (unsigned)src * 16u) : "memory");
     diag = lds64(tbl_sa + (unsigned)src * 16u + 8u);
-    const int lr = lo & 0xffff, own = lo >> 16;
+    const int lr = lo & 0xff, own = (lo >> 16) & 0xff;
     for (int ss = sl; ss < lr; ss += lpr) {
       const double v = fma(scale, acc[ss * kAS + src], ss == own ? diag : 0.0);
 #pragma unroll

@@ -27,7 +27,8 @@ module cgasm_interface
        & cgasm_nccl_unique_id, cgasm_last_error, cgasm_set_surface, cgasm_advdiff_surface_dev, &
        & cgasm_advdiff_dirichlet_dev, cgasm_momentum_surface_dev, cgasm_momentum_dirichlet_dev, &
        & cgasm_correct_masslumped_velocity, cgasm_cmc_build_sparsity, &
-       & cgasm_cmc_get_sparsity, cgasm_cmc_set_sparsity, cgasm_cmc_dev, cgasm_cmc_fetch
+       & cgasm_cmc_get_sparsity, cgasm_cmc_set_sparsity, cgasm_cmc_dev, cgasm_cmc_fetch, &
+       & cgasm_kmk_dev, cgasm_kmk_fetch
   public :: CGASM_OK, CGASM_EUNSUPPORTED
   public :: CGASM_F_NU, CGASM_F_OLDU, CGASM_F_DENSITY, CGASM_F_VISCOSITY, CGASM_F_BUOYANCY, &
        & CGASM_F_HB_DENSITY, CGASM_F_GRAVITY, CGASM_F_ABSORPTION, CGASM_F_SOURCE, CGASM_F_T, &
@@ -358,6 +359,23 @@ module cgasm_interface
        real(c_double), dimension(*), intent(out) :: cmc_val
        integer(c_int) :: stat
      end function cgasm_cmc_fetch
+
+     !! P1-P1 stabilisation (assemble_kmk_matrix, Momentum_CG.F90:2707-2766) on the same second-order sparsity;
+     !! kt / p_masslump: c_null_ptr to skip
+     function cgasm_kmk_dev(id, theta_pg) bind(c, name="cgasm_kmk_dev") result(stat)
+       use iso_c_binding
+       integer(c_int), value :: id
+       real(c_double), value :: theta_pg
+       integer(c_int) :: stat
+     end function cgasm_kmk_dev
+
+     function cgasm_kmk_fetch(id, kmk, kt, p_masslump) bind(c, name="cgasm_kmk_fetch") result(stat)
+       use iso_c_binding
+       integer(c_int), value :: id
+       real(c_double), dimension(*), intent(out) :: kmk
+       type(c_ptr), value :: kt, p_masslump
+       integer(c_int) :: stat
+     end function cgasm_kmk_fetch
 
      !! on /= 0: uploads and result downloads are queued (two streams); cgasm_synchronize waits
      function cgasm_set_async(id, on) bind(c, name="cgasm_set_async") result(stat)

@@ -346,6 +346,16 @@ int cgasm_cmc_set_sparsity(int id, int rows, int nnz2, const int* findrm2, const
 int cgasm_cmc_dev(int id, const double* ct_m, const double* inverse_masslump);
 int cgasm_cmc_fetch(int id, double* cmc_val);            /* nnz2 values in the order of the second-order colm */
 int cgasm_cmc_result_dev(int id, double** cmc_val_dev);  /* raw device pointer of the last result */
+/* P1-P1 pressure stabilisation on the same second-order sparsity: assemble_kmk_matrix
+ * (assemble/Momentum_CG.F90:2707-2766). kt = sum_e 0.5 dshape_tensor_dshape(dp, h_bar, dp, detwei) with h_bar the
+ * element's edge-length tensor (get_edge_lengths -> simplex_tensor, femtools/Metric_tools.F90:852-941), then
+ * kmk = kt diag(1 / (theta_pg p_masslump)) kt^T (mult_div_invscalar_div_T, femtools/Sparse_Matrices_Fields.F90:673-748)
+ * with p_masslump = get_lumped_mass(pressure mesh). Needs coordinates, the first-order sparsity (the pressure mesh is
+ * the P1 mesh of the handle) and the second-order one. cgasm_kmk_fetch: kmk (nnz2 values, colm2 order), and if not
+ * NULL kt (nnz) and p_masslump (n_nodes). add_kmk_matrix / add_kmk_rhs (:2768-2790) stay with the caller. */
+int cgasm_kmk_dev(int id, double theta_pg);
+int cgasm_kmk_fetch(int id, double* kmk, double* kt, double* p_masslump);
+int cgasm_kmk_result_dev(int id, double** kmk_dev);
 /* Diagnostics (host only, no GPU): the second-order pattern of a first-order one (both 1-based). findrm2
  * (n_nodes+1) is always written; colm2 only if *needed <= capacity. */
 int cgasm_cmc_sparsity_host(int n_nodes, const int* findrm, const int* colm, int* findrm2, int* colm2,

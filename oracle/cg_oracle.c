@@ -1699,6 +1699,193 @@ void orc_mult_div_vector_div_T(int dim, int n_nodes, const int* findrm, const in
 }
 
 
+/* ------------------------------------------------------------------------------------
+ * P1-P1 pressure stabilisation, assemble_kmk_matrix (assemble/Momentum_CG.F90:2707-2766):
+ *   kt = sum_e 0.5 dshape_tensor_dshape(dp_t, h_bar, dp_t, detwei)      on the first-order pressure sparsity,
+ *   h_bar = edge_length_from_eigenvalue(simplex_tensor(X, ele))  (error_measures/Edge_lengths.F90:68-79),
+ *   kmk = kt diag(1 / (theta_pg p_masslump)) kt^T  (mult_div_invscalar_div_T, femtools/Sparse_Matrices_Fields.F90:673-748).
+ * The reference solves the metric's linear system with LAPACK DGESV (femtools/Vector_Tools.F90 solve) and takes the
+ * eigen-decomposition with DSPEV (:401-440). LAPACK is an external library absent from the reference tree: both are
+ * restated by their textbook algorithms (LU with partial pivoting; cyclic Jacobi rotations) and pinned by
+ * tests/test_kmk.py against numpy.linalg (LAPACK itself) and the reference's own known answers
+ * (error_measures/tests/test_simplex_tensor.F90, test_simplex_tensor_edgelens.F90).
+ * ------------------------------------------------------------------------------------ */
+
+/* simplex_tensor without `power`, femtools/Metric_tools.F90:852-941: the symmetric M with e^T M e = 1 for every edge e.
+ * pos_ele(dim, loc); m(dim, dim). Returns 0, or 1 if the system is singular (degenerate element). */
+int orc_simplex_tensor(int dim, const double* pos_ele, double* m) {
+  const int loc = dim + 1, d = dim * (dim + 1) / 2;
+  double A[36], x[6];
+  /* idx(k,l) :919-933 (1-based) */
+#define IDX_(k, l) ((((k) < (l) ? (k) : (l)) == 1) ? ((k) > (l) ? (k) : (l)) : ((k) > (l) ? (k) : (l)) + ((k) < (l) ? (k) : (l)) - (dim == 3 ? 0 : 1))
+  int n = 0;
+  for (int i = 0; i < loc; i++)
+    for (int j = i + 1; j < loc; j++) {
+      double diff[MAXDIM];
+      for (int a = 0; a < dim; a++) diff[a] = pos_ele[a + dim * j] - pos_ele[a + dim * i];
+      for (int k = 1; k <= dim; k++)
+        for (int l = 1; l <= dim; l++) A[n + d * (IDX_(k, l) - 1)] = diff[k - 1] * diff[l - 1] * (k == l ? 1.0 : 2.0);
+      n++;
+    }
+  for (int i = 0; i < d; i++) x[i] = 1.0;
+  /* solve(A, x): LU with partial pivoting (DGESV) */
+  for (int c = 0; c < d; c++) {
+    int piv = c;
+    for (int r = c + 1; r < d; r++)
+      if (fabs(A[r + d * c]) > fabs(A[piv + d * c])) piv = r;
+    if (A[piv + d * c] == 0.0) return 1;
+    if (piv != c) {
+      for (int q = 0; q < d; q++) {
+        const double t = A[c + d * q];
+        A[c + d * q] = A[piv + d * q];
+        A[piv + d * q] = t;
+      }
+      const double t = x[c];
+      x[c] = x[piv];
+      x[piv] = t;
+    }
+    for (int r = c + 1; r < d; r++) {
+      const double f = A[r + d * c] / A[c + d * c];
+      for (int q = c + 1; q < d; q++) A[r + d * q] -= f * A[c + d * q];
+      x[r] -= f * x[c];
+    }
+  }
+  for (int c = d - 1; c >= 0; c--) {
+    double t = x[c];
+    for (int q = c + 1; q < d; q++) t -= A[c + d * q] * x[q];
+    x[c] = t / A[c + d * c];
+  }
+  for (int i = 1; i <= dim; i++)
+    for (int j = 1; j <= dim; j++) m[(i - 1) + dim * (j - 1)] = x[IDX_(i, j) - 1];
+#undef IDX_
+  return 0;
+}
+
+/* eigendecomposition_symmetric (Vector_Tools.F90:401-440: DSPEV) by cyclic Jacobi rotations. V: columns = eigenvectors. */
+void orc_eig_symmetric(int dim, const double* M, double* V, double* evals) {
+  double A[9];
+  for (int i = 0; i < dim * dim; i++) {
+    A[i] = M[i];
+    V[i] = 0.0;
+  }
+  for (int i = 0; i < dim; i++) V[i + dim * i] = 1.0;
+  for (int sweep = 0; sweep < 60; sweep++) {
+    double off = 0.0, diag = 0.0;
+    for (int i = 0; i < dim; i++)
+      for (int j = 0; j < dim; j++) {
+        if (i != j) off += A[i + dim * j] * A[i + dim * j];
+        else diag += A[i + dim * i] * A[i + dim * i];
+      }
+    if (off <= 1e-32 * diag || off == 0.0) break;
+    for (int p = 0; p < dim; p++)
+      for (int q = p + 1; q < dim; q++) {
+        const double apq = A[p + dim * q];
+        if (apq == 0.0) continue;
+        const double theta = (A[q + dim * q] - A[p + dim * p]) / (2.0 * apq);
+        const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+        const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+        for (int k = 0; k < dim; k++) { /* A <- A J */
+          const double akp = A[k + dim * p], akq = A[k + dim * q];
+          A[k + dim * p] = c * akp - sn * akq;
+          A[k + dim * q] = sn * akp + c * akq;
+        }
+        for (int k = 0; k < dim; k++) { /* A <- J^T A */
+          const double apk = A[p + dim * k], aqk = A[q + dim * k];
+          A[p + dim * k] = c * apk - sn * aqk;
+          A[q + dim * k] = sn * apk + c * aqk;
+        }
+        for (int k = 0; k < dim; k++) {
+          const double vkp = V[k + dim * p], vkq = V[k + dim * q];
+          V[k + dim * p] = c * vkp - sn * vkq;
+          V[k + dim * q] = sn * vkp + c * vkq;
+        }
+      }
+  }
+  for (int i = 0; i < dim; i++) evals[i] = A[i + dim * i];
+}
+
+/* edge_length_from_eigenvalue_metric, femtools/Metric_tools.F90:157-164: V diag(1/sqrt|lambda|) V^T */
+void orc_edge_length_from_metric(int dim, const double* metric, double* edge) {
+  double V[9], ev[3];
+  orc_eig_symmetric(dim, metric, V, ev);
+  for (int i = 0; i < dim; i++) ev[i] = 1.0 / sqrt(fabs(ev[i])); /* :145-155 */
+  for (int i = 0; i < dim; i++)
+    for (int j = 0; j < dim; j++) { /* eigenrecomposition: M = V A V^T */
+      double s = 0.0;
+      for (int k = 0; k < dim; k++) s += V[i + dim * k] * ev[k] * V[j + dim * k];
+      edge[i + dim * j] = s;
+    }
+}
+
+/* The element loop of assemble_kmk_matrix (:2748-2753) on the pressure (= coordinate, P1) mesh, plus the lumped
+ * pressure mass it divides by (get_lumped_mass -> compute_lumped_mass: row sums of shape_shape). kt(nnz), p_masslump(N)
+ * are overwritten. */
+int orc_assemble_kt(const orc_mesh* m, const int* findrm, const int* colm, double* kt, double* p_masslump) {
+  const int dim = m->dim, loc = m->loc, ngi = m->ngi;
+  const size_t nnz = (size_t)(findrm[m->n_nodes] - 1);
+  memset(kt, 0, sizeof(double) * nnz);
+  memset(p_masslump, 0, sizeof(double) * (size_t)m->n_nodes);
+  for (int ele = 1; ele <= m->n_elements; ele++) {
+    const int* nd = ele_nodes(m, ele);
+    double X_val[MAXDIM * MAXLOC], dp_t[MAXLOC * MAXNGI * MAXDIM], detwei[MAXNGI], h_bar[MAXDIM * MAXDIM * MAXNGI],
+        ele_tensor[MAXDIM * MAXDIM], edge[MAXDIM * MAXDIM], little[MAXLOC * MAXLOC];
+    for (int i = 0; i < loc; i++)
+      for (int a = 0; a < dim; a++) X_val[a + dim * i] = m->X[a + dim * (size_t)(nd[i] - 1)];
+    orc_transform_to_physical(dim, ngi, X_val, m->dn, m->weight, dp_t, detwei, NULL);
+    if (orc_simplex_tensor(dim, X_val, ele_tensor)) return CGASM_EARG;
+    orc_edge_length_from_metric(dim, ele_tensor, edge);
+    for (int g = 0; g < ngi; g++) /* spread(..., 3, ngi) */
+      for (int a = 0; a < dim * dim; a++) h_bar[a + dim * dim * g] = edge[a];
+    dshape_tensor_dshape(dim, loc, ngi, dp_t, h_bar, detwei, little);
+    for (int i = 0; i < loc; i++)
+      for (int j = 0; j < loc; j++) {
+        const double v = 0.5 * little[i + loc * j];
+        if (v == 0) continue;
+        kt[csr_sparsity_pos(findrm, colm, nd[i], nd[j]) - 1] += v;
+      }
+    for (int i = 0; i < loc; i++) {
+      double rowsum = 0.0;
+      for (int j = 0; j < loc; j++) {
+        double mij = 0.0;
+        for (int g = 0; g < ngi; g++) mij += m->n[i + loc * g] * m->n[j + loc * g] * detwei[g];
+        rowsum += mij;
+      }
+      p_masslump[nd[i] - 1] += rowsum;
+    }
+  }
+  return 0;
+}
+
+/* mult_div_invscalar_div_T, femtools/Sparse_Matrices_Fields.F90:673-748: product = m1 diag(1/s) m2^T on the
+ * second-order sparsity; entry0 + row_val(k1)*col_val(k2)/s(row(k1)) (:729-730), rows walked left to right. */
+void orc_mult_div_invscalar_div_T(int n_nodes, const int* findrm, const int* colm, const double* m1, const double* sfield,
+                                  const double* m2, const int* findrm2, const int* colm2, double* product) {
+  size_t nentry0 = 0;
+  for (int i = 1; i <= n_nodes; i++) {
+    const int r0 = findrm[i - 1] - 1, rn = findrm[i] - findrm[i - 1];
+    for (int jcol = findrm2[i - 1] - 1; jcol < findrm2[i] - 1; jcol++) {
+      const int j = colm2[jcol];
+      const int c0 = findrm[j - 1] - 1, cn = findrm[j] - findrm[j - 1];
+      double entry0 = 0.0;
+      int k1 = 1, k2 = 1;
+      while (k1 <= rn && k2 <= cn) {
+        const int a = colm[r0 + k1 - 1], b = colm[c0 + k2 - 1];
+        if (a < b) {
+          k1 = k1 + 1;
+        } else if (a == b) {
+          entry0 = entry0 + m1[r0 + k1 - 1] * m2[c0 + k2 - 1] / sfield[a - 1];
+          k1 = k1 + 1;
+          k2 = k2 + 1;
+        } else {
+          k2 = k2 + 1;
+        }
+      }
+      product[nentry0++] = entry0;
+    }
+  }
+}
+
+
 /* The continuity half of construct_momentum_surface_element_cg, assemble/Momentum_CG.F90:1073-1111, taken when
  * integrate_continuity_by_parts and (assemble_ct_matrix_here or include_pressure_and_continuity_bcs): on faces that are
  * neither no-normal-flow nor free-surface (:1075) ct_mat_bdy = shape_shape_vector(p_shape, u_shape, detwei_bdy,

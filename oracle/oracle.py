@@ -453,6 +453,57 @@ def mult_div_vector_div_T(findrm, colm, ct1, ct2, vfield, findrm2, colm2):
     return out
 
 
+# ---- P1-P1 pressure stabilisation (assemble_kmk_matrix) ---------------------------------------------------------
+def simplex_tensor(pos_ele):
+    """pos_ele (loc, dim) -> the element's metric tensor (dim, dim)."""
+    pos = np.ascontiguousarray(pos_ele, dtype=np.float64)
+    dim = pos.shape[1]
+    m = np.zeros((dim, dim))
+    lib().orc_simplex_tensor.restype = C.c_int
+    if lib().orc_simplex_tensor(C.c_int(dim), _dp(pos), _dp(m)):
+        raise RuntimeError("degenerate element")
+    return m
+
+
+def edge_length_from_metric(metric):
+    m = np.ascontiguousarray(metric, dtype=np.float64)
+    out = np.zeros_like(m)
+    lib().orc_edge_length_from_metric(C.c_int(m.shape[0]), _dp(m), _dp(out))
+    return out
+
+
+def assemble_kt(mesh, findrm, colm):
+    """The pressure diffusion matrix kt (nnz) of assemble_kmk_matrix and the lumped pressure mass (n_nodes)."""
+    ctx = _Ctx(mesh, None)
+    nnz = int(findrm[-1]) - 1
+    kt, ml = np.zeros(nnz), np.zeros(mesh.n_nodes)
+    lib().orc_assemble_kt.restype = C.c_int
+    st = lib().orc_assemble_kt(C.byref(ctx.mesh), _ip(np.ascontiguousarray(findrm, dtype=np.int32)),
+                               _ip(np.ascontiguousarray(colm, dtype=np.int32)), _dp(kt), _dp(ml))
+    if st:
+        raise RuntimeError("oracle status %d" % st)
+    return kt, ml
+
+
+def mult_div_invscalar_div_T(findrm, colm, m1, sfield, m2, findrm2, colm2):
+    out = np.zeros(len(colm2))
+    lib().orc_mult_div_invscalar_div_T(C.c_int(len(findrm) - 1), _ip(np.ascontiguousarray(findrm, dtype=np.int32)),
+                                       _ip(np.ascontiguousarray(colm, dtype=np.int32)),
+                                       _dp(np.ascontiguousarray(m1, dtype=np.float64)),
+                                       _dp(np.ascontiguousarray(sfield, dtype=np.float64)),
+                                       _dp(np.ascontiguousarray(m2, dtype=np.float64)),
+                                       _ip(np.ascontiguousarray(findrm2, dtype=np.int32)),
+                                       _ip(np.ascontiguousarray(colm2, dtype=np.int32)), _dp(out))
+    return out
+
+
+def assemble_kmk(mesh, findrm, colm, findrm2, colm2, theta_pg=1.0):
+    """kmk = kt diag(1 / (theta_pg p_masslump)) kt^T on the second-order sparsity (Momentum_CG.F90:2755-2763)."""
+    kt, ml = assemble_kt(mesh, findrm, colm)
+    s = ml if abs(theta_pg - 1.0) < np.finfo(float).eps else ml * theta_pg
+    return mult_div_invscalar_div_T(findrm, colm, kt, s, kt, findrm2, colm2), kt, ml
+
+
 def momentum_face_ct(mesh, fields, opts, sndgln, face_ele, face, velocity_bc_type, velocity_bc=None, pressure_bc_type=0,
                      pressure_bc=None, hb_pressure=None, include_pressure_and_continuity_bcs=False):
     """Continuity half of the momentum surface element: ct_addto (dim, sloc [p], sloc [u]), ct_rhs_addto (sloc),
