@@ -78,6 +78,9 @@ struct Handle {
   // node -> element adjacency (host)
   I64Vec n2e_ptr;
   IVec n2e;
+  // lexicographic key of every node's lattice point (made with the row blocks, gather.cu): orders the rows of a block,
+  // the block's staged node list and the labels of the strip builder independently of the caller's numbering
+  std::vector<int64_t> geokey;
 
   // sparsity, 0-based
   bool have_sparsity = false;
@@ -200,6 +203,9 @@ void morton_order(const Handle* h, std::vector<int>& order, MortonFrame& F);
 // -1 = padding at the end of a block); returns the number of blocks. Needs the sparsity.
 int form_row_blocks(const Handle* h, const std::vector<int>& order, const MortonFrame& F, int block_rows,
                     std::vector<int>& rows);
+
+// geometric keys of the nodes (h->geokey) and the order of the rows inside every block (host_mesh.cpp)
+void order_block_rows(Handle* h, const MortonFrame& F, std::vector<int>& rows, int nblocks);
 
 // tiled.cu
 int tiles_build(Handle* h);

@@ -263,6 +263,7 @@ int gather_build_rows(Handle* h) {
   morton_order(h, order, F);
   std::vector<int> rows;
   P->nblocks = form_row_blocks(h, order, F, kBR, rows);
+  order_block_rows(h, F, rows, P->nblocks);
   std::vector<long long> block_ptr((size_t)P->nblocks + 1, 0);
   int maxlen = 0;
 #pragma omp parallel for schedule(static) reduction(max : maxlen)
@@ -273,19 +274,6 @@ int gather_build_rows(Handle* h) {
       if (r < 0) continue;
       deg = std::max(deg, (int)(h->n2e_ptr[r + 1] - h->n2e_ptr[r]));
       maxlen = std::max(maxlen, h->h_findrm[r + 1] - h->h_findrm[r]);
-    }
-    // Rows of a block: by descending number of incident elements, then by global id. Rows with equally long
-    // element lists share a warp, so a warp of the row-owner kernels stops after ITS longest row instead of the
-    // block's (unstructured meshes: node degrees 8-58 made a warp execute 1.9x the element computations its lanes
-    // needed); where the degree is uniform (the interior of a structured mesh) this is the plain order by global id,
-    // in which neighbouring threads write neighbouring rows.
-    {
-      int* rb = rows.data() + (size_t)b * kBR;
-      const int64_t* np = h->n2e_ptr.data();
-      std::sort(rb, std::find(rb, rb + kBR, -1), [np](int x, int y) {
-        const int64_t dx = np[x + 1] - np[x], dy = np[y + 1] - np[y];
-        return dx != dy ? dx > dy : x < y;
-      });
     }
     block_ptr[b + 1] = (long long)deg * kBR;
   }

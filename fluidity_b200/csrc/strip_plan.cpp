@@ -235,7 +235,7 @@ struct FastSeq {
 // false if the link does not fit the fixed-size tables (the generic path handles it). The link's vertices are
 // the row's columns minus r itself (already sorted and distinct), so local ids come from the CSR row.
 bool fast_link(int loc, const int* nd0, const int64_t* n2e_ptr, const int* n2e, const int* findrm, const int* colm, int r,
-               FastLink& L) {
+               FastLink& L, const int64_t* geokey = nullptr) {
   const int64_t k0 = n2e_ptr[r];
   const int m = (int)(n2e_ptr[r + 1] - k0);
   if (m > kFastMaxTri) return false;
@@ -254,7 +254,23 @@ bool fast_link(int loc, const int* nd0, const int64_t* n2e_ptr, const int* n2e, 
   }
   L.m = m;
   L.nv = nv;
-  std::fill(L.ninc, L.ninc + nv, 0);
+  // Canonical labels (build_strip_row_keyed): vertices by geometric key instead of id, triangles sorted by their labels
+  int byid[kFastMaxVert];
+  unsigned char label[kFastMaxVert];  // position in the id-sorted row -> label
+  if (geokey) {
+    std::copy(L.vid, L.vid + nv, byid);
+    unsigned char ord[kFastMaxVert];
+    for (int k = 0; k < nv; k++) ord[k] = (unsigned char)k;
+    std::sort(ord, ord + nv, [&](unsigned char a, unsigned char b) {
+      const int64_t ka = geokey[byid[a]], kb = geokey[byid[b]];
+      return ka != kb ? ka < kb : a < b;
+    });
+    for (int k = 0; k < nv; k++) {
+      label[ord[k]] = (unsigned char)k;
+      L.vid[k] = byid[ord[k]];
+    }
+  }
+  const int* ids = geokey ? byid : L.vid;
   for (int k = 0; k < m; k++) {
     const int* nd = nd0 + (size_t)4 * n2e[k0 + k];
     unsigned char* t = L.tri[k];
@@ -262,15 +278,35 @@ bool fast_link(int loc, const int* nd0, const int64_t* n2e_ptr, const int* n2e, 
     for (int i = 0; i < loc; i++) {
       if (nd[i] == r) continue;
       if (q == 3) return false;
-      const int* f = std::lower_bound(L.vid, L.vid + nv, nd[i]);
-      if (f == L.vid + nv || *f != nd[i]) return false;  // the sparsity does not hold this element pair
-      t[q++] = (unsigned char)(f - L.vid);
+      const int* f = std::lower_bound(ids, ids + nv, nd[i]);
+      if (f == ids + nv || *f != nd[i]) return false;  // the sparsity does not hold this element pair
+      t[q++] = geokey ? label[f - ids] : (unsigned char)(f - ids);
     }
     if (q != 3) return false;  // degenerate element (repeated node)
     if (t[0] > t[1]) std::swap(t[0], t[1]);
     if (t[1] > t[2]) std::swap(t[1], t[2]);
     if (t[0] > t[1]) std::swap(t[0], t[1]);
     if (t[0] == t[1] || t[1] == t[2]) return false;
+  }
+  if (geokey) {  // m is ~24: insertion sort of the label triples
+    for (int a = 1; a < m; a++) {
+      unsigned char cur[3] = {L.tri[a][0], L.tri[a][1], L.tri[a][2]};
+      int b = a - 1;
+      while (b >= 0 && (L.tri[b][0] > cur[0] || (L.tri[b][0] == cur[0] && (L.tri[b][1] > cur[1] ||
+                                                (L.tri[b][1] == cur[1] && L.tri[b][2] > cur[2]))))) {
+        L.tri[b + 1][0] = L.tri[b][0];
+        L.tri[b + 1][1] = L.tri[b][1];
+        L.tri[b + 1][2] = L.tri[b][2];
+        b--;
+      }
+      L.tri[b + 1][0] = cur[0];
+      L.tri[b + 1][1] = cur[1];
+      L.tri[b + 1][2] = cur[2];
+    }
+  }
+  std::fill(L.ninc, L.ninc + nv, 0);
+  for (int k = 0; k < m; k++) {
+    const unsigned char* t = L.tri[k];
     for (int i = 0; i < 3; i++) {
       if (L.ninc[t[i]] == kFastMaxInc) return false;
       L.inc[t[i]][L.ninc[t[i]]++] = (unsigned char)k;
@@ -508,9 +544,9 @@ struct StripMemo {
 
 // the 3-D strip of row r on the fast path; false = use the generic one
 bool fast_strip_row(int loc, const int* nd0, const int64_t* n2e_ptr, const int* n2e, const int* findrm, const int* colm, int r,
-                    std::vector<int>& nodes, std::vector<char>& comp) {
+                    std::vector<int>& nodes, std::vector<char>& comp, const int64_t* geokey = nullptr) {
   FastLink L;
-  if (!fast_link(loc, nd0, n2e_ptr, n2e, findrm, colm, r, L)) return false;
+  if (!fast_link(loc, nd0, n2e_ptr, n2e, findrm, colm, r, L, geokey)) return false;
   static const int perms[6][3] = {{0, 1, 2}, {0, 2, 1}, {1, 0, 2}, {1, 2, 0}, {2, 0, 1}, {2, 1, 0}};
   if (L.m <= 64) {
     static thread_local StripMemo memo;
@@ -658,6 +694,107 @@ void build_strip_row_generic(int loc, const int* nd0, const int64_t* n2e_ptr, co
   build_strip_row_impl(loc, nd0, n2e_ptr, n2e, findrm, colm, r, out, false);
 }
 
+// The strip of row r built on a CANONICAL copy of its link: the link's vertices are relabelled by the rank of their
+// geometric key (lexicographic lattice coordinates, ties by id) and its simplices sorted by their relabelled vertex
+// tuples, so the result depends on the geometry around r and not on how the mesh generator numbered nodes and
+// elements. Rows with congruent neighbourhoods then walk their neighbours in the same relative order: on a renumbered
+// structured mesh the lanes of a warp read the staged records at a common offset again (shared-memory bank conflicts
+// measured on the B200 with id-ordered strips: 2.1x the wavefronts of the lexicographically numbered mesh), and the
+// per-thread memo of finished strips hits as on the unshuffled mesh. With a lexicographic numbering the keyed and the
+// id-ordered labels coincide.
+void build_strip_row_keyed(int loc, const int* nd0, const int64_t* n2e_ptr, const int* n2e, const int* findrm, const int* colm,
+                           const int64_t* geokey, int r, std::vector<StripEntry>& out) {
+  if (!geokey) return build_strip_row(loc, nd0, n2e_ptr, n2e, findrm, colm, r, out);
+  if (loc == 4) {  // 3-D links that fit the fixed-size tables are relabelled inside fast_link (no copy of the link)
+    static thread_local std::vector<int> nodes;
+    static thread_local std::vector<char> comp;
+    if (n2e_ptr[r + 1] > n2e_ptr[r] && fast_strip_row(loc, nd0, n2e_ptr, n2e, findrm, colm, r, nodes, comp, geokey)) {
+      const int* cb = colm + findrm[r];
+      const int* ce = colm + findrm[r + 1];
+      out.resize(nodes.size());
+      for (size_t k = 0; k < nodes.size(); k++) {
+        out[k].node = nodes[k];
+        out[k].meta = ((int)(std::lower_bound(cb, ce, nodes[k]) - cb) & 0xff) | (comp[k] ? kStripCompute : 0);
+      }
+      return;
+    }
+  }
+  const int s0 = findrm[r], len = findrm[r + 1] - s0;
+  const int64_t k0 = n2e_ptr[r];
+  const int m = (int)(n2e_ptr[r + 1] - k0);
+  out.clear();
+  if (m == 0) return;
+  constexpr int kMaxV = 512;
+  if (len < 2 || len > kMaxV) return build_strip_row(loc, nd0, n2e_ptr, n2e, findrm, colm, r, out);
+  const int nv = len - 1;
+  int byid[kMaxV], rank_of[kMaxV], verts[kMaxV];  // byid: the row minus r (ascending ids); verts: the same by key
+  {
+    int q = 0;
+    for (int k = 0; k < len; k++)
+      if (colm[s0 + k] != r && q < nv) byid[q++] = colm[s0 + k];
+    if (q != nv) return build_strip_row(loc, nd0, n2e_ptr, n2e, findrm, colm, r, out);
+  }
+  {
+    int ord[kMaxV];
+    for (int k = 0; k < nv; k++) ord[k] = k;
+    std::sort(ord, ord + nv, [&](int a, int b) {
+      const int64_t ka = geokey[byid[a]], kb = geokey[byid[b]];
+      return ka != kb ? ka < kb : byid[a] < byid[b];
+    });
+    for (int k = 0; k < nv; k++) {
+      rank_of[ord[k]] = k;
+      verts[k] = byid[ord[k]];
+    }
+  }
+  // the link in local labels: element k = {nv (the row's own node), ranks of its other nodes ascending}, sorted
+  const int w = loc - 1;
+  // per-thread scratch: this runs once per row of the mesh
+  static thread_local std::vector<int> tri, tord, nd_l, n2e_l, colm_l, findrm_l;
+  static thread_local std::vector<int64_t> ptr_l;
+  static thread_local std::vector<StripEntry> loc_out;
+  tri.assign((size_t)m * 3, 0);
+  for (int k = 0; k < m; k++) {
+    const int* nd = nd0 + (size_t)4 * n2e[k0 + k];
+    int q = 0;
+    for (int i = 0; i < loc; i++) {
+      if (nd[i] == r) continue;
+      const int* f = std::lower_bound(byid, byid + nv, nd[i]);
+      if (q == w || f == byid + nv || *f != nd[i]) return build_strip_row(loc, nd0, n2e_ptr, n2e, findrm, colm, r, out);
+      tri[(size_t)3 * k + q++] = rank_of[f - byid];
+    }
+    if (q != w) return build_strip_row(loc, nd0, n2e_ptr, n2e, findrm, colm, r, out);
+    std::sort(&tri[(size_t)3 * k], &tri[(size_t)3 * k] + w);
+  }
+  tord.resize((size_t)m);
+  for (int k = 0; k < m; k++) tord[k] = k;
+  std::sort(tord.begin(), tord.end(), [&](int a, int b) {
+    for (int i = 0; i < w; i++)
+      if (tri[(size_t)3 * a + i] != tri[(size_t)3 * b + i]) return tri[(size_t)3 * a + i] < tri[(size_t)3 * b + i];
+    return a < b;
+  });
+  nd_l.assign((size_t)m * 4, -1);
+  n2e_l.resize((size_t)m);
+  colm_l.resize((size_t)nv + 1);
+  ptr_l.assign((size_t)nv + 2, 0);
+  findrm_l.assign((size_t)nv + 2, 0);
+  for (int k = 0; k < m; k++) {
+    nd_l[(size_t)4 * k] = nv;
+    for (int i = 0; i < w; i++) nd_l[(size_t)4 * k + 1 + i] = tri[(size_t)3 * tord[k] + i];
+    n2e_l[k] = k;
+  }
+  ptr_l[(size_t)nv + 1] = m;
+  findrm_l[(size_t)nv + 1] = nv + 1;
+  for (int k = 0; k <= nv; k++) colm_l[k] = k;
+  build_strip_row(loc, nd_l.data(), ptr_l.data(), n2e_l.data(), findrm_l.data(), colm_l.data(), nv, loc_out);
+  out.resize(loc_out.size());
+  for (size_t k = 0; k < loc_out.size(); k++) {
+    const int node = verts[loc_out[k].node];
+    const int slot = (int)(std::lower_bound(colm + s0, colm + s0 + len, node) - (colm + s0));
+    out[k].node = node;
+    out[k].meta = (slot & 0xff) | (loc_out[k].meta & kStripCompute);
+  }
+}
+
 // ---- staged plan ------------------------------------------------------------------------------------------
 namespace {
 // node -> small index, O(1) clear by generation stamps (a block touches a few hundred nodes)
@@ -712,6 +849,7 @@ void build_staged_plan_host(const Handle* h, const std::vector<int>& rows, int n
                             const std::vector<int>& perm, StagedPlanHost& out) {
   const bool permuted = !perm.empty();
   const int loc = h->loc, dim = h->dim;
+  const int64_t* gk = (h->geokey.empty() || getenv("CGASM_STRIP_NOKEY")) ? nullptr : h->geokey.data();
   constexpr int kTask = 128;  // blocks per task: fixed, so the layout does not depend on the thread count
   const int ntasks = (nblocks + kTask - 1) / kTask;
   out.nblocks = nblocks;
@@ -729,6 +867,7 @@ void build_staged_plan_host(const Handle* h, const std::vector<int>& rows, int n
     std::vector<StripEntry> rp[kBR];
     NodeIndexMap map;
     std::vector<int> bn;
+    std::vector<std::pair<int64_t, int>> bk;
 #pragma omp for schedule(dynamic, 1)
     for (int task = 0; task < ntasks; task++) {
       std::vector<unsigned>& ent = out.ent[task];
@@ -739,13 +878,14 @@ void build_staged_plan_host(const Handle* h, const std::vector<int>& rows, int n
         int deg = 0;
         map.clear();
         bn.clear();
+        bk.clear();
         // the map and the block list are keyed by the record position (perm[node] when the records are permuted)
         auto key_of = [&](int node) { return permuted ? perm[node] : node; };
         auto note = [&](int node) {
           int* v = map.slot(key_of(node));
           if (*v < 0) {
             *v = 0;
-            bn.push_back(key_of(node));
+            bk.emplace_back(gk ? gk[node] : 0, key_of(node));
           }
         };
         for (int t = 0; t < kBR; t++) {
@@ -753,12 +893,17 @@ void build_staged_plan_host(const Handle* h, const std::vector<int>& rows, int n
           rp[t].clear();
           note(r >= 0 ? r : 0);
           if (r < 0) continue;
-          build_strip_row(loc, h->h_nd0.data(), h->n2e_ptr.data(), h->n2e.data(), h->h_findrm.data(), h->h_colm.data(), r, rp[t]);
+          build_strip_row_keyed(loc, h->h_nd0.data(), h->n2e_ptr.data(), h->n2e.data(), h->h_findrm.data(), h->h_colm.data(),
+                                gk, r, rp[t]);
           deg = std::max(deg, (int)rp[t].size());
           total_real += (long long)rp[t].size();
           for (const StripEntry& e : rp[t]) note(e.node);
         }
-        std::sort(bn.begin(), bn.end());
+        // local indices follow the geometric key (the lexicographic order of the touched region: what the id order is on
+        // a lexicographically numbered mesh, whose staged reads are bank-conflict free), then the record position
+        std::sort(bk.begin(), bk.end());
+        bn.resize(bk.size());
+        for (size_t i = 0; i < bk.size(); i++) bn[i] = bk[i].second;
         for (size_t i = 0; i < bn.size(); i++) *map.slot(bn[i]) = (int)i;
         block_nn[b] = (int)bn.size();
         tn.insert(tn.end(), bn.begin(), bn.end());
@@ -941,6 +1086,7 @@ extern "C" int cgasm_plan_host_timing(int dim, int n_nodes, int n_elements, cons
   times[3] = now() - t0;
   t0 = now();
   const int nb = form_row_blocks(&h, order, F, 128, rows);
+  order_block_rows(&h, F, rows, nb);
   times[4] = now() - t0;
   t0 = now();
   h.h_nd0.shrink_to_fit();
@@ -949,5 +1095,81 @@ extern "C" int cgasm_plan_host_timing(int dim, int n_nodes, int n_elements, cons
   const long long total = sp.total_real;
   times[5] = now() - t0;
   if (entries_per_pair) *entries_per_pair = h.n2e.empty() ? 0.0 : (double)total / (double)h.n2e.size();
+  return CGASM_OK;
+}
+
+// ---- diagnostics ABI: shape of the staged STRIP plan of a mesh, built on the host (no GPU needed) ----------------
+// stats[0] strip entries per (row, element) pair; [1] largest number of distinct nodes a block touches;
+// [2] shared-memory wavefronts per quarter-warp LDS.128 of the staged records (1 = bank-conflict free: the 8 lanes
+//     read 8 different 16-byte bank groups, lanes on the same node broadcast);
+// [3] entries a warp walks / entries its rows need (1 = every lane busy until the warp's last step);
+// [4] element computations a warp executes / computations its rows need (a step computes if any lane does).
+extern "C" int cgasm_plan_host_stats(int dim, int n_nodes, int n_elements, const int* ndglno, const double* X, double* stats) {
+  using namespace cgasm;
+  const int loc = dim + 1;
+  if ((dim != 2 && dim != 3) || n_nodes <= 0 || n_elements <= 0 || !ndglno || !X || !stats)
+    CG_FAIL(CGASM_EARG, "cgasm_plan_host_stats: bad argument");
+  Handle h;
+  h.dim = dim;
+  h.loc = loc;
+  h.n_nodes = n_nodes;
+  h.n_elements = n_elements;
+  h.h_nd0.resize((size_t)4 * n_elements);
+  for (int e = 0; e < n_elements; e++)
+    for (int i = 0; i < 4; i++) h.h_nd0[(size_t)4 * e + i] = i < loc ? ndglno[(size_t)loc * e + i] - 1 : -1;
+  h.h_X.assign(X, X + (size_t)dim * n_nodes);
+  build_node_to_element(n_nodes, n_elements, loc, h.h_nd0.data(), h.n2e_ptr, h.n2e);
+  build_sparsity(n_nodes, n_elements, loc, h.h_nd0.data(), h.n2e_ptr, h.n2e, h.h_findrm, h.h_colm);
+  std::vector<int> order, rows;
+  MortonFrame F;
+  morton_order(&h, order, F);
+  const int nb = form_row_blocks(&h, order, F, kBR, rows);
+  order_block_rows(&h, F, rows, nb);
+  StagedPlanHost sp;
+  build_staged_plan_host(&h, rows, nb, 64, std::vector<int>(), sp);
+  stats[0] = h.n2e.empty() ? 0.0 : (double)sp.total_real / (double)h.n2e.size();
+  stats[1] = sp.blk_nodes_max;
+  double wf = 0, groups = 0, walked = 0, needed = 0, comp_exec = 0, comp_need = 0;
+  for (int b = 0; b < nb; b++) {
+    const int task = b / sp.task_blocks;
+    const long long base = sp.ptr[b] - sp.ptr[(size_t)task * sp.task_blocks];
+    const int ldeg = (int)((sp.ptr[(size_t)b + 1] - sp.ptr[b]) / kBR);
+    const unsigned* ent = sp.ent[task].data() + base;
+    for (int w = 0; w < kBR / 32; w++) {
+      int steps = 0;
+      for (int t = 32 * w; t < 32 * w + 32; t++) steps = std::max(steps, (sp.row_meta[4 * ((size_t)b * kBR + t) + 2] >> 24) & 0xff);
+      const int wdeg = std::min(ldeg, steps * dim);
+      for (int t = 32 * w; t < 32 * w + 32; t++) {
+        const int mine = ((sp.row_meta[4 * ((size_t)b * kBR + t) + 2] >> 24) & 0xff) * dim;
+        needed += mine;
+        walked += wdeg;
+      }
+      for (int k = 0; k < wdeg; k++) {
+        int anyc = 0;
+        for (int t = 32 * w; t < 32 * w + 32; t++) {
+          const unsigned e = ent[(size_t)k * kBR + t];
+          comp_need += e & kStagedCompute;
+          anyc |= (int)(e & kStagedCompute);
+        }
+        comp_exec += 32.0 * anyc;
+        for (int q = 0; q < 4; q++) {
+          int idx[8], cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+          for (int l = 0; l < 8; l++) idx[l] = (int)((ent[(size_t)k * kBR + 32 * w + 8 * q + l] >> 4) & 0xfff);
+          for (int l = 0; l < 8; l++) {
+            bool dup = false;
+            for (int m = 0; m < l; m++) dup |= idx[m] == idx[l];
+            if (!dup) cnt[idx[l] & 7]++;
+          }
+          int mx = 0;
+          for (int c = 0; c < 8; c++) mx = std::max(mx, cnt[c]);
+          wf += mx;
+          groups += 1;
+        }
+      }
+    }
+  }
+  stats[2] = groups > 0 ? wf / groups : 0.0;
+  stats[3] = needed > 0 ? walked / needed : 0.0;
+  stats[4] = comp_need > 0 ? comp_exec / comp_need : 0.0;
   return CGASM_OK;
 }

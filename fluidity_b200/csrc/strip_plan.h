@@ -30,6 +30,10 @@ void build_strip_row(int loc, const int* nd0, const int64_t* n2e_ptr, const int*
 void build_strip_row_generic(int loc, const int* nd0, const int64_t* n2e_ptr, const int* n2e, const int* findrm,
                              const int* colm, int r, std::vector<StripEntry>& out);
 
+// The same on a canonical relabelling of the link by geometric keys (geokey[node], nullptr = build_strip_row).
+void build_strip_row_keyed(int loc, const int* nd0, const int64_t* n2e_ptr, const int* n2e, const int* findrm, const int* colm,
+                           const int64_t* geokey, int r, std::vector<StripEntry>& out);
+
 // ---- staged strip plan (host side of strip_staged.cu) ---------------------------------------------------
 constexpr unsigned kStagedCompute = 1u;
 constexpr int kStagedNL[] = {128, 256, 384, 512, 768, 1024};  // chunk strides the staged kernels are instantiated for

@@ -448,6 +448,12 @@ int cgasm_coo_fetch(int id, int which, long long ncoo, int* coo_i, int* coo_j, d
 int cgasm_plan_host_timing(int dim, int n_nodes, int n_elements, const int* ndglno, const double* X,
                            double* times, double* entries_per_pair);
 
+/* Diagnostics (host only, no GPU): shape of the staged STRIP plan of a mesh -- stats(5) = strip entries per (row, element)
+ * pair, largest number of distinct nodes a row block touches, shared-memory wavefronts per quarter-warp read of the
+ * staged node records (1 = bank-conflict free), entries a warp walks / entries its rows need, element computations a
+ * warp executes / computations its rows need (SIMT efficiency of the row-owner loop on unstructured meshes). */
+int cgasm_plan_host_stats(int dim, int n_nodes, int n_elements, const int* ndglno, const double* X, double* stats);
+
 /* ---- halo update (femtools/Halos_Communications.F90:320-412,497-567) -------------------
  * nprocs neighbours; sends/recvs are the concatenated 1-based node lists of
  * halo%sends(p) / halo%receives(p), nsend/nrecv their lengths per process p = 0..nprocs-1

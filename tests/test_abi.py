@@ -90,7 +90,7 @@ FORTRAN = os.path.join(ROOT, "fluidity_b200", "fortran", "cgasm_fortran.F90")
 # diagnostics / device-pointer accessors a Fortran caller has no use for
 _NOT_BOUND_IN_FORTRAN = {"cgasm_advdiff_result_dev", "cgasm_momentum_result_dev", "cgasm_last_kernel_ms",
                          "cgasm_launch_count", "cgasm_row_blocks_host", "cgasm_strip_plan_host", "cgasm_stream",
-                         "cgasm_plan_host_timing", "cgasm_last_path", "cgasm_plan_stats", "cgasm_cmc_result_dev", "cgasm_kmk_result_dev", "cgasm_cmc_sparsity_host", "cgasm_cmc_expand_plan_host"}
+                         "cgasm_plan_host_timing", "cgasm_plan_host_stats", "cgasm_last_path", "cgasm_plan_stats", "cgasm_cmc_result_dev", "cgasm_kmk_result_dev", "cgasm_cmc_sparsity_host", "cgasm_cmc_expand_plan_host"}
 
 
 def _fortran_type_fields(txt, name):

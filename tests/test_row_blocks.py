@@ -91,3 +91,32 @@ def test_lattice_from_the_hashed_edge_sample():
     rows, scale = row_blocks(mesh)
     assert np.allclose(scale, c)
     assert rows.shape[0] <= 1.15 * (-(-mesh.n_nodes // BR)) + 1
+
+
+def plan_stats(mesh):
+    lib = cgasm.load()
+    nd = np.ascontiguousarray(mesh.ndglno, dtype=np.int32)
+    X = np.ascontiguousarray(mesh.X, dtype=np.float64)
+    st = (C.c_double * 5)()
+    rc = lib.cgasm_plan_host_stats(C.c_int(mesh.dim), C.c_int(mesh.n_nodes), C.c_int(mesh.n_elements),
+                                   nd.ctypes.data_as(C.POINTER(C.c_int)), X.ctypes.data_as(C.POINTER(C.c_double)), st)
+    assert rc == 0, lib.cgasm_last_error()
+    return dict(zip(("entries_per_pair", "max_nodes_per_block", "lds128_wavefronts", "walk_ratio", "compute_ratio"), st))
+
+
+def test_renumbering_does_not_change_the_plan_shape():
+    """The staged STRIP plan is built on geometric keys (rows of a block, the block's node list, the labels of the strip
+    builder): a randomly renumbered structured mesh gets the plan of the lexicographically numbered one -- same strip
+    lengths, the same (near conflict-free) shared-memory access pattern, no extra divergence. With id-ordered labels the
+    renumbered mesh read its staged records with 2.5 wavefronts per quarter-warp (2.1x measured on the B200)."""
+    box = syn.box_mesh((40, 40, 40))
+    a, b = plan_stats(box), plan_stats(syn.shuffled(box, seed=3))
+    for k in a:
+        assert abs(a[k] - b[k]) <= 1e-3 * max(1.0, abs(a[k])), (k, a[k], b[k])  # (ties between equal keys go by id)
+    assert a["lds128_wavefronts"] < 1.4 and a["compute_ratio"] < 1.1
+
+
+def test_unstructured_plan_stats_are_sane():
+    st = plan_stats(syn.delaunay_mesh(6000, seed=2))
+    assert 1.0 <= st["entries_per_pair"] < 1.6 and st["max_nodes_per_block"] <= 1024
+    assert 1.0 <= st["walk_ratio"] < 1.6 and 1.0 <= st["compute_ratio"] < 2.0 and 1.0 <= st["lds128_wavefronts"] <= 8.0
