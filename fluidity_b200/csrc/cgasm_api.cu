@@ -729,7 +729,9 @@ int cgasm_set_field(int id, int slot, int rank, int field_type, const double* va
   if (field_type == CGASM_FIELD_CONSTANT) {
     if (n_val_nodes != 1) CG_FAIL(CGASM_EARG, "a CONSTANT field has one node");
   } else if (field_type == CGASM_FIELD_NORMAL) {
-    if (n_val_nodes != h->n_nodes) CG_FAIL(CGASM_EARG, "a NORMAL field must live on the velocity mesh nodes");
+    // a field on another mesh (P2 density, P0 viscosity ...) is an option set outside the device path, not a caller bug:
+    // the shim keeps the Fortran loop
+    if (n_val_nodes != h->n_nodes) CG_FAIL(CGASM_EUNSUPPORTED, "a NORMAL field must live on the velocity mesh nodes");
   } else {
     CG_FAIL(CGASM_EUNSUPPORTED, "only NORMAL and CONSTANT fields are on the device path");
   }

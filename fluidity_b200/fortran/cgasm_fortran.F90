@@ -24,7 +24,7 @@ module cgasm_interface
        & cgasm_momentum_fetch_blocks, cgasm_momentum_element, &
        & cgasm_advdiff_element, cgasm_synchronize, cgasm_set_async, cgasm_halo_create, cgasm_halo_update, cgasm_halo_set_overlap, &
        & cgasm_coo_pattern_dev, cgasm_coo_values_dev, cgasm_coo_fetch, &
-       & cgasm_nccl_unique_id, cgasm_last_error, cgasm_set_surface, cgasm_advdiff_surface_dev, &
+       & cgasm_nccl_unique_id, cgasm_last_error, cgasm_last_error_string, cgasm_set_surface, cgasm_advdiff_surface_dev, &
        & cgasm_advdiff_dirichlet_dev, cgasm_momentum_surface_dev, cgasm_momentum_dirichlet_dev, &
        & cgasm_correct_masslumped_velocity, cgasm_cmc_build_sparsity, &
        & cgasm_cmc_get_sparsity, cgasm_cmc_set_sparsity, cgasm_cmc_dev, cgasm_cmc_fetch, &
@@ -468,5 +468,24 @@ module cgasm_interface
        integer(c_int) :: stat
      end function cgasm_coo_fetch
   end interface
+
+contains
+
+  !! cgasm_last_error as a Fortran string (for FLAbort in the shim, INTEGRATION.md section 3)
+  function cgasm_last_error_string() result(msg)
+    use iso_c_binding
+    character(len=512) :: msg
+    type(c_ptr) :: p
+    character(kind=c_char), pointer :: c(:)
+    integer :: i
+    msg = ""
+    p = cgasm_last_error()
+    if (.not. c_associated(p)) return
+    call c_f_pointer(p, c, (/ 512 /))
+    do i = 1, 512
+       if (c(i) == c_null_char) exit
+       msg(i:i) = c(i)
+    end do
+  end function cgasm_last_error_string
 
 end module cgasm_interface
