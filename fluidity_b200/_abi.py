@@ -27,7 +27,7 @@ SCATTER_ATOMIC, SCATTER_COLOURED, SCATTER_WARPAGG, SCATTER_TILED, SCATTER_GATHER
 TBC_NONE, TBC_NEUMANN, TBC_WEAKDIRICHLET, TBC_INTERNAL, TBC_ROBIN = range(5)
 VBC_NONE, VBC_WEAKDIRICHLET, VBC_NO_NORMAL_FLOW, VBC_INTERNAL, VBC_FREE_SURFACE, VBC_FLUX = range(6)
 
-_M_DOUBLES = ["dt", "theta", "beta", "gravity_magnitude", "nu_bar_scale"]
+_M_DOUBLES = ["dt", "theta", "beta", "gravity_magnitude", "nu_bar_scale", "fs_sf"]
 _M_INTS = [
     "lump_mass", "exclude_mass", "exclude_advection", "integrate_advection_by_parts",
     "have_source", "lump_source", "have_gravity", "subtract_out_reference_profile",
@@ -42,7 +42,7 @@ _M_INTS = [
     "cmc_lump_on_submesh", "abs_lump_on_submesh",
     # implemented since round 2
     "assemble_mass_matrix", "integrate_continuity_by_parts",
-    # surface loop only: free-surface stabilisation (unsupported)
+    # surface loop only: free-surface stabilisation (scale factor fs_sf)
     "have_surface_fs_stabilisation",
 ]
 

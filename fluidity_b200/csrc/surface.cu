@@ -135,26 +135,29 @@ __global__ void advdiff_surface_kernel(const SurfTables t, const FaceMesh m, con
 
 template <int DIM>
 __global__ void momentum_surface_kernel(const SurfTables t, const FaceMesh m, const cgasm_momentum_opts o, const RawField U,
-                                        const RawField O, const RawField R, const int* __restrict__ vtype,
+                                        const RawField O, const RawField R, const RawField G, const int* __restrict__ vtype,
                                         const double* __restrict__ vbc, const int* __restrict__ ptype, size_t nnz,
-                                        double* __restrict__ big_m, double* __restrict__ rhs, double* __restrict__ ct_m) {
+                                        double* __restrict__ big_m, double* __restrict__ rhs, double* __restrict__ ct_m,
+                                        double* __restrict__ masslump) {
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
   if (f >= m.n_faces) return;
   int bt[DIM];
   for (int d = 0; d < DIM; d++) bt[d] = vtype[(size_t)DIM * f + d];
   if (momentum_face_skipped<DIM>(bt, ptype ? ptype[f] : 0)) return;
   int nodes[DIM];
-  double Xf[DIM][DIM], Xc[DIM], Uf[DIM][DIM], Of[DIM][DIM], rho[DIM], bc[DIM][DIM], B[DIM][DIM][DIM], r[DIM][DIM];
+  double Xf[DIM][DIM], Xc[DIM], Uf[DIM][DIM], Of[DIM][DIM], rho[DIM], bc[DIM][DIM], Gf[DIM][DIM], B[DIM][DIM][DIM], r[DIM][DIM],
+      ml[DIM][DIM];
   load_face<DIM>(m, f, nodes, Xf, Xc);
   for (int i = 0; i < DIM; i++) {
     rho[i] = R.val[(size_t)R.stride * nodes[i]];
     for (int a = 0; a < DIM; a++) {
       Uf[i][a] = U.val[(size_t)U.stride * nodes[i] + a];
       Of[i][a] = O.val[(size_t)O.stride * nodes[i] + a];
+      Gf[i][a] = G.val ? G.val[(size_t)G.stride * nodes[i] + a] : 0.0;
       bc[i][a] = vbc ? vbc[((size_t)f * DIM + i) * DIM + a] : 0.0;  // velocity_bc(dim, sloc, n_faces)
     }
   }
-  momentum_face<DIM>(t, o, bt, Xf, Xc, Uf, Of, rho, bc, B, r);
+  momentum_face<DIM>(t, o, bt, Xf, Xc, Uf, Of, rho, bc, Gf, B, r, ml);
   for (int i = 0; i < DIM; i++) {
     for (int j = 0; j < DIM; j++) {
       const int pos = csr_pos0(m.findrm, m.colm, nodes[i], nodes[j]);
@@ -162,8 +165,10 @@ __global__ void momentum_surface_kernel(const SurfTables t, const FaceMesh m, co
       for (int d = 0; d < DIM; d++)
         if (B[d][i][j] != 0.0) atomicAdd(big_m + (size_t)d * nnz + pos, B[d][i][j]);
     }
-    for (int d = 0; d < DIM; d++)
+    for (int d = 0; d < DIM; d++) {
       if (r[d][i] != 0.0) atomicAdd(rhs + (size_t)DIM * nodes[i] + d, r[d][i]);
+      if (masslump && ml[d][i] != 0.0) atomicAdd(masslump + (size_t)DIM * nodes[i] + d, ml[d][i]);
+    }
   }
   // continuity by parts: the boundary blocks of ct_m (:1073-1088; weak-Dirichlet ct_rhs and pressure conditions are
   // outside the device path: cgasm_momentum_surface_dev refuses them)
@@ -360,15 +365,24 @@ int cgasm_momentum_surface_dev(int id, const cgasm_momentum_opts* opts, const in
   if (S->n_faces == 0) return CGASM_OK;
   if (!velocity_bc_type) CG_FAIL(CGASM_EARG, "null velocity_bc_type");
   const int dim = h->dim;
-  bool need_bc = false, adds_matrix = false;
+  bool need_bc = false, adds_matrix = false, fs_faces = false;
   const bool by_parts = opts->integrate_advection_by_parts && !opts->exclude_advection;
   for (size_t k = 0; k < (size_t)S->n_faces * dim; k++) {
     const int t = velocity_bc_type[k];
     if (t < CGASM_VBC_NONE || t > CGASM_VBC_FLUX) CG_FAIL(CGASM_EARG, "bad velocity boundary-condition type");
     need_bc = need_bc || t == CGASM_VBC_FLUX || (t == CGASM_VBC_WEAKDIRICHLET && by_parts);
     adds_matrix = adds_matrix || (by_parts && t != CGASM_VBC_WEAKDIRICHLET);
-    if (t == CGASM_VBC_FREE_SURFACE && opts->have_surface_fs_stabilisation)
-      CG_FAIL(CGASM_EUNSUPPORTED, "free-surface stabilisation (have_fs_stab) is outside the device path; keep the Fortran surface loop");
+    fs_faces = fs_faces || (t == CGASM_VBC_FREE_SURFACE && opts->have_surface_fs_stabilisation && k % dim == 0);
+  }
+  // free-surface stabilisation (:1108-1176): needs the gravity direction; the reference exits on a consistent mass with
+  // pressure-corrected absorption (:1161-1163) and adds to masslump only when it assembles one (:1168-1172)
+  if (fs_faces) {
+    if (!h->fields[CGASM_F_GRAVITY].set) CG_FAIL(CGASM_ESTATE, "free-surface stabilisation needs the gravity direction field");
+    if (!opts->lump_mass && opts->pressure_corrected_absorption)
+      CG_FAIL(CGASM_EUNSUPPORTED, "free-surface stabilisation requires a lumped mass or absorption outside the pressure correction");
+    if (opts->lump_mass && opts->pressure_corrected_absorption && !(opts->assemble_inverse_masslump && h->mom_has_masslump))
+      CG_FAIL(CGASM_ESTATE, "free-surface stabilisation with pressure-corrected absorption adds to masslump: assemble it");
+    adds_matrix = true;
   }
   if (need_bc && !velocity_bc) CG_FAIL(CGASM_EARG, "a face needs boundary values that were not given");
   const size_t nf = (size_t)S->n_faces;
@@ -388,16 +402,18 @@ int cgasm_momentum_surface_dev(int id, const cgasm_momentum_opts* opts, const in
     h->mom_copy_pending = false;
   }
   const RawField U = raw_of(h, CGASM_F_NU, dim), O = raw_of(h, CGASM_F_OLDU, dim), R = raw_of(h, CGASM_F_DENSITY, 1);
+  const RawField G = fs_faces ? raw_of(h, CGASM_F_GRAVITY, dim) : RawField{nullptr, 0};
+  double* ml_out = (fs_faces && opts->lump_mass && opts->pressure_corrected_absorption) ? h->d_masslump : nullptr;
   const int threads = 128, blocks = (S->n_faces + threads - 1) / threads;
   const FaceMesh m = face_mesh(h);
   if (dim == 3)
-    momentum_surface_kernel<3><<<blocks, threads, 0, h->stream>>>(S->tab, m, *opts, U, O, R, S->d_itype, need_bc ? S->d_bc : nullptr,
+    momentum_surface_kernel<3><<<blocks, threads, 0, h->stream>>>(S->tab, m, *opts, U, O, R, G, S->d_itype, need_bc ? S->d_bc : nullptr,
                                                                   pressure_bc_type ? S->d_ptype : nullptr, (size_t)h->nnz,
-                                                                  h->d_big_m, h->d_mom_rhs, ct_bdy ? h->d_ct_m : nullptr);
+                                                                  h->d_big_m, h->d_mom_rhs, ct_bdy ? h->d_ct_m : nullptr, ml_out);
   else
-    momentum_surface_kernel<2><<<blocks, threads, 0, h->stream>>>(S->tab, m, *opts, U, O, R, S->d_itype, need_bc ? S->d_bc : nullptr,
+    momentum_surface_kernel<2><<<blocks, threads, 0, h->stream>>>(S->tab, m, *opts, U, O, R, G, S->d_itype, need_bc ? S->d_bc : nullptr,
                                                                   pressure_bc_type ? S->d_ptype : nullptr, (size_t)h->nnz,
-                                                                  h->d_big_m, h->d_mom_rhs, ct_bdy ? h->d_ct_m : nullptr);
+                                                                  h->d_big_m, h->d_mom_rhs, ct_bdy ? h->d_ct_m : nullptr, ml_out);
   h->launches++;
   CG_CUDA(cudaGetLastError());
   // weak Dirichlet on some components only makes the diagonal blocks differ

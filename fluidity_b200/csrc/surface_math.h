@@ -161,18 +161,61 @@ CG_HD bool momentum_face_skipped(const int (&bt)[DIM], int pressure_bc_type) {
 // construct_momentum_surface_element_cg (assemble/Momentum_CG.F90:959-1191): by-parts advection boundary
 // term :1029-1071 and flux conditions :1180-1187. Uf: nu, Of: oldu, rho: density at the face nodes;
 // bc[i][d] = velocity_bc(d, i). B[d][i][j] (added to block (d,d)), r[d][i] overwritten.
+// Free-surface stabilisation (:1108-1176, not on the sphere) on faces of type FREE_SURFACE: Gf = gravity direction at
+// the face nodes, ml[d][i] = what goes to masslump (pressure-corrected absorption with lumped mass).
 template <int DIM>
 CG_HD void momentum_face(const SurfTables& t, const cgasm_momentum_opts& o, const int (&bt)[DIM],
                          const double (&Xf)[DIM][DIM], const double (&Xc)[DIM], const double (&Uf)[DIM][DIM],
                          const double (&Of)[DIM][DIM], const double (&rho)[DIM], const double (&bc)[DIM][DIM],
-                         double (&B)[DIM][DIM][DIM], double (&r)[DIM][DIM]) {
+                         const double (&Gf)[DIM][DIM], double (&B)[DIM][DIM][DIM], double (&r)[DIM][DIM],
+                         double (&ml)[DIM][DIM]) {
   for (int d = 0; d < DIM; d++)
     for (int i = 0; i < DIM; i++) {
-      r[d][i] = 0.0;
+      r[d][i] = ml[d][i] = 0.0;
       for (int j = 0; j < DIM; j++) B[d][i][j] = 0.0;
     }
   double detJ, nrm[DIM], c[kMaxSngi], M[DIM][DIM];
   facet_geometry<DIM>(t, Xf, Xc, detJ, nrm);
+  if (bt[0] == CGASM_VBC_FREE_SURFACE && o.have_surface_fs_stabilisation) {
+    // fs_surfacestab(d,i,j) = sum_g N_i N_j detwei rho_g dt g_mag fs_sf (n . up_g) up_g(d), up = -gravity direction
+    const double dtt = o.dt * o.theta;
+    double fs[DIM][DIM][DIM];
+    for (int d = 0; d < DIM; d++)
+      for (int i = 0; i < DIM; i++)
+        for (int j = 0; j < DIM; j++) fs[d][i][j] = 0.0;
+    for (int g = 0; g < t.sngi; g++) {
+      double up[DIM], nk = 0.0;
+      for (int a = 0; a < DIM; a++) {
+        double gcol[DIM];
+        for (int i = 0; i < DIM; i++) gcol[i] = Gf[i][a];
+        up[a] = -face_at_quad<DIM>(t, gcol, g);
+        nk += nrm[a] * up[a];
+      }
+      const double cg = detJ * t.w[g] * face_at_quad<DIM>(t, rho, g);
+      for (int d = 0; d < DIM; d++) {
+        const double vec = o.dt * o.gravity_magnitude * (o.fs_sf * nk * up[d]);
+        for (int i = 0; i < DIM; i++)
+          for (int j = 0; j < DIM; j++) fs[d][i][j] += t.n[i + DIM * g] * t.n[j + DIM * g] * cg * vec;
+      }
+    }
+    for (int d = 0; d < DIM; d++)
+      for (int i = 0; i < DIM; i++) {
+        if (o.lump_mass) {
+          double l = 0.0;
+          for (int j = 0; j < DIM; j++) l += fs[d][i][j];
+          B[d][i][i] += dtt * l;
+          r[d][i] -= l * Of[i][d];
+          if (o.pressure_corrected_absorption) ml[d][i] += dtt * l;
+        } else {
+          double v = 0.0;
+          for (int j = 0; j < DIM; j++) {
+            B[d][i][j] += dtt * fs[d][i][j];
+            v += fs[d][i][j] * Of[j][d];
+          }
+          r[d][i] -= v;
+        }
+      }
+  }
   if (bt[0] != CGASM_VBC_NO_NORMAL_FLOW && o.integrate_advection_by_parts && !o.exclude_advection) {
     double un[DIM];
     for (int i = 0; i < DIM; i++) {

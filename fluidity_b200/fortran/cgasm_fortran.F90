@@ -48,7 +48,7 @@ module cgasm_interface
   !! Mirrors struct cgasm_momentum_opts: the module-level switches of
   !! assemble/Momentum_CG.F90:83-178. Logicals travel as integer(c_int) (0/1).
   type, bind(c) :: cgasm_momentum_opts
-     real(c_double) :: dt, theta, beta, gravity_magnitude, nu_bar_scale
+     real(c_double) :: dt, theta, beta, gravity_magnitude, nu_bar_scale, fs_sf
      integer(c_int) :: lump_mass, exclude_mass, exclude_advection, integrate_advection_by_parts
      integer(c_int) :: have_source, lump_source, have_gravity, subtract_out_reference_profile
      integer(c_int) :: have_absorption, lump_absorption, pressure_corrected_absorption

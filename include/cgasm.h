@@ -101,6 +101,7 @@ typedef struct cgasm_momentum_opts {
   double beta;                 /* conservative_advection                             */
   double gravity_magnitude;
   double nu_bar_scale;
+  double fs_sf;                /* get_surface_stab_scale_factor(u), Momentum_CG.F90:782 (surface loop) */
   int lump_mass;
   int exclude_mass;
   int exclude_advection;
@@ -128,8 +129,9 @@ typedef struct cgasm_momentum_opts {
   /* implemented since round 2 (they keep their place in the struct): the `mass` matrix (cgasm_momentum_mass_fetch) and
    * continuity by parts (volume form in the element loop, boundary blocks in cgasm_momentum_surface_dev) */
   int assemble_mass_matrix, integrate_continuity_by_parts;
-  /* have_fs_stab(u): free-surface stabilisation of the surface loop (Momentum_CG.F90:1108-1178). Not implemented:
-   * cgasm_momentum_surface_dev answers CGASM_EUNSUPPORTED when it is set and a face has type FREE_SURFACE. */
+  /* have_fs_stab(u): free-surface stabilisation of the surface loop (Momentum_CG.F90:1108-1178, scale fs_sf above) on
+   * faces of type FREE_SURFACE: cgasm_momentum_surface_dev adds it to big_m, rhs and (pressure-corrected absorption
+   * with lumped mass) masslump; needs the gravity direction field and have_gravity. on_sphere stays unsupported. */
   int have_surface_fs_stabilisation;
 } cgasm_momentum_opts;
 

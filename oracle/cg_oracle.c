@@ -1541,14 +1541,27 @@ void orc_apply_dirichlet_scalar(int n, const int* nodes, const double* values, c
  * velocity_bc_type(dim): 0, BC_TYPE_WEAKDIRICHLET = 1, NO_NORMAL_FLOW = 2, INTERNAL = 3, FREE_SURFACE = 4,
  * FLUX = 5 (:138-140). velocity_bc(dim, sloc): ele_val of the surface field. Outputs overwritten:
  * big_m_addto(dim, sloc, sloc) (diagonal blocks only), rhs_addto(dim, sloc). */
+int orc_momentum_face_ml(const orc_mesh* m, const orc_surface* s, const orc_momentum_fields* f,
+                         const cgasm_momentum_opts* o, int face, const int* velocity_bc_type, const double* velocity_bc,
+                         double* big_m_addto, double* rhs_addto, double* masslump_addto);
+
 int orc_momentum_face(const orc_mesh* m, const orc_surface* s, const orc_momentum_fields* f,
                       const cgasm_momentum_opts* o, int face, const int* velocity_bc_type, const double* velocity_bc,
                       double* big_m_addto, double* rhs_addto) {
+  return orc_momentum_face_ml(m, s, f, o, face, velocity_bc_type, velocity_bc, big_m_addto, rhs_addto, NULL);
+}
+
+/* masslump_addto(dim, sloc) (may be NULL): what the free-surface stabilisation adds to masslump (:1167-1173) */
+int orc_momentum_face_ml(const orc_mesh* m, const orc_surface* s, const orc_momentum_fields* f,
+                         const cgasm_momentum_opts* o, int face, const int* velocity_bc_type, const double* velocity_bc,
+                         double* big_m_addto, double* rhs_addto, double* masslump_addto) {
   const int dim = m->dim, sloc = s->sloc, sngi = s->sngi;
   if (momentum_opts_unsupported(o)) return CGASM_EUNSUPPORTED;
   double detwei[MAXSNGI], normal[MAXDIM * MAXSNGI], c_g[MAXSNGI], mat[MAXSLOC * MAXSLOC];
   for (int k = 0; k < dim * sloc * sloc; k++) big_m_addto[k] = 0.0;
   for (int k = 0; k < dim * sloc; k++) rhs_addto[k] = 0.0;
+  if (masslump_addto)
+    for (int k = 0; k < dim * sloc; k++) masslump_addto[k] = 0.0;
   face_geometry(m, s, face, detwei, normal);
   double oldu_val[MAXDIM * MAXSLOC];
   face_val_multi(s, &f->oldu, dim, face, oldu_val);
@@ -1583,6 +1596,55 @@ int orc_momentum_face(const orc_mesh* m, const orc_surface* s, const orc_momentu
       }
     }
   }
+  /* Free-surface stabilisation, :1108-1176 (not on the sphere): upwards = -gravity direction at the quadrature points,
+   * ndotk_k(:,g) = fs_sf (normal . upwards) upwards, fs_surfacestab = shape_shape_vector(u_shape, u_shape,
+   * detwei_bdy*density_gi, dt*gravity_magnitude*ndotk_k); lumped (lump_mass) or full (no pressure-corrected absorption). */
+  if (velocity_bc_type[0] == 4 && o->have_surface_fs_stabilisation) {
+    double grav_f[MAXDIM * MAXSLOC], up_gi[MAXDIM * MAXSNGI], rho_f[MAXSLOC], rho_q[MAXSNGI], ndotk[MAXDIM * MAXSNGI];
+    double fs[MAXDIM * MAXSLOC * MAXSLOC];
+    if (o->on_sphere) return CGASM_EUNSUPPORTED;
+    if (!o->lump_mass && o->pressure_corrected_absorption) return CGASM_EUNSUPPORTED; /* FLExit :1161-1163 */
+    face_val_multi(s, &f->gravity, dim, face, grav_f);
+    face_at_quad(s, dim, grav_f, up_gi);
+    for (int k = 0; k < dim * sngi; k++) up_gi[k] = -up_gi[k];
+    face_val_multi(s, &f->density, 1, face, rho_f);
+    face_at_quad(s, 1, rho_f, rho_q);
+    for (int g = 0; g < sngi; g++) {
+      double nk = 0.0;
+      for (int a = 0; a < dim; a++) nk += normal[a + dim * g] * up_gi[a + dim * g];
+      for (int a = 0; a < dim; a++) ndotk[a + dim * g] = o->fs_sf * nk * up_gi[a + dim * g];
+      c_g[g] = detwei[g] * rho_q[g];
+    }
+    /* shape_shape_vector: R(d,i,j) = sum_g n_i n_j detwei_g vector(d,g) */
+    for (int d = 0; d < dim; d++)
+      for (int i = 0; i < sloc; i++)
+        for (int j = 0; j < sloc; j++) {
+          double v = 0.0;
+          for (int g = 0; g < sngi; g++)
+            v += s->n_f[i + sloc * g] * s->n_f[j + sloc * g] * c_g[g] * (o->dt * o->gravity_magnitude * ndotk[d + dim * g]);
+          fs[d + dim * (i + sloc * j)] = v;
+        }
+    if (o->lump_mass) {
+      for (int d = 0; d < dim; d++)
+        for (int i = 0; i < sloc; i++) {
+          double l = 0.0;
+          for (int j = 0; j < sloc; j++) l += fs[d + dim * (i + sloc * j)];
+          big_m_addto[d + dim * (i + sloc * i)] += o->dt * o->theta * l;
+          rhs_addto[d + dim * i] += -l * oldu_val[d + dim * i];
+          if (o->pressure_corrected_absorption && masslump_addto) masslump_addto[d + dim * i] += o->dt * o->theta * l;
+        }
+    } else {
+      for (int d = 0; d < dim; d++)
+        for (int i = 0; i < sloc; i++) {
+          double v = 0.0;
+          for (int j = 0; j < sloc; j++) {
+            big_m_addto[d + dim * (i + sloc * j)] += o->dt * o->theta * fs[d + dim * (i + sloc * j)];
+            v += fs[d + dim * (i + sloc * j)] * oldu_val[d + dim * j];
+          }
+          rhs_addto[d + dim * i] += -v;
+        }
+    }
+  }
   for (int d = 0; d < dim; d++)
     if (velocity_bc_type[d] == 5) { /* shape_rhs(u_shape, ele_val_at_quad(velocity_bc, sele, dim)*detwei_bdy) */
       double bc_d[MAXSLOC], q[MAXSNGI] = {0, 0, 0, 0}, r[MAXSLOC];
@@ -1598,10 +1660,23 @@ int orc_momentum_face(const orc_mesh* m, const orc_surface* s, const orc_momentu
 /* surface_element_loop of construct_momentum_cg, assemble/Momentum_CG.F90:795-812: faces whose only
  * condition is no-normal-flow, or that are internal, are skipped unless they carry a pressure condition
  * (:799-803). pressure_bc_type may be NULL (= all zero). ADDS to big_m [dim][nnz] and rhs (dim, N). */
+int orc_assemble_momentum_surface_ml(const orc_mesh* m, const orc_surface* s, const orc_momentum_fields* f,
+                                     const cgasm_momentum_opts* o, const int* findrm, const int* colm,
+                                     const int* velocity_bc_type, const double* velocity_bc, const int* pressure_bc_type,
+                                     double* big_m, double* rhs, double* masslump);
+
 int orc_assemble_momentum_surface(const orc_mesh* m, const orc_surface* s, const orc_momentum_fields* f,
                                   const cgasm_momentum_opts* o, const int* findrm, const int* colm,
                                   const int* velocity_bc_type /*(dim,n_faces)*/, const double* velocity_bc /*(dim,sloc,n_faces)*/,
                                   const int* pressure_bc_type, double* big_m, double* rhs) {
+  return orc_assemble_momentum_surface_ml(m, s, f, o, findrm, colm, velocity_bc_type, velocity_bc, pressure_bc_type, big_m, rhs, NULL);
+}
+
+/* the same with masslump(dim, N) (may be NULL), which the free-surface stabilisation adds to (:1167-1173) */
+int orc_assemble_momentum_surface_ml(const orc_mesh* m, const orc_surface* s, const orc_momentum_fields* f,
+                                     const cgasm_momentum_opts* o, const int* findrm, const int* colm,
+                                     const int* velocity_bc_type, const double* velocity_bc, const int* pressure_bc_type,
+                                     double* big_m, double* rhs, double* masslump) {
   const int dim = m->dim, sloc = s->sloc;
   const size_t nnz = (size_t)(findrm[m->n_nodes] - 1);
   for (int face = 1; face <= s->n_faces; face++) {
@@ -1612,8 +1687,8 @@ int orc_assemble_momentum_surface(const orc_mesh* m, const orc_surface* s, const
       any_internal |= bt[d] == 3;
     }
     if (((bt[0] == 2 && sum == 2) || any_internal) && (!pressure_bc_type || pressure_bc_type[face - 1] == 0)) continue;
-    double B[MAXDIM * MAXSLOC * MAXSLOC], r[MAXDIM * MAXSLOC];
-    int st = orc_momentum_face(m, s, f, o, face, bt, velocity_bc + (size_t)dim * sloc * (face - 1), B, r);
+    double B[MAXDIM * MAXSLOC * MAXSLOC], r[MAXDIM * MAXSLOC], ml[MAXDIM * MAXSLOC];
+    int st = orc_momentum_face_ml(m, s, f, o, face, bt, velocity_bc + (size_t)dim * sloc * (face - 1), B, r, ml);
     if (st) return st;
     const int* fn = s->sndgln + (size_t)sloc * (size_t)(face - 1);
     for (int i = 0; i < sloc; i++)
@@ -1622,7 +1697,10 @@ int orc_assemble_momentum_surface(const orc_mesh* m, const orc_surface* s, const
         for (int d = 0; d < dim; d++) big_m[d * nnz + (size_t)(pos - 1)] += B[d + dim * (i + sloc * j)];
       }
     for (int i = 0; i < sloc; i++)
-      for (int d = 0; d < dim; d++) rhs[d + (size_t)dim * (fn[i] - 1)] += r[d + dim * i];
+      for (int d = 0; d < dim; d++) {
+        rhs[d + (size_t)dim * (fn[i] - 1)] += r[d + dim * i];
+        if (masslump) masslump[d + (size_t)dim * (fn[i] - 1)] += ml[d + dim * i];
+      }
   }
   return 0;
 }

@@ -392,35 +392,38 @@ def apply_dirichlet_scalar(nodes, values, field, dt, rhs, inactive=None):
                                      C.c_double(dt or 0.0), _dp(rhs), _ip(inactive))
 
 
-def momentum_face(mesh, fields, opts, sndgln, face_ele, face, velocity_bc_type, velocity_bc=None):
-    """big_m_addto (dim, sloc, sloc), rhs_addto (dim, sloc) of one face. velocity_bc (sloc, dim)."""
+def momentum_face(mesh, fields, opts, sndgln, face_ele, face, velocity_bc_type, velocity_bc=None, want_masslump=False):
+    """big_m_addto (dim, sloc, sloc), rhs_addto (dim, sloc) of one face (+ masslump_addto (dim, sloc) if asked: the
+    free-surface stabilisation adds to it). velocity_bc (sloc, dim)."""
     ctx = _SurfCtx(mesh, fields, sndgln, face_ele)
     dim = sloc = mesh.dim
     B = np.zeros(dim * sloc * sloc)
     r = np.zeros(dim * sloc)
+    ml = np.zeros(dim * sloc)
     bt = np.ascontiguousarray(velocity_bc_type, dtype=np.int32)
     bv = np.ascontiguousarray(velocity_bc if velocity_bc is not None else np.zeros((sloc, dim)), dtype=np.float64)
     mf = ctx.mom()
-    st = lib().orc_momentum_face(C.byref(ctx.mesh), C.byref(ctx.surface), C.byref(mf), C.byref(opts), C.c_int(face),
-                                 _ip(bt), _dp(bv), _dp(B), _dp(r))
+    st = lib().orc_momentum_face_ml(C.byref(ctx.mesh), C.byref(ctx.surface), C.byref(mf), C.byref(opts), C.c_int(face),
+                                    _ip(bt), _dp(bv), _dp(B), _dp(r), _dp(ml))
     if st:
         raise RuntimeError("oracle status %d" % st)
-    return B.reshape(sloc, sloc, dim).transpose(2, 1, 0).copy(), r.reshape(sloc, dim).T.copy()
+    out = (B.reshape(sloc, sloc, dim).transpose(2, 1, 0).copy(), r.reshape(sloc, dim).T.copy())
+    return out + (ml.reshape(sloc, dim).T.copy(),) if want_masslump else out
 
 
 def assemble_momentum_surface(mesh, fields, opts, findrm, colm, sndgln, face_ele, velocity_bc_type, velocity_bc,
-                              big_m, rhs, pressure_bc_type=None):
-    """ADDS the surface loop to big_m (dim, nnz) / rhs (n_nodes, dim) in place. velocity_bc_type (n_faces, dim),
-    velocity_bc (n_faces, sloc, dim)."""
+                              big_m, rhs, pressure_bc_type=None, masslump=None):
+    """ADDS the surface loop to big_m (dim, nnz) / rhs (n_nodes, dim) / masslump (n_nodes, dim; free-surface
+    stabilisation only) in place. velocity_bc_type (n_faces, dim), velocity_bc (n_faces, sloc, dim)."""
     ctx = _SurfCtx(mesh, fields, sndgln, face_ele)
     bt = np.ascontiguousarray(velocity_bc_type, dtype=np.int32)
     bv = np.ascontiguousarray(velocity_bc, dtype=np.float64)
     pt = np.ascontiguousarray(pressure_bc_type, dtype=np.int32) if pressure_bc_type is not None else None
     mf = ctx.mom()
-    st = lib().orc_assemble_momentum_surface(C.byref(ctx.mesh), C.byref(ctx.surface), C.byref(mf), C.byref(opts),
-                                             _ip(np.ascontiguousarray(findrm, dtype=np.int32)),
-                                             _ip(np.ascontiguousarray(colm, dtype=np.int32)), _ip(bt), _dp(bv), _ip(pt),
-                                             _dp(big_m), _dp(rhs))
+    st = lib().orc_assemble_momentum_surface_ml(C.byref(ctx.mesh), C.byref(ctx.surface), C.byref(mf), C.byref(opts),
+                                                _ip(np.ascontiguousarray(findrm, dtype=np.int32)),
+                                                _ip(np.ascontiguousarray(colm, dtype=np.int32)), _ip(bt), _dp(bv), _ip(pt),
+                                                _dp(big_m), _dp(rhs), _dp(masslump))
     if st:
         raise RuntimeError("oracle status %d" % st)
 

@@ -40,7 +40,7 @@ static void adv(int sngi, const double* n, const double* dn, const double* w, co
 template <int DIM>
 static int mom(int sngi, const double* n, const double* dn, const double* w, const cgasm_momentum_opts* o, const int* bt_,
                int ptype, const double* Xf_, const double* Xc_, const double* Uf_, const double* Of_, const double* rho_,
-               const double* bc_, double* B_, double* r_) {
+               const double* bc_, double* B_, double* r_, const double* Gf_ = nullptr, double* ml_ = nullptr) {
   SurfTables t;
   fill<DIM>(t, sngi, n, dn, w);
   int bt[DIM];
@@ -57,9 +57,13 @@ static int mom(int sngi, const double* n, const double* dn, const double* w, con
     }
   }
   if (momentum_face_skipped<DIM>(bt, ptype)) return 1;
-  momentum_face<DIM>(t, *o, bt, Xf, Xc, Uf, Of, rho, bc, B, r);
+  double Gf[DIM][DIM], ml[DIM][DIM];
+  for (int i = 0; i < DIM; i++)
+    for (int a = 0; a < DIM; a++) Gf[i][a] = Gf_ ? Gf_[i * DIM + a] : 0.0;
+  momentum_face<DIM>(t, *o, bt, Xf, Xc, Uf, Of, rho, bc, Gf, B, r, ml);
   for (int d = 0; d < DIM; d++)
     for (int i = 0; i < DIM; i++) {
+      if (ml_) ml_[d * DIM + i] = ml[d][i];
       r_[d * DIM + i] = r[d][i];
       for (int j = 0; j < DIM; j++) B_[(d * DIM + i) * DIM + j] = B[d][i][j];
     }
@@ -78,6 +82,13 @@ int harness_momentum_face(int dim, int sngi, const double* n, const double* dn, 
                           const double* rho, const double* bc, double* B, double* r) {
   return dim == 3 ? mom<3>(sngi, n, dn, w, o, bt, ptype, Xf, Xc, Uf, Of, rho, bc, B, r)
                   : mom<2>(sngi, n, dn, w, o, bt, ptype, Xf, Xc, Uf, Of, rho, bc, B, r);
+}
+// with the gravity direction at the face nodes (free-surface stabilisation) and the masslump contribution
+int harness_momentum_face_fs(int dim, int sngi, const double* n, const double* dn, const double* w, const cgasm_momentum_opts* o,
+                             const int* bt, int ptype, const double* Xf, const double* Xc, const double* Uf, const double* Of,
+                             const double* rho, const double* bc, const double* Gf, double* B, double* r, double* ml) {
+  return dim == 3 ? mom<3>(sngi, n, dn, w, o, bt, ptype, Xf, Xc, Uf, Of, rho, bc, B, r, Gf, ml)
+                  : mom<2>(sngi, n, dn, w, o, bt, ptype, Xf, Xc, Uf, Of, rho, bc, B, r, Gf, ml);
 }
 int harness_csr_pos0(const int* findrm, const int* colm, int i, int j) { return csr_pos0(findrm, colm, i, j); }
 }

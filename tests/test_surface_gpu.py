@@ -121,6 +121,49 @@ def test_momentum_surface_loop(orc, scatter, name):
     assert not asm.momentum_identical_blocks()
 
 
+@pytest.mark.parametrize("scatter", SCATTERS)
+@pytest.mark.parametrize("name", ["box2", "box3", "cube-parallel"])
+@pytest.mark.parametrize("case", ["lumped", "lumped_pressure_corrected", "consistent"])
+def test_free_surface_stabilisation(orc, scatter, name, case):
+    """Momentum_CG.F90:1108-1176: faces of type FREE_SURFACE with have_fs_stab add dt g fs_sf (n . k) k mass terms to
+    big_m, rhs and -- pressure-corrected absorption on a lumped mass -- masslump."""
+    mesh = meshes()[name]
+    dim = mesh.dim
+    fs = syn.standard_fields(mesh)
+    asm, sn, fe = make(mesh, fs, scatter)
+    findrm, colm, _ = asm.get_sparsity()
+    rng = np.random.default_rng(4)
+    nf = len(fe)
+    vt = np.zeros((nf, dim), dtype=np.int32)
+    top = rng.random(nf) < 0.5
+    vt[top] = abi.VBC_FREE_SURFACE
+    pc = int(case == "lumped_pressure_corrected")
+    o = abi.common_momentum_opts(have_surface_fs_stabilisation=1, fs_sf=0.6, lump_mass=int(case != "consistent"),
+                                 have_absorption=pc, lump_absorption=pc, pressure_corrected_absorption=pc,
+                                 integrate_advection_by_parts=1)
+    ref = orc.assemble_momentum(mesh, fs, o, findrm, colm)
+    before = ref["masslump"].copy()
+    orc.assemble_momentum_surface(mesh, fs, o, findrm, colm, sn, fe, vt, np.zeros((nf, dim, dim)), ref["big_m"], ref["rhs"],
+                                  masslump=ref["masslump"])
+    assert (np.abs(ref["masslump"] - before).max() > 0) == bool(pc)
+    asm.momentum_dev(o)
+    asm.momentum_surface_dev(o, vt)
+    got = asm.momentum_fetch()
+    for d in range(dim):
+        assert rel_err(got["big_m"][d], ref["big_m"][d]) < TOL
+        assert row_rel_err(got["big_m"][d], ref["big_m"][d], findrm) < TOL
+        assert rel_err(got["rhs"][:, d], ref["rhs"][:, d]) < TOL
+        assert rel_err(got["masslump"][:, d], ref["masslump"][:, d]) < TOL
+    assert not asm.momentum_identical_blocks()
+    # the reference exits on a consistent mass with pressure-corrected absorption (:1161-1163): so does the library
+    bad = abi.common_momentum_opts(have_surface_fs_stabilisation=1, fs_sf=0.6, lump_mass=0, have_absorption=1,
+                                   pressure_corrected_absorption=1)
+    asm.momentum_dev(bad)
+    with pytest.raises(cgasm.CgasmError) as e:
+        asm.momentum_surface_dev(bad, vt)
+    assert e.value.code == abi.EUNSUPPORTED
+
+
 def test_surface_calls_refuse_what_they_must():
     mesh = syn.box_mesh((3, 3), seed=1)
     fs = syn.standard_fields(mesh)

@@ -25,6 +25,7 @@ def harness(tmp_path_factory):
                     os.path.join(ROOT, "tests", "surface_harness.cpp"), "-o", str(out)], check=True)
     lib = C.CDLL(str(out))
     lib.harness_momentum_face.restype = C.c_int
+    lib.harness_momentum_face_fs.restype = C.c_int
     lib.harness_csr_pos0.restype = C.c_int
     return lib
 
@@ -114,3 +115,50 @@ def test_csr_position_search(orc, harness):
             got = harness.harness_csr_pos0(f0.ctypes.data_as(c_ip), c0.ctypes.data_as(c_ip), C.c_int(int(i)), C.c_int(int(j)))
             hit = np.flatnonzero(row == j)
             assert got == (f0[i] + hit[0] if len(hit) else -1)
+
+
+@pytest.mark.parametrize("name", ["box2", "box3"])
+@pytest.mark.parametrize("case", ["lumped", "lumped_pressure_corrected", "consistent"])
+def test_free_surface_stabilisation_face_math_equals_the_oracle(orc, harness, name, case):
+    """Momentum_CG.F90:1108-1176 on faces of type FREE_SURFACE: shape_shape_vector with dt g fs_sf (n . k) k, lumped onto
+    the diagonal (lump_mass; into masslump too with pressure-corrected absorption) or as a full face matrix."""
+    mesh = _cases()[name]
+    dim = mesh.dim
+    fs = syn.standard_fields(mesh)
+    rng = np.random.default_rng(5)
+    nodal_g = rng.normal(size=(mesh.n_nodes, dim))
+    nodal_g /= np.linalg.norm(nodal_g, axis=1)[:, None]
+    sn, fe = syn.boundary_faces(mesh)
+    n, dn, w = tables.p1_face_tables(dim)
+    U, O, R = fs.get(abi.F_NU)[0], fs.get(abi.F_OLDU)[0], fs.get(abi.F_DENSITY)[0]
+    o = abi.common_momentum_opts(have_surface_fs_stabilisation=1, fs_sf=0.7, lump_mass=int(case != "consistent"),
+                                 pressure_corrected_absorption=int(case == "lumped_pressure_corrected"),
+                                 have_absorption=int(case == "lumped_pressure_corrected"),
+                                 lump_absorption=int(case == "lumped_pressure_corrected"))
+    bta = np.array([abi.VBC_FREE_SURFACE] * dim, dtype=np.int32)
+    nonzero = 0
+    for gravity, ftype in ((np.eye(dim)[dim - 1:dim] * -1.0, abi.FIELD_CONSTANT), (nodal_g, abi.FIELD_NORMAL)):
+        fs.set(abi.F_GRAVITY, np.ascontiguousarray(gravity), ftype)
+        for f in rng.choice(len(fe), size=min(10, len(fe)), replace=False):
+            Xf = np.ascontiguousarray(mesh.X[sn[f] - 1])
+            Xc = mesh.X[mesh.ndglno[fe[f] - 1] - 1].mean(0)
+            Uf, Of, rho = (np.ascontiguousarray(a[sn[f] - 1]) for a in (U, O, R))
+            Gf = np.ascontiguousarray(gravity[sn[f] - 1] if ftype == abi.FIELD_NORMAL else np.repeat(gravity, dim, axis=0))
+            B, r, ml = np.zeros((dim, dim, dim)), np.zeros((dim, dim)), np.zeros((dim, dim))
+            bc = np.zeros((dim, dim))
+            assert harness.harness_momentum_face_fs(C.c_int(dim), C.c_int(len(w)), _dp(n), _dp(dn), _dp(w), C.byref(o),
+                                                    bta.ctypes.data_as(c_ip), C.c_int(0), _dp(Xf), _dp(Xc), _dp(Uf), _dp(Of),
+                                                    _dp(rho), _dp(bc), _dp(Gf), _dp(B), _dp(r), _dp(ml)) == 0
+            oB, orr, oml = orc.momentum_face(mesh, fs, o, sn, fe, f + 1, bta, want_masslump=True)
+            scale = max(np.abs(oB).max(), 1e-300)
+            assert np.abs(B - oB).max() <= TOL * scale and np.abs(r - orr).max() <= TOL * max(np.abs(orr).max(), 1e-300)
+            assert np.abs(ml - oml).max() <= TOL * scale
+            nonzero += int(np.abs(oB).max() > 0)
+            if case == "lumped_pressure_corrected":
+                assert np.abs(oml).max() > 0 or np.abs(oB).max() == 0
+            else:
+                assert np.abs(oml).max() == 0
+            if case != "consistent":   # lumped: diagonal only
+                for d in range(dim):
+                    assert np.abs(oB[d] - np.diag(np.diag(oB[d]))).max() == 0
+    assert nonzero > 0  # (faces whose normal is orthogonal to gravity contribute nothing)

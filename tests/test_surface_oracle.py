@@ -285,3 +285,43 @@ def test_continuity_by_parts_plus_boundary_blocks_equals_the_plain_form(orc, nam
             assert np.abs(Cb[d]).max() == 0.0 and rel_err(cr, -(blk @ bc[:, 0])) < TOL
         else:
             assert rel_err(Cb[d], blk) < TOL
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_free_surface_stabilisation_against_exact_moments(orc, dim):
+    """Momentum_CG.F90:1108-1176 on the flat top of the unit box with constant density and vertical gravity: the face
+    matrices sum to dt theta * rho dt g fs_sf * area in the vertical block and vanish in the others; side faces
+    (normal orthogonal to gravity) contribute nothing; the lumped form is the row sums on the diagonal."""
+    mesh = syn.box_mesh((3,) * dim, jitter=0.0)
+    fs = syn.standard_fields(mesh)
+    rho, g_mag, fs_sf = 1.7, 9.81, 0.35
+    fs.set(abi.F_DENSITY, np.array([rho]), abi.FIELD_CONSTANT)
+    grav = np.zeros((1, dim))
+    grav[0, dim - 1] = -1.0
+    fs.set(abi.F_GRAVITY, grav, abi.FIELD_CONSTANT)
+    sn, fe = syn.boundary_faces(mesh)
+    bt = np.array([abi.VBC_FREE_SURFACE] * dim, dtype=np.int32)
+    o = abi.common_momentum_opts(have_surface_fs_stabilisation=1, fs_sf=fs_sf, lump_mass=0, gravity_magnitude=g_mag)
+    ol = abi.common_momentum_opts(have_surface_fs_stabilisation=1, fs_sf=fs_sf, lump_mass=1, gravity_magnitude=g_mag)
+    total = np.zeros(dim)
+    for f in range(len(fe)):
+        X = mesh.X[sn[f] - 1]
+        B, r = orc.momentum_face(mesh, fs, o, sn, fe, f + 1, bt)
+        Bl, rl = orc.momentum_face(mesh, fs, ol, sn, fe, f + 1, bt)
+        on_top = np.allclose(X[:, dim - 1], 1.0)
+        on_bottom = np.allclose(X[:, dim - 1], 0.0)
+        if not (on_top or on_bottom):
+            assert np.abs(B).max() == 0 and np.abs(Bl).max() == 0
+            continue
+        # n . up = +1 on the top, -1 on the bottom; the sign of the vertical block follows it
+        for d in range(dim - 1):
+            assert np.abs(B[d]).max() == 0
+        assert np.allclose(np.diag(Bl[dim - 1]), B[dim - 1].sum(axis=1), rtol=1e-13, atol=0)
+        assert np.abs(Bl[dim - 1] - np.diag(np.diag(Bl[dim - 1]))).max() == 0
+        if on_top:
+            total += [B[d].sum() for d in range(dim)]
+            assert B[dim - 1].sum() > 0
+        else:
+            assert B[dim - 1].sum() < 0
+    want = o.dt * o.theta * rho * o.dt * g_mag * fs_sf * 1.0
+    assert abs(total[dim - 1] - want) <= 1e-13 * want and np.abs(total[:dim - 1]).max() == 0
