@@ -425,6 +425,7 @@ int cgasm_momentum_surface_dev(int id, const cgasm_momentum_opts* opts, const in
                               (velocity_bc_type[f * dim] == CGASM_VBC_WEAKDIRICHLET));
     if (!uniform) h->mom_identical_blocks = false;
   }
+  if (fs_faces) h->mom_identical_blocks = false;  // the stabilisation acts along the gravity direction only
   return CGASM_OK;
 }
 
