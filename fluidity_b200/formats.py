@@ -571,3 +571,54 @@ def dump_name_parts(path):
     base = os.path.basename(path)
     m = _DUMP_RE.match(base)
     return (m.group("field"), int(m.group("index"))) if m else (base, None)
+
+
+# ---- .stat files (diagnostics/Diagnostic_variables.F90 writes them; python/fluidity_tools.py stat_parser reads) -----
+def read_stat(path, subsample=1):
+    """A Fluidity `.stat` file: an XML `<header>` naming every column (`<field column= name= statistic=
+    [material_phase=] [components=]/>`, `<constant name= type= value=/>`), then one line of reals per dump -- or, when the
+    header holds the constant format = "binary", raw reals of `real_size` bytes in `<path>.dat`. Returns the hierarchy
+    the reference's stat_parser builds: result[material_phase][field][statistic] (or result[field][statistic] for
+    columns without a phase) -> array over the dumps, (components, dumps) for multi-component columns; the constants
+    are kept under result["__constants__"]."""
+    import xml.dom.minidom
+    assert subsample > 0
+    with open(path, "rb") as f:
+        xml_lines = []
+        while True:
+            line = f.readline()
+            if not line:
+                raise FormatError("%s: no </header> in the .stat file" % path)
+            xml_lines.append(line.decode())
+            if "</header>" in xml_lines[-1]:
+                break
+        body = f.read().decode()
+    dom = xml.dom.minidom.parseString("".join(xml_lines))
+    constants = {}
+    for el in dom.getElementsByTagName("constant"):
+        constants[el.getAttribute("name")] = (el.getAttribute("type"), el.getAttribute("value"))
+    fields = dom.getElementsByTagName("field")
+    ncol = sum(int(el.getAttribute("components") or 1) for el in fields)
+    if constants.get("format", ("", ""))[1] == "binary":
+        real_size = int(constants.get("real_size", ("integer", "8"))[1])
+        if real_size not in (4, 8):
+            raise FormatError("%s: unexpected real size %d" % (path, real_size))
+        raw = np.fromfile(path + ".dat", dtype=np.float32 if real_size == 4 else np.float64)
+        rows = raw[: (raw.size // ncol) * ncol].reshape(-1, ncol)  # an incomplete last line is ignored
+        columns = rows[::subsample].T.astype(np.float64)
+    else:
+        rows = []
+        for n, line in enumerate(l for l in body.splitlines()):
+            entries = line.split()
+            if len(entries) != ncol:
+                raise FormatError("%s: incomplete line %d: expected %d columns, got %d" % (path, n, ncol, len(entries)))
+            if n % subsample == 0:
+                rows.append([float(e) for e in entries])
+        columns = np.array(rows, dtype=np.float64).reshape(len(rows), ncol).T
+    out = {"__constants__": constants}
+    for el in fields:
+        phase, name = el.getAttribute("material_phase"), el.getAttribute("name")
+        col, stat, comps = int(el.getAttribute("column")), el.getAttribute("statistic"), el.getAttribute("components")
+        d = out.setdefault(phase, {}) if phase else out
+        d.setdefault(name, {})[stat] = columns[col - 1: col - 1 + int(comps)] if comps else columns[col - 1]
+    return out

@@ -521,3 +521,66 @@ def test_reference_decomposition_writer_with_pathological_owner_maps(tmp_path, k
     for r in range(nparts):
         for ext in (".msh", ".halo"):
             assert open(fmt.parallel_filename(theirs, r, ext), "rb").read() == open(fmt.parallel_filename(ours, r, ext), "rb").read()
+
+
+# ---- .stat files ---------------------------------------------------------------------------------------------------
+def _same_tree(mine, ref, path=""):
+    n = 0
+    for k, v in ref.items():
+        if isinstance(v, dict):
+            n += _same_tree(mine[k], v, path + "/" + k)
+        else:
+            assert np.array_equal(np.asarray(mine[k]), np.asarray(v)), path + "/" + k
+            n += 1
+    return n
+
+
+@needs_reference
+@pytest.mark.parametrize("rel", ["tests/Instability/Reference.stat",
+                                 "tests/backward_facing_step_2d_zoltan_sam/sam_output/backward_facing_step_2d_sam.stat"])
+def test_read_stat_equals_the_reference_stat_parser(rel):
+    """formats.read_stat against the reference's own python/fluidity_tools.py stat_parser (imported unmodified; its
+    module imports vtk for unrelated helpers, absent here: a MagicMock stands in) on the reference's .stat fixtures."""
+    import sys
+    from unittest import mock
+    path = os.path.join(REF, rel)
+    stub_vtk = "vtk" not in sys.modules
+    if stub_vtk:
+        sys.modules["vtk"] = mock.MagicMock()
+    sys.path.insert(0, os.path.join(REF, "python"))
+    try:
+        import fluidity_tools
+        ref = fluidity_tools.stat_parser(path)
+    finally:
+        sys.path.remove(os.path.join(REF, "python"))
+        if stub_vtk:
+            del sys.modules["vtk"]
+    mine = fmt.read_stat(path)
+    assert _same_tree(mine, ref) >= 20
+    sub = fmt.read_stat(path, subsample=3)
+    assert np.array_equal(sub["ElapsedTime"]["value"], mine["ElapsedTime"]["value"][::3])
+
+
+def test_read_stat_plain_and_binary(tmp_path):
+    header = ('<header>\n<constant name="FluidityVersion" type="string" value="x" />\n%s'
+              '<field column="1" name="ElapsedTime" statistic="value"/>\n'
+              '<field column="2" name="Velocity" statistic="max" material_phase="Water" components="3"/>\n'
+              '<field column="5" name="Tracer" statistic="l2norm" material_phase="Water"/>\n</header>\n')
+    data = np.arange(20, dtype=np.float64).reshape(4, 5) * 0.25
+    p = tmp_path / "a.stat"
+    p.write_text(header % "" + "".join(" ".join("%.17g" % v for v in row) + "\n" for row in data))
+    s = fmt.read_stat(str(p))
+    assert np.array_equal(s["ElapsedTime"]["value"], data[:, 0])
+    assert np.array_equal(s["Water"]["Velocity"]["max"], data[:, 1:4].T) and np.array_equal(s["Water"]["Tracer"]["l2norm"], data[:, 4])
+    assert s["__constants__"]["FluidityVersion"] == ("string", "x")
+    b = tmp_path / "b.stat"
+    b.write_text(header % ('<constant name="format" type="string" value="binary" />\n'
+                           '<constant name="real_size" type="integer" value="8" />\n'
+                           '<constant name="integer_size" type="integer" value="4" />\n'))
+    np.concatenate([data.ravel(), [1.0, 2.0]]).tofile(str(b) + ".dat")  # + an incomplete last line, ignored
+    sb = fmt.read_stat(str(b))
+    assert np.array_equal(sb["Water"]["Velocity"]["max"], data[:, 1:4].T) and len(sb["ElapsedTime"]["value"]) == 4
+    bad = tmp_path / "c.stat"
+    bad.write_text(header % "" + "1 2 3\n")
+    with pytest.raises(fmt.FormatError):
+        fmt.read_stat(str(bad))
