@@ -428,7 +428,12 @@ def example_configs(device, cells3, cells2, reps=5, delaunay=None):
         if keym not in meshes:
             if shuffle == "delaunay":
                 proc, base, t_start = delaunay
-                proc.wait()
+                try:
+                    proc.wait(timeout=300)   # it has been running beside everything above; a slow host must not stall the line
+                except subprocess.TimeoutExpired:
+                    proc.kill()
+                    out.append({"config": name, "error": "Delaunay triangulation not ready after %.0f s: skipped" % (time.perf_counter() - t_start)})
+                    continue
                 if proc.returncode != 0:
                     out.append({"config": name, "error": "Delaunay child process failed (%d)" % proc.returncode})
                     continue
