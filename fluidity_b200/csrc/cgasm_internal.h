@@ -238,11 +238,6 @@ void* rec_array(const Handle* h, int k);
 int rec_width(int k);
 unsigned slot_record_mask(int slot);  // bit k = record k mirrors the slot (-1 = coordinates)
 
-// strip_pipe.cu: staged STRIP kernels with the shared-memory reads issued one strip step ahead (dim + 1 register buffers)
-bool strip_piped_ok(const Handle* h, bool momentum);
-int strip_piped_momentum(Handle* h, const MomentumArgs& args);
-int strip_piped_advdiff(Handle* h, const AdvDiffArgs& args);
-
 // strip_fused.cu: both element loops in one kernel (common STRIP option sets)
 bool strip_fused_ok(const Handle* h, const MomentumArgs& m, const AdvDiffArgs& a);
 int strip_fused(Handle* h, const MomentumArgs& m, const AdvDiffArgs& a);

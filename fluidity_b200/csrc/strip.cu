@@ -443,8 +443,7 @@ int strip_momentum(Handle* h, const MomentumArgs& A) {
     h->mom_path = CGASM_PATH_STRIP_STAGED;
     // full absorption matrix: carried by the common kernel's own loop (strip_absorb.cu) where it fits
     const bool absorb = strip_extra_needed(A) && strip_absorb_ok(h, A);
-    int st = absorb ? strip_absorb_momentum(h, A)
-                    : (strip_piped_ok(h, true) ? strip_piped_momentum(h, A) : strip_staged_momentum(h, A));
+    int st = absorb ? strip_absorb_momentum(h, A) : strip_staged_momentum(h, A);
     if (st == CGASM_OK && strip_extra_needed(A)) st = strip_extra(h, A, absorb);  // adds to the common result in place
     return st;
   }
@@ -480,7 +479,6 @@ int strip_advdiff(Handle* h, const AdvDiffArgs& A) {
   h->adv_path = CGASM_PATH_STRIP;
   if (strip_staged_ok(h, false)) {
     h->adv_path = CGASM_PATH_STRIP_STAGED;
-    if (!strip_advdiff_needs_extra(A) && strip_piped_ok(h, false)) return strip_piped_advdiff(h, A);
     return strip_staged_advdiff(h, A);
   }
   if (int js = halo_join(h)) return js;

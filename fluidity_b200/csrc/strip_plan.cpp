@@ -908,9 +908,7 @@ void build_staged_plan_host(const Handle* h, const std::vector<int>& rows, int n
         block_nn[b] = (int)bn.size();
         tn.insert(tn.end(), bn.begin(), bn.end());
         if (bn.size() > 4095) overflow++;
-        // a multiple of dim (FIFO kernels: dim rotating buffers) and of dim + 1 (pipelined kernels: one more buffer)
-        const int lcm = dim * (dim + 1);
-        const int ldeg = (deg + lcm - 1) / lcm * lcm;
+        const int ldeg = (deg + dim - 1) / dim * dim;
         block_ldeg[b] = ldeg;
         const size_t base = ent.size();
         ent.resize(base + (size_t)ldeg * kBR);
@@ -926,8 +924,8 @@ void build_staged_plan_host(const Handle* h, const std::vector<int>& rows, int n
           out.own_local[q] = ol;
           out.row_meta[4 * q + 0] = r;
           out.row_meta[4 * q + 1] = r >= 0 ? h->h_findrm[r] : 0;
-          // bits 0-7 row length, 16-23 own slot, 24-31 strip length in entries (the warps take their trip counts from it)
-          const int steps = (int)rp[t].size();
+          // bits 0-7 row length, 16-23 own slot, 24-31 strip length in units of dim entries (the warp's trip count)
+          const int steps = ((int)rp[t].size() + dim - 1) / dim;
           if (steps > 255) overflow++;
           out.row_meta[4 * q + 2] = (r >= 0 ? h->h_findrm[r + 1] - h->h_findrm[r] : 0) | own << 16 | (int)((unsigned)(steps & 0xff) << 24);
           out.row_meta[4 * q + 3] = (int)ol;
@@ -1140,9 +1138,9 @@ extern "C" int cgasm_plan_host_stats(int dim, int n_nodes, int n_elements, const
     for (int w = 0; w < kBR / 32; w++) {
       int steps = 0;
       for (int t = 32 * w; t < 32 * w + 32; t++) steps = std::max(steps, (sp.row_meta[4 * ((size_t)b * kBR + t) + 2] >> 24) & 0xff);
-      const int wdeg = std::min(ldeg, (steps + dim - 1) / dim * dim);
+      const int wdeg = std::min(ldeg, steps * dim);
       for (int t = 32 * w; t < 32 * w + 32; t++) {
-        const int mine = ((((sp.row_meta[4 * ((size_t)b * kBR + t) + 2] >> 24) & 0xff) + dim - 1) / dim) * dim;
+        const int mine = ((sp.row_meta[4 * ((size_t)b * kBR + t) + 2] >> 24) & 0xff) * dim;
         needed += mine;
         walked += wdeg;
       }

@@ -150,13 +150,11 @@ __device__ __forceinline__ void prefetch_next_block(const StagedView& P, int b, 
   else if (t == 16 + NL / 32) prefetch_l2(P.ptr + nb);
 }
 
-// Strip entries this WARP walks: its longest row's (bits 24-31 of the row record), rounded up to the kernel's unroll factor
-// U (the plan pads every row of the block to the block's longest, a multiple of dim (dim + 1), with no-op entries; a warp
-// whose rows are shorter skips them).
-template <int U>
+// Strip entries this WARP walks: its longest row's, in the row record's bits 24-31 in units of DIM entries (the plan pads
+// every row of the block to the block's longest with no-op entries; a warp whose rows are shorter skips them).
+template <int DIM>
 __device__ __forceinline__ int warp_trip_count(int meta_z) {
-  const int len = (int)__reduce_max_sync(0xffffffffu, (unsigned)meta_z >> 24);
-  return (len + U - 1) / U * U;
+  return (int)__reduce_max_sync(0xffffffffu, (unsigned)meta_z >> 24) * DIM;
 }
 
 // per-row table for the write-out: {first CSR entry, length | own slot << 16, value for the diagonal}, 16 bytes per row

@@ -451,41 +451,6 @@ def test_strip_additive_pass_constant_density(orc, dim, variant, in_loop, monkey
         assert (got2[k] == got[k]).all()
 
 
-# ---- STRIP: pipelined flavour of the staged kernels (strip_pipe.cu) -------------------------------------------------
-@pytest.mark.parametrize("dim", [2, 3])
-@pytest.mark.parametrize("mesh_kind", ["box", "shuffled", "delaunay"])
-def test_pipelined_strip_kernels_equal_the_fifo_kernels(orc, dim, mesh_kind, monkeypatch):
-    """CGASM_STRIP_PIPE=1: dim + 1 register buffers, every shared-memory read issued one strip step ahead. Same plan, same
-    arithmetic per element, same order of additions per slot: bitwise the FIFO kernels' results (and the oracle's to 1e-12)."""
-    if mesh_kind == "delaunay":
-        mesh = syn.delaunay_mesh(3000 if dim == 3 else 4000, dim=dim, seed=9)
-    else:
-        mesh = syn.box_mesh((9, 8, 7)[:dim] if dim == 3 else (21, 17), seed=12)
-        if mesh_kind == "shuffled":
-            mesh = syn.shuffled(mesh, seed=2)
-    fs = syn.standard_fields(mesh)
-    asm = make_asm(mesh, fs, abi.SCATTER_STRIP)
-    findrm, colm, _ = asm.get_sparsity()
-    cases = [(abi.common_momentum_opts(), abi.common_advdiff_opts()),
-             (abi.common_momentum_opts(have_gravity=0, assemble_inverse_masslump=0, exclude_mass=1),
-              abi.common_advdiff_opts(lump_mass=1))]
-    for om, oa in cases:
-        monkeypatch.delenv("CGASM_STRIP_PIPE", raising=False)
-        m0, a0 = asm.momentum(om), asm.advdiff(oa)
-        monkeypatch.setenv("CGASM_STRIP_PIPE", "1")
-        l0 = asm.launch_count()
-        m1, a1 = asm.momentum(om), asm.advdiff(oa)
-        assert asm.launch_count() - l0 == 2 and asm.last_path() == ("strip_staged", "strip_staged")
-        for k in ("big_m", "rhs", "masslump"):
-            if m0[k] is not None:
-                assert np.array_equal(m0[k], m1[k]), k
-        assert np.array_equal(a0["matrix"], a1["matrix"]) and np.array_equal(a0["rhs"], a1["rhs"])
-        ref = orc.assemble_momentum(mesh, fs, om, findrm, colm, want_masslump=bool(om.assemble_inverse_masslump))
-        check_momentum(m1, ref, findrm, dim)
-        ra = orc.assemble_advdiff(mesh, fs, oa, findrm, colm)
-        assert rel_err(a1["matrix"], ra["matrix"]) < TOL and rel_err(a1["rhs"], ra["rhs"]) < TOL
-
-
 # ---- both loops in one call ---------------------------------------------------------------------------------------
 @pytest.mark.parametrize("dim", [2, 3])
 @pytest.mark.parametrize("case", ["common", "excluded_mass_lumped_tracer", "no_gravity_no_ml", "fallback_absorption",
