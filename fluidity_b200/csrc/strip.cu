@@ -92,6 +92,7 @@ strip_momentum_kernel(const StripConsts k_, const StripPlanView P, const double4
   MomState<DIM, N> s;
   unpack<DIM>(ld256(rX + r0), s.X0, s.b0);
   unpack<DIM>(ld256(rU + r0), s.U0, s.rho0);
+  mom_row_consts<DIM, N>(s, k_);
   s.a0 = s.msum = s.nbsum = 0.0;
 #pragma unroll
   for (int q = 0; q < N; q++) {
@@ -155,6 +156,7 @@ __device__ __forceinline__ void adv_step(AdvState<DIM, N>& s, const StripConsts&
   {
     double* sl = acc_t + (s.meta[QE] & 0xff) * kAS;
     *sl += fma(k_.dtt, s.A[QE], k_.mPo * s.C[QE]);
+    adv_evict_rhs(s.rhs, s.A[QE], s.T[QE]);
     s.A[QE] = 0.0;
     s.C[QE] = 0.0;
   }
@@ -219,7 +221,11 @@ strip_advdiff_kernel(const StripConsts k_, const StripPlanView P, const double4*
   int2 pq1 = PD + 1 < deg ? ldg_stream2(p + (long long)(PD + 1) * kBR) : pad;
   for (int j0 = 0; j0 < deg; j0 += N) AdvUnroll<DIM, N, 0>::run(s, k_, j0, deg, p, pq0, pq1, pad, acc_t, rX, rU);
 #pragma unroll
-  for (int q = 0; q < N; q++) acc_t[(s.meta[q] & 0xff) * kAS] += fma(k_.dtt, s.A[q], k_.mPo * s.C[q]);
+  for (int q = 0; q < N; q++) {
+    acc_t[(s.meta[q] & 0xff) * kAS] += fma(k_.dtt, s.A[q], k_.mPo * s.C[q]);
+    adv_evict_rhs(s.rhs, s.A[q], s.T[q]);
+  }
+  adv_finish_rhs(s.rhs, s.a0, s.T0);
   acc_t[own * kAS] += fma(k_.dtt, s.a0, k_.mPd * s.c0);
   int my_s0 = 0, my_len = 0;
   if (r >= 0) {

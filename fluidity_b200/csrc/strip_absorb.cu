@@ -162,6 +162,7 @@ staged_momentum_absorb_kernel(const StripConsts k_, const AbsorbConsts ka, const
   AbsorbState<DIM> ab;
   load_rec<DIM, NL>(nsa + own_off, 0, s.X0, s.b0);
   load_rec<DIM, NL>(nsa + own_off, 1, s.U0, s.rho0);
+  mom_row_consts<DIM, DIM>(s, k_);
   load_absorption<DIM, NL>(nsa + own_off, ab.sg0);
   s.a0 = s.msum = s.nbsum = 0.0;
   ab.c0 = 0.0;

@@ -93,7 +93,17 @@ struct MomState {
   int meta[N];
   double X0[DIM], U0[DIM], rho0, b0;
   double a0, msum, nbsum;
+  double qa_rho0, qd_rho0, pm_rho0, pm_b0;  // row constants of the moments (mom_row_consts)
 };
+
+// products of the row's own density / buoyancy with the quadrature moments: once per row instead of once per element
+template <int DIM, int N>
+__device__ __forceinline__ void mom_row_consts(MomState<DIM, N>& s, const StripConsts& k_) {
+  s.qa_rho0 = k_.Qa * s.rho0;
+  s.qd_rho0 = k_.Qd * s.rho0;
+  s.pm_rho0 = k_.PdPo * s.rho0;
+  s.pm_b0 = k_.PdPo * s.b0;
+}
 
 // row 0 (the row's own node) of the element {r, window}: Momentum_CG.F90:1535-1552 (lumped mass),
 // :1675-1680 with beta = 0 (advection), :2304-2317 (constant isotropic viscosity), :1770-1789 (buoyancy)
@@ -137,39 +147,43 @@ __device__ __forceinline__ void window_geom(const double (&X)[N][DIM], WindowGeo
 
 template <int DIM, int N, int QC, bool FULLV>
 __device__ __forceinline__ void mom_terms(MomState<DIM, N>& s, const StripConsts& k_, const WindowGeom<DIM>& g) {
+  // density-weighted mass row M_0k = |J| sum_l Q_0kl rho_l (without |J|): M_00 = Qa rho_0 + Qaab S,
+  // M_0k = Qd (rho_0 + rho_k) + Qabc S with S = rho_0 + sum_k rho_k; the products with rho_0 are row constants
   double S = s.rho0;
 #pragma unroll
   for (int k = 0; k < DIM; k++) S += s.R[WQ(k)];
-  const double QS = k_.Qabc * S;
-  const double M0 = fma(k_.Qa, s.rho0, k_.Qaab * S);
+  const double tS = fma(k_.Qabc, S, s.qd_rho0);
+  const double M0 = fma(k_.Qaab, S, s.qa_rho0);
   double w[DIM];
 #pragma unroll
   for (int a = 0; a < DIM; a++) w[a] = M0 * s.U0[a];
 #pragma unroll
   for (int k = 0; k < DIM; k++) {
-    const double Mk = fma(k_.Qd, s.rho0 + s.R[WQ(k)], QS);
+    const double Mk = fma(k_.Qd, s.R[WQ(k)], tS);
 #pragma unroll
     for (int a = 0; a < DIM; a++) w[a] = fma(Mk, s.U[WQ(k)][a], w[a]);
   }
   // v / det with v = |det| (w + Wsum V gradN_0), gradN_0 = -sc / det
   double u[DIM];
   row_vector<DIM, FULLV>(k_, w, g.sc, g.rd, g.det, u);
-  double tot = 0.0;
+  // entry (0, k) = u . c_k accumulates straight into the column's register; the diagonal takes -sum_k u . c_k = -u . sc
 #pragma unroll
   for (int k = 0; k < DIM; k++) {
-    double sk = 0.0;
+    double ak = s.A[WQ(k)];
 #pragma unroll
-    for (int a = 0; a < DIM; a++) sk = fma(u[a], g.c[k][a], sk);
-    s.A[WQ(k)] += sk;
-    tot += sk;
+    for (int a = 0; a < DIM; a++) ak = fma(u[a], g.c[k][a], ak);
+    s.A[WQ(k)] = ak;
   }
+  double tot = u[0] * g.sc[0];
+#pragma unroll
+  for (int a = 1; a < DIM; a++) tot = fma(u[a], g.sc[a], tot);
   s.a0 -= tot;
   const double ad = fabs(g.det);
-  s.msum = fma(ad, fma(k_.PdPo, s.rho0, k_.Po * S), s.msum);
+  s.msum = fma(ad, fma(k_.Po, S, s.pm_rho0), s.msum);
   double Sb = s.b0;
 #pragma unroll
   for (int k = 0; k < DIM; k++) Sb += s.B[WQ(k)];
-  s.nbsum = fma(ad, fma(k_.PdPo, s.b0, k_.Po * Sb), s.nbsum);
+  s.nbsum = fma(ad, fma(k_.Po, Sb, s.pm_b0), s.nbsum);
 }
 
 template <int DIM, int N, int QC, bool FULLV>
@@ -220,8 +234,7 @@ __device__ __forceinline__ void adv_row_const(const StripConsts& k_, const doubl
 // velocity buffers and the geometry)
 template <int DIM, int N, int QC, bool FULLV>
 __device__ __forceinline__ void adv_terms(const StripConsts& k_, const WindowGeom<DIM>& g, const double (&U)[N][DIM],
-                                          const double (&cU0)[DIM], const double (&T)[N], double T0, double (&A)[N],
-                                          double (&C)[N], double& a0, double& c0, double& rhs) {
+                                          const double (&cU0)[DIM], double (&A)[N], double (&C)[N], double& a0, double& c0) {
   // v = (Pd - Po) nu_0 + Po (nu_0 + sum_k nu_k); cU0 = Pd nu_0 is the same for every element of the row
   double v[DIM];
 #pragma unroll
@@ -234,28 +247,35 @@ __device__ __forceinline__ void adv_terms(const StripConsts& k_, const WindowGeo
   double u[DIM];
   row_vector<DIM, FULLV>(k_, v, g.sc, g.rd, g.det, u);
   const double ad = fabs(g.det);
-  double tot = 0.0;
+  // entry (0, k) = u . c_k accumulates straight into the column's register, the diagonal takes -u . sc; the products with
+  // T (rhs -= (A + D) T, Advection_Diffusion_CG.F90:1125,1200) are taken once per column when it leaves the FIFO
+  // (adv_evict_rhs) and once per row for the diagonal (adv_finish_rhs): the right-hand side is linear in the entries
 #pragma unroll
   for (int k = 0; k < DIM; k++) {
-    double sk = 0.0;
+    double ak = A[WQ(k)];
 #pragma unroll
-    for (int a = 0; a < DIM; a++) sk = fma(u[a], g.c[k][a], sk);
-    A[WQ(k)] += sk;
+    for (int a = 0; a < DIM; a++) ak = fma(u[a], g.c[k][a], ak);
+    A[WQ(k)] = ak;
     C[WQ(k)] += ad;
-    rhs = fma(-sk, T[WQ(k)], rhs);
-    tot += sk;
   }
+  double tot = u[0] * g.sc[0];
+#pragma unroll
+  for (int a = 1; a < DIM; a++) tot = fma(u[a], g.sc[a], tot);
   a0 -= tot;
   c0 += ad;
-  rhs = fma(tot, T0, rhs);
 }
 
 template <int DIM, int N, int QC, bool FULLV>
 __device__ __forceinline__ void adv_compute(AdvState<DIM, N>& s, const StripConsts& k_) {
   WindowGeom<DIM> g;
   window_geom<DIM, N, QC>(s.X, g);
-  adv_terms<DIM, N, QC, FULLV>(k_, g, s.U, s.cU0, s.T, s.T0, s.A, s.C, s.a0, s.c0, s.rhs);
+  adv_terms<DIM, N, QC, FULLV>(k_, g, s.U, s.cU0, s.A, s.C, s.a0, s.c0);
 }
+
+// rhs -= entry * T(column) for the column leaving the FIFO (a = its accumulated, unscaled entry, tk = its T) ...
+__device__ __forceinline__ void adv_evict_rhs(double& rhs, double a, double tk) { rhs = fma(-a, tk, rhs); }
+// ... and for the diagonal, after the row's last element
+__device__ __forceinline__ void adv_finish_rhs(double& rhs, double a0, double t0) { rhs = fma(-a0, t0, rhs); }
 
 // the row's own absorption / source values (tracer kernel with ABS)
 struct AdvOwnExtra {
@@ -292,23 +312,20 @@ __device__ __forceinline__ void adv_compute_abs(AdvState<DIM, N>& s, const doubl
     Sq += sq[WQ(k)];
   }
   const double QS = k_.Qabc * Ss;
-  double tot = 0.0;
 #pragma unroll
   for (int k = 0; k < DIM; k++) {
-    double sk = 0.0;
+    double ak = fma(ad, fma(k_.Qd, ox.sg0 + sg[WQ(k)], QS), s.A[WQ(k)]);
 #pragma unroll
-    for (int a = 0; a < DIM; a++) sk = fma(u[a], c[k][a], sk);
-    const double e = fma(ad, fma(k_.Qd, ox.sg0 + sg[WQ(k)], QS), sk);
-    s.A[WQ(k)] += e;
+    for (int a = 0; a < DIM; a++) ak = fma(u[a], c[k][a], ak);
+    s.A[WQ(k)] = ak;
     s.C[WQ(k)] += ad;
-    s.rhs = fma(-e, s.T[WQ(k)], s.rhs);
-    tot += sk;
   }
-  const double d0 = fma(ad, fma(k_.Qa, ox.sg0, k_.Qaab * Ss), -tot);
-  s.a0 += d0;
+  double tot = u[0] * sc[0];
+#pragma unroll
+  for (int a = 1; a < DIM; a++) tot = fma(u[a], sc[a], tot);
+  s.a0 += fma(ad, fma(k_.Qa, ox.sg0, k_.Qaab * Ss), -tot);
   s.c0 += ad;
-  s.rhs = fma(-d0, s.T0, s.rhs);
-  s.rhs = fma(ad, fma(k_.sPdPo, ox.sq0, k_.sPo * Sq), s.rhs);
+  s.rhs = fma(ad, fma(k_.sPdPo, ox.sq0, k_.sPo * Sq), s.rhs);  // the source; the products with T: adv_evict_rhs / adv_finish_rhs
 }
 
 #undef WQ

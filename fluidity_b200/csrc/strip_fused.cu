@@ -66,6 +66,7 @@ __device__ __forceinline__ void fused_step(MomState<DIM, DIM>& s, TracerSide<DIM
     sts64(acc2_sa + so, slot2 + fma(ka.dtt, q.A[QC], ka.mPo * q.C[QC]));
 #pragma unroll
     for (int d = 0; d < DIM; d++) rh[d] = fma(-a, on[d], rh[d]);
+    adv_evict_rhs(q.rhs, q.A[QC], q.T[QC]);
     s.A[QC] = 0.0;
     q.A[QC] = 0.0;
     q.C[QC] = 0.0;
@@ -77,7 +78,7 @@ __device__ __forceinline__ void fused_step(MomState<DIM, DIM>& s, TracerSide<DIM
     WindowGeom<DIM> g;
     window_geom<DIM, DIM, QC>(s.X, g);
     mom_terms<DIM, DIM, QC, false>(s, km, g);
-    adv_terms<DIM, DIM, QC, false>(ka, g, s.U, q.cU0, q.T, q.T0, q.A, q.C, q.a0, q.c0, q.rhs);
+    adv_terms<DIM, DIM, QC, false>(ka, g, s.U, q.cU0, q.A, q.C, q.a0, q.c0);
   }
 }
 
@@ -129,6 +130,7 @@ staged_fused_kernel(const StripConsts km, const StripConsts ka, const StagedView
   TracerSide<DIM> q;
   load_rec<DIM, NL>(nsa + own_off, 0, s.X0, s.b0);
   load_rec<DIM, NL>(nsa + own_off, 1, s.U0, s.rho0);
+  mom_row_consts<DIM, DIM>(s, km);
   q.T0 = lds64(fused_t_sa<NL>(nsa, own_off));
   adv_row_const<DIM>(ka, s.U0, q.cU0);
   s.a0 = s.msum = s.nbsum = 0.0;
@@ -152,6 +154,7 @@ staged_fused_kernel(const StripConsts km, const StripConsts ka, const StagedView
     const unsigned m = (unsigned)s.meta[k];
     acc_t[m >> 16] += s.A[k];
     acc2_t[m >> 16] += fma(ka.dtt, q.A[k], ka.mPo * q.C[k]);
+    adv_evict_rhs(q.rhs, q.A[k], q.T[k]);
     double o[DIM];
     load_oldu<DIM, NL>(nsa, m & 0xfff0u, o);
 #pragma unroll
@@ -167,6 +170,7 @@ staged_fused_kernel(const StripConsts km, const StripConsts ka, const StagedView
       rhs[(size_t)DIM * r + d] = fma(-s.a0, ou[d], fma(km.grav[d], s.nbsum, rh[d]));
       if (masslump) masslump[(size_t)DIM * r + d] = s.msum;
     }
+    adv_finish_rhs(q.rhs, q.a0, q.T0);
     arhs[r] = q.rhs;
   }
   // rows of the warp: the dim identical momentum blocks (dt*theta * entry + lumped mass on the diagonal), then the tracer matrix

@@ -131,6 +131,7 @@ staged_momentum_kernel(const StripConsts k_, const StagedView P, const double4* 
   MomState<DIM, DIM> s;
   load_rec<DIM, NL>(nsa + own_off, 0, s.X0, s.b0);
   load_rec<DIM, NL>(nsa + own_off, 1, s.U0, s.rho0);
+  mom_row_consts<DIM, DIM>(s, k_);
   s.a0 = s.msum = s.nbsum = 0.0;
   double rh[DIM];
 #pragma unroll
@@ -181,6 +182,7 @@ __device__ __forceinline__ void sadv_step(AdvState<DIM, DIM>& s, double (&sg)[AB
   const double slot = lds64(sa);
   const unsigned nb = nsa + (en & 0xfff0u);
   double unused;
+  adv_evict_rhs(s.rhs, s.A[QC], s.T[QC]);
   load_rec<DIM, NL>(nb, 0, s.X[QC], s.T[QC]);
   load_rec<DIM, NL>(nb, 1, s.U[QC], unused);
   sts64(sa, slot + fma(k_.dtt, s.A[QC], k_.mPo * s.C[QC]));
@@ -271,7 +273,11 @@ staged_advdiff_kernel(const StripConsts k_, const StagedView P, const double4* _
   for (int j0 = 0; j0 < deg; j0 += DIM, p += DIM * kBR)
     SAdvUnroll<DIM, 0, NL, FULLV, ABS>::run(s, sg, sq, ox, k_, p, pq, acc_sa, nsa);
 #pragma unroll
-  for (int q = 0; q < DIM; q++) acc_t[(unsigned)s.meta[q] >> 16] += fma(k_.dtt, s.A[q], k_.mPo * s.C[q]);
+  for (int q = 0; q < DIM; q++) {
+    acc_t[(unsigned)s.meta[q] >> 16] += fma(k_.dtt, s.A[q], k_.mPo * s.C[q]);
+    adv_evict_rhs(s.rhs, s.A[q], s.T[q]);
+  }
+  adv_finish_rhs(s.rhs, s.a0, s.T0);
   acc_t[own * kAS] += fma(k_.dtt, s.a0, k_.mPd * s.c0);
   if (r >= 0) rhs[r] = s.rhs;
   row_table_store(tbl_sa, t, meta.y, meta.z, 0.0);
