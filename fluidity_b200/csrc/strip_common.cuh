@@ -6,6 +6,11 @@
 
 namespace cgasm {
 
+#ifndef CGASM_V_SEPARATE_SUMS
+#define CGASM_V_SEPARATE_SUMS 0
+#endif
+constexpr bool kStripSeparateSums = CGASM_V_SEPARATE_SUMS != 0;  // A/B switch (scripts/ab_kernels.py)
+
 struct StripConsts {  // passed by value: operands are read straight from the constant bank
   // Option switches are folded into these numbers on the host (consts_momentum / consts_advdiff): a term
   // that is switched off has zero coefficients, so one kernel serves every combination.
@@ -99,10 +104,12 @@ struct MomState {
 // products of the row's own density / buoyancy with the quadrature moments: once per row instead of once per element
 template <int DIM, int N>
 __device__ __forceinline__ void mom_row_consts(MomState<DIM, N>& s, const StripConsts& k_) {
-  s.qa_rho0 = k_.Qa * s.rho0;
-  s.qd_rho0 = k_.Qd * s.rho0;
-  s.pm_rho0 = k_.PdPo * s.rho0;
-  s.pm_b0 = k_.PdPo * s.b0;
+  if constexpr (DIM == 3 && !kStripSeparateSums) {  // (2-D keeps the per-element products: measured faster there)
+    s.qa_rho0 = k_.Qa * s.rho0;
+    s.qd_rho0 = k_.Qd * s.rho0;
+    s.pm_rho0 = k_.PdPo * s.rho0;
+    s.pm_b0 = k_.PdPo * s.b0;
+  }
 }
 
 // row 0 (the row's own node) of the element {r, window}: Momentum_CG.F90:1535-1552 (lumped mass),
@@ -152,38 +159,70 @@ __device__ __forceinline__ void mom_terms(MomState<DIM, N>& s, const StripConsts
   double S = s.rho0;
 #pragma unroll
   for (int k = 0; k < DIM; k++) S += s.R[WQ(k)];
-  const double tS = fma(k_.Qabc, S, s.qd_rho0);
-  const double M0 = fma(k_.Qaab, S, s.qa_rho0);
   double w[DIM];
+  if constexpr (DIM == 3 && !kStripSeparateSums) {
+    const double tS = fma(k_.Qabc, S, s.qd_rho0);
+    const double M0 = fma(k_.Qaab, S, s.qa_rho0);
 #pragma unroll
-  for (int a = 0; a < DIM; a++) w[a] = M0 * s.U0[a];
+    for (int a = 0; a < DIM; a++) w[a] = M0 * s.U0[a];
 #pragma unroll
-  for (int k = 0; k < DIM; k++) {
-    const double Mk = fma(k_.Qd, s.R[WQ(k)], tS);
+    for (int k = 0; k < DIM; k++) {
+      const double Mk = fma(k_.Qd, s.R[WQ(k)], tS);
 #pragma unroll
-    for (int a = 0; a < DIM; a++) w[a] = fma(Mk, s.U[WQ(k)][a], w[a]);
+      for (int a = 0; a < DIM; a++) w[a] = fma(Mk, s.U[WQ(k)][a], w[a]);
+    }
+  } else {
+    const double QS = k_.Qabc * S;
+    const double M0 = fma(k_.Qa, s.rho0, k_.Qaab * S);
+#pragma unroll
+    for (int a = 0; a < DIM; a++) w[a] = M0 * s.U0[a];
+#pragma unroll
+    for (int k = 0; k < DIM; k++) {
+      const double Mk = fma(k_.Qd, s.rho0 + s.R[WQ(k)], QS);
+#pragma unroll
+      for (int a = 0; a < DIM; a++) w[a] = fma(Mk, s.U[WQ(k)][a], w[a]);
+    }
   }
   // v / det with v = |det| (w + Wsum V gradN_0), gradN_0 = -sc / det
   double u[DIM];
   row_vector<DIM, FULLV>(k_, w, g.sc, g.rd, g.det, u);
   // entry (0, k) = u . c_k accumulates straight into the column's register; the diagonal takes -sum_k u . c_k = -u . sc
+  // (3-D; in 2-D, where the dot products are two terms long, the separate sum measured faster on the B200)
+  if constexpr (DIM == 3 && !kStripSeparateSums) {
 #pragma unroll
-  for (int k = 0; k < DIM; k++) {
-    double ak = s.A[WQ(k)];
+    for (int k = 0; k < DIM; k++) {
+      double ak = s.A[WQ(k)];
 #pragma unroll
-    for (int a = 0; a < DIM; a++) ak = fma(u[a], g.c[k][a], ak);
-    s.A[WQ(k)] = ak;
+      for (int a = 0; a < DIM; a++) ak = fma(u[a], g.c[k][a], ak);
+      s.A[WQ(k)] = ak;
+    }
+    double tot = u[0] * g.sc[0];
+#pragma unroll
+    for (int a = 1; a < DIM; a++) tot = fma(u[a], g.sc[a], tot);
+    s.a0 -= tot;
+  } else {
+    double tot = 0.0;
+#pragma unroll
+    for (int k = 0; k < DIM; k++) {
+      double sk = 0.0;
+#pragma unroll
+      for (int a = 0; a < DIM; a++) sk = fma(u[a], g.c[k][a], sk);
+      s.A[WQ(k)] += sk;
+      tot += sk;
+    }
+    s.a0 -= tot;
   }
-  double tot = u[0] * g.sc[0];
-#pragma unroll
-  for (int a = 1; a < DIM; a++) tot = fma(u[a], g.sc[a], tot);
-  s.a0 -= tot;
   const double ad = fabs(g.det);
-  s.msum = fma(ad, fma(k_.Po, S, s.pm_rho0), s.msum);
   double Sb = s.b0;
 #pragma unroll
   for (int k = 0; k < DIM; k++) Sb += s.B[WQ(k)];
-  s.nbsum = fma(ad, fma(k_.Po, Sb, s.pm_b0), s.nbsum);
+  if constexpr (DIM == 3 && !kStripSeparateSums) {
+    s.msum = fma(ad, fma(k_.Po, S, s.pm_rho0), s.msum);
+    s.nbsum = fma(ad, fma(k_.Po, Sb, s.pm_b0), s.nbsum);
+  } else {
+    s.msum = fma(ad, fma(k_.PdPo, s.rho0, k_.Po * S), s.msum);
+    s.nbsum = fma(ad, fma(k_.PdPo, s.b0, k_.Po * Sb), s.nbsum);
+  }
 }
 
 template <int DIM, int N, int QC, bool FULLV>
@@ -250,18 +289,32 @@ __device__ __forceinline__ void adv_terms(const StripConsts& k_, const WindowGeo
   // entry (0, k) = u . c_k accumulates straight into the column's register, the diagonal takes -u . sc; the products with
   // T (rhs -= (A + D) T, Advection_Diffusion_CG.F90:1125,1200) are taken once per column when it leaves the FIFO
   // (adv_evict_rhs) and once per row for the diagonal (adv_finish_rhs): the right-hand side is linear in the entries
+  if constexpr (DIM == 3 && !kStripSeparateSums) {
 #pragma unroll
-  for (int k = 0; k < DIM; k++) {
-    double ak = A[WQ(k)];
+    for (int k = 0; k < DIM; k++) {
+      double ak = A[WQ(k)];
 #pragma unroll
-    for (int a = 0; a < DIM; a++) ak = fma(u[a], g.c[k][a], ak);
-    A[WQ(k)] = ak;
-    C[WQ(k)] += ad;
+      for (int a = 0; a < DIM; a++) ak = fma(u[a], g.c[k][a], ak);
+      A[WQ(k)] = ak;
+      C[WQ(k)] += ad;
+    }
+    double tot = u[0] * g.sc[0];
+#pragma unroll
+    for (int a = 1; a < DIM; a++) tot = fma(u[a], g.sc[a], tot);
+    a0 -= tot;
+  } else {
+    double tot = 0.0;
+#pragma unroll
+    for (int k = 0; k < DIM; k++) {
+      double sk = 0.0;
+#pragma unroll
+      for (int a = 0; a < DIM; a++) sk = fma(u[a], g.c[k][a], sk);
+      A[WQ(k)] += sk;
+      C[WQ(k)] += ad;
+      tot += sk;
+    }
+    a0 -= tot;
   }
-  double tot = u[0] * g.sc[0];
-#pragma unroll
-  for (int a = 1; a < DIM; a++) tot = fma(u[a], g.sc[a], tot);
-  a0 -= tot;
   c0 += ad;
 }
 
@@ -312,17 +365,16 @@ __device__ __forceinline__ void adv_compute_abs(AdvState<DIM, N>& s, const doubl
     Sq += sq[WQ(k)];
   }
   const double QS = k_.Qabc * Ss;
+  double tot = 0.0;
 #pragma unroll
   for (int k = 0; k < DIM; k++) {
-    double ak = fma(ad, fma(k_.Qd, ox.sg0 + sg[WQ(k)], QS), s.A[WQ(k)]);
+    double sk = 0.0;
 #pragma unroll
-    for (int a = 0; a < DIM; a++) ak = fma(u[a], c[k][a], ak);
-    s.A[WQ(k)] = ak;
+    for (int a = 0; a < DIM; a++) sk = fma(u[a], c[k][a], sk);
+    s.A[WQ(k)] += fma(ad, fma(k_.Qd, ox.sg0 + sg[WQ(k)], QS), sk);
     s.C[WQ(k)] += ad;
+    tot += sk;
   }
-  double tot = u[0] * sc[0];
-#pragma unroll
-  for (int a = 1; a < DIM; a++) tot = fma(u[a], sc[a], tot);
   s.a0 += fma(ad, fma(k_.Qa, ox.sg0, k_.Qaab * Ss), -tot);
   s.c0 += ad;
   s.rhs = fma(ad, fma(k_.sPdPo, ox.sq0, k_.sPo * Sq), s.rhs);  // the source; the products with T: adv_evict_rhs / adv_finish_rhs

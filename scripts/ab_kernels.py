@@ -6,12 +6,15 @@ import numpy as np
 from fluidity_b200 import synthetic as syn, _abi as abi, cgasm, tables
 
 cells = int(sys.argv[1]) if len(sys.argv) > 1 else 128
-mesh = syn.box_mesh((cells,) * 3)
-asm = cgasm.Assembler(mesh, tables.p1_tables(3), device=0)
+mode = sys.argv[2] if len(sys.argv) > 2 else "s3"   # s3 | 2d (cells^2 triangles) | abs (tracer with absorption + source)
+mesh = syn.box_mesh((cells,) * (2 if mode == "2d" else 3))
+asm = cgasm.Assembler(mesh, tables.p1_tables(mesh.dim), device=0)
 asm.build_sparsity()
 asm.set_fields(syn.standard_fields(mesh))
 asm.set_scatter(abi.SCATTER_STRIP)
 om, oa = abi.common_momentum_opts(), abi.common_advdiff_opts()
+if mode == "abs":
+    oa = abi.common_advdiff_opts(have_absorption=1, have_source=1)
 mom, adv, fus = [], [], []
 for i in range(9):
     asm.momentum_dev(om); m = asm.last_kernel_ms()
@@ -20,6 +23,6 @@ for i in range(9):
     if i >= 2:
         mom.append(m); adv.append(a); fus.append(f)
 chk = float(np.abs(asm.momentum_fetch()["rhs"]).sum()) if hasattr(asm, "momentum_fetch") else 0.0
-print("%-28s cells %d  momentum %.4f  tracer %.4f  fused %.4f ms   checksum %.12e" % (
-    os.path.basename(os.environ.get("CGASM_LIB", "libcgasm.so")), cells, statistics.median(mom), statistics.median(adv),
+print("%-28s %s cells %d  momentum %.4f  tracer %.4f  fused %.4f ms   checksum %.12e" % (
+    os.path.basename(os.environ.get("CGASM_LIB", "libcgasm.so")), mode, cells, statistics.median(mom), statistics.median(adv),
     statistics.median(fus), chk))
