@@ -3,7 +3,11 @@
 #include "strip_plan.h"
 
 #include <algorithm>
+#include <atomic>
+#include <mutex>
+#include <unordered_set>
 #include <cstdint>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -498,6 +502,229 @@ void mask_strip3(const MaskLink& L, int start, const int* perm, MaskSeq& S) {
   }
 }
 
+// ---- strip search: fewer pushes than the greedy ---------------------------------------------------------------
+// The kernels walk a row's strip in trips of `dim` entries, every non-computing push still pays its shared-memory reads
+// and the flush, and the greedy needs 33 pushes for the 24 elements around an interior node of a Kuhn mesh where 30
+// are enough (three bands of eight triangles, found by exhaustive search: 29 is infeasible). On meshes whose rows fall
+// into a few congruence classes (strip_search_prescan) the strip of every class is improved once by a bounded
+// branch-and-bound over {computing push | one-push restart that keeps the newest node | fresh triangle in any of its
+// six orders}: depth-first from every (first triangle, order) root with a growing per-root budget -- a third of the
+// roots of the Kuhn link reach 30 within ~12 000 states while others exhaust millions -- pruned by
+// pushes + pending + (components of the pending triangles' dual graph that miss the window edge) > limit and by a
+// table of visited (window, pending set) states. The target is the next multiple of 3 below the greedy's length:
+// anything in between saves no trip. Results are shared between threads (one search per class per process).
+std::atomic<int> g_strip_search{0};
+std::atomic<long> g_strip_search_states{0};  // states left for this plan build (all classes together)  // set per plan build by strip_search_prescan (CGASM_STRIP_SEARCH=0/1 overrides)
+
+struct StripSearch {
+  const MaskLink* L = nullptr;
+  int m = 0, limit = 0;
+  long states = 0, budget = 0, spent = 0;
+  uint64_t adj[64];
+  unsigned char seq[4 * 64 + 8];
+  int n = 0;
+  unsigned char best[4 * 64 + 8];
+  int best_n = 0;
+  struct Ent {
+    uint64_t todo;
+    uint32_t tag;  // epoch << 20 | a << 14 | b << 8 | pushes
+  };
+  static constexpr int kTabBits = 18;
+  std::vector<Ent> tab;
+  uint32_t epoch = 0;
+
+  void init(const MaskLink& M) {
+    L = &M;
+    m = M.m;
+    for (int i = 0; i < m; i++) {
+      uint64_t w = 0;
+      for (int e = 0; e < 3; e++) w |= M.vm[M.tri[i][e]] & M.vm[M.tri[i][(e + 1) % 3]];
+      adj[i] = w & ~(1ull << i);
+    }
+    if (tab.empty()) tab.assign((size_t)1 << kTabBits, Ent{0, 0});
+  }
+  void next_epoch() {
+    if (++epoch >= (1u << 12)) {
+      epoch = 1;
+      std::fill(tab.begin(), tab.end(), Ent{0, 0});
+    }
+  }
+  // components of the dual graph of the pending triangles that do not touch edge (a, b): one non-computing push each at least
+  int stranded(uint64_t todo, int a, int b) const {
+    const uint64_t onedge = L->vm[a] & L->vm[b];
+    int comps = 0;
+    while (todo) {
+      uint64_t c = todo & (~todo + 1), f = c;
+      while (f) {
+        uint64_t nx = 0;
+        for (uint64_t q = f; q; q &= q - 1) nx |= adj[__builtin_ctzll(q)];
+        nx &= todo & ~c;
+        c |= nx;
+        f = nx;
+      }
+      todo &= ~c;
+      comps += (c & onedge) == 0;
+    }
+    return comps;
+  }
+  bool dfs(int a, int b, uint64_t todo, int used) {
+    if (!todo) {
+      memcpy(best, seq, (size_t)n);
+      best_n = n;
+      return true;
+    }
+    const int rem = __builtin_popcountll(todo);
+    if (used + rem > limit || states > budget) return false;
+    if (used + rem + stranded(todo, a, b) > limit) return false;
+    ++states;
+    {
+      const uint64_t hsh = (todo ^ (todo >> 29) ^ ((uint64_t)(a * 64 + b) << 40)) * 0x9e3779b97f4a7c15ull;
+      Ent& e = tab[hsh >> (64 - kTabBits)];
+      const uint32_t key = epoch << 20 | (uint32_t)a << 14 | (uint32_t)b << 8;
+      if (e.todo == todo && (e.tag & ~0xffu) == key && (int)(e.tag & 0xffu) <= used) return false;
+      e.todo = todo;
+      e.tag = key | (uint32_t)used;
+    }
+    const MaskLink& M = *L;
+    {  // computing pushes: the triangle whose new edge has more pending triangles first
+      int cand[2], sc[2], nc = 0;
+      for (uint64_t c = todo & M.vm[a] & M.vm[b]; c && nc < 2; c &= c - 1) {
+        const int t = __builtin_ctzll(c), d = M.third(t, a, b);
+        cand[nc] = t;
+        sc[nc++] = __builtin_popcountll(todo & M.vm[b] & M.vm[d] & ~(1ull << t));
+      }
+      if (nc == 2 && sc[1] > sc[0]) std::swap(cand[0], cand[1]);
+      for (int i = 0; i < nc; i++) {
+        const int t = cand[i], d = M.third(t, a, b);
+        seq[n++] = (unsigned char)d;
+        if (dfs(b, d, todo & ~(1ull << t), used + 1)) return true;
+        n--;
+      }
+    }
+    if (used + rem + 1 > limit) return false;
+    for (uint64_t c = todo & M.vm[b] & ~M.vm[a]; c; c &= c - 1) {  // restart keeping b: push x, then d computes {b, x, d}
+      const int t = __builtin_ctzll(c);
+      int o[2], q = 0;
+      for (int i = 0; i < 3; i++)
+        if (M.tri[t][i] != b) o[q++] = M.tri[t][i];
+      for (int s2 = 0; s2 < 2; s2++) {
+        seq[n++] = (unsigned char)o[s2];
+        seq[n++] = (unsigned char)o[1 - s2];
+        if (dfs(o[s2], o[1 - s2], todo & ~(1ull << t), used + 2)) return true;
+        n -= 2;
+      }
+    }
+    if (used + rem + 2 > limit) return false;
+    static const int P[6][3] = {{0, 1, 2}, {0, 2, 1}, {1, 0, 2}, {1, 2, 0}, {2, 0, 1}, {2, 1, 0}};
+    for (uint64_t c = todo; c; c &= c - 1) {  // fresh triangle
+      const int t = __builtin_ctzll(c);
+      for (const auto& p : P) {
+        const int x = M.tri[t][p[0]], y = M.tri[t][p[1]], z = M.tri[t][p[2]];
+        if (rem > 1 && !(todo & ~(1ull << t) & M.vm[y] & M.vm[z])) continue;  // a strip of one triangle: never cheaper than elsewhere
+        seq[n++] = (unsigned char)x;
+        seq[n++] = (unsigned char)y;
+        seq[n++] = (unsigned char)z;
+        if (dfs(y, z, todo & ~(1ull << t), used + 3)) return true;
+        n -= 3;
+      }
+    }
+    return false;
+  }
+  // a node sequence of at most `lim` pushes covering every triangle, or false
+  bool run(int lim, long total_budget) {
+    static const int P[6][3] = {{0, 1, 2}, {0, 2, 1}, {1, 0, 2}, {1, 2, 0}, {2, 0, 1}, {2, 1, 0}};
+    const uint64_t full = m == 64 ? ~0ull : ((1ull << m) - 1);
+    limit = lim;
+    spent = 0;
+    for (long slice = 16000; spent < total_budget; slice *= 8) {
+      bool exhausted_all = true;
+      for (int t = 0; t < m; t++)
+        for (const auto& p : P) {
+          next_epoch();
+          states = 0;
+          budget = slice;
+          n = 0;
+          seq[n++] = L->tri[t][p[0]];
+          seq[n++] = L->tri[t][p[1]];
+          seq[n++] = L->tri[t][p[2]];
+          const bool ok = dfs(L->tri[t][p[1]], L->tri[t][p[2]], full & ~(1ull << t), 3);
+          spent += states;
+          if (ok) return true;
+          exhausted_all = exhausted_all && states <= budget;
+          if (spent >= total_budget) return false;
+        }
+      if (exhausted_all) return false;  // every root searched to the end: infeasible
+    }
+    return false;
+  }
+};
+
+struct SearchedStrip {
+  uint64_t hash;
+  int m, n;
+  std::vector<unsigned char> key, node;
+  std::vector<bool> comp;
+};
+std::mutex g_search_mu;
+std::vector<SearchedStrip> g_searched;  // a few dozen classes per structured mesh: linear scan under the lock
+StripSearch g_search;
+
+// best: the greedy's strip on entry, a shorter one (by whole trips of 3) on return if the search finds it
+void improve_strip(const MaskLink& M, const unsigned char* key, uint64_t hk, MaskSeq& best) {
+  const int floor_n = M.m + 2;
+  int target = (best.n - 1) / 3 * 3;
+  if (target < floor_n || M.m > 64 || M.m < 2) return;
+  std::lock_guard<std::mutex> lock(g_search_mu);
+  for (const SearchedStrip& it : g_searched)
+    if (it.hash == hk && it.m == M.m && !memcmp(it.key.data(), key, (size_t)3 * M.m)) {
+      if (it.n < best.n) {
+        best.n = it.n;
+        for (int k = 0; k < it.n; k++) {
+          best.node[k] = it.node[k];
+          best.comp[k] = it.comp[k];
+        }
+      }
+      return;
+    }
+  // Whatever happens below is final for this class in this process (the strip must be a function of the link alone: the
+  // per-thread memos and the two passes of cgasm_strip_plan_host rely on it), so the outcome is recorded even when the
+  // budget is gone; a full table answers with the greedy for every class it does not hold.
+  if (g_searched.size() >= 4096) return;
+  g_search.init(M);
+  long budget = std::min(1500000L, g_strip_search_states.load(std::memory_order_relaxed));
+  if (budget <= 0) target = -1;
+  const int greedy_n = best.n;
+  const double t_log = getenv("CGASM_STRIP_SEARCH_LOG") ? omp_get_wtime() : 0.0;
+  auto run = [&](int lim, long b) {
+    const bool ok = g_search.run(lim, b);
+    g_strip_search_states.fetch_sub(g_search.spent, std::memory_order_relaxed);
+    return ok;
+  };
+  while (target >= floor_n && run(target, budget)) {
+    // replay through mask_push: it computes a pending triangle whenever the window forms one, so every triangle of
+    // the found cover is computed at the planned push or earlier
+    MaskSeq S;
+    uint64_t todo = M.m == 64 ? ~0ull : ((1ull << M.m) - 1);
+    for (int k = 0; k < g_search.best_n; k++) mask_push(M, todo, S, g_search.best[k]);
+    if (todo != 0 || S.n >= best.n) break;
+    best = S;
+    target -= 3;
+    budget = std::min(200000L, g_strip_search_states.load(std::memory_order_relaxed));  // a second trip saved is rare: look, but briefly
+  }
+  if (t_log != 0.0)
+    fprintf(stderr, "strip search: link of %d triangles, greedy %d -> %d pushes, %.3f s\n", M.m, greedy_n, best.n, omp_get_wtime() - t_log);
+  {
+    SearchedStrip it;
+    it.hash = hk;
+    it.m = M.m;
+    it.n = best.n;
+    it.key.assign(key, key + (size_t)3 * M.m);
+    it.node.assign(best.node, best.node + best.n);
+    it.comp.assign(best.comp, best.comp + best.n);
+    g_searched.push_back(std::move(it));
+  }
+}
+
 // Per-thread memo of finished strips keyed by the link's local triangle list: the strip (as local ids) is a
 // function of that list alone, and on structured meshes a few dozen lists cover every row.
 struct StripMemo {
@@ -551,7 +778,8 @@ bool fast_strip_row(int loc, const int* nd0, const int64_t* n2e_ptr, const int* 
   if (L.m <= 64) {
     static thread_local StripMemo memo;
     const unsigned char* key = &L.tri[0][0];
-    const uint64_t hk = StripMemo::hash_of(key, 3 * L.m);
+    // (a strip memoised while the search was off must not answer for a build that has it on, and vice versa)
+    const uint64_t hk = StripMemo::hash_of(key, 3 * L.m) ^ (g_strip_search.load(std::memory_order_relaxed) ? 0xb5297a4d3f84d5b4ull : 0ull);
     if (const StripMemo::Item* it = memo.find(hk, key, L.m)) {
       nodes.resize((size_t)it->n);
       comp.resize((size_t)it->n);
@@ -585,6 +813,7 @@ bool fast_strip_row(int loc, const int* nd0, const int64_t* n2e_ptr, const int* 
       if (p == 0 || S.n < best.n) best = S;
       if (best.n == L.m + 2) break;  // one push per triangle after the first: cannot be shorter
     }
+    if (g_strip_search.load(std::memory_order_relaxed)) improve_strip(M, key, hk, best);
     memo.store(hk, key, L.m, best);
     nodes.resize((size_t)best.n);
     comp.resize((size_t)best.n);
@@ -623,6 +852,31 @@ bool fast_strip_row(int loc, const int* nd0, const int64_t* n2e_ptr, const int* 
     comp[k] = best.comp[k] ? 1 : 0;
   }
   return true;
+}
+
+// Decides whether the strips of this mesh are worth searching (improve_strip): the links of up to 2048 evenly spaced
+// rows are canonicalised as the builder will see them; a mesh whose sample falls into a few classes is structured
+// enough for one search per class to pay. CGASM_STRIP_SEARCH=0 / 1 forces the answer.
+void strip_search_prescan(int loc, const int* nd0, const int64_t* n2e_ptr, const int* n2e, const int* findrm, const int* colm,
+                          const int64_t* geokey, int n_nodes) {
+  int on = 0;
+  if (const char* e = getenv("CGASM_STRIP_SEARCH")) {
+    on = atoi(e) != 0;
+  } else if (loc == 4 && n_nodes > 0) {
+    const int samples = std::min(n_nodes, 2048);
+    std::unordered_set<uint64_t> classes;
+    int ok = 0;
+    for (int q = 0; q < samples; q++) {
+      const int r = (int)((int64_t)q * n_nodes / samples);
+      FastLink L;
+      if (n2e_ptr[r + 1] == n2e_ptr[r] || !fast_link(loc, nd0, n2e_ptr, n2e, findrm, colm, r, L, geokey) || L.m > 64) continue;
+      ok++;
+      classes.insert(StripMemo::hash_of(&L.tri[0][0], 3 * L.m) ^ (uint64_t)L.m << 56);
+    }
+    on = ok > 0 && (int)classes.size() <= std::max(48, ok / 8);
+  }
+  g_strip_search.store(on, std::memory_order_relaxed);
+  g_strip_search_states.store(4000000, std::memory_order_relaxed);  // ~2 s of search per build at most
 }
 
 }  // namespace
@@ -850,6 +1104,7 @@ void build_staged_plan_host(const Handle* h, const std::vector<int>& rows, int n
   const bool permuted = !perm.empty();
   const int loc = h->loc, dim = h->dim;
   const int64_t* gk = (h->geokey.empty() || getenv("CGASM_STRIP_NOKEY")) ? nullptr : h->geokey.data();
+  strip_search_prescan(loc, h->h_nd0.data(), h->n2e_ptr.data(), h->n2e.data(), h->h_findrm.data(), h->h_colm.data(), gk, h->n_nodes);
   constexpr int kTask = 128;  // blocks per task: fixed, so the layout does not depend on the thread count
   const int ntasks = (nblocks + kTask - 1) / kTask;
   out.nblocks = nblocks;
@@ -986,6 +1241,7 @@ extern "C" int cgasm_strip_plan_host(int loc, int n_nodes, int n_elements, const
   build_sparsity(n_nodes, n_elements, loc, nd0.data(), n2e_ptr, n2e, findrm, colm);
   // CGASM_STRIP_GENERIC=1: the O(m^2) reference implementation of the same greedy (equivalence tests)
   const bool generic = getenv("CGASM_STRIP_GENERIC") != nullptr;
+  strip_search_prescan(generic ? 0 : loc, nd0.data(), n2e_ptr.data(), n2e.data(), findrm.data(), colm.data(), nullptr, n_nodes);
   std::vector<int> len((size_t)n_nodes, 0);
 #pragma omp parallel
   {
