@@ -2,6 +2,8 @@
 #pragma once
 #include "cgasm_internal.h"
 
+#include <vector>
+
 namespace cgasm {
 
 constexpr int kBR = 128;  // rows (= threads) per gather block
@@ -48,6 +50,18 @@ struct GatherPlan {
   int4* d_row_meta = nullptr;        // [nblocks*kBR] {row node, first CSR entry, length | own slot << 16, own_local}
   int blk_nodes_max = 0;
   int nl = 0;                        // chunk stride of the staged records (one of kStagedNL)
+  // Occupancy classes (strip_staged.cuh staged_classes): on an unstructured mesh ONE crowded block sets nl and maxlen --
+  // and with them the shared memory of every block. The blocks that fit a smaller chunk stride and a shorter
+  // accumulator are launched as a class of their own with more blocks per SM.
+  std::vector<int> h_blk_nn, h_blk_ml;  // per block: distinct nodes touched, longest CSR row
+  struct StagedClass {
+    int bytes_per_node = 0, nacc = 0;  // the kernel family the split was made for
+    int nl_small = 0, ml_small = 0;    // 0: no split pays
+    int n_small = 0, n_large = 0;
+    int* d_small = nullptr;            // block ids
+    int* d_large = nullptr;
+  };
+  std::vector<StagedClass> classes;
   bool staged_ok = false;            // the mesh fits the staged encoding
   double* d_stage = nullptr;       // staging buffer (grown on demand)
   size_t stage_doubles = 0;

@@ -378,6 +378,8 @@ int strip_build(Handle* h) {
     CG_CUDA(cudaMemcpyAsync(P->d_row_meta, sp.row_meta.data(), sizeof(int) * sp.row_meta.size(), cudaMemcpyHostToDevice, h->stream));
     CG_CUDA(cudaStreamSynchronize(h->stream));  // the host vectors go out of scope
     P->nl = sp.nl;
+    P->h_blk_nn = std::move(sp.blk_nn);
+    P->h_blk_ml = std::move(sp.blk_ml);
     P->staged_ok = true;
   }
   if (!strip_staged_ok(h, true) || !strip_staged_ok(h, false)) return strip_build_global(h);
@@ -385,6 +387,13 @@ int strip_build(Handle* h) {
 }
 
 void strip_free(GatherPlan* P) {
+  for (GatherPlan::StagedClass& c : P->classes) {
+    if (c.d_small) cudaFree(c.d_small);
+    if (c.d_large) cudaFree(c.d_large);
+  }
+  P->classes.clear();
+  P->h_blk_nn.clear();
+  P->h_blk_ml.clear();
   if (P->d_strip_ptr) cudaFree(P->d_strip_ptr);
   if (P->d_strip) cudaFree(P->d_strip);
   if (P->d_strip_local_ptr) cudaFree(P->d_strip_local_ptr);

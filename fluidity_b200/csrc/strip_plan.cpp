@@ -1200,6 +1200,17 @@ void build_staged_plan_host(const Handle* h, const std::vector<int>& rows, int n
   }
   for (int b = 0; b < nblocks; b++) out.ptr[(size_t)b + 1] = out.ptr[b] + (long long)block_ldeg[b] * kBR;
   out.total_real = total_real;
+  out.blk_nn = block_nn;
+  out.blk_ml.assign((size_t)nblocks, 0);
+#pragma omp parallel for schedule(static)
+  for (int b = 0; b < nblocks; b++) {
+    int ml = 0;
+    for (int t = 0; t < kBR; t++) {
+      const int r = rows[(size_t)b * kBR + t];
+      if (r >= 0) ml = std::max(ml, h->h_findrm[r + 1] - h->h_findrm[r]);
+    }
+    out.blk_ml[b] = ml;
+  }
   out.blk_nodes_max = 0;
   for (int b = 0; b < nblocks; b++) out.blk_nodes_max = std::max(out.blk_nodes_max, block_nn[b]);
   out.nl = 0;

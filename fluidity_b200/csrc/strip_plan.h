@@ -42,6 +42,7 @@ constexpr int kStagedTailRows = 16;  // rows of padding behind the last block: t
 struct StagedPlanHost {
   int nblocks = 0;
   int blk_nodes_max = 0, nl = 0;
+  std::vector<int> blk_nn, blk_ml;     // per block: distinct nodes touched, longest CSR row (occupancy classes)
   bool ok = false;                     // false: the mesh does not fit the encoding (use the per-entry-fetch kernels)
   std::vector<long long> ptr;          // [nblocks+1] first entry of a block; degrees padded to a multiple of dim
   int task_blocks = 0;                 // blocks per chunk of `ent`

@@ -300,7 +300,7 @@ bool strip_staged_ok(const Handle* h, bool momentum) {
 template <int DIM>
 static int staged_momentum_dim(Handle* h, const MomentumArgs& A) {
   GatherPlan* P = h->gather;
-  const size_t smem = staged_smem(P, true, false);
+  size_t smem = staged_smem(P, true, false);
   const StripConsts c = consts_momentum(h, A);
   StagedView v = staged_view(h);
   const bool fullv = strip_full_tensor(A.o.have_viscosity, A.o.viscosity_shape);
@@ -332,6 +332,20 @@ static int staged_momentum_dim(Handle* h, const MomentumArgs& A) {
   if (split) {
     v.blocks = ib;
     grid = nb;
+  } else if (const GatherPlan::StagedClass* cls = staged_classes(h, 88, 1)) {
+    // the blocks that fit a smaller chunk stride and accumulator first, at more blocks per SM; then the crowded rest
+    const StagedView whole = v;
+    const size_t smem_whole = smem;
+    v.blocks = cls->d_small;
+    v.maxlen = cls->ml_small;
+    v.acc_bytes = (int)staged_acc_bytes_of(cls->ml_small, 1);
+    grid = cls->n_small;
+    smem = (size_t)v.acc_bytes + (size_t)cls->nl_small * 88 + kBR * 16;
+    if (grid > 0) CGASM_FOR_NL_OF(cls->nl_small, LAUNCH_NL);
+    v = whole;
+    smem = smem_whole;
+    v.blocks = cls->d_large;
+    grid = cls->n_large;
   }
   if (grid > 0) CGASM_FOR_NL(LAUNCH_NL);
 #undef LAUNCH_NL
@@ -348,7 +362,7 @@ template <int DIM>
 static int staged_advdiff_dim(Handle* h, const AdvDiffArgs& A) {
   GatherPlan* P = h->gather;
   const bool abs = A.o.have_absorption || A.o.have_source;
-  const size_t smem = staged_smem(P, false, abs);
+  size_t smem = staged_smem(P, false, abs);
   const StripConsts c = consts_advdiff(h, A);
   StagedView v = staged_view(h);
   const bool fullv = strip_full_tensor(A.o.have_diffusivity, A.o.diffusivity_shape);
@@ -383,6 +397,19 @@ static int staged_advdiff_dim(Handle* h, const AdvDiffArgs& A) {
   if (split) {
     v.blocks = ib;
     grid = nb;
+  } else if (const GatherPlan::StagedClass* cls = staged_classes(h, abs ? 80 : 64, 1)) {
+    const StagedView whole = v;
+    const size_t smem_whole = smem;
+    v.blocks = cls->d_small;
+    v.maxlen = cls->ml_small;
+    v.acc_bytes = (int)staged_acc_bytes_of(cls->ml_small, 1);
+    grid = cls->n_small;
+    smem = (size_t)v.acc_bytes + (size_t)cls->nl_small * (abs ? 80 : 64) + kBR * 16;
+    if (grid > 0) CGASM_FOR_NL_OF(cls->nl_small, LAUNCH_NL);
+    v = whole;
+    smem = smem_whole;
+    v.blocks = cls->d_large;
+    grid = cls->n_large;
   }
   if (grid > 0) CGASM_FOR_NL(LAUNCH_NL);
 #undef LAUNCH_NL

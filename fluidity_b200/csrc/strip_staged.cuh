@@ -16,6 +16,7 @@ struct StagedView {
   const int* __restrict__ blocks;         // the row blocks this launch works on (nullptr: all, in order)
   const int4* __restrict__ row_meta;      // {row node, first CSR entry, length | own slot << 16, own_local}
   int nblocks, ahead;                     // blocks in the plan; how far ahead a block pulls its successor's metadata into L2
+  int nl_stride;                          // ints between the node lists of consecutive blocks (>= the kernel's NL)
   int maxlen, lpr_shift;
   int acc_bytes;  // bytes of the accumulator in front of the staged records (multiple of 16)
 };
@@ -122,7 +123,7 @@ struct BlockIds {
 
 template <int NL>
 __device__ __forceinline__ void issue_block_ids(const StagedView& P, int b, int t, BlockIds<NL>& ids) {
-  const int* p = P.blk_nodes + (size_t)b * NL + (t >> 1);  // fixed stride: no pointer load in front of the id loads
+  const int* p = P.blk_nodes + (size_t)b * P.nl_stride + (t >> 1);  // no pointer load in front of the id loads
 #pragma unroll
   for (int v = 0; v < BlockIds<NL>::PER; v++) ids.node[v] = ldg_nc_s32(p + v * (kBR / 2));
 }
@@ -146,7 +147,7 @@ __device__ __forceinline__ void prefetch_next_block(const StagedView& P, int b, 
   const int nb = b + P.ahead;
   if (nb >= P.nblocks) return;
   if (t < 16) prefetch_l2(P.row_meta + (size_t)nb * kBR + t * 8);                      // 128 rows x 16 bytes
-  else if (t < 16 + NL / 32) prefetch_l2(P.blk_nodes + (size_t)nb * NL + (t - 16) * 32);  // NL ids
+  else if (t < 16 + NL / 32) prefetch_l2(P.blk_nodes + (size_t)nb * P.nl_stride + (t - 16) * 32);  // NL ids
   else if (t == 16 + NL / 32) prefetch_l2(P.ptr + nb);
 }
 
@@ -186,9 +187,10 @@ __device__ __forceinline__ void write_rows_table(const double* __restrict__ acc,
   }
 }
 
-static inline size_t staged_acc_bytes(const GatherPlan* P, int nblocks_acc) {
-  return (sizeof(double) * (size_t)nblocks_acc * P->maxlen * kAS + 15) & ~(size_t)15;
+static inline size_t staged_acc_bytes_of(int maxlen, int nblocks_acc) {
+  return (sizeof(double) * (size_t)nblocks_acc * maxlen * kAS + 15) & ~(size_t)15;
 }
+static inline size_t staged_acc_bytes(const GatherPlan* P, int nblocks_acc) { return staged_acc_bytes_of(P->maxlen, nblocks_acc); }
 
 static inline StagedView staged_view(const Handle* h, int nblocks_acc = 1) {
   const GatherPlan* P = h->gather;
@@ -202,6 +204,7 @@ static inline StagedView staged_view(const Handle* h, int nblocks_acc = 1) {
   v.blocks = nullptr;
   v.row_meta = P->d_row_meta;
   v.nblocks = P->nblocks;
+  v.nl_stride = P->nl;
   v.ahead = 4 * 148;  // about the number of blocks resident on the chip
   v.maxlen = P->maxlen;
   int sh = 0;
@@ -211,10 +214,71 @@ static inline StagedView staged_view(const Handle* h, int nblocks_acc = 1) {
   return v;
 }
 
+// Occupancy classes of a kernel family (bytes of staged records per node, accumulator columns per thread): nullptr if the
+// whole plan already runs at the blocks per SM a smaller class would reach, or if too few blocks would gain. The small
+// class keeps the plan's node lists (stride nl) and entries -- local indices do not depend on the chunk stride -- and
+// only needs nl_small >= its blocks' node counts and ml_small >= their longest rows.
+static inline const GatherPlan::StagedClass* staged_classes(Handle* h, int bytes_per_node, int nacc) {
+  GatherPlan* P = h->gather;
+  if (P->h_blk_nn.empty() || getenv("CGASM_STRIP_NOCLASSES")) return nullptr;
+  for (const GatherPlan::StagedClass& c : P->classes)
+    if (c.bytes_per_node == bytes_per_node && c.nacc == nacc) return c.nl_small ? &c : nullptr;
+  GatherPlan::StagedClass c;
+  c.bytes_per_node = bytes_per_node;
+  c.nacc = nacc;
+  const size_t sm_bytes = 227 * 1024, reserved = 1024, table = kBR * 16;
+  auto per_sm = [&](int nl, int ml) {
+    const size_t b = ((sizeof(double) * (size_t)nacc * ml * kAS + 15) & ~(size_t)15) + (size_t)nl * bytes_per_node + table + reserved;
+    return (int)std::min<size_t>(4, sm_bytes / b);  // the kernels are built for at most four blocks per SM
+  };
+  const int now = per_sm(P->nl, P->maxlen);
+  int best_cover = 0;
+  for (int nl : kStagedNL) {
+    if (nl > P->nl) break;
+    for (int k = now + 1; k <= 4; k++) {
+      const long long room = (long long)(sm_bytes / k) - (long long)reserved - (long long)table - (long long)nl * bytes_per_node;
+      const int ml = (int)std::min<long long>(P->maxlen, room / (long long)(sizeof(double) * nacc * kAS));
+      if (ml < 4 || (nl == P->nl && ml == P->maxlen)) continue;
+      int cover = 0;
+      for (int b = 0; b < P->nblocks; b++) cover += P->h_blk_nn[b] <= nl && P->h_blk_ml[b] <= ml;
+      // weigh a class by the blocks it holds times the residency it buys
+      const int score = (int)((long long)cover * (k - now) / k);
+      if (2 * cover >= P->nblocks && score > best_cover) {
+        best_cover = score;
+        c.nl_small = nl;
+        c.ml_small = ml;
+      }
+    }
+  }
+  if (c.nl_small) {
+    std::vector<int> small, large;
+    for (int b = 0; b < P->nblocks; b++)
+      (P->h_blk_nn[b] <= c.nl_small && P->h_blk_ml[b] <= c.ml_small ? small : large).push_back(b);
+    c.n_small = (int)small.size();
+    c.n_large = (int)large.size();
+    if (cudaMalloc(&c.d_small, sizeof(int) * std::max<size_t>(1, small.size())) != cudaSuccess ||
+        cudaMalloc(&c.d_large, sizeof(int) * std::max<size_t>(1, large.size())) != cudaSuccess ||
+        cudaMemcpy(c.d_small, small.data(), sizeof(int) * small.size(), cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemcpy(c.d_large, large.data(), sizeof(int) * large.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+      cudaGetLastError();
+      if (c.d_small) cudaFree(c.d_small);
+      if (c.d_large) cudaFree(c.d_large);
+      c.d_small = c.d_large = nullptr;
+      c.nl_small = 0;
+    }
+    if (getenv("CGASM_VERBOSE"))
+      fprintf(stderr, "cgasm: occupancy class (%d B/node, %d accumulators): %d of %d blocks at nl %d / maxlen %d (%d blocks per SM, plan: nl %d / maxlen %d, %d per SM)\n",
+              bytes_per_node, nacc, c.n_small, P->nblocks, c.nl_small, c.ml_small, per_sm(c.nl_small, c.ml_small), P->nl, P->maxlen, now);
+  }
+  P->classes.push_back(c);
+  return P->classes.back().nl_small ? &P->classes.back() : nullptr;
+}
+
 // the chunk strides of 2-D meshes stay small (a 128-row brick of a triangulation touches ~200 nodes)
-#define CGASM_FOR_NL(X)                                        \
+#define CGASM_FOR_NL(X) CGASM_FOR_NL_OF(P->nl, X)
+#define CGASM_FOR_NL_OF(NLV, X)                                \
   do {                                                         \
-    switch (P->nl) {                                           \
+    switch (NLV) {                                             \
       case 128: X(128); break;                                 \
       case 256: X(256); break;                                 \
       case 384: X(384); break;                                 \
