@@ -397,7 +397,7 @@ def start_delaunay(points):
     return proc, base, time.perf_counter()
 
 
-def example_configs(device, cells3, cells2, reps=5, delaunay=None):
+def example_configs(device, cells3, cells2, reps=5, delaunay=None, peak_gbs=None):
     """Kernel time of the two element loops for the option sets of BASELINE.json configs[0..3] (their meshes are not
     in the reference tree: option sets on synthetic meshes of the same dimension), plus the S3 option set on a randomly
     renumbered mesh. STRIP variant, CUDA events on the handle's stream."""
@@ -474,6 +474,14 @@ def example_configs(device, cells3, cells2, reps=5, delaunay=None):
                "gel_s": mesh.n_elements / ((mm + aa) * 1e-3) / 1e9, "kernel_launches_per_step": launches,
                "momentum_path": paths[0], "tracer_path": paths[1],
                "library_setup_s": setup}
+        if peak_gbs:
+            # the same roofline as the headline's: algorithmic bytes of this mesh (synthetic.algorithmic_bytes) / kernel time / peak
+            bm = syn.algorithmic_bytes(dim, mesh.n_nodes, mesh.n_elements, asm.nnz, "momentum")
+            bt = syn.algorithmic_bytes(dim, mesh.n_nodes, mesh.n_elements, asm.nnz, "tracer")
+            rec["roofline_frac"] = {"momentum": bm * mesh.n_elements / (mm * 1e-3) / 1e9 / peak_gbs,
+                                    "tracer": bt * mesh.n_elements / (aa * 1e-3) / 1e9 / peak_gbs,
+                                    "both": (bm + bt) * mesh.n_elements / ((mm + aa) * 1e-3) / 1e9 / peak_gbs,
+                                    "algorithmic_bytes_per_element": [bm, bt]}
         if shuffle:
             nnz = asm.nnz
             rec.update({"nodes": mesh.n_nodes, "nnz": int(nnz), "mean_row_length": nnz / mesh.n_nodes,
@@ -571,14 +579,24 @@ def run_graft(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    marks = None   # inside the timed region: CUDA events on the handle's stream around each of the two calls of a step
+
     def step_resident():
         if world > 1:
             asm.halo_update(halo_slots)
         if args.step == "fused":
             asm.momentum_advdiff_dev(om, oa)
-        else:
+        elif marks is None:
             asm.momentum_dev(om)
             asm.advdiff_dev(oa)
+        else:
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            e[0].record(stream)
+            asm.momentum_dev(om)
+            e[1].record(stream)
+            asm.advdiff_dev(oa)
+            e[2].record(stream)
+            marks.append(e)
 
     # ---- value: inputs resident in HBM ---------------------------------------------------
     sampler = ClockSampler(local_rank)
@@ -597,12 +615,18 @@ def run_graft(args):
     mom_ms, adv_ms = [], []
     if rank == 0:
         sampler.mark()
+    marks = [] if args.step == "separate" else None
     ev0.record(stream)
     for _ in range(args.steps):
         step_resident()
     ev1.record(stream)
     barrier()
     my_total_ms = ev0.elapsed_time(ev1)
+    in_region = None
+    if marks:
+        # the roofline's kernel times: average launch duration INSIDE the K timed steps (events only, no host wait)
+        in_region = (float(np.mean([e[0].elapsed_time(e[1]) for e in marks])), float(np.mean([e[1].elapsed_time(e[2]) for e in marks])))
+    marks = None
     launches = asm.launch_count() - l0
     clocks = sampler.stop() if rank == 0 else None
     # per-kernel device times (separate pass so the event queries do not perturb the timed region)
@@ -649,7 +673,12 @@ def run_graft(args):
         dist.all_reduce(tot_el, op=dist.ReduceOp.SUM)
         total_elements = float(tot_el.item())
     value = total_elements / (ms_per_step * 1e-3) / 1e6
-    m_ms, a_ms = float(np.mean(mom_ms)), float(np.mean(adv_ms))
+    # per-kernel times: from inside the timed region where the step is the two calls; else the separate pass (median:
+    # the first launch after an idle gap is an outlier that a mean of five does not absorb)
+    alone_ms = (float(np.median(mom_ms)), float(np.median(adv_ms)))
+    if rank == 0:
+        print("bench: kernels timed alone (ms): momentum %s  tracer %s" % (["%.3f" % x for x in mom_ms], ["%.3f" % x for x in adv_ms]), file=sys.stderr)
+    m_ms, a_ms = in_region if in_region else alone_ms
     per_rank = None
     if world > 1:
         mine = dict(rank=rank, step_ms=my_total_ms / args.steps, momentum_ms=m_ms, tracer_ms=a_ms, fused_ms=fused_ms, halo_ms=halo_ms,
@@ -762,7 +791,7 @@ def run_graft(args):
         cpu = cpu_baseline_block(args.cpu_cells)
     configs = None
     if world == 1 and not args.no_configs:
-        configs = example_configs(local_rank, 128, 2048, delaunay=delaunay)
+        configs = example_configs(local_rank, 128, 2048, delaunay=delaunay, peak_gbs=peak)
     elif delaunay is not None:
         delaunay[0].kill()
 
@@ -775,6 +804,9 @@ def run_graft(args):
         "host_peak_rss_gb_rank0": resource.getrusage(resource.RUSAGE_SELF).ru_maxrss / 1048576.0,
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         "step_flavour": args.step, "separate_kernels_ms_rank0": m_ms + a_ms, "fused_kernel_ms_rank0": fused_ms,
+        "kernel_ms_source": ("CUDA events on the handle's stream around each call inside the K timed steps (mean)" if in_region
+                             else "cgasm_last_kernel_ms of calls timed alone after the timed region (median)"),
+        "kernels_timed_alone_ms_rank0": list(alone_ms),
         "halo_update_ms_rank0": halo_ms, "halo_nodes_sent_rank0": n_sent, "halo_overlap": overlap,
         "multi_gpu_parity_max_rel_err": parity, "per_rank": per_rank, "configs": configs,
     }

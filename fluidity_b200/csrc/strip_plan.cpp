@@ -673,7 +673,7 @@ StripSearch g_search;
 void improve_strip(const MaskLink& M, const unsigned char* key, uint64_t hk, MaskSeq& best) {
   const int floor_n = M.m + 2;
   int target = (best.n - 1) / 3 * 3;
-  if (target < floor_n || M.m > 64 || M.m < 2) return;
+  if (target < floor_n || M.m > 64 || M.m < 2 || best.n > 250) return;  // (the state table keeps the push count in 8 bits)
   std::lock_guard<std::mutex> lock(g_search_mu);
   for (const SearchedStrip& it : g_searched)
     if (it.hash == hk && it.m == M.m && !memcmp(it.key.data(), key, (size_t)3 * M.m)) {
