@@ -167,34 +167,54 @@ __device__ __forceinline__ void at_quad(const Tables& t, const double (&f)[DIM +
 // have_diff false => NU_BAR_UNITY (:248-251). inverse() of the dim x dim diffusivity by cofactors.
 template <int DIM>
 __device__ __forceinline__ void small_inverse(const double (&A)[DIM * DIM], double (&B)[DIM * DIM]) {
+  // cofactors times ONE reciprocal of the determinant (the reference's inverse() divides entry by entry: the results
+  // differ in the last bit, inside the 1e-12 of the parity tests; nine divisions per quadrature point were a fifth of
+  // the stabilised element kernels' instructions)
   if constexpr (DIM == 2) {
-    const double det = A[0] * A[3] - A[2] * A[1];
-    B[0] = A[3] / det;
-    B[1] = -A[1] / det;
-    B[2] = -A[2] / det;
-    B[3] = A[0] / det;
+    const double rd = 1.0 / (A[0] * A[3] - A[2] * A[1]);
+    B[0] = A[3] * rd;
+    B[1] = -A[1] * rd;
+    B[2] = -A[2] * rd;
+    B[3] = A[0] * rd;
   } else {
 #define A_(i, j) A[(i) + 3 * (j)]
     const double c00 = A_(1, 1) * A_(2, 2) - A_(1, 2) * A_(2, 1);
     const double c01 = A_(1, 2) * A_(2, 0) - A_(1, 0) * A_(2, 2);
     const double c02 = A_(1, 0) * A_(2, 1) - A_(1, 1) * A_(2, 0);
-    const double det = A_(0, 0) * c00 + A_(0, 1) * c01 + A_(0, 2) * c02;
-    B[0 + 3 * 0] = c00 / det;
-    B[1 + 3 * 0] = c01 / det;
-    B[2 + 3 * 0] = c02 / det;
-    B[0 + 3 * 1] = (A_(0, 2) * A_(2, 1) - A_(0, 1) * A_(2, 2)) / det;
-    B[1 + 3 * 1] = (A_(0, 0) * A_(2, 2) - A_(0, 2) * A_(2, 0)) / det;
-    B[2 + 3 * 1] = (A_(0, 1) * A_(2, 0) - A_(0, 0) * A_(2, 1)) / det;
-    B[0 + 3 * 2] = (A_(0, 1) * A_(1, 2) - A_(0, 2) * A_(1, 1)) / det;
-    B[1 + 3 * 2] = (A_(0, 2) * A_(1, 0) - A_(0, 0) * A_(1, 2)) / det;
-    B[2 + 3 * 2] = (A_(0, 0) * A_(1, 1) - A_(0, 1) * A_(1, 0)) / det;
+    const double rd = 1.0 / (A_(0, 0) * c00 + A_(0, 1) * c01 + A_(0, 2) * c02);
+    B[0 + 3 * 0] = c00 * rd;
+    B[1 + 3 * 0] = c01 * rd;
+    B[2 + 3 * 0] = c02 * rd;
+    B[0 + 3 * 1] = (A_(0, 2) * A_(2, 1) - A_(0, 1) * A_(2, 2)) * rd;
+    B[1 + 3 * 1] = (A_(0, 0) * A_(2, 2) - A_(0, 2) * A_(2, 0)) * rd;
+    B[2 + 3 * 1] = (A_(0, 1) * A_(2, 0) - A_(0, 0) * A_(2, 1)) * rd;
+    B[0 + 3 * 2] = (A_(0, 1) * A_(1, 2) - A_(0, 2) * A_(1, 1)) * rd;
+    B[1 + 3 * 2] = (A_(0, 2) * A_(1, 0) - A_(0, 0) * A_(1, 2)) * rd;
+    B[2 + 3 * 2] = (A_(0, 0) * A_(1, 1) - A_(0, 1) * A_(1, 0)) * rd;
 #undef A_
   }
 }
 
+// JD = J . inverse(diff): constant over the element when the diffusivity is (P1: J is), so hoisted out of the
+// quadrature loop by Stabilisation::setup
+template <int DIM>
+__device__ __forceinline__ void j_inverse_diff(const double (&Jm)[DIM][DIM], const double (&diff)[DIM * DIM], double (&JD)[DIM][DIM]) {
+  double inv[DIM * DIM];
+  small_inverse<DIM>(diff, inv);
+#pragma unroll
+  for (int a = 0; a < DIM; a++)
+#pragma unroll
+    for (int k = 0; k < DIM; k++) {
+      double jd = 0.0;
+#pragma unroll
+      for (int b = 0; b < DIM; b++) jd += Jm[a][b] * inv[b + DIM * k];
+      JD[a][k] = jd;
+    }
+}
+
 template <int DIM>
 __device__ __forceinline__ double nu_bar_scaled(const double (&u)[DIM], const double (&Jm)[DIM][DIM], bool have_diff,
-                                                const double (&diff)[DIM * DIM], int scheme, double scale) {
+                                                const double (&JD)[DIM][DIM], int scheme, double scale) {
   const double tolerance = 1.0e-10, tanh_tolerance = 11.859499013855018;  // :50-51
   double norm_u = 0.0;
 #pragma unroll
@@ -213,25 +233,22 @@ __device__ __forceinline__ double nu_bar_scaled(const double (&u)[DIM], const do
 #pragma unroll
     for (int k = 0; k < DIM; k++) val += fabs(uJ[k]);
   } else {
-    double inv[DIM * DIM];
-    small_inverse<DIM>(diff, inv);
 #pragma unroll
     for (int k = 0; k < DIM; k++) {
       double p = 0.0;  // pe = 0.5 * u . (J . inverse(diff))
 #pragma unroll
-      for (int a = 0; a < DIM; a++) {
-        double jd = 0.0;
-#pragma unroll
-        for (int b = 0; b < DIM; b++) jd += Jm[a][b] * inv[b + DIM * k];
-        p += u[a] * jd;
-      }
+      for (int a = 0; a < DIM; a++) p += u[a] * JD[a][k];
       p *= 0.5;
       double xi;
       if (scheme == CGASM_NU_BAR_OPTIMAL) {
         if (fabs(p) < tolerance) xi = 0.0;
         else if (p > tanh_tolerance) xi = 1.0 - (1.0 / p);
         else if (p < -tanh_tolerance) xi = -1.0 - (1.0 / p);
-        else xi = (1.0 / tanh(p)) - (1.0 / p);
+        else {
+          // 1 / tanh(p) - 1 / p on one denominator: one division instead of two, the same cancellation for small p
+          const double th = tanh(p);
+          xi = (p - th) / (p * th);
+        }
       } else if (scheme == CGASM_NU_BAR_DOUBLY_ASYMPTOTIC) {
         if (fabs(p) <= 3.0) xi = p / 3.0;
         else xi = p > 0.0 ? 1.0 : -1.0;
@@ -259,22 +276,39 @@ struct Stabilisation {
     else return t.N[i * NGI + g];
   }
   // ug: u at quadrature points; diffq(g): diffusivity at g (dim x dim, column-major) if have_diff
+  // diff_const: the diffusivity does not vary over the element (a constant field): J . inverse(diff) once per element
   template <class DiffAt>
   __device__ __forceinline__ void setup(const Tables& t, const Geom<DIM>& G, const double (&ug)[NGI][DIM], bool have_diff,
-                                        DiffAt diff_at, int scheme, double scale) {
+                                        bool diff_const, DiffAt diff_at, int scheme, double scale) {
     if constexpr (STAB != 0) {
       double Jm[DIM][DIM];  // J(:,:,gi) = transpose(J_local_T), Transform_elements.F90:878-882
 #pragma unroll
       for (int a = 0; a < DIM; a++)
 #pragma unroll
         for (int k = 0; k < DIM; k++) Jm[a][k] = G.JT[k][a];
+      const bool need_inv = have_diff && scheme != CGASM_NU_BAR_UNITY;
+      double JD[DIM][DIM];
 #pragma unroll
-      for (int g = 0; g < NGI; g++) {
+      for (int a = 0; a < DIM; a++)
+#pragma unroll
+        for (int k = 0; k < DIM; k++) JD[a][k] = 0.0;
+      if (need_inv && diff_const) {
         double dq[DIM * DIM];
 #pragma unroll
         for (int ab = 0; ab < DIM * DIM; ab++) dq[ab] = 0.0;
-        if (have_diff) diff_at(g, dq);
-        const double nb = nu_bar_scaled<DIM>(ug[g], Jm, have_diff, dq, scheme, scale);
+        diff_at(0, dq);
+        j_inverse_diff<DIM>(Jm, dq, JD);
+      }
+#pragma unroll
+      for (int g = 0; g < NGI; g++) {
+        if (need_inv && !diff_const) {
+          double dq[DIM * DIM];
+#pragma unroll
+          for (int ab = 0; ab < DIM * DIM; ab++) dq[ab] = 0.0;
+          diff_at(g, dq);
+          j_inverse_diff<DIM>(Jm, dq, JD);
+        }
+        const double nb = nu_bar_scaled<DIM>(ug[g], Jm, have_diff, JD, scheme, scale);
 #pragma unroll
         for (int i = 0; i < LOC; i++) {
           double s = 0.0;
@@ -383,7 +417,7 @@ __device__ __forceinline__ void momentum_element(const MomentumArgs& A, const in
         dq[a + DIM * a] = vv;
       }
     };
-    ST.setup(t, G, ug, o.have_viscosity != 0, diff_at, o.nu_bar_scheme, o.nu_bar_scale);
+    ST.setup(t, G, ug, o.have_viscosity != 0, A.viscosity.stride == 0, diff_at, o.nu_bar_scheme, o.nu_bar_scale);
   }
 
   // v[i] accumulates the vector such that (A + K)_ij = v[i] . gradN_j
@@ -754,7 +788,7 @@ __device__ __forceinline__ void advdiff_element(const AdvDiffArgs& P, const int4
         dq[ab] = vv;
       }
     };
-    ST.setup(t, G, uq, o.have_diffusivity != 0, diff_at, o.nu_bar_scheme, o.nu_bar_scale);
+    ST.setup(t, G, uq, o.have_diffusivity != 0, P.diffusivity.stride == 0, diff_at, o.nu_bar_scheme, o.nu_bar_scale);
   }
 
   // Mass (:867-941): M_ij = |detJ| sum_g N_ig N_jg w_g ; lumped -> |detJ| sum_g N_ig w_g

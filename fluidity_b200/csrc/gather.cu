@@ -370,8 +370,11 @@ __device__ __forceinline__ void store_rec(double* dst, const double (&v)[RS]) {
 
 // ---- pass A ----------------------------------------------------------------------------------------
 // momentum, generic options: NB = 1 (no absorption) or DIM; NV = DIM + MLC
+#ifndef CGASM_SU_MINB
+#define CGASM_SU_MINB 1
+#endif
 template <int DIM, bool LABS, int NB, int MLC, int STAB>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, STAB != 0 ? CGASM_SU_MINB : 1)
 gather_momentum_stage_kernel(const MomentumArgs A, double* __restrict__ stage) {
   constexpr int LOC = DIM + 1;
   using R_ = Rec<LOC, NB, DIM + MLC>;
@@ -464,7 +467,7 @@ __global__ void __launch_bounds__(128) gather_ct_stage_kernel(const MomentumArgs
 }
 
 template <int DIM, int STAB>
-__global__ void __launch_bounds__(128) gather_advdiff_stage_kernel(const AdvDiffArgs A, double* __restrict__ stage) {
+__global__ void __launch_bounds__(128, STAB != 0 ? CGASM_SU_MINB : 1) gather_advdiff_stage_kernel(const AdvDiffArgs A, double* __restrict__ stage) {
   constexpr int LOC = DIM + 1;
   using R_ = Rec<LOC, 1, 1>;
   const int e = blockIdx.x * blockDim.x + threadIdx.x;

@@ -13,4 +13,5 @@ oa = abi.common_advdiff_opts(stabilisation_scheme=abi.STAB_STREAMLINE_UPWIND)
 for i in range(3):
     asm.momentum_dev(om); m = asm.last_kernel_ms()
     asm.advdiff_dev(oa); a = asm.last_kernel_ms()
-print("su", n, m, a, asm.last_path())
+import os
+print("%-24s su %d  momentum %.4f  tracer %.4f ms  paths %s" % (os.path.basename(os.environ.get("CGASM_LIB", "libcgasm.so")), n, m, a, asm.last_path()))
