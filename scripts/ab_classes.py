@@ -1,11 +1,12 @@
 """A/B on one GPU of the occupancy classes of the staged STRIP kernels on an unstructured (Delaunay) mesh: the same
-handle with CGASM_STRIP_NOCLASSES set and unset. usage: python scripts/ab_classes.py [points]"""
+handle with CGASM_STRIP_NOCLASSES set and unset. usage: python scripts/ab_classes.py [points [repetitions]]"""
 import os, sys, statistics, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from fluidity_b200 import synthetic as syn, _abi as abi, cgasm, tables
 
 npts = int(sys.argv[1]) if len(sys.argv) > 1 else 400000
+reps = int(sys.argv[2]) if len(sys.argv) > 2 else 8   # 3 under compute-sanitizer
 t0 = time.perf_counter()
 mesh = syn.delaunay_mesh(npts)
 print("Delaunay mesh: %d nodes, %d tets, %.1f s" % (mesh.n_nodes, mesh.n_elements, time.perf_counter() - t0), flush=True)
@@ -26,10 +27,10 @@ for rep in range(2):
             os.environ.pop("CGASM_STRIP_NOCLASSES", None)
         for name, (om, oa) in sets.items():
             mom, adv = [], []
-            for i in range(8):
+            for i in range(reps):
                 asm.momentum_dev(om); m = asm.last_kernel_ms()
                 asm.advdiff_dev(oa); a = asm.last_kernel_ms()
-                if i >= 2:
+                if i >= min(2, reps - 1):
                     mom.append(m); adv.append(a)
             got = asm.momentum_fetch(); ga = asm.advdiff_fetch()
             chk = (float(np.abs(got["big_m"]).sum()), float(np.abs(got["rhs"]).sum()), float(np.abs(ga["matrix"]).sum()), float(np.abs(ga["rhs"]).sum()))

@@ -227,6 +227,35 @@ def test_delaunay_unstructured_mesh(orc, scatter, dim):
         check_momentum(asm.momentum(o), orc.assemble_momentum(mesh, fs, o, findrm, colm), findrm, dim)
 
 
+def test_occupancy_classes_change_where_a_block_runs_not_what_it_computes(orc, monkeypatch):
+    """On an unstructured mesh the most crowded row block sets the chunk stride and the accumulator length of the staged
+    STRIP kernels; the blocks that fit smaller ones are launched as a class of their own at more blocks per SM
+    (strip_staged.cuh, staged_classes). Same node lists, same entries: the results are bitwise those of the single launch
+    (CGASM_STRIP_NOCLASSES), and they match the oracle."""
+    mesh = syn.delaunay_mesh(30000, dim=3, seed=5)
+    fs = syn.standard_fields(mesh)
+    asm = make_asm(mesh, fs, abi.SCATTER_STRIP)
+    findrm, colm, _ = asm.get_sparsity()
+    om, oa = abi.common_momentum_opts(), abi.common_advdiff_opts(have_absorption=1, have_source=1)
+    monkeypatch.setenv("CGASM_STRIP_NOCLASSES", "1")
+    l0 = asm.launch_count()
+    m_one, a_one = asm.momentum(om), asm.advdiff(oa)
+    one = asm.launch_count() - l0
+    monkeypatch.delenv("CGASM_STRIP_NOCLASSES")
+    l0 = asm.launch_count()
+    m_cls, a_cls = asm.momentum(om), asm.advdiff(oa)
+    cls = asm.launch_count() - l0
+    assert asm.last_path() == ("strip_staged", "strip_staged")
+    assert cls > one, "this mesh is meant to split into occupancy classes (plan: %s)" % asm.plan_stats()
+    for k in ("big_m", "rhs", "masslump"):
+        assert np.array_equal(m_one[k], m_cls[k])
+    for k in ("matrix", "rhs"):
+        assert np.array_equal(a_one[k], a_cls[k])
+    check_momentum(m_cls, orc.assemble_momentum(mesh, fs, om, findrm, colm), findrm, 3)
+    ref = orc.assemble_advdiff(mesh, fs, oa, findrm, colm)
+    assert rel_err(a_cls["matrix"], ref["matrix"]) < TOL and rel_err(a_cls["rhs"], ref["rhs"]) < TOL
+
+
 # ---- golden vectors from the reference's own Python element machinery ------------------------------
 @pytest.mark.parametrize("name", ["cube.1", "cube-parallel", "square-cavity-2d", "prectangle_0"])
 def test_element_matrices_match_reference_python(name):
