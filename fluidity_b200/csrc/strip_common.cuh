@@ -10,6 +10,14 @@ namespace cgasm {
 #define CGASM_V_SEPARATE_SUMS 0
 #endif
 constexpr bool kStripSeparateSums = CGASM_V_SEPARATE_SUMS != 0;  // A/B switch (scripts/ab_kernels.py)
+// Carried cross product (window_geom_carry): measured on the B200 (profiles/r2_ab_carry.txt) -1.1 ... -3.9 % for the tracer
+// kernel (118 registers: room for the three carried values), +1.3 ... +3 % for the momentum kernel (at its 128-register
+// ceiling): on for the tracer, off for the momentum loop. CGASM_V_CARRY=0/1 forces both (A/B builds).
+#ifdef CGASM_V_CARRY
+constexpr bool kStripCarryMomentum = CGASM_V_CARRY != 0, kStripCarryTracer = CGASM_V_CARRY != 0;
+#else
+constexpr bool kStripCarryMomentum = false, kStripCarryTracer = true;
+#endif
 
 struct StripConsts {  // passed by value: operands are read straight from the constant bank
   // Option switches are folded into these numbers on the host (consts_momentum / consts_advdiff): a term
@@ -152,6 +160,40 @@ __device__ __forceinline__ void window_geom(const double (&X)[N][DIM], WindowGeo
   }
 }
 
+// Carried flavour (3-D): the cofactor of the window's OLDEST node, c[0] = e_mid x e_new, is next step's c[2] (the window
+// slides by one node), operand for operand -- so every step computes only c[0] (also a non-computing one: its successor
+// needs it) and a computing step one more cross product instead of three. Bitwise the same numbers.
+template <int N, int QC>
+__device__ __forceinline__ void window_cross_new(const double (&X)[N][3], double (&cn)[3]) {
+  constexpr int DIM = 3;
+  const double(&p)[3] = X[WQ(1)];
+  const double(&q)[3] = X[WQ(2)];
+  cn[0] = p[1] * q[2] - p[2] * q[1];
+  cn[1] = p[2] * q[0] - p[0] * q[2];
+  cn[2] = p[0] * q[1] - p[1] * q[0];
+}
+template <int N, int QC>
+__device__ __forceinline__ void window_geom_carry(const double (&X)[N][3], const double (&carry)[3], const double (&cn)[3],
+                                                  WindowGeom<3>& g) {
+  constexpr int DIM = 3;
+  const double(&p)[3] = X[WQ(2)];
+  const double(&q)[3] = X[WQ(0)];
+  g.c[1][0] = p[1] * q[2] - p[2] * q[1];
+  g.c[1][1] = p[2] * q[0] - p[0] * q[2];
+  g.c[1][2] = p[0] * q[1] - p[1] * q[0];
+  double det = 0.0;
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+    g.c[0][a] = cn[a];
+    g.c[2][a] = carry[a];
+    det = fma(X[WQ(0)][a], cn[a], det);
+  }
+  g.det = det;
+  g.rd = rcp_nr(det);
+#pragma unroll
+  for (int a = 0; a < 3; a++) g.sc[a] = (g.c[0][a] + g.c[1][a]) + g.c[2][a];
+}
+
 template <int DIM, int N, int QC, bool FULLV>
 __device__ __forceinline__ void mom_terms(MomState<DIM, N>& s, const StripConsts& k_, const WindowGeom<DIM>& g) {
   // density-weighted mass row M_0k = |J| sum_l Q_0kl rho_l (without |J|): M_00 = Qa rho_0 + Qaab S,
@@ -258,6 +300,7 @@ struct AdvState {
   int meta[N];
   double X0[DIM], cU0[DIM], T0;  // cU0 = Pd * nu(row node): adv_row_const
   double a0, c0, rhs;
+  double cc[DIM];  // carried cross product (kStripCarry)
 };
 
 // the row-constant part of the advecting-velocity moment: (Pd - Po) nu_0 + Po nu_0

@@ -56,7 +56,7 @@ __device__ __forceinline__ void stage_nodes(const BlockIds<NL>& ids, int t, unsi
 // (slot accumulator and rhs -= entry * oldu of the evicted node), request the records of entry j and
 // plan entry j + 3, then install and compute entry j.
 template <int DIM, int QC, int NL, bool FULLV>
-__device__ __forceinline__ void smom_step(MomState<DIM, DIM>& s, double (&rh)[DIM], const StripConsts& k_,
+__device__ __forceinline__ void smom_step(MomState<DIM, DIM>& s, double (&rh)[DIM], double (&cc)[DIM], const StripConsts& k_,
                                           const unsigned* __restrict__ p, unsigned (&pq)[DIM], unsigned acc_sa, unsigned nsa) {
   // plan queue: slot QC holds entry j, refilled with entry j + DIM (static indices: the unroll factor is the queue
   // length, so nothing is moved between registers at the loop's back edge)
@@ -83,15 +83,27 @@ __device__ __forceinline__ void smom_step(MomState<DIM, DIM>& s, double (&rh)[DI
   }
 #pragma unroll
   for (int a = 0; a < DIM; a++) s.X[QC][a] -= s.X0[a];
-  if (en & kStagedCompute) mom_compute<DIM, DIM, QC, FULLV>(s, k_);
+  if constexpr (kStripCarryMomentum && DIM == 3) {
+    double cn[3];
+    window_cross_new<DIM, QC>(s.X, cn);
+    if (en & kStagedCompute) {
+      WindowGeom<3> g;
+      window_geom_carry<DIM, QC>(s.X, cc, cn, g);
+      mom_terms<DIM, DIM, QC, FULLV>(s, k_, g);
+    }
+#pragma unroll
+    for (int a = 0; a < 3; a++) cc[a] = cn[a];
+  } else {
+    if (en & kStagedCompute) mom_compute<DIM, DIM, QC, FULLV>(s, k_);
+  }
 }
 
 template <int DIM, int Q, int NL, bool FULLV>
 struct SMomUnroll {
   template <class... Args>
-  static __device__ __forceinline__ void run(MomState<DIM, DIM>& s, double (&rh)[DIM], const StripConsts& k_, Args&&... args) {
-    smom_step<DIM, Q, NL, FULLV>(s, rh, k_, args...);
-    if constexpr (Q + 1 < DIM) SMomUnroll<DIM, Q + 1, NL, FULLV>::run(s, rh, k_, args...);
+  static __device__ __forceinline__ void run(MomState<DIM, DIM>& s, double (&rh)[DIM], double (&cc)[DIM], const StripConsts& k_, Args&&... args) {
+    smom_step<DIM, Q, NL, FULLV>(s, rh, cc, k_, args...);
+    if constexpr (Q + 1 < DIM) SMomUnroll<DIM, Q + 1, NL, FULLV>::run(s, rh, cc, k_, args...);
   }
 };
 
@@ -133,9 +145,9 @@ staged_momentum_kernel(const StripConsts k_, const StagedView P, const double4* 
   load_rec<DIM, NL>(nsa + own_off, 1, s.U0, s.rho0);
   mom_row_consts<DIM, DIM>(s, k_);
   s.a0 = s.msum = s.nbsum = 0.0;
-  double rh[DIM];
+  double rh[DIM], cc[DIM];
 #pragma unroll
-  for (int d = 0; d < DIM; d++) rh[d] = 0.0;
+  for (int d = 0; d < DIM; d++) rh[d] = cc[d] = 0.0;
 #pragma unroll
   for (int q = 0; q < DIM; q++) {
 #pragma unroll
@@ -143,7 +155,7 @@ staged_momentum_kernel(const StripConsts k_, const StagedView P, const double4* 
     s.R[q] = s.B[q] = s.A[q] = 0.0;
     s.meta[q] = (int)pad;
   }
-  for (int j0 = 0; j0 < deg; j0 += DIM, p += DIM * kBR) SMomUnroll<DIM, 0, NL, FULLV>::run(s, rh, k_, p, pq, acc_sa, nsa);
+  for (int j0 = 0; j0 < deg; j0 += DIM, p += DIM * kBR) SMomUnroll<DIM, 0, NL, FULLV>::run(s, rh, cc, k_, p, pq, acc_sa, nsa);
   // drain the FIFO, then the diagonal (the row's own node never leaves)
 #pragma unroll
   for (int q = 0; q < DIM; q++) {
@@ -198,9 +210,21 @@ __device__ __forceinline__ void sadv_step(AdvState<DIM, DIM>& s, double (&sg)[AB
   prefetch_l2(p + (QC + kPlanAhead) * kBR);
 #pragma unroll
   for (int a = 0; a < DIM; a++) s.X[QC][a] -= s.X0[a];
-  if (en & kStagedCompute) {
-    if constexpr (ABS) adv_compute_abs<DIM, DIM, QC, FULLV>(s, sg, sq, ox, k_);
-    else adv_compute<DIM, DIM, QC, FULLV>(s, k_);
+  if constexpr (kStripCarryTracer && DIM == 3 && !ABS) {
+    double cn[3];
+    window_cross_new<DIM, QC>(s.X, cn);
+    if (en & kStagedCompute) {
+      WindowGeom<3> g;
+      window_geom_carry<DIM, QC>(s.X, s.cc, cn, g);
+      adv_terms<DIM, DIM, QC, FULLV>(k_, g, s.U, s.cU0, s.A, s.C, s.a0, s.c0);
+    }
+#pragma unroll
+    for (int a = 0; a < 3; a++) s.cc[a] = cn[a];
+  } else {
+    if (en & kStagedCompute) {
+      if constexpr (ABS) adv_compute_abs<DIM, DIM, QC, FULLV>(s, sg, sq, ox, k_);
+      else adv_compute<DIM, DIM, QC, FULLV>(s, k_);
+    }
   }
 }
 
@@ -267,6 +291,7 @@ staged_advdiff_kernel(const StripConsts k_, const StagedView P, const double4* _
 #pragma unroll
     for (int a = 0; a < DIM; a++) s.X[q][a] = s.U[q][a] = 0.0;
     s.T[q] = s.A[q] = s.C[q] = 0.0;
+    s.cc[q] = 0.0;
     s.meta[q] = (int)pad;
     if constexpr (ABS) sg[q] = sq[q] = 0.0;
   }
