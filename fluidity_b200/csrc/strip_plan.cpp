@@ -1097,6 +1097,89 @@ struct NodeIndexMap {
     return &val[p];
   }
 };
+// Bank groups for the staged node records of one row block. groups: 8 local node indices per (quarter-warp, step) read,
+// -1 padded, distinct; a read costs max over bank groups of the nodes it touches there. Starts from index mod 8 (the
+// geometric order), then moves single nodes to the bank group that lowers the summed cost most, a few sweeps, within
+// the capacity of the chunk stride the block needs anyway. Returns false (leave the order alone) when the block is
+// conflict-light already or nothing was gained; newidx[i] = 8 * position + group otherwise.
+bool assign_banks(int nn, const std::vector<int>& groups, std::vector<int>& newidx) {
+  const int ng = (int)(groups.size() / 8);
+  if (nn < 16 || ng == 0) return false;
+  static thread_local std::vector<unsigned char> cls;
+  static thread_local std::vector<int> gptr, glist;
+  cls.resize((size_t)nn);
+  for (int i = 0; i < nn; i++) cls[i] = (unsigned char)(i & 7);
+  auto cost_of = [&](int g) {
+    int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0}, mx = 0;
+    for (int m = 0; m < 8; m++) {
+      const int i = groups[(size_t)8 * g + m];
+      if (i >= 0) mx = std::max(mx, ++cnt[cls[i]]);
+    }
+    return mx;
+  };
+  long long cost0 = 0;
+  for (int g = 0; g < ng; g++) cost0 += cost_of(g);
+  if ((double)cost0 < 1.35 * ng) return false;
+  int nl_cap = 0;
+  for (int c : kStagedNL)
+    if (!nl_cap && c >= nn) nl_cap = c;
+  if (!nl_cap) return false;
+  const int cap = nl_cap / 8;
+  gptr.assign((size_t)nn + 1, 0);
+  for (size_t q = 0; q < groups.size(); q++)
+    if (groups[q] >= 0) gptr[(size_t)groups[q] + 1]++;
+  for (int i = 0; i < nn; i++) gptr[(size_t)i + 1] += gptr[i];
+  glist.resize((size_t)gptr[nn]);
+  {
+    std::vector<int> fill(gptr.begin(), gptr.end() - 1);
+    for (int g = 0; g < ng; g++)
+      for (int m = 0; m < 8; m++) {
+        const int i = groups[(size_t)8 * g + m];
+        if (i >= 0) glist[(size_t)fill[i]++] = g;
+      }
+  }
+  int size[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int i = 0; i < nn; i++) size[cls[i]]++;
+  long long cost = cost0;
+  for (int sweep = 0; sweep < 4; sweep++) {  // (single-node moves converge after two or three sweeps: 2.54 -> 2.14 wavefronts per read)
+    long long gained = 0;
+    for (int i = 0; i < nn; i++) {
+      const int c0 = cls[i];
+      int delta[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      for (int q = gptr[i]; q < gptr[(size_t)i + 1]; q++) {
+        const int g = glist[q];
+        int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int m = 0; m < 8; m++) {
+          const int j = groups[(size_t)8 * g + m];
+          if (j >= 0) cnt[cls[j]]++;
+        }
+        int before = 0;
+        for (int c = 0; c < 8; c++) before = std::max(before, cnt[c]);
+        cnt[c0]--;
+        int rest = 0;
+        for (int c = 0; c < 8; c++) rest = std::max(rest, cnt[c]);
+        for (int c = 0; c < 8; c++) delta[c] += std::max(rest, cnt[c] + 1) - before;
+      }
+      int best = c0;
+      for (int c = 0; c < 8; c++)
+        if (c != c0 && size[c] < cap && delta[c] < delta[best]) best = c;
+      if (best != c0) {
+        gained -= delta[best] - delta[c0];
+        cls[i] = (unsigned char)best;
+        size[c0]--;
+        size[best]++;
+      }
+    }
+    cost -= gained;
+    if (gained * 200 < cost) break;  // less than half a percent: done
+  }
+  if (cost >= cost0) return false;
+  int pos[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  newidx.resize((size_t)nn);
+  for (int i = 0; i < nn; i++) newidx[i] = 8 * pos[cls[i]]++ + cls[i];
+  return true;
+}
+
 }  // namespace
 
 void build_staged_plan_host(const Handle* h, const std::vector<int>& rows, int nblocks, int maxlen,
@@ -1105,6 +1188,10 @@ void build_staged_plan_host(const Handle* h, const std::vector<int>& rows, int n
   const int loc = h->loc, dim = h->dim;
   const int64_t* gk = (h->geokey.empty() || getenv("CGASM_STRIP_NOKEY")) ? nullptr : h->geokey.data();
   strip_search_prescan(loc, h->h_nd0.data(), h->n2e_ptr.data(), h->n2e.data(), h->h_findrm.data(), h->h_colm.data(), gk, h->n_nodes);
+  // bank groups are searched on meshes that are NOT a handful of congruence classes (there the geometric order is
+  // conflict-free and keeps the staging copies contiguous); CGASM_STRIP_BANKS=0/1 overrides
+  const bool bank_search = getenv("CGASM_STRIP_BANKS") ? atoi(getenv("CGASM_STRIP_BANKS")) != 0
+                                                        : !g_strip_search.load(std::memory_order_relaxed);
   constexpr int kTask = 128;  // blocks per task: fixed, so the layout does not depend on the thread count
   const int ntasks = (nblocks + kTask - 1) / kTask;
   out.nblocks = nblocks;
@@ -1121,7 +1208,7 @@ void build_staged_plan_host(const Handle* h, const std::vector<int>& rows, int n
   {
     std::vector<StripEntry> rp[kBR];
     NodeIndexMap map;
-    std::vector<int> bn;
+    std::vector<int> bn, bn2, groups, newidx;
     std::vector<std::pair<int64_t, int>> bk;
 #pragma omp for schedule(dynamic, 1)
     for (int task = 0; task < ntasks; task++) {
@@ -1160,6 +1247,37 @@ void build_staged_plan_host(const Handle* h, const std::vector<int>& rows, int n
         bn.resize(bk.size());
         for (size_t i = 0; i < bk.size(); i++) bn[i] = bk[i].second;
         for (size_t i = 0; i < bn.size(); i++) *map.slot(bn[i]) = (int)i;
+        if (bank_search && dim == 3) {
+          // Unstructured blocks: the 8 lanes of a quarter-warp LDS.128 read 8 unrelated nodes, 2.5 wavefronts per access
+          // with indices in any fixed order (8 balls into 8 bank groups). assign_banks moves nodes between the bank
+          // groups (index mod 8) to spread every (warp, step, quarter) group of reads; a no-op where the geometric order
+          // is conflict-free already (structured bricks).
+          groups.clear();
+          for (int w8 = 0; w8 < kBR / 8; w8++)
+            for (int k = 0; k < deg; k++) {
+              int g[8], ng = 0;
+              for (int l = 0; l < 8; l++) {
+                const int t = 8 * w8 + l;
+                if (k >= (int)rp[t].size()) continue;
+                const int i = *map.slot(key_of(rp[t][k].node));
+                bool dup = false;
+                for (int m = 0; m < ng; m++) dup |= g[m] == i;
+                if (!dup) g[ng++] = i;
+              }
+              if (ng > 1) {
+                for (int m = 0; m < 8; m++) groups.push_back(m < ng ? g[m] : -1);
+              }
+            }
+          if (assign_banks((int)bn.size(), groups, newidx)) {
+            int top = 0;
+            for (size_t i = 0; i < bn.size(); i++) top = std::max(top, newidx[i] + 1);
+            bn2.assign((size_t)top, -1);
+            for (size_t i = 0; i < bn.size(); i++) bn2[(size_t)newidx[i]] = bn[i];
+            bn.swap(bn2);
+            for (size_t i = 0; i < bn.size(); i++)
+              if (bn[i] >= 0) *map.slot(bn[i]) = (int)i;
+          }
+        }
         block_nn[b] = (int)bn.size();
         tn.insert(tn.end(), bn.begin(), bn.end());
         if (bn.size() > 4095) overflow++;

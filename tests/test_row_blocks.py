@@ -120,3 +120,23 @@ def test_unstructured_plan_stats_are_sane():
     st = plan_stats(syn.delaunay_mesh(6000, seed=2))
     assert 1.0 <= st["entries_per_pair"] < 1.6 and st["max_nodes_per_block"] <= 1024
     assert 1.0 <= st["walk_ratio"] < 1.6 and 1.0 <= st["compute_ratio"] < 2.0 and 1.0 <= st["lds128_wavefronts"] <= 8.0
+
+
+def test_bank_groups_are_searched_on_unstructured_meshes_only(monkeypatch):
+    """Delaunay mesh: no two links are congruent, the 8 lanes of a quarter-warp read 8 unrelated staged records, 2.5
+    wavefronts per LDS.128 with the block's nodes in any fixed order. assign_banks (strip_plan.cpp) moves nodes between
+    the bank groups (local index mod 8): fewer wavefronts, the same strips. A structured mesh keeps its geometric order
+    (near conflict-free, contiguous staging copies)."""
+    mesh = syn.delaunay_mesh(20000, seed=4)
+    on = plan_stats(mesh)
+    monkeypatch.setenv("CGASM_STRIP_BANKS", "0")
+    off = plan_stats(mesh)
+    monkeypatch.delenv("CGASM_STRIP_BANKS")
+    assert on["lds128_wavefronts"] < 0.9 * off["lds128_wavefronts"], (on, off)
+    for k in ("entries_per_pair", "walk_ratio", "compute_ratio"):
+        assert on[k] == off[k]
+    box = syn.box_mesh((24, 24, 24))
+    a = plan_stats(box)
+    monkeypatch.setenv("CGASM_STRIP_BANKS", "0")
+    b = plan_stats(box)
+    assert a == b
