@@ -5,7 +5,7 @@ Values: the 4-point (triangle) and 5-point (tetrahedron) degree-3 rules of Strou
 tabulated in femtools/Quadrature.F90:690-708,951-970, with the point order produced by
 expand_quadrature_template (:572-605); P1 shape functions n(i,g) = l(g,i)
 (femtools/Elements.F90:511-513) and dn(i,g,k) = delta_ik, dn(loc,g,k) = -1 (:615-717).
-tests/test_tables.py checks them bit-for-bit against the oracle's restatement.
+tests/test_abi.py::test_product_tables_equal_oracle_tables checks them bit-for-bit against the oracle's restatement.
 """
 import numpy as np
 
