@@ -201,6 +201,11 @@ def cpu_baseline_block(cells):
     rate, threads, ms, ne = cpu_assembly_rate(cells, 3, 1)
     c1 = max(16, cells // 2)
     r1, _, ms1, ne1 = cpu_assembly_rate(c1, 1, 0, threads=1)
+    # the oracle and libcgasm share one OpenMP runtime: give the threads back, or every host set-up that follows
+    # (the configs block) runs single-threaded -- it did until GPU call 48 of round 2 found it (library_setup_s 4-17 s
+    # where the same calls take 0.5-2 s)
+    from oracle import oracle as orc
+    orc.set_threads(len(os.sched_getaffinity(0)))
     return {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
             "build": "oracle/liborc_fast.so: gcc -O3 -march=native -fopenmp (FMA contraction on), built on this host",
             "sample": "%d^3 x 6 = %d Kuhn tets, 3 timed passes of momentum+tracer, OpenMP over the reference colouring "
