@@ -218,3 +218,13 @@ def test_emulated_absorption_pass_matches_oracle(orc, name):
         assert rel_err(got, ref["big_m"][d]) < TOL and row_rel_err(got, ref["big_m"][d], findrm) < TOL
         assert rel_err(base["rhs"][:, d] + add["rhs"][:, d], ref["rhs"][:, d]) < TOL
     assert rel_err(base["masslump"], ref["masslump"]) < TOL
+
+
+def test_strip_search_leaves_unstructured_meshes_to_the_greedy(monkeypatch):
+    # strip_search_prescan: a Delaunay mesh's links are all different (no congruence classes to amortise a search over),
+    # so the default plan is the greedy's, entry for entry
+    mesh = syn.delaunay_mesh(3000, dim=3, seed=9)
+    rp_default, ent_default = se.strip_plan(mesh)
+    monkeypatch.setenv("CGASM_STRIP_SEARCH", "0")
+    rp_greedy, ent_greedy = se.strip_plan(mesh)
+    assert np.array_equal(rp_default, rp_greedy) and np.array_equal(ent_default, ent_greedy)
