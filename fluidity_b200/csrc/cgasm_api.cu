@@ -521,8 +521,7 @@ int cgasm_create(int* id, int device, int dim, int loc, int ngi, int n_nodes, in
       cudaMemset(h->d_rec0, 0, sizeof(double4) * (size_t)n_nodes) != cudaSuccess ||
       cudaMemset(h->d_rec1, 0, sizeof(double4) * (size_t)n_nodes) != cudaSuccess ||
       cudaMemset(h->d_rec2, 0, sizeof(double4) * (size_t)n_nodes) != cudaSuccess ||
-      cudaMemcpy(h->d_ndglno, h->h_nd0.data(), sizeof(int4) * (size_t)n_elements,
-                 cudaMemcpyHostToDevice) != cudaSuccess) {
+      cg_upload(h->d_ndglno, h->h_nd0.data(), sizeof(int4) * (size_t)n_elements) != cudaSuccess) {
     set_error(std::string("cgasm_create: ") + cudaGetErrorString(cudaGetLastError()));
     return fail(CGASM_ECUDA);
   }
@@ -644,8 +643,7 @@ int cgasm_build_colouring(int id, int* ncolours) {
   free_dev(h->d_colour_elements);
   h->d_colour_elements = nullptr;
   CG_CUDA(cudaMalloc(&h->d_colour_elements, sizeof(int) * (size_t)h->n_elements));
-  CG_CUDA(cudaMemcpy(h->d_colour_elements, h->h_colour_elements.data(), sizeof(int) * (size_t)h->n_elements,
-                     cudaMemcpyHostToDevice));
+  CG_CUDA(cg_upload(h->d_colour_elements, h->h_colour_elements.data(), sizeof(int) * (size_t)h->n_elements));
   if (ncolours) *ncolours = nc;
   return CGASM_OK;
 }
@@ -687,8 +685,7 @@ int cgasm_set_colouring(int id, int ncolours, const int* colour_ptr, const int* 
   free_dev(h->d_colour_elements);
   h->d_colour_elements = nullptr;
   CG_CUDA(cudaMalloc(&h->d_colour_elements, sizeof(int) * (size_t)h->n_elements));
-  CG_CUDA(cudaMemcpy(h->d_colour_elements, h->h_colour_elements.data(), sizeof(int) * (size_t)h->n_elements,
-                     cudaMemcpyHostToDevice));
+  CG_CUDA(cg_upload(h->d_colour_elements, h->h_colour_elements.data(), sizeof(int) * (size_t)h->n_elements));
   return CGASM_OK;
 }
 

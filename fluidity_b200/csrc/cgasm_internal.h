@@ -146,6 +146,17 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
     return (code);               \
   } while (0)
 
+// Host -> device copy that has LANDED when it returns. Plain cudaMemcpy does not promise that for pageable sources: it
+// returns once the data is staged, the DMA is ordered in the legacy default stream only, and the handles' streams are
+// cudaStreamNonBlocking -- a kernel launched there right after the call could read the destination before its tail had
+// arrived. Seen at the end of round 2 as a once-in-a-hundred-handles failure of the two-pass GATHER path on the
+// cube-parallel fixture (wrong rows at the high node numbers, illegal addresses inside gather_pairs_kernel), never under
+// compute-sanitizer or cuda-gdb, which serialise the copies (scripts/stress_surface.py reproduces it in seconds).
+inline cudaError_t cg_upload(void* dst, const void* src, size_t bytes) {
+  const cudaError_t e = cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice);
+  return e != cudaSuccess ? e : cudaStreamSynchronize(cudaStreamLegacy);
+}
+
 Handle* get_handle(int id);
 
 // host_mesh.cpp

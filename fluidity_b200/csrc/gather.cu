@@ -237,12 +237,12 @@ static int build_walk_plan(Handle* h, GatherPlan* P, const std::vector<int>& row
     fprintf(stderr, "[cgasm] walk plan: %.3f entries per (row, element) pair, %lld padded entries\n",
             P->walk_entries_per_pair, P->n_walk);
   CG_CUDA(cudaMalloc(&P->d_walk_ptr, sizeof(long long) * walk_ptr.size()));
-  CG_CUDA(cudaMemcpy(P->d_walk_ptr, walk_ptr.data(), sizeof(long long) * walk_ptr.size(), cudaMemcpyHostToDevice));
+  CG_CUDA(cg_upload(P->d_walk_ptr, walk_ptr.data(), sizeof(long long) * walk_ptr.size()));
   CG_CUDA(cudaMalloc(&P->d_walk, sizeof(int2) * walk.size()));
-  CG_CUDA(cudaMemcpy(P->d_walk, walk.data(), sizeof(int2) * walk.size(), cudaMemcpyHostToDevice));
+  CG_CUDA(cg_upload(P->d_walk, walk.data(), sizeof(int2) * walk.size()));
   if (!P->d_own_slot) {  // the STRIP plan may have made it already
     CG_CUDA(cudaMalloc(&P->d_own_slot, own_slot.size()));
-    CG_CUDA(cudaMemcpy(P->d_own_slot, own_slot.data(), own_slot.size(), cudaMemcpyHostToDevice));
+    CG_CUDA(cg_upload(P->d_own_slot, own_slot.data(), own_slot.size()));
   }
   return CGASM_OK;
 }
@@ -290,9 +290,9 @@ int gather_build_rows(Handle* h) {
     return fail(CGASM_EUNSUPPORTED);
   }
   if (cudaMalloc(&P->d_rows, sizeof(int) * rows.size()) != cudaSuccess ||
-      cudaMemcpy(P->d_rows, rows.data(), sizeof(int) * rows.size(), cudaMemcpyHostToDevice) != cudaSuccess ||
+      cg_upload(P->d_rows, rows.data(), sizeof(int) * rows.size()) != cudaSuccess ||
       cudaMalloc(&P->d_block_ptr, sizeof(long long) * block_ptr.size()) != cudaSuccess ||
-      cudaMemcpy(P->d_block_ptr, block_ptr.data(), sizeof(long long) * block_ptr.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+      cg_upload(P->d_block_ptr, block_ptr.data(), sizeof(long long) * block_ptr.size()) != cudaSuccess) {
     set_error(std::string("gather_build_rows: ") + cudaGetErrorString(cudaGetLastError()));
     return fail(CGASM_ECUDA);
   }
@@ -316,8 +316,8 @@ int gather_build_pairs(Handle* h) {
   CG_CUDA(cudaMalloc(&d_n2e_ptr, sizeof(long long) * ((size_t)n + 1)));
   CG_CUDA(cudaMalloc(&d_n2e, sizeof(int) * std::max<size_t>(h->n2e.size(), 1)));
   static_assert(sizeof(long long) == sizeof(int64_t), "int64_t is long long");
-  cudaError_t e1 = cudaMemcpy(d_n2e_ptr, h->n2e_ptr.data(), sizeof(long long) * ((size_t)n + 1), cudaMemcpyHostToDevice);
-  cudaError_t e2 = cudaMemcpy(d_n2e, h->n2e.data(), sizeof(int) * h->n2e.size(), cudaMemcpyHostToDevice);
+  cudaError_t e1 = cg_upload(d_n2e_ptr, h->n2e_ptr.data(), sizeof(long long) * ((size_t)n + 1));
+  cudaError_t e2 = cg_upload(d_n2e, h->n2e.data(), sizeof(int) * h->n2e.size());
   if (e1 == cudaSuccess && e2 == cudaSuccess) {
     gather_pairs_kernel<<<P->nblocks, kBR, 0, h->stream>>>(P->nblocks, h->loc, P->d_rows, P->d_block_ptr, d_n2e_ptr,
                                                           d_n2e, h->d_ndglno, h->d_findrm, h->d_colm, P->d_pairs,

@@ -169,7 +169,7 @@ __global__ void halo_mark_kernel(int n, const int* __restrict__ node, const int*
 
 static int upload_ints(int** d, const std::vector<int>& v) {
   CG_CUDA(cudaMalloc(d, sizeof(int) * std::max<size_t>(v.size(), 1)));
-  if (!v.empty()) CG_CUDA(cudaMemcpy(*d, v.data(), sizeof(int) * v.size(), cudaMemcpyHostToDevice));
+  if (!v.empty()) CG_CUDA(cg_upload(*d, v.data(), sizeof(int) * v.size()));
   return CGASM_OK;
 }
 

@@ -294,9 +294,9 @@ static int strip_build_global(Handle* h) {
   }
   P->strip_entries_per_pair = h->n2e.empty() ? 0.0 : (double)total_real / (double)h->n2e.size();
   CG_CUDA(cudaMalloc(&P->d_strip_ptr, sizeof(long long) * ptr.size()));
-  CG_CUDA(cudaMemcpy(P->d_strip_ptr, ptr.data(), sizeof(long long) * ptr.size(), cudaMemcpyHostToDevice));
+  CG_CUDA(cg_upload(P->d_strip_ptr, ptr.data(), sizeof(long long) * ptr.size()));
   CG_CUDA(cudaMalloc(&P->d_strip, sizeof(int2) * ent.size()));
-  CG_CUDA(cudaMemcpy(P->d_strip, ent.data(), sizeof(int2) * ent.size(), cudaMemcpyHostToDevice));
+  CG_CUDA(cg_upload(P->d_strip, ent.data(), sizeof(int2) * ent.size()));
   if (!P->d_own_slot) {
     std::vector<unsigned char> own_slot(rows.size(), 0);
     for (size_t q = 0; q < rows.size(); q++) {
@@ -306,7 +306,7 @@ static int strip_build_global(Handle* h) {
       own_slot[q] = (unsigned char)(std::lower_bound(cb, (const int*)h->h_colm.data() + h->h_findrm[r + 1], r) - cb);
     }
     CG_CUDA(cudaMalloc(&P->d_own_slot, own_slot.size()));
-    CG_CUDA(cudaMemcpy(P->d_own_slot, own_slot.data(), own_slot.size(), cudaMemcpyHostToDevice));
+    CG_CUDA(cg_upload(P->d_own_slot, own_slot.data(), own_slot.size()));
   }
   return CGASM_OK;
 }

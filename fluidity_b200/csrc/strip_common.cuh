@@ -10,6 +10,16 @@ namespace cgasm {
 #define CGASM_V_SEPARATE_SUMS 0
 #endif
 constexpr bool kStripSeparateSums = CGASM_V_SEPARATE_SUMS != 0;  // A/B switch (scripts/ab_kernels.py)
+// Diagonal by row sum (3-D staged kernels): advection and viscosity / diffusion have zero row sums (sum_j gradN_j = 0), so
+// the diagonal entry of a row is minus the sum of its off-diagonal ones -- taken when a column's accumulated entry is
+// flushed (one DADD per strip entry) instead of a dot product u . sc per (row, element) pair (four FP64). The reference
+// computes A_ii = v_i . gradN_i directly; the difference is rounding (1e-16 of the row's largest entry).
+#ifndef CGASM_V_ROWSUM
+#define CGASM_V_ROWSUM 1
+#endif
+template <int DIM>
+constexpr bool kStripRowSum = (DIM == 3) && (CGASM_V_ROWSUM != 0);
+
 // Carried cross product (window_geom_carry): measured on the B200 (profiles/r2_ab_carry.txt) -1.1 ... -3.9 % for the tracer
 // kernel (118 registers: room for the three carried values), +1.3 ... +3 % for the momentum kernel (at its 128-register
 // ceiling): on for the tracer, off for the momentum loop. CGASM_V_CARRY=0/1 forces both (A/B builds).
@@ -194,7 +204,7 @@ __device__ __forceinline__ void window_geom_carry(const double (&X)[N][3], const
   for (int a = 0; a < 3; a++) g.sc[a] = (g.c[0][a] + g.c[1][a]) + g.c[2][a];
 }
 
-template <int DIM, int N, int QC, bool FULLV>
+template <int DIM, int N, int QC, bool FULLV, bool ROWSUM = false>
 __device__ __forceinline__ void mom_terms(MomState<DIM, N>& s, const StripConsts& k_, const WindowGeom<DIM>& g) {
   // density-weighted mass row M_0k = |J| sum_l Q_0kl rho_l (without |J|): M_00 = Qa rho_0 + Qaab S,
   // M_0k = Qd (rho_0 + rho_k) + Qabc S with S = rho_0 + sum_k rho_k; the products with rho_0 are row constants
@@ -238,10 +248,12 @@ __device__ __forceinline__ void mom_terms(MomState<DIM, N>& s, const StripConsts
       for (int a = 0; a < DIM; a++) ak = fma(u[a], g.c[k][a], ak);
       s.A[WQ(k)] = ak;
     }
-    double tot = u[0] * g.sc[0];
+    if constexpr (!ROWSUM) {  // (ROWSUM: the caller subtracts every flushed column from a0)
+      double tot = u[0] * g.sc[0];
 #pragma unroll
-    for (int a = 1; a < DIM; a++) tot = fma(u[a], g.sc[a], tot);
-    s.a0 -= tot;
+      for (int a = 1; a < DIM; a++) tot = fma(u[a], g.sc[a], tot);
+      s.a0 -= tot;
+    }
   } else {
     double tot = 0.0;
 #pragma unroll
@@ -267,11 +279,11 @@ __device__ __forceinline__ void mom_terms(MomState<DIM, N>& s, const StripConsts
   }
 }
 
-template <int DIM, int N, int QC, bool FULLV>
+template <int DIM, int N, int QC, bool FULLV, bool ROWSUM = false>
 __device__ __forceinline__ void mom_compute(MomState<DIM, N>& s, const StripConsts& k_) {
   WindowGeom<DIM> g;
   window_geom<DIM, N, QC>(s.X, g);
-  mom_terms<DIM, N, QC, FULLV>(s, k_, g);
+  mom_terms<DIM, N, QC, FULLV, ROWSUM>(s, k_, g);
 }
 
 // rows of the warp -> global memory, LPR = 1 << lpr_shift lanes per row
@@ -314,7 +326,7 @@ __device__ __forceinline__ void adv_row_const(const StripConsts& k_, const doubl
 // isotropic diffusivity), :1125,1200 (rhs -= (A + D) T)
 // the tracer terms of one window on explicit operands (the fused momentum + tracer kernel shares the momentum state's
 // velocity buffers and the geometry)
-template <int DIM, int N, int QC, bool FULLV>
+template <int DIM, int N, int QC, bool FULLV, bool ROWSUM = false>
 __device__ __forceinline__ void adv_terms(const StripConsts& k_, const WindowGeom<DIM>& g, const double (&U)[N][DIM],
                                           const double (&cU0)[DIM], double (&A)[N], double (&C)[N], double& a0, double& c0) {
   // v = (Pd - Po) nu_0 + Po (nu_0 + sum_k nu_k); cU0 = Pd nu_0 is the same for every element of the row
@@ -341,10 +353,12 @@ __device__ __forceinline__ void adv_terms(const StripConsts& k_, const WindowGeo
       A[WQ(k)] = ak;
       C[WQ(k)] += ad;
     }
-    double tot = u[0] * g.sc[0];
+    if constexpr (!ROWSUM) {
+      double tot = u[0] * g.sc[0];
 #pragma unroll
-    for (int a = 1; a < DIM; a++) tot = fma(u[a], g.sc[a], tot);
-    a0 -= tot;
+      for (int a = 1; a < DIM; a++) tot = fma(u[a], g.sc[a], tot);
+      a0 -= tot;
+    }
   } else {
     double tot = 0.0;
 #pragma unroll
@@ -361,11 +375,11 @@ __device__ __forceinline__ void adv_terms(const StripConsts& k_, const WindowGeo
   c0 += ad;
 }
 
-template <int DIM, int N, int QC, bool FULLV>
+template <int DIM, int N, int QC, bool FULLV, bool ROWSUM = false>
 __device__ __forceinline__ void adv_compute(AdvState<DIM, N>& s, const StripConsts& k_) {
   WindowGeom<DIM> g;
   window_geom<DIM, N, QC>(s.X, g);
-  adv_terms<DIM, N, QC, FULLV>(k_, g, s.U, s.cU0, s.A, s.C, s.a0, s.c0);
+  adv_terms<DIM, N, QC, FULLV, ROWSUM>(k_, g, s.U, s.cU0, s.A, s.C, s.a0, s.c0);
 }
 
 // rhs -= entry * T(column) for the column leaving the FIFO (a = its accumulated, unscaled entry, tk = its T) ...

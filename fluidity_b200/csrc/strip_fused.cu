@@ -67,6 +67,10 @@ __device__ __forceinline__ void fused_step(MomState<DIM, DIM>& s, TracerSide<DIM
 #pragma unroll
     for (int d = 0; d < DIM; d++) rh[d] = fma(-a, on[d], rh[d]);
     adv_evict_rhs(q.rhs, q.A[QC], q.T[QC]);
+    if constexpr (kStripRowSum<DIM>) {  // as the two separate kernels do (bitwise the same diagonals)
+      s.a0 -= a;
+      q.a0 -= q.A[QC];
+    }
     s.A[QC] = 0.0;
     q.A[QC] = 0.0;
     q.C[QC] = 0.0;
@@ -77,8 +81,8 @@ __device__ __forceinline__ void fused_step(MomState<DIM, DIM>& s, TracerSide<DIM
   if (en & kStagedCompute) {
     WindowGeom<DIM> g;
     window_geom<DIM, DIM, QC>(s.X, g);
-    mom_terms<DIM, DIM, QC, false>(s, km, g);
-    adv_terms<DIM, DIM, QC, false>(ka, g, s.U, q.cU0, q.A, q.C, q.a0, q.c0);
+    mom_terms<DIM, DIM, QC, false, kStripRowSum<DIM>>(s, km, g);
+    adv_terms<DIM, DIM, QC, false, kStripRowSum<DIM>>(ka, g, s.U, q.cU0, q.A, q.C, q.a0, q.c0);
   }
 }
 
@@ -155,6 +159,10 @@ staged_fused_kernel(const StripConsts km, const StripConsts ka, const StagedView
     acc_t[m >> 16] += s.A[k];
     acc2_t[m >> 16] += fma(ka.dtt, q.A[k], ka.mPo * q.C[k]);
     adv_evict_rhs(q.rhs, q.A[k], q.T[k]);
+    if constexpr (kStripRowSum<DIM>) {
+      s.a0 -= s.A[k];
+      q.a0 -= q.A[k];
+    }
     double o[DIM];
     load_oldu<DIM, NL>(nsa, m & 0xfff0u, o);
 #pragma unroll

@@ -79,6 +79,7 @@ __device__ __forceinline__ void smom_step(MomState<DIM, DIM>& s, double (&rh)[DI
     sts64(sa, slot + a);
 #pragma unroll
     for (int d = 0; d < DIM; d++) rh[d] = fma(-a, on[d], rh[d]);
+    if constexpr (kStripRowSum<DIM>) s.a0 -= a;
     s.A[QC] = 0.0;
   }
 #pragma unroll
@@ -89,12 +90,12 @@ __device__ __forceinline__ void smom_step(MomState<DIM, DIM>& s, double (&rh)[DI
     if (en & kStagedCompute) {
       WindowGeom<3> g;
       window_geom_carry<DIM, QC>(s.X, cc, cn, g);
-      mom_terms<DIM, DIM, QC, FULLV>(s, k_, g);
+      mom_terms<DIM, DIM, QC, FULLV, kStripRowSum<DIM>>(s, k_, g);
     }
 #pragma unroll
     for (int a = 0; a < 3; a++) cc[a] = cn[a];
   } else {
-    if (en & kStagedCompute) mom_compute<DIM, DIM, QC, FULLV>(s, k_);
+    if (en & kStagedCompute) mom_compute<DIM, DIM, QC, FULLV, kStripRowSum<DIM>>(s, k_);
   }
 }
 
@@ -161,6 +162,7 @@ staged_momentum_kernel(const StripConsts k_, const StagedView P, const double4* 
   for (int q = 0; q < DIM; q++) {
     const unsigned m = (unsigned)s.meta[q];
     acc_t[m >> 16] += s.A[q];
+    if constexpr (kStripRowSum<DIM>) s.a0 -= s.A[q];
     double o[DIM];
     load_oldu<DIM, NL>(nsa, m & 0xfff0u, o);
 #pragma unroll
@@ -198,6 +200,7 @@ __device__ __forceinline__ void sadv_step(AdvState<DIM, DIM>& s, double (&sg)[AB
   load_rec<DIM, NL>(nb, 0, s.X[QC], s.T[QC]);
   load_rec<DIM, NL>(nb, 1, s.U[QC], unused);
   sts64(sa, slot + fma(k_.dtt, s.A[QC], k_.mPo * s.C[QC]));
+  if constexpr (kStripRowSum<DIM> && !ABS) s.a0 -= s.A[QC];
   s.A[QC] = 0.0;
   s.C[QC] = 0.0;
   if constexpr (ABS) {
@@ -216,14 +219,14 @@ __device__ __forceinline__ void sadv_step(AdvState<DIM, DIM>& s, double (&sg)[AB
     if (en & kStagedCompute) {
       WindowGeom<3> g;
       window_geom_carry<DIM, QC>(s.X, s.cc, cn, g);
-      adv_terms<DIM, DIM, QC, FULLV>(k_, g, s.U, s.cU0, s.A, s.C, s.a0, s.c0);
+      adv_terms<DIM, DIM, QC, FULLV, kStripRowSum<DIM>>(k_, g, s.U, s.cU0, s.A, s.C, s.a0, s.c0);
     }
 #pragma unroll
     for (int a = 0; a < 3; a++) s.cc[a] = cn[a];
   } else {
     if (en & kStagedCompute) {
       if constexpr (ABS) adv_compute_abs<DIM, DIM, QC, FULLV>(s, sg, sq, ox, k_);
-      else adv_compute<DIM, DIM, QC, FULLV>(s, k_);
+      else adv_compute<DIM, DIM, QC, FULLV, kStripRowSum<DIM>>(s, k_);
     }
   }
 }
@@ -301,6 +304,7 @@ staged_advdiff_kernel(const StripConsts k_, const StagedView P, const double4* _
   for (int q = 0; q < DIM; q++) {
     acc_t[(unsigned)s.meta[q] >> 16] += fma(k_.dtt, s.A[q], k_.mPo * s.C[q]);
     adv_evict_rhs(s.rhs, s.A[q], s.T[q]);
+    if constexpr (kStripRowSum<DIM> && !ABS) s.a0 -= s.A[q];
   }
   adv_finish_rhs(s.rhs, s.a0, s.T0);
   acc_t[own * kAS] += fma(k_.dtt, s.a0, k_.mPd * s.c0);

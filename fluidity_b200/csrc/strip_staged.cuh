@@ -258,8 +258,8 @@ static inline const GatherPlan::StagedClass* staged_classes(Handle* h, int bytes
     c.n_large = (int)large.size();
     if (cudaMalloc(&c.d_small, sizeof(int) * std::max<size_t>(1, small.size())) != cudaSuccess ||
         cudaMalloc(&c.d_large, sizeof(int) * std::max<size_t>(1, large.size())) != cudaSuccess ||
-        cudaMemcpy(c.d_small, small.data(), sizeof(int) * small.size(), cudaMemcpyHostToDevice) != cudaSuccess ||
-        cudaMemcpy(c.d_large, large.data(), sizeof(int) * large.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+        cg_upload(c.d_small, small.data(), sizeof(int) * small.size()) != cudaSuccess ||
+        cg_upload(c.d_large, large.data(), sizeof(int) * large.size()) != cudaSuccess) {
       cudaGetLastError();
       if (c.d_small) cudaFree(c.d_small);
       if (c.d_large) cudaFree(c.d_large);

@@ -77,7 +77,7 @@ void tiles_free(Handle* h) {
 template <class T>
 static int upload(T** d, const std::vector<T>& v) {
   CG_CUDA(cudaMalloc(d, sizeof(T) * std::max<size_t>(v.size(), 1)));
-  if (!v.empty()) CG_CUDA(cudaMemcpy(*d, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice));
+  if (!v.empty()) CG_CUDA(cg_upload(*d, v.data(), sizeof(T) * v.size()));
   return CGASM_OK;
 }
 
