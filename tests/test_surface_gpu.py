@@ -282,3 +282,38 @@ def test_vector_dirichlet_lifting_and_velocity_correction(orc, name):
     assert rel_err(got_u, want_u) < TOL
     got_u2 = asm.correct_masslumped_velocity(iml, dp, u0.copy(), ct_m=ref["ct_m"])
     assert (got_u2 == want_u).all()      # same inputs, same summation order, explicit multiplies and adds: bitwise
+
+
+def test_many_handles_in_one_process_give_the_same_bits(orc):
+    """Regression test of the upload race found at the end of round 2: plan arrays went up with plain cudaMemcpy from
+    pageable memory, which returns once the data is STAGED -- its DMA is ordered in the legacy stream only, the handles'
+    streams are non-blocking, so a kernel launched right after could read a destination whose tail had not landed. It took
+    ~100 handles in one process to show (wrong rows at the high node numbers of this mesh on the two-pass GATHER path,
+    sometimes an illegal address in gather_pairs_kernel). scripts/stress_surface.py is the long version."""
+    mesh = load_golden_mesh("cube-parallel")
+    fs = syn.standard_fields(mesh)
+    o = abi.common_momentum_opts(lump_mass=1, integrate_advection_by_parts=1)   # outside the STRIP kernels: pair lists + two passes
+    first = None
+    keep = []
+    for it in range(160):
+        asm = cgasm.Assembler(mesh, tables.p1_tables(3))
+        asm.build_sparsity()
+        asm.set_fields(fs)
+        asm.set_scatter(abi.SCATTER_GATHER)
+        asm.momentum_dev(o)
+        got = asm.momentum_fetch()
+        if first is None:
+            first = got
+            findrm, colm, _ = asm.get_sparsity()
+            ref = orc.assemble_momentum(mesh, fs, o, findrm, colm)
+            for d in range(3):
+                assert rel_err(got["big_m"][d], ref["big_m"][d]) < TOL
+        else:
+            for k in ("big_m", "rhs", "masslump"):
+                assert np.array_equal(got[k], first[k]), "handle %d: %s differs from the first handle's" % (it, k)
+        if it % 3 == 0:
+            keep.append(asm)   # some handles stay open, as in the rest of the suite
+        else:
+            asm.close()
+    for asm in keep:
+        asm.close()
